@@ -1,0 +1,137 @@
+"""ctypes bindings for the oracle libraries (TEST INFRASTRUCTURE ONLY).
+
+  liboracle_lra.so  -- the plain-C restatement in oracle/*.c ("port")
+  libref_lra.so     -- extern "C" wrappers around the UNMODIFIED reference headers ("reference");
+                       exists only where /root/reference was present at build time (or was shipped
+                       prebuilt in oracle/_ref/ to the GPU box).
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+REFERENCE_SRC = "/root/reference"
+
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+def build(want_ref=None):
+    """(Re)build the oracle libraries.  The reference-backed targets are built only when the reference
+    sources are present; otherwise the prebuilt files in oracle/_ref/ are used as they are."""
+    if want_ref is None:
+        want_ref = os.path.isdir(REFERENCE_SRC)
+    targets = ["restatement"] + (["ref"] if want_ref else [])
+    subprocess.run(["make", "-C", HERE, "-j4"] + targets, check=True, stdout=subprocess.DEVNULL)
+
+
+def _load(name):
+    path = os.path.join(REF_DIR, name)
+    if not os.path.exists(path):
+        return None
+    return C.CDLL(path)
+
+
+_port = None
+_ref = None
+
+
+def port():
+    global _port
+    if _port is None:
+        if not os.path.exists(os.path.join(REF_DIR, "liboracle_lra.so")):
+            build(want_ref=False)
+        _port = _load("liboracle_lra.so")
+        L = _port
+        L.lra_oracle_aog.restype = C.c_int
+        L.lra_oracle_aog.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     _u32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.lra_oracle_aog_batch.restype = C.c_int
+        L.lra_oracle_aog_batch.argtypes = [_u8p, _u8p, _u32p, _u32p, _i32p, _i32p, _i32p, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, _i32p, _i32p, _i64p, _i32p, _u32p, _i32p]
+    return _port
+
+
+def ref():
+    """The reference-backed library, or None if it was never built."""
+    global _ref
+    if _ref is None:
+        L = _load("libref_lra.so")
+        if L is None:
+            return None
+        L.ref_aog.restype = C.c_int
+        L.ref_aog.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                              _u32p, C.c_int, C.POINTER(C.c_int)]
+        L.ref_aog_batch.restype = C.c_int
+        L.ref_aog_batch.argtypes = [_u8p, _u8p, _u32p, _u32p, _i32p, _i32p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    _i32p, _i32p, _i64p, C.c_void_p, C.c_int]
+        _ref = L
+    return _ref
+
+
+# ---------------------------------------------------------------- a18 AffineOneGapAlign
+
+def aog_port(q, t, m, mm, indel, k):
+    """One job through the C restatement.  Returns (score, blocks[n,3] uint32, status)."""
+    cap = min(len(q), len(t)) + 2
+    blocks = np.zeros(cap * 3, dtype=np.uint32)
+    nb, st = C.c_int(0), C.c_int(0)
+    s = port().lra_oracle_aog(bytes(q), len(q), bytes(t), len(t), m, mm, indel, k, blocks, cap, C.byref(nb), C.byref(st))
+    return s, blocks[: 3 * min(nb.value, cap)].reshape(-1, 3).copy(), st.value
+
+
+def aog_ref(q, t, m, mm, indel, k):
+    """One job through the real reference header.  Returns (score, blocks[n,3])."""
+    cap = min(len(q), len(t)) + 2
+    blocks = np.zeros(cap * 3, dtype=np.uint32)
+    nb = C.c_int(0)
+    s = ref().ref_aog(bytes(q), len(q), bytes(t), len(t), m, mm, indel, k, blocks, cap, C.byref(nb))
+    return s, blocks[: 3 * min(nb.value, cap)].reshape(-1, 3).copy()
+
+
+def block_layout(q_len, t_len):
+    """Per-job worst-case block capacity and exclusive prefix (shared by all batch back-ends)."""
+    cap = (np.minimum(q_len, t_len) + 1).astype(np.int32)
+    off = np.zeros(len(cap), dtype=np.int64)
+    np.cumsum(cap[:-1], out=off[1:])
+    return cap, off, int(cap.sum())
+
+
+def aog_batch_port(q_arena, t_arena, q_off, t_off, q_len, t_len, k, m, mm, indel, want_blocks=True):
+    n = len(q_off)
+    cap, off, total = block_layout(q_len, t_len)
+    score = np.zeros(n, np.int32); nb = np.zeros(n, np.int32); st = np.zeros(n, np.int32)
+    blocks = np.zeros(max(1, total) * 3, np.uint32)
+    port().lra_oracle_aog_batch(q_arena, t_arena, q_off, t_off, q_len, t_len, k, n, m, mm, indel, score, nb, off, cap,
+                                blocks, st)
+    return score, nb, off, blocks.reshape(-1, 3), st
+
+
+def aog_batch_ref(q_arena, t_arena, q_off, t_off, q_len, t_len, k, m, mm, indel, nthreads=1, want_blocks=True):
+    n = len(q_off)
+    cap, off, total = block_layout(q_len, t_len)
+    score = np.zeros(n, np.int32); nb = np.zeros(n, np.int32)
+    blocks = np.zeros(max(1, total) * 3, np.uint32) if want_blocks else None
+    ref().ref_aog_batch(q_arena, t_arena, q_off, t_off, q_len, t_len, k, n, m, mm, indel, score, nb, off,
+                        blocks.ctypes.data if want_blocks else None, nthreads)
+    return score, nb, off, (blocks.reshape(-1, 3) if want_blocks else None)
+
+
+# ---------------------------------------------------------------- capture files (oracle/lra_capture.cpp)
+
+def read_aog_capture(path, limit=None):
+    """Parse an LRA_CAPTURE_AOG file -> list of dict(q,t,m,mm,indel,k,score,blocks)."""
+    data = open(path, "rb").read()
+    out, p = [], 0
+    while p < len(data) and (limit is None or len(out) < limit):
+        h = np.frombuffer(data, dtype=np.int32, count=8, offset=p); p += 32
+        ql, tl, m, mm, indel, k, score, nb = (int(x) for x in h)
+        q = data[p:p + ql]; p += ql
+        t = data[p:p + tl]; p += tl
+        b = np.frombuffer(data, dtype=np.uint32, count=3 * nb, offset=p).reshape(-1, 3).copy(); p += 12 * nb
+        out.append(dict(q=q, t=t, m=m, mm=mm, indel=indel, k=k, score=score, blocks=b))
+    return out

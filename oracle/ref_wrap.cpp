@@ -1,0 +1,75 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into, loaded by, or shipped with liblra_b200.so.
+//
+// Thin extern "C" entry points around the UNMODIFIED reference headers, compiled from
+// /root/reference where they lie (see oracle/Makefile) into oracle/_ref/libref_lra.so.
+// Used (a) to pin the C restatement in oracle/*.c, (b) to generate tests/golden/*, and
+// (c) as the "reference" CPU arm of bench.py (cpu_baseline.kind == "reference").
+//
+// Reference entry points wrapped here:
+//   AffineOneGapAlign            AffineOneGapAlign.h:157-649
+#include <string>
+#include <vector>
+#include <thread>
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include "AffineOneGapAlign.h"
+
+extern "C" {
+
+// One call. blocks_out receives up to cap (qPos,tPos,length) triples; *n_blocks the true count.
+int ref_aog(const char *q, int qLen, const char *t, int tLen, int m, int mm, int indel, int k,
+            uint32_t *blocks_out, int cap, int *n_blocks) {
+  std::string qs(q, qLen), ts(t, tLen);
+  Alignment aln;
+  AffineAlignBuffers buf;
+  int score = AffineOneGapAlign(qs, qLen, ts, tLen, m, mm, indel, k, aln, buf);
+  int n = (int)aln.blocks.size();
+  *n_blocks = n;
+  for (int i = 0; i < n && i < cap; i++) {
+    blocks_out[3 * i] = aln.blocks[i].qPos;
+    blocks_out[3 * i + 1] = aln.blocks[i].tPos;
+    blocks_out[3 * i + 2] = aln.blocks[i].length;
+  }
+  return score;
+}
+
+// Batch over SoA job arrays on `nthreads` host threads (each with its own, re-used
+// AffineAlignBuffers, the favourable case for the reference: LocalRefineAlignment.h:114 passes a
+// long-lived buffer).  block_off[j] = index of job j's first triple in blocks_out, laid out with the
+// caller-provided per-job capacity prefix (block_off is an input).  Returns 0.
+int ref_aog_batch(const char *q_arena, const char *t_arena, const uint32_t *q_off,
+                  const uint32_t *t_off, const int32_t *q_len, const int32_t *t_len,
+                  const int32_t *k, int n_jobs, int m, int mm, int indel, int32_t *score,
+                  int32_t *n_blocks, const int64_t *block_off, uint32_t *blocks_out, int nthreads) {
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    AffineAlignBuffers buf;
+    Alignment aln;
+    const int CH = 64;
+    for (;;) {
+      int s = next.fetch_add(CH);
+      if (s >= n_jobs) break;
+      int e = s + CH < n_jobs ? s + CH : n_jobs;
+      for (int j = s; j < e; j++) {
+        std::string qs(q_arena + q_off[j], q_len[j]), ts(t_arena + t_off[j], t_len[j]);
+        aln.blocks.clear();
+        score[j] = AffineOneGapAlign(qs, q_len[j], ts, t_len[j], m, mm, indel, k[j], aln, buf);
+        n_blocks[j] = (int)aln.blocks.size();
+        if (blocks_out) {
+          uint32_t *o = blocks_out + 3 * block_off[j];
+          for (size_t i = 0; i < aln.blocks.size(); i++) {
+            o[3 * i] = aln.blocks[i].qPos; o[3 * i + 1] = aln.blocks[i].tPos; o[3 * i + 2] = aln.blocks[i].length;
+          }
+        }
+      }
+    }
+  };
+  if (nthreads <= 1) { work(); return 0; }
+  std::vector<std::thread> th;
+  for (int i = 0; i < nthreads; i++) th.emplace_back(work);
+  for (auto &x : th) x.join();
+  return 0;
+}
+
+}  // extern "C"

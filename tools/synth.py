@@ -1,0 +1,129 @@
+#!/usr/bin/env python
+"""Seeded synthetic references and reads for the BASELINE.json configs.
+
+Reference: uniform i.i.d. ACGT, upper-case, 80-column FASTA, contigs chr1..chrN.
+Reads: start uniform over a contig, strand 50/50, i.i.d. per-base errors with
+sub:ins:del = 1:1:1, FASTA, names r<idx>_<chr>_<start>_<strand>.
+
+Used by tests (small sizes), by bench.py (to draw job shapes) and by tools/make_golden.py.
+"""
+import argparse
+import numpy as np
+
+BASES = np.frombuffer(b"ACGT", dtype=np.uint8)
+COMP = np.zeros(256, dtype=np.uint8)
+for a, b in zip(b"ACGTN", b"TGCAN"):
+    COMP[a] = b
+
+
+def gen_ref(total_len, n_contigs=1, seed=1234):
+    """Return list of (name, uint8 array of ASCII bases)."""
+    rng = np.random.default_rng(seed)
+    per = total_len // n_contigs
+    out = []
+    for c in range(n_contigs):
+        n = per if c < n_contigs - 1 else total_len - per * (n_contigs - 1)
+        out.append(("chr%d" % (c + 1), BASES[rng.integers(0, 4, size=n, dtype=np.uint8)]))
+    return out
+
+
+def write_fasta(path, records, width=80):
+    with open(path, "wb") as f:
+        for name, seq in records:
+            f.write(b">" + name.encode() + b"\n")
+            n = len(seq)
+            full = (n // width) * width
+            if full:
+                body = np.empty((full // width, width + 1), dtype=np.uint8)
+                body[:, :width] = seq[:full].reshape(-1, width)
+                body[:, width] = 10
+                f.write(body.tobytes())
+            if n > full:
+                f.write(seq[full:].tobytes() + b"\n")
+
+
+def mutate(seq, err, rng):
+    """Apply i.i.d. errors (sub:ins:del = 1:1:1) at total rate `err`."""
+    n = len(seq)
+    if err <= 0:
+        return seq.copy()
+    r = rng.random(n)
+    kind = np.zeros(n, dtype=np.uint8)  # 0 keep, 1 sub, 2 ins (after base), 3 del
+    kind[r < err] = 1
+    kind[r < 2 * err / 3] = 2
+    kind[r < err / 3] = 3
+    sub_shift = rng.integers(1, 4, size=n, dtype=np.uint8)
+    ins_base = BASES[rng.integers(0, 4, size=n, dtype=np.uint8)]
+    code = np.searchsorted(BASES, seq).astype(np.uint8) & 3
+    subbed = BASES[(code + sub_shift) & 3]
+    base = np.where(kind == 1, subbed, seq)
+    cnt = np.ones(n, dtype=np.int64)
+    cnt[kind == 3] = 0
+    cnt[kind == 2] = 2
+    total = int(cnt.sum())
+    out = np.empty(total, dtype=np.uint8)
+    pos = np.cumsum(cnt) - cnt
+    keep = kind != 3
+    out[pos[keep]] = base[keep]
+    ins = kind == 2
+    out[pos[ins] + 1] = ins_base[ins]
+    return out
+
+
+def read_lengths(profile, n, rng):
+    if profile == "ccs10k":
+        return np.full(n, 10000, dtype=np.int64)
+    if profile == "hifi":
+        return np.maximum(5000, rng.normal(15000, 2000, size=n)).astype(np.int64)
+    if profile == "ont":  # log-normal, N50 ~ 20 kb, sigma 0.5, min 1 kb
+        sigma = 0.5
+        mu = np.log(20000.0) - sigma * sigma  # N50 of a log-normal = exp(mu + sigma^2)
+        return np.maximum(1000, rng.lognormal(mu, sigma, size=n)).astype(np.int64)
+    if profile == "clr":
+        sigma = 0.5
+        mu = np.log(12000.0) - sigma * sigma
+        return np.maximum(1000, rng.lognormal(mu, sigma, size=n)).astype(np.int64)
+    raise ValueError(profile)
+
+
+PROFILE_ERR = {"ccs10k": 0.01, "hifi": 0.005, "ont": 0.08, "clr": 0.12}
+
+
+def gen_reads(ref, n_reads, profile, seed, err=None):
+    """Return list of (name, uint8 seq). `ref` is the list from gen_ref."""
+    rng = np.random.default_rng(seed)
+    err = PROFILE_ERR[profile] if err is None else err
+    lens = read_lengths(profile, n_reads, rng)
+    sizes = np.array([len(s) for _, s in ref], dtype=np.float64)
+    contig = rng.choice(len(ref), size=n_reads, p=sizes / sizes.sum())
+    out = []
+    for i in range(n_reads):
+        name, seq = ref[contig[i]]
+        L = int(min(lens[i], len(seq)))
+        start = int(rng.integers(0, len(seq) - L + 1))
+        frag = seq[start:start + L]
+        strand = int(rng.integers(0, 2))
+        if strand:
+            frag = COMP[frag[::-1]]
+        out.append(("r%d_%s_%d_%s" % (i, name, start, "-" if strand else "+"), mutate(frag, err, rng)))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref-len", type=int, default=5_000_000)
+    ap.add_argument("--contigs", type=int, default=1)
+    ap.add_argument("--ref-seed", type=int, default=1234)
+    ap.add_argument("--reads", type=int, default=1000)
+    ap.add_argument("--profile", default="ccs10k")
+    ap.add_argument("--seed", type=int, default=11)
+    ap.add_argument("--ref-out", required=True)
+    ap.add_argument("--reads-out", required=True)
+    a = ap.parse_args()
+    ref = gen_ref(a.ref_len, a.contigs, a.ref_seed)
+    write_fasta(a.ref_out, ref)
+    write_fasta(a.reads_out, gen_reads(ref, a.reads, a.profile, a.seed), width=1 << 30)
+
+
+if __name__ == "__main__":
+    main()
