@@ -1,0 +1,104 @@
+/* lra_b200 -- C ABI of the B200-native MapRead hot path (drop-in boundary).
+ *
+ * Plain C, no STL / torch types across the boundary.  One context per GPU; calls on one context are serialised on the
+ * context's stream (thread-compatible, like one reference worker thread, lra.cpp:103-172).  All functions return
+ * LRA_B200_OK (0) or a non-zero error code; the message is available from lra_b200_last_error().  Nothing here ever
+ * calls exit() (the reference does, lra.cpp:42-45), and there is no CPU fallback: without a CUDA device every compute
+ * entry point fails with LRA_B200_ECUDA.
+ *
+ * Each entry point names the reference interface it replaces (file:line under the reference tree).
+ */
+#ifndef LRA_B200_H_
+#define LRA_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRA_B200_OK 0
+#define LRA_B200_EINVAL 1     /* bad argument / job outside the domain (empty sequence, window outside its arena) */
+#define LRA_B200_ECUDA 2      /* CUDA runtime error or no device */
+#define LRA_B200_EOVERFLOW 3  /* caller-provided output capacity too small; required size is reported */
+#define LRA_B200_EINTERNAL 4  /* kernel self-check failed (never expected) */
+
+typedef struct lra_b200_ctx lra_b200_ctx;
+typedef struct lra_b200_seq lra_b200_seq;
+
+int lra_b200_version(void);
+
+/* Context = one GPU + one stream + grow-only scratch.  Replaces the per-thread state the reference threads through
+ * MapRead (IndelRefineBuffers / AffineAlignBuffers / Timing: lra.cpp:106-108, AffineOneGapAlign.h:141-154). */
+int lra_b200_create(lra_b200_ctx **ctx, int device);
+void lra_b200_destroy(lra_b200_ctx *ctx);
+/* Last error message of this context (or of the failed lra_b200_create when ctx == NULL). */
+const char *lra_b200_last_error(const lra_b200_ctx *ctx);
+/* Run this context's work on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the own stream. */
+int lra_b200_set_stream(lra_b200_ctx *ctx, void *cuda_stream);
+int lra_b200_synchronize(lra_b200_ctx *ctx);
+
+/* ---- sequences -------------------------------------------------------------------------------------------------
+ * A device-resident packed sequence arena: 2 bits per base + a 1-bit mask of non-ACGT symbols, i.e. exactly the
+ * comparison alphabet of the reference's seqMapN table (SeqUtils.h:42-75).  Replaces the `char*` read / readRC buffers
+ * (Read.h:6-74, MapRead.h:169) and the per-contig genome strings (Genome.h:94-138) on the device side. */
+int lra_b200_seq_upload(lra_b200_ctx *ctx, const char *ascii_host, uint64_t n, lra_b200_seq **out);
+int lra_b200_seq_from_device(lra_b200_ctx *ctx, const void *ascii_dev, uint64_t n, lra_b200_seq **out);
+/* Re-use an existing arena's storage when it is large enough (per-batch read arenas). */
+int lra_b200_seq_reupload(lra_b200_ctx *ctx, lra_b200_seq *seq, const char *ascii_host, uint64_t n);
+void lra_b200_seq_free(lra_b200_ctx *ctx, lra_b200_seq *seq);
+uint64_t lra_b200_seq_length(const lra_b200_seq *seq);
+/* Test aid: copy the packed words back (b2: ceil(n/16) words, nmask: ceil(n/32) words). */
+int lra_b200_seq_download(lra_b200_ctx *ctx, const lra_b200_seq *seq, uint32_t *b2, uint32_t *nmask);
+
+/* ---- a18  AffineOneGapAlign, batched ---------------------------------------------------------------------------
+ * Replaces   int AffineOneGapAlign(string &qSeq, int qLen, string &tSeq, int tLen, int m, int mm, int indel, int k,
+ *                                  Alignment &aln, AffineAlignBuffers &b)            AffineOneGapAlign.h:157-649
+ * for a whole batch of calls.  Job j aligns q[q_off[j] .. +q_len[j]) against t[t_off[j] .. +t_len[j]) with band
+ * parameter k[j]; (match, mismatch, indel) are the reference's (m, mm, indel) = opts.localMatch / localMismatch /
+ * localIndel.  Results per job: the return value (score) and the blocks appended to aln.blocks, as (qPos,tPos,length)
+ * triples starting at blocks[3*block_off[j]], n_blocks[j] of them, in the reference's order.  Bit-exact.
+ * Domain: q_len >= 1, t_len >= 1, windows inside their arenas (else LRA_B200_EINVAL). */
+typedef struct lra_b200_aog_jobs {
+  const uint32_t *q_off;
+  const uint32_t *t_off;
+  const int32_t *q_len;
+  const int32_t *t_len;
+  const int32_t *k;
+  int32_t n_jobs;
+  int32_t match, mismatch, indel;
+} lra_b200_aog_jobs;
+
+typedef struct lra_b200_aog_result {
+  int32_t *score;          /* [n_jobs] */
+  int32_t *n_blocks;       /* [n_jobs] */
+  uint64_t *block_off;     /* [n_jobs] */
+  uint32_t *blocks;        /* [block_cap * 3] */
+  uint64_t block_cap;      /* in triples */
+  uint64_t n_blocks_total; /* out: triples produced (== required capacity on LRA_B200_EOVERFLOW) */
+  uint64_t cells;          /* out: reference-equivalent DP cells of the batch */
+} lra_b200_aog_result;
+
+/* Host buffers in, host buffers out (the copies are part of the call). */
+int lra_b200_aog_batch(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_aog_jobs *jobs,
+                       lra_b200_aog_result *res);
+/* Same with every array already resident in device memory (pointers are device pointers). */
+int lra_b200_aog_batch_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t,
+                              const lra_b200_aog_jobs *jobs_dev, lra_b200_aog_result *res_dev);
+
+/* ---- per-kernel timing of the last batch call (CUDA events on the context's stream) ---------------------------- */
+typedef struct lra_b200_kernel_stat {
+  char name[48];
+  float ms;             /* device time of the launch */
+  uint64_t jobs;        /* units processed */
+  uint64_t cells;       /* DP cells (0 if not a DP kernel) */
+  uint64_t algo_bytes;  /* algorithmic HBM bytes */
+} lra_b200_kernel_stat;
+/* Returns the number of records available; fills up to cap. */
+int lra_b200_last_kernel_stats(lra_b200_ctx *ctx, lra_b200_kernel_stat *out, int cap);
+/* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
+uint64_t lra_b200_launch_count(const lra_b200_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

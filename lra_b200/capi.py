@@ -1,0 +1,219 @@
+"""ctypes binding of include/lra_b200.h plus the host-side mirror of the reference interface for the hot path."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class LraB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("lra_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+OK, EINVAL, ECUDA, EOVERFLOW, EINTERNAL = 0, 1, 2, 3, 4
+
+
+class _AogJobs(C.Structure):
+    _fields_ = [("q_off", C.c_void_p), ("t_off", C.c_void_p), ("q_len", C.c_void_p), ("t_len", C.c_void_p),
+                ("k", C.c_void_p), ("n_jobs", C.c_int32), ("match", C.c_int32), ("mismatch", C.c_int32),
+                ("indel", C.c_int32)]
+
+
+class _AogResult(C.Structure):
+    _fields_ = [("score", C.c_void_p), ("n_blocks", C.c_void_p), ("block_off", C.c_void_p), ("blocks", C.c_void_p),
+                ("block_cap", C.c_uint64), ("n_blocks_total", C.c_uint64), ("cells", C.c_uint64)]
+
+
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("ms", C.c_float), ("jobs", C.c_uint64), ("cells", C.c_uint64),
+                ("algo_bytes", C.c_uint64)]
+
+
+def library_path():
+    return os.path.join(_HERE, "liblra_b200.so")
+
+
+def load_library():
+    """Load liblra_b200.so (built in-tree by lra_b200/build.py).  Fails loudly if it is missing: no fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise LraB200Error(ECUDA, "CUDA library %s is missing; run `python -m lra_b200.build` (there is no CPU fallback)" % path)
+    L = C.CDLL(path)
+    L.lra_b200_version.restype = C.c_int
+    L.lra_b200_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.lra_b200_destroy.argtypes = [C.c_void_p]
+    L.lra_b200_destroy.restype = None
+    L.lra_b200_last_error.argtypes = [C.c_void_p]
+    L.lra_b200_last_error.restype = C.c_char_p
+    L.lra_b200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.lra_b200_synchronize.argtypes = [C.c_void_p]
+    L.lra_b200_seq_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    L.lra_b200_seq_from_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    L.lra_b200_seq_reupload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.lra_b200_seq_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.lra_b200_seq_free.restype = None
+    L.lra_b200_seq_length.argtypes = [C.c_void_p]
+    L.lra_b200_seq_length.restype = C.c_uint64
+    L.lra_b200_seq_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lra_b200_aog_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_AogJobs), C.POINTER(_AogResult)]
+    L.lra_b200_aog_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_AogJobs), C.POINTER(_AogResult)]
+    L.lra_b200_last_kernel_stats.argtypes = [C.c_void_p, C.POINTER(KernelStat), C.c_int]
+    L.lra_b200_launch_count.argtypes = [C.c_void_p]
+    L.lra_b200_launch_count.restype = C.c_uint64
+    _LIB = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data if isinstance(a, np.ndarray) else int(a)
+
+
+class SeqArena:
+    """Device-resident packed sequence arena (lra_b200_seq)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.handle = ctx, handle
+
+    def __len__(self):
+        return int(self.ctx.lib.lra_b200_seq_length(self.handle))
+
+    def reupload(self, ascii_bytes):
+        buf = np.frombuffer(ascii_bytes, dtype=np.uint8) if not isinstance(ascii_bytes, np.ndarray) else ascii_bytes
+        self.ctx._check(self.ctx.lib.lra_b200_seq_reupload(self.ctx.h, self.handle, _ptr(buf), len(buf)))
+
+    def download(self):
+        n = len(self)
+        b2 = np.zeros((n + 15) // 16, np.uint32); nm = np.zeros((n + 31) // 32, np.uint32)
+        self.ctx._check(self.ctx.lib.lra_b200_seq_download(self.ctx.h, self.handle, _ptr(b2), _ptr(nm)))
+        return b2, nm
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.lra_b200_seq_free(self.ctx.h, self.handle)
+            self.handle = None
+
+
+class Context:
+    """One GPU context (lra_b200_ctx)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.lra_b200_create(C.byref(h), device)
+        if rc != OK:
+            raise LraB200Error(rc, self.lib.lra_b200_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lra_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise LraB200Error(rc, self.lib.lra_b200_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.lra_b200_set_stream(self.h, cuda_stream_ptr))
+
+    def synchronize(self):
+        self._check(self.lib.lra_b200_synchronize(self.h))
+
+    def launch_count(self):
+        return int(self.lib.lra_b200_launch_count(self.h))
+
+    def seq_upload(self, ascii_bytes):
+        buf = np.frombuffer(ascii_bytes, dtype=np.uint8) if not isinstance(ascii_bytes, np.ndarray) else ascii_bytes
+        h = C.c_void_p()
+        self._check(self.lib.lra_b200_seq_upload(self.h, _ptr(buf), len(buf), C.byref(h)))
+        return SeqArena(self, h)
+
+    def seq_from_device(self, dev_ptr, n):
+        h = C.c_void_p()
+        self._check(self.lib.lra_b200_seq_from_device(self.h, dev_ptr, n, C.byref(h)))
+        return SeqArena(self, h)
+
+    def kernel_stats(self):
+        arr = (KernelStat * 32)()
+        n = self.lib.lra_b200_last_kernel_stats(self.h, arr, 32)
+        return [dict(name=arr[i].name.decode(), ms=float(arr[i].ms), jobs=int(arr[i].jobs), cells=int(arr[i].cells),
+                     algo_bytes=int(arr[i].algo_bytes)) for i in range(min(n, 32))]
+
+    # ---- a18
+    def aog_batch(self, q, t, q_off, t_off, q_len, t_len, k, m, mm, indel, block_cap=None, out=None):
+        """Host arrays in / host arrays out.  Returns dict(score, n_blocks, block_off, blocks[n,3], cells)."""
+        n = len(q_off)
+        q_off = np.ascontiguousarray(q_off, np.uint32); t_off = np.ascontiguousarray(t_off, np.uint32)
+        q_len = np.ascontiguousarray(q_len, np.int32); t_len = np.ascontiguousarray(t_len, np.int32)
+        k = np.ascontiguousarray(k, np.int32)
+        if block_cap is None:
+            block_cap = int(np.minimum(q_len, t_len).clip(min=0).sum()) + 1
+        if out is None:
+            out = dict(score=np.zeros(n, np.int32), n_blocks=np.zeros(n, np.int32), block_off=np.zeros(n, np.uint64),
+                       blocks=np.zeros((max(1, block_cap), 3), np.uint32))
+        jobs = _AogJobs(_ptr(q_off), _ptr(t_off), _ptr(q_len), _ptr(t_len), _ptr(k), n, m, mm, indel)
+        res = _AogResult(_ptr(out["score"]), _ptr(out["n_blocks"]), _ptr(out["block_off"]), _ptr(out["blocks"]),
+                         block_cap, 0, 0)
+        rc = self.lib.lra_b200_aog_batch(self.h, q.handle, t.handle, C.byref(jobs), C.byref(res))
+        out["n_blocks_total"] = int(res.n_blocks_total)
+        out["cells"] = int(res.cells)
+        self._last_needed = int(res.n_blocks_total)
+        self._check(rc)
+        return out
+
+    def aog_batch_device(self, q, t, d_q_off, d_t_off, d_q_len, d_t_len, d_k, n, m, mm, indel, d_score, d_n_blocks,
+                         d_block_off, d_blocks, block_cap):
+        """Everything resident: arguments are raw device pointers (ints).  Returns (n_blocks_total, cells)."""
+        jobs = _AogJobs(d_q_off, d_t_off, d_q_len, d_t_len, d_k, n, m, mm, indel)
+        res = _AogResult(d_score, d_n_blocks, d_block_off, d_blocks, block_cap, 0, 0)
+        self._check(self.lib.lra_b200_aog_batch_device(self.h, q.handle, t.handle, C.byref(jobs), C.byref(res)))
+        return int(res.n_blocks_total), int(res.cells)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Host-side mirror of the reference interface (same names / argument meaning), used by the parity tests.
+
+_default_ctx = None
+
+
+def _ctx():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def AffineOneGapAlign(qSeq, qLen, tSeq, tLen, m, mm, indel, k, ctx=None):
+    """Mirror of `int AffineOneGapAlign(string &qSeq, int qLen, string &tSeq, int tLen, int m, int mm, int indel, int k,
+    Alignment &aln, AffineAlignBuffers &b)` (reference AffineOneGapAlign.h:157).  Returns (score, blocks) where blocks
+    is what the reference appends to aln.blocks, as an [n,3] array of (qPos, tPos, length)."""
+    ctx = ctx or _ctx()
+    q = ctx.seq_upload(bytes(qSeq[:qLen])); t = ctx.seq_upload(bytes(tSeq[:tLen]))
+    try:
+        r = ctx.aog_batch(q, t, [0], [0], [qLen], [tLen], [k], m, mm, indel)
+    finally:
+        q.free(); t.free()
+    nb = int(r["n_blocks"][0]); off = int(r["block_off"][0])
+    return int(r["score"][0]), r["blocks"][off:off + nb].copy()
+
+
+def AffineOneGapAlignBatch(q_arena, t_arena, q_off, t_off, q_len, t_len, k, m, mm, indel, ctx=None):
+    """Batched form over SoA job arrays (ASCII arenas as bytes / uint8 arrays)."""
+    ctx = ctx or _ctx()
+    q = ctx.seq_upload(q_arena); t = ctx.seq_upload(t_arena)
+    try:
+        return ctx.aog_batch(q, t, q_off, t_off, q_len, t_len, k, m, mm, indel)
+    finally:
+        q.free(); t.free()

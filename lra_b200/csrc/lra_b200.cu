@@ -1,0 +1,400 @@
+// liblra_b200.so -- host side of the C ABI declared in include/lra_b200.h: context, packed-sequence arenas and the
+// batched AffineOneGapAlign launcher.  CUDA only: every compute entry point fails loudly without a device.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/lra_b200.h"
+#include "aog_band_kernel.cuh"
+#include "aog_kernels.cuh"
+#include "seq_kernels.cuh"
+
+using namespace lra;
+
+struct lra_b200_seq {
+  uint32_t *b2 = nullptr, *nm = nullptr;
+  uint8_t *ascii_dev = nullptr;   // staging for uploads (kept for re-use)
+  uint64_t n = 0, cap_groups = 0, ascii_cap = 0;
+};
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct lra_b200_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::string err;
+  int n_sm = 148;
+  uint64_t launches = 0;
+  // grow-only scratch
+  DevBuf plan, bin_of_job, sorted, lit_slab, band_slab, misc;  // misc: block cursor (8 B) + err flag (4 B)
+  DevBuf d_qoff, d_toff, d_qlen, d_tlen, d_k, d_score, d_nb, d_boff, d_blocks;
+  AogPlan *h_plan = nullptr;            // pinned
+  unsigned long long *h_misc = nullptr;  // pinned (2 x u64)
+  std::vector<lra_b200_kernel_stat> stats;
+  std::vector<cudaEvent_t> ev;
+};
+
+static std::string g_create_err;
+
+static int fail(lra_b200_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_err = buf;
+  return code;
+}
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(ctx, LRA_B200_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static int ensure(lra_b200_ctx *ctx, DevBuf &b, size_t bytes) {
+  if (b.cap >= bytes && b.p) return 0;
+  if (b.p) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+  size_t want = bytes + bytes / 4 + 256;
+  CU(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return 0;
+}
+
+extern "C" int lra_b200_version(void) { return 100; }
+
+extern "C" int lra_b200_create(lra_b200_ctx **out, int device) {
+  lra_b200_ctx *ctx = nullptr;
+  if (!out) return fail(nullptr, LRA_B200_EINVAL, "ctx out pointer is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, LRA_B200_ECUDA, "no CUDA device available (%s); lra_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(nullptr, LRA_B200_EINVAL, "device %d out of range [0,%d)", device, n);
+  ctx = new lra_b200_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return fail(nullptr, LRA_B200_ECUDA, "cudaSetDevice(%d) failed", device); }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->n_sm = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx; return fail(nullptr, LRA_B200_ECUDA, "cudaStreamCreate failed");
+  }
+  ctx->stream = ctx->own_stream;
+  if (cudaHostAlloc((void **)&ctx->h_plan, sizeof(AogPlan), cudaHostAllocDefault) != cudaSuccess ||
+      cudaHostAlloc((void **)&ctx->h_misc, 64, cudaHostAllocDefault) != cudaSuccess) {
+    delete ctx; return fail(nullptr, LRA_B200_ECUDA, "cudaHostAlloc failed");
+  }
+  ctx->ev.resize(40);
+  for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+  *out = ctx;
+  return LRA_B200_OK;
+}
+
+extern "C" void lra_b200_destroy(lra_b200_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf *bufs[] = {&ctx->plan, &ctx->bin_of_job, &ctx->sorted, &ctx->lit_slab, &ctx->band_slab, &ctx->misc, &ctx->d_qoff,
+                    &ctx->d_toff, &ctx->d_qlen, &ctx->d_tlen, &ctx->d_k, &ctx->d_score, &ctx->d_nb, &ctx->d_boff, &ctx->d_blocks};
+  for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+  for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+  if (ctx->h_plan) cudaFreeHost(ctx->h_plan);
+  if (ctx->h_misc) cudaFreeHost(ctx->h_misc);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+extern "C" const char *lra_b200_last_error(const lra_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int lra_b200_set_stream(lra_b200_ctx *ctx, void *s) {
+  if (!ctx) return LRA_B200_EINVAL;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  return LRA_B200_OK;
+}
+extern "C" int lra_b200_synchronize(lra_b200_ctx *ctx) {
+  if (!ctx) return LRA_B200_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LRA_B200_OK;
+}
+extern "C" uint64_t lra_b200_launch_count(const lra_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------- sequences
+static int seq_reserve(lra_b200_ctx *ctx, lra_b200_seq *s, uint64_t n) {
+  uint64_t groups = (n + 31) / 32 + 1;
+  if (groups > s->cap_groups) {
+    if (s->b2) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(s->b2)); CU(cudaFree(s->nm)); s->b2 = s->nm = nullptr; }
+    uint64_t cap = groups + groups / 4 + 8;
+    CU(cudaMalloc((void **)&s->b2, (cap * 2 + 8) * 4));
+    CU(cudaMalloc((void **)&s->nm, (cap + 8) * 4));
+    CU(cudaMemsetAsync(s->b2, 0, (cap * 2 + 8) * 4, ctx->stream));
+    CU(cudaMemsetAsync(s->nm, 0xFF, (cap + 8) * 4, ctx->stream));
+    s->cap_groups = cap;
+  }
+  return 0;
+}
+static int seq_pack_launch(lra_b200_ctx *ctx, lra_b200_seq *s, const uint8_t *ascii_dev, uint64_t n) {
+  int rc = seq_reserve(ctx, s, n);
+  if (rc) return rc;
+  uint64_t groups = (n + 31) / 32 + 1;  // one extra all-N group as padding
+  unsigned blocks = (unsigned)((groups + 255) / 256);
+  seq_pack_kernel<<<blocks, 256, 0, ctx->stream>>>(ascii_dev, n, s->b2, s->nm, groups);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  s->n = n;
+  return 0;
+}
+
+extern "C" int lra_b200_seq_from_device(lra_b200_ctx *ctx, const void *ascii_dev, uint64_t n, lra_b200_seq **out) {
+  if (!ctx || !out || (!ascii_dev && n)) return fail(ctx, LRA_B200_EINVAL, "seq_from_device: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  if (((uintptr_t)ascii_dev) & 15) return fail(ctx, LRA_B200_EINVAL, "seq_from_device: device pointer must be 16-byte aligned");
+  lra_b200_seq *s = new lra_b200_seq();
+  int rc = seq_pack_launch(ctx, s, (const uint8_t *)ascii_dev, n);
+  if (rc) { delete s; return rc; }
+  *out = s;
+  return LRA_B200_OK;
+}
+
+extern "C" int lra_b200_seq_reupload(lra_b200_ctx *ctx, lra_b200_seq *s, const char *ascii_host, uint64_t n) {
+  if (!ctx || !s || (!ascii_host && n)) return fail(ctx, LRA_B200_EINVAL, "seq_reupload: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  if (n + 64 > s->ascii_cap) {
+    if (s->ascii_dev) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(s->ascii_dev)); s->ascii_dev = nullptr; }
+    uint64_t cap = n + n / 4 + 256;
+    CU(cudaMalloc((void **)&s->ascii_dev, cap));
+    s->ascii_cap = cap;
+  }
+  if (n) CU(cudaMemcpyAsync(s->ascii_dev, ascii_host, n, cudaMemcpyHostToDevice, ctx->stream));
+  return seq_pack_launch(ctx, s, s->ascii_dev, n);
+}
+
+extern "C" int lra_b200_seq_upload(lra_b200_ctx *ctx, const char *ascii_host, uint64_t n, lra_b200_seq **out) {
+  if (!ctx || !out) return fail(ctx, LRA_B200_EINVAL, "seq_upload: bad argument");
+  lra_b200_seq *s = new lra_b200_seq();
+  int rc = lra_b200_seq_reupload(ctx, s, ascii_host, n);
+  if (rc) { lra_b200_seq_free(ctx, s); return rc; }
+  *out = s;
+  return LRA_B200_OK;
+}
+
+extern "C" void lra_b200_seq_free(lra_b200_ctx *ctx, lra_b200_seq *s) {
+  if (!s) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  if (s->b2) cudaFree(s->b2);
+  if (s->nm) cudaFree(s->nm);
+  if (s->ascii_dev) cudaFree(s->ascii_dev);
+  delete s;
+}
+extern "C" uint64_t lra_b200_seq_length(const lra_b200_seq *s) { return s ? s->n : 0; }
+
+extern "C" int lra_b200_seq_download(lra_b200_ctx *ctx, const lra_b200_seq *s, uint32_t *b2, uint32_t *nmask) {
+  if (!ctx || !s || !b2 || !nmask) return fail(ctx, LRA_B200_EINVAL, "seq_download: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(b2, s->b2, ((s->n + 15) / 16) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(nmask, s->nm, ((s->n + 31) / 32) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LRA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- a18 launcher
+static const char *kClsName[kAogNumClasses] = {"aog_thread<K=2>", "aog_thread<K=4>", "aog_thread<K=6>", "aog_thread<K=8>",
+                                               "aog_thread<K=10>", "aog_thread<K=12>", "aog_thread<K=14>", "aog_warp_literal",
+                                               "aog_warp_band<C=1>", "aog_warp_band<C=2>", "aog_warp_band<C=4>", "aog_warp_band<C=8>"};
+
+template <int K>
+static void launch_thread(lra_b200_ctx *ctx, const AogBatch &b, AogPlan *plan, const uint32_t *sorted, uint32_t n) {
+  unsigned blocks = (n + 127) / 128;
+  unsigned cap = (unsigned)ctx->n_sm * 16u;
+  if (blocks > cap) blocks = cap;
+  aog_thread_kernel<K><<<blocks, 128, 0, ctx->stream>>>(b, plan, sorted);
+}
+template <int C>
+static void launch_band(lra_b200_ctx *ctx, const AogBatch &b, AogPlan *plan, const uint32_t *sorted, unsigned blocks, AogBandScratch sc) {
+  aog_warp_band_kernel<C><<<blocks, 128, 0, ctx->stream>>>(b, plan, sorted, sc);
+}
+
+static int aog_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_aog_jobs *jobs,
+                          lra_b200_aog_result *res) {
+  const int n = jobs->n_jobs;
+  ctx->stats.clear();
+  res->n_blocks_total = 0;
+  res->cells = 0;
+  if (n == 0) return LRA_B200_OK;
+  int rc;
+  if ((rc = ensure(ctx, ctx->plan, sizeof(AogPlan)))) return rc;
+  if ((rc = ensure(ctx, ctx->bin_of_job, (size_t)n * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->sorted, (size_t)n * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->misc, 64))) return rc;
+  AogPlan *plan = (AogPlan *)ctx->plan.p;
+  unsigned long long *cursor = (unsigned long long *)ctx->misc.p;
+  int *errflag = (int *)((char *)ctx->misc.p + 8);
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemsetAsync(plan, 0, sizeof(AogPlan), st));
+  CU(cudaMemsetAsync(ctx->misc.p, 0, 64, st));
+
+  AogBatch b;
+  b.q = SeqView{q->b2, q->nm, q->n};
+  b.t = SeqView{t->b2, t->nm, t->n};
+  b.q_off = jobs->q_off; b.t_off = jobs->t_off; b.q_len = jobs->q_len; b.t_len = jobs->t_len; b.k = jobs->k;
+  b.n_jobs = n; b.m = jobs->match; b.mm = jobs->mismatch; b.indel = jobs->indel;
+  b.score = res->score; b.n_blocks = res->n_blocks; b.block_off = (unsigned long long *)res->block_off;
+  b.blocks = res->blocks; b.block_cap = res->block_cap; b.block_cursor = cursor; b.err = errflag;
+
+  int evi = 0;
+  auto rec = [&]() { cudaEventRecord(ctx->ev[evi++], st); };
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  rec();
+  aog_classify_kernel<<<nb, 256, 0, st>>>(b, plan, (uint32_t *)ctx->bin_of_job.p, 1);
+  aog_scan_kernel<<<1, 512, 0, st>>>(plan);
+  aog_scatter_kernel<<<nb, 256, 0, st>>>(n, plan, (const uint32_t *)ctx->bin_of_job.p, (uint32_t *)ctx->sorted.p);
+  ctx->launches += 3;
+  rec();
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ctx->h_plan, plan, sizeof(AogPlan), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const AogPlan &hp = *ctx->h_plan;
+  uint32_t cnt[kAogNumClasses];
+  for (int c = 0; c < kAogNumClasses; c++) cnt[c] = hp.bin_start[(c + 1) * kAogBuckets] - hp.bin_start[c * kAogBuckets];
+  const uint32_t *sorted = (const uint32_t *)ctx->sorted.p;
+
+  struct Launched { int cls; int ev0; };
+  std::vector<Launched> launched;
+  auto begin_cls = [&](int c) { launched.push_back({c, evi}); rec(); };
+  auto end_cls = [&]() { rec(); ctx->launches++; };
+
+  if (cnt[0]) { begin_cls(0); launch_thread<2>(ctx, b, plan, sorted, cnt[0]); end_cls(); }
+  if (cnt[1]) { begin_cls(1); launch_thread<4>(ctx, b, plan, sorted, cnt[1]); end_cls(); }
+  if (cnt[2]) { begin_cls(2); launch_thread<6>(ctx, b, plan, sorted, cnt[2]); end_cls(); }
+  if (cnt[3]) { begin_cls(3); launch_thread<8>(ctx, b, plan, sorted, cnt[3]); end_cls(); }
+  if (cnt[4]) { begin_cls(4); launch_thread<10>(ctx, b, plan, sorted, cnt[4]); end_cls(); }
+  if (cnt[5]) { begin_cls(5); launch_thread<12>(ctx, b, plan, sorted, cnt[5]); end_cls(); }
+  if (cnt[6]) { begin_cls(6); launch_thread<14>(ctx, b, plan, sorted, cnt[6]); end_cls(); }
+  // band classes
+  uint32_t nband = cnt[8] + cnt[9] + cnt[10] + cnt[11];
+  if (nband) {
+    AogBandScratch sc;
+    sc.max_rows = hp.max_rows_band; sc.max_qlen = hp.max_qlen_band;
+    sc.slab_bytes = (aog_band_slab_bytes(sc.max_rows, sc.max_qlen) + 127ull) & ~127ull;
+    unsigned max_blocks = (unsigned)ctx->n_sm * 4u;
+    uint32_t biggest = cnt[8];
+    for (int c = 9; c < 12; c++) if (cnt[c] > biggest) biggest = cnt[c];
+    unsigned blocks_cap = (biggest + 3) / 4;
+    if (blocks_cap > max_blocks) blocks_cap = max_blocks;
+    while (blocks_cap > 1 && (unsigned long long)blocks_cap * 4ull * sc.slab_bytes > (8ull << 30)) blocks_cap /= 2;
+    if ((rc = ensure(ctx, ctx->band_slab, (size_t)blocks_cap * 4 * sc.slab_bytes))) return rc;
+    sc.base = (unsigned char *)ctx->band_slab.p;
+    auto blocks_for = [&](uint32_t c) { unsigned x = (c + 3) / 4; return x > blocks_cap ? blocks_cap : x; };
+    if (cnt[8]) { begin_cls(8); launch_band<1>(ctx, b, plan, sorted, blocks_for(cnt[8]), sc); end_cls(); }
+    if (cnt[9]) { begin_cls(9); launch_band<2>(ctx, b, plan, sorted, blocks_for(cnt[9]), sc); end_cls(); }
+    if (cnt[10]) { begin_cls(10); launch_band<4>(ctx, b, plan, sorted, blocks_for(cnt[10]), sc); end_cls(); }
+    if (cnt[11]) { begin_cls(11); launch_band<8>(ctx, b, plan, sorted, blocks_for(cnt[11]), sc); end_cls(); }
+  }
+  if (cnt[kAogClsLiteral]) {
+    AogLiteralScratch sc;
+    sc.max_mat = hp.max_mat; sc.max_diag = hp.max_diag;
+    sc.slab_bytes = (aog_literal_slab_bytes(sc.max_mat, sc.max_diag) + 127ull) & ~127ull;
+    unsigned blocks = (cnt[kAogClsLiteral] + 3) / 4;
+    unsigned max_blocks = (unsigned)ctx->n_sm * 3u;
+    if (blocks > max_blocks) blocks = max_blocks;
+    while (blocks > 1 && (unsigned long long)blocks * 4ull * sc.slab_bytes > (8ull << 30)) blocks /= 2;
+    if ((rc = ensure(ctx, ctx->lit_slab, (size_t)blocks * 4 * sc.slab_bytes))) return rc;
+    sc.base = (unsigned char *)ctx->lit_slab.p;
+    begin_cls(kAogClsLiteral);
+    aog_warp_literal_kernel<<<blocks, 128, 0, st>>>(b, plan, sorted, sc);
+    end_cls();
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ctx->h_plan, plan, sizeof(AogPlan), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(ctx->h_misc, ctx->misc.p, 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  res->n_blocks_total = ctx->h_misc[0];
+  res->cells = ctx->h_plan->cells;
+  const int err = *(int *)((char *)ctx->h_misc + 8);
+  // stats
+  {
+    lra_b200_kernel_stat s;
+    memset(&s, 0, sizeof s);
+    snprintf(s.name, sizeof s.name, "aog_plan(classify+scan+scatter)");
+    cudaEventElapsedTime(&s.ms, ctx->ev[0], ctx->ev[1]);
+    s.jobs = (uint64_t)n;
+    s.algo_bytes = (uint64_t)n * (20 + 4 + 4);
+    ctx->stats.push_back(s);
+    for (auto &L : launched) {
+      memset(&s, 0, sizeof s);
+      snprintf(s.name, sizeof s.name, "%s", kClsName[L.cls]);
+      cudaEventElapsedTime(&s.ms, ctx->ev[L.ev0], ctx->ev[L.ev0 + 1]);
+      s.jobs = cnt[L.cls];
+      s.cells = ctx->h_plan->cls_cells[L.cls];
+      s.algo_bytes = ctx->h_plan->cls_bytes[L.cls] + 12ull * ctx->h_plan->cls_blocks[L.cls];
+      ctx->stats.push_back(s);
+    }
+  }
+  if (err & 8) return fail(ctx, LRA_B200_EINVAL, "aog_batch: at least one job has an empty sequence or a window outside its arena");
+  if (err & 1) return fail(ctx, LRA_B200_EOVERFLOW, "aog_batch: block capacity %llu too small, %llu needed",
+                           (unsigned long long)res->block_cap, (unsigned long long)res->n_blocks_total);
+  if (err & 6) return fail(ctx, LRA_B200_EINTERNAL, "aog_batch: kernel self-check failed (flags 0x%x)", err);
+  return LRA_B200_OK;
+}
+
+extern "C" int lra_b200_aog_batch_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t,
+                                         const lra_b200_aog_jobs *jobs, lra_b200_aog_result *res) {
+  if (!ctx || !q || !t || !jobs || !res) return fail(ctx, LRA_B200_EINVAL, "aog_batch_device: NULL argument");
+  if (jobs->n_jobs < 0) return fail(ctx, LRA_B200_EINVAL, "aog_batch_device: negative job count");
+  CU(cudaSetDevice(ctx->device));
+  return aog_run_device(ctx, q, t, jobs, res);
+}
+
+extern "C" int lra_b200_aog_batch(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_aog_jobs *jobs,
+                                  lra_b200_aog_result *res) {
+  if (!ctx || !q || !t || !jobs || !res) return fail(ctx, LRA_B200_EINVAL, "aog_batch: NULL argument");
+  const int n = jobs->n_jobs;
+  if (n < 0) return fail(ctx, LRA_B200_EINVAL, "aog_batch: negative job count");
+  CU(cudaSetDevice(ctx->device));
+  if (n == 0) { res->n_blocks_total = 0; res->cells = 0; ctx->stats.clear(); return LRA_B200_OK; }
+  int rc;
+  const size_t nb4 = (size_t)n * 4;
+  if ((rc = ensure(ctx, ctx->d_qoff, nb4)) || (rc = ensure(ctx, ctx->d_toff, nb4)) || (rc = ensure(ctx, ctx->d_qlen, nb4)) ||
+      (rc = ensure(ctx, ctx->d_tlen, nb4)) || (rc = ensure(ctx, ctx->d_k, nb4)) || (rc = ensure(ctx, ctx->d_score, nb4)) ||
+      (rc = ensure(ctx, ctx->d_nb, nb4)) || (rc = ensure(ctx, ctx->d_boff, (size_t)n * 8)) ||
+      (rc = ensure(ctx, ctx->d_blocks, (size_t)(res->block_cap ? res->block_cap : 1) * 12)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(ctx->d_qoff.p, jobs->q_off, nb4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_toff.p, jobs->t_off, nb4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_qlen.p, jobs->q_len, nb4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_tlen.p, jobs->t_len, nb4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_k.p, jobs->k, nb4, cudaMemcpyHostToDevice, st));
+  lra_b200_aog_jobs dj = *jobs;
+  dj.q_off = (const uint32_t *)ctx->d_qoff.p; dj.t_off = (const uint32_t *)ctx->d_toff.p;
+  dj.q_len = (const int32_t *)ctx->d_qlen.p; dj.t_len = (const int32_t *)ctx->d_tlen.p; dj.k = (const int32_t *)ctx->d_k.p;
+  lra_b200_aog_result dr = *res;
+  dr.score = (int32_t *)ctx->d_score.p; dr.n_blocks = (int32_t *)ctx->d_nb.p; dr.block_off = (uint64_t *)ctx->d_boff.p;
+  dr.blocks = (uint32_t *)ctx->d_blocks.p;
+  rc = aog_run_device(ctx, q, t, &dj, &dr);
+  res->n_blocks_total = dr.n_blocks_total;
+  res->cells = dr.cells;
+  if (rc != LRA_B200_OK && rc != LRA_B200_EOVERFLOW) return rc;
+  CU(cudaMemcpyAsync(res->score, dr.score, nb4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->n_blocks, dr.n_blocks, nb4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->block_off, dr.block_off, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (rc == LRA_B200_OK && dr.n_blocks_total)
+    CU(cudaMemcpyAsync(res->blocks, dr.blocks, (size_t)dr.n_blocks_total * 12, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return rc;
+}
+
+extern "C" int lra_b200_last_kernel_stats(lra_b200_ctx *ctx, lra_b200_kernel_stat *out, int cap) {
+  if (!ctx) return 0;
+  int n = (int)ctx->stats.size();
+  for (int i = 0; i < n && i < cap; i++) out[i] = ctx->stats[i];
+  return n;
+}

@@ -1,0 +1,49 @@
+"""Builds and binds tests/simt/libemu_lra.so: the device code of lra_b200/csrc/*.cuh compiled for the CPU through the
+lock-step SIMT emulator (TEST INFRASTRUCTURE; lets the CPU suite check kernel logic where no GPU exists)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SIMT = os.path.join(HERE, "simt")
+CSRC = os.path.join(os.path.dirname(HERE), "lra_b200", "csrc")
+_lib = None
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    so = os.path.join(SIMT, "libemu_lra.so")
+    srcs = [os.path.join(SIMT, f) for f in os.listdir(SIMT) if f.endswith((".cpp", ".h"))]
+    srcs += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        cpps = [s for s in srcs if s.endswith(".cpp")]
+        subprocess.run(["g++", "-std=c++17", "-O1", "-DLRA_EMU", "-I" + SIMT, "-I" + CSRC, "-fPIC", "-shared"] + cpps +
+                       ["-o", so], check=True)
+    L = C.CDLL(so)
+    L.emu_aog_batch.restype = C.c_int
+    L.emu_aog_batch.argtypes = [_u8p, C.c_uint64, _u8p, C.c_uint64, _u32p, _u32p, _i32p, _i32p, _i32p, C.c_int, C.c_int,
+                                C.c_int, C.c_int, _i32p, _i32p, _u64p, _u32p, C.c_uint64, C.c_int, C.c_int,
+                                C.POINTER(C.c_uint64)]
+    L.emu_seq_pack.restype = C.c_int
+    L.emu_seq_pack.argtypes = [_u8p, C.c_uint64, _u32p, _u32p]
+    _lib = L
+    return L
+
+
+def aog_batch(qa, ta, qo, to, ql, tl, k, m, mm, indel, use_band=1, force_literal=0, block_cap=None):
+    n = len(qo)
+    if block_cap is None:
+        block_cap = int((np.minimum(ql, tl) + 1).sum())
+    score = np.zeros(n, np.int32); nb = np.zeros(n, np.int32); off = np.zeros(n, np.uint64)
+    blocks = np.zeros(max(1, block_cap) * 3, np.uint32)
+    cells = C.c_uint64(0)
+    err = lib().emu_aog_batch(qa, len(qa) - 16, ta, len(ta) - 16, qo, to, ql, tl, k, n, m, mm, indel, score, nb, off, blocks,
+                              block_cap, use_band, force_literal, C.byref(cells))
+    return err, score, nb, off, blocks.reshape(-1, 3), cells.value

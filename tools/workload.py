@@ -1,0 +1,133 @@
+"""Synthetic AffineOneGapAlign job streams for bench.py and the full-size parity tests.
+
+Job SHAPES (qLen, tLen, k) are drawn from the tables captured from the reference on synthetic reads of the named
+profile (tests/golden/aog_shapes_<profile>.npy, made by tools/make_golden.py); job CONTENT is synthetic: the target
+window is a random window of the synthetic genome and the query is that sequence with i.i.d. errors at the profile's
+rate (sub:ins:del = 1:1:1), cut to the drawn query length.
+"""
+import json
+import os
+import numpy as np
+
+import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+PROFILE_ERR = {"ccs": 0.01, "ont": 0.08, "clr": 0.12}
+PROFILE_SCORING = {"ccs": (4, -3, -4), "ont": (4, -1, -2), "clr": (4, -1, -2)}  # localMatch/Mismatch/Indel presets
+
+
+def meta():
+    return json.load(open(os.path.join(GOLD, "aog_shapes_meta.json")))
+
+
+def draw_shapes(profile, n_jobs, rng):
+    tab = np.load(os.path.join(GOLD, "aog_shapes_%s.npy" % profile))
+    tab = tab[(tab[:, 0] >= 1) & (tab[:, 1] >= 1)]
+    s = tab[rng.integers(0, len(tab), size=n_jobs)]
+    return s[:, 0].astype(np.int32), s[:, 1].astype(np.int32), s[:, 2].astype(np.int32)
+
+
+def make_jobs(profile, n_jobs, seed, genome_len, fetch_windows):
+    """fetch_windows(starts[int64], lengths[int64]) -> (concatenated uint8 ASCII, offsets) of genome windows.
+    Returns dict with q_arena (uint8 ASCII, padded), q_off, t_off (GLOBAL genome positions), q_len, t_len, k and
+    t_arena_compact/t_off_compact (the same target windows concatenated, for CPU arms that have no genome)."""
+    rng = np.random.default_rng(seed)
+    ql, tl, k = draw_shapes(profile, n_jobs, rng)
+    src_len = (np.maximum(ql, tl).astype(np.int64) * 13) // 10 + 48
+    t_pos = rng.integers(0, genome_len - int(src_len.max()) - 1, size=n_jobs, dtype=np.int64)
+    src, src_off = fetch_windows(t_pos, src_len)
+    # mutate the whole concatenation at once, then find where each job's segment starts in the mutated text
+    err = PROFILE_ERR[profile]
+    n = len(src)
+    r = rng.random(n)
+    kind = np.zeros(n, np.uint8)
+    kind[r < err] = 1; kind[r < 2 * err / 3] = 2; kind[r < err / 3] = 3
+    cnt = np.ones(n, np.int64); cnt[kind == 3] = 0; cnt[kind == 2] = 2
+    pos = np.cumsum(cnt) - cnt
+    total = int(pos[-1] + cnt[-1])
+    code = (np.searchsorted(synth.BASES, src) & 3).astype(np.uint8)
+    sub = synth.BASES[(code + rng.integers(1, 4, size=n, dtype=np.uint8)) & 3]
+    base = np.where(kind == 1, sub, src)
+    mut = np.empty(total + 16, np.uint8); mut[total:] = ord("A")
+    keep = kind != 3
+    mut[pos[keep]] = base[keep]
+    ins = kind == 2
+    mut[pos[ins] + 1] = synth.BASES[rng.integers(0, 4, size=int(ins.sum()), dtype=np.uint8)]
+    seg_start = pos[src_off]
+    seg_end = np.append(seg_start[1:], total)
+    avail = seg_end - seg_start
+    ql = np.minimum(ql, np.maximum(avail, 1)).astype(np.int32)
+    # compact the query arena: job j = mut[seg_start[j] : seg_start[j]+ql[j]]
+    q_off = np.zeros(n_jobs, np.int64); np.cumsum(ql[:-1], out=q_off[1:])
+    qtot = int(ql.sum())
+    gather = np.repeat(seg_start - q_off, ql) + np.arange(qtot, dtype=np.int64)
+    q_arena = np.empty(qtot + 16, np.uint8); q_arena[qtot:] = ord("A")
+    q_arena[:qtot] = mut[gather]
+    # compact target arena
+    t_off_c = np.zeros(n_jobs, np.int64); np.cumsum(tl[:-1], out=t_off_c[1:])
+    ttot = int(tl.sum())
+    gather_t = np.repeat(src_off - t_off_c, tl) + np.arange(ttot, dtype=np.int64)
+    t_arena = np.empty(ttot + 16, np.uint8); t_arena[ttot:] = ord("A")
+    t_arena[:ttot] = src[gather_t]
+    return dict(q_arena=q_arena, q_off=q_off.astype(np.uint32), t_off=t_pos.astype(np.uint32), q_len=ql, t_len=tl, k=k,
+                t_arena_compact=t_arena, t_off_compact=t_off_c.astype(np.uint32), scoring=PROFILE_SCORING[profile])
+
+
+def host_genome_fetcher(genome):
+    """fetch_windows over a host uint8 genome array."""
+    def fetch(starts, lengths):
+        off = np.zeros(len(starts), np.int64); np.cumsum(lengths[:-1], out=off[1:])
+        tot = int(lengths.sum())
+        idx = np.repeat(starts - off, lengths) + np.arange(tot, dtype=np.int64)
+        return genome[idx], off
+    return fetch
+
+
+def torch_genome_fetcher(genome_dev):
+    """fetch_windows over a device-resident torch uint8 genome tensor (gathers on the GPU, returns host arrays)."""
+    import torch
+
+    def fetch(starts, lengths):
+        off = np.zeros(len(starts), np.int64); np.cumsum(lengths[:-1], out=off[1:])
+        tot = int(lengths.sum())
+        dev = genome_dev.device
+        s = torch.from_numpy(starts - off).to(dev)
+        idx = torch.repeat_interleave(s, torch.from_numpy(lengths).to(dev)) + torch.arange(tot, device=dev)
+        return genome_dev[idx].cpu().numpy(), off
+    return fetch
+
+
+def check_blocks_property(jobs, res, m, mm, indel):
+    """Size-independent self-check of a batch result for jobs in the one-sided mode: blocks are ordered, inside the
+    windows and non-overlapping, and the score equals the score recomputed from the blocks (matches/mismatches inside
+    blocks + indel per gap base along the path from the origin to the traceback start cell).  Returns #jobs checked."""
+    ql = jobs["q_len"].astype(np.int64); tl = jobs["t_len"].astype(np.int64); kin = jobs["k"].astype(np.int64)
+    diag = np.maximum(1, np.minimum(ql, tl)); k0 = np.minimum(diag, kin)
+    one = diag + 2 * k0 >= np.maximum(ql, tl)
+    k = 2 * k0
+    qB = np.minimum(diag + k, ql + 1); tB = np.minimum(diag + k, tl + 1)
+    nb = res["n_blocks"].astype(np.int64); off = res["block_off"].astype(np.int64)
+    blk = res["blocks"]
+    jid = np.repeat(np.arange(len(nb)), nb)
+    bi = np.repeat(off, nb) + (np.arange(int(nb.sum())) - np.repeat(np.cumsum(nb) - nb, nb))
+    b = blk[bi].astype(np.int64)
+    qp, tp, ln = b[:, 0], b[:, 1], b[:, 2]
+    assert (ln > 0).all()
+    assert (qp + ln <= ql[jid]).all() and (tp + ln <= tl[jid]).all()
+    same = jid[1:] == jid[:-1]
+    assert (qp[1:][same] >= (qp + ln)[:-1][same]).all() and (tp[1:][same] >= (tp + ln)[:-1][same]).all()
+    # recompute the score of one-sided jobs
+    qa = jobs["q_arena"]; ta = jobs["t_arena_compact"]
+    tot = int(ln.sum())
+    boff = np.cumsum(ln) - ln
+    within = np.arange(tot, dtype=np.int64) - np.repeat(boff, ln)
+    qi = np.repeat(jobs["q_off"].astype(np.int64)[jid] + qp, ln) + within
+    ti = np.repeat(jobs["t_off_compact"].astype(np.int64)[jid] + tp, ln) + within
+    eq = qa[qi] == ta[ti]
+    per_block = np.add.reduceat(np.where(eq, m, mm), boff) if tot else np.zeros(0, np.int64)
+    sc = np.zeros(len(nb), np.int64); np.add.at(sc, jid, per_block)
+    cov = np.zeros(len(nb), np.int64); np.add.at(cov, jid, ln)
+    expect = sc + indel * ((qB - 1 - cov) + (tB - 1 - cov))
+    assert (res["score"].astype(np.int64)[one] == expect[one]).all()
+    return int(one.sum())
