@@ -17,7 +17,7 @@ extern "C" {
 #endif
 
 #define LRA_B200_OK 0
-#define LRA_B200_EINVAL 1     /* bad argument / job outside the domain (empty sequence, window outside its arena) */
+#define LRA_B200_EINVAL 1     /* bad argument / job outside the domain (negative length, window outside its arena) */
 #define LRA_B200_ECUDA 2      /* CUDA runtime error or no device */
 #define LRA_B200_EOVERFLOW 3  /* caller-provided output capacity too small; required size is reported */
 #define LRA_B200_EINTERNAL 4  /* kernel self-check failed (never expected) */
@@ -57,7 +57,8 @@ int lra_b200_seq_download(lra_b200_ctx *ctx, const lra_b200_seq *seq, uint32_t *
  * parameter k[j]; (match, mismatch, indel) are the reference's (m, mm, indel) = opts.localMatch / localMismatch /
  * localIndel.  Results per job: the return value (score) and the blocks appended to aln.blocks, as (qPos,tPos,length)
  * triples starting at blocks[3*block_off[j]], n_blocks[j] of them, in the reference's order.  Bit-exact.
- * Domain: q_len >= 1, t_len >= 1, windows inside their arenas (else LRA_B200_EINVAL). */
+ * Domain: q_len >= 0, t_len >= 0 (the reference does call it with empty windows), windows inside their arenas (else
+ * LRA_B200_EINVAL). */
 typedef struct lra_b200_aog_jobs {
   const uint32_t *q_off;
   const uint32_t *t_off;

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(128) aog_warp_band_kernel(AogBatch b, AogPlan 
     const int job = (int)sorted[begin + w];
     const int qLen = b.q_len[job], tLen = b.t_len[job];
     const uint32_t qoff = b.q_off[job], toff = b.t_off[job];
-    const int diag = imin(qLen, tLen);
+    const int diag = imax(1, imin(qLen, tLen));
     const int k = 2 * imin(diag, b.k[job]);
     const int qB = imin(diag + k, qLen + 1), tB = imin(diag + k, tLen + 1);
     const int rows = tB - 1;

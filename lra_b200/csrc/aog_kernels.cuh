@@ -101,14 +101,14 @@ __global__ void aog_classify_kernel(AogBatch b, AogPlan *plan, uint32_t *bin_of_
   long long cells = 0;
   if (j < b.n_jobs) {
     int qLen = b.q_len[j], tLen = b.t_len[j];
-    if (qLen < 1 || tLen < 1 || (uint64_t)b.q_off[j] + (uint64_t)qLen > b.q.n || (uint64_t)b.t_off[j] + (uint64_t)tLen > b.t.n) {
+    if (qLen < 0 || tLen < 0 || (uint64_t)b.q_off[j] + (uint64_t)qLen > b.q.n || (uint64_t)b.t_off[j] + (uint64_t)tLen > b.t.n) {
       // outside the domain: reported as LRA_B200_EINVAL by the host, job is skipped
       atomicOr(b.err, 8);
       bin_of_job[j] = 0xFFFFFFFFu;
       b.score[j] = 0; b.n_blocks[j] = 0; b.block_off[j] = 0;
-      qLen = tLen = 0;
+      qLen = tLen = -1;
     }
-  if (qLen > 0) {
+  if (qLen >= 0) {
     AogShape s = aog_shape(qLen, tLen, b.k[j], use_band);
     uint32_t bin = (uint32_t)(s.cls * kAogBuckets + s.bucket);
     bin_of_job[j] = bin;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(128) aog_thread_kernel(AogBatch b, AogPlan *pl
     if (active) {
       job = (int)sorted[idx];
       qLen = b.q_len[job]; tLen = b.t_len[job];
-      const int diag = imin(qLen, tLen);
+      const int diag = imax(1, imin(qLen, tLen));
       qB = imin(diag + K, qLen + 1);
       tB = imin(diag + K, tLen + 1);
       // (0,K+1) keeps its boundary value only if no rail loop overwrote it (AffineOneGapAlign.h:248-306)

@@ -338,7 +338,7 @@ static int aog_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b2
       ctx->stats.push_back(s);
     }
   }
-  if (err & 8) return fail(ctx, LRA_B200_EINVAL, "aog_batch: at least one job has an empty sequence or a window outside its arena");
+  if (err & 8) return fail(ctx, LRA_B200_EINVAL, "aog_batch: at least one job has a negative length or a window outside its arena");
   if (err & 1) return fail(ctx, LRA_B200_EOVERFLOW, "aog_batch: block capacity %llu too small, %llu needed",
                            (unsigned long long)res->block_cap, (unsigned long long)res->n_blocks_total);
   if (err & 6) return fail(ctx, LRA_B200_EINTERNAL, "aog_batch: kernel self-check failed (flags 0x%x)", err);

@@ -23,7 +23,7 @@ def random_job(rng, kind=None):
     """Returns (q bytes, t bytes, k)."""
     kind = kind or rng.choice(["similar", "similar", "similar", "lopsided", "tiny", "junk", "lowrep"])
     if kind == "tiny":
-        ql, tl = int(rng.integers(1, 12)), int(rng.integers(1, 12))
+        ql, tl = int(rng.integers(0, 12)), int(rng.integers(0, 12))  # the reference is called with empty windows too
         q = ALPHA[rng.integers(0, 4, ql)]; t = ALPHA[rng.integers(0, 4, tl)]
     elif kind == "junk":
         ql, tl = int(rng.integers(1, 120)), int(rng.integers(1, 120))
@@ -45,10 +45,11 @@ def random_job(rng, kind=None):
         n = int(np.exp(rng.uniform(np.log(2), np.log(1000))))
         t = ALPHA[rng.integers(0, 4, n)]
         q = _mutate(t, float(rng.choice([0.0, 0.01, 0.08, 0.15, 0.3])), rng)
-    if len(q) == 0:
-        q = ALPHA[rng.integers(0, 4, 1)]
-    if len(t) == 0:
-        t = ALPHA[rng.integers(0, 4, 1)]
+    if kind != "tiny":
+        if len(q) == 0:
+            q = ALPHA[rng.integers(0, 4, 1)]
+        if len(t) == 0:
+            t = ALPHA[rng.integers(0, 4, 1)]
     q = q.copy(); t = t.copy()
     if rng.random() < 0.1:  # non-ACGT symbols compare equal to each other (seqMapN, SeqUtils.h:42-75)
         for s in (q, t):

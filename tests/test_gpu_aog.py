@@ -106,8 +106,12 @@ def test_edge_cases(ctx):
     r = ctx.aog_batch(q, t, np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.int32), np.zeros(0, np.int32),
                       np.zeros(0, np.int32), 4, -3, -4)
     assert r["n_blocks_total"] == 0
-    with pytest.raises(capi.LraB200Error) as e:   # empty query: outside the domain
-        ctx.aog_batch(q, t, [0], [0], [0], [5], [3], 4, -3, -4)
+    r = ctx.aog_batch(q, t, [0, 0, 3], [0, 2, 0], [0, 1, 0], [5, 0, 0], [3, 3, 1], 4, -3, -4)   # empty windows are in the domain
+    for j, (qq, tt, kk) in enumerate([(b"", b"ACGTA", 3), (b"A", b"", 3), (b"", b"", 1)]):
+        es, eb, st = po.aog_port(qq, tt, 4, -3, -4, kk)
+        assert r["score"][j] == es and r["n_blocks"][j] == len(eb) == 0
+    with pytest.raises(capi.LraB200Error) as e:   # negative length: outside the domain
+        ctx.aog_batch(q, t, [0], [0], [-1], [5], [3], 4, -3, -4)
     assert e.value.code == capi.EINVAL
     with pytest.raises(capi.LraB200Error) as e:   # window runs past the arena
         ctx.aog_batch(q, t, [5], [0], [9], [5], [3], 4, -3, -4)

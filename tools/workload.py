@@ -23,7 +23,6 @@ def meta():
 
 def draw_shapes(profile, n_jobs, rng):
     tab = np.load(os.path.join(GOLD, "aog_shapes_%s.npy" % profile))
-    tab = tab[(tab[:, 0] >= 1) & (tab[:, 1] >= 1)]
     s = tab[rng.integers(0, len(tab), size=n_jobs)]
     return s[:, 0].astype(np.int32), s[:, 1].astype(np.int32), s[:, 2].astype(np.int32)
 
@@ -57,7 +56,7 @@ def make_jobs(profile, n_jobs, seed, genome_len, fetch_windows):
     seg_start = pos[src_off]
     seg_end = np.append(seg_start[1:], total)
     avail = seg_end - seg_start
-    ql = np.minimum(ql, np.maximum(avail, 1)).astype(np.int32)
+    ql = np.minimum(ql, np.maximum(avail, 0)).astype(np.int32)
     # compact the query arena: job j = mut[seg_start[j] : seg_start[j]+ql[j]]
     q_off = np.zeros(n_jobs, np.int64); np.cumsum(ql[:-1], out=q_off[1:])
     qtot = int(ql.sum())
