@@ -33,7 +33,7 @@ import workload  # noqa: E402
 PROFILE = "ont"
 STAGES = ["a18:AffineOneGapAlign"]
 METRIC = "reads/sec (MapRead stages on GPU so far: %s)" % ",".join(STAGES)
-WORKLOAD = ("BASELINE configs[1]: synthetic ONT reads (N50 20 kb, 8% err) vs 3 Gb synthetic ref (24 x 125 Mb), -ONT; "
+WORKLOAD = ("BASELINE configs[1]: synthetic ONT reads (N50 20 kb, 8%% err) vs 3 Gb synthetic ref (24 x 125 Mb), -ONT; "
             "per step the AffineOneGapAlign job stream of %d reads (%.1f jobs/read, shapes captured from the reference)")
 
 

@@ -96,39 +96,87 @@ __device__ __forceinline__ AogShape aog_shape(int qLen, int tLen, int k_in, int 
   return s;
 }
 
-__global__ void aog_classify_kernel(AogBatch b, AogPlan *plan, uint32_t *bin_of_job, int use_band) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  long long cells = 0;
+// Warp-aggregated shared-memory add: lanes with the same key elect a leader that adds the group's count.
+__device__ __forceinline__ uint32_t aog_group_rank(uint32_t key, bool valid, uint32_t *leader_lane, uint32_t *group_size) {
+#ifdef LRA_EMU
+  // emulator: ballot-based equivalent of __match_any_sync
+  uint32_t peers = 0;
+  for (int l = 0; l < 32; l++) {
+    uint32_t k2 = __shfl_sync(0xffffffffu, key, l);
+    int v2 = __shfl_sync(0xffffffffu, valid ? 1 : 0, l);
+    if (v2 && valid && k2 == key) peers |= 1u << l;
+  }
+#else
+  uint32_t peers = __match_any_sync(0xffffffffu, valid ? key : 0xFFFFFFFFu);
+  if (!valid) peers = 0;
+#endif
+  const uint32_t lane = threadIdx.x & 31;
+  *leader_lane = peers ? (uint32_t)(__ffs((int)peers) - 1) : lane;
+  *group_size = (uint32_t)__popc(peers);
+  return (uint32_t)__popc(peers & ((1u << lane) - 1u));
+}
+
+// classify: per-block histogram in shared memory (warp-aggregated), flushed once per block
+__global__ void __launch_bounds__(256) aog_classify_kernel(AogBatch b, AogPlan *plan, uint32_t *bin_of_job, int use_band) {
+  __shared__ uint32_t s_hist[kAogBins];
+  __shared__ uint32_t s_cells[kAogNumClasses], s_bytes[kAogNumClasses];
+  __shared__ uint32_t s_maxmat, s_maxdiag, s_maxrows, s_maxq;
+  for (int i = threadIdx.x; i < kAogBins; i += blockDim.x) s_hist[i] = 0;
+  if (threadIdx.x < kAogNumClasses) { s_cells[threadIdx.x] = 0; s_bytes[threadIdx.x] = 0; }
+  if (threadIdx.x == 0) { s_maxmat = 0; s_maxdiag = 0; s_maxrows = 0; s_maxq = 0; }
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = false;
+  uint32_t bin = 0;
+  AogShape s;
+  s.cls = 0; s.cells = 0;
+  int qLen = 0, tLen = 0;
   if (j < b.n_jobs) {
-    int qLen = b.q_len[j], tLen = b.t_len[j];
+    qLen = b.q_len[j]; tLen = b.t_len[j];
     if (qLen < 0 || tLen < 0 || (uint64_t)b.q_off[j] + (uint64_t)qLen > b.q.n || (uint64_t)b.t_off[j] + (uint64_t)tLen > b.t.n) {
       // outside the domain: reported as LRA_B200_EINVAL by the host, job is skipped
       atomicOr(b.err, 8);
       bin_of_job[j] = 0xFFFFFFFFu;
       b.score[j] = 0; b.n_blocks[j] = 0; b.block_off[j] = 0;
-      qLen = tLen = -1;
+    } else {
+      valid = true;
+      s = aog_shape(qLen, tLen, b.k[j], use_band);
+      bin = (uint32_t)(s.cls * kAogBuckets + s.bucket);
+      bin_of_job[j] = bin;
     }
-  if (qLen >= 0) {
-    AogShape s = aog_shape(qLen, tLen, b.k[j], use_band);
-    uint32_t bin = (uint32_t)(s.cls * kAogBuckets + s.bucket);
-    bin_of_job[j] = bin;
-    atomicAdd(&plan->hist[bin], 1u);
-    atomicAdd(&plan->cls_cells[s.cls], (unsigned long long)s.cells);
+  }
+  uint32_t leader, gsz;
+  const uint32_t rank = aog_group_rank(bin, valid, &leader, &gsz);
+  if (valid && rank == 0) atomicAdd(&s_hist[bin], gsz);
+  if (valid) {
+    // per-class work counters (fit 32 bits per block: <= 256 jobs x <= 2^22 cells)
+    atomicAdd(&s_cells[s.cls], (uint32_t)s.cells);
     // algorithmic bytes per job: 2-bit windows + 20 B SoA descriptor + 4 B score (+12 B per block, counted at output)
-    atomicAdd(&plan->cls_bytes[s.cls], (unsigned long long)((qLen + 3) / 4 + (tLen + 3) / 4 + 20 + 4));
+    atomicAdd(&s_bytes[s.cls], (uint32_t)((qLen + 3) / 4 + (tLen + 3) / 4 + 20 + 4));
     if (s.cls == kAogClsLiteral) {
-      atomicMax(&plan->max_mat, (uint32_t)((3 + s.k + s.diag) * (2 * s.k + 3)));
-      atomicMax(&plan->max_diag, (uint32_t)s.diag);
+      atomicMax(&s_maxmat, (uint32_t)((3 + s.k + s.diag) * (2 * s.k + 3)));
+      atomicMax(&s_maxdiag, (uint32_t)s.diag);
     } else if (s.cls >= kAogClsBand1) {
-      atomicMax(&plan->max_rows_band, (uint32_t)s.rows);
-      atomicMax(&plan->max_qlen_band, (uint32_t)qLen);
+      atomicMax(&s_maxrows, (uint32_t)s.rows);
+      atomicMax(&s_maxq, (uint32_t)qLen);
     }
-    cells = s.cells;
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kAogBins; i += blockDim.x) {
+    const uint32_t v = s_hist[i];
+    if (v) atomicAdd(&plan->hist[i], v);
   }
-  // warp-aggregate the cell counter
-  for (int o = 16; o > 0; o >>= 1) cells += __shfl_down_sync(0xffffffffu, cells, o);
-  if ((threadIdx.x & 31) == 0 && cells) atomicAdd(&plan->cells, (unsigned long long)cells);
+  if (threadIdx.x < kAogNumClasses) {
+    const uint32_t c = s_cells[threadIdx.x];
+    if (c) { atomicAdd(&plan->cls_cells[threadIdx.x], (unsigned long long)c); atomicAdd(&plan->cells, (unsigned long long)c); }
+    if (s_bytes[threadIdx.x]) atomicAdd(&plan->cls_bytes[threadIdx.x], (unsigned long long)s_bytes[threadIdx.x]);
+  }
+  if (threadIdx.x == 0) {
+    if (s_maxmat) atomicMax(&plan->max_mat, s_maxmat);
+    if (s_maxdiag) atomicMax(&plan->max_diag, s_maxdiag);
+    if (s_maxrows) atomicMax(&plan->max_rows_band, s_maxrows);
+    if (s_maxq) atomicMax(&plan->max_qlen_band, s_maxq);
+  }
 }
 
 // one block of kAogBins/ITEMS threads: exclusive scan of the histogram
@@ -170,12 +218,29 @@ __global__ void aog_scan_kernel(AogPlan *plan) {
   if (tid == 511) plan->bin_start[kAogBins] = run;
 }
 
-__global__ void aog_scatter_kernel(int n_jobs, AogPlan *plan, const uint32_t *bin_of_job, uint32_t *sorted) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n_jobs && bin_of_job[j] != 0xFFFFFFFFu) {
-    uint32_t pos = atomicAdd(&plan->cursor[bin_of_job[j]], 1u);
-    sorted[pos] = (uint32_t)j;
+// scatter: each block counts its jobs per bin in shared memory, reserves one range per non-empty bin with a single
+// global atomic, then places its jobs (order inside a bin is arbitrary; results are written back by job id).
+__global__ void __launch_bounds__(256) aog_scatter_kernel(int n_jobs, AogPlan *plan, const uint32_t *bin_of_job, uint32_t *sorted) {
+  __shared__ uint32_t s_cnt[kAogBins];
+  __shared__ uint32_t s_base[kAogBins];
+  for (int i = threadIdx.x; i < kAogBins; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t bin = 0xFFFFFFFFu;
+  if (j < n_jobs) bin = bin_of_job[j];
+  const bool valid = bin != 0xFFFFFFFFu;
+  uint32_t leader, gsz;
+  const uint32_t rank = aog_group_rank(bin, valid, &leader, &gsz);
+  uint32_t first = 0;
+  if (valid && rank == 0) first = atomicAdd(&s_cnt[bin], gsz);
+  first = __shfl_sync(0xffffffffu, first, (int)leader);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kAogBins; i += blockDim.x) {
+    const uint32_t c = s_cnt[i];
+    if (c) s_base[i] = atomicAdd(&plan->cursor[i], c);
   }
+  __syncthreads();
+  if (valid) sorted[s_base[bin] + first + rank] = (uint32_t)j;
 }
 
 // ---------------------------------------------------------------------------------------------------- output helper

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -38,6 +39,8 @@ struct lra_b200_ctx {
   unsigned long long *h_misc = nullptr;  // pinned (2 x u64)
   std::vector<lra_b200_kernel_stat> stats;
   std::vector<cudaEvent_t> ev;
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};  // kernel classes of one batch run concurrently
+  cudaEvent_t fork_ev = nullptr, join_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 static std::string g_create_err;
@@ -93,6 +96,11 @@ extern "C" int lra_b200_create(lra_b200_ctx **out, int device) {
   }
   ctx->ev.resize(40);
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+  for (int i = 0; i < 4; i++) {
+    cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->join_ev[i], cudaEventDisableTiming);
+  }
+  cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
   *out = ctx;
   return LRA_B200_OK;
 }
@@ -105,6 +113,8 @@ extern "C" void lra_b200_destroy(lra_b200_ctx *ctx) {
                     &ctx->d_toff, &ctx->d_qlen, &ctx->d_tlen, &ctx->d_k, &ctx->d_score, &ctx->d_nb, &ctx->d_boff, &ctx->d_blocks};
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
   for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+  for (int i = 0; i < 4; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]); }
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   if (ctx->h_plan) cudaFreeHost(ctx->h_plan);
   if (ctx->h_misc) cudaFreeHost(ctx->h_misc);
   cudaStreamDestroy(ctx->own_stream);
@@ -211,15 +221,15 @@ static const char *kClsName[kAogNumClasses] = {"aog_thread<K=2>", "aog_thread<K=
                                                "aog_warp_band<C=1>", "aog_warp_band<C=2>", "aog_warp_band<C=4>", "aog_warp_band<C=8>"};
 
 template <int K>
-static void launch_thread(lra_b200_ctx *ctx, const AogBatch &b, AogPlan *plan, const uint32_t *sorted, uint32_t n) {
+static void launch_thread(lra_b200_ctx *ctx, cudaStream_t st, const AogBatch &b, AogPlan *plan, const uint32_t *sorted, uint32_t n) {
   unsigned blocks = (n + 127) / 128;
   unsigned cap = (unsigned)ctx->n_sm * 16u;
   if (blocks > cap) blocks = cap;
-  aog_thread_kernel<K><<<blocks, 128, 0, ctx->stream>>>(b, plan, sorted);
+  aog_thread_kernel<K><<<blocks, 128, 0, st>>>(b, plan, sorted);
 }
 template <int C>
-static void launch_band(lra_b200_ctx *ctx, const AogBatch &b, AogPlan *plan, const uint32_t *sorted, unsigned blocks, AogBandScratch sc) {
-  aog_warp_band_kernel<C><<<blocks, 128, 0, ctx->stream>>>(b, plan, sorted, sc);
+static void launch_band(cudaStream_t st, const AogBatch &b, AogPlan *plan, const uint32_t *sorted, unsigned blocks, AogBandScratch sc) {
+  aog_warp_band_kernel<C><<<blocks, 128, 0, st>>>(b, plan, sorted, sc);
 }
 
 static int aog_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_aog_jobs *jobs,
@@ -268,17 +278,35 @@ static int aog_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b2
 
   struct Launched { int cls; int ev0; };
   std::vector<Launched> launched;
-  auto begin_cls = [&](int c) { launched.push_back({c, evi}); rec(); };
-  auto end_cls = [&]() { rec(); ctx->launches++; };
+  // The classes are independent: latency-bound warp kernels (few long jobs) overlap with the throughput-bound thread
+  // kernels on side streams.  LRA_B200_SERIAL=1 keeps everything on the main stream (per-kernel timing without overlap).
+  static const bool serial = getenv("LRA_B200_SERIAL") != nullptr;
+  cudaStream_t S[4];
+  for (int i = 0; i < 4; i++) S[i] = serial ? st : ctx->side[i];
+  if (!serial) {
+    CU(cudaEventRecord(ctx->fork_ev, st));
+    for (int i = 0; i < 4; i++) CU(cudaStreamWaitEvent(S[i], ctx->fork_ev, 0));
+  }
+  cudaStream_t cur = st;
+  auto begin_cls = [&](int c, cudaStream_t s2) { cur = s2; launched.push_back({c, evi}); cudaEventRecord(ctx->ev[evi++], cur); };
+  auto end_cls = [&]() { cudaEventRecord(ctx->ev[evi++], cur); ctx->launches++; };
 
-  if (cnt[0]) { begin_cls(0); launch_thread<2>(ctx, b, plan, sorted, cnt[0]); end_cls(); }
-  if (cnt[1]) { begin_cls(1); launch_thread<4>(ctx, b, plan, sorted, cnt[1]); end_cls(); }
-  if (cnt[2]) { begin_cls(2); launch_thread<6>(ctx, b, plan, sorted, cnt[2]); end_cls(); }
-  if (cnt[3]) { begin_cls(3); launch_thread<8>(ctx, b, plan, sorted, cnt[3]); end_cls(); }
-  if (cnt[4]) { begin_cls(4); launch_thread<10>(ctx, b, plan, sorted, cnt[4]); end_cls(); }
-  if (cnt[5]) { begin_cls(5); launch_thread<12>(ctx, b, plan, sorted, cnt[5]); end_cls(); }
-  if (cnt[6]) { begin_cls(6); launch_thread<14>(ctx, b, plan, sorted, cnt[6]); end_cls(); }
-  // band classes
+  // stream 0: literal kernel (longest jobs, launched first)
+  if (cnt[kAogClsLiteral]) {
+    AogLiteralScratch sc;
+    sc.max_mat = hp.max_mat; sc.max_diag = hp.max_diag;
+    sc.slab_bytes = (aog_literal_slab_bytes(sc.max_mat, sc.max_diag) + 127ull) & ~127ull;
+    unsigned blocks = (cnt[kAogClsLiteral] + 3) / 4;
+    unsigned max_blocks = (unsigned)ctx->n_sm * 4u;
+    if (blocks > max_blocks) blocks = max_blocks;
+    while (blocks > 1 && (unsigned long long)blocks * 4ull * sc.slab_bytes > (8ull << 30)) blocks /= 2;
+    if ((rc = ensure(ctx, ctx->lit_slab, (size_t)blocks * 4 * sc.slab_bytes))) return rc;
+    sc.base = (unsigned char *)ctx->lit_slab.p;
+    begin_cls(kAogClsLiteral, S[0]);
+    aog_warp_literal_kernel<<<blocks, 128, 0, cur>>>(b, plan, sorted, sc);
+    end_cls();
+  }
+  // stream 1: band classes, widest first
   uint32_t nband = cnt[8] + cnt[9] + cnt[10] + cnt[11];
   if (nband) {
     AogBandScratch sc;
@@ -290,27 +318,25 @@ static int aog_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b2
     unsigned blocks_cap = (biggest + 3) / 4;
     if (blocks_cap > max_blocks) blocks_cap = max_blocks;
     while (blocks_cap > 1 && (unsigned long long)blocks_cap * 4ull * sc.slab_bytes > (8ull << 30)) blocks_cap /= 2;
+    // the band classes run one after another on one stream, so they can share the slabs
     if ((rc = ensure(ctx, ctx->band_slab, (size_t)blocks_cap * 4 * sc.slab_bytes))) return rc;
     sc.base = (unsigned char *)ctx->band_slab.p;
     auto blocks_for = [&](uint32_t c) { unsigned x = (c + 3) / 4; return x > blocks_cap ? blocks_cap : x; };
-    if (cnt[8]) { begin_cls(8); launch_band<1>(ctx, b, plan, sorted, blocks_for(cnt[8]), sc); end_cls(); }
-    if (cnt[9]) { begin_cls(9); launch_band<2>(ctx, b, plan, sorted, blocks_for(cnt[9]), sc); end_cls(); }
-    if (cnt[10]) { begin_cls(10); launch_band<4>(ctx, b, plan, sorted, blocks_for(cnt[10]), sc); end_cls(); }
-    if (cnt[11]) { begin_cls(11); launch_band<8>(ctx, b, plan, sorted, blocks_for(cnt[11]), sc); end_cls(); }
+    if (cnt[11]) { begin_cls(11, S[1]); launch_band<8>(cur, b, plan, sorted, blocks_for(cnt[11]), sc); end_cls(); }
+    if (cnt[10]) { begin_cls(10, S[1]); launch_band<4>(cur, b, plan, sorted, blocks_for(cnt[10]), sc); end_cls(); }
+    if (cnt[9]) { begin_cls(9, S[1]); launch_band<2>(cur, b, plan, sorted, blocks_for(cnt[9]), sc); end_cls(); }
+    if (cnt[8]) { begin_cls(8, S[1]); launch_band<1>(cur, b, plan, sorted, blocks_for(cnt[8]), sc); end_cls(); }
   }
-  if (cnt[kAogClsLiteral]) {
-    AogLiteralScratch sc;
-    sc.max_mat = hp.max_mat; sc.max_diag = hp.max_diag;
-    sc.slab_bytes = (aog_literal_slab_bytes(sc.max_mat, sc.max_diag) + 127ull) & ~127ull;
-    unsigned blocks = (cnt[kAogClsLiteral] + 3) / 4;
-    unsigned max_blocks = (unsigned)ctx->n_sm * 3u;
-    if (blocks > max_blocks) blocks = max_blocks;
-    while (blocks > 1 && (unsigned long long)blocks * 4ull * sc.slab_bytes > (8ull << 30)) blocks /= 2;
-    if ((rc = ensure(ctx, ctx->lit_slab, (size_t)blocks * 4 * sc.slab_bytes))) return rc;
-    sc.base = (unsigned char *)ctx->lit_slab.p;
-    begin_cls(kAogClsLiteral);
-    aog_warp_literal_kernel<<<blocks, 128, 0, st>>>(b, plan, sorted, sc);
-    end_cls();
+  // streams 2,3: thread-per-job classes
+  if (cnt[6]) { begin_cls(6, S[2]); launch_thread<14>(ctx, cur, b, plan, sorted, cnt[6]); end_cls(); }
+  if (cnt[4]) { begin_cls(4, S[3]); launch_thread<10>(ctx, cur, b, plan, sorted, cnt[4]); end_cls(); }
+  if (cnt[2]) { begin_cls(2, S[2]); launch_thread<6>(ctx, cur, b, plan, sorted, cnt[2]); end_cls(); }
+  if (cnt[0]) { begin_cls(0, S[3]); launch_thread<2>(ctx, cur, b, plan, sorted, cnt[0]); end_cls(); }
+  if (cnt[5]) { begin_cls(5, S[2]); launch_thread<12>(ctx, cur, b, plan, sorted, cnt[5]); end_cls(); }
+  if (cnt[3]) { begin_cls(3, S[3]); launch_thread<8>(ctx, cur, b, plan, sorted, cnt[3]); end_cls(); }
+  if (cnt[1]) { begin_cls(1, S[2]); launch_thread<4>(ctx, cur, b, plan, sorted, cnt[1]); end_cls(); }
+  if (!serial) {
+    for (int i = 0; i < 4; i++) { CU(cudaEventRecord(ctx->join_ev[i], S[i])); CU(cudaStreamWaitEvent(st, ctx->join_ev[i], 0)); }
   }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(ctx->h_plan, plan, sizeof(AogPlan), cudaMemcpyDeviceToHost, st));
