@@ -86,6 +86,45 @@ int lra_b200_aog_batch(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_
 int lra_b200_aog_batch_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t,
                               const lra_b200_aog_jobs *jobs_dev, lra_b200_aog_result *res_dev);
 
+/* ---- a19  IndelRefineAlignment: the banded 3-state DP, batched --------------------------------------------------
+ * Replaces the per-group body of  void IndelRefineAlignment(Read&, Genome&, Alignment&, const Options&,
+ * IndelRefineBuffers&, bool endAlign)   IndelRefine.h:359-745  (matrices :383-431, recurrence :438-622, traceback
+ * :626-674, path -> blocks :702-745) for a batch of groups.  A group is one banded window of a segment, as the
+ * reference builds it in IndelRefine.h:132-333: rows t = 0..t_len-1 are the target bases tSeq[t_start+t], row t spans
+ * the read positions qS[t]..qE[t] (band[band_off .. +t_len) = qS, band[band_off+t_len .. +2 t_len) = qE; absolute read
+ * coordinates).  qSeq[i] = q arena [q_base + i], tSeq[i] = t arena [t_base + i] (32-bit wrap-around arithmetic, so a
+ * contig-relative t with a window-relative arena works).  Scoring: gap = indel, gapOpen = 2*indel+1, gapExtend = 0.
+ * Output per group: the blocks the reference pushes to `refined` for it (including its zero-length blocks), in order.
+ * Characters are compared through the packed alphabet: identical to the reference's raw comparison for A,C,G,T,N. */
+typedef struct lra_b200_ir_groups {
+  const uint32_t *q_base;
+  const uint32_t *t_base;
+  const int32_t *q_start;
+  const int32_t *t_start;
+  const int32_t *t_len;
+  const int32_t *q_seq_len;
+  const int32_t *t_seq_len;
+  const uint32_t *band_off;
+  const int32_t *band;
+  uint64_t band_len;      /* number of int32 in band */
+  int32_t n_groups;
+  int32_t match, mismatch, indel;
+} lra_b200_ir_groups;
+
+typedef struct lra_b200_ir_result {
+  int32_t *n_blocks;       /* [n_groups] */
+  uint64_t *block_off;     /* [n_groups] */
+  uint32_t *blocks;        /* [block_cap * 3] */
+  uint64_t block_cap;
+  uint64_t n_blocks_total; /* out */
+  uint64_t cells;          /* out: DP cells (matSize summed over groups) */
+} lra_b200_ir_result;
+
+int lra_b200_indel_dp_batch(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_ir_groups *groups,
+                            lra_b200_ir_result *res);
+int lra_b200_indel_dp_batch_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t,
+                                   const lra_b200_ir_groups *groups_dev, lra_b200_ir_result *res_dev);
+
 /* ---- per-kernel timing of the last batch call (CUDA events on the context's stream) ---------------------------- */
 typedef struct lra_b200_kernel_stat {
   char name[48];

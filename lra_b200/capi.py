@@ -27,6 +27,18 @@ class _AogResult(C.Structure):
                 ("block_cap", C.c_uint64), ("n_blocks_total", C.c_uint64), ("cells", C.c_uint64)]
 
 
+class _IrGroups(C.Structure):
+    _fields_ = [("q_base", C.c_void_p), ("t_base", C.c_void_p), ("q_start", C.c_void_p), ("t_start", C.c_void_p),
+                ("t_len", C.c_void_p), ("q_seq_len", C.c_void_p), ("t_seq_len", C.c_void_p), ("band_off", C.c_void_p),
+                ("band", C.c_void_p), ("band_len", C.c_uint64), ("n_groups", C.c_int32), ("match", C.c_int32),
+                ("mismatch", C.c_int32), ("indel", C.c_int32)]
+
+
+class _IrResult(C.Structure):
+    _fields_ = [("n_blocks", C.c_void_p), ("block_off", C.c_void_p), ("blocks", C.c_void_p), ("block_cap", C.c_uint64),
+                ("n_blocks_total", C.c_uint64), ("cells", C.c_uint64)]
+
+
 class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("ms", C.c_float), ("jobs", C.c_uint64), ("cells", C.c_uint64),
                 ("algo_bytes", C.c_uint64)]
@@ -63,6 +75,8 @@ def load_library():
     L.lra_b200_seq_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lra_b200_aog_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_AogJobs), C.POINTER(_AogResult)]
     L.lra_b200_aog_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_AogJobs), C.POINTER(_AogResult)]
+    L.lra_b200_indel_dp_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrGroups), C.POINTER(_IrResult)]
+    L.lra_b200_indel_dp_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrGroups), C.POINTER(_IrResult)]
     L.lra_b200_last_kernel_stats.argtypes = [C.c_void_p, C.POINTER(KernelStat), C.c_int]
     L.lra_b200_launch_count.argtypes = [C.c_void_p]
     L.lra_b200_launch_count.restype = C.c_uint64
@@ -179,6 +193,33 @@ class Context:
         jobs = _AogJobs(d_q_off, d_t_off, d_q_len, d_t_len, d_k, n, m, mm, indel)
         res = _AogResult(d_score, d_n_blocks, d_block_off, d_blocks, block_cap, 0, 0)
         self._check(self.lib.lra_b200_aog_batch_device(self.h, q.handle, t.handle, C.byref(jobs), C.byref(res)))
+        return int(res.n_blocks_total), int(res.cells)
+
+
+    # ---- a19
+    def indel_dp_batch(self, q, t, g, block_cap=None, out=None):
+        """g: dict of host arrays (q_base,t_base,q_start,t_start,t_len,q_seq_len,t_seq_len,band_off,band) + match/mismatch/indel.
+        Returns dict(n_blocks, block_off, blocks[n,3], n_blocks_total, cells)."""
+        n = len(g["t_len"])
+        arr = {k: np.ascontiguousarray(g[k], np.uint32 if k in ("q_base", "t_base", "band_off") else np.int32)
+               for k in ("q_base", "t_base", "q_start", "t_start", "t_len", "q_seq_len", "t_seq_len", "band_off", "band")}
+        if block_cap is None:
+            block_cap = int(arr["q_seq_len"].sum() + arr["t_seq_len"].sum()) + 8
+        if out is None:
+            out = dict(n_blocks=np.zeros(n, np.int32), block_off=np.zeros(n, np.uint64), blocks=np.zeros((max(1, block_cap), 3), np.uint32))
+        gs = _IrGroups(*[_ptr(arr[k]) for k in ("q_base", "t_base", "q_start", "t_start", "t_len", "q_seq_len", "t_seq_len", "band_off", "band")],
+                       len(arr["band"]), n, g["match"], g["mismatch"], g["indel"])
+        res = _IrResult(_ptr(out["n_blocks"]), _ptr(out["block_off"]), _ptr(out["blocks"]), block_cap, 0, 0)
+        rc = self.lib.lra_b200_indel_dp_batch(self.h, q.handle, t.handle, C.byref(gs), C.byref(res))
+        out["n_blocks_total"] = int(res.n_blocks_total); out["cells"] = int(res.cells)
+        self._check(rc)
+        return out
+
+    def indel_dp_batch_device(self, q, t, ptrs, n, band_len, match, mismatch, indel, d_n_blocks, d_block_off, d_blocks, block_cap):
+        """ptrs: device pointers in the order q_base,t_base,q_start,t_start,t_len,q_seq_len,t_seq_len,band_off,band."""
+        gs = _IrGroups(*ptrs, band_len, n, match, mismatch, indel)
+        res = _IrResult(d_n_blocks, d_block_off, d_blocks, block_cap, 0, 0)
+        self._check(self.lib.lra_b200_indel_dp_batch_device(self.h, q.handle, t.handle, C.byref(gs), C.byref(res)))
         return int(res.n_blocks_total), int(res.cells)
 
 

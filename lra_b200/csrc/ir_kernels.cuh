@@ -1,0 +1,432 @@
+// a19  IndelRefineAlignment -- banded 3-state (match / ins / del) DP over a ragged band, batched.
+// Reference: IndelRefine.h:359-745 (matrix set-up :383-431, recurrence :438-622, traceback :626-674, path->blocks :702-745).
+//
+// A "group" is one banded window of a segment: rows t = 0..tLen-1 (target bases tStart+t), row t covers the query
+// positions qS[t]..qE[t] (absolute read coordinates, both non-decreasing in t).  Scoring: gap = indel,
+// gapOpen = 2*indel+1, gapExtend = 0 (IndelRefine.h:338-340).  Boundary cells: the first cell of every row >= 1 and
+// the last cell of every row but the last are "bound" (never computed, never a valid predecessor); row 0 is a pure
+// insertion ramp from its first cell.  Tie order M: diag, left, down, delClose, insClose; del/ins: open before extend.
+//
+// ir_dp_thread_kernel<WMAX>: ONE GROUP PER THREAD (long thin bands: ONT/CLR groups are 10^4 rows x 15..57 cells; CCS
+// groups are 10^2 rows).  The previous row of M and D lives in shared memory ([cell][thread], conflict-free), updated in
+// place; the query window is a packed shift register and the row's match mask is computed bit-parallel; arrows are 5 bits
+// per cell (3 for M, 1 for del, 1 for ins), 6 cells per 32-bit word, streamed to HBM once per row.  This is the part
+// of the hot path whose traffic is real: ~10^5..10^6 cells per group spill 0.67 B/cell of traceback.
+// ir_dp_generic_kernel: any width, rows and byte arrows in a per-thread scratch slab (slow, exact, rare).
+#pragma once
+#include "aog_kernels.cuh"
+
+namespace lra {
+
+constexpr int kIrBad = -999999999;
+enum IrArrow : int { IR_DIAG = 0, IR_LEFT = 1, IR_DOWN = 2, IR_DELCLOSE = 3, IR_INSCLOSE = 4 };
+
+struct IrBatch {
+  SeqView q, t;
+  const uint32_t *q_base;   // arena offset of qSeq[0] (the read strand the blocks refer to)
+  const uint32_t *t_base;   // arena offset of tSeq[0] (contig start)
+  const int32_t *q_start, *t_start, *t_len, *q_seq_len, *t_seq_len;
+  const uint32_t *band_off; // band[off .. off+tLen) = qS, band[off+tLen .. off+2 tLen) = qE
+  const int32_t *band;
+  int n_groups;
+  int match, mismatch, gap;
+  int32_t *n_blocks;
+  unsigned long long *block_off;
+  uint32_t *blocks;
+  unsigned long long block_cap;
+  unsigned long long *block_cursor;
+  int *err;                 // bit0 block overflow, bit4 traceback failed, bit5 path end mismatch
+  // scratch
+  uint32_t *tb;             // arrows
+  unsigned long long *tb_off;  // per group, in 32-bit words (assigned by the classify kernel)
+  int32_t *max_width;       // per group
+};
+
+constexpr int kIrClsW24 = 0, kIrClsW64 = 1, kIrClsGeneric = 2;
+__host__ __device__ inline int ir_words(int wmax) { return (wmax + 5) / 6; }
+
+// one warp per group: band maximum width -> class; reserves traceback storage; fills the planner histogram
+__global__ void __launch_bounds__(128) ir_classify_kernel(IrBatch b, AogPlan *plan, uint32_t *bin_of_group, unsigned long long *tb_cursor,
+                                                          unsigned long long *cells_total) {
+  const int lane = threadIdx.x & 31;
+  const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (g >= b.n_groups) return;
+  const int rows = b.t_len[g];
+  const int32_t *qS = b.band + b.band_off[g];
+  const int32_t *qE = qS + rows;
+  int mw = 0;
+  long long cells = 0;
+  int bad = 0;
+  for (int r = lane; r < rows; r += 32) {
+    const int w = qE[r] - qS[r] + 1;
+    mw = imax(mw, w);
+    cells += w;
+    if (w < 2) bad = 1;
+    if (r > 0 && (qS[r] < qS[r - 1] || qE[r] < qE[r - 1])) bad = 1;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mw = imax(mw, __shfl_down_sync(0xffffffffu, mw, o));
+    cells += __shfl_down_sync(0xffffffffu, cells, o);
+    bad |= __shfl_down_sync(0xffffffffu, bad, o);
+  }
+  if (lane == 0) {
+    if (bad || rows < 2) {
+      atomicOr(b.err, 8);
+      bin_of_group[g] = 0xFFFFFFFFu;
+      b.n_blocks[g] = 0; b.block_off[g] = 0;
+      return;
+    }
+    const int cls = mw <= 24 ? kIrClsW24 : (mw <= 64 ? kIrClsW64 : kIrClsGeneric);
+    const unsigned long long words = cls == kIrClsGeneric ? ((unsigned long long)rows * (unsigned long long)mw + 3ull) / 4ull + 2ull * (unsigned long long)mw + 4ull
+                                                           : (unsigned long long)rows * (unsigned long long)ir_words(cls == kIrClsW24 ? 24 : 64);
+    b.tb_off[g] = atomicAdd(tb_cursor, words);
+    b.max_width[g] = mw;
+    const int bucket = kAogBuckets - 1 - imin(rows >> 8, kAogBuckets - 1);
+    const uint32_t bin = (uint32_t)(cls * kAogBuckets + bucket);
+    bin_of_group[g] = bin;
+    atomicAdd(&plan->hist[bin], 1u);
+    atomicAdd(&plan->cls_cells[cls], (unsigned long long)cells);
+    // algorithmic bytes: 2-bit windows + 8 B per band row + 32 B descriptor + arrows spilled at 5 bit/cell
+    atomicAdd(&plan->cls_bytes[cls], (unsigned long long)((b.q_seq_len[g] + 3) / 4 + (b.t_seq_len[g] + 3) / 4 + 8 * rows + 32) + (unsigned long long)((5 * cells + 7) / 8));
+    atomicAdd(cells_total, (unsigned long long)cells);
+  }
+}
+
+// Walks the stored arrows backwards.  WRITE == false counts the blocks the reference's path->blocks loop would emit,
+// WRITE == true stores them (last block first) at out[nb-1], out[nb-2], ...  Returns the number of blocks or -1.
+template <int WORDS, bool WRITE>
+__device__ __forceinline__ int ir_walk(const uint32_t *tb, const int32_t *qS, const int32_t *qE, int rows, int tStart, uint32_t *out, int nb) {
+  int t = rows - 1;
+  int qs = qS[t];
+  int x = qE[t] - qs;
+  int mat = 0;            // 0 M, 1 del, 2 ins
+  int run = 0;            // length of the diagonal run being walked (backwards)
+  int lastOp = -1;        // type of the previous op in walk order (= the NEXT op in forward order)
+  int count = 0;
+  long guard = 0;
+  const long guardMax = 4L * rows + 4L * (qE[rows - 1] - qS[0]) + 64;
+  // forward semantics: blocks = one per diagonal run, plus a zero-length block for a gap run that directly follows
+  // another gap run.  Walking backwards, an op `op` at a cell with forward start coordinates (qb, tb0) closes things:
+  auto emit = [&](uint32_t qq, uint32_t tt, uint32_t ln) {
+    if (WRITE) { const int r = nb - 1 - count; out[3 * r] = qq; out[3 * r + 1] = tt; out[3 * r + 2] = ln; }
+    count++;
+  };
+  // coordinates of the forward-first cell of the current diagonal run are known when the run ends (see below)
+  while (true) {
+    if (++guard > guardMax) return -1;
+    if (t == 0) {
+      // row 0: `x` insertion ops back to the origin cell, then the origin diagonal (IndelRefine.h:420-424, :674)
+      int op;
+      if (x > 0) {
+        if (mat != 0) return -1;
+        // a left run of length x at row 0; forward start of its first op: q = qs+1, t = tStart+1
+        if (run > 0) { emit((uint32_t)(qs + x + 1), (uint32_t)(tStart + 1), (uint32_t)run); run = 0; }
+        else if (lastOp == IR_DOWN) emit((uint32_t)(qs + x + 1), (uint32_t)(tStart + 1), 0u);
+        lastOp = IR_LEFT;
+        x = 0;
+      }
+      op = IR_DIAG;  // origin
+      if (lastOp != IR_DIAG && lastOp != -1 && run == 0) { /* gap run precedes: absorbed by this diagonal block */ }
+      run += 1;
+      emit((uint32_t)qs, (uint32_t)tStart, (uint32_t)run);
+      (void)op;
+      break;
+    }
+    const uint32_t word = tb[(unsigned long long)t * WORDS + (unsigned)(x / 6)];
+    const int a5 = (int)((word >> (5 * (x % 6))) & 31u);
+    int op;          // op pushed by the reference at this step (or -1 for a matrix hop)
+    int nt = t, nx = x, nmat = mat;
+    if (mat == 0) {
+      const int a = a5 & 7;
+      if (a == IR_DELCLOSE) { op = -1; nmat = 1; }
+      else if (a == IR_INSCLOSE) { op = -1; nmat = 2; }
+      else if (a == IR_DIAG) { op = IR_DIAG; nt = t - 1; }
+      else if (a == IR_LEFT) { op = IR_LEFT; nx = x - 1; }
+      else if (a == IR_DOWN) { op = IR_DOWN; nt = t - 1; }
+      else return -1;
+    } else if (mat == 1) {
+      op = IR_DOWN; nmat = ((a5 >> 3) & 1) ? 1 : 0; nt = t - 1;
+    } else {
+      op = IR_LEFT; nmat = ((a5 >> 4) & 1) ? 2 : 0; nx = x - 1;
+    }
+    if (op >= 0) {
+      const int q = qs + x;
+      if (op == IR_DIAG) {
+        run++;
+      } else {
+        // a gap op; forward start coordinates of THIS op: left: (q, tStart+t+1), down: (q+1, tStart+t)
+        if (run > 0) {
+          // the diagonal run that follows this gap op in forward order starts right after it
+          const uint32_t qb = (uint32_t)(q + 1), tb0 = (uint32_t)(tStart + t + 1);
+          emit(qb, tb0, (uint32_t)run);
+          run = 0;
+        } else if (lastOp != -1 && lastOp != op) {
+          // forward order: this gap run, then a different gap run (lastOp) with no diagonal between -> the later run got a
+          // zero-length block at its own start = the position after this op
+          const uint32_t qb = (uint32_t)(q + 1), tb0 = (uint32_t)(tStart + t + 1);
+          emit(qb, tb0, 0u);
+        }
+      }
+      lastOp = op;
+    }
+    if (nt != t) {
+      // moving up one row: diag -> (t-1, q-1), down -> (t-1, q)
+      const int pqs = qS[t - 1];
+      const int q = qs + x;
+      nx = (op == IR_DIAG ? q - 1 : q) - pqs;
+      qs = pqs;
+    }
+    t = nt; x = nx; mat = nmat;
+    if (x < 0) return -1;
+  }
+  return count;
+}
+
+template <int WMAX> struct IrWin { typedef unsigned long long type; };
+template <> struct IrWin<64> { typedef unsigned __int128 type; };
+
+template <int WMAX>
+__global__ void __launch_bounds__(64) ir_dp_thread_kernel(IrBatch b, AogPlan *plan, const uint32_t *sorted, int cls) {
+  typedef typename IrWin<WMAX>::type BT;
+  constexpr int WORDS = (WMAX + 5) / 6;
+  __shared__ int sM[WMAX + 1][64];
+  __shared__ int sD[WMAX + 1][64];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const uint32_t begin = plan->bin_start[cls * kAogBuckets];
+  const uint32_t end = plan->bin_start[(cls + 1) * kAogBuckets];
+  BT kOdd = 0;
+#pragma unroll
+  for (int i = 0; i < WMAX; i++) kOdd |= (BT)1 << (2 * i);
+  const int match = b.match, mismatch = b.mismatch, gap = b.gap, gapOpen = 2 * b.gap + 1;
+
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&plan->work[cls], 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (begin + base >= end) break;
+    const uint32_t idx = begin + base + lane;
+    const bool active = idx < end;
+    int g = 0, nb = 0, rows = 0, tStart = 0;
+    const int32_t *qS = nullptr, *qE = nullptr;
+    const uint32_t *tbp = nullptr;
+    if (active) {
+      g = (int)sorted[idx];
+      rows = b.t_len[g];
+      tStart = b.t_start[g];
+      qS = b.band + b.band_off[g];
+      qE = qS + rows;
+      uint32_t *tbw = b.tb + b.tb_off[g];
+      tbp = tbw;
+      // ---- row 0: M[0] = 0 (done), ramp, last cell bound; D = BAD
+      int qsPrev = qS[0], qePrev = qE[0];
+      int lenPrev = qePrev - qsPrev + 1;
+      for (int x = 0; x < lenPrev; x++) { sM[x][tid] = x * gap; sD[x][tid] = kIrBad; }
+      SeqStream qst, tst;
+      qst.init(b.q, (uint64_t)b.q_base[g] + (uint64_t)qsPrev);
+      tst.init(b.t, (uint64_t)(uint32_t)(b.t_base[g] + (uint32_t)(tStart + 1)));  // 32-bit wrap-around: t_base may be 'negative'
+      BT qw = 0, qn = 0;
+      for (int x = 0; x < lenPrev; x++) {
+        const int code = qst.next();
+        qw |= (BT)(code & 3) << (2 * x);
+        qn |= (BT)(code == 4 ? 1 : 0) << (2 * x);
+      }
+      for (int t = 1; t < rows; t++) {
+        const int qs = qS[t], qe = qE[t];
+        const int len = qe - qs + 1;
+        const int off = qs - qsPrev;
+        const int rowEnd = (t == rows - 1) ? len : len - 1;
+        // slide the query window
+        if (off >= WMAX) { qw = 0; qn = 0; } else { qw >>= (2 * off); qn >>= (2 * off); }
+        {
+          int qnext = qePrev + 1;
+          for (; qnext < qs; qnext++) (void)qst.next();  // (never in practice: bands overlap)
+          for (; qnext <= qe; qnext++) {
+            const int code = qst.next();
+            const int xx = qnext - qs;
+            qw |= (BT)(code & 3) << (2 * xx);
+            qn |= (BT)(code == 4 ? 1 : 0) << (2 * xx);
+          }
+        }
+        const int tc = tst.next();
+        BT e;
+        if (tc == 4) e = qn;
+        else { BT xr = qw ^ ((BT)tc * kOdd); e = ~(xr | (xr >> 1)) & kOdd & ~qn; }
+        // in-place row update, left to right
+        int Mdiag = (off < lenPrev) ? sM[off][tid] : kIrBad;  // prev-row cell under x = 0, diagonal predecessor of x = 1
+        int Mleft = kIrBad, Ileft = kIrBad;
+        sM[0][tid] = kIrBad;             // first cell of rows >= 1 is bound
+        uint32_t words[WORDS];
+#pragma unroll
+        for (int w = 0; w < WORDS; w++) words[w] = 0;
+        const bool prevIsRow0 = (t == 1);
+#pragma unroll
+        for (int x = 1; x < WMAX; x++) {
+          if (x >= rowEnd) break;
+          const int xp = x + off;
+          const bool upIn = xp <= lenPrev - 1;
+          const bool upOk = xp < lenPrev - 1;     // in range and not the bound last cell of the (non-final) previous row
+          const bool diagOk = upIn && !(xp - 1 == 0 && !prevIsRow0);
+          int Mup = kIrBad, Dup = kIrBad;
+          if (upIn) { Mup = sM[xp][tid]; Dup = sD[xp][tid]; }
+          const int delOpen = upOk ? Mup + gapOpen : kIrBad;
+          const int delExt = upOk ? Dup : kIrBad;
+          const int D = imax(delOpen, delExt);
+          const int dbit = (D == delOpen) ? 0 : 1;
+          const int insOpen = Mleft + gapOpen;
+          const int I = imax(insOpen, Ileft);
+          const int ibit = (I == insOpen) ? 0 : 1;
+          const int mS = diagOk ? Mdiag + (((e >> (2 * x)) & 1) ? match : mismatch) : kIrBad;
+          const int iS = Mleft + gap;
+          const int dS = upOk ? Mup + gap : kIrBad;
+          const int mx = imax(imax(mS, iS), imax(dS, imax(D, I)));
+          const int a = (mx == mS) ? IR_DIAG : (mx == iS) ? IR_LEFT : (mx == dS) ? IR_DOWN : (mx == D) ? IR_DELCLOSE : IR_INSCLOSE;
+          words[x / 6] |= (uint32_t)(a | (dbit << 3) | (ibit << 4)) << (5 * (x % 6));
+          sM[x][tid] = mx;
+          sD[x][tid] = D;
+          Mdiag = Mup;
+          Mleft = mx;
+          Ileft = I;
+        }
+#pragma unroll
+        for (int w = 0; w < WORDS; w++)
+          if (w * 6 < rowEnd) tbw[(unsigned long long)t * WORDS + w] = words[w];
+        qsPrev = qs; qePrev = qe; lenPrev = len;
+      }
+      nb = ir_walk<WORDS, false>(tbp, qS, qE, rows, tStart, nullptr, 0);
+      if (nb < 0) { atomicOr(b.err, 16); nb = 0; }
+    }
+    const unsigned long long slot = aog_reserve_blocks(AogBatch{b.q, b.t, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, nullptr,
+                                                                nullptr, b.blocks, b.block_cap, b.block_cursor, b.err},
+                                                       nb, lane, &plan->cls_blocks[cls]);
+    if (active) {
+      b.n_blocks[g] = nb;
+      b.block_off[g] = slot;
+      if (slot != ~0ull && nb > 0) ir_walk<WORDS, true>(tbp, qS, qE, rows, tStart, b.blocks + 3ull * slot, nb);
+    }
+  }
+}
+
+// ---- generic width: one group per thread, rows and byte arrows in the group's scratch region (exact, slow, rare)
+__device__ __forceinline__ int ir_walk_bytes(const uint8_t *ar, int W, const int32_t *qS, const int32_t *qE, int rows, int tStart,
+                                             uint32_t *out, int nb, bool write) {
+  int t = rows - 1, qs = qS[t], x = qE[t] - qs, mat = 0, run = 0, lastOp = -1, count = 0;
+  long guard = 0;
+  const long guardMax = 4L * rows + 4L * (qE[rows - 1] - qS[0]) + 64;
+  auto emit = [&](uint32_t qq, uint32_t tt, uint32_t ln) {
+    if (write) { const int r = nb - 1 - count; out[3 * r] = qq; out[3 * r + 1] = tt; out[3 * r + 2] = ln; }
+    count++;
+  };
+  while (true) {
+    if (++guard > guardMax) return -1;
+    if (t == 0) {
+      if (x > 0) {
+        if (mat != 0) return -1;
+        if (run > 0) { emit((uint32_t)(qs + x + 1), (uint32_t)(tStart + 1), (uint32_t)run); run = 0; }
+        else if (lastOp == IR_DOWN) emit((uint32_t)(qs + x + 1), (uint32_t)(tStart + 1), 0u);
+        lastOp = IR_LEFT; x = 0;
+      }
+      run += 1;
+      emit((uint32_t)qs, (uint32_t)tStart, (uint32_t)run);
+      break;
+    }
+    const int a5 = ar[(unsigned long long)t * W + x];
+    int op, nt = t, nx = x, nmat = mat;
+    if (mat == 0) {
+      const int a = a5 & 7;
+      if (a == IR_DELCLOSE) { op = -1; nmat = 1; }
+      else if (a == IR_INSCLOSE) { op = -1; nmat = 2; }
+      else if (a == IR_DIAG) { op = IR_DIAG; nt = t - 1; }
+      else if (a == IR_LEFT) { op = IR_LEFT; nx = x - 1; }
+      else if (a == IR_DOWN) { op = IR_DOWN; nt = t - 1; }
+      else return -1;
+    } else if (mat == 1) { op = IR_DOWN; nmat = ((a5 >> 3) & 1) ? 1 : 0; nt = t - 1; }
+    else { op = IR_LEFT; nmat = ((a5 >> 4) & 1) ? 2 : 0; nx = x - 1; }
+    if (op >= 0) {
+      const int q = qs + x;
+      if (op == IR_DIAG) run++;
+      else {
+        if (run > 0) { emit((uint32_t)(q + 1), (uint32_t)(tStart + t + 1), (uint32_t)run); run = 0; }
+        else if (lastOp != -1 && lastOp != op) emit((uint32_t)(q + 1), (uint32_t)(tStart + t + 1), 0u);
+      }
+      lastOp = op;
+    }
+    if (nt != t) { const int pqs = qS[t - 1]; const int q = qs + x; nx = (op == IR_DIAG ? q - 1 : q) - pqs; qs = pqs; }
+    t = nt; x = nx; mat = nmat;
+    if (x < 0) return -1;
+  }
+  return count;
+}
+
+__global__ void __launch_bounds__(64) ir_dp_generic_kernel(IrBatch b, AogPlan *plan, const uint32_t *sorted) {
+  const int cls = kIrClsGeneric;
+  const int lane = threadIdx.x & 31;
+  const uint32_t begin = plan->bin_start[cls * kAogBuckets];
+  const uint32_t end = plan->bin_start[(cls + 1) * kAogBuckets];
+  const int match = b.match, mismatch = b.mismatch, gap = b.gap, gapOpen = 2 * b.gap + 1;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&plan->work[cls], 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (begin + base >= end) break;
+    const uint32_t idx = begin + base + lane;
+    const bool active = idx < end;
+    int g = 0, nb = 0, rows = 0, tStart = 0, W = 0;
+    const int32_t *qS = nullptr, *qE = nullptr;
+    uint8_t *ar = nullptr;
+    if (active) {
+      g = (int)sorted[idx];
+      rows = b.t_len[g]; tStart = b.t_start[g]; W = b.max_width[g];
+      qS = b.band + b.band_off[g]; qE = qS + rows;
+      uint32_t *region = b.tb + b.tb_off[g];
+      int *M = (int *)region;                    // [W]
+      int *D = M + W;                            // [W]
+      ar = (uint8_t *)(D + W);                   // [rows][W]
+      int qsPrev = qS[0], lenPrev = qE[0] - qS[0] + 1;
+      for (int x = 0; x < lenPrev; x++) { M[x] = x * gap; D[x] = kIrBad; }
+      for (int t = 1; t < rows; t++) {
+        const int qs = qS[t], len = qE[t] - qs + 1, off = qs - qsPrev;
+        const int rowEnd = (t == rows - 1) ? len : len - 1;
+        const int tc = seq_code(b.t, (uint64_t)(uint32_t)(b.t_base[g] + (uint32_t)(tStart + t)));
+        int Mdiag = off <= lenPrev - 1 ? M[off] : kIrBad;
+        int Mleft = kIrBad, Ileft = kIrBad;
+        M[0] = kIrBad;
+        for (int x = 1; x < rowEnd; x++) {
+          const int xp = x + off;
+          const bool upIn = xp <= lenPrev - 1, upOk = xp < lenPrev - 1;
+          const bool diagOk = upIn && !(xp - 1 == 0 && t != 1);
+          int Mup = kIrBad, Dup = kIrBad;
+          if (upIn) { Mup = M[xp]; Dup = D[xp]; }
+          const int delOpen = upOk ? Mup + gapOpen : kIrBad, delExt = upOk ? Dup : kIrBad;
+          const int Dv = imax(delOpen, delExt);
+          const int dbit = (Dv == delOpen) ? 0 : 1;
+          const int insOpen = Mleft + gapOpen;
+          const int Iv = imax(insOpen, Ileft);
+          const int ibit = (Iv == insOpen) ? 0 : 1;
+          const int qc = seq_code(b.q, (uint64_t)b.q_base[g] + (uint64_t)(qs + x));
+          const int mS = diagOk ? Mdiag + (qc == tc ? match : mismatch) : kIrBad;
+          const int iS = Mleft + gap;
+          const int dS = upOk ? Mup + gap : kIrBad;
+          const int mx = imax(imax(mS, iS), imax(dS, imax(Dv, Iv)));
+          const int a = (mx == mS) ? IR_DIAG : (mx == iS) ? IR_LEFT : (mx == dS) ? IR_DOWN : (mx == Dv) ? IR_DELCLOSE : IR_INSCLOSE;
+          ar[(unsigned long long)t * W + x] = (uint8_t)(a | (dbit << 3) | (ibit << 4));
+          M[x] = mx; D[x] = Dv;
+          Mdiag = Mup; Mleft = mx; Ileft = Iv;
+        }
+        qsPrev = qs; lenPrev = len;
+      }
+      nb = ir_walk_bytes(ar, W, qS, qE, rows, tStart, nullptr, 0, false);
+      if (nb < 0) { atomicOr(b.err, 16); nb = 0; }
+    }
+    const unsigned long long slot = aog_reserve_blocks(AogBatch{b.q, b.t, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, nullptr,
+                                                                nullptr, b.blocks, b.block_cap, b.block_cursor, b.err},
+                                                       nb, lane, &plan->cls_blocks[cls]);
+    if (active) {
+      b.n_blocks[g] = nb;
+      b.block_off[g] = slot;
+      if (slot != ~0ull && nb > 0) ir_walk_bytes(ar, W, qS, qE, rows, tStart, b.blocks + 3ull * slot, nb, true);
+    }
+  }
+}
+
+}  // namespace lra

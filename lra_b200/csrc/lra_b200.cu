@@ -11,6 +11,7 @@
 #include "../../include/lra_b200.h"
 #include "aog_band_kernel.cuh"
 #include "aog_kernels.cuh"
+#include "ir_kernels.cuh"
 #include "seq_kernels.cuh"
 
 using namespace lra;
@@ -35,6 +36,7 @@ struct lra_b200_ctx {
   // grow-only scratch
   DevBuf plan, bin_of_job, sorted, lit_slab, band_slab, misc;  // misc: block cursor (8 B) + err flag (4 B)
   DevBuf d_qoff, d_toff, d_qlen, d_tlen, d_k, d_score, d_nb, d_boff, d_blocks;
+  DevBuf ir_tb, ir_tboff, ir_maxw, ir_in[9], ir_band;
   AogPlan *h_plan = nullptr;            // pinned
   unsigned long long *h_misc = nullptr;  // pinned (2 x u64)
   std::vector<lra_b200_kernel_stat> stats;
@@ -110,7 +112,9 @@ extern "C" void lra_b200_destroy(lra_b200_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf *bufs[] = {&ctx->plan, &ctx->bin_of_job, &ctx->sorted, &ctx->lit_slab, &ctx->band_slab, &ctx->misc, &ctx->d_qoff,
-                    &ctx->d_toff, &ctx->d_qlen, &ctx->d_tlen, &ctx->d_k, &ctx->d_score, &ctx->d_nb, &ctx->d_boff, &ctx->d_blocks};
+                    &ctx->d_toff, &ctx->d_qlen, &ctx->d_tlen, &ctx->d_k, &ctx->d_score, &ctx->d_nb, &ctx->d_boff, &ctx->d_blocks,
+                    &ctx->ir_tb, &ctx->ir_tboff, &ctx->ir_maxw, &ctx->ir_band, &ctx->ir_in[0], &ctx->ir_in[1], &ctx->ir_in[2], &ctx->ir_in[3],
+                    &ctx->ir_in[4], &ctx->ir_in[5], &ctx->ir_in[6], &ctx->ir_in[7], &ctx->ir_in[8]};
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
   for (auto &ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < 4; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]); }
@@ -423,4 +427,138 @@ extern "C" int lra_b200_last_kernel_stats(lra_b200_ctx *ctx, lra_b200_kernel_sta
   int n = (int)ctx->stats.size();
   for (int i = 0; i < n && i < cap; i++) out[i] = ctx->stats[i];
   return n;
+}
+
+
+// ---------------------------------------------------------------------------------------------------- a19 launcher
+static int ir_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_ir_groups *gr,
+                         lra_b200_ir_result *res) {
+  const int n = gr->n_groups;
+  ctx->stats.clear();
+  res->n_blocks_total = 0;
+  res->cells = 0;
+  if (n == 0) return LRA_B200_OK;
+  int rc;
+  if ((rc = ensure(ctx, ctx->plan, sizeof(AogPlan))) || (rc = ensure(ctx, ctx->bin_of_job, (size_t)n * 4)) ||
+      (rc = ensure(ctx, ctx->sorted, (size_t)n * 4)) || (rc = ensure(ctx, ctx->misc, 64)) ||
+      (rc = ensure(ctx, ctx->ir_tboff, (size_t)n * 8)) || (rc = ensure(ctx, ctx->ir_maxw, (size_t)n * 4)))
+    return rc;
+  AogPlan *plan = (AogPlan *)ctx->plan.p;
+  unsigned long long *cursor = (unsigned long long *)ctx->misc.p;          // [0] block cursor
+  int *errflag = (int *)((char *)ctx->misc.p + 8);
+  unsigned long long *tb_cursor = (unsigned long long *)((char *)ctx->misc.p + 16);
+  unsigned long long *cells_total = (unsigned long long *)((char *)ctx->misc.p + 24);
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemsetAsync(plan, 0, sizeof(AogPlan), st));
+  CU(cudaMemsetAsync(ctx->misc.p, 0, 64, st));
+  IrBatch b;
+  b.q = SeqView{q->b2, q->nm, q->n};
+  b.t = SeqView{t->b2, t->nm, t->n};
+  b.q_base = gr->q_base; b.t_base = gr->t_base; b.q_start = gr->q_start; b.t_start = gr->t_start; b.t_len = gr->t_len;
+  b.q_seq_len = gr->q_seq_len; b.t_seq_len = gr->t_seq_len; b.band_off = gr->band_off; b.band = gr->band;
+  b.n_groups = n; b.match = gr->match; b.mismatch = gr->mismatch; b.gap = gr->indel;
+  b.n_blocks = res->n_blocks; b.block_off = (unsigned long long *)res->block_off; b.blocks = res->blocks;
+  b.block_cap = res->block_cap; b.block_cursor = cursor; b.err = errflag;
+  b.tb = nullptr; b.tb_off = (unsigned long long *)ctx->ir_tboff.p; b.max_width = (int32_t *)ctx->ir_maxw.p;
+  int evi = 0;
+  auto rec = [&]() { cudaEventRecord(ctx->ev[evi++], st); };
+  rec();
+  ir_classify_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(b, plan, (uint32_t *)ctx->bin_of_job.p, tb_cursor, cells_total);
+  aog_scan_kernel<<<1, 512, 0, st>>>(plan);
+  aog_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, plan, (const uint32_t *)ctx->bin_of_job.p, (uint32_t *)ctx->sorted.p);
+  ctx->launches += 3;
+  rec();
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ctx->h_plan, plan, sizeof(AogPlan), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(ctx->h_misc, ctx->misc.p, 32, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (*(int *)((char *)ctx->h_misc + 8) & 8)
+    return fail(ctx, LRA_B200_EINVAL, "indel_dp_batch: a group has fewer than 2 rows, a row narrower than 2 cells or a non-monotone band");
+  const AogPlan &hp = *ctx->h_plan;
+  uint32_t cnt[3];
+  for (int c = 0; c < 3; c++) cnt[c] = hp.bin_start[(c + 1) * kAogBuckets] - hp.bin_start[c * kAogBuckets];
+  const unsigned long long tb_words = ctx->h_misc[2];
+  if ((rc = ensure(ctx, ctx->ir_tb, (size_t)(tb_words + 64) * 4))) return rc;
+  b.tb = (uint32_t *)ctx->ir_tb.p;
+  const uint32_t *sorted = (const uint32_t *)ctx->sorted.p;
+  struct Launched { int cls; int ev0; };
+  std::vector<Launched> launched;
+  auto blocks_for = [&](uint32_t c) { unsigned x = (c + 63) / 64; unsigned cap = (unsigned)ctx->n_sm * 8u; return x > cap ? cap : x; };
+  if (cnt[kIrClsGeneric]) { launched.push_back({kIrClsGeneric, evi}); rec(); ir_dp_generic_kernel<<<blocks_for(cnt[kIrClsGeneric]), 64, 0, st>>>(b, plan, sorted); rec(); ctx->launches++; }
+  if (cnt[kIrClsW64]) { launched.push_back({kIrClsW64, evi}); rec(); ir_dp_thread_kernel<64><<<blocks_for(cnt[kIrClsW64]), 64, 0, st>>>(b, plan, sorted, kIrClsW64); rec(); ctx->launches++; }
+  if (cnt[kIrClsW24]) { launched.push_back({kIrClsW24, evi}); rec(); ir_dp_thread_kernel<24><<<blocks_for(cnt[kIrClsW24]), 64, 0, st>>>(b, plan, sorted, kIrClsW24); rec(); ctx->launches++; }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ctx->h_plan, plan, sizeof(AogPlan), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(ctx->h_misc, ctx->misc.p, 32, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  res->n_blocks_total = ctx->h_misc[0];
+  res->cells = ctx->h_misc[3];
+  const int err = *(int *)((char *)ctx->h_misc + 8);
+  static const char *names[3] = {"ir_dp_thread<W=24>", "ir_dp_thread<W=64>", "ir_dp_generic"};
+  {
+    lra_b200_kernel_stat s;
+    memset(&s, 0, sizeof s);
+    snprintf(s.name, sizeof s.name, "ir_plan(classify+scan+scatter)");
+    cudaEventElapsedTime(&s.ms, ctx->ev[0], ctx->ev[1]);
+    s.jobs = (uint64_t)n;
+    ctx->stats.push_back(s);
+    for (auto &L : launched) {
+      memset(&s, 0, sizeof s);
+      snprintf(s.name, sizeof s.name, "%s", names[L.cls]);
+      cudaEventElapsedTime(&s.ms, ctx->ev[L.ev0], ctx->ev[L.ev0 + 1]);
+      s.jobs = cnt[L.cls];
+      s.cells = ctx->h_plan->cls_cells[L.cls];
+      s.algo_bytes = ctx->h_plan->cls_bytes[L.cls] + 12ull * ctx->h_plan->cls_blocks[L.cls];
+      ctx->stats.push_back(s);
+    }
+  }
+  if (err & 1) return fail(ctx, LRA_B200_EOVERFLOW, "indel_dp_batch: block capacity %llu too small, %llu needed",
+                           (unsigned long long)res->block_cap, (unsigned long long)res->n_blocks_total);
+  if (err & ~1) return fail(ctx, LRA_B200_EINTERNAL, "indel_dp_batch: kernel self-check failed (flags 0x%x)", err);
+  return LRA_B200_OK;
+}
+
+extern "C" int lra_b200_indel_dp_batch_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t,
+                                              const lra_b200_ir_groups *gr, lra_b200_ir_result *res) {
+  if (!ctx || !q || !t || !gr || !res) return fail(ctx, LRA_B200_EINVAL, "indel_dp_batch_device: NULL argument");
+  if (gr->n_groups < 0) return fail(ctx, LRA_B200_EINVAL, "indel_dp_batch_device: negative group count");
+  CU(cudaSetDevice(ctx->device));
+  return ir_run_device(ctx, q, t, gr, res);
+}
+
+extern "C" int lra_b200_indel_dp_batch(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_ir_groups *gr,
+                                       lra_b200_ir_result *res) {
+  if (!ctx || !q || !t || !gr || !res) return fail(ctx, LRA_B200_EINVAL, "indel_dp_batch: NULL argument");
+  const int n = gr->n_groups;
+  if (n < 0) return fail(ctx, LRA_B200_EINVAL, "indel_dp_batch: negative group count");
+  CU(cudaSetDevice(ctx->device));
+  if (n == 0) { res->n_blocks_total = 0; res->cells = 0; ctx->stats.clear(); return LRA_B200_OK; }
+  int rc;
+  const size_t nb4 = (size_t)n * 4;
+  for (int i = 0; i < 8; i++) if ((rc = ensure(ctx, ctx->ir_in[i], nb4))) return rc;
+  if ((rc = ensure(ctx, ctx->ir_band, (size_t)gr->band_len * 4 + 16)) || (rc = ensure(ctx, ctx->d_nb, nb4)) ||
+      (rc = ensure(ctx, ctx->d_boff, (size_t)n * 8)) || (rc = ensure(ctx, ctx->d_blocks, (size_t)(res->block_cap ? res->block_cap : 1) * 12)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  const void *src[8] = {gr->q_base, gr->t_base, gr->q_start, gr->t_start, gr->t_len, gr->q_seq_len, gr->t_seq_len, gr->band_off};
+  for (int i = 0; i < 8; i++) CU(cudaMemcpyAsync(ctx->ir_in[i].p, src[i], nb4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->ir_band.p, gr->band, (size_t)gr->band_len * 4, cudaMemcpyHostToDevice, st));
+  lra_b200_ir_groups dg = *gr;
+  dg.q_base = (const uint32_t *)ctx->ir_in[0].p; dg.t_base = (const uint32_t *)ctx->ir_in[1].p;
+  dg.q_start = (const int32_t *)ctx->ir_in[2].p; dg.t_start = (const int32_t *)ctx->ir_in[3].p;
+  dg.t_len = (const int32_t *)ctx->ir_in[4].p; dg.q_seq_len = (const int32_t *)ctx->ir_in[5].p;
+  dg.t_seq_len = (const int32_t *)ctx->ir_in[6].p; dg.band_off = (const uint32_t *)ctx->ir_in[7].p;
+  dg.band = (const int32_t *)ctx->ir_band.p;
+  lra_b200_ir_result dr = *res;
+  dr.n_blocks = (int32_t *)ctx->d_nb.p; dr.block_off = (uint64_t *)ctx->d_boff.p; dr.blocks = (uint32_t *)ctx->d_blocks.p;
+  rc = ir_run_device(ctx, q, t, &dg, &dr);
+  res->n_blocks_total = dr.n_blocks_total;
+  res->cells = dr.cells;
+  if (rc != LRA_B200_OK && rc != LRA_B200_EOVERFLOW) return rc;
+  CU(cudaMemcpyAsync(res->n_blocks, dr.n_blocks, nb4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->block_off, dr.block_off, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (rc == LRA_B200_OK && dr.n_blocks_total)
+    CU(cudaMemcpyAsync(res->blocks, dr.blocks, (size_t)dr.n_blocks_total * 12, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return rc;
 }

@@ -36,4 +36,43 @@ static inline int AffineOneGapAlign_logged(string &qSeq, int qLen, string &tSeq,
   return score;
 }
 #define AffineOneGapAlign AffineOneGapAlign_logged
+
+// ---- IndelRefineAlignment (IndelRefine.h:53): log the segment before and after.  $LRA_CAPTURE_IR
+// record: int32 {readLen, contigLen, k, match, mismatch, indel, endAlign, nIn, nOut, tWinOff, tWinLen, strandFlag}
+//         ; read strand bytes [readLen] ; contig window bytes [tWinLen] ; nIn x 3 uint32 ; nOut x 3 uint32
+#include <zlib.h>
+#include <string>
+#include <vector>
+#include <iomanip>
+#include "htslib/sam.h"
+#include "Input.h"       // declares KSEQ_INIT(gzFile, gzread), which Genome.h (pulled in by IndelRefine.h) relies on
+#include "IndelRefine.h"
+static FILE *lra_cap_ir_fp() {
+  static FILE *fp = NULL; static bool init = false;
+  if (!init) { init = true; const char *p = getenv("LRA_CAPTURE_IR"); if (p) fp = fopen(p, "wb"); }
+  return fp;
+}
+static inline void IndelRefineAlignment_logged(Read &read, Genome &genome, Alignment &alignment, const Options &opts,
+                                               IndelRefineBuffers &buffers, bool endAlign = false) {
+  std::vector<Block> before = alignment.blocks;
+  IndelRefineAlignment(read, genome, alignment, opts, buffers, endAlign);
+  FILE *fp = lra_cap_ir_fp();
+  if (fp && before.size() > 0) {
+    long contigLen = genome.lengths[alignment.chromIndex];
+    long lo = before[0].tPos, hi = before.back().tPos + before.back().length;
+    for (size_t i = 0; i < alignment.blocks.size(); i++) {
+      if ((long)alignment.blocks[i].tPos < lo) lo = alignment.blocks[i].tPos;
+      long e = (long)alignment.blocks[i].tPos + alignment.blocks[i].length; if (e > hi) hi = e;
+    }
+    lo = lo - 64 < 0 ? 0 : lo - 64; hi = hi + 64 > contigLen ? contigLen : hi + 64;
+    int32_t h[12] = {(int32_t)read.length, (int32_t)contigLen, opts.refineBand, opts.localMatch, opts.localMismatch, opts.localIndel,
+                     endAlign ? 1 : 0, (int32_t)before.size(), (int32_t)alignment.blocks.size(), (int32_t)lo, (int32_t)(hi - lo), alignment.strand};
+    fwrite(h, 4, 12, fp);
+    fwrite(alignment.read, 1, read.length, fp);
+    fwrite(genome.seqs[alignment.chromIndex] + lo, 1, hi - lo, fp);
+    for (size_t i = 0; i < before.size(); i++) { uint32_t v[3] = {before[i].qPos, before[i].tPos, before[i].length}; fwrite(v, 4, 3, fp); }
+    for (size_t i = 0; i < alignment.blocks.size(); i++) { uint32_t v[3] = {alignment.blocks[i].qPos, alignment.blocks[i].tPos, alignment.blocks[i].length}; fwrite(v, 4, 3, fp); }
+  }
+}
+#define IndelRefineAlignment IndelRefineAlignment_logged
 #include "lra.cpp"

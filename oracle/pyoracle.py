@@ -135,3 +135,71 @@ def read_aog_capture(path, limit=None):
         b = np.frombuffer(data, dtype=np.uint32, count=3 * nb, offset=p).reshape(-1, 3).copy(); p += 12 * nb
         out.append(dict(q=q, t=t, m=m, mm=mm, indel=indel, k=k, score=score, blocks=b))
     return out
+
+
+# ---------------------------------------------------------------- a19 IndelRefineAlignment
+
+def _bind_ir(L):
+    if getattr(L, "_ir_bound", False):
+        return
+    L.lra_oracle_indel_refine.restype = C.c_int
+    L.lra_oracle_indel_refine.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_long, C.c_long, _u32p, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_int, C.c_int, _u32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_long)]
+    L._ir_bound = True
+
+
+def indel_refine_port(read, twin, t_win_off, contig_len, blocks_in, k, match, mismatch, indel, end_align):
+    """One segment through the C restatement.  Returns (blocks_out[n,3], status, cells)."""
+    L = port(); _bind_ir(L)
+    bi = np.ascontiguousarray(blocks_in, dtype=np.uint32).reshape(-1)
+    cap = len(read) + 8
+    out = np.zeros(cap * 3, np.uint32)
+    n, st, cells = C.c_int(0), C.c_int(0), C.c_long(0)
+    L.lra_oracle_indel_refine(bytes(read), len(read), bytes(twin), t_win_off, contig_len, bi, len(bi) // 3, k, match, mismatch,
+                              indel, 1 if end_align else 0, out, cap, C.byref(n), C.byref(st), C.byref(cells))
+    return out[: 3 * n.value].reshape(-1, 3).copy(), st.value, cells.value
+
+
+def read_ir_capture(path, limit=None):
+    """Parse an LRA_CAPTURE_IR file (oracle/lra_capture.cpp) -> list of dicts."""
+    data = open(path, "rb").read()
+    out, p = [], 0
+    while p < len(data) and (limit is None or len(out) < limit):
+        h = np.frombuffer(data, dtype=np.int32, count=12, offset=p); p += 48
+        rl, cl, k, m, mm, indel, ea, nin, nout, woff, wlen, strand = (int(x) for x in h)
+        read = data[p:p + rl]; p += rl
+        twin = data[p:p + wlen]; p += wlen
+        bi = np.frombuffer(data, dtype=np.uint32, count=3 * nin, offset=p).reshape(-1, 3).copy(); p += 12 * nin
+        bo = np.frombuffer(data, dtype=np.uint32, count=3 * nout, offset=p).reshape(-1, 3).copy(); p += 12 * nout
+        out.append(dict(read=read, twin=twin, t_win_off=woff, contig_len=cl, k=k, match=m, mismatch=mm, indel=indel,
+                        end_align=ea, blocks_in=bi, blocks_out=bo, strand=strand))
+    return out
+
+
+def indel_refine_groups_port(read, twin, t_win_off, contig_len, blocks_in, k, match, mismatch, indel, end_align, max_groups=4096):
+    """Like indel_refine_port, also returning the banded DP groups: list of dict(qStart,tStart,tLen,qSeqLen,tSeqLen,qS,qE,blocks)."""
+    L = port(); _bind_ir(L)
+    if not getattr(L, "_irg_bound", False):
+        L.lra_oracle_indel_refine_groups.restype = C.c_int
+        L.lra_oracle_indel_refine_groups.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_long, C.c_long, _u32p, C.c_int, C.c_int,
+                                                     C.c_int, C.c_int, C.c_int, C.c_int, _u32p, C.c_int, C.POINTER(C.c_int),
+                                                     C.POINTER(C.c_int), _i32p, C.c_int, _i32p, C.c_long]
+        L._irg_bound = True
+    bi = np.ascontiguousarray(blocks_in, dtype=np.uint32).reshape(-1)
+    cap = len(read) + 8
+    out = np.zeros(cap * 3, np.uint32)
+    meta = np.zeros(max_groups * 8, np.int32)
+    band_cap = 4 * (len(read) + len(twin)) + 1024
+    band = np.zeros(band_cap, np.int32)
+    n, st = C.c_int(0), C.c_int(0)
+    ng = L.lra_oracle_indel_refine_groups(bytes(read), len(read), bytes(twin), t_win_off, contig_len, bi, len(bi) // 3, k, match,
+                                          mismatch, indel, 1 if end_align else 0, out, cap, C.byref(n), C.byref(st), meta, max_groups,
+                                          band, band_cap)
+    blocks = out[: 3 * n.value].reshape(-1, 3).copy()
+    groups = []
+    for g in range(ng):
+        qs, ts, tl, qsl, tsl, boff, fo, no = (int(x) for x in meta[8 * g: 8 * g + 8])
+        groups.append(dict(qStart=qs, tStart=ts, tLen=tl, qSeqLen=qsl, tSeqLen=tsl, qS=band[boff:boff + tl].copy(),
+                           qE=band[boff + tl:boff + 2 * tl].copy(), blocks=blocks[fo:fo + no].copy()))
+    return blocks, st.value, groups

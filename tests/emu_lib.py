@@ -33,8 +33,25 @@ def lib():
                                 C.POINTER(C.c_uint64)]
     L.emu_seq_pack.restype = C.c_int
     L.emu_seq_pack.argtypes = [_u8p, C.c_uint64, _u32p, _u32p]
+    L.emu_ir_dp_batch.restype = C.c_int
+    L.emu_ir_dp_batch.argtypes = [_u8p, C.c_uint64, _u8p, C.c_uint64, _u32p, _u32p, _i32p, _i32p, _i32p, _i32p, _i32p, _u32p, _i32p,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _u64p, _u32p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     _lib = L
     return L
+
+
+def ir_dp_batch(gb, force_generic=0, block_cap=None):
+    """gb: dict from irgen.pack_groups.  Returns (err, n_blocks, block_off, blocks, cells)."""
+    n = len(gb["t_len"])
+    if block_cap is None:
+        block_cap = int(gb["q_seq_len"].sum() + gb["t_seq_len"].sum()) + 8
+    nb = np.zeros(n, np.int32); off = np.zeros(n, np.uint64); blocks = np.zeros(block_cap * 3, np.uint32)
+    cells = C.c_uint64(0)
+    err = lib().emu_ir_dp_batch(gb["q_arena"], len(gb["q_arena"]) - 16, gb["t_arena"], len(gb["t_arena"]) - 16, gb["q_base"],
+                                gb["t_base"], gb["q_start"], gb["t_start"], gb["t_len"], gb["q_seq_len"], gb["t_seq_len"],
+                                gb["band_off"], gb["band"], n, gb["match"], gb["mismatch"], gb["indel"], nb, off, blocks, block_cap,
+                                force_generic, C.byref(cells))
+    return err, nb, off, blocks.reshape(-1, 3), cells.value
 
 
 def aog_batch(qa, ta, qo, to, ql, tl, k, m, mm, indel, use_band=1, force_literal=0, block_cap=None):

@@ -19,7 +19,7 @@
 
 #define __device__
 #define __host__
-#define __global__
+#define __global__ static
 #define __forceinline__ inline __attribute__((always_inline))
 #define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)

@@ -1,0 +1,43 @@
+"""Kernel-logic parity on the CPU for a19: the IndelRefine DP kernels (lra_b200/csrc/ir_kernels.cuh) executed through the
+SIMT emulator must reproduce, group by group, the blocks of the pinned oracle on segments captured from the reference."""
+import os
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+import irgen
+import emu_lib
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def run(name, n_rec, force_generic=0, max_groups=None):
+    recs = po.read_ir_capture(os.path.join(GOLD, name + ".bin"))[:n_rec]
+    rg = irgen.groups_of_records(recs)
+    if max_groups:
+        rg = rg[:max_groups]
+    r0 = recs[0]
+    gb, expect = irgen.pack_groups(recs, rg, (r0["match"], r0["mismatch"], r0["indel"]))
+    err, nb, off, blk, cells = emu_lib.ir_dp_batch(gb, force_generic=force_generic)
+    assert err == 0
+    assert cells == int(sum((g["qE"] - g["qS"] + 1).sum() for _, g in rg))
+    for j, e in enumerate(expect):
+        assert nb[j] == len(e), (name, j, nb[j], len(e))
+        assert (blk[int(off[j]):int(off[j]) + nb[j]] == e).all(), (name, j)
+    return len(expect)
+
+
+def test_emu_ir_ccs():
+    assert run("ir_ccs", 4) > 50
+
+
+def test_emu_ir_ont():
+    assert run("ir_ont", 1) >= 1
+
+
+def test_emu_ir_clr_w64():
+    assert run("ir_clr", 1) >= 1
+
+
+def test_emu_ir_generic_kernel():
+    assert run("ir_ccs", 2, force_generic=1, max_groups=40) > 10

@@ -8,6 +8,8 @@ Golden sets for a18 AffineOneGapAlign (record format = oracle/lra_capture.cpp):
   aog_{ccs,ont,clr}.bin   calls captured from `lra align -MODE` on seeded synthetic reads (tools/synth.py)
                      vs a 5 Mb synthetic reference: every two-sided ("alignTop") call + a seeded subsample
   aog_shapes_{ccs,ont,clr}.npy  (qLen,tLen,k) of every captured call: the job-shape table bench.py draws from
+Golden sets for a19 IndelRefineAlignment:
+  ir_{ccs,ont,clr}.bin    whole segments (read strand, contig window, blocks before / after) captured from the same runs
 Run:  python tools/make_golden.py
 """
 import os, re, subprocess, sys, tempfile
@@ -29,6 +31,15 @@ def write_records(path, recs):
             f.write(np.array([len(r["q"]), len(r["t"]), r["m"], r["mm"], r["indel"], r["k"], r["score"], len(b)],
                              dtype=np.int32).tobytes())
             f.write(bytes(r["q"])); f.write(bytes(r["t"])); f.write(b.tobytes())
+
+
+def write_ir_records(path, recs):
+    with open(path, "wb") as f:
+        for r in recs:
+            f.write(np.array([len(r["read"]), r["contig_len"], r["k"], r["match"], r["mismatch"], r["indel"], r["end_align"],
+                              len(r["blocks_in"]), len(r["blocks_out"]), r["t_win_off"], len(r["twin"]), r["strand"]], dtype=np.int32).tobytes())
+            f.write(bytes(r["read"])); f.write(bytes(r["twin"]))
+            f.write(np.asarray(r["blocks_in"], np.uint32).tobytes()); f.write(np.asarray(r["blocks_out"], np.uint32).tobytes())
 
 
 def kat20():
@@ -56,7 +67,7 @@ def captured():
         os.symlink(os.path.join(tmp, "ref.fa"), os.path.join(d, "ref.fa"))
         synth.write_fasta(os.path.join(d, "reads.fa"), synth.gen_reads(ref, n, prof, seed), width=1 << 30)
         subprocess.run([CAP, "index", mode, "ref.fa"], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        env = dict(os.environ, LRA_CAPTURE_AOG=os.path.join(d, "aog.cap"))
+        env = dict(os.environ, LRA_CAPTURE_AOG=os.path.join(d, "aog.cap"), LRA_CAPTURE_IR=os.path.join(d, "ir.cap"))
         subprocess.run([CAP, "align", mode, "ref.fa", "reads.fa", "-t", "1", "-p", "s", "-o", "out.sam"], cwd=d, env=env,
                        check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         recs = po.read_aog_capture(os.path.join(d, "aog.cap"))
@@ -72,6 +83,12 @@ def captured():
         sel = [recs[i] for i in sorted(pick)]
         write_records(os.path.join(GOLD, "aog_%s.bin" % name), sel)
         print("aog_%s: %d of %d calls (%d two-sided)" % (name, len(sel), len(recs), int(two.sum())))
+        # a19 IndelRefineAlignment: whole-segment before/after records (record format: oracle/lra_capture.cpp)
+        irs = po.read_ir_capture(os.path.join(d, "ir.cap"))
+        keep = {"ccs": 24, "ont": 10, "clr": 10}[name]
+        pick = sorted(np.random.default_rng(9).choice(len(irs), size=min(keep, len(irs)), replace=False).tolist())
+        write_ir_records(os.path.join(GOLD, "ir_%s.bin" % name), [irs[i] for i in pick])
+        print("ir_%s: %d of %d segments" % (name, len(pick), len(irs)))
 
 
 if __name__ == "__main__":
