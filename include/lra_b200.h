@@ -125,6 +125,44 @@ int lra_b200_indel_dp_batch(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_
 int lra_b200_indel_dp_batch_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t,
                                    const lra_b200_ir_groups *groups_dev, lra_b200_ir_result *res_dev);
 
+/* The whole function, batched over segments:
+ *   void IndelRefineAlignment(Read &read, Genome &genome, Alignment &alignment, const Options &opts,
+ *                             IndelRefineBuffers &buffers, bool endAlign)                    IndelRefine.h:53-784
+ * Segment s has blk_cnt[s] blocks (alignment.blocks, (qPos,tPos,length) triples) starting at triple blk_off[s] of
+ * blocks_in (blk_off = exclusive prefix sum of blk_cnt); qSeq = alignment.read = q arena + q_base[s] (the strand the
+ * blocks refer to), tSeq = genome.seqs[alignment.chromIndex] = t arena + t_base[s]; read_len = read.length,
+ * contig_len = genome.lengths[chromIndex]; refine_band = opts.refineBand, (match, mismatch, indel) = opts.localMatch /
+ * localMismatch / localIndel.  Output: the segment's new alignment.blocks.  Small windows go through the batched
+ * AffineOneGapAlign exactly as the reference's fallback (IndelRefine.h:344-357). */
+typedef struct lra_b200_ir_segments {
+  const uint32_t *blocks_in;
+  const uint64_t *blk_off;
+  const int32_t *blk_cnt;
+  const uint32_t *q_base;
+  const uint32_t *t_base;
+  const int32_t *read_len;
+  const int32_t *contig_len;
+  uint64_t n_blocks_in;   /* total triples in blocks_in */
+  int32_t n_segments;
+  int32_t refine_band, match, mismatch, indel, end_align;
+} lra_b200_ir_segments;
+
+typedef struct lra_b200_ir_seg_result {
+  int32_t *n_blocks;       /* [n_segments] */
+  uint64_t *block_off;     /* [n_segments] */
+  uint32_t *blocks;        /* [block_cap * 3] */
+  uint64_t block_cap;
+  uint64_t n_blocks_total; /* out */
+  uint64_t cells;          /* out: banded DP cells */
+  uint64_t n_dp_groups;    /* out */
+  uint64_t n_aog_jobs;     /* out */
+} lra_b200_ir_seg_result;
+
+int lra_b200_indel_refine_batch(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_ir_segments *segs,
+                                lra_b200_ir_seg_result *res);
+int lra_b200_indel_refine_batch_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t,
+                                       const lra_b200_ir_segments *segs_dev, lra_b200_ir_seg_result *res_dev);
+
 /* ---- per-kernel timing of the last batch call (CUDA events on the context's stream) ---------------------------- */
 typedef struct lra_b200_kernel_stat {
   char name[48];

@@ -39,6 +39,18 @@ class _IrResult(C.Structure):
                 ("n_blocks_total", C.c_uint64), ("cells", C.c_uint64)]
 
 
+class _IrSegments(C.Structure):
+    _fields_ = [("blocks_in", C.c_void_p), ("blk_off", C.c_void_p), ("blk_cnt", C.c_void_p), ("q_base", C.c_void_p),
+                ("t_base", C.c_void_p), ("read_len", C.c_void_p), ("contig_len", C.c_void_p), ("n_blocks_in", C.c_uint64),
+                ("n_segments", C.c_int32), ("refine_band", C.c_int32), ("match", C.c_int32), ("mismatch", C.c_int32),
+                ("indel", C.c_int32), ("end_align", C.c_int32)]
+
+
+class _IrSegResult(C.Structure):
+    _fields_ = [("n_blocks", C.c_void_p), ("block_off", C.c_void_p), ("blocks", C.c_void_p), ("block_cap", C.c_uint64),
+                ("n_blocks_total", C.c_uint64), ("cells", C.c_uint64), ("n_dp_groups", C.c_uint64), ("n_aog_jobs", C.c_uint64)]
+
+
 class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("ms", C.c_float), ("jobs", C.c_uint64), ("cells", C.c_uint64),
                 ("algo_bytes", C.c_uint64)]
@@ -77,6 +89,8 @@ def load_library():
     L.lra_b200_aog_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_AogJobs), C.POINTER(_AogResult)]
     L.lra_b200_indel_dp_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrGroups), C.POINTER(_IrResult)]
     L.lra_b200_indel_dp_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrGroups), C.POINTER(_IrResult)]
+    L.lra_b200_indel_refine_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrSegments), C.POINTER(_IrSegResult)]
+    L.lra_b200_indel_refine_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrSegments), C.POINTER(_IrSegResult)]
     L.lra_b200_last_kernel_stats.argtypes = [C.c_void_p, C.POINTER(KernelStat), C.c_int]
     L.lra_b200_launch_count.argtypes = [C.c_void_p]
     L.lra_b200_launch_count.restype = C.c_uint64
@@ -215,6 +229,34 @@ class Context:
         self._check(rc)
         return out
 
+    def indel_refine_batch(self, q, t, sb, block_cap=None, out=None):
+        """Whole IndelRefineAlignment over segments.  sb: dict(blocks_in[T,3], blk_off, blk_cnt, q_base, t_base, read_len,
+        contig_len, k, match, mismatch, indel, end_align).  Returns dict(n_blocks, block_off, blocks, ...)."""
+        S = len(sb["blk_cnt"])
+        bi = np.ascontiguousarray(sb["blocks_in"], np.uint32)
+        a = dict(blk_off=np.ascontiguousarray(sb["blk_off"], np.uint64), blk_cnt=np.ascontiguousarray(sb["blk_cnt"], np.int32),
+                 q_base=np.ascontiguousarray(sb["q_base"], np.uint32), t_base=np.ascontiguousarray(sb["t_base"], np.uint32),
+                 read_len=np.ascontiguousarray(sb["read_len"], np.int32), contig_len=np.ascontiguousarray(sb["contig_len"], np.int32))
+        if block_cap is None:
+            block_cap = int(a["read_len"].sum()) + 16
+        if out is None:
+            out = dict(n_blocks=np.zeros(S, np.int32), block_off=np.zeros(S, np.uint64), blocks=np.zeros((max(1, block_cap), 3), np.uint32))
+        sg = _IrSegments(_ptr(bi), _ptr(a["blk_off"]), _ptr(a["blk_cnt"]), _ptr(a["q_base"]), _ptr(a["t_base"]), _ptr(a["read_len"]),
+                         _ptr(a["contig_len"]), bi.size // 3, S, sb["k"], sb["match"], sb["mismatch"], sb["indel"], sb["end_align"])
+        res = _IrSegResult(_ptr(out["n_blocks"]), _ptr(out["block_off"]), _ptr(out["blocks"]), block_cap, 0, 0, 0, 0)
+        rc = self.lib.lra_b200_indel_refine_batch(self.h, q.handle, t.handle, C.byref(sg), C.byref(res))
+        out.update(n_blocks_total=int(res.n_blocks_total), cells=int(res.cells), n_dp_groups=int(res.n_dp_groups), n_aog_jobs=int(res.n_aog_jobs))
+        self._check(rc)
+        return out
+
+    def indel_refine_batch_device(self, q, t, ptrs, n_blocks_in, S, k, match, mismatch, indel, end_align, d_n_blocks, d_block_off,
+                                  d_blocks, block_cap):
+        """ptrs: device pointers blocks_in, blk_off, blk_cnt, q_base, t_base, read_len, contig_len."""
+        sg = _IrSegments(*ptrs, n_blocks_in, S, k, match, mismatch, indel, end_align)
+        res = _IrSegResult(d_n_blocks, d_block_off, d_blocks, block_cap, 0, 0, 0, 0)
+        self._check(self.lib.lra_b200_indel_refine_batch_device(self.h, q.handle, t.handle, C.byref(sg), C.byref(res)))
+        return dict(n_blocks_total=int(res.n_blocks_total), cells=int(res.cells), n_dp_groups=int(res.n_dp_groups), n_aog_jobs=int(res.n_aog_jobs))
+
     def indel_dp_batch_device(self, q, t, ptrs, n, band_len, match, mismatch, indel, d_n_blocks, d_block_off, d_blocks, block_cap):
         """ptrs: device pointers in the order q_base,t_base,q_start,t_start,t_len,q_seq_len,t_seq_len,band_off,band."""
         gs = _IrGroups(*ptrs, band_len, n, match, mismatch, indel)
@@ -248,6 +290,26 @@ def AffineOneGapAlign(qSeq, qLen, tSeq, tLen, m, mm, indel, k, ctx=None):
         q.free(); t.free()
     nb = int(r["n_blocks"][0]); off = int(r["block_off"][0])
     return int(r["score"][0]), r["blocks"][off:off + nb].copy()
+
+
+def IndelRefineAlignment(read, tSeq, contigLen, blocks, refineBand, localMatch, localMismatch, localIndel, endAlign=False, tWinOff=0,
+                         ctx=None):
+    """Mirror of `void IndelRefineAlignment(Read &read, Genome &genome, Alignment &alignment, const Options &opts,
+    IndelRefineBuffers &buffers, bool endAlign)` (reference IndelRefine.h:53) for one segment: `read` is alignment.read (the
+    strand the blocks refer to), `tSeq` the contig (or a window of it starting at contig offset tWinOff), `blocks` the
+    segment's alignment.blocks.  Returns the refined blocks."""
+    ctx = ctx or _ctx()
+    q = ctx.seq_upload(bytes(read)); t = ctx.seq_upload(bytes(tSeq))
+    try:
+        b = np.ascontiguousarray(blocks, np.uint32).reshape(-1, 3)
+        sb = dict(blocks_in=b, blk_off=np.zeros(1, np.uint64), blk_cnt=np.array([len(b)], np.int32), q_base=np.zeros(1, np.uint32),
+                  t_base=np.array([(-tWinOff) & 0xFFFFFFFF], np.uint32), read_len=np.array([len(read)], np.int32),
+                  contig_len=np.array([contigLen], np.int32), k=refineBand, match=localMatch, mismatch=localMismatch,
+                  indel=localIndel, end_align=1 if endAlign else 0)
+        r = ctx.indel_refine_batch(q, t, sb)
+    finally:
+        q.free(); t.free()
+    return r["blocks"][int(r["block_off"][0]):int(r["block_off"][0]) + int(r["n_blocks"][0])].copy()
 
 
 def AffineOneGapAlignBatch(q_arena, t_arena, q_off, t_off, q_len, t_len, k, m, mm, indel, ctx=None):

@@ -1,0 +1,287 @@
+// a19  IndelRefineAlignment -- the segment-level part: end padding, grouping of blocks, band construction and the final
+// assembly of the refined block list.  Reference: IndelRefine.h:53-784 (end padding :89-130, grouping :132-211, band
+// :220-333, small-window fallback to AffineOneGapAlign :344-357, stitching :761-771).
+//
+//   ir_group_kernel     one thread per segment: replays the (sequential, cheap) grouping loop on a scratch copy of the
+//                       segment's blocks and emits an ordered list of PIECES (literal block | AffineOneGapAlign job |
+//                       banded DP group) plus the job / group descriptors.
+//   ir_band_kernel      one warp per DP group: the reference's band construction, steps in order, the inner +-k
+//                       neighbourhood update spread over the lanes; then the monotone fix-ups as warp scans.
+//   ir_assemble_kernel  one thread per segment: concatenates the pieces' blocks in order into the output arena.
+#pragma once
+#include "ir_kernels.cuh"
+
+namespace lra {
+
+enum IrPiece : uint32_t { IR_PIECE_LITERAL = 0, IR_PIECE_AOG = 1, IR_PIECE_DP = 2 };
+
+struct IrSegBatch {
+  // input (device)
+  const uint32_t *blocks_in;        // [total_in][3]
+  const unsigned long long *blk_off;  // [n_seg] first triple of the segment (exclusive prefix of blk_cnt)
+  const int32_t *blk_cnt;           // [n_seg]
+  const uint32_t *q_base, *t_base;  // [n_seg] arena offsets of qSeq[0] / tSeq[0]
+  const int32_t *read_len, *contig_len;
+  int n_seg;
+  int k, end_align;
+  // scratch (device)
+  uint32_t *work;                   // [total_in + 2 n_seg][3] mutable copy of the blocks (with end padding)
+  uint32_t *pieces;                 // [2 total_in + 8 n_seg][4]
+  int32_t *n_pieces;                // [n_seg]
+  // AffineOneGapAlign fallback jobs (SoA, capacity total_in + n_seg)
+  uint32_t *aog_q_off, *aog_t_off;
+  int32_t *aog_q_len, *aog_t_len, *aog_k;
+  // DP groups (SoA, capacity total_in + n_seg)
+  uint32_t *g_q_base, *g_t_base;
+  int32_t *g_q_start, *g_t_start, *g_t_len, *g_q_seq_len, *g_t_seq_len;
+  uint32_t *g_band_off;
+  int32_t *g_seg, *g_first_block, *g_last_block;   // indices into the segment's work copy
+  uint32_t *g_first;                // [n][3] the (trimmed) first block as the band builder must see it
+  uint32_t *g_last;                 // [n][3] the last block (q, t, trimmed length) as seen by the band builder
+  unsigned long long *counters;     // [0] n_aog, [1] n_groups, [2] band ints, [3] status flags
+};
+
+__device__ __forceinline__ unsigned long long ir_work_off(const IrSegBatch &b, int s) { return b.blk_off[s] + 2ull * (unsigned long long)s; }
+__device__ __forceinline__ unsigned long long ir_piece_off(const IrSegBatch &b, int s) { return 2ull * b.blk_off[s] + 8ull * (unsigned long long)s; }
+
+__global__ void __launch_bounds__(128) ir_group_kernel(IrSegBatch b) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= b.n_seg) return;
+  const int n_in = b.blk_cnt[s];
+  const uint32_t *in = b.blocks_in + 3ull * b.blk_off[s];
+  uint32_t *W = b.work + 3ull * ir_work_off(b, s);
+  uint32_t *P = b.pieces + 4ull * ir_piece_off(b, s);
+  int np = 0;
+  auto piece = [&](uint32_t kind, uint32_t a, uint32_t c, uint32_t d) { P[4 * np] = kind; P[4 * np + 1] = a; P[4 * np + 2] = c; P[4 * np + 3] = d; np++; };
+  if (n_in <= 1) {
+    for (int i = 0; i < n_in; i++) piece(IR_PIECE_LITERAL, in[3 * i], in[3 * i + 1], in[3 * i + 2]);
+    b.n_pieces[s] = np;
+    return;
+  }
+  const int k = b.k, maxGap = b.k - 1;
+  int nb = 0;
+  {
+    long qS0 = in[0], tS0 = in[1];
+    const long qAlnEnd = (long)in[3 * (n_in - 1)] + in[3 * (n_in - 1) + 2];
+    const long tAlnEnd = (long)in[3 * (n_in - 1) + 1] + in[3 * (n_in - 1) + 2];
+    int addStart = 0, addEnd = 0, startMatch = 0, endMatch = 0;
+    if (b.end_align) {
+      const int minStart = (int)(qS0 < tS0 ? qS0 : tS0);
+      if (minStart < 40) { tS0 -= minStart; qS0 -= minStart; startMatch = minStart; addStart = 1; }
+      const long a = (long)b.read_len[s] - qAlnEnd, c = (long)b.contig_len[s] - tAlnEnd;
+      const int minEnd = (int)(a < c ? a : c);
+      if (minEnd < 40) { endMatch = minEnd; addEnd = 1; }
+    }
+    if (addStart) { W[0] = (uint32_t)qS0; W[1] = (uint32_t)tS0; W[2] = (uint32_t)startMatch; nb++; }
+    for (int i = 0; i < n_in; i++, nb++) { W[3 * nb] = in[3 * i]; W[3 * nb + 1] = in[3 * i + 1]; W[3 * nb + 2] = in[3 * i + 2]; }
+    if (addEnd) { W[3 * nb] = (uint32_t)qAlnEnd; W[3 * nb + 1] = (uint32_t)tAlnEnd; W[3 * nb + 2] = (uint32_t)endMatch; nb++; }
+  }
+#define BQ(i) W[3 * (i)]
+#define BT_(i) W[3 * (i) + 1]
+#define BL(i) W[3 * (i) + 2]
+  int startBlock = 0, endBlock = 0;
+  while (endBlock < nb) {
+    long qStart = BQ(startBlock), tStart = BT_(startBlock);
+    long qPos = (long)BQ(startBlock) + (int)BL(startBlock), tPos = (long)BT_(startBlock) + (int)BL(startBlock);
+    int tGap = 0, qGap = 0;
+    if (endBlock < nb - 1) { tGap = (int)(BT_(endBlock + 1) - (uint32_t)tPos); qGap = (int)(BQ(endBlock + 1) - (uint32_t)qPos); }
+    while (endBlock < nb - 1 && qGap < maxGap && tGap < maxGap && (startBlock == endBlock || BL(endBlock) < 100u)) {
+      endBlock++;
+      const int bl = (int)BL(endBlock);
+      qPos = (long)BQ(endBlock) + bl; tPos = (long)BT_(endBlock) + bl;
+      if (endBlock + 1 < nb - 1) { tGap = (int)(BT_(endBlock + 1) - (uint32_t)tPos); qGap = (int)(BQ(endBlock + 1) - (uint32_t)qPos); }
+    }
+    uint32_t altQ = 0, altT = 0, altL = 0;
+    bool usedAlt = false;
+    if (endBlock == startBlock) {
+      piece(IR_PIECE_LITERAL, BQ(startBlock), BT_(startBlock), BL(startBlock));
+    } else {
+      if ((long)BL(startBlock) > maxGap) {
+        const int advanced = (int)BL(startBlock) - maxGap;
+        BL(startBlock) -= (uint32_t)maxGap;
+        piece(IR_PIECE_LITERAL, BQ(startBlock), BT_(startBlock), BL(startBlock));
+        BQ(startBlock) += (uint32_t)advanced; BT_(startBlock) += (uint32_t)advanced; BL(startBlock) = (uint32_t)maxGap;
+        qStart += advanced; tStart += advanced;
+      }
+      if ((long)BL(endBlock) > maxGap) {
+        usedAlt = true;
+        altQ = BQ(endBlock) + (uint32_t)maxGap; altT = BT_(endBlock) + (uint32_t)maxGap; altL = BL(endBlock) - (uint32_t)maxGap;
+        BL(endBlock) = (uint32_t)maxGap;
+        qPos = (long)BQ(endBlock) + maxGap; tPos = (long)BT_(endBlock) + maxGap;
+      }
+      const long qEnd = (long)BQ(endBlock) + BL(endBlock), tEnd = (long)BT_(endBlock) + BL(endBlock);
+      const long tLen = tPos - tStart;
+      const long tSeqLen = tEnd - tStart, qSeqLen = qEnd - qStart;
+      if (tSeqLen < k || qSeqLen < k) {
+        const unsigned long long j = atomicAdd(&b.counters[0], 1ull);
+        b.aog_q_off[j] = b.q_base[s] + (uint32_t)qStart;
+        b.aog_t_off[j] = b.t_base[s] + (uint32_t)tStart;
+        b.aog_q_len[j] = (int32_t)qSeqLen; b.aog_t_len[j] = (int32_t)tSeqLen; b.aog_k[j] = k;
+        piece(IR_PIECE_AOG, (uint32_t)j, (uint32_t)qStart, (uint32_t)tStart);
+      } else {
+        const unsigned long long g = atomicAdd(&b.counters[1], 1ull);
+        b.g_q_base[g] = b.q_base[s]; b.g_t_base[g] = b.t_base[s];
+        b.g_q_start[g] = (int32_t)qStart; b.g_t_start[g] = (int32_t)tStart; b.g_t_len[g] = (int32_t)tLen;
+        b.g_q_seq_len[g] = (int32_t)qSeqLen; b.g_t_seq_len[g] = (int32_t)tSeqLen;
+        b.g_band_off[g] = (uint32_t)atomicAdd(&b.counters[2], (unsigned long long)(2 * tLen));
+        b.g_seg[g] = s; b.g_first_block[g] = startBlock; b.g_last_block[g] = endBlock;
+        b.g_first[3 * g] = BQ(startBlock); b.g_first[3 * g + 1] = BT_(startBlock); b.g_first[3 * g + 2] = BL(startBlock);
+        b.g_last[3 * g] = BQ(endBlock); b.g_last[3 * g + 1] = BT_(endBlock); b.g_last[3 * g + 2] = BL(endBlock);
+        piece(IR_PIECE_DP, (uint32_t)g, 0u, 0u);
+      }
+    }
+    if (!usedAlt) endBlock++;
+    else { BQ(endBlock) = altQ; BT_(endBlock) = altT; BL(endBlock) = altL; }
+    startBlock = endBlock;
+  }
+#undef BQ
+#undef BT_
+#undef BL
+  b.n_pieces[s] = np;
+}
+
+// One warp per DP group.  The work copy of the segment's blocks may have moved on (later groups trim / restore their own
+// boundary blocks), so the first block and the last block's length come from the group record; inner blocks are untouched.
+__global__ void __launch_bounds__(128) ir_band_kernel(IrSegBatch b, int n_groups, int32_t *band) {
+  const int lane = threadIdx.x & 31;
+  const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (g >= n_groups) return;
+  const int s = b.g_seg[g];
+  const uint32_t *W = b.work + 3ull * ir_work_off(b, s);
+  const int startBlock = b.g_first_block[g], endBlock = b.g_last_block[g];
+  const int k = b.k;
+  const long tLen = b.g_t_len[g];
+  const long qStart = b.g_q_start[g];
+  const long qEnd = qStart + b.g_q_seq_len[g];
+  int32_t *qS = band + b.g_band_off[g];
+  int32_t *qE = qS + tLen;
+  for (long x = lane; x < tLen; x += 32) { qS[x] = -1; qE[x] = -1; }
+  __syncwarp();
+  auto blkq = [&](int i) -> long { return i == startBlock ? (long)b.g_first[3 * g] : (i == endBlock ? (long)b.g_last[3 * g] : (long)W[3 * i]); };
+  auto blkt = [&](int i) -> long { return i == startBlock ? (long)b.g_first[3 * g + 1] : (i == endBlock ? (long)b.g_last[3 * g + 1] : (long)W[3 * i + 1]); };
+  auto blkl = [&](int i) -> long { return i == startBlock ? (long)b.g_first[3 * g + 2] : (i == endBlock ? (long)b.g_last[3 * g + 2] : (long)W[3 * i + 2]); };
+  long q = blkq(startBlock);
+  long tOff = 0;
+  for (int bb = startBlock; bb <= endBlock; bb++) {
+    int qGap = 0, tGap = 0;
+    int blockLength = (int)blkl(bb);
+    if (bb < endBlock) {
+      qGap = (int)(blkq(bb + 1) - (blkq(bb) + blockLength));
+      tGap = (int)(blkt(bb + 1) - (blkt(bb) + blockLength));
+      if (qGap > 0 && tGap > 0) { const int c = qGap < tGap ? qGap : tGap; qGap -= c; tGap -= c; blockLength += c; }
+    }
+    for (int bi = 0; bi < blockLength; tOff++, bi++, q++) {
+      if (lane == 0 && tOff < tLen) {
+        const long lo = (q - k > qStart) ? q - k : qStart;
+        if (qS[tOff] == -1) qS[tOff] = (int32_t)lo;
+        else if (lo < (long)qS[tOff]) qS[tOff] = (int32_t)lo;
+        if (qE[tOff] == -1 || qE[tOff] < q + k) qE[tOff] = (int32_t)((qEnd - 1 < q + k) ? qEnd - 1 : q + k);
+      }
+      __syncwarp();
+      for (int ki = lane; ki < k; ki += 32) {
+        if (tOff - ki >= 0 && tOff - ki < tLen) { if (qE[tOff - ki] < q) qE[tOff - ki] = (int32_t)q; }
+        if (tOff + ki < tLen) { const int v = qS[tOff + ki]; if (v == -1 || v > q) qS[tOff + ki] = (int32_t)q; }
+      }
+      __syncwarp();
+    }
+    if (qGap > tGap) {
+      for (int qi = 0; qi < qGap; qi++, q++) {
+        for (int ki = lane; ki < k; ki += 32) {
+          if (tOff - ki >= 0 && tOff - ki < tLen) { if (qE[tOff - ki] < q) qE[tOff - ki] = (int32_t)q; }
+          if (tOff + ki < tLen) { const int v = qS[tOff + ki]; if (v == 0 || v > q) qS[tOff + ki] = (int32_t)q; }
+        }
+        __syncwarp();
+      }
+    }
+    if (tGap > qGap) {
+      const long lo = (q - k > qStart) ? q - k : qStart;
+      const long hi = (qEnd - 1 < q + k) ? qEnd - 1 : q + k;
+      for (int ti = lane; ti < tGap; ti += 32) if (tOff + ti < tLen) { qS[tOff + ti] = (int32_t)lo; qE[tOff + ti] = (int32_t)hi; }
+      tOff += tGap;
+      __syncwarp();
+    }
+  }
+  // monotone fix-ups (IndelRefine.h:318-325): qS := suffix minimum, qE := prefix maximum
+  {
+    int carry = 0x7fffffff;
+    for (long base = ((tLen - 1) / 32) * 32; base >= 0; base -= 32) {
+      const long i = base + lane;
+      int v = (i < tLen) ? qS[i] : 0x7fffffff;
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_down_sync(0xffffffffu, v, o); if (lane + o < 32) v = imin(v, u); }
+      v = imin(v, carry);
+      if (i < tLen) qS[i] = v;
+      carry = __shfl_sync(0xffffffffu, v, 0);
+    }
+    carry = -0x7fffffff;
+    for (long base = 0; base < tLen; base += 32) {
+      const long i = base + lane;
+      int v = (i < tLen) ? qE[i] : -0x7fffffff;
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = imax(v, u); }
+      v = imax(v, carry);
+      if (i < tLen) qE[i] = v;
+      carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+  }
+}
+
+struct IrAssemble {
+  const int32_t *aog_n_blocks; const unsigned long long *aog_block_off; const uint32_t *aog_blocks;
+  const int32_t *dp_n_blocks; const unsigned long long *dp_block_off; const uint32_t *dp_blocks;
+  int32_t *out_n; unsigned long long *out_off; uint32_t *out_blocks;
+  unsigned long long out_cap; unsigned long long *out_cursor; int *err;
+};
+
+__global__ void __launch_bounds__(128) ir_assemble_kernel(IrSegBatch b, IrAssemble a) {
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = s < b.n_seg;
+  int total = 0, np = 0;
+  const uint32_t *P = nullptr;
+  if (active) {
+    np = b.n_pieces[s];
+    P = b.pieces + 4ull * ir_piece_off(b, s);
+    for (int p = 0; p < np; p++) {
+      const uint32_t kind = P[4 * p];
+      total += kind == IR_PIECE_LITERAL ? 1 : (kind == IR_PIECE_AOG ? a.aog_n_blocks[P[4 * p + 1]] : a.dp_n_blocks[P[4 * p + 1]]);
+    }
+  }
+  // warp-aggregated reservation
+  int inc = total;
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+  const int wtotal = __shfl_sync(0xffffffffu, inc, 31);
+  unsigned long long base = 0;
+  if (lane == 0 && wtotal > 0) base = atomicAdd(a.out_cursor, (unsigned long long)wtotal);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  const bool over = base + (unsigned long long)wtotal > a.out_cap;
+  if (over && lane == 0) atomicOr(a.err, 1);
+  if (!active) return;
+  const unsigned long long slot = base + (unsigned long long)(inc - total);
+  a.out_n[s] = total;
+  a.out_off[s] = slot;
+  if (over) return;
+  uint32_t *out = a.out_blocks + 3ull * slot;
+  int o = 0;
+  for (int p = 0; p < np; p++) {
+    const uint32_t kind = P[4 * p];
+    if (kind == IR_PIECE_LITERAL) { out[3 * o] = P[4 * p + 1]; out[3 * o + 1] = P[4 * p + 2]; out[3 * o + 2] = P[4 * p + 3]; o++; }
+    else if (kind == IR_PIECE_AOG) {
+      const uint32_t j = P[4 * p + 1];
+      const uint32_t *src = a.aog_blocks + 3ull * a.aog_block_off[j];
+      const int n = a.aog_n_blocks[j];
+      for (int i = 0; i < n; i++, o++) { out[3 * o] = src[3 * i] + P[4 * p + 2]; out[3 * o + 1] = src[3 * i + 1] + P[4 * p + 3]; out[3 * o + 2] = src[3 * i + 2]; }
+    } else {
+      const uint32_t g = P[4 * p + 1];
+      const uint32_t *src = a.dp_blocks + 3ull * a.dp_block_off[g];
+      const int n = a.dp_n_blocks[g];
+      for (int i = 0; i < n; i++, o++) { out[3 * o] = src[3 * i]; out[3 * o + 1] = src[3 * i + 1]; out[3 * o + 2] = src[3 * i + 2]; }
+    }
+  }
+  // "ERROR with alignment consistency" check of the reference (IndelRefine.h:772-782): reported as a status flag
+  for (int i = 0; i + 1 < total; i++)
+    if ((unsigned long long)out[3 * i] + out[3 * i + 2] > out[3 * (i + 1)] || (unsigned long long)out[3 * i + 1] + out[3 * i + 2] > out[3 * (i + 1) + 1]) {
+      atomicOr(a.err, 64);
+      break;
+    }
+}
+
+}  // namespace lra

@@ -12,6 +12,7 @@
 #include "aog_band_kernel.cuh"
 #include "aog_kernels.cuh"
 #include "ir_kernels.cuh"
+#include "ir_segment_kernels.cuh"
 #include "seq_kernels.cuh"
 
 using namespace lra;
@@ -37,6 +38,8 @@ struct lra_b200_ctx {
   DevBuf plan, bin_of_job, sorted, lit_slab, band_slab, misc;  // misc: block cursor (8 B) + err flag (4 B)
   DevBuf d_qoff, d_toff, d_qlen, d_tlen, d_k, d_score, d_nb, d_boff, d_blocks;
   DevBuf ir_tb, ir_tboff, ir_maxw, ir_in[9], ir_band;
+  DevBuf sg[40];          // segment-level IndelRefine scratch
+  bool keep_stats = false;  // sub-launchers append to stats instead of clearing
   AogPlan *h_plan = nullptr;            // pinned
   unsigned long long *h_misc = nullptr;  // pinned (2 x u64)
   std::vector<lra_b200_kernel_stat> stats;
@@ -116,6 +119,7 @@ extern "C" void lra_b200_destroy(lra_b200_ctx *ctx) {
                     &ctx->ir_tb, &ctx->ir_tboff, &ctx->ir_maxw, &ctx->ir_band, &ctx->ir_in[0], &ctx->ir_in[1], &ctx->ir_in[2], &ctx->ir_in[3],
                     &ctx->ir_in[4], &ctx->ir_in[5], &ctx->ir_in[6], &ctx->ir_in[7], &ctx->ir_in[8]};
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+  for (DevBuf &b : ctx->sg) if (b.p) cudaFree(b.p);
   for (auto &ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < 4; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]); }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
@@ -239,7 +243,7 @@ static void launch_band(cudaStream_t st, const AogBatch &b, AogPlan *plan, const
 static int aog_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_aog_jobs *jobs,
                           lra_b200_aog_result *res) {
   const int n = jobs->n_jobs;
-  ctx->stats.clear();
+  if (!ctx->keep_stats) ctx->stats.clear();
   res->n_blocks_total = 0;
   res->cells = 0;
   if (n == 0) return LRA_B200_OK;
@@ -434,7 +438,7 @@ extern "C" int lra_b200_last_kernel_stats(lra_b200_ctx *ctx, lra_b200_kernel_sta
 static int ir_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_ir_groups *gr,
                          lra_b200_ir_result *res) {
   const int n = gr->n_groups;
-  ctx->stats.clear();
+  if (!ctx->keep_stats) ctx->stats.clear();
   res->n_blocks_total = 0;
   res->cells = 0;
   if (n == 0) return LRA_B200_OK;
@@ -557,6 +561,180 @@ extern "C" int lra_b200_indel_dp_batch(lra_b200_ctx *ctx, const lra_b200_seq *q,
   if (rc != LRA_B200_OK && rc != LRA_B200_EOVERFLOW) return rc;
   CU(cudaMemcpyAsync(res->n_blocks, dr.n_blocks, nb4, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(res->block_off, dr.block_off, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (rc == LRA_B200_OK && dr.n_blocks_total)
+    CU(cudaMemcpyAsync(res->blocks, dr.blocks, (size_t)dr.n_blocks_total * 12, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return rc;
+}
+
+
+// ---------------------------------------------------------------------------------------------------- a19 whole function
+static int ir_segments_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_ir_segments *sg,
+                                  lra_b200_ir_seg_result *res) {
+  const int S = sg->n_segments;
+  const size_t T = (size_t)sg->n_blocks_in;
+  ctx->stats.clear();
+  res->n_blocks_total = 0; res->cells = 0; res->n_dp_groups = 0; res->n_aog_jobs = 0;
+  if (S == 0) return LRA_B200_OK;
+  if (sg->refine_band < 2) return fail(ctx, LRA_B200_EINVAL, "indel_refine_batch: refine_band must be >= 2");
+  int rc;
+  const size_t nd = T + 2 * (size_t)S + 8;   // capacity of job / group descriptor arrays
+  enum { WORK, PIECES, NPIECES, AQ, AT, AQL, ATL, AK, GQB, GTB, GQS, GTS, GTL, GQSL, GTSL, GBO, GSEG, GFB, GLB, GFIRST, GLAST, CNT,
+         A_SCORE, A_NB, A_BOFF, A_BLK, D_NB, D_BOFF, D_BLK, BAND, OUTCUR };
+  DevBuf *B = ctx->sg;
+  if ((rc = ensure(ctx, B[WORK], (T + 2 * (size_t)S + 4) * 12)) || (rc = ensure(ctx, B[PIECES], (2 * T + 8 * (size_t)S + 8) * 16)) ||
+      (rc = ensure(ctx, B[NPIECES], (size_t)S * 4)) || (rc = ensure(ctx, B[CNT], 64)) || (rc = ensure(ctx, B[OUTCUR], 64)))
+    return rc;
+  for (int i : {AQ, AT, AQL, ATL, AK, GQB, GTB, GQS, GTS, GTL, GQSL, GTSL, GBO, GSEG, GFB, GLB}) if ((rc = ensure(ctx, B[i], nd * 4))) return rc;
+  if ((rc = ensure(ctx, B[GFIRST], nd * 12)) || (rc = ensure(ctx, B[GLAST], nd * 12))) return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemsetAsync(B[CNT].p, 0, 64, st));
+  CU(cudaMemsetAsync(B[OUTCUR].p, 0, 64, st));
+  IrSegBatch b;
+  b.blocks_in = sg->blocks_in; b.blk_off = (const unsigned long long *)sg->blk_off; b.blk_cnt = sg->blk_cnt;
+  b.q_base = sg->q_base; b.t_base = sg->t_base; b.read_len = sg->read_len; b.contig_len = sg->contig_len;
+  b.n_seg = S; b.k = sg->refine_band; b.end_align = sg->end_align;
+  b.work = (uint32_t *)B[WORK].p; b.pieces = (uint32_t *)B[PIECES].p; b.n_pieces = (int32_t *)B[NPIECES].p;
+  b.aog_q_off = (uint32_t *)B[AQ].p; b.aog_t_off = (uint32_t *)B[AT].p; b.aog_q_len = (int32_t *)B[AQL].p;
+  b.aog_t_len = (int32_t *)B[ATL].p; b.aog_k = (int32_t *)B[AK].p;
+  b.g_q_base = (uint32_t *)B[GQB].p; b.g_t_base = (uint32_t *)B[GTB].p; b.g_q_start = (int32_t *)B[GQS].p;
+  b.g_t_start = (int32_t *)B[GTS].p; b.g_t_len = (int32_t *)B[GTL].p; b.g_q_seq_len = (int32_t *)B[GQSL].p;
+  b.g_t_seq_len = (int32_t *)B[GTSL].p; b.g_band_off = (uint32_t *)B[GBO].p; b.g_seg = (int32_t *)B[GSEG].p;
+  b.g_first_block = (int32_t *)B[GFB].p; b.g_last_block = (int32_t *)B[GLB].p; b.g_first = (uint32_t *)B[GFIRST].p;
+  b.g_last = (uint32_t *)B[GLAST].p; b.counters = (unsigned long long *)B[CNT].p;
+
+  cudaEvent_t e0 = ctx->ev[36], e1 = ctx->ev[37], e2 = ctx->ev[38], e3 = ctx->ev[39];
+  cudaEventRecord(e0, st);
+  ir_group_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(b);
+  ctx->launches++;
+  cudaEventRecord(e1, st);
+  CU(cudaGetLastError());
+  unsigned long long hc[8];
+  CU(cudaMemcpyAsync(ctx->h_misc, B[CNT].p, 32, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  memcpy(hc, ctx->h_misc, 32);
+  const int nA = (int)hc[0], nG = (int)hc[1];
+  const unsigned long long bandInts = hc[2];
+  if (bandInts > 0xFFFFFFF0ull) return fail(ctx, LRA_B200_EINVAL, "indel_refine_batch: batch too large (band offsets exceed 32 bits); split it");
+  res->n_dp_groups = (uint64_t)nG; res->n_aog_jobs = (uint64_t)nA;
+  std::vector<lra_b200_kernel_stat> all;
+  auto stat = [&](const char *name, cudaEvent_t a, cudaEvent_t c, uint64_t jobs) {
+    lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "%s", name);
+    cudaEventElapsedTime(&s2.ms, a, c); s2.jobs = jobs; all.push_back(s2);
+  };
+  stat("ir_group", e0, e1, (uint64_t)S);
+  // ---- band construction for the DP groups
+  if (nG) {
+    if ((rc = ensure(ctx, B[BAND], (size_t)(bandInts + 16) * 4))) return rc;
+    cudaEventRecord(e2, st);
+    ir_band_kernel<<<(unsigned)((nG + 3) / 4), 128, 0, st>>>(b, nG, (int32_t *)B[BAND].p);
+    ctx->launches++;
+    cudaEventRecord(e3, st);
+    CU(cudaGetLastError());
+  }
+  // ---- small windows: AffineOneGapAlign
+  lra_b200_aog_result ar; memset(&ar, 0, sizeof ar);
+  if (nA) {
+    const size_t acap = (size_t)nA * (size_t)sg->refine_band + 16;
+    if ((rc = ensure(ctx, B[A_SCORE], (size_t)nA * 4)) || (rc = ensure(ctx, B[A_NB], (size_t)nA * 4)) ||
+        (rc = ensure(ctx, B[A_BOFF], (size_t)nA * 8)) || (rc = ensure(ctx, B[A_BLK], acap * 12)))
+      return rc;
+    lra_b200_aog_jobs aj = {b.aog_q_off, b.aog_t_off, b.aog_q_len, b.aog_t_len, b.aog_k, nA, sg->match, sg->mismatch, sg->indel};
+    ar.score = (int32_t *)B[A_SCORE].p; ar.n_blocks = (int32_t *)B[A_NB].p; ar.block_off = (uint64_t *)B[A_BOFF].p;
+    ar.blocks = (uint32_t *)B[A_BLK].p; ar.block_cap = acap;
+    rc = aog_run_device(ctx, q, t, &aj, &ar);
+    for (auto &s2 : ctx->stats) all.push_back(s2);
+    if (rc) return rc;
+  }
+  // ---- banded DP
+  lra_b200_ir_result dr; memset(&dr, 0, sizeof dr);
+  if (nG) {
+    if ((rc = ensure(ctx, B[D_NB], (size_t)nG * 4)) || (rc = ensure(ctx, B[D_BOFF], (size_t)nG * 8))) return rc;
+    lra_b200_ir_groups dg;
+    dg.q_base = b.g_q_base; dg.t_base = b.g_t_base; dg.q_start = b.g_q_start; dg.t_start = b.g_t_start; dg.t_len = b.g_t_len;
+    dg.q_seq_len = b.g_q_seq_len; dg.t_seq_len = b.g_t_seq_len; dg.band_off = b.g_band_off; dg.band = (const int32_t *)B[BAND].p;
+    dg.band_len = bandInts; dg.n_groups = nG; dg.match = sg->match; dg.mismatch = sg->mismatch; dg.indel = sg->indel;
+    size_t dcap = 2 * T + 64 * (size_t)nG + 1024;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      if ((rc = ensure(ctx, B[D_BLK], dcap * 12))) return rc;
+      dr.n_blocks = (int32_t *)B[D_NB].p; dr.block_off = (uint64_t *)B[D_BOFF].p; dr.blocks = (uint32_t *)B[D_BLK].p; dr.block_cap = dcap;
+      rc = ir_run_device(ctx, q, t, &dg, &dr);
+      if (rc != LRA_B200_EOVERFLOW) break;
+      dcap = (size_t)dr.n_blocks_total + 64;
+    }
+    {
+      lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "ir_band");
+      cudaEventElapsedTime(&s2.ms, e2, e3); s2.jobs = (uint64_t)nG; s2.algo_bytes = bandInts * 4; all.push_back(s2);
+    }
+    for (auto &s2 : ctx->stats) all.push_back(s2);
+    if (rc) return rc;
+    res->cells = dr.cells;
+  }
+  // ---- assembly
+  IrAssemble a;
+  a.aog_n_blocks = ar.n_blocks; a.aog_block_off = (const unsigned long long *)ar.block_off; a.aog_blocks = ar.blocks;
+  a.dp_n_blocks = dr.n_blocks; a.dp_block_off = (const unsigned long long *)dr.block_off; a.dp_blocks = dr.blocks;
+  a.out_n = res->n_blocks; a.out_off = (unsigned long long *)res->block_off; a.out_blocks = res->blocks; a.out_cap = res->block_cap;
+  a.out_cursor = (unsigned long long *)B[OUTCUR].p; a.err = (int *)((char *)B[OUTCUR].p + 8);
+  cudaEventRecord(e0, st);
+  ir_assemble_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(b, a);
+  ctx->launches++;
+  cudaEventRecord(e1, st);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ctx->h_misc, B[OUTCUR].p, 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  stat("ir_assemble", e0, e1, (uint64_t)S);
+  ctx->stats = all;
+  res->n_blocks_total = ctx->h_misc[0];
+  const int err = *(int *)((char *)ctx->h_misc + 8);
+  if (err & 1) return fail(ctx, LRA_B200_EOVERFLOW, "indel_refine_batch: block capacity %llu too small, %llu needed",
+                           (unsigned long long)res->block_cap, (unsigned long long)res->n_blocks_total);
+  if (err & 64) return fail(ctx, LRA_B200_EINTERNAL, "indel_refine_batch: refined blocks overlap (the reference prints 'ERROR with alignment consistency')");
+  return LRA_B200_OK;
+}
+
+extern "C" int lra_b200_indel_refine_batch_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t,
+                                                  const lra_b200_ir_segments *sg, lra_b200_ir_seg_result *res) {
+  if (!ctx || !q || !t || !sg || !res) return fail(ctx, LRA_B200_EINVAL, "indel_refine_batch_device: NULL argument");
+  if (sg->n_segments < 0) return fail(ctx, LRA_B200_EINVAL, "indel_refine_batch_device: negative segment count");
+  CU(cudaSetDevice(ctx->device));
+  return ir_segments_run_device(ctx, q, t, sg, res);
+}
+
+extern "C" int lra_b200_indel_refine_batch(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t,
+                                           const lra_b200_ir_segments *sg, lra_b200_ir_seg_result *res) {
+  if (!ctx || !q || !t || !sg || !res) return fail(ctx, LRA_B200_EINVAL, "indel_refine_batch: NULL argument");
+  const int S = sg->n_segments;
+  if (S < 0) return fail(ctx, LRA_B200_EINVAL, "indel_refine_batch: negative segment count");
+  CU(cudaSetDevice(ctx->device));
+  if (S == 0) { res->n_blocks_total = 0; res->cells = 0; res->n_dp_groups = 0; res->n_aog_jobs = 0; ctx->stats.clear(); return LRA_B200_OK; }
+  int rc;
+  DevBuf *H = ctx->sg + 31;  // host-variant staging: 31..39
+  const size_t T = (size_t)sg->n_blocks_in;
+  if ((rc = ensure(ctx, H[0], T * 12 + 16)) || (rc = ensure(ctx, H[1], (size_t)S * 8)) || (rc = ensure(ctx, H[2], (size_t)S * 4)) ||
+      (rc = ensure(ctx, H[3], (size_t)S * 4)) || (rc = ensure(ctx, H[4], (size_t)S * 4)) || (rc = ensure(ctx, H[5], (size_t)S * 4)) ||
+      (rc = ensure(ctx, H[6], (size_t)S * 4)) || (rc = ensure(ctx, H[7], (size_t)S * 12)) ||
+      (rc = ensure(ctx, H[8], (size_t)(res->block_cap ? res->block_cap : 1) * 12)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(H[0].p, sg->blocks_in, T * 12, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(H[1].p, sg->blk_off, (size_t)S * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(H[2].p, sg->blk_cnt, (size_t)S * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(H[3].p, sg->q_base, (size_t)S * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(H[4].p, sg->t_base, (size_t)S * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(H[5].p, sg->read_len, (size_t)S * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(H[6].p, sg->contig_len, (size_t)S * 4, cudaMemcpyHostToDevice, st));
+  lra_b200_ir_segments ds = *sg;
+  ds.blocks_in = (const uint32_t *)H[0].p; ds.blk_off = (const uint64_t *)H[1].p; ds.blk_cnt = (const int32_t *)H[2].p;
+  ds.q_base = (const uint32_t *)H[3].p; ds.t_base = (const uint32_t *)H[4].p; ds.read_len = (const int32_t *)H[5].p;
+  ds.contig_len = (const int32_t *)H[6].p;
+  lra_b200_ir_seg_result dr = *res;
+  dr.n_blocks = (int32_t *)H[7].p; dr.block_off = (uint64_t *)((char *)H[7].p + (size_t)S * 4); dr.blocks = (uint32_t *)H[8].p;
+  rc = ir_segments_run_device(ctx, q, t, &ds, &dr);
+  res->n_blocks_total = dr.n_blocks_total; res->cells = dr.cells; res->n_dp_groups = dr.n_dp_groups; res->n_aog_jobs = dr.n_aog_jobs;
+  if (rc != LRA_B200_OK && rc != LRA_B200_EOVERFLOW) return rc;
+  CU(cudaMemcpyAsync(res->n_blocks, dr.n_blocks, (size_t)S * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->block_off, dr.block_off, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
   if (rc == LRA_B200_OK && dr.n_blocks_total)
     CU(cudaMemcpyAsync(res->blocks, dr.blocks, (size_t)dr.n_blocks_total * 12, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));

@@ -36,8 +36,24 @@ def lib():
     L.emu_ir_dp_batch.restype = C.c_int
     L.emu_ir_dp_batch.argtypes = [_u8p, C.c_uint64, _u8p, C.c_uint64, _u32p, _u32p, _i32p, _i32p, _i32p, _i32p, _i32p, _u32p, _i32p,
                                   C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _u64p, _u32p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
+    L.emu_ir_segments.restype = C.c_int
+    L.emu_ir_segments.argtypes = [_u8p, C.c_uint64, _u8p, C.c_uint64, _u32p, _u64p, _i32p, _u32p, _u32p, _i32p, _i32p, C.c_uint64, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _u64p, _u32p, C.c_uint64, _u64p]
     _lib = L
     return L
+
+
+def ir_segments(sb, out_cap=None):
+    """sb: dict from irgen.pack_segments.  Returns (err, n_blocks, block_off, blocks, info[n_aog,n_groups,cells])."""
+    S = len(sb["blk_cnt"])
+    if out_cap is None:
+        out_cap = int(sb["read_len"].sum()) + 16
+    n = np.zeros(S, np.int32); off = np.zeros(S, np.uint64); blocks = np.zeros(out_cap * 3, np.uint32); info = np.zeros(3, np.uint64)
+    err = lib().emu_ir_segments(sb["q_arena"], len(sb["q_arena"]) - 16, sb["t_arena"], len(sb["t_arena"]) - 16, sb["blocks_in"].reshape(-1),
+                                sb["blk_off"], sb["blk_cnt"], sb["q_base"], sb["t_base"], sb["read_len"], sb["contig_len"],
+                                len(sb["blocks_in"]), S, sb["k"], sb["match"], sb["mismatch"], sb["indel"], sb["end_align"], n, off,
+                                blocks, out_cap, info)
+    return err, n, off, blocks.reshape(-1, 3), info
 
 
 def ir_dp_batch(gb, force_generic=0, block_cap=None):

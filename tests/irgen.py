@@ -42,3 +42,21 @@ def pack_groups(recs, rec_groups, scoring):
         expect.append(g["blocks"])
     gb["band"] = np.concatenate(band + [np.zeros(4, np.int32)]).astype(np.int32)
     return gb, expect
+
+
+def pack_segments(recs):
+    """Whole-function batch (lra_b200_indel_refine_batch) over captured segments that share k / scoring / endAlign."""
+    r0 = recs[0]
+    assert all((r["k"], r["match"], r["mismatch"], r["indel"], r["end_align"]) == (r0["k"], r0["match"], r0["mismatch"], r0["indel"], r0["end_align"]) for r in recs)
+    q_parts, t_parts, qb, tb, qo, to = [], [], [], [], 0, 0
+    for r in recs:
+        qb.append(qo); q_parts.append(r["read"]); qo += len(r["read"])
+        tb.append((to - r["t_win_off"]) & 0xFFFFFFFF); t_parts.append(r["twin"]); to += len(r["twin"])
+    cnt = np.array([len(r["blocks_in"]) for r in recs], np.int32)
+    off = np.zeros(len(recs), np.uint64); off[1:] = np.cumsum(cnt[:-1])
+    return dict(q_arena=np.frombuffer(b"".join(q_parts) + b"N" * 16, dtype=np.uint8).copy(),
+                t_arena=np.frombuffer(b"".join(t_parts) + b"N" * 16, dtype=np.uint8).copy(),
+                blocks_in=np.concatenate([r["blocks_in"] for r in recs]).astype(np.uint32), blk_off=off, blk_cnt=cnt,
+                q_base=np.array(qb, np.uint32), t_base=np.array(tb, np.uint32),
+                read_len=np.array([len(r["read"]) for r in recs], np.int32), contig_len=np.array([r["contig_len"] for r in recs], np.int32),
+                k=r0["k"], match=r0["match"], mismatch=r0["mismatch"], indel=r0["indel"], end_align=r0["end_align"])

@@ -41,3 +41,17 @@ def test_emu_ir_clr_w64():
 
 def test_emu_ir_generic_kernel():
     assert run("ir_ccs", 2, force_generic=1, max_groups=40) > 10
+
+
+@pytest.mark.parametrize("name,n", [("ir_ccs", 6), ("ir_ont", 2), ("ir_clr", 2)])
+def test_emu_whole_function_on_captured_segments(name, n):
+    """group + band + AffineOneGapAlign fallback + DP + assemble == the reference's IndelRefineAlignment output."""
+    recs = po.read_ir_capture(os.path.join(GOLD, name + ".bin"))[:n]
+    sb = irgen.pack_segments(recs)
+    err, nb, off, blk, info = emu_lib.ir_segments(sb)
+    assert err == 0
+    assert info[1] > 0
+    for s, r in enumerate(recs):
+        e = r["blocks_out"]
+        assert nb[s] == len(e), (name, s, nb[s], len(e))
+        assert (blk[int(off[s]):int(off[s]) + nb[s]] == e).all(), (name, s)

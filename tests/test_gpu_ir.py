@@ -52,3 +52,30 @@ def test_ir_dp_errors(ctx):
         ctx.indel_dp_batch(q, t, bad)
     assert e.value.code == capi.EINVAL
     q.free(); t.free()
+
+
+@pytest.mark.parametrize("name", ["ir_ccs", "ir_ont", "ir_clr"])
+def test_whole_function_golden_segments(ctx, name):
+    """lra_b200_indel_refine_batch (group + band + AffineOneGapAlign fallback + DP + assemble on the GPU) must return the
+    reference's refined alignment.blocks for every captured segment."""
+    recs = po.read_ir_capture(os.path.join(GOLD, name + ".bin"))
+    sb = irgen.pack_segments(recs)
+    q = ctx.seq_upload(sb["q_arena"][:-16]); t = ctx.seq_upload(sb["t_arena"][:-16])
+    r = ctx.indel_refine_batch(q, t, sb)
+    q.free(); t.free()
+    assert r["n_dp_groups"] > 0
+    names = [s["name"] for s in ctx.kernel_stats()]
+    assert "ir_group" in names and "ir_band" in names and "ir_assemble" in names
+    for s, rec in enumerate(recs):
+        e = rec["blocks_out"]
+        assert r["n_blocks"][s] == len(e), (name, s)
+        o = int(r["block_off"][s])
+        assert (r["blocks"][o:o + len(e)] == e).all(), (name, s)
+
+
+def test_single_segment_mirror(ctx):
+    import lra_b200
+    r = po.read_ir_capture(os.path.join(GOLD, "ir_ccs.bin"))[0]
+    out = lra_b200.IndelRefineAlignment(r["read"], r["twin"], r["contig_len"], r["blocks_in"], r["k"], r["match"], r["mismatch"],
+                                        r["indel"], endAlign=bool(r["end_align"]), tWinOff=r["t_win_off"], ctx=ctx)
+    assert out.shape == r["blocks_out"].shape and (out == r["blocks_out"]).all()
