@@ -729,7 +729,7 @@ extern "C" int lra_b200_indel_refine_batch(lra_b200_ctx *ctx, const lra_b200_seq
   ds.q_base = (const uint32_t *)H[3].p; ds.t_base = (const uint32_t *)H[4].p; ds.read_len = (const int32_t *)H[5].p;
   ds.contig_len = (const int32_t *)H[6].p;
   lra_b200_ir_seg_result dr = *res;
-  dr.n_blocks = (int32_t *)H[7].p; dr.block_off = (uint64_t *)((char *)H[7].p + (size_t)S * 4); dr.blocks = (uint32_t *)H[8].p;
+  dr.block_off = (uint64_t *)H[7].p; dr.n_blocks = (int32_t *)((char *)H[7].p + (size_t)S * 8); dr.blocks = (uint32_t *)H[8].p;
   rc = ir_segments_run_device(ctx, q, t, &ds, &dr);
   res->n_blocks_total = dr.n_blocks_total; res->cells = dr.cells; res->n_dp_groups = dr.n_dp_groups; res->n_aog_jobs = dr.n_aog_jobs;
   if (rc != LRA_B200_OK && rc != LRA_B200_EOVERFLOW) return rc;

@@ -18,6 +18,7 @@ _u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 _i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 _u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 
 
 def build(want_ref=None):
@@ -203,3 +204,39 @@ def indel_refine_groups_port(read, twin, t_win_off, contig_len, blocks_in, k, ma
         groups.append(dict(qStart=qs, tStart=ts, tLen=tl, qSeqLen=qsl, tSeqLen=tsl, qS=band[boff:boff + tl].copy(),
                            qE=band[boff + tl:boff + 2 * tl].copy(), blocks=blocks[fo:fo + no].copy()))
     return blocks, st.value, groups
+
+
+def indel_refine_batch_ref(sb, t_arena, t_base, nthreads=1, want_blocks=True):
+    """Whole-function batch through the UNMODIFIED reference (libref_lra.so).  sb as for lra_b200_indel_refine_batch but with the
+    target arena / bases given explicitly (CPU arms use compact window arenas).  Returns (n_blocks, out_off, blocks)."""
+    L = ref()
+    if not getattr(L, "_irb_bound", False):
+        L.ref_indel_refine_batch.restype = C.c_int
+        L.ref_indel_refine_batch.argtypes = [_u8p, _u8p, _u32p, _u64p, _i32p, _u32p, _u32p, _i32p, _i32p, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, _i32p, _u64p, C.c_void_p, C.c_int]
+        L._irb_bound = True
+    S = len(sb["blk_cnt"])
+    cap = (sb["read_len"].astype(np.int64) + sb["contig_len"]).astype(np.uint64)
+    off = np.zeros(S, np.uint64); off[1:] = np.cumsum(cap[:-1])
+    n = np.zeros(S, np.int32)
+    blocks = np.zeros((int(cap.sum()) + 1) * 3, np.uint32) if want_blocks else None
+    L.ref_indel_refine_batch(sb["q_arena"], t_arena, np.ascontiguousarray(sb["blocks_in"], np.uint32).reshape(-1),
+                             np.ascontiguousarray(sb["blk_off"], np.uint64), sb["blk_cnt"], sb["q_base"], t_base, sb["read_len"],
+                             sb["contig_len"], S, sb["k"], sb["match"], sb["mismatch"], sb["indel"], sb["end_align"], n, off,
+                             blocks.ctypes.data if want_blocks else None, nthreads)
+    return n, off, (blocks.reshape(-1, 3) if want_blocks else None)
+
+
+def indel_refine_batch_port(sb, t_arena, t_base):
+    """Same through the C restatement (single thread)."""
+    S = len(sb["blk_cnt"])
+    outs = []
+    for s in range(S):
+        o, c = int(sb["blk_off"][s]), int(sb["blk_cnt"][s])
+        qb, tb = int(sb["q_base"][s]), int(t_base[s])
+        bo, st, cells = indel_refine_port(sb["q_arena"][qb:qb + sb["read_len"][s]].tobytes(), t_arena[tb:tb + sb["contig_len"][s]].tobytes(), 0,
+                                          int(sb["contig_len"][s]), sb["blocks_in"][o:o + c], sb["k"], sb["match"], sb["mismatch"], sb["indel"],
+                                          sb["end_align"])
+        assert st == 0
+        outs.append(bo)
+    return outs

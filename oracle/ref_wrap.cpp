@@ -7,13 +7,20 @@
 //
 // Reference entry points wrapped here:
 //   AffineOneGapAlign            AffineOneGapAlign.h:157-649
+//   IndelRefineAlignment         IndelRefine.h:53-784
 #include <string>
 #include <vector>
 #include <thread>
 #include <atomic>
 #include <cstdint>
 #include <cstring>
+#include <zlib.h>
+#include <iomanip>
+#include "htslib/kseq.h"
+#include "htslib/sam.h"
 #include "AffineOneGapAlign.h"
+#include "Input.h"         // declares KSEQ_INIT(gzFile, gzread) for Genome.h
+#include "IndelRefine.h"
 
 extern "C" {
 
@@ -63,6 +70,53 @@ int ref_aog_batch(const char *q_arena, const char *t_arena, const uint32_t *q_of
           }
         }
       }
+    }
+  };
+  if (nthreads <= 1) { work(); return 0; }
+  std::vector<std::thread> th;
+  for (int i = 0; i < nthreads; i++) th.emplace_back(work);
+  for (auto &x : th) x.join();
+  return 0;
+}
+
+// IndelRefineAlignment over a batch of segments on `nthreads` host threads.  Segment s: blocks_in[blk_off[s] .. +blk_cnt[s]),
+// read strand = q_arena + q_base[s] (read_len[s] bases), contig = t_arena + t_base[s] (contig_len[s] bases; block tPos
+// are contig-relative).  Output blocks at out_blocks[3*out_off[s]] with capacity read_len[s]+contig_len[s] each (out_off is an
+// input).  Returns 0.
+int ref_indel_refine_batch(const char *q_arena, const char *t_arena, const uint32_t *blocks_in, const uint64_t *blk_off,
+                           const int32_t *blk_cnt, const uint32_t *q_base, const uint32_t *t_base, const int32_t *read_len,
+                           const int32_t *contig_len, int n_seg, int refineBand, int match, int mismatch, int indel, int endAlign,
+                           int32_t *out_n, const uint64_t *out_off, uint32_t *out_blocks, int nthreads) {
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    Options opts;
+    opts.refineBand = refineBand; opts.localMatch = match; opts.localMismatch = mismatch; opts.localIndel = indel;
+    IndelRefineBuffers buffers;
+    for (;;) {
+      int s = next.fetch_add(1);
+      if (s >= n_seg) break;
+      Read read;
+      read.length = read_len[s];
+      read.name = "r";
+      Genome genome;
+      genome.seqs.push_back((char *)t_arena + t_base[s]);
+      genome.lengths.push_back(contig_len[s]);
+      Alignment aln;
+      aln.chromIndex = 0;
+      aln.read = (char *)q_arena + q_base[s];
+      aln.blocks.resize(blk_cnt[s]);
+      for (int i = 0; i < blk_cnt[s]; i++) {
+        const uint32_t *b = blocks_in + 3 * (blk_off[s] + i);
+        aln.blocks[i] = Block(b[0], b[1], b[2]);
+      }
+      IndelRefineAlignment(read, genome, aln, opts, buffers, endAlign != 0);
+      out_n[s] = (int32_t)aln.blocks.size();
+      if (out_blocks) {
+        uint32_t *o = out_blocks + 3 * out_off[s];
+        for (size_t i = 0; i < aln.blocks.size(); i++) { o[3 * i] = aln.blocks[i].qPos; o[3 * i + 1] = aln.blocks[i].tPos; o[3 * i + 2] = aln.blocks[i].length; }
+      }
+      genome.seqs.clear();   // the arena is not ours: keep ~Genome from delete[]-ing it
+      read.seq = NULL; read.qual = NULL;
     }
   };
   if (nthreads <= 1) { work(); return 0; }

@@ -79,3 +79,31 @@ def test_single_segment_mirror(ctx):
     out = lra_b200.IndelRefineAlignment(r["read"], r["twin"], r["contig_len"], r["blocks_in"], r["k"], r["match"], r["mismatch"],
                                         r["indel"], endAlign=bool(r["end_align"]), tWinOff=r["t_win_off"], ctx=ctx)
     assert out.shape == r["blocks_out"].shape and (out == r["blocks_out"]).all()
+
+
+@pytest.mark.parametrize("profile,n", [("ont", 400), ("ccs", 3000), ("clr", 250)])
+def test_whole_function_synthetic_segments_vs_reference(ctx, profile, n):
+    """Bench-shaped synthetic segments: the GPU path vs the reference header itself (prebuilt oracle/_ref/libref_lra.so, all host
+    threads) or, if that did not travel, the C restatement on a sample."""
+    import synth, workload
+    genome = synth.gen_ref(30_000_000, 1, 78)[0][1]
+    sb = workload.make_segments(profile, n, 6, len(genome), workload.host_genome_fetcher(genome))
+    q = ctx.seq_upload(sb["q_arena"][:-16]); t = ctx.seq_upload(genome)
+    r = ctx.indel_refine_batch(q, t, sb)
+    q.free(); t.free()
+    assert r["n_dp_groups"] >= n * 0.9
+    if po.ref() is not None:
+        nref, off, blk = po.indel_refine_batch_ref(sb, sb["t_arena_compact"], sb["t_base_compact"], nthreads=os.cpu_count() or 1)
+        assert (r["n_blocks"] == nref).all()
+        tot = int(nref.sum())
+        within = np.arange(tot) - np.repeat(np.cumsum(nref) - nref, nref)
+        got = r["blocks"][np.repeat(r["block_off"].astype(np.int64), nref) + within]
+        exp = blk[np.repeat(off.astype(np.int64), nref) + within]
+        # the reference sees contig-relative t; both use window-relative blocks here
+        assert (got == exp).all()
+    else:
+        sub = {k: (v[:20] if isinstance(v, np.ndarray) and len(v) == n else v) for k, v in sb.items()}
+        outs = po.indel_refine_batch_port(sub, sb["t_arena_compact"], sb["t_base_compact"][:20])
+        for s, o in enumerate(outs):
+            oo = int(r["block_off"][s])
+            assert r["n_blocks"][s] == len(o) and (r["blocks"][oo:oo + len(o)] == o).all()

@@ -34,3 +34,16 @@ def test_group_dump_is_consistent():
             b = g["blocks"]
             assert b[0, 0] == g["qStart"] and b[0, 1] == g["tStart"]
             assert b[-1, 0] + b[-1, 2] == g["qStart"] + g["qSeqLen"] and b[-1, 1] + b[-1, 2] == g["tStart"] + g["tSeqLen"]
+
+
+@pytest.mark.skipif(po.ref() is None, reason="oracle/_ref/libref_lra.so not built (no /root/reference)")
+@pytest.mark.parametrize("profile,n", [("ont", 12), ("ccs", 40), ("clr", 10)])
+def test_restatement_matches_live_reference_on_synthetic_segments(profile, n):
+    """Whole IndelRefineAlignment through the unmodified reference header (oracle/ref_wrap.cpp) vs the restatement."""
+    import synth, workload
+    genome = synth.gen_ref(3_000_000, 1, 77)[0][1]
+    sb = workload.make_segments(profile, n, 5, len(genome), workload.host_genome_fetcher(genome))
+    nref, off, blk = po.indel_refine_batch_ref(sb, sb["t_arena_compact"], sb["t_base_compact"], nthreads=2)
+    outs = po.indel_refine_batch_port(sb, sb["t_arena_compact"], sb["t_base_compact"])
+    for s, o in enumerate(outs):
+        assert len(o) == nref[s] and (o == blk[int(off[s]):int(off[s]) + nref[s]]).all(), (profile, s)

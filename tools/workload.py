@@ -130,3 +130,57 @@ def check_blocks_property(jobs, res, m, mm, indel):
     expect = sc + indel * ((qB - 1 - cov) + (tB - 1 - cov))
     assert (res["score"].astype(np.int64)[one] == expect[one]).all()
     return int(one.sum())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# a19 IndelRefineAlignment: synthetic SEGMENTS.  One segment per read: the target is a random genome window of the read's
+# length, the read is that window with i.i.d. errors, and the segment's input blocks are the maximal gap-free runs of the
+# true alignment (what the upstream chain refinement hands to IndelRefineAlignment: blocks separated by small indels).
+PROFILE_REFINE_BAND = {"ccs": 7, "ont": 7, "clr": 20}
+PROFILE_END_ALIGN = {"ccs": 1, "ont": 0, "clr": 0}
+
+
+def make_segments(profile, n_reads, seed, genome_len, fetch_windows, max_len=None):
+    rng = np.random.default_rng(seed)
+    lens = synth.read_lengths({"ccs": "ccs10k", "ont": "ont", "clr": "clr"}[profile], n_reads, rng).astype(np.int64)
+    if max_len:
+        lens = np.minimum(lens, max_len)
+    t_pos = rng.integers(0, genome_len - int(lens.max()) - 1, size=n_reads, dtype=np.int64)
+    src, src_off = fetch_windows(t_pos, lens)
+    n = len(src)
+    err = PROFILE_ERR[profile]
+    r = rng.random(n)
+    kind = np.zeros(n, np.uint8)
+    kind[r < err] = 1; kind[r < 2 * err / 3] = 2; kind[r < err / 3] = 3
+    first = np.zeros(n, bool); first[src_off] = True
+    last = np.zeros(n, bool); last[src_off + lens - 1] = True
+    kind[first | last] = 0                      # segments start and end on an aligned base
+    cnt = np.ones(n, np.int64); cnt[kind == 3] = 0; cnt[kind == 2] = 2
+    pos = np.cumsum(cnt) - cnt
+    total = int(pos[-1] + cnt[-1])
+    code = (np.searchsorted(synth.BASES, src) & 3).astype(np.uint8)
+    sub = synth.BASES[(code + rng.integers(1, 4, size=n, dtype=np.uint8)) & 3]
+    q_arena = np.empty(total + 16, np.uint8); q_arena[total:] = ord("A")
+    keep = kind != 3
+    q_arena[pos[keep]] = np.where(kind == 1, sub, src)[keep]
+    ins = kind == 2
+    q_arena[pos[ins] + 1] = synth.BASES[rng.integers(0, 4, size=int(ins.sum()), dtype=np.uint8)]
+    q_base = pos[src_off]
+    read_len = np.append(q_base[1:], total) - q_base
+    # blocks: maximal runs of emitted bases not interrupted by an insertion or a deletion
+    prev_kind = np.concatenate([[0], kind[:-1]])
+    prev_keep = np.concatenate([[False], keep[:-1]])
+    start = keep & (first | ~prev_keep | (prev_kind == 2))
+    run_id = np.cumsum(start) - 1
+    blen = np.bincount(run_id[keep], minlength=int(start.sum()))
+    sidx = np.flatnonzero(start)
+    seg_of = np.searchsorted(src_off, sidx, side="right") - 1
+    blocks = np.stack([pos[sidx] - q_base[seg_of], sidx - src_off[seg_of], blen], 1).astype(np.uint32)
+    blk_cnt = np.bincount(seg_of, minlength=n_reads).astype(np.int32)
+    blk_off = np.zeros(n_reads, np.uint64); blk_off[1:] = np.cumsum(blk_cnt[:-1])
+    t_arena = np.empty(n + 16, np.uint8); t_arena[:n] = src; t_arena[n:] = ord("A")
+    m, mm, indel = PROFILE_SCORING[profile]
+    return dict(q_arena=q_arena, blocks_in=blocks, blk_off=blk_off, blk_cnt=blk_cnt, q_base=q_base.astype(np.uint32),
+                t_base=t_pos.astype(np.uint32), read_len=read_len.astype(np.int32), contig_len=lens.astype(np.int32),
+                t_arena_compact=t_arena, t_base_compact=src_off.astype(np.uint32), k=PROFILE_REFINE_BAND[profile], match=m, mismatch=mm,
+                indel=indel, end_align=PROFILE_END_ALIGN[profile], bases=int(lens.sum()))
