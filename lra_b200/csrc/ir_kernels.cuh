@@ -42,12 +42,13 @@ struct IrBatch {
   int32_t *max_width;       // per group
 };
 
-constexpr int kIrClsW24 = 0, kIrClsW64 = 1, kIrClsGeneric = 2;
+constexpr int kIrClsW24 = 0, kIrClsW64 = 1, kIrClsGeneric = 2, kIrClsWarp32 = 3;
+constexpr int kIrWarpMinRows = 192;   // longer groups of width <= 32 go to the warp-per-group kernel
 __host__ __device__ inline int ir_words(int wmax) { return (wmax + 5) / 6; }
 
 // one warp per group: band maximum width -> class; reserves traceback storage; fills the planner histogram
 __global__ void __launch_bounds__(128) ir_classify_kernel(IrBatch b, AogPlan *plan, uint32_t *bin_of_group, unsigned long long *tb_cursor,
-                                                          unsigned long long *cells_total) {
+                                                          unsigned long long *cells_total, int no_warp) {
   const int lane = threadIdx.x & 31;
   const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   if (g >= b.n_groups) return;
@@ -76,12 +77,12 @@ __global__ void __launch_bounds__(128) ir_classify_kernel(IrBatch b, AogPlan *pl
       b.n_blocks[g] = 0; b.block_off[g] = 0;
       return;
     }
-    const int cls = mw <= 24 ? kIrClsW24 : (mw <= 64 ? kIrClsW64 : kIrClsGeneric);
-    const unsigned long long words = cls == kIrClsGeneric ? ((unsigned long long)rows * (unsigned long long)mw + 3ull) / 4ull + 2ull * (unsigned long long)mw + 4ull
+    const int cls = (mw <= 32 && rows >= kIrWarpMinRows && !no_warp) ? kIrClsWarp32 : mw <= 24 ? kIrClsW24 : (mw <= 64 ? kIrClsW64 : kIrClsGeneric);
+    const unsigned long long words = cls == kIrClsWarp32 ? (unsigned long long)rows * 5ull + 8ull : cls == kIrClsGeneric ? ((unsigned long long)rows * (unsigned long long)mw + 3ull) / 4ull + 2ull * (unsigned long long)mw + 4ull
                                                            : (unsigned long long)rows * (unsigned long long)ir_words(cls == kIrClsW24 ? 24 : 64);
     b.tb_off[g] = atomicAdd(tb_cursor, words);
     b.max_width[g] = mw;
-    const int bucket = kAogBuckets - 1 - imin(rows >> 8, kAogBuckets - 1);
+    const int bucket = kAogBuckets - 1 - imin(cls == kIrClsWarp32 ? rows >> 8 : rows >> 3, kAogBuckets - 1);
     const uint32_t bin = (uint32_t)(cls * kAogBuckets + bucket);
     bin_of_group[g] = bin;
     atomicAdd(&plan->hist[bin], 1u);
@@ -304,6 +305,186 @@ __global__ void __launch_bounds__(64) ir_dp_thread_kernel(IrBatch b, AogPlan *pl
       b.block_off[g] = slot;
       if (slot != ~0ull && nb > 0) ir_walk<WORDS, true>(tbp, qS, qE, rows, tStart, b.blocks + 3ull * slot, nb);
     }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------- warp per group
+// Long groups (ONT/CLR: 10^3..10^4 rows).  Lane x owns band cell x of the current row (width <= 32).  With
+//   a[x] = max(match, down, delClose)            (candidates that come from the previous row),
+// the in-row recurrences  I[x] = max(M[x-1]+gapOpen, I[x-1]),  M[x] = max(a[x], M[x-1]+gap, I[x])  have the closed form
+//   M[x] = max( max_{y<=x} a[y] + (x-y)*gap ,  max_{y<x} a[y] + gapOpen ,  BAD ),   I[x] = max(BAD, max_{y<x} a[y] + gapOpen)
+// (gapExtend = 0 and gapOpen < gap < 0), i.e. two independent 5-step prefix-max scans per row instead of a serial chain.
+// Arrows are then decided per cell from the exact M[x-1], I[x].  The previous row is exchanged through shared memory;
+// arrows are stored as 5 bit-planes (one ballot each) = 5 words per row; the traceback is walked by the whole warp with
+// 32 rows of planes held in registers at a time.
+constexpr int kIrNeg = -1073741824;
+
+template <bool WRITE>
+__device__ __forceinline__ int ir_walk_planes(const uint32_t *tb, const int32_t *qS, const int32_t *qE, int rows, int tStart, uint32_t *out,
+                                              int nb, int lane) {
+  int t = rows - 1;
+  int qs = qS[t];
+  int x = qE[t] - qs;
+  int mat = 0, run = 0, lastOp = -1, count = 0;
+  long guard = 0;
+  const long guardMax = 4L * rows + 4L * (qE[rows - 1] - qS[0]) + 64;
+  auto emit = [&](uint32_t qq, uint32_t tt, uint32_t ln) {
+    if (WRITE && lane == 0) { const int r = nb - 1 - count; out[3 * r] = qq; out[3 * r + 1] = tt; out[3 * r + 2] = ln; }
+    count++;
+  };
+  int top = -1;                 // rows [top-31, top] are held: lane l has row top-l
+  uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0;
+  int rqs = 0;
+  while (true) {
+    if (++guard > guardMax) return -1;
+    if (t == 0) {
+      if (x > 0) {
+        if (mat != 0) return -1;
+        if (run > 0) { emit((uint32_t)(qs + x + 1), (uint32_t)(tStart + 1), (uint32_t)run); run = 0; }
+        else if (lastOp == IR_DOWN) emit((uint32_t)(qs + x + 1), (uint32_t)(tStart + 1), 0u);
+        lastOp = IR_LEFT; x = 0;
+      }
+      run += 1;
+      emit((uint32_t)qs, (uint32_t)tStart, (uint32_t)run);
+      break;
+    }
+    if (top < 0 || t > top || t < top - 31) {
+      top = t;
+      const int r = top - lane;
+      if (r >= 1) {
+        const uint32_t *w = tb + (unsigned long long)r * 5ull;
+        p0 = w[0]; p1 = w[1]; p2 = w[2]; p3 = w[3]; p4 = w[4];
+      }
+      rqs = (r >= 1) ? qS[r - 1] : 0;   // qS of the row above row r
+    }
+    const int src = top - t;
+    const uint32_t w0 = __shfl_sync(0xffffffffu, p0, src), w1 = __shfl_sync(0xffffffffu, p1, src), w2 = __shfl_sync(0xffffffffu, p2, src);
+    const uint32_t w3 = __shfl_sync(0xffffffffu, p3, src), w4 = __shfl_sync(0xffffffffu, p4, src);
+    const int pqs = __shfl_sync(0xffffffffu, rqs, src);
+    const int a = (int)(((w0 >> x) & 1u) | (((w1 >> x) & 1u) << 1) | (((w2 >> x) & 1u) << 2));
+    const int dbit = (int)((w3 >> x) & 1u), ibit = (int)((w4 >> x) & 1u);
+    int op, nt = t, nx = x, nmat = mat;
+    if (mat == 0) {
+      if (a == IR_DELCLOSE) { op = -1; nmat = 1; }
+      else if (a == IR_INSCLOSE) { op = -1; nmat = 2; }
+      else if (a == IR_DIAG) { op = IR_DIAG; nt = t - 1; }
+      else if (a == IR_LEFT) { op = IR_LEFT; nx = x - 1; }
+      else if (a == IR_DOWN) { op = IR_DOWN; nt = t - 1; }
+      else return -1;
+    } else if (mat == 1) { op = IR_DOWN; nmat = dbit ? 1 : 0; nt = t - 1; }
+    else { op = IR_LEFT; nmat = ibit ? 2 : 0; nx = x - 1; }
+    if (op >= 0) {
+      const int q = qs + x;
+      if (op == IR_DIAG) run++;
+      else {
+        if (run > 0) { emit((uint32_t)(q + 1), (uint32_t)(tStart + t + 1), (uint32_t)run); run = 0; }
+        else if (lastOp != -1 && lastOp != op) emit((uint32_t)(q + 1), (uint32_t)(tStart + t + 1), 0u);
+      }
+      lastOp = op;
+    }
+    if (nt != t) { const int q = qs + x; nx = (op == IR_DIAG ? q - 1 : q) - pqs; qs = pqs; }
+    t = nt; x = nx; mat = nmat;
+    if (x < 0 || x > 31) return -1;
+  }
+  return count;
+}
+
+__global__ void __launch_bounds__(128) ir_dp_warp_kernel(IrBatch b, AogPlan *plan, const uint32_t *sorted) {
+  constexpr int cls = kIrClsWarp32;
+  __shared__ int sM[4][33];
+  __shared__ int sD[4][33];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  int *rowM = sM[wib], *rowD = sD[wib];
+  const uint32_t begin = plan->bin_start[cls * kAogBuckets];
+  const uint32_t end = plan->bin_start[(cls + 1) * kAogBuckets];
+  const int match = b.match, mismatch = b.mismatch, gap = b.gap, gapOpen = 2 * b.gap + 1;
+  for (;;) {
+    uint32_t w = 0;
+    if (lane == 0) w = atomicAdd(&plan->work[cls], 1u);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (begin + w >= end) break;
+    const int g = (int)sorted[begin + w];
+    const int rows = b.t_len[g];
+    const int tStart = b.t_start[g];
+    const int32_t *qS = b.band + b.band_off[g];
+    const int32_t *qE = qS + rows;
+    uint32_t *tbw = b.tb + b.tb_off[g];
+    const uint64_t qbase = (uint64_t)b.q_base[g];
+    const uint32_t tbase = b.t_base[g];
+    int qsPrev = qS[0];
+    int lenPrev = qE[0] - qsPrev + 1;
+    __syncwarp();
+    rowM[lane] = lane * gap;
+    rowD[lane] = kIrBad;
+    __syncwarp();
+    int qsN = rows > 1 ? qS[1] : 0, qeN = rows > 1 ? qE[1] : 0;
+    for (int t = 1; t < rows; t++) {
+      const int qs = qsN, qe = qeN;
+      if (t + 1 < rows) { qsN = qS[t + 1]; qeN = qE[t + 1]; }
+      const int len = qe - qs + 1;
+      const int off = qs - qsPrev;
+      const int rowEnd = (t == rows - 1) ? len : len - 1;
+      const int x = lane;
+      const int xp = x + off;
+      const bool upIn = xp <= lenPrev - 1;
+      const bool upOk = xp < lenPrev - 1;
+      const bool diagOk = upIn && !(xp - 1 == 0 && t != 1);
+      const int Mup = upIn ? rowM[xp] : kIrBad;
+      const int Dup = upIn ? rowD[xp] : kIrBad;
+      const int Mdg = (upIn && xp >= 1) ? rowM[xp - 1] : kIrBad;
+      const bool valid = x >= 1 && x < rowEnd;
+      const int tc = seq_code(b.t, (uint64_t)(uint32_t)(tbase + (uint32_t)(tStart + t)));
+      const int qc = valid ? seq_code(b.q, qbase + (uint64_t)(qs + x)) : 5;
+      __syncwarp();
+      const int delOpen = upOk ? Mup + gapOpen : kIrBad;
+      const int delExt = upOk ? Dup : kIrBad;
+      const int D = imax(delOpen, delExt);
+      const int dbit = (D == delOpen) ? 0 : 1;
+      const int mS = diagOk ? Mdg + (qc == tc ? match : mismatch) : kIrBad;
+      const int dS = upOk ? Mup + gap : kIrBad;
+      const int a = valid ? imax(imax(mS, dS), D) : (x == 0 ? kIrBad : kIrNeg);
+      // two prefix scans: linear-gap chain and running maximum
+      int u = a - x * gap;         // L[x] = x*gap + max_{y<=x}(a[y] - y*gap)
+      int pm = a;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int uu = __shfl_up_sync(0xffffffffu, u, o);
+        const int pp = __shfl_up_sync(0xffffffffu, pm, o);
+        if (lane >= o) { u = imax(u, uu); pm = imax(pm, pp); }
+      }
+      int pmx = __shfl_up_sync(0xffffffffu, pm, 1);
+      if (lane == 0) pmx = kIrNeg;
+      const int L = u + x * gap;
+      const int I = imax(kIrBad, pmx + gapOpen);
+      const int M = (x == 0) ? kIrBad : imax(imax(L, pmx + gapOpen), kIrBad);
+      int Mleft = __shfl_up_sync(0xffffffffu, M, 1);
+      if (lane == 0) Mleft = kIrBad;
+      const int iS = Mleft + gap;
+      const int ibit = (I == Mleft + gapOpen) ? 0 : 1;
+      const int arrow = (M == mS) ? IR_DIAG : (M == iS) ? IR_LEFT : (M == dS) ? IR_DOWN : (M == D) ? IR_DELCLOSE : IR_INSCLOSE;
+      const uint32_t b0 = __ballot_sync(0xffffffffu, valid && (arrow & 1));
+      const uint32_t b1 = __ballot_sync(0xffffffffu, valid && (arrow & 2));
+      const uint32_t b2 = __ballot_sync(0xffffffffu, valid && (arrow & 4));
+      const uint32_t b3 = __ballot_sync(0xffffffffu, valid && dbit);
+      const uint32_t b4 = __ballot_sync(0xffffffffu, valid && ibit);
+      if (lane < 5) tbw[(unsigned long long)t * 5ull + lane] = lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : lane == 3 ? b3 : b4;
+      rowM[lane] = M;
+      rowD[lane] = valid ? D : kIrBad;
+      __syncwarp();
+      qsPrev = qs; lenPrev = len;
+    }
+    __syncwarp();
+    int nb = ir_walk_planes<false>(tbw, qS, qE, rows, tStart, nullptr, 0, lane);
+    if (nb < 0) { if (lane == 0) atomicOr(b.err, 16); nb = 0; }
+    unsigned long long slot = aog_reserve_blocks(AogBatch{b.q, b.t, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, nullptr,
+                                                          nullptr, b.blocks, b.block_cap, b.block_cursor, b.err},
+                                                 lane == 0 ? nb : 0, lane, &plan->cls_blocks[cls]);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (lane == 0) { b.n_blocks[g] = nb; b.block_off[g] = slot; }
+    if (slot != ~0ull && nb > 0) ir_walk_planes<true>(tbw, qS, qE, rows, tStart, b.blocks + 3ull * slot, nb, lane);
+    __syncwarp();
   }
 }
 

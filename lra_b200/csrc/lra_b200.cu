@@ -467,7 +467,8 @@ static int ir_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b20
   int evi = 0;
   auto rec = [&]() { cudaEventRecord(ctx->ev[evi++], st); };
   rec();
-  ir_classify_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(b, plan, (uint32_t *)ctx->bin_of_job.p, tb_cursor, cells_total);
+  static const int no_warp = getenv("LRA_B200_IR_NO_WARP") ? 1 : 0;
+  ir_classify_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(b, plan, (uint32_t *)ctx->bin_of_job.p, tb_cursor, cells_total, no_warp);
   aog_scan_kernel<<<1, 512, 0, st>>>(plan);
   aog_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, plan, (const uint32_t *)ctx->bin_of_job.p, (uint32_t *)ctx->sorted.p);
   ctx->launches += 3;
@@ -479,8 +480,8 @@ static int ir_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b20
   if (*(int *)((char *)ctx->h_misc + 8) & 8)
     return fail(ctx, LRA_B200_EINVAL, "indel_dp_batch: a group has fewer than 2 rows, a row narrower than 2 cells or a non-monotone band");
   const AogPlan &hp = *ctx->h_plan;
-  uint32_t cnt[3];
-  for (int c = 0; c < 3; c++) cnt[c] = hp.bin_start[(c + 1) * kAogBuckets] - hp.bin_start[c * kAogBuckets];
+  uint32_t cnt[4];
+  for (int c = 0; c < 4; c++) cnt[c] = hp.bin_start[(c + 1) * kAogBuckets] - hp.bin_start[c * kAogBuckets];
   const unsigned long long tb_words = ctx->h_misc[2];
   if ((rc = ensure(ctx, ctx->ir_tb, (size_t)(tb_words + 64) * 4))) return rc;
   b.tb = (uint32_t *)ctx->ir_tb.p;
@@ -488,6 +489,10 @@ static int ir_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b20
   struct Launched { int cls; int ev0; };
   std::vector<Launched> launched;
   auto blocks_for = [&](uint32_t c) { unsigned x = (c + 63) / 64; unsigned cap = (unsigned)ctx->n_sm * 8u; return x > cap ? cap : x; };
+  if (cnt[kIrClsWarp32]) {
+    unsigned wb = (cnt[kIrClsWarp32] + 3) / 4; const unsigned wcap = (unsigned)ctx->n_sm * 12u; if (wb > wcap) wb = wcap;
+    launched.push_back({kIrClsWarp32, evi}); rec(); ir_dp_warp_kernel<<<wb, 128, 0, st>>>(b, plan, sorted); rec(); ctx->launches++;
+  }
   if (cnt[kIrClsGeneric]) { launched.push_back({kIrClsGeneric, evi}); rec(); ir_dp_generic_kernel<<<blocks_for(cnt[kIrClsGeneric]), 64, 0, st>>>(b, plan, sorted); rec(); ctx->launches++; }
   if (cnt[kIrClsW64]) { launched.push_back({kIrClsW64, evi}); rec(); ir_dp_thread_kernel<64><<<blocks_for(cnt[kIrClsW64]), 64, 0, st>>>(b, plan, sorted, kIrClsW64); rec(); ctx->launches++; }
   if (cnt[kIrClsW24]) { launched.push_back({kIrClsW24, evi}); rec(); ir_dp_thread_kernel<24><<<blocks_for(cnt[kIrClsW24]), 64, 0, st>>>(b, plan, sorted, kIrClsW24); rec(); ctx->launches++; }
@@ -498,7 +503,7 @@ static int ir_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b20
   res->n_blocks_total = ctx->h_misc[0];
   res->cells = ctx->h_misc[3];
   const int err = *(int *)((char *)ctx->h_misc + 8);
-  static const char *names[3] = {"ir_dp_thread<W=24>", "ir_dp_thread<W=64>", "ir_dp_generic"};
+  static const char *names[4] = {"ir_dp_thread<W=24>", "ir_dp_thread<W=64>", "ir_dp_generic", "ir_dp_warp<W=32>"};
   {
     lra_b200_kernel_stat s;
     memset(&s, 0, sizeof s);

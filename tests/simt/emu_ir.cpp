@@ -14,8 +14,8 @@ static uint64_t run_ir_dp(IrBatch &b, int force_generic, std::vector<uint32_t> &
   unsigned long long tb_cursor = 0, cells = 0;
   std::vector<AogPlan> planv(1); AogPlan *plan = planv.data(); memset(plan, 0, sizeof(AogPlan));
   std::vector<uint32_t> bin(n_groups + 1), sorted(n_groups + 1);
-  emu::launch(dim3((unsigned)((n_groups + 3) / 4)), dim3(128), 0, [&] { ir_classify_kernel(b, plan, bin.data(), &tb_cursor, &cells); });
-  if (force_generic) {
+  emu::launch(dim3((unsigned)((n_groups + 3) / 4)), dim3(128), 0, [&] { ir_classify_kernel(b, plan, bin.data(), &tb_cursor, &cells, force_generic == 3 ? 1 : 0); });
+  if (force_generic == 1) {
     memset(plan->hist, 0, sizeof plan->hist);
     tb_cursor = 0;
     for (int g = 0; g < n_groups; g++) if (bin[g] != 0xFFFFFFFFu) {
@@ -34,10 +34,11 @@ static uint64_t run_ir_dp(IrBatch &b, int force_generic, std::vector<uint32_t> &
   if (cnt(kIrClsW24)) emu::launch(dim3(2), dim3(64), 0, [&] { ir_dp_thread_kernel<24>(b, plan, sorted.data(), kIrClsW24); });
   if (cnt(kIrClsW64)) emu::launch(dim3(2), dim3(64), 0, [&] { ir_dp_thread_kernel<64>(b, plan, sorted.data(), kIrClsW64); });
   if (cnt(kIrClsGeneric)) emu::launch(dim3(2), dim3(64), 0, [&] { ir_dp_generic_kernel(b, plan, sorted.data()); });
+  if (cnt(kIrClsWarp32)) emu::launch(dim3(2), dim3(128), 0, [&] { ir_dp_warp_kernel(b, plan, sorted.data()); });
   return cells;
 }
 
-// force_generic: send everything to the generic kernel
+// force_generic: 1 = send everything to the generic kernel, 3 = never use the warp kernel (thread kernels only)
 extern "C" int emu_ir_dp_batch(const uint8_t *q_arena, uint64_t qn, const uint8_t *t_arena, uint64_t tn, const uint32_t *q_base,
                                const uint32_t *t_base, const int32_t *q_start, const int32_t *t_start, const int32_t *t_len,
                                const int32_t *q_seq_len, const int32_t *t_seq_len, const uint32_t *band_off, const int32_t *band,

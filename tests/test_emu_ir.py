@@ -39,6 +39,11 @@ def test_emu_ir_clr_w64():
     assert run("ir_clr", 1) >= 1
 
 
+def test_emu_ir_thread_kernels_only():
+    assert run("ir_ont", 1, force_generic=3) >= 1
+    assert run("ir_ccs", 2, force_generic=3) > 20
+
+
 def test_emu_ir_generic_kernel():
     assert run("ir_ccs", 2, force_generic=1, max_groups=40) > 10
 
