@@ -163,6 +163,47 @@ int lra_b200_indel_refine_batch(lra_b200_ctx *ctx, const lra_b200_seq *q, const 
 int lra_b200_indel_refine_batch_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t,
                                        const lra_b200_ir_segments *segs_dev, lra_b200_ir_seg_result *res_dev);
 
+/* ---- a1-a5  the seeding prefix of MapRead, batched over reads --------------------------------------------------
+ * Replaces, for a batch of reads, MapRead.h:169-203:
+ *   CreateRC (SeqUtils.h:151)  ->  lra_b200_seq_revcomp
+ *   StoreMinimizers<GenomeTuple,Tuple>(read.seq, read.length, opts.globalK, opts.globalW, readmm, true)   MinCount.h:7
+ *   sort(readmm.begin(), readmm.end())                                                                   MapRead.h:185
+ *   CompareLists<GenomeTuple,Tuple>(readmm, genomemm, allMatches, opts, true)                            CompareLists.h:148
+ *   SeparateMatchesByStrand(read, genome, opts.globalK, allMatches, forMatches, revMatches, baseName)    MapRead.h:109
+ * The global index image is the array of GenomeTuple{t,pos} of a `<ref>.mms` file (MMIndex.h:402-424), uploaded once.
+ * Output: for read r the matches match_off[r] .. match_off[r+1] in the reference's allMatches order, each with the read
+ * tuple (q_t, q_pos), the index tuple (t_t, t_pos) and strand = 0 (goes to forMatches) or 1 (revMatches). */
+typedef struct lra_b200_index lra_b200_index;
+int lra_b200_index_upload(lra_b200_ctx *ctx, const uint64_t *t, const uint32_t *pos, uint64_t n, lra_b200_index **out);
+void lra_b200_index_free(lra_b200_ctx *ctx, lra_b200_index *idx);
+
+/* reads: a packed arena holding the forward strands; read r = [read_off[r], read_off[r] + read_len[r]) */
+int lra_b200_seq_revcomp(lra_b200_ctx *ctx, const lra_b200_seq *reads, const uint64_t *read_off, const uint32_t *read_len,
+                         int32_t n_reads, lra_b200_seq **out_rc);
+
+typedef struct lra_b200_seed_reads {
+  const uint64_t *read_off;
+  const uint32_t *read_len;
+  int32_t n_reads;
+  int32_t k, w;          /* opts.globalK (from the index file), opts.globalW (align preset) */
+  int64_t max_freq;      /* opts.globalMaxFreq */
+} lra_b200_seed_reads;
+
+typedef struct lra_b200_seed_result {
+  uint64_t *match_off;   /* [n_reads + 1] */
+  uint64_t *q_t;         /* [match_cap] */
+  uint32_t *q_pos;
+  uint64_t *t_t;
+  uint32_t *t_pos;
+  uint8_t *strand;
+  uint64_t match_cap;
+  uint64_t n_matches;    /* out (== required capacity on LRA_B200_EOVERFLOW) */
+  uint32_t *n_minimizers; /* [n_reads], may be NULL */
+} lra_b200_seed_result;
+
+int lra_b200_seed_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_index *index,
+                        const lra_b200_seed_reads *in, lra_b200_seed_result *res);
+
 /* ---- per-kernel timing of the last batch call (CUDA events on the context's stream) ---------------------------- */
 typedef struct lra_b200_kernel_stat {
   char name[48];

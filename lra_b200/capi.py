@@ -51,6 +51,16 @@ class _IrSegResult(C.Structure):
                 ("n_blocks_total", C.c_uint64), ("cells", C.c_uint64), ("n_dp_groups", C.c_uint64), ("n_aog_jobs", C.c_uint64)]
 
 
+class _SeedReads(C.Structure):
+    _fields_ = [("read_off", C.c_void_p), ("read_len", C.c_void_p), ("n_reads", C.c_int32), ("k", C.c_int32), ("w", C.c_int32),
+                ("max_freq", C.c_int64)]
+
+
+class _SeedResult(C.Structure):
+    _fields_ = [("match_off", C.c_void_p), ("q_t", C.c_void_p), ("q_pos", C.c_void_p), ("t_t", C.c_void_p), ("t_pos", C.c_void_p),
+                ("strand", C.c_void_p), ("match_cap", C.c_uint64), ("n_matches", C.c_uint64), ("n_minimizers", C.c_void_p)]
+
+
 class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("ms", C.c_float), ("jobs", C.c_uint64), ("cells", C.c_uint64),
                 ("algo_bytes", C.c_uint64)]
@@ -91,6 +101,11 @@ def load_library():
     L.lra_b200_indel_dp_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrGroups), C.POINTER(_IrResult)]
     L.lra_b200_indel_refine_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrSegments), C.POINTER(_IrSegResult)]
     L.lra_b200_indel_refine_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrSegments), C.POINTER(_IrSegResult)]
+    L.lra_b200_index_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    L.lra_b200_index_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.lra_b200_index_free.restype = None
+    L.lra_b200_seq_revcomp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+    L.lra_b200_seed_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_SeedReads), C.POINTER(_SeedResult)]
     L.lra_b200_last_kernel_stats.argtypes = [C.c_void_p, C.POINTER(KernelStat), C.c_int]
     L.lra_b200_launch_count.argtypes = [C.c_void_p]
     L.lra_b200_launch_count.restype = C.c_uint64
@@ -209,6 +224,42 @@ class Context:
         self._check(self.lib.lra_b200_aog_batch_device(self.h, q.handle, t.handle, C.byref(jobs), C.byref(res)))
         return int(res.n_blocks_total), int(res.cells)
 
+
+    # ---- a1-a5
+    def index_upload(self, t, pos):
+        t = np.ascontiguousarray(t, np.uint64); pos = np.ascontiguousarray(pos, np.uint32)
+        h = C.c_void_p()
+        self._check(self.lib.lra_b200_index_upload(self.h, _ptr(t), _ptr(pos), len(t), C.byref(h)))
+        return h
+
+    def index_free(self, h):
+        self.lib.lra_b200_index_free(self.h, h)
+
+    def seq_revcomp(self, reads, read_off, read_len):
+        ro = np.ascontiguousarray(read_off, np.uint64); rl = np.ascontiguousarray(read_len, np.uint32)
+        h = C.c_void_p()
+        self._check(self.lib.lra_b200_seq_revcomp(self.h, reads.handle, _ptr(ro), _ptr(rl), len(ro), C.byref(h)))
+        return SeqArena(self, h)
+
+    def seed_batch(self, reads, genome, index, read_off, read_len, k, w, max_freq, match_cap=None):
+        """a2-a5 for a batch of reads.  Returns dict(match_off, q_t, q_pos, t_t, t_pos, strand, n_minimizers, n_matches)."""
+        ro = np.ascontiguousarray(read_off, np.uint64); rl = np.ascontiguousarray(read_len, np.uint32)
+        R = len(ro)
+        cap = match_cap if match_cap is not None else int(rl.sum()) + 1024
+        for _ in range(2):
+            o = dict(match_off=np.zeros(R + 1, np.uint64), q_t=np.zeros(cap, np.uint64), q_pos=np.zeros(cap, np.uint32), t_t=np.zeros(cap, np.uint64),
+                     t_pos=np.zeros(cap, np.uint32), strand=np.zeros(cap, np.uint8), n_minimizers=np.zeros(R, np.uint32))
+            rd = _SeedReads(_ptr(ro), _ptr(rl), R, k, w, max_freq)
+            res = _SeedResult(_ptr(o["match_off"]), _ptr(o["q_t"]), _ptr(o["q_pos"]), _ptr(o["t_t"]), _ptr(o["t_pos"]), _ptr(o["strand"]), cap, 0,
+                              _ptr(o["n_minimizers"]))
+            rc = self.lib.lra_b200_seed_batch(self.h, reads.handle, genome.handle, index, C.byref(rd), C.byref(res))
+            o["n_matches"] = int(res.n_matches)
+            if rc == EOVERFLOW and match_cap is None:
+                cap = int(res.n_matches) + 16
+                continue
+            self._check(rc)
+            return o
+        self._check(rc)
 
     # ---- a19
     def indel_dp_batch(self, q, t, g, block_cap=None, out=None):

@@ -14,6 +14,7 @@
 #include "ir_kernels.cuh"
 #include "ir_segment_kernels.cuh"
 #include "seq_kernels.cuh"
+#include "seed_kernels.cuh"
 
 using namespace lra;
 
@@ -39,6 +40,7 @@ struct lra_b200_ctx {
   DevBuf d_qoff, d_toff, d_qlen, d_tlen, d_k, d_score, d_nb, d_boff, d_blocks;
   DevBuf ir_tb, ir_tboff, ir_maxw, ir_in[9], ir_band;
   DevBuf sg[40];          // segment-level IndelRefine scratch
+  DevBuf sd[12];          // seeding scratch
   bool keep_stats = false;  // sub-launchers append to stats instead of clearing
   AogPlan *h_plan = nullptr;            // pinned
   unsigned long long *h_misc = nullptr;  // pinned (2 x u64)
@@ -120,6 +122,7 @@ extern "C" void lra_b200_destroy(lra_b200_ctx *ctx) {
                     &ctx->ir_in[4], &ctx->ir_in[5], &ctx->ir_in[6], &ctx->ir_in[7], &ctx->ir_in[8]};
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
   for (DevBuf &b : ctx->sg) if (b.p) cudaFree(b.p);
+  for (DevBuf &b : ctx->sd) if (b.p) cudaFree(b.p);
   for (auto &ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < 4; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]); }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
@@ -744,4 +747,125 @@ extern "C" int lra_b200_indel_refine_batch(lra_b200_ctx *ctx, const lra_b200_seq
     CU(cudaMemcpyAsync(res->blocks, dr.blocks, (size_t)dr.n_blocks_total * 12, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return rc;
+}
+
+
+// ---------------------------------------------------------------------------------------------------- a1-a5 seeding
+struct lra_b200_index {
+  unsigned long long *t = nullptr;
+  uint32_t *pos = nullptr;
+  uint64_t n = 0;
+};
+
+extern "C" int lra_b200_index_upload(lra_b200_ctx *ctx, const uint64_t *t, const uint32_t *pos, uint64_t n, lra_b200_index **out) {
+  if (!ctx || !out || (n && (!t || !pos))) return fail(ctx, LRA_B200_EINVAL, "index_upload: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  lra_b200_index *ix = new lra_b200_index();
+  ix->n = n;
+  CU(cudaMalloc((void **)&ix->t, (n + 4) * 8));
+  CU(cudaMalloc((void **)&ix->pos, (n + 4) * 4));
+  CU(cudaMemcpyAsync(ix->t, t, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ix->pos, pos, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *out = ix;
+  return LRA_B200_OK;
+}
+extern "C" void lra_b200_index_free(lra_b200_ctx *ctx, lra_b200_index *ix) {
+  if (!ix) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  if (ix->t) cudaFree(ix->t);
+  if (ix->pos) cudaFree(ix->pos);
+  delete ix;
+}
+
+extern "C" int lra_b200_seq_revcomp(lra_b200_ctx *ctx, const lra_b200_seq *reads, const uint64_t *read_off, const uint32_t *read_len,
+                                    int32_t n_reads, lra_b200_seq **out_rc) {
+  if (!ctx || !reads || !out_rc || n_reads < 0 || (n_reads && (!read_off || !read_len))) return fail(ctx, LRA_B200_EINVAL, "seq_revcomp: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  lra_b200_seq *o = new lra_b200_seq();
+  if ((rc = seq_reserve(ctx, o, reads->n))) { delete o; return rc; }
+  o->n = reads->n;
+  // positions outside every read keep the padding value (N)
+  CU(cudaMemsetAsync(o->b2, 0, (o->cap_groups * 2 + 8) * 4, ctx->stream));
+  CU(cudaMemsetAsync(o->nm, 0xFF, (o->cap_groups + 8) * 4, ctx->stream));
+  if (n_reads) {
+    if ((rc = ensure(ctx, ctx->sd[0], (size_t)n_reads * 8)) || (rc = ensure(ctx, ctx->sd[1], (size_t)n_reads * 4))) { lra_b200_seq_free(ctx, o); return rc; }
+    CU(cudaMemcpyAsync(ctx->sd[0].p, read_off, (size_t)n_reads * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->sd[1].p, read_len, (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
+    seq_revcomp_kernel<<<(unsigned)((n_reads + 7) / 8), 256, 0, ctx->stream>>>(SeqView{reads->b2, reads->nm, reads->n}, (const unsigned long long *)ctx->sd[0].p,
+                                                                                (const uint32_t *)ctx->sd[1].p, n_reads, o->b2, o->nm);
+    ctx->launches++;
+    CU(cudaGetLastError());
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  *out_rc = o;
+  return LRA_B200_OK;
+}
+
+extern "C" int lra_b200_seed_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_index *index,
+                                   const lra_b200_seed_reads *in, lra_b200_seed_result *res) {
+  if (!ctx || !reads || !genome || !index || !in || !res) return fail(ctx, LRA_B200_EINVAL, "seed_batch: NULL argument");
+  const int R = in->n_reads;
+  if (R < 0 || in->k < 1 || in->k > 31 || in->w < 1 || in->w > kSeedMaxW) return fail(ctx, LRA_B200_EINVAL, "seed_batch: need 1 <= k <= 31, 1 <= w <= %d", kSeedMaxW);
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  res->n_matches = 0;
+  if (R == 0) return LRA_B200_OK;
+  int rc;
+  DevBuf *B = ctx->sd;
+  const size_t mmcap = (size_t)reads->n + 64;
+  const size_t mcap = (size_t)(res->match_cap ? res->match_cap : 1);
+  if ((rc = ensure(ctx, B[0], (size_t)R * 8)) || (rc = ensure(ctx, B[1], (size_t)R * 4)) || (rc = ensure(ctx, B[2], mmcap * 8)) ||
+      (rc = ensure(ctx, B[3], mmcap * 4)) || (rc = ensure(ctx, B[4], (size_t)R * 4)) || (rc = ensure(ctx, B[5], ((size_t)R + 1) * 8)) ||
+      (rc = ensure(ctx, B[6], mcap * 8)) || (rc = ensure(ctx, B[7], mcap * 8)) || (rc = ensure(ctx, B[8], mcap * 4)) ||
+      (rc = ensure(ctx, B[9], mcap * 4)) || (rc = ensure(ctx, B[10], mcap)) || (rc = ensure(ctx, B[11], 64)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(B[0].p, in->read_off, (size_t)R * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[1].p, in->read_len, (size_t)R * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(B[11].p, 0, 64, st));
+  SeedBatch b;
+  b.reads = SeqView{reads->b2, reads->nm, reads->n};
+  b.read_off = (const unsigned long long *)B[0].p; b.read_len = (const uint32_t *)B[1].p; b.n_reads = R;
+  b.k = in->k; b.w = in->w; b.max_freq = in->max_freq;
+  b.idx_t = index->t; b.idx_pos = index->pos; b.n_idx = (long long)index->n;
+  b.genome = SeqView{genome->b2, genome->nm, genome->n};
+  b.mm_t = (unsigned long long *)B[2].p; b.mm_pos = (uint32_t *)B[3].p; b.mm_n = (uint32_t *)B[4].p;
+  b.match_cnt = (unsigned long long *)B[5].p;
+  b.m_qt = (unsigned long long *)B[6].p; b.m_tt = (unsigned long long *)B[7].p; b.m_qpos = (uint32_t *)B[8].p; b.m_tpos = (uint32_t *)B[9].p;
+  b.m_strand = (uint8_t *)B[10].p; b.match_cap = res->match_cap; b.err = (int *)B[11].p;
+  const unsigned nb = (unsigned)((R + 127) / 128);
+  int evi = 0;
+  auto rec = [&]() { cudaEventRecord(ctx->ev[evi++], st); };
+  rec(); seed_minimizers_kernel<<<nb, 128, 0, st>>>(b);
+  rec(); seed_sort_kernel<<<nb, 128, 0, st>>>(b);
+  rec(); seed_compare_kernel<false><<<nb, 128, 0, st>>>(b);
+  rec(); seed_scan_kernel<<<1, 1024, 0, st>>>(b.match_cnt, R, b.match_cap, b.err);
+  rec(); seed_compare_kernel<true><<<nb, 128, 0, st>>>(b);
+  rec();
+  ctx->launches += 5;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(res->match_off, b.match_cnt, ((size_t)R + 1) * 8, cudaMemcpyDeviceToHost, st));
+  if (res->n_minimizers) CU(cudaMemcpyAsync(res->n_minimizers, b.mm_n, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const uint64_t total = res->match_off[R];
+  res->n_matches = total;
+  static const char *names[5] = {"seed_minimizers", "seed_sort", "seed_compare<count>", "seed_scan", "seed_compare<emit>"};
+  for (int i = 0; i < 5; i++) {
+    lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "%s", names[i]);
+    cudaEventElapsedTime(&s2.ms, ctx->ev[i], ctx->ev[i + 1]); s2.jobs = (uint64_t)R;
+    ctx->stats.push_back(s2);
+  }
+  if (total > res->match_cap) return fail(ctx, LRA_B200_EOVERFLOW, "seed_batch: match capacity %llu too small, %llu needed",
+                                         (unsigned long long)res->match_cap, (unsigned long long)total);
+  if (total) {
+    CU(cudaMemcpyAsync(res->q_t, b.m_qt, total * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->t_t, b.m_tt, total * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->q_pos, b.m_qpos, total * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->t_pos, b.m_tpos, total * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->strand, b.m_strand, total, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return LRA_B200_OK;
 }

@@ -240,3 +240,93 @@ def indel_refine_batch_port(sb, t_arena, t_base):
         assert st == 0
         outs.append(bo)
     return outs
+
+
+# ---------------------------------------------------------------- a1-a5 seeding prefix of MapRead
+
+def _bind_seed(L, prefix):
+    if getattr(L, "_seed_bound", False):
+        return
+    f = getattr(L, prefix + "store_minimizers"); f.restype = C.c_long
+    f.argtypes = [_u8p, C.c_uint32, C.c_int, C.c_int, _u64p, _u32p, C.c_long]
+    f = getattr(L, prefix + "sort_minimizers"); f.restype = None
+    f.argtypes = [_u64p, _u32p, C.c_long]
+    f = getattr(L, prefix + "compare_lists"); f.restype = C.c_long
+    f.argtypes = [_u64p, _u32p, C.c_long, _u64p, _u32p, C.c_long, C.c_long if prefix.startswith("lra_oracle") else C.c_int, _u64p, _u32p, _u64p, _u32p, C.c_long]
+    f = getattr(L, prefix + "seed_read"); f.restype = C.c_long
+    f.argtypes = [_u8p, C.c_uint32, _u8p, _u64p, _u32p, C.c_long, C.c_int, C.c_int, C.c_long if prefix.startswith("lra_oracle") else C.c_int,
+                  _u64p, _u32p, _u64p, _u32p, _u8p, C.c_long]
+    L._seed_bound = True
+
+
+def _seed_lib(which):
+    if which == "ref":
+        L = ref(); _bind_seed(L, "ref_"); return L, "ref_"
+    L = port(); _bind_seed(L, "lra_oracle_"); return L, "lra_oracle_"
+
+
+def _u8(a):
+    return np.frombuffer(a, dtype=np.uint8).copy() if isinstance(a, (bytes, bytearray)) else np.ascontiguousarray(a, np.uint8)
+
+
+def store_minimizers(seq, k, w, which="port"):
+    L, p = _seed_lib(which)
+    s = _u8(seq); n = len(s)
+    s = np.concatenate([s, np.zeros(8, np.uint8)])
+    t = np.zeros(n + 16, np.uint64); pos = np.zeros(n + 16, np.uint32)
+    m = getattr(L, p + "store_minimizers")(s, n, k, w, t, pos, n + 16)
+    return t[:m].copy(), pos[:m].copy()
+
+
+def sort_minimizers(t, pos, which="port"):
+    L, p = _seed_lib(which)
+    t = np.ascontiguousarray(t, np.uint64).copy(); pos = np.ascontiguousarray(pos, np.uint32).copy()
+    getattr(L, p + "sort_minimizers")(t, pos, len(t))
+    return t, pos
+
+
+def compare_lists(qt, qpos, tt, tpos, max_freq, which="port"):
+    L, p = _seed_lib(which)
+    cap = 4 * (len(qt) + 16) * 8 + 1024
+    for _ in range(3):
+        r = [np.zeros(cap, np.uint64), np.zeros(cap, np.uint32), np.zeros(cap, np.uint64), np.zeros(cap, np.uint32)]
+        n = getattr(L, p + "compare_lists")(np.ascontiguousarray(qt, np.uint64), np.ascontiguousarray(qpos, np.uint32), len(qt),
+                                            np.ascontiguousarray(tt, np.uint64), np.ascontiguousarray(tpos, np.uint32), len(tt), max_freq,
+                                            r[0], r[1], r[2], r[3], cap)
+        if n <= cap:
+            return [x[:n].copy() for x in r]
+        cap = n + 16
+    raise RuntimeError("compare_lists capacity")
+
+
+def seed_read(read, genome_concat, tt, tpos, k, w, max_freq, which="port"):
+    """a2..a5 for one read.  Returns (q_t, q_pos, t_t, t_pos, strand) in the reference's allMatches order."""
+    L, p = _seed_lib(which)
+    rd = _u8(read); n = len(rd)
+    rd = np.concatenate([rd, np.zeros(8, np.uint8)])
+    cap = 8 * n + 1024
+    for _ in range(3):
+        r = [np.zeros(cap, np.uint64), np.zeros(cap, np.uint32), np.zeros(cap, np.uint64), np.zeros(cap, np.uint32), np.zeros(cap, np.uint8)]
+        m = getattr(L, p + "seed_read")(rd, n, _u8(genome_concat) if not isinstance(genome_concat, np.ndarray) else genome_concat,
+                                        np.ascontiguousarray(tt, np.uint64), np.ascontiguousarray(tpos, np.uint32), len(tt), k, w, max_freq,
+                                        r[0], r[1], r[2], r[3], r[4], cap)
+        if m <= cap:
+            return [x[:m].copy() for x in r]
+        cap = m + 16
+    raise RuntimeError("seed_read capacity")
+
+
+def read_mms(path):
+    """Parse a reference global index file (<ref>.mms, MMIndex.h:416-424).
+    Returns dict(k, names, pos (cumulative contig offsets), t (uint64), tpos (uint32))."""
+    data = open(path, "rb").read()
+    n = int(np.frombuffer(data, np.int64, 1, 0)[0]); k = int(np.frombuffer(data, np.int32, 1, 8)[0])
+    p = 12
+    nc = int(np.frombuffer(data, np.int32, 1, p)[0]); p += 4
+    names = []
+    for _ in range(nc):
+        ln = int(np.frombuffer(data, np.int32, 1, p)[0]); p += 4
+        names.append(data[p:p + ln].decode()); p += ln
+    pos = np.frombuffer(data, np.uint64, nc + 1, p).copy(); p += 8 * (nc + 1)
+    rec = np.frombuffer(data, np.dtype([("t", "<u8"), ("pos", "<u4"), ("pad", "<u4")]), n, p)
+    return dict(k=k, names=names, pos=pos, t=rec["t"].copy(), tpos=rec["pos"].copy())

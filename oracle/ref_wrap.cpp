@@ -8,6 +8,8 @@
 // Reference entry points wrapped here:
 //   AffineOneGapAlign            AffineOneGapAlign.h:157-649
 //   IndelRefineAlignment         IndelRefine.h:53-784
+//   StoreMinimizers / std::sort / CompareLists / SeparateMatchesByStrand semantics   MinCount.h:7-179, MapRead.h:185,
+//                                CompareLists.h:8-151, MapRead.h:109-150   (the seeding prefix of MapRead, MapRead.h:169-203)
 #include <string>
 #include <vector>
 #include <thread>
@@ -21,6 +23,8 @@
 #include "AffineOneGapAlign.h"
 #include "Input.h"         // declares KSEQ_INIT(gzFile, gzread) for Genome.h
 #include "IndelRefine.h"
+#include "MinCount.h"
+#include "CompareLists.h"
 
 extern "C" {
 
@@ -124,6 +128,66 @@ int ref_indel_refine_batch(const char *q_arena, const char *t_arena, const uint3
   for (int i = 0; i < nthreads; i++) th.emplace_back(work);
   for (auto &x : th) x.join();
   return 0;
+}
+
+static void ref_init_static() {   // lra.cpp:1008-1012 (InitStatic)
+  Tuple mask = 1;
+  GenomeTuple::for_mask_s = ~(mask << (sizeof(mask) * 8 - 1));
+  GenomeTuple::rev_mask_s = (mask << (sizeof(mask) * 8 - 1));
+}
+
+// canonical (w,k) minimizers of one sequence, in the reference's emission order (MinCount.h:7-179)
+long ref_store_minimizers(const char *seq, uint32_t len, int k, int w, uint64_t *t_out, uint32_t *pos_out, long cap) {
+  ref_init_static();
+  std::vector<GenomeTuple> mm;
+  StoreMinimizers<GenomeTuple, Tuple>((char *)seq, len, k, w, mm, true);
+  for (size_t i = 0; i < mm.size() && (long)i < cap; i++) { t_out[i] = mm[i].t; pos_out[i] = mm[i].pos; }
+  return (long)mm.size();
+}
+
+// std::sort with GenomeTuple::operator< (masked key), exactly as MapRead.h:185
+void ref_sort_minimizers(uint64_t *t, uint32_t *pos, long n) {
+  ref_init_static();
+  std::vector<GenomeTuple> mm(n);
+  for (long i = 0; i < n; i++) { mm[i].t = t[i]; mm[i].pos = pos[i]; }
+  std::sort(mm.begin(), mm.end());
+  for (long i = 0; i < n; i++) { t[i] = mm[i].t; pos[i] = mm[i].pos; }
+}
+
+// CompareLists<GenomeTuple,Tuple>(query, target, result, opts, Global=true)  (CompareLists.h:148-151): pairs as 4 arrays
+long ref_compare_lists(const uint64_t *qt, const uint32_t *qpos, long nq, const uint64_t *tt, const uint32_t *tpos, long nt, int maxFreq,
+                       uint64_t *r_qt, uint32_t *r_qpos, uint64_t *r_tt, uint32_t *r_tpos, long cap) {
+  ref_init_static();
+  std::vector<GenomeTuple> q(nq), t(nt);
+  for (long i = 0; i < nq; i++) { q[i].t = qt[i]; q[i].pos = qpos[i]; }
+  for (long i = 0; i < nt; i++) { t[i].t = tt[i]; t[i].pos = tpos[i]; }
+  Options opts; opts.globalMaxFreq = maxFreq;
+  std::vector<std::pair<GenomeTuple, GenomeTuple> > res;
+  CompareLists<GenomeTuple, Tuple>(q, t, res, opts, true);
+  for (size_t i = 0; i < res.size() && (long)i < cap; i++) {
+    r_qt[i] = res[i].first.t; r_qpos[i] = res[i].first.pos; r_tt[i] = res[i].second.t; r_tpos[i] = res[i].second.pos;
+  }
+  return (long)res.size();
+}
+
+// The seeding prefix of MapRead for one read (MapRead.h:169-203): minimizers, sort, CompareLists against the global index,
+// strand split by strncmp against the genome (contigs concatenated; the reference resolves the contig through
+// Genome::GlobalIndexToSeq, which addresses the same bytes).  strand_out[i] = 0 forward, 1 reverse, in allMatches order.
+long ref_seed_read(const char *read, uint32_t len, const char *genome_concat, const uint64_t *tt, const uint32_t *tpos, long nt,
+                   int k, int w, int maxFreq, uint64_t *r_qt, uint32_t *r_qpos, uint64_t *r_tt, uint32_t *r_tpos, uint8_t *strand_out, long cap) {
+  ref_init_static();
+  std::vector<GenomeTuple> mm, t(nt);
+  StoreMinimizers<GenomeTuple, Tuple>((char *)read, len, k, w, mm, true);
+  std::sort(mm.begin(), mm.end());
+  for (long i = 0; i < nt; i++) { t[i].t = tt[i]; t[i].pos = tpos[i]; }
+  Options opts; opts.globalMaxFreq = maxFreq;
+  std::vector<std::pair<GenomeTuple, GenomeTuple> > res;
+  CompareLists<GenomeTuple, Tuple>(mm, t, res, opts, true);
+  for (size_t i = 0; i < res.size() && (long)i < cap; i++) {
+    r_qt[i] = res[i].first.t; r_qpos[i] = res[i].first.pos; r_tt[i] = res[i].second.t; r_tpos[i] = res[i].second.pos;
+    strand_out[i] = strncmp(read + res[i].first.pos, genome_concat + res[i].second.pos, k) == 0 ? 0 : 1;   // MapRead.h:125
+  }
+  return (long)res.size();
 }
 
 }  // extern "C"

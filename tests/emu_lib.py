@@ -39,8 +39,35 @@ def lib():
     L.emu_ir_segments.restype = C.c_int
     L.emu_ir_segments.argtypes = [_u8p, C.c_uint64, _u8p, C.c_uint64, _u32p, _u64p, _i32p, _u32p, _u32p, _i32p, _i32p, C.c_uint64, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _u64p, _u32p, C.c_uint64, _u64p]
+    L.emu_seed_batch.restype = C.c_long
+    L.emu_seed_batch.argtypes = [_u8p, C.c_uint64, _u64p, _u32p, C.c_int, _u8p, C.c_uint64, _u64p, _u32p, C.c_long, C.c_int, C.c_int, C.c_long,
+                                 _u64p, _u64p, _u32p, _u64p, _u32p, _u8p, C.c_uint64, _u32p, _u64p, _u32p]
+    L.emu_seq_revcomp.restype = C.c_int
+    L.emu_seq_revcomp.argtypes = [_u8p, C.c_uint64, _u64p, _u32p, C.c_int, _u32p, _u32p]
     _lib = L
     return L
+
+
+def seed_batch(reads_arena, read_off, read_len, genome, idx_t, idx_pos, k, w, max_freq, cap=None):
+    """Returns dict(match_off, q_t, q_pos, t_t, t_pos, strand, n_mm, mm_t, mm_pos)."""
+    R = len(read_off)
+    rn = len(reads_arena) - 16
+    cap = cap or (8 * rn + 1024)
+    o = dict(match_off=np.zeros(R + 1, np.uint64), q_t=np.zeros(cap, np.uint64), q_pos=np.zeros(cap, np.uint32), t_t=np.zeros(cap, np.uint64),
+             t_pos=np.zeros(cap, np.uint32), strand=np.zeros(cap, np.uint8), n_mm=np.zeros(R, np.uint32), mm_t=np.zeros(rn + 8, np.uint64),
+             mm_pos=np.zeros(rn + 8, np.uint32))
+    n = lib().emu_seed_batch(reads_arena, rn, np.ascontiguousarray(read_off, np.uint64), np.ascontiguousarray(read_len, np.uint32), R, genome,
+                             len(genome) - 16, np.ascontiguousarray(idx_t, np.uint64), np.ascontiguousarray(idx_pos, np.uint32), len(idx_t), k, w,
+                             max_freq, o["match_off"], o["q_t"], o["q_pos"], o["t_t"], o["t_pos"], o["strand"], cap, o["n_mm"], o["mm_t"], o["mm_pos"])
+    o["n"] = n
+    return o
+
+
+def seq_revcomp(arena, read_off, read_len):
+    n = len(arena) - 16
+    b2 = np.zeros((n + 15) // 16, np.uint32); nm = np.zeros((n + 31) // 32, np.uint32)
+    lib().emu_seq_revcomp(arena, n, np.ascontiguousarray(read_off, np.uint64), np.ascontiguousarray(read_len, np.uint32), len(read_off), b2, nm)
+    return b2, nm
 
 
 def ir_segments(sb, out_cap=None):
