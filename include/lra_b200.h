@@ -204,6 +204,28 @@ typedef struct lra_b200_seed_result {
 int lra_b200_seed_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_index *index,
                         const lra_b200_seed_reads *in, lra_b200_seed_result *res);
 
+/* ---- a21  Alignment::CalculateStatistics, batched over segments ------------------------------------------------
+ * Replaces  void Alignment::CalculateStatistics(const Options&, ostream*, const std::vector<float> &LookUpTable)
+ * (Alignment.h:513-531, with CreateAlignmentStrings :247-333 and AlignStringsToCigar :414-504; opts.showmm == true, the
+ * default) for a batch of segments given as in lra_b200_ir_segments (blocks, blk_off, blk_cnt, q_base, t_base,
+ * read_len).  log_lut = the caller's LookUpTable (2001 floats built by CreateLookUpTable with the host logf,
+ * LogLookUpTable.h:9-15).  Outputs per segment: CIGAR ops (BAM encoding len<<4|op with '='=7 'X'=8 'I'=1 'D'=2),
+ * `value` (the NV tag, bit-identical float) and stats[16] = nm, nmm, n_D, n_I, tdel, tins, nSmallDel, nMedDel, nLargeDel,
+ * nSmallIns, nMedIns, nLargeIns, refLen, preClip, sufClip, n_cigar -- the quantities of ONE call; the reference stores
+ * n_D into Alignment::nins and n_I into Alignment::ndel (Alignment.h:414 vs :516) and keeps adding tdel..nLargeIns across
+ * calls; that bookkeeping stays with the caller. */
+typedef struct lra_b200_stats_result {
+  int32_t *stats;        /* [n_segments * 16] */
+  float *value;          /* [n_segments] */
+  uint64_t *cigar_off;   /* [n_segments + 1] */
+  uint32_t *cigar;       /* [cigar_cap] */
+  uint64_t cigar_cap;
+  uint64_t n_cigar_total; /* out */
+} lra_b200_stats_result;
+
+int lra_b200_calc_stats_batch(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_ir_segments *segs,
+                              const float *log_lut, lra_b200_stats_result *res);
+
 /* ---- per-kernel timing of the last batch call (CUDA events on the context's stream) ---------------------------- */
 typedef struct lra_b200_kernel_stat {
   char name[48];

@@ -61,6 +61,11 @@ class _SeedResult(C.Structure):
                 ("strand", C.c_void_p), ("match_cap", C.c_uint64), ("n_matches", C.c_uint64), ("n_minimizers", C.c_void_p)]
 
 
+class _StatsResult(C.Structure):
+    _fields_ = [("stats", C.c_void_p), ("value", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p), ("cigar_cap", C.c_uint64),
+                ("n_cigar_total", C.c_uint64)]
+
+
 class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("ms", C.c_float), ("jobs", C.c_uint64), ("cells", C.c_uint64),
                 ("algo_bytes", C.c_uint64)]
@@ -106,6 +111,7 @@ def load_library():
     L.lra_b200_index_free.restype = None
     L.lra_b200_seq_revcomp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
     L.lra_b200_seed_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_SeedReads), C.POINTER(_SeedResult)]
+    L.lra_b200_calc_stats_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrSegments), C.c_void_p, C.POINTER(_StatsResult)]
     L.lra_b200_last_kernel_stats.argtypes = [C.c_void_p, C.POINTER(KernelStat), C.c_int]
     L.lra_b200_launch_count.argtypes = [C.c_void_p]
     L.lra_b200_launch_count.restype = C.c_uint64
@@ -260,6 +266,28 @@ class Context:
             self._check(rc)
             return o
         self._check(rc)
+
+    # ---- a21
+    def calc_stats_batch(self, q, t, sb, log_lut, cigar_cap=None):
+        """Alignment::CalculateStatistics over segments (sb as for indel_refine_batch: blocks_in, blk_off, blk_cnt, q_base, t_base,
+        read_len).  Returns dict(stats[S,16], value[S], cigar_off[S+1], cigar)."""
+        S = len(sb["blk_cnt"])
+        bi = np.ascontiguousarray(sb["blocks_in"], np.uint32)
+        a = dict(blk_off=np.ascontiguousarray(sb["blk_off"], np.uint64), blk_cnt=np.ascontiguousarray(sb["blk_cnt"], np.int32),
+                 q_base=np.ascontiguousarray(sb["q_base"], np.uint32), t_base=np.ascontiguousarray(sb["t_base"], np.uint32),
+                 read_len=np.ascontiguousarray(sb["read_len"], np.int32))
+        cl = np.zeros(S, np.int32)
+        lut = np.ascontiguousarray(log_lut, np.float32)
+        assert len(lut) == 2001
+        cap = cigar_cap if cigar_cap is not None else 4 * (bi.size // 3) + 16 * S + 16
+        o = dict(stats=np.zeros((S, 16), np.int32), value=np.zeros(S, np.float32), cigar_off=np.zeros(S + 1, np.uint64), cigar=np.zeros(cap, np.uint32))
+        sg = _IrSegments(_ptr(bi), _ptr(a["blk_off"]), _ptr(a["blk_cnt"]), _ptr(a["q_base"]), _ptr(a["t_base"]), _ptr(a["read_len"]), _ptr(cl),
+                         bi.size // 3, S, 0, 0, 0, 0, 0)
+        res = _StatsResult(_ptr(o["stats"]), _ptr(o["value"]), _ptr(o["cigar_off"]), _ptr(o["cigar"]), cap, 0)
+        rc = self.lib.lra_b200_calc_stats_batch(self.h, q.handle, t.handle, C.byref(sg), _ptr(lut), C.byref(res))
+        o["n_cigar_total"] = int(res.n_cigar_total)
+        self._check(rc)
+        return o
 
     # ---- a19
     def indel_dp_batch(self, q, t, g, block_cap=None, out=None):

@@ -15,6 +15,7 @@
 #include "ir_segment_kernels.cuh"
 #include "seq_kernels.cuh"
 #include "seed_kernels.cuh"
+#include "stats_kernels.cuh"
 
 using namespace lra;
 
@@ -41,6 +42,7 @@ struct lra_b200_ctx {
   DevBuf ir_tb, ir_tboff, ir_maxw, ir_in[9], ir_band;
   DevBuf sg[40];          // segment-level IndelRefine scratch
   DevBuf sd[12];          // seeding scratch
+  DevBuf stt[12];         // statistics scratch
   bool keep_stats = false;  // sub-launchers append to stats instead of clearing
   AogPlan *h_plan = nullptr;            // pinned
   unsigned long long *h_misc = nullptr;  // pinned (2 x u64)
@@ -123,6 +125,7 @@ extern "C" void lra_b200_destroy(lra_b200_ctx *ctx) {
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
   for (DevBuf &b : ctx->sg) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->sd) if (b.p) cudaFree(b.p);
+  for (DevBuf &b : ctx->stt) if (b.p) cudaFree(b.p);
   for (auto &ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < 4; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]); }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
@@ -865,6 +868,67 @@ extern "C" int lra_b200_seed_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads,
     CU(cudaMemcpyAsync(res->q_pos, b.m_qpos, total * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(res->t_pos, b.m_tpos, total * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(res->strand, b.m_strand, total, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return LRA_B200_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------- a21 statistics
+extern "C" int lra_b200_calc_stats_batch(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_ir_segments *sg,
+                                         const float *log_lut, lra_b200_stats_result *res) {
+  if (!ctx || !q || !t || !sg || !log_lut || !res) return fail(ctx, LRA_B200_EINVAL, "calc_stats_batch: NULL argument");
+  const int S = sg->n_segments;
+  if (S < 0) return fail(ctx, LRA_B200_EINVAL, "calc_stats_batch: negative segment count");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  res->n_cigar_total = 0;
+  if (S == 0) return LRA_B200_OK;
+  int rc;
+  DevBuf *B = ctx->stt;
+  const size_t T = (size_t)sg->n_blocks_in;
+  const size_t ccap = (size_t)(res->cigar_cap ? res->cigar_cap : 1);
+  if ((rc = ensure(ctx, B[0], T * 12 + 16)) || (rc = ensure(ctx, B[1], (size_t)S * 8)) || (rc = ensure(ctx, B[2], (size_t)S * 4)) ||
+      (rc = ensure(ctx, B[3], (size_t)S * 4)) || (rc = ensure(ctx, B[4], (size_t)S * 4)) || (rc = ensure(ctx, B[5], (size_t)S * 4)) ||
+      (rc = ensure(ctx, B[6], 2001 * 4)) || (rc = ensure(ctx, B[7], (size_t)S * 64)) || (rc = ensure(ctx, B[8], (size_t)S * 4)) ||
+      (rc = ensure(ctx, B[9], ((size_t)S + 1) * 8)) || (rc = ensure(ctx, B[10], ccap * 4)) || (rc = ensure(ctx, B[11], 64)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(B[0].p, sg->blocks_in, T * 12, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[1].p, sg->blk_off, (size_t)S * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[2].p, sg->blk_cnt, (size_t)S * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[3].p, sg->q_base, (size_t)S * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[4].p, sg->t_base, (size_t)S * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[5].p, sg->read_len, (size_t)S * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[6].p, log_lut, 2001 * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(B[11].p, 0, 64, st));
+  StatsBatch b;
+  b.q = SeqView{q->b2, q->nm, q->n}; b.t = SeqView{t->b2, t->nm, t->n};
+  b.blocks = (const uint32_t *)B[0].p; b.blk_off = (const unsigned long long *)B[1].p; b.blk_cnt = (const int32_t *)B[2].p;
+  b.q_base = (const uint32_t *)B[3].p; b.t_base = (const uint32_t *)B[4].p; b.read_len = (const int32_t *)B[5].p; b.n_seg = S;
+  b.lut = (const float *)B[6].p; b.stats = (int32_t *)B[7].p; b.value = (float *)B[8].p; b.cig_off = (unsigned long long *)B[9].p;
+  b.cigar = (uint32_t *)B[10].p; b.cigar_cap = res->cigar_cap;
+  const unsigned nb = (unsigned)((S + 127) / 128);
+  cudaEventRecord(ctx->ev[0], st);
+  stats_kernel<false><<<nb, 128, 0, st>>>(b);
+  seed_scan_kernel<<<1, 1024, 0, st>>>(b.cig_off, S, b.cigar_cap, (int *)B[11].p);
+  stats_kernel<true><<<nb, 128, 0, st>>>(b);
+  cudaEventRecord(ctx->ev[1], st);
+  ctx->launches += 3;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(res->cigar_off, b.cig_off, ((size_t)S + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->stats, b.stats, (size_t)S * 64, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->value, b.value, (size_t)S * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  res->n_cigar_total = res->cigar_off[S];
+  {
+    lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "stats(count+scan+emit)");
+    cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]); s2.jobs = (uint64_t)S; ctx->stats.push_back(s2);
+  }
+  if (res->n_cigar_total > res->cigar_cap) return fail(ctx, LRA_B200_EOVERFLOW, "calc_stats_batch: cigar capacity %llu too small, %llu needed",
+                                                      (unsigned long long)res->cigar_cap, (unsigned long long)res->n_cigar_total);
+  if (res->n_cigar_total) {
+    CU(cudaMemcpyAsync(res->cigar, b.cigar, (size_t)res->n_cigar_total * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
   }
   return LRA_B200_OK;

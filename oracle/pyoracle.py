@@ -330,3 +330,49 @@ def read_mms(path):
     pos = np.frombuffer(data, np.uint64, nc + 1, p).copy(); p += 8 * (nc + 1)
     rec = np.frombuffer(data, np.dtype([("t", "<u8"), ("pos", "<u4"), ("pad", "<u4")]), n, p)
     return dict(k=k, names=names, pos=pos, t=rec["t"].copy(), tpos=rec["pos"].copy())
+
+
+# ---------------------------------------------------------------- a21 CalculateStatistics
+
+def log_lut():
+    """The reference's LookUpTable: logf(i) for i = 1, 6, ..., 10001 (LogLookUpTable.h:9-15), built with the HOST libm."""
+    L = port()
+    if getattr(L, "_lut", None) is None:
+        libm = C.CDLL("libm.so.6"); libm.logf.restype = C.c_float; libm.logf.argtypes = [C.c_float]
+        L._lut = np.array([libm.logf(float(i)) for i in range(1, 10002, 5)], np.float32)
+    return L._lut
+
+
+_CIG = {0: "M", 1: "I", 2: "D", 7: "=", 8: "X"}
+
+
+def cigar_string(ops):
+    return "".join("%d%s" % (int(o) >> 4, _CIG[int(o) & 15]) for o in ops)
+
+
+def calc_stats_port(read, text, t_win_off, blocks):
+    L = port()
+    if not getattr(L, "_st_bound", False):
+        L.lra_oracle_calc_stats.restype = C.c_long
+        L.lra_oracle_calc_stats.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_long, _u32p, C.c_int, np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"),
+                                            _u32p, C.c_long, _i32p, C.POINTER(C.c_float)]
+        L._st_bound = True
+    b = np.ascontiguousarray(blocks, np.uint32).reshape(-1)
+    cap = 2 * (len(read) + len(text)) + 16
+    cig = np.zeros(cap, np.uint32); st = np.zeros(16, np.int32); v = C.c_float(0)
+    n = L.lra_oracle_calc_stats(bytes(read), len(read), bytes(text), t_win_off, b, len(b) // 3, log_lut(), cig, cap, st, C.byref(v))
+    return st, np.float32(v.value), cig[:n].copy()
+
+
+def calc_stats_ref(read, text, blocks):
+    """Through the unmodified reference; blocks' tPos index `text` directly.  Returns (stats, value, cigar string)."""
+    L = ref()
+    if not getattr(L, "_st_bound", False):
+        L.ref_calc_stats.restype = C.c_int
+        L.ref_calc_stats.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, _u32p, C.c_int, _i32p, C.POINTER(C.c_float), C.c_char_p, C.c_int]
+        L._st_bound = True
+    b = np.ascontiguousarray(blocks, np.uint32).reshape(-1)
+    st = np.zeros(16, np.int32); v = C.c_float(0)
+    buf = C.create_string_buffer(12 * (len(read) + len(text)) + 64)
+    L.ref_calc_stats(bytes(read), len(read), bytes(text), len(text), b, len(b) // 3, st, C.byref(v), buf, len(buf))
+    return st, np.float32(v.value), buf.value.decode()

@@ -130,6 +130,26 @@ int ref_indel_refine_batch(const char *q_arena, const char *t_arena, const uint3
   return 0;
 }
 
+// Alignment::CalculateStatistics for one segment (Alignment.h:513-531).  stats as in oracle/stats.c, but taken from the
+// MEMBERS after one call on a fresh Alignment: stats[2] (n_D) = member nins, stats[3] (n_I) = member ndel (the swap).
+int ref_calc_stats(const char *read, int readLen, const char *text, int textLen, const uint32_t *blocks, int nb, int32_t *stats, float *value_out,
+                   char *cigar_out, int cigar_cap) {
+  Alignment a;
+  a.read = (char *)read; a.genome = (char *)text; a.readLen = readLen; a.genomeLen = textLen;
+  a.blocks.resize(nb);
+  for (int i = 0; i < nb; i++) a.blocks[i] = Block(blocks[3 * i], blocks[3 * i + 1], blocks[3 * i + 2]);
+  Options opts;
+  std::vector<float> lut;
+  for (int i = 1; i <= 10001; i = i + 5) lut.push_back(logf(i));     // LogLookUpTable.h:9-15
+  a.CalculateStatistics(opts, NULL, lut);
+  stats[0] = a.nm; stats[1] = a.nmm; stats[2] = a.nins; stats[3] = a.ndel; stats[4] = a.tdel; stats[5] = a.tins;
+  stats[6] = a.nSmallDel; stats[7] = a.nMedDel; stats[8] = a.nLargeDel; stats[9] = a.nSmallIns; stats[10] = a.nMedIns; stats[11] = a.nLargeIns;
+  stats[12] = a.refLen; stats[13] = a.preClip; stats[14] = a.sufClip; stats[15] = 0;
+  *value_out = a.value;
+  snprintf(cigar_out, cigar_cap, "%s", a.cigar.c_str());
+  return 0;
+}
+
 static void ref_init_static() {   // lra.cpp:1008-1012 (InitStatic)
   Tuple mask = 1;
   GenomeTuple::for_mask_s = ~(mask << (sizeof(mask) * 8 - 1));

@@ -44,8 +44,23 @@ def lib():
                                  _u64p, _u64p, _u32p, _u64p, _u32p, _u8p, C.c_uint64, _u32p, _u64p, _u32p]
     L.emu_seq_revcomp.restype = C.c_int
     L.emu_seq_revcomp.argtypes = [_u8p, C.c_uint64, _u64p, _u32p, C.c_int, _u32p, _u32p]
+    L.emu_calc_stats.restype = C.c_long
+    L.emu_calc_stats.argtypes = [_u8p, C.c_uint64, _u8p, C.c_uint64, _u32p, _u64p, _i32p, _u32p, _u32p, _i32p, C.c_int,
+                                 np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"), _i32p, np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"),
+                                 _u64p, _u32p, C.c_uint64]
     _lib = L
     return L
+
+
+def calc_stats(sb, t_arena, t_base, lut):
+    S = len(sb["blk_cnt"])
+    bi = np.ascontiguousarray(sb["blocks_in"], np.uint32)
+    cap = 4 * (bi.size // 3) + 16 * S + 16
+    o = dict(stats=np.zeros((S, 16), np.int32), value=np.zeros(S, np.float32), cigar_off=np.zeros(S + 1, np.uint64), cigar=np.zeros(cap, np.uint32))
+    lib().emu_calc_stats(sb["q_arena"], len(sb["q_arena"]) - 16, t_arena, len(t_arena) - 16, bi.reshape(-1), np.ascontiguousarray(sb["blk_off"], np.uint64),
+                         sb["blk_cnt"], sb["q_base"], np.ascontiguousarray(t_base, np.uint32), sb["read_len"], S, np.ascontiguousarray(lut, np.float32),
+                         o["stats"].reshape(-1), o["value"], o["cigar_off"], o["cigar"], cap)
+    return o
 
 
 def seed_batch(reads_arena, read_off, read_len, genome, idx_t, idx_pos, k, w, max_freq, cap=None):

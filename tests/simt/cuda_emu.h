@@ -253,5 +253,8 @@ inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s) {
   uint64_t v = ((uint64_t)hi << 32) | lo;
   return (unsigned)((v << (s & 31)) >> 32);
 }
+inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 template <class T> inline T __ldg(const T *p) { return *p; }
 template <class T> inline T __ldcg(const T *p) { return *p; }
