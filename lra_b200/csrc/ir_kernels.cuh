@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128) ir_classify_kernel(IrBatch b, AogPlan *pl
       return;
     }
     const int cls = (mw <= 32 && rows >= kIrWarpMinRows && !no_warp) ? kIrClsWarp32 : mw <= 24 ? kIrClsW24 : (mw <= 64 ? kIrClsW64 : kIrClsGeneric);
-    const unsigned long long words = cls == kIrClsWarp32 ? (unsigned long long)rows * 5ull + 8ull : cls == kIrClsGeneric ? ((unsigned long long)rows * (unsigned long long)mw + 3ull) / 4ull + 2ull * (unsigned long long)mw + 4ull
+    const unsigned long long words = cls == kIrClsWarp32 ? (unsigned long long)rows * 5ull + 8ull + 3ull * ((unsigned long long)rows + (unsigned long long)b.q_seq_len[g] + 4ull) : cls == kIrClsGeneric ? ((unsigned long long)rows * (unsigned long long)mw + 3ull) / 4ull + 2ull * (unsigned long long)mw + 4ull
                                                            : (unsigned long long)rows * (unsigned long long)ir_words(cls == kIrClsW24 ? 24 : 64);
     b.tb_off[g] = atomicAdd(tb_cursor, words);
     b.max_width[g] = mw;
@@ -320,7 +320,8 @@ __global__ void __launch_bounds__(64) ir_dp_thread_kernel(IrBatch b, AogPlan *pl
 // 32 rows of planes held in registers at a time.
 constexpr int kIrNeg = -1073741824;
 
-template <bool WRITE>
+// MODE 0: count only; MODE 1: write forward (needs nb); MODE 2: write in walk order (last block first) at out[0..)
+template <int MODE>
 __device__ __forceinline__ int ir_walk_planes(const uint32_t *tb, const int32_t *qS, const int32_t *qE, int rows, int tStart, uint32_t *out,
                                               int nb, int lane) {
   int t = rows - 1;
@@ -330,7 +331,7 @@ __device__ __forceinline__ int ir_walk_planes(const uint32_t *tb, const int32_t 
   long guard = 0;
   const long guardMax = 4L * rows + 4L * (qE[rows - 1] - qS[0]) + 64;
   auto emit = [&](uint32_t qq, uint32_t tt, uint32_t ln) {
-    if (WRITE && lane == 0) { const int r = nb - 1 - count; out[3 * r] = qq; out[3 * r + 1] = tt; out[3 * r + 2] = ln; }
+    if (MODE != 0 && lane == 0) { const int r = (MODE == 1) ? nb - 1 - count : count; out[3 * r] = qq; out[3 * r + 1] = tt; out[3 * r + 2] = ln; }
     count++;
   };
   int top = -1;                 // rows [top-31, top] are held: lane l has row top-l
@@ -419,71 +420,87 @@ __global__ void __launch_bounds__(128) ir_dp_warp_kernel(IrBatch b, AogPlan *pla
     rowM[lane] = lane * gap;
     rowD[lane] = kIrBad;
     __syncwarp();
-    int qsN = rows > 1 ? qS[1] : 0, qeN = rows > 1 ? qE[1] : 0;
-    for (int t = 1; t < rows; t++) {
-      const int qs = qsN, qe = qeN;
-      if (t + 1 < rows) { qsN = qS[t + 1]; qeN = qE[t + 1]; }
-      const int len = qe - qs + 1;
-      const int off = qs - qsPrev;
-      const int rowEnd = (t == rows - 1) ? len : len - 1;
-      const int x = lane;
-      const int xp = x + off;
-      const bool upIn = xp <= lenPrev - 1;
-      const bool upOk = xp < lenPrev - 1;
-      const bool diagOk = upIn && !(xp - 1 == 0 && t != 1);
-      const int Mup = upIn ? rowM[xp] : kIrBad;
-      const int Dup = upIn ? rowD[xp] : kIrBad;
-      const int Mdg = (upIn && xp >= 1) ? rowM[xp - 1] : kIrBad;
-      const bool valid = x >= 1 && x < rowEnd;
-      const int tc = seq_code(b.t, (uint64_t)(uint32_t)(tbase + (uint32_t)(tStart + t)));
-      const int qc = valid ? seq_code(b.q, qbase + (uint64_t)(qs + x)) : 5;
-      __syncwarp();
-      const int delOpen = upOk ? Mup + gapOpen : kIrBad;
-      const int delExt = upOk ? Dup : kIrBad;
-      const int D = imax(delOpen, delExt);
-      const int dbit = (D == delOpen) ? 0 : 1;
-      const int mS = diagOk ? Mdg + (qc == tc ? match : mismatch) : kIrBad;
-      const int dS = upOk ? Mup + gap : kIrBad;
-      const int a = valid ? imax(imax(mS, dS), D) : (x == 0 ? kIrBad : kIrNeg);
-      // two prefix scans: linear-gap chain and running maximum
-      int u = a - x * gap;         // L[x] = x*gap + max_{y<=x}(a[y] - y*gap)
-      int pm = a;
+    // query code held by this lane: position qsPrev + lane (refreshed by a shuffle when the band moves)
+    auto qcode_at = [&](int pos) -> int { const uint64_t p = qbase + (uint64_t)pos; return p < b.q.n ? seq_code(b.q, p) : 5; };
+    int qc = qcode_at(qsPrev + lane);
+    for (int t0 = 1; t0 < rows; t0 += 32) {
+      // band limits and target codes of the next 32 rows, one row per lane
+      const int rr = t0 + lane;
+      const int pqs = rr < rows ? qS[rr] : 0, pqe = rr < rows ? qE[rr] : 0;
+      const int ptc = rr < rows ? seq_code(b.t, (uint64_t)(uint32_t)(tbase + (uint32_t)(tStart + rr))) : 5;
+      const int nrow = imin(32, rows - t0);
+      for (int l = 0; l < nrow; l++) {
+        const int t = t0 + l;
+        const int qs = __shfl_sync(0xffffffffu, pqs, l), qe = __shfl_sync(0xffffffffu, pqe, l), tc = __shfl_sync(0xffffffffu, ptc, l);
+        const int len = qe - qs + 1;
+        const int off = qs - qsPrev;
+        const int rowEnd = (t == rows - 1) ? len : len - 1;
+        if (off > 0) {
+          const int moved = __shfl_down_sync(0xffffffffu, qc, (unsigned)(off & 31));
+          qc = (off < 32 && lane + off < 32) ? moved : qcode_at(qs + lane);
+        }
+        const int x = lane;
+        const int xp = x + off;
+        const bool upIn = xp <= lenPrev - 1;
+        const bool upOk = xp < lenPrev - 1;
+        const bool diagOk = upIn && !(xp - 1 == 0 && t != 1);
+        const int Mup = upIn ? rowM[xp] : kIrBad;
+        const int Dup = upIn ? rowD[xp] : kIrBad;
+        const int Mdg = (upIn && xp >= 1) ? rowM[xp - 1] : kIrBad;
+        const bool valid = x >= 1 && x < rowEnd;
+        __syncwarp();
+        const int delOpen = upOk ? Mup + gapOpen : kIrBad;
+        const int delExt = upOk ? Dup : kIrBad;
+        const int D = imax(delOpen, delExt);
+        const int dbit = (D == delOpen) ? 0 : 1;
+        const int mS = diagOk ? Mdg + (qc == tc ? match : mismatch) : kIrBad;
+        const int dS = upOk ? Mup + gap : kIrBad;
+        const int a = valid ? imax(imax(mS, dS), D) : (x == 0 ? kIrBad : kIrNeg);
+        int u = a - x * gap;         // L[x] = x*gap + max_{y<=x}(a[y] - y*gap)
+        int pm = a;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int uu = __shfl_up_sync(0xffffffffu, u, o);
-        const int pp = __shfl_up_sync(0xffffffffu, pm, o);
-        if (lane >= o) { u = imax(u, uu); pm = imax(pm, pp); }
+        for (int o = 1; o < 32; o <<= 1) {
+          const int uu = __shfl_up_sync(0xffffffffu, u, o);
+          const int pp = __shfl_up_sync(0xffffffffu, pm, o);
+          if (lane >= o) { u = imax(u, uu); pm = imax(pm, pp); }
+        }
+        int pmx = __shfl_up_sync(0xffffffffu, pm, 1);
+        if (lane == 0) pmx = kIrNeg;
+        const int L = u + x * gap;
+        const int I = imax(kIrBad, pmx + gapOpen);
+        const int M = (x == 0) ? kIrBad : imax(imax(L, pmx + gapOpen), kIrBad);
+        int Mleft = __shfl_up_sync(0xffffffffu, M, 1);
+        if (lane == 0) Mleft = kIrBad;
+        const int iS = Mleft + gap;
+        const int ibit = (I == Mleft + gapOpen) ? 0 : 1;
+        const int arrow = (M == mS) ? IR_DIAG : (M == iS) ? IR_LEFT : (M == dS) ? IR_DOWN : (M == D) ? IR_DELCLOSE : IR_INSCLOSE;
+        const uint32_t b0 = __ballot_sync(0xffffffffu, valid && (arrow & 1));
+        const uint32_t b1 = __ballot_sync(0xffffffffu, valid && (arrow & 2));
+        const uint32_t b2 = __ballot_sync(0xffffffffu, valid && (arrow & 4));
+        const uint32_t b3 = __ballot_sync(0xffffffffu, valid && dbit);
+        const uint32_t b4 = __ballot_sync(0xffffffffu, valid && ibit);
+        if (lane < 5) tbw[(unsigned)t * 5u + lane] = lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : lane == 3 ? b3 : b4;
+        rowM[lane] = M;
+        rowD[lane] = valid ? D : kIrBad;
+        __syncwarp();
+        qsPrev = qs; lenPrev = len;
       }
-      int pmx = __shfl_up_sync(0xffffffffu, pm, 1);
-      if (lane == 0) pmx = kIrNeg;
-      const int L = u + x * gap;
-      const int I = imax(kIrBad, pmx + gapOpen);
-      const int M = (x == 0) ? kIrBad : imax(imax(L, pmx + gapOpen), kIrBad);
-      int Mleft = __shfl_up_sync(0xffffffffu, M, 1);
-      if (lane == 0) Mleft = kIrBad;
-      const int iS = Mleft + gap;
-      const int ibit = (I == Mleft + gapOpen) ? 0 : 1;
-      const int arrow = (M == mS) ? IR_DIAG : (M == iS) ? IR_LEFT : (M == dS) ? IR_DOWN : (M == D) ? IR_DELCLOSE : IR_INSCLOSE;
-      const uint32_t b0 = __ballot_sync(0xffffffffu, valid && (arrow & 1));
-      const uint32_t b1 = __ballot_sync(0xffffffffu, valid && (arrow & 2));
-      const uint32_t b2 = __ballot_sync(0xffffffffu, valid && (arrow & 4));
-      const uint32_t b3 = __ballot_sync(0xffffffffu, valid && dbit);
-      const uint32_t b4 = __ballot_sync(0xffffffffu, valid && ibit);
-      if (lane < 5) tbw[(unsigned long long)t * 5ull + lane] = lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : lane == 3 ? b3 : b4;
-      rowM[lane] = M;
-      rowD[lane] = valid ? D : kIrBad;
-      __syncwarp();
-      qsPrev = qs; lenPrev = len;
     }
     __syncwarp();
-    int nb = ir_walk_planes<false>(tbw, qS, qE, rows, tStart, nullptr, 0, lane);
+    // one traceback walk: blocks come out last-first into the group's scratch, then are copied in forward order
+    uint32_t *rb = tbw + (unsigned long long)rows * 5ull + 8ull;
+    int nb = ir_walk_planes<2>(tbw, qS, qE, rows, tStart, rb, 0, lane);
     if (nb < 0) { if (lane == 0) atomicOr(b.err, 16); nb = 0; }
     unsigned long long slot = aog_reserve_blocks(AogBatch{b.q, b.t, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, nullptr,
                                                           nullptr, b.blocks, b.block_cap, b.block_cursor, b.err},
                                                  lane == 0 ? nb : 0, lane, &plan->cls_blocks[cls]);
     slot = __shfl_sync(0xffffffffu, slot, 0);
     if (lane == 0) { b.n_blocks[g] = nb; b.block_off[g] = slot; }
-    if (slot != ~0ull && nb > 0) ir_walk_planes<true>(tbw, qS, qE, rows, tStart, b.blocks + 3ull * slot, nb, lane);
+    __syncwarp();
+    if (slot != ~0ull) {
+      uint32_t *out = b.blocks + 3ull * slot;
+      for (int i = lane; i < 3 * nb; i += 32) { const int r = i / 3, c = i - 3 * r; out[i] = rb[3 * (nb - 1 - r) + c]; }
+    }
     __syncwarp();
   }
 }

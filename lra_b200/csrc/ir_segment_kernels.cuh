@@ -160,8 +160,13 @@ __global__ void __launch_bounds__(128) ir_band_kernel(IrSegBatch b, int n_groups
   auto blkq = [&](int i) -> long { return i == startBlock ? (long)b.g_first[3 * g] : (i == endBlock ? (long)b.g_last[3 * g] : (long)W[3 * i]); };
   auto blkt = [&](int i) -> long { return i == startBlock ? (long)b.g_first[3 * g + 1] : (i == endBlock ? (long)b.g_last[3 * g + 1] : (long)W[3 * i + 1]); };
   auto blkl = [&](int i) -> long { return i == startBlock ? (long)b.g_first[3 * g + 2] : (i == endBlock ? (long)b.g_last[3 * g + 2] : (long)W[3 * i + 2]); };
-  long q = blkq(startBlock);
-  long tOff = 0;
+  // Steps run in path order.  Within one step the lanes touch distinct rows (lane ki: rows tOff-ki and tOff+ki), and the
+  // row's own update (IndelRefine.h:253-266) is done by lane 0 right before its ki = 0 neighbourhood update, so one warp
+  // barrier per step orders everything.
+  const int tl = (int)tLen;
+  int q = (int)blkq(startBlock);
+  int tOff = 0;
+  const int qStartI = (int)qStart, qEndI = (int)qEnd;
   for (int bb = startBlock; bb <= endBlock; bb++) {
     int qGap = 0, tGap = 0;
     int blockLength = (int)blkl(bb);
@@ -171,32 +176,34 @@ __global__ void __launch_bounds__(128) ir_band_kernel(IrSegBatch b, int n_groups
       if (qGap > 0 && tGap > 0) { const int c = qGap < tGap ? qGap : tGap; qGap -= c; tGap -= c; blockLength += c; }
     }
     for (int bi = 0; bi < blockLength; tOff++, bi++, q++) {
-      if (lane == 0 && tOff < tLen) {
-        const long lo = (q - k > qStart) ? q - k : qStart;
-        if (qS[tOff] == -1) qS[tOff] = (int32_t)lo;
-        else if (lo < (long)qS[tOff]) qS[tOff] = (int32_t)lo;
-        if (qE[tOff] == -1 || qE[tOff] < q + k) qE[tOff] = (int32_t)((qEnd - 1 < q + k) ? qEnd - 1 : q + k);
-      }
-      __syncwarp();
       for (int ki = lane; ki < k; ki += 32) {
-        if (tOff - ki >= 0 && tOff - ki < tLen) { if (qE[tOff - ki] < q) qE[tOff - ki] = (int32_t)q; }
-        if (tOff + ki < tLen) { const int v = qS[tOff + ki]; if (v == -1 || v > q) qS[tOff + ki] = (int32_t)q; }
+        const int im = tOff - ki, ip = tOff + ki;
+        if (ki == 0 && tOff < tl) {
+          const int lo = imax(q - k, qStartI);
+          const int cs = qS[tOff];
+          if (cs == -1 || lo < cs) qS[tOff] = lo;
+          const int ce = qE[tOff];
+          if (ce == -1 || ce < q + k) qE[tOff] = imin(qEndI - 1, q + k);
+        }
+        if (im >= 0 && im < tl) { if (qE[im] < q) qE[im] = q; }
+        if (ip < tl) { const int v = qS[ip]; if (v == -1 || v > q) qS[ip] = q; }
       }
       __syncwarp();
     }
     if (qGap > tGap) {
       for (int qi = 0; qi < qGap; qi++, q++) {
         for (int ki = lane; ki < k; ki += 32) {
-          if (tOff - ki >= 0 && tOff - ki < tLen) { if (qE[tOff - ki] < q) qE[tOff - ki] = (int32_t)q; }
-          if (tOff + ki < tLen) { const int v = qS[tOff + ki]; if (v == 0 || v > q) qS[tOff + ki] = (int32_t)q; }
+          const int im = tOff - ki, ip = tOff + ki;
+          if (im >= 0 && im < tl) { if (qE[im] < q) qE[im] = q; }
+          if (ip < tl) { const int v = qS[ip]; if (v == 0 || v > q) qS[ip] = q; }
         }
         __syncwarp();
       }
     }
     if (tGap > qGap) {
-      const long lo = (q - k > qStart) ? q - k : qStart;
-      const long hi = (qEnd - 1 < q + k) ? qEnd - 1 : q + k;
-      for (int ti = lane; ti < tGap; ti += 32) if (tOff + ti < tLen) { qS[tOff + ti] = (int32_t)lo; qE[tOff + ti] = (int32_t)hi; }
+      const int lo = imax(q - k, qStartI);
+      const int hi = imin(qEndI - 1, q + k);
+      for (int ti = lane; ti < tGap; ti += 32) if (tOff + ti < tl) { qS[tOff + ti] = lo; qE[tOff + ti] = hi; }
       tOff += tGap;
       __syncwarp();
     }
@@ -231,57 +238,56 @@ struct IrAssemble {
   unsigned long long out_cap; unsigned long long *out_cursor; int *err;
 };
 
+// one WARP per segment: lanes sum the piece sizes, lane 0 reserves the output range, then every piece is copied cooperatively
 __global__ void __launch_bounds__(128) ir_assemble_kernel(IrSegBatch b, IrAssemble a) {
   const int lane = threadIdx.x & 31;
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = s < b.n_seg;
-  int total = 0, np = 0;
-  const uint32_t *P = nullptr;
-  if (active) {
-    np = b.n_pieces[s];
-    P = b.pieces + 4ull * ir_piece_off(b, s);
-    for (int p = 0; p < np; p++) {
-      const uint32_t kind = P[4 * p];
-      total += kind == IR_PIECE_LITERAL ? 1 : (kind == IR_PIECE_AOG ? a.aog_n_blocks[P[4 * p + 1]] : a.dp_n_blocks[P[4 * p + 1]]);
-    }
+  const int s = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (s >= b.n_seg) return;
+  const int np = b.n_pieces[s];
+  const uint32_t *P = b.pieces + 4ull * ir_piece_off(b, s);
+  int total = 0;
+  for (int p = lane; p < np; p += 32) {
+    const uint32_t kind = P[4 * p];
+    total += kind == IR_PIECE_LITERAL ? 1 : (kind == IR_PIECE_AOG ? a.aog_n_blocks[P[4 * p + 1]] : a.dp_n_blocks[P[4 * p + 1]]);
   }
-  // warp-aggregated reservation
-  int inc = total;
-  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-  const int wtotal = __shfl_sync(0xffffffffu, inc, 31);
-  unsigned long long base = 0;
-  if (lane == 0 && wtotal > 0) base = atomicAdd(a.out_cursor, (unsigned long long)wtotal);
-  base = __shfl_sync(0xffffffffu, base, 0);
-  const bool over = base + (unsigned long long)wtotal > a.out_cap;
-  if (over && lane == 0) atomicOr(a.err, 1);
-  if (!active) return;
-  const unsigned long long slot = base + (unsigned long long)(inc - total);
-  a.out_n[s] = total;
-  a.out_off[s] = slot;
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  unsigned long long slot = 0;
+  if (lane == 0 && total > 0) slot = atomicAdd(a.out_cursor, (unsigned long long)total);
+  slot = __shfl_sync(0xffffffffu, slot, 0);
+  const bool over = slot + (unsigned long long)total > a.out_cap;
+  if (lane == 0) {
+    a.out_n[s] = total;
+    a.out_off[s] = slot;
+    if (over) atomicOr(a.err, 1);
+  }
   if (over) return;
   uint32_t *out = a.out_blocks + 3ull * slot;
   int o = 0;
   for (int p = 0; p < np; p++) {
     const uint32_t kind = P[4 * p];
-    if (kind == IR_PIECE_LITERAL) { out[3 * o] = P[4 * p + 1]; out[3 * o + 1] = P[4 * p + 2]; out[3 * o + 2] = P[4 * p + 3]; o++; }
-    else if (kind == IR_PIECE_AOG) {
+    if (kind == IR_PIECE_LITERAL) {
+      if (lane < 3) out[3 * o + lane] = P[4 * p + 1 + lane];
+      o++;
+    } else if (kind == IR_PIECE_AOG) {
       const uint32_t j = P[4 * p + 1];
       const uint32_t *src = a.aog_blocks + 3ull * a.aog_block_off[j];
       const int n = a.aog_n_blocks[j];
-      for (int i = 0; i < n; i++, o++) { out[3 * o] = src[3 * i] + P[4 * p + 2]; out[3 * o + 1] = src[3 * i + 1] + P[4 * p + 3]; out[3 * o + 2] = src[3 * i + 2]; }
+      for (int i = lane; i < 3 * n; i += 32) { const int c = i % 3; out[3 * o + i] = src[i] + (c == 0 ? P[4 * p + 2] : (c == 1 ? P[4 * p + 3] : 0u)); }
+      o += n;
     } else {
       const uint32_t g = P[4 * p + 1];
       const uint32_t *src = a.dp_blocks + 3ull * a.dp_block_off[g];
       const int n = a.dp_n_blocks[g];
-      for (int i = 0; i < n; i++, o++) { out[3 * o] = src[3 * i]; out[3 * o + 1] = src[3 * i + 1]; out[3 * o + 2] = src[3 * i + 2]; }
+      for (int i = lane; i < 3 * n; i += 32) out[3 * o + i] = src[i];
+      o += n;
     }
   }
+  __syncwarp();
   // "ERROR with alignment consistency" check of the reference (IndelRefine.h:772-782): reported as a status flag
-  for (int i = 0; i + 1 < total; i++)
-    if ((unsigned long long)out[3 * i] + out[3 * i + 2] > out[3 * (i + 1)] || (unsigned long long)out[3 * i + 1] + out[3 * i + 2] > out[3 * (i + 1) + 1]) {
-      atomicOr(a.err, 64);
-      break;
-    }
+  int bad = 0;
+  for (int i = lane; i + 1 < total; i += 32)
+    if ((unsigned long long)out[3 * i] + out[3 * i + 2] > out[3 * (i + 1)] || (unsigned long long)out[3 * i + 1] + out[3 * i + 2] > out[3 * (i + 1) + 1]) bad = 1;
+  if (bad) atomicOr(a.err, 64);
 }
 
 }  // namespace lra

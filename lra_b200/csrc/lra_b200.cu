@@ -688,7 +688,7 @@ static int ir_segments_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, cons
   a.out_n = res->n_blocks; a.out_off = (unsigned long long *)res->block_off; a.out_blocks = res->blocks; a.out_cap = res->block_cap;
   a.out_cursor = (unsigned long long *)B[OUTCUR].p; a.err = (int *)((char *)B[OUTCUR].p + 8);
   cudaEventRecord(e0, st);
-  ir_assemble_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(b, a);
+  ir_assemble_kernel<<<(unsigned)((S + 3) / 4), 128, 0, st>>>(b, a);
   ctx->launches++;
   cudaEventRecord(e1, st);
   CU(cudaGetLastError());

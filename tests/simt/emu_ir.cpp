@@ -103,7 +103,7 @@ extern "C" int emu_ir_segments(const uint8_t *q_arena, uint64_t qn, const uint8_
   unsigned long long out_cursor = 0;
   IrAssemble a{a_nb.data(), a_off.data(), a_blk.data(), d_nb.data(), d_off.data(), d_blk.data(), out_n, (unsigned long long *)out_off, out_blocks,
                out_cap, &out_cursor, &err};
-  emu::launch(dim3((unsigned)((S + 127) / 128)), dim3(128), 0, [&] { ir_assemble_kernel(b, a); });
+  emu::launch(dim3((unsigned)((S + 3) / 4)), dim3(128), 0, [&] { ir_assemble_kernel(b, a); });
   if (info) { info[0] = nA; info[1] = nG; info[2] = cells; }
   return err;
 }
