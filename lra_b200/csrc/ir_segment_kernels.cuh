@@ -155,18 +155,82 @@ __global__ void __launch_bounds__(128) ir_band_kernel(IrSegBatch b, int n_groups
   const long qEnd = qStart + b.g_q_seq_len[g];
   int32_t *qS = band + b.g_band_off[g];
   int32_t *qE = qS + tLen;
-  for (long x = lane; x < tLen; x += 32) { qS[x] = -1; qE[x] = -1; }
-  __syncwarp();
   auto blkq = [&](int i) -> long { return i == startBlock ? (long)b.g_first[3 * g] : (i == endBlock ? (long)b.g_last[3 * g] : (long)W[3 * i]); };
   auto blkt = [&](int i) -> long { return i == startBlock ? (long)b.g_first[3 * g + 1] : (i == endBlock ? (long)b.g_last[3 * g + 1] : (long)W[3 * i + 1]); };
   auto blkl = [&](int i) -> long { return i == startBlock ? (long)b.g_first[3 * g + 2] : (i == endBlock ? (long)b.g_last[3 * g + 2] : (long)W[3 * i + 2]); };
   // Steps run in path order.  Within one step the lanes touch distinct rows (lane ki: rows tOff-ki and tOff+ki), and the
   // row's own update (IndelRefine.h:253-266) is done by lane 0 right before its ki = 0 neighbourhood update, so one warp
-  // barrier per step orders everything.
+  // barrier per step orders everything.  Only the rows [tOff-k+1, tOff+k-1] (+ a target gap) are live at any time: they are
+  // kept in a shared-memory ring (row & 255) and flushed to HBM once the path has moved k rows past them.
+  __shared__ int ringS[4][256];
+  __shared__ int ringE[4][256];
   const int tl = (int)tLen;
+  const int qStartI = (int)qStart, qEndI = (int)qEnd;
+  if (2 * k + (k - 1) <= 250) {
+    int *rS = ringS[threadIdx.x >> 5], *rE = ringE[threadIdx.x >> 5];
+    for (int x = lane; x < 256; x += 32) { rS[x] = -1; rE[x] = -1; }
+    __syncwarp();
+    int q = (int)blkq(startBlock);
+    int tOff = 0;
+    int nextFlush = 0;     // rows < nextFlush are final and in HBM
+    auto flush_to = [&](int upto) {   // make rows < upto final (upto <= first row that can still change)
+      if (upto > tl) upto = tl;
+      if (upto > nextFlush) {
+        for (int r = nextFlush + lane; r < upto; r += 32) { qS[r] = rS[r & 255]; qE[r] = rE[r & 255]; rS[r & 255] = -1; rE[r & 255] = -1; }
+        nextFlush = upto;
+        __syncwarp();
+      }
+    };
+    for (int bb = startBlock; bb <= endBlock; bb++) {
+      int qGap = 0, tGap = 0;
+      int blockLength = (int)blkl(bb);
+      if (bb < endBlock) {
+        qGap = (int)(blkq(bb + 1) - (blkq(bb) + blockLength));
+        tGap = (int)(blkt(bb + 1) - (blkt(bb) + blockLength));
+        if (qGap > 0 && tGap > 0) { const int c = qGap < tGap ? qGap : tGap; qGap -= c; tGap -= c; blockLength += c; }
+      }
+      for (int bi = 0; bi < blockLength; tOff++, bi++, q++) {
+        flush_to(tOff - k + 1);
+        for (int ki = lane; ki < k; ki += 32) {
+          const int im = tOff - ki, ip = tOff + ki;
+          if (ki == 0 && tOff < tl) {
+            const int lo = imax(q - k, qStartI);
+            const int cs = rS[tOff & 255];
+            if (cs == -1 || lo < cs) rS[tOff & 255] = lo;
+            const int ce = rE[tOff & 255];
+            if (ce == -1 || ce < q + k) rE[tOff & 255] = imin(qEndI - 1, q + k);
+          }
+          if (im >= 0 && im < tl) { if (rE[im & 255] < q) rE[im & 255] = q; }
+          if (ip < tl) { const int v = rS[ip & 255]; if (v == -1 || v > q) rS[ip & 255] = q; }
+        }
+        __syncwarp();
+      }
+      if (qGap > tGap) {
+        flush_to(tOff - k + 1);
+        for (int qi = 0; qi < qGap; qi++, q++) {
+          for (int ki = lane; ki < k; ki += 32) {
+            const int im = tOff - ki, ip = tOff + ki;
+            if (im >= 0 && im < tl) { if (rE[im & 255] < q) rE[im & 255] = q; }
+            if (ip < tl) { const int v = rS[ip & 255]; if (v == 0 || v > q) rS[ip & 255] = q; }
+          }
+          __syncwarp();
+        }
+      }
+      if (tGap > qGap) {
+        flush_to(tOff - k + 1);
+        const int lo = imax(q - k, qStartI);
+        const int hi = imin(qEndI - 1, q + k);
+        for (int ti = lane; ti < tGap; ti += 32) if (tOff + ti < tl) { rS[(tOff + ti) & 255] = lo; rE[(tOff + ti) & 255] = hi; }
+        tOff += tGap;
+        __syncwarp();
+      }
+    }
+    flush_to(tl);
+  } else {
+  for (long x = lane; x < tLen; x += 32) { qS[x] = -1; qE[x] = -1; }
+  __syncwarp();
   int q = (int)blkq(startBlock);
   int tOff = 0;
-  const int qStartI = (int)qStart, qEndI = (int)qEnd;
   for (int bb = startBlock; bb <= endBlock; bb++) {
     int qGap = 0, tGap = 0;
     int blockLength = (int)blkl(bb);
@@ -208,6 +272,8 @@ __global__ void __launch_bounds__(128) ir_band_kernel(IrSegBatch b, int n_groups
       __syncwarp();
     }
   }
+  }
+  __syncwarp();
   // monotone fix-ups (IndelRefine.h:318-325): qS := suffix minimum, qE := prefix maximum
   {
     int carry = 0x7fffffff;

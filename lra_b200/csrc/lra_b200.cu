@@ -496,7 +496,7 @@ static int ir_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b20
   std::vector<Launched> launched;
   auto blocks_for = [&](uint32_t c) { unsigned x = (c + 63) / 64; unsigned cap = (unsigned)ctx->n_sm * 8u; return x > cap ? cap : x; };
   if (cnt[kIrClsWarp32]) {
-    unsigned wb = (cnt[kIrClsWarp32] + 3) / 4; const unsigned wcap = (unsigned)ctx->n_sm * 12u; if (wb > wcap) wb = wcap;
+    unsigned wb = (cnt[kIrClsWarp32] + 3) / 4; const unsigned wcap = (unsigned)ctx->n_sm * 16u; if (wb > wcap) wb = wcap;
     launched.push_back({kIrClsWarp32, evi}); rec(); ir_dp_warp_kernel<<<wb, 128, 0, st>>>(b, plan, sorted); rec(); ctx->launches++;
   }
   if (cnt[kIrClsGeneric]) { launched.push_back({kIrClsGeneric, evi}); rec(); ir_dp_generic_kernel<<<blocks_for(cnt[kIrClsGeneric]), 64, 0, st>>>(b, plan, sorted); rec(); ctx->launches++; }
