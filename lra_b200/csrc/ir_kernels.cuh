@@ -420,24 +420,33 @@ __global__ void __launch_bounds__(128) ir_dp_warp_kernel(IrBatch b, AogPlan *pla
     rowM[lane] = lane * gap;
     rowD[lane] = kIrBad;
     __syncwarp();
-    // query code held by this lane: position qsPrev + lane (refreshed by a shuffle when the band moves)
     auto qcode_at = [&](int pos) -> int { const uint64_t p = qbase + (uint64_t)pos; return p < b.q.n ? seq_code(b.q, p) : 5; };
-    int qc = qcode_at(qsPrev + lane);
     for (int t0 = 1; t0 < rows; t0 += 32) {
-      // band limits and target codes of the next 32 rows, one row per lane
+      // band limits and target codes of the next 32 rows, one row per lane; query codes of the positions those rows
+      // can touch, three per lane (the band advances about one position per row, so 96 positions cover 32 rows)
       const int rr = t0 + lane;
       const int pqs = rr < rows ? qS[rr] : 0, pqe = rr < rows ? qE[rr] : 0;
       const int ptc = rr < rows ? seq_code(b.t, (uint64_t)(uint32_t)(tbase + (uint32_t)(tStart + rr))) : 5;
       const int nrow = imin(32, rows - t0);
+      const int p0 = __shfl_sync(0xffffffffu, pqs, 0);
+      const int pend = __shfl_sync(0xffffffffu, pqe, nrow - 1);
+      const bool inRegs = pend - p0 < 96;
+      int qr0 = 5, qr1 = 5, qr2 = 5;
+      if (inRegs) { qr0 = qcode_at(p0 + lane); qr1 = qcode_at(p0 + 32 + lane); qr2 = qcode_at(p0 + 64 + lane); }
       for (int l = 0; l < nrow; l++) {
         const int t = t0 + l;
         const int qs = __shfl_sync(0xffffffffu, pqs, l), qe = __shfl_sync(0xffffffffu, pqe, l), tc = __shfl_sync(0xffffffffu, ptc, l);
         const int len = qe - qs + 1;
         const int off = qs - qsPrev;
         const int rowEnd = (t == rows - 1) ? len : len - 1;
-        if (off > 0) {
-          const int moved = __shfl_down_sync(0xffffffffu, qc, (unsigned)(off & 31));
-          qc = (off < 32 && lane + off < 32) ? moved : qcode_at(qs + lane);
+        int qc;
+        if (inRegs) {
+          const int idx = qs + lane - p0;          // 0 .. 95+31: lanes beyond the band read garbage that is never used
+          const int src = idx & 31;
+          const int c0 = __shfl_sync(0xffffffffu, qr0, src), c1 = __shfl_sync(0xffffffffu, qr1, src), c2 = __shfl_sync(0xffffffffu, qr2, src);
+          qc = idx < 32 ? c0 : (idx < 64 ? c1 : (idx < 96 ? c2 : 5));
+        } else {
+          qc = qcode_at(qs + lane);
         }
         const int x = lane;
         const int xp = x + off;
@@ -479,7 +488,7 @@ __global__ void __launch_bounds__(128) ir_dp_warp_kernel(IrBatch b, AogPlan *pla
         const uint32_t b2 = __ballot_sync(0xffffffffu, valid && (arrow & 4));
         const uint32_t b3 = __ballot_sync(0xffffffffu, valid && dbit);
         const uint32_t b4 = __ballot_sync(0xffffffffu, valid && ibit);
-        if (lane < 5) tbw[(unsigned)t * 5u + lane] = lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : lane == 3 ? b3 : b4;
+        if (lane == 0) { uint32_t *w5 = tbw + (unsigned)t * 5u; w5[0] = b0; w5[1] = b1; w5[2] = b2; w5[3] = b3; w5[4] = b4; }
         rowM[lane] = M;
         rowD[lane] = valid ? D : kIrBad;
         __syncwarp();

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(128) ir_group_kernel(IrSegBatch b) {
 
 // One warp per DP group.  The work copy of the segment's blocks may have moved on (later groups trim / restore their own
 // boundary blocks), so the first block and the last block's length come from the group record; inner blocks are untouched.
-__global__ void __launch_bounds__(128) ir_band_kernel(IrSegBatch b, int n_groups, int32_t *band) {
+__global__ void __launch_bounds__(128) ir_band_literal_kernel(IrSegBatch b, int n_groups, int32_t *band) {
   const int lane = threadIdx.x & 31;
   const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   if (g >= n_groups) return;
@@ -292,6 +292,105 @@ __global__ void __launch_bounds__(128) ir_band_kernel(IrSegBatch b, int n_groups
       for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = imax(v, u); }
       v = imax(v, carry);
       if (i < tLen) qE[i] = v;
+      carry = __shfl_sync(0xffffffffu, v, 31);
+    }
+  }
+}
+
+
+// Closed form of the band construction (default).  The reference walks the old path step by step (IndelRefine.h:232-315);
+// because q and the row index never decrease along the path, every update it makes is a running min / max whose winner is
+// known in O(1) per row from two per-row arrays:
+//   Q[r]  = query position of the path at row r   (diagonal rows: the step's q; target-gap rows: the q the gap sits at)
+//   F[r]  = bit0: row r lies in a target gap; bit1: a query gap precedes the diagonal step of row r
+// With R2 = min(r+k-1, tLen-1) and a = max(0, r-k+1):
+//   qE[r] = max( min(qEnd-1, Q[r]+k),  Q[R2] - (F[R2]&1) )                      (last step at or before row r+k-1)
+//   qS[r] = max(Q[r]-k, qStart)                                  on target-gap rows (the gap overwrites earlier touches)
+//   qS[r] = min( v, max(Q[r]-k, qStart) ),  v = Q[a]             on diagonal rows r >= 1 (first step at or after row a);
+//           if v == 0 and a query gap precedes a row R in (a, r], v becomes that gap's first q  (the `== 0` test of :298)
+//           row 0: v does not exist, qS[0] = max(Q[0]-k, qStart)
+// followed by the same monotone fix-ups.  Validated against the step-by-step kernel (ir_band_literal_kernel) and the oracle.
+__global__ void __launch_bounds__(128) ir_band_kernel(IrSegBatch b, int n_groups, int32_t *band, int32_t *tmp) {
+  const int lane = threadIdx.x & 31;
+  const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (g >= n_groups) return;
+  const int s = b.g_seg[g];
+  const uint32_t *W = b.work + 3ull * ir_work_off(b, s);
+  const int startBlock = b.g_first_block[g], endBlock = b.g_last_block[g];
+  const int k = b.k;
+  const int tl = b.g_t_len[g];
+  const int qStart = b.g_q_start[g];
+  const int qEnd = qStart + b.g_q_seq_len[g];
+  const int tStart = b.g_t_start[g];
+  int32_t *qS = band + b.g_band_off[g];
+  int32_t *qE = qS + tl;
+  int32_t *Q = tmp + b.g_band_off[g];
+  int32_t *F = Q + tl;
+  auto blkq = [&](int i) -> int { return i == startBlock ? (int)b.g_first[3 * g] : (i == endBlock ? (int)b.g_last[3 * g] : (int)W[3 * i]); };
+  auto blkt = [&](int i) -> int { return i == startBlock ? (int)b.g_first[3 * g + 1] : (i == endBlock ? (int)b.g_last[3 * g + 1] : (int)W[3 * i + 1]); };
+  auto blkl = [&](int i) -> int { return i == startBlock ? (int)b.g_first[3 * g + 2] : (i == endBlock ? (int)b.g_last[3 * g + 2] : (int)W[3 * i + 2]); };
+  // phase 1: per-row path description, one block per lane
+  for (int bb = startBlock + lane; bb <= endBlock; bb += 32) {
+    int len = blkl(bb), qGap = 0, tGap = 0;
+    const int q0 = blkq(bb), r0 = blkt(bb) - tStart;
+    if (bb < endBlock) {
+      qGap = blkq(bb + 1) - (q0 + len);
+      tGap = blkt(bb + 1) - (blkt(bb) + len);
+      if (qGap > 0 && tGap > 0) { const int c = qGap < tGap ? qGap : tGap; qGap -= c; tGap -= c; len += c; }
+    }
+    for (int i = 0; i < len; i++) if (r0 + i < tl) { Q[r0 + i] = q0 + i; F[r0 + i] = (i == 0 && bb > startBlock) ? (F[r0] & 2) : 0; }
+    if (tGap > qGap) for (int i = 0; i < tGap; i++) if (r0 + len + i < tl) { Q[r0 + len + i] = q0 + len; F[r0 + len + i] = 1; }
+  }
+  __syncwarp();
+  // query-gap markers (second pass so that they are not overwritten by the row fill above)
+  for (int bb = startBlock + lane; bb < endBlock; bb += 32) {
+    int len = blkl(bb);
+    int qGap = blkq(bb + 1) - (blkq(bb) + len), tGap = blkt(bb + 1) - (blkt(bb) + len);
+    if (qGap > 0 && tGap > 0) { const int c = qGap < tGap ? qGap : tGap; qGap -= c; tGap -= c; }
+    const int rn = blkt(bb + 1) - tStart;
+    if (qGap > tGap && rn < tl) F[rn] |= 2;
+  }
+  __syncwarp();
+  // phase 2: every row independently
+  for (int r = lane; r < tl; r += 32) {
+    const int Qr = Q[r], Fr = F[r];
+    const int R2 = imin(r + k - 1, tl - 1);
+    const int lastQ = Q[R2] - (F[R2] & 1);
+    const int e = imax(imin(qEnd - 1, Qr + k), lastQ);
+    const int lo = imax(Qr - k, qStart);
+    int v;
+    if (Fr & 1) v = lo;
+    else if (r == 0) v = lo;
+    else {
+      const int a = imax(0, r - k + 1);
+      v = Q[a];
+      if (v == 0) {
+        for (int R = a + 1; R <= r; R++) if (F[R] & 2) { v = Q[R - 1] + 1; break; }
+      }
+      v = imin(v, lo);
+    }
+    qS[r] = v;
+    qE[r] = e;
+  }
+  __syncwarp();
+  // monotone fix-ups (IndelRefine.h:318-325): qS := suffix minimum, qE := prefix maximum
+  {
+    int carry = 0x7fffffff;
+    for (int base = ((tl - 1) / 32) * 32; base >= 0; base -= 32) {
+      const int i = base + lane;
+      int v = (i < tl) ? qS[i] : 0x7fffffff;
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_down_sync(0xffffffffu, v, o); if (lane + o < 32) v = imin(v, u); }
+      v = imin(v, carry);
+      if (i < tl) qS[i] = v;
+      carry = __shfl_sync(0xffffffffu, v, 0);
+    }
+    carry = -0x7fffffff;
+    for (int base = 0; base < tl; base += 32) {
+      const int i = base + lane;
+      int v = (i < tl) ? qE[i] : -0x7fffffff;
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = imax(v, u); }
+      v = imax(v, carry);
+      if (i < tl) qE[i] = v;
       carry = __shfl_sync(0xffffffffu, v, 31);
     }
   }

@@ -636,9 +636,11 @@ static int ir_segments_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, cons
   stat("ir_group", e0, e1, (uint64_t)S);
   // ---- band construction for the DP groups
   if (nG) {
-    if ((rc = ensure(ctx, B[BAND], (size_t)(bandInts + 16) * 4))) return rc;
+    if ((rc = ensure(ctx, B[BAND], (size_t)(2 * bandInts + 32) * 4))) return rc;
+    static const bool band_literal = getenv("LRA_B200_IR_BAND_LITERAL") != nullptr;
     cudaEventRecord(e2, st);
-    ir_band_kernel<<<(unsigned)((nG + 3) / 4), 128, 0, st>>>(b, nG, (int32_t *)B[BAND].p);
+    if (band_literal) ir_band_literal_kernel<<<(unsigned)((nG + 3) / 4), 128, 0, st>>>(b, nG, (int32_t *)B[BAND].p);
+    else ir_band_kernel<<<(unsigned)((nG + 3) / 4), 128, 0, st>>>(b, nG, (int32_t *)B[BAND].p, (int32_t *)B[BAND].p + bandInts + 16);
     ctx->launches++;
     cudaEventRecord(e3, st);
     CU(cudaGetLastError());

@@ -78,8 +78,13 @@ extern "C" int emu_ir_segments(const uint8_t *q_arena, uint64_t qn, const uint8_
   b.g_first_block = gfb.data(); b.g_last_block = glb.data(); b.g_first = gfirst.data(); b.g_last = glast.data(); b.counters = counters;
   emu::launch(dim3((unsigned)((S + 127) / 128)), dim3(128), 0, [&] { ir_group_kernel(b); });
   const int nA = (int)counters[0], nG = (int)counters[1];
-  std::vector<int32_t> band(counters[2] + 16);
-  if (nG) emu::launch(dim3((unsigned)((nG + 3) / 4)), dim3(128), 0, [&] { ir_band_kernel(b, nG, band.data()); });
+  std::vector<int32_t> band(counters[2] + 16), band_lit(counters[2] + 16), tmpb(counters[2] + 16);
+  if (nG) {
+    emu::launch(dim3((unsigned)((nG + 3) / 4)), dim3(128), 0, [&] { ir_band_kernel(b, nG, band.data(), tmpb.data()); });
+    // cross-check the closed form against the step-by-step kernel on every group
+    emu::launch(dim3((unsigned)((nG + 3) / 4)), dim3(128), 0, [&] { ir_band_literal_kernel(b, nG, band_lit.data()); });
+    for (size_t i = 0; i < (size_t)counters[2]; i++) if (band[i] != band_lit[i]) return 1 << 20;
+  }
   int err = 0;
   // AffineOneGapAlign fallback
   std::vector<int32_t> a_score(nA + 1), a_nb(nA + 1); std::vector<unsigned long long> a_off(nA + 1);

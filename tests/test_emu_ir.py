@@ -60,3 +60,18 @@ def test_emu_whole_function_on_captured_segments(name, n):
         e = r["blocks_out"]
         assert nb[s] == len(e), (name, s, nb[s], len(e))
         assert (blk[int(off[s]):int(off[s]) + nb[s]] == e).all(), (name, s)
+
+
+@pytest.mark.parametrize("profile,n", [("ccs", 30), ("ont", 2)])
+def test_emu_whole_function_on_synthetic_segments(profile, n):
+    """Bench-shaped synthetic segments (CCS ones start at read position 0 with end padding: the band builder's `== 0` quirk).
+    The harness also cross-checks the closed-form band kernel against the step-by-step one on every group (error bit 20)."""
+    import synth, workload
+    genome = synth.gen_ref(2_000_000, 1, 31)[0][1]
+    sb = workload.make_segments(profile, n, 8, len(genome), workload.host_genome_fetcher(genome), max_len=6000)
+    sb2 = dict(sb); sb2["t_arena"] = sb["t_arena_compact"]; sb2["t_base"] = sb["t_base_compact"]
+    err, nb, off, blk, info = emu_lib.ir_segments(sb2)
+    assert err == 0
+    outs = po.indel_refine_batch_port(sb, sb["t_arena_compact"], sb["t_base_compact"])
+    for s, e in enumerate(outs):
+        assert nb[s] == len(e) and (blk[int(off[s]):int(off[s]) + nb[s]] == e).all(), (profile, s)
