@@ -44,18 +44,25 @@ struct IrSegBatch {
 __device__ __forceinline__ unsigned long long ir_work_off(const IrSegBatch &b, int s) { return b.blk_off[s] + 2ull * (unsigned long long)s; }
 __device__ __forceinline__ unsigned long long ir_piece_off(const IrSegBatch &b, int s) { return 2ull * b.blk_off[s] + 8ull * (unsigned long long)s; }
 
+// One WARP per segment.  The grouping loop is sequential, but it only ever modifies the block that currently starts a
+// group (trimmed head / restored tail), so the loop runs on the read-only padded copy plus one override block held in
+// registers; all lanes execute it uniformly, block fields come from a 32-block register chunk by shuffle, lane 0 writes.
 __global__ void __launch_bounds__(128) ir_group_kernel(IrSegBatch b) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int s = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   if (s >= b.n_seg) return;
   const int n_in = b.blk_cnt[s];
   const uint32_t *in = b.blocks_in + 3ull * b.blk_off[s];
   uint32_t *W = b.work + 3ull * ir_work_off(b, s);
   uint32_t *P = b.pieces + 4ull * ir_piece_off(b, s);
   int np = 0;
-  auto piece = [&](uint32_t kind, uint32_t a, uint32_t c, uint32_t d) { P[4 * np] = kind; P[4 * np + 1] = a; P[4 * np + 2] = c; P[4 * np + 3] = d; np++; };
+  auto piece = [&](uint32_t kind, uint32_t a, uint32_t c, uint32_t d) {
+    if (lane == 0) { P[4 * np] = kind; P[4 * np + 1] = a; P[4 * np + 2] = c; P[4 * np + 3] = d; }
+    np++;
+  };
   if (n_in <= 1) {
     for (int i = 0; i < n_in; i++) piece(IR_PIECE_LITERAL, in[3 * i], in[3 * i + 1], in[3 * i + 2]);
-    b.n_pieces[s] = np;
+    if (lane == 0) b.n_pieces[s] = np;
     return;
   }
   const int k = b.k, maxGap = b.k - 1;
@@ -72,72 +79,94 @@ __global__ void __launch_bounds__(128) ir_group_kernel(IrSegBatch b) {
       const int minEnd = (int)(a < c ? a : c);
       if (minEnd < 40) { endMatch = minEnd; addEnd = 1; }
     }
-    if (addStart) { W[0] = (uint32_t)qS0; W[1] = (uint32_t)tS0; W[2] = (uint32_t)startMatch; nb++; }
-    for (int i = 0; i < n_in; i++, nb++) { W[3 * nb] = in[3 * i]; W[3 * nb + 1] = in[3 * i + 1]; W[3 * nb + 2] = in[3 * i + 2]; }
-    if (addEnd) { W[3 * nb] = (uint32_t)qAlnEnd; W[3 * nb + 1] = (uint32_t)tAlnEnd; W[3 * nb + 2] = (uint32_t)endMatch; nb++; }
+    if (addStart && lane == 0) { W[0] = (uint32_t)qS0; W[1] = (uint32_t)tS0; W[2] = (uint32_t)startMatch; }
+    for (int i = lane; i < 3 * n_in; i += 32) W[3 * addStart + i] = in[i];
+    nb = n_in + addStart;
+    if (addEnd) { if (lane == 0) { W[3 * nb] = (uint32_t)qAlnEnd; W[3 * nb + 1] = (uint32_t)tAlnEnd; W[3 * nb + 2] = (uint32_t)endMatch; } nb++; }
   }
-#define BQ(i) W[3 * (i)]
-#define BT_(i) W[3 * (i) + 1]
-#define BL(i) W[3 * (i) + 2]
+  __syncwarp();
+  // register chunk of 32 blocks + the override block
+  int cbase = -1000;
+  uint32_t cq = 0, ct = 0, cl = 0;
+  int ovIdx = -1;
+  uint32_t ovQ = 0, ovT = 0, ovL = 0;
+  auto fetch = [&](int i, uint32_t &q, uint32_t &t, uint32_t &l) {
+    if (i < cbase || i >= cbase + 32) {
+      cbase = i;
+      const int j = cbase + lane;
+      if (j < nb) { cq = W[3 * j]; ct = W[3 * j + 1]; cl = W[3 * j + 2]; }
+    }
+    q = __shfl_sync(0xffffffffu, cq, i - cbase); t = __shfl_sync(0xffffffffu, ct, i - cbase); l = __shfl_sync(0xffffffffu, cl, i - cbase);
+    if (i == ovIdx) { q = ovQ; t = ovT; l = ovL; }
+  };
   int startBlock = 0, endBlock = 0;
   while (endBlock < nb) {
-    long qStart = BQ(startBlock), tStart = BT_(startBlock);
-    long qPos = (long)BQ(startBlock) + (int)BL(startBlock), tPos = (long)BT_(startBlock) + (int)BL(startBlock);
+    uint32_t sQ, sT, sL;
+    fetch(startBlock, sQ, sT, sL);
+    long qStart = sQ, tStart = sT;
+    long qPos = (long)sQ + (int)sL, tPos = (long)sT + (int)sL;
     int tGap = 0, qGap = 0;
-    if (endBlock < nb - 1) { tGap = (int)(BT_(endBlock + 1) - (uint32_t)tPos); qGap = (int)(BQ(endBlock + 1) - (uint32_t)qPos); }
-    while (endBlock < nb - 1 && qGap < maxGap && tGap < maxGap && (startBlock == endBlock || BL(endBlock) < 100u)) {
+    uint32_t eQ = sQ, eT = sT, eL = sL;      // block endBlock
+    uint32_t nQ = 0, nT = 0, nL = 0;         // block endBlock + 1
+    if (endBlock < nb - 1) { fetch(endBlock + 1, nQ, nT, nL); tGap = (int)(nT - (uint32_t)tPos); qGap = (int)(nQ - (uint32_t)qPos); }
+    while (endBlock < nb - 1 && qGap < maxGap && tGap < maxGap && (startBlock == endBlock || eL < 100u)) {
       endBlock++;
-      const int bl = (int)BL(endBlock);
-      qPos = (long)BQ(endBlock) + bl; tPos = (long)BT_(endBlock) + bl;
-      if (endBlock + 1 < nb - 1) { tGap = (int)(BT_(endBlock + 1) - (uint32_t)tPos); qGap = (int)(BQ(endBlock + 1) - (uint32_t)qPos); }
+      eQ = nQ; eT = nT; eL = nL;
+      qPos = (long)eQ + (int)eL; tPos = (long)eT + (int)eL;
+      if (endBlock + 1 < nb - 1) { fetch(endBlock + 1, nQ, nT, nL); tGap = (int)(nT - (uint32_t)tPos); qGap = (int)(nQ - (uint32_t)qPos); }
+      else if (endBlock + 1 < nb) fetch(endBlock + 1, nQ, nT, nL);   // keep (n*) = block endBlock+1 for the next iteration; gaps stay stale as in the reference
     }
     uint32_t altQ = 0, altT = 0, altL = 0;
     bool usedAlt = false;
     if (endBlock == startBlock) {
-      piece(IR_PIECE_LITERAL, BQ(startBlock), BT_(startBlock), BL(startBlock));
+      piece(IR_PIECE_LITERAL, sQ, sT, sL);
     } else {
-      if ((long)BL(startBlock) > maxGap) {
-        const int advanced = (int)BL(startBlock) - maxGap;
-        BL(startBlock) -= (uint32_t)maxGap;
-        piece(IR_PIECE_LITERAL, BQ(startBlock), BT_(startBlock), BL(startBlock));
-        BQ(startBlock) += (uint32_t)advanced; BT_(startBlock) += (uint32_t)advanced; BL(startBlock) = (uint32_t)maxGap;
+      if ((long)sL > maxGap) {
+        const int advanced = (int)sL - maxGap;
+        piece(IR_PIECE_LITERAL, sQ, sT, sL - (uint32_t)maxGap);
+        sQ += (uint32_t)advanced; sT += (uint32_t)advanced; sL = (uint32_t)maxGap;
         qStart += advanced; tStart += advanced;
       }
-      if ((long)BL(endBlock) > maxGap) {
+      if ((long)eL > maxGap) {
         usedAlt = true;
-        altQ = BQ(endBlock) + (uint32_t)maxGap; altT = BT_(endBlock) + (uint32_t)maxGap; altL = BL(endBlock) - (uint32_t)maxGap;
-        BL(endBlock) = (uint32_t)maxGap;
-        qPos = (long)BQ(endBlock) + maxGap; tPos = (long)BT_(endBlock) + maxGap;
+        altQ = eQ + (uint32_t)maxGap; altT = eT + (uint32_t)maxGap; altL = eL - (uint32_t)maxGap;
+        eL = (uint32_t)maxGap;
+        qPos = (long)eQ + maxGap; tPos = (long)eT + maxGap;
       }
-      const long qEnd = (long)BQ(endBlock) + BL(endBlock), tEnd = (long)BT_(endBlock) + BL(endBlock);
+      const long qEnd = (long)eQ + eL, tEnd = (long)eT + eL;
       const long tLen = tPos - tStart;
       const long tSeqLen = tEnd - tStart, qSeqLen = qEnd - qStart;
       if (tSeqLen < k || qSeqLen < k) {
-        const unsigned long long j = atomicAdd(&b.counters[0], 1ull);
-        b.aog_q_off[j] = b.q_base[s] + (uint32_t)qStart;
-        b.aog_t_off[j] = b.t_base[s] + (uint32_t)tStart;
-        b.aog_q_len[j] = (int32_t)qSeqLen; b.aog_t_len[j] = (int32_t)tSeqLen; b.aog_k[j] = k;
+        unsigned long long j = 0;
+        if (lane == 0) {
+          j = atomicAdd(&b.counters[0], 1ull);
+          b.aog_q_off[j] = b.q_base[s] + (uint32_t)qStart;
+          b.aog_t_off[j] = b.t_base[s] + (uint32_t)tStart;
+          b.aog_q_len[j] = (int32_t)qSeqLen; b.aog_t_len[j] = (int32_t)tSeqLen; b.aog_k[j] = k;
+        }
+        j = __shfl_sync(0xffffffffu, j, 0);
         piece(IR_PIECE_AOG, (uint32_t)j, (uint32_t)qStart, (uint32_t)tStart);
       } else {
-        const unsigned long long g = atomicAdd(&b.counters[1], 1ull);
-        b.g_q_base[g] = b.q_base[s]; b.g_t_base[g] = b.t_base[s];
-        b.g_q_start[g] = (int32_t)qStart; b.g_t_start[g] = (int32_t)tStart; b.g_t_len[g] = (int32_t)tLen;
-        b.g_q_seq_len[g] = (int32_t)qSeqLen; b.g_t_seq_len[g] = (int32_t)tSeqLen;
-        b.g_band_off[g] = (uint32_t)atomicAdd(&b.counters[2], (unsigned long long)(2 * tLen));
-        b.g_seg[g] = s; b.g_first_block[g] = startBlock; b.g_last_block[g] = endBlock;
-        b.g_first[3 * g] = BQ(startBlock); b.g_first[3 * g + 1] = BT_(startBlock); b.g_first[3 * g + 2] = BL(startBlock);
-        b.g_last[3 * g] = BQ(endBlock); b.g_last[3 * g + 1] = BT_(endBlock); b.g_last[3 * g + 2] = BL(endBlock);
+        unsigned long long g = 0;
+        if (lane == 0) {
+          g = atomicAdd(&b.counters[1], 1ull);
+          b.g_q_base[g] = b.q_base[s]; b.g_t_base[g] = b.t_base[s];
+          b.g_q_start[g] = (int32_t)qStart; b.g_t_start[g] = (int32_t)tStart; b.g_t_len[g] = (int32_t)tLen;
+          b.g_q_seq_len[g] = (int32_t)qSeqLen; b.g_t_seq_len[g] = (int32_t)tSeqLen;
+          b.g_band_off[g] = (uint32_t)atomicAdd(&b.counters[2], (unsigned long long)(2 * tLen));
+          b.g_seg[g] = s; b.g_first_block[g] = startBlock; b.g_last_block[g] = endBlock;
+          b.g_first[3 * g] = sQ; b.g_first[3 * g + 1] = sT; b.g_first[3 * g + 2] = sL;
+          b.g_last[3 * g] = eQ; b.g_last[3 * g + 1] = eT; b.g_last[3 * g + 2] = eL;
+        }
+        g = __shfl_sync(0xffffffffu, g, 0);
         piece(IR_PIECE_DP, (uint32_t)g, 0u, 0u);
       }
     }
-    if (!usedAlt) endBlock++;
-    else { BQ(endBlock) = altQ; BT_(endBlock) = altT; BL(endBlock) = altL; }
+    if (!usedAlt) { endBlock++; ovIdx = -1; }
+    else { ovIdx = endBlock; ovQ = altQ; ovT = altT; ovL = altL; }
     startBlock = endBlock;
   }
-#undef BQ
-#undef BT_
-#undef BL
-  b.n_pieces[s] = np;
+  if (lane == 0) b.n_pieces[s] = np;
 }
 
 // One warp per DP group.  The work copy of the segment's blocks may have moved on (later groups trim / restore their own

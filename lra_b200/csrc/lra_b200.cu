@@ -616,7 +616,7 @@ static int ir_segments_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, cons
 
   cudaEvent_t e0 = ctx->ev[36], e1 = ctx->ev[37], e2 = ctx->ev[38], e3 = ctx->ev[39];
   cudaEventRecord(e0, st);
-  ir_group_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(b);
+  ir_group_kernel<<<(unsigned)((S + 3) / 4), 128, 0, st>>>(b);
   ctx->launches++;
   cudaEventRecord(e1, st);
   CU(cudaGetLastError());

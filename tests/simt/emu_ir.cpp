@@ -76,7 +76,7 @@ extern "C" int emu_ir_segments(const uint8_t *q_arena, uint64_t qn, const uint8_
   b.g_q_base = gqb.data(); b.g_t_base = gtb.data(); b.g_q_start = gqs.data(); b.g_t_start = gts.data(); b.g_t_len = gtl.data();
   b.g_q_seq_len = gqsl.data(); b.g_t_seq_len = gtsl.data(); b.g_band_off = gbo.data(); b.g_seg = gseg.data();
   b.g_first_block = gfb.data(); b.g_last_block = glb.data(); b.g_first = gfirst.data(); b.g_last = glast.data(); b.counters = counters;
-  emu::launch(dim3((unsigned)((S + 127) / 128)), dim3(128), 0, [&] { ir_group_kernel(b); });
+  emu::launch(dim3((unsigned)((S + 3) / 4)), dim3(128), 0, [&] { ir_group_kernel(b); });
   const int nA = (int)counters[0], nG = (int)counters[1];
   std::vector<int32_t> band(counters[2] + 16), band_lit(counters[2] + 16), tmpb(counters[2] + 16);
   if (nG) {
