@@ -42,7 +42,9 @@ struct IrBatch {
   int32_t *max_width;       // per group
 };
 
-constexpr int kIrClsW24 = 0, kIrClsW64 = 1, kIrClsGeneric = 2, kIrClsWarp32 = 3;
+constexpr int kIrClsW24 = 0, kIrClsW64 = 1, kIrClsGeneric = 2, kIrClsWarp32 = 3, kIrClsPipe = 4, kIrNumCls = 5;
+constexpr int kIrPipeSpan = 24;        // rows over which the band may advance at most kIrPipeMaxAdvance for the pipeline kernel
+constexpr int kIrPipeMaxAdvance = 64;
 constexpr int kIrWarpMinRows = 192;   // longer groups of width <= 32 go to the warp-per-group kernel
 __host__ __device__ inline int ir_words(int wmax) { return (wmax + 5) / 6; }
 
@@ -64,6 +66,7 @@ __global__ void __launch_bounds__(128) ir_classify_kernel(IrBatch b, AogPlan *pl
     cells += w;
     if (w < 2) bad = 1;
     if (r > 0 && (qS[r] < qS[r - 1] || qE[r] < qE[r - 1])) bad = 1;
+    if (qE[imin(r + kIrPipeSpan, rows - 1)] - qS[r] > kIrPipeMaxAdvance) bad |= 2;   // too steep for the pipeline kernel's query ring
   }
   for (int o = 16; o > 0; o >>= 1) {
     mw = imax(mw, __shfl_down_sync(0xffffffffu, mw, o));
@@ -71,18 +74,21 @@ __global__ void __launch_bounds__(128) ir_classify_kernel(IrBatch b, AogPlan *pl
     bad |= __shfl_down_sync(0xffffffffu, bad, o);
   }
   if (lane == 0) {
-    if (bad || rows < 2) {
+    if ((bad & 1) || rows < 2) {
       atomicOr(b.err, 8);
       bin_of_group[g] = 0xFFFFFFFFu;
       b.n_blocks[g] = 0; b.block_off[g] = 0;
       return;
     }
-    const int cls = (mw <= 32 && rows >= kIrWarpMinRows && !no_warp) ? kIrClsWarp32 : mw <= 24 ? kIrClsW24 : (mw <= 64 ? kIrClsW64 : kIrClsGeneric);
-    const unsigned long long words = cls == kIrClsWarp32 ? (unsigned long long)rows * 5ull + 8ull + 3ull * ((unsigned long long)rows + (unsigned long long)b.q_seq_len[g] + 4ull) : cls == kIrClsGeneric ? ((unsigned long long)rows * (unsigned long long)mw + 3ull) / 4ull + 2ull * (unsigned long long)mw + 4ull
+    // no_warp: 1 = thread kernels only, 2 = long groups through the scan kernel only
+    const bool longGroup = mw <= 32 && rows >= kIrWarpMinRows && no_warp != 1;
+    const int cls = longGroup ? ((no_warp == 2 || (bad & 2)) ? kIrClsWarp32 : kIrClsPipe) : mw <= 24 ? kIrClsW24 : (mw <= 64 ? kIrClsW64 : kIrClsGeneric);
+    unsigned long long words = longGroup ? (unsigned long long)rows * 6ull + 8ull + 3ull * ((unsigned long long)rows + (unsigned long long)b.q_seq_len[g] + 4ull) : cls == kIrClsGeneric ? ((unsigned long long)rows * (unsigned long long)mw + 3ull) / 4ull + 2ull * (unsigned long long)mw + 4ull
                                                            : (unsigned long long)rows * (unsigned long long)ir_words(cls == kIrClsW24 ? 24 : 64);
+    words = (words + 1ull) & ~1ull;   // keep every group's arrows 8-byte aligned
     b.tb_off[g] = atomicAdd(tb_cursor, words);
     b.max_width[g] = mw;
-    const int bucket = kAogBuckets - 1 - imin(cls == kIrClsWarp32 ? rows >> 8 : rows >> 3, kAogBuckets - 1);
+    const int bucket = kAogBuckets - 1 - imin(longGroup ? rows >> 8 : rows >> 3, kAogBuckets - 1);
     const uint32_t bin = (uint32_t)(cls * kAogBuckets + bucket);
     bin_of_group[g] = bin;
     atomicAdd(&plan->hist[bin], 1u);
@@ -509,6 +515,287 @@ __global__ void __launch_bounds__(128) ir_dp_warp_kernel(IrBatch b, AogPlan *pla
     if (slot != ~0ull) {
       uint32_t *out = b.blocks + 3ull * slot;
       for (int i = lane; i < 3 * nb; i += 32) { const int r = i / 3, c = i - 3 * r; out[i] = rb[3 * (nb - 1 - r) + c]; }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- 8-lane row pipeline
+// Long groups, default kernel.  EIGHT lanes own one group and four groups share a warp.  Sub-lane j computes the rows
+// t = j+1 (mod 8) cell by cell -- the in-row chain (I, M) is a plain serial recurrence again, no scans -- one row behind its
+// left neighbour: cell (t, x) may run once row t-1 has produced cell x+off (off = qS[t]-qS[t-1]).  Each lane does up to two
+// cells per lock step; rows are 15..20 cells, so all eight rows in flight keep their lanes busy and a warp retires up to 64
+// cells per step.  Rows are exchanged through shared memory (one M/D row buffer per lane, reused every 8 rows: a lane may
+// overwrite cell x only after the right neighbour, which still reads the old row, is past it), progress (row id, last cell)
+// through shuffles.  Row descriptors (band limits + the target base's packed words) and the packed query window are
+// prefetched into shared-memory rings with cp.async, a whole row-round ahead, so no global load sits in the dependent chain.
+// Arrows: 5 bits per cell (3 M, 1 del, 1 ins), 12 cells per 64-bit word, 3 words per row, cell x >= 1 of a row in word
+// (x-1)/12 at bit 5*(11-(x-1)%12).  The traceback is walked by the 8 lanes with 8 rows of arrow words in registers and the
+// next 8 rows prefetched behind them.
+__device__ __forceinline__ uint32_t ir_pipe_code(unsigned long long a0, unsigned long long a1, unsigned long long a2, int x) {
+  if (x <= 0) return 0u;
+  const int kb = (x - 1) / 12, i = (x - 1) - 12 * kb;
+  const unsigned long long wv = kb == 0 ? a0 : (kb == 1 ? a1 : a2);
+  return (uint32_t)(wv >> (5 * (11 - i))) & 31u;
+}
+
+// MODE 2: write in walk order (last block first) at out[0..); MODE 0: count only
+template <int MODE>
+__device__ __forceinline__ int ir_walk_pipe(const uint32_t *tb, const int32_t *qS, const int32_t *qE, int rows, int tStart, uint32_t *out,
+                                            int sl, int sbase, bool have) {
+  int t = 0, qs = 0, x = 0, mat = 0, run = 0, lastOp = -1, count = 0;
+  long guard = 0, guardMax = 0;
+  bool done = !have;
+  if (have) { t = rows - 1; qs = qS[t]; x = qE[t] - qs; guardMax = 4L * rows + 4L * (qE[rows - 1] - qS[0]) + 64; }
+  auto emit = [&](uint32_t qq, uint32_t tt, uint32_t ln) {
+    if (MODE != 0 && sl == 0) { out[3 * count] = qq; out[3 * count + 1] = tt; out[3 * count + 2] = ln; }
+    count++;
+  };
+  const unsigned long long *tb64 = (const unsigned long long *)tb;
+  int top = have ? rows - 1 : 0;
+  unsigned long long c0 = 0, c1 = 0, c2 = 0, n0 = 0, n1 = 0, n2 = 0;
+  int rqs = 0, nqs = 0;
+  if (have) {
+    int r = top - sl;
+    if (r >= 1) { const unsigned long long *w = tb64 + (unsigned long long)r * 3ull; c0 = w[0]; c1 = w[1]; c2 = w[2]; rqs = qS[r - 1]; }
+    r -= 8;
+    if (r >= 1) { const unsigned long long *w = tb64 + (unsigned long long)r * 3ull; n0 = w[0]; n1 = w[1]; n2 = w[2]; nqs = qS[r - 1]; }
+  }
+  while (__any_sync(0xffffffffu, !done)) {
+    bool step = !done;
+    if (step && ++guard > guardMax) { count = -1; done = true; step = false; }
+    if (step && t == 0) {
+      if (x > 0) {
+        if (mat != 0) { count = -1; }
+        else {
+          if (run > 0) { emit((uint32_t)(qs + x + 1), (uint32_t)(tStart + 1), (uint32_t)run); run = 0; }
+          else if (lastOp == IR_DOWN) emit((uint32_t)(qs + x + 1), (uint32_t)(tStart + 1), 0u);
+          lastOp = IR_LEFT; x = 0;
+        }
+      }
+      if (count >= 0) { run += 1; emit((uint32_t)qs, (uint32_t)tStart, (uint32_t)run); }
+      done = true; step = false;
+    }
+    if (step && t < top - 7) {     // the walk leaves a chunk one row at a time, so the next chunk is always top - 8
+      top -= 8;
+      c0 = n0; c1 = n1; c2 = n2; rqs = nqs;
+      const int r = top - 8 - sl;
+      if (r >= 1) { const unsigned long long *w = tb64 + (unsigned long long)r * 3ull; n0 = w[0]; n1 = w[1]; n2 = w[2]; nqs = qS[r - 1]; }
+    }
+    // every lane decodes the cell of ITS row at the walker's column; the walker's row owner is picked by shuffle
+    const uint32_t mine = ir_pipe_code(c0, c1, c2, x);
+    const int src = step ? (top - t) : 0;
+    const uint32_t a5 = __shfl_sync(0xffffffffu, mine, sbase + src);
+    const int pqs = __shfl_sync(0xffffffffu, rqs, sbase + src);
+    if (step) {
+      const int a = (int)(a5 & 7u);
+      const int dbit = (int)((a5 >> 3) & 1u), ibit = (int)((a5 >> 4) & 1u);
+      int op = -2, nt = t, nx = x, nmat = mat;
+      if (mat == 0) {
+        if (a == IR_DELCLOSE) { op = -1; nmat = 1; }
+        else if (a == IR_INSCLOSE) { op = -1; nmat = 2; }
+        else if (a == IR_DIAG) { op = IR_DIAG; nt = t - 1; }
+        else if (a == IR_LEFT) { op = IR_LEFT; nx = x - 1; }
+        else if (a == IR_DOWN) { op = IR_DOWN; nt = t - 1; }
+      } else if (mat == 1) { op = IR_DOWN; nmat = dbit ? 1 : 0; nt = t - 1; }
+      else { op = IR_LEFT; nmat = ibit ? 2 : 0; nx = x - 1; }
+      if (op == -2) { count = -1; done = true; }
+      else {
+        if (op >= 0) {
+          const int q = qs + x;
+          if (op == IR_DIAG) run++;
+          else {
+            if (run > 0) { emit((uint32_t)(q + 1), (uint32_t)(tStart + t + 1), (uint32_t)run); run = 0; }
+            else if (lastOp != -1 && lastOp != op) emit((uint32_t)(q + 1), (uint32_t)(tStart + t + 1), 0u);
+          }
+          lastOp = op;
+        }
+        if (nt != t) { const int q = qs + x; nx = (op == IR_DIAG ? q - 1 : q) - pqs; qs = pqs; }
+        t = nt; x = nx; mat = nmat;
+        if (x < 0 || x > 32) { count = -1; done = true; }
+      }
+    }
+  }
+  return count;
+}
+
+struct IrPipeSmem {          // per group (8 lanes)
+  int M[8][33];
+  int D[8][33];
+  uint32_t row[32][4];       // ring of row descriptors {qS, qE, target b2 word, target mask word}, slot = row & 31
+  uint32_t qb2[16];          // ring of packed query words (256 bases), slot = word index & 15
+  uint32_t qnm[8];           // ring of query mask words (256 bases), slot = word index & 7
+};
+constexpr int kIrPipeAhead = 160;   // query bases kept prefetched beyond the row that sub-lane 0 is starting
+constexpr int kIrPipeDone = 1 << 20;
+
+template <int CPS>   // cells per lane per lock step
+__global__ void __launch_bounds__(128) ir_dp_pipe_kernel(IrBatch b, AogPlan *plan, const uint32_t *sorted, int cls) {
+  __shared__ IrPipeSmem sm[4][4];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int sg = lane >> 3, sl = lane & 7, sbase = sg << 3;
+  const int prevLane = sbase + ((sl + 7) & 7), nextLane = sbase + ((sl + 1) & 7);
+  IrPipeSmem &S = sm[wib][sg];
+  const int ps = (sl + 7) & 7;
+  const uint32_t begin = plan->bin_start[cls * kAogBuckets];
+  const uint32_t end = plan->bin_start[(cls + 1) * kAogBuckets];
+  const int match = b.match, mismatch = b.mismatch, gap = b.gap, gapOpen = 2 * b.gap + 1;
+  const uint32_t qWordMax = (uint32_t)(b.q.n >> 4) + 3u, qMaskMax = (uint32_t)(b.q.n >> 5) + 3u;
+  for (;;) {
+    uint32_t w = 0;
+    if (lane == 0) w = atomicAdd(&plan->work[cls], 4u);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (begin + w >= end) break;
+    const bool have = begin + w + (uint32_t)sg < end;
+    int g = 0, rows = 0, tStart = 0;
+    const int32_t *qS = nullptr, *qE = nullptr;
+    uint32_t *tbw = nullptr;
+    uint32_t qbase = 0, tbase = 0;     // arenas are < 2^32 bases (uint32 offsets in the ABI)
+    if (have) {
+      g = (int)sorted[begin + w + sg];
+      rows = b.t_len[g]; tStart = b.t_start[g];
+      qS = b.band + b.band_off[g]; qE = qS + rows;
+      tbw = b.tb + b.tb_off[g];
+      qbase = b.q_base[g]; tbase = b.t_base[g] + (uint32_t)tStart;
+    }
+    unsigned long long *tb64 = (unsigned long long *)tbw;
+    __syncwarp();
+    auto issue_row = [&](int r) {     // asynchronous fetch of the descriptor of row r
+      uint32_t *e = S.row[r & 31];
+      cp_async4(e, qS + r);
+      cp_async4(e + 1, qE + r);
+      const uint32_t tp = tbase + (uint32_t)r;
+      cp_async4(e + 2, b.t.b2 + (tp >> 4));
+      cp_async4(e + 3, b.t.nm + (tp >> 5));
+    };
+    uint32_t qwNext = 0, qmNext = 0;   // sub-lane 0: next query word / mask word to request
+    auto issue_query = [&](int qs) {   // keep the query ring filled up to qs + kIrPipeAhead
+      const uint32_t last = qbase + (uint32_t)qs + (uint32_t)kIrPipeAhead;
+      for (; qwNext <= (last >> 4); qwNext++) cp_async4(&S.qb2[qwNext & 15], b.q.b2 + (qwNext < qWordMax ? qwNext : qWordMax));
+      for (; qmNext <= (last >> 5); qmNext++) cp_async4(&S.qnm[qmNext & 7], b.q.nm + (qmNext < qMaskMax ? qmNext : qMaskMax));
+    };
+    int prow = -1, pdone = 0;     // progress of this lane: row it works on / last cell it finished (kIrPipeDone: row complete)
+    int t = sl + 1;
+    if (have) {
+      const int q0 = qS[0], e0 = qE[0];
+      for (int xx = sl; xx <= e0 - q0 && xx < 33; xx += 8) { S.M[7][xx] = xx * gap; S.D[7][xx] = kIrBad; }
+      if (sl == 7) { prow = 0; pdone = kIrPipeDone; S.row[0][0] = (uint32_t)q0; S.row[0][1] = (uint32_t)e0; }
+      if (t < rows) issue_row(t);
+      if (t + 8 < rows) issue_row(t + 8);
+      if (sl == 0) { qwNext = (qbase + (uint32_t)q0) >> 4; qmNext = (qbase + (uint32_t)q0) >> 5; issue_query(q0); }
+      cp_async_wait_all();
+    }
+    __syncwarp();
+    bool started = false;
+    int x = 1, rowEnd = 0, off = 0, lenPrev = 0, tc = 5;
+    uint32_t qp = 0;                  // arena position of band cell 0 of the current row
+    int Mleft = kIrBad, Ileft = kIrBad, Mdiag = kIrBad;
+    unsigned long long acc0 = 0, acc1 = 0, acc2 = 0;
+    long guard = 0;
+    const long guardMax = 64L * (long)__reduce_max_sync(0xffffffffu, rows) + 4096;
+    while (__any_sync(0xffffffffu, have && t < rows)) {
+      if (++guard > guardMax) { if (lane == 0) atomicOr(b.err, 32); break; }
+      const int pr = __shfl_sync(0xffffffffu, prow, prevLane);
+      const int pd = __shfl_sync(0xffffffffu, pdone, prevLane);
+      // (one cell per step never overwrites a cell the right neighbour still needs: it reads strictly beyond its own column)
+      const int nr = CPS > 1 ? __shfl_sync(0xffffffffu, prow, nextLane) : -1;
+      const int nd = CPS > 1 ? __shfl_sync(0xffffffffu, pdone, nextLane) : 0;
+      if (have && t < rows) {
+        if (!started && pr == t - 1) {
+          cp_async_wait_all();              // my own copies: rows t and t+8 (issued >= 8 rows ago), query words (sub-lane 0)
+          const uint32_t *e = S.row[t & 31];
+          const uint32_t *pe = S.row[(t - 1) & 31];
+          const int qs = (int)e[0], qe = (int)e[1];
+          const uint32_t tw = e[2], tm = e[3];
+          const int pqs = (int)pe[0], pqe = (int)pe[1];
+          const int len = qe - qs + 1;
+          off = qs - pqs;
+          lenPrev = pqe - pqs + 1;
+          rowEnd = (t == rows - 1) ? len : len - 1;
+          const uint32_t tp = tbase + (uint32_t)t;
+          tc = ((tm >> (tp & 31)) & 1u) ? 4 : (int)((tw >> ((tp & 15) * 2)) & 3u);
+          qp = qbase + (uint32_t)qs;
+          x = 1; Mleft = kIrBad; Ileft = kIrBad;
+          Mdiag = (off < lenPrev && off >= 0) ? kIrNeg : kIrBad;   // marker: load on the first cell
+          acc0 = acc1 = acc2 = 0;
+          started = true;
+          prow = t; pdone = 0;
+          if (t + 16 < rows) issue_row(t + 16);
+          if (sl == 0) issue_query(qs);
+        }
+        if (started) {
+          // cells of the previous row that are final / cells of my old row the right neighbour no longer reads
+          const int avail = (pr > t - 1) ? kIrPipeDone : pd;
+          const int safe = (CPS > 1 && nr == t - 7) ? nd : kIrPipeDone;
+#pragma unroll
+          for (int c = 0; c < CPS; c++) {
+            const int xp = x + off;
+            if (x < rowEnd && imin(xp, lenPrev - 2) <= avail && x <= safe) {
+              const bool upIn = xp <= lenPrev - 1;
+              const bool upOk = xp < lenPrev - 1;
+              const bool diagOk = upIn && !(xp - 1 == 0 && t != 1);
+              if (Mdiag == kIrNeg) Mdiag = S.M[ps][off];
+              int Mup = kIrBad, Dup = kIrBad;
+              if (upIn) { Mup = S.M[ps][xp]; Dup = S.D[ps][xp]; }
+              const uint32_t p = qp + (uint32_t)x;
+              const int qc = ((S.qnm[(p >> 5) & 7] >> (p & 31)) & 1u) ? 4 : (int)((S.qb2[(p >> 4) & 15] >> ((p & 15) * 2)) & 3u);
+              const int delOpen = upOk ? Mup + gapOpen : kIrBad;
+              const int delExt = upOk ? Dup : kIrBad;
+              const int D = imax(delOpen, delExt);
+              const uint32_t dbit = (D == delOpen) ? 0u : 8u;
+              const int insOpen = Mleft + gapOpen;
+              const int I = imax(insOpen, Ileft);
+              const uint32_t ibit = (I == insOpen) ? 0u : 16u;
+              const int mS = diagOk ? Mdiag + (qc == tc ? match : mismatch) : kIrBad;
+              const int iS = Mleft + gap;
+              const int dS = upOk ? Mup + gap : kIrBad;
+              const int mx = imax(imax(mS, iS), imax(dS, imax(D, I)));
+              const uint32_t a = (mx == mS) ? IR_DIAG : (mx == iS) ? IR_LEFT : (mx == dS) ? IR_DOWN : (mx == D) ? IR_DELCLOSE : IR_INSCLOSE;
+              if (x == 13 || x == 25) { acc2 = acc1; acc1 = acc0; acc0 = 0; }
+              acc0 = (acc0 << 5) | (unsigned long long)(a | dbit | ibit);
+              S.M[sl][x] = mx; S.D[sl][x] = D;
+              Mdiag = Mup; Mleft = mx; Ileft = I;
+              pdone = x;
+              x++;
+            }
+          }
+          if (x >= rowEnd) {
+            // row complete (possibly without any computed cell): publish its arrows, take the next row of this lane
+            const int n = rowEnd - 1;
+            unsigned long long v0 = 0, v1 = 0, v2 = 0;     // cells never computed read as 0, like untouched bit planes
+            if (n >= 1) {
+              const int kb = (n - 1) / 12, m = n - 12 * kb;
+              const unsigned long long last = acc0 << (5 * (12 - m));
+              if (kb == 0) v0 = last;
+              else if (kb == 1) { v0 = acc1; v1 = last; }
+              else { v0 = acc2; v1 = acc1; v2 = last; }
+            }
+            unsigned long long *w3 = tb64 + (unsigned)t * 3u;
+            w3[0] = v0; w3[1] = v1; w3[2] = v2;
+            pdone = kIrPipeDone;
+            t += 8; started = false;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    // traceback, all four groups of the warp in lock step, each walked by its own 8 lanes
+    uint32_t *rb = have ? tbw + (unsigned long long)rows * 6ull + 8ull : nullptr;
+    int nb = ir_walk_pipe<2>(tbw, qS, qE, rows, tStart, rb, sl, sbase, have);
+    if (have && nb < 0) { if (sl == 0) atomicOr(b.err, 16); nb = 0; }
+    if (!have) nb = 0;
+    unsigned long long slot = aog_reserve_blocks(AogBatch{b.q, b.t, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, nullptr,
+                                                          nullptr, b.blocks, b.block_cap, b.block_cursor, b.err},
+                                                 (have && sl == 0) ? nb : 0, lane, &plan->cls_blocks[cls]);
+    slot = __shfl_sync(0xffffffffu, slot, sbase);
+    if (have && sl == 0) { b.n_blocks[g] = nb; b.block_off[g] = slot; }
+    __syncwarp();
+    if (have && slot != ~0ull) {
+      uint32_t *out = b.blocks + 3ull * slot;
+      for (int i = sl; i < 3 * nb; i += 8) { const int r = i / 3, c = i - 3 * r; out[i] = rb[3 * (nb - 1 - r) + c]; }
     }
     __syncwarp();
   }

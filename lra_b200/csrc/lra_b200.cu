@@ -473,7 +473,7 @@ static int ir_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b20
   int evi = 0;
   auto rec = [&]() { cudaEventRecord(ctx->ev[evi++], st); };
   rec();
-  static const int no_warp = getenv("LRA_B200_IR_NO_WARP") ? 1 : 0;
+  static const int no_warp = getenv("LRA_B200_IR_NO_WARP") ? 1 : getenv("LRA_B200_IR_SCAN_KERNEL") ? 2 : 0;
   ir_classify_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(b, plan, (uint32_t *)ctx->bin_of_job.p, tb_cursor, cells_total, no_warp);
   aog_scan_kernel<<<1, 512, 0, st>>>(plan);
   aog_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, plan, (const uint32_t *)ctx->bin_of_job.p, (uint32_t *)ctx->sorted.p);
@@ -486,8 +486,8 @@ static int ir_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b20
   if (*(int *)((char *)ctx->h_misc + 8) & 8)
     return fail(ctx, LRA_B200_EINVAL, "indel_dp_batch: a group has fewer than 2 rows, a row narrower than 2 cells or a non-monotone band");
   const AogPlan &hp = *ctx->h_plan;
-  uint32_t cnt[4];
-  for (int c = 0; c < 4; c++) cnt[c] = hp.bin_start[(c + 1) * kAogBuckets] - hp.bin_start[c * kAogBuckets];
+  uint32_t cnt[kIrNumCls];
+  for (int c = 0; c < kIrNumCls; c++) cnt[c] = hp.bin_start[(c + 1) * kAogBuckets] - hp.bin_start[c * kAogBuckets];
   const unsigned long long tb_words = ctx->h_misc[2];
   if ((rc = ensure(ctx, ctx->ir_tb, (size_t)(tb_words + 64) * 4))) return rc;
   b.tb = (uint32_t *)ctx->ir_tb.p;
@@ -495,6 +495,11 @@ static int ir_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b20
   struct Launched { int cls; int ev0; };
   std::vector<Launched> launched;
   auto blocks_for = [&](uint32_t c) { unsigned x = (c + 63) / 64; unsigned cap = (unsigned)ctx->n_sm * 8u; return x > cap ? cap : x; };
+  if (cnt[kIrClsPipe]) {
+    unsigned pb = (cnt[kIrClsPipe] + 15) / 16; const unsigned pcap = (unsigned)ctx->n_sm * 5u; if (pb > pcap) pb = pcap;
+    launched.push_back({kIrClsPipe, evi}); rec(); { static const bool two = getenv("LRA_B200_IR_PIPE2") != nullptr;
+      if (two) ir_dp_pipe_kernel<2><<<pb, 128, 0, st>>>(b, plan, sorted, kIrClsPipe); else ir_dp_pipe_kernel<1><<<pb, 128, 0, st>>>(b, plan, sorted, kIrClsPipe); } rec(); ctx->launches++;
+  }
   if (cnt[kIrClsWarp32]) {
     unsigned wb = (cnt[kIrClsWarp32] + 3) / 4; const unsigned wcap = (unsigned)ctx->n_sm * 16u; if (wb > wcap) wb = wcap;
     launched.push_back({kIrClsWarp32, evi}); rec(); ir_dp_warp_kernel<<<wb, 128, 0, st>>>(b, plan, sorted); rec(); ctx->launches++;
@@ -509,7 +514,7 @@ static int ir_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b20
   res->n_blocks_total = ctx->h_misc[0];
   res->cells = ctx->h_misc[3];
   const int err = *(int *)((char *)ctx->h_misc + 8);
-  static const char *names[4] = {"ir_dp_thread<W=24>", "ir_dp_thread<W=64>", "ir_dp_generic", "ir_dp_warp<W=32>"};
+  static const char *names[kIrNumCls] = {"ir_dp_thread<W=24>", "ir_dp_thread<W=64>", "ir_dp_generic", "ir_dp_warp<W=32>", "ir_dp_pipe<W=32>"};
   {
     lra_b200_kernel_stat s;
     memset(&s, 0, sizeof s);

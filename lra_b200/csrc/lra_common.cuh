@@ -60,6 +60,22 @@ struct SeqStream {
   }
 };
 
+// 4-byte asynchronous global -> shared copy (LDGSTS): the prefetches of the row-pipeline kernel never pass through registers,
+// so no scoreboard wait can end up in the dependent chain.  Completion: cp_async_wait_all() by the issuing thread, then a
+// warp barrier before other lanes read.  (The emulator copies at issue time.)
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+#ifdef LRA_EMU
+  *(uint32_t *)smem_dst = *(const uint32_t *)gsrc;
+#else
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#ifndef LRA_EMU
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
 __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
 __device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
 

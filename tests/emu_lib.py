@@ -15,6 +15,10 @@ _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 _u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 
 
+def set_lane_order(mode):
+    lib().emu_set_lane_order(C.c_long(mode))
+
+
 def lib():
     global _lib
     if _lib is not None:

@@ -62,10 +62,12 @@ struct BlockState {
   int bar_count = 0;
   uint64_t bar_gen = 0;
   int live = 0;
+  std::vector<int> order;
   std::function<void()> body;
 };
 
 inline BlockState *&B() { static BlockState *b = nullptr; return b; }
+inline long &g_order_mode() { static long m = getenv("LRA_EMU_ORDER") ? atol(getenv("LRA_EMU_ORDER")) : 0; return m; }
 inline uint3 &g_blockIdx() { static uint3 v{0, 0, 0}; return v; }
 inline dim3 &g_blockDim() { static dim3 v; return v; }
 inline dim3 &g_gridDim() { static dim3 v; return v; }
@@ -120,7 +122,17 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem, F &&body) {
         long idle_rounds = 0;
         while (bs.live > 0) {
           int before = bs.live;
-          for (int t = 0; t < nth; t++) {
+          // LRA_EMU_ORDER: 0 ascending (default), 1 descending, >= 2 a fresh pseudo-random permutation every round (seed) --
+          // the order lanes run between two collectives is unspecified on hardware, tests replay kernels under several orders
+          const long order_mode = g_order_mode();
+          static unsigned long long rng = 0x9E3779B97F4A7C15ull;
+          rng ^= (unsigned long long)order_mode;
+          std::vector<int> &ord = bs.order;
+          if ((int)ord.size() != nth) { ord.resize(nth); for (int t = 0; t < nth; t++) ord[t] = t; }
+          if (order_mode >= 2)
+            for (int t = nth - 1; t > 0; t--) { rng = rng * 6364136223846793005ull + 1442695040888963407ull; std::swap(ord[t], ord[(int)((rng >> 33) % (unsigned)(t + 1))]); }
+          for (int k = 0; k < nth; k++) {
+            const int t = order_mode == 1 ? nth - 1 - k : ord[k];
             if (bs.th[t].done) continue;
             bs.cur = t;
             swapcontext(&bs.sched, &bs.th[t].ctx);
@@ -223,6 +235,14 @@ inline void __syncthreads() {
     if (b->bar_count >= b->live) { b->bar_count = 0; b->bar_gen++; break; }
     emu::yield();
   }
+}
+inline int __reduce_max_sync(unsigned mask, int v) {
+  uint64_t vals[32];
+  emu::warp_arrive(mask, emu::to_bits(v), 0, vals, nullptr);
+  int m = v;
+  int nth = (int)emu::B()->th.size(), base = emu::self().warp * 32;
+  for (int l = 0; l < 32; l++) if (((mask >> l) & 1u) && base + l < nth) { int o = emu::from_bits<int>(vals[l]); if (o > m) m = o; }
+  return m;
 }
 inline void __threadfence() {}
 inline void __threadfence_block() {}

@@ -26,3 +26,6 @@ extern "C" int emu_aog_batch(const uint8_t *q_arena, uint64_t qn, const uint8_t 
   if (cells_out) *cells_out = cells;
   return err;
 }
+
+// lane scheduling order of the emulator between collectives (0 ascending, 1 descending, >= 2 random with that seed)
+extern "C" void emu_set_lane_order(long mode) { emu::g_order_mode() = mode; }

@@ -14,7 +14,7 @@ static uint64_t run_ir_dp(IrBatch &b, int force_generic, std::vector<uint32_t> &
   unsigned long long tb_cursor = 0, cells = 0;
   std::vector<AogPlan> planv(1); AogPlan *plan = planv.data(); memset(plan, 0, sizeof(AogPlan));
   std::vector<uint32_t> bin(n_groups + 1), sorted(n_groups + 1);
-  emu::launch(dim3((unsigned)((n_groups + 3) / 4)), dim3(128), 0, [&] { ir_classify_kernel(b, plan, bin.data(), &tb_cursor, &cells, force_generic == 3 ? 1 : 0); });
+  emu::launch(dim3((unsigned)((n_groups + 3) / 4)), dim3(128), 0, [&] { ir_classify_kernel(b, plan, bin.data(), &tb_cursor, &cells, force_generic == 3 ? 1 : force_generic == 4 ? 2 : 0); });
   if (force_generic == 1) {
     memset(plan->hist, 0, sizeof plan->hist);
     tb_cursor = 0;
@@ -35,10 +35,12 @@ static uint64_t run_ir_dp(IrBatch &b, int force_generic, std::vector<uint32_t> &
   if (cnt(kIrClsW64)) emu::launch(dim3(2), dim3(64), 0, [&] { ir_dp_thread_kernel<64>(b, plan, sorted.data(), kIrClsW64); });
   if (cnt(kIrClsGeneric)) emu::launch(dim3(2), dim3(64), 0, [&] { ir_dp_generic_kernel(b, plan, sorted.data()); });
   if (cnt(kIrClsWarp32)) emu::launch(dim3(2), dim3(128), 0, [&] { ir_dp_warp_kernel(b, plan, sorted.data()); });
+  if (cnt(kIrClsPipe)) emu::launch(dim3(2), dim3(128), 0, [&] { if (force_generic == 5) ir_dp_pipe_kernel<2>(b, plan, sorted.data(), kIrClsPipe); else ir_dp_pipe_kernel<1>(b, plan, sorted.data(), kIrClsPipe); });
   return cells;
 }
 
-// force_generic: 1 = send everything to the generic kernel, 3 = never use the warp kernel (thread kernels only)
+// force_generic: 1 = send everything to the generic kernel, 3 = thread kernels only, 4 = long groups through the scan-based warp kernel, 5 = pipeline kernel with two cells per step
+// (default: the 8-lane row-pipeline kernel)
 extern "C" int emu_ir_dp_batch(const uint8_t *q_arena, uint64_t qn, const uint8_t *t_arena, uint64_t tn, const uint32_t *q_base,
                                const uint32_t *t_base, const int32_t *q_start, const int32_t *t_start, const int32_t *t_len,
                                const int32_t *q_seq_len, const int32_t *t_seq_len, const uint32_t *band_off, const int32_t *band,

@@ -39,6 +39,25 @@ def test_emu_ir_clr_w64():
     assert run("ir_clr", 1) >= 1
 
 
+def test_emu_ir_pipe_kernel_lane_orders():
+    """the row-pipeline kernel exchanges rows through shared memory between warp barriers: replay it with the lanes
+    scheduled in descending and in random order between collectives (hardware leaves that order unspecified)"""
+    try:
+        for mode in (1, 20261017):
+            emu_lib.set_lane_order(mode)
+            assert run("ir_ont", 1) >= 1
+    finally:
+        emu_lib.set_lane_order(0)
+
+
+def test_emu_ir_pipe_two_cells_per_step():
+    assert run("ir_ont", 1, force_generic=5) >= 1
+
+
+def test_emu_ir_scan_warp_kernel():
+    assert run("ir_ont", 1, force_generic=4) >= 1
+
+
 def test_emu_ir_thread_kernels_only():
     assert run("ir_ont", 1, force_generic=3) >= 1
     assert run("ir_ccs", 2, force_generic=3) > 20

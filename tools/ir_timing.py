@@ -9,7 +9,9 @@ import synth, workload, lra_b200
 profile = sys.argv[1] if len(sys.argv) > 1 else "ont"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
 genome = synth.gen_ref(100_000_000, 1, 78)[0][1]
-sb = workload.make_segments(profile, n, 6, len(genome), workload.host_genome_fetcher(genome))
+max_len = int(sys.argv[3]) if len(sys.argv) > 3 else None
+sb = workload.make_segments(profile, n, 6, len(genome), workload.host_genome_fetcher(genome), max_len=max_len)
+print("read_len max", int(sb["read_len"].max()), "mean", float(sb["read_len"].mean()))
 ctx = lra_b200.Context(0)
 q = ctx.seq_upload(sb["q_arena"][:-16]); t = ctx.seq_upload(genome)
 for it in range(3):
