@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads-per-step", type=int, default=4096)
+    ap.add_argument("--reads-per-step", type=int, default=16384)
     ap.add_argument("--genome-len", type=int, default=3_000_000_000)
     ap.add_argument("--cpu-sample-jobs", type=int, default=400_000)
     ap.add_argument("--cpu-sample-segments", type=int, default=256)

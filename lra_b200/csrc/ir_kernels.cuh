@@ -50,7 +50,7 @@ __host__ __device__ inline int ir_words(int wmax) { return (wmax + 5) / 6; }
 
 // one warp per group: band maximum width -> class; reserves traceback storage; fills the planner histogram
 __global__ void __launch_bounds__(128) ir_classify_kernel(IrBatch b, AogPlan *plan, uint32_t *bin_of_group, unsigned long long *tb_cursor,
-                                                          unsigned long long *cells_total, int no_warp) {
+                                                          unsigned long long *cells_total, int no_warp, int long_rows) {
   const int lane = threadIdx.x & 31;
   const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   if (g >= b.n_groups) return;
@@ -80,9 +80,10 @@ __global__ void __launch_bounds__(128) ir_classify_kernel(IrBatch b, AogPlan *pl
       b.n_blocks[g] = 0; b.block_off[g] = 0;
       return;
     }
-    // no_warp: 1 = thread kernels only, 2 = long groups through the scan kernel only
+    // no_warp: 1 = thread kernels only, 2 = long groups through the scan kernel only.  The longest groups (rows >= long_rows)
+    // take the scan kernel, whose latency per row is lower; the row-pipeline kernel has the higher throughput for the rest.
     const bool longGroup = mw <= 32 && rows >= kIrWarpMinRows && no_warp != 1;
-    const int cls = longGroup ? ((no_warp == 2 || (bad & 2)) ? kIrClsWarp32 : kIrClsPipe) : mw <= 24 ? kIrClsW24 : (mw <= 64 ? kIrClsW64 : kIrClsGeneric);
+    const int cls = longGroup ? ((no_warp == 2 || (bad & 2) || rows >= long_rows) ? kIrClsWarp32 : kIrClsPipe) : mw <= 24 ? kIrClsW24 : (mw <= 64 ? kIrClsW64 : kIrClsGeneric);
     unsigned long long words = longGroup ? (unsigned long long)rows * 6ull + 8ull + 3ull * ((unsigned long long)rows + (unsigned long long)b.q_seq_len[g] + 4ull) : cls == kIrClsGeneric ? ((unsigned long long)rows * (unsigned long long)mw + 3ull) / 4ull + 2ull * (unsigned long long)mw + 4ull
                                                            : (unsigned long long)rows * (unsigned long long)ir_words(cls == kIrClsW24 ? 24 : 64);
     words = (words + 1ull) & ~1ull;   // keep every group's arrows 8-byte aligned

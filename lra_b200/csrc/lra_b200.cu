@@ -474,7 +474,11 @@ static int ir_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b20
   auto rec = [&]() { cudaEventRecord(ctx->ev[evi++], st); };
   rec();
   static const int no_warp = getenv("LRA_B200_IR_NO_WARP") ? 1 : getenv("LRA_B200_IR_SCAN_KERNEL") ? 2 : 0;
-  ir_classify_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(b, plan, (uint32_t *)ctx->bin_of_job.p, tb_cursor, cells_total, no_warp);
+  // measured on B200 (tools/ir_sweep.sh): a small batch is bound by the row chain of its longest groups, which the scan kernel
+  // walks at half the latency per row; a large batch is bound by throughput, where the row-pipeline kernel is ahead
+  static const int long_rows_env = getenv("LRA_B200_IR_LONG_ROWS") ? atoi(getenv("LRA_B200_IR_LONG_ROWS")) : 0;
+  const int long_rows = long_rows_env > 0 ? long_rows_env : (n < 40000 ? 6000 : 24576);
+  ir_classify_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(b, plan, (uint32_t *)ctx->bin_of_job.p, tb_cursor, cells_total, no_warp, long_rows);
   aog_scan_kernel<<<1, 512, 0, st>>>(plan);
   aog_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, plan, (const uint32_t *)ctx->bin_of_job.p, (uint32_t *)ctx->sorted.p);
   ctx->launches += 3;
@@ -495,18 +499,29 @@ static int ir_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b20
   struct Launched { int cls; int ev0; };
   std::vector<Launched> launched;
   auto blocks_for = [&](uint32_t c) { unsigned x = (c + 63) / 64; unsigned cap = (unsigned)ctx->n_sm * 8u; return x > cap ? cap : x; };
+  // the DP classes are independent: each runs on its own side stream (LRA_B200_SERIAL=1 keeps them on the main stream)
+  static const bool ir_serial = getenv("LRA_B200_SERIAL") != nullptr;
+  cudaStream_t S[4];
+  for (int i = 0; i < 4; i++) S[i] = ir_serial ? st : ctx->side[i];
+  if (!ir_serial) {
+    CU(cudaEventRecord(ctx->fork_ev, st));
+    for (int i = 0; i < 4; i++) CU(cudaStreamWaitEvent(S[i], ctx->fork_ev, 0));
+  }
+  auto recs = [&](cudaStream_t s) { cudaEventRecord(ctx->ev[evi++], s); };
+  if (cnt[kIrClsWarp32]) {   // the longest groups first: their row chains are the critical path of the batch
+    unsigned wb = (cnt[kIrClsWarp32] + 3) / 4; const unsigned wcap = (unsigned)ctx->n_sm * 16u; if (wb > wcap) wb = wcap;
+    launched.push_back({kIrClsWarp32, evi}); recs(S[0]); ir_dp_warp_kernel<<<wb, 128, 0, S[0]>>>(b, plan, sorted); recs(S[0]); ctx->launches++;
+  }
   if (cnt[kIrClsPipe]) {
     unsigned pb = (cnt[kIrClsPipe] + 15) / 16; const unsigned pcap = (unsigned)ctx->n_sm * 5u; if (pb > pcap) pb = pcap;
-    launched.push_back({kIrClsPipe, evi}); rec(); { static const bool two = getenv("LRA_B200_IR_PIPE2") != nullptr;
-      if (two) ir_dp_pipe_kernel<2><<<pb, 128, 0, st>>>(b, plan, sorted, kIrClsPipe); else ir_dp_pipe_kernel<1><<<pb, 128, 0, st>>>(b, plan, sorted, kIrClsPipe); } rec(); ctx->launches++;
+    launched.push_back({kIrClsPipe, evi}); recs(S[1]); { static const bool two = getenv("LRA_B200_IR_PIPE2") != nullptr;
+      if (two) ir_dp_pipe_kernel<2><<<pb, 128, 0, S[1]>>>(b, plan, sorted, kIrClsPipe); else ir_dp_pipe_kernel<1><<<pb, 128, 0, S[1]>>>(b, plan, sorted, kIrClsPipe); } recs(S[1]); ctx->launches++;
   }
-  if (cnt[kIrClsWarp32]) {
-    unsigned wb = (cnt[kIrClsWarp32] + 3) / 4; const unsigned wcap = (unsigned)ctx->n_sm * 16u; if (wb > wcap) wb = wcap;
-    launched.push_back({kIrClsWarp32, evi}); rec(); ir_dp_warp_kernel<<<wb, 128, 0, st>>>(b, plan, sorted); rec(); ctx->launches++;
-  }
-  if (cnt[kIrClsGeneric]) { launched.push_back({kIrClsGeneric, evi}); rec(); ir_dp_generic_kernel<<<blocks_for(cnt[kIrClsGeneric]), 64, 0, st>>>(b, plan, sorted); rec(); ctx->launches++; }
-  if (cnt[kIrClsW64]) { launched.push_back({kIrClsW64, evi}); rec(); ir_dp_thread_kernel<64><<<blocks_for(cnt[kIrClsW64]), 64, 0, st>>>(b, plan, sorted, kIrClsW64); rec(); ctx->launches++; }
-  if (cnt[kIrClsW24]) { launched.push_back({kIrClsW24, evi}); rec(); ir_dp_thread_kernel<24><<<blocks_for(cnt[kIrClsW24]), 64, 0, st>>>(b, plan, sorted, kIrClsW24); rec(); ctx->launches++; }
+  if (cnt[kIrClsGeneric]) { launched.push_back({kIrClsGeneric, evi}); recs(S[2]); ir_dp_generic_kernel<<<blocks_for(cnt[kIrClsGeneric]), 64, 0, S[2]>>>(b, plan, sorted); recs(S[2]); ctx->launches++; }
+  if (cnt[kIrClsW64]) { launched.push_back({kIrClsW64, evi}); recs(S[3]); ir_dp_thread_kernel<64><<<blocks_for(cnt[kIrClsW64]), 64, 0, S[3]>>>(b, plan, sorted, kIrClsW64); recs(S[3]); ctx->launches++; }
+  if (cnt[kIrClsW24]) { launched.push_back({kIrClsW24, evi}); recs(S[2]); ir_dp_thread_kernel<24><<<blocks_for(cnt[kIrClsW24]), 64, 0, S[2]>>>(b, plan, sorted, kIrClsW24); recs(S[2]); ctx->launches++; }
+  if (!ir_serial)
+    for (int i = 0; i < 4; i++) { CU(cudaEventRecord(ctx->join_ev[i], S[i])); CU(cudaStreamWaitEvent(st, ctx->join_ev[i], 0)); }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(ctx->h_plan, plan, sizeof(AogPlan), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(ctx->h_misc, ctx->misc.p, 32, cudaMemcpyDeviceToHost, st));

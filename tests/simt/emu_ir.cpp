@@ -14,7 +14,7 @@ static uint64_t run_ir_dp(IrBatch &b, int force_generic, std::vector<uint32_t> &
   unsigned long long tb_cursor = 0, cells = 0;
   std::vector<AogPlan> planv(1); AogPlan *plan = planv.data(); memset(plan, 0, sizeof(AogPlan));
   std::vector<uint32_t> bin(n_groups + 1), sorted(n_groups + 1);
-  emu::launch(dim3((unsigned)((n_groups + 3) / 4)), dim3(128), 0, [&] { ir_classify_kernel(b, plan, bin.data(), &tb_cursor, &cells, force_generic == 3 ? 1 : force_generic == 4 ? 2 : 0); });
+  emu::launch(dim3((unsigned)((n_groups + 3) / 4)), dim3(128), 0, [&] { ir_classify_kernel(b, plan, bin.data(), &tb_cursor, &cells, force_generic == 3 ? 1 : force_generic == 4 ? 2 : 0, 1 << 30); });
   if (force_generic == 1) {
     memset(plan->hist, 0, sizeof plan->hist);
     tb_cursor = 0;
