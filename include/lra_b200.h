@@ -226,6 +226,68 @@ typedef struct lra_b200_stats_result {
 int lra_b200_calc_stats_batch(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_ir_segments *segs,
                               const float *log_lut, lra_b200_stats_result *res);
 
+/* ---- a12  LocalIndex::IndexSeq, batched over sequences ---------------------------------------------------------
+ * Replaces  void LocalIndex::IndexSeq(char *seq, int seqLen)  (MMIndex.h:200-245; StoreMinimizers_noncanonical
+ * MinCount.h:181-338, std::sort on LocalTuple::operator< TupleOps.h:30-32, RemoveFrequent MMIndex.h:69-85) for any number of
+ * sequences of one packed arena: the forward strands of a read batch (Map_highacc.h:401, Map_lowacc.h:249), their reverse
+ * complements (:402 / :250; the arena made by lra_b200_seq_revcomp), or the contigs of the genome (IndexFile, MMIndex.h:246-253:
+ * the image of <ref>.gli).  Sequence s = [seq_start[s], seq_start[s] + seq_len[s]) is cut into windows of `window` bases
+ * (<= 2048); the image holds, like the reference's LocalIndex, the window offsets (arena-relative), the tuple boundaries and
+ * the LocalTuples (uint32: tuple in bits 0..19, window-relative position in bits 20..31 -- the <ref>.gli layout, MMIndex.h:138-151). */
+typedef struct lra_b200_lindex lra_b200_lindex;
+int lra_b200_lindex_build(lra_b200_ctx *ctx, const lra_b200_seq *seq, const uint64_t *seq_start, const uint32_t *seq_len, int32_t n_seqs,
+                          int32_t k, int32_t w, int32_t window, int32_t max_freq, lra_b200_lindex **out);
+/* an image from host arrays (a <ref>.gli read by the caller): win_off[n_win + 1], bnd[n_win + 1], mins[bnd[n_win]] */
+int lra_b200_lindex_upload(lra_b200_ctx *ctx, const uint64_t *seq_start, const uint32_t *seq_len, int32_t n_seqs, int32_t window,
+                           const uint64_t *win_off, const uint64_t *bnd, const uint32_t *mins, uint64_t n_win, lra_b200_lindex **out);
+void lra_b200_lindex_sizes(const lra_b200_lindex *li, uint64_t *n_win, uint64_t *n_mins);
+/* copies the image to host arrays: win_off[n_win + 1], bnd[n_win + 1], mins[n_mins] (any may be NULL) */
+int lra_b200_lindex_download(lra_b200_ctx *ctx, const lra_b200_lindex *li, uint64_t *win_off, uint64_t *bnd, uint32_t *mins);
+void lra_b200_lindex_free(lra_b200_ctx *ctx, lra_b200_lindex *li);
+
+/* ---- a13  REFINEclusters, batched over clusters ------------------------------------------------------------------
+ * Replaces  int REFINEclusters(vector<Cluster> &clusters, vector<Cluster> &refinedclusters, Genome&, Read&, LocalIndex &glIndex,
+ *                              LocalIndex *localIndexes[2], const Options &smallOpts, const Options &opts)
+ * (ClusterRefine.h:50-240) for the clusters of a whole batch of reads.  Cluster c: anchors m_q/m_t[m_off[c] .. m_off[c+1])
+ * (read position on the cluster's strand, GLOBAL genome position), box[4c..] = qStart, qEnd, tStart, tEnd, strand[c], and
+ * read_id[c] = the sequence index of its read in reads_fwd / reads_rc.  hdr_pos = genome.header.pos (n_hdr = contigs + 1).
+ * Outputs per cluster: status (0 refined, 1 skipped: no anchors, 2 dropped by CHROMIndex: spans two contigs), chrom, the
+ * diagonal band diag[2c..] = minDiagNum, maxDiagNum, the refined anchors r_off[c] .. r_off[c+1] in the reference's order
+ * (r_q on the cluster's strand, r_t chromosome-relative, r_tup the 20-bit tuple), the refined cluster's boundaries rbox and
+ * refineEffiency (bit-identical float); m_q_out / m_t_out / box_out (may be NULL) receive what the reference leaves in clusters[ph]
+ * (chromosome-relative, forward coordinates, sorted by (t, q)). */
+typedef struct lra_b200_clusters {
+  int32_t n_clusters;
+  const uint32_t *m_q, *m_t;
+  const uint64_t *m_off;        /* [n_clusters + 1] */
+  const uint32_t *box;          /* [n_clusters * 4] */
+  const uint8_t *strand;        /* [n_clusters] */
+  const uint32_t *read_id;      /* [n_clusters] */
+  const uint64_t *hdr_pos;
+  int32_t n_hdr;
+  int32_t global_k;             /* opts.globalK */
+  int32_t small_k;              /* smallOpts.globalK (= glIndex.k) */
+  int32_t window;               /* smallOpts.window */
+  int64_t local_max_freq;       /* smallOpts.localMaxFreq */
+} lra_b200_clusters;
+
+typedef struct lra_b200_refined {
+  int32_t *status, *chrom;      /* [n_clusters] */
+  int64_t *diag;                /* [n_clusters * 2] */
+  uint64_t *r_off;              /* [n_clusters + 1] */
+  uint32_t *r_q, *r_t, *r_tup;  /* [anchor_cap] */
+  uint64_t anchor_cap;
+  uint64_t n_anchors;           /* out (== required capacity on LRA_B200_EOVERFLOW) */
+  uint32_t *rbox;               /* [n_clusters * 4] */
+  float *eff;                   /* [n_clusters] */
+  uint32_t *m_q_out, *m_t_out;  /* [m_off[n_clusters]] or NULL */
+  uint32_t *box_out;            /* [n_clusters * 4] or NULL */
+  uint64_t n_units, n_tasks;    /* out: (cluster, genome window) pairs and (cluster, genome window, read window) triples */
+} lra_b200_refined;
+
+int lra_b200_refine_clusters_batch(lra_b200_ctx *ctx, const lra_b200_lindex *genome_li, const lra_b200_lindex *reads_fwd,
+                                   const lra_b200_lindex *reads_rc, const lra_b200_clusters *cl, lra_b200_refined *res);
+
 /* ---- per-kernel timing of the last batch call (CUDA events on the context's stream) ---------------------------- */
 typedef struct lra_b200_kernel_stat {
   char name[48];

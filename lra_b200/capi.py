@@ -66,6 +66,19 @@ class _StatsResult(C.Structure):
                 ("n_cigar_total", C.c_uint64)]
 
 
+class _Clusters(C.Structure):
+    _fields_ = [("n_clusters", C.c_int32), ("m_q", C.c_void_p), ("m_t", C.c_void_p), ("m_off", C.c_void_p), ("box", C.c_void_p),
+                ("strand", C.c_void_p), ("read_id", C.c_void_p), ("hdr_pos", C.c_void_p), ("n_hdr", C.c_int32), ("global_k", C.c_int32),
+                ("small_k", C.c_int32), ("window", C.c_int32), ("local_max_freq", C.c_int64)]
+
+
+class _Refined(C.Structure):
+    _fields_ = [("status", C.c_void_p), ("chrom", C.c_void_p), ("diag", C.c_void_p), ("r_off", C.c_void_p), ("r_q", C.c_void_p),
+                ("r_t", C.c_void_p), ("r_tup", C.c_void_p), ("anchor_cap", C.c_uint64), ("n_anchors", C.c_uint64), ("rbox", C.c_void_p),
+                ("eff", C.c_void_p), ("m_q_out", C.c_void_p), ("m_t_out", C.c_void_p), ("box_out", C.c_void_p), ("n_units", C.c_uint64),
+                ("n_tasks", C.c_uint64)]
+
+
 class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("ms", C.c_float), ("jobs", C.c_uint64), ("cells", C.c_uint64),
                 ("algo_bytes", C.c_uint64)]
@@ -112,6 +125,16 @@ def load_library():
     L.lra_b200_seq_revcomp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
     L.lra_b200_seed_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_SeedReads), C.POINTER(_SeedResult)]
     L.lra_b200_calc_stats_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrSegments), C.c_void_p, C.POINTER(_StatsResult)]
+    L.lra_b200_lindex_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.POINTER(C.c_void_p)]
+    L.lra_b200_lindex_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                         C.POINTER(C.c_void_p)]
+    L.lra_b200_lindex_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.lra_b200_lindex_sizes.restype = None
+    L.lra_b200_lindex_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lra_b200_lindex_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.lra_b200_lindex_free.restype = None
+    L.lra_b200_refine_clusters_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Clusters), C.POINTER(_Refined)]
     L.lra_b200_last_kernel_stats.argtypes = [C.c_void_p, C.POINTER(KernelStat), C.c_int]
     L.lra_b200_launch_count.argtypes = [C.c_void_p]
     L.lra_b200_launch_count.restype = C.c_uint64
@@ -145,6 +168,30 @@ class SeqArena:
     def free(self):
         if self.handle:
             self.ctx.lib.lra_b200_seq_free(self.ctx.h, self.handle)
+            self.handle = None
+
+
+class LocalIndexImage:
+    """A LocalIndex resident on the device (lra_b200_lindex)."""
+    def __init__(self, ctx, handle):
+        self.ctx, self.handle = ctx, handle
+
+    def sizes(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self.ctx.lib.lra_b200_lindex_sizes(self.handle, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
+    def download(self):
+        """(win_off[n_win + 1], bnd[n_win + 1], mins) as in the reference's LocalIndex (seqOffsets without the leading 0 when the arena
+        starts at 0; tupleBoundaries; minimizers as uint32)."""
+        nw, nm = self.sizes()
+        wo = np.zeros(nw + 1, np.uint64); bd = np.zeros(nw + 1, np.uint64); mn = np.zeros(max(nm, 1), np.uint32)
+        self.ctx._check(self.ctx.lib.lra_b200_lindex_download(self.ctx.h, self.handle, _ptr(wo), _ptr(bd), _ptr(mn)))
+        return wo, bd, mn[:nm]
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.lra_b200_lindex_free(self.ctx.h, self.handle)
             self.handle = None
 
 
@@ -262,6 +309,49 @@ class Context:
             o["n_matches"] = int(res.n_matches)
             if rc == EOVERFLOW and match_cap is None:
                 cap = int(res.n_matches) + 16
+                continue
+            self._check(rc)
+            return o
+        self._check(rc)
+
+    # ---- a12
+    def lindex_build(self, seq, seq_start, seq_len, k=10, w=5, window=2048, max_freq=15):
+        """LocalIndex::IndexSeq for every sequence [seq_start[s], +seq_len[s]) of a packed arena.  Returns a LocalIndexImage."""
+        ss = np.ascontiguousarray(seq_start, np.uint64); sl = np.ascontiguousarray(seq_len, np.uint32)
+        h = C.c_void_p()
+        self._check(self.lib.lra_b200_lindex_build(self.h, seq.handle, _ptr(ss), _ptr(sl), len(ss), k, w, window, max_freq, C.byref(h)))
+        return LocalIndexImage(self, h)
+
+    def lindex_upload(self, seq_start, seq_len, window, win_off, bnd, mins):
+        ss = np.ascontiguousarray(seq_start, np.uint64); sl = np.ascontiguousarray(seq_len, np.uint32)
+        wo = np.ascontiguousarray(win_off, np.uint64); bd = np.ascontiguousarray(bnd, np.uint64); mn = np.ascontiguousarray(mins, np.uint32)
+        h = C.c_void_p()
+        self._check(self.lib.lra_b200_lindex_upload(self.h, _ptr(ss), _ptr(sl), len(ss), window, _ptr(wo), _ptr(bd), _ptr(mn) if len(mn) else None,
+                                                    len(wo) - 1, C.byref(h)))
+        return LocalIndexImage(self, h)
+
+    # ---- a13
+    def refine_clusters_batch(self, genome_li, reads_fwd, reads_rc, cl, anchor_cap=None):
+        """REFINEclusters over a batch (cl: dict(m_q, m_t, m_off, box[n,4], strand, read_id, hdr_pos, global_k, small_k, window,
+        local_max_freq)).  Returns dict(status, chrom, diag, r_off, r_q, r_t, r_tup, rbox, eff, m_q_out, m_t_out, box_out, n_anchors, ...)."""
+        n = len(cl["strand"])
+        a = dict(m_q=np.ascontiguousarray(cl["m_q"], np.uint32), m_t=np.ascontiguousarray(cl["m_t"], np.uint32), m_off=np.ascontiguousarray(cl["m_off"], np.uint64),
+                 box=np.ascontiguousarray(cl["box"], np.uint32).reshape(-1), strand=np.ascontiguousarray(cl["strand"], np.uint8),
+                 read_id=np.ascontiguousarray(cl["read_id"], np.uint32), hdr=np.ascontiguousarray(cl["hdr_pos"], np.uint64))
+        M = int(a["m_off"][n]) if n else 0
+        cap = anchor_cap if anchor_cap is not None else 4 * M + 4096
+        for _ in range(2):
+            o = dict(status=np.zeros(n, np.int32), chrom=np.zeros(n, np.int32), diag=np.zeros(2 * n, np.int64), r_off=np.zeros(n + 1, np.uint64),
+                     r_q=np.zeros(cap, np.uint32), r_t=np.zeros(cap, np.uint32), r_tup=np.zeros(cap, np.uint32), rbox=np.zeros(4 * n, np.uint32),
+                     eff=np.zeros(n, np.float32), m_q_out=np.zeros(M + 1, np.uint32), m_t_out=np.zeros(M + 1, np.uint32), box_out=np.zeros(4 * n, np.uint32))
+            c = _Clusters(n, _ptr(a["m_q"]) if M else None, _ptr(a["m_t"]) if M else None, _ptr(a["m_off"]), _ptr(a["box"]), _ptr(a["strand"]),
+                          _ptr(a["read_id"]), _ptr(a["hdr"]), len(a["hdr"]), cl["global_k"], cl["small_k"], cl["window"], cl["local_max_freq"])
+            r = _Refined(_ptr(o["status"]), _ptr(o["chrom"]), _ptr(o["diag"]), _ptr(o["r_off"]), _ptr(o["r_q"]), _ptr(o["r_t"]), _ptr(o["r_tup"]), cap, 0,
+                         _ptr(o["rbox"]), _ptr(o["eff"]), _ptr(o["m_q_out"]), _ptr(o["m_t_out"]), _ptr(o["box_out"]), 0, 0)
+            rc = self.lib.lra_b200_refine_clusters_batch(self.h, genome_li.handle, reads_fwd.handle, reads_rc.handle, C.byref(c), C.byref(r))
+            o["n_anchors"], o["n_units"], o["n_tasks"] = int(r.n_anchors), int(r.n_units), int(r.n_tasks)
+            if rc == EOVERFLOW and anchor_cap is None:
+                cap = int(r.n_anchors) + 16
                 continue
             self._check(rc)
             return o

@@ -16,6 +16,8 @@
 #include "seq_kernels.cuh"
 #include "seed_kernels.cuh"
 #include "stats_kernels.cuh"
+#include "lidx_kernels.cuh"
+#include "lref_kernels.cuh"
 
 using namespace lra;
 
@@ -43,6 +45,7 @@ struct lra_b200_ctx {
   DevBuf sg[40];          // segment-level IndelRefine scratch
   DevBuf sd[12];          // seeding scratch
   DevBuf stt[12];         // statistics scratch
+  DevBuf lr[32];          // local index / cluster refinement scratch
   bool keep_stats = false;  // sub-launchers append to stats instead of clearing
   AogPlan *h_plan = nullptr;            // pinned
   unsigned long long *h_misc = nullptr;  // pinned (2 x u64)
@@ -126,6 +129,7 @@ extern "C" void lra_b200_destroy(lra_b200_ctx *ctx) {
   for (DevBuf &b : ctx->sg) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->sd) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->stt) if (b.p) cudaFree(b.p);
+  for (DevBuf &b : ctx->lr) if (b.p) cudaFree(b.p);
   for (auto &ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < 4; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]); }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
@@ -955,3 +959,5 @@ extern "C" int lra_b200_calc_stats_batch(lra_b200_ctx *ctx, const lra_b200_seq *
   }
   return LRA_B200_OK;
 }
+
+#include "lref_host.cuh"

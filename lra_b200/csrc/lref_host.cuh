@@ -1,0 +1,283 @@
+// Host side of the C ABI for a12 (lra_b200_lindex_*) and a13 (lra_b200_refine_clusters_batch); included by lra_b200.cu.
+#pragma once
+
+struct lra_b200_lindex {
+  unsigned long long *win_off = nullptr, *bnd = nullptr, *seq_start = nullptr;
+  uint32_t *win_len = nullptr, *mins = nullptr, *win_first = nullptr, *seq_len = nullptr;
+  uint64_t n_win = 0, n_mins = 0;
+  int n_seq = 0, window = 0;
+};
+
+static void lindex_release(lra_b200_lindex *li) {
+  void *p[] = {li->win_off, li->bnd, li->seq_start, li->win_len, li->mins, li->win_first, li->seq_len};
+  for (void *x : p) if (x) cudaFree(x);
+  delete li;
+}
+
+extern "C" void lra_b200_lindex_free(lra_b200_ctx *ctx, lra_b200_lindex *li) {
+  if (!li) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  lindex_release(li);
+}
+
+extern "C" void lra_b200_lindex_sizes(const lra_b200_lindex *li, uint64_t *n_win, uint64_t *n_mins) {
+  if (n_win) *n_win = li ? li->n_win : 0;
+  if (n_mins) *n_mins = li ? li->n_mins : 0;
+}
+
+// window table of n_seqs sequences cut into `window`-base pieces (IndexSeq, MMIndex.h:200-206,227-232)
+static int lindex_layout(lra_b200_ctx *ctx, lra_b200_lindex *li, const uint64_t *seq_start, const uint32_t *seq_len, int n_seqs, int window,
+                         std::vector<unsigned long long> &win_off, std::vector<uint32_t> &win_len) {
+  std::vector<uint32_t> win_first((size_t)n_seqs + 1);
+  for (int s = 0; s < n_seqs; s++) {
+    win_first[s] = (uint32_t)win_off.size();
+    for (uint32_t p = 0; p < seq_len[s]; p += (uint32_t)window) {
+      win_off.push_back(seq_start[s] + p);
+      win_len.push_back(seq_len[s] - p < (uint32_t)window ? seq_len[s] - p : (uint32_t)window);
+    }
+  }
+  win_first[n_seqs] = (uint32_t)win_off.size();
+  li->n_win = win_off.size();
+  li->n_seq = n_seqs; li->window = window;
+  win_off.push_back(n_seqs ? seq_start[n_seqs - 1] + seq_len[n_seqs - 1] : 0ull);     // the closing offset of the last sequence
+  const size_t W = li->n_win;
+  CU(cudaMalloc(&li->win_off, (W + 1) * 8)); CU(cudaMalloc(&li->win_len, (W + 1) * 4)); CU(cudaMalloc(&li->bnd, (W + 2) * 8));
+  CU(cudaMalloc(&li->win_first, ((size_t)n_seqs + 1) * 4)); CU(cudaMalloc(&li->seq_start, ((size_t)n_seqs + 1) * 8)); CU(cudaMalloc(&li->seq_len, ((size_t)n_seqs + 1) * 4));
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(li->win_off, win_off.data(), (W + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (W) CU(cudaMemcpyAsync(li->win_len, win_len.data(), W * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(li->win_first, win_first.data(), ((size_t)n_seqs + 1) * 4, cudaMemcpyHostToDevice, st));
+  if (n_seqs) {
+    CU(cudaMemcpyAsync(li->seq_start, seq_start, (size_t)n_seqs * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(li->seq_len, seq_len, (size_t)n_seqs * 4, cudaMemcpyHostToDevice, st));
+  }
+  CU(cudaStreamSynchronize(st));     // the host vectors go out of scope with the caller
+  return LRA_B200_OK;
+}
+
+extern "C" int lra_b200_lindex_build(lra_b200_ctx *ctx, const lra_b200_seq *seq, const uint64_t *seq_start, const uint32_t *seq_len, int32_t n_seqs,
+                                     int32_t k, int32_t w, int32_t window, int32_t max_freq, lra_b200_lindex **out) {
+  if (!ctx || !seq || !out || n_seqs < 0 || (n_seqs && (!seq_start || !seq_len))) return fail(ctx, LRA_B200_EINVAL, "lindex_build: bad argument");
+  if (k < 1 || k > 10 || w < 1 || window < 1 || window > kLidxMaxWindow || max_freq < 1)
+    return fail(ctx, LRA_B200_EINVAL, "lindex_build: need 1 <= k <= 10 (20-bit LocalTuple), w >= 1, 1 <= window <= %d, max_freq >= 1", kLidxMaxWindow);
+  for (int s = 0; s < n_seqs; s++)
+    if (seq_start[s] + seq_len[s] > seq->n) return fail(ctx, LRA_B200_EINVAL, "lindex_build: sequence %d ends beyond the arena", s);
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  *out = nullptr;
+  lra_b200_lindex *li = new lra_b200_lindex();
+  std::vector<unsigned long long> win_off; std::vector<uint32_t> win_len;
+  int rc = lindex_layout(ctx, li, seq_start, seq_len, n_seqs, window, win_off, win_len);
+  if (rc) { lindex_release(li); return rc; }
+  const size_t W = li->n_win;
+  cudaStream_t st = ctx->stream;
+  if (W == 0) { CU(cudaMemsetAsync(li->bnd, 0, 16, st)); CU(cudaStreamSynchronize(st)); *out = li; return LRA_B200_OK; }
+  // staging: one slot per arena base (transient; 4 B/base -- 12 GB for a 3 Gb genome, freed below)
+  uint32_t *tmp = nullptr;
+  if (cudaMalloc(&tmp, ((size_t)seq->n + 64) * 4) != cudaSuccess) { lindex_release(li); return fail(ctx, LRA_B200_ECUDA, "lindex_build: cannot allocate %zu bytes of staging", ((size_t)seq->n + 64) * 4); }
+  LidxBuild b;
+  b.seq = SeqView{seq->b2, seq->nm, seq->n};
+  b.win_off = li->win_off; b.win_len = li->win_len; b.n_win = (int)W; b.k = k; b.w = w; b.max_freq = max_freq;
+  b.tmp = tmp; b.cnt = li->bnd; b.mins = nullptr;
+  if ((rc = ensure(ctx, ctx->lr[0], 64))) { cudaFree(tmp); lindex_release(li); return rc; }
+  cudaMemsetAsync(ctx->lr[0].p, 0, 64, st);
+  cudaEventRecord(ctx->ev[0], st);
+  lidx_window_kernel<<<(unsigned)((W + kLidxWarps - 1) / kLidxWarps), 32 * kLidxWarps, 0, st>>>(b);
+  cudaEventRecord(ctx->ev[1], st);
+  seed_scan_kernel<<<1, 1024, 0, st>>>(li->bnd, (int)W, ~0ull, (int *)ctx->lr[0].p);
+  ctx->launches += 2;
+  unsigned long long total = 0;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&total, li->bnd + W, 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaMalloc(&li->mins, ((size_t)total + 16) * 4);
+  if (e != cudaSuccess) { cudaFree(tmp); lindex_release(li); return fail(ctx, LRA_B200_ECUDA, "lindex_build: %s", cudaGetErrorString(e)); }
+  li->n_mins = total;
+  b.mins = li->mins;
+  cudaEventRecord(ctx->ev[2], st);
+  lidx_compact_kernel<<<(unsigned)((W + 7) / 8), 256, 0, st>>>(b);
+  cudaEventRecord(ctx->ev[3], st);
+  ctx->launches++;
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(tmp);
+  if (e != cudaSuccess) { lindex_release(li); return fail(ctx, LRA_B200_ECUDA, "lindex_build: %s", cudaGetErrorString(e)); }
+  {
+    lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "lidx_window");
+    cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]); s2.jobs = W;
+    // algorithmic bytes: 2-bit bases + mask read once, the kept tuples written once
+    s2.algo_bytes = (seq->n * 3) / 8 + 12 * W + 4ull * total;
+    ctx->stats.push_back(s2);
+    memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "lidx_scan+compact");
+    cudaEventElapsedTime(&s2.ms, ctx->ev[1], ctx->ev[3]); s2.jobs = W; s2.algo_bytes = 8ull * total + 16 * W;
+    ctx->stats.push_back(s2);
+  }
+  *out = li;
+  return LRA_B200_OK;
+}
+
+extern "C" int lra_b200_lindex_upload(lra_b200_ctx *ctx, const uint64_t *seq_start, const uint32_t *seq_len, int32_t n_seqs, int32_t window,
+                                      const uint64_t *win_off, const uint64_t *bnd, const uint32_t *mins, uint64_t n_win, lra_b200_lindex **out) {
+  if (!ctx || !out || n_seqs < 0 || !seq_start || !seq_len || !win_off || !bnd || (bnd[n_win] && !mins) || window < 1 || window > kLidxMaxWindow)
+    return fail(ctx, LRA_B200_EINVAL, "lindex_upload: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  *out = nullptr;
+  lra_b200_lindex *li = new lra_b200_lindex();
+  std::vector<unsigned long long> wo; std::vector<uint32_t> wl;
+  int rc = lindex_layout(ctx, li, seq_start, seq_len, n_seqs, window, wo, wl);
+  if (rc) { lindex_release(li); return rc; }
+  if (li->n_win != n_win) { lindex_release(li); return fail(ctx, LRA_B200_EINVAL, "lindex_upload: %llu windows given, the sequences have %llu", (unsigned long long)n_win, (unsigned long long)wo.size() - 1); }
+  for (uint64_t i = 0; i <= n_win; i++)
+    if (win_off[i] != wo[i]) { lindex_release(li); return fail(ctx, LRA_B200_EINVAL, "lindex_upload: window offset %llu differs from the sequence layout", (unsigned long long)i); }
+  li->n_mins = bnd[n_win];
+  cudaStream_t st = ctx->stream;
+  cudaError_t e = cudaMalloc(&li->mins, ((size_t)li->n_mins + 16) * 4);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(li->bnd, bnd, (n_win + 1) * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && li->n_mins) e = cudaMemcpyAsync(li->mins, mins, (size_t)li->n_mins * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { lindex_release(li); return fail(ctx, LRA_B200_ECUDA, "lindex_upload: %s", cudaGetErrorString(e)); }
+  *out = li;
+  return LRA_B200_OK;
+}
+
+extern "C" int lra_b200_lindex_download(lra_b200_ctx *ctx, const lra_b200_lindex *li, uint64_t *win_off, uint64_t *bnd, uint32_t *mins) {
+  if (!ctx || !li) return fail(ctx, LRA_B200_EINVAL, "lindex_download: NULL argument");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (win_off) CU(cudaMemcpyAsync(win_off, li->win_off, (li->n_win + 1) * 8, cudaMemcpyDeviceToHost, st));
+  if (bnd) CU(cudaMemcpyAsync(bnd, li->bnd, (li->n_win + 1) * 8, cudaMemcpyDeviceToHost, st));
+  if (mins && li->n_mins) CU(cudaMemcpyAsync(mins, li->mins, (size_t)li->n_mins * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return LRA_B200_OK;
+}
+
+static LidxView lidx_view(const lra_b200_lindex *li) {
+  return LidxView{li->win_off, li->win_len, li->bnd, li->mins, li->win_first, li->seq_start, li->seq_len, (int)li->n_win, li->n_seq};
+}
+
+extern "C" int lra_b200_refine_clusters_batch(lra_b200_ctx *ctx, const lra_b200_lindex *gl, const lra_b200_lindex *rf, const lra_b200_lindex *rr,
+                                              const lra_b200_clusters *cl, lra_b200_refined *res) {
+  if (!ctx || !gl || !rf || !rr || !cl || !res) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: NULL argument");
+  const int n = cl->n_clusters;
+  if (n < 0 || cl->n_hdr < 2 || !cl->hdr_pos) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: bad cluster batch");
+  if (rf->n_seq != rr->n_seq) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: the two read images differ in their number of reads");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  res->n_anchors = 0; res->n_units = 0; res->n_tasks = 0;
+  if (n == 0) { if (res->r_off) res->r_off[0] = 0; return LRA_B200_OK; }
+  for (int c = 0; c < n; c++)
+    if (cl->read_id[c] >= (uint32_t)rf->n_seq) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: cluster %d names read %u of %d", c, cl->read_id[c], rf->n_seq);
+  const size_t M = (size_t)cl->m_off[n];
+  std::vector<unsigned long long> key_off((size_t)n);
+  size_t keys_total = 0;
+  for (int c = 0; c < n; c++) {
+    const size_t nm = (size_t)(cl->m_off[c + 1] - cl->m_off[c]);
+    size_t P = 1; while (P < nm) P <<= 1;
+    key_off[c] = keys_total; keys_total += P;
+  }
+  int rc;
+  DevBuf *B = ctx->lr;
+  const size_t acap = (size_t)(res->anchor_cap ? res->anchor_cap : 1);
+  if ((rc = ensure(ctx, B[1], M * 4 + 16)) || (rc = ensure(ctx, B[2], M * 4 + 16)) || (rc = ensure(ctx, B[3], ((size_t)n + 1) * 8)) ||
+      (rc = ensure(ctx, B[4], (size_t)n * 16)) || (rc = ensure(ctx, B[5], (size_t)n)) || (rc = ensure(ctx, B[6], (size_t)n * 4)) ||
+      (rc = ensure(ctx, B[7], (size_t)cl->n_hdr * 8)) || (rc = ensure(ctx, B[8], M * 4 + 16)) || (rc = ensure(ctx, B[9], M * 4 + 16)) ||
+      (rc = ensure(ctx, B[10], (size_t)n * 16)) || (rc = ensure(ctx, B[11], keys_total * 8 + 16)) || (rc = ensure(ctx, B[12], (size_t)n * 8)) ||
+      (rc = ensure(ctx, B[13], (size_t)n * 4)) || (rc = ensure(ctx, B[14], (size_t)n * 4)) || (rc = ensure(ctx, B[15], (size_t)n * 16)) ||
+      (rc = ensure(ctx, B[16], (size_t)n * 4)) || (rc = ensure(ctx, B[17], (size_t)n * 4)) || (rc = ensure(ctx, B[18], ((size_t)n + 1) * 8)) ||
+      (rc = ensure(ctx, B[24], acap * 4)) || (rc = ensure(ctx, B[25], acap * 4)) || (rc = ensure(ctx, B[26], acap * 4)) ||
+      (rc = ensure(ctx, B[27], ((size_t)n + 1) * 8)) || (rc = ensure(ctx, B[28], (size_t)n * 16)) || (rc = ensure(ctx, B[29], (size_t)n * 4)) ||
+      (rc = ensure(ctx, B[0], 64)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  if (M) { CU(cudaMemcpyAsync(B[1].p, cl->m_q, M * 4, cudaMemcpyHostToDevice, st)); CU(cudaMemcpyAsync(B[2].p, cl->m_t, M * 4, cudaMemcpyHostToDevice, st)); }
+  CU(cudaMemcpyAsync(B[3].p, cl->m_off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[4].p, cl->box, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[5].p, cl->strand, (size_t)n, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[6].p, cl->read_id, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[7].p, cl->hdr_pos, (size_t)cl->n_hdr * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[12].p, key_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(B[0].p, 0, 64, st));
+  LrefBatch b;
+  memset(&b, 0, sizeof b);
+  b.n_clusters = n;
+  b.in_q = (const uint32_t *)B[1].p; b.in_t = (const uint32_t *)B[2].p; b.m_off = (const unsigned long long *)B[3].p; b.in_box = (const uint32_t *)B[4].p;
+  b.strand = (const uint8_t *)B[5].p; b.read_id = (const uint32_t *)B[6].p; b.hdr_pos = (const unsigned long long *)B[7].p; b.n_hdr = cl->n_hdr;
+  b.gl = lidx_view(gl); b.rd[0] = lidx_view(rf); b.rd[1] = lidx_view(rr);
+  b.global_k = cl->global_k; b.small_k = cl->small_k; b.window = cl->window; b.local_max_freq = cl->local_max_freq;
+  b.m_q = (uint32_t *)B[8].p; b.m_t = (uint32_t *)B[9].p; b.box = (uint32_t *)B[10].p; b.keys = (unsigned long long *)B[11].p;
+  b.key_off = (const unsigned long long *)B[12].p; b.status = (int32_t *)B[13].p; b.chrom = (int32_t *)B[14].p; b.diag = (long long *)B[15].p;
+  b.chrom_off = (uint32_t *)B[16].p; b.ls = (int32_t *)B[17].p; b.unit_off = (unsigned long long *)B[18].p;
+  b.r_q = (uint32_t *)B[24].p; b.r_t = (uint32_t *)B[25].p; b.r_tup = (uint32_t *)B[26].p; b.out_cap = res->anchor_cap;
+  b.r_off = (unsigned long long *)B[27].p; b.rbox = (uint32_t *)B[28].p; b.eff = (float *)B[29].p;
+  int *errflag = (int *)B[0].p;
+  int evi = 0;
+  auto rec = [&]() { cudaEventRecord(ctx->ev[evi++], st); };
+  rec();
+  lref_prep_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(b);
+  seed_scan_kernel<<<1, 1024, 0, st>>>(b.unit_off, n, ~0ull, errflag);
+  ctx->launches += 2;
+  rec();
+  CU(cudaGetLastError());
+  unsigned long long n_units = 0, n_tasks = 0, n_out = 0;
+  CU(cudaMemcpyAsync(&n_units, b.unit_off + n, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if ((rc = ensure(ctx, B[19], (size_t)(n_units + 1) * 4)) || (rc = ensure(ctx, B[20], (size_t)(n_units + 1) * 4)) ||
+      (rc = ensure(ctx, B[21], (size_t)(n_units + 1) * 4)) || (rc = ensure(ctx, B[22], (size_t)(n_units + 2) * 8)))
+    return rc;
+  b.u_cluster = (uint32_t *)B[19].p; b.u_qis = (uint32_t *)B[20].p; b.u_gstart = (uint32_t *)B[21].p; b.task_off = (unsigned long long *)B[22].p;
+  CU(cudaMemsetAsync(b.task_off, 0, (size_t)(n_units + 2) * 8, st));
+  if (n_units) {
+    if (n_units > 0x7FFFFFFFull) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: %llu (cluster, window) units in one batch", n_units);
+    lref_unit_kernel<<<(unsigned)((n_units + 127) / 128), 128, 0, st>>>(b, n_units);
+    seed_scan_kernel<<<1, 1024, 0, st>>>(b.task_off, (int)n_units, ~0ull, errflag);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&n_tasks, b.task_off + n_units, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  rec();
+  if ((rc = ensure(ctx, B[23], (size_t)(n_tasks + 2) * 8))) return rc;
+  b.out_off = (unsigned long long *)B[23].p;
+  CU(cudaMemsetAsync(b.out_off, 0, (size_t)(n_tasks + 2) * 8, st));
+  if (n_tasks) {
+    if (n_tasks > 0x7FFFFFFFull) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: %llu window pairs in one batch", n_tasks);
+    lref_task_kernel<false><<<(unsigned)((n_tasks + 127) / 128), 128, 0, st>>>(b, n_units, n_tasks);
+    seed_scan_kernel<<<1, 1024, 0, st>>>(b.out_off, (int)n_tasks, res->anchor_cap, errflag);
+    rec();
+    lref_task_kernel<true><<<(unsigned)((n_tasks + 127) / 128), 128, 0, st>>>(b, n_units, n_tasks);
+    ctx->launches += 3;
+  } else rec();
+  rec();
+  lref_finish_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(b, n_units, n_tasks);
+  ctx->launches++;
+  rec();
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(&n_out, b.out_off + n_tasks, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->status, b.status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->chrom, b.chrom, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->diag, b.diag, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->r_off, b.r_off, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->rbox, b.rbox, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->eff, b.eff, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (res->box_out) CU(cudaMemcpyAsync(res->box_out, b.box, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+  if (M && res->m_q_out) CU(cudaMemcpyAsync(res->m_q_out, b.m_q, M * 4, cudaMemcpyDeviceToHost, st));
+  if (M && res->m_t_out) CU(cudaMemcpyAsync(res->m_t_out, b.m_t, M * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  res->n_anchors = n_out; res->n_units = n_units; res->n_tasks = n_tasks;
+  static const char *names[5] = {"lref_prep(+sort)", "lref_unit", "lref_task<count>", "lref_task<emit>", "lref_finish"};
+  const uint64_t jobs[5] = {(uint64_t)n, n_units, n_tasks, n_tasks, (uint64_t)n};
+  for (int i = 0; i < 5; i++) {
+    lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "%s", names[i]);
+    cudaEventElapsedTime(&s2.ms, ctx->ev[i], ctx->ev[i + 1]); s2.jobs = jobs[i];
+    ctx->stats.push_back(s2);
+  }
+  if (n_out > res->anchor_cap) return fail(ctx, LRA_B200_EOVERFLOW, "refine_clusters_batch: anchor capacity %llu too small, %llu needed",
+                                           (unsigned long long)res->anchor_cap, n_out);
+  if (n_out) {
+    CU(cudaMemcpyAsync(res->r_q, b.r_q, (size_t)n_out * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->r_t, b.r_t, (size_t)n_out * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->r_tup, b.r_tup, (size_t)n_out * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return LRA_B200_OK;
+}

@@ -1,0 +1,340 @@
+// a13: REFINEclusters (reference ClusterRefine.h:50-240), batched over clusters.
+//   Cluster::CHROMIndex / Header::Find / GetNextOffset   Clustering.h:326-336, Genome.h:19-47
+//   SwapStrand                                           ClusterRefine.h:24-31
+//   CartesianTargetSort / LowerBound / UpperBound        Sorting.h:182-224      (a total order on (t, q): any correct sort)
+//   LocalIndex::LookupIndex                              MMIndex.h:175-190
+//   CompareLists<LocalTuple,SmallTuple>(Global = false)  CompareLists.h:8-146   (literal: front/back galloping, emission order kept)
+//   AppendValues (diagonal band + cluster box)           TupleOps.h:159-195
+//   Cluster::SetClusterBoundariesFromMatches             Clustering.h:308-322
+//
+// The reference's triple loop  cluster -> genome window lsi -> read window qi  is flattened into three launches:
+//   lref_prep_kernel     one warp per cluster: contig, strand swap, diagonal band, sort by (t, q), window range [ls, le]
+//   lref_unit_kernel     one thread per (cluster, lsi): anchors inside the window -> read interval -> read windows [qis, qie]
+//   lref_task_kernel<E>  one thread per (cluster, lsi, qi): CompareLists of two ~700-tuple lists + the band/box filter;
+//                        count pass, scan, emit pass: refined anchors land in the reference's order
+//   lref_finish_kernel   one warp per cluster: strand swap back, boundaries, refineEffiency (binary32 division)
+#pragma once
+#include "lra_common.cuh"
+#include "lidx_kernels.cuh"
+
+namespace lra {
+
+struct LidxView {                      // a LocalIndex image (lidx_kernels.cuh)
+  const unsigned long long *win_off;   // [n_win + 1] arena position of each window; last entry = end of the last sequence
+  const uint32_t *win_len;             // [n_win]
+  const unsigned long long *bnd;       // [n_win + 1] tuple boundaries
+  const uint32_t *mins;
+  const uint32_t *win_first;           // [n_seq + 1] first window of each sequence
+  const unsigned long long *seq_start; // [n_seq] arena position of each sequence
+  const uint32_t *seq_len;             // [n_seq]
+  int n_win, n_seq;
+};
+
+struct LrefBatch {
+  int n_clusters;
+  // clusters (input)
+  const uint32_t *in_q, *in_t;         // anchors, concatenated
+  const unsigned long long *m_off;     // [n_clusters + 1]
+  const uint32_t *in_box;              // [n_clusters][4] qStart, qEnd, tStart, tEnd (tStart / tEnd global)
+  const uint8_t *strand;               // [n_clusters]
+  const uint32_t *read_id;             // [n_clusters] sequence index in the read LocalIndex images
+  const unsigned long long *hdr_pos;   // genome.header.pos
+  int n_hdr;
+  LidxView gl, rd[2];                  // genome; reads forward / reverse complement
+  int global_k, small_k, window;
+  long long local_max_freq;
+  // working copy of the clusters = what the reference leaves in clusters[ph] (output)
+  uint32_t *m_q, *m_t;
+  uint32_t *box;                       // [n_clusters][4]
+  unsigned long long *keys;            // sort scratch, key_off[c] .. (power-of-two sized slots)
+  const unsigned long long *key_off;   // [n_clusters]
+  // per cluster
+  int32_t *status, *chrom;             // status: 0 refined, 1 no anchors, 2 spans two contigs
+  long long *diag;                     // [n_clusters][2] minDiagNum, maxDiagNum
+  uint32_t *chrom_off;                 // [n_clusters]
+  int32_t *ls;                         // [n_clusters]
+  unsigned long long *unit_off;        // [n_clusters + 1] number of windows le - ls + 1, then offsets
+  // per unit (cluster, lsi)
+  uint32_t *u_cluster, *u_qis, *u_gstart;
+  unsigned long long *task_off;        // [n_units + 1]
+  // per task
+  unsigned long long *out_off;         // [n_tasks + 1]
+  // refined anchors
+  uint32_t *r_q, *r_t, *r_tup;
+  unsigned long long out_cap;
+  unsigned long long *r_off;           // [n_clusters + 1] first refined anchor of each cluster
+  uint32_t *rbox;                      // [n_clusters][4]
+  float *eff;                          // [n_clusters]
+};
+
+__device__ __forceinline__ int lref_hdr_find(const unsigned long long *pos, int n, unsigned long long query) {   // Header::Find
+  if (n > 0 && query == pos[0]) return 0;
+  int lo = 0, len = n;
+  while (len > 0) { const int half = len >> 1; if (pos[lo + half] < query) { lo += half + 1; len -= half + 1; } else len = half; }
+  if (lo < n && query == pos[lo]) return lo;
+  return lo - 1;
+}
+
+// LocalIndex::LookupIndex over the offsets {off[0], .., off[n_win - 1], end} minus `base`
+__device__ __forceinline__ int lref_lookup(const unsigned long long *off, int n_win, unsigned long long base, unsigned long long end, unsigned long long query) {
+  int lo = 0, len = n_win + 1;
+  while (len > 0) {
+    const int half = len >> 1, mid = lo + half;
+    const unsigned long long o = (mid < n_win ? off[mid] : end) - base;
+    if (o < query) { lo = mid + 1; len -= half + 1; } else len = half;
+  }
+  if (lo <= n_win && ((lo < n_win ? off[lo] : end) - base) == query) return lo;
+  return lo - 1;
+}
+
+__global__ void __launch_bounds__(128) lref_prep_kernel(LrefBatch b) {
+  const int lane = threadIdx.x & 31;
+  const int c = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (c >= b.n_clusters) return;
+  const unsigned long long m0 = b.m_off[c];
+  const int nm = (int)(b.m_off[c + 1] - m0);
+  uint32_t *mq = b.m_q + m0, *mt = b.m_t + m0;
+  uint32_t *box = b.box + 4 * c;
+  if (lane < 4) box[lane] = b.in_box[4 * c + lane];
+  if (lane == 0) { b.unit_off[c] = 0; b.chrom[c] = 0; b.diag[2 * c] = 0; b.diag[2 * c + 1] = 0; b.chrom_off[c] = 0; b.ls[c] = 0; }
+  __syncwarp();
+  if (nm == 0) { if (lane == 0) b.status[c] = 1; return; }
+  const uint32_t tStart = box[2], tEnd = box[3];
+  const int first = lref_hdr_find(b.hdr_pos, b.n_hdr, (unsigned long long)tStart + 1), last = lref_hdr_find(b.hdr_pos, b.n_hdr, (unsigned long long)tEnd);
+  if (first != last) {
+    if (lane == 0) b.status[c] = 2;
+    for (int i = lane; i < nm; i += 32) { mq[i] = b.in_q[m0 + i]; mt[i] = b.in_t[m0 + i]; }
+    return;
+  }
+  const uint32_t chromOffset = (uint32_t)b.hdr_pos[first];
+  const uint32_t chromEndOffset = (uint32_t)b.hdr_pos[last + 1];
+  const int strand = b.strand[c];
+  const uint32_t readLen = b.rd[0].seq_len[b.read_id[c]];
+  long long maxDN = -(1ll << 62), minDN = (1ll << 62);
+  unsigned long long *keys = b.keys + b.key_off[c];
+  int P = 1;
+  while (P < nm) P <<= 1;
+  for (int i = lane; i < P; i += 32) {
+    if (i < nm) {
+      uint32_t q = b.in_q[m0 + i];
+      const uint32_t t = b.in_t[m0 + i] - chromOffset;
+      if (strand == 1) q = readLen - (q + (uint32_t)b.global_k);
+      const long long d = (long long)t - (long long)q;
+      maxDN = d > maxDN ? d : maxDN; minDN = d < minDN ? d : minDN;
+      keys[i] = ((unsigned long long)t << 32) | q;
+    } else keys[i] = ~0ull;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long a = __shfl_xor_sync(0xffffffffu, maxDN, o), bb = __shfl_xor_sync(0xffffffffu, minDN, o);
+    maxDN = a > maxDN ? a : maxDN; minDN = bb < minDN ? bb : minDN;
+  }
+  maxDN += 100; minDN -= 100;
+  __syncwarp();
+  for (int kk = 2; kk <= P; kk <<= 1) {          // CartesianTargetSort
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < P; i += 32) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], cc = keys[ixj];
+          const bool up = (i & kk) == 0;
+          if ((a > cc) == up) { keys[i] = cc; keys[ixj] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < nm; i += 32) { const unsigned long long kx = keys[i]; mt[i] = (uint32_t)(kx >> 32); mq[i] = (uint32_t)kx; }
+  if (lane == 0) {
+    if (strand == 1) { const uint32_t r = box[0]; box[0] = readLen - box[1]; box[1] = readLen - r; }
+    uint32_t wts, wte;
+    if (chromOffset + (uint32_t)b.window > tStart) wts = chromOffset; else wts = tStart - (uint32_t)b.window;
+    if (tEnd + (uint32_t)b.window > chromEndOffset) wte = chromEndOffset - 1; else wte = tEnd + (uint32_t)b.window;
+    const unsigned long long gend = b.gl.win_off[b.gl.n_win];
+    const int ls = lref_lookup(b.gl.win_off, b.gl.n_win, 0ull, gend, wts), le = lref_lookup(b.gl.win_off, b.gl.n_win, 0ull, gend, wte);
+    b.status[c] = 0; b.chrom[c] = first; b.diag[2 * c] = minDN; b.diag[2 * c + 1] = maxDN; b.chrom_off[c] = chromOffset; b.ls[c] = ls;
+    b.unit_off[c] = le >= ls ? (unsigned long long)(le - ls + 1) : 0ull;
+  }
+}
+
+// one thread per (cluster, lsi)
+__global__ void __launch_bounds__(128) lref_unit_kernel(LrefBatch b, unsigned long long n_units) {
+  const unsigned long long u = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_units) return;
+  int c;
+  { int lo = 0, len = b.n_clusters;      // the cluster whose unit range contains u: last c with unit_off[c] <= u
+    while (len > 0) { const int half = len >> 1; if (b.unit_off[lo + half] <= u) { lo += half + 1; len -= half + 1; } else len = half; }
+    c = lo - 1; }
+  const int ls = b.ls[c];
+  const int lsi = ls + (int)(u - b.unit_off[c]);
+  const int le = ls + (int)(b.unit_off[c + 1] - b.unit_off[c]) - 1;
+  b.u_cluster[u] = (uint32_t)c; b.u_qis[u] = 0; b.u_gstart[u] = 0; b.task_off[u] = 0;
+  const uint32_t chromOffset = b.chrom_off[c];
+  const unsigned long long o0 = b.gl.win_off[lsi], o1 = b.gl.win_off[lsi + 1];
+  if (o0 < chromOffset || o1 < chromOffset) return;
+  const uint32_t gStart = (uint32_t)(o0 - chromOffset), gEnd = (uint32_t)(o1 - 1 - chromOffset);
+  if (gStart >= gEnd) return;
+  const unsigned long long m0 = b.m_off[c];
+  const int nm = (int)(b.m_off[c + 1] - m0);
+  const uint32_t *mq = b.m_q + m0, *mt = b.m_t + m0;
+  int matchStart, matchEnd;
+  { int lo = 0, len = nm;
+    while (len > 0) { const int half = len >> 1; if (mt[lo + half] < gStart) { lo += half + 1; len -= half + 1; } else len = half; }
+    matchStart = lo; }
+  { int lo = matchStart, len = nm - matchStart;
+    while (len > 0) {
+      const int half = len >> 1, mid = lo + half;
+      const bool less = (gEnd != mt[mid]) ? (gEnd < mt[mid]) : (0u < mq[mid]);
+      if (less) len = half; else { lo = mid + 1; len -= half + 1; }
+    }
+    matchEnd = lo; }
+  if (matchEnd == nm) matchEnd--;
+  if (matchStart >= nm) return;
+  const int s = b.strand[c];
+  const uint32_t rid = b.read_id[c];
+  const uint32_t readLen = b.rd[s].seq_len[rid];
+  uint32_t readStart = mq[matchStart], readEnd = mq[matchEnd];
+  if (readStart == readEnd) { if (lsi > ls && readStart > 0u) readStart = 0u; }   // prev_readEnd is 0 at its only read (ClusterRefine.h:152,162)
+  if (lsi == ls) { if (readStart < (uint32_t)b.window) readStart = 0; else readStart -= (uint32_t)b.window; }
+  if (lsi == le) { if (readEnd + (uint32_t)b.window > readLen) readEnd = readLen; else readEnd += (uint32_t)b.window; }
+  if (readStart > readEnd) return;
+  const LidxView &rd = b.rd[s];
+  const int wf = (int)rd.win_first[rid], nw = (int)rd.win_first[rid + 1] - wf;
+  const unsigned long long base = rd.seq_start[rid], end = base + readLen;
+  const int qis = lref_lookup(rd.win_off + wf, nw, base, end, readStart);
+  const int qie = lref_lookup(rd.win_off + wf, nw, base, end, readEnd < readLen - 1 ? readEnd : readLen - 1);
+  b.u_qis[u] = (uint32_t)qis; b.u_gstart[u] = gStart;
+  b.task_off[u] = qie >= qis ? (unsigned long long)(qie - qis + 1) : 0ull;
+}
+
+// one thread per (cluster, lsi, qi): CompareLists<LocalTuple,SmallTuple>(Global = false) + AppendValues
+template <bool EMIT>
+__global__ void __launch_bounds__(128) lref_task_kernel(LrefBatch b, unsigned long long n_units, unsigned long long n_tasks) {
+  const unsigned long long task = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (task >= n_tasks) return;
+  unsigned long long u;
+  { unsigned long long lo = 0, len = n_units;
+    while (len > 0) { const unsigned long long half = len >> 1; if (b.task_off[lo + half] <= task) { lo += half + 1; len -= half + 1; } else len = half; }
+    u = lo - 1; }
+  const int c = (int)b.u_cluster[u];
+  const int lsi = b.ls[c] + (int)(u - b.unit_off[c]);
+  const int s = b.strand[c];
+  const uint32_t rid = b.read_id[c];
+  const LidxView &rd = b.rd[s];
+  const int qw = (int)rd.win_first[rid] + (int)b.u_qis[u] + (int)(task - b.task_off[u]);
+  const uint32_t *q = rd.mins + rd.bnd[qw];
+  const long nq = (long)(rd.bnd[qw + 1] - rd.bnd[qw]);
+  const uint32_t *t = b.gl.mins + b.gl.bnd[lsi];
+  const long nt = (long)(b.gl.bnd[lsi + 1] - b.gl.bnd[lsi]);
+  const uint32_t readSegmentStart = (uint32_t)(rd.win_off[qw] - rd.seq_start[rid]);
+  const uint32_t gStart = b.u_gstart[u];
+  const long long minDN = b.diag[2 * c], maxDN = b.diag[2 * c + 1];
+  const uint32_t *box = b.box + 4 * c;
+  const uint32_t chromOffset = b.chrom_off[c];
+  const uint32_t bqs = box[0], bqe = box[1], bts = box[2] - chromOffset, bte = box[3] - chromOffset;
+  const long maxFreq = (long)b.local_max_freq;
+  unsigned long long n_out = 0;
+  const unsigned long long obase = EMIT ? b.out_off[task] : 0ull;
+  auto push = [&](long qi, long ti) {
+    const uint32_t qv = q[qi], tv = t[ti];
+    const uint32_t qp = (qv >> 20) + readSegmentStart, tp = (tv >> 20) + gStart;
+    const long long d = (long long)tp - (long long)qp;
+    if (d >= minDN && d <= maxDN && qp >= bqs && qp < bqe && tp >= bts && tp < bte) {
+      if (EMIT) {
+        const unsigned long long o = obase + n_out;
+        if (o < b.out_cap) { b.r_q[o] = qp; b.r_t[o] = tp; b.r_tup[o] = lt_t(qv); }
+      }
+      n_out++;
+    }
+  };
+#define QK(i) lt_t(q[i])
+#define TK(i) lt_t(t[i])
+  if (nq > 0 && nt > 0) {
+    long qs = 0, qe = nq - 1, ts = 0, te = nt;
+    do {
+      while (qs <= qe && QK(qs) < TK(ts)) qs++;
+      if (qs >= qe) break;
+      const uint32_t startGap = (QK(qs) - TK(ts)) & 0xFFFFFu;       // LocalTuple bit-field arithmetic: 20 bits
+      while (qe > qs && te > ts && QK(qe) > TK(te - 1)) qe--;
+      const uint32_t endGap = (TK(te - 1) - QK(qe)) & 0xFFFFFu;
+      if (startGap == 0 || startGap > endGap) {
+        const long tsOrig = ts, qsOrig = qs;
+        { long lo = ts, len = te - ts;
+          const uint32_t key = QK(qs);
+          while (len > 0) { const long half = len >> 1, mid = lo + half; if (TK(mid) < key) { lo = mid + 1; len = len - half - 1; } else len = half; }
+          ts = lo; }
+        if (ts < nt && TK(ts) == QK(qs)) {
+          const long tsStart = ts;
+          long tsi = ts;
+          while (tsi != te && QK(qs) == TK(tsi)) tsi++;
+          const long qsStart = qs;
+          while (qs < qe && QK(qs + 1) == QK(qs)) qs++;
+          for (long ti = tsStart; ti != tsi; ti++)
+            if (qs - qsStart < maxFreq)
+              for (long qi = qsStart; qi <= qs; qi++) push(qi, ti);
+        }
+        { const uint32_t k0 = TK(tsOrig); while (ts < te && TK(ts) == k0) ts++; }
+        { const uint32_t k0 = QK(qsOrig); while (qs < qe && QK(qs) == k0) qs++; }
+      } else {
+        if (te != nt && TK(te - 1) == QK(qe)) { /* pass */ }
+        else {
+          long lo = ts, len = te - ts;
+          const uint32_t key = QK(qe);
+          while (len > 0) { const long half = len >> 1, mid = lo + half; if (key < TK(mid)) len = half; else { lo = mid + 1; len = len - half - 1; } }
+          te = lo;
+        }
+        const long teStart = te;
+        long tei = te;
+        while (tei > ts && TK(tei - 1) == QK(qe)) tei--;
+        if (tei < teStart && teStart > 0) {
+          const long qeStart = qe;
+          while (qe > qs && QK(qe) == QK(qe - 1)) qe--;
+          for (long ti = tei; ti < teStart; ti++)
+            if (qeStart - qe < maxFreq)
+              for (long qi = qe; qi <= qeStart; qi++) push(qi, ti);
+        }
+        te = tei;
+      }
+    } while (qs < qe && ts < te);
+  }
+#undef QK
+#undef TK
+  if (!EMIT) b.out_off[task] = n_out;
+}
+
+// one warp per cluster: range of its refined anchors, strand swap back, boundaries, efficiency
+__global__ void __launch_bounds__(128) lref_finish_kernel(LrefBatch b, unsigned long long n_units, unsigned long long n_tasks) {
+  const int lane = threadIdx.x & 31;
+  const int c = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (c >= b.n_clusters) return;
+  // first task of the cluster's first unit / of the next cluster's first unit
+  const unsigned long long u0 = b.unit_off[c], u1 = b.unit_off[c + 1];
+  const unsigned long long t0 = u0 < n_units ? b.task_off[u0] : n_tasks, t1 = u1 < n_units ? b.task_off[u1] : n_tasks;
+  const unsigned long long o0 = b.out_off[t0], o1 = b.out_off[t1];
+  if (lane == 0) { b.r_off[c] = o0; if (c == b.n_clusters - 1) b.r_off[c + 1] = b.out_off[n_tasks]; }
+  const unsigned long long n = o1 - o0;
+  uint32_t *rb = b.rbox + 4 * c;
+  if (n == 0 || o1 > b.out_cap) { if (lane < 4) rb[lane] = 0; if (lane == 0) b.eff[c] = 0.0f; return; }
+  const int s = b.strand[c];
+  const uint32_t readLen = b.rd[0].seq_len[b.read_id[c]];
+  const uint32_t K = (uint32_t)b.small_k;
+  uint32_t qS = 0xFFFFFFFFu, qE = 0, tS = 0xFFFFFFFFu, tE = 0;
+  for (unsigned long long i = o0 + lane; i < o1; i += 32) {
+    uint32_t qp = b.r_q[i];
+    if (s == 1) { qp = readLen - (qp + K); b.r_q[i] = qp; }
+    const uint32_t tp = b.r_t[i];
+    qS = qp < qS ? qp : qS; qE = qp + K > qE ? qp + K : qE;
+    tS = tp < tS ? tp : tS; tE = tp + K > tE ? tp + K : tE;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint32_t a = __shfl_xor_sync(0xffffffffu, qS, o), bb = __shfl_xor_sync(0xffffffffu, qE, o);
+    const uint32_t cc = __shfl_xor_sync(0xffffffffu, tS, o), d = __shfl_xor_sync(0xffffffffu, tE, o);
+    qS = a < qS ? a : qS; qE = bb > qE ? bb : qE; tS = cc < tS ? cc : tS; tE = d > tE ? d : tE;
+  }
+  if (lane == 0) {
+    rb[0] = qS; rb[1] = qE; rb[2] = tS; rb[3] = tE;
+    const uint32_t den = (qE - qS) < (tE - tS) ? (qE - qS) : (tE - tS);
+    b.eff[c] = __fdiv_rn((float)(unsigned long long)n, (float)den);      // ((float) matches.size()) / min(..): binary32, round to nearest
+  }
+}
+
+}  // namespace lra

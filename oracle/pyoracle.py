@@ -376,3 +376,130 @@ def calc_stats_ref(read, text, blocks):
     buf = C.create_string_buffer(12 * (len(read) + len(text)) + 64)
     L.ref_calc_stats(bytes(read), len(read), bytes(text), len(text), b, len(b) // 3, st, C.byref(v), buf, len(buf))
     return st, np.float32(v.value), buf.value.decode()
+
+
+# ---------------------------------------------------------------- a12 LocalIndex::IndexSeq, a13 REFINEclusters
+
+class LocalIndexData:
+    """A LocalIndex as three arrays: seq_off (uint64, leading 0), bnd (uint64, leading 0), mins (uint32: tuple | pos << 20)."""
+    def __init__(self, seq_off, bnd, mins, k=10, w=5, window=2048, max_freq=15):
+        self.seq_off, self.bnd, self.mins = seq_off, bnd, mins
+        self.k, self.w, self.window, self.max_freq = k, w, window, max_freq
+
+
+def local_index(seqs, k=10, w=5, window=2048, max_freq=15, which="port"):
+    """LocalIndex of one sequence (a read strand) or of a list of contigs (the genome: IndexFile calls IndexSeq per contig)."""
+    if isinstance(seqs, (bytes, bytearray, np.ndarray)):
+        seqs = [seqs]
+    seqs = [np.frombuffer(s, np.uint8) if isinstance(s, (bytes, bytearray)) else np.ascontiguousarray(s, np.uint8) for s in seqs]
+    if which == "ref":
+        L = ref()
+        L.ref_lidx_new.restype = C.c_void_p; L.ref_lidx_new.argtypes = [C.c_int] * 4
+        L.ref_lidx_index_seq.argtypes = [C.c_void_p, _u8p, C.c_int]
+        L.ref_lidx_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long)]
+        L.ref_lidx_copy.argtypes = [C.c_void_p, _u64p, _u64p, _u32p]
+        L.ref_lidx_free.argtypes = [C.c_void_p]
+        h = L.ref_lidx_new(k, w, window, max_freq)
+        for s in seqs:
+            L.ref_lidx_index_seq(h, np.concatenate([s, np.zeros(8, np.uint8)]), len(s))
+        a, b, c = C.c_long(), C.c_long(), C.c_long()
+        L.ref_lidx_sizes(h, C.byref(a), C.byref(b), C.byref(c))
+        off = np.zeros(a.value, np.uint64); bnd = np.zeros(b.value, np.uint64); mins = np.zeros(max(c.value, 1), np.uint32)
+        L.ref_lidx_copy(h, off, bnd, mins)
+        L.ref_lidx_free(h)
+        return LocalIndexData(off, bnd, mins[:c.value], k, w, window, max_freq)
+    L = port()
+    L.lra_oracle_index_seq.restype = C.c_long
+    L.lra_oracle_index_seq.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u64p, _u64p, _u32p, C.c_long, C.POINTER(C.c_int)]
+    offs, bnds, minss = [np.zeros(1, np.uint64)], [np.zeros(1, np.uint64)], []
+    base, nmin = 0, 0
+    for s in seqs:
+        nwin = (len(s) + window - 1) // window
+        off = np.zeros(nwin + 1, np.uint64); bnd = np.zeros(nwin + 1, np.uint64); mins = np.zeros(len(s) + 16, np.uint32)
+        ni = C.c_int()
+        n = L.lra_oracle_index_seq(np.concatenate([s, np.zeros(8, np.uint8)]), len(s), k, w, window, max_freq, off, bnd, mins, len(mins), C.byref(ni))
+        assert n >= 0 and ni.value == nwin
+        offs.append(off[1:] + np.uint64(base)); bnds.append(bnd[1:] + np.uint64(nmin)); minss.append(mins[:n])
+        base += len(s); nmin += n
+    return LocalIndexData(np.concatenate(offs), np.concatenate(bnds), np.concatenate(minss) if minss else np.zeros(0, np.uint32), k, w, window, max_freq)
+
+
+def local_minimizers_port(seq, k=10, w=5):
+    L = port()
+    L.lra_oracle_local_minimizers.restype = C.c_long
+    L.lra_oracle_local_minimizers.argtypes = [_u8p, C.c_uint32, C.c_int, C.c_int, _u32p, C.c_long]
+    s = np.frombuffer(seq, np.uint8) if isinstance(seq, (bytes, bytearray)) else seq
+    out = np.zeros(len(s) + 8, np.uint32)
+    n = L.lra_oracle_local_minimizers(np.concatenate([s, np.zeros(8, np.uint8)]), len(s), k, w, out, len(out))
+    return out[:n]
+
+
+def compare_lists_local_port(q, t, max_freq):
+    L = port()
+    L.lra_oracle_compare_lists_local.restype = C.c_long
+    L.lra_oracle_compare_lists_local.argtypes = [_u32p, C.c_long, _u32p, C.c_long, C.c_long, _u32p, _u32p, C.c_long]
+    q = np.ascontiguousarray(q, np.uint32); t = np.ascontiguousarray(t, np.uint32)
+    cap = 4 * (len(q) + len(t)) + 64
+    while True:
+        rq = np.zeros(cap, np.uint32); rt = np.zeros(cap, np.uint32)
+        n = L.lra_oracle_compare_lists_local(q if len(q) else np.zeros(1, np.uint32), len(q), t if len(t) else np.zeros(1, np.uint32), len(t), max_freq, rq, rt, cap)
+        if n <= cap:
+            return rq[:n], rt[:n]
+        cap = n
+
+
+def refine_cluster(mq, mt, box, strand, read_len, hdr_pos, gl, rd_fwd, rd_rev, global_k, small_k=10, window=100, local_max_freq=15, which="port",
+                   ref_handles=None):
+    """One cluster through REFINEclusters.  Returns a dict: status, chrom, mq/mt/box (as the reference leaves them), diag (min,max),
+    rq/rt/rtup (refined anchors), rbox (qStart,qEnd,tStart,tEnd of the refined cluster), eff (float32)."""
+    mq = np.array(mq, np.uint32); mt = np.array(mt, np.uint32); box = np.array(box, np.uint32)
+    hdr = np.ascontiguousarray(hdr_pos, np.uint64)
+    info = np.zeros(8, np.int32); diag = np.zeros(2, np.int64); eff = C.c_float()
+    cap = 1 << 16
+    mq1 = mq if len(mq) else np.zeros(1, np.uint32); mt1 = mt if len(mt) else np.zeros(1, np.uint32)
+    while True:
+        a, b, bx = mq1.copy(), mt1.copy(), box.copy()
+        rq = np.zeros(cap, np.uint32); rt = np.zeros(cap, np.uint32); ru = np.zeros(cap, np.uint32)
+        if which == "ref":
+            L = ref()
+            L.ref_refine_cluster.restype = C.c_long
+            L.ref_refine_cluster.argtypes = [_u32p, _u32p, C.c_long, _u32p, C.c_int, C.c_uint32, _u64p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_int, C.c_int, C.c_int, C.c_long, _u32p, _u32p, _u32p, C.c_long, _i32p, _i64p, C.POINTER(C.c_float)]
+            n = L.ref_refine_cluster(a, b, len(mq), bx, strand, read_len, hdr, len(hdr), ref_handles[0], ref_handles[1], ref_handles[2],
+                                     global_k, small_k, window, local_max_freq, rq, rt, ru, cap, info, diag, C.byref(eff))
+        else:
+            L = port()
+            L.lra_oracle_refine_cluster.restype = C.c_long
+            L.lra_oracle_refine_cluster.argtypes = [_u32p, _u32p, C.c_long, _u32p, C.c_int, C.c_uint32, _u64p, C.c_int,
+                                                    _u64p, C.c_long, _u64p, _u32p, _u64p, C.c_long, _u64p, _u32p,
+                                                    C.c_int, C.c_int, C.c_int, C.c_long, _u32p, _u32p, _u32p, C.c_long, _i32p, _i64p, C.POINTER(C.c_float)]
+            rd = rd_rev if strand else rd_fwd
+            pad = lambda m: m if len(m) else np.zeros(1, np.uint32)
+            n = L.lra_oracle_refine_cluster(a, b, len(mq), bx, strand, read_len, hdr, len(hdr), gl.seq_off, len(gl.seq_off), gl.bnd, pad(gl.mins),
+                                            rd.seq_off, len(rd.seq_off), rd.bnd, pad(rd.mins), global_k, small_k, window, local_max_freq,
+                                            rq, rt, ru, cap, info, diag, C.byref(eff))
+        if n <= cap:
+            break
+        cap = n
+    return dict(status=int(info[0]), chrom=int(info[1]), mq=a[:len(mq)], mt=b[:len(mq)], box=bx, diag=diag.copy(), rq=rq[:n], rt=rt[:n], rtup=ru[:n],
+                rbox=info[2:6].astype(np.uint32), eff=np.float32(eff.value))
+
+
+class RefLocalIndexHandle:
+    """A live reference LocalIndex (for ref_refine_cluster)."""
+    def __init__(self, seqs, k=10, w=5, window=2048, max_freq=15):
+        L = ref()
+        L.ref_lidx_new.restype = C.c_void_p; L.ref_lidx_new.argtypes = [C.c_int] * 4
+        L.ref_lidx_index_seq.argtypes = [C.c_void_p, _u8p, C.c_int]
+        L.ref_lidx_free.argtypes = [C.c_void_p]
+        self.L = L
+        self.h = C.c_void_p(L.ref_lidx_new(k, w, window, max_freq))
+        if isinstance(seqs, (bytes, bytearray, np.ndarray)):
+            seqs = [seqs]
+        for s in seqs:
+            s = np.frombuffer(s, np.uint8) if isinstance(s, (bytes, bytearray)) else np.ascontiguousarray(s, np.uint8)
+            L.ref_lidx_index_seq(self.h, np.concatenate([s, np.zeros(8, np.uint8)]), len(s))
+
+    def close(self):
+        if self.h:
+            self.L.ref_lidx_free(self.h); self.h = None

@@ -10,6 +10,8 @@
 //   IndelRefineAlignment         IndelRefine.h:53-784
 //   StoreMinimizers / std::sort / CompareLists / SeparateMatchesByStrand semantics   MinCount.h:7-179, MapRead.h:185,
 //                                CompareLists.h:8-151, MapRead.h:109-150   (the seeding prefix of MapRead, MapRead.h:169-203)
+//   LocalIndex::IndexSeq         MMIndex.h:200-245
+//   REFINEclusters               ClusterRefine.h:50-240
 #include <string>
 #include <vector>
 #include <thread>
@@ -20,11 +22,16 @@
 #include <iomanip>
 #include "htslib/kseq.h"
 #include "htslib/sam.h"
-#include "AffineOneGapAlign.h"
+// the reference's headers only compile in the include order of its own translation unit (lra.cpp:18-29)
 #include "Input.h"         // declares KSEQ_INIT(gzFile, gzread) for Genome.h
-#include "IndelRefine.h"
+#include "MMIndex.h"
+#include "TupleOps.h"
 #include "MinCount.h"
-#include "CompareLists.h"
+#include "MapRead.h"
+#include "SeqUtils.h"
+#include "Options.h"
+#include "Alignment.h"
+#include "LogLookUpTable.h"
 
 extern "C" {
 
@@ -150,10 +157,67 @@ int ref_calc_stats(const char *read, int readLen, const char *text, int textLen,
   return 0;
 }
 
-static void ref_init_static() {   // lra.cpp:1008-1012 (InitStatic)
+static void ref_init_static() {   // lra.cpp:1008-1018 (InitStatic)
   Tuple mask = 1;
   GenomeTuple::for_mask_s = ~(mask << (sizeof(mask) * 8 - 1));
   GenomeTuple::rev_mask_s = (mask << (sizeof(mask) * 8 - 1));
+  LocalTuple::for_mask_s = 1;
+  for (int i = 1; i < 32 - LOCAL_POS_BITS; i++) { LocalTuple::for_mask_s = LocalTuple::for_mask_s << 1; LocalTuple::for_mask_s += 1; }
+  LocalTuple::rev_mask_s = 0;
+}
+
+// ---- a12: LocalIndex.  A handle owns one LocalIndex; IndexSeq may be called once per contig (IndexFile, MMIndex.h:246-253).
+void *ref_lidx_new(int k, int w, int window, int maxFreq) {
+  ref_init_static();
+  LocalIndex *li = new LocalIndex(window);
+  li->k = k; li->w = w; li->maxFreq = maxFreq;
+  return li;
+}
+void ref_lidx_index_seq(void *h, const char *seq, int len) { ((LocalIndex *)h)->IndexSeq((char *)seq, len); }
+void ref_lidx_sizes(void *h, long *n_off, long *n_bnd, long *n_min) {
+  LocalIndex *li = (LocalIndex *)h;
+  *n_off = (long)li->seqOffsets.size(); *n_bnd = (long)li->tupleBoundaries.size(); *n_min = (long)li->minimizers.size();
+}
+void ref_lidx_copy(void *h, uint64_t *off, uint64_t *bnd, uint32_t *mins) {
+  LocalIndex *li = (LocalIndex *)h;
+  memcpy(off, li->seqOffsets.data(), sizeof(uint64_t) * li->seqOffsets.size());
+  memcpy(bnd, li->tupleBoundaries.data(), sizeof(uint64_t) * li->tupleBoundaries.size());
+  static_assert(sizeof(LocalTuple) == 4, "LocalTuple is one 32-bit word");
+  memcpy(mins, li->minimizers.data(), sizeof(uint32_t) * li->minimizers.size());
+}
+void ref_lidx_free(void *h) { delete (LocalIndex *)h; }
+
+// ---- a13: REFINEclusters on ONE cluster (ClusterRefine.h:50-240).  Arguments as oracle/local_refine.c: lra_oracle_refine_cluster;
+// gl / rd_fwd / rd_rev are LocalIndex handles.  mq/mt/box are updated to what the reference leaves in clusters[0].
+long ref_refine_cluster(uint32_t *mq, uint32_t *mt, long nm, uint32_t *box, int strand, uint32_t readLen, const uint64_t *hdr_pos, int n_hdr,
+                        void *gl, void *rd_fwd, void *rd_rev, int globalK, int smallK, int window, long localMaxFreq,
+                        uint32_t *rq, uint32_t *rt, uint32_t *rtup, long cap, int32_t *info, int64_t *diag, float *eff) {
+  ref_init_static();
+  Options opts; opts.globalK = globalK;
+  Options smallOpts = opts; smallOpts.globalK = smallK; smallOpts.window = window; smallOpts.localMaxFreq = (int)localMaxFreq;
+  Genome genome;
+  genome.header.pos.assign(hdr_pos, hdr_pos + n_hdr);
+  Read read; read.length = (int)readLen; read.unaligned = 0;
+  std::vector<Cluster> clusters(1), refined(1);
+  Cluster &c = clusters[0];
+  c.matches.resize(nm);
+  for (long i = 0; i < nm; i++) { c.matches[i].first.pos = mq[i]; c.matches[i].second.pos = mt[i]; }
+  c.qStart = box[0]; c.qEnd = box[1]; c.tStart = box[2]; c.tEnd = box[3]; c.strand = strand; c.refined = 0;
+  LocalIndex *lis[2] = {(LocalIndex *)rd_fwd, (LocalIndex *)rd_rev};
+  for (int i = 0; i < 8; i++) info[i] = 0;
+  diag[0] = diag[1] = 0; *eff = 0;
+  REFINEclusters(clusters, refined, genome, read, *(LocalIndex *)gl, lis, smallOpts, opts);
+  if (nm == 0) { info[0] = 1; return 0; }
+  if (c.matches.size() == 0) { info[0] = 2; return 0; }
+  for (long i = 0; i < nm; i++) { mq[i] = c.matches[i].first.pos; mt[i] = c.matches[i].second.pos; }
+  box[0] = c.qStart; box[1] = c.qEnd; box[2] = c.tStart; box[3] = c.tEnd;
+  Cluster &r = refined[0];
+  info[1] = r.chromIndex; info[6] = (int32_t)r.matches.size();
+  diag[0] = c.minDiagNum; diag[1] = c.maxDiagNum;
+  long n = (long)r.matches.size();
+  for (long i = 0; i < n && i < cap; i++) { rq[i] = r.matches[i].first.pos; rt[i] = r.matches[i].second.pos; rtup[i] = (uint32_t)r.matches[i].first.t; }
+  if (n > 0) { info[2] = r.qStart; info[3] = r.qEnd; info[4] = r.tStart; info[5] = r.tEnd; *eff = r.refineEffiency; }
+  return n;
 }
 
 // canonical (w,k) minimizers of one sequence, in the reference's emission order (MinCount.h:7-179)

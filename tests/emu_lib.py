@@ -126,3 +126,72 @@ def aog_batch(qa, ta, qo, to, ql, tl, k, m, mm, indel, use_band=1, force_literal
     err = lib().emu_aog_batch(qa, len(qa) - 16, ta, len(ta) - 16, qo, to, ql, tl, k, n, m, mm, indel, score, nb, off, blocks,
                               block_cap, use_band, force_literal, C.byref(cells))
     return err, score, nb, off, blocks.reshape(-1, 3), cells.value
+
+
+# ---------------------------------------------------------------- a12 / a13
+
+class EmuLidx(C.Structure):
+    _fields_ = [("win_off", C.c_void_p), ("win_len", C.c_void_p), ("bnd", C.c_void_p), ("mins", C.c_void_p), ("win_first", C.c_void_p),
+                ("seq_start", C.c_void_p), ("seq_len", C.c_void_p), ("n_win", C.c_int32), ("n_seq", C.c_int32)]
+
+
+def lindex_layout(seq_start, seq_len, window=2048):
+    """The window table of lra_b200/csrc/lref_host.cuh: lindex_layout."""
+    win_off, win_len, win_first = [], [], []
+    for s, L in zip(seq_start, seq_len):
+        win_first.append(len(win_off))
+        for p in range(0, int(L), window):
+            win_off.append(int(s) + p); win_len.append(min(window, int(L) - p))
+    win_first.append(len(win_off))
+    win_off.append(int(seq_start[-1]) + int(seq_len[-1]) if len(seq_start) else 0)
+    return np.array(win_off, np.uint64), np.array(win_len + [0], np.uint32), np.array(win_first, np.uint32)
+
+
+def lindex_build(arena, seq_start, seq_len, k=10, w=5, window=2048, max_freq=15):
+    """arena: ASCII + 16 bytes of padding.  Returns a dict image (win_off, win_len, bnd, mins, win_first, seq_start, seq_len)."""
+    L = lib()
+    L.emu_lindex_build.restype = C.c_long
+    L.emu_lindex_build.argtypes = [_u8p, C.c_uint64, _u64p, _u32p, C.c_int, C.c_int, C.c_int, C.c_int, _u64p, _u32p]
+    seq_start = np.ascontiguousarray(seq_start, np.uint64); seq_len = np.ascontiguousarray(seq_len, np.uint32)
+    win_off, win_len, win_first = lindex_layout(seq_start, seq_len, window)
+    nw = len(win_off) - 1
+    bnd = np.zeros(nw + 2, np.uint64); mins = np.zeros(len(arena) + 16, np.uint32)
+    n = L.emu_lindex_build(arena, len(arena) - 16, win_off, win_len, nw, k, w, max_freq, bnd, mins)
+    return dict(win_off=win_off, win_len=win_len, bnd=bnd[:nw + 1].copy(), mins=mins[:max(n, 1)].copy(), n_mins=n, win_first=win_first, seq_start=seq_start,
+                seq_len=seq_len, n_win=nw, n_seq=len(seq_start))
+
+
+def _emu_lidx(img):
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    return EmuLidx(p(img["win_off"]), p(img["win_len"]), p(img["bnd"]), p(img["mins"]), p(img["win_first"]), p(img["seq_start"]), p(img["seq_len"]),
+                   img["n_win"], img["n_seq"])
+
+
+def refine_clusters(gl, rf, rr, cl, cap=None):
+    """cl: dict(m_q, m_t, m_off, box[n,4], strand, read_id, hdr_pos, global_k, small_k, window, local_max_freq).  Returns a result dict."""
+    L = lib()
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"); i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+    L.emu_refine_clusters.restype = C.c_long
+    L.emu_refine_clusters.argtypes = [C.POINTER(EmuLidx)] * 3 + [C.c_int, _u32p, _u32p, _u64p, _u32p, _u8p, _u32p, _u64p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                                 C.c_long, _i32p, _i32p, i64p, _u64p, _u32p, _u32p, _u32p, C.c_uint64, _u32p, f32p, _u32p, _u32p,
+                                                                 _u32p, _u64p]
+    n = len(cl["strand"])
+    M = int(cl["m_off"][n])
+    cap = cap or 1 << 18
+    pad = lambda a, dt: np.ascontiguousarray(a, dt) if len(a) else np.zeros(1, dt)
+    while True:
+        o = dict(status=np.zeros(n, np.int32), chrom=np.zeros(n, np.int32), diag=np.zeros(2 * n, np.int64), r_off=np.zeros(n + 1, np.uint64),
+                 r_q=np.zeros(cap, np.uint32), r_t=np.zeros(cap, np.uint32), r_tup=np.zeros(cap, np.uint32), rbox=np.zeros(4 * n, np.uint32),
+                 eff=np.zeros(n, np.float32), m_q_out=np.zeros(M + 1, np.uint32), m_t_out=np.zeros(M + 1, np.uint32), box_out=np.zeros(4 * n, np.uint32))
+        counts = np.zeros(2, np.uint64)
+        a, b_, c = _emu_lidx(gl), _emu_lidx(rf), _emu_lidx(rr)
+        tot = L.emu_refine_clusters(C.byref(a), C.byref(b_), C.byref(c), n, pad(cl["m_q"], np.uint32), pad(cl["m_t"], np.uint32),
+                                    np.ascontiguousarray(cl["m_off"], np.uint64), np.ascontiguousarray(cl["box"], np.uint32).reshape(-1),
+                                    np.ascontiguousarray(cl["strand"], np.uint8), np.ascontiguousarray(cl["read_id"], np.uint32),
+                                    np.ascontiguousarray(cl["hdr_pos"], np.uint64), len(cl["hdr_pos"]), cl["global_k"], cl["small_k"], cl["window"],
+                                    cl["local_max_freq"], o["status"], o["chrom"], o["diag"], o["r_off"], o["r_q"], o["r_t"], o["r_tup"], cap,
+                                    o["rbox"], o["eff"], o["m_q_out"], o["m_t_out"], o["box_out"], counts)
+        if tot <= cap:
+            o["n_anchors"] = tot; o["n_units"], o["n_tasks"] = int(counts[0]), int(counts[1])
+            return o
+        cap = tot

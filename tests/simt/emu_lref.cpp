@@ -1,0 +1,87 @@
+// TEST INFRASTRUCTURE ONLY: runs lra_b200/csrc/lidx_kernels.cuh and lref_kernels.cuh on the CPU through the SIMT emulator,
+// with the launch sequence of lra_b200/csrc/lref_host.cuh.
+#include "emu_common.h"
+#include "seed_kernels.cuh"
+#include "lidx_kernels.cuh"
+#include "lref_kernels.cuh"
+
+using namespace lra;
+using namespace emuh;
+
+struct EmuLidx {              // host arrays of one LocalIndex image
+  const uint64_t *win_off;    // [n_win + 1]
+  const uint32_t *win_len;    // [n_win]
+  const uint64_t *bnd;        // [n_win + 1]
+  const uint32_t *mins;
+  const uint32_t *win_first;  // [n_seq + 1]
+  const uint64_t *seq_start;  // [n_seq]
+  const uint32_t *seq_len;    // [n_seq]
+  int32_t n_win, n_seq;
+};
+
+// win_off[n_win] / win_len[n_win] are inputs (the layout of lindex_layout); bnd[n_win + 1] and mins[<= arena length] are outputs.
+extern "C" long emu_lindex_build(const uint8_t *ascii, uint64_t n, const uint64_t *win_off, const uint32_t *win_len, int n_win, int k, int w,
+                                 int max_freq, uint64_t *bnd, uint32_t *mins) {
+  Packed p; pack(ascii, n, p);
+  std::vector<uint32_t> tmp(n + 64);
+  int err = 0;
+  LidxBuild b;
+  b.seq = p.view; b.win_off = (const unsigned long long *)win_off; b.win_len = win_len; b.n_win = n_win; b.k = k; b.w = w; b.max_freq = max_freq;
+  b.tmp = tmp.data(); b.cnt = (unsigned long long *)bnd; b.mins = mins;
+  if (n_win == 0) { bnd[0] = 0; return 0; }
+  emu::launch(dim3((unsigned)((n_win + kLidxWarps - 1) / kLidxWarps)), dim3(32 * kLidxWarps), 0, [&] { lidx_window_kernel(b); });
+  emu::launch(dim3(1), dim3(1024), 0, [&] { seed_scan_kernel(b.cnt, n_win, ~0ull, &err); });
+  emu::launch(dim3((unsigned)((n_win + 7) / 8)), dim3(256), 0, [&] { lidx_compact_kernel(b); });
+  return (long)bnd[n_win];
+}
+
+static LidxView view(const EmuLidx *x) {
+  return LidxView{(const unsigned long long *)x->win_off, x->win_len, (const unsigned long long *)x->bnd, x->mins, x->win_first,
+                  (const unsigned long long *)x->seq_start, x->seq_len, x->n_win, x->n_seq};
+}
+
+extern "C" long emu_refine_clusters(const EmuLidx *gl, const EmuLidx *rf, const EmuLidx *rr, int n, const uint32_t *m_q, const uint32_t *m_t,
+                                    const uint64_t *m_off, const uint32_t *box, const uint8_t *strand, const uint32_t *read_id,
+                                    const uint64_t *hdr_pos, int n_hdr, int global_k, int small_k, int window, long local_max_freq,
+                                    int32_t *status, int32_t *chrom, int64_t *diag, uint64_t *r_off, uint32_t *r_q, uint32_t *r_t, uint32_t *r_tup,
+                                    uint64_t cap, uint32_t *rbox, float *eff, uint32_t *m_q_out, uint32_t *m_t_out, uint32_t *box_out, uint64_t *counts) {
+  const size_t M = (size_t)m_off[n];
+  std::vector<unsigned long long> key_off(n + 1), keys, unit_off(n + 2, 0);
+  size_t kt = 0;
+  for (int c = 0; c < n; c++) { size_t nm = m_off[c + 1] - m_off[c], P = 1; while (P < nm) P <<= 1; key_off[c] = kt; kt += P; }
+  keys.resize(kt + 2);
+  std::vector<uint32_t> chrom_off(n + 1);
+  std::vector<int32_t> ls(n + 1);
+  int err = 0;
+  LrefBatch b;
+  memset(&b, 0, sizeof b);
+  b.n_clusters = n; b.in_q = m_q; b.in_t = m_t; b.m_off = (const unsigned long long *)m_off; b.in_box = box; b.strand = strand; b.read_id = read_id;
+  b.hdr_pos = (const unsigned long long *)hdr_pos; b.n_hdr = n_hdr; b.gl = view(gl); b.rd[0] = view(rf); b.rd[1] = view(rr);
+  b.global_k = global_k; b.small_k = small_k; b.window = window; b.local_max_freq = local_max_freq;
+  std::vector<uint32_t> mqv(M + 4), mtv(M + 4);
+  b.m_q = m_q_out ? m_q_out : mqv.data(); b.m_t = m_t_out ? m_t_out : mtv.data(); b.box = box_out; b.keys = keys.data(); b.key_off = key_off.data();
+  b.status = status; b.chrom = chrom; b.diag = (long long *)diag; b.chrom_off = chrom_off.data(); b.ls = ls.data(); b.unit_off = unit_off.data();
+  b.r_q = r_q; b.r_t = r_t; b.r_tup = r_tup; b.out_cap = cap; b.r_off = (unsigned long long *)r_off; b.rbox = rbox; b.eff = eff;
+  emu::launch(dim3((unsigned)((n + 3) / 4)), dim3(128), 0, [&] { lref_prep_kernel(b); });
+  emu::launch(dim3(1), dim3(1024), 0, [&] { seed_scan_kernel(b.unit_off, n, ~0ull, &err); });
+  const unsigned long long n_units = unit_off[n];
+  std::vector<uint32_t> uc(n_units + 1), uq(n_units + 1), ug(n_units + 1);
+  std::vector<unsigned long long> task_off(n_units + 2, 0);
+  b.u_cluster = uc.data(); b.u_qis = uq.data(); b.u_gstart = ug.data(); b.task_off = task_off.data();
+  unsigned long long n_tasks = 0;
+  if (n_units) {
+    emu::launch(dim3((unsigned)((n_units + 127) / 128)), dim3(128), 0, [&] { lref_unit_kernel(b, n_units); });
+    emu::launch(dim3(1), dim3(1024), 0, [&] { seed_scan_kernel(b.task_off, (int)n_units, ~0ull, &err); });
+    n_tasks = task_off[n_units];
+  }
+  std::vector<unsigned long long> out_off(n_tasks + 2, 0);
+  b.out_off = out_off.data();
+  if (n_tasks) {
+    emu::launch(dim3((unsigned)((n_tasks + 127) / 128)), dim3(128), 0, [&] { lref_task_kernel<false>(b, n_units, n_tasks); });
+    emu::launch(dim3(1), dim3(1024), 0, [&] { seed_scan_kernel(b.out_off, (int)n_tasks, cap, &err); });
+    emu::launch(dim3((unsigned)((n_tasks + 127) / 128)), dim3(128), 0, [&] { lref_task_kernel<true>(b, n_units, n_tasks); });
+  }
+  emu::launch(dim3((unsigned)((n + 3) / 4)), dim3(128), 0, [&] { lref_finish_kernel(b, n_units, n_tasks); });
+  counts[0] = n_units; counts[1] = n_tasks;
+  return (long)out_off[n_tasks];
+}
