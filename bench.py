@@ -8,6 +8,10 @@ over the work those reads generate in the reference:
   a18  AffineOneGapAlign      the job stream of the reads (job shapes drawn from tables captured from the reference on reads
                               of this profile, job content synthetic; tools/workload.py make_jobs)
   a19  IndelRefineAlignment   one segment per read (block list = gap-free runs of the read's true alignment; make_segments)
+  a12  LocalIndex::IndexSeq   both strands of every read (CreateRC included): the per-read two-strand local index
+  a13  REFINEclusters         one cluster per read (anchors = the exact >= 17-base stretches of its alignment; make_clusters) against the
+                              LocalIndex of the 3 Gb genome (built once, on the GPU, outside the timed region like the reference's .gli load)
+  a21  CalculateStatistics    CIGAR + NV of every segment a19 refined
 The metric is named "reads/sec (<stages>)" until every stage of MapRead is covered: it is NOT a whole-aligner reads/sec
 yet and is not presented as one.  `--impl reference` runs the reference's own CPU code for the same stages on the same
 kind of work, with all host threads.
@@ -34,10 +38,11 @@ for p in (ROOT, os.path.join(ROOT, "tools")):
 import workload  # noqa: E402
 
 PROFILE = "ont"
-STAGES = ["a18:AffineOneGapAlign", "a19:IndelRefineAlignment"]
+STAGES = ["a12:LocalIndex::IndexSeq", "a13:REFINEclusters", "a18:AffineOneGapAlign", "a19:IndelRefineAlignment", "a21:CalculateStatistics"]
 WORKLOAD = ("BASELINE configs[1]: synthetic ONT reads (N50 20 kb, 8%% err) vs 3 Gb synthetic ref (24 x 125 Mb), -ONT; per step %d reads: "
             "their AffineOneGapAlign job stream (%.1f jobs/read, shapes captured from the reference) and one IndelRefineAlignment "
-            "segment per read")
+            "segment per read; local index of both strands of every read, one cluster per read refined against the genome's local index, "
+            "CIGAR/NV statistics of every refined segment")
 
 
 def metric_name(stages):
@@ -55,7 +60,7 @@ def parse():
     ap.add_argument("--cpu-sample-jobs", type=int, default=400_000)
     ap.add_argument("--cpu-sample-segments", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--stages", default="a18,a19")
+    ap.add_argument("--stages", default="a12,a13,a18,a19,a21")
     return ap.parse_args()
 
 
@@ -160,7 +165,7 @@ def cpu_stage_rates(args, jobs, segs, jobs_per_read, budget_s):
         rate = n * len(ts) / tot
         per_read += jobs_per_read / rate
         parts["a18"] = {"jobs_per_s": rate, "sample": "%d jobs x %d passes" % (n, len(ts))}
-    if segs is not None:
+    if segs is not None and "a19" in args.stages.split(","):
         n = min(args.cpu_sample_segments, len(segs["blk_cnt"]))
         sub = dict(segs)
         for k in ["blk_off", "blk_cnt", "q_base", "read_len", "contig_len"]:
@@ -182,6 +187,86 @@ def cpu_stage_rates(args, jobs, segs, jobs_per_read, budget_s):
         rate = n * len(ts) / tot
         per_read += 1.0 / rate
         parts["a19"] = {"segments_per_s": rate, "sample": "%d segments x %d passes" % (n, len(ts))}
+    stages = args.stages.split(",")
+    if segs is not None and ("a12" in stages or "a13" in stages):
+        # the reference's LocalIndex::IndexSeq on both strands of every read + REFINEclusters on its cluster, all host threads
+        # (one ctypes call per read and stage: the GIL is released inside); the genome's LocalIndex is built once, untimed
+        from concurrent.futures import ThreadPoolExecutor
+        n = min(args.cpu_sample_segments, len(segs["blk_cnt"]))
+        which = "ref" if kind == "reference" else "port"
+        cl = workload.make_clusters(segs, compact=True)
+        comp = np.zeros(256, np.uint8); comp[[65, 67, 71, 84, 78]] = [84, 71, 67, 65, 78]
+        ta = segs["t_arena_compact"]; hdr = cl["hdr_pos"]
+        contigs = [ta[int(hdr[i]):int(hdr[i + 1])] for i in range(n)]
+        glh = po.RefLocalIndexHandle(contigs) if which == "ref" else None
+        gl = po.local_index(contigs, which="port") if which == "port" else None
+        hdr_n = np.ascontiguousarray(hdr[:n + 1])
+
+        def one_read(i):
+            qb = int(segs["q_base"][i]); L = int(segs["read_len"][i])
+            r = segs["q_arena"][qb:qb + L]; rc = comp[r[::-1]]
+            a, b = int(cl["m_off"][i]), int(cl["m_off"][i + 1])
+            if which == "ref":
+                f = po.RefLocalIndexHandle(r); v = po.RefLocalIndexHandle(rc)
+                if "a13" in stages:
+                    po.refine_cluster(cl["m_q"][a:b], cl["m_t"][a:b], cl["box"][i], 0, L, hdr_n, None, None, None, 17, which="ref", ref_handles=(glh.h, f.h, v.h))
+                f.close(); v.close()
+            else:
+                f = po.local_index(r); v = po.local_index(rc)
+                if "a13" in stages:
+                    po.refine_cluster(cl["m_q"][a:b], cl["m_t"][a:b], cl["box"][i], 0, L, hdr_n, gl, f, v, 17, which="port")
+
+        def one3():
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(cores if which == "ref" else 1) as ex:
+                list(ex.map(one_read, range(n)))
+            return time.perf_counter() - t0
+        one3()
+        ts = [one3()]
+        tot = ts[0]
+        while tot < budget_s and len(ts) < 200:
+            ts.append(one3()); tot += ts[-1]
+        rate = n * len(ts) / tot
+        per_read += 1.0 / rate
+        parts["a12+a13"] = {"reads_per_s": rate, "sample": "%d reads x %d passes" % (n, len(ts))}
+        if glh:
+            glh.close()
+    if segs is not None and "a21" in stages:
+        from concurrent.futures import ThreadPoolExecutor
+        n = min(args.cpu_sample_segments, len(segs["blk_cnt"]))
+        sub = dict(segs)
+        for k in ["blk_off", "blk_cnt", "q_base", "read_len", "contig_len"]:
+            sub[k] = np.ascontiguousarray(segs[k][:n])
+        tb = np.ascontiguousarray(segs["t_base_compact"][:n])
+        if kind == "reference":
+            nb, off, blk = po.indel_refine_batch_ref(sub, segs["t_arena_compact"], tb, nthreads=cores, want_blocks=True)
+            refined = [blk[int(off[i]):int(off[i]) + int(nb[i])] for i in range(n)]
+        else:
+            refined = po.indel_refine_batch_port(sub, segs["t_arena_compact"], tb)
+        items = []
+        for i in range(n):
+            qb, t0_ = int(segs["q_base"][i]), int(tb[i])
+            items.append((segs["q_arena"][qb:qb + int(segs["read_len"][i])].tobytes(), segs["t_arena_compact"][t0_:t0_ + int(segs["contig_len"][i])].tobytes(), refined[i]))
+
+        def one_seg(it):
+            if kind == "reference":
+                po.calc_stats_ref(it[0], it[1], it[2])
+            else:
+                po.calc_stats_port(it[0], it[1], 0, it[2])
+
+        def one4():
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(cores if kind == "reference" else 1) as ex:
+                list(ex.map(one_seg, items))
+            return time.perf_counter() - t0
+        one4()
+        ts = [one4()]
+        tot = ts[0]
+        while tot < budget_s and len(ts) < 200:
+            ts.append(one4()); tot += ts[-1]
+        rate = n * len(ts) / tot
+        per_read += 1.0 / rate
+        parts["a21"] = {"segments_per_s": rate, "sample": "%d segments x %d passes" % (n, len(ts))}
     desc = {"kind": kind, "cores": cores if kind == "reference" else 1, "parts": parts}
     return 1.0 / per_read, desc
 
@@ -192,7 +277,7 @@ def run_reference(args, jobs_per_read, stages):
     fetch = workload.host_genome_fetcher(genome)
     n_jobs = min(args.cpu_sample_jobs, int(round(args.reads_per_step * jobs_per_read)))
     jobs = workload.make_jobs(PROFILE, n_jobs, 1000, len(genome), fetch) if "a18" in stages else None
-    segs = workload.make_segments(PROFILE, min(args.cpu_sample_segments, args.reads_per_step), 1001, len(genome), fetch) if "a19" in stages else None
+    segs = workload.make_segments(PROFILE, min(args.cpu_sample_segments, args.reads_per_step), 1001, len(genome), fetch) if any(x in stages for x in ("a19", "a12", "a13", "a21")) else None
     rates, desc = [], None
     for i in range(args.warmup + args.steps):       # each step = one pass over the bounded samples
         r, desc = cpu_stage_rates(args, jobs, segs, jobs_per_read, budget_s=0.0)
@@ -232,6 +317,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     R = args.reads_per_step
     n_jobs = int(round(R * jobs_per_read))
+    need_reads = any(x in stages for x in ("a19", "a12", "a13", "a21"))
+    if "a21" in stages and "a19" not in stages:
+        raise SystemExit("stage a21 (statistics) runs on the segments a19 refines: add a19 to --stages")
 
     # all device work (torch's and the library's) goes to ONE explicit stream, so the CUDA events below see it all
     stream = torch.cuda.Stream(device=dev)
@@ -267,7 +355,7 @@ def main():
             hb["aog"] = A
             if bi == 0 and rank == 0:
                 hb["jobs0"] = j
-        if "a19" in stages:
+        if need_reads:
             sg = workload.make_segments(PROFILE, R, seed + 17, args.genome_len, fetch)
             I = {k: sg[k] for k in ["k", "match", "mismatch", "indel", "end_align"]}
             I["T"] = len(sg["blocks_in"])
@@ -285,6 +373,24 @@ def main():
             d["n_blocks"] = torch.empty(R, dtype=torch.int32, device=dev)
             d["block_off"] = torch.empty(R, dtype=torch.int64, device=dev)
             d["blocks"] = torch.empty((I["cap"], 3), dtype=torch.int32, device=dev)
+            if "a12" in stages or "a13" in stages:
+                I["read_off"] = np.ascontiguousarray(sg["q_base"].astype(np.uint64)); I["read_len_u"] = np.ascontiguousarray(sg["read_len"].astype(np.uint32))
+            if "a13" in stages:
+                cl = workload.make_clusters(sg, genome_len=args.genome_len)
+                I["cl"] = cl
+                I["M"] = int(cl["m_off"][-1])
+                I["acap"] = int(sg["read_len"].sum()) // 2 + 4096
+                dc = {key: torch.from_numpy(np.ascontiguousarray(cl[key]).view(np.int32 if cl[key].dtype == np.uint32 else (np.int64 if cl[key].dtype == np.uint64 else np.uint8))).to(dev)
+                      for key in ["m_q", "m_t", "m_off", "box", "strand", "read_id", "hdr_pos"]}
+                for key, shape, dt in [("status", R, torch.int32), ("chrom", R, torch.int32), ("diag", 2 * R, torch.int64), ("r_off", R + 1, torch.int64),
+                                       ("r_q", I["acap"], torch.int32), ("r_t", I["acap"], torch.int32), ("r_tup", I["acap"], torch.int32),
+                                       ("rbox", 4 * R, torch.int32), ("eff", R, torch.float32)]:
+                    dc["o_" + key] = torch.empty(shape, dtype=dt, device=dev)
+                I["dcl"] = dc
+            if "a21" in stages:
+                I["ccap"] = 4 * I["T"] + 64 * R + 1024
+                d["st_stats"] = torch.empty(16 * R, dtype=torch.int32, device=dev); d["st_value"] = torch.empty(R, dtype=torch.float32, device=dev)
+                d["st_off"] = torch.empty(R + 1, dtype=torch.int64, device=dev); d["st_cigar"] = torch.empty(I["ccap"], dtype=torch.int32, device=dev)
             I["dev"] = d
             hb["ir"] = I
             if bi == 0 and rank == 0:
@@ -293,7 +399,13 @@ def main():
     del genome, fetch
     torch.cuda.empty_cache()
     eseq_a = ctx.seq_upload(batches[0]["aog"]["q_arena"][:-16]) if "a18" in stages else None
-    eseq_i = ctx.seq_upload(batches[0]["ir"]["q_arena"][:-16]) if "a19" in stages else None
+    eseq_i = ctx.seq_upload(batches[0]["ir"]["q_arena"][:-16]) if need_reads else None
+    # the genome's LocalIndex (<ref>.gli): built once on the GPU, like the reference loads it once
+    gli = None
+    if "a13" in stages:
+        hdr = batches[0]["ir"]["cl"]["hdr_pos"]
+        gli = ctx.lindex_build(tseq, hdr[:-1], np.diff(hdr).astype(np.uint32))
+    log_lut = lra_b200.CreateLookUpTable() if "a21" in stages else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step_value(hb):
@@ -310,6 +422,29 @@ def main():
                                               I["T"], R, I["k"], I["match"], I["mismatch"], I["indel"], I["end_align"], d["n_blocks"].data_ptr(),
                                               d["block_off"].data_ptr(), d["blocks"].data_ptr(), I["cap"])
             out["cells"] += r["cells"]; out["stats"] += ctx.kernel_stats()
+        if "a21" in stages:
+            I = hb["ir"]; d = I["dev"]
+            ctx.calc_stats_batch_device(d["qseq"], tseq, [d[k].data_ptr() for k in ["blocks", "block_off", "n_blocks", "q_base", "t_base", "read_len"]],
+                                        I["cap"], R, log_lut, d["st_stats"].data_ptr(), d["st_value"].data_ptr(), d["st_off"].data_ptr(),
+                                        d["st_cigar"].data_ptr(), I["ccap"])
+            out["stats"] += ctx.kernel_stats()
+        if "a12" in stages or "a13" in stages:
+            I = hb["ir"]; d = I["dev"]
+            rc = ctx.seq_revcomp(d["qseq"], I["read_off"], I["read_len_u"])
+            rf = ctx.lindex_build(d["qseq"], I["read_off"], I["read_len_u"]); st1 = ctx.kernel_stats()
+            rr = ctx.lindex_build(rc, I["read_off"], I["read_len_u"]); st2 = ctx.kernel_stats()
+            for a, b2 in zip(st1, st2):
+                a["ms"] += b2["ms"]; a["jobs"] += b2["jobs"]; a["algo_bytes"] += b2["algo_bytes"]
+            out["stats"] += st1
+            if "a13" in stages:
+                dc = I["dcl"]; cl = I["cl"]
+                ctx.refine_clusters_batch_device(gli, rf, rr, dict(m_q=dc["m_q"].data_ptr(), m_t=dc["m_t"].data_ptr(), m_off=dc["m_off"].data_ptr(),
+                                                                   box=dc["box"].data_ptr(), strand=dc["strand"].data_ptr(), read_id=dc["read_id"].data_ptr(),
+                                                                   hdr_pos=dc["hdr_pos"].data_ptr(), n_hdr=len(cl["hdr_pos"])),
+                                                 R, I["M"], (cl["global_k"], cl["small_k"], cl["window"], cl["local_max_freq"]),
+                                                 {k: dc["o_" + k].data_ptr() for k in ["status", "chrom", "diag", "r_off", "r_q", "r_t", "r_tup", "rbox", "eff"]}, I["acap"])
+                out["stats"] += ctx.kernel_stats()
+            rf.free(); rr.free(); rc.free()
         return out
 
     io = {"h2d": 0, "d2h": 0}
@@ -328,6 +463,24 @@ def main():
             r = ctx.indel_refine_batch(eseq_i, tseq, I, block_cap=I["cap"], out=I["out"])
             h2d += len(I["q_arena"]) - 16 + 12 * I["T"] + R * (8 + 5 * 4)
             d2h += R * 12 + 12 * r["n_blocks_total"]
+            if "a21" in stages:
+                nb = I["out"]["n_blocks"]; tot = int(r["n_blocks_total"])
+                o = ctx.calc_stats_batch(eseq_i, tseq, dict(blocks_in=I["out"]["blocks"][:tot], blk_off=I["out"]["block_off"], blk_cnt=nb, q_base=I["q_base"],
+                                                             t_base=I["t_base"], read_len=I["read_len"]), log_lut, cigar_cap=I["ccap"])
+                h2d += 12 * tot + R * 24 + 2001 * 4
+                d2h += R * (64 + 4 + 8) + 4 * o["n_cigar_total"]
+        if "a12" in stages or "a13" in stages:
+            I = hb["ir"]
+            if "a19" not in stages:
+                eseq_i.reupload(I["q_arena"][:-16]); h2d += len(I["q_arena"]) - 16
+            rc = ctx.seq_revcomp(eseq_i, I["read_off"], I["read_len_u"])
+            rf = ctx.lindex_build(eseq_i, I["read_off"], I["read_len_u"]); rr = ctx.lindex_build(rc, I["read_off"], I["read_len_u"])
+            h2d += 2 * 12 * R
+            if "a13" in stages:
+                o = ctx.refine_clusters_batch(gli, rf, rr, I["cl"], anchor_cap=I["acap"])
+                h2d += 8 * I["M"] + R * (8 + 16 + 1 + 4)
+                d2h += R * (4 + 4 + 16 + 8 + 16 + 4 + 16) + 8 * I["M"] + 12 * o["n_anchors"]
+            rf.free(); rr.free(); rc.free()
         io["h2d"], io["d2h"] = h2d, d2h
         return None
 

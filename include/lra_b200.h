@@ -225,6 +225,10 @@ typedef struct lra_b200_stats_result {
 
 int lra_b200_calc_stats_batch(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_ir_segments *segs,
                               const float *log_lut, lra_b200_stats_result *res);
+/* the same with the array pointers of segs / res in device memory (log_lut stays a host pointer: 8 KB, uploaded per call);
+ * blk_cnt / blk_off may be the n_blocks / block_off outputs of lra_b200_indel_refine_batch_device */
+int lra_b200_calc_stats_batch_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_ir_segments *segs_dev,
+                                     const float *log_lut, lra_b200_stats_result *res_dev);
 
 /* ---- a12  LocalIndex::IndexSeq, batched over sequences ---------------------------------------------------------
  * Replaces  void LocalIndex::IndexSeq(char *seq, int seqLen)  (MMIndex.h:200-245; StoreMinimizers_noncanonical
@@ -287,6 +291,10 @@ typedef struct lra_b200_refined {
 
 int lra_b200_refine_clusters_batch(lra_b200_ctx *ctx, const lra_b200_lindex *genome_li, const lra_b200_lindex *reads_fwd,
                                    const lra_b200_lindex *reads_rc, const lra_b200_clusters *cl, lra_b200_refined *res);
+/* the same with every array pointer of cl / res (hdr_pos included) in device memory; n_anchors_in = m_off[n_clusters] */
+int lra_b200_refine_clusters_batch_device(lra_b200_ctx *ctx, const lra_b200_lindex *genome_li, const lra_b200_lindex *reads_fwd,
+                                          const lra_b200_lindex *reads_rc, const lra_b200_clusters *cl_dev, uint64_t n_anchors_in,
+                                          lra_b200_refined *res_dev);
 
 /* ---- per-kernel timing of the last batch call (CUDA events on the context's stream) ---------------------------- */
 typedef struct lra_b200_kernel_stat {

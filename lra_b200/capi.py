@@ -135,6 +135,8 @@ def load_library():
     L.lra_b200_lindex_free.argtypes = [C.c_void_p, C.c_void_p]
     L.lra_b200_lindex_free.restype = None
     L.lra_b200_refine_clusters_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Clusters), C.POINTER(_Refined)]
+    L.lra_b200_refine_clusters_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Clusters), C.c_uint64, C.POINTER(_Refined)]
+    L.lra_b200_calc_stats_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrSegments), C.c_void_p, C.POINTER(_StatsResult)]
     L.lra_b200_last_kernel_stats.argtypes = [C.c_void_p, C.POINTER(KernelStat), C.c_int]
     L.lra_b200_launch_count.argtypes = [C.c_void_p]
     L.lra_b200_launch_count.restype = C.c_uint64
@@ -357,6 +359,25 @@ class Context:
             return o
         self._check(rc)
 
+    def refine_clusters_batch_device(self, genome_li, reads_fwd, reads_rc, p, n, n_anchors_in, consts, out, anchor_cap):
+        """Device-pointer variant.  p: dict of device pointers m_q, m_t, m_off, box, strand, read_id, hdr_pos (+ n_hdr); consts: (global_k,
+        small_k, window, local_max_freq); out: dict of device pointers status, chrom, diag, r_off, r_q, r_t, r_tup, rbox, eff.
+        Returns dict(n_anchors, n_units, n_tasks)."""
+        c = _Clusters(n, p["m_q"], p["m_t"], p["m_off"], p["box"], p["strand"], p["read_id"], p["hdr_pos"], p["n_hdr"], consts[0], consts[1], consts[2], consts[3])
+        r = _Refined(out["status"], out["chrom"], out["diag"], out["r_off"], out["r_q"], out["r_t"], out["r_tup"], anchor_cap, 0, out["rbox"], out["eff"],
+                     None, None, None, 0, 0)
+        self._check(self.lib.lra_b200_refine_clusters_batch_device(self.h, genome_li.handle, reads_fwd.handle, reads_rc.handle, C.byref(c), n_anchors_in, C.byref(r)))
+        return dict(n_anchors=int(r.n_anchors), n_units=int(r.n_units), n_tasks=int(r.n_tasks))
+
+    def calc_stats_batch_device(self, q, t, ptrs, n_blocks_in, S, log_lut, d_stats, d_value, d_cigar_off, d_cigar, cigar_cap):
+        """Device-pointer variant.  ptrs = [blocks, blk_off, blk_cnt, q_base, t_base, read_len] (blk_off uint64, blk_cnt int32: the
+        block_off / n_blocks outputs of indel_refine_batch_device fit).  Returns the number of CIGAR ops."""
+        lut = np.ascontiguousarray(log_lut, np.float32)
+        sg = _IrSegments(ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[5], None, n_blocks_in, S, 0, 0, 0, 0, 0)
+        res = _StatsResult(d_stats, d_value, d_cigar_off, d_cigar, cigar_cap, 0)
+        self._check(self.lib.lra_b200_calc_stats_batch_device(self.h, q.handle, t.handle, C.byref(sg), _ptr(lut), C.byref(res)))
+        return int(res.n_cigar_total)
+
     # ---- a21
     def calc_stats_batch(self, q, t, sb, log_lut, cigar_cap=None):
         """Alignment::CalculateStatistics over segments (sb as for indel_refine_batch: blocks_in, blk_off, blk_cnt, q_base, t_base,
@@ -438,6 +459,14 @@ class Context:
 # Host-side mirror of the reference interface (same names / argument meaning), used by the parity tests.
 
 _default_ctx = None
+
+
+def CreateLookUpTable():
+    """The reference's LogLookUpTable (LogLookUpTable.h:9-15): logf(i) for i = 1, 6, ..., 10001, built with the HOST libm so that the NV
+    tag is bit-identical (never a device logf for anything that reaches the output)."""
+    libm = C.CDLL("libm.so.6")
+    libm.logf.restype = C.c_float; libm.logf.argtypes = [C.c_float]
+    return np.array([libm.logf(float(i)) for i in range(1, 10002, 5)], np.float32)
 
 
 def _ctx():

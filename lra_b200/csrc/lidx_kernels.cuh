@@ -188,6 +188,7 @@ __device__ __noinline__ int lt_scan_window(uint32_t *v, const SeqView &seq, unsi
 
 __global__ void __launch_bounds__(32 * kLidxWarps) lidx_window_kernel(LidxBuild b) {
   __shared__ uint32_t sm[kLidxWarps][kLidxMaxWindow];
+  __shared__ uint32_t nm_sm[kLidxWarps][68];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int wi = (int)(blockIdx.x * kLidxWarps + wib);
   if (wi >= b.n_win) return;
@@ -210,13 +211,76 @@ __global__ void __launch_bounds__(32 * kLidxWarps) lidx_window_kernel(LidxBuild 
     }
   }
   __syncwarp();
-  // 2. the reference's scan, in place
-  int n = 0;
-  if (lane == 0) n = lt_scan_window(v, b.seq, off, len, k, b.w);
-  n = __shfl_sync(0xffffffffu, n, 0);
-  __syncwarp();
+  // 2. the minimizers of the window.
+  // Lane-parallel form: where the minimum of every w-window is attained once, the reference's active minimizer at p is simply the
+  // argmin of [p-w+1, p], and it emits exactly where the argmin changes (a rescan always moves it, a strictly smaller newcomer moves
+  // it, nothing else does).  An emission is allowed iff the bases [p-w+1, p+k-1] hold no N and the N-free run they lie in starts
+  // before seqLen - windowSpan (the reference only looks for a new run while nextValidWindowStart < seqLen - windowSpan).  A tied
+  // minimum anywhere (low-complexity sequence) makes the active position depend on history: lane 0 then replays the reference's scan.
   uint32_t *stage = b.tmp + off;
-  for (int i = lane; i < n; i += 32) stage[i] = v[i];          // the unsorted list, for the introsort replay
+  int n = 0;
+  const int w = b.w;
+  const int windowSpan = w + k - 1;
+  bool tie = false;
+  if (len > (uint32_t)windowSpan) {
+    const int npos = (int)len - k + 1;
+    // N mask of the window, bit p = base off+p is not A/C/G/T (65 words cover 2048 + 32 bases)
+    uint32_t *nmw = nm_sm[wib];
+    for (int j = lane; j < 65; j += 32) {
+      const unsigned long long a = off + 32ull * j;
+      const uint32_t w0 = b.seq.nm[a >> 5], w1 = b.seq.nm[(a >> 5) + 1];
+      const unsigned long long two = ((unsigned long long)w1 << 32) | w0;
+      uint32_t bits = (uint32_t)(two >> (uint32_t)(a & 31));
+      const int rem = (int)len - 32 * j;               // bases beyond the window count as N-free here (never inside a span)
+      if (rem < 32) bits &= rem <= 0 ? 0u : ((1u << rem) - 1u);
+      nmw[j] = bits;
+    }
+    __syncwarp();
+    auto has_n = [&](int lo, int hi) {                 // any N in [lo, hi], 0 <= lo <= hi < len, hi - lo < 64
+      const unsigned long long two = ((unsigned long long)nmw[(lo >> 5) + 1] << 32) | nmw[lo >> 5];
+      const unsigned long long m = (two >> (lo & 31)) & ((hi - lo + 1) >= 64 ? ~0ull : ((1ull << (hi - lo + 1)) - 1ull));
+      return m != 0ull;
+    };
+    auto argmin = [&](int p, bool &tied) {             // leftmost minimum of v[p-w+1 .. p]; tied: attained more than once
+      uint32_t bt = v[p - w + 1]; int bp = p - w + 1; bool td = false;
+      for (int j = p - w + 2; j <= p; j++) { const uint32_t x = v[j]; if (x < bt) { bt = x; bp = j; td = false; } else if (x == bt) td = true; }
+      tied = td;
+      return bp;
+    };
+    for (int base = w - 1; base < npos; base += 32) {
+      const int p = base + lane;
+      bool emit = false;
+      uint32_t val = 0;
+      if (p < npos) {
+        bool t1 = false, t0 = false;
+        const int a = argmin(p, t1);
+        if (p == w - 1) { emit = true; }                                  // the first window: leftmost minimum, no history
+        else { const int a0 = argmin(p - 1, t0); emit = a != a0; if (t1) tie = true; }
+        if (emit) {
+          const int lo = p - w + 1, hi = p + k - 1;
+          bool ok = !has_n(lo, hi);
+          if (ok && (uint32_t)lo == len - (uint32_t)windowSpan) ok = lo > 0 && !has_n(lo - 1, lo - 1);   // run must start before seqLen - windowSpan
+          emit = ok;
+          val = v[a] | (((uint32_t)a & 0xFFFu) << 20);
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, emit);
+      if (emit) stage[n + __popc(m & ((1u << lane) - 1u))] = val;
+      n += __popc(m);
+    }
+    tie = __any_sync(0xffffffffu, tie);
+  }
+  __syncwarp();
+  if (tie) {
+    if (lane == 0) n = lt_scan_window(v, b.seq, off, len, k, w);
+    n = __shfl_sync(0xffffffffu, n, 0);
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) stage[i] = v[i];          // the unsorted list, for the introsort replay
+  } else {
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) v[i] = stage[i];
+  }
+  __syncwarp();
   // 3. bitonic sort on (tuple << 12 | position)
   int P = 1;
   while (P < n) P <<= 1;

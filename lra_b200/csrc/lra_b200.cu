@@ -46,6 +46,7 @@ struct lra_b200_ctx {
   DevBuf sd[12];          // seeding scratch
   DevBuf stt[12];         // statistics scratch
   DevBuf lr[32];          // local index / cluster refinement scratch
+  DevBuf li_tmp;          // LocalIndex staging (one slot per arena base)
   bool keep_stats = false;  // sub-launchers append to stats instead of clearing
   AogPlan *h_plan = nullptr;            // pinned
   unsigned long long *h_misc = nullptr;  // pinned (2 x u64)
@@ -130,6 +131,7 @@ extern "C" void lra_b200_destroy(lra_b200_ctx *ctx) {
   for (DevBuf &b : ctx->sd) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->stt) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->lr) if (b.p) cudaFree(b.p);
+  if (ctx->li_tmp.p) cudaFree(ctx->li_tmp.p);
   for (auto &ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < 4; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]); }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
@@ -957,6 +959,50 @@ extern "C" int lra_b200_calc_stats_batch(lra_b200_ctx *ctx, const lra_b200_seq *
     CU(cudaMemcpyAsync(res->cigar, b.cigar, (size_t)res->n_cigar_total * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
   }
+  return LRA_B200_OK;
+}
+
+extern "C" int lra_b200_calc_stats_batch_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_ir_segments *sg,
+                                                const float *log_lut, lra_b200_stats_result *res) {
+  if (!ctx || !q || !t || !sg || !log_lut || !res) return fail(ctx, LRA_B200_EINVAL, "calc_stats_batch_device: NULL argument");
+  const int S = sg->n_segments;
+  if (S < 0) return fail(ctx, LRA_B200_EINVAL, "calc_stats_batch_device: negative segment count");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  res->n_cigar_total = 0;
+  if (S == 0) return LRA_B200_OK;
+  int rc;
+  DevBuf *B = ctx->stt;
+  if ((rc = ensure(ctx, B[6], 2001 * 4)) || (rc = ensure(ctx, B[11], 64))) return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(B[6].p, log_lut, 2001 * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(B[11].p, 0, 64, st));
+  StatsBatch b;
+  b.q = SeqView{q->b2, q->nm, q->n}; b.t = SeqView{t->b2, t->nm, t->n};
+  b.blocks = sg->blocks_in; b.blk_off = (const unsigned long long *)sg->blk_off; b.blk_cnt = sg->blk_cnt;
+  b.q_base = sg->q_base; b.t_base = sg->t_base; b.read_len = sg->read_len; b.n_seg = S;
+  b.lut = (const float *)B[6].p; b.stats = res->stats; b.value = res->value; b.cig_off = (unsigned long long *)res->cigar_off;
+  b.cigar = res->cigar; b.cigar_cap = res->cigar_cap;
+  const unsigned nb = (unsigned)((S + 127) / 128);
+  cudaEventRecord(ctx->ev[0], st);
+  stats_kernel<false><<<nb, 128, 0, st>>>(b);
+  seed_scan_kernel<<<1, 1024, 0, st>>>(b.cig_off, S, b.cigar_cap, (int *)B[11].p);
+  stats_kernel<true><<<nb, 128, 0, st>>>(b);
+  cudaEventRecord(ctx->ev[1], st);
+  ctx->launches += 3;
+  CU(cudaGetLastError());
+  unsigned long long total = 0;
+  CU(cudaMemcpyAsync(&total, b.cig_off + S, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  res->n_cigar_total = total;
+  {
+    lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "stats(count+scan+emit)");
+    cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]); s2.jobs = (uint64_t)S;
+    s2.algo_bytes = 12ull * sg->n_blocks_in + 4ull * total + 100ull * (uint64_t)S;     // blocks in, CIGAR out, descriptors + counters (bases: see DESIGN.md)
+    ctx->stats.push_back(s2);
+  }
+  if (total > res->cigar_cap) return fail(ctx, LRA_B200_EOVERFLOW, "calc_stats_batch_device: cigar capacity %llu too small, %llu needed",
+                                         (unsigned long long)res->cigar_cap, total);
   return LRA_B200_OK;
 }
 

@@ -58,8 +58,8 @@ static int lindex_layout(lra_b200_ctx *ctx, lra_b200_lindex *li, const uint64_t 
 extern "C" int lra_b200_lindex_build(lra_b200_ctx *ctx, const lra_b200_seq *seq, const uint64_t *seq_start, const uint32_t *seq_len, int32_t n_seqs,
                                      int32_t k, int32_t w, int32_t window, int32_t max_freq, lra_b200_lindex **out) {
   if (!ctx || !seq || !out || n_seqs < 0 || (n_seqs && (!seq_start || !seq_len))) return fail(ctx, LRA_B200_EINVAL, "lindex_build: bad argument");
-  if (k < 1 || k > 10 || w < 1 || window < 1 || window > kLidxMaxWindow || max_freq < 1)
-    return fail(ctx, LRA_B200_EINVAL, "lindex_build: need 1 <= k <= 10 (20-bit LocalTuple), w >= 1, 1 <= window <= %d, max_freq >= 1", kLidxMaxWindow);
+  if (k < 1 || k > 10 || w < 1 || w + k - 1 > 60 || window < 1 || window > kLidxMaxWindow || max_freq < 1)
+    return fail(ctx, LRA_B200_EINVAL, "lindex_build: need 1 <= k <= 10 (20-bit LocalTuple), w >= 1, w + k <= 61, 1 <= window <= %d, max_freq >= 1", kLidxMaxWindow);
   for (int s = 0; s < n_seqs; s++)
     if (seq_start[s] + seq_len[s] > seq->n) return fail(ctx, LRA_B200_EINVAL, "lindex_build: sequence %d ends beyond the arena", s);
   CU(cudaSetDevice(ctx->device));
@@ -73,13 +73,21 @@ extern "C" int lra_b200_lindex_build(lra_b200_ctx *ctx, const lra_b200_seq *seq,
   cudaStream_t st = ctx->stream;
   if (W == 0) { CU(cudaMemsetAsync(li->bnd, 0, 16, st)); CU(cudaStreamSynchronize(st)); *out = li; return LRA_B200_OK; }
   // staging: one slot per arena base (transient; 4 B/base -- 12 GB for a 3 Gb genome, freed below)
+  // (read batches re-use a grow-only context buffer; anything above 4 GB is allocated for this call only)
   uint32_t *tmp = nullptr;
-  if (cudaMalloc(&tmp, ((size_t)seq->n + 64) * 4) != cudaSuccess) { lindex_release(li); return fail(ctx, LRA_B200_ECUDA, "lindex_build: cannot allocate %zu bytes of staging", ((size_t)seq->n + 64) * 4); }
+  const size_t tmp_bytes = ((size_t)seq->n + 64) * 4;
+  const bool own_tmp = tmp_bytes > (4ull << 30);
+  if (own_tmp) {
+    if (cudaMalloc(&tmp, tmp_bytes) != cudaSuccess) { lindex_release(li); return fail(ctx, LRA_B200_ECUDA, "lindex_build: cannot allocate %zu bytes of staging", tmp_bytes); }
+  } else {
+    if ((rc = ensure(ctx, ctx->li_tmp, tmp_bytes))) { lindex_release(li); return rc; }
+    tmp = (uint32_t *)ctx->li_tmp.p;
+  }
   LidxBuild b;
   b.seq = SeqView{seq->b2, seq->nm, seq->n};
   b.win_off = li->win_off; b.win_len = li->win_len; b.n_win = (int)W; b.k = k; b.w = w; b.max_freq = max_freq;
   b.tmp = tmp; b.cnt = li->bnd; b.mins = nullptr;
-  if ((rc = ensure(ctx, ctx->lr[0], 64))) { cudaFree(tmp); lindex_release(li); return rc; }
+  if ((rc = ensure(ctx, ctx->lr[0], 64))) { if (own_tmp) cudaFree(tmp); lindex_release(li); return rc; }
   cudaMemsetAsync(ctx->lr[0].p, 0, 64, st);
   cudaEventRecord(ctx->ev[0], st);
   lidx_window_kernel<<<(unsigned)((W + kLidxWarps - 1) / kLidxWarps), 32 * kLidxWarps, 0, st>>>(b);
@@ -91,7 +99,7 @@ extern "C" int lra_b200_lindex_build(lra_b200_ctx *ctx, const lra_b200_seq *seq,
   if (e == cudaSuccess) e = cudaMemcpyAsync(&total, li->bnd + W, 8, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaMalloc(&li->mins, ((size_t)total + 16) * 4);
-  if (e != cudaSuccess) { cudaFree(tmp); lindex_release(li); return fail(ctx, LRA_B200_ECUDA, "lindex_build: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { if (own_tmp) cudaFree(tmp); lindex_release(li); return fail(ctx, LRA_B200_ECUDA, "lindex_build: %s", cudaGetErrorString(e)); }
   li->n_mins = total;
   b.mins = li->mins;
   cudaEventRecord(ctx->ev[2], st);
@@ -100,7 +108,7 @@ extern "C" int lra_b200_lindex_build(lra_b200_ctx *ctx, const lra_b200_seq *seq,
   ctx->launches++;
   e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(tmp);
+  if (own_tmp) cudaFree(tmp);
   if (e != cudaSuccess) { lindex_release(li); return fail(ctx, LRA_B200_ECUDA, "lindex_build: %s", cudaGetErrorString(e)); }
   {
     lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "lidx_window");
@@ -155,67 +163,53 @@ static LidxView lidx_view(const lra_b200_lindex *li) {
   return LidxView{li->win_off, li->win_len, li->bnd, li->mins, li->win_first, li->seq_start, li->seq_len, (int)li->n_win, li->n_seq};
 }
 
-extern "C" int lra_b200_refine_clusters_batch(lra_b200_ctx *ctx, const lra_b200_lindex *gl, const lra_b200_lindex *rf, const lra_b200_lindex *rr,
-                                              const lra_b200_clusters *cl, lra_b200_refined *res) {
-  if (!ctx || !gl || !rf || !rr || !cl || !res) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: NULL argument");
+// pow2ceil(anchors of cluster c) -> key_off[c] (scanned afterwards): slots of the bitonic sort scratch
+__global__ void lref_keyslots_kernel(const unsigned long long *m_off, int n, unsigned long long *key_off) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const unsigned long long nm = m_off[c + 1] - m_off[c];
+  unsigned long long P = 1;
+  while (P < nm) P <<= 1;
+  key_off[c] = P;
+}
+
+// The launch sequence of a13 on device-resident clusters (cl: device pointers) into device-resident results (res: device pointers;
+// m_q_out / m_t_out / box_out may be NULL).  M = total number of input anchors.
+static int lref_run(lra_b200_ctx *ctx, const lra_b200_lindex *gl, const lra_b200_lindex *rf, const lra_b200_lindex *rr, const lra_b200_clusters *cl,
+                    size_t M, lra_b200_refined *res) {
   const int n = cl->n_clusters;
-  if (n < 0 || cl->n_hdr < 2 || !cl->hdr_pos) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: bad cluster batch");
-  if (rf->n_seq != rr->n_seq) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: the two read images differ in their number of reads");
-  CU(cudaSetDevice(ctx->device));
-  ctx->stats.clear();
-  res->n_anchors = 0; res->n_units = 0; res->n_tasks = 0;
-  if (n == 0) { if (res->r_off) res->r_off[0] = 0; return LRA_B200_OK; }
-  for (int c = 0; c < n; c++)
-    if (cl->read_id[c] >= (uint32_t)rf->n_seq) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: cluster %d names read %u of %d", c, cl->read_id[c], rf->n_seq);
-  const size_t M = (size_t)cl->m_off[n];
-  std::vector<unsigned long long> key_off((size_t)n);
-  size_t keys_total = 0;
-  for (int c = 0; c < n; c++) {
-    const size_t nm = (size_t)(cl->m_off[c + 1] - cl->m_off[c]);
-    size_t P = 1; while (P < nm) P <<= 1;
-    key_off[c] = keys_total; keys_total += P;
-  }
   int rc;
   DevBuf *B = ctx->lr;
-  const size_t acap = (size_t)(res->anchor_cap ? res->anchor_cap : 1);
-  if ((rc = ensure(ctx, B[1], M * 4 + 16)) || (rc = ensure(ctx, B[2], M * 4 + 16)) || (rc = ensure(ctx, B[3], ((size_t)n + 1) * 8)) ||
-      (rc = ensure(ctx, B[4], (size_t)n * 16)) || (rc = ensure(ctx, B[5], (size_t)n)) || (rc = ensure(ctx, B[6], (size_t)n * 4)) ||
-      (rc = ensure(ctx, B[7], (size_t)cl->n_hdr * 8)) || (rc = ensure(ctx, B[8], M * 4 + 16)) || (rc = ensure(ctx, B[9], M * 4 + 16)) ||
-      (rc = ensure(ctx, B[10], (size_t)n * 16)) || (rc = ensure(ctx, B[11], keys_total * 8 + 16)) || (rc = ensure(ctx, B[12], (size_t)n * 8)) ||
-      (rc = ensure(ctx, B[13], (size_t)n * 4)) || (rc = ensure(ctx, B[14], (size_t)n * 4)) || (rc = ensure(ctx, B[15], (size_t)n * 16)) ||
+  if ((rc = ensure(ctx, B[8], M * 4 + 16)) || (rc = ensure(ctx, B[9], M * 4 + 16)) || (rc = ensure(ctx, B[10], (size_t)n * 16)) ||
+      (rc = ensure(ctx, B[11], (2 * M + (size_t)n + 2) * 8)) || (rc = ensure(ctx, B[12], ((size_t)n + 1) * 8)) ||
       (rc = ensure(ctx, B[16], (size_t)n * 4)) || (rc = ensure(ctx, B[17], (size_t)n * 4)) || (rc = ensure(ctx, B[18], ((size_t)n + 1) * 8)) ||
-      (rc = ensure(ctx, B[24], acap * 4)) || (rc = ensure(ctx, B[25], acap * 4)) || (rc = ensure(ctx, B[26], acap * 4)) ||
-      (rc = ensure(ctx, B[27], ((size_t)n + 1) * 8)) || (rc = ensure(ctx, B[28], (size_t)n * 16)) || (rc = ensure(ctx, B[29], (size_t)n * 4)) ||
       (rc = ensure(ctx, B[0], 64)))
     return rc;
   cudaStream_t st = ctx->stream;
-  if (M) { CU(cudaMemcpyAsync(B[1].p, cl->m_q, M * 4, cudaMemcpyHostToDevice, st)); CU(cudaMemcpyAsync(B[2].p, cl->m_t, M * 4, cudaMemcpyHostToDevice, st)); }
-  CU(cudaMemcpyAsync(B[3].p, cl->m_off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(B[4].p, cl->box, (size_t)n * 16, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(B[5].p, cl->strand, (size_t)n, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(B[6].p, cl->read_id, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(B[7].p, cl->hdr_pos, (size_t)cl->n_hdr * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(B[12].p, key_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(B[0].p, 0, 64, st));
   LrefBatch b;
   memset(&b, 0, sizeof b);
   b.n_clusters = n;
-  b.in_q = (const uint32_t *)B[1].p; b.in_t = (const uint32_t *)B[2].p; b.m_off = (const unsigned long long *)B[3].p; b.in_box = (const uint32_t *)B[4].p;
-  b.strand = (const uint8_t *)B[5].p; b.read_id = (const uint32_t *)B[6].p; b.hdr_pos = (const unsigned long long *)B[7].p; b.n_hdr = cl->n_hdr;
+  b.in_q = cl->m_q; b.in_t = cl->m_t; b.m_off = (const unsigned long long *)cl->m_off; b.in_box = cl->box;
+  b.strand = cl->strand; b.read_id = cl->read_id; b.hdr_pos = (const unsigned long long *)cl->hdr_pos; b.n_hdr = cl->n_hdr;
   b.gl = lidx_view(gl); b.rd[0] = lidx_view(rf); b.rd[1] = lidx_view(rr);
   b.global_k = cl->global_k; b.small_k = cl->small_k; b.window = cl->window; b.local_max_freq = cl->local_max_freq;
-  b.m_q = (uint32_t *)B[8].p; b.m_t = (uint32_t *)B[9].p; b.box = (uint32_t *)B[10].p; b.keys = (unsigned long long *)B[11].p;
-  b.key_off = (const unsigned long long *)B[12].p; b.status = (int32_t *)B[13].p; b.chrom = (int32_t *)B[14].p; b.diag = (long long *)B[15].p;
+  b.m_q = res->m_q_out ? res->m_q_out : (uint32_t *)B[8].p; b.m_t = res->m_t_out ? res->m_t_out : (uint32_t *)B[9].p;
+  b.box = res->box_out ? res->box_out : (uint32_t *)B[10].p;
+  b.keys = (unsigned long long *)B[11].p; b.key_off = (const unsigned long long *)B[12].p;
+  b.status = res->status; b.chrom = res->chrom; b.diag = (long long *)res->diag;
   b.chrom_off = (uint32_t *)B[16].p; b.ls = (int32_t *)B[17].p; b.unit_off = (unsigned long long *)B[18].p;
-  b.r_q = (uint32_t *)B[24].p; b.r_t = (uint32_t *)B[25].p; b.r_tup = (uint32_t *)B[26].p; b.out_cap = res->anchor_cap;
-  b.r_off = (unsigned long long *)B[27].p; b.rbox = (uint32_t *)B[28].p; b.eff = (float *)B[29].p;
+  b.r_q = res->r_q; b.r_t = res->r_t; b.r_tup = res->r_tup; b.out_cap = res->anchor_cap;
+  b.r_off = (unsigned long long *)res->r_off; b.rbox = res->rbox; b.eff = res->eff;
   int *errflag = (int *)B[0].p;
   int evi = 0;
   auto rec = [&]() { cudaEventRecord(ctx->ev[evi++], st); };
   rec();
+  lref_keyslots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.m_off, n, (unsigned long long *)B[12].p);
+  seed_scan_kernel<<<1, 1024, 0, st>>>((unsigned long long *)B[12].p, n, ~0ull, errflag);
   lref_prep_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(b);
   seed_scan_kernel<<<1, 1024, 0, st>>>(b.unit_off, n, ~0ull, errflag);
-  ctx->launches += 2;
+  ctx->launches += 4;
   rec();
   CU(cudaGetLastError());
   unsigned long long n_units = 0, n_tasks = 0, n_out = 0;
@@ -241,10 +235,15 @@ extern "C" int lra_b200_refine_clusters_batch(lra_b200_ctx *ctx, const lra_b200_
   CU(cudaMemsetAsync(b.out_off, 0, (size_t)(n_tasks + 2) * 8, st));
   if (n_tasks) {
     if (n_tasks > 0x7FFFFFFFull) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: %llu window pairs in one batch", n_tasks);
-    lref_task_kernel<false><<<(unsigned)((n_tasks + 127) / 128), 128, 0, st>>>(b, n_units, n_tasks);
+    // measured on B200 (tools/lref_timing.py): one task per THREAD (3.7 ms per pass for 74 k window pairs) beats one task per warp
+    // (16 ms): the stage is bound by instruction issue, not by latency, and the lock-step warp form issues 8x more instructions
+    static const bool literal = getenv("LRA_B200_LREF_WARP") == nullptr;
+    if (literal) lref_task_literal_kernel<false><<<(unsigned)((n_tasks + 127) / 128), 128, 0, st>>>(b, n_units, n_tasks);
+    else lref_task_kernel<false><<<(unsigned)((n_tasks + 3) / 4), 128, 0, st>>>(b, n_units, n_tasks);
     seed_scan_kernel<<<1, 1024, 0, st>>>(b.out_off, (int)n_tasks, res->anchor_cap, errflag);
     rec();
-    lref_task_kernel<true><<<(unsigned)((n_tasks + 127) / 128), 128, 0, st>>>(b, n_units, n_tasks);
+    if (literal) lref_task_literal_kernel<true><<<(unsigned)((n_tasks + 127) / 128), 128, 0, st>>>(b, n_units, n_tasks);
+    else lref_task_kernel<true><<<(unsigned)((n_tasks + 3) / 4), 128, 0, st>>>(b, n_units, n_tasks);
     ctx->launches += 3;
   } else rec();
   rec();
@@ -253,31 +252,94 @@ extern "C" int lra_b200_refine_clusters_batch(lra_b200_ctx *ctx, const lra_b200_
   rec();
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(&n_out, b.out_off + n_tasks, 8, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(res->status, b.status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(res->chrom, b.chrom, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(res->diag, b.diag, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(res->r_off, b.r_off, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(res->rbox, b.rbox, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(res->eff, b.eff, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  if (res->box_out) CU(cudaMemcpyAsync(res->box_out, b.box, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
-  if (M && res->m_q_out) CU(cudaMemcpyAsync(res->m_q_out, b.m_q, M * 4, cudaMemcpyDeviceToHost, st));
-  if (M && res->m_t_out) CU(cudaMemcpyAsync(res->m_t_out, b.m_t, M * 4, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   res->n_anchors = n_out; res->n_units = n_units; res->n_tasks = n_tasks;
   static const char *names[5] = {"lref_prep(+sort)", "lref_unit", "lref_task<count>", "lref_task<emit>", "lref_finish"};
   const uint64_t jobs[5] = {(uint64_t)n, n_units, n_tasks, n_tasks, (uint64_t)n};
+  const uint64_t nmins_q = rf->n_mins + rr->n_mins;
   for (int i = 0; i < 5; i++) {
     lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "%s", names[i]);
     cudaEventElapsedTime(&s2.ms, ctx->ev[i], ctx->ev[i + 1]); s2.jobs = jobs[i];
+    // algorithmic bytes of a task pass: both tuple lists of every window pair once (~2 x 700 x 4 B), 24 B of descriptors, anchors out
+    if (i == 2 || i == 3) s2.algo_bytes = n_tasks * 24 + (n_tasks ? (uint64_t)((double)n_tasks * 4.0 * ((double)nmins_q / (double)(rf->n_win + rr->n_win + 1) + (double)gl->n_mins / (double)(gl->n_win + 1))) : 0)
+                                          + (i == 3 ? 12 * n_out : 0);
     ctx->stats.push_back(s2);
   }
   if (n_out > res->anchor_cap) return fail(ctx, LRA_B200_EOVERFLOW, "refine_clusters_batch: anchor capacity %llu too small, %llu needed",
                                            (unsigned long long)res->anchor_cap, n_out);
-  if (n_out) {
-    CU(cudaMemcpyAsync(res->r_q, b.r_q, (size_t)n_out * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(res->r_t, b.r_t, (size_t)n_out * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(res->r_tup, b.r_tup, (size_t)n_out * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-  }
   return LRA_B200_OK;
+}
+
+extern "C" int lra_b200_refine_clusters_batch_device(lra_b200_ctx *ctx, const lra_b200_lindex *gl, const lra_b200_lindex *rf, const lra_b200_lindex *rr,
+                                                     const lra_b200_clusters *cl, uint64_t n_anchors_in, lra_b200_refined *res) {
+  if (!ctx || !gl || !rf || !rr || !cl || !res) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch_device: NULL argument");
+  if (cl->n_clusters < 0 || cl->n_hdr < 2 || !cl->hdr_pos) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch_device: bad cluster batch");
+  if (rf->n_seq != rr->n_seq) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch_device: the two read images differ in their number of reads");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  res->n_anchors = 0; res->n_units = 0; res->n_tasks = 0;
+  if (cl->n_clusters == 0) return LRA_B200_OK;
+  return lref_run(ctx, gl, rf, rr, cl, (size_t)n_anchors_in, res);
+}
+
+extern "C" int lra_b200_refine_clusters_batch(lra_b200_ctx *ctx, const lra_b200_lindex *gl, const lra_b200_lindex *rf, const lra_b200_lindex *rr,
+                                              const lra_b200_clusters *cl, lra_b200_refined *res) {
+  if (!ctx || !gl || !rf || !rr || !cl || !res) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: NULL argument");
+  const int n = cl->n_clusters;
+  if (n < 0 || cl->n_hdr < 2 || !cl->hdr_pos) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: bad cluster batch");
+  if (rf->n_seq != rr->n_seq) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: the two read images differ in their number of reads");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  res->n_anchors = 0; res->n_units = 0; res->n_tasks = 0;
+  if (n == 0) { if (res->r_off) res->r_off[0] = 0; return LRA_B200_OK; }
+  for (int c = 0; c < n; c++)
+    if (cl->read_id[c] >= (uint32_t)rf->n_seq) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: cluster %d names read %u of %d", c, cl->read_id[c], rf->n_seq);
+  const size_t M = (size_t)cl->m_off[n];
+  int rc;
+  DevBuf *B = ctx->lr;
+  const size_t acap = (size_t)(res->anchor_cap ? res->anchor_cap : 1);
+  if ((rc = ensure(ctx, B[1], M * 4 + 16)) || (rc = ensure(ctx, B[2], M * 4 + 16)) || (rc = ensure(ctx, B[3], ((size_t)n + 1) * 8)) ||
+      (rc = ensure(ctx, B[4], (size_t)n * 16)) || (rc = ensure(ctx, B[5], (size_t)n)) || (rc = ensure(ctx, B[6], (size_t)n * 4)) ||
+      (rc = ensure(ctx, B[7], (size_t)cl->n_hdr * 8)) || (rc = ensure(ctx, B[13], (size_t)n * 4)) || (rc = ensure(ctx, B[14], (size_t)n * 4)) ||
+      (rc = ensure(ctx, B[15], (size_t)n * 16)) || (rc = ensure(ctx, B[24], acap * 4)) || (rc = ensure(ctx, B[25], acap * 4)) ||
+      (rc = ensure(ctx, B[26], acap * 4)) || (rc = ensure(ctx, B[27], ((size_t)n + 1) * 8)) || (rc = ensure(ctx, B[28], (size_t)n * 16)) ||
+      (rc = ensure(ctx, B[29], (size_t)n * 4)) || (rc = ensure(ctx, B[30], M * 4 + 16)) || (rc = ensure(ctx, B[31], M * 4 + 16)) ||
+      (rc = ensure(ctx, B[10], (size_t)n * 16)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  if (M) { CU(cudaMemcpyAsync(B[1].p, cl->m_q, M * 4, cudaMemcpyHostToDevice, st)); CU(cudaMemcpyAsync(B[2].p, cl->m_t, M * 4, cudaMemcpyHostToDevice, st)); }
+  CU(cudaMemcpyAsync(B[3].p, cl->m_off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[4].p, cl->box, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[5].p, cl->strand, (size_t)n, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[6].p, cl->read_id, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[7].p, cl->hdr_pos, (size_t)cl->n_hdr * 8, cudaMemcpyHostToDevice, st));
+  lra_b200_clusters dcl = *cl;
+  dcl.m_q = (const uint32_t *)B[1].p; dcl.m_t = (const uint32_t *)B[2].p; dcl.m_off = (const uint64_t *)B[3].p; dcl.box = (const uint32_t *)B[4].p;
+  dcl.strand = (const uint8_t *)B[5].p; dcl.read_id = (const uint32_t *)B[6].p; dcl.hdr_pos = (const uint64_t *)B[7].p;
+  lra_b200_refined dres;
+  memset(&dres, 0, sizeof dres);
+  dres.status = (int32_t *)B[13].p; dres.chrom = (int32_t *)B[14].p; dres.diag = (int64_t *)B[15].p; dres.r_off = (uint64_t *)B[27].p;
+  dres.r_q = (uint32_t *)B[24].p; dres.r_t = (uint32_t *)B[25].p; dres.r_tup = (uint32_t *)B[26].p; dres.anchor_cap = res->anchor_cap;
+  dres.rbox = (uint32_t *)B[28].p; dres.eff = (float *)B[29].p; dres.m_q_out = (uint32_t *)B[30].p; dres.m_t_out = (uint32_t *)B[31].p;
+  dres.box_out = (uint32_t *)B[10].p;
+  rc = lref_run(ctx, gl, rf, rr, &dcl, M, &dres);
+  res->n_anchors = dres.n_anchors; res->n_units = dres.n_units; res->n_tasks = dres.n_tasks;
+  if (rc != LRA_B200_OK && rc != LRA_B200_EOVERFLOW) return rc;
+  CU(cudaMemcpyAsync(res->status, dres.status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->chrom, dres.chrom, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->diag, dres.diag, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->r_off, dres.r_off, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->rbox, dres.rbox, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->eff, dres.eff, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (res->box_out) CU(cudaMemcpyAsync(res->box_out, dres.box_out, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+  if (M && res->m_q_out) CU(cudaMemcpyAsync(res->m_q_out, dres.m_q_out, M * 4, cudaMemcpyDeviceToHost, st));
+  if (M && res->m_t_out) CU(cudaMemcpyAsync(res->m_t_out, dres.m_t_out, M * 4, cudaMemcpyDeviceToHost, st));
+  const uint64_t n_out = dres.n_anchors;
+  if (rc == LRA_B200_OK && n_out) {
+    CU(cudaMemcpyAsync(res->r_q, dres.r_q, (size_t)n_out * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->r_t, dres.r_t, (size_t)n_out * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->r_tup, dres.r_tup, (size_t)n_out * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  return rc;
 }

@@ -10,8 +10,9 @@
 // The reference's triple loop  cluster -> genome window lsi -> read window qi  is flattened into three launches:
 //   lref_prep_kernel     one warp per cluster: contig, strand swap, diagonal band, sort by (t, q), window range [ls, le]
 //   lref_unit_kernel     one thread per (cluster, lsi): anchors inside the window -> read interval -> read windows [qis, qie]
-//   lref_task_kernel<E>  one thread per (cluster, lsi, qi): CompareLists of two ~700-tuple lists + the band/box filter;
+//   lref_task_literal_kernel<E>  one thread per (cluster, lsi, qi): CompareLists of two ~700-tuple lists + the band/box filter;
 //                        count pass, scan, emit pass: refined anchors land in the reference's order
+//                        (lref_task_kernel<E>: the same per warp with shared searches -- slower, kept as a cross-check)
 //   lref_finish_kernel   one warp per cluster: strand swap back, boundaries, refineEffiency (binary32 division)
 #pragma once
 #include "lra_common.cuh"
@@ -206,9 +207,10 @@ __global__ void __launch_bounds__(128) lref_unit_kernel(LrefBatch b, unsigned lo
   b.task_off[u] = qie >= qis ? (unsigned long long)(qie - qis + 1) : 0ull;
 }
 
-// one thread per (cluster, lsi, qi): CompareLists<LocalTuple,SmallTuple>(Global = false) + AppendValues
+// one THREAD per (cluster, lsi, qi): CompareLists<LocalTuple,SmallTuple>(Global = false) + AppendValues, statement by statement
+// (the default: measured 4x faster than the warp form below, which LRA_B200_LREF_WARP=1 selects)
 template <bool EMIT>
-__global__ void __launch_bounds__(128) lref_task_kernel(LrefBatch b, unsigned long long n_units, unsigned long long n_tasks) {
+__global__ void __launch_bounds__(128) lref_task_literal_kernel(LrefBatch b, unsigned long long n_units, unsigned long long n_tasks) {
   const unsigned long long task = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (task >= n_tasks) return;
   unsigned long long u;
@@ -299,6 +301,136 @@ __global__ void __launch_bounds__(128) lref_task_kernel(LrefBatch b, unsigned lo
 #undef QK
 #undef TK
   if (!EMIT) b.out_off[task] = n_out;
+}
+
+// ---- one WARP per (cluster, lsi, qi).  The control flow of CompareLists is replayed by all lanes in lock step on uniform state
+// (no divergence, every load a broadcast out of L1); the lanes share the two searches that dominate it: the binary searches
+// become 32-ary searches (one ballot per level), the "skip what cannot match" loops advance 32 tuples per ballot.
+__device__ __forceinline__ long lref_warp_bound(const uint32_t *t, long lo, long hi, uint32_t key, bool upper, int lane) {
+  // first index in [lo, hi) whose tuple is >= key (upper: > key); the list is sorted, so the result is that of std::lower/upper_bound
+  while (hi - lo > 32) {
+    const long stride = (hi - lo + 31) >> 5;
+    const long idx = lo + (long)lane * stride;
+    bool before = false;
+    if (idx < hi) { const uint32_t x = lt_t(t[idx]); before = upper ? (x <= key) : (x < key); }
+    const int c = __popc(__ballot_sync(0xffffffffu, before));
+    if (c == 0) return lo;
+    const long nlo = lo + (long)(c - 1) * stride + 1;
+    const long nhi = lo + (long)c * stride;
+    lo = nlo; hi = nhi < hi ? nhi : hi;
+  }
+  bool before = false;
+  if (lo + lane < hi) { const uint32_t x = lt_t(t[lo + lane]); before = upper ? (x <= key) : (x < key); }
+  return lo + __popc(__ballot_sync(0xffffffffu, before));
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(128) lref_task_kernel(LrefBatch b, unsigned long long n_units, unsigned long long n_tasks) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long task = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (task >= n_tasks) return;
+  unsigned long long u;
+  { unsigned long long lo = 0, len = n_units;
+    while (len > 0) { const unsigned long long half = len >> 1; if (b.task_off[lo + half] <= task) { lo += half + 1; len -= half + 1; } else len = half; }
+    u = lo - 1; }
+  const int c = (int)b.u_cluster[u];
+  const int lsi = b.ls[c] + (int)(u - b.unit_off[c]);
+  const int s = b.strand[c];
+  const uint32_t rid = b.read_id[c];
+  const LidxView &rd = b.rd[s];
+  const int qw = (int)rd.win_first[rid] + (int)b.u_qis[u] + (int)(task - b.task_off[u]);
+  const uint32_t *q = rd.mins + rd.bnd[qw];
+  const long nq = (long)(rd.bnd[qw + 1] - rd.bnd[qw]);
+  const uint32_t *t = b.gl.mins + b.gl.bnd[lsi];
+  const long nt = (long)(b.gl.bnd[lsi + 1] - b.gl.bnd[lsi]);
+  const uint32_t readSegmentStart = (uint32_t)(rd.win_off[qw] - rd.seq_start[rid]);
+  const uint32_t gStart = b.u_gstart[u];
+  const long long minDN = b.diag[2 * c], maxDN = b.diag[2 * c + 1];
+  const uint32_t *box = b.box + 4 * c;
+  const uint32_t chromOffset = b.chrom_off[c];
+  const uint32_t bqs = box[0], bqe = box[1], bts = box[2] - chromOffset, bte = box[3] - chromOffset;
+  const long maxFreq = (long)b.local_max_freq;
+  unsigned long long n_out = 0;
+  const unsigned long long obase = EMIT ? b.out_off[task] : 0ull;
+  auto push = [&](long qi, long ti) {       // uniform: every lane sees the same pair, lane 0 stores it
+    const uint32_t qv = q[qi], tv = t[ti];
+    const uint32_t qp = (qv >> 20) + readSegmentStart, tp = (tv >> 20) + gStart;
+    const long long d = (long long)tp - (long long)qp;
+    if (d >= minDN && d <= maxDN && qp >= bqs && qp < bqe && tp >= bts && tp < bte) {
+      if (EMIT && lane == 0) {
+        const unsigned long long o = obase + n_out;
+        if (o < b.out_cap) { b.r_q[o] = qp; b.r_t[o] = tp; b.r_tup[o] = lt_t(qv); }
+      }
+      n_out++;
+    }
+  };
+#define QK(i) lt_t(q[i])
+#define TK(i) lt_t(t[i])
+  if (nq > 0 && nt > 0) {
+    long qs = 0, qe = nq - 1, ts = 0, te = nt;
+    do {
+      { // while (qs <= qe && QK(qs) < TK(ts)) qs++;
+        const uint32_t k0 = TK(ts);
+        for (;;) {
+          const long i = qs + lane;
+          const bool adv = i <= qe && QK(i) < k0;
+          const unsigned m = __ballot_sync(0xffffffffu, adv);
+          const int run = (m == 0xffffffffu) ? 32 : __ffs(~m) - 1;     // tuples are sorted: the predicate holds for a prefix
+          qs += run;
+          if (run < 32) break;
+        }
+      }
+      if (qs >= qe) break;
+      const uint32_t startGap = (QK(qs) - TK(ts)) & 0xFFFFFu;       // LocalTuple bit-field arithmetic: 20 bits
+      { // while (qe > qs && te > ts && QK(qe) > TK(te - 1)) qe--;
+        if (te > ts) {
+          const uint32_t k1 = TK(te - 1);
+          for (;;) {
+            const long i = qe - lane;
+            const bool adv = i > qs && QK(i) > k1;
+            const unsigned m = __ballot_sync(0xffffffffu, adv);
+            const int run = (m == 0xffffffffu) ? 32 : __ffs(~m) - 1;
+            qe -= run;
+            if (run < 32) break;
+          }
+        }
+      }
+      const uint32_t endGap = (TK(te - 1) - QK(qe)) & 0xFFFFFu;
+      if (startGap == 0 || startGap > endGap) {
+        const long tsOrig = ts, qsOrig = qs;
+        ts = lref_warp_bound(t, ts, te, QK(qs), false, lane);
+        if (ts < nt && TK(ts) == QK(qs)) {
+          const long tsStart = ts;
+          long tsi = ts;
+          while (tsi != te && QK(qs) == TK(tsi)) tsi++;
+          const long qsStart = qs;
+          while (qs < qe && QK(qs + 1) == QK(qs)) qs++;
+          for (long ti = tsStart; ti != tsi; ti++)
+            if (qs - qsStart < maxFreq)
+              for (long qi = qsStart; qi <= qs; qi++) push(qi, ti);
+        }
+        { const uint32_t k0 = TK(tsOrig); while (ts < te && TK(ts) == k0) ts++; }
+        { const uint32_t k0 = QK(qsOrig); while (qs < qe && QK(qs) == k0) qs++; }
+      } else {
+        if (te != nt && TK(te - 1) == QK(qe)) { /* pass */ }
+        else te = lref_warp_bound(t, ts, te, QK(qe), true, lane);
+        const long teStart = te;
+        long tei = te;
+        while (tei > ts && TK(tei - 1) == QK(qe)) tei--;
+        if (tei < teStart && teStart > 0) {
+          const long qeStart = qe;
+          while (qe > qs && QK(qe) == QK(qe - 1)) qe--;
+          for (long ti = tei; ti < teStart; ti++)
+            if (qeStart - qe < maxFreq)
+              for (long qi = qe; qi <= qeStart; qi++) push(qi, ti);
+        }
+        te = tei;
+      }
+    } while (qs < qe && ts < te);
+  }
+#undef QK
+#undef TK
+  if (!EMIT && lane == 0) b.out_off[task] = n_out;
 }
 
 // one warp per cluster: range of its refined anchors, strand swap back, boundaries, efficiency

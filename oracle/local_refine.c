@@ -387,3 +387,108 @@ long lra_oracle_refine_cluster(uint32_t *mq, uint32_t *mt, long nm, uint32_t *bo
   }
   return n_out;
 }
+
+/* ---- a13 (low-accuracy pipeline): one iteration (one split chain) of the loop of Refine_splitchain, ChainRefine.h:383-576.
+ *   mq / mt / mlen / mstrand [n]   the chain's anchors in chain order: read position and GLOBAL genome position as stored in the clusters,
+ *                                  anchor length (matchesLengths) and the strand of the cluster the anchor comes from.  The reference flips
+ *                                  the clusters in place for the duration of the call (t -= chromOffset; q = L - (q + opts.globalK) on
+ *                                  strand-1 clusters, ChainRefine.h:399-411) and restores them before returning (:554-565).
+ *   box[4]                         QStart, QEnd, TStart, TEnd of the split chain (T global), chrom = its chromIndex, strand = its Strand
+ *   limitrefine                    opts.limitrefine (default true): the band of every genome window is [min diag of the anchors in the
+ *                                  window - 100, +inf): the upper bound `miniMaxDiag` is read uninitialised in the reference (:493) and holds
+ *                                  a stack address in the stock build, i.e. it never filters
+ *   info / diag / eff as in lra_oracle_refine_cluster (status 1: empty chain).  A window index past the genome's last window (le can be one
+ *   past it when TEnd + window reaches the end of the last contig; the reference then reads past seqOffsets) is skipped. */
+long lra_oracle_refine_splitchain(const uint32_t *mq_in, const uint32_t *mt_in, const uint32_t *mlen, const uint8_t *mstrand, long n, const uint32_t *box,
+                                  int chrom, int strand, uint32_t readLen, const uint64_t *hdr_pos, int n_hdr,
+                                  const uint64_t *gl_off, long gl_noff, const uint64_t *gl_bnd, const uint32_t *gl_min,
+                                  const uint64_t *rd_off, long rd_noff, const uint64_t *rd_bnd, const uint32_t *rd_min,
+                                  int globalK, int smallK, int window, long localMaxFreq, int limitrefine,
+                                  uint32_t *rq, uint32_t *rt, uint32_t *rtup, long cap, int32_t *info, int64_t *diag, float *eff) {
+  for (int i = 0; i < 8; i++) info[i] = 0;
+  diag[0] = diag[1] = 0; *eff = 0;
+  if (n == 0) { info[0] = 1; return 0; }
+  info[1] = chrom;
+  const uint32_t chromOffset = (uint32_t)hdr_pos[chrom];
+  uint32_t *mq = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)n), *mt = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)n);
+  for (long i = 0; i < n; i++) { mt[i] = mt_in[i] - chromOffset; mq[i] = mstrand[i] ? readLen - (mq_in[i] + (uint32_t)globalK) : mq_in[i]; }
+  const uint32_t QStart = box[0], QEnd = box[1], TStart = box[2], TEnd = box[3];
+  const uint32_t chromEndOffset = (uint32_t)hdr_pos[hdr_find(hdr_pos, n_hdr, (uint64_t)TEnd) + 1];
+  int64_t maxDN = (int64_t)mt[0] - (int64_t)mq[0], minDN = maxDN;
+  for (long i = 0; i < n; i++) { int64_t d = (int64_t)mt[i] - (int64_t)mq[i]; if (d > maxDN) maxDN = d; if (d < minDN) minDN = d; }
+  maxDN += 50; minDN -= 50;
+  diag[0] = minDN; diag[1] = maxDN;
+  const uint32_t wts = (TStart >= chromOffset + (uint32_t)window) ? TStart - (uint32_t)window : chromOffset;
+  const uint32_t wte = (TEnd + (uint32_t)window < chromEndOffset) ? TEnd + (uint32_t)window : chromEndOffset;
+  const long ls = lra_oracle_lookup_index(gl_off, gl_noff, wts), le = lra_oracle_lookup_index(gl_off, gl_noff, wte);
+  long n_out = 0, scap = 65536;
+  uint32_t *sq = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)scap), *st = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)scap);
+  long matchStart = 0, matchEnd = 0;
+  uint32_t bqs, bqe;
+  if (strand == 0) { bqs = QStart; bqe = QEnd; } else { bqs = readLen - QEnd; bqe = readLen - QStart; }
+  const uint32_t bts = TStart - chromOffset, bte = TEnd - chromOffset;
+  for (long lsi = ls; lsi <= le; lsi++) {
+    if (lsi + 1 >= gl_noff) continue;
+    if (gl_off[lsi] < chromOffset || gl_off[lsi + 1] < chromOffset) continue;
+    const uint32_t gStart = (uint32_t)(gl_off[lsi] - chromOffset), gEnd = (uint32_t)(gl_off[lsi + 1] - 1 - chromOffset);
+    if (gStart >= gEnd) continue;
+    while (matchStart < n && mt[matchStart] <= gStart) matchStart++;
+    matchEnd = matchStart;
+    while (matchEnd < n && mt[matchEnd] < gEnd) matchEnd++;
+    if (matchStart >= n) continue;
+    if (matchEnd == matchStart) continue;
+    uint32_t readStart = mq[matchStart], readEnd = mq[matchEnd - 1];
+    for (long mi = matchStart; mi < matchEnd; mi++) {
+      if (mq[mi] < readStart) readStart = mq[mi];
+      if (mq[mi] + mlen[mi] > readEnd) readEnd = mq[mi] + mlen[mi];
+    }
+    if (readStart == readEnd) { if (lsi > ls && readStart > 0u) readStart = 0u; }
+    int64_t bandMin = minDN, bandMax = maxDN;
+    if (limitrefine) {
+      int64_t mn = (int64_t)mt[matchStart] - (int64_t)mq[matchStart];
+      for (long mi = matchStart; mi < matchEnd; mi++) { int64_t d = (int64_t)mt[mi] - (int64_t)mq[mi]; if (d < mn) mn = d; }
+      bandMin = mn - 100; bandMax = INT64_MAX;
+    }
+    const uint32_t sow = 500;
+    if (lsi == ls) readStart = (readStart < sow) ? 0 : readStart - sow;
+    if (lsi == le) readEnd = (readEnd + sow > readLen) ? readLen : readEnd + sow;
+    if (readStart > readEnd) continue;
+    const long qis = lra_oracle_lookup_index(rd_off, rd_noff, readStart);
+    const long qie = lra_oracle_lookup_index(rd_off, rd_noff, readEnd < readLen - 1 ? readEnd : readLen - 1);
+    for (long qi = qis; qi <= qie; ++qi) {
+      const uint32_t qb0 = (uint32_t)rd_bnd[qi], qb1 = (uint32_t)rd_bnd[qi + 1];
+      const uint32_t readSegmentStart = (uint32_t)rd_off[qi];
+      long m = lra_oracle_compare_lists_local(rd_min + qb0, (long)qb1 - (long)qb0, gl_min + gl_bnd[lsi], (long)(gl_bnd[lsi + 1] - gl_bnd[lsi]), localMaxFreq, sq, st, scap);
+      if (m > scap) {
+        scap = m; sq = (uint32_t *)realloc(sq, sizeof(uint32_t) * (size_t)scap); st = (uint32_t *)realloc(st, sizeof(uint32_t) * (size_t)scap);
+        lra_oracle_compare_lists_local(rd_min + qb0, (long)qb1 - (long)qb0, gl_min + gl_bnd[lsi], (long)(gl_bnd[lsi + 1] - gl_bnd[lsi]), localMaxFreq, sq, st, scap);
+      }
+      for (long i = 0; i < m; i++) {
+        const uint32_t qp = LP(sq[i]) + readSegmentStart, tp = LP(st[i]) + gStart;
+        const int64_t d = (int64_t)tp - (int64_t)qp;
+        if (d >= bandMin && d <= bandMax && qp >= bqs && qp < bqe && tp >= bts && tp < bte) {
+          if (n_out < cap) { rq[n_out] = qp; rt[n_out] = tp; rtup[n_out] = LT(sq[i]); }
+          n_out++;
+        }
+      }
+    }
+  }
+  free(sq); free(st); free(mq); free(mt);
+  info[6] = (int32_t)n_out;
+  if (n_out == 0) return 0;
+  const long ns = n_out < cap ? n_out : cap;
+  if (strand == 1) for (long i = 0; i < ns; i++) rq[i] = readLen - (rq[i] + (uint32_t)smallK);
+  if (n_out <= cap) {
+    uint32_t qS = rq[0], qE = qS + (uint32_t)smallK, tS = rt[0], tE = tS + (uint32_t)smallK;
+    for (long i = 1; i < n_out; i++) {
+      if (rt[i] + (uint32_t)smallK > tE) tE = rt[i] + (uint32_t)smallK;
+      if (rt[i] < tS) tS = rt[i];
+      if (rq[i] + (uint32_t)smallK > qE) qE = rq[i] + (uint32_t)smallK;
+      if (rq[i] < qS) qS = rq[i];
+    }
+    info[2] = (int32_t)qS; info[3] = (int32_t)qE; info[4] = (int32_t)tS; info[5] = (int32_t)tE;
+    const uint32_t den = (qE - qS) < (tE - tS) ? (qE - qS) : (tE - tS);
+    *eff = ((float)n_out) / den;
+  }
+  return n_out;
+}

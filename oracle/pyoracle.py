@@ -503,3 +503,44 @@ class RefLocalIndexHandle:
     def close(self):
         if self.h:
             self.L.ref_lidx_free(self.h); self.h = None
+
+
+def refine_splitchain(mq, mt, mlen, mstrand, box, chrom, strand, read_len, hdr_pos, gl, rd_fwd, rd_rev, global_k, small_k=10, window=100, local_max_freq=15,
+                      limitrefine=1, which="port", ref_handles=None):
+    """One split chain through Refine_splitchain (ChainRefine.h:383-576).  mstrand: strand of the cluster each anchor comes from.
+    Returns dict(status, chrom, diag, rq, rt, rtup, rbox, eff)."""
+    mq = np.ascontiguousarray(mq, np.uint32); mt = np.ascontiguousarray(mt, np.uint32); mlen = np.ascontiguousarray(mlen, np.uint32)
+    mstrand = np.ascontiguousarray(mstrand, np.uint8); box = np.ascontiguousarray(box, np.uint32)
+    hdr = np.ascontiguousarray(hdr_pos, np.uint64)
+    info = np.zeros(8, np.int32); diag = np.zeros(2, np.int64); eff = C.c_float()
+    n = len(mq)
+    pad = lambda a, dt: a if len(a) else np.zeros(1, dt)
+    cap = 1 << 16
+    while True:
+        rq = np.zeros(cap, np.uint32); rt = np.zeros(cap, np.uint32); ru = np.zeros(cap, np.uint32)
+        if which == "ref":
+            L = ref()
+            L.ref_refine_splitchain.restype = C.c_long
+            L.ref_refine_splitchain.argtypes = [_u32p, _u32p, _u32p, _i32p, C.c_long, _u8p, C.c_int, _u32p, C.c_int, C.c_int, C.c_uint32, _u64p, C.c_int,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, _u32p, _u32p, _u32p, C.c_long,
+                                                _i32p, _i64p, C.POINTER(C.c_float)]
+            # anchors of strand s live in cluster s: two clusters, each flipped once by the reference
+            cluster_of = mstrand.astype(np.int32)
+            m = L.ref_refine_splitchain(pad(mq, np.uint32), pad(mt, np.uint32), pad(mlen, np.uint32), pad(cluster_of, np.int32), n, np.array([0, 1], np.uint8), 2,
+                                        box, chrom, strand, read_len, hdr, len(hdr), ref_handles[0], ref_handles[1], ref_handles[2], global_k, small_k, window,
+                                        local_max_freq, limitrefine, rq, rt, ru, cap, info, diag, C.byref(eff))
+            assert m >= 0, "the reference did not restore the clusters"
+        else:
+            L = port()
+            L.lra_oracle_refine_splitchain.restype = C.c_long
+            L.lra_oracle_refine_splitchain.argtypes = [_u32p, _u32p, _u32p, _u8p, C.c_long, _u32p, C.c_int, C.c_int, C.c_uint32, _u64p, C.c_int,
+                                                       _u64p, C.c_long, _u64p, _u32p, _u64p, C.c_long, _u64p, _u32p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int,
+                                                       _u32p, _u32p, _u32p, C.c_long, _i32p, _i64p, C.POINTER(C.c_float)]
+            rd = rd_rev if strand else rd_fwd
+            m = L.lra_oracle_refine_splitchain(pad(mq, np.uint32), pad(mt, np.uint32), pad(mlen, np.uint32), pad(mstrand, np.uint8), n, box, chrom, strand, read_len,
+                                               hdr, len(hdr), gl.seq_off, len(gl.seq_off), gl.bnd, pad(gl.mins, np.uint32), rd.seq_off, len(rd.seq_off), rd.bnd,
+                                               pad(rd.mins, np.uint32), global_k, small_k, window, local_max_freq, limitrefine, rq, rt, ru, cap, info, diag, C.byref(eff))
+        if m <= cap:
+            break
+        cap = m
+    return dict(status=int(info[0]), chrom=int(info[1]), diag=diag.copy(), rq=rq[:m], rt=rt[:m], rtup=ru[:m], rbox=info[2:6].astype(np.uint32), eff=np.float32(eff.value))

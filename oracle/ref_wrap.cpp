@@ -274,4 +274,54 @@ long ref_seed_read(const char *read, uint32_t len, const char *genome_concat, co
   return (long)res.size();
 }
 
+// ---- a13, low-accuracy pipeline: Refine_splitchain on ONE split chain (ChainRefine.h:383-576).  The chain's anchors live in clusters
+// (cluster_of[i] = index of the cluster anchor i belongs to, n_clusters of them, strand per cluster); arguments otherwise as
+// oracle/local_refine.c: lra_oracle_refine_splitchain.
+long ref_refine_splitchain(const uint32_t *mq, const uint32_t *mt, const uint32_t *mlen, const int32_t *cluster_of, long n, const uint8_t *cluster_strand,
+                           int n_clusters, const uint32_t *box, int chrom, int strand, uint32_t readLen, const uint64_t *hdr_pos, int n_hdr,
+                           void *gl, void *rd_fwd, void *rd_rev, int globalK, int smallK, int window, long localMaxFreq, int limitrefine,
+                           uint32_t *rq, uint32_t *rt, uint32_t *rtup, long cap, int32_t *info, int64_t *diag, float *eff) {
+  ref_init_static();
+  Options opts; opts.globalK = globalK; opts.limitrefine = limitrefine != 0;
+  Options smallOpts = opts; smallOpts.globalK = smallK; smallOpts.window = window; smallOpts.localMaxFreq = (int)localMaxFreq;
+  Genome genome;
+  genome.header.pos.assign(hdr_pos, hdr_pos + n_hdr);
+  Read read; read.length = (int)readLen; read.unaligned = 0;
+  std::vector<Cluster> clusters(n_clusters), refined(1);
+  for (int c = 0; c < n_clusters; c++) { clusters[c].strand = cluster_strand[c]; clusters[c].flip = 0; }
+  UltimateChain chain(&clusters);
+  std::vector<int> sptc;
+  std::vector<bool> link;
+  for (long i = 0; i < n; i++) {
+    Cluster &c = clusters[cluster_of[i]];
+    GenomePair gp; gp.first.pos = mq[i]; gp.second.pos = mt[i];
+    chain.chain.push_back((unsigned)c.matches.size());
+    chain.ClusterIndex.push_back(cluster_of[i]);
+    c.matches.push_back(gp); c.matchesLengths.push_back((int)mlen[i]);
+    sptc.push_back((int)i);
+  }
+  std::vector<SplitChain> sps;
+  sps.push_back(SplitChain(sptc, link, &chain, strand != 0));
+  SplitChain &sp = sps[0];
+  sp.QStart = box[0]; sp.QEnd = box[1]; sp.TStart = box[2]; sp.TEnd = box[3]; sp.chromIndex = chrom;
+  for (int c = 0; c < n_clusters; c++) sp.ClusterIndex.push_back(c);
+  LocalIndex *lis[2] = {(LocalIndex *)rd_fwd, (LocalIndex *)rd_rev};
+  for (int i = 0; i < 8; i++) info[i] = 0;
+  diag[0] = diag[1] = 0; *eff = 0;
+  Refine_splitchain(sps, chain, refined, clusters, genome, read, *(LocalIndex *)gl, lis, smallOpts, opts);
+  if (n == 0) { info[0] = 1; return 0; }
+  Cluster &r = refined[0];
+  info[1] = r.chromIndex; info[6] = (int32_t)r.matches.size();
+  diag[0] = r.minDiagNum; diag[1] = r.maxDiagNum;
+  long m = (long)r.matches.size();
+  for (long i = 0; i < m && i < cap; i++) { rq[i] = r.matches[i].first.pos; rt[i] = r.matches[i].second.pos; rtup[i] = (uint32_t)r.matches[i].first.t; }
+  if (m > 0) { info[2] = r.qStart; info[3] = r.qEnd; info[4] = r.tStart; info[5] = r.tEnd; *eff = r.refineEffiency; }
+  // the clusters must be back in their original coordinates (ChainRefine.h:554-565)
+  for (long i = 0; i < n; i++) {
+    const GenomePair &gp = clusters[cluster_of[i]].matches[chain.chain[i]];
+    if (gp.first.pos != mq[i] || gp.second.pos != mt[i]) return -1;
+  }
+  return m;
+}
+
 }  // extern "C"

@@ -167,14 +167,14 @@ def _emu_lidx(img):
                    img["n_win"], img["n_seq"])
 
 
-def refine_clusters(gl, rf, rr, cl, cap=None):
+def refine_clusters(gl, rf, rr, cl, cap=None, literal=0):
     """cl: dict(m_q, m_t, m_off, box[n,4], strand, read_id, hdr_pos, global_k, small_k, window, local_max_freq).  Returns a result dict."""
     L = lib()
     f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"); i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
     L.emu_refine_clusters.restype = C.c_long
     L.emu_refine_clusters.argtypes = [C.POINTER(EmuLidx)] * 3 + [C.c_int, _u32p, _u32p, _u64p, _u32p, _u8p, _u32p, _u64p, C.c_int, C.c_int, C.c_int, C.c_int,
                                                                  C.c_long, _i32p, _i32p, i64p, _u64p, _u32p, _u32p, _u32p, C.c_uint64, _u32p, f32p, _u32p, _u32p,
-                                                                 _u32p, _u64p]
+                                                                 _u32p, _u64p, C.c_int]
     n = len(cl["strand"])
     M = int(cl["m_off"][n])
     cap = cap or 1 << 18
@@ -190,7 +190,7 @@ def refine_clusters(gl, rf, rr, cl, cap=None):
                                     np.ascontiguousarray(cl["strand"], np.uint8), np.ascontiguousarray(cl["read_id"], np.uint32),
                                     np.ascontiguousarray(cl["hdr_pos"], np.uint64), len(cl["hdr_pos"]), cl["global_k"], cl["small_k"], cl["window"],
                                     cl["local_max_freq"], o["status"], o["chrom"], o["diag"], o["r_off"], o["r_q"], o["r_t"], o["r_tup"], cap,
-                                    o["rbox"], o["eff"], o["m_q_out"], o["m_t_out"], o["box_out"], counts)
+                                    o["rbox"], o["eff"], o["m_q_out"], o["m_t_out"], o["box_out"], counts, literal)
         if tot <= cap:
             o["n_anchors"] = tot; o["n_units"], o["n_tasks"] = int(counts[0]), int(counts[1])
             return o

@@ -130,3 +130,65 @@ def check_batch(o, cl, exp):
         if b > a:
             assert (o["rbox"].reshape(-1, 4)[c] == e["rbox"]).all(), c
             assert o["eff"][c] == e["eff"], (c, o["eff"][c], e["eff"])
+
+
+# ---- Refine_splitchain (the low-accuracy pipeline's a13)
+
+def make_chains(case, seed=0):
+    """Split chains for the clusters of make_case(): the anchors of a cluster in chain order (ascending genome position; every fifth
+    chain keeps an unsorted order -- the reference scans anchors sequentially), anchor lengths 17..60, boundaries from the anchors.
+    A reverse chain (Strand 1) takes its anchors from strand-1 clusters; every seventh chain mixes in anchors of the other strand."""
+    rng = np.random.default_rng(seed)
+    hdr = case["hdr"]
+    chains = []
+    for ci, c in enumerate(case["clusters"]):
+        n = len(c["mq"])
+        if n == 0:
+            chains.append(dict(read=c["read"], strand=0, chrom=0, mq=c["mq"], mt=c["mt"], mlen=np.zeros(0, np.uint32), mstrand=np.zeros(0, np.uint8), box=np.zeros(4, np.uint32)))
+            continue
+        chrom = int(np.searchsorted(hdr, c["mt"].min(), side="right") - 1)
+        if int(np.searchsorted(hdr, c["mt"].max() + 60, side="right") - 1) != chrom:
+            continue                                                  # a split chain lives on one contig
+        order = np.argsort(c["mt"], kind="stable") if ci % 5 else rng.permutation(n)
+        mq, mt = c["mq"][order], c["mt"][order]
+        mlen = rng.integers(17, 61, n).astype(np.uint32)
+        mstrand = np.full(n, c["strand"], np.uint8)
+        if ci % 7 == 3:
+            mstrand[rng.random(n) < 0.1] ^= 1
+        L = len(case["reads"][c["read"]])
+        mlen = np.minimum(mlen, np.maximum(17, L - mq.astype(np.int64) - 1)).astype(np.uint32)
+        box = np.array([mq.min(), (mq + mlen).max(), mt.min(), (mt + mlen).max()], np.uint32)
+        chains.append(dict(read=c["read"], strand=c["strand"], chrom=chrom, mq=mq, mt=mt, mlen=mlen, mstrand=mstrand, box=box))
+    return chains
+
+
+def expected_chains(case, chains, which="port", small_k=10, window=100, local_max_freq=15, limitrefine=1):
+    gl = po.local_index(case["contigs"], max_freq=local_max_freq, which="port")
+    glh = po.RefLocalIndexHandle(case["contigs"], max_freq=local_max_freq) if which == "ref" else None
+    out, handles = [], {}
+    for c in chains:
+        r = case["reads"][c["read"]]; rc = COMP[r[::-1]]
+        if which == "ref":
+            if c["read"] not in handles:
+                handles[c["read"]] = (po.RefLocalIndexHandle(r, max_freq=local_max_freq), po.RefLocalIndexHandle(rc, max_freq=local_max_freq))
+            f, v = handles[c["read"]]
+            out.append(po.refine_splitchain(c["mq"], c["mt"], c["mlen"], c["mstrand"], c["box"], c["chrom"], c["strand"], len(r), case["hdr"], None, None, None,
+                                            case["k"], small_k, window, local_max_freq, limitrefine, "ref", (glh.h, f.h, v.h)))
+        else:
+            rf = po.local_index(r, max_freq=local_max_freq); rr = po.local_index(rc, max_freq=local_max_freq)
+            out.append(po.refine_splitchain(c["mq"], c["mt"], c["mlen"], c["mstrand"], c["box"], c["chrom"], c["strand"], len(r), case["hdr"], gl, rf, rr,
+                                            case["k"], small_k, window, local_max_freq, limitrefine, "port"))
+    for f, v in handles.values():
+        f.close(); v.close()
+    if glh:
+        glh.close()
+    return out
+
+
+def same_chain(a, b):
+    if a["status"] != b["status"]:
+        return False
+    if a["status"] != 0:
+        return True
+    return (a["chrom"] == b["chrom"] and (a["diag"] == b["diag"]).all() and len(a["rq"]) == len(b["rq"]) and (a["rq"] == b["rq"]).all()
+            and (a["rt"] == b["rt"]).all() and (a["rtup"] == b["rtup"]).all() and (len(a["rq"]) == 0 or ((a["rbox"] == b["rbox"]).all() and a["eff"] == b["eff"])))

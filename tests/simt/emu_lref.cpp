@@ -44,7 +44,7 @@ extern "C" long emu_refine_clusters(const EmuLidx *gl, const EmuLidx *rf, const 
                                     const uint64_t *m_off, const uint32_t *box, const uint8_t *strand, const uint32_t *read_id,
                                     const uint64_t *hdr_pos, int n_hdr, int global_k, int small_k, int window, long local_max_freq,
                                     int32_t *status, int32_t *chrom, int64_t *diag, uint64_t *r_off, uint32_t *r_q, uint32_t *r_t, uint32_t *r_tup,
-                                    uint64_t cap, uint32_t *rbox, float *eff, uint32_t *m_q_out, uint32_t *m_t_out, uint32_t *box_out, uint64_t *counts) {
+                                    uint64_t cap, uint32_t *rbox, float *eff, uint32_t *m_q_out, uint32_t *m_t_out, uint32_t *box_out, uint64_t *counts, int literal) {
   const size_t M = (size_t)m_off[n];
   std::vector<unsigned long long> key_off(n + 1), keys, unit_off(n + 2, 0);
   size_t kt = 0;
@@ -77,9 +77,11 @@ extern "C" long emu_refine_clusters(const EmuLidx *gl, const EmuLidx *rf, const 
   std::vector<unsigned long long> out_off(n_tasks + 2, 0);
   b.out_off = out_off.data();
   if (n_tasks) {
-    emu::launch(dim3((unsigned)((n_tasks + 127) / 128)), dim3(128), 0, [&] { lref_task_kernel<false>(b, n_units, n_tasks); });
+    if (literal) emu::launch(dim3((unsigned)((n_tasks + 127) / 128)), dim3(128), 0, [&] { lref_task_literal_kernel<false>(b, n_units, n_tasks); });
+    else emu::launch(dim3((unsigned)((n_tasks + 3) / 4)), dim3(128), 0, [&] { lref_task_kernel<false>(b, n_units, n_tasks); });
     emu::launch(dim3(1), dim3(1024), 0, [&] { seed_scan_kernel(b.out_off, (int)n_tasks, cap, &err); });
-    emu::launch(dim3((unsigned)((n_tasks + 127) / 128)), dim3(128), 0, [&] { lref_task_kernel<true>(b, n_units, n_tasks); });
+    if (literal) emu::launch(dim3((unsigned)((n_tasks + 127) / 128)), dim3(128), 0, [&] { lref_task_literal_kernel<true>(b, n_units, n_tasks); });
+    else emu::launch(dim3((unsigned)((n_tasks + 3) / 4)), dim3(128), 0, [&] { lref_task_kernel<true>(b, n_units, n_tasks); });
   }
   emu::launch(dim3((unsigned)((n + 3) / 4)), dim3(128), 0, [&] { lref_finish_kernel(b, n_units, n_tasks); });
   counts[0] = n_units; counts[1] = n_tasks;

@@ -25,6 +25,15 @@ def test_emu_lindex_contigs():
         if L == 4099:
             s[:2100] = ord("A")
         contigs.append(s)
+    # N handling on the lane-parallel path (no tied minima): sporadic N's, a valid run that starts exactly at seqLen - windowSpan
+    # (never used by the reference), one that starts one base earlier (used), N as the very last base, a sequence of windowSpan bases
+    for L, ns in ((3000, None), (500, [485]), (500, [484]), (500, [499]), (14, []), (15, []), (15, [0]), (2048 + 14, [2047]), (2048 + 15, [2048])):
+        s = B[rng.integers(0, 4, L)].copy()
+        if ns is None:
+            s[rng.random(L) < 0.04] = ord("N")
+        else:
+            s[ns] = ord("N")
+        contigs.append(s)
     lens = np.array([len(c) for c in contigs], np.uint32)
     start = np.zeros(len(contigs), np.uint64); start[1:] = np.cumsum(lens[:-1])
     arena = np.concatenate(contigs + [np.full(16, ord("N"), np.uint8)])
@@ -48,7 +57,8 @@ def test_emu_refine_clusters():
         w0, w1 = int(rf["win_first"][i]), int(rf["win_first"][i + 1])
         a, b = int(rf["bnd"][w0]), int(rf["bnd"][w1])
         assert w1 - w0 == len(li.seq_off) - 1 and (rf["mins"][a:b] == li.mins).all()
-    o = emu_lib.refine_clusters(gl, rf, rr, pk["cl"])
     exp = refinegen.expected(case, "port")
-    assert o["n_anchors"] == sum(len(e["rq"]) for e in exp) and o["n_anchors"] > 200
-    refinegen.check_batch(o, pk["cl"], exp)
+    for literal in (0, 1):       # the warp kernel and the statement-by-statement thread kernel
+        o = emu_lib.refine_clusters(gl, rf, rr, pk["cl"], literal=literal)
+        assert o["n_anchors"] == sum(len(e["rq"]) for e in exp) and o["n_anchors"] > 200
+        refinegen.check_batch(o, pk["cl"], exp)

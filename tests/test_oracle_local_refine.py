@@ -56,3 +56,15 @@ def test_compare_lists_local_small():
     assert pairs == [(1, 300), (2, 300), (7, 100), (7, 200)]
     rq, rt = po.compare_lists_local_port(q, t, 1)     # a tuple occurring more than maxFreq times IN THE QUERY is skipped
     assert sorted(zip((rq >> 20).tolist(), (rt >> 20).tolist())) == [(7, 100), (7, 200)]
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,limit", [(13, 1), (14, 1), (13, 0)])
+def test_refine_splitchain_matches_reference(seed, limit):
+    case = refinegen.make_case(seed)
+    chains = refinegen.make_chains(case, seed)
+    a = refinegen.expected_chains(case, chains, "port", limitrefine=limit); b = refinegen.expected_chains(case, chains, "ref", limitrefine=limit)
+    assert len(a) == len(b) and len(a) >= 8
+    assert sum(len(x["rq"]) for x in b) > 1000
+    bad = [i for i, (x, y) in enumerate(zip(a, b)) if not refinegen.same_chain(x, y)]
+    assert not bad, (bad, [(len(a[i]["rq"]), len(b[i]["rq"])) for i in bad])

@@ -184,3 +184,28 @@ def make_segments(profile, n_reads, seed, genome_len, fetch_windows, max_len=Non
                 t_base=t_pos.astype(np.uint32), read_len=read_len.astype(np.int32), contig_len=lens.astype(np.int32),
                 t_arena_compact=t_arena, t_base_compact=src_off.astype(np.uint32), k=PROFILE_REFINE_BAND[profile], match=m, mismatch=mm,
                 indel=indel, end_align=PROFILE_END_ALIGN[profile], bases=int(lens.sum()))
+
+
+def make_clusters(sg, global_k=17, compact=False, contig=125_000_000, genome_len=None):
+    """The cluster batch REFINEclusters / Refine_splitchain would see for the reads of make_segments(): one cluster per read whose anchors
+    are the exact stretches of at least global_k bases of the read's alignment (what minimizer seeding + clustering hand over on a
+    repeat-free genome: ONT ~380 anchors per 20 kb read).  compact=False: genome positions in the full genome
+    (contigs of `contig` bases); compact=True: positions in sg["t_arena_compact"], every read's window its own contig (the CPU arm)."""
+    blocks = sg["blocks_in"]; n = len(sg["blk_cnt"])
+    seg_of = np.repeat(np.arange(n), sg["blk_cnt"])
+    keep = blocks[:, 2] >= global_k
+    first = np.zeros(len(blocks), bool); first[sg["blk_off"].astype(np.int64)] = True        # every read keeps at least its first block
+    keep |= first
+    t_base = (sg["t_base_compact"] if compact else sg["t_base"]).astype(np.int64)
+    m_q = blocks[keep, 0].astype(np.uint32)
+    m_t = (blocks[keep, 1].astype(np.int64) + t_base[seg_of[keep]]).astype(np.uint32)
+    cnt = np.bincount(seg_of[keep], minlength=n)
+    m_off = np.zeros(n + 1, np.uint64); m_off[1:] = np.cumsum(cnt)
+    lo = m_off[:-1].astype(np.int64); hi = m_off[1:].astype(np.int64) - 1
+    box = np.stack([m_q[lo], m_q[hi] + global_k, m_t[lo], m_t[hi] + global_k], 1).astype(np.uint32)
+    if compact:
+        hdr = np.append(sg["t_base_compact"].astype(np.uint64), np.uint64(len(sg["t_arena_compact"]) - 16))
+    else:
+        hdr = np.append(np.arange(0, genome_len, contig, dtype=np.uint64), np.uint64(genome_len))
+    return dict(m_q=m_q, m_t=m_t, m_off=m_off, box=box, strand=np.zeros(n, np.uint8), read_id=np.arange(n, dtype=np.uint32), hdr_pos=hdr,
+                global_k=global_k, small_k=10, window=100, local_max_freq=15)
