@@ -408,6 +408,8 @@ def main():
     log_lut = lra_b200.CreateLookUpTable() if "a21" in stages else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    keep = {"rc": None, "rf": None, "rr": None}      # the reverse-complement arena and the two read LocalIndex images are rebuilt in place every step
+
     def step_value(hb):
         out = {"cells": 0, "stats": []}
         if "a18" in stages:
@@ -430,9 +432,9 @@ def main():
             out["stats"] += ctx.kernel_stats()
         if "a12" in stages or "a13" in stages:
             I = hb["ir"]; d = I["dev"]
-            rc = ctx.seq_revcomp(d["qseq"], I["read_off"], I["read_len_u"])
-            rf = ctx.lindex_build(d["qseq"], I["read_off"], I["read_len_u"]); st1 = ctx.kernel_stats()
-            rr = ctx.lindex_build(rc, I["read_off"], I["read_len_u"]); st2 = ctx.kernel_stats()
+            rc = keep["rc"] = ctx.seq_revcomp(d["qseq"], I["read_off"], I["read_len_u"], reuse=keep["rc"])
+            rf = keep["rf"] = ctx.lindex_build(d["qseq"], I["read_off"], I["read_len_u"], reuse=keep["rf"]); st1 = ctx.kernel_stats()
+            rr = keep["rr"] = ctx.lindex_build(rc, I["read_off"], I["read_len_u"], reuse=keep["rr"]); st2 = ctx.kernel_stats()
             for a, b2 in zip(st1, st2):
                 a["ms"] += b2["ms"]; a["jobs"] += b2["jobs"]; a["algo_bytes"] += b2["algo_bytes"]
             out["stats"] += st1
@@ -444,7 +446,6 @@ def main():
                                                  R, I["M"], (cl["global_k"], cl["small_k"], cl["window"], cl["local_max_freq"]),
                                                  {k: dc["o_" + k].data_ptr() for k in ["status", "chrom", "diag", "r_off", "r_q", "r_t", "r_tup", "rbox", "eff"]}, I["acap"])
                 out["stats"] += ctx.kernel_stats()
-            rf.free(); rr.free(); rc.free()
         return out
 
     io = {"h2d": 0, "d2h": 0}
@@ -473,14 +474,14 @@ def main():
             I = hb["ir"]
             if "a19" not in stages:
                 eseq_i.reupload(I["q_arena"][:-16]); h2d += len(I["q_arena"]) - 16
-            rc = ctx.seq_revcomp(eseq_i, I["read_off"], I["read_len_u"])
-            rf = ctx.lindex_build(eseq_i, I["read_off"], I["read_len_u"]); rr = ctx.lindex_build(rc, I["read_off"], I["read_len_u"])
+            rc = keep["rc"] = ctx.seq_revcomp(eseq_i, I["read_off"], I["read_len_u"], reuse=keep["rc"])
+            rf = keep["rf"] = ctx.lindex_build(eseq_i, I["read_off"], I["read_len_u"], reuse=keep["rf"])
+            rr = keep["rr"] = ctx.lindex_build(rc, I["read_off"], I["read_len_u"], reuse=keep["rr"])
             h2d += 2 * 12 * R
             if "a13" in stages:
                 o = ctx.refine_clusters_batch(gli, rf, rr, I["cl"], anchor_cap=I["acap"])
                 h2d += 8 * I["M"] + R * (8 + 16 + 1 + 4)
                 d2h += R * (4 + 4 + 16 + 8 + 16 + 4 + 16) + 8 * I["M"] + 12 * o["n_anchors"]
-            rf.free(); rr.free(); rc.free()
         io["h2d"], io["d2h"] = h2d, d2h
         return None
 
@@ -541,7 +542,10 @@ def main():
     e2e = reads_total / (ms_e2e / 1000.0)
     peak, peak_src = peaks()
     dp = {k: v for k, v in kstats.items() if v["algo_bytes"] > 0} or kstats
-    dom_name = max(dp, key=lambda k: dp[k]["ms"])
+    # kernel classes of one stage run concurrently on side streams, so their event times overlap: among the kernels within 10 % of the
+    # longest, the dominant one is the one moving the most algorithmic bytes
+    top = max(v["ms"] for v in dp.values())
+    dom_name = max((k for k in dp if dp[k]["ms"] >= 0.9 * top), key=lambda k: dp[k]["algo_bytes"])
     dom = kstats[dom_name]
     achieved = dom["algo_bytes"] / (dom["ms"] / 1000.0) / 1e9
     traffic = None

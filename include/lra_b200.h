@@ -177,7 +177,8 @@ typedef struct lra_b200_index lra_b200_index;
 int lra_b200_index_upload(lra_b200_ctx *ctx, const uint64_t *t, const uint32_t *pos, uint64_t n, lra_b200_index **out);
 void lra_b200_index_free(lra_b200_ctx *ctx, lra_b200_index *idx);
 
-/* reads: a packed arena holding the forward strands; read r = [read_off[r], read_off[r] + read_len[r]) */
+/* reads: a packed arena holding the forward strands; read r = [read_off[r], read_off[r] + read_len[r]).  *out_rc must be NULL or an
+ * arena of an earlier call, which is then re-used (no allocation in the steady state of a batch loop). */
 int lra_b200_seq_revcomp(lra_b200_ctx *ctx, const lra_b200_seq *reads, const uint64_t *read_off, const uint32_t *read_len,
                          int32_t n_reads, lra_b200_seq **out_rc);
 
@@ -238,6 +239,7 @@ int lra_b200_calc_stats_batch_device(lra_b200_ctx *ctx, const lra_b200_seq *q, c
  * the image of <ref>.gli).  Sequence s = [seq_start[s], seq_start[s] + seq_len[s]) is cut into windows of `window` bases
  * (<= 2048); the image holds, like the reference's LocalIndex, the window offsets (arena-relative), the tuple boundaries and
  * the LocalTuples (uint32: tuple in bits 0..19, window-relative position in bits 20..31 -- the <ref>.gli layout, MMIndex.h:138-151). */
+/* *out must be NULL or an image of an earlier call, which is then rebuilt in place (its device buffers are re-used). */
 typedef struct lra_b200_lindex lra_b200_lindex;
 int lra_b200_lindex_build(lra_b200_ctx *ctx, const lra_b200_seq *seq, const uint64_t *seq_start, const uint32_t *seq_len, int32_t n_seqs,
                           int32_t k, int32_t w, int32_t window, int32_t max_freq, lra_b200_lindex **out);
@@ -295,6 +297,39 @@ int lra_b200_refine_clusters_batch(lra_b200_ctx *ctx, const lra_b200_lindex *gen
 int lra_b200_refine_clusters_batch_device(lra_b200_ctx *ctx, const lra_b200_lindex *genome_li, const lra_b200_lindex *reads_fwd,
                                           const lra_b200_lindex *reads_rc, const lra_b200_clusters *cl_dev, uint64_t n_anchors_in,
                                           lra_b200_refined *res_dev);
+
+/* ---- a13 (low-accuracy pipeline)  Refine_splitchain, batched over split chains ------------------------------------
+ * Replaces  int Refine_splitchain(vector<SplitChain> &splitchains, UltimateChain &chain, vector<Cluster> &refinedclusters,
+ *                                 vector<Cluster> &clusters, Genome&, Read&, LocalIndex &glIndex, LocalIndex *localIndexes[2],
+ *                                 const Options &smallOpts, const Options &opts)
+ * (ChainRefine.h:383-576) for the split chains of a whole batch of reads.  Chain c: anchors m_off[c] .. m_off[c+1] IN CHAIN ORDER, each
+ * with the read / GLOBAL genome position stored in its cluster (m_q, m_t), its length (matchesLengths, m_len) and the strand of the
+ * cluster it comes from (m_strand); box[4c..] = QStart, QEnd, TStart, TEnd; strand[c] = Strand; chrom[c] = chromIndex.  limitrefine =
+ * opts.limitrefine (default 1): per genome window the band is [min diagonal of the window's anchors - 100, +inf) -- the reference's
+ * upper bound is an uninitialised variable that never filters in the stock build (ChainRefine.h:491-501).  Results as for
+ * lra_b200_refine_clusters_batch (status 1: empty chain; diag = the refined cluster's minDiagNum / maxDiagNum; m_q_out / m_t_out /
+ * box_out are not written: the reference restores the clusters before it returns). */
+typedef struct lra_b200_splitchains {
+  int32_t n_chains;
+  const uint32_t *m_q, *m_t, *m_len;
+  const uint8_t *m_strand;
+  const uint64_t *m_off;        /* [n_chains + 1] */
+  const uint32_t *box;          /* [n_chains * 4] */
+  const uint8_t *strand;        /* [n_chains] */
+  const int32_t *chrom;         /* [n_chains] */
+  const uint32_t *read_id;      /* [n_chains] */
+  const uint64_t *hdr_pos;
+  int32_t n_hdr;
+  int32_t global_k, small_k, window;
+  int64_t local_max_freq;
+  int32_t limitrefine;
+} lra_b200_splitchains;
+
+int lra_b200_refine_splitchains_batch(lra_b200_ctx *ctx, const lra_b200_lindex *genome_li, const lra_b200_lindex *reads_fwd,
+                                      const lra_b200_lindex *reads_rc, const lra_b200_splitchains *sc, lra_b200_refined *res);
+int lra_b200_refine_splitchains_batch_device(lra_b200_ctx *ctx, const lra_b200_lindex *genome_li, const lra_b200_lindex *reads_fwd,
+                                             const lra_b200_lindex *reads_rc, const lra_b200_splitchains *sc_dev, uint64_t n_anchors_in,
+                                             lra_b200_refined *res_dev);
 
 /* ---- per-kernel timing of the last batch call (CUDA events on the context's stream) ---------------------------- */
 typedef struct lra_b200_kernel_stat {

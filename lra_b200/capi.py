@@ -72,6 +72,12 @@ class _Clusters(C.Structure):
                 ("small_k", C.c_int32), ("window", C.c_int32), ("local_max_freq", C.c_int64)]
 
 
+class _SplitChains(C.Structure):
+    _fields_ = [("n_chains", C.c_int32), ("m_q", C.c_void_p), ("m_t", C.c_void_p), ("m_len", C.c_void_p), ("m_strand", C.c_void_p), ("m_off", C.c_void_p),
+                ("box", C.c_void_p), ("strand", C.c_void_p), ("chrom", C.c_void_p), ("read_id", C.c_void_p), ("hdr_pos", C.c_void_p), ("n_hdr", C.c_int32),
+                ("global_k", C.c_int32), ("small_k", C.c_int32), ("window", C.c_int32), ("local_max_freq", C.c_int64), ("limitrefine", C.c_int32)]
+
+
 class _Refined(C.Structure):
     _fields_ = [("status", C.c_void_p), ("chrom", C.c_void_p), ("diag", C.c_void_p), ("r_off", C.c_void_p), ("r_q", C.c_void_p),
                 ("r_t", C.c_void_p), ("r_tup", C.c_void_p), ("anchor_cap", C.c_uint64), ("n_anchors", C.c_uint64), ("rbox", C.c_void_p),
@@ -136,6 +142,8 @@ def load_library():
     L.lra_b200_lindex_free.restype = None
     L.lra_b200_refine_clusters_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Clusters), C.POINTER(_Refined)]
     L.lra_b200_refine_clusters_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Clusters), C.c_uint64, C.POINTER(_Refined)]
+    L.lra_b200_refine_splitchains_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_SplitChains), C.POINTER(_Refined)]
+    L.lra_b200_refine_splitchains_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_SplitChains), C.c_uint64, C.POINTER(_Refined)]
     L.lra_b200_calc_stats_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrSegments), C.c_void_p, C.POINTER(_StatsResult)]
     L.lra_b200_last_kernel_stats.argtypes = [C.c_void_p, C.POINTER(KernelStat), C.c_int]
     L.lra_b200_launch_count.argtypes = [C.c_void_p]
@@ -290,9 +298,11 @@ class Context:
     def index_free(self, h):
         self.lib.lra_b200_index_free(self.h, h)
 
-    def seq_revcomp(self, reads, read_off, read_len):
+    def seq_revcomp(self, reads, read_off, read_len, reuse=None):
         ro = np.ascontiguousarray(read_off, np.uint64); rl = np.ascontiguousarray(read_len, np.uint32)
-        h = C.c_void_p()
+        h = C.c_void_p(reuse.handle.value) if reuse is not None else C.c_void_p()
+        if reuse is not None:
+            reuse.handle = None
         self._check(self.lib.lra_b200_seq_revcomp(self.h, reads.handle, _ptr(ro), _ptr(rl), len(ro), C.byref(h)))
         return SeqArena(self, h)
 
@@ -317,10 +327,13 @@ class Context:
         self._check(rc)
 
     # ---- a12
-    def lindex_build(self, seq, seq_start, seq_len, k=10, w=5, window=2048, max_freq=15):
-        """LocalIndex::IndexSeq for every sequence [seq_start[s], +seq_len[s]) of a packed arena.  Returns a LocalIndexImage."""
+    def lindex_build(self, seq, seq_start, seq_len, k=10, w=5, window=2048, max_freq=15, reuse=None):
+        """LocalIndex::IndexSeq for every sequence [seq_start[s], +seq_len[s]) of a packed arena.  Returns a LocalIndexImage (`reuse`: an
+        image of an earlier call, rebuilt in place)."""
         ss = np.ascontiguousarray(seq_start, np.uint64); sl = np.ascontiguousarray(seq_len, np.uint32)
-        h = C.c_void_p()
+        h = C.c_void_p(reuse.handle.value) if reuse is not None else C.c_void_p()
+        if reuse is not None:
+            reuse.handle = None
         self._check(self.lib.lra_b200_lindex_build(self.h, seq.handle, _ptr(ss), _ptr(sl), len(ss), k, w, window, max_freq, C.byref(h)))
         return LocalIndexImage(self, h)
 
@@ -367,6 +380,45 @@ class Context:
         r = _Refined(out["status"], out["chrom"], out["diag"], out["r_off"], out["r_q"], out["r_t"], out["r_tup"], anchor_cap, 0, out["rbox"], out["eff"],
                      None, None, None, 0, 0)
         self._check(self.lib.lra_b200_refine_clusters_batch_device(self.h, genome_li.handle, reads_fwd.handle, reads_rc.handle, C.byref(c), n_anchors_in, C.byref(r)))
+        return dict(n_anchors=int(r.n_anchors), n_units=int(r.n_units), n_tasks=int(r.n_tasks))
+
+    def refine_splitchains_batch(self, genome_li, reads_fwd, reads_rc, sc, anchor_cap=None):
+        """Refine_splitchain over a batch (sc: dict(m_q, m_t, m_len, m_strand, m_off, box[n,4], strand, chrom, read_id, hdr_pos, global_k, small_k,
+        window, local_max_freq, limitrefine)).  Returns dict(status, chrom, diag, r_off, r_q, r_t, r_tup, rbox, eff, n_anchors, n_units, n_tasks)."""
+        n = len(sc["strand"])
+        a = dict(m_q=np.ascontiguousarray(sc["m_q"], np.uint32), m_t=np.ascontiguousarray(sc["m_t"], np.uint32), m_len=np.ascontiguousarray(sc["m_len"], np.uint32),
+                 m_strand=np.ascontiguousarray(sc["m_strand"], np.uint8), m_off=np.ascontiguousarray(sc["m_off"], np.uint64),
+                 box=np.ascontiguousarray(sc["box"], np.uint32).reshape(-1), strand=np.ascontiguousarray(sc["strand"], np.uint8),
+                 chrom=np.ascontiguousarray(sc["chrom"], np.int32), read_id=np.ascontiguousarray(sc["read_id"], np.uint32),
+                 hdr=np.ascontiguousarray(sc["hdr_pos"], np.uint64))
+        M = int(a["m_off"][n]) if n else 0
+        cap = anchor_cap if anchor_cap is not None else 4 * M + 4096
+        for _ in range(2):
+            o = dict(status=np.zeros(n, np.int32), chrom=np.zeros(n, np.int32), diag=np.zeros(2 * n, np.int64), r_off=np.zeros(n + 1, np.uint64),
+                     r_q=np.zeros(cap, np.uint32), r_t=np.zeros(cap, np.uint32), r_tup=np.zeros(cap, np.uint32), rbox=np.zeros(4 * n, np.uint32),
+                     eff=np.zeros(n, np.float32))
+            c = _SplitChains(n, _ptr(a["m_q"]) if M else None, _ptr(a["m_t"]) if M else None, _ptr(a["m_len"]) if M else None, _ptr(a["m_strand"]) if M else None,
+                             _ptr(a["m_off"]), _ptr(a["box"]), _ptr(a["strand"]), _ptr(a["chrom"]), _ptr(a["read_id"]), _ptr(a["hdr"]), len(a["hdr"]),
+                             sc["global_k"], sc["small_k"], sc["window"], sc["local_max_freq"], sc.get("limitrefine", 1))
+            r = _Refined(_ptr(o["status"]), _ptr(o["chrom"]), _ptr(o["diag"]), _ptr(o["r_off"]), _ptr(o["r_q"]), _ptr(o["r_t"]), _ptr(o["r_tup"]), cap, 0,
+                         _ptr(o["rbox"]), _ptr(o["eff"]), None, None, None, 0, 0)
+            rc = self.lib.lra_b200_refine_splitchains_batch(self.h, genome_li.handle, reads_fwd.handle, reads_rc.handle, C.byref(c), C.byref(r))
+            o["n_anchors"], o["n_units"], o["n_tasks"] = int(r.n_anchors), int(r.n_units), int(r.n_tasks)
+            if rc == EOVERFLOW and anchor_cap is None:
+                cap = int(r.n_anchors) + 16
+                continue
+            self._check(rc)
+            return o
+        self._check(rc)
+
+    def refine_splitchains_batch_device(self, genome_li, reads_fwd, reads_rc, p, n, n_anchors_in, consts, out, anchor_cap):
+        """Device-pointer variant.  p: device pointers m_q, m_t, m_len, m_strand, m_off, box, strand, chrom, read_id, hdr_pos (+ n_hdr); consts:
+        (global_k, small_k, window, local_max_freq, limitrefine); out: device pointers status, chrom, diag, r_off, r_q, r_t, r_tup, rbox, eff."""
+        c = _SplitChains(n, p["m_q"], p["m_t"], p["m_len"], p["m_strand"], p["m_off"], p["box"], p["strand"], p["chrom"], p["read_id"], p["hdr_pos"], p["n_hdr"],
+                         consts[0], consts[1], consts[2], consts[3], consts[4])
+        r = _Refined(out["status"], out["chrom"], out["diag"], out["r_off"], out["r_q"], out["r_t"], out["r_tup"], anchor_cap, 0, out["rbox"], out["eff"],
+                     None, None, None, 0, 0)
+        self._check(self.lib.lra_b200_refine_splitchains_batch_device(self.h, genome_li.handle, reads_fwd.handle, reads_rc.handle, C.byref(c), n_anchors_in, C.byref(r)))
         return dict(n_anchors=int(r.n_anchors), n_units=int(r.n_units), n_tasks=int(r.n_tasks))
 
     def calc_stats_batch_device(self, q, t, ptrs, n_blocks_in, S, log_lut, d_stats, d_value, d_cigar_off, d_cigar, cigar_cap):

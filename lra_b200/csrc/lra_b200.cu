@@ -47,6 +47,7 @@ struct lra_b200_ctx {
   DevBuf stt[12];         // statistics scratch
   DevBuf lr[32];          // local index / cluster refinement scratch
   DevBuf li_tmp;          // LocalIndex staging (one slot per arena base)
+  DevBuf lr_x[8];         // more cluster refinement scratch
   bool keep_stats = false;  // sub-launchers append to stats instead of clearing
   AogPlan *h_plan = nullptr;            // pinned
   unsigned long long *h_misc = nullptr;  // pinned (2 x u64)
@@ -132,6 +133,7 @@ extern "C" void lra_b200_destroy(lra_b200_ctx *ctx) {
   for (DevBuf &b : ctx->stt) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->lr) if (b.p) cudaFree(b.p);
   if (ctx->li_tmp.p) cudaFree(ctx->li_tmp.p);
+  for (DevBuf &b : ctx->lr_x) if (b.p) cudaFree(b.p);
   for (auto &ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < 4; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]); }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
@@ -814,8 +816,10 @@ extern "C" int lra_b200_seq_revcomp(lra_b200_ctx *ctx, const lra_b200_seq *reads
   if (!ctx || !reads || !out_rc || n_reads < 0 || (n_reads && (!read_off || !read_len))) return fail(ctx, LRA_B200_EINVAL, "seq_revcomp: bad argument");
   CU(cudaSetDevice(ctx->device));
   int rc;
-  lra_b200_seq *o = new lra_b200_seq();
-  if ((rc = seq_reserve(ctx, o, reads->n))) { delete o; return rc; }
+  lra_b200_seq *o = *out_rc ? *out_rc : new lra_b200_seq();     // an arena passed in is re-used (re-sized if needed)
+  const bool fresh = *out_rc == nullptr;
+  *out_rc = nullptr;
+  if ((rc = seq_reserve(ctx, o, reads->n))) { if (fresh) delete o; return rc; }
   o->n = reads->n;
   // positions outside every read keep the padding value (N)
   CU(cudaMemsetAsync(o->b2, 0, (o->cap_groups * 2 + 8) * 4, ctx->stream));

@@ -6,6 +6,7 @@ struct lra_b200_lindex {
   uint32_t *win_len = nullptr, *mins = nullptr, *win_first = nullptr, *seq_len = nullptr;
   uint64_t n_win = 0, n_mins = 0;
   int n_seq = 0, window = 0;
+  size_t cap_win = 0, cap_seq = 0, cap_mins = 0;     // allocated entries (an image handed back to lindex_build is re-used)
 };
 
 static void lindex_release(lra_b200_lindex *li) {
@@ -41,8 +42,16 @@ static int lindex_layout(lra_b200_ctx *ctx, lra_b200_lindex *li, const uint64_t 
   li->n_seq = n_seqs; li->window = window;
   win_off.push_back(n_seqs ? seq_start[n_seqs - 1] + seq_len[n_seqs - 1] : 0ull);     // the closing offset of the last sequence
   const size_t W = li->n_win;
-  CU(cudaMalloc(&li->win_off, (W + 1) * 8)); CU(cudaMalloc(&li->win_len, (W + 1) * 4)); CU(cudaMalloc(&li->bnd, (W + 2) * 8));
-  CU(cudaMalloc(&li->win_first, ((size_t)n_seqs + 1) * 4)); CU(cudaMalloc(&li->seq_start, ((size_t)n_seqs + 1) * 8)); CU(cudaMalloc(&li->seq_len, ((size_t)n_seqs + 1) * 4));
+  if (W + 2 > li->cap_win) {
+    if (li->win_off) { CU(cudaStreamSynchronize(ctx->stream)); cudaFree(li->win_off); cudaFree(li->win_len); cudaFree(li->bnd); }
+    li->cap_win = W + W / 4 + 16;
+    CU(cudaMalloc(&li->win_off, li->cap_win * 8)); CU(cudaMalloc(&li->win_len, li->cap_win * 4)); CU(cudaMalloc(&li->bnd, li->cap_win * 8));
+  }
+  if ((size_t)n_seqs + 1 > li->cap_seq) {
+    if (li->win_first) { CU(cudaStreamSynchronize(ctx->stream)); cudaFree(li->win_first); cudaFree(li->seq_start); cudaFree(li->seq_len); }
+    li->cap_seq = (size_t)n_seqs + (size_t)n_seqs / 4 + 16;
+    CU(cudaMalloc(&li->win_first, li->cap_seq * 4)); CU(cudaMalloc(&li->seq_start, li->cap_seq * 8)); CU(cudaMalloc(&li->seq_len, li->cap_seq * 4));
+  }
   cudaStream_t st = ctx->stream;
   CU(cudaMemcpyAsync(li->win_off, win_off.data(), (W + 1) * 8, cudaMemcpyHostToDevice, st));
   if (W) CU(cudaMemcpyAsync(li->win_len, win_len.data(), W * 4, cudaMemcpyHostToDevice, st));
@@ -64,8 +73,8 @@ extern "C" int lra_b200_lindex_build(lra_b200_ctx *ctx, const lra_b200_seq *seq,
     if (seq_start[s] + seq_len[s] > seq->n) return fail(ctx, LRA_B200_EINVAL, "lindex_build: sequence %d ends beyond the arena", s);
   CU(cudaSetDevice(ctx->device));
   ctx->stats.clear();
+  lra_b200_lindex *li = *out ? *out : new lra_b200_lindex();     // an image passed in is rebuilt in place (its buffers are re-used)
   *out = nullptr;
-  lra_b200_lindex *li = new lra_b200_lindex();
   std::vector<unsigned long long> win_off; std::vector<uint32_t> win_len;
   int rc = lindex_layout(ctx, li, seq_start, seq_len, n_seqs, window, win_off, win_len);
   if (rc) { lindex_release(li); return rc; }
@@ -98,7 +107,12 @@ extern "C" int lra_b200_lindex_build(lra_b200_ctx *ctx, const lra_b200_seq *seq,
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(&total, li->bnd + W, 8, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e == cudaSuccess) e = cudaMalloc(&li->mins, ((size_t)total + 16) * 4);
+  if (e == cudaSuccess && (size_t)total + 16 > li->cap_mins) {
+    if (li->mins) cudaFree(li->mins);
+    li->mins = nullptr;
+    li->cap_mins = (size_t)total + (size_t)total / 8 + 16;
+    e = cudaMalloc(&li->mins, li->cap_mins * 4);
+  }
   if (e != cudaSuccess) { if (own_tmp) cudaFree(tmp); lindex_release(li); return fail(ctx, LRA_B200_ECUDA, "lindex_build: %s", cudaGetErrorString(e)); }
   li->n_mins = total;
   b.mins = li->mins;
@@ -139,7 +153,8 @@ extern "C" int lra_b200_lindex_upload(lra_b200_ctx *ctx, const uint64_t *seq_sta
     if (win_off[i] != wo[i]) { lindex_release(li); return fail(ctx, LRA_B200_EINVAL, "lindex_upload: window offset %llu differs from the sequence layout", (unsigned long long)i); }
   li->n_mins = bnd[n_win];
   cudaStream_t st = ctx->stream;
-  cudaError_t e = cudaMalloc(&li->mins, ((size_t)li->n_mins + 16) * 4);
+  li->cap_mins = (size_t)li->n_mins + 16;
+  cudaError_t e = cudaMalloc(&li->mins, li->cap_mins * 4);
   if (e == cudaSuccess) e = cudaMemcpyAsync(li->bnd, bnd, (n_win + 1) * 8, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess && li->n_mins) e = cudaMemcpyAsync(li->mins, mins, (size_t)li->n_mins * 4, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -175,21 +190,25 @@ __global__ void lref_keyslots_kernel(const unsigned long long *m_off, int n, uns
 
 // The launch sequence of a13 on device-resident clusters (cl: device pointers) into device-resident results (res: device pointers;
 // m_q_out / m_t_out / box_out may be NULL).  M = total number of input anchors.
+struct LrefChainExtra { const uint32_t *m_len; const uint8_t *m_strand; const int32_t *chrom; int limitrefine; };   // device pointers (mode 1)
+
 static int lref_run(lra_b200_ctx *ctx, const lra_b200_lindex *gl, const lra_b200_lindex *rf, const lra_b200_lindex *rr, const lra_b200_clusters *cl,
-                    size_t M, lra_b200_refined *res) {
+                    size_t M, lra_b200_refined *res, const LrefChainExtra *chain = nullptr) {
   const int n = cl->n_clusters;
   int rc;
   DevBuf *B = ctx->lr;
   if ((rc = ensure(ctx, B[8], M * 4 + 16)) || (rc = ensure(ctx, B[9], M * 4 + 16)) || (rc = ensure(ctx, B[10], (size_t)n * 16)) ||
       (rc = ensure(ctx, B[11], (2 * M + (size_t)n + 2) * 8)) || (rc = ensure(ctx, B[12], ((size_t)n + 1) * 8)) ||
       (rc = ensure(ctx, B[16], (size_t)n * 4)) || (rc = ensure(ctx, B[17], (size_t)n * 4)) || (rc = ensure(ctx, B[18], ((size_t)n + 1) * 8)) ||
-      (rc = ensure(ctx, B[0], 64)))
+      (rc = ensure(ctx, B[0], 64)) || (rc = ensure(ctx, ctx->lr_x[0], (size_t)n * 16)))
     return rc;
   cudaStream_t st = ctx->stream;
   CU(cudaMemsetAsync(B[0].p, 0, 64, st));
   LrefBatch b;
   memset(&b, 0, sizeof b);
   b.n_clusters = n;
+  b.fbox = (uint32_t *)ctx->lr_x[0].p;
+  if (chain) { b.mode = 1; b.limitrefine = chain->limitrefine; b.in_len = chain->m_len; b.in_mstrand = chain->m_strand; b.in_chrom = chain->chrom; }
   b.in_q = cl->m_q; b.in_t = cl->m_t; b.m_off = (const unsigned long long *)cl->m_off; b.in_box = cl->box;
   b.strand = cl->strand; b.read_id = cl->read_id; b.hdr_pos = (const unsigned long long *)cl->hdr_pos; b.n_hdr = cl->n_hdr;
   b.gl = lidx_view(gl); b.rd[0] = lidx_view(rf); b.rd[1] = lidx_view(rr);
@@ -205,8 +224,10 @@ static int lref_run(lra_b200_ctx *ctx, const lra_b200_lindex *gl, const lra_b200
   int evi = 0;
   auto rec = [&]() { cudaEventRecord(ctx->ev[evi++], st); };
   rec();
-  lref_keyslots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.m_off, n, (unsigned long long *)B[12].p);
-  seed_scan_kernel<<<1, 1024, 0, st>>>((unsigned long long *)B[12].p, n, ~0ull, errflag);
+  if (!chain) {
+    lref_keyslots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.m_off, n, (unsigned long long *)B[12].p);
+    seed_scan_kernel<<<1, 1024, 0, st>>>((unsigned long long *)B[12].p, n, ~0ull, errflag);
+  }
   lref_prep_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(b);
   seed_scan_kernel<<<1, 1024, 0, st>>>(b.unit_off, n, ~0ull, errflag);
   ctx->launches += 4;
@@ -216,13 +237,16 @@ static int lref_run(lra_b200_ctx *ctx, const lra_b200_lindex *gl, const lra_b200
   CU(cudaMemcpyAsync(&n_units, b.unit_off + n, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if ((rc = ensure(ctx, B[19], (size_t)(n_units + 1) * 4)) || (rc = ensure(ctx, B[20], (size_t)(n_units + 1) * 4)) ||
-      (rc = ensure(ctx, B[21], (size_t)(n_units + 1) * 4)) || (rc = ensure(ctx, B[22], (size_t)(n_units + 2) * 8)))
+      (rc = ensure(ctx, B[21], (size_t)(n_units + 1) * 4)) || (rc = ensure(ctx, B[22], (size_t)(n_units + 2) * 8)) ||
+      (rc = ensure(ctx, ctx->lr_x[1], (size_t)(n_units + 1) * 16)))
     return rc;
   b.u_cluster = (uint32_t *)B[19].p; b.u_qis = (uint32_t *)B[20].p; b.u_gstart = (uint32_t *)B[21].p; b.task_off = (unsigned long long *)B[22].p;
+  b.u_band = (long long *)ctx->lr_x[1].p;
   CU(cudaMemsetAsync(b.task_off, 0, (size_t)(n_units + 2) * 8, st));
   if (n_units) {
     if (n_units > 0x7FFFFFFFull) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: %llu (cluster, window) units in one batch", n_units);
-    lref_unit_kernel<<<(unsigned)((n_units + 127) / 128), 128, 0, st>>>(b, n_units);
+    if (chain) lref_chain_unit_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b);
+    else lref_unit_kernel<<<(unsigned)((n_units + 127) / 128), 128, 0, st>>>(b, n_units);
     seed_scan_kernel<<<1, 1024, 0, st>>>(b.task_off, (int)n_units, ~0ull, errflag);
     ctx->launches += 2;
     CU(cudaGetLastError());
@@ -254,7 +278,7 @@ static int lref_run(lra_b200_ctx *ctx, const lra_b200_lindex *gl, const lra_b200
   CU(cudaMemcpyAsync(&n_out, b.out_off + n_tasks, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   res->n_anchors = n_out; res->n_units = n_units; res->n_tasks = n_tasks;
-  static const char *names[5] = {"lref_prep(+sort)", "lref_unit", "lref_task<count>", "lref_task<emit>", "lref_finish"};
+  const char *names[5] = {chain ? "lref_prep(chain)" : "lref_prep(+sort)", chain ? "lref_chain_unit" : "lref_unit", "lref_task<count>", "lref_task<emit>", "lref_finish"};
   const uint64_t jobs[5] = {(uint64_t)n, n_units, n_tasks, n_tasks, (uint64_t)n};
   const uint64_t nmins_q = rf->n_mins + rr->n_mins;
   for (int i = 0; i < 5; i++) {
@@ -282,8 +306,9 @@ extern "C" int lra_b200_refine_clusters_batch_device(lra_b200_ctx *ctx, const lr
   return lref_run(ctx, gl, rf, rr, cl, (size_t)n_anchors_in, res);
 }
 
-extern "C" int lra_b200_refine_clusters_batch(lra_b200_ctx *ctx, const lra_b200_lindex *gl, const lra_b200_lindex *rf, const lra_b200_lindex *rr,
-                                              const lra_b200_clusters *cl, lra_b200_refined *res) {
+// host-buffer front end shared by REFINEclusters (hchain == NULL) and Refine_splitchain (hchain: HOST pointers)
+static int lref_host_batch(lra_b200_ctx *ctx, const lra_b200_lindex *gl, const lra_b200_lindex *rf, const lra_b200_lindex *rr,
+                           const lra_b200_clusters *cl, lra_b200_refined *res, const LrefChainExtra *hchain) {
   if (!ctx || !gl || !rf || !rr || !cl || !res) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: NULL argument");
   const int n = cl->n_clusters;
   if (n < 0 || cl->n_hdr < 2 || !cl->hdr_pos) return fail(ctx, LRA_B200_EINVAL, "refine_clusters_batch: bad cluster batch");
@@ -307,6 +332,16 @@ extern "C" int lra_b200_refine_clusters_batch(lra_b200_ctx *ctx, const lra_b200_
       (rc = ensure(ctx, B[10], (size_t)n * 16)))
     return rc;
   cudaStream_t st = ctx->stream;
+  LrefChainExtra dchain;
+  if (hchain) {
+    if ((rc = ensure(ctx, ctx->lr_x[2], M * 4 + 16)) || (rc = ensure(ctx, ctx->lr_x[3], M + 16)) || (rc = ensure(ctx, ctx->lr_x[4], (size_t)n * 4))) return rc;
+    for (int c = 0; c < n; c++)
+      if (cl->m_off[c + 1] > cl->m_off[c] && (hchain->chrom[c] < 0 || hchain->chrom[c] + 1 >= cl->n_hdr))
+        return fail(ctx, LRA_B200_EINVAL, "refine_splitchains_batch: chain %d names contig %d of %d", c, hchain->chrom[c], cl->n_hdr - 1);
+    if (M) { CU(cudaMemcpyAsync(ctx->lr_x[2].p, hchain->m_len, M * 4, cudaMemcpyHostToDevice, st)); CU(cudaMemcpyAsync(ctx->lr_x[3].p, hchain->m_strand, M, cudaMemcpyHostToDevice, st)); }
+    CU(cudaMemcpyAsync(ctx->lr_x[4].p, hchain->chrom, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    dchain = LrefChainExtra{(const uint32_t *)ctx->lr_x[2].p, (const uint8_t *)ctx->lr_x[3].p, (const int32_t *)ctx->lr_x[4].p, hchain->limitrefine};
+  }
   if (M) { CU(cudaMemcpyAsync(B[1].p, cl->m_q, M * 4, cudaMemcpyHostToDevice, st)); CU(cudaMemcpyAsync(B[2].p, cl->m_t, M * 4, cudaMemcpyHostToDevice, st)); }
   CU(cudaMemcpyAsync(B[3].p, cl->m_off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(B[4].p, cl->box, (size_t)n * 16, cudaMemcpyHostToDevice, st));
@@ -322,7 +357,7 @@ extern "C" int lra_b200_refine_clusters_batch(lra_b200_ctx *ctx, const lra_b200_
   dres.r_q = (uint32_t *)B[24].p; dres.r_t = (uint32_t *)B[25].p; dres.r_tup = (uint32_t *)B[26].p; dres.anchor_cap = res->anchor_cap;
   dres.rbox = (uint32_t *)B[28].p; dres.eff = (float *)B[29].p; dres.m_q_out = (uint32_t *)B[30].p; dres.m_t_out = (uint32_t *)B[31].p;
   dres.box_out = (uint32_t *)B[10].p;
-  rc = lref_run(ctx, gl, rf, rr, &dcl, M, &dres);
+  rc = lref_run(ctx, gl, rf, rr, &dcl, M, &dres, hchain ? &dchain : nullptr);
   res->n_anchors = dres.n_anchors; res->n_units = dres.n_units; res->n_tasks = dres.n_tasks;
   if (rc != LRA_B200_OK && rc != LRA_B200_EOVERFLOW) return rc;
   CU(cudaMemcpyAsync(res->status, dres.status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
@@ -342,4 +377,40 @@ extern "C" int lra_b200_refine_clusters_batch(lra_b200_ctx *ctx, const lra_b200_
   }
   CU(cudaStreamSynchronize(st));
   return rc;
+}
+
+extern "C" int lra_b200_refine_clusters_batch(lra_b200_ctx *ctx, const lra_b200_lindex *gl, const lra_b200_lindex *rf, const lra_b200_lindex *rr,
+                                              const lra_b200_clusters *cl, lra_b200_refined *res) {
+  return lref_host_batch(ctx, gl, rf, rr, cl, res, nullptr);
+}
+
+static lra_b200_clusters chains_as_clusters(const lra_b200_splitchains *sc) {
+  lra_b200_clusters cl;
+  memset(&cl, 0, sizeof cl);
+  cl.n_clusters = sc->n_chains; cl.m_q = sc->m_q; cl.m_t = sc->m_t; cl.m_off = sc->m_off; cl.box = sc->box; cl.strand = sc->strand; cl.read_id = sc->read_id;
+  cl.hdr_pos = sc->hdr_pos; cl.n_hdr = sc->n_hdr; cl.global_k = sc->global_k; cl.small_k = sc->small_k; cl.window = sc->window; cl.local_max_freq = sc->local_max_freq;
+  return cl;
+}
+
+extern "C" int lra_b200_refine_splitchains_batch(lra_b200_ctx *ctx, const lra_b200_lindex *gl, const lra_b200_lindex *rf, const lra_b200_lindex *rr,
+                                                 const lra_b200_splitchains *sc, lra_b200_refined *res) {
+  if (!sc || (sc->n_chains > 0 && (!sc->m_off || !sc->chrom || (sc->m_off[sc->n_chains] && (!sc->m_len || !sc->m_strand)))))
+    return fail(ctx, LRA_B200_EINVAL, "refine_splitchains_batch: NULL argument");
+  const lra_b200_clusters cl = chains_as_clusters(sc);
+  const LrefChainExtra ex{sc->m_len, sc->m_strand, sc->chrom, sc->limitrefine};
+  return lref_host_batch(ctx, gl, rf, rr, &cl, res, &ex);
+}
+
+extern "C" int lra_b200_refine_splitchains_batch_device(lra_b200_ctx *ctx, const lra_b200_lindex *gl, const lra_b200_lindex *rf, const lra_b200_lindex *rr,
+                                                        const lra_b200_splitchains *sc, uint64_t n_anchors_in, lra_b200_refined *res) {
+  if (!ctx || !gl || !rf || !rr || !sc || !res) return fail(ctx, LRA_B200_EINVAL, "refine_splitchains_batch_device: NULL argument");
+  if (sc->n_chains < 0 || sc->n_hdr < 2 || !sc->hdr_pos) return fail(ctx, LRA_B200_EINVAL, "refine_splitchains_batch_device: bad chain batch");
+  if (rf->n_seq != rr->n_seq) return fail(ctx, LRA_B200_EINVAL, "refine_splitchains_batch_device: the two read images differ in their number of reads");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  res->n_anchors = 0; res->n_units = 0; res->n_tasks = 0;
+  if (sc->n_chains == 0) return LRA_B200_OK;
+  const lra_b200_clusters cl = chains_as_clusters(sc);
+  const LrefChainExtra ex{sc->m_len, sc->m_strand, sc->chrom, sc->limitrefine};
+  return lref_run(ctx, gl, rf, rr, &cl, (size_t)n_anchors_in, res, &ex);
 }

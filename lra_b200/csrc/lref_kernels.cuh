@@ -44,9 +44,16 @@ struct LrefBatch {
   LidxView gl, rd[2];                  // genome; reads forward / reverse complement
   int global_k, small_k, window;
   long long local_max_freq;
+  // mode 1 = Refine_splitchain (ChainRefine.h:383-576): the units are split chains; anchors in chain order with their lengths and the
+  // strand of the cluster each comes from, chromIndex given, per-window diagonal bands (opts.limitrefine)
+  int mode, limitrefine;
+  const uint32_t *in_len;
+  const uint8_t *in_mstrand;
+  const int32_t *in_chrom;
   // working copy of the clusters = what the reference leaves in clusters[ph] (output)
   uint32_t *m_q, *m_t;
   uint32_t *box;                       // [n_clusters][4]
+  uint32_t *fbox;                      // [n_clusters][4] the box AppendValues filters with: read start/end on the unit's strand, target chromosome-relative
   unsigned long long *keys;            // sort scratch, key_off[c] .. (power-of-two sized slots)
   const unsigned long long *key_off;   // [n_clusters]
   // per cluster
@@ -57,6 +64,7 @@ struct LrefBatch {
   unsigned long long *unit_off;        // [n_clusters + 1] number of windows le - ls + 1, then offsets
   // per unit (cluster, lsi)
   uint32_t *u_cluster, *u_qis, *u_gstart;
+  long long *u_band;                   // [n_units][2] diagonal band of the unit's anchors
   unsigned long long *task_off;        // [n_units + 1]
   // per task
   unsigned long long *out_off;         // [n_tasks + 1]
@@ -100,6 +108,41 @@ __global__ void __launch_bounds__(128) lref_prep_kernel(LrefBatch b) {
   if (lane == 0) { b.unit_off[c] = 0; b.chrom[c] = 0; b.diag[2 * c] = 0; b.diag[2 * c + 1] = 0; b.chrom_off[c] = 0; b.ls[c] = 0; }
   __syncwarp();
   if (nm == 0) { if (lane == 0) b.status[c] = 1; return; }
+  if (b.mode == 1) {
+    // Refine_splitchain: flip the anchors for the duration of the call (ChainRefine.h:399-411), band +-50 over the whole chain (:417-428)
+    const int chrom = b.in_chrom[c];
+    const uint32_t chromOffset = (uint32_t)b.hdr_pos[chrom];
+    const uint32_t QStart = box[0], QEnd = box[1], TStart = box[2], TEnd = box[3];
+    const uint32_t chromEndOffset = (uint32_t)b.hdr_pos[lref_hdr_find(b.hdr_pos, b.n_hdr, (unsigned long long)TEnd) + 1];
+    const uint32_t readLen = b.rd[0].seq_len[b.read_id[c]];
+    long long maxDN = -(1ll << 62), minDN = (1ll << 62);
+    for (int i = lane; i < nm; i += 32) {
+      uint32_t q = b.in_q[m0 + i];
+      const uint32_t t = b.in_t[m0 + i] - chromOffset;
+      if (b.in_mstrand[m0 + i]) q = readLen - (q + (uint32_t)b.global_k);
+      mq[i] = q; mt[i] = t;
+      const long long d = (long long)t - (long long)q;
+      maxDN = d > maxDN ? d : maxDN; minDN = d < minDN ? d : minDN;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const long long a = __shfl_xor_sync(0xffffffffu, maxDN, o), bb = __shfl_xor_sync(0xffffffffu, minDN, o);
+      maxDN = a > maxDN ? a : maxDN; minDN = bb < minDN ? bb : minDN;
+    }
+    maxDN += 50; minDN -= 50;
+    if (lane == 0) {
+      const int strand = b.strand[c];
+      uint32_t *fb = b.fbox + 4 * c;
+      if (strand == 0) { fb[0] = QStart; fb[1] = QEnd; } else { fb[0] = readLen - QEnd; fb[1] = readLen - QStart; }
+      fb[2] = TStart - chromOffset; fb[3] = TEnd - chromOffset;
+      const uint32_t wts = (TStart >= chromOffset + (uint32_t)b.window) ? TStart - (uint32_t)b.window : chromOffset;
+      const uint32_t wte = (TEnd + (uint32_t)b.window < chromEndOffset) ? TEnd + (uint32_t)b.window : chromEndOffset;
+      const unsigned long long gend = b.gl.win_off[b.gl.n_win];
+      const int ls = lref_lookup(b.gl.win_off, b.gl.n_win, 0ull, gend, wts), le = lref_lookup(b.gl.win_off, b.gl.n_win, 0ull, gend, wte);
+      b.status[c] = 0; b.chrom[c] = chrom; b.diag[2 * c] = minDN; b.diag[2 * c + 1] = maxDN; b.chrom_off[c] = chromOffset; b.ls[c] = ls;
+      b.unit_off[c] = le >= ls ? (unsigned long long)(le - ls + 1) : 0ull;
+    }
+    return;
+  }
   const uint32_t tStart = box[2], tEnd = box[3];
   const int first = lref_hdr_find(b.hdr_pos, b.n_hdr, (unsigned long long)tStart + 1), last = lref_hdr_find(b.hdr_pos, b.n_hdr, (unsigned long long)tEnd);
   if (first != last) {
@@ -147,6 +190,8 @@ __global__ void __launch_bounds__(128) lref_prep_kernel(LrefBatch b) {
   for (int i = lane; i < nm; i += 32) { const unsigned long long kx = keys[i]; mt[i] = (uint32_t)(kx >> 32); mq[i] = (uint32_t)kx; }
   if (lane == 0) {
     if (strand == 1) { const uint32_t r = box[0]; box[0] = readLen - box[1]; box[1] = readLen - r; }
+    uint32_t *fb = b.fbox + 4 * c;
+    fb[0] = box[0]; fb[1] = box[1]; fb[2] = box[2] - chromOffset; fb[3] = box[3] - chromOffset;
     uint32_t wts, wte;
     if (chromOffset + (uint32_t)b.window > tStart) wts = chromOffset; else wts = tStart - (uint32_t)b.window;
     if (tEnd + (uint32_t)b.window > chromEndOffset) wte = chromEndOffset - 1; else wte = tEnd + (uint32_t)b.window;
@@ -204,7 +249,67 @@ __global__ void __launch_bounds__(128) lref_unit_kernel(LrefBatch b, unsigned lo
   const int qis = lref_lookup(rd.win_off + wf, nw, base, end, readStart);
   const int qie = lref_lookup(rd.win_off + wf, nw, base, end, readEnd < readLen - 1 ? readEnd : readLen - 1);
   b.u_qis[u] = (uint32_t)qis; b.u_gstart[u] = gStart;
+  b.u_band[2 * u] = b.diag[2 * c]; b.u_band[2 * u + 1] = b.diag[2 * c + 1];
   b.task_off[u] = qie >= qis ? (unsigned long long)(qie - qis + 1) : 0ull;
+}
+
+// Refine_splitchain: one thread per split chain walks its genome windows in order -- the anchor cursor (matchStart) is carried from
+// window to window and the anchors are scanned sequentially, in chain order (ChainRefine.h:451-521)
+__global__ void __launch_bounds__(128) lref_chain_unit_kernel(LrefBatch b) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= b.n_clusters) return;
+  const unsigned long long u0 = b.unit_off[c];
+  const int nu = (int)(b.unit_off[c + 1] - u0);
+  if (nu == 0) return;
+  const int ls = b.ls[c], le = ls + nu - 1;
+  const uint32_t chromOffset = b.chrom_off[c];
+  const unsigned long long m0 = b.m_off[c];
+  const int nm = (int)(b.m_off[c + 1] - m0);
+  const uint32_t *mq = b.m_q + m0, *mt = b.m_t + m0, *ml = b.in_len + m0;
+  const int s = b.strand[c];
+  const uint32_t rid = b.read_id[c];
+  const uint32_t readLen = b.rd[s].seq_len[rid];
+  const LidxView &rd = b.rd[s];
+  const int wf = (int)rd.win_first[rid], nw = (int)rd.win_first[rid + 1] - wf;
+  const unsigned long long base = rd.seq_start[rid], end = base + readLen;
+  int matchStart = 0, matchEnd = 0;
+  for (int lsi = ls; lsi <= le; lsi++) {
+    const unsigned long long u = u0 + (unsigned long long)(lsi - ls);
+    b.u_cluster[u] = (uint32_t)c; b.u_qis[u] = 0; b.u_gstart[u] = 0; b.task_off[u] = 0; b.u_band[2 * u] = 0; b.u_band[2 * u + 1] = 0;
+    if (lsi >= b.gl.n_win) continue;          // (one past the last window: the reference reads past seqOffsets there)
+    const unsigned long long o0 = b.gl.win_off[lsi], o1 = b.gl.win_off[lsi + 1];
+    if (o0 < chromOffset || o1 < chromOffset) continue;
+    const uint32_t gStart = (uint32_t)(o0 - chromOffset), gEnd = (uint32_t)(o1 - 1 - chromOffset);
+    if (gStart >= gEnd) continue;
+    while (matchStart < nm && mt[matchStart] <= gStart) matchStart++;
+    matchEnd = matchStart;
+    while (matchEnd < nm && mt[matchEnd] < gEnd) matchEnd++;
+    if (matchStart >= nm) continue;
+    if (matchEnd == matchStart) continue;
+    uint32_t readStart = mq[matchStart], readEnd = mq[matchEnd - 1];
+    long long mn = (long long)mt[matchStart] - (long long)mq[matchStart];
+    for (int mi = matchStart; mi < matchEnd; mi++) {
+      const uint32_t q = mq[mi];
+      if (q < readStart) readStart = q;
+      if (q + ml[mi] > readEnd) readEnd = q + ml[mi];
+      const long long d = (long long)mt[mi] - (long long)q;
+      mn = d < mn ? d : mn;
+    }
+    if (readStart == readEnd) { if (lsi > ls && readStart > 0u) readStart = 0u; }
+    long long bandMin = b.diag[2 * c], bandMax = b.diag[2 * c + 1];
+    // opts.limitrefine: [min diagonal of the window's anchors - 100, +inf) -- the reference's upper bound is an uninitialised variable
+    // that holds a stack address in the stock build (ChainRefine.h:491-501): it never filters
+    if (b.limitrefine) { bandMin = mn - 100; bandMax = 0x7FFFFFFFFFFFFFFFll; }
+    const uint32_t sow = 500;
+    if (lsi == ls) readStart = (readStart < sow) ? 0 : readStart - sow;
+    if (lsi == le) readEnd = (readEnd + sow > readLen) ? readLen : readEnd + sow;
+    if (readStart > readEnd) continue;
+    const int qis = lref_lookup(rd.win_off + wf, nw, base, end, readStart);
+    const int qie = lref_lookup(rd.win_off + wf, nw, base, end, readEnd < readLen - 1 ? readEnd : readLen - 1);
+    b.u_qis[u] = (uint32_t)qis; b.u_gstart[u] = gStart;
+    b.u_band[2 * u] = bandMin; b.u_band[2 * u + 1] = bandMax;
+    b.task_off[u] = qie >= qis ? (unsigned long long)(qie - qis + 1) : 0ull;
+  }
 }
 
 // one THREAD per (cluster, lsi, qi): CompareLists<LocalTuple,SmallTuple>(Global = false) + AppendValues, statement by statement
@@ -229,10 +334,9 @@ __global__ void __launch_bounds__(128) lref_task_literal_kernel(LrefBatch b, uns
   const long nt = (long)(b.gl.bnd[lsi + 1] - b.gl.bnd[lsi]);
   const uint32_t readSegmentStart = (uint32_t)(rd.win_off[qw] - rd.seq_start[rid]);
   const uint32_t gStart = b.u_gstart[u];
-  const long long minDN = b.diag[2 * c], maxDN = b.diag[2 * c + 1];
-  const uint32_t *box = b.box + 4 * c;
-  const uint32_t chromOffset = b.chrom_off[c];
-  const uint32_t bqs = box[0], bqe = box[1], bts = box[2] - chromOffset, bte = box[3] - chromOffset;
+  const long long minDN = b.u_band[2 * u], maxDN = b.u_band[2 * u + 1];
+  const uint32_t *box = b.fbox + 4 * c;
+  const uint32_t bqs = box[0], bqe = box[1], bts = box[2], bte = box[3];
   const long maxFreq = (long)b.local_max_freq;
   unsigned long long n_out = 0;
   const unsigned long long obase = EMIT ? b.out_off[task] : 0ull;
@@ -345,10 +449,9 @@ __global__ void __launch_bounds__(128) lref_task_kernel(LrefBatch b, unsigned lo
   const long nt = (long)(b.gl.bnd[lsi + 1] - b.gl.bnd[lsi]);
   const uint32_t readSegmentStart = (uint32_t)(rd.win_off[qw] - rd.seq_start[rid]);
   const uint32_t gStart = b.u_gstart[u];
-  const long long minDN = b.diag[2 * c], maxDN = b.diag[2 * c + 1];
-  const uint32_t *box = b.box + 4 * c;
-  const uint32_t chromOffset = b.chrom_off[c];
-  const uint32_t bqs = box[0], bqe = box[1], bts = box[2] - chromOffset, bte = box[3] - chromOffset;
+  const long long minDN = b.u_band[2 * u], maxDN = b.u_band[2 * u + 1];
+  const uint32_t *box = b.fbox + 4 * c;
+  const uint32_t bqs = box[0], bqe = box[1], bts = box[2], bte = box[3];
   const long maxFreq = (long)b.local_max_freq;
   unsigned long long n_out = 0;
   const unsigned long long obase = EMIT ? b.out_off[task] : 0ull;

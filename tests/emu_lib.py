@@ -174,7 +174,7 @@ def refine_clusters(gl, rf, rr, cl, cap=None, literal=0):
     L.emu_refine_clusters.restype = C.c_long
     L.emu_refine_clusters.argtypes = [C.POINTER(EmuLidx)] * 3 + [C.c_int, _u32p, _u32p, _u64p, _u32p, _u8p, _u32p, _u64p, C.c_int, C.c_int, C.c_int, C.c_int,
                                                                  C.c_long, _i32p, _i32p, i64p, _u64p, _u32p, _u32p, _u32p, C.c_uint64, _u32p, f32p, _u32p, _u32p,
-                                                                 _u32p, _u64p, C.c_int]
+                                                                 _u32p, _u64p, C.c_int, C.c_int, _u32p, _u8p, _i32p, C.c_int]
     n = len(cl["strand"])
     M = int(cl["m_off"][n])
     cap = cap or 1 << 18
@@ -190,7 +190,9 @@ def refine_clusters(gl, rf, rr, cl, cap=None, literal=0):
                                     np.ascontiguousarray(cl["strand"], np.uint8), np.ascontiguousarray(cl["read_id"], np.uint32),
                                     np.ascontiguousarray(cl["hdr_pos"], np.uint64), len(cl["hdr_pos"]), cl["global_k"], cl["small_k"], cl["window"],
                                     cl["local_max_freq"], o["status"], o["chrom"], o["diag"], o["r_off"], o["r_q"], o["r_t"], o["r_tup"], cap,
-                                    o["rbox"], o["eff"], o["m_q_out"], o["m_t_out"], o["box_out"], counts, literal)
+                                    o["rbox"], o["eff"], o["m_q_out"], o["m_t_out"], o["box_out"], counts, literal,
+                                    1 if "m_len" in cl else 0, pad(cl.get("m_len", []), np.uint32), pad(cl.get("m_strand", []), np.uint8),
+                                    pad(cl.get("chrom", []), np.int32), cl.get("limitrefine", 1))
         if tot <= cap:
             o["n_anchors"] = tot; o["n_units"], o["n_tasks"] = int(counts[0]), int(counts[1])
             return o

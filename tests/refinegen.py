@@ -192,3 +192,29 @@ def same_chain(a, b):
         return True
     return (a["chrom"] == b["chrom"] and (a["diag"] == b["diag"]).all() and len(a["rq"]) == len(b["rq"]) and (a["rq"] == b["rq"]).all()
             and (a["rt"] == b["rt"]).all() and (a["rtup"] == b["rtup"]).all() and (len(a["rq"]) == 0 or ((a["rbox"] == b["rbox"]).all() and a["eff"] == b["eff"])))
+
+
+def pack_chains(case, chains, small_k=10, window=100, local_max_freq=15, limitrefine=1):
+    """The split-chain batch of the C ABI (lra_b200_splitchains) on the arenas of pack_case()."""
+    pk = pack_case(case, small_k, window, local_max_freq)
+    m_off = np.zeros(len(chains) + 1, np.uint64); m_off[1:] = np.cumsum([len(c["mq"]) for c in chains])
+    cat = lambda key, dt: np.concatenate([c[key] for c in chains]).astype(dt) if len(chains) else np.zeros(0, dt)
+    pk["cl"] = dict(m_q=cat("mq", np.uint32), m_t=cat("mt", np.uint32), m_len=cat("mlen", np.uint32), m_strand=cat("mstrand", np.uint8), m_off=m_off,
+                    box=np.array([c["box"] for c in chains], np.uint32).reshape(-1, 4), strand=np.array([c["strand"] for c in chains], np.uint8),
+                    chrom=np.array([c["chrom"] for c in chains], np.int32), read_id=np.array([c["read"] for c in chains], np.uint32), hdr_pos=case["hdr"],
+                    global_k=case["k"], small_k=small_k, window=window, local_max_freq=local_max_freq, limitrefine=limitrefine)
+    return pk
+
+
+def check_chain_batch(o, exp):
+    for c, e in enumerate(exp):
+        assert o["status"][c] == e["status"], (c, o["status"][c], e["status"])
+        a, b = int(o["r_off"][c]), int(o["r_off"][c + 1])
+        if e["status"] != 0:
+            assert a == b, c
+            continue
+        assert o["chrom"][c] == e["chrom"] and (o["diag"][2 * c:2 * c + 2] == e["diag"]).all(), c
+        assert b - a == len(e["rq"]), (c, b - a, len(e["rq"]))
+        assert (o["r_q"][a:b] == e["rq"]).all() and (o["r_t"][a:b] == e["rt"]).all() and (o["r_tup"][a:b] == e["rtup"]).all(), c
+        if b > a:
+            assert (o["rbox"].reshape(-1, 4)[c] == e["rbox"]).all() and o["eff"][c] == e["eff"], c

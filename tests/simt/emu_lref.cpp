@@ -44,7 +44,8 @@ extern "C" long emu_refine_clusters(const EmuLidx *gl, const EmuLidx *rf, const 
                                     const uint64_t *m_off, const uint32_t *box, const uint8_t *strand, const uint32_t *read_id,
                                     const uint64_t *hdr_pos, int n_hdr, int global_k, int small_k, int window, long local_max_freq,
                                     int32_t *status, int32_t *chrom, int64_t *diag, uint64_t *r_off, uint32_t *r_q, uint32_t *r_t, uint32_t *r_tup,
-                                    uint64_t cap, uint32_t *rbox, float *eff, uint32_t *m_q_out, uint32_t *m_t_out, uint32_t *box_out, uint64_t *counts, int literal) {
+                                    uint64_t cap, uint32_t *rbox, float *eff, uint32_t *m_q_out, uint32_t *m_t_out, uint32_t *box_out, uint64_t *counts, int literal,
+                                    int mode, const uint32_t *m_len, const uint8_t *m_strand, const int32_t *chrom_in, int limitrefine) {
   const size_t M = (size_t)m_off[n];
   std::vector<unsigned long long> key_off(n + 1), keys, unit_off(n + 2, 0);
   size_t kt = 0;
@@ -58,6 +59,9 @@ extern "C" long emu_refine_clusters(const EmuLidx *gl, const EmuLidx *rf, const 
   b.n_clusters = n; b.in_q = m_q; b.in_t = m_t; b.m_off = (const unsigned long long *)m_off; b.in_box = box; b.strand = strand; b.read_id = read_id;
   b.hdr_pos = (const unsigned long long *)hdr_pos; b.n_hdr = n_hdr; b.gl = view(gl); b.rd[0] = view(rf); b.rd[1] = view(rr);
   b.global_k = global_k; b.small_k = small_k; b.window = window; b.local_max_freq = local_max_freq;
+  b.mode = mode; b.limitrefine = limitrefine; b.in_len = m_len; b.in_mstrand = m_strand; b.in_chrom = chrom_in;
+  std::vector<uint32_t> fbox(4 * (size_t)n + 4);
+  b.fbox = fbox.data();
   std::vector<uint32_t> mqv(M + 4), mtv(M + 4);
   b.m_q = m_q_out ? m_q_out : mqv.data(); b.m_t = m_t_out ? m_t_out : mtv.data(); b.box = box_out; b.keys = keys.data(); b.key_off = key_off.data();
   b.status = status; b.chrom = chrom; b.diag = (long long *)diag; b.chrom_off = chrom_off.data(); b.ls = ls.data(); b.unit_off = unit_off.data();
@@ -67,10 +71,13 @@ extern "C" long emu_refine_clusters(const EmuLidx *gl, const EmuLidx *rf, const 
   const unsigned long long n_units = unit_off[n];
   std::vector<uint32_t> uc(n_units + 1), uq(n_units + 1), ug(n_units + 1);
   std::vector<unsigned long long> task_off(n_units + 2, 0);
+  std::vector<long long> uband(2 * n_units + 2, 0);
+  b.u_band = uband.data();
   b.u_cluster = uc.data(); b.u_qis = uq.data(); b.u_gstart = ug.data(); b.task_off = task_off.data();
   unsigned long long n_tasks = 0;
   if (n_units) {
-    emu::launch(dim3((unsigned)((n_units + 127) / 128)), dim3(128), 0, [&] { lref_unit_kernel(b, n_units); });
+    if (mode == 1) emu::launch(dim3((unsigned)((n + 127) / 128)), dim3(128), 0, [&] { lref_chain_unit_kernel(b); });
+    else emu::launch(dim3((unsigned)((n_units + 127) / 128)), dim3(128), 0, [&] { lref_unit_kernel(b, n_units); });
     emu::launch(dim3(1), dim3(1024), 0, [&] { seed_scan_kernel(b.task_off, (int)n_units, ~0ull, &err); });
     n_tasks = task_off[n_units];
   }

@@ -62,3 +62,18 @@ def test_emu_refine_clusters():
         o = emu_lib.refine_clusters(gl, rf, rr, pk["cl"], literal=literal)
         assert o["n_anchors"] == sum(len(e["rq"]) for e in exp) and o["n_anchors"] > 200
         refinegen.check_batch(o, pk["cl"], exp)
+
+
+def test_emu_refine_splitchains():
+    case = refinegen.make_case(22, n_reads=5, contig_lens=(30000, 9000, 12000), read_lens=(700, 2500, 5000))
+    chains = refinegen.make_chains(case, 22)
+    hdr = case["hdr"]
+    for limit in (1, 0):
+        pk = refinegen.pack_chains(case, chains, limitrefine=limit)
+        gl = emu_lib.lindex_build(pk["genome"], hdr[:-1], np.diff(hdr).astype(np.uint32))
+        rf = emu_lib.lindex_build(pk["arena"], pk["read_off"], pk["read_len"])
+        rr = emu_lib.lindex_build(pk["rc_arena"], pk["read_off"], pk["read_len"])
+        o = emu_lib.refine_clusters(gl, rf, rr, pk["cl"], literal=1)
+        exp = refinegen.expected_chains(case, chains, "port", limitrefine=limit)
+        assert o["n_anchors"] == sum(len(e["rq"]) for e in exp) and o["n_anchors"] > 200
+        refinegen.check_chain_batch(o, exp)

@@ -67,3 +67,27 @@ def test_gpu_refine_clusters(seed, n_reads):
     for x in (gl, rf, rr, g, rd, rc):
         x.free()
     ctx.close()
+
+
+@pytest.mark.parametrize("seed,n_reads,limit", [(41, 16, 1), (42, 30, 1), (41, 16, 0)])
+def test_gpu_refine_splitchains(seed, n_reads, limit):
+    import lra_b200
+    ctx = lra_b200.Context(0)
+    case = refinegen.make_case(seed, n_reads=n_reads)
+    chains = refinegen.make_chains(case, seed)
+    pk = refinegen.pack_chains(case, chains, limitrefine=limit)
+    hdr = case["hdr"]
+    g = ctx.seq_upload(pk["genome"][:-16]); rd = ctx.seq_upload(pk["arena"][:-16])
+    rc = ctx.seq_revcomp(rd, pk["read_off"], pk["read_len"])
+    gl = ctx.lindex_build(g, hdr[:-1], np.diff(hdr).astype(np.uint32))
+    rf = ctx.lindex_build(rd, pk["read_off"], pk["read_len"]); rr = ctx.lindex_build(rc, pk["read_off"], pk["read_len"])
+    # images rebuilt in place give the same result (the steady state of a batch loop)
+    rf = ctx.lindex_build(rd, pk["read_off"], pk["read_len"], reuse=rf); rc = ctx.seq_revcomp(rd, pk["read_off"], pk["read_len"], reuse=rc)
+    rr = ctx.lindex_build(rc, pk["read_off"], pk["read_len"], reuse=rr)
+    o = ctx.refine_splitchains_batch(gl, rf, rr, pk["cl"])
+    exp = refinegen.expected_chains(case, chains, WHICH, limitrefine=limit)
+    assert o["n_anchors"] == sum(len(e["rq"]) for e in exp) and o["n_anchors"] > 1000
+    refinegen.check_chain_batch(o, exp)
+    for x in (gl, rf, rr, g, rd, rc):
+        x.free()
+    ctx.close()
