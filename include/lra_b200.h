@@ -231,6 +231,15 @@ int lra_b200_calc_stats_batch(lra_b200_ctx *ctx, const lra_b200_seq *q, const lr
 int lra_b200_calc_stats_batch_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_ir_segments *segs_dev,
                                      const float *log_lut, lra_b200_stats_result *res_dev);
 
+/* ---- a6  DiagonalSort / AntiDiagonalSort / CartesianSort / CartesianTargetSort, batched over segments ------------------
+ * Replaces the anchor sorts of Sorting.h (:49-75, :111-139, :155-169, :196-209) for any number of anchor lists at once: segment s =
+ * anchors seg_off[s] .. seg_off[s+1] of (q, t) = (first.pos, second.pos).  mode 0 DiagonalSort ((long) q - (long) t, then q),
+ * 1 AntiDiagonalSort ((GenomePos)(q + t), then q), 2 CartesianSort (q, then t), 3 CartesianTargetSort (t, then q).  q and t are sorted in
+ * place; perm (may be NULL) receives, for every output position, the batch-wide index of the anchor that moved there, so that the
+ * caller can permute the rest of the GenomePair (tuple values) or any side array (strands, lengths).  Every comparator is a total order
+ * on the position pair, so the result is the reference's for any input order. */
+int lra_b200_sort_matches_batch(lra_b200_ctx *ctx, int32_t mode, uint32_t *q, uint32_t *t, const uint64_t *seg_off, int32_t n_seg, uint32_t *perm);
+
 /* ---- a12  LocalIndex::IndexSeq, batched over sequences ---------------------------------------------------------
  * Replaces  void LocalIndex::IndexSeq(char *seq, int seqLen)  (MMIndex.h:200-245; StoreMinimizers_noncanonical
  * MinCount.h:181-338, std::sort on LocalTuple::operator< TupleOps.h:30-32, RemoveFrequent MMIndex.h:69-85) for any number of

@@ -131,6 +131,7 @@ def load_library():
     L.lra_b200_seq_revcomp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
     L.lra_b200_seed_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_SeedReads), C.POINTER(_SeedResult)]
     L.lra_b200_calc_stats_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrSegments), C.c_void_p, C.POINTER(_StatsResult)]
+    L.lra_b200_sort_matches_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_lindex_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.POINTER(C.c_void_p)]
     L.lra_b200_lindex_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
@@ -325,6 +326,15 @@ class Context:
             self._check(rc)
             return o
         self._check(rc)
+
+    # ---- a6
+    def sort_matches_batch(self, mode, q, t, seg_off, want_perm=True):
+        """DiagonalSort (mode 0) / AntiDiagonalSort (1) / CartesianSort (2) / CartesianTargetSort (3) of every segment.  Returns (q, t, perm)."""
+        q = np.array(q, np.uint32); t = np.array(t, np.uint32); so = np.ascontiguousarray(seg_off, np.uint64)
+        perm = np.zeros(max(len(q), 1), np.uint32) if want_perm else None
+        self._check(self.lib.lra_b200_sort_matches_batch(self.h, mode, _ptr(q) if len(q) else None, _ptr(t) if len(t) else None, _ptr(so), len(so) - 1,
+                                                         _ptr(perm) if want_perm else None))
+        return q, t, (perm[:len(q)] if want_perm else None)
 
     # ---- a12
     def lindex_build(self, seq, seq_start, seq_len, k=10, w=5, window=2048, max_freq=15, reuse=None):

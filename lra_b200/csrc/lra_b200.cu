@@ -18,6 +18,7 @@
 #include "stats_kernels.cuh"
 #include "lidx_kernels.cuh"
 #include "lref_kernels.cuh"
+#include "sort_kernels.cuh"
 
 using namespace lra;
 
@@ -45,9 +46,11 @@ struct lra_b200_ctx {
   DevBuf sg[40];          // segment-level IndelRefine scratch
   DevBuf sd[12];          // seeding scratch
   DevBuf stt[12];         // statistics scratch
+  DevBuf stt_x[2];        // statistics: block offsets, per-lane op indices
   DevBuf lr[32];          // local index / cluster refinement scratch
   DevBuf li_tmp;          // LocalIndex staging (one slot per arena base)
   DevBuf lr_x[8];         // more cluster refinement scratch
+  DevBuf so[8];           // anchor sort scratch
   bool keep_stats = false;  // sub-launchers append to stats instead of clearing
   AogPlan *h_plan = nullptr;            // pinned
   unsigned long long *h_misc = nullptr;  // pinned (2 x u64)
@@ -131,9 +134,11 @@ extern "C" void lra_b200_destroy(lra_b200_ctx *ctx) {
   for (DevBuf &b : ctx->sg) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->sd) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->stt) if (b.p) cudaFree(b.p);
+  for (DevBuf &b : ctx->stt_x) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->lr) if (b.p) cudaFree(b.p);
   if (ctx->li_tmp.p) cudaFree(ctx->li_tmp.p);
   for (DevBuf &b : ctx->lr_x) if (b.p) cudaFree(b.p);
+  for (DevBuf &b : ctx->so) if (b.p) cudaFree(b.p);
   for (auto &ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < 4; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]); }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
@@ -906,6 +911,30 @@ extern "C" int lra_b200_seed_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads,
 }
 
 
+// count -> scan -> emit of a21.  One warp per segment (stats_warp_kernel); LRA_B200_STATS_THREAD=1 selects the statement-by-statement
+// one-segment-per-thread kernels, which are kept as the cross-check.
+static int stats_launch(lra_b200_ctx *ctx, StatsBatch &b, int S, size_t n_blocks_in, int *errflag) {
+  int rc;
+  if ((rc = ensure(ctx, ctx->stt_x[0], n_blocks_in * 12 + 64)) || (rc = ensure(ctx, ctx->stt_x[1], (size_t)S * 256))) return rc;
+  b.pre = (uint32_t *)ctx->stt_x[0].p; b.lane_info = (uint32_t *)ctx->stt_x[1].p;
+  cudaStream_t st = ctx->stream;
+  static const bool thread_kernels = getenv("LRA_B200_STATS_THREAD") != nullptr;
+  cudaEventRecord(ctx->ev[0], st);
+  if (thread_kernels) {
+    const unsigned nb = (unsigned)((S + 127) / 128);
+    stats_kernel<false><<<nb, 128, 0, st>>>(b);
+    seed_scan_kernel<<<1, 1024, 0, st>>>(b.cig_off, S, b.cigar_cap, errflag);
+    stats_kernel<true><<<nb, 128, 0, st>>>(b);
+  } else {
+    const unsigned nb = (unsigned)((S + 3) / 4);
+    stats_warp_kernel<false><<<nb, 128, 0, st>>>(b);
+    seed_scan_kernel<<<1, 1024, 0, st>>>(b.cig_off, S, b.cigar_cap, errflag);
+    stats_warp_kernel<true><<<nb, 128, 0, st>>>(b);
+  }
+  cudaEventRecord(ctx->ev[1], st);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------- a21 statistics
 extern "C" int lra_b200_calc_stats_batch(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b200_seq *t, const lra_b200_ir_segments *sg,
                                          const float *log_lut, lra_b200_stats_result *res) {
@@ -940,12 +969,7 @@ extern "C" int lra_b200_calc_stats_batch(lra_b200_ctx *ctx, const lra_b200_seq *
   b.q_base = (const uint32_t *)B[3].p; b.t_base = (const uint32_t *)B[4].p; b.read_len = (const int32_t *)B[5].p; b.n_seg = S;
   b.lut = (const float *)B[6].p; b.stats = (int32_t *)B[7].p; b.value = (float *)B[8].p; b.cig_off = (unsigned long long *)B[9].p;
   b.cigar = (uint32_t *)B[10].p; b.cigar_cap = res->cigar_cap;
-  const unsigned nb = (unsigned)((S + 127) / 128);
-  cudaEventRecord(ctx->ev[0], st);
-  stats_kernel<false><<<nb, 128, 0, st>>>(b);
-  seed_scan_kernel<<<1, 1024, 0, st>>>(b.cig_off, S, b.cigar_cap, (int *)B[11].p);
-  stats_kernel<true><<<nb, 128, 0, st>>>(b);
-  cudaEventRecord(ctx->ev[1], st);
+  if ((rc = stats_launch(ctx, b, S, (size_t)sg->n_blocks_in, (int *)B[11].p))) return rc;
   ctx->launches += 3;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(res->cigar_off, b.cig_off, ((size_t)S + 1) * 8, cudaMemcpyDeviceToHost, st));
@@ -987,12 +1011,7 @@ extern "C" int lra_b200_calc_stats_batch_device(lra_b200_ctx *ctx, const lra_b20
   b.q_base = sg->q_base; b.t_base = sg->t_base; b.read_len = sg->read_len; b.n_seg = S;
   b.lut = (const float *)B[6].p; b.stats = res->stats; b.value = res->value; b.cig_off = (unsigned long long *)res->cigar_off;
   b.cigar = res->cigar; b.cigar_cap = res->cigar_cap;
-  const unsigned nb = (unsigned)((S + 127) / 128);
-  cudaEventRecord(ctx->ev[0], st);
-  stats_kernel<false><<<nb, 128, 0, st>>>(b);
-  seed_scan_kernel<<<1, 1024, 0, st>>>(b.cig_off, S, b.cigar_cap, (int *)B[11].p);
-  stats_kernel<true><<<nb, 128, 0, st>>>(b);
-  cudaEventRecord(ctx->ev[1], st);
+  if ((rc = stats_launch(ctx, b, S, (size_t)sg->n_blocks_in, (int *)B[11].p))) return rc;
   ctx->launches += 3;
   CU(cudaGetLastError());
   unsigned long long total = 0;

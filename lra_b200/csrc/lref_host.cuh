@@ -414,3 +414,51 @@ extern "C" int lra_b200_refine_splitchains_batch_device(lra_b200_ctx *ctx, const
   const LrefChainExtra ex{sc->m_len, sc->m_strand, sc->chrom, sc->limitrefine};
   return lref_run(ctx, gl, rf, rr, &cl, (size_t)n_anchors_in, res, &ex);
 }
+
+// ---------------------------------------------------------------------------------------------------- a6 anchor sorts
+extern "C" int lra_b200_sort_matches_batch(lra_b200_ctx *ctx, int32_t mode, uint32_t *q, uint32_t *t, const uint64_t *seg_off, int32_t n_seg, uint32_t *perm) {
+  if (!ctx || !seg_off || n_seg < 0 || mode < 0 || mode > 3) return fail(ctx, LRA_B200_EINVAL, "sort_matches_batch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  if (n_seg == 0) return LRA_B200_OK;
+  const size_t N = (size_t)seg_off[n_seg];
+  if (N == 0) return LRA_B200_OK;
+  if (!q || !t) return fail(ctx, LRA_B200_EINVAL, "sort_matches_batch: NULL anchors");
+  if (N > 0xFFFFFFF0ull) return fail(ctx, LRA_B200_EINVAL, "sort_matches_batch: more than 2^32 anchors in one batch");
+  std::vector<unsigned long long> slot((size_t)n_seg);
+  size_t slots = 0;
+  for (int s = 0; s < n_seg; s++) {
+    if (seg_off[s + 1] < seg_off[s]) return fail(ctx, LRA_B200_EINVAL, "sort_matches_batch: segment offsets not ascending");
+    const size_t n = (size_t)(seg_off[s + 1] - seg_off[s]);
+    size_t P = 1; while (P < n) P <<= 1;
+    slot[s] = slots;
+    if (P > (size_t)kSortSmem) slots += P;
+  }
+  int rc;
+  DevBuf *B = ctx->so;
+  if ((rc = ensure(ctx, B[0], N * 4)) || (rc = ensure(ctx, B[1], N * 4)) || (rc = ensure(ctx, B[2], ((size_t)n_seg + 1) * 8)) || (rc = ensure(ctx, B[3], N * 4)) ||
+      (rc = ensure(ctx, B[4], slots * 8 + 16)) || (rc = ensure(ctx, B[5], slots * 4 + 16)) || (rc = ensure(ctx, B[6], slots * 4 + 16)) || (rc = ensure(ctx, B[7], (size_t)n_seg * 8)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(B[0].p, q, N * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[1].p, t, N * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[2].p, seg_off, ((size_t)n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[7].p, slot.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+  SortBatch b;
+  b.n_seg = n_seg; b.mode = mode; b.seg_off = (const unsigned long long *)B[2].p; b.q = (uint32_t *)B[0].p; b.t = (uint32_t *)B[1].p;
+  b.perm = perm ? (uint32_t *)B[3].p : nullptr; b.kp = (unsigned long long *)B[4].p; b.ks = (uint32_t *)B[5].p; b.ki = (uint32_t *)B[6].p;
+  b.slot_off = (const unsigned long long *)B[7].p;
+  cudaEventRecord(ctx->ev[0], st);
+  sort_pairs_kernel<<<(unsigned)n_seg, 256, 0, st>>>(b);
+  cudaEventRecord(ctx->ev[1], st);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(q, b.q, N * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(t, b.t, N * 4, cudaMemcpyDeviceToHost, st));
+  if (perm) CU(cudaMemcpyAsync(perm, b.perm, N * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "sort_pairs<mode=%d>", mode);
+  cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]); s2.jobs = (uint64_t)n_seg; s2.algo_bytes = 16ull * N + (perm ? 4ull * N : 0ull) + 8ull * (uint64_t)n_seg;
+  ctx->stats.push_back(s2);
+  return LRA_B200_OK;
+}

@@ -544,3 +544,23 @@ def refine_splitchain(mq, mt, mlen, mstrand, box, chrom, strand, read_len, hdr_p
             break
         cap = m
     return dict(status=int(info[0]), chrom=int(info[1]), diag=diag.copy(), rq=rq[:m], rt=rt[:m], rtup=ru[:m], rbox=info[2:6].astype(np.uint32), eff=np.float32(eff.value))
+
+
+# ---------------------------------------------------------------- a6 anchor sorts (Sorting.h)
+
+def sort_matches(mode, q, t, which="port"):
+    """mode 0 DiagonalSort, 1 AntiDiagonalSort, 2 CartesianSort, 3 CartesianTargetSort on one anchor list.  Returns (q, t[, perm])."""
+    q = np.array(q, np.uint32); t = np.array(t, np.uint32)
+    n = len(q)
+    if n == 0:
+        return q, t, np.zeros(0, np.uint32)
+    if which == "ref":
+        L = ref()
+        L.ref_sort_matches.argtypes = [C.c_int, _u32p, _u32p, C.c_long]; L.ref_sort_matches.restype = None
+        L.ref_sort_matches(mode, q, t, n)
+        return q, t, None
+    L = port()
+    L.lra_oracle_sort_matches.argtypes = [C.c_int, _u32p, _u32p, C.c_long, _u32p]; L.lra_oracle_sort_matches.restype = None
+    perm = np.zeros(n, np.uint32)
+    L.lra_oracle_sort_matches(mode, q, t, n, perm)
+    return q, t, perm

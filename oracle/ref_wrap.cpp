@@ -324,4 +324,19 @@ long ref_refine_splitchain(const uint32_t *mq, const uint32_t *mt, const uint32_
   return m;
 }
 
+// ---- a6: the anchor sorts of Sorting.h on a vector of GenomePairs (tuple values derived from the positions, as in real anchors)
+void ref_sort_matches(int mode, uint32_t *q, uint32_t *t, long n) {
+  ref_init_static();
+  GenomePairs v(n);
+  for (long i = 0; i < n; i++) {
+    v[i].first.pos = q[i]; v[i].second.pos = t[i];
+    v[i].first.t = (Tuple)q[i] * 0x9E3779B97F4A7C15ull; v[i].second.t = v[i].first.t;
+  }
+  if (mode == 0) DiagonalSort<GenomeTuple>(v);
+  else if (mode == 1) AntiDiagonalSort<GenomeTuple>(v);
+  else if (mode == 2) CartesianSort<GenomeTuple>(v);
+  else CartesianTargetSort<GenomeTuple>(v.begin(), v.end());
+  for (long i = 0; i < n; i++) { q[i] = v[i].first.pos; t[i] = v[i].second.pos; }
+}
+
 }  // extern "C"

@@ -51,19 +51,19 @@ def lib():
     L.emu_calc_stats.restype = C.c_long
     L.emu_calc_stats.argtypes = [_u8p, C.c_uint64, _u8p, C.c_uint64, _u32p, _u64p, _i32p, _u32p, _u32p, _i32p, C.c_int,
                                  np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"), _i32p, np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"),
-                                 _u64p, _u32p, C.c_uint64]
+                                 _u64p, _u32p, C.c_uint64, C.c_int]
     _lib = L
     return L
 
 
-def calc_stats(sb, t_arena, t_base, lut):
+def calc_stats(sb, t_arena, t_base, lut, thread_kernels=0):
     S = len(sb["blk_cnt"])
     bi = np.ascontiguousarray(sb["blocks_in"], np.uint32)
     cap = 4 * (bi.size // 3) + 16 * S + 16
     o = dict(stats=np.zeros((S, 16), np.int32), value=np.zeros(S, np.float32), cigar_off=np.zeros(S + 1, np.uint64), cigar=np.zeros(cap, np.uint32))
     lib().emu_calc_stats(sb["q_arena"], len(sb["q_arena"]) - 16, t_arena, len(t_arena) - 16, bi.reshape(-1), np.ascontiguousarray(sb["blk_off"], np.uint64),
                          sb["blk_cnt"], sb["q_base"], np.ascontiguousarray(t_base, np.uint32), sb["read_len"], S, np.ascontiguousarray(lut, np.float32),
-                         o["stats"].reshape(-1), o["value"], o["cigar_off"], o["cigar"], cap)
+                         o["stats"].reshape(-1), o["value"], o["cigar_off"], o["cigar"], cap, thread_kernels)
     return o
 
 
@@ -197,3 +197,12 @@ def refine_clusters(gl, rf, rr, cl, cap=None, literal=0):
             o["n_anchors"] = tot; o["n_units"], o["n_tasks"] = int(counts[0]), int(counts[1])
             return o
         cap = tot
+
+
+def sort_matches(mode, q, t, seg_off):
+    L = lib()
+    L.emu_sort_matches.argtypes = [C.c_int, _u32p, _u32p, _u64p, C.c_int, _u32p]
+    q = np.array(q, np.uint32); t = np.array(t, np.uint32); perm = np.zeros(max(len(q), 1), np.uint32)
+    seg_off = np.ascontiguousarray(seg_off, np.uint64)
+    L.emu_sort_matches(mode, q if len(q) else np.zeros(1, np.uint32), t if len(t) else np.zeros(1, np.uint32), seg_off, len(seg_off) - 1, perm)
+    return q, t, perm[:len(q)]

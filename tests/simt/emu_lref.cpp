@@ -94,3 +94,16 @@ extern "C" long emu_refine_clusters(const EmuLidx *gl, const EmuLidx *rf, const 
   counts[0] = n_units; counts[1] = n_tasks;
   return (long)out_off[n_tasks];
 }
+
+// ---- a6 anchor sorts
+#include "sort_kernels.cuh"
+extern "C" int emu_sort_matches(int mode, uint32_t *q, uint32_t *t, const uint64_t *seg_off, int n_seg, uint32_t *perm) {
+  std::vector<unsigned long long> slot(n_seg + 1);
+  size_t slots = 0;
+  for (int s = 0; s < n_seg; s++) { size_t n = seg_off[s + 1] - seg_off[s], P = 1; while (P < n) P <<= 1; slot[s] = slots; if (P > (size_t)kSortSmem) slots += P; }
+  std::vector<unsigned long long> kp(slots + 2);
+  std::vector<uint32_t> ks(slots + 2), ki(slots + 2);
+  SortBatch b{n_seg, mode, (const unsigned long long *)seg_off, q, t, perm, kp.data(), ks.data(), ki.data(), slot.data()};
+  if (n_seg) emu::launch(dim3((unsigned)n_seg), dim3(256), 0, [&] { sort_pairs_kernel(b); });
+  return 0;
+}

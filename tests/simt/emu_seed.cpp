@@ -47,14 +47,24 @@ extern "C" long emu_seed_batch(const uint8_t *reads_ascii, uint64_t rn, const ui
 #include "stats_kernels.cuh"
 extern "C" long emu_calc_stats(const uint8_t *q_arena, uint64_t qn, const uint8_t *t_arena, uint64_t tn, const uint32_t *blocks, const uint64_t *blk_off,
                                const int32_t *blk_cnt, const uint32_t *q_base, const uint32_t *t_base, const int32_t *read_len, int S, const float *lut,
-                               int32_t *stats, float *value, uint64_t *cig_off, uint32_t *cigar, uint64_t cap) {
+                               int32_t *stats, float *value, uint64_t *cig_off, uint32_t *cigar, uint64_t cap, int thread_kernels) {
   Packed q, t; pack(q_arena, qn, q); pack(t_arena, tn, t);
   int err = 0;
+  size_t T = 0;
+  for (int s = 0; s < S; s++) T = std::max(T, (size_t)(blk_off[s] + (uint64_t)blk_cnt[s]));
+  std::vector<uint32_t> pre(3 * T + 16), lane_info((size_t)S * 64 + 16);
   StatsBatch b{q.view, t.view, blocks, (const unsigned long long *)blk_off, blk_cnt, q_base, t_base, read_len, S, lut, stats, value,
-               (unsigned long long *)cig_off, cigar, cap};
-  unsigned nb = (unsigned)((S + 127) / 128);
-  emu::launch(dim3(nb), dim3(128), 0, [&] { stats_kernel<false>(b); });
-  emu::launch(dim3(1), dim3(1024), 0, [&] { seed_scan_kernel(b.cig_off, S, cap, &err); });
-  emu::launch(dim3(nb), dim3(128), 0, [&] { stats_kernel<true>(b); });
+               (unsigned long long *)cig_off, cigar, cap, pre.data(), lane_info.data()};
+  if (thread_kernels) {
+    unsigned nb = (unsigned)((S + 127) / 128);
+    emu::launch(dim3(nb), dim3(128), 0, [&] { stats_kernel<false>(b); });
+    emu::launch(dim3(1), dim3(1024), 0, [&] { seed_scan_kernel(b.cig_off, S, cap, &err); });
+    emu::launch(dim3(nb), dim3(128), 0, [&] { stats_kernel<true>(b); });
+  } else {
+    unsigned nb = (unsigned)((S + 3) / 4);
+    emu::launch(dim3(nb), dim3(128), 0, [&] { stats_warp_kernel<false>(b); });
+    emu::launch(dim3(1), dim3(1024), 0, [&] { seed_scan_kernel(b.cig_off, S, cap, &err); });
+    emu::launch(dim3(nb), dim3(128), 0, [&] { stats_warp_kernel<true>(b); });
+  }
   return (long)cig_off[S];
 }
