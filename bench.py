@@ -221,6 +221,7 @@ def cpu_stage_rates(args, jobs, segs, jobs_per_read, budget_s):
             with ThreadPoolExecutor(cores if which == "ref" else 1) as ex:
                 list(ex.map(one_read, range(n)))
             return time.perf_counter() - t0
+        one_read(0)      # (binds the ctypes prototypes on this thread before the pool starts)
         one3()
         ts = [one3()]
         tot = ts[0]
@@ -259,6 +260,7 @@ def cpu_stage_rates(args, jobs, segs, jobs_per_read, budget_s):
             with ThreadPoolExecutor(cores if kind == "reference" else 1) as ex:
                 list(ex.map(one_seg, items))
             return time.perf_counter() - t0
+        one_seg(items[0])
         one4()
         ts = [one4()]
         tot = ts[0]

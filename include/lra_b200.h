@@ -340,6 +340,15 @@ int lra_b200_refine_splitchains_batch_device(lra_b200_ctx *ctx, const lra_b200_l
                                              const lra_b200_lindex *reads_rc, const lra_b200_splitchains *sc_dev, uint64_t n_anchors_in,
                                              lra_b200_refined *res_dev);
 
+/* ---- a24  GlobalChain over a PrioritySearchTree, batched over independent problems --------------------------------------
+ * Replaces  int GlobalChain(vector<T_Fragment> &fragments, vector<int> &optFragmentChainIndices, vector<T_Endpoint> &endpoints)
+ * (GlobalChain.h:88-189, with PrioritySearchTree.h:47-291) as the reference's driver TestGlobalChain.cpp:9-27 calls it.  Problem p:
+ * fragments frag_off[p] .. frag_off[p+1], frag[4i..] = xl, yl, xh, yh.  score: in = each fragment's own score, out = the score of the
+ * best chain ending in it (Fragment::score); prev: Fragment::prev (problem-local index, -1 = none); chain[frag_off[p] ..] = the optimal
+ * chain of problem p, first fragment first, chain_len[p] fragments.  (`lra` itself never calls GlobalChain.) */
+int lra_b200_global_chain_batch(lra_b200_ctx *ctx, const int32_t *frag, const uint64_t *frag_off, int32_t n_prob, int32_t *score, int32_t *prev,
+                                int32_t *chain, int32_t *chain_len);
+
 /* ---- per-kernel timing of the last batch call (CUDA events on the context's stream) ---------------------------- */
 typedef struct lra_b200_kernel_stat {
   char name[48];

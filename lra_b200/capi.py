@@ -132,6 +132,7 @@ def load_library():
     L.lra_b200_seed_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_SeedReads), C.POINTER(_SeedResult)]
     L.lra_b200_calc_stats_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrSegments), C.c_void_p, C.POINTER(_StatsResult)]
     L.lra_b200_sort_matches_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.lra_b200_global_chain_batch.argtypes = [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 4
     L.lra_b200_lindex_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.POINTER(C.c_void_p)]
     L.lra_b200_lindex_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
@@ -335,6 +336,19 @@ class Context:
         self._check(self.lib.lra_b200_sort_matches_batch(self.h, mode, _ptr(q) if len(q) else None, _ptr(t) if len(t) else None, _ptr(so), len(so) - 1,
                                                          _ptr(perm) if want_perm else None))
         return q, t, (perm[:len(q)] if want_perm else None)
+
+    # ---- a24
+    def global_chain_batch(self, frag, frag_off, score):
+        """GlobalChain for every problem (frag[n,4] int32, frag_off[n_prob+1], score[n]).  Returns dict(score, prev, chain, chain_len)."""
+        f = np.ascontiguousarray(frag, np.int32).reshape(-1); fo = np.ascontiguousarray(frag_off, np.uint64)
+        n = len(f) // 4
+        o = dict(score=np.array(score, np.int32), prev=np.zeros(max(n, 1), np.int32), chain=np.zeros(max(n, 1), np.int32), chain_len=np.zeros(max(len(fo) - 1, 1), np.int32))
+        if n == 0:
+            o["score"] = np.zeros(1, np.int32)
+        self._check(self.lib.lra_b200_global_chain_batch(self.h, _ptr(f) if n else None, _ptr(fo), len(fo) - 1, _ptr(o["score"]), _ptr(o["prev"]), _ptr(o["chain"]),
+                                                         _ptr(o["chain_len"])))
+        o["score"] = o["score"][:n]; o["prev"] = o["prev"][:n]; o["chain_len"] = o["chain_len"][:len(fo) - 1]
+        return o
 
     # ---- a12
     def lindex_build(self, seq, seq_start, seq_len, k=10, w=5, window=2048, max_freq=15, reuse=None):

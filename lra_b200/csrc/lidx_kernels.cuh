@@ -288,13 +288,12 @@ __global__ void __launch_bounds__(32 * kLidxWarps) lidx_window_kernel(LidxBuild 
   __syncwarp();
   for (int kk = 2; kk <= P; kk <<= 1) {
     for (int j = kk >> 1; j > 0; j >>= 1) {
-      for (int i = lane; i < P; i += 32) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const uint32_t a = v[i], c = v[ixj];
-          const bool up = (i & kk) == 0;
-          if ((a > c) == up) { v[i] = c; v[ixj] = a; }
-        }
+      for (int x = lane; x < (P >> 1); x += 32) {
+        const int i = ((x & ~(j - 1)) << 1) | (x & (j - 1));      // lower index of the x-th compare-exchange pair of this stage
+        const int ixj = i | j;
+        const uint32_t a = v[i], c = v[ixj];
+        const bool up = (i & kk) == 0;
+        if ((a > c) == up) { v[i] = c; v[ixj] = a; }
       }
       __syncwarp();
     }

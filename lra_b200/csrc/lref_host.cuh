@@ -462,3 +462,45 @@ extern "C" int lra_b200_sort_matches_batch(lra_b200_ctx *ctx, int32_t mode, uint
   ctx->stats.push_back(s2);
   return LRA_B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- a24 GlobalChain
+extern "C" int lra_b200_global_chain_batch(lra_b200_ctx *ctx, const int32_t *frag, const uint64_t *frag_off, int32_t n_prob, int32_t *score, int32_t *prev,
+                                           int32_t *chain, int32_t *chain_len) {
+  if (!ctx || !frag_off || n_prob < 0 || !chain_len) return fail(ctx, LRA_B200_EINVAL, "global_chain_batch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  if (n_prob == 0) return LRA_B200_OK;
+  const size_t N = (size_t)frag_off[n_prob];
+  for (int p = 0; p < n_prob; p++) {
+    if (frag_off[p + 1] < frag_off[p]) return fail(ctx, LRA_B200_EINVAL, "global_chain_batch: problem offsets not ascending");
+    if (frag_off[p + 1] - frag_off[p] > (1ull << 28)) return fail(ctx, LRA_B200_EINVAL, "global_chain_batch: problem %d has more than 2^28 fragments", p);
+  }
+  if (N && (!frag || !score || !prev || !chain)) return fail(ctx, LRA_B200_EINVAL, "global_chain_batch: NULL fragment arrays");
+  int rc;
+  DevBuf *B = ctx->gc;
+  if ((rc = ensure(ctx, B[0], N * 16 + 16)) || (rc = ensure(ctx, B[1], ((size_t)n_prob + 1) * 8)) || (rc = ensure(ctx, B[2], N * 4 + 16)) || (rc = ensure(ctx, B[3], N * 4 + 16)) ||
+      (rc = ensure(ctx, B[4], N * 4 + 16)) || (rc = ensure(ctx, B[5], (size_t)n_prob * 4)) || (rc = ensure(ctx, B[6], 2 * N * sizeof(GcEndpoint) + 64)) ||
+      (rc = ensure(ctx, B[7], 4 * N * sizeof(GcVertex) + 64)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  if (N) { CU(cudaMemcpyAsync(B[0].p, frag, N * 16, cudaMemcpyHostToDevice, st)); CU(cudaMemcpyAsync(B[2].p, score, N * 4, cudaMemcpyHostToDevice, st)); }
+  CU(cudaMemcpyAsync(B[1].p, frag_off, ((size_t)n_prob + 1) * 8, cudaMemcpyHostToDevice, st));
+  GcBatch b;
+  b.n_prob = n_prob; b.frag_off = (const unsigned long long *)B[1].p; b.frag = (const int32_t *)B[0].p; b.score = (int32_t *)B[2].p; b.prev = (int32_t *)B[3].p;
+  b.chain = (int32_t *)B[4].p; b.chain_len = (int32_t *)B[5].p; b.ep = (GcEndpoint *)B[6].p; b.tree = (GcVertex *)B[7].p;
+  cudaEventRecord(ctx->ev[0], st);
+  gchain_kernel<<<(unsigned)((n_prob + 63) / 64), 64, 0, st>>>(b);
+  cudaEventRecord(ctx->ev[1], st);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  if (N) {
+    CU(cudaMemcpyAsync(score, b.score, N * 4, cudaMemcpyDeviceToHost, st)); CU(cudaMemcpyAsync(prev, b.prev, N * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(chain, b.chain, N * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaMemcpyAsync(chain_len, b.chain_len, (size_t)n_prob * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "gchain");
+  cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]); s2.jobs = (uint64_t)n_prob; s2.algo_bytes = 32ull * N;
+  ctx->stats.push_back(s2);
+  return LRA_B200_OK;
+}

@@ -380,6 +380,21 @@ def calc_stats_ref(read, text, blocks):
 
 # ---------------------------------------------------------------- a12 LocalIndex::IndexSeq, a13 REFINEclusters
 
+import threading
+_bind_lock = threading.Lock()
+
+
+def _bind_once(L, name, restype, argtypes):
+    """ctypes prototypes are set once per library object: bench.py calls these wrappers from a thread pool, and re-assigning argtypes
+    while another thread is inside a call is a race."""
+    f = getattr(L, name)
+    if not getattr(f, "_lra_bound", False):
+        with _bind_lock:
+            if not getattr(f, "_lra_bound", False):
+                f.restype = restype; f.argtypes = argtypes; f._lra_bound = True
+    return f
+
+
 class LocalIndexData:
     """A LocalIndex as three arrays: seq_off (uint64, leading 0), bnd (uint64, leading 0), mins (uint32: tuple | pos << 20)."""
     def __init__(self, seq_off, bnd, mins, k=10, w=5, window=2048, max_freq=15):
@@ -394,12 +409,12 @@ def local_index(seqs, k=10, w=5, window=2048, max_freq=15, which="port"):
     seqs = [np.frombuffer(s, np.uint8) if isinstance(s, (bytes, bytearray)) else np.ascontiguousarray(s, np.uint8) for s in seqs]
     if which == "ref":
         L = ref()
-        L.ref_lidx_new.restype = C.c_void_p; L.ref_lidx_new.argtypes = [C.c_int] * 4
-        L.ref_lidx_index_seq.argtypes = [C.c_void_p, _u8p, C.c_int]
-        L.ref_lidx_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long)]
-        L.ref_lidx_copy.argtypes = [C.c_void_p, _u64p, _u64p, _u32p]
-        L.ref_lidx_free.argtypes = [C.c_void_p]
-        h = L.ref_lidx_new(k, w, window, max_freq)
+        _bind_once(L, "ref_lidx_new", C.c_void_p, [C.c_int] * 4)
+        _bind_once(L, "ref_lidx_index_seq", None, [C.c_void_p, _u8p, C.c_int])
+        _bind_once(L, "ref_lidx_sizes", None, [C.c_void_p, C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long)])
+        _bind_once(L, "ref_lidx_copy", None, [C.c_void_p, _u64p, _u64p, _u32p])
+        _bind_once(L, "ref_lidx_free", None, [C.c_void_p])
+        h = C.c_void_p(L.ref_lidx_new(k, w, window, max_freq))
         for s in seqs:
             L.ref_lidx_index_seq(h, np.concatenate([s, np.zeros(8, np.uint8)]), len(s))
         a, b, c = C.c_long(), C.c_long(), C.c_long()
@@ -409,8 +424,7 @@ def local_index(seqs, k=10, w=5, window=2048, max_freq=15, which="port"):
         L.ref_lidx_free(h)
         return LocalIndexData(off, bnd, mins[:c.value], k, w, window, max_freq)
     L = port()
-    L.lra_oracle_index_seq.restype = C.c_long
-    L.lra_oracle_index_seq.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u64p, _u64p, _u32p, C.c_long, C.POINTER(C.c_int)]
+    _bind_once(L, "lra_oracle_index_seq", C.c_long, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u64p, _u64p, _u32p, C.c_long, C.POINTER(C.c_int)])
     offs, bnds, minss = [np.zeros(1, np.uint64)], [np.zeros(1, np.uint64)], []
     base, nmin = 0, 0
     for s in seqs:
@@ -462,17 +476,15 @@ def refine_cluster(mq, mt, box, strand, read_len, hdr_pos, gl, rd_fwd, rd_rev, g
         rq = np.zeros(cap, np.uint32); rt = np.zeros(cap, np.uint32); ru = np.zeros(cap, np.uint32)
         if which == "ref":
             L = ref()
-            L.ref_refine_cluster.restype = C.c_long
-            L.ref_refine_cluster.argtypes = [_u32p, _u32p, C.c_long, _u32p, C.c_int, C.c_uint32, _u64p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                             C.c_int, C.c_int, C.c_int, C.c_long, _u32p, _u32p, _u32p, C.c_long, _i32p, _i64p, C.POINTER(C.c_float)]
+            _bind_once(L, "ref_refine_cluster", C.c_long, [_u32p, _u32p, C.c_long, _u32p, C.c_int, C.c_uint32, _u64p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                            C.c_int, C.c_int, C.c_int, C.c_long, _u32p, _u32p, _u32p, C.c_long, _i32p, _i64p, C.POINTER(C.c_float)])
             n = L.ref_refine_cluster(a, b, len(mq), bx, strand, read_len, hdr, len(hdr), ref_handles[0], ref_handles[1], ref_handles[2],
                                      global_k, small_k, window, local_max_freq, rq, rt, ru, cap, info, diag, C.byref(eff))
         else:
             L = port()
-            L.lra_oracle_refine_cluster.restype = C.c_long
-            L.lra_oracle_refine_cluster.argtypes = [_u32p, _u32p, C.c_long, _u32p, C.c_int, C.c_uint32, _u64p, C.c_int,
-                                                    _u64p, C.c_long, _u64p, _u32p, _u64p, C.c_long, _u64p, _u32p,
-                                                    C.c_int, C.c_int, C.c_int, C.c_long, _u32p, _u32p, _u32p, C.c_long, _i32p, _i64p, C.POINTER(C.c_float)]
+            _bind_once(L, "lra_oracle_refine_cluster", C.c_long, [_u32p, _u32p, C.c_long, _u32p, C.c_int, C.c_uint32, _u64p, C.c_int,
+                                                                   _u64p, C.c_long, _u64p, _u32p, _u64p, C.c_long, _u64p, _u32p,
+                                                                   C.c_int, C.c_int, C.c_int, C.c_long, _u32p, _u32p, _u32p, C.c_long, _i32p, _i64p, C.POINTER(C.c_float)])
             rd = rd_rev if strand else rd_fwd
             pad = lambda m: m if len(m) else np.zeros(1, np.uint32)
             n = L.lra_oracle_refine_cluster(a, b, len(mq), bx, strand, read_len, hdr, len(hdr), gl.seq_off, len(gl.seq_off), gl.bnd, pad(gl.mins),
@@ -489,9 +501,9 @@ class RefLocalIndexHandle:
     """A live reference LocalIndex (for ref_refine_cluster)."""
     def __init__(self, seqs, k=10, w=5, window=2048, max_freq=15):
         L = ref()
-        L.ref_lidx_new.restype = C.c_void_p; L.ref_lidx_new.argtypes = [C.c_int] * 4
-        L.ref_lidx_index_seq.argtypes = [C.c_void_p, _u8p, C.c_int]
-        L.ref_lidx_free.argtypes = [C.c_void_p]
+        _bind_once(L, "ref_lidx_new", C.c_void_p, [C.c_int] * 4)
+        _bind_once(L, "ref_lidx_index_seq", None, [C.c_void_p, _u8p, C.c_int])
+        _bind_once(L, "ref_lidx_free", None, [C.c_void_p])
         self.L = L
         self.h = C.c_void_p(L.ref_lidx_new(k, w, window, max_freq))
         if isinstance(seqs, (bytes, bytearray, np.ndarray)):
@@ -564,3 +576,16 @@ def sort_matches(mode, q, t, which="port"):
     perm = np.zeros(n, np.uint32)
     L.lra_oracle_sort_matches(mode, q, t, n, perm)
     return q, t, perm
+
+
+# ---------------------------------------------------------------- a24 GlobalChain / PrioritySearchTree
+
+def global_chain(frag, score, which="port"):
+    """frag[n,4] = xl, yl, xh, yh (int32), score[n].  Returns (chain indices, final scores, prev)."""
+    frag = np.ascontiguousarray(frag, np.int32).reshape(-1, 4); n = len(frag)
+    sc = np.array(score, np.int32); prev = np.full(max(n, 1), -1, np.int32); chain = np.zeros(max(n, 1), np.int32)
+    L = ref() if which == "ref" else port()
+    f = L.ref_global_chain if which == "ref" else L.lra_oracle_global_chain
+    f.restype = C.c_long; f.argtypes = [_i32p, _i32p, _i32p, C.c_long, _i32p]
+    m = f(frag.reshape(-1) if n else np.zeros(4, np.int32), sc if n else np.zeros(1, np.int32), prev, n, chain)
+    return chain[:m].copy(), sc, prev[:n]

@@ -32,6 +32,8 @@
 #include "Options.h"
 #include "Alignment.h"
 #include "LogLookUpTable.h"
+#include "GlobalChain.h"
+#include "Fragment.h"
 
 extern "C" {
 
@@ -337,6 +339,18 @@ void ref_sort_matches(int mode, uint32_t *q, uint32_t *t, long n) {
   else if (mode == 2) CartesianSort<GenomeTuple>(v);
   else CartesianTargetSort<GenomeTuple>(v.begin(), v.end());
   for (long i = 0; i < n; i++) { q[i] = v[i].first.pos; t[i] = v[i].second.pos; }
+}
+
+// ---- a24: GlobalChain<Fragment,Endpoint> (GlobalChain.h:88-189) as the reference's driver calls it (TestGlobalChain.cpp:9-27)
+long ref_global_chain(const int32_t *frag, int32_t *score, int32_t *prev, long n, int32_t *chain_out) {
+  std::vector<Endpoint> endpoints;
+  std::vector<Fragment> fragments;
+  std::vector<int> opt;
+  for (long i = 0; i < n; i++) fragments.push_back(Fragment(frag[4 * i], frag[4 * i + 1], frag[4 * i + 2], frag[4 * i + 3], score[i], 0));
+  GlobalChain(fragments, opt, endpoints);
+  for (long i = 0; i < n; i++) { score[i] = fragments[i].score; prev[i] = fragments[i].prev; }
+  for (size_t i = 0; i < opt.size(); i++) chain_out[i] = opt[i];
+  return (long)opt.size();
 }
 
 }  // extern "C"

@@ -206,3 +206,13 @@ def sort_matches(mode, q, t, seg_off):
     seg_off = np.ascontiguousarray(seg_off, np.uint64)
     L.emu_sort_matches(mode, q if len(q) else np.zeros(1, np.uint32), t if len(t) else np.zeros(1, np.uint32), seg_off, len(seg_off) - 1, perm)
     return q, t, perm[:len(q)]
+
+
+def global_chain(frag, frag_off, score):
+    L = lib()
+    L.emu_global_chain.argtypes = [_i32p, _u64p, C.c_int, _i32p, _i32p, _i32p, _i32p]
+    f = np.ascontiguousarray(frag, np.int32).reshape(-1); fo = np.ascontiguousarray(frag_off, np.uint64)
+    n = len(f) // 4
+    sc = np.array(score, np.int32); prev = np.zeros(max(n, 1), np.int32); chain = np.zeros(max(n, 1), np.int32); cl = np.zeros(max(len(fo) - 1, 1), np.int32)
+    L.emu_global_chain(f if n else np.zeros(4, np.int32), fo, len(fo) - 1, sc if n else np.zeros(1, np.int32), prev, chain, cl)
+    return dict(score=sc, prev=prev[:n], chain=chain, chain_len=cl[:len(fo) - 1])

@@ -107,3 +107,14 @@ extern "C" int emu_sort_matches(int mode, uint32_t *q, uint32_t *t, const uint64
   if (n_seg) emu::launch(dim3((unsigned)n_seg), dim3(256), 0, [&] { sort_pairs_kernel(b); });
   return 0;
 }
+
+// ---- a24 GlobalChain
+#include "gchain_kernels.cuh"
+extern "C" int emu_global_chain(const int32_t *frag, const uint64_t *frag_off, int n_prob, int32_t *score, int32_t *prev, int32_t *chain, int32_t *chain_len) {
+  const size_t N = (size_t)frag_off[n_prob];
+  std::vector<GcEndpoint> ep(2 * N + 2);
+  std::vector<GcVertex> tree(4 * N + 2);
+  GcBatch b{n_prob, (const unsigned long long *)frag_off, frag, score, prev, chain, chain_len, ep.data(), tree.data()};
+  if (n_prob) emu::launch(dim3((unsigned)((n_prob + 63) / 64)), dim3(64), 0, [&] { gchain_kernel(b); });
+  return 0;
+}

@@ -5,7 +5,10 @@ TAG=${1:-r01}
 ARGS="--steps 2 --warmup 1 --no-cpu-baseline --reads-per-step 4096"
 export LRA_B200_SERIAL=1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py $ARGS > gpurun_out/launches_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"ir_dp_pipe|ir_dp_warp|ir_band|lidx_window|lref_task_literal|stats_warp|aog_thread_kernel|aog_warp_literal|lref_prep|ir_group" \
-    -c 36 -f -o gpurun_out/prof_$TAG python bench.py --steps 1 --warmup 1 --no-cpu-baseline --reads-per-step 4096 > gpurun_out/prof_$TAG.log 2>&1
-ncu -i gpurun_out/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2> /dev/null
-ls -la gpurun_out/prof_$TAG.ncu-rep gpurun_out/launches_$TAG.csv gpurun_out/prof_${TAG}_raw.csv
+ncu --set full --clock-control none --import-source on -k regex:"ir_dp_pipe|ir_band|lidx_window|lref_task_literal|stats_warp|aog_thread_kernel|aog_warp_literal|lref_prep|ir_group" \
+    -c 24 -f -o /tmp/prof_$TAG python bench.py --steps 1 --warmup 1 --no-cpu-baseline --reads-per-step 2048 > gpurun_out/prof_$TAG.log 2>&1
+ncu -i /tmp/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2> /dev/null
+# source-level hot spots of the two heaviest kernels (the report itself is too large to bring back: gpurun_out is capped at 64 MiB)
+ncu -i /tmp/prof_$TAG.ncu-rep --page source --csv -k regex:"lidx_window" > gpurun_out/prof_${TAG}_src_lidx.csv 2> /dev/null
+ncu -i /tmp/prof_$TAG.ncu-rep --page source --csv -k regex:"ir_dp_pipe" > gpurun_out/prof_${TAG}_src_irpipe.csv 2> /dev/null
+ls -la /tmp/prof_$TAG.ncu-rep gpurun_out/launches_$TAG.csv gpurun_out/prof_${TAG}_raw.csv gpurun_out/prof_${TAG}_src_*.csv
