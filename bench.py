@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--cpu-sample-segments", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stages", default="a12,a13,a18,a19,a21")
+    ap.add_argument("--serial-stages", action="store_true", help="run the two stage groups back to back on one context instead of concurrently on two")
     return ap.parse_args()
 
 
@@ -411,9 +412,19 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     keep = {"rc": None, "rf": None, "rr": None}      # the reverse-complement arena and the two read LocalIndex images are rebuilt in place every step
+    io = {"h2d": 0, "d2h": 0}
+    # second context for the stage group a12+a13 (one context per worker thread)
+    two = (not args.serial_stages) and ("a12" in stages or "a13" in stages) and any(x in stages for x in ("a18", "a19", "a21"))
+    if two:
+        from concurrent.futures import ThreadPoolExecutor
+        stream_b = torch.cuda.Stream(device=dev)
+        ctxb = lra_b200.Context(local)
+        ctxb.set_stream(stream_b.cuda_stream)
+        pool = ThreadPoolExecutor(1)
+    else:
+        ctxb, pool = ctx, None
 
-    def step_value(hb):
-        out = {"cells": 0, "stats": []}
+    def value_group_a(hb, out):          # a18, a19, a21 on the first context
         if "a18" in stages:
             A = hb["aog"]; d = A["dev"]; m, mm, indel = A["scoring"]
             nbt, cells = ctx.aog_batch_device(d["qseq"], tseq, d["q_off"].data_ptr(), d["t_off"].data_ptr(), d["q_len"].data_ptr(),
@@ -432,27 +443,41 @@ def main():
                                         I["cap"], R, log_lut, d["st_stats"].data_ptr(), d["st_value"].data_ptr(), d["st_off"].data_ptr(),
                                         d["st_cigar"].data_ptr(), I["ccap"])
             out["stats"] += ctx.kernel_stats()
+
+    def value_group_b(hb, out):          # a12, a13 on the second context (its own stream): independent of group a within a batch
         if "a12" in stages or "a13" in stages:
             I = hb["ir"]; d = I["dev"]
-            rc = keep["rc"] = ctx.seq_revcomp(d["qseq"], I["read_off"], I["read_len_u"], reuse=keep["rc"])
-            rf = keep["rf"] = ctx.lindex_build(d["qseq"], I["read_off"], I["read_len_u"], reuse=keep["rf"]); st1 = ctx.kernel_stats()
-            rr = keep["rr"] = ctx.lindex_build(rc, I["read_off"], I["read_len_u"], reuse=keep["rr"]); st2 = ctx.kernel_stats()
+            rc = keep["rc"] = ctxb.seq_revcomp(d["qseq"], I["read_off"], I["read_len_u"], reuse=keep["rc"])
+            rf = keep["rf"] = ctxb.lindex_build(d["qseq"], I["read_off"], I["read_len_u"], reuse=keep["rf"]); st1 = ctxb.kernel_stats()
+            rr = keep["rr"] = ctxb.lindex_build(rc, I["read_off"], I["read_len_u"], reuse=keep["rr"]); st2 = ctxb.kernel_stats()
             for a, b2 in zip(st1, st2):
                 a["ms"] += b2["ms"]; a["jobs"] += b2["jobs"]; a["algo_bytes"] += b2["algo_bytes"]
             out["stats"] += st1
             if "a13" in stages:
                 dc = I["dcl"]; cl = I["cl"]
-                ctx.refine_clusters_batch_device(gli, rf, rr, dict(m_q=dc["m_q"].data_ptr(), m_t=dc["m_t"].data_ptr(), m_off=dc["m_off"].data_ptr(),
-                                                                   box=dc["box"].data_ptr(), strand=dc["strand"].data_ptr(), read_id=dc["read_id"].data_ptr(),
-                                                                   hdr_pos=dc["hdr_pos"].data_ptr(), n_hdr=len(cl["hdr_pos"])),
-                                                 R, I["M"], (cl["global_k"], cl["small_k"], cl["window"], cl["local_max_freq"]),
-                                                 {k: dc["o_" + k].data_ptr() for k in ["status", "chrom", "diag", "r_off", "r_q", "r_t", "r_tup", "rbox", "eff"]}, I["acap"])
-                out["stats"] += ctx.kernel_stats()
-        return out
+                ctxb.refine_clusters_batch_device(gli, rf, rr, dict(m_q=dc["m_q"].data_ptr(), m_t=dc["m_t"].data_ptr(), m_off=dc["m_off"].data_ptr(),
+                                                                    box=dc["box"].data_ptr(), strand=dc["strand"].data_ptr(), read_id=dc["read_id"].data_ptr(),
+                                                                    hdr_pos=dc["hdr_pos"].data_ptr(), n_hdr=len(cl["hdr_pos"])),
+                                                  R, I["M"], (cl["global_k"], cl["small_k"], cl["window"], cl["local_max_freq"]),
+                                                  {k: dc["o_" + k].data_ptr() for k in ["status", "chrom", "diag", "r_off", "r_q", "r_t", "r_tup", "rbox", "eff"]}, I["acap"])
+                out["stats"] += ctxb.kernel_stats()
 
-    io = {"h2d": 0, "d2h": 0}
+    def run_groups(fa, fb, hb, oa, ob):
+        """The two stage groups of a batch are independent: like two of the reference's worker threads, each drives its own context
+        (stream); --serial-stages runs them back to back on one."""
+        if pool is not None:
+            fut = pool.submit(fb, hb, ob)
+            fa(hb, oa)
+            fut.result()
+        else:
+            fa(hb, oa); fb(hb, ob)
 
-    def step_e2e(hb):
+    def step_value(hb):
+        oa, ob = {"cells": 0, "stats": []}, {"cells": 0, "stats": []}
+        run_groups(value_group_a, value_group_b, hb, oa, ob)
+        return {"cells": oa["cells"] + ob["cells"], "stats": oa["stats"] + ob["stats"]}
+
+    def e2e_group_a(hb, acc):
         h2d = d2h = 0
         if "a18" in stages:
             A = hb["aog"]; m, mm, indel = A["scoring"]
@@ -462,9 +487,8 @@ def main():
             d2h += n_jobs * 16 + 12 * r["n_blocks_total"]
         if "a19" in stages:
             I = hb["ir"]
-            eseq_i.reupload(I["q_arena"][:-16])
             r = ctx.indel_refine_batch(eseq_i, tseq, I, block_cap=I["cap"], out=I["out"])
-            h2d += len(I["q_arena"]) - 16 + 12 * I["T"] + R * (8 + 5 * 4)
+            h2d += 12 * I["T"] + R * (8 + 5 * 4)
             d2h += R * 12 + 12 * r["n_blocks_total"]
             if "a21" in stages:
                 nb = I["out"]["n_blocks"]; tot = int(r["n_blocks_total"])
@@ -472,19 +496,30 @@ def main():
                                                              t_base=I["t_base"], read_len=I["read_len"]), log_lut, cigar_cap=I["ccap"])
                 h2d += 12 * tot + R * 24 + 2001 * 4
                 d2h += R * (64 + 4 + 8) + 4 * o["n_cigar_total"]
+        acc["h2d"] += h2d; acc["d2h"] += d2h
+
+    def e2e_group_b(hb, acc):
+        h2d = d2h = 0
         if "a12" in stages or "a13" in stages:
             I = hb["ir"]
-            if "a19" not in stages:
-                eseq_i.reupload(I["q_arena"][:-16]); h2d += len(I["q_arena"]) - 16
-            rc = keep["rc"] = ctx.seq_revcomp(eseq_i, I["read_off"], I["read_len_u"], reuse=keep["rc"])
-            rf = keep["rf"] = ctx.lindex_build(eseq_i, I["read_off"], I["read_len_u"], reuse=keep["rf"])
-            rr = keep["rr"] = ctx.lindex_build(rc, I["read_off"], I["read_len_u"], reuse=keep["rr"])
+            rc = keep["rc"] = ctxb.seq_revcomp(eseq_i, I["read_off"], I["read_len_u"], reuse=keep["rc"])
+            rf = keep["rf"] = ctxb.lindex_build(eseq_i, I["read_off"], I["read_len_u"], reuse=keep["rf"])
+            rr = keep["rr"] = ctxb.lindex_build(rc, I["read_off"], I["read_len_u"], reuse=keep["rr"])
             h2d += 2 * 12 * R
             if "a13" in stages:
-                o = ctx.refine_clusters_batch(gli, rf, rr, I["cl"], anchor_cap=I["acap"])
+                o = ctxb.refine_clusters_batch(gli, rf, rr, I["cl"], anchor_cap=I["acap"])
                 h2d += 8 * I["M"] + R * (8 + 16 + 1 + 4)
                 d2h += R * (4 + 4 + 16 + 8 + 16 + 4 + 16) + 8 * I["M"] + 12 * o["n_anchors"]
-        io["h2d"], io["d2h"] = h2d, d2h
+        acc["h2d"] += h2d; acc["d2h"] += d2h
+
+    def step_e2e(hb):
+        a, b2 = {"h2d": 0, "d2h": 0}, {"h2d": 0, "d2h": 0}
+        if need_reads:       # the read arena of the batch: uploaded (and packed) once, used by both groups
+            I = hb["ir"]
+            eseq_i.reupload(I["q_arena"][:-16]); ctx.synchronize()
+            a["h2d"] += len(I["q_arena"]) - 16
+        run_groups(e2e_group_a, e2e_group_b, hb, a, b2)
+        io["h2d"], io["d2h"] = a["h2d"] + b2["h2d"], a["d2h"] + b2["d2h"]
         return None
 
     def timed(fn, steps, collect=None):
@@ -518,12 +553,12 @@ def main():
             a["ms"] += s["ms"]; a["jobs"] += s["jobs"]; a["cells"] += s["cells"]; a["algo_bytes"] += s["algo_bytes"]; a["launches"] += 1
     sync_all()
     sampler = ClockSampler(local) if rank == 0 else None
-    l0 = ctx.launch_count()
+    l0 = ctx.launch_count() + (ctxb.launch_count() if two else 0)
     t0 = time.time()
     ms_value = timed(step_value, args.steps, collect)
     sync_all()
     t1 = time.time()
-    launches = ctx.launch_count() - l0
+    launches = ctx.launch_count() + (ctxb.launch_count() if two else 0) - l0
     clocks = sampler.stop(t0, t1) if sampler else None
     # ---- end to end through the host-buffer C ABI
     timed(step_e2e, max(1, args.warmup))
@@ -552,7 +587,10 @@ def main():
     achieved = dom["algo_bytes"] / (dom["ms"] / 1000.0) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom_name)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(dom_name)
+        if traffic is not None:        # measured at a smaller batch: per-launch traffic scales with the reads of a launch
+            traffic = int(traffic * R / float(tj.get("_captured_at_reads_per_step", R)))
     except Exception:
         pass
     line = {"metric": metric_name(stages), "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -561,6 +599,7 @@ def main():
             "config": {"workload": WORKLOAD % (R, jobs_per_read), "stages": [s for s in STAGES if s[:3] in stages], "profile": PROFILE,
                        "reads_per_step": R, "aog_jobs_per_step": n_jobs if "a18" in stages else 0, "genome_len": args.genome_len,
                        "l2": "flushed between timed steps (256 MiB fill)",
+                       "stage_groups": "a18+a19+a21 and a12+a13 run concurrently on two contexts (streams)" if two else "one context, stages back to back",
                        "parallelism": "reads sharded over %d GPU(s), no data-path collective" % world},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(io["h2d"]), "d2h_bytes_per_step": int(io["d2h"]),

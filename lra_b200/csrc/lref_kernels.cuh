@@ -318,6 +318,7 @@ template <bool EMIT>
 __global__ void __launch_bounds__(128) lref_task_literal_kernel(LrefBatch b, unsigned long long n_units, unsigned long long n_tasks) {
   const unsigned long long task = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (task >= n_tasks) return;
+  if (EMIT && b.out_off[task + 1] == b.out_off[task]) return;      // the count pass found nothing for this window pair
   unsigned long long u;
   { unsigned long long lo = 0, len = n_units;
     while (len > 0) { const unsigned long long half = len >> 1; if (b.task_off[lo + half] <= task) { lo += half + 1; len -= half + 1; } else len = half; }
@@ -433,6 +434,7 @@ __global__ void __launch_bounds__(128) lref_task_kernel(LrefBatch b, unsigned lo
   const int lane = threadIdx.x & 31;
   const unsigned long long task = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (task >= n_tasks) return;
+  if (EMIT && b.out_off[task + 1] == b.out_off[task]) return;
   unsigned long long u;
   { unsigned long long lo = 0, len = n_units;
     while (len > 0) { const unsigned long long half = len >> 1; if (b.task_off[lo + half] <= task) { lo += half + 1; len -= half + 1; } else len = half; }

@@ -18,7 +18,8 @@ def short(name):
 
 def num(x):
     try:
-        return float(x.replace(",", ""))
+        v = float(x.replace(",", ""))
+        return v if v == v else None
     except Exception:
         return None
 
@@ -86,7 +87,7 @@ def main():
             lines.append("| %s | %s | %s | %s | %s | %s | %s | %s | %s | %s | %s | %s | %s |" % (
                 r["name"], f(r["us"]), f(r["regs"], 0), f(r["grid"], 0), f(r["occ"]), f(r["ipc"], 2), f(r["dram_r"], 2), f(r["dram_w"], 2),
                 f(r["dram_pct"]), f(r["sm_pct"]), f(r["l1_hit"]), f(r["l2_hit"]), f(r["lanes"])))
-            if r["dram_r"] is not None and r["name"] not in traffic:
+            if r["dram_r"] is not None and r["dram_r"] == r["dram_r"] and r["name"] not in traffic:
                 traffic[r["name"]] = int((r["dram_r"] + (r["dram_w"] or 0)) * 1e6)
         lines.append("")
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
