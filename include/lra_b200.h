@@ -340,6 +340,35 @@ int lra_b200_refine_splitchains_batch_device(lra_b200_ctx *ctx, const lra_b200_l
                                              const lra_b200_lindex *reads_rc, const lra_b200_splitchains *sc_dev, uint64_t n_anchors_in,
                                              lra_b200_refined *res_dev);
 
+/* ---- a20  RefineBreakpoint, batched over pairs of adjacent segments --------------------------------------------------
+ * Replaces  void RefineBreakpoint(Read &read, Genome &genome, Alignment &leftAln, Alignment &rightAln, const Options &opts)
+ * (RefineBreakpoint.h:212-462; called for consecutive segments of a split read, Map_highacc.h:725, Map_lowacc.h:592).  Pair p: the left /
+ * right alignment enter through their first and last block (lf, ll, rf, rl: q, t, len -- GetQStart/GetQEnd/GetTStart/GetTEnd and the
+ * block Prepend/AppendBlocks may merge into), their strand, and the contig they lie on (arena position and length in the packed genome);
+ * the read is at read_off[p] in both strand arenas (Alignment::read is one or the other).  Results per side s in {0 left, 1 right}:
+ * mode[2p+s] = 0 nothing (the two segments are not within MAX_GAP = 500 of each other), 1 AppendBlocks, 2 PrependBlocks;
+ * out[(2p+s) * 512 * 3 ..] the n_out[2p+s] blocks to splice in, bound[(2p+s) * 3 ..] the alignment's boundary block (the last block for an
+ * append, the first for a prepend) after a possible gapless merge; refined[p] = 1 if the pair was refined. */
+typedef struct lra_b200_breakpoints {
+  int32_t n_pairs;
+  const uint32_t *lf, *ll, *rf, *rl;           /* [n_pairs * 3] */
+  const uint8_t *lstrand, *rstrand;            /* [n_pairs] */
+  const uint64_t *read_off;                    /* [n_pairs] */
+  const uint32_t *read_len;
+  const uint64_t *lchrom_off, *rchrom_off;     /* [n_pairs] */
+  const uint32_t *lchrom_len, *rchrom_len;
+} lra_b200_breakpoints;
+
+typedef struct lra_b200_breakpoint_result {
+  int32_t *mode, *n_out;        /* [n_pairs * 2] */
+  uint32_t *bound;              /* [n_pairs * 2 * 3] */
+  uint32_t *out;                /* [n_pairs * 2 * 512 * 3] */
+  int32_t *refined;             /* [n_pairs] */
+} lra_b200_breakpoint_result;
+
+int lra_b200_refine_breakpoint_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads_fwd, const lra_b200_seq *reads_rc, const lra_b200_seq *genome,
+                                     const lra_b200_breakpoints *bp, lra_b200_breakpoint_result *res);
+
 /* ---- a24  GlobalChain over a PrioritySearchTree, batched over independent problems --------------------------------------
  * Replaces  int GlobalChain(vector<T_Fragment> &fragments, vector<int> &optFragmentChainIndices, vector<T_Endpoint> &endpoints)
  * (GlobalChain.h:88-189, with PrioritySearchTree.h:47-291) as the reference's driver TestGlobalChain.cpp:9-27 calls it.  Problem p:

@@ -78,6 +78,16 @@ class _SplitChains(C.Structure):
                 ("global_k", C.c_int32), ("small_k", C.c_int32), ("window", C.c_int32), ("local_max_freq", C.c_int64), ("limitrefine", C.c_int32)]
 
 
+class _Breakpoints(C.Structure):
+    _fields_ = [("n_pairs", C.c_int32), ("lf", C.c_void_p), ("ll", C.c_void_p), ("rf", C.c_void_p), ("rl", C.c_void_p), ("lstrand", C.c_void_p),
+                ("rstrand", C.c_void_p), ("read_off", C.c_void_p), ("read_len", C.c_void_p), ("lchrom_off", C.c_void_p), ("rchrom_off", C.c_void_p),
+                ("lchrom_len", C.c_void_p), ("rchrom_len", C.c_void_p)]
+
+
+class _BreakpointResult(C.Structure):
+    _fields_ = [("mode", C.c_void_p), ("n_out", C.c_void_p), ("bound", C.c_void_p), ("out", C.c_void_p), ("refined", C.c_void_p)]
+
+
 class _Refined(C.Structure):
     _fields_ = [("status", C.c_void_p), ("chrom", C.c_void_p), ("diag", C.c_void_p), ("r_off", C.c_void_p), ("r_q", C.c_void_p),
                 ("r_t", C.c_void_p), ("r_tup", C.c_void_p), ("anchor_cap", C.c_uint64), ("n_anchors", C.c_uint64), ("rbox", C.c_void_p),
@@ -133,6 +143,7 @@ def load_library():
     L.lra_b200_calc_stats_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrSegments), C.c_void_p, C.POINTER(_StatsResult)]
     L.lra_b200_sort_matches_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_global_chain_batch.argtypes = [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 4
+    L.lra_b200_refine_breakpoint_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Breakpoints), C.POINTER(_BreakpointResult)]
     L.lra_b200_lindex_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.POINTER(C.c_void_p)]
     L.lra_b200_lindex_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
@@ -336,6 +347,22 @@ class Context:
         self._check(self.lib.lra_b200_sort_matches_batch(self.h, mode, _ptr(q) if len(q) else None, _ptr(t) if len(t) else None, _ptr(so), len(so) - 1,
                                                          _ptr(perm) if want_perm else None))
         return q, t, (perm[:len(q)] if want_perm else None)
+
+    # ---- a20
+    def refine_breakpoint_batch(self, reads_fwd, reads_rc, genome, bp):
+        """RefineBreakpoint for every pair (bp: dict(lf, ll, rf, rl [n,3]; lstrand, rstrand, read_off, read_len, lchrom_off, rchrom_off,
+        lchrom_len, rchrom_len)).  Returns dict(mode[n,2], n_out[n,2], bound[n,2,3], out[n,2,512,3], refined[n])."""
+        n = len(bp["lstrand"])
+        a = {k: np.ascontiguousarray(bp[k], np.uint32).reshape(-1) for k in ["lf", "ll", "rf", "rl", "read_len", "lchrom_len", "rchrom_len"]}
+        a.update({k: np.ascontiguousarray(bp[k], np.uint8) for k in ["lstrand", "rstrand"]})
+        a.update({k: np.ascontiguousarray(bp[k], np.uint64) for k in ["read_off", "lchrom_off", "rchrom_off"]})
+        o = dict(mode=np.zeros((max(n, 1), 2), np.int32), n_out=np.zeros((max(n, 1), 2), np.int32), bound=np.zeros((max(n, 1), 2, 3), np.uint32),
+                 out=np.zeros((max(n, 1), 2, 512, 3), np.uint32), refined=np.zeros(max(n, 1), np.int32))
+        b = _Breakpoints(n, _ptr(a["lf"]), _ptr(a["ll"]), _ptr(a["rf"]), _ptr(a["rl"]), _ptr(a["lstrand"]), _ptr(a["rstrand"]), _ptr(a["read_off"]), _ptr(a["read_len"]),
+                         _ptr(a["lchrom_off"]), _ptr(a["rchrom_off"]), _ptr(a["lchrom_len"]), _ptr(a["rchrom_len"]))
+        r = _BreakpointResult(_ptr(o["mode"]), _ptr(o["n_out"]), _ptr(o["bound"]), _ptr(o["out"]), _ptr(o["refined"]))
+        self._check(self.lib.lra_b200_refine_breakpoint_batch(self.h, reads_fwd.handle, reads_rc.handle, genome.handle, C.byref(b), C.byref(r)))
+        return {k: v[:n] for k, v in o.items()}
 
     # ---- a24
     def global_chain_batch(self, frag, frag_off, score):

@@ -504,3 +504,62 @@ extern "C" int lra_b200_global_chain_batch(lra_b200_ctx *ctx, const int32_t *fra
   ctx->stats.push_back(s2);
   return LRA_B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- a20 RefineBreakpoint
+extern "C" int lra_b200_refine_breakpoint_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads_fwd, const lra_b200_seq *reads_rc, const lra_b200_seq *genome,
+                                                const lra_b200_breakpoints *bp, lra_b200_breakpoint_result *res) {
+  if (!ctx || !reads_fwd || !reads_rc || !genome || !bp || !res) return fail(ctx, LRA_B200_EINVAL, "refine_breakpoint_batch: NULL argument");
+  const int n = bp->n_pairs;
+  if (n < 0) return fail(ctx, LRA_B200_EINVAL, "refine_breakpoint_batch: negative pair count");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  if (n == 0) return LRA_B200_OK;
+  for (int p = 0; p < n; p++) {
+    if (bp->read_off[p] + bp->read_len[p] > reads_fwd->n || bp->read_off[p] + bp->read_len[p] > reads_rc->n)
+      return fail(ctx, LRA_B200_EINVAL, "refine_breakpoint_batch: read of pair %d ends beyond the arena", p);
+    if (bp->lchrom_off[p] + bp->lchrom_len[p] > genome->n || bp->rchrom_off[p] + bp->rchrom_len[p] > genome->n)
+      return fail(ctx, LRA_B200_EINVAL, "refine_breakpoint_batch: contig of pair %d ends beyond the genome arena", p);
+  }
+  const int slabs = n < 512 ? n : 512;
+  int rc;
+  DevBuf *B = ctx->rb;
+  const size_t N = (size_t)n;
+  if ((rc = ensure(ctx, B[0], N * 12)) || (rc = ensure(ctx, B[1], N * 12)) || (rc = ensure(ctx, B[2], N * 12)) || (rc = ensure(ctx, B[3], N * 12)) ||
+      (rc = ensure(ctx, B[4], N)) || (rc = ensure(ctx, B[5], N)) || (rc = ensure(ctx, B[6], N * 8)) || (rc = ensure(ctx, B[7], N * 4)) ||
+      (rc = ensure(ctx, B[8], N * 8)) || (rc = ensure(ctx, B[9], N * 8)) || (rc = ensure(ctx, B[10], N * 4)) || (rc = ensure(ctx, B[11], N * 4)) ||
+      (rc = ensure(ctx, B[12], (size_t)slabs * 2 * kRbpCells * 4)) || (rc = ensure(ctx, B[13], (size_t)slabs * 2 * kRbpCells)) ||
+      (rc = ensure(ctx, B[14], (size_t)slabs * 8 * 512 * 4)) || (rc = ensure(ctx, B[15], N * 8)) || (rc = ensure(ctx, B[16], N * 8)) ||
+      (rc = ensure(ctx, B[17], N * 24)) || (rc = ensure(ctx, B[18], N * 2 * kRbpCap * 12)) || (rc = ensure(ctx, B[19], N * 4)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  const void *src[12] = {bp->lf, bp->ll, bp->rf, bp->rl, bp->lstrand, bp->rstrand, bp->read_off, bp->read_len, bp->lchrom_off, bp->rchrom_off, bp->lchrom_len, bp->rchrom_len};
+  const size_t sz[12] = {N * 12, N * 12, N * 12, N * 12, N, N, N * 8, N * 4, N * 8, N * 8, N * 4, N * 4};
+  for (int i = 0; i < 12; i++) CU(cudaMemcpyAsync(B[i].p, src[i], sz[i], cudaMemcpyHostToDevice, st));
+  RbpBatch b;
+  b.n_pairs = n;
+  b.reads_fwd = SeqView{reads_fwd->b2, reads_fwd->nm, reads_fwd->n}; b.reads_rc = SeqView{reads_rc->b2, reads_rc->nm, reads_rc->n};
+  b.genome = SeqView{genome->b2, genome->nm, genome->n};
+  b.lf = (const uint32_t *)B[0].p; b.ll = (const uint32_t *)B[1].p; b.rf = (const uint32_t *)B[2].p; b.rl = (const uint32_t *)B[3].p;
+  b.lstrand = (const uint8_t *)B[4].p; b.rstrand = (const uint8_t *)B[5].p; b.read_off = (const unsigned long long *)B[6].p; b.read_len = (const uint32_t *)B[7].p;
+  b.lchrom_off = (const unsigned long long *)B[8].p; b.rchrom_off = (const unsigned long long *)B[9].p; b.lchrom_len = (const uint32_t *)B[10].p; b.rchrom_len = (const uint32_t *)B[11].p;
+  b.score = (int32_t *)B[12].p; b.path = (uint8_t *)B[13].p; b.walk = (int32_t *)B[14].p;
+  b.mode = (int32_t *)B[15].p; b.n_out = (int32_t *)B[16].p; b.bound = (uint32_t *)B[17].p; b.out = (uint32_t *)B[18].p; b.refined = (int32_t *)B[19].p;
+  cudaEventRecord(ctx->ev[0], st);
+  for (int first = 0; first < n; first += slabs) {
+    const int here = n - first < slabs ? n - first : slabs;
+    rbp_kernel<<<(unsigned)((here + 3) / 4), 128, 0, st>>>(b, first, here);
+    ctx->launches++;
+  }
+  cudaEventRecord(ctx->ev[1], st);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(res->mode, b.mode, N * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->n_out, b.n_out, N * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->bound, b.bound, N * 24, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->out, b.out, N * 2 * kRbpCap * 12, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->refined, b.refined, N * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "rbp");
+  cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]); s2.jobs = (uint64_t)n; s2.algo_bytes = 128ull * N;
+  ctx->stats.push_back(s2);
+  return LRA_B200_OK;
+}

@@ -589,3 +589,48 @@ def global_chain(frag, score, which="port"):
     f.restype = C.c_long; f.argtypes = [_i32p, _i32p, _i32p, C.c_long, _i32p]
     m = f(frag.reshape(-1) if n else np.zeros(4, np.int32), sc if n else np.zeros(1, np.int32), prev, n, chain)
     return chain[:m].copy(), sc, prev[:n]
+
+
+# ---------------------------------------------------------------- a20 RefineBreakpoint
+
+def refine_breakpoint_ref(lread, rread, read_len, lchrom, rchrom, lblocks, lstrand, rblocks, rstrand):
+    """Through the unmodified reference.  Returns the two updated block lists."""
+    L = ref()
+    _bind_once(L, "ref_refine_breakpoint", C.c_int, [_u8p, _u8p, C.c_int, _u8p, C.c_int, _u8p, C.c_int, _u32p, C.POINTER(C.c_int), C.c_int, _u32p,
+                                                     C.POINTER(C.c_int), C.c_int, C.c_int])
+    cap = len(lblocks) + len(rblocks) + 1200
+    lb = np.zeros((cap, 3), np.uint32); rb = np.zeros((cap, 3), np.uint32)
+    lb[:len(lblocks)] = lblocks; rb[:len(rblocks)] = rblocks
+    ln, rn = C.c_int(len(lblocks)), C.c_int(len(rblocks))
+    pad = lambda a: np.concatenate([np.ascontiguousarray(a, np.uint8), np.zeros(8, np.uint8)])
+    rc = L.ref_refine_breakpoint(pad(lread), pad(rread), read_len, pad(lchrom), len(lchrom), pad(rchrom), len(rchrom), lb.reshape(-1), C.byref(ln), lstrand,
+                                 rb.reshape(-1), C.byref(rn), rstrand, cap)
+    assert rc == 0
+    return lb[:ln.value].copy(), rb[:rn.value].copy()
+
+
+def splice_blocks(blocks, mode, bound, new):
+    """Apply one side of a refine-breakpoint result (mode 1 append / 2 prepend, boundary block after the merge, blocks to splice in)."""
+    b = np.array(blocks, np.uint32).reshape(-1, 3)
+    if mode == 1:
+        b[-1] = bound
+        return np.concatenate([b, np.asarray(new, np.uint32).reshape(-1, 3)])
+    if mode == 2:
+        b[0] = bound
+        return np.concatenate([np.asarray(new, np.uint32).reshape(-1, 3), b])
+    return b
+
+
+def refine_breakpoint_port(lread, rread, read_len, lchrom, rchrom, lblocks, lstrand, rblocks, rstrand):
+    """Through the C restatement.  Returns (refined?, left blocks, right blocks)."""
+    L = port()
+    _bind_once(L, "lra_oracle_refine_breakpoint", C.c_int, [_u8p, _u8p, C.c_int, _u8p, C.c_int, _u8p, C.c_int, _u32p, _u32p, C.c_int, _u32p, _u32p, C.c_int,
+                                                            _i32p, _i32p, _u32p, _u32p, C.c_int])
+    cap = 600
+    mode = np.zeros(2, np.int32); n_out = np.zeros(2, np.int32); bound = np.zeros(6, np.uint32); out = np.zeros(2 * cap * 3, np.uint32)
+    pad = lambda a: np.concatenate([np.ascontiguousarray(a, np.uint8), np.zeros(8, np.uint8)])
+    lb = np.ascontiguousarray(lblocks, np.uint32).reshape(-1, 3); rb = np.ascontiguousarray(rblocks, np.uint32).reshape(-1, 3)
+    r = L.lra_oracle_refine_breakpoint(pad(lread), pad(rread), read_len, pad(lchrom), len(lchrom), pad(rchrom), len(rchrom), lb[0].copy(), lb[-1].copy(), lstrand,
+                                       rb[0].copy(), rb[-1].copy(), rstrand, mode, n_out, bound, out, cap)
+    o = out.reshape(2, cap, 3)
+    return r, splice_blocks(lb, mode[0], bound[:3], o[0, :n_out[0]]), splice_blocks(rb, mode[1], bound[3:], o[1, :n_out[1]]), (mode.copy(), n_out.copy(), bound.copy(), o)

@@ -353,4 +353,27 @@ long ref_global_chain(const int32_t *frag, int32_t *score, int32_t *prev, long n
   return (long)opt.size();
 }
 
+// ---- a20: RefineBreakpoint (RefineBreakpoint.h:212-462) on two alignments given by their block lists.  The block lists are updated in
+// place (capacity cap blocks each); returns 0.
+int ref_refine_breakpoint(const char *lread, const char *rread, int readLen, const char *lchrom, int lchromLen, const char *rchrom, int rchromLen,
+                          uint32_t *lblocks, int *ln, int lstrand, uint32_t *rblocks, int *rn, int rstrand, int cap) {
+  Read read; read.length = readLen;
+  Genome genome;
+  genome.seqs.push_back((char *)lchrom); genome.lengths.push_back(lchromLen);
+  genome.seqs.push_back((char *)rchrom); genome.lengths.push_back(rchromLen);
+  Alignment L, R;
+  L.read = (char *)lread; R.read = (char *)rread; L.strand = lstrand; R.strand = rstrand; L.chromIndex = 0; R.chromIndex = 1;
+  for (int i = 0; i < *ln; i++) L.blocks.push_back(Block(lblocks[3 * i], lblocks[3 * i + 1], lblocks[3 * i + 2]));
+  for (int i = 0; i < *rn; i++) R.blocks.push_back(Block(rblocks[3 * i], rblocks[3 * i + 1], rblocks[3 * i + 2]));
+  Options opts;
+  RefineBreakpoint(read, genome, L, R, opts);
+  genome.seqs.clear();
+  read.seq = NULL; read.qual = NULL;
+  if ((int)L.blocks.size() > cap || (int)R.blocks.size() > cap) return -1;
+  *ln = (int)L.blocks.size(); *rn = (int)R.blocks.size();
+  for (int i = 0; i < *ln; i++) { lblocks[3 * i] = L.blocks[i].qPos; lblocks[3 * i + 1] = L.blocks[i].tPos; lblocks[3 * i + 2] = L.blocks[i].length; }
+  for (int i = 0; i < *rn; i++) { rblocks[3 * i] = R.blocks[i].qPos; rblocks[3 * i + 1] = R.blocks[i].tPos; rblocks[3 * i + 2] = R.blocks[i].length; }
+  return 0;
+}
+
 }  // extern "C"

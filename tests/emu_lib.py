@@ -216,3 +216,19 @@ def global_chain(frag, frag_off, score):
     sc = np.array(score, np.int32); prev = np.zeros(max(n, 1), np.int32); chain = np.zeros(max(n, 1), np.int32); cl = np.zeros(max(len(fo) - 1, 1), np.int32)
     L.emu_global_chain(f if n else np.zeros(4, np.int32), fo, len(fo) - 1, sc if n else np.zeros(1, np.int32), prev, chain, cl)
     return dict(score=sc, prev=prev[:n], chain=chain, chain_len=cl[:len(fo) - 1])
+
+
+def refine_breakpoint(fwd, rcs, genome, bp):
+    """fwd / rcs / genome: ASCII arenas with 16 bytes of padding; bp as for Context.refine_breakpoint_batch."""
+    L = lib()
+    L.emu_refine_breakpoint.argtypes = [_u8p, _u8p, C.c_uint64, _u8p, C.c_uint64, C.c_int, _u32p, _u32p, _u32p, _u32p, _u8p, _u8p, _u64p, _u32p, _u64p, _u64p, _u32p,
+                                        _u32p, _i32p, _i32p, _u32p, _u32p, _i32p]
+    n = len(bp["lstrand"])
+    u32 = lambda k: np.ascontiguousarray(bp[k], np.uint32).reshape(-1)
+    u64 = lambda k: np.ascontiguousarray(bp[k], np.uint64)
+    o = dict(mode=np.zeros((n, 2), np.int32), n_out=np.zeros((n, 2), np.int32), bound=np.zeros((n, 2, 3), np.uint32), out=np.zeros((n, 2, 512, 3), np.uint32),
+             refined=np.zeros(n, np.int32))
+    L.emu_refine_breakpoint(fwd, rcs, len(fwd) - 16, genome, len(genome) - 16, n, u32("lf"), u32("ll"), u32("rf"), u32("rl"), np.ascontiguousarray(bp["lstrand"], np.uint8),
+                            np.ascontiguousarray(bp["rstrand"], np.uint8), u64("read_off"), u32("read_len"), u64("lchrom_off"), u64("rchrom_off"), u32("lchrom_len"),
+                            u32("rchrom_len"), o["mode"].reshape(-1), o["n_out"].reshape(-1), o["bound"].reshape(-1), o["out"].reshape(-1), o["refined"])
+    return o

@@ -118,3 +118,22 @@ extern "C" int emu_global_chain(const int32_t *frag, const uint64_t *frag_off, i
   if (n_prob) emu::launch(dim3((unsigned)((n_prob + 63) / 64)), dim3(64), 0, [&] { gchain_kernel(b); });
   return 0;
 }
+
+// ---- a20 RefineBreakpoint
+#include "rbp_kernels.cuh"
+extern "C" int emu_refine_breakpoint(const uint8_t *fwd, const uint8_t *rcs, uint64_t rn, const uint8_t *genome, uint64_t gn, int n, const uint32_t *lf, const uint32_t *ll,
+                                     const uint32_t *rf, const uint32_t *rl, const uint8_t *lstrand, const uint8_t *rstrand, const uint64_t *read_off,
+                                     const uint32_t *read_len, const uint64_t *lchrom_off, const uint64_t *rchrom_off, const uint32_t *lchrom_len,
+                                     const uint32_t *rchrom_len, int32_t *mode, int32_t *n_out, uint32_t *bound, uint32_t *out, int32_t *refined) {
+  Packed pf, pr, pg; pack(fwd, rn, pf); pack(rcs, rn, pr); pack(genome, gn, pg);
+  const int slabs = n < 4 ? n : 4;
+  std::vector<int32_t> score((size_t)slabs * 2 * kRbpCells), walk((size_t)slabs * 8 * 512);
+  std::vector<uint8_t> path((size_t)slabs * 2 * kRbpCells);
+  RbpBatch b{n, pf.view, pr.view, pg.view, lf, ll, rf, rl, lstrand, rstrand, (const unsigned long long *)read_off, read_len, (const unsigned long long *)lchrom_off,
+             (const unsigned long long *)rchrom_off, lchrom_len, rchrom_len, score.data(), path.data(), walk.data(), mode, n_out, bound, out, refined};
+  for (int first = 0; first < n; first += slabs) {
+    const int here = n - first < slabs ? n - first : slabs;
+    emu::launch(dim3((unsigned)((here + 3) / 4)), dim3(128), 0, [&] { rbp_kernel(b, first, here); });
+  }
+  return 0;
+}
