@@ -340,6 +340,17 @@ int lra_b200_refine_splitchains_batch_device(lra_b200_ctx *ctx, const lra_b200_l
                                              const lra_b200_lindex *reads_rc, const lra_b200_splitchains *sc_dev, uint64_t n_anchors_in,
                                              lra_b200_refined *res_dev);
 
+/* ---- a16  chain filters, batched over chains --------------------------------------------------------------------------
+ * Replaces, for any number of chains at once (chain c = anchors chain_off[c] .. chain_off[c+1] in chain order: q = qStart, t = tStart,
+ * len = length, strand), the remove-mask computation of
+ *   mode 0  RemoveSmallPairedIndels<Tup>(chain)                 Chain.h:546-606      mode 3  RemovePairedIndels(matches, chain, lengths)  :754-822
+ *   mode 1  RemovePairedIndels<Tup>(chain, refineEnds = true)   Chain.h:611-748      mode 4  RemoveSpuriousAnchors<Tup>(chain)             :828-890
+ *   mode 2  RemovePairedIndels<Tup>(chain, refineEnds = false)                       mode 5  RemoveSpuriousJump<Tup>(chain)                :896-960
+ * keep[i] = 0 for the anchors the reference removes.  The caller compacts chain.chain / ClusterIndex with it, and link as the reference
+ * does: link[m-1] = link[i-1] for every kept anchor i that has m >= 1 kept anchors before it.  strand may be NULL for mode 3. */
+int lra_b200_chain_filter_batch(lra_b200_ctx *ctx, int32_t mode, const uint32_t *q, const uint32_t *t, const uint32_t *len, const uint8_t *strand,
+                                const uint64_t *chain_off, int32_t n_chains, uint8_t *keep);
+
 /* ---- a20  RefineBreakpoint, batched over pairs of adjacent segments --------------------------------------------------
  * Replaces  void RefineBreakpoint(Read &read, Genome &genome, Alignment &leftAln, Alignment &rightAln, const Options &opts)
  * (RefineBreakpoint.h:212-462; called for consecutive segments of a split read, Map_highacc.h:725, Map_lowacc.h:592).  Pair p: the left /

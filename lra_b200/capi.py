@@ -144,6 +144,7 @@ def load_library():
     L.lra_b200_sort_matches_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_global_chain_batch.argtypes = [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 4
     L.lra_b200_refine_breakpoint_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Breakpoints), C.POINTER(_BreakpointResult)]
+    L.lra_b200_chain_filter_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_lindex_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.POINTER(C.c_void_p)]
     L.lra_b200_lindex_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
@@ -347,6 +348,17 @@ class Context:
         self._check(self.lib.lra_b200_sort_matches_batch(self.h, mode, _ptr(q) if len(q) else None, _ptr(t) if len(t) else None, _ptr(so), len(so) - 1,
                                                          _ptr(perm) if want_perm else None))
         return q, t, (perm[:len(q)] if want_perm else None)
+
+    # ---- a16
+    def chain_filter_batch(self, mode, q, t, length, strand, chain_off):
+        """The keep mask of every chain under one of the reference's chain filters (modes in include/lra_b200.h)."""
+        q = np.ascontiguousarray(q, np.uint32); t = np.ascontiguousarray(t, np.uint32); ln = np.ascontiguousarray(length, np.uint32)
+        st = np.ascontiguousarray(strand, np.uint8); co = np.ascontiguousarray(chain_off, np.uint64)
+        keep = np.zeros(max(len(q), 1), np.uint8)
+        n = len(q)
+        self._check(self.lib.lra_b200_chain_filter_batch(self.h, mode, _ptr(q) if n else None, _ptr(t) if n else None, _ptr(ln) if n else None, _ptr(st) if n else None,
+                                                         _ptr(co), len(co) - 1, _ptr(keep)))
+        return keep[:n]
 
     # ---- a20
     def refine_breakpoint_batch(self, reads_fwd, reads_rc, genome, bp):

@@ -563,3 +563,41 @@ extern "C" int lra_b200_refine_breakpoint_batch(lra_b200_ctx *ctx, const lra_b20
   ctx->stats.push_back(s2);
   return LRA_B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- a16 chain filters
+extern "C" int lra_b200_chain_filter_batch(lra_b200_ctx *ctx, int32_t mode, const uint32_t *q, const uint32_t *t, const uint32_t *len, const uint8_t *strand,
+                                           const uint64_t *chain_off, int32_t n_chains, uint8_t *keep) {
+  if (!ctx || !chain_off || n_chains < 0 || mode < 0 || mode > 5) return fail(ctx, LRA_B200_EINVAL, "chain_filter_batch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  if (n_chains == 0) return LRA_B200_OK;
+  const size_t N = (size_t)chain_off[n_chains];
+  if (N == 0) return LRA_B200_OK;
+  if (!q || !t || !len || !keep || (mode != 3 && !strand)) return fail(ctx, LRA_B200_EINVAL, "chain_filter_batch: NULL anchor arrays");
+  for (int c = 0; c < n_chains; c++)
+    if (chain_off[c + 1] < chain_off[c] || chain_off[c + 1] - chain_off[c] > 0x7FFFFFF0ull) return fail(ctx, LRA_B200_EINVAL, "chain_filter_batch: bad chain offsets");
+  int rc;
+  DevBuf *B = ctx->cf;
+  if ((rc = ensure(ctx, B[0], N * 4)) || (rc = ensure(ctx, B[1], N * 4)) || (rc = ensure(ctx, B[2], N * 4)) || (rc = ensure(ctx, B[3], N + 16)) ||
+      (rc = ensure(ctx, B[4], ((size_t)n_chains + 1) * 8)) || (rc = ensure(ctx, B[5], N + 16)) || (rc = ensure(ctx, B[6], N * 4)) || (rc = ensure(ctx, B[7], N * 4)) ||
+      (rc = ensure(ctx, B[8], N * 4)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(B[0].p, q, N * 4, cudaMemcpyHostToDevice, st)); CU(cudaMemcpyAsync(B[1].p, t, N * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[2].p, len, N * 4, cudaMemcpyHostToDevice, st));
+  if (strand) CU(cudaMemcpyAsync(B[3].p, strand, N, cudaMemcpyHostToDevice, st)); else CU(cudaMemsetAsync(B[3].p, 0, N, st));
+  CU(cudaMemcpyAsync(B[4].p, chain_off, ((size_t)n_chains + 1) * 8, cudaMemcpyHostToDevice, st));
+  ChainfBatch b{n_chains, mode, (const unsigned long long *)B[4].p, (const uint32_t *)B[0].p, (const uint32_t *)B[1].p, (const uint32_t *)B[2].p, (const uint8_t *)B[3].p,
+                (uint8_t *)B[5].p, (int32_t *)B[6].p, (int32_t *)B[7].p, (int32_t *)B[8].p};
+  cudaEventRecord(ctx->ev[0], st);
+  chainf_kernel<<<(unsigned)((n_chains + 127) / 128), 128, 0, st>>>(b);
+  cudaEventRecord(ctx->ev[1], st);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(keep, b.keep, N, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "chainf<mode=%d>", mode);
+  cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]); s2.jobs = (uint64_t)n_chains; s2.algo_bytes = 14ull * N;
+  ctx->stats.push_back(s2);
+  return LRA_B200_OK;
+}

@@ -634,3 +634,19 @@ def refine_breakpoint_port(lread, rread, read_len, lchrom, rchrom, lblocks, lstr
                                        rb[0].copy(), rb[-1].copy(), rstrand, mode, n_out, bound, out, cap)
     o = out.reshape(2, cap, 3)
     return r, splice_blocks(lb, mode[0], bound[:3], o[0, :n_out[0]]), splice_blocks(rb, mode[1], bound[3:], o[1, :n_out[1]]), (mode.copy(), n_out.copy(), bound.copy(), o)
+
+
+# ---------------------------------------------------------------- a16 chain filters (Chain.h:546-960)
+
+def chain_filter(mode, q, t, length, strand, which="port"):
+    """keep mask of one chain (anchors in chain order).  mode 0 RemoveSmallPairedIndels, 1 RemovePairedIndels(refineEnds), 2 RemovePairedIndels(no
+    refineEnds), 3 RemovePairedIndels(matches, chain, lengths), 4 RemoveSpuriousAnchors, 5 RemoveSpuriousJump."""
+    q = np.ascontiguousarray(q, np.uint32); t = np.ascontiguousarray(t, np.uint32); length = np.ascontiguousarray(length, np.uint32)
+    strand = np.ascontiguousarray(strand, np.uint8)
+    n = len(q)
+    keep = np.zeros(max(n, 1), np.uint8)
+    L = ref() if which == "ref" else port()
+    f = _bind_once(L, "ref_chain_filter" if which == "ref" else "lra_oracle_chain_filter", None, [C.c_int, _u32p, _u32p, _u32p, _u8p, C.c_long, _u8p])
+    pad = lambda a, dt: a if n else np.zeros(1, dt)
+    f(mode, pad(q, np.uint32), pad(t, np.uint32), pad(length, np.uint32), pad(strand, np.uint8), n, keep)
+    return keep[:n]

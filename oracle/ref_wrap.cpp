@@ -35,6 +35,19 @@
 #include "GlobalChain.h"
 #include "Fragment.h"
 
+// A chain type for the unmodified filter templates of Chain.h (they only use these members)
+struct WrapChain {
+  std::vector<uint32_t> q, t, len; std::vector<uint8_t> st;
+  std::vector<unsigned int> chain; std::vector<int> ClusterIndex; std::vector<bool> link;
+  int size() { return (int)chain.size(); }
+  bool strand(int i) { return st[chain[i]] != 0; }
+  GenomePos &qStart(int i) { return q[chain[i]]; }
+  GenomePos &tStart(int i) { return t[chain[i]]; }
+  GenomePos qEnd(int i) { return q[chain[i]] + len[chain[i]]; }
+  GenomePos tEnd(int i) { return t[chain[i]] + len[chain[i]]; }
+  int length(int i) { return (int)len[chain[i]]; }
+};
+
 extern "C" {
 
 // One call. blocks_out receives up to cap (qPos,tPos,length) triples; *n_blocks the true count.
@@ -374,6 +387,30 @@ int ref_refine_breakpoint(const char *lread, const char *rread, int readLen, con
   for (int i = 0; i < *ln; i++) { lblocks[3 * i] = L.blocks[i].qPos; lblocks[3 * i + 1] = L.blocks[i].tPos; lblocks[3 * i + 2] = L.blocks[i].length; }
   for (int i = 0; i < *rn; i++) { rblocks[3 * i] = R.blocks[i].qPos; rblocks[3 * i + 1] = R.blocks[i].tPos; rblocks[3 * i + 2] = R.blocks[i].length; }
   return 0;
+}
+
+// ---- a16: the chain filters of Chain.h:546-960 (modes as in oracle/chain_filters.c).  keep[i] = 1 if anchor i survives.
+void ref_chain_filter(int mode, const uint32_t *q, const uint32_t *t, const uint32_t *len, const uint8_t *strand, long n, uint8_t *keep) {
+  for (long i = 0; i < n; i++) keep[i] = 0;
+  if (mode == 3) {
+    GenomePairs matches(n);
+    std::vector<unsigned int> chain(n);
+    std::vector<int> lengths(n);
+    for (long i = 0; i < n; i++) { matches[i].first.pos = q[i]; matches[i].second.pos = t[i]; chain[i] = (unsigned)i; lengths[i] = (int)len[i]; }
+    RemovePairedIndels(matches, chain, lengths);
+    for (size_t i = 0; i < chain.size(); i++) keep[chain[i]] = 1;
+    return;
+  }
+  WrapChain c;
+  c.q.assign(q, q + n); c.t.assign(t, t + n); c.len.assign(len, len + n); c.st.assign(strand, strand + n);
+  c.chain.resize(n); c.ClusterIndex.assign(n, 0);
+  for (long i = 0; i < n; i++) c.chain[i] = (unsigned)i;
+  if (mode == 0) RemoveSmallPairedIndels<WrapChain>(c);
+  else if (mode == 1) RemovePairedIndels<WrapChain>(c, true);
+  else if (mode == 2) RemovePairedIndels<WrapChain>(c, false);
+  else if (mode == 4) RemoveSpuriousAnchors<WrapChain>(c);
+  else RemoveSpuriousJump<WrapChain>(c);
+  for (size_t i = 0; i < c.chain.size(); i++) keep[c.chain[i]] = 1;
 }
 
 }  // extern "C"

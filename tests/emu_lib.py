@@ -232,3 +232,14 @@ def refine_breakpoint(fwd, rcs, genome, bp):
                             np.ascontiguousarray(bp["rstrand"], np.uint8), u64("read_off"), u32("read_len"), u64("lchrom_off"), u64("rchrom_off"), u32("lchrom_len"),
                             u32("rchrom_len"), o["mode"].reshape(-1), o["n_out"].reshape(-1), o["bound"].reshape(-1), o["out"].reshape(-1), o["refined"])
     return o
+
+
+def chain_filter(mode, q, t, length, strand, chain_off):
+    L = lib()
+    L.emu_chain_filter.argtypes = [C.c_int, _u32p, _u32p, _u32p, _u8p, _u64p, C.c_int, _u8p]
+    n = len(q)
+    pad = lambda a, dt: np.ascontiguousarray(a, dt) if n else np.zeros(1, dt)
+    keep = np.zeros(max(n, 1), np.uint8)
+    co = np.ascontiguousarray(chain_off, np.uint64)
+    L.emu_chain_filter(mode, pad(q, np.uint32), pad(t, np.uint32), pad(length, np.uint32), pad(strand, np.uint8), co, len(co) - 1, keep)
+    return keep[:n]

@@ -277,5 +277,7 @@ inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+inline float __fsqrt_rn(float a) { volatile float r = __builtin_sqrtf(a); return r; }
+inline float __ll2float_rn(long long a) { volatile float r = (float)a; return r; }
 template <class T> inline T __ldg(const T *p) { return *p; }
 template <class T> inline T __ldcg(const T *p) { return *p; }

@@ -137,3 +137,13 @@ extern "C" int emu_refine_breakpoint(const uint8_t *fwd, const uint8_t *rcs, uin
   }
   return 0;
 }
+
+// ---- a16 chain filters
+#include "chainf_kernels.cuh"
+extern "C" int emu_chain_filter(int mode, const uint32_t *q, const uint32_t *t, const uint32_t *len, const uint8_t *strand, const uint64_t *off, int n_chains, uint8_t *keep) {
+  const size_t N = (size_t)off[n_chains];
+  std::vector<int32_t> sv(N + 1), svpos(N + 1), svg(N + 1);
+  ChainfBatch b{n_chains, mode, (const unsigned long long *)off, q, t, len, strand, keep, sv.data(), svpos.data(), svg.data()};
+  if (n_chains) emu::launch(dim3((unsigned)((n_chains + 127) / 128)), dim3(128), 0, [&] { chainf_kernel(b); });
+  return 0;
+}
