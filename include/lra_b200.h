@@ -240,6 +240,42 @@ int lra_b200_calc_stats_batch_device(lra_b200_ctx *ctx, const lra_b200_seq *q, c
  * on the position pair, so the result is the reference's for any input order. */
 int lra_b200_sort_matches_batch(lra_b200_ctx *ctx, int32_t mode, uint32_t *q, uint32_t *t, const uint64_t *seg_off, int32_t n_seg, uint32_t *perm);
 
+/* ---- a7  CleanOffDiagonal, batched over anchor lists ------------------------------------------------------------------------
+ * Replaces  void CleanOffDiagonal(Genome&, vector<Cluster> &clusters, vector<pair<Tup,Tup>> &matches, vector<float> &matches_freq,
+ *                                 const Options&, Read&, int strand = 0, int diagOrigin = -1, int diagDrift = -1)
+ * (Clustering.h:565-800, with SecondRoundCleanOffDiagonal :801-868 and AVGfreq :549-563; every call site leaves diagOrigin / diagDrift at
+ * -1) for the forward and reverse anchor lists of a whole batch of reads.  List s = anchors list_off[s] .. list_off[s+1], already sorted by
+ * DiagonalSort (strand 0) / AntiDiagonalSort (strand 1): q = first.pos, t = second.pos, qt = first.t (the read tuple AVGfreq counts).
+ * Per INPUT anchor: keep (the reference erases the others), freq = matches_freq, cnt = the run counter.  With ExtractDiagonalFromClean the
+ * clusters of list s, over its COMPACTED anchors, are cl[7 * (list_off[s] + k) ..] = start, end, qStart, qEnd, tStart, tEnd, chromIndex
+ * (chromIndex only with bypassClustering) and cl_freq[list_off[s] + k] = anchorfreq, k < n_cl[s]; with bypassClustering the reference also
+ * copies the anchors start .. end into the cluster. */
+typedef struct lra_b200_anchor_lists {
+  int32_t n_lists;
+  const uint32_t *q, *t;
+  const uint64_t *qt;
+  const uint64_t *list_off;     /* [n_lists + 1] */
+  const uint8_t *strand;        /* [n_lists] */
+  const uint64_t *hdr_pos;      /* genome.header.pos (needed with bypassClustering) */
+  int32_t n_hdr;
+} lra_b200_anchor_lists;
+
+typedef struct lra_b200_clean_opts {      /* Options fields read by CleanOffDiagonal */
+  int32_t cleanMaxDiag, minDiagCluster, bypassClustering, cleanClustersize, SecondCleanMinDiagCluster, punish_anchorfreq, anchorPerlength,
+          SecondCleanMaxDiag, ExtractDiagonalFromClean, globalK;
+} lra_b200_clean_opts;
+
+typedef struct lra_b200_clean_result {
+  uint8_t *keep;                /* [total anchors] */
+  float *freq;
+  int32_t *cnt;
+  int32_t *cl;                  /* [total anchors * 7] or NULL */
+  float *cl_freq;               /* [total anchors] or NULL */
+  int32_t *n_cl;                /* [n_lists] */
+} lra_b200_clean_result;
+
+int lra_b200_clean_off_diagonal_batch(lra_b200_ctx *ctx, const lra_b200_anchor_lists *al, const lra_b200_clean_opts *opts, lra_b200_clean_result *res);
+
 /* ---- a12  LocalIndex::IndexSeq, batched over sequences ---------------------------------------------------------
  * Replaces  void LocalIndex::IndexSeq(char *seq, int seqLen)  (MMIndex.h:200-245; StoreMinimizers_noncanonical
  * MinCount.h:181-338, std::sort on LocalTuple::operator< TupleOps.h:30-32, RemoveFrequent MMIndex.h:69-85) for any number of

@@ -88,6 +88,20 @@ class _BreakpointResult(C.Structure):
     _fields_ = [("mode", C.c_void_p), ("n_out", C.c_void_p), ("bound", C.c_void_p), ("out", C.c_void_p), ("refined", C.c_void_p)]
 
 
+class _AnchorLists(C.Structure):
+    _fields_ = [("n_lists", C.c_int32), ("q", C.c_void_p), ("t", C.c_void_p), ("qt", C.c_void_p), ("list_off", C.c_void_p), ("strand", C.c_void_p),
+                ("hdr_pos", C.c_void_p), ("n_hdr", C.c_int32)]
+
+
+class _CleanOpts(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ["cleanMaxDiag", "minDiagCluster", "bypassClustering", "cleanClustersize", "SecondCleanMinDiagCluster", "punish_anchorfreq",
+                                         "anchorPerlength", "SecondCleanMaxDiag", "ExtractDiagonalFromClean", "globalK"]]
+
+
+class _CleanResult(C.Structure):
+    _fields_ = [("keep", C.c_void_p), ("freq", C.c_void_p), ("cnt", C.c_void_p), ("cl", C.c_void_p), ("cl_freq", C.c_void_p), ("n_cl", C.c_void_p)]
+
+
 class _Refined(C.Structure):
     _fields_ = [("status", C.c_void_p), ("chrom", C.c_void_p), ("diag", C.c_void_p), ("r_off", C.c_void_p), ("r_q", C.c_void_p),
                 ("r_t", C.c_void_p), ("r_tup", C.c_void_p), ("anchor_cap", C.c_uint64), ("n_anchors", C.c_uint64), ("rbox", C.c_void_p),
@@ -145,6 +159,7 @@ def load_library():
     L.lra_b200_global_chain_batch.argtypes = [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 4
     L.lra_b200_refine_breakpoint_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Breakpoints), C.POINTER(_BreakpointResult)]
     L.lra_b200_chain_filter_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.lra_b200_clean_off_diagonal_batch.argtypes = [C.c_void_p, C.POINTER(_AnchorLists), C.POINTER(_CleanOpts), C.POINTER(_CleanResult)]
     L.lra_b200_lindex_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.POINTER(C.c_void_p)]
     L.lra_b200_lindex_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
@@ -348,6 +363,21 @@ class Context:
         self._check(self.lib.lra_b200_sort_matches_batch(self.h, mode, _ptr(q) if len(q) else None, _ptr(t) if len(t) else None, _ptr(so), len(so) - 1,
                                                          _ptr(perm) if want_perm else None))
         return q, t, (perm[:len(q)] if want_perm else None)
+
+    # ---- a7
+    def clean_off_diagonal_batch(self, q, t, qt, list_off, strand, opts, hdr_pos):
+        """CleanOffDiagonal of every anchor list (opts: dict of the Options fields, see include/lra_b200.h).  Returns dict(keep, freq, cnt, cl[N,7],
+        cl_freq, n_cl)."""
+        q = np.ascontiguousarray(q, np.uint32); t = np.ascontiguousarray(t, np.uint32); qt = np.ascontiguousarray(qt, np.uint64)
+        lo = np.ascontiguousarray(list_off, np.uint64); st = np.ascontiguousarray(strand, np.uint8); hdr = np.ascontiguousarray(hdr_pos, np.uint64)
+        N, n = len(q), len(lo) - 1
+        o = dict(keep=np.zeros(max(N, 1), np.uint8), freq=np.zeros(max(N, 1), np.float32), cnt=np.zeros(max(N, 1), np.int32), cl=np.zeros((max(N, 1), 7), np.int32),
+                 cl_freq=np.zeros(max(N, 1), np.float32), n_cl=np.zeros(max(n, 1), np.int32))
+        al = _AnchorLists(n, _ptr(q) if N else None, _ptr(t) if N else None, _ptr(qt) if N else None, _ptr(lo), _ptr(st) if n else None, _ptr(hdr), len(hdr))
+        op = _CleanOpts(*[int(opts[k]) for k, _ in _CleanOpts._fields_])
+        r = _CleanResult(_ptr(o["keep"]), _ptr(o["freq"]), _ptr(o["cnt"]), _ptr(o["cl"]), _ptr(o["cl_freq"]), _ptr(o["n_cl"]))
+        self._check(self.lib.lra_b200_clean_off_diagonal_batch(self.h, C.byref(al), C.byref(op), C.byref(r)))
+        return {k: (v[:n] if k == "n_cl" else v[:N]) for k, v in o.items()}
 
     # ---- a16
     def chain_filter_batch(self, mode, q, t, length, strand, chain_off):

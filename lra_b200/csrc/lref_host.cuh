@@ -601,3 +601,58 @@ extern "C" int lra_b200_chain_filter_batch(lra_b200_ctx *ctx, int32_t mode, cons
   ctx->stats.push_back(s2);
   return LRA_B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- a7 CleanOffDiagonal
+extern "C" int lra_b200_clean_off_diagonal_batch(lra_b200_ctx *ctx, const lra_b200_anchor_lists *al, const lra_b200_clean_opts *opts, lra_b200_clean_result *res) {
+  if (!ctx || !al || !opts || !res || al->n_lists < 0 || !al->list_off) return fail(ctx, LRA_B200_EINVAL, "clean_off_diagonal_batch: bad argument");
+  const int n = al->n_lists;
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  if (n == 0) return LRA_B200_OK;
+  const size_t N = (size_t)al->list_off[n];
+  for (int s = 0; s < n; s++)
+    if (al->list_off[s + 1] < al->list_off[s] || al->list_off[s + 1] - al->list_off[s] > 0x3FFFFFFFull) return fail(ctx, LRA_B200_EINVAL, "clean_off_diagonal_batch: bad list offsets");
+  if (N && (!al->q || !al->t || !al->qt)) return fail(ctx, LRA_B200_EINVAL, "clean_off_diagonal_batch: NULL anchors");
+  if (opts->bypassClustering && opts->ExtractDiagonalFromClean && (!al->hdr_pos || al->n_hdr < 1)) return fail(ctx, LRA_B200_EINVAL, "clean_off_diagonal_batch: genome header needed");
+  int rc;
+  DevBuf *B = ctx->cd;
+  const size_t H = al->n_hdr > 0 ? (size_t)al->n_hdr : 1;
+  if ((rc = ensure(ctx, B[0], N * 4 + 16)) || (rc = ensure(ctx, B[1], N * 4 + 16)) || (rc = ensure(ctx, B[2], N * 8 + 16)) || (rc = ensure(ctx, B[3], (size_t)n)) ||
+      (rc = ensure(ctx, B[4], ((size_t)n + 1) * 8)) || (rc = ensure(ctx, B[5], H * 8)) || (rc = ensure(ctx, B[6], N + 16)) || (rc = ensure(ctx, B[7], N * 4 + 16)) ||
+      (rc = ensure(ctx, B[8], N * 4 + 16)) || (rc = ensure(ctx, B[9], N * 28 + 64)) || (rc = ensure(ctx, B[10], N * 4 + 16)) || (rc = ensure(ctx, B[11], (size_t)n * 4)) ||
+      (rc = ensure(ctx, B[12], N * 3 + 64)) || (rc = ensure(ctx, B[13], N * 32 + 64)) || (rc = ensure(ctx, B[14], N * 4 + 64)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  if (N) {
+    CU(cudaMemcpyAsync(B[0].p, al->q, N * 4, cudaMemcpyHostToDevice, st)); CU(cudaMemcpyAsync(B[1].p, al->t, N * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B[2].p, al->qt, N * 8, cudaMemcpyHostToDevice, st));
+  }
+  CU(cudaMemcpyAsync(B[3].p, al->strand, (size_t)n, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[4].p, al->list_off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (al->n_hdr > 0) CU(cudaMemcpyAsync(B[5].p, al->hdr_pos, (size_t)al->n_hdr * 8, cudaMemcpyHostToDevice, st));
+  CodBatch b;
+  b.n_lists = n; b.off = (const unsigned long long *)B[4].p; b.q = (const uint32_t *)B[0].p; b.t = (const uint32_t *)B[1].p; b.qt = (const unsigned long long *)B[2].p;
+  b.strand = (const uint8_t *)B[3].p;
+  b.o = CodOpts{opts->cleanMaxDiag, opts->minDiagCluster, opts->bypassClustering, opts->cleanClustersize, opts->SecondCleanMinDiagCluster, opts->punish_anchorfreq,
+                opts->anchorPerlength, opts->SecondCleanMaxDiag, opts->ExtractDiagonalFromClean, opts->globalK};
+  b.hdr_pos = (const unsigned long long *)B[5].p; b.n_hdr = al->n_hdr;
+  b.keep = (uint8_t *)B[6].p; b.freq = (float *)B[7].p; b.cnt = (int32_t *)B[8].p; b.cl = (int32_t *)B[9].p; b.cl_freq = (float *)B[10].p; b.n_cl = (int32_t *)B[11].p;
+  b.flags = (uint8_t *)B[12].p; b.hkeys = (unsigned long long *)B[13].p; b.hused = (uint8_t *)B[14].p;
+  cudaEventRecord(ctx->ev[0], st);
+  cod_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(b);
+  cudaEventRecord(ctx->ev[1], st);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  if (N) {
+    CU(cudaMemcpyAsync(res->keep, b.keep, N, cudaMemcpyDeviceToHost, st)); CU(cudaMemcpyAsync(res->freq, b.freq, N * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->cnt, b.cnt, N * 4, cudaMemcpyDeviceToHost, st));
+    if (res->cl) CU(cudaMemcpyAsync(res->cl, b.cl, N * 28, cudaMemcpyDeviceToHost, st));
+    if (res->cl_freq) CU(cudaMemcpyAsync(res->cl_freq, b.cl_freq, N * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaMemcpyAsync(res->n_cl, b.n_cl, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "cod");
+  cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]); s2.jobs = (uint64_t)n; s2.algo_bytes = 25ull * N;
+  ctx->stats.push_back(s2);
+  return LRA_B200_OK;
+}

@@ -650,3 +650,47 @@ def chain_filter(mode, q, t, length, strand, which="port"):
     pad = lambda a, dt: a if n else np.zeros(1, dt)
     f(mode, pad(q, np.uint32), pad(t, np.uint32), pad(length, np.uint32), pad(strand, np.uint8), n, keep)
     return keep[:n]
+
+
+# ---------------------------------------------------------------- a7 CleanOffDiagonal (Clustering.h:565-868)
+
+COD_FIELDS = ["cleanMaxDiag", "minDiagCluster", "bypassClustering", "cleanClustersize", "SecondCleanMinDiagCluster", "punish_anchorfreq", "anchorPerlength",
+              "SecondCleanMaxDiag", "ExtractDiagonalFromClean", "globalK"]
+COD_PRESETS = {      # lra.cpp:268-431 (align presets) / Options.h:123-240
+    "ccs": dict(cleanMaxDiag=150, minDiagCluster=30, bypassClustering=0, cleanClustersize=100, SecondCleanMinDiagCluster=30, punish_anchorfreq=10, anchorPerlength=10,
+                SecondCleanMaxDiag=100, ExtractDiagonalFromClean=1, globalK=17),
+    "clr": dict(cleanMaxDiag=150, minDiagCluster=10, bypassClustering=1, cleanClustersize=100, SecondCleanMinDiagCluster=30, punish_anchorfreq=10, anchorPerlength=10,
+                SecondCleanMaxDiag=100, ExtractDiagonalFromClean=1, globalK=15),
+    "ont": dict(cleanMaxDiag=200, minDiagCluster=3, bypassClustering=1, cleanClustersize=100, SecondCleanMinDiagCluster=10, punish_anchorfreq=5, anchorPerlength=5,
+                SecondCleanMaxDiag=120, ExtractDiagonalFromClean=1, globalK=17),
+    "noextract": dict(cleanMaxDiag=100, minDiagCluster=10, bypassClustering=0, cleanClustersize=100, SecondCleanMinDiagCluster=40, punish_anchorfreq=10, anchorPerlength=10,
+                      SecondCleanMaxDiag=10, ExtractDiagonalFromClean=0, globalK=17),
+}
+
+
+def clean_off_diagonal(q, t, qt, strand, opts, hdr_pos, which="port"):
+    """One anchor list (sorted by DiagonalSort / AntiDiagonalSort) through CleanOffDiagonal.  Returns dict(kq, kt, kfreq (the surviving anchors),
+    cl[ncl,7] (start, end, qStart, qEnd, tStart, tEnd, chromIndex), cl_freq) and, for the port, keep / freq / cnt per input anchor."""
+    q = np.array(q, np.uint32); t = np.array(t, np.uint32); qt = np.ascontiguousarray(qt, np.uint64)
+    n = len(q)
+    hdr = np.ascontiguousarray(hdr_pos, np.uint64)
+    ov = np.array([opts[k] for k in COD_FIELDS], np.int32)
+    cl = np.zeros(7 * (n + 1), np.int32); clf = np.zeros(n + 1, np.float32)
+    pad = lambda a, dt: a if n else np.zeros(1, dt)
+    if which == "ref":
+        L = ref()
+        f = _bind_once(L, "ref_clean_off_diagonal", C.c_long, [_u32p, _u32p, _u64p, C.c_long, C.c_int, _i32p, _u64p, C.c_int, np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"),
+                                                               C.POINTER(C.c_long), _i32p, np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")])
+        freq = np.zeros(n + 1, np.float32); nk = C.c_long(0)
+        qq, tt = pad(q, np.uint32), pad(t, np.uint32)
+        ncl = f(qq, tt, pad(qt, np.uint64), n, strand, ov, hdr, len(hdr), freq, C.byref(nk), cl, clf)
+        k = nk.value
+        return dict(kq=qq[:k].copy(), kt=tt[:k].copy(), kfreq=freq[:k].copy(), cl=cl[:7 * ncl].reshape(-1, 7).copy(), cl_freq=clf[:ncl].copy())
+    L = port()
+    f = _bind_once(L, "lra_oracle_clean_off_diagonal", C.c_long, [_u32p, _u32p, _u64p, C.c_long, C.c_int, _i32p, _u64p, C.c_int, _u8p,
+                                                                  np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"), _i32p, _i32p,
+                                                                  np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")])
+    keep = np.zeros(n + 1, np.uint8); freq = np.zeros(n + 1, np.float32); cnt = np.zeros(n + 1, np.int32)
+    ncl = f(pad(q, np.uint32), pad(t, np.uint32), pad(qt, np.uint64), n, strand, ov, hdr, len(hdr), keep, freq, cnt, cl, clf)
+    m = keep[:n] == 1
+    return dict(kq=q[m], kt=t[m], kfreq=freq[:n][m], cl=cl[:7 * ncl].reshape(-1, 7).copy(), cl_freq=clf[:ncl].copy(), keep=keep[:n].copy(), freq=freq[:n].copy(), cnt=cnt[:n].copy())

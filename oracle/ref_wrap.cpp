@@ -413,4 +413,33 @@ void ref_chain_filter(int mode, const uint32_t *q, const uint32_t *t, const uint
   for (size_t i = 0; i < c.chain.size(); i++) keep[c.chain[i]] = 1;
 }
 
+// ---- a7: CleanOffDiagonal (Clustering.h:565-800) on the anchors of one read strand.  opt[10] as cod_opts in oracle/clean_off_diagonal.c.
+// Outputs the surviving anchors (q, t, freq) and the clusters (cl[7k..] = start, end, qStart, qEnd, tStart, tEnd, chromIndex; cl_freq).
+long ref_clean_off_diagonal(uint32_t *q, uint32_t *t, const uint64_t *qt, long n, int strand, const int32_t *opt, const uint64_t *hdr_pos, int n_hdr,
+                            float *freq, long *n_kept, int32_t *cl, float *cl_freq) {
+  ref_init_static();
+  Options opts;
+  opts.cleanMaxDiag = opt[0]; opts.minDiagCluster = opt[1]; opts.bypassClustering = opt[2] != 0; opts.cleanClustersize = opt[3];
+  opts.SecondCleanMinDiagCluster = opt[4]; opts.punish_anchorfreq = opt[5]; opts.anchorPerlength = opt[6]; opts.SecondCleanMaxDiag = opt[7];
+  opts.ExtractDiagonalFromClean = opt[8] != 0; opts.globalK = opt[9];
+  opts.readname = "\x01not-a-read-name"; opts.dotPlot = false;
+  Genome genome;
+  genome.header.pos.assign(hdr_pos, hdr_pos + n_hdr);
+  Read read; read.name = "r";
+  std::vector<Cluster> clusters;
+  GenomePairs matches(n);
+  for (long i = 0; i < n; i++) { matches[i].first.pos = q[i]; matches[i].second.pos = t[i]; matches[i].first.t = qt[i]; matches[i].second.t = qt[i]; }
+  std::vector<float> mf(n, 0.0f);
+  CleanOffDiagonal(genome, clusters, matches, mf, opts, read, strand);
+  *n_kept = (long)matches.size();
+  for (size_t i = 0; i < matches.size(); i++) { q[i] = matches[i].first.pos; t[i] = matches[i].second.pos; freq[i] = mf[i]; }
+  for (size_t k = 0; k < clusters.size(); k++) {
+    cl[7 * k] = clusters[k].start; cl[7 * k + 1] = clusters[k].end; cl[7 * k + 2] = (int32_t)clusters[k].qStart; cl[7 * k + 3] = (int32_t)clusters[k].qEnd;
+    cl[7 * k + 4] = (int32_t)clusters[k].tStart; cl[7 * k + 5] = (int32_t)clusters[k].tEnd; cl[7 * k + 6] = opts.bypassClustering ? clusters[k].chromIndex : 0;
+    cl_freq[k] = clusters[k].anchorfreq;
+  }
+  read.seq = NULL; read.qual = NULL;
+  return (long)clusters.size();
+}
+
 }  // extern "C"

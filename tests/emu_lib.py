@@ -243,3 +243,19 @@ def chain_filter(mode, q, t, length, strand, chain_off):
     co = np.ascontiguousarray(chain_off, np.uint64)
     L.emu_chain_filter(mode, pad(q, np.uint32), pad(t, np.uint32), pad(length, np.uint32), pad(strand, np.uint8), co, len(co) - 1, keep)
     return keep[:n]
+
+
+def clean_off_diagonal(q, t, qt, list_off, strand, opt_values, hdr_pos):
+    """opt_values: the ten Options fields in the order of lra_b200_clean_opts."""
+    L = lib()
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    L.emu_clean_off_diagonal.argtypes = [_u32p, _u32p, _u64p, _u64p, _u8p, C.c_int, _i32p, _u64p, C.c_int, _u8p, f32p, _i32p, _i32p, f32p, _i32p]
+    N, n = len(q), len(list_off) - 1
+    pad = lambda a, dt: np.ascontiguousarray(a, dt) if len(a) else np.zeros(1, dt)
+    o = dict(keep=np.zeros(max(N, 1), np.uint8), freq=np.zeros(max(N, 1), np.float32), cnt=np.zeros(max(N, 1), np.int32), cl=np.zeros(7 * max(N, 1), np.int32),
+             cl_freq=np.zeros(max(N, 1), np.float32), n_cl=np.zeros(max(n, 1), np.int32))
+    hdr = np.ascontiguousarray(hdr_pos, np.uint64)
+    L.emu_clean_off_diagonal(pad(q, np.uint32), pad(t, np.uint32), pad(qt, np.uint64), np.ascontiguousarray(list_off, np.uint64), pad(strand, np.uint8), n,
+                             np.ascontiguousarray(opt_values, np.int32), hdr, len(hdr), o["keep"], o["freq"], o["cnt"], o["cl"], o["cl_freq"], o["n_cl"])
+    o["cl"] = o["cl"].reshape(-1, 7)
+    return {k: (v[:n] if k == "n_cl" else v[:N]) for k, v in o.items()}

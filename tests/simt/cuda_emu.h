@@ -8,6 +8,7 @@
 // (reported), as they would be undefined behaviour on the device.
 #pragma once
 #include <ucontext.h>
+#include <math.h>
 #include <algorithm>
 #include <cassert>
 #include <cstdint>
@@ -277,6 +278,9 @@ inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 inline float __fsqrt_rn(float a) { volatile float r = __builtin_sqrtf(a); return r; }
 inline float __ll2float_rn(long long a) { volatile float r = (float)a; return r; }
 template <class T> inline T __ldg(const T *p) { return *p; }

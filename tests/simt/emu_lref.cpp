@@ -147,3 +147,19 @@ extern "C" int emu_chain_filter(int mode, const uint32_t *q, const uint32_t *t, 
   if (n_chains) emu::launch(dim3((unsigned)((n_chains + 127) / 128)), dim3(128), 0, [&] { chainf_kernel(b); });
   return 0;
 }
+
+// ---- a7 CleanOffDiagonal
+#include "cod_kernels.cuh"
+extern "C" int emu_clean_off_diagonal(const uint32_t *q, const uint32_t *t, const uint64_t *qt, const uint64_t *off, const uint8_t *strand, int n_lists, const int32_t *opt,
+                                      const uint64_t *hdr_pos, int n_hdr, uint8_t *keep, float *freq, int32_t *cnt, int32_t *cl, float *cl_freq, int32_t *n_cl) {
+  const size_t N = (size_t)off[n_lists];
+  std::vector<uint8_t> flags(3 * N + 8), hused(4 * N + 8);
+  std::vector<unsigned long long> hkeys(4 * N + 8);
+  CodBatch b;
+  b.n_lists = n_lists; b.off = (const unsigned long long *)off; b.q = q; b.t = t; b.qt = (const unsigned long long *)qt; b.strand = strand;
+  b.o = CodOpts{opt[0], opt[1], opt[2], opt[3], opt[4], opt[5], opt[6], opt[7], opt[8], opt[9]};
+  b.hdr_pos = (const unsigned long long *)hdr_pos; b.n_hdr = n_hdr; b.keep = keep; b.freq = freq; b.cnt = cnt; b.cl = cl; b.cl_freq = cl_freq; b.n_cl = n_cl;
+  b.flags = flags.data(); b.hkeys = hkeys.data(); b.hused = hused.data();
+  if (n_lists) emu::launch(dim3((unsigned)((n_lists + 63) / 64)), dim3(64), 0, [&] { cod_kernel(b); });
+  return 0;
+}
