@@ -39,7 +39,10 @@ __global__ void __launch_bounds__(128) chainf_kernel(ChainfBatch b) {
   if (n < 2) return;
   int ns = 0;
   const int thr = mode == 0 ? 5 : (mode == 4 ? 499 : (mode == 5 ? 100 : 30));
-  long long totalDist = 0, totDistSq = 0;
+  // `long` sums in the reference; dist * dist overflows 64 bits when an anchor pair is out of order (dist is then an unsigned 32-bit
+  // wrap-around near 2^32), and the stock build simply wraps (the mean / sd then turn negative / NaN, which is observable: no distance
+  // is "valid" and every short anchor goes).  Unsigned arithmetic makes that wrap well defined here.
+  unsigned long long totalDist = 0, totDistSq = 0;
   auto dists = [&](int c, long long &tDist, long long &qDist) {       // unsigned 32-bit differences widened, as in the reference
     const uint32_t te1 = t[c - 1] + len[c - 1], qe1 = q[c - 1] + len[c - 1], tec = t[c] + len[c], qec = q[c] + len[c];
     tDist = t[c] > te1 ? (long long)(uint32_t)(t[c] - te1) : (long long)(uint32_t)(t[c - 1] - tec);
@@ -50,7 +53,7 @@ __global__ void __launch_bounds__(128) chainf_kernel(ChainfBatch b) {
       long long tDist, qDist;
       dists(c, tDist, qDist);
       const long long dist = tDist < qDist ? tDist : qDist;
-      totDistSq += dist * dist; totalDist += dist;
+      totDistSq += (unsigned long long)dist * (unsigned long long)dist; totalDist += (unsigned long long)dist;
     }
     if (mode == 3) {
       const int Gap = (int)(((long long)t[c] - (long long)q[c]) - ((long long)t[c - 1] - (long long)q[c - 1]));
@@ -77,8 +80,8 @@ __global__ void __launch_bounds__(128) chainf_kernel(ChainfBatch b) {
     }
     if (mode == 1) {
       const float nDist = (float)(n - 1);
-      const float meanDist = __fdiv_rn(__ll2float_rn(totalDist), nDist);
-      const float varDist = __fsub_rn(__fdiv_rn(__ll2float_rn(totDistSq), nDist), __fmul_rn(meanDist, meanDist));
+      const float meanDist = __fdiv_rn(__ll2float_rn((long long)totalDist), nDist);
+      const float varDist = __fsub_rn(__fdiv_rn(__ll2float_rn((long long)totDistSq), nDist), __fmul_rn(meanDist, meanDist));
       const float sdDist = __fsqrt_rn(varDist);
       const float bound = __fadd_rn(meanDist, __fmul_rn(4.0f, sdDist));
       int firstValidDist = -1, lastValidDist = -1;

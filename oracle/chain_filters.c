@@ -23,7 +23,8 @@ void lra_oracle_chain_filter(int mode, const uint32_t *q, const uint32_t *t, con
   long *SVg = (long *)malloc(sizeof(long) * (size_t)n);
   long ns = 0;
   const int thr = mode == 0 ? 5 : (mode == 4 ? 499 : (mode == 5 ? 100 : 30));      /* |Gap| > thr  (mode 4: >= 500) */
-  long totalDist = 0, totDistSq = 0;
+  /* `long` in the reference: dist * dist overflows for out-of-order anchor pairs and the stock build wraps; unsigned makes the wrap defined */
+  unsigned long totalDist = 0, totDistSq = 0;
 #define QE(i) (q[i] + len[i])
 #define TE(i) (t[i] + len[i])
   for (long c = 1; c < n; c++) {
@@ -32,7 +33,7 @@ void lra_oracle_chain_filter(int mode, const uint32_t *q, const uint32_t *t, con
       if (t[c] > TE(c - 1)) tDist = (uint32_t)(t[c] - TE(c - 1)); else tDist = (uint32_t)(t[c - 1] - TE(c));
       if (q[c] > QE(c - 1)) qDist = (uint32_t)(q[c] - TE(c - 1)); else qDist = (uint32_t)(q[c - 1] - QE(c));
       long dist = tDist < qDist ? tDist : qDist;
-      totDistSq += dist * dist; totalDist += dist;
+      totDistSq += (unsigned long)dist * (unsigned long)dist; totalDist += (unsigned long)dist;
     }
     if (mode == 3) {
       int Gap = (int)(((long)t[c] - (long)q[c]) - ((long)t[c - 1] - (long)q[c - 1]));
@@ -53,8 +54,8 @@ void lra_oracle_chain_filter(int mode, const uint32_t *q, const uint32_t *t, con
         for (int i = SVpos[c - 1]; i < SVpos[c]; i++) if (len[i] <= 50) keep[i] = 0;
   } else if (mode == 1 || mode == 2) {
     const float nDist = (float)(n - 1);
-    const float meanDist = (float)totalDist / nDist;
-    const float varDist = (float)totDistSq / (float)nDist - meanDist * meanDist;
+    const float meanDist = (float)(long)totalDist / nDist;
+    const float varDist = (float)(long)totDistSq / (float)nDist - meanDist * meanDist;
     const float sdDist = sqrtf(varDist);
     int firstValidDist = -1, lastValidDist = -1;
     for (long c = 1; c < ns; c++) {
