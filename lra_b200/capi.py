@@ -614,6 +614,27 @@ def CreateLookUpTable():
     return np.array([libm.logf(float(i)) for i in range(1, 10002, 5)], np.float32)
 
 
+def write_gli(path, k, w, window, seq_offsets, tuple_boundaries, minimizers):
+    """<ref>.gli as LocalIndex::Write lays it out (MMIndex.h:138-151): int k, w, localIndexWindow, nRegions; uint64 seqOffsets[nRegions];
+    uint64 tupleBoundaries[nRegions]; uint64 nMin; LocalTuple minimizers[nMin] (uint32: tuple | pos << 20).  seq_offsets / tuple_boundaries
+    include the leading 0 (what LocalIndexImage.download() returns for an arena that starts at 0)."""
+    so = np.ascontiguousarray(seq_offsets, np.uint64); tb = np.ascontiguousarray(tuple_boundaries, np.uint64); mn = np.ascontiguousarray(minimizers, np.uint32)
+    assert len(so) == len(tb)
+    with open(path, "wb") as f:
+        f.write(np.array([k, w, window, len(so)], np.int32).tobytes())
+        f.write(so.tobytes()); f.write(tb.tobytes())
+        f.write(np.array([len(mn)], np.uint64).tobytes()); f.write(mn.tobytes())
+
+
+def read_gli(path):
+    """Inverse of write_gli (LocalIndex::Read, MMIndex.h:154-173).  Returns dict(k, w, window, seq_offsets, tuple_boundaries, minimizers)."""
+    d = open(path, "rb").read()
+    k, w, window, n = (int(x) for x in np.frombuffer(d, np.int32, 4, 0))
+    so = np.frombuffer(d, np.uint64, n, 16).copy(); tb = np.frombuffer(d, np.uint64, n, 16 + 8 * n).copy()
+    nm = int(np.frombuffer(d, np.uint64, 1, 16 + 16 * n)[0])
+    return dict(k=k, w=w, window=window, seq_offsets=so, tuple_boundaries=tb, minimizers=np.frombuffer(d, np.uint32, nm, 24 + 16 * n).copy())
+
+
 def _ctx():
     global _default_ctx
     if _default_ctx is None:
