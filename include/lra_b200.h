@@ -276,6 +276,37 @@ typedef struct lra_b200_clean_result {
 
 int lra_b200_clean_off_diagonal_batch(lra_b200_ctx *ctx, const lra_b200_anchor_lists *al, const lra_b200_clean_opts *opts, lra_b200_clean_result *res);
 
+/* ---- a9  SplitClusters + DecideSplitClustersValue, batched over reads ----------------------------------------------------
+ * Replaces  void SplitClusters(vector<Cluster> &clusters, vector<Cluster> &splitclusters, Read&, const Options&)   (SplitClusters.h:63-171)
+ * and       void DecideSplitClustersValue(vector<Cluster> &clusters, vector<Cluster> &splitclusters, const Options&, Read&)   (:174-248)
+ * for the clusters of a whole batch of reads (Map_highacc.h:154-155).  Read r owns clusters cl_off[r] .. cl_off[r+1]; cluster c: box[4c..] =
+ * qStart, qEnd, tStart, tEnd, strand[c], freq[c] = anchorfreq, and the read positions of its anchors m_q[m_off[c] .. m_off[c+1]) in
+ * CartesianSort order.  contig = (opts.readType == Options::contig).  Results: split[c] = Cluster::split, val_cluster[c] = Cluster::Val; the
+ * pieces of read r are sp_off[r] .. sp_off[r+1] in the reference's order: sp[6k..] = qStart, qEnd, tStart, tEnd, strand, coarse (index of the
+ * cluster WITHIN its read), sp_val[k] = Val, sp_n0[k] = NumofAnchors0. */
+typedef struct lra_b200_read_clusters {
+  int32_t n_reads;
+  const uint64_t *cl_off;       /* [n_reads + 1] */
+  const uint32_t *box;          /* [clusters * 4] */
+  const uint8_t *strand;        /* [clusters] */
+  const float *freq;            /* [clusters] */
+  const uint64_t *m_off;        /* [clusters + 1] */
+  const uint32_t *m_q;
+  int32_t contig, global_k;
+} lra_b200_read_clusters;
+
+typedef struct lra_b200_split_result {
+  uint8_t *split;               /* [clusters] */
+  int32_t *val_cluster;         /* [clusters] */
+  uint64_t *sp_off;             /* [n_reads + 1] */
+  uint32_t *sp;                 /* [piece_cap * 6] */
+  int32_t *sp_val, *sp_n0;      /* [piece_cap] */
+  uint64_t piece_cap;
+  uint64_t n_pieces;            /* out (== required capacity on LRA_B200_EOVERFLOW) */
+} lra_b200_split_result;
+
+int lra_b200_split_clusters_batch(lra_b200_ctx *ctx, const lra_b200_read_clusters *rc, lra_b200_split_result *res);
+
 /* ---- a12  LocalIndex::IndexSeq, batched over sequences ---------------------------------------------------------
  * Replaces  void LocalIndex::IndexSeq(char *seq, int seqLen)  (MMIndex.h:200-245; StoreMinimizers_noncanonical
  * MinCount.h:181-338, std::sort on LocalTuple::operator< TupleOps.h:30-32, RemoveFrequent MMIndex.h:69-85) for any number of

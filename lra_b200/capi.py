@@ -102,6 +102,16 @@ class _CleanResult(C.Structure):
     _fields_ = [("keep", C.c_void_p), ("freq", C.c_void_p), ("cnt", C.c_void_p), ("cl", C.c_void_p), ("cl_freq", C.c_void_p), ("n_cl", C.c_void_p)]
 
 
+class _ReadClusters(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("cl_off", C.c_void_p), ("box", C.c_void_p), ("strand", C.c_void_p), ("freq", C.c_void_p), ("m_off", C.c_void_p),
+                ("m_q", C.c_void_p), ("contig", C.c_int32), ("global_k", C.c_int32)]
+
+
+class _SplitResult(C.Structure):
+    _fields_ = [("split", C.c_void_p), ("val_cluster", C.c_void_p), ("sp_off", C.c_void_p), ("sp", C.c_void_p), ("sp_val", C.c_void_p), ("sp_n0", C.c_void_p),
+                ("piece_cap", C.c_uint64), ("n_pieces", C.c_uint64)]
+
+
 class _Refined(C.Structure):
     _fields_ = [("status", C.c_void_p), ("chrom", C.c_void_p), ("diag", C.c_void_p), ("r_off", C.c_void_p), ("r_q", C.c_void_p),
                 ("r_t", C.c_void_p), ("r_tup", C.c_void_p), ("anchor_cap", C.c_uint64), ("n_anchors", C.c_uint64), ("rbox", C.c_void_p),
@@ -160,6 +170,7 @@ def load_library():
     L.lra_b200_refine_breakpoint_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Breakpoints), C.POINTER(_BreakpointResult)]
     L.lra_b200_chain_filter_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_clean_off_diagonal_batch.argtypes = [C.c_void_p, C.POINTER(_AnchorLists), C.POINTER(_CleanOpts), C.POINTER(_CleanResult)]
+    L.lra_b200_split_clusters_batch.argtypes = [C.c_void_p, C.POINTER(_ReadClusters), C.POINTER(_SplitResult)]
     L.lra_b200_lindex_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.POINTER(C.c_void_p)]
     L.lra_b200_lindex_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
@@ -378,6 +389,29 @@ class Context:
         r = _CleanResult(_ptr(o["keep"]), _ptr(o["freq"]), _ptr(o["cnt"]), _ptr(o["cl"]), _ptr(o["cl_freq"]), _ptr(o["n_cl"]))
         self._check(self.lib.lra_b200_clean_off_diagonal_batch(self.h, C.byref(al), C.byref(op), C.byref(r)))
         return {k: (v[:n] if k == "n_cl" else v[:N]) for k, v in o.items()}
+
+    # ---- a9
+    def split_clusters_batch(self, cl_off, box, strand, freq, m_off, m_q, contig, global_k, piece_cap=None):
+        """SplitClusters + DecideSplitClustersValue for every read.  Returns dict(split, val_cluster, sp_off, sp[k,6], sp_val, sp_n0, n_pieces)."""
+        co = np.ascontiguousarray(cl_off, np.uint64); bx = np.ascontiguousarray(box, np.uint32).reshape(-1); st = np.ascontiguousarray(strand, np.uint8)
+        fr = np.ascontiguousarray(freq, np.float32); mo = np.ascontiguousarray(m_off, np.uint64); mq = np.ascontiguousarray(m_q, np.uint32)
+        R, Cn = len(co) - 1, len(st)
+        cap = piece_cap if piece_cap is not None else 8 * Cn + 64
+        for _ in range(2):
+            o = dict(split=np.zeros(max(Cn, 1), np.uint8), val_cluster=np.zeros(max(Cn, 1), np.int32), sp_off=np.zeros(R + 1, np.uint64), sp=np.zeros((cap, 6), np.uint32),
+                     sp_val=np.zeros(cap, np.int32), sp_n0=np.zeros(cap, np.int32))
+            rcs = _ReadClusters(R, _ptr(co), _ptr(bx) if Cn else None, _ptr(st) if Cn else None, _ptr(fr) if Cn else None, _ptr(mo), _ptr(mq) if len(mq) else None, contig, global_k)
+            res = _SplitResult(_ptr(o["split"]), _ptr(o["val_cluster"]), _ptr(o["sp_off"]), _ptr(o["sp"]), _ptr(o["sp_val"]), _ptr(o["sp_n0"]), cap, 0)
+            rc = self.lib.lra_b200_split_clusters_batch(self.h, C.byref(rcs), C.byref(res))
+            o["n_pieces"] = int(res.n_pieces)
+            if rc == EOVERFLOW and piece_cap is None:
+                cap = int(res.n_pieces) + 16
+                continue
+            self._check(rc)
+            n = o["n_pieces"]
+            o["split"] = o["split"][:Cn]; o["val_cluster"] = o["val_cluster"][:Cn]; o["sp"] = o["sp"][:n]; o["sp_val"] = o["sp_val"][:n]; o["sp_n0"] = o["sp_n0"][:n]
+            return o
+        self._check(rc)
 
     # ---- a16
     def chain_filter_batch(self, mode, q, t, length, strand, chain_off):

@@ -23,6 +23,7 @@
 #include "rbp_kernels.cuh"
 #include "chainf_kernels.cuh"
 #include "cod_kernels.cuh"
+#include "split_kernels.cuh"
 
 using namespace lra;
 
@@ -59,6 +60,7 @@ struct lra_b200_ctx {
   DevBuf rb[20];          // RefineBreakpoint scratch
   DevBuf cf[9];           // chain filter scratch
   DevBuf cd[15];          // CleanOffDiagonal scratch
+  DevBuf sc[15];          // SplitClusters scratch
   bool keep_stats = false;  // sub-launchers append to stats instead of clearing
   AogPlan *h_plan = nullptr;            // pinned
   unsigned long long *h_misc = nullptr;  // pinned (2 x u64)
@@ -151,6 +153,7 @@ extern "C" void lra_b200_destroy(lra_b200_ctx *ctx) {
   for (DevBuf &b : ctx->rb) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->cf) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->cd) if (b.p) cudaFree(b.p);
+  for (DevBuf &b : ctx->sc) if (b.p) cudaFree(b.p);
   for (auto &ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < 4; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]); }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);

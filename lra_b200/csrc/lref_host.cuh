@@ -656,3 +656,61 @@ extern "C" int lra_b200_clean_off_diagonal_batch(lra_b200_ctx *ctx, const lra_b2
   ctx->stats.push_back(s2);
   return LRA_B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- a9 SplitClusters
+extern "C" int lra_b200_split_clusters_batch(lra_b200_ctx *ctx, const lra_b200_read_clusters *rc_, lra_b200_split_result *res) {
+  if (!ctx || !rc_ || !res || rc_->n_reads < 0 || !rc_->cl_off) return fail(ctx, LRA_B200_EINVAL, "split_clusters_batch: bad argument");
+  const int R = rc_->n_reads;
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  res->n_pieces = 0;
+  if (R == 0) return LRA_B200_OK;
+  const size_t Cn = (size_t)rc_->cl_off[R];
+  if (Cn == 0) { for (int r = 0; r <= R; r++) res->sp_off[r] = 0; return LRA_B200_OK; }
+  if (!rc_->box || !rc_->strand || !rc_->freq || !rc_->m_off) return fail(ctx, LRA_B200_EINVAL, "split_clusters_batch: NULL cluster arrays");
+  const size_t M = (size_t)rc_->m_off[Cn];
+  if (M && !rc_->m_q) return fail(ctx, LRA_B200_EINVAL, "split_clusters_batch: NULL anchors");
+  int rc;
+  DevBuf *B = ctx->sc;
+  const size_t cap = (size_t)(res->piece_cap ? res->piece_cap : 1);
+  if ((rc = ensure(ctx, B[0], ((size_t)R + 1) * 8)) || (rc = ensure(ctx, B[1], Cn * 16)) || (rc = ensure(ctx, B[2], Cn)) || (rc = ensure(ctx, B[3], Cn * 4)) ||
+      (rc = ensure(ctx, B[4], (Cn + 1) * 8)) || (rc = ensure(ctx, B[5], M * 4 + 16)) || (rc = ensure(ctx, B[6], Cn)) || (rc = ensure(ctx, B[7], Cn * 4)) ||
+      (rc = ensure(ctx, B[8], ((size_t)R + 2) * 8)) || (rc = ensure(ctx, B[9], cap * 24)) || (rc = ensure(ctx, B[10], cap * 4)) || (rc = ensure(ctx, B[11], cap * 4)) ||
+      (rc = ensure(ctx, B[12], Cn * 16 + 64)) || (rc = ensure(ctx, B[13], Cn * 4 * sizeof(ScPoint) + 64)) || (rc = ensure(ctx, B[14], 64)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(B[0].p, rc_->cl_off, ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[1].p, rc_->box, Cn * 16, cudaMemcpyHostToDevice, st)); CU(cudaMemcpyAsync(B[2].p, rc_->strand, Cn, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[3].p, rc_->freq, Cn * 4, cudaMemcpyHostToDevice, st)); CU(cudaMemcpyAsync(B[4].p, rc_->m_off, (Cn + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (M) CU(cudaMemcpyAsync(B[5].p, rc_->m_q, M * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(B[14].p, 0, 64, st));
+  SplitBatch b;
+  b.n_reads = R; b.contig = rc_->contig; b.globalK = rc_->global_k;
+  b.cl_off = (const unsigned long long *)B[0].p; b.box = (const uint32_t *)B[1].p; b.strand = (const uint8_t *)B[2].p; b.freq = (const float *)B[3].p;
+  b.m_off = (const unsigned long long *)B[4].p; b.mq = (const uint32_t *)B[5].p; b.split = (uint8_t *)B[6].p; b.val_cluster = (int32_t *)B[7].p;
+  b.sp_off = (unsigned long long *)B[8].p; b.sp = (uint32_t *)B[9].p; b.sp_val = (int32_t *)B[10].p; b.sp_n0 = (int32_t *)B[11].p; b.sp_cap = res->piece_cap;
+  b.sets = (uint32_t *)B[12].p; b.pts = (ScPoint *)B[13].p;
+  cudaEventRecord(ctx->ev[0], st);
+  split_kernel<false><<<(unsigned)((R + 63) / 64), 64, 0, st>>>(b);
+  seed_scan_kernel<<<1, 1024, 0, st>>>(b.sp_off, R, res->piece_cap, (int *)B[14].p);
+  split_kernel<true><<<(unsigned)((R + 63) / 64), 64, 0, st>>>(b);
+  cudaEventRecord(ctx->ev[1], st);
+  ctx->launches += 3;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(res->sp_off, b.sp_off, ((size_t)R + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->split, b.split, Cn, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->val_cluster, b.val_cluster, Cn * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const uint64_t total = res->sp_off[R];
+  res->n_pieces = total;
+  lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "split(count+scan+emit)");
+  cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]); s2.jobs = (uint64_t)R; s2.algo_bytes = 30ull * Cn + 4ull * M + 32ull * total;
+  ctx->stats.push_back(s2);
+  if (total > res->piece_cap) return fail(ctx, LRA_B200_EOVERFLOW, "split_clusters_batch: piece capacity %llu too small, %llu needed", (unsigned long long)res->piece_cap, (unsigned long long)total);
+  if (total) {
+    CU(cudaMemcpyAsync(res->sp, b.sp, total * 24, cudaMemcpyDeviceToHost, st)); CU(cudaMemcpyAsync(res->sp_val, b.sp_val, total * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->sp_n0, b.sp_n0, total * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return LRA_B200_OK;
+}

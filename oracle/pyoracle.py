@@ -694,3 +694,25 @@ def clean_off_diagonal(q, t, qt, strand, opts, hdr_pos, which="port"):
     ncl = f(pad(q, np.uint32), pad(t, np.uint32), pad(qt, np.uint64), n, strand, ov, hdr, len(hdr), keep, freq, cnt, cl, clf)
     m = keep[:n] == 1
     return dict(kq=q[m], kt=t[m], kfreq=freq[:n][m], cl=cl[:7 * ncl].reshape(-1, 7).copy(), cl_freq=clf[:ncl].copy(), keep=keep[:n].copy(), freq=freq[:n].copy(), cnt=cnt[:n].copy())
+
+
+# ---------------------------------------------------------------- a9 SplitClusters + DecideSplitClustersValue (SplitClusters.h)
+
+def split_clusters(box, strand, freq, contig, mq, m_off, global_k, which="port"):
+    """The clusters of one read (box[n,4] = qStart,qEnd,tStart,tEnd; anchors' read positions mq per cluster, CartesianSort order).
+    Returns dict(split, val_cluster, sp[k,6] (qStart,qEnd,tStart,tEnd,strand,coarse), sp_val, sp_n0)."""
+    box = np.ascontiguousarray(box, np.uint32).reshape(-1); strand = np.ascontiguousarray(strand, np.uint8); freq = np.ascontiguousarray(freq, np.float32)
+    mq = np.ascontiguousarray(mq, np.uint32); m_off = np.ascontiguousarray(m_off, np.uint64)
+    n = len(strand)
+    L = ref() if which == "ref" else port()
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    f = _bind_once(L, "ref_split_clusters" if which == "ref" else "lra_oracle_split_clusters", C.c_long,
+                   [_u32p, _u8p, f32p, C.c_long, C.c_int, _u32p, _u64p, C.c_int, _u8p, _i32p, _u32p, _i32p, _i32p, C.c_long])
+    cap = 64 * (n + 1)
+    pad = lambda a, dt: a if len(a) else np.zeros(1, dt)
+    while True:
+        split = np.zeros(max(n, 1), np.uint8); vc = np.zeros(max(n, 1), np.int32); sp = np.zeros(6 * cap, np.uint32); sv = np.zeros(cap, np.int32); s0 = np.zeros(cap, np.int32)
+        ns = f(pad(box, np.uint32), pad(strand, np.uint8), pad(freq, np.float32), n, contig, pad(mq, np.uint32), m_off, global_k, split, vc, sp, sv, s0, cap)
+        if ns <= cap:
+            return dict(split=split[:n], val_cluster=vc[:n], sp=sp[:6 * ns].reshape(-1, 6).copy(), sp_val=sv[:ns].copy(), sp_n0=s0[:ns].copy())
+        cap = ns

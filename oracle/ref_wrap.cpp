@@ -442,4 +442,30 @@ long ref_clean_off_diagonal(uint32_t *q, uint32_t *t, const uint64_t *qt, long n
   return (long)clusters.size();
 }
 
+// ---- a9: SplitClusters + DecideSplitClustersValue (SplitClusters.h:63-248) on the clusters of one read.  Arguments as
+// oracle/split_clusters.c: lra_oracle_split_clusters (mt: genome positions of the anchors, only carried along).
+long ref_split_clusters(const uint32_t *box, const uint8_t *strand, const float *freq, long n, int contig, const uint32_t *mq, const uint64_t *m_off, int globalK,
+                        uint8_t *split, int32_t *val_cluster, uint32_t *sp, int32_t *sp_val, int32_t *sp_n0, long cap) {
+  ref_init_static();
+  Options opts; opts.globalK = globalK; opts.readType = contig ? Options::contig : Options::ccs;
+  Read read; read.unaligned = 0;
+  std::vector<Cluster> clusters(n), splitclusters;
+  for (long m = 0; m < n; m++) {
+    Cluster &c = clusters[m];
+    c.qStart = box[4 * m]; c.qEnd = box[4 * m + 1]; c.tStart = box[4 * m + 2]; c.tEnd = box[4 * m + 3]; c.strand = strand[m]; c.anchorfreq = freq[m]; c.Val = 0;
+    for (uint64_t i = m_off[m]; i < m_off[m + 1]; i++) { GenomePair gp; gp.first.pos = mq[i]; gp.second.pos = 0; c.matches.push_back(gp); }
+  }
+  SplitClusters(clusters, splitclusters, read, opts);
+  DecideSplitClustersValue(clusters, splitclusters, opts, read);
+  for (long m = 0; m < n; m++) { split[m] = clusters[m].split; val_cluster[m] = clusters[m].Val; }
+  const long ns = (long)splitclusters.size();
+  for (long k = 0; k < ns && k < cap; k++) {
+    const Cluster &c = splitclusters[k];
+    sp[6 * k] = c.qStart; sp[6 * k + 1] = c.qEnd; sp[6 * k + 2] = c.tStart; sp[6 * k + 3] = c.tEnd; sp[6 * k + 4] = c.strand; sp[6 * k + 5] = (uint32_t)c.coarse;
+    sp_val[k] = c.Val; sp_n0[k] = c.NumofAnchors0;
+  }
+  read.seq = NULL; read.qual = NULL;
+  return ns;
+}
+
 }  // extern "C"

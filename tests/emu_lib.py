@@ -259,3 +259,18 @@ def clean_off_diagonal(q, t, qt, list_off, strand, opt_values, hdr_pos):
                              np.ascontiguousarray(opt_values, np.int32), hdr, len(hdr), o["keep"], o["freq"], o["cnt"], o["cl"], o["cl_freq"], o["n_cl"])
     o["cl"] = o["cl"].reshape(-1, 7)
     return {k: (v[:n] if k == "n_cl" else v[:N]) for k, v in o.items()}
+
+
+def split_clusters(cl_off, box, strand, freq, m_off, mq, contig, global_k, cap=1 << 16):
+    L = lib()
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    L.emu_split_clusters.restype = C.c_long
+    L.emu_split_clusters.argtypes = [C.c_int, _u64p, _u32p, _u8p, f32p, _u64p, _u32p, C.c_int, C.c_int, _u8p, _i32p, _u64p, _u32p, _i32p, _i32p, C.c_uint64]
+    co = np.ascontiguousarray(cl_off, np.uint64); R, Cn = len(co) - 1, int(co[-1])
+    pad = lambda a, dt: np.ascontiguousarray(a, dt).reshape(-1) if len(a) else np.zeros(1, dt)
+    o = dict(split=np.zeros(max(Cn, 1), np.uint8), val_cluster=np.zeros(max(Cn, 1), np.int32), sp_off=np.zeros(R + 2, np.uint64), sp=np.zeros(6 * cap, np.uint32),
+             sp_val=np.zeros(cap, np.int32), sp_n0=np.zeros(cap, np.int32))
+    n = L.emu_split_clusters(R, co, pad(box, np.uint32), pad(strand, np.uint8), pad(freq, np.float32), np.ascontiguousarray(m_off, np.uint64), pad(mq, np.uint32), contig, global_k,
+                             o["split"], o["val_cluster"], o["sp_off"], o["sp"], o["sp_val"], o["sp_n0"], cap)
+    assert n <= cap
+    return dict(split=o["split"][:Cn], val_cluster=o["val_cluster"][:Cn], sp_off=o["sp_off"][:R + 1], sp=o["sp"][:6 * n].reshape(-1, 6), sp_val=o["sp_val"][:n], sp_n0=o["sp_n0"][:n])

@@ -280,6 +280,7 @@ inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 inline float __fsqrt_rn(float a) { volatile float r = __builtin_sqrtf(a); return r; }
 inline float __ll2float_rn(long long a) { volatile float r = (float)a; return r; }

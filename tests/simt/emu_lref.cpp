@@ -163,3 +163,20 @@ extern "C" int emu_clean_off_diagonal(const uint32_t *q, const uint32_t *t, cons
   if (n_lists) emu::launch(dim3((unsigned)((n_lists + 63) / 64)), dim3(64), 0, [&] { cod_kernel(b); });
   return 0;
 }
+
+// ---- a9 SplitClusters
+#include "split_kernels.cuh"
+extern "C" long emu_split_clusters(int R, const uint64_t *cl_off, const uint32_t *box, const uint8_t *strand, const float *freq, const uint64_t *m_off, const uint32_t *mq,
+                                   int contig, int globalK, uint8_t *split, int32_t *val_cluster, uint64_t *sp_off, uint32_t *sp, int32_t *sp_val, int32_t *sp_n0, uint64_t cap) {
+  const size_t Cn = (size_t)cl_off[R];
+  std::vector<uint32_t> sets(4 * Cn + 8);
+  std::vector<ScPoint> pts(4 * Cn + 8);
+  int err = 0;
+  SplitBatch b{R, contig, globalK, (const unsigned long long *)cl_off, box, strand, freq, (const unsigned long long *)m_off, mq, split, val_cluster,
+               (unsigned long long *)sp_off, sp, sp_val, sp_n0, cap, sets.data(), pts.data()};
+  if (R == 0) return 0;
+  emu::launch(dim3((unsigned)((R + 63) / 64)), dim3(64), 0, [&] { split_kernel<false>(b); });
+  emu::launch(dim3(1), dim3(1024), 0, [&] { seed_scan_kernel(b.sp_off, R, cap, &err); });
+  emu::launch(dim3((unsigned)((R + 63) / 64)), dim3(64), 0, [&] { split_kernel<true>(b); });
+  return (long)sp_off[R];
+}
