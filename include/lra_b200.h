@@ -447,6 +447,40 @@ typedef struct lra_b200_breakpoint_result {
 int lra_b200_refine_breakpoint_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads_fwd, const lra_b200_seq *reads_rc, const lra_b200_seq *genome,
                                      const lra_b200_breakpoints *bp, lra_b200_breakpoint_result *res);
 
+/* ---- a22  SetFromSegAlignment + AlignmentsOrder::Update + SimpleMapQV, batched over reads ------------------------------------
+ * Replaces, for every read of a batch, the tail of MapRead after the statistics: SegAlignmentGroup::SetFromSegAlignment (Alignment.h:944-983)
+ * for each alignment, AlignmentsOrder::Update (Alignment.h:1024-1062) at the points the pipeline calls it, and SimpleMapQV
+ * (Mapping_ultility.h:497-589).  Read r owns alignments grp_off[r] .. grp_off[r+1]; alignment g owns segments seg_off[g] .. seg_off[g+1] (the
+ * Alignment members value, NumOfAnchors0 / 1, nm, nmm, ndel, nins, strand).  update_at[upd_off[r] .. upd_off[r+1]) = how many of the read's
+ * alignments exist at each Update call, ascending (Map_lowacc.h:609: one entry, the total; Map_highacc.h:737,743: one per primary chain, then
+ * the total again); an Update that finds nothing new is a no-op (the reference reads past its index vector there).  bypass_clustering /
+ * read_type (0 ont, 1 clr, 2 ccs, 3 contig) / global_k are the Options fields SimpleMapQV reads (smallOpts at the call sites).
+ * In / out per segment: flag, typeofaln, issec (ISsecondary), supp (Supplymentary); out: mapq (mapqv).  Out per alignment: g_issec, g_value,
+ * g_n0, g_n1, g_nm[4] (nm, nmm, ndel, nins) and order (AlignmentsOrder::index, positions within the read).  The two logf terms are evaluated
+ * on the host with its libm, as in the reference. */
+typedef struct lra_b200_alignment_groups {
+  int32_t n_reads;
+  const int32_t *grp_off;       /* [n_reads + 1] */
+  const int32_t *seg_off;       /* [alignments + 1] */
+  const int32_t *upd_off;       /* [n_reads + 1] */
+  const int32_t *update_at;
+  const float *value;           /* per segment */
+  const int32_t *n0, *n1, *nm, *nmm, *ndel, *nins;
+  const uint8_t *strand;
+  int32_t bypass_clustering, read_type, global_k;
+} lra_b200_alignment_groups;
+
+typedef struct lra_b200_mapq_result {
+  int32_t *flag, *typeofaln;    /* per segment, in / out */
+  uint8_t *issec, *supp;        /* per segment, in / out */
+  int32_t *mapq;                /* per segment */
+  uint8_t *g_issec;             /* per alignment */
+  float *g_value;
+  int32_t *g_n0, *g_n1, *g_nm /* [alignments * 4] */, *order;
+} lra_b200_mapq_result;
+
+int lra_b200_mapq_batch(lra_b200_ctx *ctx, const lra_b200_alignment_groups *ag, lra_b200_mapq_result *res);
+
 /* ---- a24  GlobalChain over a PrioritySearchTree, batched over independent problems --------------------------------------
  * Replaces  int GlobalChain(vector<T_Fragment> &fragments, vector<int> &optFragmentChainIndices, vector<T_Endpoint> &endpoints)
  * (GlobalChain.h:88-189, with PrioritySearchTree.h:47-291) as the reference's driver TestGlobalChain.cpp:9-27 calls it.  Problem p:

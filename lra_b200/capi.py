@@ -112,6 +112,15 @@ class _SplitResult(C.Structure):
                 ("piece_cap", C.c_uint64), ("n_pieces", C.c_uint64)]
 
 
+class _AlignmentGroups(C.Structure):
+    _fields_ = [("n_reads", C.c_int32)] + [(k, C.c_void_p) for k in ["grp_off", "seg_off", "upd_off", "update_at", "value", "n0", "n1", "nm", "nmm", "ndel", "nins", "strand"]] + \
+               [("bypass_clustering", C.c_int32), ("read_type", C.c_int32), ("global_k", C.c_int32)]
+
+
+class _MapqResult(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ["flag", "typeofaln", "issec", "supp", "mapq", "g_issec", "g_value", "g_n0", "g_n1", "g_nm", "order"]]
+
+
 class _Refined(C.Structure):
     _fields_ = [("status", C.c_void_p), ("chrom", C.c_void_p), ("diag", C.c_void_p), ("r_off", C.c_void_p), ("r_q", C.c_void_p),
                 ("r_t", C.c_void_p), ("r_tup", C.c_void_p), ("anchor_cap", C.c_uint64), ("n_anchors", C.c_uint64), ("rbox", C.c_void_p),
@@ -171,6 +180,7 @@ def load_library():
     L.lra_b200_chain_filter_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_clean_off_diagonal_batch.argtypes = [C.c_void_p, C.POINTER(_AnchorLists), C.POINTER(_CleanOpts), C.POINTER(_CleanResult)]
     L.lra_b200_split_clusters_batch.argtypes = [C.c_void_p, C.POINTER(_ReadClusters), C.POINTER(_SplitResult)]
+    L.lra_b200_mapq_batch.argtypes = [C.c_void_p, C.POINTER(_AlignmentGroups), C.POINTER(_MapqResult)]
     L.lra_b200_lindex_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.POINTER(C.c_void_p)]
     L.lra_b200_lindex_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
@@ -439,6 +449,28 @@ class Context:
         r = _BreakpointResult(_ptr(o["mode"]), _ptr(o["n_out"]), _ptr(o["bound"]), _ptr(o["out"]), _ptr(o["refined"]))
         self._check(self.lib.lra_b200_refine_breakpoint_batch(self.h, reads_fwd.handle, reads_rc.handle, genome.handle, C.byref(b), C.byref(r)))
         return {k: v[:n] for k, v in o.items()}
+
+    # ---- a22
+    def mapq_batch(self, ag, bypass, read_type, global_k):
+        """SetFromSegAlignment + AlignmentsOrder::Update + SimpleMapQV for every read.  ag: dict(grp_off, seg_off, upd_off, update_at, value, n0, n1, nm,
+        nmm, ndel, nins, strand, flag, typeofaln, issec, supp).  Returns dict(flag, typeofaln, issec, supp, mapq, g_issec, g_value, g_n0, g_n1, g_nm, order)."""
+        i32 = lambda k: np.ascontiguousarray(ag[k], np.int32)
+        a = {k: i32(k) for k in ["grp_off", "seg_off", "upd_off", "update_at", "n0", "n1", "nm", "nmm", "ndel", "nins"]}
+        a["value"] = np.ascontiguousarray(ag["value"], np.float32); a["strand"] = np.ascontiguousarray(ag["strand"], np.uint8)
+        R = len(a["grp_off"]) - 1; G = int(a["grp_off"][-1]); S = int(a["seg_off"][G]) if G else 0
+        o = dict(flag=np.array(ag["flag"], np.int32), typeofaln=np.array(ag["typeofaln"], np.int32), issec=np.array(ag["issec"], np.uint8), supp=np.array(ag["supp"], np.uint8),
+                 mapq=np.zeros(max(S, 1), np.int32), g_issec=np.zeros(max(G, 1), np.uint8), g_value=np.zeros(max(G, 1), np.float32), g_n0=np.zeros(max(G, 1), np.int32),
+                 g_n1=np.zeros(max(G, 1), np.int32), g_nm=np.zeros((max(G, 1), 4), np.int32), order=np.zeros(max(G, 1), np.int32))
+        p = lambda x: _ptr(x) if x.size else None
+        g = _AlignmentGroups(R, p(a["grp_off"]), p(a["seg_off"]), p(a["upd_off"]), p(a["update_at"]), p(a["value"]), p(a["n0"]), p(a["n1"]), p(a["nm"]), p(a["nmm"]),
+                             p(a["ndel"]), p(a["nins"]), p(a["strand"]), bypass, read_type, global_k)
+        r = _MapqResult(p(o["flag"]), p(o["typeofaln"]), p(o["issec"]), p(o["supp"]), _ptr(o["mapq"]), _ptr(o["g_issec"]), _ptr(o["g_value"]), _ptr(o["g_n0"]),
+                        _ptr(o["g_n1"]), _ptr(o["g_nm"]), _ptr(o["order"]))
+        self._check(self.lib.lra_b200_mapq_batch(self.h, C.byref(g), C.byref(r)))
+        o["mapq"] = o["mapq"][:S]
+        for k in ("g_issec", "g_value", "g_n0", "g_n1", "g_nm", "order"):
+            o[k] = o[k][:G]
+        return o
 
     # ---- a24
     def global_chain_batch(self, frag, frag_off, score):

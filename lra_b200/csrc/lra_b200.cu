@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include <string>
 #include <vector>
 
@@ -24,6 +25,7 @@
 #include "chainf_kernels.cuh"
 #include "cod_kernels.cuh"
 #include "split_kernels.cuh"
+#include "mapq_kernels.cuh"
 
 using namespace lra;
 
@@ -61,6 +63,7 @@ struct lra_b200_ctx {
   DevBuf cf[9];           // chain filter scratch
   DevBuf cd[15];          // CleanOffDiagonal scratch
   DevBuf sc[15];          // SplitClusters scratch
+  DevBuf mq[25];          // ordering / MAPQ scratch
   bool keep_stats = false;  // sub-launchers append to stats instead of clearing
   AogPlan *h_plan = nullptr;            // pinned
   unsigned long long *h_misc = nullptr;  // pinned (2 x u64)
@@ -154,6 +157,7 @@ extern "C" void lra_b200_destroy(lra_b200_ctx *ctx) {
   for (DevBuf &b : ctx->cf) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->cd) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->sc) if (b.p) cudaFree(b.p);
+  for (DevBuf &b : ctx->mq) if (b.p) cudaFree(b.p);
   for (auto &ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < 4; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]); }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);

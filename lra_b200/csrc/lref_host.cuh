@@ -714,3 +714,76 @@ extern "C" int lra_b200_split_clusters_batch(lra_b200_ctx *ctx, const lra_b200_r
   }
   return LRA_B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- a22 ordering + MAPQ
+extern "C" int lra_b200_mapq_batch(lra_b200_ctx *ctx, const lra_b200_alignment_groups *ag, lra_b200_mapq_result *res) {
+  if (!ctx || !ag || !res || ag->n_reads < 0 || !ag->grp_off) return fail(ctx, LRA_B200_EINVAL, "mapq_batch: bad argument");
+  const int R = ag->n_reads;
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  if (R == 0) return LRA_B200_OK;
+  const size_t G = (size_t)ag->grp_off[R];
+  if (G == 0) return LRA_B200_OK;
+  if (!ag->seg_off || !ag->upd_off) return fail(ctx, LRA_B200_EINVAL, "mapq_batch: NULL offsets");
+  const size_t S = (size_t)ag->seg_off[G], U = (size_t)ag->upd_off[R];
+  // the two logf terms of SimpleMapQV, with the host libm (Mapping_ultility.h:527,563,576)
+  std::vector<float> logv(S + 1);
+  for (size_t s = 0; s < S; s++) logv[s] = ag->value[s] > 3 ? logf(ag->value[s] / ag->global_k) : 0;
+  std::vector<int32_t> lenpen((size_t)R);
+  for (int r = 0; r < R; r++) {
+    int len = 0, old = 0;
+    for (int u = ag->upd_off[r]; u < ag->upd_off[r + 1]; u++) {
+      const int c = ag->update_at[u];
+      if (c < old || c > ag->grp_off[r + 1] - ag->grp_off[r]) return fail(ctx, LRA_B200_EINVAL, "mapq_batch: update schedule of read %d not ascending / beyond its alignments", r);
+      old = c; len = c;
+    }
+    lenpen[r] = len > 0 ? (int)(4.343f * logf(len) + .499f) : 0;
+  }
+  int rc;
+  DevBuf *B = ctx->mq;
+  const size_t sz4 = S * 4 + 16;
+  if ((rc = ensure(ctx, B[0], ((size_t)R + 1) * 4)) || (rc = ensure(ctx, B[1], (G + 1) * 4)) || (rc = ensure(ctx, B[2], ((size_t)R + 1) * 4)) || (rc = ensure(ctx, B[3], U * 4 + 16)))
+    return rc;
+  for (int i = 4; i <= 12; i++) if ((rc = ensure(ctx, B[i], sz4))) return rc;       // value n0 n1 nm nmm ndel nins logv flag
+  if ((rc = ensure(ctx, B[13], sz4)) || (rc = ensure(ctx, B[14], S + 16)) || (rc = ensure(ctx, B[15], S + 16)) || (rc = ensure(ctx, B[16], S + 16)) || (rc = ensure(ctx, B[17], sz4)) ||
+      (rc = ensure(ctx, B[18], (size_t)R * 4)) || (rc = ensure(ctx, B[19], G + 16)) || (rc = ensure(ctx, B[20], G * 4 + 16)) || (rc = ensure(ctx, B[21], G * 4 + 16)) ||
+      (rc = ensure(ctx, B[22], G * 4 + 16)) || (rc = ensure(ctx, B[23], G * 16 + 16)) || (rc = ensure(ctx, B[24], G * 4 + 16)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(B[0].p, ag->grp_off, ((size_t)R + 1) * 4, cudaMemcpyHostToDevice, st)); CU(cudaMemcpyAsync(B[1].p, ag->seg_off, (G + 1) * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[2].p, ag->upd_off, ((size_t)R + 1) * 4, cudaMemcpyHostToDevice, st));
+  if (U) CU(cudaMemcpyAsync(B[3].p, ag->update_at, U * 4, cudaMemcpyHostToDevice, st));
+  const void *src4[9] = {ag->value, ag->n0, ag->n1, ag->nm, ag->nmm, ag->ndel, ag->nins, logv.data(), res->flag};
+  if (S) {
+    for (int i = 0; i < 9; i++) CU(cudaMemcpyAsync(B[4 + i].p, src4[i], S * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B[13].p, res->typeofaln, S * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B[14].p, ag->strand, S, cudaMemcpyHostToDevice, st)); CU(cudaMemcpyAsync(B[15].p, res->issec, S, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B[16].p, res->supp, S, cudaMemcpyHostToDevice, st));
+  }
+  CU(cudaMemcpyAsync(B[18].p, lenpen.data(), (size_t)R * 4, cudaMemcpyHostToDevice, st));
+  MapqBatch b;
+  b.n_reads = R; b.bypass = ag->bypass_clustering; b.read_type = ag->read_type;
+  b.grp_off = (const int32_t *)B[0].p; b.seg_off = (const int32_t *)B[1].p; b.upd_off = (const int32_t *)B[2].p; b.update_at = (const int32_t *)B[3].p;
+  b.value = (const float *)B[4].p; b.n0 = (const int32_t *)B[5].p; b.n1 = (const int32_t *)B[6].p; b.nm = (const int32_t *)B[7].p; b.nmm = (const int32_t *)B[8].p;
+  b.ndel = (const int32_t *)B[9].p; b.nins = (const int32_t *)B[10].p; b.logv = (const float *)B[11].p; b.flag = (int32_t *)B[12].p; b.typeofaln = (int32_t *)B[13].p;
+  b.strand = (const uint8_t *)B[14].p; b.issec = (uint8_t *)B[15].p; b.supp = (uint8_t *)B[16].p; b.mapq = (int32_t *)B[17].p; b.lenpen = (const int32_t *)B[18].p;
+  b.g_issec = (uint8_t *)B[19].p; b.g_value = (float *)B[20].p; b.g_n0 = (int32_t *)B[21].p; b.g_n1 = (int32_t *)B[22].p; b.g_nm = (int32_t *)B[23].p; b.order = (int32_t *)B[24].p;
+  cudaEventRecord(ctx->ev[0], st);
+  mapq_kernel<<<(unsigned)((R + 63) / 64), 64, 0, st>>>(b);
+  cudaEventRecord(ctx->ev[1], st);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  if (S) {
+    CU(cudaMemcpyAsync(res->flag, b.flag, S * 4, cudaMemcpyDeviceToHost, st)); CU(cudaMemcpyAsync(res->typeofaln, b.typeofaln, S * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->issec, b.issec, S, cudaMemcpyDeviceToHost, st)); CU(cudaMemcpyAsync(res->supp, b.supp, S, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->mapq, b.mapq, S * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaMemcpyAsync(res->g_issec, b.g_issec, G, cudaMemcpyDeviceToHost, st)); CU(cudaMemcpyAsync(res->g_value, b.g_value, G * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->g_n0, b.g_n0, G * 4, cudaMemcpyDeviceToHost, st)); CU(cudaMemcpyAsync(res->g_n1, b.g_n1, G * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->g_nm, b.g_nm, G * 16, cudaMemcpyDeviceToHost, st)); CU(cudaMemcpyAsync(res->order, b.order, G * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "mapq");
+  cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]); s2.jobs = (uint64_t)R; s2.algo_bytes = 60ull * S + 40ull * G;
+  ctx->stats.push_back(s2);
+  return LRA_B200_OK;
+}

@@ -716,3 +716,30 @@ def split_clusters(box, strand, freq, contig, mq, m_off, global_k, which="port")
         if ns <= cap:
             return dict(split=split[:n], val_cluster=vc[:n], sp=sp[:6 * ns].reshape(-1, 6).copy(), sp_val=sv[:ns].copy(), sp_n0=s0[:ns].copy())
         cap = ns
+
+
+# ---------------------------------------------------------------- a22 SetFromSegAlignment / AlignmentsOrder / SimpleMapQV
+
+def mapq(rd, bypass, read_type, K, which="port"):
+    """One read: rd = dict(seg_off, value, n0, n1, nm, nmm, ndel, nins, strand, flag, typeofaln, issec, supp, update_at).
+    Returns dict(flag, typeofaln, issec, supp, mapq per segment; g_issec, g_value, g_n0, g_n1, g_nm[g,4], order per group)."""
+    so = np.ascontiguousarray(rd["seg_off"], np.int32); G = len(so) - 1; S = int(so[-1])
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    L = ref() if which == "ref" else port()
+    f = _bind_once(L, "ref_mapq" if which == "ref" else "lra_oracle_mapq", None,
+                   [C.c_int, _i32p, f32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _u8p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                    _i32p, _i32p, _u8p, _u8p, _i32p, _u8p, f32p, _i32p, _i32p, _i32p, _i32p])
+    pad = lambda a, dt: np.ascontiguousarray(a, dt).copy() if len(a) else np.zeros(1, dt)
+    i32 = lambda k: pad(rd[k], np.int32)
+    o = dict(flag=i32("flag"), typeofaln=i32("typeofaln"), issec=pad(rd["issec"], np.uint8), supp=pad(rd["supp"], np.uint8), mapq=np.zeros(max(S, 1), np.int32),
+             g_issec=np.zeros(max(G, 1), np.uint8), g_value=np.zeros(max(G, 1), np.float32), g_n0=np.zeros(max(G, 1), np.int32), g_n1=np.zeros(max(G, 1), np.int32),
+             g_nm=np.zeros(4 * max(G, 1), np.int32), order=np.full(max(G, 1), -1, np.int32))
+    ua = pad(rd["update_at"], np.int32)
+    f(G, so, pad(rd["value"], np.float32), i32("n0"), i32("n1"), i32("nm"), i32("nmm"), i32("ndel"), i32("nins"), pad(rd["strand"], np.uint8), ua, len(rd["update_at"]),
+      bypass, read_type, K, o["flag"], o["typeofaln"], o["issec"], o["supp"], o["mapq"], o["g_issec"], o["g_value"], o["g_n0"], o["g_n1"], o["g_nm"], o["order"])
+    for k in ("flag", "typeofaln", "issec", "supp", "mapq"):
+        o[k] = o[k][:S]
+    for k in ("g_issec", "g_value", "g_n0", "g_n1", "order"):
+        o[k] = o[k][:G]
+    o["g_nm"] = o["g_nm"][:4 * G].reshape(-1, 4)
+    return o

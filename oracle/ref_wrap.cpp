@@ -468,4 +468,43 @@ long ref_split_clusters(const uint32_t *box, const uint8_t *strand, const float 
   return ns;
 }
 
+// ---- a22: SetFromSegAlignment / AlignmentsOrder::Update / SimpleMapQV (Alignment.h:944-1062, Mapping_ultility.h:497-589) for one read.
+// Arguments as oracle/mapq.c: lra_oracle_mapq.
+void ref_mapq(int n_groups, const int32_t *seg_off, const float *value, const int32_t *n0, const int32_t *n1, const int32_t *nm, const int32_t *nmm, const int32_t *ndel,
+              const int32_t *nins, const uint8_t *strand, const int32_t *update_at, int n_updates, int bypass, int read_type, int K,
+              int32_t *flag, int32_t *typeofaln, uint8_t *issec, uint8_t *supp, int32_t *mapq,
+              uint8_t *g_issec, float *g_value, int32_t *g_n0, int32_t *g_n1, int32_t *g_nm, int32_t *order) {
+  Options opts; opts.bypassClustering = bypass != 0; opts.globalK = K;
+  opts.readType = read_type == 0 ? Options::ont : read_type == 1 ? Options::clr : read_type == 2 ? Options::ccs : Options::contig;
+  Read read; read.unaligned = 0;
+  std::vector<SegAlignmentGroup> alignments;
+  alignments.reserve(n_groups + 1);
+  AlignmentsOrder ao(&alignments);
+  std::vector<Alignment *> all;
+  int u = 0;
+  for (int g = 0; g <= n_groups; g++) {
+    while (u < n_updates && update_at[u] == g) { if (g > ao.Oldend) ao.Update(&alignments); u++; }
+    if (g == n_groups) break;
+    alignments.resize(alignments.size() + 1);
+    for (int s = seg_off[g]; s < seg_off[g + 1]; s++) {
+      Alignment *a = new Alignment();
+      a->value = value[s]; a->NumOfAnchors0 = n0[s]; a->NumOfAnchors1 = n1[s]; a->nm = nm[s]; a->nmm = nmm[s]; a->ndel = ndel[s]; a->nins = nins[s];
+      a->strand = strand[s]; a->flag = flag[s]; a->typeofaln = typeofaln[s]; a->ISsecondary = issec[s]; a->Supplymentary = supp[s];
+      alignments.back().SegAlignment.push_back(a); all.push_back(a);
+    }
+    alignments.back().SetFromSegAlignment(opts);
+  }
+  SimpleMapQV(ao, read, opts);
+  for (size_t s = 0; s < all.size(); s++) {
+    flag[s] = all[s]->flag; typeofaln[s] = all[s]->typeofaln; issec[s] = all[s]->ISsecondary; supp[s] = all[s]->Supplymentary; mapq[s] = all[s]->mapqv;
+  }
+  for (int g = 0; g < n_groups; g++) {
+    g_issec[g] = alignments[g].ISsecondary; g_value[g] = alignments[g].value; g_n0[g] = alignments[g].NumOfAnchors0; g_n1[g] = alignments[g].NumOfAnchors1;
+    g_nm[4 * g] = alignments[g].nm; g_nm[4 * g + 1] = alignments[g].nmm; g_nm[4 * g + 2] = alignments[g].ndel; g_nm[4 * g + 3] = alignments[g].nins;
+  }
+  for (size_t i = 0; i < ao.index.size(); i++) order[i] = ao.index[i];
+  for (Alignment *a : all) delete a;
+  read.seq = NULL; read.qual = NULL;
+}
+
 }  // extern "C"

@@ -274,3 +274,20 @@ def split_clusters(cl_off, box, strand, freq, m_off, mq, contig, global_k, cap=1
                              o["split"], o["val_cluster"], o["sp_off"], o["sp"], o["sp_val"], o["sp_n0"], cap)
     assert n <= cap
     return dict(split=o["split"][:Cn], val_cluster=o["val_cluster"][:Cn], sp_off=o["sp_off"][:R + 1], sp=o["sp"][:6 * n].reshape(-1, 6), sp_val=o["sp_val"][:n], sp_n0=o["sp_n0"][:n])
+
+
+def mapq(ag, logv, lenpen, bypass, read_type):
+    L = lib()
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    L.emu_mapq.argtypes = [C.c_int, _i32p, _i32p, _i32p, _i32p, f32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _u8p, f32p, _i32p, C.c_int, C.c_int, _i32p, _i32p, _u8p, _u8p,
+                           _i32p, _u8p, f32p, _i32p, _i32p, _i32p, _i32p]
+    i32 = lambda k: np.ascontiguousarray(ag[k], np.int32)
+    G = int(ag["grp_off"][-1]); S = int(ag["seg_off"][G]); R = len(ag["grp_off"]) - 1
+    o = dict(flag=np.array(ag["flag"], np.int32), typeofaln=np.array(ag["typeofaln"], np.int32), issec=np.array(ag["issec"], np.uint8), supp=np.array(ag["supp"], np.uint8),
+             mapq=np.zeros(S, np.int32), g_issec=np.zeros(G, np.uint8), g_value=np.zeros(G, np.float32), g_n0=np.zeros(G, np.int32), g_n1=np.zeros(G, np.int32),
+             g_nm=np.zeros(4 * G, np.int32), order=np.zeros(G, np.int32))
+    L.emu_mapq(R, i32("grp_off"), i32("seg_off"), i32("upd_off"), i32("update_at"), np.ascontiguousarray(ag["value"], np.float32), i32("n0"), i32("n1"), i32("nm"), i32("nmm"),
+               i32("ndel"), i32("nins"), np.ascontiguousarray(ag["strand"], np.uint8), np.ascontiguousarray(logv, np.float32), np.ascontiguousarray(lenpen, np.int32), bypass,
+               read_type, o["flag"], o["typeofaln"], o["issec"], o["supp"], o["mapq"], o["g_issec"], o["g_value"], o["g_n0"], o["g_n1"], o["g_nm"], o["order"])
+    o["g_nm"] = o["g_nm"].reshape(-1, 4)
+    return o

@@ -180,3 +180,15 @@ extern "C" long emu_split_clusters(int R, const uint64_t *cl_off, const uint32_t
   emu::launch(dim3((unsigned)((R + 63) / 64)), dim3(64), 0, [&] { split_kernel<true>(b); });
   return (long)sp_off[R];
 }
+
+// ---- a22 ordering + MAPQ (logv / lenpen are host-computed inputs, as in lref_host.cuh)
+#include "mapq_kernels.cuh"
+extern "C" int emu_mapq(int R, const int32_t *grp_off, const int32_t *seg_off, const int32_t *upd_off, const int32_t *update_at, const float *value, const int32_t *n0,
+                        const int32_t *n1, const int32_t *nm, const int32_t *nmm, const int32_t *ndel, const int32_t *nins, const uint8_t *strand, const float *logv,
+                        const int32_t *lenpen, int bypass, int read_type, int32_t *flag, int32_t *typeofaln, uint8_t *issec, uint8_t *supp, int32_t *mapq, uint8_t *g_issec,
+                        float *g_value, int32_t *g_n0, int32_t *g_n1, int32_t *g_nm, int32_t *order) {
+  MapqBatch b{R, bypass, read_type, grp_off, seg_off, upd_off, update_at, value, n0, n1, nm, nmm, ndel, nins, strand, logv, lenpen, flag, typeofaln, issec, supp, mapq,
+              g_issec, g_value, g_n0, g_n1, g_nm, order};
+  if (R) emu::launch(dim3((unsigned)((R + 63) / 64)), dim3(64), 0, [&] { mapq_kernel(b); });
+  return 0;
+}
