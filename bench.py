@@ -9,8 +9,9 @@ over the work those reads generate in the reference:
                               of this profile, job content synthetic; tools/workload.py make_jobs)
   a19  IndelRefineAlignment   one segment per read (block list = gap-free runs of the read's true alignment; make_segments)
   a12  LocalIndex::IndexSeq   both strands of every read (CreateRC included): the per-read two-strand local index
-  a13  REFINEclusters         one cluster per read (anchors = the exact >= 17-base stretches of its alignment; make_clusters) against the
-                              LocalIndex of the 3 Gb genome (built once, on the GPU, outside the timed region like the reference's .gli load)
+  a13  Refine_splitchain      (the low-accuracy pipeline's local refinement, ONT is low-accuracy) one split chain per read (anchors = the exact
+                              >= 17-base stretches of its alignment with their lengths; make_clusters) against the LocalIndex of the 3 Gb genome
+                              (built once, on the GPU, outside the timed region like the reference's .gli load)
   a21  CalculateStatistics    CIGAR + NV of every segment a19 refined
 The metric is named "reads/sec (<stages>)" until every stage of MapRead is covered: it is NOT a whole-aligner reads/sec
 yet and is not presented as one.  `--impl reference` runs the reference's own CPU code for the same stages on the same
@@ -38,7 +39,7 @@ for p in (ROOT, os.path.join(ROOT, "tools")):
 import workload  # noqa: E402
 
 PROFILE = "ont"
-STAGES = ["a12:LocalIndex::IndexSeq", "a13:REFINEclusters", "a18:AffineOneGapAlign", "a19:IndelRefineAlignment", "a21:CalculateStatistics"]
+STAGES = ["a12:LocalIndex::IndexSeq", "a13:Refine_splitchain", "a18:AffineOneGapAlign", "a19:IndelRefineAlignment", "a21:CalculateStatistics"]
 WORKLOAD = ("BASELINE configs[1]: synthetic ONT reads (N50 20 kb, 8%% err) vs 3 Gb synthetic ref (24 x 125 Mb), -ONT; per step %d reads: "
             "their AffineOneGapAlign job stream (%.1f jobs/read, shapes captured from the reference) and one IndelRefineAlignment "
             "segment per read; local index of both strands of every read, one cluster per read refined against the genome's local index, "
@@ -198,10 +199,11 @@ def cpu_stage_rates(args, jobs, segs, jobs_per_read, budget_s):
         cl = workload.make_clusters(segs, compact=True)
         comp = np.zeros(256, np.uint8); comp[[65, 67, 71, 84, 78]] = [84, 71, 67, 65, 78]
         ta = segs["t_arena_compact"]; hdr = cl["hdr_pos"]
-        contigs = [ta[int(hdr[i]):int(hdr[i + 1])] for i in range(n)]
+        contigs = [ta[int(hdr[i]):int(hdr[i + 1])] for i in range(n)] + [ta[int(hdr[-2]):int(hdr[-1])]]
+        hdr = np.concatenate([hdr[:n + 1], [hdr[n] + np.uint64(len(contigs[-1]))]]).astype(np.uint64)
         glh = po.RefLocalIndexHandle(contigs) if which == "ref" else None
         gl = po.local_index(contigs, which="port") if which == "port" else None
-        hdr_n = np.ascontiguousarray(hdr[:n + 1])
+        hdr_n = np.ascontiguousarray(hdr)
 
         def one_read(i):
             qb = int(segs["q_base"][i]); L = int(segs["read_len"][i])
@@ -209,13 +211,15 @@ def cpu_stage_rates(args, jobs, segs, jobs_per_read, budget_s):
             a, b = int(cl["m_off"][i]), int(cl["m_off"][i + 1])
             if which == "ref":
                 f = po.RefLocalIndexHandle(r); v = po.RefLocalIndexHandle(rc)
-                if "a13" in stages:
-                    po.refine_cluster(cl["m_q"][a:b], cl["m_t"][a:b], cl["box"][i], 0, L, hdr_n, None, None, None, 17, which="ref", ref_handles=(glh.h, f.h, v.h))
+                if "a13" in stages and cl["chain_ok"][i]:
+                    po.refine_splitchain(cl["m_q"][a:b], cl["m_t"][a:b], cl["m_len"][a:b], cl["m_strand"][a:b], cl["chain_box"][i], int(cl["chrom"][i]), 0, L, hdr_n,
+                                         None, None, None, 17, which="ref", ref_handles=(glh.h, f.h, v.h))
                 f.close(); v.close()
             else:
                 f = po.local_index(r); v = po.local_index(rc)
-                if "a13" in stages:
-                    po.refine_cluster(cl["m_q"][a:b], cl["m_t"][a:b], cl["box"][i], 0, L, hdr_n, gl, f, v, 17, which="port")
+                if "a13" in stages and cl["chain_ok"][i]:
+                    po.refine_splitchain(cl["m_q"][a:b], cl["m_t"][a:b], cl["m_len"][a:b], cl["m_strand"][a:b], cl["chain_box"][i], int(cl["chrom"][i]), 0, L, hdr_n,
+                                         gl, f, v, 17, which="port")
 
         def one3():
             t0 = time.perf_counter()
@@ -380,11 +384,23 @@ def main():
                 I["read_off"] = np.ascontiguousarray(sg["q_base"].astype(np.uint64)); I["read_len_u"] = np.ascontiguousarray(sg["read_len"].astype(np.uint32))
             if "a13" in stages:
                 cl = workload.make_clusters(sg, genome_len=args.genome_len)
+                if not cl["chain_ok"].all():          # a chain across a contig boundary never reaches Refine_splitchain: make it empty
+                    keepa = np.repeat(cl["chain_ok"], np.diff(cl["m_off"].astype(np.int64)))
+                    for key in ["m_q", "m_t", "m_len", "m_strand"]:
+                        cl[key] = cl[key][keepa]
+                    cnt = np.where(cl["chain_ok"], np.diff(cl["m_off"].astype(np.int64)), 0)
+                    cl["m_off"] = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint64)
+                cl["box"] = cl["chain_box"]
                 I["cl"] = cl
                 I["M"] = int(cl["m_off"][-1])
+                cl["chrom"] = np.ascontiguousarray(cl["chrom"], np.int32)
                 I["acap"] = int(sg["read_len"].sum()) // 2 + 4096
-                dc = {key: torch.from_numpy(np.ascontiguousarray(cl[key]).view(np.int32 if cl[key].dtype == np.uint32 else (np.int64 if cl[key].dtype == np.uint64 else np.uint8))).to(dev)
-                      for key in ["m_q", "m_t", "m_off", "box", "strand", "read_id", "hdr_pos"]}
+                I["rf_out"] = {}
+                for key, shape, dt in [("status", R, np.int32), ("chrom", R, np.int32), ("diag", 2 * R, np.int64), ("r_off", R + 1, np.uint64), ("r_q", I["acap"], np.uint32),
+                                       ("r_t", I["acap"], np.uint32), ("r_tup", I["acap"], np.uint32), ("rbox", 4 * R, np.uint32), ("eff", R, np.float32)]:
+                    I["rf_" + key + "_ot"], I["rf_out"][key] = pinned(np.zeros(shape, dt))
+                dc = {key: torch.from_numpy(np.ascontiguousarray(cl[key]).view(np.int32 if cl[key].dtype in (np.uint32, np.int32) else (np.int64 if cl[key].dtype == np.uint64 else np.uint8))).to(dev)
+                      for key in ["m_q", "m_t", "m_len", "m_strand", "m_off", "box", "strand", "chrom", "read_id", "hdr_pos"]}
                 for key, shape, dt in [("status", R, torch.int32), ("chrom", R, torch.int32), ("diag", 2 * R, torch.int64), ("r_off", R + 1, torch.int64),
                                        ("r_q", I["acap"], torch.int32), ("r_t", I["acap"], torch.int32), ("r_tup", I["acap"], torch.int32),
                                        ("rbox", 4 * R, torch.int32), ("eff", R, torch.float32)]:
@@ -392,6 +408,9 @@ def main():
                 I["dcl"] = dc
             if "a21" in stages:
                 I["ccap"] = 4 * I["T"] + 64 * R + 1024
+                I["st_out"] = {}
+                for key, shape, dt in [("stats", (R, 16), np.int32), ("value", R, np.float32), ("cigar_off", R + 1, np.uint64), ("cigar", I["ccap"], np.uint32)]:
+                    I["st_" + key + "_ot"], I["st_out"][key] = pinned(np.zeros(shape, dt))
                 d["st_stats"] = torch.empty(16 * R, dtype=torch.int32, device=dev); d["st_value"] = torch.empty(R, dtype=torch.float32, device=dev)
                 d["st_off"] = torch.empty(R + 1, dtype=torch.int64, device=dev); d["st_cigar"] = torch.empty(I["ccap"], dtype=torch.int32, device=dev)
             I["dev"] = d
@@ -455,11 +474,12 @@ def main():
             out["stats"] += st1
             if "a13" in stages:
                 dc = I["dcl"]; cl = I["cl"]
-                ctxb.refine_clusters_batch_device(gli, rf, rr, dict(m_q=dc["m_q"].data_ptr(), m_t=dc["m_t"].data_ptr(), m_off=dc["m_off"].data_ptr(),
-                                                                    box=dc["box"].data_ptr(), strand=dc["strand"].data_ptr(), read_id=dc["read_id"].data_ptr(),
-                                                                    hdr_pos=dc["hdr_pos"].data_ptr(), n_hdr=len(cl["hdr_pos"])),
-                                                  R, I["M"], (cl["global_k"], cl["small_k"], cl["window"], cl["local_max_freq"]),
-                                                  {k: dc["o_" + k].data_ptr() for k in ["status", "chrom", "diag", "r_off", "r_q", "r_t", "r_tup", "rbox", "eff"]}, I["acap"])
+                ctxb.refine_splitchains_batch_device(gli, rf, rr, dict(m_q=dc["m_q"].data_ptr(), m_t=dc["m_t"].data_ptr(), m_len=dc["m_len"].data_ptr(),
+                                                                       m_strand=dc["m_strand"].data_ptr(), m_off=dc["m_off"].data_ptr(), box=dc["box"].data_ptr(),
+                                                                       strand=dc["strand"].data_ptr(), chrom=dc["chrom"].data_ptr(), read_id=dc["read_id"].data_ptr(),
+                                                                       hdr_pos=dc["hdr_pos"].data_ptr(), n_hdr=len(cl["hdr_pos"])),
+                                                     R, I["M"], (cl["global_k"], cl["small_k"], cl["window"], cl["local_max_freq"], cl["limitrefine"]),
+                                                     {k: dc["o_" + k].data_ptr() for k in ["status", "chrom", "diag", "r_off", "r_q", "r_t", "r_tup", "rbox", "eff"]}, I["acap"])
                 out["stats"] += ctxb.kernel_stats()
 
     def run_groups(fa, fb, hb, oa, ob):
@@ -493,7 +513,7 @@ def main():
             if "a21" in stages:
                 nb = I["out"]["n_blocks"]; tot = int(r["n_blocks_total"])
                 o = ctx.calc_stats_batch(eseq_i, tseq, dict(blocks_in=I["out"]["blocks"][:tot], blk_off=I["out"]["block_off"], blk_cnt=nb, q_base=I["q_base"],
-                                                             t_base=I["t_base"], read_len=I["read_len"]), log_lut, cigar_cap=I["ccap"])
+                                                             t_base=I["t_base"], read_len=I["read_len"]), log_lut, cigar_cap=I["ccap"], out=I["st_out"])
                 h2d += 12 * tot + R * 24 + 2001 * 4
                 d2h += R * (64 + 4 + 8) + 4 * o["n_cigar_total"]
         acc["h2d"] += h2d; acc["d2h"] += d2h
@@ -507,9 +527,9 @@ def main():
             rr = keep["rr"] = ctxb.lindex_build(rc, I["read_off"], I["read_len_u"], reuse=keep["rr"])
             h2d += 2 * 12 * R
             if "a13" in stages:
-                o = ctxb.refine_clusters_batch(gli, rf, rr, I["cl"], anchor_cap=I["acap"])
-                h2d += 8 * I["M"] + R * (8 + 16 + 1 + 4)
-                d2h += R * (4 + 4 + 16 + 8 + 16 + 4 + 16) + 8 * I["M"] + 12 * o["n_anchors"]
+                o = ctxb.refine_splitchains_batch(gli, rf, rr, I["cl"], anchor_cap=I["acap"], out=I["rf_out"])
+                h2d += 13 * I["M"] + R * (8 + 16 + 1 + 4 + 4)
+                d2h += R * (4 + 4 + 16 + 8 + 16 + 4) + 12 * o["n_anchors"]
         acc["h2d"] += h2d; acc["d2h"] += d2h
 
     def step_e2e(hb):

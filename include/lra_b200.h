@@ -418,6 +418,45 @@ int lra_b200_refine_splitchains_batch_device(lra_b200_ctx *ctx, const lra_b200_l
 int lra_b200_chain_filter_batch(lra_b200_ctx *ctx, int32_t mode, const uint32_t *q, const uint32_t *t, const uint32_t *len, const uint8_t *strand,
                                 const uint64_t *chain_off, int32_t n_chains, uint8_t *keep);
 
+/* ---- a15  LinearExtend (low-accuracy pipeline), batched over reads --------------------------------------------------
+ * Replaces  void LinearExtend(GenomePairs *pairs, GenomePairs &Extendpairs, vector<int> &ExtendpairsMatchesLength, const Options&, Genome&, Read&,
+ *                             int chromIndex, bool strand, bool skipsorting, int K)            (LinearExtend.h:658-716, with Checkbp :50-84)
+ * followed by DecideCoordinates (:104-128) and, when trim != 0, TrimOverlappedAnchors(vector<Cluster>&, 0) (:573-647), as the two call sites
+ * of the low-accuracy pipeline use them: Map_lowacc.h:132-136 (every cluster, skipsorting = 1, trim = 0) and Map_lowacc.h:460-474 (the
+ * refined clusters of one split chain appended into one extended cluster: several parts per group, skipsorting = 0, trim = 1).
+ * Group g (one extended cluster) owns parts g_off[g] .. g_off[g+1]; part p (one input cluster) owns anchors p_off[p] .. p_off[p+1] of
+ * (q, t) -- t relative to the part's contig, which lies at chrom_off[p] (length chrom_len[p]) of the packed genome -- on strand
+ * p_strand[p] of the read at read_off[p] (length read_len[p]) of the read arena.  Strand and contig of a group are those of its last part.
+ * Results: extended anchors e_off[g] .. e_off[g+1] as (q, t, len) and box[4g..] = qStart, qEnd, tStart, tEnd (computed before trimming,
+ * as in the reference; zeros for a group without anchors).  The result arrays must hold one entry per input anchor (cap >= p_off[n_parts]);
+ * n_total = the number produced.  The input anchors are not modified (with skipsorting = 0 the reference leaves them diagonal-sorted). */
+typedef struct lra_b200_extend_parts {
+  int32_t n_groups;
+  const uint64_t *g_off;        /* [n_groups + 1] */
+  const uint64_t *p_off;        /* [n_parts + 1] */
+  const uint8_t *p_strand;      /* [n_parts] */
+  const uint64_t *chrom_off;    /* [n_parts] */
+  const uint32_t *chrom_len;
+  const uint64_t *read_off;     /* [n_parts] */
+  const uint32_t *read_len;
+  const uint32_t *q, *t;        /* [p_off[n_parts]] */
+  int32_t K;                    /* opts.globalK */
+  int32_t skipsorting;          /* 0: DiagonalSort every part first */
+  int32_t trim;                 /* 1: TrimOverlappedAnchors over every group */
+} lra_b200_extend_parts;
+
+typedef struct lra_b200_extended {
+  uint64_t *e_off;              /* [n_groups + 1] */
+  uint32_t *q, *t;              /* [cap] */
+  int32_t *len;                 /* [cap] */
+  uint64_t cap;
+  uint64_t n_total;             /* out */
+  uint32_t *box;                /* [n_groups * 4] */
+} lra_b200_extended;
+
+int lra_b200_linear_extend_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_extend_parts *in,
+                                 lra_b200_extended *res);
+
 /* ---- a20  RefineBreakpoint, batched over pairs of adjacent segments --------------------------------------------------
  * Replaces  void RefineBreakpoint(Read &read, Genome &genome, Alignment &leftAln, Alignment &rightAln, const Options &opts)
  * (RefineBreakpoint.h:212-462; called for consecutive segments of a split read, Map_highacc.h:725, Map_lowacc.h:592).  Pair p: the left /

@@ -78,6 +78,15 @@ class _SplitChains(C.Structure):
                 ("global_k", C.c_int32), ("small_k", C.c_int32), ("window", C.c_int32), ("local_max_freq", C.c_int64), ("limitrefine", C.c_int32)]
 
 
+class _ExtendParts(C.Structure):
+    _fields_ = [("n_groups", C.c_int32), ("g_off", C.c_void_p), ("p_off", C.c_void_p), ("p_strand", C.c_void_p), ("chrom_off", C.c_void_p), ("chrom_len", C.c_void_p),
+                ("read_off", C.c_void_p), ("read_len", C.c_void_p), ("q", C.c_void_p), ("t", C.c_void_p), ("K", C.c_int32), ("skipsorting", C.c_int32), ("trim", C.c_int32)]
+
+
+class _Extended(C.Structure):
+    _fields_ = [("e_off", C.c_void_p), ("q", C.c_void_p), ("t", C.c_void_p), ("len", C.c_void_p), ("cap", C.c_uint64), ("n_total", C.c_uint64), ("box", C.c_void_p)]
+
+
 class _Breakpoints(C.Structure):
     _fields_ = [("n_pairs", C.c_int32), ("lf", C.c_void_p), ("ll", C.c_void_p), ("rf", C.c_void_p), ("rl", C.c_void_p), ("lstrand", C.c_void_p),
                 ("rstrand", C.c_void_p), ("read_off", C.c_void_p), ("read_len", C.c_void_p), ("lchrom_off", C.c_void_p), ("rchrom_off", C.c_void_p),
@@ -177,6 +186,7 @@ def load_library():
     L.lra_b200_sort_matches_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_global_chain_batch.argtypes = [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 4
     L.lra_b200_refine_breakpoint_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Breakpoints), C.POINTER(_BreakpointResult)]
+    L.lra_b200_linear_extend_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_ExtendParts), C.POINTER(_Extended)]
     L.lra_b200_chain_filter_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_clean_off_diagonal_batch.argtypes = [C.c_void_p, C.POINTER(_AnchorLists), C.POINTER(_CleanOpts), C.POINTER(_CleanResult)]
     L.lra_b200_split_clusters_batch.argtypes = [C.c_void_p, C.POINTER(_ReadClusters), C.POINTER(_SplitResult)]
@@ -450,6 +460,27 @@ class Context:
         self._check(self.lib.lra_b200_refine_breakpoint_batch(self.h, reads_fwd.handle, reads_rc.handle, genome.handle, C.byref(b), C.byref(r)))
         return {k: v[:n] for k, v in o.items()}
 
+    # ---- a15
+    def linear_extend_batch(self, reads, genome, ep, K, skipsorting, trim):
+        """LinearExtend (GenomePairs overload) + DecideCoordinates [+ TrimOverlappedAnchors] for every group of parts (ep: dict(g_off, p_off, p_strand,
+        chrom_off, chrom_len, read_off, read_len, q, t)).  Returns dict(e_off, q, t, len, box[g,4])."""
+        a = {k: np.ascontiguousarray(ep[k], np.uint64) for k in ["g_off", "p_off", "chrom_off", "read_off"]}
+        a.update({k: np.ascontiguousarray(ep[k], np.uint32) for k in ["chrom_len", "read_len", "q", "t"]})
+        a["p_strand"] = np.ascontiguousarray(ep["p_strand"], np.uint8)
+        G = len(a["g_off"]) - 1; N = len(a["q"])
+        o = dict(e_off=np.zeros(G + 1, np.uint64), q=np.zeros(max(N, 1), np.uint32), t=np.zeros(max(N, 1), np.uint32), len=np.zeros(max(N, 1), np.int32),
+                 box=np.zeros((max(G, 1), 4), np.uint32))
+        p = lambda x: _ptr(x) if x.size else None
+        e = _ExtendParts(G, _ptr(a["g_off"]), p(a["p_off"]), p(a["p_strand"]), p(a["chrom_off"]), p(a["chrom_len"]), p(a["read_off"]), p(a["read_len"]), p(a["q"]), p(a["t"]),
+                         K, int(skipsorting), int(trim))
+        r = _Extended(_ptr(o["e_off"]), _ptr(o["q"]), _ptr(o["t"]), _ptr(o["len"]), max(N, 1), 0, _ptr(o["box"]))
+        self._check(self.lib.lra_b200_linear_extend_batch(self.h, reads.handle, genome.handle, C.byref(e), C.byref(r)))
+        n = int(r.n_total)
+        for k in ("q", "t", "len"):
+            o[k] = o[k][:n]
+        o["box"] = o["box"][:G]
+        return o
+
     # ---- a22
     def mapq_batch(self, ag, bypass, read_type, global_k):
         """SetFromSegAlignment + AlignmentsOrder::Update + SimpleMapQV for every read.  ag: dict(grp_off, seg_off, upd_off, update_at, value, n0, n1, nm,
@@ -541,7 +572,7 @@ class Context:
         self._check(self.lib.lra_b200_refine_clusters_batch_device(self.h, genome_li.handle, reads_fwd.handle, reads_rc.handle, C.byref(c), n_anchors_in, C.byref(r)))
         return dict(n_anchors=int(r.n_anchors), n_units=int(r.n_units), n_tasks=int(r.n_tasks))
 
-    def refine_splitchains_batch(self, genome_li, reads_fwd, reads_rc, sc, anchor_cap=None):
+    def refine_splitchains_batch(self, genome_li, reads_fwd, reads_rc, sc, anchor_cap=None, out=None):
         """Refine_splitchain over a batch (sc: dict(m_q, m_t, m_len, m_strand, m_off, box[n,4], strand, chrom, read_id, hdr_pos, global_k, small_k,
         window, local_max_freq, limitrefine)).  Returns dict(status, chrom, diag, r_off, r_q, r_t, r_tup, rbox, eff, n_anchors, n_units, n_tasks)."""
         n = len(sc["strand"])
@@ -553,9 +584,10 @@ class Context:
         M = int(a["m_off"][n]) if n else 0
         cap = anchor_cap if anchor_cap is not None else 4 * M + 4096
         for _ in range(2):
-            o = dict(status=np.zeros(n, np.int32), chrom=np.zeros(n, np.int32), diag=np.zeros(2 * n, np.int64), r_off=np.zeros(n + 1, np.uint64),
-                     r_q=np.zeros(cap, np.uint32), r_t=np.zeros(cap, np.uint32), r_tup=np.zeros(cap, np.uint32), rbox=np.zeros(4 * n, np.uint32),
-                     eff=np.zeros(n, np.float32))
+            # `out`: caller-owned (e.g. pinned) result arrays of the right sizes, re-used across batches
+            o = out if out is not None else dict(status=np.zeros(n, np.int32), chrom=np.zeros(n, np.int32), diag=np.zeros(2 * n, np.int64), r_off=np.zeros(n + 1, np.uint64),
+                                                 r_q=np.zeros(cap, np.uint32), r_t=np.zeros(cap, np.uint32), r_tup=np.zeros(cap, np.uint32), rbox=np.zeros(4 * n, np.uint32),
+                                                 eff=np.zeros(n, np.float32))
             c = _SplitChains(n, _ptr(a["m_q"]) if M else None, _ptr(a["m_t"]) if M else None, _ptr(a["m_len"]) if M else None, _ptr(a["m_strand"]) if M else None,
                              _ptr(a["m_off"]), _ptr(a["box"]), _ptr(a["strand"]), _ptr(a["chrom"]), _ptr(a["read_id"]), _ptr(a["hdr"]), len(a["hdr"]),
                              sc["global_k"], sc["small_k"], sc["window"], sc["local_max_freq"], sc.get("limitrefine", 1))
@@ -590,7 +622,7 @@ class Context:
         return int(res.n_cigar_total)
 
     # ---- a21
-    def calc_stats_batch(self, q, t, sb, log_lut, cigar_cap=None):
+    def calc_stats_batch(self, q, t, sb, log_lut, cigar_cap=None, out=None):
         """Alignment::CalculateStatistics over segments (sb as for indel_refine_batch: blocks_in, blk_off, blk_cnt, q_base, t_base,
         read_len).  Returns dict(stats[S,16], value[S], cigar_off[S+1], cigar)."""
         S = len(sb["blk_cnt"])
@@ -602,7 +634,7 @@ class Context:
         lut = np.ascontiguousarray(log_lut, np.float32)
         assert len(lut) == 2001
         cap = cigar_cap if cigar_cap is not None else 4 * (bi.size // 3) + 16 * S + 16
-        o = dict(stats=np.zeros((S, 16), np.int32), value=np.zeros(S, np.float32), cigar_off=np.zeros(S + 1, np.uint64), cigar=np.zeros(cap, np.uint32))
+        o = out if out is not None else dict(stats=np.zeros((S, 16), np.int32), value=np.zeros(S, np.float32), cigar_off=np.zeros(S + 1, np.uint64), cigar=np.zeros(cap, np.uint32))
         sg = _IrSegments(_ptr(bi), _ptr(a["blk_off"]), _ptr(a["blk_cnt"]), _ptr(a["q_base"]), _ptr(a["t_base"]), _ptr(a["read_len"]), _ptr(cl),
                          bi.size // 3, S, 0, 0, 0, 0, 0)
         res = _StatsResult(_ptr(o["stats"]), _ptr(o["value"]), _ptr(o["cigar_off"]), _ptr(o["cigar"]), cap, 0)

@@ -787,3 +787,117 @@ extern "C" int lra_b200_mapq_batch(lra_b200_ctx *ctx, const lra_b200_alignment_g
   ctx->stats.push_back(s2);
   return LRA_B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- a15 LinearExtend (low-accuracy pipeline)
+extern "C" int lra_b200_linear_extend_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_extend_parts *in,
+                                            lra_b200_extended *res) {
+  if (!ctx || !reads || !genome || !in || !res) return fail(ctx, LRA_B200_EINVAL, "linear_extend_batch: NULL argument");
+  const int G = in->n_groups;
+  if (G < 0 || !in->g_off || in->K <= 0) return fail(ctx, LRA_B200_EINVAL, "linear_extend_batch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  res->n_total = 0;
+  if (G == 0) { if (res->e_off) res->e_off[0] = 0; return LRA_B200_OK; }
+  const size_t P = (size_t)in->g_off[G];
+  if (P > 0x7FFFFFFFull) return fail(ctx, LRA_B200_EINVAL, "linear_extend_batch: more than 2^31 parts");
+  if (P && (!in->p_off || !in->p_strand || !in->chrom_off || !in->chrom_len || !in->read_off || !in->read_len))
+    return fail(ctx, LRA_B200_EINVAL, "linear_extend_batch: NULL part array");
+  const size_t N = P ? (size_t)in->p_off[P] : 0;
+  if (N > 0x7FFFFFF0ull) return fail(ctx, LRA_B200_EINVAL, "linear_extend_batch: more than 2^31 anchors in one batch");
+  if (N && (!in->q || !in->t)) return fail(ctx, LRA_B200_EINVAL, "linear_extend_batch: NULL anchors");
+  if (res->cap < N) { res->n_total = N; return fail(ctx, LRA_B200_EOVERFLOW, "linear_extend_batch: result arrays hold %llu anchors, %llu may be needed",
+                                                     (unsigned long long)res->cap, (unsigned long long)N); }
+  for (int g = 0; g < G; g++) if (in->g_off[g + 1] < in->g_off[g]) return fail(ctx, LRA_B200_EINVAL, "linear_extend_batch: group offsets not ascending");
+  std::vector<unsigned long long> slot(P ? P : 1);
+  size_t slots = 0;
+  for (size_t p = 0; p < P; p++) {
+    if (in->p_off[p + 1] < in->p_off[p]) return fail(ctx, LRA_B200_EINVAL, "linear_extend_batch: part offsets not ascending");
+    if (in->chrom_off[p] + in->chrom_len[p] > genome->n) return fail(ctx, LRA_B200_EINVAL, "linear_extend_batch: contig of part %zu ends beyond the genome arena", p);
+    if (in->read_off[p] + in->read_len[p] > reads->n) return fail(ctx, LRA_B200_EINVAL, "linear_extend_batch: read of part %zu ends beyond the read arena", p);
+    if (in->chrom_len[p] == 0) return fail(ctx, LRA_B200_EINVAL, "linear_extend_batch: part %zu lies on an empty contig", p);
+    const size_t n = (size_t)(in->p_off[p + 1] - in->p_off[p]);
+    size_t P2 = 1; while (P2 < n) P2 <<= 1;
+    slot[p] = slots;
+    if (!in->skipsorting && P2 > (size_t)kSortSmem) slots += P2;
+  }
+  int rc;
+  DevBuf *B = ctx->le;
+  const size_t Np = N ? N : 1, Pp = P ? P : 1;
+  if ((rc = ensure(ctx, B[0], ((size_t)G + 1) * 8)) || (rc = ensure(ctx, B[1], (Pp + 1) * 8)) || (rc = ensure(ctx, B[2], Pp)) || (rc = ensure(ctx, B[3], Pp * 8)) ||
+      (rc = ensure(ctx, B[4], Pp * 4)) || (rc = ensure(ctx, B[5], Pp * 8)) || (rc = ensure(ctx, B[6], Pp * 4)) || (rc = ensure(ctx, B[7], Np * 4)) ||
+      (rc = ensure(ctx, B[8], Np * 4)) || (rc = ensure(ctx, B[9], Np * 4)) || (rc = ensure(ctx, B[10], (Np + 2) * 8)) || (rc = ensure(ctx, B[11], Np * 4)) ||
+      (rc = ensure(ctx, B[12], Np * 4)) || (rc = ensure(ctx, B[13], Np * 4)) || (rc = ensure(ctx, B[14], ((size_t)G + 1) * 8)) || (rc = ensure(ctx, B[15], Np * 4)) ||
+      (rc = ensure(ctx, B[16], Np * 4)) || (rc = ensure(ctx, B[17], Np * 4)) || (rc = ensure(ctx, B[18], (size_t)G * 16)) || (rc = ensure(ctx, B[19], slots * 8 + 16)) ||
+      (rc = ensure(ctx, B[20], slots * 4 + 16)) || (rc = ensure(ctx, B[21], slots * 4 + 16)) || (rc = ensure(ctx, B[22], Pp * 8)) || (rc = ensure(ctx, B[23], 16)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(B[0].p, in->g_off, ((size_t)G + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (P) {
+    CU(cudaMemcpyAsync(B[1].p, in->p_off, (P + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B[2].p, in->p_strand, P, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B[3].p, in->chrom_off, P * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B[4].p, in->chrom_len, P * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B[5].p, in->read_off, P * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B[6].p, in->read_len, P * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B[22].p, slot.data(), P * 8, cudaMemcpyHostToDevice, st));
+  } else {
+    CU(cudaMemsetAsync(B[1].p, 0, 8, st));
+  }
+  if (N) {
+    CU(cudaMemcpyAsync(B[7].p, in->q, N * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B[8].p, in->t, N * 4, cudaMemcpyHostToDevice, st));
+  }
+  LextBatch b;
+  b.n_groups = G; b.n_parts = (long long)P; b.N = N; b.K = in->K; b.trim = in->trim;
+  b.reads = SeqView{reads->b2, reads->nm, reads->n}; b.genome = SeqView{genome->b2, genome->nm, genome->n};
+  b.g_off = (const unsigned long long *)B[0].p; b.p_off = (const unsigned long long *)B[1].p; b.p_strand = (const uint8_t *)B[2].p;
+  b.chrom_off = (const unsigned long long *)B[3].p; b.chrom_len = (const uint32_t *)B[4].p; b.read_off = (const unsigned long long *)B[5].p;
+  b.read_len = (const uint32_t *)B[6].p; b.q = (const uint32_t *)B[7].p; b.t = (const uint32_t *)B[8].p; b.part_of = (uint32_t *)B[9].p;
+  b.run = (unsigned long long *)B[10].p; b.end_q = (uint32_t *)B[11].p; b.end_t = (uint32_t *)B[12].p; b.lidx = (int *)B[13].p;
+  b.e_off = (unsigned long long *)B[14].p; b.eq = (uint32_t *)B[15].p; b.et = (uint32_t *)B[16].p; b.elen = (int32_t *)B[17].p; b.box = (uint32_t *)B[18].p;
+  auto rec = [&](int i) { cudaEventRecord(ctx->ev[i], st); };
+  rec(0);
+  if (!in->skipsorting && N) {                   // DiagonalSort<GenomeTuple> of every part (LinearExtend.h:663; Sorting.h:33-60)
+    SortBatch sb;
+    sb.n_seg = (int)P; sb.mode = 0; sb.seg_off = b.p_off; sb.q = (uint32_t *)B[7].p; sb.t = (uint32_t *)B[8].p; sb.perm = nullptr;
+    sb.kp = (unsigned long long *)B[19].p; sb.ks = (uint32_t *)B[20].p; sb.ki = (uint32_t *)B[21].p; sb.slot_off = (const unsigned long long *)B[22].p;
+    sort_pairs_kernel<<<(unsigned)P, 256, 0, st>>>(sb);
+    ctx->launches++;
+  }
+  rec(1);
+  if (N) {
+    const unsigned blocks = (unsigned)((N + 255) / 256);
+    lext_link_kernel<<<blocks, 256, 0, st>>>(b);
+    CU(cudaMemsetAsync(b.run + N, 0, 16, st));
+    seed_scan_kernel<<<1, 1024, 0, st>>>(b.run, (int)N, ~0ull, (int *)B[23].p);
+    lext_emit_kernel<<<blocks, 256, 0, st>>>(b);
+    ctx->launches += 3;
+  } else {
+    CU(cudaMemsetAsync(b.run, 0, 16, st));
+  }
+  rec(2);
+  lext_group_kernel<<<(unsigned)((G + 3) / 4), 128, 0, st>>>(b);
+  ctx->launches++;
+  rec(3);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(res->e_off, b.e_off, ((size_t)G + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->box, b.box, (size_t)G * 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const size_t n_out = (size_t)res->e_off[G];
+  res->n_total = n_out;
+  if (n_out) {
+    CU(cudaMemcpyAsync(res->q, b.eq, n_out * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->t, b.et, n_out * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->len, b.elen, n_out * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  const char *names[3] = {"lext_sort", "lext_link+scan+emit", "lext_group"};
+  for (int i = 0; i < 3; i++) {
+    if (i == 0 && (in->skipsorting || !N)) continue;
+    lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "%s", names[i]);
+    cudaEventElapsedTime(&s2.ms, ctx->ev[i], ctx->ev[i + 1]); s2.jobs = i == 2 ? (uint64_t)G : (uint64_t)N;
+    s2.algo_bytes = i == 0 ? 16ull * N : i == 1 ? 8ull * N + 12ull * n_out : 12ull * n_out + 16ull * (uint64_t)G;
+    ctx->stats.push_back(s2);
+  }
+  return LRA_B200_OK;
+}

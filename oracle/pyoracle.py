@@ -532,10 +532,10 @@ def refine_splitchain(mq, mt, mlen, mstrand, box, chrom, strand, read_len, hdr_p
         rq = np.zeros(cap, np.uint32); rt = np.zeros(cap, np.uint32); ru = np.zeros(cap, np.uint32)
         if which == "ref":
             L = ref()
-            L.ref_refine_splitchain.restype = C.c_long
-            L.ref_refine_splitchain.argtypes = [_u32p, _u32p, _u32p, _i32p, C.c_long, _u8p, C.c_int, _u32p, C.c_int, C.c_int, C.c_uint32, _u64p, C.c_int,
-                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, _u32p, _u32p, _u32p, C.c_long,
-                                                _i32p, _i64p, C.POINTER(C.c_float)]
+            _bind_once(L, "ref_refine_splitchain", C.c_long,
+                       [_u32p, _u32p, _u32p, _i32p, C.c_long, _u8p, C.c_int, _u32p, C.c_int, C.c_int, C.c_uint32, _u64p, C.c_int,
+                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, _u32p, _u32p, _u32p, C.c_long,
+                        _i32p, _i64p, C.POINTER(C.c_float)])
             # anchors of strand s live in cluster s: two clusters, each flipped once by the reference
             cluster_of = mstrand.astype(np.int32)
             m = L.ref_refine_splitchain(pad(mq, np.uint32), pad(mt, np.uint32), pad(mlen, np.uint32), pad(cluster_of, np.int32), n, np.array([0, 1], np.uint8), 2,
@@ -544,10 +544,10 @@ def refine_splitchain(mq, mt, mlen, mstrand, box, chrom, strand, read_len, hdr_p
             assert m >= 0, "the reference did not restore the clusters"
         else:
             L = port()
-            L.lra_oracle_refine_splitchain.restype = C.c_long
-            L.lra_oracle_refine_splitchain.argtypes = [_u32p, _u32p, _u32p, _u8p, C.c_long, _u32p, C.c_int, C.c_int, C.c_uint32, _u64p, C.c_int,
-                                                       _u64p, C.c_long, _u64p, _u32p, _u64p, C.c_long, _u64p, _u32p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int,
-                                                       _u32p, _u32p, _u32p, C.c_long, _i32p, _i64p, C.POINTER(C.c_float)]
+            _bind_once(L, "lra_oracle_refine_splitchain", C.c_long,
+                       [_u32p, _u32p, _u32p, _u8p, C.c_long, _u32p, C.c_int, C.c_int, C.c_uint32, _u64p, C.c_int,
+                        _u64p, C.c_long, _u64p, _u32p, _u64p, C.c_long, _u64p, _u32p, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int,
+                        _u32p, _u32p, _u32p, C.c_long, _i32p, _i64p, C.POINTER(C.c_float)])
             rd = rd_rev if strand else rd_fwd
             m = L.lra_oracle_refine_splitchain(pad(mq, np.uint32), pad(mt, np.uint32), pad(mlen, np.uint32), pad(mstrand, np.uint8), n, box, chrom, strand, read_len,
                                                hdr, len(hdr), gl.seq_off, len(gl.seq_off), gl.bnd, pad(gl.mins, np.uint32), rd.seq_off, len(rd.seq_off), rd.bnd,
@@ -742,4 +742,28 @@ def mapq(rd, bypass, read_type, K, which="port"):
     for k in ("g_issec", "g_value", "g_n0", "g_n1", "order"):
         o[k] = o[k][:G]
     o["g_nm"] = o["g_nm"][:4 * G].reshape(-1, 4)
+    return o
+
+
+# ---------------------------------------------------------------- a15 LinearExtend (pairs) / DecideCoordinates / TrimOverlappedAnchors (clusters)
+
+def linear_extend(read, genome, rd, K, skipsorting, trim, which="port"):
+    """One read (ASCII bytes / uint8 array) against `genome` (uint8 arena).  rd = dict(g_off[n_groups+1], p_off[n_parts+1], p_strand, chrom_off,
+    chrom_len (per part), q, t).  Returns dict(e_off, q, t, len, box[g,4], sorted_q, sorted_t)."""
+    go = np.ascontiguousarray(rd["g_off"], np.int32); po_ = np.ascontiguousarray(rd["p_off"], np.int32)
+    G = len(go) - 1; N = int(po_[-1])
+    L = ref() if which == "ref" else port()
+    f = _bind_once(L, "ref_linear_extend" if which == "ref" else "lra_oracle_linear_extend", C.c_long,
+                   [_u8p, C.c_int, _u8p, _u64p, _i32p, C.c_int, _i32p, _i32p, _u8p, _u32p, _u32p, C.c_int, C.c_int, C.c_int, _i32p, _u32p, _u32p, _i32p, _u32p])
+    pad = lambda a, dt: np.ascontiguousarray(a, dt).copy() if len(a) else np.zeros(1, dt)
+    q = pad(rd["q"], np.uint32); t = pad(rd["t"], np.uint32)
+    r = np.frombuffer(read, np.uint8) if isinstance(read, (bytes, bytearray)) else np.ascontiguousarray(read, np.uint8)
+    o = dict(e_off=np.zeros(G + 1, np.int32), q=np.zeros(max(N, 1), np.uint32), t=np.zeros(max(N, 1), np.uint32), len=np.zeros(max(N, 1), np.int32),
+             box=np.zeros(4 * max(G, 1), np.uint32))
+    n = f(r, len(r), np.ascontiguousarray(genome, np.uint8), pad(rd["chrom_off"], np.uint64), pad(rd["chrom_len"], np.int32), G, go, po_, pad(rd["p_strand"], np.uint8),
+          q, t, K, int(skipsorting), int(trim), o["e_off"], o["q"], o["t"], o["len"], o["box"])
+    for k in ("q", "t", "len"):
+        o[k] = o[k][:n]
+    o["box"] = o["box"][:4 * G].reshape(-1, 4)
+    o["sorted_q"], o["sorted_t"] = q[:N], t[:N]
     return o

@@ -507,4 +507,42 @@ void ref_mapq(int n_groups, const int32_t *seg_off, const float *value, const in
   read.seq = NULL; read.qual = NULL;
 }
 
+// ---- a15: LinearExtend (GenomePairs overload) + DecideCoordinates + TrimOverlappedAnchors(vector<Cluster>&) for one read, as Map_lowacc.h:132-136
+// (skipsorting = 1, trim = 0) and Map_lowacc.h:460-474 (skipsorting = 0, trim = 1) call them.  Arguments as oracle/linear_extend.c.
+long ref_linear_extend(const uint8_t *readseq, int read_len, const uint8_t *genome_arena, const uint64_t *chrom_off, const int32_t *chrom_len, int n_groups,
+                       const int32_t *g_off, const int32_t *p_off, const uint8_t *p_strand, uint32_t *q, uint32_t *t, int K, int skipsorting, int trim,
+                       int32_t *e_off, uint32_t *eq, uint32_t *et, int32_t *elen, uint32_t *box) {
+  ref_init_static();
+  Options opts; opts.globalK = K;
+  Read read; read.seq = (char *)readseq; read.length = read_len; read.unaligned = 0;
+  const int n_parts = g_off[n_groups];
+  Genome genome;
+  for (int p = 0; p < n_parts; p++) { genome.seqs.push_back((char *)genome_arena + chrom_off[p]); genome.lengths.push_back(chrom_len[p]); }
+  std::vector<Cluster> ext(n_groups);
+  for (int g = 0; g < n_groups; g++) {
+    bool st = 0; int chromIndex = 0;
+    for (int p = g_off[g]; p < g_off[g + 1]; p++) {
+      GenomePairs pairs(p_off[p + 1] - p_off[p]);
+      for (size_t i = 0; i < pairs.size(); i++) { pairs[i].first.pos = q[p_off[p] + i]; pairs[i].second.pos = t[p_off[p] + i]; }
+      st = p_strand[p]; chromIndex = p;       // every part carries its own contig entry
+      LinearExtend(&pairs, ext[g].matches, ext[g].matchesLengths, opts, genome, read, chromIndex, st, skipsorting != 0, K);
+      for (size_t i = 0; i < pairs.size(); i++) { q[p_off[p] + i] = pairs[i].first.pos; t[p_off[p] + i] = pairs[i].second.pos; }
+    }
+    ext[g].qStart = ext[g].qEnd = ext[g].tStart = ext[g].tEnd = 0;
+    DecideCoordinates(ext[g], st, chromIndex, 0.0f);
+    box[4 * g] = ext[g].qStart; box[4 * g + 1] = ext[g].qEnd; box[4 * g + 2] = ext[g].tStart; box[4 * g + 3] = ext[g].tEnd;
+    if (ext[g].matches.size() == 0) ext[g].strand = st;
+  }
+  if (trim) TrimOverlappedAnchors(ext, 0);
+  long no = 0;
+  for (int g = 0; g < n_groups; g++) {
+    e_off[g] = (int32_t)no;
+    for (size_t i = 0; i < ext[g].matches.size(); i++, no++) { eq[no] = ext[g].matches[i].first.pos; et[no] = ext[g].matches[i].second.pos; elen[no] = ext[g].matchesLengths[i]; }
+  }
+  e_off[n_groups] = (int32_t)no;
+  genome.seqs.clear();
+  read.seq = NULL; read.qual = NULL;
+  return no;
+}
+
 }  // extern "C"

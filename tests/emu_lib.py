@@ -291,3 +291,23 @@ def mapq(ag, logv, lenpen, bypass, read_type):
                read_type, o["flag"], o["typeofaln"], o["issec"], o["supp"], o["mapq"], o["g_issec"], o["g_value"], o["g_n0"], o["g_n1"], o["g_nm"], o["order"])
     o["g_nm"] = o["g_nm"].reshape(-1, 4)
     return o
+
+
+def linear_extend(read_arena, genome, ep, K, skipsorting, trim):
+    """read_arena / genome: ASCII arenas with 16 bytes of padding; ep as for Context.linear_extend_batch."""
+    L = lib()
+    L.emu_linear_extend.argtypes = [_u8p, C.c_uint64, _u8p, C.c_uint64, C.c_int, _u64p, _u64p, _u8p, _u64p, _u32p, _u64p, _u32p, _u32p, _u32p, C.c_int, C.c_int, C.c_int,
+                                    _u64p, _u32p, _u32p, _i32p, _u32p]
+    G = len(ep["g_off"]) - 1; N = len(ep["q"])
+    pad = lambda a, dt: np.ascontiguousarray(a, dt).copy() if len(a) else np.zeros(1, dt)
+    o = dict(e_off=np.zeros(G + 1, np.uint64), q=np.zeros(max(N, 1), np.uint32), t=np.zeros(max(N, 1), np.uint32), len=np.zeros(max(N, 1), np.int32),
+             box=np.zeros(4 * max(G, 1), np.uint32))
+    L.emu_linear_extend(read_arena, len(read_arena) - 16, genome, len(genome) - 16, G, np.ascontiguousarray(ep["g_off"], np.uint64), pad(ep["p_off"], np.uint64),
+                        pad(ep["p_strand"], np.uint8), pad(ep["chrom_off"], np.uint64), pad(ep["chrom_len"], np.uint32), pad(ep["read_off"], np.uint64),
+                        pad(ep["read_len"], np.uint32), pad(ep["q"], np.uint32), pad(ep["t"], np.uint32), K, int(skipsorting), int(trim), o["e_off"], o["q"], o["t"],
+                        o["len"], o["box"])
+    n = int(o["e_off"][G])
+    for k in ("q", "t", "len"):
+        o[k] = o[k][:n]
+    o["box"] = o["box"][:4 * G].reshape(-1, 4)
+    return o

@@ -192,3 +192,37 @@ extern "C" int emu_mapq(int R, const int32_t *grp_off, const int32_t *seg_off, c
   if (R) emu::launch(dim3((unsigned)((R + 63) / 64)), dim3(64), 0, [&] { mapq_kernel(b); });
   return 0;
 }
+
+// ---- a15 LinearExtend (pairs) + DecideCoordinates + TrimOverlappedAnchors
+#include "lext_kernels.cuh"
+extern "C" int emu_linear_extend(const uint8_t *reads, uint64_t rn, const uint8_t *genome, uint64_t gn, int n_groups, const uint64_t *g_off, const uint64_t *p_off,
+                                 const uint8_t *p_strand, const uint64_t *chrom_off, const uint32_t *chrom_len, const uint64_t *read_off, const uint32_t *read_len,
+                                 uint32_t *q, uint32_t *t, int K, int skipsorting, int trim, uint64_t *e_off, uint32_t *eq, uint32_t *et, int32_t *elen, uint32_t *box) {
+  Packed pr, pg; pack(reads, rn, pr); pack(genome, gn, pg);
+  const size_t P = (size_t)g_off[n_groups], N = P ? (size_t)p_off[P] : 0;
+  std::vector<uint32_t> part_of(N + 1), end_q(N + 1), end_t(N + 1);
+  std::vector<unsigned long long> run(N + 2, 0ull);
+  std::vector<int> lidx(N + 1);
+  if (!skipsorting && N) {
+    std::vector<unsigned long long> slot(P), kp; std::vector<uint32_t> ks, ki;
+    size_t slots = 0;
+    for (size_t p = 0; p < P; p++) { size_t n = p_off[p + 1] - p_off[p], P2 = 1; while (P2 < n) P2 <<= 1; slot[p] = slots; if (P2 > (size_t)kSortSmem) slots += P2; }
+    kp.resize(slots + 2); ks.resize(slots + 2); ki.resize(slots + 2);
+    SortBatch sb{(int)P, 0, (const unsigned long long *)p_off, q, t, nullptr, kp.data(), ks.data(), ki.data(), slot.data()};
+    emu::launch(dim3((unsigned)P), dim3(256), 0, [&] { sort_pairs_kernel(sb); });
+  }
+  LextBatch b;
+  b.n_groups = n_groups; b.n_parts = (long long)P; b.N = N; b.K = K; b.trim = trim; b.reads = pr.view; b.genome = pg.view;
+  b.g_off = (const unsigned long long *)g_off; b.p_off = (const unsigned long long *)p_off; b.p_strand = p_strand; b.chrom_off = (const unsigned long long *)chrom_off;
+  b.chrom_len = chrom_len; b.read_off = (const unsigned long long *)read_off; b.read_len = read_len; b.q = q; b.t = t; b.part_of = part_of.data(); b.run = run.data();
+  b.end_q = end_q.data(); b.end_t = end_t.data(); b.lidx = lidx.data(); b.e_off = (unsigned long long *)e_off; b.eq = eq; b.et = et; b.elen = elen; b.box = box;
+  if (N) {
+    const unsigned blocks = (unsigned)((N + 255) / 256);
+    int err = 0;
+    emu::launch(dim3(blocks), dim3(256), 0, [&] { lext_link_kernel(b); });
+    emu::launch(dim3(1), dim3(1024), 0, [&] { seed_scan_kernel(b.run, (int)N, ~0ull, &err); });
+    emu::launch(dim3(blocks), dim3(256), 0, [&] { lext_emit_kernel(b); });
+  }
+  if (n_groups) emu::launch(dim3((unsigned)((n_groups + 3) / 4)), dim3(128), 0, [&] { lext_group_kernel(b); });
+  return 0;
+}

@@ -199,13 +199,22 @@ def make_clusters(sg, global_k=17, compact=False, contig=125_000_000, genome_len
     t_base = (sg["t_base_compact"] if compact else sg["t_base"]).astype(np.int64)
     m_q = blocks[keep, 0].astype(np.uint32)
     m_t = (blocks[keep, 1].astype(np.int64) + t_base[seg_of[keep]]).astype(np.uint32)
+    m_len = blocks[keep, 2].astype(np.uint32)
     cnt = np.bincount(seg_of[keep], minlength=n)
     m_off = np.zeros(n + 1, np.uint64); m_off[1:] = np.cumsum(cnt)
     lo = m_off[:-1].astype(np.int64); hi = m_off[1:].astype(np.int64) - 1
     box = np.stack([m_q[lo], m_q[hi] + global_k, m_t[lo], m_t[hi] + global_k], 1).astype(np.uint32)
-    if compact:
-        hdr = np.append(sg["t_base_compact"].astype(np.uint64), np.uint64(len(sg["t_arena_compact"]) - 16))
+    if compact:      # one contig per read window, plus the 16 padding bases as a last dummy contig (no chain touches the genome's very last window)
+        hdr = np.append(sg["t_base_compact"].astype(np.uint64), [np.uint64(len(sg["t_arena_compact"]) - 16), np.uint64(len(sg["t_arena_compact"]))])
     else:
         hdr = np.append(np.arange(0, genome_len, contig, dtype=np.uint64), np.uint64(genome_len))
+    # the same anchors as a split chain of the low-accuracy pipeline (Refine_splitchain): anchor lengths = the exact stretches, boundaries with
+    # the lengths, the contig each chain lies on (chains across a contig boundary are dropped by the reference before this stage: empty here)
+    m_len[hi] = np.maximum(m_len[hi], 2) - 1          # keep TEnd strictly inside the contig (Header::Find(TEnd) of a chain ending exactly at a contig
+    last_len = m_len[hi]                                # end names the NEXT contig, and the reference drops such chains before this stage)
+    cbox = np.stack([m_q[lo], m_q[hi] + last_len, m_t[lo], m_t[hi] + last_len], 1).astype(np.uint32)
+    chrom = (np.searchsorted(hdr, cbox[:, 2], side="right") - 1).astype(np.int32)
+    ok = (np.searchsorted(hdr, cbox[:, 3], side="left") - 1) == chrom
     return dict(m_q=m_q, m_t=m_t, m_off=m_off, box=box, strand=np.zeros(n, np.uint8), read_id=np.arange(n, dtype=np.uint32), hdr_pos=hdr,
-                global_k=global_k, small_k=10, window=100, local_max_freq=15)
+                global_k=global_k, small_k=10, window=100, local_max_freq=15,
+                m_len=m_len, m_strand=np.zeros(len(m_q), np.uint8), chain_box=cbox, chrom=np.where(ok, chrom, 0).astype(np.int32), chain_ok=ok, limitrefine=1)
