@@ -442,7 +442,8 @@ typedef struct lra_b200_extend_parts {
   const uint32_t *q, *t;        /* [p_off[n_parts]] */
   int32_t K;                    /* opts.globalK */
   int32_t skipsorting;          /* 0: DiagonalSort every part first */
-  int32_t trim;                 /* 1: TrimOverlappedAnchors over every group */
+  int32_t trim;                 /* 1: TrimOverlappedAnchors(vector<Cluster>&) over every group; 2: its GenomePairs overload (anchors >= 50, forward;
+                                   LinearExtend.h:724-777, as LocalRefineAlignment.h:358-373 uses it on the anchors of one gap) */
 } lra_b200_extend_parts;
 
 typedef struct lra_b200_extended {
@@ -456,6 +457,53 @@ typedef struct lra_b200_extended {
 
 int lra_b200_linear_extend_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_extend_parts *in,
                                  lra_b200_extended *res);
+
+/* ---- a15  LinearExtend (high-accuracy pipeline: the vector<Cluster*> + chain overload), batched over chains --------------
+ * Replaces  LinearExtend_chain(chain, ExtendClusters, RefinedClusters, smallOpts, genome, read, start, overlap, skiprepetitive, K)
+ * (LinearExtend.h:782-792 = LinearExtend(vector<Cluster*>, vector<Cluster>&, vector<Tup> &chain, ...) :134-350 with CheckOverlap :87-101 and
+ * DecideCoordinates, then TrimOverlappedAnchors(ExtendClusters, start) :573-647; trim = 0 leaves the trimming out) for every chain of a batch
+ * (Map_highacc.h:571-582), and MergeMatchesSameDiag (:794-823, Map_highacc.h:642) over the result.
+ * Chain k owns entries ch_off[k] .. ch_off[k+1] of ch[] = cluster indices; cluster c owns anchors cl_off[c] .. cl_off[c+1] of (q, t) (t relative
+ * to its contig), cl_box[4c..] = qStart, qEnd, tStart, tEnd, strand, anchorfreq, contig and read as in lra_b200_extend_parts.  The anchors need
+ * not be sorted (DiagonalSort / AntiDiagonalSort by strand is part of the call; the input arrays are not modified).
+ * Results, one extended cluster per chain entry u (= ExtendClusters[start + c]): anchors e_off[u] .. e_off[u+1] as (q, t, len), ovp =
+ * Cluster::overlap, md_head = 1 where MergeMatchesSameDiag starts a new run (start[] = positions of the ones, end[] = the next one or the
+ * cluster's size), box, overlap[u] = what the entry adds to the reference's `overlap` counter.  An entry whose cluster has no anchors yields an
+ * empty extended cluster with a zero box.  cap must be >= the sum over entries of their clusters' sizes (n_total = that sum on
+ * LRA_B200_EOVERFLOW, else the number of anchors produced). */
+typedef struct lra_b200_extend_chains {
+  int32_t n_chains;
+  const uint64_t *ch_off;       /* [n_chains + 1] */
+  const uint32_t *ch;           /* [ch_off[n_chains]] */
+  int32_t n_clusters;
+  const uint64_t *cl_off;       /* [n_clusters + 1] */
+  const uint32_t *q, *t;        /* [cl_off[n_clusters]] */
+  const uint32_t *cl_box;       /* [n_clusters * 4] */
+  const uint8_t *cl_strand;     /* [n_clusters] */
+  const float *cl_freq;         /* [n_clusters] anchorfreq */
+  const uint64_t *chrom_off;    /* [n_clusters] */
+  const uint32_t *chrom_len;
+  const uint64_t *read_off;     /* [n_clusters] */
+  const uint32_t *read_len;
+  int32_t K;                    /* the K LinearExtend_chain is called with */
+  int32_t skiprepetitive;
+  int32_t trim;
+  int32_t merge_dist;           /* opts.merge_dist */
+} lra_b200_extend_chains;
+
+typedef struct lra_b200_extended_chains {
+  uint64_t *e_off;              /* [n_entries + 1] */
+  uint32_t *q, *t;              /* [cap] */
+  int32_t *len;                 /* [cap] */
+  uint8_t *ovp, *md_head;       /* [cap] */
+  uint64_t cap;
+  uint64_t n_total;             /* out */
+  uint32_t *box;                /* [n_entries * 4] */
+  int32_t *overlap;             /* [n_entries] */
+} lra_b200_extended_chains;
+
+int lra_b200_linear_extend_chains_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_extend_chains *in,
+                                        lra_b200_extended_chains *res);
 
 /* ---- a20  RefineBreakpoint, batched over pairs of adjacent segments --------------------------------------------------
  * Replaces  void RefineBreakpoint(Read &read, Genome &genome, Alignment &leftAln, Alignment &rightAln, const Options &opts)

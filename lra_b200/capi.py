@@ -87,6 +87,17 @@ class _Extended(C.Structure):
     _fields_ = [("e_off", C.c_void_p), ("q", C.c_void_p), ("t", C.c_void_p), ("len", C.c_void_p), ("cap", C.c_uint64), ("n_total", C.c_uint64), ("box", C.c_void_p)]
 
 
+class _ExtendChains(C.Structure):
+    _fields_ = [("n_chains", C.c_int32), ("ch_off", C.c_void_p), ("ch", C.c_void_p), ("n_clusters", C.c_int32), ("cl_off", C.c_void_p), ("q", C.c_void_p), ("t", C.c_void_p),
+                ("cl_box", C.c_void_p), ("cl_strand", C.c_void_p), ("cl_freq", C.c_void_p), ("chrom_off", C.c_void_p), ("chrom_len", C.c_void_p), ("read_off", C.c_void_p),
+                ("read_len", C.c_void_p), ("K", C.c_int32), ("skiprepetitive", C.c_int32), ("trim", C.c_int32), ("merge_dist", C.c_int32)]
+
+
+class _ExtendedChains(C.Structure):
+    _fields_ = [("e_off", C.c_void_p), ("q", C.c_void_p), ("t", C.c_void_p), ("len", C.c_void_p), ("ovp", C.c_void_p), ("md_head", C.c_void_p), ("cap", C.c_uint64),
+                ("n_total", C.c_uint64), ("box", C.c_void_p), ("overlap", C.c_void_p)]
+
+
 class _Breakpoints(C.Structure):
     _fields_ = [("n_pairs", C.c_int32), ("lf", C.c_void_p), ("ll", C.c_void_p), ("rf", C.c_void_p), ("rl", C.c_void_p), ("lstrand", C.c_void_p),
                 ("rstrand", C.c_void_p), ("read_off", C.c_void_p), ("read_len", C.c_void_p), ("lchrom_off", C.c_void_p), ("rchrom_off", C.c_void_p),
@@ -187,6 +198,7 @@ def load_library():
     L.lra_b200_global_chain_batch.argtypes = [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 4
     L.lra_b200_refine_breakpoint_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Breakpoints), C.POINTER(_BreakpointResult)]
     L.lra_b200_linear_extend_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_ExtendParts), C.POINTER(_Extended)]
+    L.lra_b200_linear_extend_chains_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_ExtendChains), C.POINTER(_ExtendedChains)]
     L.lra_b200_chain_filter_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_clean_off_diagonal_batch.argtypes = [C.c_void_p, C.POINTER(_AnchorLists), C.POINTER(_CleanOpts), C.POINTER(_CleanResult)]
     L.lra_b200_split_clusters_batch.argtypes = [C.c_void_p, C.POINTER(_ReadClusters), C.POINTER(_SplitResult)]
@@ -479,6 +491,28 @@ class Context:
         for k in ("q", "t", "len"):
             o[k] = o[k][:n]
         o["box"] = o["box"][:G]
+        return o
+
+    def linear_extend_chains_batch(self, reads, genome, cd, K, skiprepetitive=1, trim=1, merge_dist=100):
+        """LinearExtend_chain (the high-accuracy overload) + MergeMatchesSameDiag for every chain (cd: dict(ch_off, ch, cl_off, q, t, box[n,4], strand, freq,
+        chrom_off, chrom_len, read_off, read_len)).  Returns dict(e_off, q, t, len, ovp, md_head, box[u,4], overlap[u])."""
+        a = {k: np.ascontiguousarray(cd[k], np.uint64) for k in ["ch_off", "cl_off", "chrom_off", "read_off"]}
+        a.update({k: np.ascontiguousarray(cd[k], np.uint32).reshape(-1) for k in ["ch", "chrom_len", "read_len", "q", "t", "box"]})
+        a["strand"] = np.ascontiguousarray(cd["strand"], np.uint8); a["freq"] = np.ascontiguousarray(cd["freq"], np.float32)
+        NC = len(a["ch_off"]) - 1; CL = len(a["cl_off"]) - 1; U = len(a["ch"])
+        sizes = np.diff(a["cl_off"].astype(np.int64))
+        cap = int(sizes[a["ch"]].sum()) if U else 0
+        o = dict(e_off=np.zeros(U + 1, np.uint64), q=np.zeros(max(cap, 1), np.uint32), t=np.zeros(max(cap, 1), np.uint32), len=np.zeros(max(cap, 1), np.int32),
+                 ovp=np.zeros(max(cap, 1), np.uint8), md_head=np.zeros(max(cap, 1), np.uint8), box=np.zeros((max(U, 1), 4), np.uint32), overlap=np.zeros(max(U, 1), np.int32))
+        p = lambda x: _ptr(x) if x.size else None
+        e = _ExtendChains(NC, _ptr(a["ch_off"]), p(a["ch"]), CL, _ptr(a["cl_off"]), p(a["q"]), p(a["t"]), p(a["box"]), p(a["strand"]), p(a["freq"]), p(a["chrom_off"]),
+                          p(a["chrom_len"]), p(a["read_off"]), p(a["read_len"]), K, int(skiprepetitive), int(trim), int(merge_dist))
+        r = _ExtendedChains(_ptr(o["e_off"]), _ptr(o["q"]), _ptr(o["t"]), _ptr(o["len"]), _ptr(o["ovp"]), _ptr(o["md_head"]), max(cap, 1), 0, _ptr(o["box"]), _ptr(o["overlap"]))
+        self._check(self.lib.lra_b200_linear_extend_chains_batch(self.h, reads.handle, genome.handle, C.byref(e), C.byref(r)))
+        n = int(r.n_total)
+        for k in ("q", "t", "len", "ovp", "md_head"):
+            o[k] = o[k][:n]
+        o["box"] = o["box"][:U]; o["overlap"] = o["overlap"][:U]
         return o
 
     # ---- a22

@@ -117,6 +117,39 @@ struct LextLongLess {
   }
 };
 
+// TrimOverlappedAnchors for one extended cluster, by one warp (see the header of this file)
+__device__ __forceinline__ void lext_trim_warp(uint32_t *Q, uint32_t *T, int32_t *L, int cnt, int *idx, int strand, int thr, int lane) {
+  int nl = 0;
+  for (int base = 0; base < cnt; base += 32) {  // ordered compaction of the long anchors
+    const int i = base + lane;
+    const bool is_long = i < cnt && L[i] >= thr;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, is_long);
+    if (is_long) idx[nl + __popc(m & ((1u << lane) - 1u))] = i;
+    nl += __popc(m);
+  }
+  __syncwarp();
+  if (lane == 0) std_sort_replay(idx, nl, LextLongLess{Q, T, L, strand});
+  __syncwarp();
+  for (int base = 1; base < nl; base += 32) {
+    const int ln = base + lane;
+    int prev = 0, cut = 0;
+    if (ln < nl) {
+      prev = idx[ln - 1];
+      const int cur = idx[ln];
+      int overlap_r = 0, overlap_g = 0;
+      const uint32_t pend = Q[prev] + (uint32_t)L[prev];
+      if (strand == 0) { if (Q[cur] < pend && Q[cur] >= pend - 30u) overlap_r = (int)(pend - Q[cur]); }
+      else { const uint32_t cend = Q[cur] + (uint32_t)L[cur]; if (cend > Q[prev] && cend <= Q[prev] + 30u) overlap_r = (int)(cend - Q[prev]); }
+      const uint32_t ptend = T[prev] + (uint32_t)L[prev];
+      if (T[cur] < ptend && T[cur] >= ptend - 30u) overlap_g = (int)(ptend - T[cur]);
+      if (overlap_r > 0 || overlap_g > 0) cut = (overlap_r > overlap_g ? overlap_r : overlap_g) + 1;
+    }
+    __syncwarp();
+    if (cut) { if (strand == 1) Q[prev] += (uint32_t)cut; L[prev] -= cut; }
+    __syncwarp();
+  }
+}
+
 // one warp per group
 __global__ void __launch_bounds__(128) lext_group_kernel(LextBatch b) {
   const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
@@ -144,36 +177,166 @@ __global__ void __launch_bounds__(128) lext_group_kernel(LextBatch b) {
   }
   if (!b.trim || cnt == 0) return;
   __syncwarp();
-  const int strand = b.p_strand[pb - 1];        // the reference's `st` after the loop over the merged clusters: the last part's strand
-  int *idx = b.lidx + e0;
-  int nl = 0;
-  for (int base = 0; base < cnt; base += 32) {  // ordered compaction of the anchors >= 40
-    const int i = base + lane;
-    const bool is_long = i < cnt && L[i] >= 40;
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, is_long);
-    if (is_long) idx[nl + __popc(m & ((1u << lane) - 1u))] = i;
-    nl += __popc(m);
+  // trim 1: the vector<Cluster> overload (anchors >= 40, strand = the reference's `st` after its loop over the merged clusters: the last part's);
+  // trim 2: the GenomePairs overload (LinearExtend.h:724-777: anchors >= 50, forward only)
+  lext_trim_warp(Q, T, L, cnt, b.lidx + e0, b.trim == 2 ? 0 : (int)b.p_strand[pb - 1], b.trim == 2 ? 50 : 40, lane);
+}
+
+// ---- the high-accuracy overload: LinearExtend(vector<Cluster*> clusters, vector<Cluster> &extCluster, vector<Tup> &chain, ...) (LinearExtend.h:134-350),
+// TrimOverlappedAnchors from `start` (LinearExtend_chain :782-792) and MergeMatchesSameDiag (:794-823).
+// A unit = one chain entry (chain c of a read, position e): it extends cluster chain[e] with the overlap points of clusters chain[e-1] and
+// chain[e+1] in its Set.  The walk carries state from anchor to anchor (m, n, chm; an anchor that covers a Set point consumes its successor's
+// turn), so it is replayed literally by one thread per unit into the unit's slot (at most one output per input anchor); the counts are scanned,
+// and one warp per unit compacts the slot, reduces the box, trims, and flags the heads of the same-diagonal runs.
+struct LextChainBatch {
+  int n_units;
+  int K, skiprepetitive, trim;
+  long long merge_dist;
+  SeqView reads, genome;
+  const uint32_t *unit_cl;                      // [n_units] cluster of the unit
+  const uint8_t *unit_edge;                     // [n_units] bit 0: first entry of its chain, bit 1: last
+  const unsigned long long *slot_off;           // [n_units + 1] exclusive scan of the units' cluster sizes
+  const unsigned long long *cl_off;             // [n_clusters + 1]
+  const uint32_t *cq, *ct;                      // cluster anchors, already sorted (DiagonalSort / AntiDiagonalSort by strand)
+  const uint32_t *cl_box;                       // [n_clusters * 4] qStart, qEnd, tStart, tEnd
+  const uint8_t *cl_strand;
+  const float *cl_freq;
+  const unsigned long long *cl_chrom_off;       // contig of the cluster in the packed genome
+  const uint32_t *cl_chrom_len;
+  const unsigned long long *cl_read_off;        // the read of the cluster in the read arena
+  const uint32_t *cl_read_len;
+  uint32_t *sq, *st;                            // [slot_off[n_units]] slot scratch
+  int32_t *sl;
+  uint8_t *so;
+  unsigned long long *cnt;                      // [n_units + 1] outputs per unit, then their exclusive scan
+  int32_t *u_overlap;                           // [n_units] out: increments of the reference's `overlap` counter
+  int *lidx;                                    // [slot_off[n_units]] scratch
+  uint32_t *eq, *et;                            // out, compacted
+  int32_t *elen;
+  uint8_t *eovp;                                // out: Cluster::overlap
+  uint8_t *md_head;                             // out: 1 = the anchor starts a new same-diagonal run (MergeMatchesSameDiag's start[] entries)
+  uint32_t *box;                                // [n_units * 4]
+};
+
+__device__ __forceinline__ bool lext_check_overlap(uint32_t q, uint32_t t, uint32_t K, const uint32_t *sp, const uint32_t sf, int ns) {   // CheckOverlap
+  for (int i = 0; i < ns; i++) {
+    const bool on_t = (sf >> i) & 1u;
+    const uint32_t lo = on_t ? t : q;
+    if (sp[i] >= lo && sp[i] < lo + K) return true;
   }
-  __syncwarp();
-  if (lane == 0) std_sort_replay(idx, nl, LextLongLess{Q, T, L, strand});
-  __syncwarp();
-  for (int base = 1; base < nl; base += 32) {
-    const int ln = base + lane;
-    int prev = 0, cut = 0;
-    if (ln < nl) {
-      prev = idx[ln - 1];
-      const int cur = idx[ln];
-      int overlap_r = 0, overlap_g = 0;
-      const uint32_t pend = Q[prev] + (uint32_t)L[prev];
-      if (strand == 0) { if (Q[cur] < pend && Q[cur] >= pend - 30u) overlap_r = (int)(pend - Q[cur]); }
-      else { const uint32_t cend = Q[cur] + (uint32_t)L[cur]; if (cend > Q[prev] && cend <= Q[prev] + 30u) overlap_r = (int)(cend - Q[prev]); }
-      const uint32_t ptend = T[prev] + (uint32_t)L[prev];
-      if (T[cur] < ptend && T[cur] >= ptend - 30u) overlap_g = (int)(ptend - T[cur]);
-      if (overlap_r > 0 || overlap_g > 0) cut = (overlap_r > overlap_g ? overlap_r : overlap_g) + 1;
+  return false;
+}
+
+__global__ void __launch_bounds__(128) lextc_walk_kernel(LextChainBatch b) {
+  const int u = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x);
+  if (u >= b.n_units) return;
+  const uint32_t cm = b.unit_cl[u];
+  const unsigned long long a = b.cl_off[cm];
+  const long size = (long)(b.cl_off[cm + 1] - a);
+  unsigned long long no = 0;
+  int ovl = 0;
+  if (size > 0) {
+    const uint32_t K = (uint32_t)b.K;
+    const int strand = b.cl_strand[cm];
+    uint32_t sp[8]; uint32_t sf = 0; int ns = 0;
+    const uint32_t *bx = b.cl_box + 4 * (size_t)cm;
+    const uint32_t qsb = bx[0], qeb = bx[1], tsb = bx[2], teb = bx[3];
+    if (b.skiprepetitive && b.cl_freq[cm] <= 1.1f) {
+      const int edge = b.unit_edge[u];
+#pragma unroll
+      for (int side = 0; side < 2; side++) {
+        if (side == 0 ? (edge & 1) : (edge & 2)) continue;
+        const uint32_t *ob = b.cl_box + 4 * (size_t)b.unit_cl[side == 0 ? u - 1 : u + 1];
+        if (ob[0] > qsb && ob[0] < qeb) { sp[ns++] = ob[0]; }
+        if (ob[1] > qsb && ob[1] < qeb) { sp[ns++] = ob[1]; }
+        if (ob[2] > tsb && ob[2] < teb) { sf |= 1u << ns; sp[ns++] = ob[2]; }
+        if (ob[3] > tsb && ob[3] < teb) { sf |= 1u << ns; sp[ns++] = ob[3]; }
+      }
     }
-    __syncwarp();
-    if (cut) { if (strand == 1) Q[prev] += (uint32_t)cut; L[prev] -= cut; }
-    __syncwarp();
+    const uint32_t *pq = b.cq + a, *pt = b.ct + a;
+    const unsigned long long so = b.slot_off[u];
+    uint32_t *oq = b.sq + so, *ot = b.st + so; int32_t *ol = b.sl + so; uint8_t *oo = b.so + so;
+    const unsigned long long coff = b.cl_chrom_off[cm], roff = b.cl_read_off[cm];
+    const uint32_t clen = b.cl_chrom_len[cm], rlen = b.cl_read_len[cm];
+    // the walk only needs the fields LextBatch's Checkbp reads
+    LextBatch lb; lb.K = b.K; lb.reads = b.reads; lb.genome = b.genome;
+    auto push = [&](uint32_t q, uint32_t t, uint32_t len, uint8_t o) { oq[no] = q; ot[no] = t; ol[no] = (int32_t)len; oo[no] = o; no++; };
+    long n = 1, m = 0;
+    bool chm = true;
+    while (n < size) {
+      if (chm) {
+        if (lext_check_overlap(pq[m], pt[m], K, sp, sf, ns)) { push(pq[m], pt[m], K, 1); ovl++; m = n; n++; chm = true; continue; }
+        chm = false;
+      }
+      if (lext_check_overlap(pq[n], pt[n], K, sp, sf, ns)) {
+        push(pq[m], strand == 0 ? pt[m] : pt[n - 1], pq[n - 1] + K - pq[m], 0);
+        push(pq[n], pt[n], K, 1); ovl++;
+        m = n + 1; n = m + 1; chm = true;
+        continue;
+      }
+      long long curDiag, nextDiag;
+      if (strand == 0) { curDiag = (long long)pq[n - 1] - (long long)pt[n - 1]; nextDiag = (long long)pq[n] - (long long)pt[n]; }
+      else { curDiag = (long long)pq[n - 1] + (long long)pt[n - 1]; nextDiag = (long long)pq[n] + (long long)pt[n]; }
+      if (curDiag == nextDiag) {
+        if (pq[n] < pq[n - 1] + K) n++;
+        else {
+          uint32_t qe, te;
+          lext_checkbp(lb, pq[n - 1], pt[n - 1], pq[n], pt[n], coff, clen, roff, rlen, strand, qe, te);
+          if (strand == 0 ? (qe == pq[n] && te == pt[n]) : (qe == pq[n] && te == pt[n] + K - 1u)) n++;
+          else { push(pq[m], strand == 0 ? pt[m] : te + 1u, qe - pq[m], 0); m = n; n++; }
+        }
+      } else { push(pq[m], strand == 0 ? pt[m] : pt[n - 1], pq[n - 1] + K - pq[m], 0); m = n; n++; }
+      chm = false;
+    }
+    if (n == size) push(pq[m], strand == 0 ? pt[m] : pt[n - 1], pq[n - 1] + K - pq[m], 0);
+  }
+  b.cnt[u] = no;
+  b.u_overlap[u] = ovl;
+}
+
+// one warp per unit, after the scan of cnt[]
+__global__ void __launch_bounds__(128) lextc_group_kernel(LextChainBatch b) {
+  const int u = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (u >= b.n_units) return;
+  const unsigned long long e0 = b.cnt[u], so = b.slot_off[u];
+  const int cnt = (int)(b.cnt[u + 1] - e0);
+  uint32_t *Q = b.eq + e0, *T = b.et + e0;
+  int32_t *L = b.elen + e0;
+  uint8_t *O = b.eovp + e0;
+  uint32_t qs = 0xFFFFFFFFu, qe = 0, ts = 0xFFFFFFFFu, te = 0;
+  for (int i = lane; i < cnt; i += 32) {
+    const uint32_t q = b.sq[so + i], t = b.st[so + i];
+    const int32_t len = b.sl[so + i];
+    Q[i] = q; T[i] = t; L[i] = len; O[i] = b.so[so + i];
+    qs = lext_umin(qs, q); qe = lext_umax(qe, q + (uint32_t)len); ts = lext_umin(ts, t); te = lext_umax(te, t + (uint32_t)len);
+  }
+  for (int d = 16; d; d >>= 1) {
+    qs = lext_umin(qs, __shfl_xor_sync(0xFFFFFFFFu, qs, d)); qe = lext_umax(qe, __shfl_xor_sync(0xFFFFFFFFu, qe, d));
+    ts = lext_umin(ts, __shfl_xor_sync(0xFFFFFFFFu, ts, d)); te = lext_umax(te, __shfl_xor_sync(0xFFFFFFFFu, te, d));
+  }
+  if (lane == 0) {
+    uint32_t *bx = b.box + 4 * (size_t)u;
+    if (cnt > 0) { bx[0] = qs; bx[1] = qe; bx[2] = ts; bx[3] = te; } else { bx[0] = bx[1] = bx[2] = bx[3] = 0; }
+  }
+  if (cnt == 0) return;
+  __syncwarp();
+  const int strand = b.cl_strand[b.unit_cl[u]];
+  if (b.trim) lext_trim_warp(Q, T, L, cnt, b.lidx + so, strand, 40, lane);
+  __syncwarp();
+  // MergeMatchesSameDiag: anchor i continues the run of i-1 iff neither is an overlap anchor, they share GetDiag, i starts after i-1 ends on the
+  // read and the read gap is <= merge_dist
+  for (int i = lane; i < cnt; i += 32) {
+    bool head = true;
+    if (i > 0) {
+      const long long dp = strand == 0 ? (long long)T[i - 1] - (long long)Q[i - 1] : (long long)Q[i - 1] + (long long)T[i - 1] + (long long)L[i - 1];
+      const long long dc = strand == 0 ? (long long)T[i] - (long long)Q[i] : (long long)Q[i] + (long long)T[i] + (long long)L[i];
+      const uint32_t prev_qEnd = Q[i - 1] + (uint32_t)L[i - 1];
+      long long gd = (long long)Q[i] - ((long long)Q[i - 1] + (long long)L[i - 1]);
+      if (gd < 0) gd = -gd;
+      if (O[i - 1] == 0 && O[i] == 0 && dp == dc && prev_qEnd < Q[i] && gd <= b.merge_dist) head = false;
+    }
+    b.md_head[e0 + i] = head ? 1 : 0;
   }
 }
 

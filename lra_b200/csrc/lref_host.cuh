@@ -901,3 +901,119 @@ extern "C" int lra_b200_linear_extend_batch(lra_b200_ctx *ctx, const lra_b200_se
   }
   return LRA_B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- a15 LinearExtend (high-accuracy overload)
+extern "C" int lra_b200_linear_extend_chains_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_extend_chains *in,
+                                                   lra_b200_extended_chains *res) {
+  if (!ctx || !reads || !genome || !in || !res) return fail(ctx, LRA_B200_EINVAL, "linear_extend_chains_batch: NULL argument");
+  const int NC = in->n_chains, CL = in->n_clusters;
+  if (NC < 0 || CL < 0 || !in->ch_off || in->K <= 0) return fail(ctx, LRA_B200_EINVAL, "linear_extend_chains_batch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  res->n_total = 0;
+  const size_t U = NC ? (size_t)in->ch_off[NC] : 0;
+  if (U == 0) { if (res->e_off) res->e_off[0] = 0; return LRA_B200_OK; }
+  if (U > 0x7FFFFFF0ull) return fail(ctx, LRA_B200_EINVAL, "linear_extend_chains_batch: more than 2^31 chain entries");
+  if (!in->ch || !in->cl_off || !in->cl_box || !in->cl_strand || !in->cl_freq || !in->chrom_off || !in->chrom_len || !in->read_off || !in->read_len || CL == 0)
+    return fail(ctx, LRA_B200_EINVAL, "linear_extend_chains_batch: NULL cluster array");
+  const size_t N = (size_t)in->cl_off[CL];
+  if (N > 0x7FFFFFF0ull) return fail(ctx, LRA_B200_EINVAL, "linear_extend_chains_batch: more than 2^31 anchors in one batch");
+  if (N && (!in->q || !in->t)) return fail(ctx, LRA_B200_EINVAL, "linear_extend_chains_batch: NULL anchors");
+  std::vector<unsigned long long> slot((size_t)CL), slot_off(U + 1);
+  std::vector<uint8_t> edge(U, 0);
+  size_t slots = 0;
+  for (int c = 0; c < CL; c++) {
+    if (in->cl_off[c + 1] < in->cl_off[c]) return fail(ctx, LRA_B200_EINVAL, "linear_extend_chains_batch: cluster offsets not ascending");
+    if (in->chrom_off[c] + in->chrom_len[c] > genome->n) return fail(ctx, LRA_B200_EINVAL, "linear_extend_chains_batch: contig of cluster %d ends beyond the genome arena", c);
+    if (in->read_off[c] + in->read_len[c] > reads->n) return fail(ctx, LRA_B200_EINVAL, "linear_extend_chains_batch: read of cluster %d ends beyond the read arena", c);
+    if (in->chrom_len[c] == 0) return fail(ctx, LRA_B200_EINVAL, "linear_extend_chains_batch: cluster %d lies on an empty contig", c);
+    if (in->cl_strand[c] > 1) return fail(ctx, LRA_B200_EINVAL, "linear_extend_chains_batch: strand of cluster %d is not 0 / 1", c);
+    const size_t n = (size_t)(in->cl_off[c + 1] - in->cl_off[c]);
+    size_t P2 = 1; while (P2 < n) P2 <<= 1;
+    slot[c] = slots;
+    if (P2 > (size_t)kSortSmem) slots += P2;
+  }
+  size_t S = 0;
+  for (int k = 0; k < NC; k++) {
+    if (in->ch_off[k + 1] < in->ch_off[k]) return fail(ctx, LRA_B200_EINVAL, "linear_extend_chains_batch: chain offsets not ascending");
+    for (size_t u = (size_t)in->ch_off[k]; u < (size_t)in->ch_off[k + 1]; u++) {
+      if (in->ch[u] >= (uint32_t)CL) return fail(ctx, LRA_B200_EINVAL, "linear_extend_chains_batch: chain entry %zu names cluster %u of %d", u, in->ch[u], CL);
+      edge[u] = (uint8_t)((u == (size_t)in->ch_off[k] ? 1 : 0) | (u + 1 == (size_t)in->ch_off[k + 1] ? 2 : 0));
+      slot_off[u] = S;
+      S += (size_t)(in->cl_off[in->ch[u] + 1] - in->cl_off[in->ch[u]]);
+    }
+  }
+  slot_off[U] = S;
+  if (res->cap < S) { res->n_total = S; return fail(ctx, LRA_B200_EOVERFLOW, "linear_extend_chains_batch: result arrays hold %llu anchors, %llu may be needed",
+                                                     (unsigned long long)res->cap, (unsigned long long)S); }
+  int rc;
+  DevBuf *B = ctx->lc;
+  const size_t Np = N ? N : 1, Sp = S ? S : 1, C1 = (size_t)CL;
+  if ((rc = ensure(ctx, B[0], U * 4)) || (rc = ensure(ctx, B[1], U)) || (rc = ensure(ctx, B[2], (U + 1) * 8)) || (rc = ensure(ctx, B[3], (C1 + 1) * 8)) ||
+      (rc = ensure(ctx, B[4], Np * 4)) || (rc = ensure(ctx, B[5], Np * 4)) || (rc = ensure(ctx, B[6], C1 * 16)) || (rc = ensure(ctx, B[7], C1)) ||
+      (rc = ensure(ctx, B[8], C1 * 4)) || (rc = ensure(ctx, B[9], C1 * 8)) || (rc = ensure(ctx, B[10], C1 * 4)) || (rc = ensure(ctx, B[11], C1 * 8)) ||
+      (rc = ensure(ctx, B[12], C1 * 4)) || (rc = ensure(ctx, B[13], Sp * 4)) || (rc = ensure(ctx, B[14], Sp * 4)) || (rc = ensure(ctx, B[15], Sp * 4)) ||
+      (rc = ensure(ctx, B[16], Sp)) || (rc = ensure(ctx, B[17], (U + 2) * 8)) || (rc = ensure(ctx, B[18], U * 4)) || (rc = ensure(ctx, B[19], Sp * 4)) ||
+      (rc = ensure(ctx, B[20], Sp * 4)) || (rc = ensure(ctx, B[21], Sp * 4)) || (rc = ensure(ctx, B[22], Sp * 4)) || (rc = ensure(ctx, B[23], Sp)) ||
+      (rc = ensure(ctx, B[24], Sp)) || (rc = ensure(ctx, B[25], U * 16)) || (rc = ensure(ctx, B[26], slots * 8 + 16)) || (rc = ensure(ctx, B[27], slots * 4 + 16)) ||
+      (rc = ensure(ctx, B[28], slots * 4 + 16)) || (rc = ensure(ctx, B[29], C1 * 8)) || (rc = ensure(ctx, B[30], 16)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  const void *src[13] = {in->ch, edge.data(), slot_off.data(), in->cl_off, in->q, in->t, in->cl_box, in->cl_strand, in->cl_freq, in->chrom_off, in->chrom_len,
+                         in->read_off, in->read_len};
+  const size_t sz[13] = {U * 4, U, (U + 1) * 8, (C1 + 1) * 8, N * 4, N * 4, C1 * 16, C1, C1 * 4, C1 * 8, C1 * 4, C1 * 8, C1 * 4};
+  for (int i = 0; i < 13; i++) if (sz[i]) CU(cudaMemcpyAsync(B[i].p, src[i], sz[i], cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[29].p, slot.data(), C1 * 8, cudaMemcpyHostToDevice, st));
+  LextChainBatch b;
+  b.n_units = (int)U; b.K = in->K; b.skiprepetitive = in->skiprepetitive; b.trim = in->trim; b.merge_dist = in->merge_dist;
+  b.reads = SeqView{reads->b2, reads->nm, reads->n}; b.genome = SeqView{genome->b2, genome->nm, genome->n};
+  b.unit_cl = (const uint32_t *)B[0].p; b.unit_edge = (const uint8_t *)B[1].p; b.slot_off = (const unsigned long long *)B[2].p;
+  b.cl_off = (const unsigned long long *)B[3].p; b.cq = (const uint32_t *)B[4].p; b.ct = (const uint32_t *)B[5].p; b.cl_box = (const uint32_t *)B[6].p;
+  b.cl_strand = (const uint8_t *)B[7].p; b.cl_freq = (const float *)B[8].p; b.cl_chrom_off = (const unsigned long long *)B[9].p;
+  b.cl_chrom_len = (const uint32_t *)B[10].p; b.cl_read_off = (const unsigned long long *)B[11].p; b.cl_read_len = (const uint32_t *)B[12].p;
+  b.sq = (uint32_t *)B[13].p; b.st = (uint32_t *)B[14].p; b.sl = (int32_t *)B[15].p; b.so = (uint8_t *)B[16].p; b.cnt = (unsigned long long *)B[17].p;
+  b.u_overlap = (int32_t *)B[18].p; b.lidx = (int *)B[19].p; b.eq = (uint32_t *)B[20].p; b.et = (uint32_t *)B[21].p; b.elen = (int32_t *)B[22].p;
+  b.eovp = (uint8_t *)B[23].p; b.md_head = (uint8_t *)B[24].p; b.box = (uint32_t *)B[25].p;
+  auto rec = [&](int i) { cudaEventRecord(ctx->ev[i], st); };
+  rec(0);
+  if (N) {   // DiagonalSort<GenomeTuple>(matches, 500) on strand 0, AntiDiagonalSort<GenomeTuple>(matches, 500) on strand 1 (LinearExtend.h:196-205)
+    SortBatch sb;
+    sb.n_seg = CL; sb.mode = 0; sb.seg_off = b.cl_off; sb.q = (uint32_t *)B[4].p; sb.t = (uint32_t *)B[5].p; sb.perm = nullptr;
+    sb.kp = (unsigned long long *)B[26].p; sb.ks = (uint32_t *)B[27].p; sb.ki = (uint32_t *)B[28].p; sb.slot_off = (const unsigned long long *)B[29].p;
+    sb.seg_mode = b.cl_strand;
+    sort_pairs_kernel<<<(unsigned)CL, 256, 0, st>>>(sb);
+    ctx->launches++;
+  }
+  rec(1);
+  lextc_walk_kernel<<<(unsigned)((U + 127) / 128), 128, 0, st>>>(b);
+  CU(cudaMemsetAsync(b.cnt + U, 0, 16, st));
+  seed_scan_kernel<<<1, 1024, 0, st>>>(b.cnt, (int)U, ~0ull, (int *)B[30].p);
+  rec(2);
+  lextc_group_kernel<<<(unsigned)((U + 3) / 4), 128, 0, st>>>(b);
+  ctx->launches += 3;
+  rec(3);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(res->e_off, b.cnt, (U + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->box, b.box, U * 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->overlap, b.u_overlap, U * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const size_t n_out = (size_t)res->e_off[U];
+  res->n_total = n_out;
+  if (n_out) {
+    CU(cudaMemcpyAsync(res->q, b.eq, n_out * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->t, b.et, n_out * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->len, b.elen, n_out * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->ovp, b.eovp, n_out, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->md_head, b.md_head, n_out, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  const char *names[3] = {"lextc_sort", "lextc_walk+scan", "lextc_group"};
+  for (int i = 0; i < 3; i++) {
+    if (i == 0 && !N) continue;
+    lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "%s", names[i]);
+    cudaEventElapsedTime(&s2.ms, ctx->ev[i], ctx->ev[i + 1]); s2.jobs = i == 0 ? (uint64_t)CL : (uint64_t)U;
+    s2.algo_bytes = i == 0 ? 16ull * N : i == 1 ? 8ull * S + 13ull * n_out : 27ull * n_out + 16ull * U;
+    ctx->stats.push_back(s2);
+  }
+  return LRA_B200_OK;
+}

@@ -23,6 +23,7 @@ struct SortBatch {
   unsigned long long *kp;              // scratch: primary keys,   slot_off[s] .. (power-of-two sized slots, large segments only)
   uint32_t *ks, *ki;                   // scratch: secondary keys, source indices
   const unsigned long long *slot_off;  // [n_seg]
+  const uint8_t *seg_mode = nullptr;   // [n_seg] per-segment mode (a15: DiagonalSort on strand 0, AntiDiagonalSort on strand 1), or nullptr: `mode` for all
 };
 
 constexpr int kSortSmem = 2048;
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(256) sort_pairs_kernel(SortBatch b) {
   if (s >= b.n_seg) return;
   const unsigned long long o = b.seg_off[s];
   const int n = (int)(b.seg_off[s + 1] - o);
+  const int mode = b.seg_mode ? (int)b.seg_mode[s] : b.mode;
   if (n <= 1) { if (n == 1 && b.perm && threadIdx.x == 0) b.perm[o] = (uint32_t)o; return; }
   int P = 1;
   while (P < n) P <<= 1;
@@ -49,7 +51,7 @@ __global__ void __launch_bounds__(256) sort_pairs_kernel(SortBatch b) {
   uint32_t *ks = in_smem ? ss : b.ks + b.slot_off[s];
   uint32_t *ki = in_smem ? si : b.ki + b.slot_off[s];
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    if (i < n) { unsigned long long p; uint32_t s2; sort_keys(b.mode, b.q[o + i], b.t[o + i], p, s2); kp[i] = p; ks[i] = s2; ki[i] = (uint32_t)i; }
+    if (i < n) { unsigned long long p; uint32_t s2; sort_keys(mode, b.q[o + i], b.t[o + i], p, s2); kp[i] = p; ks[i] = s2; ki[i] = (uint32_t)i; }
     else { kp[i] = ~0ull; ks[i] = 0xFFFFFFFFu; ki[i] = 0xFFFFFFFFu; }
   }
   __syncthreads();
@@ -76,9 +78,9 @@ __global__ void __launch_bounds__(256) sort_pairs_kernel(SortBatch b) {
     const unsigned long long p = kp[i];
     const uint32_t s2 = ks[i];
     uint32_t nq, nt;
-    if (b.mode == 0) { nq = s2; nt = (uint32_t)((long long)s2 - ((long long)p - (1ll << 32))); }
-    else if (b.mode == 1) { nq = s2; nt = (uint32_t)p - s2; }
-    else if (b.mode == 2) { nq = (uint32_t)p; nt = s2; }
+    if (mode == 0) { nq = s2; nt = (uint32_t)((long long)s2 - ((long long)p - (1ll << 32))); }
+    else if (mode == 1) { nq = s2; nt = (uint32_t)p - s2; }
+    else if (mode == 2) { nq = (uint32_t)p; nt = s2; }
     else { nt = (uint32_t)p; nq = s2; }
     oq[i] = nq; ot[i] = nt;
     if (b.perm) b.perm[o + i] = (uint32_t)(o + ki[i]);

@@ -11,7 +11,11 @@
  * parts of a group are appended in order; strand and contig of the group are those of its last part (the reference's loop variables).
  * The reference compares genome.seqs[chrom][curT] with read.seq[curQ] directly on BOTH strands (no complement on strand 1) -- restated as is.
  * All position arithmetic is GenomePos (uint32) arithmetic as in the reference; lengths are int.
- * Pinned by tests/test_linear_extend.py against the unmodified reference (oracle/ref_wrap.cpp: ref_linear_extend). */
+ * trim: 0 none, 1 the vector<Cluster> overload of TrimOverlappedAnchors, 2 its GenomePairs overload (LocalRefineAlignment.h:358-373).
+ * lra_oracle_linear_extend_chain restates the high-accuracy pipeline's overload LinearExtend(vector<Cluster*>, ..., chain, ...)
+ * (LinearExtend.h:134-350, with CheckOverlap :87-101) as LinearExtend_chain (:782-792) and Map_highacc.h:571-582 call it, followed by
+ * MergeMatchesSameDiag (:794-823, Map_highacc.h:642).
+ * Pinned by tests/test_linear_extend.py against the unmodified reference (oracle/ref_wrap.cpp: ref_linear_extend, ref_linear_extend_chain). */
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -100,6 +104,32 @@ static void checkbp(uint32_t cq, uint32_t ct, uint32_t nq, uint32_t nt, const ui
   *qe = curQ; *te = curT;
 }
 
+/* TrimOverlappedAnchors: the vector<Cluster> overload (LinearExtend.h:573-647; thr 40, strand-aware) and the GenomePairs overload (:724-777; thr 50,
+ * forward only = strand 0 here) */
+static void trim_group(uint32_t *Q, uint32_t *T, int32_t *L, long cnt, int st, int thr) {
+  int *idx = (int *)malloc((size_t)(cnt > 0 ? cnt : 1) * sizeof(int));
+  long nl = 0;
+  for (long i = 0; i < cnt; i++) if (L[i] >= thr) idx[nl++] = (int)i;
+  la_ctx c = {Q, T, L, st};
+  la_sort(&c, idx, nl);
+  for (long ln = 1; ln < nl; ln++) {
+    const int prev = idx[ln - 1], cur = idx[ln];
+    int overlap_r = 0, overlap_g = 0;
+    if (st == 0) {
+      if (Q[cur] < Q[prev] + (uint32_t)L[prev] && Q[cur] >= Q[prev] + (uint32_t)L[prev] - 30u) overlap_r = (int)(Q[prev] + (uint32_t)L[prev] - Q[cur]);
+    } else {
+      if (Q[cur] + (uint32_t)L[cur] > Q[prev] && Q[cur] + (uint32_t)L[cur] <= Q[prev] + 30u) overlap_r = (int)(Q[cur] + (uint32_t)L[cur] - Q[prev]);
+    }
+    if (T[cur] < T[prev] + (uint32_t)L[prev] && T[cur] >= T[prev] + (uint32_t)L[prev] - 30u) overlap_g = (int)(T[prev] + (uint32_t)L[prev] - T[cur]);
+    if (overlap_r > 0 || overlap_g > 0) {
+      const int overlap = overlap_r > overlap_g ? overlap_r : overlap_g;
+      if (st == 1) Q[prev] += (uint32_t)(overlap + 1);
+      L[prev] -= overlap + 1;
+    }
+  }
+  free(idx);
+}
+
 /* Returns the number of extended anchors (== e_off[n_groups]).  q, t are sorted in place per part when skipsorting == 0.
  * box[4g..] = qStart, qEnd, tStart, tEnd (DecideCoordinates, before trimming; zeros for a group without anchors). */
 long lra_oracle_linear_extend(const uint8_t *read, int read_len, const uint8_t *genome, const uint64_t *chrom_off, const int32_t *chrom_len, int n_groups,
@@ -161,31 +191,138 @@ long lra_oracle_linear_extend(const uint8_t *read, int read_len, const uint8_t *
       }
       box[4 * g] = qs; box[4 * g + 1] = qe2; box[4 * g + 2] = ts; box[4 * g + 3] = te2;
     }
-    if (trim && cnt > 0) {
-      int *idx = (int *)malloc((size_t)cnt * sizeof(int));
-      long nl = 0;
-      for (long i = 0; i < cnt; i++) if (elen[b + i] >= 40) idx[nl++] = (int)i;
-      la_ctx c = {eq + b, et + b, elen + b, st};
-      la_sort(&c, idx, nl);
-      uint32_t *Q = eq + b, *T = et + b; int32_t *L = elen + b;
-      for (long ln = 1; ln < nl; ln++) {
-        const int prev = idx[ln - 1], cur = idx[ln];
-        int overlap_r = 0, overlap_g = 0;
-        if (st == 0) {
-          if (Q[cur] < Q[prev] + (uint32_t)L[prev] && Q[cur] >= Q[prev] + (uint32_t)L[prev] - 30u) overlap_r = (int)(Q[prev] + (uint32_t)L[prev] - Q[cur]);
-        } else {
-          if (Q[cur] + (uint32_t)L[cur] > Q[prev] && Q[cur] + (uint32_t)L[cur] <= Q[prev] + 30u) overlap_r = (int)(Q[cur] + (uint32_t)L[cur] - Q[prev]);
-        }
-        if (T[cur] < T[prev] + (uint32_t)L[prev] && T[cur] >= T[prev] + (uint32_t)L[prev] - 30u) overlap_g = (int)(T[prev] + (uint32_t)L[prev] - T[cur]);
-        if (overlap_r > 0 || overlap_g > 0) {
-          const int overlap = overlap_r > overlap_g ? overlap_r : overlap_g;
-          if (st == 1) Q[prev] += (uint32_t)(overlap + 1);
-          L[prev] -= overlap + 1;
-        }
-      }
-      free(idx);
-    }
+    if (trim && cnt > 0) trim_group(eq + b, et + b, elen + b, cnt, trim == 2 ? 0 : st, trim == 2 ? 50 : 40);
   }
   e_off[n_groups] = (int32_t)no;
+  return no;
+}
+
+static int adiag_cmp(const void *a, const void *b) {       /* AntiDiagonalSortOp (Sorting.h:77-90): (GenomePos)(q + t), then q */
+  const le_pair *x = (const le_pair *)a, *y = (const le_pair *)b;
+  const uint32_t dx = x->q + x->t, dy = y->q + y->t;
+  if (dx != dy) return dx < dy ? -1 : 1;
+  return x->q < y->q ? -1 : (x->q > y->q ? 1 : 0);
+}
+
+static int check_overlap(uint32_t q, uint32_t t, int K, const uint32_t *set_pos, const uint8_t *set_flag, int ns) {   /* CheckOverlap */
+  for (int i = 0; i < ns; i++) {
+    if (set_flag[i] == 0 && set_pos[i] >= q && set_pos[i] < q + (uint32_t)K) return 1;
+    if (set_flag[i] == 1 && set_pos[i] >= t && set_pos[i] < t + (uint32_t)K) return 1;
+  }
+  return 0;
+}
+
+/* One chain of one read.  Clusters: anchors cl_off[c] .. cl_off[c+1] of (cq, ct) (sorted in place: DiagonalSort on strand 0, AntiDiagonalSort on
+ * strand 1), cl_box[4c..] = qStart, qEnd, tStart, tEnd, strand, contig (arena position, length), anchorfreq.  chain[0..n_chain) = cluster indices.
+ * Out per chain entry e: extended anchors e_off[e] .. e_off[e+1] (q, t, len, overlap flag), box, and the same-diagonal runs md_off[e] ..
+ * md_off[e+1] as (md_start, md_end) -- one run (0, 1) for an entry without anchors, where the reference reads matches[0] of an empty vector.
+ * *overlap_count = the reference's `overlap` counter.  Returns the number of extended anchors. */
+long lra_oracle_linear_extend_chain(const uint8_t *read, int read_len, const uint8_t *genome, int n_cl, const int32_t *cl_off, uint32_t *cq, uint32_t *ct,
+                                    const uint32_t *cl_box, const uint8_t *cl_strand, const uint64_t *cl_chrom_off, const int32_t *cl_chrom_len, const float *cl_freq,
+                                    int n_chain, const int32_t *chain, int K, int skiprepetitive, int trim, int merge_dist,
+                                    int32_t *e_off, uint32_t *eq, uint32_t *et, int32_t *elen, uint8_t *eovp, uint32_t *box, int32_t *overlap_count,
+                                    int32_t *md_off, int32_t *md_start, int32_t *md_end) {
+  (void)n_cl;
+  long no = 0, nmd = 0;
+  int overlap = 0;
+  for (int c = 0; c < n_chain; c++) {
+    e_off[c] = (int32_t)no;
+    md_off[c] = (int32_t)nmd;
+    const int cm = chain[c];
+    const long a = cl_off[cm], size = cl_off[cm + 1] - a;
+    box[4 * c] = box[4 * c + 1] = box[4 * c + 2] = box[4 * c + 3] = 0;
+    const int strand = cl_strand[cm];
+    if (size > 0) {
+      uint32_t set_pos[8]; uint8_t set_flag[8]; int ns = 0;
+      const uint32_t qsb = cl_box[4 * cm], qeb = cl_box[4 * cm + 1], tsb = cl_box[4 * cm + 2], teb = cl_box[4 * cm + 3];
+      if (skiprepetitive && cl_freq[cm] <= 1.1f) {
+        for (int side = 0; side < 2; side++) {
+          const int o = side == 0 ? c - 1 : c + 1;
+          if (o < 0 || o >= n_chain) continue;
+          const uint32_t *ob = cl_box + 4 * chain[o];
+          if (ob[0] > qsb && ob[0] < qeb) { set_pos[ns] = ob[0]; set_flag[ns++] = 0; }
+          if (ob[1] > qsb && ob[1] < qeb) { set_pos[ns] = ob[1]; set_flag[ns++] = 0; }
+          if (ob[2] > tsb && ob[2] < teb) { set_pos[ns] = ob[2]; set_flag[ns++] = 1; }
+          if (ob[3] > tsb && ob[3] < teb) { set_pos[ns] = ob[3]; set_flag[ns++] = 1; }
+        }
+      }
+      uint32_t *pq = cq + a, *pt = ct + a;
+      if (size > 1) {
+        le_pair *v = (le_pair *)malloc((size_t)size * sizeof(le_pair));
+        for (long i = 0; i < size; i++) { v[i].q = pq[i]; v[i].t = pt[i]; }
+        qsort(v, (size_t)size, sizeof(le_pair), strand == 0 ? diag_cmp : adiag_cmp);
+        for (long i = 0; i < size; i++) { pq[i] = v[i].q; pt[i] = v[i].t; }
+        free(v);
+      }
+      const uint8_t *contig = genome + cl_chrom_off[cm];
+      long n = 1, m = 0;
+      int chm = 1;
+#define PUSH(Q_, T_, L_, O_) do { eq[no] = (Q_); et[no] = (T_); elen[no] = (int32_t)(L_); eovp[no] = (O_); no++; } while (0)
+      while (n < size) {
+        if (chm == 1) {
+          if (check_overlap(pq[m], pt[m], K, set_pos, set_flag, ns)) {
+            PUSH(pq[m], pt[m], K, 1); overlap++;
+            m = n; n++; chm = 1;
+            continue;
+          } else chm = 0;
+        }
+        if (check_overlap(pq[n], pt[n], K, set_pos, set_flag, ns)) {
+          PUSH(pq[m], strand == 0 ? pt[m] : pt[n - 1], pq[n - 1] + (uint32_t)K - pq[m], 0);
+          PUSH(pq[n], pt[n], K, 1); overlap++;
+          m = n + 1; n = m + 1; chm = 1;
+          continue;
+        }
+        long curDiag, nextDiag;
+        if (strand == 0) { curDiag = (long)pq[n - 1] - (long)pt[n - 1]; nextDiag = (long)pq[n] - (long)pt[n]; }
+        else { curDiag = (long)pq[n - 1] + (long)pt[n - 1]; nextDiag = (long)pq[n] + (long)pt[n]; }
+        if (curDiag == nextDiag) {
+          if (pq[n] < pq[n - 1] + (uint32_t)K) n++;
+          else {
+            uint32_t qe, te;
+            checkbp(pq[n - 1], pt[n - 1], pq[n], pt[n], contig, cl_chrom_len[cm], read, read_len, strand, K, &qe, &te);
+            if (strand == 0 && qe == pq[n] && te == pt[n]) n++;
+            else if (strand == 1 && qe == pq[n] && te == pt[n] + (uint32_t)K - 1u) n++;
+            else { PUSH(pq[m], strand == 0 ? pt[m] : te + 1u, qe - pq[m], 0); m = n; n++; }
+          }
+        } else { PUSH(pq[m], strand == 0 ? pt[m] : pt[n - 1], pq[n - 1] + (uint32_t)K - pq[m], 0); m = n; n++; }
+        chm = 0;
+      }
+      if (n == size) PUSH(pq[m], strand == 0 ? pt[m] : pt[n - 1], pq[n - 1] + (uint32_t)K - pq[m], 0);
+#undef PUSH
+      const long b = e_off[c], cnt = no - b;
+      if (cnt > 0) {
+        uint32_t qs = eq[b], qe2 = qs + (uint32_t)elen[b], ts = et[b], te2 = ts + (uint32_t)elen[b];
+        for (long i = b + 1; i < no; i++) {
+          if (eq[i] < qs) qs = eq[i];
+          if (eq[i] + (uint32_t)elen[i] > qe2) qe2 = eq[i] + (uint32_t)elen[i];
+          if (et[i] < ts) ts = et[i];
+          if (et[i] + (uint32_t)elen[i] > te2) te2 = et[i] + (uint32_t)elen[i];
+        }
+        box[4 * c] = qs; box[4 * c + 1] = qe2; box[4 * c + 2] = ts; box[4 * c + 3] = te2;
+        if (trim) trim_group(eq + b, et + b, elen + b, cnt, strand, 40);
+      }
+    }
+    /* MergeMatchesSameDiag */
+    const long b = e_off[c], cnt = no - b;
+    md_start[nmd] = 0; md_end[nmd] = 1; nmd++;
+    if (cnt > 0) {
+      const uint32_t *Q = eq + b, *T = et + b; const int32_t *L = elen + b; const uint8_t *O = eovp + b;
+#define GDIAG(i) (strand == 0 ? (long)T[i] - (long)Q[i] : (long)Q[i] + (long)T[i] + (long)L[i])
+      long prev_diag = GDIAG(0);
+      uint32_t prev_qEnd = Q[0] + (uint32_t)L[0];
+      for (long qi = 1; qi < cnt; qi++) {
+        const long cur_diag = GDIAG(qi);
+        long gd = (long)Q[qi] - ((long)Q[qi - 1] + (long)L[qi - 1]); if (gd < 0) gd = -gd;
+        if (O[qi - 1] == 0 && O[qi] == 0 && prev_diag == cur_diag && prev_qEnd < Q[qi] && gd <= merge_dist) md_end[nmd - 1] = (int32_t)(qi + 1);
+        else { md_start[nmd] = (int32_t)qi; md_end[nmd] = (int32_t)(qi + 1); nmd++; }
+        prev_qEnd = Q[qi] + (uint32_t)L[qi];
+        prev_diag = cur_diag;
+      }
+#undef GDIAG
+    }
+  }
+  e_off[n_chain] = (int32_t)no;
+  md_off[n_chain] = (int32_t)nmd;
+  *overlap_count = overlap;
   return no;
 }

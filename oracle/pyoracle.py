@@ -767,3 +767,33 @@ def linear_extend(read, genome, rd, K, skipsorting, trim, which="port"):
     o["box"] = o["box"][:4 * G].reshape(-1, 4)
     o["sorted_q"], o["sorted_t"] = q[:N], t[:N]
     return o
+
+
+def linear_extend_chain(read, genome, cd, chain, K, skiprepetitive=1, trim=1, merge_dist=100, which="port"):
+    """High-accuracy overload for one chain.  cd = dict(cl_off, q, t, box[n,4], strand, chrom_off, chrom_len, freq); chain = cluster indices.
+    Returns dict(e_off, q, t, len, ovp, box[e,4], overlap, md_off, md_start, md_end, sorted_q, sorted_t)."""
+    co = np.ascontiguousarray(cd["cl_off"], np.int32); ncl = len(co) - 1
+    ch = np.ascontiguousarray(chain, np.int32); E = len(ch)
+    cap = int(sum(int(co[c + 1] - co[c]) for c in ch)) + 1
+    L = ref() if which == "ref" else port()
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    f = _bind_once(L, "ref_linear_extend_chain" if which == "ref" else "lra_oracle_linear_extend_chain", C.c_long,
+                   [_u8p, C.c_int, _u8p, C.c_int, _i32p, _u32p, _u32p, _u32p, _u8p, _u64p, _i32p, f32p, C.c_int, _i32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                    _i32p, _u32p, _u32p, _i32p, _u8p, _u32p, _i32p, _i32p, _i32p, _i32p])
+    pad = lambda a, dt: np.ascontiguousarray(a, dt).reshape(-1).copy() if len(a) else np.zeros(1, dt)
+    q = pad(cd["q"], np.uint32); t = pad(cd["t"], np.uint32)
+    r = np.frombuffer(read, np.uint8) if isinstance(read, (bytes, bytearray)) else np.ascontiguousarray(read, np.uint8)
+    o = dict(e_off=np.zeros(E + 1, np.int32), q=np.zeros(cap, np.uint32), t=np.zeros(cap, np.uint32), len=np.zeros(cap, np.int32), ovp=np.zeros(cap, np.uint8),
+             box=np.zeros(4 * max(E, 1), np.uint32), md_off=np.zeros(E + 1, np.int32), md_start=np.zeros(cap + E, np.int32), md_end=np.zeros(cap + E, np.int32))
+    ov = np.zeros(1, np.int32)
+    n = f(r, len(r), np.ascontiguousarray(genome, np.uint8), ncl, co, q, t, pad(cd["box"], np.uint32), pad(cd["strand"], np.uint8), pad(cd["chrom_off"], np.uint64),
+          pad(cd["chrom_len"], np.int32), pad(cd["freq"], np.float32), E, pad(ch, np.int32), K, int(skiprepetitive), int(trim), int(merge_dist),
+          o["e_off"], o["q"], o["t"], o["len"], o["ovp"], o["box"], ov, o["md_off"], o["md_start"], o["md_end"])
+    for k in ("q", "t", "len", "ovp"):
+        o[k] = o[k][:n]
+    nm = int(o["md_off"][E])
+    o["md_start"] = o["md_start"][:nm]; o["md_end"] = o["md_end"][:nm]
+    o["box"] = o["box"][:4 * E].reshape(-1, 4)
+    o["overlap"] = int(ov[0])
+    o["sorted_q"], o["sorted_t"] = q[:len(cd["q"])], t[:len(cd["t"])]
+    return o

@@ -545,4 +545,55 @@ long ref_linear_extend(const uint8_t *readseq, int read_len, const uint8_t *geno
   return no;
 }
 
+// ---- a15 (high-accuracy overload): LinearExtend_chain (LinearExtend.h:782-792 = LinearExtend(vector<Cluster*>, ..., chain, ...) + TrimOverlappedAnchors
+// from `start`) for ONE chain, as Map_highacc.h:571-582 calls it with skiprepetitive = 1, then MergeMatchesSameDiag (Map_highacc.h:642).
+// Arguments as oracle/linear_extend.c: lra_oracle_linear_extend_chain.  trim = 0 calls LinearExtend alone.  Entries whose cluster has no anchors are
+// left out of MergeMatchesSameDiag (the reference would index an empty vector there) and reported as one run (0, 1).
+long ref_linear_extend_chain(const uint8_t *readseq, int read_len, const uint8_t *genome_arena, int n_cl, const int32_t *cl_off, uint32_t *cq, uint32_t *ct,
+                             const uint32_t *cl_box, const uint8_t *cl_strand, const uint64_t *cl_chrom_off, const int32_t *cl_chrom_len, const float *cl_freq,
+                             int n_chain, const int32_t *chain, int K, int skiprepetitive, int trim, int merge_dist,
+                             int32_t *e_off, uint32_t *eq, uint32_t *et, int32_t *elen, uint8_t *eovp, uint32_t *box, int32_t *overlap_count,
+                             int32_t *md_off, int32_t *md_start, int32_t *md_end) {
+  ref_init_static();
+  Options opts; opts.globalK = K; opts.merge_dist = merge_dist;
+  Read read; read.seq = (char *)readseq; read.length = read_len; read.unaligned = 0;
+  Genome genome;
+  std::vector<Cluster> cl(n_cl);
+  std::vector<Cluster *> clp(n_cl);
+  for (int c = 0; c < n_cl; c++) {
+    genome.seqs.push_back((char *)genome_arena + cl_chrom_off[c]); genome.lengths.push_back(cl_chrom_len[c]);
+    cl[c].qStart = cl_box[4 * c]; cl[c].qEnd = cl_box[4 * c + 1]; cl[c].tStart = cl_box[4 * c + 2]; cl[c].tEnd = cl_box[4 * c + 3];
+    cl[c].strand = cl_strand[c]; cl[c].chromIndex = c; cl[c].anchorfreq = cl_freq[c];
+    cl[c].matches.resize(cl_off[c + 1] - cl_off[c]);
+    for (size_t i = 0; i < cl[c].matches.size(); i++) { cl[c].matches[i].first.pos = cq[cl_off[c] + i]; cl[c].matches[i].second.pos = ct[cl_off[c] + i]; }
+    clp[c] = &cl[c];
+  }
+  std::vector<unsigned int> ch(chain, chain + n_chain);
+  std::vector<Cluster> ext(n_chain);
+  for (int e = 0; e < n_chain; e++) { ext[e].qStart = ext[e].qEnd = ext[e].tStart = ext[e].tEnd = 0; }
+  int overlap = 0;
+  if (trim) LinearExtend_chain<unsigned int>(ch, ext, clp, opts, genome, read, 0, overlap, skiprepetitive != 0, K);
+  else LinearExtend<unsigned int>(clp, ext, ch, opts, genome, read, 0, overlap, skiprepetitive != 0, K);
+  *overlap_count = overlap;
+  for (int c = 0; c < n_cl; c++)
+    for (size_t i = 0; i < cl[c].matches.size(); i++) { cq[cl_off[c] + i] = cl[c].matches[i].first.pos; ct[cl_off[c] + i] = cl[c].matches[i].second.pos; }
+  long no = 0, nmd = 0;
+  for (int e = 0; e < n_chain; e++) {
+    e_off[e] = (int32_t)no; md_off[e] = (int32_t)nmd;
+    for (size_t i = 0; i < ext[e].matches.size(); i++, no++) {
+      eq[no] = ext[e].matches[i].first.pos; et[no] = ext[e].matches[i].second.pos; elen[no] = ext[e].matchesLengths[i]; eovp[no] = ext[e].overlap[i];
+    }
+    box[4 * e] = ext[e].qStart; box[4 * e + 1] = ext[e].qEnd; box[4 * e + 2] = ext[e].tStart; box[4 * e + 3] = ext[e].tEnd;
+    if (ext[e].matches.size() == 0) { md_start[nmd] = 0; md_end[nmd] = 1; nmd++; continue; }
+    std::vector<Cluster> one(1); one[0] = ext[e];
+    std::vector<Cluster_SameDiag> merged;
+    MergeMatchesSameDiag(one, merged, opts);
+    for (size_t i = 0; i < merged[0].start.size(); i++, nmd++) { md_start[nmd] = merged[0].start[i]; md_end[nmd] = merged[0].end[i]; }
+  }
+  e_off[n_chain] = (int32_t)no; md_off[n_chain] = (int32_t)nmd;
+  genome.seqs.clear();
+  read.seq = NULL; read.qual = NULL;
+  return no;
+}
+
 }  // extern "C"

@@ -311,3 +311,26 @@ def linear_extend(read_arena, genome, ep, K, skipsorting, trim):
         o[k] = o[k][:n]
     o["box"] = o["box"][:4 * G].reshape(-1, 4)
     return o
+
+
+def linear_extend_chains(read_arena, genome, cd, K, skiprepetitive=1, trim=1, merge_dist=100):
+    """cd as for Context.linear_extend_chains_batch."""
+    L = lib()
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    L.emu_linear_extend_chains.argtypes = [_u8p, C.c_uint64, _u8p, C.c_uint64, C.c_int, _u64p, _u32p, C.c_int, _u64p, _u32p, _u32p, _u32p, _u8p, f32p, _u64p, _u32p, _u64p,
+                                           _u32p, C.c_int, C.c_int, C.c_int, C.c_int, _u64p, _u32p, _u32p, _i32p, _u8p, _u8p, _u32p, _i32p]
+    pad = lambda a, dt: np.ascontiguousarray(a, dt).reshape(-1).copy() if len(a) else np.zeros(1, dt)
+    cho = np.ascontiguousarray(cd["ch_off"], np.uint64); clo = np.ascontiguousarray(cd["cl_off"], np.uint64)
+    ch = pad(cd["ch"], np.uint32); U = int(cho[-1])
+    cap = int(np.diff(clo.astype(np.int64))[ch[:U]].sum()) if U else 0
+    o = dict(e_off=np.zeros(U + 1, np.uint64), q=np.zeros(max(cap, 1), np.uint32), t=np.zeros(max(cap, 1), np.uint32), len=np.zeros(max(cap, 1), np.int32),
+             ovp=np.zeros(max(cap, 1), np.uint8), md_head=np.zeros(max(cap, 1), np.uint8), box=np.zeros(4 * max(U, 1), np.uint32), overlap=np.zeros(max(U, 1), np.int32))
+    L.emu_linear_extend_chains(read_arena, len(read_arena) - 16, genome, len(genome) - 16, len(cho) - 1, cho, ch, len(clo) - 1, clo, pad(cd["q"], np.uint32),
+                               pad(cd["t"], np.uint32), pad(cd["box"], np.uint32), pad(cd["strand"], np.uint8), pad(cd["freq"], np.float32), pad(cd["chrom_off"], np.uint64),
+                               pad(cd["chrom_len"], np.uint32), pad(cd["read_off"], np.uint64), pad(cd["read_len"], np.uint32), K, int(skiprepetitive), int(trim),
+                               int(merge_dist), o["e_off"], o["q"], o["t"], o["len"], o["ovp"], o["md_head"], o["box"], o["overlap"])
+    n = int(o["e_off"][U])
+    for k in ("q", "t", "len", "ovp", "md_head"):
+        o[k] = o[k][:n]
+    o["box"] = o["box"][:4 * U].reshape(-1, 4); o["overlap"] = o["overlap"][:U]
+    return o

@@ -152,3 +152,84 @@ def to_batch(items):
     return read_arena, dict(g_off=np.array(g_off, np.uint64), p_off=np.array(p_off, np.uint64), p_strand=np.array(st, np.uint8), chrom_off=np.array(co, np.uint64),
                             chrom_len=np.array(cl, np.uint32), read_off=np.array(pro, np.uint64), read_len=np.array(prl, np.uint32),
                             q=np.concatenate(q).astype(np.uint32) if q else np.zeros(0, np.uint32), t=np.concatenate(t).astype(np.uint32) if t else np.zeros(0, np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------ the high-accuracy overload (chains of clusters)
+
+def chain_read(rng, arena, c_off, c_len, K, read_len, sub=0.02, indel=0.02):
+    """One read with 1-2 chains over clusters cut from mutated windows with OVERLAPPING read ranges (so that the neighbours' box corners fall
+    inside a cluster and CheckOverlap has work).  Returns (read, dict(cl_off, q, t, box, strand, freq, chrom_off, chrom_len), [chain, ...])."""
+    pieces, clusters, chains = [], [], []
+    qbase = 0
+    for _ in range(int(rng.integers(1, 3))):
+        c = int(rng.integers(0, len(c_len))); L = int(rng.integers(read_len // 2, read_len))
+        s = int(rng.integers(0, int(c_len[c]) - L))
+        win = arena[int(c_off[c]) + s:int(c_off[c]) + s + L]
+        strand = int(rng.random() < 0.35)
+        src = win[::-1] if strand else win
+        piece, pairs = mutate(rng, src, sub, indel)
+        qs = np.array([a for a, _ in pairs]); ts = np.array([b for _, b in pairs])
+        eq = piece[qs] == src[ts]
+        anchors = []
+        i = 0
+        while i + K <= len(pairs):
+            j = i + K - 1
+            if qs[j] - qs[i] == K - 1 and ts[j] - ts[i] == K - 1 and eq[i:j + 1].all():
+                tt = s + int(ts[i]) if strand == 0 else s + (L - 1 - int(ts[i])) - (K - 1)
+                anchors.append((qbase + int(qs[i]), tt)); i += int(rng.integers(1, 10))
+            else:
+                i += 1
+        a = np.array(anchors, np.int64).reshape(-1, 2)
+        ncl = int(rng.integers(1, 5))
+        cuts = np.sort(rng.integers(qbase, qbase + len(piece), ncl - 1)) if ncl > 1 else np.zeros(0, np.int64)
+        bounds = np.concatenate([[qbase], cuts, [qbase + len(piece)]])
+        chain = []
+        for k in range(ncl):
+            ov = int(rng.integers(0, 90))
+            sel = a[(a[:, 0] >= bounds[k] - ov) & (a[:, 0] < bounds[k + 1] + ov)] if len(a) else a
+            if len(sel) == 0:
+                continue
+            sel = sel[rng.permutation(len(sel))]
+            box = [int(sel[:, 0].min()), int(sel[:, 0].max()) + K, int(sel[:, 1].min()), int(sel[:, 1].max()) + K]
+            chain.append(len(clusters))
+            clusters.append((sel, box, strand, float(rng.choice([1.0, 1.05, 1.1, 1.3])), int(c_off[c]), int(c_len[c])))
+        if rng.random() < 0.3:
+            chain = chain[::-1]
+        if chain:
+            chains.append(np.array(chain, np.int32))
+        pieces.append(piece); qbase += len(piece)
+    read = np.concatenate(pieces)
+    if not clusters:
+        return chain_read(rng, arena, c_off, c_len, K, read_len, sub, indel)
+    cl_off = np.zeros(len(clusters) + 1, np.int32); cl_off[1:] = np.cumsum([len(c[0]) for c in clusters])
+    cd = dict(cl_off=cl_off, q=np.concatenate([c[0][:, 0] for c in clusters]).astype(np.uint32), t=np.concatenate([c[0][:, 1] for c in clusters]).astype(np.uint32),
+              box=np.array([c[1] for c in clusters], np.uint32), strand=np.array([c[2] for c in clusters], np.uint8), freq=np.array([c[3] for c in clusters], np.float32),
+              chrom_off=np.array([c[4] for c in clusters], np.uint64), chrom_len=np.array([c[5] for c in clusters], np.int32))
+    return read, cd, chains
+
+
+def chain_reads(seed, n_reads, K=17, read_len=3000):
+    rng = np.random.default_rng(seed)
+    arena, c_off, c_len = make_genome(rng)
+    return arena, [chain_read(rng, arena, c_off, c_len, K, read_len) for _ in range(n_reads)]
+
+
+def chains_to_batch(items):
+    """Concatenate per-read (read, cd, chains) into the batch layout of lra_b200_linear_extend_chains_batch."""
+    roff = np.zeros(len(items), np.uint64); rlen = np.array([len(r) for r, _, _ in items], np.uint32)
+    roff[1:] = np.cumsum(rlen[:-1])
+    read_arena = np.concatenate([r for r, _, _ in items] + [np.full(16, ord("A"), np.uint8)])
+    ch_off, ch, cl_off = [0], [], [0]
+    cols = {k: [] for k in ["q", "t", "box", "strand", "freq", "chrom_off", "chrom_len", "read_off", "read_len"]}
+    for i, (_, cd, chains) in enumerate(items):
+        base = len(cl_off) - 1
+        ncl = len(cd["strand"])
+        cl_off += [cl_off[-1] + int(cd["cl_off"][k + 1]) for k in range(ncl)]
+        for c in chains:
+            ch += [base + int(x) for x in c]; ch_off.append(len(ch))
+        for k in ["q", "t", "box", "strand", "freq", "chrom_off", "chrom_len"]:
+            cols[k].append(cd[k])
+        cols["read_off"].append(np.full(ncl, roff[i], np.uint64)); cols["read_len"].append(np.full(ncl, rlen[i], np.uint32))
+    out = {k: np.concatenate(v) for k, v in cols.items()}
+    out.update(ch_off=np.array(ch_off, np.uint64), ch=np.array(ch, np.uint32), cl_off=np.array(cl_off, np.uint64))
+    return read_arena, out

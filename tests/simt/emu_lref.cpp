@@ -226,3 +226,43 @@ extern "C" int emu_linear_extend(const uint8_t *reads, uint64_t rn, const uint8_
   if (n_groups) emu::launch(dim3((unsigned)((n_groups + 3) / 4)), dim3(128), 0, [&] { lext_group_kernel(b); });
   return 0;
 }
+
+extern "C" int emu_linear_extend_chains(const uint8_t *reads, uint64_t rn, const uint8_t *genome, uint64_t gn, int n_chains, const uint64_t *ch_off, const uint32_t *ch,
+                                        int n_cl, const uint64_t *cl_off, uint32_t *q, uint32_t *t, const uint32_t *cl_box, const uint8_t *cl_strand, const float *cl_freq,
+                                        const uint64_t *chrom_off, const uint32_t *chrom_len, const uint64_t *read_off, const uint32_t *read_len, int K, int skiprepetitive,
+                                        int trim, int merge_dist, uint64_t *e_off, uint32_t *eq, uint32_t *et, int32_t *elen, uint8_t *eovp, uint8_t *md_head, uint32_t *box,
+                                        int32_t *overlap) {
+  Packed pr, pg; pack(reads, rn, pr); pack(genome, gn, pg);
+  const size_t U = (size_t)ch_off[n_chains], N = (size_t)cl_off[n_cl];
+  if (U == 0) { e_off[0] = 0; return 0; }
+  std::vector<unsigned long long> slot_off(U + 1), cnt(U + 2, 0ull);
+  std::vector<uint8_t> edge(U, 0);
+  size_t S = 0;
+  for (int k = 0; k < n_chains; k++)
+    for (size_t u = ch_off[k]; u < ch_off[k + 1]; u++) {
+      edge[u] = (uint8_t)((u == ch_off[k] ? 1 : 0) | (u + 1 == ch_off[k + 1] ? 2 : 0));
+      slot_off[u] = S; S += cl_off[ch[u] + 1] - cl_off[ch[u]];
+    }
+  slot_off[U] = S;
+  if (N) {
+    std::vector<unsigned long long> slot(n_cl), kp; std::vector<uint32_t> ks, ki;
+    size_t slots = 0;
+    for (int c = 0; c < n_cl; c++) { size_t n = cl_off[c + 1] - cl_off[c], P2 = 1; while (P2 < n) P2 <<= 1; slot[c] = slots; if (P2 > (size_t)kSortSmem) slots += P2; }
+    kp.resize(slots + 2); ks.resize(slots + 2); ki.resize(slots + 2);
+    SortBatch sb{n_cl, 0, (const unsigned long long *)cl_off, q, t, nullptr, kp.data(), ks.data(), ki.data(), slot.data(), cl_strand};
+    emu::launch(dim3((unsigned)n_cl), dim3(256), 0, [&] { sort_pairs_kernel(sb); });
+  }
+  std::vector<uint32_t> sq(S + 1), st(S + 1); std::vector<int32_t> sl(S + 1); std::vector<uint8_t> so(S + 1); std::vector<int> lidx(S + 1);
+  LextChainBatch b;
+  b.n_units = (int)U; b.K = K; b.skiprepetitive = skiprepetitive; b.trim = trim; b.merge_dist = merge_dist; b.reads = pr.view; b.genome = pg.view;
+  b.unit_cl = ch; b.unit_edge = edge.data(); b.slot_off = slot_off.data(); b.cl_off = (const unsigned long long *)cl_off; b.cq = q; b.ct = t; b.cl_box = cl_box;
+  b.cl_strand = cl_strand; b.cl_freq = cl_freq; b.cl_chrom_off = (const unsigned long long *)chrom_off; b.cl_chrom_len = chrom_len;
+  b.cl_read_off = (const unsigned long long *)read_off; b.cl_read_len = read_len; b.sq = sq.data(); b.st = st.data(); b.sl = sl.data(); b.so = so.data();
+  b.cnt = cnt.data(); b.u_overlap = overlap; b.lidx = lidx.data(); b.eq = eq; b.et = et; b.elen = elen; b.eovp = eovp; b.md_head = md_head; b.box = box;
+  int err = 0;
+  emu::launch(dim3((unsigned)((U + 127) / 128)), dim3(128), 0, [&] { lextc_walk_kernel(b); });
+  emu::launch(dim3(1), dim3(1024), 0, [&] { seed_scan_kernel(b.cnt, (int)U, ~0ull, &err); });
+  emu::launch(dim3((unsigned)((U + 3) / 4)), dim3(128), 0, [&] { lextc_group_kernel(b); });
+  for (size_t u = 0; u <= U; u++) e_off[u] = cnt[u];
+  return 0;
+}

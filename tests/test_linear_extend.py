@@ -110,6 +110,77 @@ def test_emu_long_anchor_lists_reach_introsort():
     check_batch(emu_lib.linear_extend(read_arena, arena, ep, K, 0, 1), with_bases(exp))
 
 
+# ---------------------------------------------------------------------------------------------- the high-accuracy overload (chains)
+
+def expected_chains(arena, items, trim, which, skiprep=1):
+    out = []
+    for read, cd, chains in items:
+        for ch in chains:
+            out.append(po.linear_extend_chain(read, arena, cd, ch, K, skiprep, trim, 100, which=which))
+    return out
+
+
+def check_chain_batch(o, exp):
+    e = u = 0
+    for x in exp:
+        E = len(x["e_off"]) - 1
+        n = len(x["q"])
+        assert (o["e_off"][u:u + E + 1].astype(np.int64) - e == x["e_off"]).all()
+        for k in ("q", "t", "len", "ovp"):
+            assert np.array_equal(o[k][e:e + n], x[k]), k
+        assert np.array_equal(o["box"][u:u + E], x["box"])
+        assert int(o["overlap"][u:u + E].sum()) == x["overlap"]
+        for j in range(E):            # md_head -> (start, end) runs of MergeMatchesSameDiag
+            a, b = int(x["e_off"][j]), int(x["e_off"][j + 1])
+            heads = np.flatnonzero(o["md_head"][e + a:e + b])
+            ms, me = x["md_start"][x["md_off"][j]:x["md_off"][j + 1]], x["md_end"][x["md_off"][j]:x["md_off"][j + 1]]
+            if b > a:
+                assert np.array_equal(heads, ms) and np.array_equal(np.append(heads[1:], b - a), me)
+            else:
+                assert ms.tolist() == [0] and me.tolist() == [1]
+        e += n; u += E
+    assert e == len(o["q"])
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref/libref_lra.so not built (no /root/reference)")
+@pytest.mark.parametrize("trim", [0, 1])
+def test_chain_oracle_matches_reference(trim):
+    arena, items = lextgen.chain_reads(21 + trim, 40)
+    ovl = runs = total = 0
+    for a, b in zip(expected_chains(arena, items, trim, "ref"), expected_chains(arena, items, trim, "port")):
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+        ovl += b["overlap"]; runs += len(b["md_start"]); total += len(b["q"])
+    assert ovl > 20 and runs < total       # overlap anchors exist, and some anchors are merged into same-diagonal runs
+
+
+def test_chain_skiprepetitive_off_has_no_overlap_anchors():
+    arena, items = lextgen.chain_reads(23, 10)
+    for x in expected_chains(arena, items, 1, "port", skiprep=0):
+        assert x["overlap"] == 0 and not x["ovp"].any()
+
+
+@pytest.mark.parametrize("trim", [0, 1])
+def test_emu_linear_extend_chains(trim):
+    import emu_lib
+    arena, items = lextgen.chain_reads(31 + trim, 12)
+    read_arena, cd = lextgen.chains_to_batch(items)
+    o = emu_lib.linear_extend_chains(read_arena, arena, cd, K, 1, trim, 100)
+    check_chain_batch(o, expected_chains(arena, items, trim, "port"))
+
+
+def test_pairs_trim_mode_2():
+    """TrimOverlappedAnchors(GenomePairs&, vector<int>&): anchors >= 50 only, forward order; the handmade first anchor (84 long) is still trimmed,
+    and a 45-long anchor would not be."""
+    import emu_lib
+    arena, read, rd, rd2 = lextgen.handmade(K)
+    b = po.linear_extend(read, arena, rd, K, 0, 2)
+    assert b["len"].tolist() == [59, 153, 116]
+    items = [(read, rd), (read, rd2)]
+    read_arena, ep = lextgen.to_batch(items)
+    check_batch(emu_lib.linear_extend(read_arena, arena, ep, K, 0, 2), with_bases(expected(arena, items, 0, 2, "port")))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", MODES)
 def test_gpu_linear_extend(mode):
@@ -135,4 +206,28 @@ def test_gpu_linear_extend(mode):
                                              chrom_len=np.zeros(0, np.uint32), read_off=np.zeros(0, np.uint64), read_len=np.zeros(0, np.uint32),
                                              q=np.zeros(0, np.uint32), t=np.zeros(0, np.uint32)), K, skip, trim)
     assert len(e["q"]) == 0
+    rs.free(); gs.free(); ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("trim", [0, 1])
+def test_gpu_linear_extend_chains(trim):
+    import lra_b200
+    ctx = lra_b200.Context(0)
+    arena, items = lextgen.chain_reads(41 + trim, 200)
+    read_arena, cd = lextgen.chains_to_batch(items)
+    rs = ctx.seq_upload(read_arena[:-16]); gs = ctx.seq_upload(arena[:-16])
+    o = ctx.linear_extend_chains_batch(rs, gs, cd, K, 1, trim, 100)
+    check_chain_batch(o, expected_chains(arena, items, trim, "ref" if HAVE_REF else "port"))
+    rs.free(); gs.free(); ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_pairs_trim_mode_2():
+    import lra_b200
+    ctx = lra_b200.Context(0)
+    arena, items = lextgen.reads(77, 100, single=False)
+    read_arena, ep = lextgen.to_batch(items)
+    rs = ctx.seq_upload(read_arena[:-16]); gs = ctx.seq_upload(arena[:-16])
+    check_batch(ctx.linear_extend_batch(rs, gs, ep, K, 0, 2), with_bases(expected(arena, items, 0, 2, "port")))
     rs.free(); gs.free(); ctx.close()
