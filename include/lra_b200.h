@@ -505,6 +505,43 @@ typedef struct lra_b200_extended_chains {
 int lra_b200_linear_extend_chains_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_extend_chains *in,
                                         lra_b200_extended_chains *res);
 
+/* ---- a11  SPLITChain on an UltimateChain (low-accuracy pipeline), batched over chains -------------------------------------
+ * Replaces  SPLITChain(genome, read, chains[p], spchain, spchain_link, opts); RemoveSpuriousSplitChain(spchain, spchain_link);
+ * (Map_lowacc.h:261-262; Mapping_ultility.h:380-437 with push_new :355-378, SplitChain::CHROMIndex Chain.h:388-396, MergeSplitchainINS
+ * Mapping_ultility.h:163-264; Map_lowacc.h:38-66).  Chain k owns anchors c_off[k] .. c_off[k+1] in chain order: qStart, tStart (global
+ * genome coordinate), length, the strand of the anchor's cluster, UltimateChain::ClusterNum, and link[i] = chain.link between anchors i and
+ * i+1.  hdr_pos = genome.header.pos.
+ * Results in slot layout (nothing is compacted across chains): chain k produced n_sp[k] split chains and n_link[k] spchain_link bits.  Its
+ * piece s has anchors  sptc[c_off[k] + o0 .. c_off[k] + o1)  with o0 = sp_off[c_off[k] + k + s], o1 = sp_off[c_off[k] + k + s + 1]
+ * (indices into the chain, already reversed for forward pieces as the reference does for refining), sp_lk at the same places = SplitChain::link
+ * (one fewer valid entry than anchors), ClusterIndex = ci[c_off[k] + ci_off[c_off[k] + k + s] ..), and at c_off[k] + s: sp_box[4*..] = QStart, QEnd,
+ * TStart, TEnd, sp_chrom, sp_type ('N', 'T' or 'I'), sp_strand; spchain_link = sp_link[c_off[k] ..]. */
+typedef struct lra_b200_anchor_chains {
+  int32_t n_chains;
+  const uint64_t *c_off;        /* [n_chains + 1] */
+  const uint32_t *q, *t;        /* [c_off[n_chains]] */
+  const int32_t *len;
+  const uint8_t *strand;
+  const int32_t *cnum;
+  const uint8_t *link;
+  const uint64_t *hdr_pos;
+  int32_t n_hdr;
+  int32_t splitdist;            /* opts.splitdist */
+  int32_t bypass_clustering;    /* opts.bypassClustering */
+} lra_b200_anchor_chains;
+
+typedef struct lra_b200_split_chains {
+  int32_t *n_sp, *n_link;       /* [n_chains] */
+  int32_t *sp_off, *ci_off;     /* [N + n_chains] */
+  int32_t *sptc, *ci;           /* [N] */
+  uint8_t *sp_lk;               /* [N] */
+  uint32_t *sp_box;             /* [N * 4] */
+  int32_t *sp_chrom;            /* [N] */
+  uint8_t *sp_type, *sp_strand, *sp_link;   /* [N] */
+} lra_b200_split_chains;
+
+int lra_b200_split_chains_batch(lra_b200_ctx *ctx, const lra_b200_anchor_chains *in, lra_b200_split_chains *res);
+
 /* ---- a20  RefineBreakpoint, batched over pairs of adjacent segments --------------------------------------------------
  * Replaces  void RefineBreakpoint(Read &read, Genome &genome, Alignment &leftAln, Alignment &rightAln, const Options &opts)
  * (RefineBreakpoint.h:212-462; called for consecutive segments of a split read, Map_highacc.h:725, Map_lowacc.h:592).  Pair p: the left /

@@ -98,6 +98,25 @@ class _ExtendedChains(C.Structure):
                 ("n_total", C.c_uint64), ("box", C.c_void_p), ("overlap", C.c_void_p)]
 
 
+class _AnchorChains(C.Structure):
+    _fields_ = [("n_chains", C.c_int32), ("c_off", C.c_void_p), ("q", C.c_void_p), ("t", C.c_void_p), ("len", C.c_void_p), ("strand", C.c_void_p), ("cnum", C.c_void_p),
+                ("link", C.c_void_p), ("hdr_pos", C.c_void_p), ("n_hdr", C.c_int32), ("splitdist", C.c_int32), ("bypass_clustering", C.c_int32)]
+
+
+class _SplitChains(C.Structure):
+    _fields_ = [("n_sp", C.c_void_p), ("n_link", C.c_void_p), ("sp_off", C.c_void_p), ("ci_off", C.c_void_p), ("sptc", C.c_void_p), ("ci", C.c_void_p), ("sp_lk", C.c_void_p),
+                ("sp_box", C.c_void_p), ("sp_chrom", C.c_void_p), ("sp_type", C.c_void_p), ("sp_strand", C.c_void_p), ("sp_link", C.c_void_p)]
+
+
+def split_chain_view(o, c_off, k):
+    """Chain k of a split_chains_batch result as the per-chain dict the oracle returns (sp_off, sptc, sp_lk, ci_off, ci, box, chrom, type, strand, link)."""
+    a = int(c_off[k]); ns = int(o["n_sp"][k])
+    so = o["sp_off"][a + k:a + k + ns + 1]; co = o["ci_off"][a + k:a + k + ns + 1]
+    m = int(so[ns]) if ns else 0; mc = int(co[ns]) if ns else 0
+    return dict(sp_off=so, sptc=o["sptc"][a:a + m], sp_lk=o["sp_lk"][a:a + m], ci_off=co, ci=o["ci"][a:a + mc], box=o["sp_box"][a:a + ns], chrom=o["sp_chrom"][a:a + ns],
+                type=o["sp_type"][a:a + ns], strand=o["sp_strand"][a:a + ns], link=o["sp_link"][a:a + int(o["n_link"][k])])
+
+
 class _Breakpoints(C.Structure):
     _fields_ = [("n_pairs", C.c_int32), ("lf", C.c_void_p), ("ll", C.c_void_p), ("rf", C.c_void_p), ("rl", C.c_void_p), ("lstrand", C.c_void_p),
                 ("rstrand", C.c_void_p), ("read_off", C.c_void_p), ("read_len", C.c_void_p), ("lchrom_off", C.c_void_p), ("rchrom_off", C.c_void_p),
@@ -198,6 +217,7 @@ def load_library():
     L.lra_b200_global_chain_batch.argtypes = [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 4
     L.lra_b200_refine_breakpoint_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Breakpoints), C.POINTER(_BreakpointResult)]
     L.lra_b200_linear_extend_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_ExtendParts), C.POINTER(_Extended)]
+    L.lra_b200_split_chains_batch.argtypes = [C.c_void_p, C.POINTER(_AnchorChains), C.POINTER(_SplitChains)]
     L.lra_b200_linear_extend_chains_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_ExtendChains), C.POINTER(_ExtendedChains)]
     L.lra_b200_chain_filter_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_clean_off_diagonal_batch.argtypes = [C.c_void_p, C.POINTER(_AnchorLists), C.POINTER(_CleanOpts), C.POINTER(_CleanResult)]
@@ -513,6 +533,25 @@ class Context:
         for k in ("q", "t", "len", "ovp", "md_head"):
             o[k] = o[k][:n]
         o["box"] = o["box"][:U]; o["overlap"] = o["overlap"][:U]
+        return o
+
+    # ---- a11
+    def split_chains_batch(self, ac, hdr_pos, splitdist=50000, bypass=0):
+        """SPLITChain(UltimateChain) + MergeSplitchainINS + RemoveSpuriousSplitChain for every chain (ac: dict(c_off, q, t, len, strand, cnum, link -- link has
+        one entry per anchor, the last of each chain unused)).  Returns the slot-layout arrays of lra_b200_split_chains; see split_chain_view."""
+        co = np.ascontiguousarray(ac["c_off"], np.uint64); NC = len(co) - 1; N = int(co[-1])
+        a = dict(q=np.ascontiguousarray(ac["q"], np.uint32), t=np.ascontiguousarray(ac["t"], np.uint32), len=np.ascontiguousarray(ac["len"], np.int32),
+                 strand=np.ascontiguousarray(ac["strand"], np.uint8), cnum=np.ascontiguousarray(ac["cnum"], np.int32), link=np.ascontiguousarray(ac["link"], np.uint8))
+        assert all(len(v) == N for v in a.values())
+        hdr = np.ascontiguousarray(hdr_pos, np.uint64)
+        Np = max(N, 1)
+        o = dict(n_sp=np.zeros(max(NC, 1), np.int32), n_link=np.zeros(max(NC, 1), np.int32), sp_off=np.zeros(Np + NC + 1, np.int32), ci_off=np.zeros(Np + NC + 1, np.int32),
+                 sptc=np.zeros(Np, np.int32), ci=np.zeros(Np, np.int32), sp_lk=np.zeros(Np, np.uint8), sp_box=np.zeros((Np, 4), np.uint32), sp_chrom=np.zeros(Np, np.int32),
+                 sp_type=np.zeros(Np, np.uint8), sp_strand=np.zeros(Np, np.uint8), sp_link=np.zeros(Np, np.uint8))
+        p = lambda x: _ptr(x) if x.size else None
+        e = _AnchorChains(NC, _ptr(co), p(a["q"]), p(a["t"]), p(a["len"]), p(a["strand"]), p(a["cnum"]), p(a["link"]), _ptr(hdr), len(hdr), int(splitdist), int(bypass))
+        r = _SplitChains(*[_ptr(o[k]) for k in ["n_sp", "n_link", "sp_off", "ci_off", "sptc", "ci", "sp_lk", "sp_box", "sp_chrom", "sp_type", "sp_strand", "sp_link"]])
+        self._check(self.lib.lra_b200_split_chains_batch(self.h, C.byref(e), C.byref(r)))
         return o
 
     # ---- a22

@@ -1017,3 +1017,67 @@ extern "C" int lra_b200_linear_extend_chains_batch(lra_b200_ctx *ctx, const lra_
   }
   return LRA_B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- a11 SPLITChain (low-accuracy pipeline)
+extern "C" int lra_b200_split_chains_batch(lra_b200_ctx *ctx, const lra_b200_anchor_chains *in, lra_b200_split_chains *res) {
+  if (!ctx || !in || !res) return fail(ctx, LRA_B200_EINVAL, "split_chains_batch: NULL argument");
+  const int NC = in->n_chains;
+  if (NC < 0 || !in->c_off || !in->hdr_pos || in->n_hdr < 1) return fail(ctx, LRA_B200_EINVAL, "split_chains_batch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  if (NC == 0) return LRA_B200_OK;
+  const size_t N = (size_t)in->c_off[NC];
+  if (N > 0x7FFFFFF0ull) return fail(ctx, LRA_B200_EINVAL, "split_chains_batch: more than 2^31 anchors in one batch");
+  for (int k = 0; k < NC; k++) if (in->c_off[k + 1] < in->c_off[k]) return fail(ctx, LRA_B200_EINVAL, "split_chains_batch: chain offsets not ascending");
+  if (N && (!in->q || !in->t || !in->len || !in->strand || !in->cnum || !in->link)) return fail(ctx, LRA_B200_EINVAL, "split_chains_batch: NULL anchor array");
+  int rc;
+  DevBuf *B = ctx->sp;
+  const size_t Np = N ? N : 1, C1 = (size_t)NC;
+  // 0 c_off, 1..6 inputs, 7 hdr, 8..15 int scratch, 16..19 uint scratch, 20..23 byte scratch, 24.. outputs
+  const size_t need[37] = {(C1 + 1) * 8, Np * 4, Np * 4, Np * 4, Np, Np * 4, Np, (size_t)in->n_hdr * 8,
+                           Np * 4, Np * 4, Np * 4, Np * 4, Np * 4, Np * 4, Np * 4, Np * 4, Np * 4, Np * 4, Np * 4, Np * 4, Np, Np, Np, Np,
+                           C1 * 4, C1 * 4, (Np + C1 + 1) * 4, (Np + C1 + 1) * 4, Np * 4, Np * 4, Np, Np * 16, Np * 4, Np, Np, Np, 16};
+  for (int i = 0; i < 37; i++) if ((rc = ensure(ctx, B[i], need[i]))) return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(B[0].p, in->c_off, (C1 + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (N) {
+    const void *src[6] = {in->q, in->t, in->len, in->strand, in->cnum, in->link};
+    const size_t sz[6] = {N * 4, N * 4, N * 4, N, N * 4, N};
+    for (int i = 0; i < 6; i++) CU(cudaMemcpyAsync(B[1 + i].p, src[i], sz[i], cudaMemcpyHostToDevice, st));
+  }
+  CU(cudaMemcpyAsync(B[7].p, in->hdr_pos, (size_t)in->n_hdr * 8, cudaMemcpyHostToDevice, st));
+  SpChainBatch b;
+  b.n_chains = NC; b.splitdist = in->splitdist; b.bypass = in->bypass_clustering;
+  b.c_off = (const unsigned long long *)B[0].p; b.q = (const uint32_t *)B[1].p; b.t = (const uint32_t *)B[2].p; b.len = (const int32_t *)B[3].p;
+  b.strand = (const uint8_t *)B[4].p; b.cnum = (const int32_t *)B[5].p; b.link = (const uint8_t *)B[6].p; b.hdr_pos = (const unsigned long long *)B[7].p; b.n_hdr = in->n_hdr;
+  b.pa = (int32_t *)B[8].p; b.pb = (int32_t *)B[9].p; b.pnext = (int32_t *)B[10].p; b.tail = (int32_t *)B[11].p; b.size = (int32_t *)B[12].p; b.chrom = (int32_t *)B[13].p;
+  b.cur_ind = (int32_t *)B[14].p; b.ord = (int32_t *)B[15].p; b.QS = (uint32_t *)B[16].p; b.QE = (uint32_t *)B[17].p; b.TS = (uint32_t *)B[18].p; b.TE = (uint32_t *)B[19].p;
+  b.type = (uint8_t *)B[20].p; b.pstrand = (uint8_t *)B[21].p; b.keep = (uint8_t *)B[22].p; b.SL = (uint8_t *)B[23].p;
+  b.n_sp = (int32_t *)B[24].p; b.n_link = (int32_t *)B[25].p; b.sp_off = (int32_t *)B[26].p; b.ci_off = (int32_t *)B[27].p; b.sptc = (int32_t *)B[28].p; b.ci = (int32_t *)B[29].p;
+  b.sp_lk = (uint8_t *)B[30].p; b.sp_box = (uint32_t *)B[31].p; b.sp_chrom = (int32_t *)B[32].p; b.sp_type = (uint8_t *)B[33].p; b.sp_strand = (uint8_t *)B[34].p;
+  b.sp_link = (uint8_t *)B[35].p;
+  cudaEventRecord(ctx->ev[0], st);
+  spchain_kernel<<<(unsigned)((NC + 63) / 64), 64, 0, st>>>(b);
+  cudaEventRecord(ctx->ev[1], st);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(res->n_sp, b.n_sp, C1 * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->n_link, b.n_link, C1 * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->sp_off, b.sp_off, (N + C1) * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->ci_off, b.ci_off, (N + C1) * 4, cudaMemcpyDeviceToHost, st));
+  if (N) {
+    CU(cudaMemcpyAsync(res->sptc, b.sptc, N * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->ci, b.ci, N * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->sp_lk, b.sp_lk, N, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->sp_box, b.sp_box, N * 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->sp_chrom, b.sp_chrom, N * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->sp_type, b.sp_type, N, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->sp_strand, b.sp_strand, N, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->sp_link, b.sp_link, N, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "spchain");
+  cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]); s2.jobs = (uint64_t)NC; s2.algo_bytes = 18ull * N + 9ull * N;
+  ctx->stats.push_back(s2);
+  return LRA_B200_OK;
+}

@@ -797,3 +797,28 @@ def linear_extend_chain(read, genome, cd, chain, K, skiprepetitive=1, trim=1, me
     o["overlap"] = int(ov[0])
     o["sorted_q"], o["sorted_t"] = q[:len(cd["q"])], t[:len(cd["t"])]
     return o
+
+
+# ---------------------------------------------------------------- a11 SPLITChain (UltimateChain) / MergeSplitchainINS / RemoveSpuriousSplitChain
+
+def split_chain(ch, hdr_pos, splitdist=50000, bypass=0, which="port"):
+    """One chain: ch = dict(q, t, len, strand, cnum, link[n-1]).  Returns dict(sp_off, sptc, sp_lk, ci_off, ci, box[k,4], chrom, type, strand, link)."""
+    n = len(ch["q"])
+    L = ref() if which == "ref" else port()
+    f = _bind_once(L, "ref_split_chain" if which == "ref" else "lra_oracle_split_chain", C.c_long,
+                   [_u32p, _u32p, _i32p, _u8p, _i32p, _u8p, C.c_int, _u64p, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _u8p, _i32p, _i32p, _u32p, _i32p, _u8p, _u8p, _u8p, _i32p])
+    pad = lambda a, dt: np.ascontiguousarray(a, dt).copy() if len(a) else np.zeros(1, dt)
+    hdr = np.ascontiguousarray(hdr_pos, np.uint64)
+    o = dict(sp_off=np.zeros(n + 2, np.int32), sptc=np.zeros(n + 1, np.int32), sp_lk=np.zeros(n + 1, np.uint8), ci_off=np.zeros(n + 2, np.int32), ci=np.zeros(n + 1, np.int32),
+             box=np.zeros(4 * (n + 1), np.uint32), chrom=np.zeros(n + 1, np.int32), type=np.zeros(n + 1, np.uint8), strand=np.zeros(n + 1, np.uint8),
+             link=np.zeros(n + 2, np.uint8))
+    nl = np.zeros(1, np.int32)
+    k = f(pad(ch["q"], np.uint32), pad(ch["t"], np.uint32), pad(ch["len"], np.int32), pad(ch["strand"], np.uint8), pad(ch["cnum"], np.int32), pad(ch["link"], np.uint8), n,
+          hdr, len(hdr), int(splitdist), int(bypass), o["sp_off"], o["sptc"], o["sp_lk"], o["ci_off"], o["ci"], o["box"], o["chrom"], o["type"], o["strand"], o["link"], nl)
+    o["sp_off"] = o["sp_off"][:k + 1]; o["ci_off"] = o["ci_off"][:k + 1]
+    m = int(o["sp_off"][k]); o["sptc"] = o["sptc"][:m]; o["sp_lk"] = o["sp_lk"][:m]; o["ci"] = o["ci"][:int(o["ci_off"][k])]
+    o["box"] = o["box"][:4 * k].reshape(-1, 4)
+    for key in ("chrom", "type", "strand"):
+        o[key] = o[key][:k]
+    o["link"] = o["link"][:int(nl[0])]
+    return o

@@ -596,4 +596,47 @@ long ref_linear_extend_chain(const uint8_t *readseq, int read_len, const uint8_t
   return no;
 }
 
+// ---- a11 (low-accuracy pipeline): SPLITChain(genome, read, UltimateChain&, splitchains, splitchains_link, opts) (Mapping_ultility.h:380-437, with push_new
+// and MergeSplitchainINS) followed by RemoveSpuriousSplitChain (Map_lowacc.h:38-66), as Map_lowacc.h:261-262.  Arguments as oracle/split_chain.c; anchor i
+// lives in cluster cnum[i] (all anchors of a cluster share its strand).
+long ref_split_chain(const uint32_t *q, const uint32_t *t, const int32_t *len, const uint8_t *strand, const int32_t *cnum, const uint8_t *link, int n,
+                     const uint64_t *hdr_pos, int n_hdr, int splitdist, int bypass,
+                     int32_t *sp_off, int32_t *sptc, uint8_t *sp_lk, int32_t *ci_off, int32_t *ci, uint32_t *sp_box, int32_t *sp_chrom, uint8_t *sp_type,
+                     uint8_t *sp_strand, uint8_t *sp_link, int32_t *n_link) {
+  ref_init_static();
+  Options opts; opts.splitdist = splitdist; opts.bypassClustering = bypass != 0;
+  Genome genome; genome.header.pos.assign(hdr_pos, hdr_pos + n_hdr);
+  Read read; read.unaligned = 0;
+  int ncl = 0;
+  for (int i = 0; i < n; i++) if (cnum[i] + 1 > ncl) ncl = cnum[i] + 1;
+  std::vector<Cluster> clusters(ncl);
+  UltimateChain chain(&clusters);
+  chain.chain.resize(n); chain.ClusterIndex.resize(n); chain.link.resize(n > 0 ? n - 1 : 0);
+  for (int i = 0; i < n; i++) {
+    Cluster &c = clusters[cnum[i]];
+    c.strand = strand[i];
+    GenomePair gp; gp.first.pos = q[i]; gp.second.pos = t[i];
+    chain.chain[i] = (unsigned)c.matches.size(); chain.ClusterIndex[i] = cnum[i];
+    c.matches.push_back(gp); c.matchesLengths.push_back(len[i]);
+    if (i + 1 < n) chain.link[i] = link[i] != 0;
+  }
+  std::vector<SplitChain> sp; std::vector<bool> spl;
+  SPLITChain(genome, read, chain, sp, spl, opts);
+  RemoveSpuriousSplitChain(sp, spl);
+  int o = 0, oc = 0;
+  for (size_t s = 0; s < sp.size(); s++) {
+    sp_off[s] = o; ci_off[s] = oc;
+    for (int i = 0; i < sp[s].size(); i++) { sptc[o + i] = sp[s].sptc[i]; sp_lk[o + i] = i + 1 < sp[s].size() ? (uint8_t)sp[s].link[i] : 0; }
+    o += sp[s].size();
+    for (size_t i = 0; i < sp[s].ClusterIndex.size(); i++) ci[oc++] = sp[s].ClusterIndex[i];
+    sp_box[4 * s] = sp[s].QStart; sp_box[4 * s + 1] = sp[s].QEnd; sp_box[4 * s + 2] = sp[s].TStart; sp_box[4 * s + 3] = sp[s].TEnd;
+    sp_chrom[s] = sp[s].chromIndex; sp_type[s] = (uint8_t)sp[s].type; sp_strand[s] = sp[s].Strand;
+  }
+  sp_off[sp.size()] = o; ci_off[sp.size()] = oc;
+  for (size_t i = 0; i < spl.size(); i++) sp_link[i] = spl[i];
+  *n_link = (int32_t)spl.size();
+  read.seq = NULL; read.qual = NULL;
+  return (long)sp.size();
+}
+
 }  // extern "C"

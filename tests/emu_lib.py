@@ -334,3 +334,21 @@ def linear_extend_chains(read_arena, genome, cd, K, skiprepetitive=1, trim=1, me
         o[k] = o[k][:n]
     o["box"] = o["box"][:4 * U].reshape(-1, 4); o["overlap"] = o["overlap"][:U]
     return o
+
+
+def split_chains(ac, hdr_pos, splitdist=50000, bypass=0):
+    """ac as for Context.split_chains_batch; returns the same slot-layout dict."""
+    L = lib()
+    L.emu_split_chains.argtypes = [C.c_int, _u64p, _u32p, _u32p, _i32p, _u8p, _i32p, _u8p, _u64p, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _u8p,
+                                   _u32p, _i32p, _u8p, _u8p, _u8p]
+    co = np.ascontiguousarray(ac["c_off"], np.uint64); NC = len(co) - 1; N = int(co[-1]); Np = max(N, 1)
+    pad = lambda a, dt: np.ascontiguousarray(a, dt).copy() if len(a) else np.zeros(1, dt)
+    o = dict(n_sp=np.zeros(max(NC, 1), np.int32), n_link=np.zeros(max(NC, 1), np.int32), sp_off=np.zeros(Np + NC + 1, np.int32), ci_off=np.zeros(Np + NC + 1, np.int32),
+             sptc=np.zeros(Np, np.int32), ci=np.zeros(Np, np.int32), sp_lk=np.zeros(Np, np.uint8), sp_box=np.zeros(4 * Np, np.uint32), sp_chrom=np.zeros(Np, np.int32),
+             sp_type=np.zeros(Np, np.uint8), sp_strand=np.zeros(Np, np.uint8), sp_link=np.zeros(Np, np.uint8))
+    hdr = np.ascontiguousarray(hdr_pos, np.uint64)
+    L.emu_split_chains(NC, co, pad(ac["q"], np.uint32), pad(ac["t"], np.uint32), pad(ac["len"], np.int32), pad(ac["strand"], np.uint8), pad(ac["cnum"], np.int32),
+                       pad(ac["link"], np.uint8), hdr, len(hdr), int(splitdist), int(bypass), o["n_sp"], o["n_link"], o["sp_off"], o["ci_off"], o["sptc"], o["ci"], o["sp_lk"],
+                       o["sp_box"], o["sp_chrom"], o["sp_type"], o["sp_strand"], o["sp_link"])
+    o["sp_box"] = o["sp_box"].reshape(-1, 4)
+    return o

@@ -266,3 +266,20 @@ extern "C" int emu_linear_extend_chains(const uint8_t *reads, uint64_t rn, const
   for (size_t u = 0; u <= U; u++) e_off[u] = cnt[u];
   return 0;
 }
+
+// ---- a11 SPLITChain (UltimateChain) + MergeSplitchainINS + RemoveSpuriousSplitChain
+#include "spchain_kernels.cuh"
+extern "C" int emu_split_chains(int n_chains, const uint64_t *c_off, const uint32_t *q, const uint32_t *t, const int32_t *len, const uint8_t *strand, const int32_t *cnum,
+                                const uint8_t *link, const uint64_t *hdr_pos, int n_hdr, int splitdist, int bypass, int32_t *n_sp, int32_t *n_link, int32_t *sp_off,
+                                int32_t *ci_off, int32_t *sptc, int32_t *ci, uint8_t *sp_lk, uint32_t *sp_box, int32_t *sp_chrom, uint8_t *sp_type, uint8_t *sp_strand,
+                                uint8_t *sp_link) {
+  const size_t N = (size_t)c_off[n_chains] + 1;
+  std::vector<int32_t> pa(N), pb(N), pnext(N), tail(N), size(N), chrom(N), cur_ind(N), ord(N);
+  std::vector<uint32_t> QS(N), QE(N), TS(N), TE(N);
+  std::vector<uint8_t> type(N), pstrand(N), keep(N), SL(N);
+  SpChainBatch b{n_chains, splitdist, bypass, (const unsigned long long *)c_off, q, t, len, strand, cnum, link, (const unsigned long long *)hdr_pos, n_hdr,
+                 pa.data(), pb.data(), pnext.data(), tail.data(), size.data(), chrom.data(), cur_ind.data(), ord.data(), QS.data(), QE.data(), TS.data(), TE.data(),
+                 type.data(), pstrand.data(), keep.data(), SL.data(), n_sp, n_link, sp_off, ci_off, sptc, ci, sp_lk, sp_box, sp_chrom, sp_type, sp_strand, sp_link};
+  if (n_chains) emu::launch(dim3((unsigned)((n_chains + 63) / 64)), dim3(64), 0, [&] { spchain_kernel(b); });
+  return 0;
+}
