@@ -542,6 +542,22 @@ typedef struct lra_b200_split_chains {
 
 int lra_b200_split_chains_batch(lra_b200_ctx *ctx, const lra_b200_anchor_chains *in, lra_b200_split_chains *res);
 
+/* ---- a11  MergeChain, batched over split chains ------------------------------------------------------------------------------
+ * Replaces  MergeChain(Refined_Clusters, mergeinfo, merge_spcluster, spcluster)  (ChainRefine.h:767-802; Map_lowacc.h:440).  Split chain k owns
+ * entries sc_off[k] .. sc_off[k+1] of sp[] = cluster indices; clusters enter as chromIndex, strand and box[4c..] = qStart, qEnd, tStart, tEnd.
+ * head[e] = 1 iff entry e starts a new Merge_SplitChain: mergeinfo[r].merged_clusterIndex = the entries from the r-th 1 up to the next one
+ * (these are the groups lra_b200_linear_extend_batch takes), merge_sp.sptc = 0 .. #groups-1. */
+int lra_b200_merge_chain_batch(lra_b200_ctx *ctx, const int32_t *sp, const uint64_t *sc_off, int32_t n_chains, const int32_t *chrom, const uint8_t *strand,
+                               const uint32_t *box, int32_t n_clusters, uint8_t *head);
+
+/* ---- a11  switchindex, batched over chains -------------------------------------------------------------------------------------
+ * Replaces  switchindex(splitclusters, Primary_chains, clusters, genome, read)  (Mapping_ultility.h:39-161; Map_highacc.h:215) for every chain
+ * Primary_chains[p].chains[h]: chain k owns entries c_off[k] .. c_off[k+1] of ch[] (split-cluster indices) and link[c_off[k] + i] = its link
+ * between entries i and i+1; coarse[] = splitclusters[].coarse, cq[2c], cq[2c+1] = clusters[c].qStart, qEnd.  ch and link are rewritten in
+ * place (slot layout): chain k keeps n_out[k] entries (cluster indices) and nl_out[k] links at the start of its slot. */
+int lra_b200_switchindex_batch(lra_b200_ctx *ctx, int32_t *ch, uint8_t *link, const uint64_t *c_off, int32_t n_chains, const int32_t *coarse,
+                               int32_t n_splitclusters, const uint32_t *cq, int32_t n_clusters, int32_t *n_out, int32_t *nl_out);
+
 /* ---- a20  RefineBreakpoint, batched over pairs of adjacent segments --------------------------------------------------
  * Replaces  void RefineBreakpoint(Read &read, Genome &genome, Alignment &leftAln, Alignment &rightAln, const Options &opts)
  * (RefineBreakpoint.h:212-462; called for consecutive segments of a split read, Map_highacc.h:725, Map_lowacc.h:592).  Pair p: the left /

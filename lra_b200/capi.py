@@ -218,6 +218,8 @@ def load_library():
     L.lra_b200_refine_breakpoint_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Breakpoints), C.POINTER(_BreakpointResult)]
     L.lra_b200_linear_extend_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_ExtendParts), C.POINTER(_Extended)]
     L.lra_b200_split_chains_batch.argtypes = [C.c_void_p, C.POINTER(_AnchorChains), C.POINTER(_SplitChains)]
+    L.lra_b200_merge_chain_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.lra_b200_switchindex_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.lra_b200_linear_extend_chains_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_ExtendChains), C.POINTER(_ExtendedChains)]
     L.lra_b200_chain_filter_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_clean_off_diagonal_batch.argtypes = [C.c_void_p, C.POINTER(_AnchorLists), C.POINTER(_CleanOpts), C.POINTER(_CleanResult)]
@@ -553,6 +555,25 @@ class Context:
         r = _SplitChains(*[_ptr(o[k]) for k in ["n_sp", "n_link", "sp_off", "ci_off", "sptc", "ci", "sp_lk", "sp_box", "sp_chrom", "sp_type", "sp_strand", "sp_link"]])
         self._check(self.lib.lra_b200_split_chains_batch(self.h, C.byref(e), C.byref(r)))
         return o
+
+    def merge_chain_batch(self, sp, sc_off, chrom, strand, box):
+        """MergeChain for every split chain; returns the head flags (1 = the entry starts a new Merge_SplitChain)."""
+        sp = np.ascontiguousarray(sp, np.int32); so = np.ascontiguousarray(sc_off, np.uint64)
+        chrom = np.ascontiguousarray(chrom, np.int32); strand = np.ascontiguousarray(strand, np.uint8); box = np.ascontiguousarray(box, np.uint32).reshape(-1)
+        head = np.zeros(max(len(sp), 1), np.uint8)
+        p = lambda x: _ptr(x) if x.size else None
+        self._check(self.lib.lra_b200_merge_chain_batch(self.h, p(sp), _ptr(so), len(so) - 1, p(chrom), p(strand), p(box), len(chrom), _ptr(head)))
+        return head[:len(sp)]
+
+    def switchindex_batch(self, ch, link, c_off, coarse, cq):
+        """switchindex for every chain (link: one byte per entry, the last of each chain unused).  Returns (ch, link, n_out, nl_out) in slot layout."""
+        ch = np.array(ch, np.int32); link = np.array(link, np.uint8); co = np.ascontiguousarray(c_off, np.uint64)
+        coarse = np.ascontiguousarray(coarse, np.int32); cq = np.ascontiguousarray(cq, np.uint32).reshape(-1)
+        NC = len(co) - 1
+        n_out = np.zeros(max(NC, 1), np.int32); nl_out = np.zeros(max(NC, 1), np.int32)
+        p = lambda x: _ptr(x) if x.size else None
+        self._check(self.lib.lra_b200_switchindex_batch(self.h, p(ch), p(link), _ptr(co), NC, p(coarse), len(coarse), p(cq), len(cq) // 2, _ptr(n_out), _ptr(nl_out)))
+        return ch, link, n_out[:NC], nl_out[:NC]
 
     # ---- a22
     def mapq_batch(self, ag, bypass, read_type, global_k):

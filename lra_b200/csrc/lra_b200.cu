@@ -28,6 +28,7 @@
 #include "mapq_kernels.cuh"
 #include "lext_kernels.cuh"
 #include "spchain_kernels.cuh"
+#include "cglue_kernels.cuh"
 
 using namespace lra;
 
@@ -69,6 +70,7 @@ struct lra_b200_ctx {
   DevBuf le[24];          // linear extension scratch
   DevBuf lc[32];          // linear extension (chain overload) scratch
   DevBuf sp[40];          // chain splitting scratch
+  DevBuf cg[16];          // MergeChain / switchindex scratch
   bool keep_stats = false;  // sub-launchers append to stats instead of clearing
   AogPlan *h_plan = nullptr;            // pinned
   unsigned long long *h_misc = nullptr;  // pinned (2 x u64)
@@ -166,6 +168,7 @@ extern "C" void lra_b200_destroy(lra_b200_ctx *ctx) {
   for (DevBuf &b : ctx->le) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->lc) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->sp) if (b.p) cudaFree(b.p);
+  for (DevBuf &b : ctx->cg) if (b.p) cudaFree(b.p);
   for (auto &ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < 4; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]); }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);

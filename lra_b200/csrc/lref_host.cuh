@@ -1081,3 +1081,91 @@ extern "C" int lra_b200_split_chains_batch(lra_b200_ctx *ctx, const lra_b200_anc
   ctx->stats.push_back(s2);
   return LRA_B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- a11 MergeChain / switchindex
+extern "C" int lra_b200_merge_chain_batch(lra_b200_ctx *ctx, const int32_t *sp, const uint64_t *sc_off, int32_t n_chains, const int32_t *chrom, const uint8_t *strand,
+                                          const uint32_t *box, int32_t n_clusters, uint8_t *head) {
+  if (!ctx || !sc_off || n_chains < 0 || n_clusters < 0) return fail(ctx, LRA_B200_EINVAL, "merge_chain_batch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  const size_t E = n_chains ? (size_t)sc_off[n_chains] : 0;
+  if (E == 0) return LRA_B200_OK;
+  if (!sp || !chrom || !strand || !box || !head || n_clusters == 0) return fail(ctx, LRA_B200_EINVAL, "merge_chain_batch: NULL array");
+  std::vector<uint8_t> first(E, 0);
+  for (int k = 0; k < n_chains; k++) {
+    if (sc_off[k + 1] < sc_off[k]) return fail(ctx, LRA_B200_EINVAL, "merge_chain_batch: chain offsets not ascending");
+    if (sc_off[k + 1] > sc_off[k]) first[(size_t)sc_off[k]] = 1;
+  }
+  for (size_t e = 0; e < E; e++) if (sp[e] < 0 || sp[e] >= n_clusters) return fail(ctx, LRA_B200_EINVAL, "merge_chain_batch: entry %zu names cluster %d of %d", e, sp[e], n_clusters);
+  int rc;
+  DevBuf *B = ctx->cg;
+  const size_t C1 = (size_t)n_clusters;
+  if ((rc = ensure(ctx, B[0], E * 4)) || (rc = ensure(ctx, B[1], E)) || (rc = ensure(ctx, B[2], C1 * 4)) || (rc = ensure(ctx, B[3], C1)) || (rc = ensure(ctx, B[4], C1 * 16)) ||
+      (rc = ensure(ctx, B[5], E)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(B[0].p, sp, E * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[1].p, first.data(), E, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[2].p, chrom, C1 * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[3].p, strand, C1, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[4].p, box, C1 * 16, cudaMemcpyHostToDevice, st));
+  MergeChainBatch b{E, (const int32_t *)B[0].p, (const uint8_t *)B[1].p, (const int32_t *)B[2].p, (const uint8_t *)B[3].p, (const uint32_t *)B[4].p, (uint8_t *)B[5].p};
+  cudaEventRecord(ctx->ev[0], st);
+  merge_chain_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(b);
+  cudaEventRecord(ctx->ev[1], st);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(head, b.head, E, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "merge_chain");
+  cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]); s2.jobs = (uint64_t)E; s2.algo_bytes = 6ull * E + 21ull * C1;
+  ctx->stats.push_back(s2);
+  return LRA_B200_OK;
+}
+
+extern "C" int lra_b200_switchindex_batch(lra_b200_ctx *ctx, int32_t *ch, uint8_t *link, const uint64_t *c_off, int32_t n_chains, const int32_t *coarse,
+                                          int32_t n_splitclusters, const uint32_t *cq, int32_t n_clusters, int32_t *n_out, int32_t *nl_out) {
+  if (!ctx || !c_off || n_chains < 0 || !n_out || !nl_out) return fail(ctx, LRA_B200_EINVAL, "switchindex_batch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  if (n_chains == 0) return LRA_B200_OK;
+  const size_t E = (size_t)c_off[n_chains];
+  for (int k = 0; k < n_chains; k++) if (c_off[k + 1] < c_off[k]) return fail(ctx, LRA_B200_EINVAL, "switchindex_batch: chain offsets not ascending");
+  if (E && (!ch || !link || !coarse || !cq)) return fail(ctx, LRA_B200_EINVAL, "switchindex_batch: NULL array");
+  for (size_t e = 0; e < E; e++) if (ch[e] < 0 || ch[e] >= n_splitclusters) return fail(ctx, LRA_B200_EINVAL, "switchindex_batch: entry %zu names split cluster %d of %d", e, ch[e], n_splitclusters);
+  for (int i = 0; i < n_splitclusters; i++) if (coarse[i] < 0 || coarse[i] >= n_clusters) return fail(ctx, LRA_B200_EINVAL, "switchindex_batch: split cluster %d maps to cluster %d of %d", i, coarse[i], n_clusters);
+  int rc;
+  DevBuf *B = ctx->cg;
+  const size_t Ep = E ? E : 1, C1 = (size_t)n_chains;
+  if ((rc = ensure(ctx, B[6], (C1 + 1) * 8)) || (rc = ensure(ctx, B[7], Ep * 4)) || (rc = ensure(ctx, B[8], Ep)) || (rc = ensure(ctx, B[9], (size_t)(n_splitclusters ? n_splitclusters : 1) * 4)) ||
+      (rc = ensure(ctx, B[10], (size_t)(n_clusters ? n_clusters : 1) * 8)) || (rc = ensure(ctx, B[11], Ep * 12)) || (rc = ensure(ctx, B[12], Ep * 2)) || (rc = ensure(ctx, B[13], C1 * 8)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(B[6].p, c_off, (C1 + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (E) {
+    CU(cudaMemcpyAsync(B[7].p, ch, E * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B[8].p, link, E, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B[9].p, coarse, (size_t)n_splitclusters * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B[10].p, cq, (size_t)n_clusters * 8, cudaMemcpyHostToDevice, st));
+  }
+  SwitchIndexBatch b;
+  b.n_chains = n_chains; b.c_off = (const unsigned long long *)B[6].p; b.ch = (int32_t *)B[7].p; b.link = (uint8_t *)B[8].p; b.coarse = (const int32_t *)B[9].p;
+  b.cq = (const uint32_t *)B[10].p; b.ss = (int32_t *)B[11].p; b.se = b.ss + Ep; b.newch = b.se + Ep; b.newlink = (uint8_t *)B[12].p; b.flag = b.newlink + Ep;
+  b.n_out = (int32_t *)B[13].p; b.nl_out = b.n_out + C1;
+  cudaEventRecord(ctx->ev[0], st);
+  switchindex_kernel<<<(unsigned)((n_chains + 63) / 64), 64, 0, st>>>(b);
+  cudaEventRecord(ctx->ev[1], st);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  if (E) {
+    CU(cudaMemcpyAsync(ch, b.ch, E * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(link, b.link, E, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaMemcpyAsync(n_out, b.n_out, C1 * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(nl_out, b.nl_out, C1 * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "switchindex");
+  cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]); s2.jobs = (uint64_t)n_chains; s2.algo_bytes = 10ull * E;
+  ctx->stats.push_back(s2);
+  return LRA_B200_OK;
+}

@@ -822,3 +822,33 @@ def split_chain(ch, hdr_pos, splitdist=50000, bypass=0, which="port"):
         o[key] = o[key][:k]
     o["link"] = o["link"][:int(nl[0])]
     return o
+
+
+# ---------------------------------------------------------------- a11 MergeChain / switchindex
+
+def merge_chain(sp, chrom, strand, box, which="port"):
+    """One split chain over clusters.  Returns head flags (1 = the entry starts a new Merge_SplitChain)."""
+    n = len(sp)
+    L = ref() if which == "ref" else port()
+    f = _bind_once(L, "ref_merge_chain" if which == "ref" else "lra_oracle_merge_chain", C.c_long, [_i32p, C.c_int, _i32p, _u8p, _u32p, _u8p])
+    head = np.zeros(max(n, 1), np.uint8)
+    g = f(np.ascontiguousarray(sp, np.int32) if n else np.zeros(1, np.int32), n, np.ascontiguousarray(chrom, np.int32), np.ascontiguousarray(strand, np.uint8),
+          np.ascontiguousarray(box, np.uint32).reshape(-1), head)
+    assert g == int(head[:n].sum())
+    return head[:n]
+
+
+def switchindex(ch, link, coarse, cq, which="port"):
+    """One chain over split clusters (link: len(ch) - 1 bits).  Returns (chain over clusters, links)."""
+    n = len(ch)
+    c = np.ascontiguousarray(ch, np.int32).copy() if n else np.zeros(1, np.int32)
+    l = np.zeros(max(n, 1), np.uint8); l[:len(link)] = link
+    nl = np.zeros(1, np.int32)
+    coarse = np.ascontiguousarray(coarse, np.int32); cq = np.ascontiguousarray(cq, np.uint32).reshape(-1)
+    if which == "ref":
+        f = _bind_once(ref(), "ref_switchindex", C.c_long, [_i32p, C.c_int, _u8p, C.c_int, _i32p, C.c_int, _u32p, C.c_int, _i32p])
+        m = f(c, n, l, len(link), coarse, len(coarse), cq, len(cq) // 2, nl)
+    else:
+        f = _bind_once(port(), "lra_oracle_switchindex", C.c_long, [_i32p, C.c_int, _u8p, C.c_int, _i32p, _u32p, _i32p])
+        m = f(c, n, l, len(link), coarse, cq, nl)
+    return c[:m].copy(), l[:int(nl[0])].copy()

@@ -639,4 +639,46 @@ long ref_split_chain(const uint32_t *q, const uint32_t *t, const int32_t *len, c
   return (long)sp.size();
 }
 
+// ---- a11: MergeChain (ChainRefine.h:767-802) for one split chain; arguments as oracle/chain_glue.c: lra_oracle_merge_chain.
+long ref_merge_chain(const int32_t *sp, int n, const int32_t *chrom, const uint8_t *strand, const uint32_t *box, uint8_t *head) {
+  ref_init_static();
+  int ncl = 0;
+  for (int i = 0; i < n; i++) if (sp[i] + 1 > ncl) ncl = sp[i] + 1;
+  std::vector<Cluster> cl(ncl); std::vector<Cluster *> clp(ncl);
+  for (int c = 0; c < ncl; c++) {
+    cl[c].chromIndex = chrom[c]; cl[c].strand = strand[c]; cl[c].qStart = box[4 * c]; cl[c].qEnd = box[4 * c + 1]; cl[c].tStart = box[4 * c + 2]; cl[c].tEnd = box[4 * c + 3];
+    clp[c] = &cl[c];
+  }
+  SplitChain spc, merged;
+  spc.sptc.assign(sp, sp + n);
+  std::vector<Merge_SplitChain> mergeinfo;
+  MergeChain(clp, mergeinfo, merged, spc);
+  int t = 0;
+  for (size_t g = 0; g < mergeinfo.size(); g++)
+    for (size_t i = 0; i < mergeinfo[g].merged_clusterIndex.size(); i++, t++) head[t] = i == 0;
+  return (long)mergeinfo.size();
+}
+
+// ---- a11: switchindex (Mapping_ultility.h:39-161) for one chain; arguments as oracle/chain_glue.c: lra_oracle_switchindex (n_cl clusters, n_sc split clusters).
+long ref_switchindex(int32_t *ch, int n, uint8_t *link, int n_link, const int32_t *coarse, int n_sc, const uint32_t *cq, int n_cl, int32_t *n_link_out) {
+  ref_init_static();
+  std::vector<Cluster> splitclusters(n_sc), clusters(n_cl);
+  for (int i = 0; i < n_sc; i++) splitclusters[i].coarse = coarse[i];
+  for (int i = 0; i < n_cl; i++) { clusters[i].qStart = cq[2 * i]; clusters[i].qEnd = cq[2 * i + 1]; }
+  std::vector<Primary_chain> pcs(1);
+  pcs[0].chains.resize(1);
+  CHain &c = pcs[0].chains[0];
+  c.ch.assign(ch, ch + n);
+  c.link.resize(n_link);
+  for (int i = 0; i < n_link; i++) c.link[i] = link[i] != 0;
+  Genome genome; Read read; read.unaligned = 0;
+  switchindex(splitclusters, pcs, clusters, genome, read);
+  CHain &r = pcs[0].chains[0];
+  for (size_t i = 0; i < r.ch.size(); i++) ch[i] = (int32_t)r.ch[i];
+  for (size_t i = 0; i < r.link.size(); i++) link[i] = r.link[i];
+  *n_link_out = (int32_t)r.link.size();
+  read.seq = NULL; read.qual = NULL;
+  return (long)r.ch.size();
+}
+
 }  // extern "C"

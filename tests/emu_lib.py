@@ -352,3 +352,23 @@ def split_chains(ac, hdr_pos, splitdist=50000, bypass=0):
                        o["sp_box"], o["sp_chrom"], o["sp_type"], o["sp_strand"], o["sp_link"])
     o["sp_box"] = o["sp_box"].reshape(-1, 4)
     return o
+
+
+def merge_chain(sp, first, chrom, strand, box):
+    L = lib()
+    L.emu_merge_chain.argtypes = [C.c_uint64, _i32p, _u8p, _i32p, _u8p, _u32p, _u8p]
+    n = len(sp)
+    head = np.zeros(max(n, 1), np.uint8)
+    pad = lambda a, dt: np.ascontiguousarray(a, dt).reshape(-1) if len(a) else np.zeros(1, dt)
+    L.emu_merge_chain(n, pad(sp, np.int32), pad(first, np.uint8), pad(chrom, np.int32), pad(strand, np.uint8), pad(box, np.uint32), head)
+    return head[:n]
+
+
+def switchindex(ch, link, c_off, coarse, cq):
+    L = lib()
+    L.emu_switchindex.argtypes = [C.c_int, _u64p, _i32p, _u8p, _i32p, _u32p, _i32p, _i32p]
+    co = np.ascontiguousarray(c_off, np.uint64); NC = len(co) - 1
+    ch = np.array(ch, np.int32) if len(ch) else np.zeros(1, np.int32); link = np.array(link, np.uint8) if len(link) else np.zeros(1, np.uint8)
+    n_out = np.zeros(max(NC, 1), np.int32); nl_out = np.zeros(max(NC, 1), np.int32)
+    L.emu_switchindex(NC, co, ch, link, np.ascontiguousarray(coarse, np.int32), np.ascontiguousarray(cq, np.uint32).reshape(-1), n_out, nl_out)
+    return ch, link, n_out[:NC], nl_out[:NC]

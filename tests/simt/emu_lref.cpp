@@ -283,3 +283,18 @@ extern "C" int emu_split_chains(int n_chains, const uint64_t *c_off, const uint3
   if (n_chains) emu::launch(dim3((unsigned)((n_chains + 63) / 64)), dim3(64), 0, [&] { spchain_kernel(b); });
   return 0;
 }
+
+// ---- a11 MergeChain / switchindex
+#include "cglue_kernels.cuh"
+extern "C" int emu_merge_chain(uint64_t n_entries, const int32_t *sp, const uint8_t *first, const int32_t *chrom, const uint8_t *strand, const uint32_t *box, uint8_t *head) {
+  MergeChainBatch b{n_entries, sp, first, chrom, strand, box, head};
+  if (n_entries) emu::launch(dim3((unsigned)((n_entries + 255) / 256)), dim3(256), 0, [&] { merge_chain_kernel(b); });
+  return 0;
+}
+extern "C" int emu_switchindex(int n_chains, const uint64_t *c_off, int32_t *ch, uint8_t *link, const int32_t *coarse, const uint32_t *cq, int32_t *n_out, int32_t *nl_out) {
+  const size_t E = (size_t)c_off[n_chains] + 1;
+  std::vector<int32_t> ss(E), se(E), newch(E); std::vector<uint8_t> newlink(E), flag(E);
+  SwitchIndexBatch b{n_chains, (const unsigned long long *)c_off, ch, link, coarse, cq, ss.data(), se.data(), newch.data(), newlink.data(), flag.data(), n_out, nl_out};
+  if (n_chains) emu::launch(dim3((unsigned)((n_chains + 63) / 64)), dim3(64), 0, [&] { switchindex_kernel(b); });
+  return 0;
+}
