@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Stand-alone timing of the small MapRead stages that are not in bench.py yet (development aid; run on the GPU box):
-a6 anchor sorts, a7 CleanOffDiagonal, a16 chain filters, a20 RefineBreakpoint, a24 GlobalChain, on ONT-shaped synthetic batches
+a6 anchor sorts, a7 CleanOffDiagonal, a11 chain splitting, a15 LinearExtend, a16 chain filters, a20 RefineBreakpoint, a24 GlobalChain, on ONT-shaped synthetic batches
 (16384 reads: two anchor lists of ~190 seeds per read, one chain of ~400 anchors per read, 2048 breakpoints, 2048 chaining problems)."""
 import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -66,3 +66,37 @@ foff = np.zeros(len(probs) + 1, np.uint64); foff[1:] = np.cumsum([len(p[0]) for 
 frag = np.concatenate([p[0] for p in probs]); sc = np.concatenate([p[1] for p in probs])
 for it in range(2):
     t0 = time.time(); o = ctx.global_chain_batch(frag, foff, sc); report("a24 GlobalChain", len(probs), t0)
+
+# a15 LinearExtend (low-accuracy): 16384 reads, one cluster each of ~3 k K-mer anchors along the read's true alignment (ONT: the exact >= 17-base stretches)
+import lextgen, spchaingen, cgluegen
+RL = min(R, 4096)
+arena, items = lextgen.reads(5, 64, read_len=20000, single=False, sub=0.04, indel=0.04, max_parts=2)
+items = (items * (RL // 64 + 1))[:RL]
+read_arena, ep = lextgen.to_batch(items)
+rs = ctx.seq_upload(read_arena[:-16]); gs = ctx.seq_upload(arena[:-16])
+for it in range(2):
+    t0 = time.time(); o = ctx.linear_extend_batch(rs, gs, ep, 17, 0, 1); report("a15 LinearExtend+Trim (%d reads)" % RL, len(ep["q"]), t0)
+print("   %d anchors -> %d extended" % (len(ep["q"]), len(o["q"])))
+carena, citems = lextgen.chain_reads(6, 64, read_len=20000)
+citems = (citems * (RL // 64 + 1))[:RL]
+cra, cd = lextgen.chains_to_batch(citems)
+rs2 = ctx.seq_upload(cra[:-16]); gs2 = ctx.seq_upload(carena[:-16])
+for it in range(2):
+    t0 = time.time(); o = ctx.linear_extend_chains_batch(rs2, gs2, cd, 17, 1, 1, 100); report("a15 LinearExtend_chain+Merge (%d reads)" % RL, len(cd["q"]), t0)
+
+# a11: one UltimateChain per read
+chs = spchaingen.chains(7, 512) * (R // 512)
+c_off = np.zeros(len(chs) + 1, np.uint64); c_off[1:] = np.cumsum([len(c["q"]) for c in chs])
+cat = lambda k, dt: np.concatenate([np.asarray(c[k], dt) for c in chs])
+ac = dict(c_off=c_off, q=cat("q", np.uint32), t=cat("t", np.uint32), len=cat("len", np.int32), strand=cat("strand", np.uint8), cnum=cat("cnum", np.int32),
+          link=np.concatenate([np.append(c["link"], 0).astype(np.uint8)[:len(c["q"])] for c in chs]))
+for it in range(2):
+    t0 = time.time(); o = ctx.split_chains_batch(ac, spchaingen.HDR, 50000, 0); report("a11 SPLITChain (%d anchors)" % int(c_off[-1]), len(chs), t0)
+rg = np.random.default_rng(3)
+mc = [cgluegen.merge_case(rg) for _ in range(512)] * (R // 512)
+sp, chrom, strand_, box, base_ = [], [], [], [], 0
+for c in mc:
+    sp.append(c["sp"] + base_); chrom.append(c["chrom"]); strand_.append(c["strand"]); box.append(c["box"]); base_ += len(c["chrom"])
+so = np.zeros(len(mc) + 1, np.uint64); so[1:] = np.cumsum([len(c["sp"]) for c in mc])
+for it in range(2):
+    t0 = time.time(); o = ctx.merge_chain_batch(np.concatenate(sp), so, np.concatenate(chrom), np.concatenate(strand_), np.concatenate(box)); report("a11 MergeChain", len(mc), t0)
