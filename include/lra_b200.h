@@ -558,6 +558,25 @@ int lra_b200_merge_chain_batch(lra_b200_ctx *ctx, const int32_t *sp, const uint6
 int lra_b200_switchindex_batch(lra_b200_ctx *ctx, int32_t *ch, uint8_t *link, const uint64_t *c_off, int32_t n_chains, const int32_t *coarse,
                                int32_t n_splitclusters, const uint32_t *cq, int32_t n_clusters, int32_t *n_out, int32_t *nl_out);
 
+/* ---- a17 (leaf)  RefineByLinearAlignment, batched over the gaps between consecutive anchors --------------------------------
+ * Replaces  RefineByLinearAlignment(btc_curReadEnd, btc_curGenomeEnd, btc_nextReadStart, btc_nextGenomeStart, str, chromIndex, alignment, read,
+ *                                   genome, strands, scoreMat, pathMat, opts, buff)      (LocalRefineAlignment.h:144-185, with SetMatchAndGaps /
+ * Matched :89-99, RefineSubstrings :131-142, AlignSubstrings :101-129; opts.refineLevel & REF_DP set, the default) for a batch of gaps:
+ * gap g aligns read[cur_read_end .. next_read_start) (the read starts at read_off[g] of `reads`, the arena of its strand) to
+ * contig[cur_genome_end .. next_genome_start) (the contig starts at chrom_off[g] of `genome`) with AffineOneGapAlign(localMatch, localMismatch,
+ * localIndel, min(2 |qLen - tLen| + 1, localBand)) when Matched() > 0, and returns the blocks the reference appends to alignment->blocks (read /
+ * contig coordinates), n_blocks[g] of them from blocks[3 * block_off[g]]; a gap with Matched() <= 0 yields none.  score[g] = the value
+ * AlignSubstrings returns (meaningful for aligned gaps only).  Capacity protocol as lra_b200_aog_batch. */
+typedef struct lra_b200_linear_gaps {
+  int32_t n_gaps;
+  const uint32_t *cur_read_end, *next_read_start, *cur_genome_end, *next_genome_start;   /* [n_gaps] */
+  const uint32_t *read_off, *chrom_off;                                                    /* [n_gaps] */
+  int32_t match, mismatch, indel, local_band;
+} lra_b200_linear_gaps;
+
+int lra_b200_refine_linear_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_linear_gaps *in,
+                                 lra_b200_aog_result *res);
+
 /* ---- a20  RefineBreakpoint, batched over pairs of adjacent segments --------------------------------------------------
  * Replaces  void RefineBreakpoint(Read &read, Genome &genome, Alignment &leftAln, Alignment &rightAln, const Options &opts)
  * (RefineBreakpoint.h:212-462; called for consecutive segments of a split read, Map_highacc.h:725, Map_lowacc.h:592).  Pair p: the left /

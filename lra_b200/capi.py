@@ -117,6 +117,11 @@ def split_chain_view(o, c_off, k):
                 type=o["sp_type"][a:a + ns], strand=o["sp_strand"][a:a + ns], link=o["sp_link"][a:a + int(o["n_link"][k])])
 
 
+class _LinearGaps(C.Structure):
+    _fields_ = [("n_gaps", C.c_int32), ("cur_read_end", C.c_void_p), ("next_read_start", C.c_void_p), ("cur_genome_end", C.c_void_p), ("next_genome_start", C.c_void_p),
+                ("read_off", C.c_void_p), ("chrom_off", C.c_void_p), ("match", C.c_int32), ("mismatch", C.c_int32), ("indel", C.c_int32), ("local_band", C.c_int32)]
+
+
 class _Breakpoints(C.Structure):
     _fields_ = [("n_pairs", C.c_int32), ("lf", C.c_void_p), ("ll", C.c_void_p), ("rf", C.c_void_p), ("rl", C.c_void_p), ("lstrand", C.c_void_p),
                 ("rstrand", C.c_void_p), ("read_off", C.c_void_p), ("read_len", C.c_void_p), ("lchrom_off", C.c_void_p), ("rchrom_off", C.c_void_p),
@@ -218,6 +223,7 @@ def load_library():
     L.lra_b200_refine_breakpoint_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Breakpoints), C.POINTER(_BreakpointResult)]
     L.lra_b200_linear_extend_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_ExtendParts), C.POINTER(_Extended)]
     L.lra_b200_split_chains_batch.argtypes = [C.c_void_p, C.POINTER(_AnchorChains), C.POINTER(_SplitChains)]
+    L.lra_b200_refine_linear_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_LinearGaps), C.POINTER(_AogResult)]
     L.lra_b200_merge_chain_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_switchindex_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.lra_b200_linear_extend_chains_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_ExtendChains), C.POINTER(_ExtendedChains)]
@@ -574,6 +580,25 @@ class Context:
         p = lambda x: _ptr(x) if x.size else None
         self._check(self.lib.lra_b200_switchindex_batch(self.h, p(ch), p(link), _ptr(co), NC, p(coarse), len(coarse), p(cq), len(cq) // 2, _ptr(n_out), _ptr(nl_out)))
         return ch, link, n_out[:NC], nl_out[:NC]
+
+    # ---- a17 (leaf)
+    def refine_linear_batch(self, reads, genome, gaps, m, mm, indel, local_band, block_cap=None):
+        """RefineByLinearAlignment for every gap (gaps: dict(cur_read_end, next_read_start, cur_genome_end, next_genome_start, read_off, chrom_off)).
+        Returns dict(score, n_blocks, block_off, blocks[n,3]) with blocks in read / contig coordinates."""
+        a = {k: np.ascontiguousarray(gaps[k], np.uint32) for k in ["cur_read_end", "next_read_start", "cur_genome_end", "next_genome_start", "read_off", "chrom_off"]}
+        n = len(a["read_off"])
+        if block_cap is None:
+            ql = (a["next_read_start"] - a["cur_read_end"]).astype(np.int32).astype(np.int64); tl = (a["next_genome_start"] - a["cur_genome_end"]).astype(np.int32).astype(np.int64)
+            block_cap = int(np.minimum(ql, tl).clip(min=0).sum()) + 1
+        out = dict(score=np.zeros(max(n, 1), np.int32), n_blocks=np.zeros(max(n, 1), np.int32), block_off=np.zeros(max(n, 1), np.uint64), blocks=np.zeros((max(1, block_cap), 3), np.uint32))
+        p = lambda x: _ptr(x) if x.size else None
+        g = _LinearGaps(n, p(a["cur_read_end"]), p(a["next_read_start"]), p(a["cur_genome_end"]), p(a["next_genome_start"]), p(a["read_off"]), p(a["chrom_off"]), m, mm, indel, local_band)
+        res = _AogResult(_ptr(out["score"]), _ptr(out["n_blocks"]), _ptr(out["block_off"]), _ptr(out["blocks"]), block_cap, 0, 0)
+        self._check(self.lib.lra_b200_refine_linear_batch(self.h, reads.handle, genome.handle, C.byref(g), C.byref(res)))
+        out["n_blocks_total"] = int(res.n_blocks_total)
+        for k in ("score", "n_blocks", "block_off"):
+            out[k] = out[k][:n]
+        return out
 
     # ---- a22
     def mapq_batch(self, ag, bypass, read_type, global_k):

@@ -29,6 +29,7 @@
 #include "lext_kernels.cuh"
 #include "spchain_kernels.cuh"
 #include "cglue_kernels.cuh"
+#include "rla_kernels.cuh"
 
 using namespace lra;
 
@@ -71,6 +72,7 @@ struct lra_b200_ctx {
   DevBuf lc[32];          // linear extension (chain overload) scratch
   DevBuf sp[40];          // chain splitting scratch
   DevBuf cg[16];          // MergeChain / switchindex scratch
+  DevBuf rl[8];           // RefineByLinearAlignment: gap descriptors
   bool keep_stats = false;  // sub-launchers append to stats instead of clearing
   AogPlan *h_plan = nullptr;            // pinned
   unsigned long long *h_misc = nullptr;  // pinned (2 x u64)
@@ -169,6 +171,7 @@ extern "C" void lra_b200_destroy(lra_b200_ctx *ctx) {
   for (DevBuf &b : ctx->lc) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->sp) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->cg) if (b.p) cudaFree(b.p);
+  for (DevBuf &b : ctx->rl) if (b.p) cudaFree(b.p);
   for (auto &ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < 4; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]); }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);

@@ -1169,3 +1169,63 @@ extern "C" int lra_b200_switchindex_batch(lra_b200_ctx *ctx, int32_t *ch, uint8_
   ctx->stats.push_back(s2);
   return LRA_B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- a17 (leaf) RefineByLinearAlignment
+extern "C" int lra_b200_refine_linear_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_linear_gaps *in,
+                                            lra_b200_aog_result *res) {
+  if (!ctx || !reads || !genome || !in || !res) return fail(ctx, LRA_B200_EINVAL, "refine_linear_batch: NULL argument");
+  const int n = in->n_gaps;
+  if (n < 0) return fail(ctx, LRA_B200_EINVAL, "refine_linear_batch: negative gap count");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  res->n_blocks_total = 0; res->cells = 0;
+  if (n == 0) return LRA_B200_OK;
+  if (!in->cur_read_end || !in->next_read_start || !in->cur_genome_end || !in->next_genome_start || !in->read_off || !in->chrom_off)
+    return fail(ctx, LRA_B200_EINVAL, "refine_linear_batch: NULL gap array");
+  for (int g = 0; g < n; g++) {       // the windows a gap with m > 0 reads must lie inside the arenas
+    const uint32_t a = in->next_read_start[g] - in->cur_read_end[g] + 1u, c = in->next_genome_start[g] - in->cur_genome_end[g] + 1u;
+    if ((int)(a < c ? a : c) <= 0) continue;
+    const int ql = (int)(in->next_read_start[g] - in->cur_read_end[g]), tl = (int)(in->next_genome_start[g] - in->cur_genome_end[g]);
+    if (ql < 0 || tl < 0 || (uint64_t)in->read_off[g] + in->next_read_start[g] > reads->n || (uint64_t)in->chrom_off[g] + in->next_genome_start[g] > genome->n)
+      return fail(ctx, LRA_B200_EINVAL, "refine_linear_batch: gap %d reaches beyond its arena", g);
+  }
+  int rc;
+  DevBuf *B = ctx->rl;
+  const size_t nb4 = (size_t)n * 4;
+  for (int i = 0; i < 6; i++) if ((rc = ensure(ctx, B[i], nb4))) return rc;
+  if ((rc = ensure(ctx, ctx->d_qoff, nb4)) || (rc = ensure(ctx, ctx->d_toff, nb4)) || (rc = ensure(ctx, ctx->d_qlen, nb4)) || (rc = ensure(ctx, ctx->d_tlen, nb4)) ||
+      (rc = ensure(ctx, ctx->d_k, nb4)) || (rc = ensure(ctx, ctx->d_score, nb4)) || (rc = ensure(ctx, ctx->d_nb, nb4)) || (rc = ensure(ctx, ctx->d_boff, (size_t)n * 8)) ||
+      (rc = ensure(ctx, ctx->d_blocks, (size_t)(res->block_cap ? res->block_cap : 1) * 12)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  const void *src[6] = {in->cur_read_end, in->next_read_start, in->cur_genome_end, in->next_genome_start, in->read_off, in->chrom_off};
+  for (int i = 0; i < 6; i++) CU(cudaMemcpyAsync(B[i].p, src[i], nb4, cudaMemcpyHostToDevice, st));
+  RlaBatch b;
+  b.n_gaps = n; b.local_band = in->local_band;
+  b.cur_read_end = (const uint32_t *)B[0].p; b.next_read_start = (const uint32_t *)B[1].p; b.cur_genome_end = (const uint32_t *)B[2].p;
+  b.next_genome_start = (const uint32_t *)B[3].p; b.read_off = (const uint32_t *)B[4].p; b.chrom_off = (const uint32_t *)B[5].p;
+  b.q_off = (uint32_t *)ctx->d_qoff.p; b.t_off = (uint32_t *)ctx->d_toff.p; b.q_len = (int32_t *)ctx->d_qlen.p; b.t_len = (int32_t *)ctx->d_tlen.p; b.k = (int32_t *)ctx->d_k.p;
+  b.n_blocks = (const int32_t *)ctx->d_nb.p; b.block_off = (const unsigned long long *)ctx->d_boff.p; b.blocks = (uint32_t *)ctx->d_blocks.p;
+  rla_jobs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  lra_b200_aog_jobs dj;
+  dj.q_off = b.q_off; dj.t_off = b.t_off; dj.q_len = b.q_len; dj.t_len = b.t_len; dj.k = b.k; dj.n_jobs = n;
+  dj.match = in->match; dj.mismatch = in->mismatch; dj.indel = in->indel;
+  lra_b200_aog_result dr = *res;
+  dr.score = (int32_t *)ctx->d_score.p; dr.n_blocks = (int32_t *)ctx->d_nb.p; dr.block_off = (uint64_t *)ctx->d_boff.p; dr.blocks = (uint32_t *)ctx->d_blocks.p;
+  rc = aog_run_device(ctx, reads, genome, &dj, &dr);
+  res->n_blocks_total = dr.n_blocks_total; res->cells = dr.cells;
+  if (rc != LRA_B200_OK && rc != LRA_B200_EOVERFLOW) return rc;
+  if (rc == LRA_B200_OK) {
+    rla_shift_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b);
+    ctx->launches++;
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(res->score, dr.score, nb4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->n_blocks, dr.n_blocks, nb4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->block_off, dr.block_off, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (rc == LRA_B200_OK && dr.n_blocks_total) CU(cudaMemcpyAsync(res->blocks, dr.blocks, (size_t)dr.n_blocks_total * 12, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return rc;
+}

@@ -852,3 +852,31 @@ def switchindex(ch, link, coarse, cq, which="port"):
         f = _bind_once(port(), "lra_oracle_switchindex", C.c_long, [_i32p, C.c_int, _u8p, C.c_int, _i32p, _u32p, _i32p])
         m = f(c, n, l, len(link), coarse, cq, nl)
     return c[:m].copy(), l[:int(nl[0])].copy()
+
+
+# ---------------------------------------------------------------- a17 (leaf) RefineByLinearAlignment
+
+def refine_linear(read, contig, qs, qe, ts, te, m, mm, indel, local_band, which="port"):
+    """One gap: read[qs, qe) against contig[ts, te).  Returns the blocks [n,3] in read / contig coordinates.
+    port: SetMatchAndGaps / Matched (LocalRefineAlignment.h:89-99) in uint32 arithmetic, AlignSubstrings' band (:101-129), the a18 oracle, the shift of
+    RefineSubstrings (:131-142)."""
+    r = np.ascontiguousarray(read, np.uint8); c = np.ascontiguousarray(contig, np.uint8)
+    if which == "ref":
+        f = _bind_once(ref(), "ref_refine_linear", C.c_long, [_u8p, C.c_int, _u8p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                              _u32p, C.c_long])
+        cap = max(int(qe) - int(qs), 1) + 16
+        out = np.zeros(3 * cap, np.uint32)
+        n = f(r, len(r), c, len(c), int(qs), int(qe), int(ts), int(te), m, mm, indel, local_band, out, cap)
+        return out[:3 * n].reshape(-1, 3)
+    a = (int(qe) - int(qs) + 1) & 0xFFFFFFFF; b = (int(te) - int(ts) + 1) & 0xFFFFFFFF
+    mt = min(a, b)
+    if mt >= 1 << 31:
+        mt -= 1 << 32
+    if mt <= 0:
+        return np.zeros((0, 3), np.uint32)
+    ql, tl = int(qe) - int(qs), int(te) - int(ts)
+    k = min(abs(ql - tl) * 2 + 1, local_band)
+    score, blocks, st = aog_port(bytes(r[qs:qe]), bytes(c[ts:te]), m, mm, indel, k)
+    assert st == 0
+    blocks[:, 0] += np.uint32(qs); blocks[:, 1] += np.uint32(ts)
+    return blocks

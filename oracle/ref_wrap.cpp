@@ -681,4 +681,25 @@ long ref_switchindex(int32_t *ch, int n, uint8_t *link, int n_link, const int32_
   return (long)r.ch.size();
 }
 
+// ---- a17 (leaf): RefineByLinearAlignment (LocalRefineAlignment.h:144-185) for one gap of a read (the strand's sequence) against its contig.
+long ref_refine_linear(const uint8_t *readseq, int read_len, const uint8_t *contig, int contig_len, uint32_t cur_read_end, uint32_t next_read_start,
+                       uint32_t cur_genome_end, uint32_t next_genome_start, int m, int mm, int indel, int local_band, uint32_t *blocks_out, long cap) {
+  ref_init_static();
+  Options opts; opts.localMatch = m; opts.localMismatch = mm; opts.localIndel = indel; opts.localBand = local_band;
+  opts.refineLevel = REF_LOC | REF_DYN | REF_DP; opts.dotPlot = false;
+  Read read; read.seq = (char *)readseq; read.length = read_len; read.unaligned = 0;
+  Genome genome; genome.seqs.push_back((char *)contig); genome.lengths.push_back(contig_len);
+  char *strands[2] = {(char *)readseq, (char *)readseq};
+  Alignment aln;
+  std::vector<int> scoreMat; std::vector<Arrow> pathMat;
+  AffineAlignBuffers buff;
+  GenomePos a = cur_read_end, b = cur_genome_end, c = next_read_start, d = next_genome_start;
+  RefineByLinearAlignment(a, b, c, d, 0, 0, &aln, read, genome, strands, scoreMat, pathMat, opts, buff);
+  const long n = (long)aln.blocks.size();
+  for (long i = 0; i < n && i < cap; i++) { blocks_out[3 * i] = aln.blocks[i].qPos; blocks_out[3 * i + 1] = aln.blocks[i].tPos; blocks_out[3 * i + 2] = aln.blocks[i].length; }
+  genome.seqs.clear();
+  read.seq = NULL; read.qual = NULL;
+  return n;
+}
+
 }  // extern "C"
