@@ -530,7 +530,7 @@ typedef struct lra_b200_anchor_chains {
   int32_t bypass_clustering;    /* opts.bypassClustering */
 } lra_b200_anchor_chains;
 
-typedef struct lra_b200_split_chains {
+typedef struct lra_b200_split_chain_result {
   int32_t *n_sp, *n_link;       /* [n_chains] */
   int32_t *sp_off, *ci_off;     /* [N + n_chains] */
   int32_t *sptc, *ci;           /* [N] */
@@ -538,9 +538,9 @@ typedef struct lra_b200_split_chains {
   uint32_t *sp_box;             /* [N * 4] */
   int32_t *sp_chrom;            /* [N] */
   uint8_t *sp_type, *sp_strand, *sp_link;   /* [N] */
-} lra_b200_split_chains;
+} lra_b200_split_chain_result;
 
-int lra_b200_split_chains_batch(lra_b200_ctx *ctx, const lra_b200_anchor_chains *in, lra_b200_split_chains *res);
+int lra_b200_split_chains_batch(lra_b200_ctx *ctx, const lra_b200_anchor_chains *in, lra_b200_split_chain_result *res);
 
 /* ---- a11  MergeChain, batched over split chains ------------------------------------------------------------------------------
  * Replaces  MergeChain(Refined_Clusters, mergeinfo, merge_spcluster, spcluster)  (ChainRefine.h:767-802; Map_lowacc.h:440).  Split chain k owns

@@ -103,7 +103,7 @@ class _AnchorChains(C.Structure):
                 ("link", C.c_void_p), ("hdr_pos", C.c_void_p), ("n_hdr", C.c_int32), ("splitdist", C.c_int32), ("bypass_clustering", C.c_int32)]
 
 
-class _SplitChains(C.Structure):
+class _SplitChainsOut(C.Structure):
     _fields_ = [("n_sp", C.c_void_p), ("n_link", C.c_void_p), ("sp_off", C.c_void_p), ("ci_off", C.c_void_p), ("sptc", C.c_void_p), ("ci", C.c_void_p), ("sp_lk", C.c_void_p),
                 ("sp_box", C.c_void_p), ("sp_chrom", C.c_void_p), ("sp_type", C.c_void_p), ("sp_strand", C.c_void_p), ("sp_link", C.c_void_p)]
 
@@ -222,7 +222,7 @@ def load_library():
     L.lra_b200_global_chain_batch.argtypes = [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 4
     L.lra_b200_refine_breakpoint_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Breakpoints), C.POINTER(_BreakpointResult)]
     L.lra_b200_linear_extend_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_ExtendParts), C.POINTER(_Extended)]
-    L.lra_b200_split_chains_batch.argtypes = [C.c_void_p, C.POINTER(_AnchorChains), C.POINTER(_SplitChains)]
+    L.lra_b200_split_chains_batch.argtypes = [C.c_void_p, C.POINTER(_AnchorChains), C.POINTER(_SplitChainsOut)]
     L.lra_b200_refine_linear_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_LinearGaps), C.POINTER(_AogResult)]
     L.lra_b200_merge_chain_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_switchindex_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
@@ -546,7 +546,7 @@ class Context:
     # ---- a11
     def split_chains_batch(self, ac, hdr_pos, splitdist=50000, bypass=0):
         """SPLITChain(UltimateChain) + MergeSplitchainINS + RemoveSpuriousSplitChain for every chain (ac: dict(c_off, q, t, len, strand, cnum, link -- link has
-        one entry per anchor, the last of each chain unused)).  Returns the slot-layout arrays of lra_b200_split_chains; see split_chain_view."""
+        one entry per anchor, the last of each chain unused)).  Returns the slot-layout arrays of lra_b200_split_chain_result; see split_chain_view."""
         co = np.ascontiguousarray(ac["c_off"], np.uint64); NC = len(co) - 1; N = int(co[-1])
         a = dict(q=np.ascontiguousarray(ac["q"], np.uint32), t=np.ascontiguousarray(ac["t"], np.uint32), len=np.ascontiguousarray(ac["len"], np.int32),
                  strand=np.ascontiguousarray(ac["strand"], np.uint8), cnum=np.ascontiguousarray(ac["cnum"], np.int32), link=np.ascontiguousarray(ac["link"], np.uint8))
@@ -558,7 +558,7 @@ class Context:
                  sp_type=np.zeros(Np, np.uint8), sp_strand=np.zeros(Np, np.uint8), sp_link=np.zeros(Np, np.uint8))
         p = lambda x: _ptr(x) if x.size else None
         e = _AnchorChains(NC, _ptr(co), p(a["q"]), p(a["t"]), p(a["len"]), p(a["strand"]), p(a["cnum"]), p(a["link"]), _ptr(hdr), len(hdr), int(splitdist), int(bypass))
-        r = _SplitChains(*[_ptr(o[k]) for k in ["n_sp", "n_link", "sp_off", "ci_off", "sptc", "ci", "sp_lk", "sp_box", "sp_chrom", "sp_type", "sp_strand", "sp_link"]])
+        r = _SplitChainsOut(*[_ptr(o[k]) for k in ["n_sp", "n_link", "sp_off", "ci_off", "sptc", "ci", "sp_lk", "sp_box", "sp_chrom", "sp_type", "sp_strand", "sp_link"]])
         self._check(self.lib.lra_b200_split_chains_batch(self.h, C.byref(e), C.byref(r)))
         return o
 

@@ -1019,7 +1019,7 @@ extern "C" int lra_b200_linear_extend_chains_batch(lra_b200_ctx *ctx, const lra_
 }
 
 // ---------------------------------------------------------------------------------------------------- a11 SPLITChain (low-accuracy pipeline)
-extern "C" int lra_b200_split_chains_batch(lra_b200_ctx *ctx, const lra_b200_anchor_chains *in, lra_b200_split_chains *res) {
+extern "C" int lra_b200_split_chains_batch(lra_b200_ctx *ctx, const lra_b200_anchor_chains *in, lra_b200_split_chain_result *res) {
   if (!ctx || !in || !res) return fail(ctx, LRA_B200_EINVAL, "split_chains_batch: NULL argument");
   const int NC = in->n_chains;
   if (NC < 0 || !in->c_off || !in->hdr_pos || in->n_hdr < 1) return fail(ctx, LRA_B200_EINVAL, "split_chains_batch: bad argument");
