@@ -577,6 +577,36 @@ typedef struct lra_b200_linear_gaps {
 int lra_b200_refine_linear_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_linear_gaps *in,
                                  lra_b200_aog_result *res);
 
+/* ---- a14 (core, small spaces)  RefineSpace, batched over spaces -------------------------------------------------------------
+ * Replaces  float RefineSpace(K, W, refineSpaceDiag, consider_str, EndPairs, opts, genome, read, strands, ChromIndex, qe, qs, te, ts, st, lrts, lrlength)
+ * (ClusterRefine.h:242-327) for spaces with qe - qs < 1000 and te - ts + lrlength < 1000: the branch that aligns the space with
+ * AffineOneGapAlign(localMatch, localMismatch, localIndel, 30) and takes the exact K-mers at multiples of K inside blocks longer than K (:262-294).
+ * Space g: read[qs, qe) on the strand whose arena holds the read at read_off[g] (length read_len[g]), contig[ts - lrts, te + lrlength - lrts) with
+ * the contig at chrom_off[g]; flip[g] = consider_str && st == 1 (read positions are reported as read_len - pos - K).  Results in slot layout:
+ * EndPairs of space g = (pq, pt)[pair_off[g] .. pair_off[g] + n_pairs[g]), identity[g] = the return value (nMatch / (float) min(|query|, |ref|)).
+ * A larger space is rejected with LRA_B200_EINVAL (the minimizer + CompareLists branch :296-305 is not built -- there is no fallback).
+ * pair_cap must cover the slots (n_pairs_total = their number, also on LRA_B200_EOVERFLOW): sum over spaces of min(qLen, tLen) / K + 1. */
+typedef struct lra_b200_spaces {
+  int32_t n_spaces;
+  const uint32_t *qs, *qe, *ts, *te, *lrts, *lrlength;      /* [n_spaces] */
+  const uint32_t *read_off, *read_len, *chrom_off;          /* [n_spaces] */
+  const uint8_t *flip;                                      /* [n_spaces] */
+  int32_t K;                                                /* the K RefineSpace is called with (opts.globalK) */
+  int32_t match, mismatch, indel;                           /* opts.localMatch, localMismatch, localIndel */
+} lra_b200_spaces;
+
+typedef struct lra_b200_space_result {
+  uint64_t *pair_off;       /* [n_spaces + 1] */
+  int32_t *n_pairs;         /* [n_spaces] */
+  float *identity;          /* [n_spaces] */
+  uint32_t *pq, *pt;        /* [pair_cap] */
+  uint64_t pair_cap;
+  uint64_t n_pairs_total;   /* out: slots used */
+} lra_b200_space_result;
+
+int lra_b200_refine_space_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_spaces *in,
+                                lra_b200_space_result *res);
+
 /* ---- a20  RefineBreakpoint, batched over pairs of adjacent segments --------------------------------------------------
  * Replaces  void RefineBreakpoint(Read &read, Genome &genome, Alignment &leftAln, Alignment &rightAln, const Options &opts)
  * (RefineBreakpoint.h:212-462; called for consecutive segments of a split read, Map_highacc.h:725, Map_lowacc.h:592).  Pair p: the left /

@@ -122,6 +122,17 @@ class _LinearGaps(C.Structure):
                 ("read_off", C.c_void_p), ("chrom_off", C.c_void_p), ("match", C.c_int32), ("mismatch", C.c_int32), ("indel", C.c_int32), ("local_band", C.c_int32)]
 
 
+class _Spaces(C.Structure):
+    _fields_ = [("n_spaces", C.c_int32), ("qs", C.c_void_p), ("qe", C.c_void_p), ("ts", C.c_void_p), ("te", C.c_void_p), ("lrts", C.c_void_p), ("lrlength", C.c_void_p),
+                ("read_off", C.c_void_p), ("read_len", C.c_void_p), ("chrom_off", C.c_void_p), ("flip", C.c_void_p), ("K", C.c_int32), ("match", C.c_int32),
+                ("mismatch", C.c_int32), ("indel", C.c_int32)]
+
+
+class _SpaceResult(C.Structure):
+    _fields_ = [("pair_off", C.c_void_p), ("n_pairs", C.c_void_p), ("identity", C.c_void_p), ("pq", C.c_void_p), ("pt", C.c_void_p), ("pair_cap", C.c_uint64),
+                ("n_pairs_total", C.c_uint64)]
+
+
 class _Breakpoints(C.Structure):
     _fields_ = [("n_pairs", C.c_int32), ("lf", C.c_void_p), ("ll", C.c_void_p), ("rf", C.c_void_p), ("rl", C.c_void_p), ("lstrand", C.c_void_p),
                 ("rstrand", C.c_void_p), ("read_off", C.c_void_p), ("read_len", C.c_void_p), ("lchrom_off", C.c_void_p), ("rchrom_off", C.c_void_p),
@@ -223,6 +234,7 @@ def load_library():
     L.lra_b200_refine_breakpoint_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Breakpoints), C.POINTER(_BreakpointResult)]
     L.lra_b200_linear_extend_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_ExtendParts), C.POINTER(_Extended)]
     L.lra_b200_split_chains_batch.argtypes = [C.c_void_p, C.POINTER(_AnchorChains), C.POINTER(_SplitChainsOut)]
+    L.lra_b200_refine_space_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Spaces), C.POINTER(_SpaceResult)]
     L.lra_b200_refine_linear_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_LinearGaps), C.POINTER(_AogResult)]
     L.lra_b200_merge_chain_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_switchindex_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
@@ -599,6 +611,24 @@ class Context:
         for k in ("score", "n_blocks", "block_off"):
             out[k] = out[k][:n]
         return out
+
+    # ---- a14 (core, small spaces)
+    def refine_space_batch(self, reads, genome, sp, K, m, mm, indel):
+        """RefineSpace (the AffineOneGapAlign branch) for every space (sp: dict(qs, qe, ts, te, lrts, lrlength, read_off, read_len, chrom_off, flip)).
+        Returns dict(pair_off, n_pairs, identity, pq, pt) in slot layout."""
+        a = {k: np.ascontiguousarray(sp[k], np.uint32) for k in ["qs", "qe", "ts", "te", "lrts", "lrlength", "read_off", "read_len", "chrom_off"]}
+        a["flip"] = np.ascontiguousarray(sp["flip"], np.uint8)
+        n = len(a["qs"])
+        ql = a["qe"].astype(np.int64) - a["qs"]; tl = a["te"].astype(np.int64) - a["ts"] + a["lrlength"]
+        cap = int((np.minimum(ql, tl).clip(min=0) // K + 1).sum()) + 1
+        o = dict(pair_off=np.zeros(n + 1, np.uint64), n_pairs=np.zeros(max(n, 1), np.int32), identity=np.zeros(max(n, 1), np.float32), pq=np.zeros(cap, np.uint32),
+                 pt=np.zeros(cap, np.uint32))
+        p = lambda x: _ptr(x) if x.size else None
+        e = _Spaces(n, *[p(a[k]) for k in ["qs", "qe", "ts", "te", "lrts", "lrlength", "read_off", "read_len", "chrom_off", "flip"]], K, m, mm, indel)
+        r = _SpaceResult(_ptr(o["pair_off"]), _ptr(o["n_pairs"]), _ptr(o["identity"]), _ptr(o["pq"]), _ptr(o["pt"]), cap, 0)
+        self._check(self.lib.lra_b200_refine_space_batch(self.h, reads.handle, genome.handle, C.byref(e), C.byref(r)))
+        o["n_pairs"] = o["n_pairs"][:n]; o["identity"] = o["identity"][:n]
+        return o
 
     # ---- a22
     def mapq_batch(self, ag, bypass, read_type, global_k):

@@ -1229,3 +1229,81 @@ extern "C" int lra_b200_refine_linear_batch(lra_b200_ctx *ctx, const lra_b200_se
   CU(cudaStreamSynchronize(st));
   return rc;
 }
+
+// ---------------------------------------------------------------------------------------------------- a14 (core, small spaces) RefineSpace
+extern "C" int lra_b200_refine_space_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_spaces *in,
+                                           lra_b200_space_result *res) {
+  if (!ctx || !reads || !genome || !in || !res) return fail(ctx, LRA_B200_EINVAL, "refine_space_batch: NULL argument");
+  const int n = in->n_spaces;
+  if (n < 0 || in->K <= 0) return fail(ctx, LRA_B200_EINVAL, "refine_space_batch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  res->n_pairs_total = 0;
+  if (n == 0) return LRA_B200_OK;
+  if (!in->qs || !in->qe || !in->ts || !in->te || !in->lrts || !in->lrlength || !in->read_off || !in->read_len || !in->chrom_off || !in->flip)
+    return fail(ctx, LRA_B200_EINVAL, "refine_space_batch: NULL space array");
+  std::vector<unsigned long long> pair_off((size_t)n + 1);
+  size_t P = 0, blk = 0;
+  for (int g = 0; g < n; g++) {
+    const long long ql = (long long)in->qe[g] - (long long)in->qs[g], tl = (long long)in->te[g] - (long long)in->ts[g] + (long long)in->lrlength[g];
+    if (ql < 0 || tl < 0 || in->lrts[g] > in->ts[g]) return fail(ctx, LRA_B200_EINVAL, "refine_space_batch: space %d has a negative extent", g);
+    if (ql >= 1000 || tl >= 1000)
+      return fail(ctx, LRA_B200_EINVAL, "refine_space_batch: space %d is %lld x %lld: only spaces below 1000 bases on both axes (the AffineOneGapAlign branch of RefineSpace) are built",
+                  g, ql, tl);
+    if ((uint64_t)in->read_off[g] + in->qe[g] > reads->n || (uint64_t)in->chrom_off[g] + in->te[g] + in->lrlength[g] > genome->n)
+      return fail(ctx, LRA_B200_EINVAL, "refine_space_batch: space %d reaches beyond its arena", g);
+    pair_off[g] = P;
+    const long long mn = ql < tl ? ql : tl;
+    P += (size_t)(mn / in->K + 1);
+    blk += (size_t)mn + 1;
+  }
+  pair_off[n] = P;
+  if (res->pair_cap < P) { res->n_pairs_total = P; return fail(ctx, LRA_B200_EOVERFLOW, "refine_space_batch: pair arrays hold %llu entries, %llu slots are needed",
+                                                                 (unsigned long long)res->pair_cap, (unsigned long long)P); }
+  int rc;
+  DevBuf *B = ctx->rs;
+  const size_t nb4 = (size_t)n * 4;
+  for (int i = 0; i < 9; i++) if ((rc = ensure(ctx, B[i], nb4))) return rc;
+  if ((rc = ensure(ctx, B[9], (size_t)n)) || (rc = ensure(ctx, B[10], ((size_t)n + 1) * 8)) || (rc = ensure(ctx, B[11], P * 4)) || (rc = ensure(ctx, B[12], P * 4)) ||
+      (rc = ensure(ctx, B[13], nb4)) || (rc = ensure(ctx, B[14], nb4)))
+    return rc;
+  if ((rc = ensure(ctx, ctx->d_qoff, nb4)) || (rc = ensure(ctx, ctx->d_toff, nb4)) || (rc = ensure(ctx, ctx->d_qlen, nb4)) || (rc = ensure(ctx, ctx->d_tlen, nb4)) ||
+      (rc = ensure(ctx, ctx->d_k, nb4)) || (rc = ensure(ctx, ctx->d_score, nb4)) || (rc = ensure(ctx, ctx->d_nb, nb4)) || (rc = ensure(ctx, ctx->d_boff, (size_t)n * 8)) ||
+      (rc = ensure(ctx, ctx->d_blocks, blk * 12)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  const void *src[9] = {in->qs, in->qe, in->ts, in->te, in->lrts, in->lrlength, in->read_off, in->read_len, in->chrom_off};
+  for (int i = 0; i < 9; i++) CU(cudaMemcpyAsync(B[i].p, src[i], nb4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[9].p, in->flip, (size_t)n, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[10].p, pair_off.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+  RspBatch b;
+  b.n = n; b.K = in->K;
+  b.reads = SeqView{reads->b2, reads->nm, reads->n}; b.genome = SeqView{genome->b2, genome->nm, genome->n};
+  b.qs = (const uint32_t *)B[0].p; b.qe = (const uint32_t *)B[1].p; b.ts = (const uint32_t *)B[2].p; b.te = (const uint32_t *)B[3].p; b.lrts = (const uint32_t *)B[4].p;
+  b.lrlength = (const uint32_t *)B[5].p; b.read_off = (const uint32_t *)B[6].p; b.read_len = (const uint32_t *)B[7].p; b.chrom_off = (const uint32_t *)B[8].p;
+  b.flip = (const uint8_t *)B[9].p; b.pair_off = (const unsigned long long *)B[10].p; b.pq = (uint32_t *)B[11].p; b.pt = (uint32_t *)B[12].p;
+  b.n_pairs = (int32_t *)B[13].p; b.identity = (float *)B[14].p;
+  b.q_off = (uint32_t *)ctx->d_qoff.p; b.t_off = (uint32_t *)ctx->d_toff.p; b.q_len = (int32_t *)ctx->d_qlen.p; b.t_len = (int32_t *)ctx->d_tlen.p; b.k = (int32_t *)ctx->d_k.p;
+  b.n_blocks = (const int32_t *)ctx->d_nb.p; b.block_off = (const unsigned long long *)ctx->d_boff.p; b.blocks = (const uint32_t *)ctx->d_blocks.p;
+  rsp_jobs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  lra_b200_aog_jobs dj;
+  dj.q_off = b.q_off; dj.t_off = b.t_off; dj.q_len = b.q_len; dj.t_len = b.t_len; dj.k = b.k; dj.n_jobs = n;
+  dj.match = in->match; dj.mismatch = in->mismatch; dj.indel = in->indel;
+  lra_b200_aog_result dr; memset(&dr, 0, sizeof dr);
+  dr.score = (int32_t *)ctx->d_score.p; dr.n_blocks = (int32_t *)ctx->d_nb.p; dr.block_off = (uint64_t *)ctx->d_boff.p; dr.blocks = (uint32_t *)ctx->d_blocks.p;
+  dr.block_cap = blk;
+  if ((rc = aog_run_device(ctx, reads, genome, &dj, &dr))) return rc;
+  rsp_harvest_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(res->pair_off, b.pair_off, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->n_pairs, b.n_pairs, nb4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->identity, b.identity, nb4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->pq, b.pq, P * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->pt, b.pt, P * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  res->n_pairs_total = P;
+  return LRA_B200_OK;
+}

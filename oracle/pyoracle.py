@@ -880,3 +880,35 @@ def refine_linear(read, contig, qs, qe, ts, te, m, mm, indel, local_band, which=
     assert st == 0
     blocks[:, 0] += np.uint32(qs); blocks[:, 1] += np.uint32(ts)
     return blocks
+
+
+# ---------------------------------------------------------------- a14 (core, small spaces) RefineSpace
+
+def refine_space(strandseq, contig, K, qs, qe, ts, te, st, consider_str, lrts, lrlength, m, mm, indel, which="port"):
+    """One space.  Returns (pq, pt, identity).  port: the AffineOneGapAlign branch of RefineSpace (ClusterRefine.h:262-294) on the a18 oracle, the K-mer
+    harvest, identity in binary32, the coordinate shift (:314-325); spaces of 1000 or more are outside the restatement."""
+    r = np.ascontiguousarray(strandseq, np.uint8); c = np.ascontiguousarray(contig, np.uint8)
+    if which == "ref":
+        f = _bind_once(ref(), "ref_refine_space", C.c_long, [_u8p, C.c_int, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                             C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, _u32p, _u32p, C.c_long, C.POINTER(C.c_float)])
+        cap = (int(qe) - int(qs)) // K + 8
+        pq = np.zeros(cap, np.uint32); pt = np.zeros(cap, np.uint32); idn = C.c_float(0)
+        n = f(r, len(r), c, len(c), K, 10, 100, int(consider_str), int(qe), int(qs), int(te), int(ts), int(st), int(lrts), int(lrlength), m, mm, indel, pq, pt, cap, C.byref(idn))
+        return pq[:n], pt[:n], np.float32(idn.value)
+    q = r[qs:qe]; t0 = int(ts) - int(lrts); t = c[t0:t0 + int(te) - int(ts) + int(lrlength)]
+    assert len(q) < 1000 and len(t) < 1000
+    score, blocks, stt = aog_port(bytes(q), bytes(t), m, mm, indel, 30)
+    assert stt == 0
+    n_match = 0; pq, pt = [], []
+    for bq, bt, ln in blocks.tolist():
+        n_match += int((q[bq:bq + ln] == t[bt:bt + ln]).sum())
+        if ln > K:
+            for bp in range(0, ln - K, K):              # bp + K < length
+                if (q[bq + bp:bq + bp + K] == t[bt + bp:bt + bp + K]).all():
+                    fq = bq + bp + int(qs)
+                    if consider_str and st == 1:
+                        fq = (len(r) - fq - K) & 0xFFFFFFFF
+                    pq.append(fq); pt.append(bt + bp + t0)
+    mn = min(len(q), len(t))
+    idn = np.float32(n_match) / np.float32(mn) if mn else np.frombuffer(np.uint32(0xFFC00000).tobytes(), np.float32)[0]
+    return np.array(pq, np.uint32), np.array(pt, np.uint32), np.float32(idn)
