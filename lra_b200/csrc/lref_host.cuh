@@ -262,10 +262,18 @@ static int lref_run(lra_b200_ctx *ctx, const lra_b200_lindex *gl, const lra_b200
     // measured on B200 (tools/lref_timing.py): one task per THREAD (3.7 ms per pass for 74 k window pairs) beats one task per warp
     // (16 ms): the stage is bound by instruction issue, not by latency, and the lock-step warp form issues 8x more instructions
     static const bool literal = getenv("LRA_B200_LREF_WARP") == nullptr;
+    // anchors per window pair parked by the count pass (0 = off: the emit pass re-runs every non-empty pair)
+    static const int slot_cap = getenv("LRA_B200_LREF_SLOT") ? atoi(getenv("LRA_B200_LREF_SLOT")) : 48;
+    b.slot = nullptr; b.slot_cap = 0;
+    if (literal && slot_cap > 0 && n_tasks * (unsigned long long)slot_cap * 12ull <= (4ull << 30)) {
+      if ((rc = ensure(ctx, ctx->lr_x[5], (size_t)n_tasks * (size_t)slot_cap * 12))) return rc;
+      b.slot = (uint32_t *)ctx->lr_x[5].p; b.slot_cap = slot_cap;
+    }
     if (literal) lref_task_literal_kernel<false><<<(unsigned)((n_tasks + 127) / 128), 128, 0, st>>>(b, n_units, n_tasks);
     else lref_task_kernel<false><<<(unsigned)((n_tasks + 3) / 4), 128, 0, st>>>(b, n_units, n_tasks);
     seed_scan_kernel<<<1, 1024, 0, st>>>(b.out_off, (int)n_tasks, res->anchor_cap, errflag);
     rec();
+    if (b.slot) { lref_task_copy_kernel<<<(unsigned)((n_tasks * 8 + 255) / 256), 256, 0, st>>>(b, n_tasks); ctx->launches++; }
     if (literal) lref_task_literal_kernel<true><<<(unsigned)((n_tasks + 127) / 128), 128, 0, st>>>(b, n_units, n_tasks);
     else lref_task_kernel<true><<<(unsigned)((n_tasks + 3) / 4), 128, 0, st>>>(b, n_units, n_tasks);
     ctx->launches += 3;

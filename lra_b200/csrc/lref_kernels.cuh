@@ -74,6 +74,10 @@ struct LrefBatch {
   unsigned long long *r_off;           // [n_clusters + 1] first refined anchor of each cluster
   uint32_t *rbox;                      // [n_clusters][4]
   float *eff;                          // [n_clusters]
+  // the count pass parks the first slot_cap anchors of every window pair here ((q, t, tuple) triples), so that the emit pass only re-runs the pairs
+  // that produced more (nullptr: every non-empty pair is re-run)
+  uint32_t *slot;
+  int slot_cap;
 };
 
 __device__ __forceinline__ int lref_hdr_find(const unsigned long long *pos, int n, unsigned long long query) {   // Header::Find
@@ -318,7 +322,10 @@ template <bool EMIT>
 __global__ void __launch_bounds__(128) lref_task_literal_kernel(LrefBatch b, unsigned long long n_units, unsigned long long n_tasks) {
   const unsigned long long task = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (task >= n_tasks) return;
-  if (EMIT && b.out_off[task + 1] == b.out_off[task]) return;      // the count pass found nothing for this window pair
+  if (EMIT) {                                                      // the count pass found nothing for this window pair, or parked all of it
+    const unsigned long long cnt = b.out_off[task + 1] - b.out_off[task];
+    if (cnt == 0 || (b.slot != nullptr && cnt <= (unsigned long long)b.slot_cap)) return;
+  }
   unsigned long long u;
   { unsigned long long lo = 0, len = n_units;
     while (len > 0) { const unsigned long long half = len >> 1; if (b.task_off[lo + half] <= task) { lo += half + 1; len -= half + 1; } else len = half; }
@@ -349,6 +356,9 @@ __global__ void __launch_bounds__(128) lref_task_literal_kernel(LrefBatch b, uns
       if (EMIT) {
         const unsigned long long o = obase + n_out;
         if (o < b.out_cap) { b.r_q[o] = qp; b.r_t[o] = tp; b.r_tup[o] = lt_t(qv); }
+      } else if (b.slot != nullptr && n_out < (unsigned long long)b.slot_cap) {
+        uint32_t *sl = b.slot + (task * (unsigned long long)b.slot_cap + n_out) * 3ull;
+        sl[0] = qp; sl[1] = tp; sl[2] = lt_t(qv);
       }
       n_out++;
     }
@@ -406,6 +416,20 @@ __global__ void __launch_bounds__(128) lref_task_literal_kernel(LrefBatch b, uns
 #undef QK
 #undef TK
   if (!EMIT) b.out_off[task] = n_out;
+}
+
+// the parked anchors of every window pair that fitted its slot go to their place in the reference's order (8 lanes per pair)
+__global__ void __launch_bounds__(256) lref_task_copy_kernel(LrefBatch b, unsigned long long n_tasks) {
+  const unsigned long long task = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  if (task >= n_tasks) return;
+  const unsigned long long o0 = b.out_off[task], cnt = b.out_off[task + 1] - o0;
+  if (cnt == 0 || cnt > (unsigned long long)b.slot_cap) return;
+  const uint32_t *sl = b.slot + task * (unsigned long long)b.slot_cap * 3ull;
+  for (unsigned long long i = sub; i < cnt; i += 8) {
+    const unsigned long long o = o0 + i;
+    if (o < b.out_cap) { b.r_q[o] = sl[3 * i]; b.r_t[o] = sl[3 * i + 1]; b.r_tup[o] = sl[3 * i + 2]; }
+  }
 }
 
 // ---- one WARP per (cluster, lsi, qi).  The control flow of CompareLists is replayed by all lanes in lock step on uniform state

@@ -83,10 +83,14 @@ extern "C" long emu_refine_clusters(const EmuLidx *gl, const EmuLidx *rf, const 
   }
   std::vector<unsigned long long> out_off(n_tasks + 2, 0);
   b.out_off = out_off.data();
+  // a small slot, so that window pairs below and above it both occur: the copy kernel and the re-run of the emit pass are both exercised
+  std::vector<uint32_t> slot(literal ? n_tasks * 6 * 3 + 3 : 3);
+  if (literal) { b.slot = slot.data(); b.slot_cap = 6; }
   if (n_tasks) {
     if (literal) emu::launch(dim3((unsigned)((n_tasks + 127) / 128)), dim3(128), 0, [&] { lref_task_literal_kernel<false>(b, n_units, n_tasks); });
     else emu::launch(dim3((unsigned)((n_tasks + 3) / 4)), dim3(128), 0, [&] { lref_task_kernel<false>(b, n_units, n_tasks); });
     emu::launch(dim3(1), dim3(1024), 0, [&] { seed_scan_kernel(b.out_off, (int)n_tasks, cap, &err); });
+    if (literal) emu::launch(dim3((unsigned)((n_tasks * 8 + 255) / 256)), dim3(256), 0, [&] { lref_task_copy_kernel(b, n_tasks); });
     if (literal) emu::launch(dim3((unsigned)((n_tasks + 127) / 128)), dim3(128), 0, [&] { lref_task_literal_kernel<true>(b, n_units, n_tasks); });
     else emu::launch(dim3((unsigned)((n_tasks + 3) / 4)), dim3(128), 0, [&] { lref_task_kernel<true>(b, n_units, n_tasks); });
   }
