@@ -607,6 +607,15 @@ typedef struct lra_b200_space_result {
 int lra_b200_refine_space_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_spaces *in,
                                 lra_b200_space_result *res);
 
+/* ---- a17  SwitchToOriginalAnchors, batched over FinalChain entries ----------------------------------------------------------
+ * Replaces  SwitchToOriginalAnchors(finalchain, ultimatechain, ExtendClusters, extend_clusters)  (LocalRefineAlignment.h:187-198, :576): entry i of the
+ * chains of a batch (concatenated) names the same-diagonal run [run_start[i], run_end[i]) = ExtendClusters[c]->start[k], ->end[k] of its extended cluster
+ * (the runs lra_b200_linear_extend_chains_batch flags with md_head) and that cluster's `coarse`.  Results: the anchors of entry i are
+ * chain[off[i] .. off[i+1]) = run_end-1 .. run_start (descending) with cluster_index[] = coarse[i]; off has n_entries + 1 elements, *n_total = off[n_entries]
+ * (the capacity needed on LRA_B200_EOVERFLOW). */
+int lra_b200_switch_to_original_batch(lra_b200_ctx *ctx, const int32_t *run_start, const int32_t *run_end, const int32_t *coarse, uint64_t n_entries,
+                                      uint64_t *off, uint32_t *chain, int32_t *cluster_index, uint64_t cap, uint64_t *n_total);
+
 /* ---- a20  RefineBreakpoint, batched over pairs of adjacent segments --------------------------------------------------
  * Replaces  void RefineBreakpoint(Read &read, Genome &genome, Alignment &leftAln, Alignment &rightAln, const Options &opts)
  * (RefineBreakpoint.h:212-462; called for consecutive segments of a split read, Map_highacc.h:725, Map_lowacc.h:592).  Pair p: the left /

@@ -236,6 +236,7 @@ def load_library():
     L.lra_b200_split_chains_batch.argtypes = [C.c_void_p, C.POINTER(_AnchorChains), C.POINTER(_SplitChainsOut)]
     L.lra_b200_refine_space_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Spaces), C.POINTER(_SpaceResult)]
     L.lra_b200_refine_linear_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_LinearGaps), C.POINTER(_AogResult)]
+    L.lra_b200_switch_to_original_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.lra_b200_merge_chain_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_switchindex_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.lra_b200_linear_extend_chains_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_ExtendChains), C.POINTER(_ExtendedChains)]
@@ -629,6 +630,16 @@ class Context:
         self._check(self.lib.lra_b200_refine_space_batch(self.h, reads.handle, genome.handle, C.byref(e), C.byref(r)))
         o["n_pairs"] = o["n_pairs"][:n]; o["identity"] = o["identity"][:n]
         return o
+
+    def switch_to_original_batch(self, run_start, run_end, coarse):
+        """SwitchToOriginalAnchors for every FinalChain entry.  Returns (off, chain, cluster_index)."""
+        rs = np.ascontiguousarray(run_start, np.int32); re_ = np.ascontiguousarray(run_end, np.int32); co = np.ascontiguousarray(coarse, np.int32)
+        n = len(rs); cap = int(np.clip(re_.astype(np.int64) - rs, 0, None).sum())
+        off = np.zeros(n + 1, np.uint64); chain = np.zeros(max(cap, 1), np.uint32); ci = np.zeros(max(cap, 1), np.int32)
+        tot = C.c_uint64(0)
+        p = lambda x: _ptr(x) if x.size else None
+        self._check(self.lib.lra_b200_switch_to_original_batch(self.h, p(rs), p(re_), p(co), n, _ptr(off), _ptr(chain), _ptr(ci), cap, C.byref(tot)))
+        return off, chain[:int(tot.value)], ci[:int(tot.value)]
 
     # ---- a22
     def mapq_batch(self, ag, bypass, read_type, global_k):

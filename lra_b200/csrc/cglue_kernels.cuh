@@ -105,4 +105,30 @@ __global__ void __launch_bounds__(64) switchindex_kernel(SwitchIndexBatch b) {
   b.n_out[k] = n; b.nl_out[k] = nl;
 }
 
+// a17: SwitchToOriginalAnchors (reference LocalRefineAlignment.h:187-198).  Entry i of a FinalChain names run k = chain[i] of the same-diagonal runs
+// (MergeMatchesSameDiag) of extended cluster c = ClusterNum(i); the UltimateChain gets the run's anchors end[k]-1 .. start[k] (descending) with
+// ClusterIndex = the cluster's `coarse`.  The entries' output ranges are an exclusive scan of end - start; one thread per entry writes its range.
+struct SwitchOrigBatch {
+  unsigned long long n_entries;
+  const int32_t *run_start, *run_end;    // [n_entries] ExtendClusters[c]->start[k], ->end[k]
+  const int32_t *coarse;                 // [n_entries] ExtendClusters[c]->coarse
+  unsigned long long *off;               // [n_entries + 1] counts, then their exclusive scan
+  uint32_t *chain;                       // out
+  int32_t *cluster_index;                // out
+};
+
+__global__ void __launch_bounds__(256) switch_orig_count_kernel(SwitchOrigBatch b) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.n_entries) return;
+  const int n = b.run_end[i] - b.run_start[i];
+  b.off[i] = n > 0 ? (unsigned long long)n : 0ull;
+}
+
+__global__ void __launch_bounds__(256) switch_orig_emit_kernel(SwitchOrigBatch b) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.n_entries) return;
+  unsigned long long o = b.off[i];
+  for (int j = b.run_end[i] - 1; j >= b.run_start[i]; j--, o++) { b.chain[o] = (uint32_t)j; b.cluster_index[o] = b.coarse[i]; }
+}
+
 }  // namespace lra

@@ -1315,3 +1315,46 @@ extern "C" int lra_b200_refine_space_batch(lra_b200_ctx *ctx, const lra_b200_seq
   res->n_pairs_total = P;
   return LRA_B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- a17 SwitchToOriginalAnchors
+extern "C" int lra_b200_switch_to_original_batch(lra_b200_ctx *ctx, const int32_t *run_start, const int32_t *run_end, const int32_t *coarse, uint64_t n_entries,
+                                                 uint64_t *off, uint32_t *chain, int32_t *cluster_index, uint64_t cap, uint64_t *n_total) {
+  if (!ctx || !n_total) return fail(ctx, LRA_B200_EINVAL, "switch_to_original_batch: NULL argument");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  *n_total = 0;
+  if (n_entries == 0) { if (off) off[0] = 0; return LRA_B200_OK; }
+  if (!run_start || !run_end || !coarse || !off) return fail(ctx, LRA_B200_EINVAL, "switch_to_original_batch: NULL array");
+  if (n_entries > 0x7FFFFFF0ull) return fail(ctx, LRA_B200_EINVAL, "switch_to_original_batch: more than 2^31 entries");
+  int rc;
+  DevBuf *B = ctx->cg;
+  const size_t E = (size_t)n_entries;
+  if ((rc = ensure(ctx, B[0], E * 4)) || (rc = ensure(ctx, B[1], E * 4)) || (rc = ensure(ctx, B[2], E * 4)) || (rc = ensure(ctx, B[3], (E + 2) * 8)) || (rc = ensure(ctx, B[14], 16)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(B[0].p, run_start, E * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[1].p, run_end, E * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[2].p, coarse, E * 4, cudaMemcpyHostToDevice, st));
+  SwitchOrigBatch b{n_entries, (const int32_t *)B[0].p, (const int32_t *)B[1].p, (const int32_t *)B[2].p, (unsigned long long *)B[3].p, nullptr, nullptr};
+  cudaEventRecord(ctx->ev[0], st);
+  switch_orig_count_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(b);
+  seed_scan_kernel<<<1, 1024, 0, st>>>(b.off, (int)E, ~0ull, (int *)B[14].p);
+  CU(cudaMemcpyAsync(off, b.off, (E + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const size_t T = (size_t)off[E];
+  *n_total = T;
+  if (T > cap) return fail(ctx, LRA_B200_EOVERFLOW, "switch_to_original_batch: result arrays hold %llu anchors, %llu needed", (unsigned long long)cap, (unsigned long long)T);
+  if (T) {
+    if (!chain || !cluster_index) return fail(ctx, LRA_B200_EINVAL, "switch_to_original_batch: NULL result array");
+    if ((rc = ensure(ctx, B[4], T * 4)) || (rc = ensure(ctx, B[5], T * 4))) return rc;
+    b.chain = (uint32_t *)B[4].p; b.cluster_index = (int32_t *)B[5].p;
+    switch_orig_emit_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(b);
+    cudaEventRecord(ctx->ev[1], st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(chain, b.chain, T * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cluster_index, b.cluster_index, T * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  } else cudaEventRecord(ctx->ev[1], st);
+  ctx->launches += 3;
+  return LRA_B200_OK;
+}

@@ -912,3 +912,23 @@ def refine_space(strandseq, contig, K, qs, qe, ts, te, st, consider_str, lrts, l
     mn = min(len(q), len(t))
     idn = np.float32(n_match) / np.float32(mn) if mn else np.frombuffer(np.uint32(0xFFC00000).tobytes(), np.float32)[0]
     return np.array(pq, np.uint32), np.array(pt, np.uint32), np.float32(idn)
+
+
+# ---------------------------------------------------------------- a17 SwitchToOriginalAnchors
+
+def switch_to_original(cnum, k, run_off, start, end, coarse, which="port"):
+    """One FinalChain: entry i names run k[i] of cluster cnum[i] (runs of cluster c: start/end[run_off[c] .. run_off[c+1])).  Returns (chain, ClusterIndex).
+    port: LocalRefineAlignment.h:187-198 restated -- every run expands to its anchors end-1 .. start, ClusterIndex = the cluster's coarse."""
+    cnum = np.ascontiguousarray(cnum, np.int32); k = np.ascontiguousarray(k, np.int32); run_off = np.ascontiguousarray(run_off, np.int32)
+    start = np.ascontiguousarray(start, np.int32); end = np.ascontiguousarray(end, np.int32); coarse = np.ascontiguousarray(coarse, np.int32)
+    if which == "ref":
+        f = _bind_once(ref(), "ref_switch_to_original", C.c_long, [_i32p, _i32p, C.c_int, _i32p, _i32p, _i32p, _i32p, C.c_int, _u32p, _i32p])
+        cap = int(sum(int(end[run_off[c] + r] - start[run_off[c] + r]) for c, r in zip(cnum, k))) + 1
+        ch = np.zeros(cap, np.uint32); ci = np.zeros(cap, np.int32)
+        n = f(cnum, k, len(cnum), run_off, start, end, coarse, len(coarse), ch, ci)
+        return ch[:n], ci[:n]
+    ch, ci = [], []
+    for c, r in zip(cnum, k):
+        for j in range(int(end[run_off[c] + r]) - 1, int(start[run_off[c] + r]) - 1, -1):
+            ch.append(j); ci.append(int(coarse[c]))
+    return np.array(ch, np.uint32), np.array(ci, np.int32)

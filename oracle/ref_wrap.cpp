@@ -722,4 +722,25 @@ long ref_refine_space(const uint8_t *strandseq, int read_len, const uint8_t *con
   return n;
 }
 
+// ---- a17: SwitchToOriginalAnchors (LocalRefineAlignment.h:187-198) for one FinalChain: entry i = (cluster cnum[i], run k[i]); clusters enter as their
+// run lists (start / end of cluster c at run_off[c] ..) and coarse.  Returns the length of the UltimateChain.
+long ref_switch_to_original(const int32_t *cnum, const int32_t *k, int n, const int32_t *run_off, const int32_t *start, const int32_t *end, const int32_t *coarse,
+                            int n_cl, uint32_t *chain_out, int32_t *ci_out) {
+  ref_init_static();
+  std::vector<Cluster> ext(n_cl);
+  std::vector<Cluster_SameDiag> sd(n_cl);
+  std::vector<Cluster_SameDiag *> sdp(n_cl);
+  for (int c = 0; c < n_cl; c++) {
+    sd[c].cluster = &ext[c]; sd[c].coarse = coarse[c];
+    sd[c].start.assign(start + run_off[c], start + run_off[c + 1]); sd[c].end.assign(end + run_off[c], end + run_off[c + 1]);
+    sdp[c] = &sd[c];
+  }
+  FinalChain prev(&sdp);
+  prev.chain.assign(k, k + n); prev.ClusterIndex.assign(cnum, cnum + n); prev.SecondSDPValue = 0;
+  UltimateChain cur;
+  SwitchToOriginalAnchors(prev, cur, sdp, ext);
+  for (size_t i = 0; i < cur.chain.size(); i++) { chain_out[i] = cur.chain[i]; ci_out[i] = cur.ClusterIndex[i]; }
+  return (long)cur.chain.size();
+}
+
 }  // extern "C"

@@ -90,3 +90,45 @@ def test_gpu_chain_glue():
     ch, link, off, coarse, cq, bases = switch_batch(sc)
     check_switch(ctx.switchindex_batch(ch, link, off, coarse, cq), off, sc, bases, which)
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------- a17 SwitchToOriginalAnchors
+
+def switch_orig_case(rng):
+    n_cl = int(rng.integers(1, 6))
+    run_off, start, end = [0], [], []
+    for _ in range(n_cl):
+        cuts = np.unique(np.concatenate([[0], rng.integers(1, 60, int(rng.integers(0, 8))), [60]]))
+        start += cuts[:-1].tolist(); end += cuts[1:].tolist(); run_off.append(len(start))
+    n = int(rng.integers(1, 30))
+    cnum = rng.integers(0, n_cl, n)
+    k = np.array([rng.integers(0, run_off[c + 1] - run_off[c]) for c in cnum])
+    return dict(cnum=cnum, k=k, run_off=run_off, start=start, end=end, coarse=rng.integers(0, 50, n_cl))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref/libref_lra.so not built (no /root/reference)")
+def test_switch_to_original_oracle_matches_reference():
+    rng = np.random.default_rng(4)
+    for _ in range(300):
+        c = switch_orig_case(rng)
+        a = po.switch_to_original(**c, which="ref"); b = po.switch_to_original(**c)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.gpu
+def test_gpu_switch_to_original():
+    import lra_b200
+    ctx = lra_b200.Context(0)
+    rng = np.random.default_rng(6)
+    cases = [switch_orig_case(rng) for _ in range(2000)]
+    rs = np.concatenate([[c["start"][c["run_off"][a] + r] for a, r in zip(c["cnum"], c["k"])] for c in cases])
+    re_ = np.concatenate([[c["end"][c["run_off"][a] + r] for a, r in zip(c["cnum"], c["k"])] for c in cases])
+    co = np.concatenate([[c["coarse"][a] for a in c["cnum"]] for c in cases])
+    off, chain, ci = ctx.switch_to_original_batch(rs, re_, co)
+    which = "ref" if HAVE_REF else "port"
+    exp = [po.switch_to_original(**c, which=which) for c in cases]
+    assert np.array_equal(chain, np.concatenate([e[0] for e in exp])) and np.array_equal(ci, np.concatenate([e[1] for e in exp]))
+    assert int(off[-1]) == len(chain)
+    o2 = ctx.switch_to_original_batch([], [], [])
+    assert len(o2[1]) == 0
+    ctx.close()
