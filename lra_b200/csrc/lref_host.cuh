@@ -263,7 +263,7 @@ static int lref_run(lra_b200_ctx *ctx, const lra_b200_lindex *gl, const lra_b200
     // (16 ms): the stage is bound by instruction issue, not by latency, and the lock-step warp form issues 8x more instructions
     static const bool literal = getenv("LRA_B200_LREF_WARP") == nullptr;
     // anchors per window pair parked by the count pass (0 = off: the emit pass re-runs every non-empty pair)
-    static const int slot_cap = getenv("LRA_B200_LREF_SLOT") ? atoi(getenv("LRA_B200_LREF_SLOT")) : 48;
+    static const int slot_cap = getenv("LRA_B200_LREF_SLOT") ? atoi(getenv("LRA_B200_LREF_SLOT")) : 256;   // measured: 48 -> 131.4, 128 -> 128.1, 256 -> 124.8 ms/step
     b.slot = nullptr; b.slot_cap = 0;
     if (literal && slot_cap > 0 && n_tasks * (unsigned long long)slot_cap * 12ull <= (4ull << 30)) {
       if ((rc = ensure(ctx, ctx->lr_x[5], (size_t)n_tasks * (size_t)slot_cap * 12))) return rc;
