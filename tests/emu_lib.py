@@ -372,3 +372,39 @@ def switchindex(ch, link, c_off, coarse, cq):
     n_out = np.zeros(max(NC, 1), np.int32); nl_out = np.zeros(max(NC, 1), np.int32)
     L.emu_switchindex(NC, co, ch, link, np.ascontiguousarray(coarse, np.int32), np.ascontiguousarray(cq, np.uint32).reshape(-1), n_out, nl_out)
     return ch, link, n_out[:NC], nl_out[:NC]
+
+
+def refine_linear(read_arena, genome, g, m, mm, indel, local_band):
+    """g as for Context.refine_linear_batch; arenas with 16 bytes of padding."""
+    L = lib()
+    L.emu_refine_linear.argtypes = [_u8p, C.c_uint64, _u8p, C.c_uint64, C.c_int, _u32p, _u32p, _u32p, _u32p, _u32p, _u32p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p,
+                                    _u64p, _u32p, C.c_uint64]
+    a = {k: np.ascontiguousarray(g[k], np.uint32) for k in ["cur_read_end", "next_read_start", "cur_genome_end", "next_genome_start", "read_off", "chrom_off"]}
+    n = len(a["read_off"])
+    ql = (a["next_read_start"] - a["cur_read_end"]).astype(np.int32).astype(np.int64); tl = (a["next_genome_start"] - a["cur_genome_end"]).astype(np.int32).astype(np.int64)
+    cap = int((np.minimum(ql, tl).clip(min=0) + 1).sum()) + 1
+    o = dict(score=np.zeros(n, np.int32), n_blocks=np.zeros(n, np.int32), block_off=np.zeros(n, np.uint64), blocks=np.zeros(3 * cap, np.uint32))
+    err = L.emu_refine_linear(read_arena, len(read_arena) - 16, genome, len(genome) - 16, n, a["cur_read_end"], a["next_read_start"], a["cur_genome_end"], a["next_genome_start"],
+                              a["read_off"], a["chrom_off"], m, mm, indel, local_band, o["score"], o["n_blocks"], o["block_off"], o["blocks"], cap)
+    assert err == 0
+    o["blocks"] = o["blocks"].reshape(-1, 3)
+    return o
+
+
+def refine_space(read_arena, genome, sp, K, m, mm, indel):
+    """sp as for Context.refine_space_batch."""
+    L = lib()
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    L.emu_refine_space.argtypes = [_u8p, C.c_uint64, _u8p, C.c_uint64, C.c_int, C.c_int] + [_u32p] * 9 + [_u8p, C.c_int, C.c_int, C.c_int, _u64p, _u32p, _u32p, _i32p, f32p, C.c_uint64]
+    a = {k: np.ascontiguousarray(sp[k], np.uint32) for k in ["qs", "qe", "ts", "te", "lrts", "lrlength", "read_off", "read_len", "chrom_off"]}
+    flip = np.ascontiguousarray(sp["flip"], np.uint8)
+    n = len(flip)
+    ql = a["qe"].astype(np.int64) - a["qs"]; tl = a["te"].astype(np.int64) - a["ts"] + a["lrlength"]
+    mn = np.minimum(ql, tl).clip(min=0)
+    pair_off = np.zeros(n + 1, np.uint64); pair_off[1:] = np.cumsum(mn // K + 1)
+    cap = int(pair_off[-1]) + 1
+    o = dict(pair_off=pair_off, n_pairs=np.zeros(n, np.int32), identity=np.zeros(n, np.float32), pq=np.zeros(cap, np.uint32), pt=np.zeros(cap, np.uint32))
+    err = L.emu_refine_space(read_arena, len(read_arena) - 16, genome, len(genome) - 16, n, K, *[a[k] for k in ["qs", "qe", "ts", "te", "lrts", "lrlength", "read_off", "read_len",
+                             "chrom_off"]], flip, m, mm, indel, pair_off, o["pq"], o["pt"], o["n_pairs"], o["identity"], int((mn + 1).sum()) + 1)
+    assert err == 0
+    return o

@@ -29,3 +29,40 @@ extern "C" int emu_aog_batch(const uint8_t *q_arena, uint64_t qn, const uint8_t 
 
 // lane scheduling order of the emulator between collectives (0 ascending, 1 descending, >= 2 random with that seed)
 extern "C" void emu_set_lane_order(long mode) { emu::g_order_mode() = mode; }
+
+// ---- a17 leaf RefineByLinearAlignment / a14 core RefineSpace: the job and post-processing kernels around the a18 kernels
+#include "rla_kernels.cuh"
+#include "rsp_kernels.cuh"
+extern "C" int emu_refine_linear(const uint8_t *q_arena, uint64_t qn, const uint8_t *t_arena, uint64_t tn, int n, const uint32_t *cre, const uint32_t *nrs,
+                                 const uint32_t *cge, const uint32_t *ngs, const uint32_t *read_off, const uint32_t *chrom_off, int m, int mm, int indel,
+                                 int local_band, int32_t *score, int32_t *n_blocks, uint64_t *block_off, uint32_t *blocks, uint64_t block_cap) {
+  Packed q, t; pack(q_arena, qn, q); pack(t_arena, tn, t);
+  std::vector<uint32_t> qo(n + 1), to(n + 1); std::vector<int32_t> ql(n + 1), tl(n + 1), kk(n + 1);
+  RlaBatch rb{n, local_band, cre, nrs, cge, ngs, read_off, chrom_off, qo.data(), to.data(), ql.data(), tl.data(), kk.data(), n_blocks,
+              (const unsigned long long *)block_off, blocks};
+  if (n) emu::launch(dim3((unsigned)((n + 255) / 256)), dim3(256), 0, [&] { rla_jobs_kernel(rb); });
+  unsigned long long cursor = 0; int err = 0;
+  AogBatch b{q.view, t.view, qo.data(), to.data(), ql.data(), tl.data(), kk.data(), n, m, mm, indel, score, n_blocks, (unsigned long long *)block_off, blocks, block_cap,
+             &cursor, &err};
+  run_aog(b, 1);
+  if (n) emu::launch(dim3((unsigned)((n + 255) / 256)), dim3(256), 0, [&] { rla_shift_kernel(rb); });
+  return err;
+}
+
+extern "C" int emu_refine_space(const uint8_t *q_arena, uint64_t qn, const uint8_t *t_arena, uint64_t tn, int n, int K, const uint32_t *qs, const uint32_t *qe,
+                                const uint32_t *ts, const uint32_t *te, const uint32_t *lrts, const uint32_t *lrlength, const uint32_t *read_off, const uint32_t *read_len,
+                                const uint32_t *chrom_off, const uint8_t *flip, int m, int mm, int indel, const uint64_t *pair_off, uint32_t *pq, uint32_t *pt,
+                                int32_t *n_pairs, float *identity, uint64_t block_cap) {
+  Packed q, t; pack(q_arena, qn, q); pack(t_arena, tn, t);
+  std::vector<uint32_t> qo(n + 1), to(n + 1), blocks(3 * block_cap + 3); std::vector<int32_t> ql(n + 1), tl(n + 1), kk(n + 1), score(n + 1), nb(n + 1);
+  std::vector<unsigned long long> boff(n + 1);
+  RspBatch rb{n, K, q.view, t.view, qs, qe, ts, te, lrts, lrlength, read_off, read_len, chrom_off, flip, qo.data(), to.data(), ql.data(), tl.data(), kk.data(),
+              nb.data(), boff.data(), blocks.data(), (const unsigned long long *)pair_off, pq, pt, n_pairs, identity};
+  if (n) emu::launch(dim3((unsigned)((n + 255) / 256)), dim3(256), 0, [&] { rsp_jobs_kernel(rb); });
+  unsigned long long cursor = 0; int err = 0;
+  AogBatch b{q.view, t.view, qo.data(), to.data(), ql.data(), tl.data(), kk.data(), n, m, mm, indel, score.data(), nb.data(), boff.data(), blocks.data(), block_cap,
+             &cursor, &err};
+  run_aog(b, 1);
+  if (n) emu::launch(dim3((unsigned)((n + 127) / 128)), dim3(128), 0, [&] { rsp_harvest_kernel(rb); });
+  return err;
+}

@@ -57,6 +57,19 @@ def test_oracle_matches_reference():
     assert nb > 500 and empty > 10
 
 
+def test_emu_refine_linear():
+    import emu_lib
+    contig, reads, gl = gaps(3, 60)
+    roff = np.zeros(len(reads), np.int64); roff[1:] = np.cumsum([len(r) for r in reads[:-1]])
+    pad = np.full(16, ord("A"), np.uint8)
+    g = dict(cur_read_end=[x[1] for x in gl], next_read_start=[x[2] & 0xFFFFFFFF for x in gl], cur_genome_end=[x[3] for x in gl], next_genome_start=[x[4] & 0xFFFFFFFF for x in gl],
+             read_off=[int(roff[x[0]]) for x in gl], chrom_off=np.zeros(len(gl), np.uint32))
+    o = emu_lib.refine_linear(np.concatenate(reads + [pad]), np.concatenate([contig, pad]), g, *SC)
+    for i, e in enumerate(expected(contig, reads, gl, "port")):
+        a = int(o["block_off"][i])
+        assert o["n_blocks"][i] == len(e) and np.array_equal(o["blocks"][a:a + len(e)], e), i
+
+
 @pytest.mark.gpu
 def test_gpu_refine_linear():
     import lra_b200

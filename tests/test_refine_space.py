@@ -53,6 +53,20 @@ def test_oracle_matches_reference():
     assert pairs > 300
 
 
+def test_emu_refine_space():
+    import emu_lib
+    contig, reads, sp = spaces(3, 50)
+    roff = np.zeros(len(reads), np.int64); roff[1:] = np.cumsum([len(r) for r in reads[:-1]])
+    pad = np.full(16, ord("A"), np.uint8)
+    col = lambda k: [x[k] for x in sp]
+    d = dict(qs=col("qs"), qe=col("qe"), ts=col("ts"), te=col("te"), lrts=col("lrts"), lrlength=col("lrlength"), read_off=[int(roff[x["read"]]) for x in sp],
+             read_len=[len(reads[x["read"]]) for x in sp], chrom_off=np.zeros(len(sp), np.uint32), flip=[x["cs"] and x["st"] for x in sp])
+    o = emu_lib.refine_space(np.concatenate(reads + [pad]), np.concatenate([contig, pad]), d, K, *SC)
+    for i, e in enumerate(expected(contig, reads, sp, "port")):
+        a = int(o["pair_off"][i]); n = int(o["n_pairs"][i])
+        assert same((o["pq"][a:a + n], o["pt"][a:a + n], o["identity"][i]), e), i
+
+
 @pytest.mark.gpu
 def test_gpu_refine_space():
     import lra_b200
