@@ -616,6 +616,38 @@ int lra_b200_refine_space_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, co
 int lra_b200_switch_to_original_batch(lra_b200_ctx *ctx, const int32_t *run_start, const int32_t *run_end, const int32_t *coarse, uint64_t n_entries,
                                       uint64_t *off, uint32_t *chain, int32_t *cluster_index, uint64_t cap, uint64_t *n_total);
 
+/* ---- a8 (first half)  SplitRoughClustersWithGaps, batched over anchor lists ---------------------------------------------------
+ * Replaces the loop  for (c ...) SplitRoughClustersWithGaps(Matches, roughClusters[c], split_roughClusters, opts, c, read, strand)
+ * (Clustering.h:1578-1581 forward, :1632-1635 reverse; the function :1358-1430 with CloseToPreviousCluster / MergeTwoClusters :1332-1356) for every list
+ * of a batch.  List l owns anchors l_off[l] .. l_off[l+1] (Cartesian-sorted inside every rough cluster: lra_b200_sort_matches_batch mode 2 with the
+ * rough clusters as segments = the CartesianSort of :1579) and rough clusters lr_off[l] .. lr_off[l+1]: start / end (relative to the list), box,
+ * strand, anchorfreq, chromIndex (-1 where CleanOffDiagonal leaves the constructor's value).
+ * Results in slot layout, base(l) = l_off[l] + lr_off[l]: split cluster i of list l at base(l) + i = start, end, box, strand, coarse (index of its
+ * rough cluster in the list), anchorfreq, chromIndex; its splitmatchindex = the anchor ranges [p_start, p_end) of the pieces j at base(l) + j with
+ * p_cluster == i, in order. */
+typedef struct lra_b200_rough_lists {
+  int32_t n_lists;
+  const uint64_t *l_off, *lr_off;       /* [n_lists + 1] */
+  const uint32_t *q, *t;
+  const int32_t *r_start, *r_end;       /* [lr_off[n_lists]] */
+  const uint32_t *r_box;
+  const uint8_t *r_strand;
+  const float *r_freq;
+  const int32_t *r_chrom;
+  int32_t globalK, rough_cluster_max_gap, min_cluster_size, max_diag;   /* opts.globalK, RoughClustermaxGap, minClusterSize, maxDiag */
+} lra_b200_rough_lists;
+
+typedef struct lra_b200_split_rough_result {
+  int32_t *n_split, *n_piece;           /* [n_lists] */
+  int32_t *s_start, *s_end, *s_coarse, *s_chrom;   /* [N + n_rough] */
+  uint32_t *s_box;                      /* [(N + n_rough) * 4] */
+  uint8_t *s_strand;
+  float *s_freq;
+  int32_t *p_cluster, *p_start, *p_end; /* [N + n_rough] */
+} lra_b200_split_rough_result;
+
+int lra_b200_split_rough_batch(lra_b200_ctx *ctx, const lra_b200_rough_lists *in, lra_b200_split_rough_result *res);
+
 /* ---- a20  RefineBreakpoint, batched over pairs of adjacent segments --------------------------------------------------
  * Replaces  void RefineBreakpoint(Read &read, Genome &genome, Alignment &leftAln, Alignment &rightAln, const Options &opts)
  * (RefineBreakpoint.h:212-462; called for consecutive segments of a split read, Map_highacc.h:725, Map_lowacc.h:592).  Pair p: the left /

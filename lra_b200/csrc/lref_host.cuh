@@ -1358,3 +1358,60 @@ extern "C" int lra_b200_switch_to_original_batch(lra_b200_ctx *ctx, const int32_
   ctx->launches += 3;
   return LRA_B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- a8 (first half) SplitRoughClustersWithGaps
+extern "C" int lra_b200_split_rough_batch(lra_b200_ctx *ctx, const lra_b200_rough_lists *in, lra_b200_split_rough_result *res) {
+  if (!ctx || !in || !res) return fail(ctx, LRA_B200_EINVAL, "split_rough_batch: NULL argument");
+  const int NL = in->n_lists;
+  if (NL < 0 || !in->l_off || !in->lr_off) return fail(ctx, LRA_B200_EINVAL, "split_rough_batch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  if (NL == 0) return LRA_B200_OK;
+  const size_t N = (size_t)in->l_off[NL], RC = (size_t)in->lr_off[NL];
+  if (N + RC > 0x7FFFFFF0ull) return fail(ctx, LRA_B200_EINVAL, "split_rough_batch: batch too large");
+  if (RC && (!in->r_start || !in->r_end || !in->r_box || !in->r_strand || !in->r_freq || !in->r_chrom)) return fail(ctx, LRA_B200_EINVAL, "split_rough_batch: NULL cluster array");
+  if (N && (!in->q || !in->t)) return fail(ctx, LRA_B200_EINVAL, "split_rough_batch: NULL anchors");
+  for (int l = 0; l < NL; l++) {
+    if (in->l_off[l + 1] < in->l_off[l] || in->lr_off[l + 1] < in->lr_off[l]) return fail(ctx, LRA_B200_EINVAL, "split_rough_batch: offsets not ascending");
+    const long long n = (long long)(in->l_off[l + 1] - in->l_off[l]);
+    for (size_t c = (size_t)in->lr_off[l]; c < (size_t)in->lr_off[l + 1]; c++)
+      if (in->r_start[c] < 0 || in->r_end[c] < in->r_start[c] || in->r_end[c] > n) return fail(ctx, LRA_B200_EINVAL, "split_rough_batch: rough cluster %zu lies outside its list", c);
+  }
+  int rc;
+  DevBuf *B = ctx->sr;
+  const size_t Np = N ? N : 1, Rp = RC ? RC : 1, S = N + RC + 1, L1 = (size_t)NL;
+  const size_t need[22] = {(L1 + 1) * 8, (L1 + 1) * 8, Np * 4, Np * 4, Rp * 4, Rp * 4, Rp * 16, Rp, Rp * 4, Rp * 4,
+                           L1 * 4, L1 * 4, S * 4, S * 4, S * 4, S * 4, S * 16, S, S * 4, S * 4, S * 4, S * 4};
+  for (int i = 0; i < 22; i++) if ((rc = ensure(ctx, B[i], need[i]))) return rc;
+  cudaStream_t st = ctx->stream;
+  const void *src[10] = {in->l_off, in->lr_off, in->q, in->t, in->r_start, in->r_end, in->r_box, in->r_strand, in->r_freq, in->r_chrom};
+  const size_t sz[10] = {(L1 + 1) * 8, (L1 + 1) * 8, N * 4, N * 4, RC * 4, RC * 4, RC * 16, RC, RC * 4, RC * 4};
+  for (int i = 0; i < 10; i++) if (sz[i]) CU(cudaMemcpyAsync(B[i].p, src[i], sz[i], cudaMemcpyHostToDevice, st));
+  SplitRoughBatch b;
+  b.n_lists = NL; b.globalK = in->globalK; b.maxGap = in->rough_cluster_max_gap; b.minClusterSize = in->min_cluster_size; b.maxDiag = in->max_diag;
+  b.l_off = (const unsigned long long *)B[0].p; b.lr_off = (const unsigned long long *)B[1].p; b.q = (const uint32_t *)B[2].p; b.t = (const uint32_t *)B[3].p;
+  b.r_start = (const int32_t *)B[4].p; b.r_end = (const int32_t *)B[5].p; b.r_box = (const uint32_t *)B[6].p; b.r_strand = (const uint8_t *)B[7].p;
+  b.r_freq = (const float *)B[8].p; b.r_chrom = (const int32_t *)B[9].p;
+  b.n_split = (int32_t *)B[10].p; b.n_piece = (int32_t *)B[11].p; b.s_start = (int32_t *)B[12].p; b.s_end = (int32_t *)B[13].p; b.s_coarse = (int32_t *)B[14].p;
+  b.s_chrom = (int32_t *)B[15].p; b.s_box = (uint32_t *)B[16].p; b.s_strand = (uint8_t *)B[17].p; b.s_freq = (float *)B[18].p; b.p_cluster = (int32_t *)B[19].p;
+  b.p_start = (int32_t *)B[20].p; b.p_end = (int32_t *)B[21].p;
+  cudaEventRecord(ctx->ev[0], st);
+  split_rough_kernel<<<(unsigned)((NL + 63) / 64), 64, 0, st>>>(b);
+  cudaEventRecord(ctx->ev[1], st);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  const size_t T = N + RC;
+  CU(cudaMemcpyAsync(res->n_split, b.n_split, L1 * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->n_piece, b.n_piece, L1 * 4, cudaMemcpyDeviceToHost, st));
+  if (T) {
+    void *dst[10] = {res->s_start, res->s_end, res->s_coarse, res->s_chrom, res->s_box, res->s_strand, res->s_freq, res->p_cluster, res->p_start, res->p_end};
+    const void *dsrc[10] = {b.s_start, b.s_end, b.s_coarse, b.s_chrom, b.s_box, b.s_strand, b.s_freq, b.p_cluster, b.p_start, b.p_end};
+    const size_t dsz[10] = {T * 4, T * 4, T * 4, T * 4, T * 16, T, T * 4, T * 4, T * 4, T * 4};
+    for (int i = 0; i < 10; i++) CU(cudaMemcpyAsync(dst[i], dsrc[i], dsz[i], cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "split_rough");
+  cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]); s2.jobs = (uint64_t)NL; s2.algo_bytes = 8ull * N + 33ull * RC;
+  ctx->stats.push_back(s2);
+  return LRA_B200_OK;
+}

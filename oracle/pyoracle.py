@@ -932,3 +932,34 @@ def switch_to_original(cnum, k, run_off, start, end, coarse, which="port"):
         for j in range(int(end[run_off[c] + r]) - 1, int(start[run_off[c] + r]) - 1, -1):
             ch.append(j); ci.append(int(coarse[c]))
     return np.array(ch, np.uint32), np.array(ci, np.int32)
+
+
+# ---------------------------------------------------------------- a8 (first half) SplitRoughClustersWithGaps
+
+def split_rough(q, t, rc, globalK, maxGap, minClusterSize, maxDiag, which="port"):
+    """One anchor list (Cartesian-sorted inside every rough cluster).  rc = dict(start, end, box[n,4], strand, freq, chrom).
+    Returns dict(start, end, box, strand, coarse, freq, chrom, smi = [splitmatchindex of every split cluster])."""
+    q = np.ascontiguousarray(q, np.uint32); t = np.ascontiguousarray(t, np.uint32)
+    n = len(rc["start"]); N = len(q)
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    L = ref() if which == "ref" else port()
+    f = _bind_once(L, "ref_split_rough" if which == "ref" else "lra_oracle_split_rough", C.c_long,
+                   [_u32p, _u32p, C.c_int, _i32p, _i32p, _u32p, _u8p, f32p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                    _i32p, _i32p, _u32p, _u8p, _i32p, f32p, _i32p, _i32p, _i32p, _i32p, _i32p])
+    pad = lambda a, dt: np.ascontiguousarray(a, dt).reshape(-1).copy() if len(a) else np.zeros(1, dt)
+    cap = N + n + 1
+    o = dict(start=np.zeros(cap, np.int32), end=np.zeros(cap, np.int32), box=np.zeros(4 * cap, np.uint32), strand=np.zeros(cap, np.uint8), coarse=np.zeros(cap, np.int32),
+             freq=np.zeros(cap, np.float32), chrom=np.zeros(cap, np.int32))
+    pc = np.zeros(cap, np.int32); ps = np.zeros(cap, np.int32); pe = np.zeros(cap, np.int32); npiece = np.zeros(1, np.int32)
+    ns = f(pad(q, np.uint32), pad(t, np.uint32), n, pad(rc["start"], np.int32), pad(rc["end"], np.int32), pad(rc["box"], np.uint32), pad(rc["strand"], np.uint8),
+           pad(rc["freq"], np.float32), pad(rc["chrom"], np.int32), globalK, maxGap, minClusterSize, maxDiag,
+           o["start"], o["end"], o["box"], o["strand"], o["coarse"], o["freq"], o["chrom"], pc, ps, pe, npiece)
+    for k in ("start", "end", "strand", "coarse", "freq", "chrom"):
+        o[k] = o[k][:ns]
+    o["box"] = o["box"][:4 * ns].reshape(-1, 4)
+    smi = [[] for _ in range(ns)]
+    for j in range(int(npiece[0])):
+        smi[pc[j]] += list(range(int(ps[j]), int(pe[j])))
+    o["smi"] = smi
+    o["n_piece"] = int(npiece[0])
+    return o

@@ -743,4 +743,45 @@ long ref_switch_to_original(const int32_t *cnum, const int32_t *k, int n, const 
   return (long)cur.chain.size();
 }
 
+// ---- a8 (first half): SplitRoughClustersWithGaps (Clustering.h:1358-1430) over all rough clusters of one anchor list into one vector, as
+// MatchesToFineClusters does (Clustering.h:1578-1581).  Arguments as oracle/split_rough.c.
+long ref_split_rough(const uint32_t *q, const uint32_t *t, int n_rough, const int32_t *r_start, const int32_t *r_end, const uint32_t *r_box,
+                     const uint8_t *r_strand, const float *r_freq, const int32_t *r_chrom, int globalK, int maxGap, int minClusterSize, int maxDiag,
+                     int32_t *s_start, int32_t *s_end, uint32_t *s_box, uint8_t *s_strand, int32_t *s_coarse, float *s_freq, int32_t *s_chrom,
+                     int32_t *p_cluster, int32_t *p_start, int32_t *p_end, int32_t *n_piece) {
+  ref_init_static();
+  Options opts; opts.globalK = globalK; opts.RoughClustermaxGap = maxGap; opts.minClusterSize = minClusterSize; opts.maxDiag = maxDiag;
+  opts.debug = false; opts.dotPlot = false;
+  Read read; read.unaligned = 0;
+  int N = 0;
+  for (int c = 0; c < n_rough; c++) if (r_end[c] > N) N = r_end[c];
+  GenomePairs matches(N);
+  for (int i = 0; i < N; i++) { matches[i].first.pos = q[i]; matches[i].second.pos = t[i]; }
+  std::vector<Cluster> split;
+  for (int c = 0; c < n_rough; c++) {
+    Cluster rc(r_start[c], r_end[c], r_box[4 * c], r_box[4 * c + 1], r_box[4 * c + 2], r_box[4 * c + 3], r_strand[c]);
+    rc.anchorfreq = r_freq[c]; rc.chromIndex = r_chrom[c];
+    int outIter = c;
+    SplitRoughClustersWithGaps(matches, rc, split, opts, outIter, read, r_strand[c]);
+  }
+  long np = 0;
+  for (size_t i = 0; i < split.size(); i++) {
+    const Cluster &x = split[i];
+    s_start[i] = x.start; s_end[i] = x.end; s_box[4 * i] = x.qStart; s_box[4 * i + 1] = x.qEnd; s_box[4 * i + 2] = x.tStart; s_box[4 * i + 3] = x.tEnd;
+    s_strand[i] = x.strand; s_coarse[i] = x.coarse; s_freq[i] = x.anchorfreq; s_chrom[i] = x.chromIndex;
+    // splitmatchindex as maximal runs of consecutive indices: every piece the reference appends is one run (pieces of one cluster never touch: a
+    // boundary exists only where a gap separated them... two appended pieces CAN be adjacent, so runs are cut at the recorded piece ends instead)
+    size_t k = 0;
+    while (k < x.splitmatchindex.size()) {
+      size_t e = k + 1;
+      while (e < x.splitmatchindex.size() && x.splitmatchindex[e] == x.splitmatchindex[e - 1] + 1) e++;
+      p_cluster[np] = (int32_t)i; p_start[np] = x.splitmatchindex[k]; p_end[np] = x.splitmatchindex[e - 1] + 1; np++;
+      k = e;
+    }
+  }
+  *n_piece = (int32_t)np;
+  read.seq = NULL; read.qual = NULL;
+  return (long)split.size();
+}
+
 }  // extern "C"

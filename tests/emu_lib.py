@@ -408,3 +408,22 @@ def refine_space(read_arena, genome, sp, K, m, mm, indel):
                              "chrom_off"]], flip, m, mm, indel, pair_off, o["pq"], o["pt"], o["n_pairs"], o["identity"], int((mn + 1).sum()) + 1)
     assert err == 0
     return o
+
+
+def split_rough(rl, globalK, max_gap, min_cluster_size, max_diag):
+    """rl as for Context.split_rough_batch; returns the same slot-layout dict."""
+    L = lib()
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    L.emu_split_rough.argtypes = [C.c_int, _u64p, _u64p, _u32p, _u32p, _i32p, _i32p, _u32p, _u8p, f32p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p,
+                                  _i32p, _i32p, _u32p, _u8p, f32p, _i32p, _i32p, _i32p]
+    lo = np.ascontiguousarray(rl["l_off"], np.uint64); lro = np.ascontiguousarray(rl["lr_off"], np.uint64)
+    NL = len(lo) - 1; T = int(lo[-1]) + int(lro[-1]) + 1
+    pad = lambda a, dt: np.ascontiguousarray(a, dt).reshape(-1) if len(a) else np.zeros(1, dt)
+    o = dict(n_split=np.zeros(max(NL, 1), np.int32), n_piece=np.zeros(max(NL, 1), np.int32), s_start=np.zeros(T, np.int32), s_end=np.zeros(T, np.int32),
+             s_coarse=np.zeros(T, np.int32), s_chrom=np.zeros(T, np.int32), s_box=np.zeros(4 * T, np.uint32), s_strand=np.zeros(T, np.uint8), s_freq=np.zeros(T, np.float32),
+             p_cluster=np.zeros(T, np.int32), p_start=np.zeros(T, np.int32), p_end=np.zeros(T, np.int32))
+    L.emu_split_rough(NL, lo, lro, pad(rl["q"], np.uint32), pad(rl["t"], np.uint32), pad(rl["r_start"], np.int32), pad(rl["r_end"], np.int32), pad(rl["r_box"], np.uint32),
+                      pad(rl["r_strand"], np.uint8), pad(rl["r_freq"], np.float32), pad(rl["r_chrom"], np.int32), globalK, max_gap, min_cluster_size, max_diag,
+                      o["n_split"], o["n_piece"], o["s_start"], o["s_end"], o["s_coarse"], o["s_chrom"], o["s_box"], o["s_strand"], o["s_freq"], o["p_cluster"], o["p_start"], o["p_end"])
+    o["s_box"] = o["s_box"].reshape(-1, 4)
+    return o

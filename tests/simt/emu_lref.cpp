@@ -302,3 +302,15 @@ extern "C" int emu_switchindex(int n_chains, const uint64_t *c_off, int32_t *ch,
   if (n_chains) emu::launch(dim3((unsigned)((n_chains + 63) / 64)), dim3(64), 0, [&] { switchindex_kernel(b); });
   return 0;
 }
+
+// ---- a8 (first half) SplitRoughClustersWithGaps
+#include "srough_kernels.cuh"
+extern "C" int emu_split_rough(int n_lists, const uint64_t *l_off, const uint64_t *lr_off, const uint32_t *q, const uint32_t *t, const int32_t *r_start, const int32_t *r_end,
+                               const uint32_t *r_box, const uint8_t *r_strand, const float *r_freq, const int32_t *r_chrom, int globalK, int maxGap, int minClusterSize, int maxDiag,
+                               int32_t *n_split, int32_t *n_piece, int32_t *s_start, int32_t *s_end, int32_t *s_coarse, int32_t *s_chrom, uint32_t *s_box, uint8_t *s_strand,
+                               float *s_freq, int32_t *p_cluster, int32_t *p_start, int32_t *p_end) {
+  SplitRoughBatch b{n_lists, globalK, maxGap, minClusterSize, maxDiag, (const unsigned long long *)l_off, (const unsigned long long *)lr_off, q, t, r_start, r_end, r_box,
+                    r_strand, r_freq, r_chrom, n_split, n_piece, s_start, s_end, s_coarse, s_chrom, s_box, s_strand, s_freq, p_cluster, p_start, p_end};
+  if (n_lists) emu::launch(dim3((unsigned)((n_lists + 63) / 64)), dim3(64), 0, [&] { split_rough_kernel(b); });
+  return 0;
+}
