@@ -577,15 +577,18 @@ typedef struct lra_b200_linear_gaps {
 int lra_b200_refine_linear_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_linear_gaps *in,
                                  lra_b200_aog_result *res);
 
-/* ---- a14 (core, small spaces)  RefineSpace, batched over spaces -------------------------------------------------------------
+/* ---- a14 (core)  RefineSpace, batched over spaces -----------------------------------------------------------------------------
  * Replaces  float RefineSpace(K, W, refineSpaceDiag, consider_str, EndPairs, opts, genome, read, strands, ChromIndex, qe, qs, te, ts, st, lrts, lrlength)
- * (ClusterRefine.h:242-327) for spaces with qe - qs < 1000 and te - ts + lrlength < 1000: the branch that aligns the space with
- * AffineOneGapAlign(localMatch, localMismatch, localIndel, 30) and takes the exact K-mers at multiples of K inside blocks longer than K (:262-294).
+ * (ClusterRefine.h:242-327), both branches: a space with qe - qs < 1000 and te - ts + lrlength < 1000 is aligned with AffineOneGapAlign(localMatch,
+ * localMismatch, localIndel, 30) and yields the exact K-mers at multiples of K inside blocks longer than K (:262-294) and the identity; a larger space
+ * yields the pairs of CompareLists over the sorted non-canonical (K, W) minimizers of its two windows inside the diagonal band
+ * [min(0, d) - refineSpaceDiag, max(0, d) + refineSpaceDiag], d = (te - (ts - lrts)) - (qe - qs), with opts.localMaxFreq (:296-305), identity = -1.
  * Space g: read[qs, qe) on the strand whose arena holds the read at read_off[g] (length read_len[g]), contig[ts - lrts, te + lrlength - lrts) with
- * the contig at chrom_off[g]; flip[g] = consider_str && st == 1 (read positions are reported as read_len - pos - K).  Results in slot layout:
- * EndPairs of space g = (pq, pt)[pair_off[g] .. pair_off[g] + n_pairs[g]), identity[g] = the return value (nMatch / (float) min(|query|, |ref|)).
- * A larger space is rejected with LRA_B200_EINVAL (the minimizer + CompareLists branch :296-305 is not built -- there is no fallback).
- * pair_cap must cover the slots (n_pairs_total = their number, also on LRA_B200_EOVERFLOW): sum over spaces of min(qLen, tLen) / K + 1. */
+ * the contig at chrom_off[g]; flip[g] = consider_str && st == 1 (read positions are reported as read_len - pos - K); diag[g] = refineSpaceDiag
+ * (read for the larger spaces only; the array may be NULL when there are none).  Results in slot layout: EndPairs of space g =
+ * (pq, pt)[pair_off[g] .. pair_off[g] + n_pairs[g]), identity[g] = the return value.
+ * pair_cap must cover the slots: min(qLen, tLen) / K + 1 per aligned space plus the pairs of the larger spaces, which are only known after their
+ * count pass -- n_pairs_total reports the requirement, also with LRA_B200_EOVERFLOW (call again with at least that). */
 typedef struct lra_b200_spaces {
   int32_t n_spaces;
   const uint32_t *qs, *qe, *ts, *te, *lrts, *lrlength;      /* [n_spaces] */
@@ -593,6 +596,9 @@ typedef struct lra_b200_spaces {
   const uint8_t *flip;                                      /* [n_spaces] */
   int32_t K;                                                /* the K RefineSpace is called with (opts.globalK) */
   int32_t match, mismatch, indel;                           /* opts.localMatch, localMismatch, localIndel */
+  int32_t W;                                                /* the W RefineSpace is called with (opts.globalW) */
+  int32_t local_max_freq;                                   /* opts.localMaxFreq */
+  const int32_t *diag;                                      /* [n_spaces] refineSpaceDiag */
 } lra_b200_spaces;
 
 typedef struct lra_b200_space_result {

@@ -125,7 +125,7 @@ class _LinearGaps(C.Structure):
 class _Spaces(C.Structure):
     _fields_ = [("n_spaces", C.c_int32), ("qs", C.c_void_p), ("qe", C.c_void_p), ("ts", C.c_void_p), ("te", C.c_void_p), ("lrts", C.c_void_p), ("lrlength", C.c_void_p),
                 ("read_off", C.c_void_p), ("read_len", C.c_void_p), ("chrom_off", C.c_void_p), ("flip", C.c_void_p), ("K", C.c_int32), ("match", C.c_int32),
-                ("mismatch", C.c_int32), ("indel", C.c_int32)]
+                ("mismatch", C.c_int32), ("indel", C.c_int32), ("W", C.c_int32), ("local_max_freq", C.c_int32), ("diag", C.c_void_p)]
 
 
 class _SpaceResult(C.Structure):
@@ -625,50 +625,29 @@ class Context:
         return out
 
     # ---- a14 (core, small spaces)
-    def refine_space_batch(self, reads, genome, sp, K, m, mm, indel):
-        """RefineSpace (the AffineOneGapAlign branch) for every space (sp: dict(qs, qe, ts, te, lrts, lrlength, read_off, read_len, chrom_off, flip)).
-        Returns dict(pair_off, n_pairs, identity, pq, pt) in slot layout."""
+    def refine_space_batch(self, reads, genome, sp, K, m, mm, indel, W=10, local_max_freq=30):
+        """RefineSpace for every space (sp: dict(qs, qe, ts, te, lrts, lrlength, read_off, read_len, chrom_off, flip[, diag = refineSpaceDiag per space, needed when a
+        space has 1000 bases or more on an axis])).  Returns dict(pair_off, n_pairs, identity, pq, pt) in slot layout."""
         a = {k: np.ascontiguousarray(sp[k], np.uint32) for k in ["qs", "qe", "ts", "te", "lrts", "lrlength", "read_off", "read_len", "chrom_off"]}
         a["flip"] = np.ascontiguousarray(sp["flip"], np.uint8)
+        diag = np.ascontiguousarray(sp["diag"], np.int32) if "diag" in sp else None
         n = len(a["qs"])
         ql = a["qe"].astype(np.int64) - a["qs"]; tl = a["te"].astype(np.int64) - a["ts"] + a["lrlength"]
         cap = int((np.minimum(ql, tl).clip(min=0) // K + 1).sum()) + 1
-        o = dict(pair_off=np.zeros(n + 1, np.uint64), n_pairs=np.zeros(max(n, 1), np.int32), identity=np.zeros(max(n, 1), np.float32), pq=np.zeros(cap, np.uint32),
-                 pt=np.zeros(cap, np.uint32))
         p = lambda x: _ptr(x) if x.size else None
-        e = _Spaces(n, *[p(a[k]) for k in ["qs", "qe", "ts", "te", "lrts", "lrlength", "read_off", "read_len", "chrom_off", "flip"]], K, m, mm, indel)
-        r = _SpaceResult(_ptr(o["pair_off"]), _ptr(o["n_pairs"]), _ptr(o["identity"]), _ptr(o["pq"]), _ptr(o["pt"]), cap, 0)
-        self._check(self.lib.lra_b200_refine_space_batch(self.h, reads.handle, genome.handle, C.byref(e), C.byref(r)))
+        for _ in range(2):
+            o = dict(pair_off=np.zeros(n + 1, np.uint64), n_pairs=np.zeros(max(n, 1), np.int32), identity=np.zeros(max(n, 1), np.float32), pq=np.zeros(cap, np.uint32),
+                     pt=np.zeros(cap, np.uint32))
+            e = _Spaces(n, *[p(a[k]) for k in ["qs", "qe", "ts", "te", "lrts", "lrlength", "read_off", "read_len", "chrom_off", "flip"]], K, m, mm, indel, W, local_max_freq,
+                        _ptr(diag) if diag is not None and diag.size else None)
+            r = _SpaceResult(_ptr(o["pair_off"]), _ptr(o["n_pairs"]), _ptr(o["identity"]), _ptr(o["pq"]), _ptr(o["pt"]), cap, 0)
+            rc = self.lib.lra_b200_refine_space_batch(self.h, reads.handle, genome.handle, C.byref(e), C.byref(r))
+            if rc == EOVERFLOW:        # the pairs of the minimizer branch are only known after its count pass
+                cap = int(r.n_pairs_total) + 1
+                continue
+            break
+        self._check(rc)
         o["n_pairs"] = o["n_pairs"][:n]; o["identity"] = o["identity"][:n]
-        return o
-
-    def switch_to_original_batch(self, run_start, run_end, coarse):
-        """SwitchToOriginalAnchors for every FinalChain entry.  Returns (off, chain, cluster_index)."""
-        rs = np.ascontiguousarray(run_start, np.int32); re_ = np.ascontiguousarray(run_end, np.int32); co = np.ascontiguousarray(coarse, np.int32)
-        n = len(rs); cap = int(np.clip(re_.astype(np.int64) - rs, 0, None).sum())
-        off = np.zeros(n + 1, np.uint64); chain = np.zeros(max(cap, 1), np.uint32); ci = np.zeros(max(cap, 1), np.int32)
-        tot = C.c_uint64(0)
-        p = lambda x: _ptr(x) if x.size else None
-        self._check(self.lib.lra_b200_switch_to_original_batch(self.h, p(rs), p(re_), p(co), n, _ptr(off), _ptr(chain), _ptr(ci), cap, C.byref(tot)))
-        return off, chain[:int(tot.value)], ci[:int(tot.value)]
-
-    # ---- a8 (first half)
-    def split_rough_batch(self, rl, globalK, max_gap, min_cluster_size, max_diag):
-        """SplitRoughClustersWithGaps for every anchor list (rl: dict(l_off, lr_off, q, t, r_start, r_end, r_box, r_strand, r_freq, r_chrom)).
-        Returns the slot-layout arrays of lra_b200_split_rough_result (base of list l = l_off[l] + lr_off[l])."""
-        lo = np.ascontiguousarray(rl["l_off"], np.uint64); lro = np.ascontiguousarray(rl["lr_off"], np.uint64)
-        NL = len(lo) - 1; T = int(lo[-1]) + int(lro[-1]) + 1
-        a = dict(q=np.ascontiguousarray(rl["q"], np.uint32), t=np.ascontiguousarray(rl["t"], np.uint32), r_start=np.ascontiguousarray(rl["r_start"], np.int32),
-                 r_end=np.ascontiguousarray(rl["r_end"], np.int32), r_box=np.ascontiguousarray(rl["r_box"], np.uint32).reshape(-1), r_strand=np.ascontiguousarray(rl["r_strand"], np.uint8),
-                 r_freq=np.ascontiguousarray(rl["r_freq"], np.float32), r_chrom=np.ascontiguousarray(rl["r_chrom"], np.int32))
-        o = dict(n_split=np.zeros(max(NL, 1), np.int32), n_piece=np.zeros(max(NL, 1), np.int32), s_start=np.zeros(T, np.int32), s_end=np.zeros(T, np.int32),
-                 s_coarse=np.zeros(T, np.int32), s_chrom=np.zeros(T, np.int32), s_box=np.zeros((T, 4), np.uint32), s_strand=np.zeros(T, np.uint8), s_freq=np.zeros(T, np.float32),
-                 p_cluster=np.zeros(T, np.int32), p_start=np.zeros(T, np.int32), p_end=np.zeros(T, np.int32))
-        p = lambda x: _ptr(x) if x.size else None
-        e = _RoughLists(NL, _ptr(lo), _ptr(lro), p(a["q"]), p(a["t"]), p(a["r_start"]), p(a["r_end"]), p(a["r_box"]), p(a["r_strand"]), p(a["r_freq"]), p(a["r_chrom"]),
-                        globalK, max_gap, min_cluster_size, max_diag)
-        r = _SplitRoughResult(*[_ptr(o[k]) for k in ["n_split", "n_piece", "s_start", "s_end", "s_coarse", "s_chrom", "s_box", "s_strand", "s_freq", "p_cluster", "p_start", "p_end"]])
-        self._check(self.lib.lra_b200_split_rough_batch(self.h, C.byref(e), C.byref(r)))
         return o
 
     # ---- a22

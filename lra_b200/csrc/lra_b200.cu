@@ -77,6 +77,7 @@ struct lra_b200_ctx {
   DevBuf rl[8];           // RefineByLinearAlignment: gap descriptors
   DevBuf rs[16];          // RefineSpace: space descriptors, pairs
   DevBuf sr[24];          // SplitRoughClustersWithGaps
+  DevBuf rs2[12];         // RefineSpace, minimizer branch
   bool keep_stats = false;  // sub-launchers append to stats instead of clearing
   AogPlan *h_plan = nullptr;            // pinned
   unsigned long long *h_misc = nullptr;  // pinned (2 x u64)
@@ -178,6 +179,7 @@ extern "C" void lra_b200_destroy(lra_b200_ctx *ctx) {
   for (DevBuf &b : ctx->rl) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->rs) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->sr) if (b.p) cudaFree(b.p);
+  for (DevBuf &b : ctx->rs2) if (b.p) cudaFree(b.p);
   for (auto &ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < 4; i++) { if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]); if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]); }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);

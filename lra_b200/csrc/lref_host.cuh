@@ -1238,7 +1238,7 @@ extern "C" int lra_b200_refine_linear_batch(lra_b200_ctx *ctx, const lra_b200_se
   return rc;
 }
 
-// ---------------------------------------------------------------------------------------------------- a14 (core, small spaces) RefineSpace
+// ---------------------------------------------------------------------------------------------------- a14 (core) RefineSpace
 extern "C" int lra_b200_refine_space_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads, const lra_b200_seq *genome, const lra_b200_spaces *in,
                                            lra_b200_space_result *res) {
   if (!ctx || !reads || !genome || !in || !res) return fail(ctx, LRA_B200_EINVAL, "refine_space_batch: NULL argument");
@@ -1250,49 +1250,95 @@ extern "C" int lra_b200_refine_space_batch(lra_b200_ctx *ctx, const lra_b200_seq
   if (n == 0) return LRA_B200_OK;
   if (!in->qs || !in->qe || !in->ts || !in->te || !in->lrts || !in->lrlength || !in->read_off || !in->read_len || !in->chrom_off || !in->flip)
     return fail(ctx, LRA_B200_EINVAL, "refine_space_batch: NULL space array");
-  std::vector<unsigned long long> pair_off((size_t)n + 1);
-  size_t P = 0, blk = 0;
+  std::vector<unsigned long long> pair_off((size_t)n + 1), mq_off, mt_off;
+  std::vector<uint8_t> large((size_t)n, 0);
+  std::vector<uint32_t> lidx;
+  size_t blk = 0, MQ = 0, MT = 0;
   for (int g = 0; g < n; g++) {
     const long long ql = (long long)in->qe[g] - (long long)in->qs[g], tl = (long long)in->te[g] - (long long)in->ts[g] + (long long)in->lrlength[g];
     if (ql < 0 || tl < 0 || in->lrts[g] > in->ts[g]) return fail(ctx, LRA_B200_EINVAL, "refine_space_batch: space %d has a negative extent", g);
-    if (ql >= 1000 || tl >= 1000)
-      return fail(ctx, LRA_B200_EINVAL, "refine_space_batch: space %d is %lld x %lld: only spaces below 1000 bases on both axes (the AffineOneGapAlign branch of RefineSpace) are built",
-                  g, ql, tl);
     if ((uint64_t)in->read_off[g] + in->qe[g] > reads->n || (uint64_t)in->chrom_off[g] + in->te[g] + in->lrlength[g] > genome->n)
       return fail(ctx, LRA_B200_EINVAL, "refine_space_batch: space %d reaches beyond its arena", g);
-    pair_off[g] = P;
-    const long long mn = ql < tl ? ql : tl;
-    P += (size_t)(mn / in->K + 1);
-    blk += (size_t)mn + 1;
+    if (in->qe[g] > in->read_len[g]) return fail(ctx, LRA_B200_EINVAL, "refine_space_batch: space %d ends at read position %u of a read of %u bases", g, in->qe[g], in->read_len[g]);
+    if (ql >= 1000 || tl >= 1000) {          // the minimizer branch (ClusterRefine.h:296-305)
+      if (!in->diag || in->W <= 0 || in->W > kSeedMaxW || in->K > 31) return fail(ctx, LRA_B200_EINVAL, "refine_space_batch: space %d needs W, localMaxFreq and refineSpaceDiag", g);
+      large[g] = 1; lidx.push_back((uint32_t)g); mq_off.push_back(MQ); mt_off.push_back(MT);
+      MQ += (size_t)ql + 1; MT += (size_t)tl + 1;
+    } else {
+      const long long mn = ql < tl ? ql : tl;
+      blk += (size_t)mn + 1;
+    }
   }
-  pair_off[n] = P;
-  if (res->pair_cap < P) { res->n_pairs_total = P; return fail(ctx, LRA_B200_EOVERFLOW, "refine_space_batch: pair arrays hold %llu entries, %llu slots are needed",
-                                                                 (unsigned long long)res->pair_cap, (unsigned long long)P); }
+  const int nl = (int)lidx.size();
   int rc;
   DevBuf *B = ctx->rs;
   const size_t nb4 = (size_t)n * 4;
   for (int i = 0; i < 9; i++) if ((rc = ensure(ctx, B[i], nb4))) return rc;
-  if ((rc = ensure(ctx, B[9], (size_t)n)) || (rc = ensure(ctx, B[10], ((size_t)n + 1) * 8)) || (rc = ensure(ctx, B[11], P * 4)) || (rc = ensure(ctx, B[12], P * 4)) ||
-      (rc = ensure(ctx, B[13], nb4)) || (rc = ensure(ctx, B[14], nb4)))
+  if ((rc = ensure(ctx, B[9], (size_t)n)) || (rc = ensure(ctx, B[10], ((size_t)n + 1) * 8)) || (rc = ensure(ctx, B[13], nb4)) || (rc = ensure(ctx, B[14], nb4)) ||
+      (rc = ensure(ctx, B[15], (size_t)n)))
     return rc;
   if ((rc = ensure(ctx, ctx->d_qoff, nb4)) || (rc = ensure(ctx, ctx->d_toff, nb4)) || (rc = ensure(ctx, ctx->d_qlen, nb4)) || (rc = ensure(ctx, ctx->d_tlen, nb4)) ||
       (rc = ensure(ctx, ctx->d_k, nb4)) || (rc = ensure(ctx, ctx->d_score, nb4)) || (rc = ensure(ctx, ctx->d_nb, nb4)) || (rc = ensure(ctx, ctx->d_boff, (size_t)n * 8)) ||
-      (rc = ensure(ctx, ctx->d_blocks, blk * 12)))
+      (rc = ensure(ctx, ctx->d_blocks, (blk ? blk : 1) * 12)))
     return rc;
   cudaStream_t st = ctx->stream;
   const void *src[9] = {in->qs, in->qe, in->ts, in->te, in->lrts, in->lrlength, in->read_off, in->read_len, in->chrom_off};
   for (int i = 0; i < 9; i++) CU(cudaMemcpyAsync(B[i].p, src[i], nb4, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(B[9].p, in->flip, (size_t)n, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(B[10].p, pair_off.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[15].p, large.data(), (size_t)n, cudaMemcpyHostToDevice, st));
   RspBatch b;
   b.n = n; b.K = in->K;
   b.reads = SeqView{reads->b2, reads->nm, reads->n}; b.genome = SeqView{genome->b2, genome->nm, genome->n};
   b.qs = (const uint32_t *)B[0].p; b.qe = (const uint32_t *)B[1].p; b.ts = (const uint32_t *)B[2].p; b.te = (const uint32_t *)B[3].p; b.lrts = (const uint32_t *)B[4].p;
   b.lrlength = (const uint32_t *)B[5].p; b.read_off = (const uint32_t *)B[6].p; b.read_len = (const uint32_t *)B[7].p; b.chrom_off = (const uint32_t *)B[8].p;
-  b.flip = (const uint8_t *)B[9].p; b.pair_off = (const unsigned long long *)B[10].p; b.pq = (uint32_t *)B[11].p; b.pt = (uint32_t *)B[12].p;
+  b.flip = (const uint8_t *)B[9].p; b.large = (const uint8_t *)B[15].p; b.pair_off = (const unsigned long long *)B[10].p;
   b.n_pairs = (int32_t *)B[13].p; b.identity = (float *)B[14].p;
   b.q_off = (uint32_t *)ctx->d_qoff.p; b.t_off = (uint32_t *)ctx->d_toff.p; b.q_len = (int32_t *)ctx->d_qlen.p; b.t_len = (int32_t *)ctx->d_tlen.p; b.k = (int32_t *)ctx->d_k.p;
   b.n_blocks = (const int32_t *)ctx->d_nb.p; b.block_off = (const unsigned long long *)ctx->d_boff.p; b.blocks = (const uint32_t *)ctx->d_blocks.p;
+  // ---- large spaces: minimizers of both windows, sort, count the pairs inside the band
+  RsplBatch lb; memset(&lb, 0, sizeof lb);
+  std::vector<unsigned long long> cnt((size_t)nl + 1, 0ull);
+  if (nl) {
+    DevBuf *L = ctx->rs2;
+    if ((rc = ensure(ctx, L[0], (size_t)nl * 4)) || (rc = ensure(ctx, L[1], (size_t)nl * 8)) || (rc = ensure(ctx, L[2], (size_t)nl * 8)) || (rc = ensure(ctx, L[3], MQ * 8)) ||
+        (rc = ensure(ctx, L[4], MT * 8)) || (rc = ensure(ctx, L[5], MQ * 4)) || (rc = ensure(ctx, L[6], MT * 4)) || (rc = ensure(ctx, L[7], (size_t)nl * 4)) ||
+        (rc = ensure(ctx, L[8], (size_t)nl * 4)) || (rc = ensure(ctx, L[9], (size_t)nl * 8)) || (rc = ensure(ctx, L[10], nb4)))
+      return rc;
+    CU(cudaMemcpyAsync(L[0].p, lidx.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(L[1].p, mq_off.data(), (size_t)nl * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(L[2].p, mt_off.data(), (size_t)nl * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(L[10].p, in->diag, nb4, cudaMemcpyHostToDevice, st));
+    lb.n_large = nl; lb.K = in->K; lb.W = in->W; lb.max_freq = in->local_max_freq; lb.reads = b.reads; lb.genome = b.genome;
+    lb.idx = (const uint32_t *)L[0].p; lb.qs = b.qs; lb.qe = b.qe; lb.ts = b.ts; lb.te = b.te; lb.lrts = b.lrts; lb.lrlength = b.lrlength; lb.read_off = b.read_off;
+    lb.read_len = b.read_len; lb.chrom_off = b.chrom_off; lb.flip = b.flip; lb.diag = (const int32_t *)L[10].p;
+    lb.mq_off = (const unsigned long long *)L[1].p; lb.mt_off = (const unsigned long long *)L[2].p; lb.mq_t = (unsigned long long *)L[3].p; lb.mt_t = (unsigned long long *)L[4].p;
+    lb.mq_p = (uint32_t *)L[5].p; lb.mt_p = (uint32_t *)L[6].p; lb.mq_n = (uint32_t *)L[7].p; lb.mt_n = (uint32_t *)L[8].p; lb.cnt = (unsigned long long *)L[9].p;
+    lb.pair_off = b.pair_off; lb.n_pairs = b.n_pairs; lb.identity = b.identity;
+    rspl_mins_kernel<<<(unsigned)((2 * nl + 63) / 64), 64, 0, st>>>(lb);
+    rspl_compare_kernel<false><<<(unsigned)((nl + 63) / 64), 64, 0, st>>>(lb);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(cnt.data(), lb.cnt, (size_t)nl * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  // ---- slots: min(qLen, tLen) / K + 1 for an aligned space, the counted pairs for a minimizer space
+  size_t P = 0;
+  { int j = 0;
+    for (int g = 0; g < n; g++) {
+      pair_off[g] = P;
+      if (large[g]) P += (size_t)cnt[j++];
+      else {
+        const long long ql = (long long)in->qe[g] - (long long)in->qs[g], tl = (long long)in->te[g] - (long long)in->ts[g] + (long long)in->lrlength[g];
+        P += (size_t)((ql < tl ? ql : tl) / in->K + 1);
+      }
+    }
+    pair_off[n] = P; }
+  res->n_pairs_total = P;
+  if (res->pair_cap < P) return fail(ctx, LRA_B200_EOVERFLOW, "refine_space_batch: pair arrays hold %llu entries, %llu slots are needed",
+                                     (unsigned long long)res->pair_cap, (unsigned long long)P);
+  if ((rc = ensure(ctx, B[11], (P ? P : 1) * 4)) || (rc = ensure(ctx, B[12], (P ? P : 1) * 4))) return rc;
+  b.pq = (uint32_t *)B[11].p; b.pt = (uint32_t *)B[12].p; lb.pq = b.pq; lb.pt = b.pt;
+  CU(cudaMemcpyAsync(B[10].p, pair_off.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
   rsp_jobs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b);
   ctx->launches++;
   CU(cudaGetLastError());
@@ -1301,18 +1347,20 @@ extern "C" int lra_b200_refine_space_batch(lra_b200_ctx *ctx, const lra_b200_seq
   dj.match = in->match; dj.mismatch = in->mismatch; dj.indel = in->indel;
   lra_b200_aog_result dr; memset(&dr, 0, sizeof dr);
   dr.score = (int32_t *)ctx->d_score.p; dr.n_blocks = (int32_t *)ctx->d_nb.p; dr.block_off = (uint64_t *)ctx->d_boff.p; dr.blocks = (uint32_t *)ctx->d_blocks.p;
-  dr.block_cap = blk;
+  dr.block_cap = blk ? blk : 1;
   if ((rc = aog_run_device(ctx, reads, genome, &dj, &dr))) return rc;
   rsp_harvest_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b);
   ctx->launches++;
+  if (nl) { rspl_compare_kernel<true><<<(unsigned)((nl + 63) / 64), 64, 0, st>>>(lb); ctx->launches++; }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(res->pair_off, b.pair_off, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(res->n_pairs, b.n_pairs, nb4, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(res->identity, b.identity, nb4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(res->pq, b.pq, P * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(res->pt, b.pt, P * 4, cudaMemcpyDeviceToHost, st));
+  if (P) {
+    CU(cudaMemcpyAsync(res->pq, b.pq, P * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->pt, b.pt, P * 4, cudaMemcpyDeviceToHost, st));
+  }
   CU(cudaStreamSynchronize(st));
-  res->n_pairs_total = P;
   return LRA_B200_OK;
 }
 

@@ -87,20 +87,14 @@ struct SeedBatch {
 
 constexpr int kSeedMaxW = 64;
 
-// ---- a2 (literal): one read per thread
-__global__ void __launch_bounds__(128) seed_minimizers_kernel(SeedBatch b) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= b.n_reads) return;
-  const unsigned long long off = b.read_off[r];
-  const uint32_t seqLen = b.read_len[r];
-  const int k = b.k, w = b.w;
-  unsigned long long *ot = b.mm_t + off;
-  uint32_t *op = b.mm_pos + off;
+// ---- a2 (literal): the minimizers of seq[off, off + seqLen) into (ot, op); returns their number.  CANON: StoreMinimizers (MinCount.h:7-179, the smaller of
+// the tuple and its reverse complement, strand in the top bit); !CANON: StoreMinimizers_noncanonical (MinCount.h:181-337, forward tuples only)
+template <bool CANON>
+__device__ uint32_t mm_scan(const SeqView &seq, unsigned long long off, uint32_t seqLen, int k, int w, unsigned long long *ot, uint32_t *op) {
   uint32_t n_out = 0;
-  b.mm_n[r] = 0;
-  if (seqLen < (uint32_t)k) return;
+  if (seqLen < (uint32_t)k) return 0;
   const int windowSpan = w + k - 1;
-  if (seqLen < (uint32_t)windowSpan) return;
+  if (seqLen < (uint32_t)windowSpan) return 0;
   unsigned long long m = 0;
   for (int i = 0; i < k; i++) { m <<= 2; m += 3; }
   int nextValidWindowEnd = 0, nextValidWindowStart = 0;
@@ -108,14 +102,14 @@ __global__ void __launch_bounds__(128) seed_minimizers_kernel(SeedBatch b) {
   while ((uint32_t)nextValidWindowStart < seqLen - (uint32_t)windowSpan && !valid) {
     valid = true;
     for (int n = nextValidWindowStart; valid && n < nextValidWindowStart + windowSpan; n++) {
-      if (seqLen < (uint32_t)n) return;
-      if (seq_code(b.reads, off + (unsigned long long)n) > 3) { nextValidWindowStart = n + 1; valid = false; }
+      if (seqLen < (uint32_t)n) return 0;
+      if (seq_code(seq, off + (unsigned long long)n) > 3) { nextValidWindowStart = n + 1; valid = false; }
     }
   }
-  if (!valid) return;
+  if (!valid) return 0;
   nextValidWindowEnd = nextValidWindowStart + windowSpan;
   SeqStream st;
-  st.init(b.reads, off);
+  st.init(seq, off);
   unsigned long long cur = 0, curRC = 0;
   for (int p = 0; p <= k - 1; p++) { const int c = st.next(); cur <<= 2; cur += (unsigned long long)(c & 3) * (c != 4); }
   { unsigned long long a = cur; for (int i = 0; i < k; i++) { const unsigned long long least = ~(a & 3ull) & 3ull; a >>= 2; curRC <<= 2; curRC += least; } }
@@ -123,7 +117,7 @@ __global__ void __launch_bounds__(128) seed_minimizers_kernel(SeedBatch b) {
   uint32_t ringP[kSeedMaxW];
   unsigned long long actT;
   uint32_t actP = 0;
-  if ((cur & kForMask) < (curRC & kForMask)) actT = cur & kForMask; else actT = curRC | kRevMask;
+  if (!CANON) actT = cur; else if ((cur & kForMask) < (curRC & kForMask)) actT = cur & kForMask; else actT = curRC | kRevMask;
   ringT[0] = actT; ringP[0] = 0;
   uint32_t p;
   for (p = 1; p < (uint32_t)w && p < seqLen - (uint32_t)k + 1; p++) {
@@ -131,7 +125,7 @@ __global__ void __launch_bounds__(128) seed_minimizers_kernel(SeedBatch b) {
     const unsigned long long n2 = (unsigned long long)(c & 3) * (c != 4);
     cur = ((cur << 2) & m) + n2;
     curRC >>= 2; curRC += ((~n2) & 3ull) << (2 * ((unsigned long long)k - 1));
-    const unsigned long long ct = ((cur & kForMask) < (curRC & kForMask)) ? (cur & kForMask) : (curRC | kRevMask);
+    const unsigned long long ct = !CANON ? (cur & kForMask) : ((cur & kForMask) < (curRC & kForMask)) ? (cur & kForMask) : (curRC | kRevMask);
     if (ct < actT) { actT = ct; actP = p; }        // first window: unmasked comparison (MinCount.h:91)
     ringT[p % (uint32_t)w] = ct; ringP[p % (uint32_t)w] = p;
   }
@@ -146,16 +140,16 @@ __global__ void __launch_bounds__(128) seed_minimizers_kernel(SeedBatch b) {
         while ((uint32_t)nextValidWindowStart < seqLen - (uint32_t)windowSpan && !valid) {
           valid = true;
           for (int n = nextValidWindowStart; valid && n < nextValidWindowStart + windowSpan; n++)
-            if (seq_code(b.reads, off + (unsigned long long)n) > 3) { nextValidWindowStart = n + 1; valid = false; }
+            if (seq_code(seq, off + (unsigned long long)n) > 3) { nextValidWindowStart = n + 1; valid = false; }
         }
-        if (!valid) { b.mm_n[r] = n_out; return; }
+        if (!valid) return n_out;
         nextValidWindowEnd = nextValidWindowStart + windowSpan;
       }
     }
     const unsigned long long n2 = (unsigned long long)(c & 3) * (c != 4);
     cur = ((cur << 2) & m) + n2;
     curRC >>= 2; curRC += ((~n2) & 3ull) << (2 * ((unsigned long long)k - 1));
-    const unsigned long long ct = ((cur & kForMask) < (curRC & kForMask)) ? (cur & kForMask) : (curRC | kRevMask);
+    const unsigned long long ct = !CANON ? (cur & kForMask) : ((cur & kForMask) < (curRC & kForMask)) ? (cur & kForMask) : (curRC | kRevMask);
     ringT[p % (uint32_t)w] = ct; ringP[p % (uint32_t)w] = p;
     if (p - (uint32_t)w >= actP) {
       actT = ringT[0]; actP = ringP[0];
@@ -166,7 +160,14 @@ __global__ void __launch_bounds__(128) seed_minimizers_kernel(SeedBatch b) {
       if ((uint32_t)nextValidWindowEnd == p + (uint32_t)k) { ot[n_out] = actT; op[n_out] = actP; n_out++; }
     }
   }
-  b.mm_n[r] = n_out;
+  return n_out;
+}
+
+__global__ void __launch_bounds__(128) seed_minimizers_kernel(SeedBatch b) {   // one read per thread
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= b.n_reads) return;
+  const unsigned long long off = b.read_off[r];
+  b.mm_n[r] = mm_scan<true>(b.reads, off, b.read_len[r], b.k, b.w, b.mm_t + off, b.mm_pos + off);
 }
 
 // ---- a3: libstdc++ std::sort (introsort) on the masked key, in place, one read per thread
@@ -229,12 +230,8 @@ __device__ __forceinline__ void mm_heap_sort(const MmRef &v, long first, long la
   }
 }
 
-__global__ void __launch_bounds__(128) seed_sort_kernel(SeedBatch b) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= b.n_reads) return;
-  const long n = (long)b.mm_n[r];
+__device__ inline void mm_sort(const MmRef &v, long n) {
   if (n <= 1) return;
-  MmRef v{b.mm_t + b.read_off[r], b.mm_pos + b.read_off[r]};
   long lg = 0;
   { unsigned long x = (unsigned long)n; while (x > 1) { x >>= 1; lg++; } }
   // __introsort_loop with an explicit stack for the recursive (right-hand) calls
@@ -274,36 +271,16 @@ __global__ void __launch_bounds__(128) seed_sort_kernel(SeedBatch b) {
   else mm_insertion_sort(v, 0, n);
 }
 
-// ---- a4 + a5: literal CompareLists; EMIT == false counts, EMIT == true writes at match offsets
-template <bool EMIT>
-__global__ void __launch_bounds__(128) seed_compare_kernel(SeedBatch b) {
+__global__ void __launch_bounds__(128) seed_sort_kernel(SeedBatch b) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= b.n_reads) return;
-  const long nq = (long)b.mm_n[r];
-  const long nt = (long)b.n_idx;
-  const unsigned long long *qt = b.mm_t + b.read_off[r];
-  const uint32_t *qpos = b.mm_pos + b.read_off[r];
-  const unsigned long long *tt = b.idx_t;
-  const uint32_t *tpos = b.idx_pos;
-  const long long maxFreq = b.max_freq;
-  unsigned long long n_out = 0;
-  const unsigned long long obase = EMIT ? b.match_cnt[r] : 0ull;
-  const unsigned long long roff = b.read_off[r];
-  const int k = b.k;
-  auto push = [&](long qi, long ti) {
-    if (EMIT) {
-      const unsigned long long o = obase + n_out;
-      if (o < b.match_cap) {
-        b.m_qt[o] = qt[qi]; b.m_qpos[o] = qpos[qi]; b.m_tt[o] = tt[ti]; b.m_tpos[o] = tpos[ti];
-        // a5: strncmp(read + q, genome + t, k) == 0 -> forward (0) else reverse (1)
-        int differ = 0;
-        for (int j = 0; j < k && !differ; j++)
-          differ = seq_code(b.reads, roff + (unsigned long long)qpos[qi] + j) != seq_code(b.genome, (unsigned long long)tpos[ti] + j);
-        b.m_strand[o] = (uint8_t)differ;
-      }
-    }
-    n_out++;
-  };
+  mm_sort(MmRef{b.mm_t + b.read_off[r], b.mm_pos + b.read_off[r]}, (long)b.mm_n[r]);
+}
+
+// ---- a4: literal CompareLists<GenomeTuple, Tuple> (CompareLists.h:8-146) of two sorted minimizer lists; push(qi, ti) receives every pair in the reference's
+// order (the caller applies its own filter: none for the global index, the diagonal band for RefineSpace)
+template <class Push>
+__device__ void mm_compare(const unsigned long long *qt, long nq, const unsigned long long *tt, long nt, long long maxFreq, Push push) {
 #define QK(i) (qt[i] & kForMask)
 #define TK(i) (tt[i] & kForMask)
   if (nq != 0 && nt != 0) {
@@ -362,6 +339,37 @@ __global__ void __launch_bounds__(128) seed_compare_kernel(SeedBatch b) {
   }
 #undef QK
 #undef TK
+}
+
+// ---- a4 + a5 against the global index: EMIT == false counts, EMIT == true writes at match offsets
+template <bool EMIT>
+__global__ void __launch_bounds__(128) seed_compare_kernel(SeedBatch b) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= b.n_reads) return;
+  const long nq = (long)b.mm_n[r];
+  const long nt = (long)b.n_idx;
+  const unsigned long long *qt = b.mm_t + b.read_off[r];
+  const uint32_t *qpos = b.mm_pos + b.read_off[r];
+  const unsigned long long *tt = b.idx_t;
+  const uint32_t *tpos = b.idx_pos;
+  unsigned long long n_out = 0;
+  const unsigned long long obase = EMIT ? b.match_cnt[r] : 0ull;
+  const unsigned long long roff = b.read_off[r];
+  const int k = b.k;
+  mm_compare(qt, nq, tt, nt, b.max_freq, [&](long qi, long ti) {
+    if (EMIT) {
+      const unsigned long long o = obase + n_out;
+      if (o < b.match_cap) {
+        b.m_qt[o] = qt[qi]; b.m_qpos[o] = qpos[qi]; b.m_tt[o] = tt[ti]; b.m_tpos[o] = tpos[ti];
+        // a5: strncmp(read + q, genome + t, k) == 0 -> forward (0) else reverse (1)
+        int differ = 0;
+        for (int j = 0; j < k && !differ; j++)
+          differ = seq_code(b.reads, roff + (unsigned long long)qpos[qi] + j) != seq_code(b.genome, (unsigned long long)tpos[ti] + j);
+        b.m_strand[o] = (uint8_t)differ;
+      }
+    }
+    n_out++;
+  });
   if (!EMIT) b.match_cnt[r] = n_out;
 }
 

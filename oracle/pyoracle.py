@@ -884,19 +884,56 @@ def refine_linear(read, contig, qs, qe, ts, te, m, mm, indel, local_band, which=
 
 # ---------------------------------------------------------------- a14 (core, small spaces) RefineSpace
 
-def refine_space(strandseq, contig, K, qs, qe, ts, te, st, consider_str, lrts, lrlength, m, mm, indel, which="port"):
+def _refine_space_large(r, q, t, t0, K, W, diag, local_max_freq, qs, qe, ts, te, st, consider_str, lrts):
+    """The branch of RefineSpace for a space of 1000 bases or more on either axis (ClusterRefine.h:296-305): non-canonical minimizers of both windows,
+    std::sort, CompareLists(Global = false) inside the diagonal band [min(0, d2) - diag, max(0, d2) + diag], d2 = (te - (ts - lrts)) - (qe - qs); identity = -1."""
+    P = port()
+    f = _bind_once(P, "lra_oracle_store_minimizers_nc", C.c_long, [_u8p, C.c_uint32, C.c_int, C.c_int, _u64p, _u32p, C.c_long])
+    g = _bind_once(P, "lra_oracle_compare_lists_band", C.c_long, [_u64p, _u32p, C.c_long, _u64p, _u32p, C.c_long, C.c_long, C.c_long, C.c_long, _u64p, _u32p, _u64p, _u32p, C.c_long])
+    srt = _bind_once(P, "lra_oracle_sort_minimizers", None, [_u64p, _u32p, C.c_long])
+
+    def mins(seq):
+        buf = np.concatenate([np.ascontiguousarray(seq, np.uint8), np.zeros(8, np.uint8)])
+        cap = len(seq) + 8
+        tt = np.zeros(cap, np.uint64); pp = np.zeros(cap, np.uint32)
+        n = f(buf, len(seq), K, W, tt, pp, cap)
+        tt, pp = tt[:n].copy(), pp[:n].copy()
+        if n:
+            srt(tt, pp, n)
+        return tt, pp
+    gt, gp = mins(t); qt, qp = mins(q)
+    d2 = (int(te) - (int(ts) - int(lrts))) - (int(qe) - int(qs))
+    mn, mx = min(0, d2) - diag, max(0, d2) + diag
+    pq, pt = np.zeros(0, np.uint32), np.zeros(0, np.uint32)
+    if len(qt) and len(gt):
+        cap = 4 * (len(qt) + len(gt)) + 1024
+        while True:
+            r4 = [np.zeros(cap, np.uint64), np.zeros(cap, np.uint32), np.zeros(cap, np.uint64), np.zeros(cap, np.uint32)]
+            n = g(qt, qp, len(qt), gt, gp, len(gt), local_max_freq, mx, mn, r4[0], r4[1], r4[2], r4[3], cap)
+            if n <= cap:
+                break
+            cap = n + 16
+        pq = r4[1][:n].astype(np.int64) + int(qs); pt = r4[3][:n].astype(np.int64) + t0
+        if consider_str and st == 1:
+            pq = len(r) - pq - K
+        pq = (pq & 0xFFFFFFFF).astype(np.uint32); pt = (pt & 0xFFFFFFFF).astype(np.uint32)
+    return pq, pt, np.float32(-1.0)
+
+
+def refine_space(strandseq, contig, K, qs, qe, ts, te, st, consider_str, lrts, lrlength, m, mm, indel, which="port", W=10, diag=100, local_max_freq=30):
     """One space.  Returns (pq, pt, identity).  port: the AffineOneGapAlign branch of RefineSpace (ClusterRefine.h:262-294) on the a18 oracle, the K-mer
     harvest, identity in binary32, the coordinate shift (:314-325); spaces of 1000 or more are outside the restatement."""
     r = np.ascontiguousarray(strandseq, np.uint8); c = np.ascontiguousarray(contig, np.uint8)
     if which == "ref":
         f = _bind_once(ref(), "ref_refine_space", C.c_long, [_u8p, C.c_int, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                                             C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, _u32p, _u32p, C.c_long, C.POINTER(C.c_float)])
-        cap = (int(qe) - int(qs)) // K + 8
+                                                             C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, _u32p, _u32p, C.c_long, C.POINTER(C.c_float), C.c_int])
+        cap = 8 * (int(qe) - int(qs)) + 1024
         pq = np.zeros(cap, np.uint32); pt = np.zeros(cap, np.uint32); idn = C.c_float(0)
-        n = f(r, len(r), c, len(c), K, 10, 100, int(consider_str), int(qe), int(qs), int(te), int(ts), int(st), int(lrts), int(lrlength), m, mm, indel, pq, pt, cap, C.byref(idn))
+        n = f(r, len(r), c, len(c), K, W, diag, int(consider_str), int(qe), int(qs), int(te), int(ts), int(st), int(lrts), int(lrlength), m, mm, indel, pq, pt, cap, C.byref(idn), local_max_freq)
         return pq[:n], pt[:n], np.float32(idn.value)
     q = r[qs:qe]; t0 = int(ts) - int(lrts); t = c[t0:t0 + int(te) - int(ts) + int(lrlength)]
-    assert len(q) < 1000 and len(t) < 1000
+    if not (len(q) < 1000 and len(t) < 1000):
+        return _refine_space_large(r, q, t, t0, K, W, diag, local_max_freq, qs, qe, ts, te, st, consider_str, lrts)
     score, blocks, stt = aog_port(bytes(q), bytes(t), m, mm, indel, 30)
     assert stt == 0
     n_match = 0; pq, pt = [], []

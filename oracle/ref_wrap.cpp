@@ -706,9 +706,9 @@ long ref_refine_linear(const uint8_t *readseq, int read_len, const uint8_t *cont
 // Returns the number of EndPairs; *identity = the function's return value.
 long ref_refine_space(const uint8_t *strandseq, int read_len, const uint8_t *contig, int contig_len, int K, int W, int refineSpaceDiag, int consider_str,
                       uint32_t qe, uint32_t qs, uint32_t te, uint32_t ts, int st, uint32_t lrts, uint32_t lrlength, int m, int mm, int indel,
-                      uint32_t *pq, uint32_t *pt, long cap, float *identity) {
+                      uint32_t *pq, uint32_t *pt, long cap, float *identity, int localMaxFreq) {
   ref_init_static();
-  Options opts; opts.localMatch = m; opts.localMismatch = mm; opts.localIndel = indel; opts.dotPlot = false;
+  Options opts; opts.localMaxFreq = localMaxFreq; opts.localMatch = m; opts.localMismatch = mm; opts.localIndel = indel; opts.dotPlot = false;
   Read read; read.seq = (char *)strandseq; read.length = read_len; read.unaligned = 0;
   Genome genome; genome.seqs.push_back((char *)contig); genome.lengths.push_back(contig_len);
   char *strands[2] = {(char *)strandseq, (char *)strandseq};

@@ -41,7 +41,7 @@ void lra_oracle_create_rc(const char *seq, long l, char *dest) {
 typedef struct { uint64_t t; uint32_t pos; } mtup;
 
 /* a2.  Returns the number of minimizers (all are counted; only the first `cap` are stored). */
-long lra_oracle_store_minimizers(const char *seq, uint32_t seqLen, int k, int w, uint64_t *t_out, uint32_t *pos_out, long cap) {
+static long store_minimizers_impl(const char *seq, uint32_t seqLen, int k, int w, uint64_t *t_out, uint32_t *pos_out, long cap, int canonical) {
   long n_out = 0;
 #define EMIT(M) do { if (n_out < cap) { t_out[n_out] = (M).t; pos_out[n_out] = (M).pos; } n_out++; } while (0)
   if (seqLen < (uint32_t)k) return 0;
@@ -63,7 +63,8 @@ long lra_oracle_store_minimizers(const char *seq, uint32_t seqLen, int k, int w,
   for (int p = 0; p <= k - 1; p++) { cur <<= 2; cur += (uint64_t)map2((unsigned char)seq[p]); }
   { uint64_t a = cur; curRC = 0; for (int i = 0; i < k; i++) { uint64_t least = ~(a & 3) & 3; a >>= 2; curRC <<= 2; curRC += least; } }
   mtup active, curM;
-  if ((cur & FOR_MASK) < (curRC & FOR_MASK)) active.t = cur & FOR_MASK; else active.t = curRC | REV_MASK;
+  if (!canonical) active.t = cur;   /* StoreMinimizers_noncanonical (MinCount.h:181-337): forward tuples only, can.t = cur.t */
+  else if ((cur & FOR_MASK) < (curRC & FOR_MASK)) active.t = cur & FOR_MASK; else active.t = curRC | REV_MASK;
   active.pos = 0;
   mtup *ring = (mtup *)calloc((size_t)w, sizeof(mtup));
   ring[0] = active;
@@ -72,7 +73,8 @@ long lra_oracle_store_minimizers(const char *seq, uint32_t seqLen, int k, int w,
     cur = ((cur << 2) & m) + (uint64_t)map2((unsigned char)seq[p + k - 1]);
     curRC >>= 2; curRC += ((~(uint64_t)map2((unsigned char)seq[p + k - 1])) & 3ull) << (2 * ((uint64_t)k - 1));
     curM.pos = p;
-    if ((cur & FOR_MASK) < (curRC & FOR_MASK)) curM.t = cur & FOR_MASK; else curM.t = curRC | REV_MASK;
+    if (!canonical) curM.t = cur & FOR_MASK;
+    else if ((cur & FOR_MASK) < (curRC & FOR_MASK)) curM.t = cur & FOR_MASK; else curM.t = curRC | REV_MASK;
     if (curM.t < active.t) { active.t = curM.t; active.pos = p; }   /* first window: UNMASKED comparison (MinCount.h:91) */
     ring[p % (uint32_t)w] = curM;
   }
@@ -94,7 +96,8 @@ long lra_oracle_store_minimizers(const char *seq, uint32_t seqLen, int k, int w,
     }
     cur = ((cur << 2) & m) + (uint64_t)map2((unsigned char)seq[p + k - 1]);
     curRC >>= 2; curRC += ((~(uint64_t)map2((unsigned char)seq[p + k - 1])) & 3ull) << (2 * ((uint64_t)k - 1));
-    if ((cur & FOR_MASK) < (curRC & FOR_MASK)) curM.t = cur & FOR_MASK; else curM.t = curRC | REV_MASK;
+    if (!canonical) curM.t = cur & FOR_MASK;
+    else if ((cur & FOR_MASK) < (curRC & FOR_MASK)) curM.t = cur & FOR_MASK; else curM.t = curRC | REV_MASK;
     curM.pos = p;
     ring[p % (uint32_t)w] = curM;
     if (p - (uint32_t)w >= active.pos) {
@@ -109,6 +112,14 @@ long lra_oracle_store_minimizers(const char *seq, uint32_t seqLen, int k, int w,
   free(ring);
   return n_out;
 #undef EMIT
+}
+
+long lra_oracle_store_minimizers(const char *seq, uint32_t seqLen, int k, int w, uint64_t *t_out, uint32_t *pos_out, long cap) {
+  return store_minimizers_impl(seq, seqLen, k, w, t_out, pos_out, cap, 1);
+}
+/* StoreMinimizers_noncanonical<GenomeTuple, Tuple>(seq, len, k, w, out, Global = false)   MinCount.h:181-337 (RefineSpace, ClusterRefine.h:297-300) */
+long lra_oracle_store_minimizers_nc(const char *seq, uint32_t seqLen, int k, int w, uint64_t *t_out, uint32_t *pos_out, long cap) {
+  return store_minimizers_impl(seq, seqLen, k, w, t_out, pos_out, cap, 0);
 }
 
 /* a3: libstdc++ introsort on (t & FOR_MASK) */
@@ -183,12 +194,14 @@ void lra_oracle_sort_minimizers(uint64_t *t, uint32_t *pos, long n) {
 }
 
 /* a4.  Returns the number of pairs (all counted; first `cap` stored). */
-long lra_oracle_compare_lists(const uint64_t *qt, const uint32_t *qpos, long nq, const uint64_t *tt, const uint32_t *tpos, long nt, long maxFreq,
-                              uint64_t *r_qt, uint32_t *r_qpos, uint64_t *r_tt, uint32_t *r_tpos, long cap) {
+static long compare_lists_impl(const uint64_t *qt, const uint32_t *qpos, long nq, const uint64_t *tt, const uint32_t *tpos, long nt, long maxFreq,
+                               long maxDiagNum, long minDiagNum, uint64_t *r_qt, uint32_t *r_qpos, uint64_t *r_tt, uint32_t *r_tpos, long cap) {
   long n_out = 0;
 #define QK(i) (qt[i] & FOR_MASK)
 #define TK(i) (tt[i] & FOR_MASK)
-#define PUSH(qi, ti) do { if (n_out < cap) { r_qt[n_out] = qt[qi]; r_qpos[n_out] = qpos[qi]; r_tt[n_out] = tt[ti]; r_tpos[n_out] = tpos[ti]; } n_out++; } while (0)
+/* the diagonal band applies only when both bounds are non-zero (CompareLists.h:86-95) */
+#define PUSH(qi, ti) do { int ok_ = 1; if (maxDiagNum != 0 && minDiagNum != 0) { const long D_ = (long)tpos[ti] - (long)qpos[qi]; ok_ = D_ <= maxDiagNum && D_ >= minDiagNum; } \
+    if (ok_) { if (n_out < cap) { r_qt[n_out] = qt[qi]; r_qpos[n_out] = qpos[qi]; r_tt[n_out] = tt[ti]; r_tpos[n_out] = tpos[ti]; } n_out++; } } while (0)
   if (nq == 0 || nt == 0) return 0;
   long qs = 0, qe = nq - 1, ts = 0, te = nt;
   do {
@@ -242,6 +255,16 @@ long lra_oracle_compare_lists(const uint64_t *qt, const uint32_t *qpos, long nq,
 #undef QK
 #undef TK
 #undef PUSH
+}
+
+long lra_oracle_compare_lists(const uint64_t *qt, const uint32_t *qpos, long nq, const uint64_t *tt, const uint32_t *tpos, long nt, long maxFreq,
+                              uint64_t *r_qt, uint32_t *r_qpos, uint64_t *r_tt, uint32_t *r_tpos, long cap) {
+  return compare_lists_impl(qt, qpos, nq, tt, tpos, nt, maxFreq, 0, 0, r_qt, r_qpos, r_tt, r_tpos, cap);
+}
+/* CompareLists<GenomeTuple, Tuple>(.., Global = false, maxDiagNum, minDiagNum, canonical = false): maxFreq = opts.localMaxFreq, banded */
+long lra_oracle_compare_lists_band(const uint64_t *qt, const uint32_t *qpos, long nq, const uint64_t *tt, const uint32_t *tpos, long nt, long maxFreq,
+                                   long maxDiagNum, long minDiagNum, uint64_t *r_qt, uint32_t *r_qpos, uint64_t *r_tt, uint32_t *r_tpos, long cap) {
+  return compare_lists_impl(qt, qpos, nq, tt, tpos, nt, maxFreq, maxDiagNum, minDiagNum, r_qt, r_qpos, r_tt, r_tpos, cap);
 }
 
 /* a5: strand of every match: 0 if the k read bases equal the k genome bases (strncmp == 0), else 1 */

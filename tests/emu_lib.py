@@ -427,3 +427,23 @@ def split_rough(rl, globalK, max_gap, min_cluster_size, max_diag):
                       o["n_split"], o["n_piece"], o["s_start"], o["s_end"], o["s_coarse"], o["s_chrom"], o["s_box"], o["s_strand"], o["s_freq"], o["p_cluster"], o["p_start"], o["p_end"])
     o["s_box"] = o["s_box"].reshape(-1, 4)
     return o
+
+
+def refine_space_large(read_arena, genome, sp, K, W, max_freq):
+    """The minimizer branch of RefineSpace for every space of sp (as Context.refine_space_batch, with diag)."""
+    L = lib()
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    L.emu_refine_space_large.restype = C.c_long
+    L.emu_refine_space_large.argtypes = [_u8p, C.c_uint64, _u8p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_longlong] + [_u32p] * 9 + [_u8p, _i32p, _u64p, _u32p, _u32p, C.c_uint64,
+                                         _i32p, f32p]
+    a = {k: np.ascontiguousarray(sp[k], np.uint32) for k in ["qs", "qe", "ts", "te", "lrts", "lrlength", "read_off", "read_len", "chrom_off"]}
+    flip = np.ascontiguousarray(sp["flip"], np.uint8); diag = np.ascontiguousarray(sp["diag"], np.int32)
+    n = len(flip)
+    cap = 1 << 16
+    while True:
+        o = dict(pair_off=np.zeros(n + 1, np.uint64), n_pairs=np.zeros(n, np.int32), identity=np.zeros(n, np.float32), pq=np.zeros(cap, np.uint32), pt=np.zeros(cap, np.uint32))
+        r = L.emu_refine_space_large(read_arena, len(read_arena) - 16, genome, len(genome) - 16, n, K, W, max_freq, *[a[k] for k in ["qs", "qe", "ts", "te", "lrts", "lrlength",
+                                     "read_off", "read_len", "chrom_off"]], flip, diag, o["pair_off"], o["pq"], o["pt"], cap, o["n_pairs"], o["identity"])
+        if r >= 0:
+            return o
+        cap = -r + 16
