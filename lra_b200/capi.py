@@ -650,6 +650,35 @@ class Context:
         o["n_pairs"] = o["n_pairs"][:n]; o["identity"] = o["identity"][:n]
         return o
 
+    def switch_to_original_batch(self, run_start, run_end, coarse):
+        """SwitchToOriginalAnchors for every FinalChain entry.  Returns (off, chain, cluster_index)."""
+        rs = np.ascontiguousarray(run_start, np.int32); re_ = np.ascontiguousarray(run_end, np.int32); co = np.ascontiguousarray(coarse, np.int32)
+        n = len(rs); cap = int(np.clip(re_.astype(np.int64) - rs, 0, None).sum())
+        off = np.zeros(n + 1, np.uint64); chain = np.zeros(max(cap, 1), np.uint32); ci = np.zeros(max(cap, 1), np.int32)
+        tot = C.c_uint64(0)
+        p = lambda x: _ptr(x) if x.size else None
+        self._check(self.lib.lra_b200_switch_to_original_batch(self.h, p(rs), p(re_), p(co), n, _ptr(off), _ptr(chain), _ptr(ci), cap, C.byref(tot)))
+        return off, chain[:int(tot.value)], ci[:int(tot.value)]
+
+    # ---- a8 (first half)
+    def split_rough_batch(self, rl, globalK, max_gap, min_cluster_size, max_diag):
+        """SplitRoughClustersWithGaps for every anchor list (rl: dict(l_off, lr_off, q, t, r_start, r_end, r_box, r_strand, r_freq, r_chrom)).
+        Returns the slot-layout arrays of lra_b200_split_rough_result (base of list l = l_off[l] + lr_off[l])."""
+        lo = np.ascontiguousarray(rl["l_off"], np.uint64); lro = np.ascontiguousarray(rl["lr_off"], np.uint64)
+        NL = len(lo) - 1; T = int(lo[-1]) + int(lro[-1]) + 1
+        a = dict(q=np.ascontiguousarray(rl["q"], np.uint32), t=np.ascontiguousarray(rl["t"], np.uint32), r_start=np.ascontiguousarray(rl["r_start"], np.int32),
+                 r_end=np.ascontiguousarray(rl["r_end"], np.int32), r_box=np.ascontiguousarray(rl["r_box"], np.uint32).reshape(-1), r_strand=np.ascontiguousarray(rl["r_strand"], np.uint8),
+                 r_freq=np.ascontiguousarray(rl["r_freq"], np.float32), r_chrom=np.ascontiguousarray(rl["r_chrom"], np.int32))
+        o = dict(n_split=np.zeros(max(NL, 1), np.int32), n_piece=np.zeros(max(NL, 1), np.int32), s_start=np.zeros(T, np.int32), s_end=np.zeros(T, np.int32),
+                 s_coarse=np.zeros(T, np.int32), s_chrom=np.zeros(T, np.int32), s_box=np.zeros((T, 4), np.uint32), s_strand=np.zeros(T, np.uint8), s_freq=np.zeros(T, np.float32),
+                 p_cluster=np.zeros(T, np.int32), p_start=np.zeros(T, np.int32), p_end=np.zeros(T, np.int32))
+        p = lambda x: _ptr(x) if x.size else None
+        e = _RoughLists(NL, _ptr(lo), _ptr(lro), p(a["q"]), p(a["t"]), p(a["r_start"]), p(a["r_end"]), p(a["r_box"]), p(a["r_strand"]), p(a["r_freq"]), p(a["r_chrom"]),
+                        globalK, max_gap, min_cluster_size, max_diag)
+        r = _SplitRoughResult(*[_ptr(o[k]) for k in ["n_split", "n_piece", "s_start", "s_end", "s_coarse", "s_chrom", "s_box", "s_strand", "s_freq", "p_cluster", "p_start", "p_end"]])
+        self._check(self.lib.lra_b200_split_rough_batch(self.h, C.byref(e), C.byref(r)))
+        return o
+
     # ---- a22
     def mapq_batch(self, ag, bypass, read_type, global_k):
         """SetFromSegAlignment + AlignmentsOrder::Update + SimpleMapQV for every read.  ag: dict(grp_off, seg_off, upd_off, update_at, value, n0, n1, nm,

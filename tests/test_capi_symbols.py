@@ -52,3 +52,11 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "pyoracle" not in src and "liboracle" not in src and "libref_lra" not in src, f
+
+
+def test_every_batch_entry_point_has_a_python_binding():
+    """Every lra_b200_*_batch[_device] the header declares is called by the ctypes layer (a binding dropped by an edit shows up here, without a GPU)."""
+    src = open(os.path.join(ROOT, "lra_b200", "capi.py")).read()
+    for s in declared_symbols():
+        if s.endswith("_batch") or s.endswith("_batch_device"):
+            assert re.search(r"self\.lib\.%s\(" % s, src), s
