@@ -100,3 +100,37 @@ for c in mc:
 so = np.zeros(len(mc) + 1, np.uint64); so[1:] = np.cumsum([len(c["sp"]) for c in mc])
 for it in range(2):
     t0 = time.time(); o = ctx.merge_chain_batch(np.concatenate(sp), so, np.concatenate(chrom), np.concatenate(strand_), np.concatenate(box)); report("a11 MergeChain", len(mc), t0)
+
+# a14 RefineSpace (both branches) and a17 RefineByLinearAlignment: spaces / gaps between anchors, a8 SplitRoughClustersWithGaps
+import test_refine_space as TRS, test_refine_linear as TRL, roughgen
+contig, reads, sp = TRS.large_spaces(7, 256)
+rng2 = np.random.default_rng(8)
+for x in sp[::3]:
+    x["qe"] = min(x["qs"] + int(rng2.integers(0, 900)), len(reads[x["read"]])); x["te"] = x["ts"] + max(0, (x["qe"] - x["qs"]) + int(rng2.integers(-20, 21)) - x["lrlength"])
+d = TRS.space_dict(reads, sp)
+d = {k: np.tile(np.asarray(v), 16) for k, v in d.items()}          # 4096 spaces (the same 256, sixteen times: the work is what counts)
+rs3 = ctx.seq_upload(np.concatenate(reads)); gs3 = ctx.seq_upload(contig)
+for it in range(2):
+    t0 = time.time(); o = ctx.refine_space_batch(rs3, gs3, d, 17, 4, -3, -4, W=10, local_max_freq=30)
+    dt = time.time() - t0
+    print("%-28s wall %8.2f ms  (%d spaces, %d pairs)" % ("a14 RefineSpace (mixed)", dt * 1e3, len(d["qs"]), int(o["n_pairs"].sum())))
+contig2, reads2, gl = TRL.gaps(2, 1500)
+roff = np.zeros(len(reads2), np.int64); roff[1:] = np.cumsum([len(r) for r in reads2[:-1]])
+g = dict(cur_read_end=[x[1] for x in gl], next_read_start=[x[2] & 0xFFFFFFFF for x in gl], cur_genome_end=[x[3] for x in gl], next_genome_start=[x[4] & 0xFFFFFFFF for x in gl],
+         read_off=[int(roff[x[0]]) for x in gl], chrom_off=np.zeros(len(gl), np.uint32))
+g = {k: np.tile(np.asarray(v, np.uint32), 64) for k, v in g.items()}
+rs4 = ctx.seq_upload(np.concatenate(reads2)); gs4 = ctx.seq_upload(contig2)
+for it in range(2):
+    t0 = time.time(); o = ctx.refine_linear_batch(rs4, gs4, g, 4, -3, -4, 15); report("a17 RefineByLinearAlignment", len(g["read_off"]), t0)
+rg2 = np.random.default_rng(4)
+cs = [roughgen.rough_list(rg2) for _ in range(512)] * (2 * R // 512)
+l_off, lr_off = [0], [0]
+cols = {k: [] for k in ["q", "t", "r_start", "r_end", "r_box", "r_strand", "r_freq", "r_chrom"]}
+for q_, t_, rc_ in cs:
+    l_off.append(l_off[-1] + len(q_)); lr_off.append(lr_off[-1] + len(rc_["start"]))
+    cols["q"].append(q_); cols["t"].append(t_)
+    for k_, kk in [("r_start", "start"), ("r_end", "end"), ("r_box", "box"), ("r_strand", "strand"), ("r_freq", "freq"), ("r_chrom", "chrom")]:
+        cols[k_].append(rc_[kk])
+rl = {k: np.concatenate(v) for k, v in cols.items()}; rl.update(l_off=np.array(l_off, np.uint64), lr_off=np.array(lr_off, np.uint64))
+for it in range(2):
+    t0 = time.time(); o = ctx.split_rough_batch(rl, 17, 1000, 2, 500); report("a8 SplitRoughClustersWithGaps (%d anchors)" % l_off[-1], len(cs), t0)
