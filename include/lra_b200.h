@@ -654,6 +654,33 @@ typedef struct lra_b200_split_rough_result {
 
 int lra_b200_split_rough_batch(lra_b200_ctx *ctx, const lra_b200_rough_lists *in, lra_b200_split_rough_result *res);
 
+/* ---- StoreDiagonalClusters (the cluster builder of CleanMatches when opts.ExtractDiagonalFromClean is off), batched over anchor lists ----------
+ * Replaces  StoreDiagonalClusters(genome, Matches_freq, Matches, clusters, opts, 0, Matches.size(), strand)  (Clustering.h:1442-1487; called
+ * :1863, :1893 after CleanOffDiagonal, and :1569, :1624) for every list of a batch: list l owns anchors l_off[l] .. l_off[l+1] (cleaned, in diagonal
+ * order) with first.pos, second.pos, first.t and matches_freq (lra_b200_clean_off_diagonal_batch's `freq`), on strand[l].
+ * Results in slot layout: cluster i of list l at l_off[l] + i = start, end (anchor range inside the list), box (qStart, qEnd, tStart, tEnd),
+ * anchorfreq (bit-identical binary32), chromIndex; n_cl[l] clusters. */
+typedef struct lra_b200_cleaned_lists {
+  int32_t n_lists;
+  const uint64_t *l_off;        /* [n_lists + 1] */
+  const uint32_t *q, *t;
+  const uint64_t *qt;
+  const float *freq;
+  const uint8_t *strand;        /* [n_lists] */
+  const uint64_t *hdr_pos;
+  int32_t n_hdr;
+  int32_t globalK, max_diag, min_cluster_size, min_cluster_length, bypass_clustering;   /* opts.globalK, maxDiag, minClusterSize, minClusterLength, bypassClustering */
+} lra_b200_cleaned_lists;
+
+typedef struct lra_b200_diag_clusters {
+  int32_t *n_cl;                /* [n_lists] */
+  int32_t *c_start, *c_end, *c_chrom;   /* [N] */
+  uint32_t *c_box;              /* [N * 4] */
+  float *c_freq;                /* [N] */
+} lra_b200_diag_clusters;
+
+int lra_b200_store_diagonal_batch(lra_b200_ctx *ctx, const lra_b200_cleaned_lists *in, lra_b200_diag_clusters *res);
+
 /* ---- a20  RefineBreakpoint, batched over pairs of adjacent segments --------------------------------------------------
  * Replaces  void RefineBreakpoint(Read &read, Genome &genome, Alignment &leftAln, Alignment &rightAln, const Options &opts)
  * (RefineBreakpoint.h:212-462; called for consecutive segments of a split read, Map_highacc.h:725, Map_lowacc.h:592).  Pair p: the left /

@@ -143,6 +143,16 @@ class _SplitRoughResult(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ["n_split", "n_piece", "s_start", "s_end", "s_coarse", "s_chrom", "s_box", "s_strand", "s_freq", "p_cluster", "p_start", "p_end"]]
 
 
+class _CleanedLists(C.Structure):
+    _fields_ = [("n_lists", C.c_int32), ("l_off", C.c_void_p), ("q", C.c_void_p), ("t", C.c_void_p), ("qt", C.c_void_p), ("freq", C.c_void_p), ("strand", C.c_void_p),
+                ("hdr_pos", C.c_void_p), ("n_hdr", C.c_int32), ("globalK", C.c_int32), ("max_diag", C.c_int32), ("min_cluster_size", C.c_int32),
+                ("min_cluster_length", C.c_int32), ("bypass_clustering", C.c_int32)]
+
+
+class _DiagClusters(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ["n_cl", "c_start", "c_end", "c_chrom", "c_box", "c_freq"]]
+
+
 class _Breakpoints(C.Structure):
     _fields_ = [("n_pairs", C.c_int32), ("lf", C.c_void_p), ("ll", C.c_void_p), ("rf", C.c_void_p), ("rl", C.c_void_p), ("lstrand", C.c_void_p),
                 ("rstrand", C.c_void_p), ("read_off", C.c_void_p), ("read_len", C.c_void_p), ("lchrom_off", C.c_void_p), ("rchrom_off", C.c_void_p),
@@ -248,6 +258,7 @@ def load_library():
     L.lra_b200_refine_linear_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_LinearGaps), C.POINTER(_AogResult)]
     L.lra_b200_switch_to_original_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.lra_b200_split_rough_batch.argtypes = [C.c_void_p, C.POINTER(_RoughLists), C.POINTER(_SplitRoughResult)]
+    L.lra_b200_store_diagonal_batch.argtypes = [C.c_void_p, C.POINTER(_CleanedLists), C.POINTER(_DiagClusters)]
     L.lra_b200_merge_chain_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_switchindex_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.lra_b200_linear_extend_chains_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_ExtendChains), C.POINTER(_ExtendedChains)]
@@ -677,6 +688,21 @@ class Context:
                         globalK, max_gap, min_cluster_size, max_diag)
         r = _SplitRoughResult(*[_ptr(o[k]) for k in ["n_split", "n_piece", "s_start", "s_end", "s_coarse", "s_chrom", "s_box", "s_strand", "s_freq", "p_cluster", "p_start", "p_end"]])
         self._check(self.lib.lra_b200_split_rough_batch(self.h, C.byref(e), C.byref(r)))
+        return o
+
+    def store_diagonal_batch(self, cl, hdr_pos, globalK, max_diag, min_cluster_size, min_cluster_length, bypass):
+        """StoreDiagonalClusters for every cleaned anchor list (cl: dict(l_off, q, t, qt, freq, strand)).  Returns the slot-layout arrays of lra_b200_diag_clusters."""
+        lo = np.ascontiguousarray(cl["l_off"], np.uint64); NL = len(lo) - 1; N = max(int(lo[-1]), 1)
+        a = dict(q=np.ascontiguousarray(cl["q"], np.uint32), t=np.ascontiguousarray(cl["t"], np.uint32), qt=np.ascontiguousarray(cl["qt"], np.uint64),
+                 freq=np.ascontiguousarray(cl["freq"], np.float32), strand=np.ascontiguousarray(cl["strand"], np.uint8))
+        hdr = np.ascontiguousarray(hdr_pos, np.uint64)
+        o = dict(n_cl=np.zeros(max(NL, 1), np.int32), c_start=np.zeros(N, np.int32), c_end=np.zeros(N, np.int32), c_chrom=np.zeros(N, np.int32), c_box=np.zeros((N, 4), np.uint32),
+                 c_freq=np.zeros(N, np.float32))
+        p = lambda x: _ptr(x) if x.size else None
+        e = _CleanedLists(NL, _ptr(lo), p(a["q"]), p(a["t"]), p(a["qt"]), p(a["freq"]), p(a["strand"]), _ptr(hdr), len(hdr), globalK, max_diag, min_cluster_size,
+                          min_cluster_length, int(bypass))
+        r = _DiagClusters(*[_ptr(o[k]) for k in ["n_cl", "c_start", "c_end", "c_chrom", "c_box", "c_freq"]])
+        self._check(self.lib.lra_b200_store_diagonal_batch(self.h, C.byref(e), C.byref(r)))
         return o
 
     # ---- a22

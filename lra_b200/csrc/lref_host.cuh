@@ -1463,3 +1463,50 @@ extern "C" int lra_b200_split_rough_batch(lra_b200_ctx *ctx, const lra_b200_roug
   ctx->stats.push_back(s2);
   return LRA_B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- StoreDiagonalClusters
+extern "C" int lra_b200_store_diagonal_batch(lra_b200_ctx *ctx, const lra_b200_cleaned_lists *in, lra_b200_diag_clusters *res) {
+  if (!ctx || !in || !res) return fail(ctx, LRA_B200_EINVAL, "store_diagonal_batch: NULL argument");
+  const int NL = in->n_lists;
+  if (NL < 0 || !in->l_off || !in->hdr_pos || in->n_hdr < 1) return fail(ctx, LRA_B200_EINVAL, "store_diagonal_batch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  if (NL == 0) return LRA_B200_OK;
+  const size_t N = (size_t)in->l_off[NL];
+  if (N > 0x7FFFFFF0ull) return fail(ctx, LRA_B200_EINVAL, "store_diagonal_batch: more than 2^31 anchors in one batch");
+  for (int l = 0; l < NL; l++) if (in->l_off[l + 1] < in->l_off[l]) return fail(ctx, LRA_B200_EINVAL, "store_diagonal_batch: list offsets not ascending");
+  if (!in->strand || (N && (!in->q || !in->t || !in->qt || !in->freq))) return fail(ctx, LRA_B200_EINVAL, "store_diagonal_batch: NULL array");
+  int rc;
+  DevBuf *B = ctx->sr;
+  const size_t Np = N ? N : 1, L1 = (size_t)NL;
+  const size_t need[13] = {(L1 + 1) * 8, Np * 4, Np * 4, Np * 8, Np * 4, L1, (size_t)in->n_hdr * 8, L1 * 4, Np * 4, Np * 4, Np * 4, Np * 16, Np * 4};
+  for (int i = 0; i < 13; i++) if ((rc = ensure(ctx, B[i], need[i]))) return rc;
+  cudaStream_t st = ctx->stream;
+  const void *src[7] = {in->l_off, in->q, in->t, in->qt, in->freq, in->strand, in->hdr_pos};
+  const size_t sz[7] = {(L1 + 1) * 8, N * 4, N * 4, N * 8, N * 4, L1, (size_t)in->n_hdr * 8};
+  for (int i = 0; i < 7; i++) if (sz[i]) CU(cudaMemcpyAsync(B[i].p, src[i], sz[i], cudaMemcpyHostToDevice, st));
+  StoreDiagBatch b;
+  b.n_lists = NL; b.globalK = in->globalK; b.maxDiag = in->max_diag; b.minClusterSize = in->min_cluster_size; b.minClusterLength = in->min_cluster_length;
+  b.bypass = in->bypass_clustering;
+  b.l_off = (const unsigned long long *)B[0].p; b.q = (const uint32_t *)B[1].p; b.t = (const uint32_t *)B[2].p; b.qt = (const unsigned long long *)B[3].p;
+  b.freq = (const float *)B[4].p; b.strand = (const uint8_t *)B[5].p; b.hdr_pos = (const unsigned long long *)B[6].p; b.n_hdr = in->n_hdr;
+  b.n_cl = (int32_t *)B[7].p; b.c_start = (int32_t *)B[8].p; b.c_end = (int32_t *)B[9].p; b.c_chrom = (int32_t *)B[10].p; b.c_box = (uint32_t *)B[11].p; b.c_freq = (float *)B[12].p;
+  cudaEventRecord(ctx->ev[0], st);
+  store_diagonal_kernel<<<(unsigned)((NL + 63) / 64), 64, 0, st>>>(b);
+  cudaEventRecord(ctx->ev[1], st);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(res->n_cl, b.n_cl, L1 * 4, cudaMemcpyDeviceToHost, st));
+  if (N) {
+    CU(cudaMemcpyAsync(res->c_start, b.c_start, N * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->c_end, b.c_end, N * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->c_chrom, b.c_chrom, N * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->c_box, b.c_box, N * 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(res->c_freq, b.c_freq, N * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "store_diagonal");
+  cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]); s2.jobs = (uint64_t)NL; s2.algo_bytes = 20ull * N;
+  ctx->stats.push_back(s2);
+  return LRA_B200_OK;
+}

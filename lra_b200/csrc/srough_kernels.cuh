@@ -97,4 +97,73 @@ __global__ void __launch_bounds__(64) split_rough_kernel(SplitRoughBatch b) {
   b.n_split[l] = ns; b.n_piece[l] = np;
 }
 
+// StoreDiagonalClusters (reference Clustering.h:1442-1487, RemoveSuperRepetitiveClusters :1432-1439): the clusters CleanMatches makes from the cleaned,
+// diagonal-sorted anchors of one strand when opts.ExtractDiagonalFromClean is off.  A run ends where the diagonal jumps by maxDiag or more; anchorfreq
+// sums matches_freq in binary32 in anchor order and is only reset when a run is KEPT, so a rejected run's frequencies leak into the next cluster: one
+// thread per anchor list, literal.
+struct StoreDiagBatch {
+  int n_lists;
+  int globalK, maxDiag, minClusterSize, minClusterLength, bypass;
+  const unsigned long long *l_off;        // [n_lists + 1]
+  const uint32_t *q, *t;
+  const unsigned long long *qt;           // first.t of every anchor
+  const float *freq;                      // matches_freq
+  const uint8_t *strand;                  // [n_lists]
+  const unsigned long long *hdr_pos;
+  int n_hdr;
+  int32_t *n_cl;                          // [n_lists] out
+  int32_t *c_start, *c_end, *c_chrom;     // out, slot layout: cluster i of list l at l_off[l] + i
+  uint32_t *c_box;
+  float *c_freq;
+};
+
+__device__ __forceinline__ int sdc_hdr_find(const unsigned long long *pos, int n, unsigned long long query) {   // Header::Find
+  if (n > 0 && query == pos[0]) return 0;
+  int lo = 0, len = n;
+  while (len > 0) { const int half = len >> 1; if (pos[lo + half] < query) { lo += half + 1; len -= half + 1; } else len = half; }
+  if (lo < n && query == pos[lo]) return lo;
+  return lo - 1;
+}
+
+__global__ void __launch_bounds__(64) store_diagonal_kernel(StoreDiagBatch b) {
+  const int l = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x);
+  if (l >= b.n_lists) return;
+  const unsigned long long a0 = b.l_off[l];
+  const int n = (int)(b.l_off[l + 1] - a0);
+  const uint32_t *q = b.q + a0, *t = b.t + a0;
+  const unsigned long long *qt = b.qt + a0;
+  const float *freq = b.freq + a0;
+  const int strand = b.strand[l];
+  const uint32_t K = (uint32_t)b.globalK;
+  int nc = 0, cs = 0;
+  float totalfreq = 0.0f;
+  while (cs < n) {
+    int ce = cs + 1;
+    uint32_t qS = q[cs], qE = q[cs] + K, tS = t[cs], tE = t[cs] + K;
+    totalfreq = __fadd_rn(totalfreq, freq[cs]);
+    const int cI = sdc_hdr_find(b.hdr_pos, b.n_hdr, (unsigned long long)tS);
+    bool rep = true;
+    while (ce < n) {
+      long long d;
+      if (strand == 0) d = ((long long)t[ce] - (long long)q[ce]) - ((long long)t[ce - 1] - (long long)q[ce - 1]);
+      else d = (long long)(uint32_t)(q[ce] + t[ce]) - (long long)(uint32_t)(q[ce - 1] + t[ce - 1]);
+      if (!((d < 0 ? -d : d) < (long long)b.maxDiag)) break;
+      if (q[ce] < qS) qS = q[ce]; if (q[ce] + K > qE) qE = q[ce] + K; if (t[ce] < tS) tS = t[ce]; if (t[ce] + K > tE) tE = t[ce] + K;
+      totalfreq = __fadd_rn(totalfreq, freq[ce]);
+      if (qt[ce] != qt[cs]) rep = false;
+      ce++;
+    }
+    if (ce - cs >= b.minClusterSize && qE - qS >= (uint32_t)b.minClusterLength && tE - tS >= (uint32_t)b.minClusterLength && !rep) {
+      const unsigned long long o = a0 + nc;
+      b.c_start[o] = cs; b.c_end[o] = ce; b.c_box[4 * o] = qS; b.c_box[4 * o + 1] = qE; b.c_box[4 * o + 2] = tS; b.c_box[4 * o + 3] = tE;
+      b.c_freq[o] = __fdiv_rn(totalfreq, (float)(ce - cs));
+      b.c_chrom[o] = b.bypass ? sdc_hdr_find(b.hdr_pos, b.n_hdr, (unsigned long long)tS) : cI;
+      totalfreq = 0.0f;
+      nc++;
+    }
+    cs = ce;
+  }
+  b.n_cl[l] = nc;
+}
+
 }  // namespace lra

@@ -1000,3 +1000,23 @@ def split_rough(q, t, rc, globalK, maxGap, minClusterSize, maxDiag, which="port"
     o["smi"] = smi
     o["n_piece"] = int(npiece[0])
     return o
+
+
+# ---------------------------------------------------------------- StoreDiagonalClusters (CleanMatches without ExtractDiagonalFromClean)
+
+def store_diagonal(q, t, qt, freq, strand, hdr_pos, globalK, maxDiag, minClusterSize, minClusterLength, bypass, which="port"):
+    """One cleaned, diagonal-sorted anchor list.  Returns dict(start, end, box[k,4], freq, chrom)."""
+    n = len(q)
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    L = ref() if which == "ref" else port()
+    f = _bind_once(L, "ref_store_diagonal" if which == "ref" else "lra_oracle_store_diagonal", C.c_long,
+                   [_u32p, _u32p, _u64p, f32p, C.c_int, C.c_int, _u64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _u32p, f32p, _i32p])
+    pad = lambda a, dt: np.ascontiguousarray(a, dt) if n else np.zeros(1, dt)
+    hdr = np.ascontiguousarray(hdr_pos, np.uint64)
+    o = dict(start=np.zeros(n + 1, np.int32), end=np.zeros(n + 1, np.int32), box=np.zeros(4 * (n + 1), np.uint32), freq=np.zeros(n + 1, np.float32), chrom=np.zeros(n + 1, np.int32))
+    k = f(pad(q, np.uint32), pad(t, np.uint32), pad(qt, np.uint64), pad(freq, np.float32), n, int(strand), hdr, len(hdr), globalK, maxDiag, minClusterSize, minClusterLength,
+          int(bypass), o["start"], o["end"], o["box"], o["freq"], o["chrom"])
+    for key in ("start", "end", "freq", "chrom"):
+        o[key] = o[key][:k]
+    o["box"] = o["box"][:4 * k].reshape(-1, 4)
+    return o

@@ -784,4 +784,24 @@ long ref_split_rough(const uint32_t *q, const uint32_t *t, int n_rough, const in
   return (long)split.size();
 }
 
+// ---- StoreDiagonalClusters (Clustering.h:1442-1487) on the cleaned anchors of one strand; arguments as oracle/store_diagonal.c.
+long ref_store_diagonal(const uint32_t *q, const uint32_t *t, const uint64_t *qt, const float *freq, int n, int strand, const uint64_t *hdr_pos, int n_hdr,
+                        int globalK, int maxDiag, int minClusterSize, int minClusterLength, int bypass,
+                        int32_t *c_start, int32_t *c_end, uint32_t *c_box, float *c_freq, int32_t *c_chrom) {
+  ref_init_static();
+  Options opts; opts.globalK = globalK; opts.maxDiag = maxDiag; opts.minClusterSize = minClusterSize; opts.minClusterLength = minClusterLength;
+  opts.bypassClustering = bypass != 0;
+  Genome genome; genome.header.pos.assign(hdr_pos, hdr_pos + n_hdr);
+  GenomePairs matches(n);
+  std::vector<float> mf(freq, freq + n);
+  for (int i = 0; i < n; i++) { matches[i].first.pos = q[i]; matches[i].second.pos = t[i]; matches[i].first.t = qt[i]; matches[i].second.t = qt[i]; }
+  std::vector<Cluster> clusters;
+  StoreDiagonalClusters(genome, mf, matches, clusters, opts, 0, n, strand);
+  for (size_t k = 0; k < clusters.size(); k++) {
+    c_start[k] = clusters[k].start; c_end[k] = clusters[k].end; c_box[4 * k] = clusters[k].qStart; c_box[4 * k + 1] = clusters[k].qEnd;
+    c_box[4 * k + 2] = clusters[k].tStart; c_box[4 * k + 3] = clusters[k].tEnd; c_freq[k] = clusters[k].anchorfreq; c_chrom[k] = clusters[k].chromIndex;
+  }
+  return (long)clusters.size();
+}
+
 }  // extern "C"

@@ -447,3 +447,19 @@ def refine_space_large(read_arena, genome, sp, K, W, max_freq):
         if r >= 0:
             return o
         cap = -r + 16
+
+
+def store_diagonal(cl, hdr_pos, globalK, max_diag, min_cluster_size, min_cluster_length, bypass):
+    L = lib()
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    L.emu_store_diagonal.argtypes = [C.c_int, _u64p, _u32p, _u32p, _u64p, f32p, _u8p, _u64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p,
+                                     _u32p, f32p]
+    lo = np.ascontiguousarray(cl["l_off"], np.uint64); NL = len(lo) - 1; N = max(int(lo[-1]), 1)
+    pad = lambda a, dt: np.ascontiguousarray(a, dt) if len(a) else np.zeros(1, dt)
+    hdr = np.ascontiguousarray(hdr_pos, np.uint64)
+    o = dict(n_cl=np.zeros(max(NL, 1), np.int32), c_start=np.zeros(N, np.int32), c_end=np.zeros(N, np.int32), c_chrom=np.zeros(N, np.int32), c_box=np.zeros(4 * N, np.uint32),
+             c_freq=np.zeros(N, np.float32))
+    L.emu_store_diagonal(NL, lo, pad(cl["q"], np.uint32), pad(cl["t"], np.uint32), pad(cl["qt"], np.uint64), pad(cl["freq"], np.float32), pad(cl["strand"], np.uint8), hdr, len(hdr),
+                         globalK, max_diag, min_cluster_size, min_cluster_length, int(bypass), o["n_cl"], o["c_start"], o["c_end"], o["c_chrom"], o["c_box"], o["c_freq"])
+    o["c_box"] = o["c_box"].reshape(-1, 4)
+    return o

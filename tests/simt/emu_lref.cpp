@@ -314,3 +314,12 @@ extern "C" int emu_split_rough(int n_lists, const uint64_t *l_off, const uint64_
   if (n_lists) emu::launch(dim3((unsigned)((n_lists + 63) / 64)), dim3(64), 0, [&] { split_rough_kernel(b); });
   return 0;
 }
+
+extern "C" int emu_store_diagonal(int n_lists, const uint64_t *l_off, const uint32_t *q, const uint32_t *t, const uint64_t *qt, const float *freq, const uint8_t *strand,
+                                  const uint64_t *hdr_pos, int n_hdr, int globalK, int maxDiag, int minClusterSize, int minClusterLength, int bypass, int32_t *n_cl,
+                                  int32_t *c_start, int32_t *c_end, int32_t *c_chrom, uint32_t *c_box, float *c_freq) {
+  StoreDiagBatch b{n_lists, globalK, maxDiag, minClusterSize, minClusterLength, bypass, (const unsigned long long *)l_off, q, t, (const unsigned long long *)qt, freq, strand,
+                   (const unsigned long long *)hdr_pos, n_hdr, n_cl, c_start, c_end, c_chrom, c_box, c_freq};
+  if (n_lists) emu::launch(dim3((unsigned)((n_lists + 63) / 64)), dim3(64), 0, [&] { store_diagonal_kernel(b); });
+  return 0;
+}
