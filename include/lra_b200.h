@@ -681,6 +681,14 @@ typedef struct lra_b200_diag_clusters {
 
 int lra_b200_store_diagonal_batch(lra_b200_ctx *ctx, const lra_b200_cleaned_lists *in, lra_b200_diag_clusters *res);
 
+/* ---- TrimSplitChainDiagonal, batched over split chains ------------------------------------------------------------------------
+ * Replaces  TrimSplitChainDiagonal(spchain, refined_clusters)  (ChainRefine.h:189-331; Map_lowacc.h:331, right after Refine_splitchain): split chain c owns
+ * chain anchors c_off[c] .. c_off[c+1] (cq / ct = SplitChain::qStart(i) / tStart(i) in sptc order) with SplitChain::Strand strand[c], and the refined anchors
+ * m_off[c] .. m_off[c+1] of (q, t) = refined_clusters[c].matches.  q and t come back in the order the reference leaves them (CartesianSort; untouched for a
+ * chain of one anchor), keep[i] = 0 marks the anchors it erases, removed[c] = its contribution to the return value. */
+int lra_b200_trim_splitchains_batch(lra_b200_ctx *ctx, const uint32_t *cq, const uint32_t *ct, const uint64_t *c_off, const uint8_t *strand, int32_t n_chains,
+                                    uint32_t *q, uint32_t *t, const uint64_t *m_off, uint8_t *keep, int32_t *removed);
+
 /* ---- a20  RefineBreakpoint, batched over pairs of adjacent segments --------------------------------------------------
  * Replaces  void RefineBreakpoint(Read &read, Genome &genome, Alignment &leftAln, Alignment &rightAln, const Options &opts)
  * (RefineBreakpoint.h:212-462; called for consecutive segments of a split read, Map_highacc.h:725, Map_lowacc.h:592).  Pair p: the left /

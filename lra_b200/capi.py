@@ -259,6 +259,7 @@ def load_library():
     L.lra_b200_switch_to_original_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.lra_b200_split_rough_batch.argtypes = [C.c_void_p, C.POINTER(_RoughLists), C.POINTER(_SplitRoughResult)]
     L.lra_b200_store_diagonal_batch.argtypes = [C.c_void_p, C.POINTER(_CleanedLists), C.POINTER(_DiagClusters)]
+    L.lra_b200_trim_splitchains_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lra_b200_merge_chain_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.lra_b200_switchindex_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.lra_b200_linear_extend_chains_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_ExtendChains), C.POINTER(_ExtendedChains)]
@@ -704,6 +705,17 @@ class Context:
         r = _DiagClusters(*[_ptr(o[k]) for k in ["n_cl", "c_start", "c_end", "c_chrom", "c_box", "c_freq"]])
         self._check(self.lib.lra_b200_store_diagonal_batch(self.h, C.byref(e), C.byref(r)))
         return o
+
+    def trim_splitchains_batch(self, cq, ct, c_off, strand, q, t, m_off):
+        """TrimSplitChainDiagonal for every split chain.  Returns (q, t, keep, removed): the anchors in the reference's order and which of them stay."""
+        cq = np.ascontiguousarray(cq, np.uint32); ct = np.ascontiguousarray(ct, np.uint32); co = np.ascontiguousarray(c_off, np.uint64)
+        st = np.ascontiguousarray(strand, np.uint8); mo = np.ascontiguousarray(m_off, np.uint64)
+        q = np.array(q, np.uint32); t = np.array(t, np.uint32)
+        n = len(co) - 1
+        keep = np.zeros(max(len(q), 1), np.uint8); removed = np.zeros(max(n, 1), np.int32)
+        p = lambda x: _ptr(x) if x.size else None
+        self._check(self.lib.lra_b200_trim_splitchains_batch(self.h, p(cq), p(ct), _ptr(co), p(st), n, p(q), p(t), _ptr(mo), _ptr(keep), _ptr(removed)))
+        return q, t, keep[:len(q)], removed[:n]
 
     # ---- a22
     def mapq_batch(self, ag, bypass, read_type, global_k):

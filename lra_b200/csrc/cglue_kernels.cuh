@@ -131,4 +131,53 @@ __global__ void __launch_bounds__(256) switch_orig_emit_kernel(SwitchOrigBatch b
   for (int j = b.run_end[i] - 1; j >= b.run_start[i]; j--, o++) { b.chain[o] = (uint32_t)j; b.cluster_index[o] = b.coarse[i]; }
 }
 
+// TrimSplitChainDiagonal (reference ChainRefine.h:189-331; Map_lowacc.h:331): the refined anchors of a split chain, Cartesian-sorted by the a6 kernel first
+// (chains of one anchor are skipped there: mode 255), are kept or dropped by the diagonal window of the two chain anchors around them.  The reference walks
+// chain anchors and refined anchors with two monotone cursors (forward chains) or only looks at the first two chain anchors from the far end (reverse
+// chains): one thread per chain replays it.  Diagonals are GenomePos differences (uint32 wrap), widened to 64 bits for the +-100 window.
+struct TrimChainBatch {
+  int n_chains;
+  const unsigned long long *c_off;      // [n_chains + 1] chain anchors
+  const uint32_t *cq, *ct;              // qStart / tStart of the chain anchors, sptc order
+  const uint8_t *strand;                // [n_chains] SplitChain::Strand
+  const unsigned long long *m_off;      // [n_chains + 1] refined anchors
+  const uint32_t *q, *t;                // sorted
+  uint8_t *keep;                        // out
+  int32_t *removed;                     // [n_chains] out
+};
+
+__global__ void __launch_bounds__(64) trim_splitchain_kernel(TrimChainBatch b) {
+  const int c = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x);
+  if (c >= b.n_chains) return;
+  const unsigned long long a0 = b.c_off[c], m0 = b.m_off[c];
+  const int nch = (int)(b.c_off[c + 1] - a0), n = (int)(b.m_off[c + 1] - m0);
+  const uint32_t *cq = b.cq + a0, *ct = b.ct + a0, *q = b.q + m0, *t = b.t + m0;
+  uint8_t *keep = b.keep + m0;
+  for (int i = 0; i < n; i++) keep[i] = 1;
+  int removed = 0;
+  if (nch != 1) {
+    auto cd = [&](int i) { return (uint32_t)(ct[i] - cq[i]); };
+    if (b.strand[c] == 0) {
+      int mi = 0;
+      for (int ci = 0; ci < nch - 1; ci++) {
+        const uint32_t m = cd(ci) < cd(ci + 1) ? cd(ci) : cd(ci + 1);
+        const long long minDiag = (long long)m - 100, maxDiag = (long long)m + 100;
+        while (mi < n && q[mi] < cq[ci + 1]) {
+          const long long d = (long long)(uint32_t)(t[mi] - q[mi]);
+          if (d < minDiag || d > maxDiag) { keep[mi] = 0; removed++; }
+          mi++;
+        }
+      }
+    } else if (nch >= 2) {
+      const uint32_t m = cd(0) < cd(1) ? cd(0) : cd(1);
+      const long long minDiag = (long long)m - 100, maxDiag = (long long)m + 100;
+      for (int mi = n - 1; mi >= 0 && q[mi] > cq[1]; mi--) {
+        const long long d = (long long)(uint32_t)(t[mi] - q[mi]);
+        if (d < minDiag || d > maxDiag) { keep[mi] = 0; removed++; }
+      }
+    }
+  }
+  b.removed[c] = removed;
+}
+
 }  // namespace lra

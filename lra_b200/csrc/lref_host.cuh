@@ -1510,3 +1510,68 @@ extern "C" int lra_b200_store_diagonal_batch(lra_b200_ctx *ctx, const lra_b200_c
   ctx->stats.push_back(s2);
   return LRA_B200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- TrimSplitChainDiagonal
+extern "C" int lra_b200_trim_splitchains_batch(lra_b200_ctx *ctx, const uint32_t *cq, const uint32_t *ct, const uint64_t *c_off, const uint8_t *strand, int32_t n_chains,
+                                               uint32_t *q, uint32_t *t, const uint64_t *m_off, uint8_t *keep, int32_t *removed) {
+  if (!ctx || !c_off || !m_off || !strand || !removed || n_chains < 0) return fail(ctx, LRA_B200_EINVAL, "trim_splitchains_batch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  ctx->stats.clear();
+  if (n_chains == 0) return LRA_B200_OK;
+  const size_t A = (size_t)c_off[n_chains], M = (size_t)m_off[n_chains], C1 = (size_t)n_chains;
+  if (M > 0x7FFFFFF0ull) return fail(ctx, LRA_B200_EINVAL, "trim_splitchains_batch: more than 2^31 anchors in one batch");
+  if ((A && (!cq || !ct)) || (M && (!q || !t || !keep))) return fail(ctx, LRA_B200_EINVAL, "trim_splitchains_batch: NULL array");
+  std::vector<uint8_t> mode(C1);
+  std::vector<unsigned long long> slot(C1);
+  size_t slots = 0;
+  for (int c = 0; c < n_chains; c++) {
+    if (c_off[c + 1] < c_off[c] || m_off[c + 1] < m_off[c]) return fail(ctx, LRA_B200_EINVAL, "trim_splitchains_batch: offsets not ascending");
+    const size_t nch = (size_t)(c_off[c + 1] - c_off[c]), n = (size_t)(m_off[c + 1] - m_off[c]);
+    if (strand[c] != 0 && nch == 0) return fail(ctx, LRA_B200_EINVAL, "trim_splitchains_batch: chain %d is empty", c);
+    mode[c] = nch == 1 ? 255 : 2;                  // chains of one anchor are left alone, the others get CartesianSort
+    size_t P2 = 1; while (P2 < n) P2 <<= 1;
+    slot[c] = slots;
+    if (mode[c] == 2 && P2 > (size_t)kSortSmem) slots += P2;
+  }
+  int rc;
+  DevBuf *B = ctx->cg;
+  const size_t Ap = A ? A : 1, Mp = M ? M : 1;
+  if ((rc = ensure(ctx, B[0], (C1 + 1) * 8)) || (rc = ensure(ctx, B[1], Ap * 4)) || (rc = ensure(ctx, B[2], Ap * 4)) || (rc = ensure(ctx, B[3], C1)) || (rc = ensure(ctx, B[4], (C1 + 1) * 8)) ||
+      (rc = ensure(ctx, B[5], Mp * 4)) || (rc = ensure(ctx, B[6], Mp * 4)) || (rc = ensure(ctx, B[7], Mp)) || (rc = ensure(ctx, B[8], C1 * 4)) || (rc = ensure(ctx, B[9], C1)) ||
+      (rc = ensure(ctx, B[10], C1 * 8)) || (rc = ensure(ctx, B[11], slots * 8 + 16)) || (rc = ensure(ctx, B[12], slots * 4 + 16)) || (rc = ensure(ctx, B[13], slots * 4 + 16)))
+    return rc;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(B[0].p, c_off, (C1 + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (A) { CU(cudaMemcpyAsync(B[1].p, cq, A * 4, cudaMemcpyHostToDevice, st)); CU(cudaMemcpyAsync(B[2].p, ct, A * 4, cudaMemcpyHostToDevice, st)); }
+  CU(cudaMemcpyAsync(B[3].p, strand, C1, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[4].p, m_off, (C1 + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (M) { CU(cudaMemcpyAsync(B[5].p, q, M * 4, cudaMemcpyHostToDevice, st)); CU(cudaMemcpyAsync(B[6].p, t, M * 4, cudaMemcpyHostToDevice, st)); }
+  CU(cudaMemcpyAsync(B[9].p, mode.data(), C1, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[10].p, slot.data(), C1 * 8, cudaMemcpyHostToDevice, st));
+  cudaEventRecord(ctx->ev[0], st);
+  if (M) {
+    SortBatch sb;
+    sb.n_seg = n_chains; sb.mode = 2; sb.seg_off = (const unsigned long long *)B[4].p; sb.q = (uint32_t *)B[5].p; sb.t = (uint32_t *)B[6].p; sb.perm = nullptr;
+    sb.kp = (unsigned long long *)B[11].p; sb.ks = (uint32_t *)B[12].p; sb.ki = (uint32_t *)B[13].p; sb.slot_off = (const unsigned long long *)B[10].p;
+    sb.seg_mode = (const uint8_t *)B[9].p;
+    sort_pairs_kernel<<<(unsigned)n_chains, 256, 0, st>>>(sb);
+    ctx->launches++;
+  }
+  TrimChainBatch b{n_chains, (const unsigned long long *)B[0].p, (const uint32_t *)B[1].p, (const uint32_t *)B[2].p, (const uint8_t *)B[3].p, (const unsigned long long *)B[4].p,
+                   (const uint32_t *)B[5].p, (const uint32_t *)B[6].p, (uint8_t *)B[7].p, (int32_t *)B[8].p};
+  trim_splitchain_kernel<<<(unsigned)((n_chains + 63) / 64), 64, 0, st>>>(b);
+  cudaEventRecord(ctx->ev[1], st);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  if (M) {
+    CU(cudaMemcpyAsync(q, B[5].p, M * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(t, B[6].p, M * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(keep, B[7].p, M, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaMemcpyAsync(removed, B[8].p, C1 * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "trim_splitchain(sort+trim)");
+  cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]); s2.jobs = (uint64_t)n_chains; s2.algo_bytes = 17ull * M + 8ull * A;
+  ctx->stats.push_back(s2);
+  return LRA_B200_OK;
+}

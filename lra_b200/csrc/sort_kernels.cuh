@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256) sort_pairs_kernel(SortBatch b) {
   const unsigned long long o = b.seg_off[s];
   const int n = (int)(b.seg_off[s + 1] - o);
   const int mode = b.seg_mode ? (int)b.seg_mode[s] : b.mode;
+  if (mode == 255) return;            // a segment its caller leaves unsorted (TrimSplitChainDiagonal: chains of one anchor)
   if (n <= 1) { if (n == 1 && b.perm && threadIdx.x == 0) b.perm[o] = (uint32_t)o; return; }
   int P = 1;
   while (P < n) P <<= 1;

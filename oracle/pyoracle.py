@@ -1020,3 +1020,22 @@ def store_diagonal(q, t, qt, freq, strand, hdr_pos, globalK, maxDiag, minCluster
         o[key] = o[key][:k]
     o["box"] = o["box"][:4 * k].reshape(-1, 4)
     return o
+
+
+# ---------------------------------------------------------------- TrimSplitChainDiagonal
+
+def trim_splitchain(cq, ct, strand, q, t, which="port"):
+    """One split chain (chain anchors cq / ct in sptc order) and its refined anchors.  Returns (kept q, kept t, nRemoved)."""
+    cq = np.ascontiguousarray(cq, np.uint32); ct = np.ascontiguousarray(ct, np.uint32)
+    n = len(q)
+    qq = np.ascontiguousarray(q, np.uint32).copy() if n else np.zeros(1, np.uint32); tt = np.ascontiguousarray(t, np.uint32).copy() if n else np.zeros(1, np.uint32)
+    if which == "ref":
+        f = _bind_once(ref(), "ref_trim_splitchain", C.c_long, [_u32p, _u32p, C.c_int, C.c_int, _u32p, _u32p, C.c_int, C.POINTER(C.c_long)])
+        rem = C.c_long(0)
+        k = f(cq, ct, len(cq), int(strand), qq, tt, n, C.byref(rem))
+        return qq[:k].copy(), tt[:k].copy(), int(rem.value)
+    f = _bind_once(port(), "lra_oracle_trim_splitchain", C.c_long, [_u32p, _u32p, C.c_int, C.c_int, _u32p, _u32p, C.c_int, _u8p])
+    keep = np.zeros(max(n, 1), np.uint8)
+    rem = f(cq, ct, len(cq), int(strand), qq, tt, n, keep)
+    m = keep[:n].astype(bool)
+    return qq[:n][m], tt[:n][m], int(rem)

@@ -804,4 +804,27 @@ long ref_store_diagonal(const uint32_t *q, const uint32_t *t, const uint64_t *qt
   return (long)clusters.size();
 }
 
+// ---- TrimSplitChainDiagonal (ChainRefine.h:189-331) for one split chain and its refined cluster; arguments as oracle/trim_splitchain.c.  Returns the number
+// of anchors kept; q/t receive them (the refined cluster's matches after the call), *removed the function's return value.
+long ref_trim_splitchain(const uint32_t *cq, const uint32_t *ct, int n_chain, int strand, uint32_t *q, uint32_t *t, int n, long *removed) {
+  ref_init_static();
+  std::vector<Cluster> cl(1);
+  cl[0].strand = strand;
+  UltimateChain chain(&cl);
+  chain.chain.resize(n_chain); chain.ClusterIndex.assign(n_chain, 0);
+  for (int i = 0; i < n_chain; i++) {
+    GenomePair gp; gp.first.pos = cq[i]; gp.second.pos = ct[i];
+    chain.chain[i] = (unsigned)i; cl[0].matches.push_back(gp); cl[0].matchesLengths.push_back(17);
+  }
+  std::vector<int> sp(n_chain); std::vector<bool> lk(n_chain > 0 ? n_chain - 1 : 0, false);
+  for (int i = 0; i < n_chain; i++) sp[i] = i;
+  std::vector<SplitChain> spchain; spchain.push_back(SplitChain(sp, lk, &chain, strand != 0));
+  std::vector<Cluster> refined(1);
+  refined[0].matches.resize(n);
+  for (int i = 0; i < n; i++) { refined[0].matches[i].first.pos = q[i]; refined[0].matches[i].second.pos = t[i]; }
+  *removed = TrimSplitChainDiagonal(spchain, refined);
+  for (size_t i = 0; i < refined[0].matches.size(); i++) { q[i] = refined[0].matches[i].first.pos; t[i] = refined[0].matches[i].second.pos; }
+  return (long)refined[0].matches.size();
+}
+
 }  // extern "C"

@@ -463,3 +463,14 @@ def store_diagonal(cl, hdr_pos, globalK, max_diag, min_cluster_size, min_cluster
                          globalK, max_diag, min_cluster_size, min_cluster_length, int(bypass), o["n_cl"], o["c_start"], o["c_end"], o["c_chrom"], o["c_box"], o["c_freq"])
     o["c_box"] = o["c_box"].reshape(-1, 4)
     return o
+
+
+def trim_splitchains(cq, ct, c_off, strand, q, t, m_off):
+    L = lib()
+    L.emu_trim_splitchains.argtypes = [C.c_int, _u64p, _u32p, _u32p, _u8p, _u64p, _u32p, _u32p, _u8p, _i32p]
+    co = np.ascontiguousarray(c_off, np.uint64); mo = np.ascontiguousarray(m_off, np.uint64); n = len(co) - 1
+    pad = lambda a, dt: np.array(a, dt) if len(a) else np.zeros(1, dt)
+    q2 = pad(q, np.uint32); t2 = pad(t, np.uint32)
+    keep = np.zeros(max(len(q), 1), np.uint8); removed = np.zeros(max(n, 1), np.int32)
+    L.emu_trim_splitchains(n, co, pad(cq, np.uint32), pad(ct, np.uint32), pad(strand, np.uint8), mo, q2, t2, keep, removed)
+    return q2[:len(q)], t2[:len(t)], keep[:len(q)], removed[:n]

@@ -323,3 +323,22 @@ extern "C" int emu_store_diagonal(int n_lists, const uint64_t *l_off, const uint
   if (n_lists) emu::launch(dim3((unsigned)((n_lists + 63) / 64)), dim3(64), 0, [&] { store_diagonal_kernel(b); });
   return 0;
 }
+
+extern "C" int emu_trim_splitchains(int n_chains, const uint64_t *c_off, const uint32_t *cq, const uint32_t *ct, const uint8_t *strand, const uint64_t *m_off, uint32_t *q,
+                                    uint32_t *t, uint8_t *keep, int32_t *removed) {
+  std::vector<uint8_t> mode(n_chains + 1);
+  std::vector<unsigned long long> slot(n_chains + 1), kp; std::vector<uint32_t> ks, ki;
+  size_t slots = 0;
+  for (int c = 0; c < n_chains; c++) {
+    mode[c] = (c_off[c + 1] - c_off[c]) == 1 ? 255 : 2;
+    size_t n = m_off[c + 1] - m_off[c], P2 = 1; while (P2 < n) P2 <<= 1; slot[c] = slots; if (mode[c] == 2 && P2 > (size_t)kSortSmem) slots += P2;
+  }
+  kp.resize(slots + 2); ks.resize(slots + 2); ki.resize(slots + 2);
+  if (n_chains && m_off[n_chains]) {
+    SortBatch sb{n_chains, 2, (const unsigned long long *)m_off, q, t, nullptr, kp.data(), ks.data(), ki.data(), slot.data(), mode.data()};
+    emu::launch(dim3((unsigned)n_chains), dim3(256), 0, [&] { sort_pairs_kernel(sb); });
+  }
+  TrimChainBatch b{n_chains, (const unsigned long long *)c_off, cq, ct, strand, (const unsigned long long *)m_off, q, t, keep, removed};
+  if (n_chains) emu::launch(dim3((unsigned)((n_chains + 63) / 64)), dim3(64), 0, [&] { trim_splitchain_kernel(b); });
+  return 0;
+}
