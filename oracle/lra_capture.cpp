@@ -75,4 +75,83 @@ static inline void IndelRefineAlignment_logged(Read &read, Genome &genome, Align
   }
 }
 #define IndelRefineAlignment IndelRefineAlignment_logged
+
+// ---- SparseDP (SparseDP.h:2139 pure matches, :2287 one cluster) and SparseDP_ForwardOnly (SparseDP_Forward.h:312): inputs and outputs of every
+// call of the low-accuracy pipeline.  $LRA_CAPTURE_SDP.  Records (all 32-bit words, little endian):
+//   kind 0: {0, n_cl, nfrag, rate(f32), alnthres(f32), NumAln, read_len} cl_off[n_cl+1] cl_strand[n_cl] q[nfrag] t[nfrag] len[nfrag]
+//           {n_chains} then per chain {n, value(f32), QStart, QEnd, TStart, TEnd} chain[n] (global fragment index) link[n-1]
+//   kind 1: {1, strand, nfrag, rate(f32)} q t len {n, value(f32)} chain[n] link[n-1]
+//   kind 2: {2, nfrag, rate} q t len {n, value(f32)} chain[n]
+#include "SparseDP.h"
+#include "SparseDP_Forward.h"
+static FILE *lra_cap_sdp_fp() {
+  static FILE *fp = NULL; static bool init = false;
+  if (!init) { init = true; const char *p = getenv("LRA_CAPTURE_SDP"); if (p) fp = fopen(p, "wb"); }
+  return fp;
+}
+static inline void cap_w32(FILE *fp, uint32_t v) { fwrite(&v, 4, 1, fp); }
+static inline void cap_wf(FILE *fp, float v) { fwrite(&v, 4, 1, fp); }
+static inline int SparseDP_logged(vector<Cluster> &FragInput, vector<UltimateChain> &chains, const Options &opts, const vector<float> &LookUpTable, Read &read, float rate) {
+  FILE *fp = lra_cap_sdp_fp();
+  size_t c0 = chains.size();
+  int un = read.unaligned;
+  int r = SparseDP(FragInput, chains, opts, LookUpTable, read, rate);
+  if (fp && !un) {
+    int nfrag = 0; for (size_t c = 0; c < FragInput.size(); c++) nfrag += FragInput[c].matches.size();
+    cap_w32(fp, 0); cap_w32(fp, FragInput.size()); cap_w32(fp, nfrag); cap_wf(fp, rate); cap_wf(fp, opts.alnthres); cap_w32(fp, opts.NumAln); cap_w32(fp, read.length);
+    std::vector<int> off(FragInput.size() + 1, 0);
+    for (size_t c = 0; c < FragInput.size(); c++) off[c + 1] = off[c] + FragInput[c].matches.size();
+    for (size_t c = 0; c <= FragInput.size(); c++) cap_w32(fp, off[c]);
+    for (size_t c = 0; c < FragInput.size(); c++) cap_w32(fp, FragInput[c].strand);
+    for (size_t c = 0; c < FragInput.size(); c++) for (size_t i = 0; i < FragInput[c].matches.size(); i++) cap_w32(fp, FragInput[c].matches[i].first.pos);
+    for (size_t c = 0; c < FragInput.size(); c++) for (size_t i = 0; i < FragInput[c].matches.size(); i++) cap_w32(fp, FragInput[c].matches[i].second.pos);
+    for (size_t c = 0; c < FragInput.size(); c++) for (size_t i = 0; i < FragInput[c].matches.size(); i++) cap_w32(fp, FragInput[c].matchesLengths[i]);
+    cap_w32(fp, chains.size() - c0);
+    for (size_t c = c0; c < chains.size(); c++) {
+      cap_w32(fp, chains[c].chain.size()); cap_wf(fp, chains[c].FirstSDPValue);
+      cap_w32(fp, chains[c].QStart); cap_w32(fp, chains[c].QEnd); cap_w32(fp, chains[c].TStart); cap_w32(fp, chains[c].TEnd);
+      for (size_t s = 0; s < chains[c].chain.size(); s++) cap_w32(fp, chains[c].chain[s] + off[chains[c].ClusterIndex[s]]);
+      for (size_t s = 0; s + 1 < chains[c].chain.size(); s++) cap_w32(fp, s < chains[c].link.size() ? (uint32_t)chains[c].link[s] : 255u);
+    }
+  }
+  return r;
+}
+static inline int SparseDP_logged(int ClusterIndex, vector<Cluster> &FragInput, UltimateChain &ultimatechain, const Options &opts, const vector<float> &LookUpTable, Read &read) {
+  FILE *fp = lra_cap_sdp_fp();
+  int un = read.unaligned;
+  int r = SparseDP(ClusterIndex, FragInput, ultimatechain, opts, LookUpTable, read);
+  if (fp && !un && FragInput[ClusterIndex].matches.size() > 0) {
+    Cluster &C = FragInput[ClusterIndex];
+    cap_w32(fp, 1); cap_w32(fp, C.strand); cap_w32(fp, C.matches.size()); cap_wf(fp, opts.second_anchorbonus);
+    for (size_t i = 0; i < C.matches.size(); i++) cap_w32(fp, C.matches[i].first.pos);
+    for (size_t i = 0; i < C.matches.size(); i++) cap_w32(fp, C.matches[i].second.pos);
+    for (size_t i = 0; i < C.matches.size(); i++) cap_w32(fp, C.matchesLengths[i]);
+    cap_w32(fp, ultimatechain.chain.size()); cap_wf(fp, ultimatechain.FirstSDPValue);
+    for (size_t s = 0; s < ultimatechain.chain.size(); s++) cap_w32(fp, ultimatechain.chain[s]);
+    for (size_t s = 0; s + 1 < ultimatechain.chain.size(); s++) cap_w32(fp, s < ultimatechain.link.size() ? (uint32_t)ultimatechain.link[s] : 255u);
+  }
+  return r;
+}
+static inline int SparseDP_logged(SplitChain &inputChain, vector<Cluster_SameDiag *> &FragInput, FinalChain &finalchain, const Options &opts, const vector<float> &LookUpTable, Read &read) {
+  return SparseDP(inputChain, FragInput, finalchain, opts, LookUpTable, read);
+}
+static inline int SparseDP_logged(vector<Cluster> &FragInput, vector<Primary_chain> &Primary_chains, const Options &opts, const vector<float> &LookUpTable, Read &read, float &rate) {
+  return SparseDP(FragInput, Primary_chains, opts, LookUpTable, read, rate);
+}
+static inline int SparseDP_ForwardOnly_logged(const GenomePairs &FragInput, const vector<int> &MatchLengths, std::vector<unsigned int> &chain, const Options &opts,
+                                              const std::vector<float> &LookUpTable, float &inv_value, int &inv_NumOfAnchors, int rate = 5) {
+  FILE *fp = lra_cap_sdp_fp();
+  int r = SparseDP_ForwardOnly(FragInput, MatchLengths, chain, opts, LookUpTable, inv_value, inv_NumOfAnchors, rate);
+  if (fp && FragInput.size() > 0) {
+    cap_w32(fp, 2); cap_w32(fp, FragInput.size()); cap_w32(fp, rate);
+    for (size_t i = 0; i < FragInput.size(); i++) cap_w32(fp, FragInput[i].first.pos);
+    for (size_t i = 0; i < FragInput.size(); i++) cap_w32(fp, FragInput[i].second.pos);
+    for (size_t i = 0; i < FragInput.size(); i++) cap_w32(fp, MatchLengths[i]);
+    cap_w32(fp, chain.size()); cap_wf(fp, inv_value);
+    for (size_t s = 0; s < chain.size(); s++) cap_w32(fp, chain[s]);
+  }
+  return r;
+}
+#define SparseDP(...) SparseDP_logged(__VA_ARGS__)
+#define SparseDP_ForwardOnly(...) SparseDP_ForwardOnly_logged(__VA_ARGS__)
 #include "lra.cpp"

@@ -827,4 +827,74 @@ long ref_trim_splitchain(const uint32_t *cq, const uint32_t *ct, int n_chain, in
   return (long)refined[0].matches.size();
 }
 
+// ---- a10: the SparseDP drivers of the low-accuracy pipeline (SparseDP.h:2139, :2287; SparseDP_Forward.h:312) -----------------------------
+// InitPWL (SubRountine.h:43-101) with the given preset values; the tables it builds are returned for upload.
+void ref_init_pwl(float gapopen, float gapextend, float gaproot, int ceil1, int ceil2, int64_t *stops, float *slope, float *inter) {
+  InitPWL(gapopen, gapextend, gaproot, ceil1, ceil2);
+  for (int i = 0; i < NUMPWL; i++) { stops[i] = STOPS[i]; slope[i] = SLOPE[i]; inter[i] = INTER[i]; }
+}
+float ref_pwl_w(long x) { return PWL_w(x); }
+
+static void ref_make_clusters(std::vector<Cluster> &cl, int n_cl, const int32_t *cl_off, const uint8_t *cl_strand, const uint32_t *q, const uint32_t *t, const int32_t *len) {
+  cl.resize(n_cl);
+  for (int c = 0; c < n_cl; c++) {
+    cl[c].strand = cl_strand[c]; cl[c].chromIndex = 0; cl[c].matchStart = -1;
+    for (int i = cl_off[c]; i < cl_off[c + 1]; i++) {
+      GenomePair gp; gp.first.pos = q[i]; gp.second.pos = t[i]; gp.first.t = 0; gp.second.t = 0;
+      cl[c].matches.push_back(gp); cl[c].matchesLengths.push_back(len[i]);
+    }
+  }
+}
+// Pure matches + DecidePrimaryChains.  Outputs per chain c (< max_aln): chain_len[c], value[c], bounds[4c..] = QStart,QEnd,TStart,TEnd, and at
+// chain[c * nfrag ..] the anchors as global fragment indices (cluster offset added back), link[c * nfrag ..] the link bits.  Returns #chains.
+int ref_sdp_pure(int n_cl, const int32_t *cl_off, const uint8_t *cl_strand, const uint32_t *q, const uint32_t *t, const int32_t *len, float rate,
+                 float alnthres, int NumAln, int read_len, int max_aln, int32_t *chain_len, float *value, uint32_t *bounds, uint32_t *chain, uint8_t *link) {
+  ref_init_static();
+  std::vector<Cluster> cl; ref_make_clusters(cl, n_cl, cl_off, cl_strand, q, t, len);
+  const int nfrag = cl_off[n_cl];
+  Options opts; opts.alnthres = alnthres; opts.NumAln = NumAln; opts.readname = "";
+  Read read; read.length = read_len; read.name = "r"; read.unaligned = 0;
+  std::vector<float> lut;
+  std::vector<UltimateChain> chains;
+  SparseDP(cl, chains, opts, lut, read, rate);
+  int n = 0;
+  for (size_t c = 0; c < chains.size() && (int)c < max_aln; c++, n++) {
+    chain_len[c] = (int)chains[c].chain.size(); value[c] = chains[c].FirstSDPValue;
+    bounds[4 * c] = chains[c].QStart; bounds[4 * c + 1] = chains[c].QEnd; bounds[4 * c + 2] = chains[c].TStart; bounds[4 * c + 3] = chains[c].TEnd;
+    for (size_t s = 0; s < chains[c].chain.size(); s++) {
+      chain[c * nfrag + s] = chains[c].chain[s] + cl_off[chains[c].ClusterIndex[s]];
+      if (s + 1 < chains[c].chain.size()) link[c * nfrag + s] = s < chains[c].link.size() ? (uint8_t)chains[c].link[s] : 255;
+    }
+  }
+  read.seq = NULL; read.qual = NULL; read.passthrough = NULL;
+  return n;
+}
+// One cluster (second SDP of the low-accuracy pipeline).  Returns the chain length; chain holds cluster-local indices.
+int ref_sdp_cluster(int n_cl, const int32_t *cl_off, const uint8_t *cl_strand, const uint32_t *q, const uint32_t *t, const int32_t *len, int cluster,
+                    float second_anchorbonus, float *value, uint32_t *chain, uint8_t *link) {
+  ref_init_static();
+  std::vector<Cluster> cl; ref_make_clusters(cl, n_cl, cl_off, cl_strand, q, t, len);
+  Options opts; opts.second_anchorbonus = second_anchorbonus;
+  Read read; read.length = 1000; read.name = "r"; read.unaligned = 0;
+  std::vector<float> lut;
+  UltimateChain uc(&cl);
+  uc.FirstSDPValue = 0;
+  SparseDP(cluster, cl, uc, opts, lut, read);
+  *value = uc.FirstSDPValue;
+  for (size_t s = 0; s < uc.chain.size(); s++) { chain[s] = uc.chain[s]; if (s < uc.link.size()) link[s] = (uint8_t)uc.link[s]; }
+  read.seq = NULL; read.qual = NULL; read.passthrough = NULL;
+  return (int)uc.chain.size();
+}
+// Forward only (third SDP).  Returns the chain length.
+int ref_sdp_forward(int n, const uint32_t *q, const uint32_t *t, const int32_t *len, int rate, float *value, uint32_t *chain) {
+  ref_init_static();
+  GenomePairs gp(n); std::vector<int> ml(n);
+  for (int i = 0; i < n; i++) { gp[i].first.pos = q[i]; gp[i].second.pos = t[i]; gp[i].first.t = 0; gp[i].second.t = 0; ml[i] = len[i]; }
+  Options opts; std::vector<float> lut; std::vector<unsigned int> ch; float v = 0; int na = 0;
+  SparseDP_ForwardOnly(gp, ml, ch, opts, lut, v, na, rate);
+  *value = v;
+  for (size_t s = 0; s < ch.size(); s++) chain[s] = ch[s];
+  return (int)ch.size();
+}
+
 }  // extern "C"
