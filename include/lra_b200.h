@@ -761,6 +761,53 @@ int lra_b200_mapq_batch(lra_b200_ctx *ctx, const lra_b200_alignment_groups *ag, 
 int lra_b200_global_chain_batch(lra_b200_ctx *ctx, const int32_t *frag, const uint64_t *frag_off, int32_t n_prob, int32_t *score, int32_t *prev,
                                 int32_t *chain, int32_t *chain_len);
 
+/* ---- a10  the SparseDP family, batched (one problem per warp) ------------------------------------------------------
+ * Replaces, for a batch of calls,
+ *   mode 0:  int SparseDP(vector<Cluster> &FragInput, vector<UltimateChain> &chains, const Options&, const vector<float>&, Read&, float rate)
+ *            SparseDP.h:2139-2282 (first SDP of MapRead_lowacc, Map_lowacc.h:188) incl. DecidePrimaryChains :1658-1765
+ *   mode 1:  int SparseDP(int ClusterIndex, vector<Cluster> &FragInput, UltimateChain&, const Options&, const vector<float>&, Read&)
+ *            SparseDP.h:2287-2440 (second SDP, Map_lowacc.h:535)
+ *   mode 2:  int SparseDP_ForwardOnly(const GenomePairs&, const vector<int> &MatchLengths, vector<unsigned int> &chain, ..., int rate)
+ *            SparseDP_Forward.h:312-490 (third SDP, LocalRefineAlignment.h:377)
+ * Problem p owns the anchors frag_off[p] .. frag_off[p+1] (q = first.pos, t = second.pos, len = matchesLengths), grouped into clusters by
+ * cl_off[cl_off_off[p] ..] (ncl + 1 problem-relative offsets) with strands cl_strand[cl_off_off[p] ..].  rate = the anchor bonus (mode 0:
+ * the `rate` argument, mode 1: opts.second_anchorbonus), irate = the integer rate of mode 2.  The gap cost is the reference's PWL_w over
+ * the tables InitPWL builds (SubRountine.h:43-126): build them on the host with lra_b200_init_pwl and pass them in.
+ * Output: chain c (< max_aln) of problem p has chain_len[p*max_aln+c] anchors at chain[max_aln*frag_off[p] + c*nfrag_p ..] (mode 0: problem-
+ * relative fragment index = MatchStart[cluster] + index in cluster; modes 1, 2: index in the cluster / list), link bits beside them,
+ * chain_val = FirstSDPValue / max_value / inv_value, bounds = QStart,QEnd,TStart,TEnd (mode 0).  Bit-exact incl. the float value. */
+typedef struct lra_b200_sdp_problems {
+  int32_t n_prob, max_aln;
+  const int32_t *mode;
+  const uint64_t *frag_off;
+  const uint32_t *q, *t;
+  const int32_t *len;
+  const uint64_t *cl_off_off;
+  const int32_t *cl_off;
+  const uint8_t *cl_strand;
+  const int32_t *only_cl;
+  const float *rate;
+  const int32_t *irate;
+  const int32_t *read_len;
+  float alnthres;          /* opts.alnthres */
+  int32_t num_aln;         /* opts.NumAln */
+  const int64_t *pwl_stops; const float *pwl_slope; const float *pwl_inter;   /* 25 entries each */
+  int32_t ceil1, ceil2;    /* opts.gapCeiling1 / 2 */
+} lra_b200_sdp_problems;
+typedef struct lra_b200_sdp_result {
+  int32_t *n_chains;       /* [n_prob] */
+  int32_t *chain_len;      /* [n_prob * max_aln] */
+  float *chain_val;        /* [n_prob * max_aln] */
+  uint32_t *bounds;        /* [n_prob * max_aln * 4] */
+  uint32_t *chain;         /* [max_aln * total anchors] */
+  uint8_t *link;           /* [max_aln * total anchors] */
+  int32_t *cl_of_frag;     /* [total anchors] (mode 0: cluster of every anchor) */
+  uint64_t arena_peak;     /* out: largest per-problem scratch use in bytes */
+} lra_b200_sdp_result;
+int lra_b200_sdp_batch(lra_b200_ctx *ctx, const lra_b200_sdp_problems *problems, lra_b200_sdp_result *res);
+/* InitPWL (SubRountine.h:43-101): the piece-wise-linear gap cost tables for (opts.gapopen, opts.gapextend, opts.gaproot), 25 entries each. */
+int lra_b200_init_pwl(float intercept, float scalar, float root, int32_t ceil1, int32_t ceil2, int64_t *stops, float *slope, float *inter);
+
 /* ---- per-kernel timing of the last batch call (CUDA events on the context's stream) ---------------------------- */
 typedef struct lra_b200_kernel_stat {
   char name[48];

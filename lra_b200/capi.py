@@ -51,6 +51,18 @@ class _IrSegResult(C.Structure):
                 ("n_blocks_total", C.c_uint64), ("cells", C.c_uint64), ("n_dp_groups", C.c_uint64), ("n_aog_jobs", C.c_uint64)]
 
 
+class _SdpProblems(C.Structure):
+    _fields_ = [("n_prob", C.c_int32), ("max_aln", C.c_int32), ("mode", C.c_void_p), ("frag_off", C.c_void_p), ("q", C.c_void_p), ("t", C.c_void_p), ("len", C.c_void_p),
+                ("cl_off_off", C.c_void_p), ("cl_off", C.c_void_p), ("cl_strand", C.c_void_p), ("only_cl", C.c_void_p), ("rate", C.c_void_p), ("irate", C.c_void_p),
+                ("read_len", C.c_void_p), ("alnthres", C.c_float), ("num_aln", C.c_int32), ("pwl_stops", C.c_void_p), ("pwl_slope", C.c_void_p), ("pwl_inter", C.c_void_p),
+                ("ceil1", C.c_int32), ("ceil2", C.c_int32)]
+
+
+class _SdpResult(C.Structure):
+    _fields_ = [("n_chains", C.c_void_p), ("chain_len", C.c_void_p), ("chain_val", C.c_void_p), ("bounds", C.c_void_p), ("chain", C.c_void_p), ("link", C.c_void_p),
+                ("cl_of_frag", C.c_void_p), ("arena_peak", C.c_uint64)]
+
+
 class _SeedReads(C.Structure):
     _fields_ = [("read_off", C.c_void_p), ("read_len", C.c_void_p), ("n_reads", C.c_int32), ("k", C.c_int32), ("w", C.c_int32),
                 ("max_freq", C.c_int64)]
@@ -281,11 +293,20 @@ def load_library():
     L.lra_b200_refine_splitchains_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_SplitChains), C.POINTER(_Refined)]
     L.lra_b200_refine_splitchains_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_SplitChains), C.c_uint64, C.POINTER(_Refined)]
     L.lra_b200_calc_stats_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrSegments), C.c_void_p, C.POINTER(_StatsResult)]
+    L.lra_b200_sdp_batch.argtypes = [C.c_void_p, C.POINTER(_SdpProblems), C.POINTER(_SdpResult)]
+    L.lra_b200_init_pwl.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lra_b200_last_kernel_stats.argtypes = [C.c_void_p, C.POINTER(KernelStat), C.c_int]
     L.lra_b200_launch_count.argtypes = [C.c_void_p]
     L.lra_b200_launch_count.restype = C.c_uint64
     _LIB = L
     return L
+
+
+def init_pwl(gapopen, gapextend, gaproot, ceil1, ceil2):
+    """InitPWL (SubRountine.h:43-101) on the host: (stops int64[25], slope f32[25], inter f32[25], ceil1, ceil2)."""
+    stops = np.zeros(25, np.int64); slope = np.zeros(25, np.float32); inter = np.zeros(25, np.float32)
+    load_library().lra_b200_init_pwl(gapopen, gapextend, gaproot, ceil1, ceil2, stops.ctypes.data, slope.ctypes.data, inter.ctypes.data)
+    return stops, slope, inter, ceil1, ceil2
 
 
 def _ptr(a):
@@ -750,6 +771,22 @@ class Context:
         self._check(self.lib.lra_b200_global_chain_batch(self.h, _ptr(f) if n else None, _ptr(fo), len(fo) - 1, _ptr(o["score"]), _ptr(o["prev"]), _ptr(o["chain"]),
                                                          _ptr(o["chain_len"])))
         o["score"] = o["score"][:n]; o["prev"] = o["prev"][:n]; o["chain_len"] = o["chain_len"][:len(fo) - 1]
+        return o
+
+    # ---- a10
+    def sdp_batch(self, pb, pwl, alnthres, num_aln, max_aln=2):
+        """The SparseDP family for a batch of problems (tests/sdpgen.pack layout).  pwl = (stops, slope, inter, ceil1, ceil2) from init_pwl."""
+        n = len(pb["mode"]); nf = int(pb["frag_off"][-1]) if n else 0
+        o = dict(n_chains=np.zeros(max(n, 1), np.int32), chain_len=np.zeros(max(n * max_aln, 1), np.int32), chain_val=np.zeros(max(n * max_aln, 1), np.float32),
+                 bounds=np.zeros(max(4 * n * max_aln, 1), np.uint32), chain=np.zeros(max(1, nf * max_aln), np.uint32), link=np.zeros(max(1, nf * max_aln), np.uint8),
+                 cl_of_frag=np.zeros(max(1, nf), np.int32))
+        keep = [np.ascontiguousarray(pwl[0], np.int64), np.ascontiguousarray(pwl[1], np.float32), np.ascontiguousarray(pwl[2], np.float32)]
+        pr = _SdpProblems(n, max_aln, _ptr(pb["mode"]), _ptr(pb["frag_off"]), _ptr(pb["q"]), _ptr(pb["t"]), _ptr(pb["len"]), _ptr(pb["cl_off_off"]), _ptr(pb["cl_off"]),
+                          _ptr(pb["cl_strand"]), _ptr(pb["only_cl"]), _ptr(pb["rate"]), _ptr(pb["irate"]), _ptr(pb["read_len"]), alnthres, num_aln,
+                          _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), int(pwl[3]), int(pwl[4]))
+        rs = _SdpResult(_ptr(o["n_chains"]), _ptr(o["chain_len"]), _ptr(o["chain_val"]), _ptr(o["bounds"]), _ptr(o["chain"]), _ptr(o["link"]), _ptr(o["cl_of_frag"]), 0)
+        self._check(self.lib.lra_b200_sdp_batch(self.h, C.byref(pr), C.byref(rs)))
+        o["peak"] = int(rs.arena_peak); o["err"] = 0
         return o
 
     # ---- a12

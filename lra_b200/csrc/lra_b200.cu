@@ -78,6 +78,7 @@ struct lra_b200_ctx {
   DevBuf rs[16];          // RefineSpace: space descriptors, pairs
   DevBuf sr[24];          // SplitRoughClustersWithGaps
   DevBuf rs2[12];         // RefineSpace, minimizer branch
+  DevBuf mp[48];          // mapper / SparseDP
   bool keep_stats = false;  // sub-launchers append to stats instead of clearing
   AogPlan *h_plan = nullptr;            // pinned
   unsigned long long *h_misc = nullptr;  // pinned (2 x u64)
@@ -167,6 +168,7 @@ extern "C" void lra_b200_destroy(lra_b200_ctx *ctx) {
   for (DevBuf &b : ctx->lr_x) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->so) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->gc) if (b.p) cudaFree(b.p);
+  for (DevBuf &b : ctx->mp) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->rb) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->cf) if (b.p) cudaFree(b.p);
   for (DevBuf &b : ctx->cd) if (b.p) cudaFree(b.p);
@@ -1071,3 +1073,4 @@ extern "C" int lra_b200_calc_stats_batch_device(lra_b200_ctx *ctx, const lra_b20
 }
 
 #include "lref_host.cuh"
+#include "mp_host.cuh"

@@ -100,14 +100,15 @@ __device__ __forceinline__ int wscan_incl(int v) {
 // ---- per-worker bump arena with stack discipline (mark / release), replaces the function-local std::vectors of the reference
 struct Arena {
   unsigned char *base;
-  unsigned long long cap, top;
+  unsigned long long cap, top, peak;
   int overflow;
-  __device__ __forceinline__ void init(void *b, unsigned long long c) { base = (unsigned char *)b; cap = c; top = 0; overflow = 0; }
+  __device__ __forceinline__ void init(void *b, unsigned long long c) { base = (unsigned char *)b; cap = c; top = 0; peak = 0; overflow = 0; }
   template <class T> __device__ __forceinline__ T *alloc(unsigned long long n) {
     unsigned long long t = (top + 15ull) & ~15ull;
     unsigned long long e = t + n * sizeof(T);
     if (e > cap) { overflow = 1; return (T *)0; }
     top = e;
+    if (e > peak) peak = e;
     return (T *)(base + t);
   }
   __device__ __forceinline__ unsigned long long mark() const { return top; }

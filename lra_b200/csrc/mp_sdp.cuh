@@ -44,7 +44,7 @@ struct SdpFam {
 // growth heap for the Block / S_1 lists: the part of the worker arena above the set-up allocations, bumped atomically because
 // lanes grow the lists of different sub-problems concurrently.  (The reference re-runs Maximization over entries it has
 // already seen whenever `now` moves backwards, so the lists have no bound in terms of m.)
-struct SdpDyn { unsigned long long *top; unsigned char *base; unsigned long long cap; int *err; };
+struct SdpDyn { unsigned long long *top; unsigned char *base; unsigned long long cap; int *err; unsigned long long base_off; };
 __device__ inline bool sdp_grow(const SdpDyn &D, int2 *&arr, int &cap, int used) {
   const int ncap = cap * 2 + 16;
   const unsigned long long bytes = ((unsigned long long)ncap * sizeof(int2) + 15ull) & ~15ull;
@@ -499,7 +499,7 @@ __device__ inline bool sdp_open_dyn(SdpWork &W, Arena &ar) {
   if (lane_id() == 0) { cell[0] = 0ull; cell[1] = 0ull; }
   wsync();
   const unsigned long long t = (ar.top + 15ull) & ~15ull;
-  W.dyn.top = cell; W.dyn.err = (int *)(cell + 1); W.dyn.base = ar.base + t; W.dyn.cap = ar.cap > t ? ar.cap - t : 0ull;
+  W.dyn.top = cell; W.dyn.err = (int *)(cell + 1); W.dyn.base = ar.base + t; W.dyn.cap = ar.cap > t ? ar.cap - t : 0ull; W.dyn.base_off = t;
   return true;
 }
 

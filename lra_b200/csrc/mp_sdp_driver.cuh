@@ -35,6 +35,7 @@ __device__ inline int sdp_pure_matches(const SdpAnchors &A, float rate, float al
   int *nch_p = ar.alloc<int>(1);
   if (ar.overflow || !sdp_open_dyn(W, ar)) { ar.release(mk); return -1; }
   sdp_process(W, A, 0, 0, rate, 0, P);
+  { const unsigned long long e = W.dyn.base_off + *W.dyn.top; if (e > ar.peak) ar.peak = e; }
   if (*W.dyn.err) { ar.release(mk); return -1; }
   for (int i = lane_id(); i < n; i += kLanes) { order[i] = i; used[i] = 0; if (cl_of_frag) cl_of_frag[i] = W.val[i].cl; }
   wsync();
@@ -86,6 +87,7 @@ __device__ inline int sdp_one_cluster(const SdpAnchors &A, int cl, float rate, c
   int *res = ar.alloc<int>(2);
   if (ar.overflow || !sdp_open_dyn(W, ar)) { ar.release(mk); return -1; }
   sdp_process(W, A, f0, 1, rate, 0, P);
+  { const unsigned long long e = W.dyn.base_off + *W.dyn.top; if (e > ar.peak) ar.peak = e; }
   if (*W.dyn.err) { ar.release(mk); return -1; }
   if (lane_id() == 0) {
     float mx = 0.0f; uint32_t pos = 0;
@@ -109,6 +111,7 @@ __device__ inline int sdp_forward_only(const SdpAnchors &A, int irate, const Pwl
   uint8_t *link = ar.alloc<uint8_t>(A.nfrag + 1);
   if (ar.overflow || !sdp_open_dyn(W, ar)) { ar.release(mk); return -1; }
   sdp_process(W, A, 0, 2, 0.0f, irate, P);
+  { const unsigned long long e = W.dyn.base_off + *W.dyn.top; if (e > ar.peak) ar.peak = e; }
   if (*W.dyn.err) { ar.release(mk); return -1; }
   if (lane_id() == 0) {
     float mx = 0.0f; uint32_t pos = 0;
@@ -136,6 +139,7 @@ struct SdpBatch {
   // out: chain c of problem p: chain / link at max_aln * frag_off[p] + c * nfrag_p; scalars at p * max_aln + c
   int *n_chains; int *chain_len; float *chain_val; uint32_t *bounds; uint32_t *chain; uint8_t *link; int *cl_of_frag;
   unsigned char *arena; unsigned long long arena_per_warp; int *err;
+  unsigned long long *peak;                // optional: high-water mark of one problem's arena use (sizing aid)
 };
 
 __global__ void __launch_bounds__(128) sdp_batch_kernel(SdpBatch b) {
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(128) sdp_batch_kernel(SdpBatch b) {
   const int nw = (int)gridDim.x * warps_per_block;
   Arena ar; ar.init(b.arena + (unsigned long long)wid * b.arena_per_warp, b.arena_per_warp);
   for (int p = wid; p < b.n_prob; p += nw) {
-    ar.top = 0; ar.overflow = 0;
+    ar.top = 0; ar.overflow = 0; ar.peak = 0;
     const unsigned long long fo = b.frag_off[p]; const int nf = (int)(b.frag_off[p + 1] - fo);
     const unsigned long long co = b.cl_off_off[p]; const int ncl = (int)(b.cl_off_off[p + 1] - co) - 1;
     SdpAnchors A; A.q = b.q + fo; A.t = b.t + fo; A.len = b.len + fo; A.nfrag = nf; A.cl_off = b.cl_off + co; A.cl_strand = b.cl_strand + co; A.ncl = ncl;
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(128) sdp_batch_kernel(SdpBatch b) {
       const int n = sdp_forward_only(A, b.irate[p], *b.pwl, ar, cb, vp);
       if (n < 0) nch = -1; else { nch = 1; if (lane_id() == 0) b.chain_len[p * b.max_aln] = n; }
     }
-    if (lane_id() == 0) { b.n_chains[p] = nch; if (nch < 0) atomicOr(b.err, 1); }
+    if (lane_id() == 0) { b.n_chains[p] = nch; if (nch < 0) atomicOr(b.err, 1); if (b.peak) atomicMax(b.peak, ar.peak); }
     wsync();
   }
 }

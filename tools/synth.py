@@ -27,6 +27,29 @@ def gen_ref(total_len, n_contigs=1, seed=1234):
     return out
 
 
+def add_repeats(ref, frac=0.05, seed=77):
+    """Repeat-enriched variant: overwrite `frac` of every contig with copies of 1-10 kb segments of the same
+    contig set at 0-2 % divergence, so that minimizers repeat and anchor / chain ties occur."""
+    rng = np.random.default_rng(seed)
+    out = [(n, s.copy()) for n, s in ref]
+    for ci, (name, seq) in enumerate(out):
+        budget = int(len(seq) * frac)
+        while budget > 0:
+            L = int(rng.integers(1000, 10001))
+            sc = int(rng.integers(0, len(out)))
+            src = out[sc][1]
+            if len(src) <= L or len(seq) <= L:
+                break
+            a = int(rng.integers(0, len(src) - L))
+            b = int(rng.integers(0, len(seq) - L))
+            piece = mutate(src[a:a + L], float(rng.uniform(0.0, 0.02)), rng)[:L]
+            if rng.integers(0, 2):
+                piece = COMP[piece[::-1]]
+            seq[b:b + len(piece)] = piece
+            budget -= L
+    return out
+
+
 def write_fasta(path, records, width=80):
     with open(path, "wb") as f:
         for name, seq in records:
