@@ -808,6 +808,69 @@ int lra_b200_sdp_batch(lra_b200_ctx *ctx, const lra_b200_sdp_problems *problems,
 /* InitPWL (SubRountine.h:43-101): the piece-wise-linear gap cost tables for (opts.gapopen, opts.gapextend, opts.gaproot), 25 entries each. */
 int lra_b200_init_pwl(float intercept, float scalar, float root, int32_t ceil1, int32_t ceil2, int64_t *stops, float *slope, float *inter);
 
+/* ---- the MapRead seam: reads in, alignment records out -------------------------------------------------
+ * Replaces the body of the worker loop  numAligned += MapRead(LookUpTable, read, genome, genomemm, glIndex, opts, &strm, ...)
+ * (lra.cpp:115-121; MapRead.h:153-263 -> MapRead_lowacc, Map_lowacc.h:69-632) for a batch of reads.  The low-accuracy presets
+ * (-ONT, -CLR) are implemented; the record is the per-segment POD the printers consume (Alignment.h:591-808), so the host formats
+ * SAM text (lra_b200_format_sam). */
+typedef struct lra_b200_map_opts {      /* the Options members the path reads (Options.h:8-241) after the align preset (lra.cpp:268-431) */
+  int32_t globalK, globalW, globalMaxFreq;
+  int32_t localW, localMaxFreq;
+  int32_t smallK, smallW;                /* k / w of the LocalIndex (<ref>.gli): smallOpts.globalK / globalW, Map_lowacc.h:232-233 */
+  int32_t cleanMaxDiag, minDiagCluster, cleanClustersize, SecondCleanMinDiagCluster, SecondCleanMaxDiag, punish_anchorfreq, anchorPerlength;
+  int32_t NumAln, PrintNumAln, splitdist, readType;      /* readType: 0 ont, 1 clr, 2 ccs, 3 contig */
+  float initial_anchorbonus, second_anchorbonus, alnthres, anchorstoosparse;
+  int32_t refineSpaceDist, window, limitrefine, RefineBySDP;
+  int32_t localMatch, localMismatch, localIndel, localBand, refineBand;
+  int32_t hardClip, bypassClustering;
+  /* host-side only (not read by the kernels) */
+  float gapopen, gapextend, gaproot;
+  int32_t gapCeiling1, gapCeiling2;
+  int32_t localIndexWindow, localIndexMaxFreq;
+} lra_b200_map_opts;
+/* the align preset of `lra align -ONT | -CLR` (lra.cpp:339-431) on top of the defaults (Options.h:123-240); globalK is overwritten
+ * by the value stored in <ref>.mms (MMIndex.h:409), smallK / smallW by the <ref>.gli header */
+int lra_b200_map_opts_preset(const char *mode, lra_b200_map_opts *opts);
+
+typedef struct lra_b200_record {         /* one segment (an Alignment) */
+  int32_t read, chain, seg, n_seg;       /* read of the batch, alignment slot (chain p), index s in SegAlignment, segments of that alignment */
+  uint32_t flag;                         /* SAM flag (READ_REVERSE | READ_SECONDARY | READ_SUPPLEMENTARY) */
+  int32_t chrom, strand, mapq, order, typeofaln, supplementary;
+  uint32_t tStart, tEnd, qStart, qEnd;
+  int32_t preClip, sufClip;
+  int32_t nm, nmm, nins, ndel, tins, tdel, nSmallDel, nMedDel, nLargeDel, nSmallIns, nMedIns, nLargeIns;   /* members of Alignment (nins / ndel swapped as in the reference) */
+  float value;
+  int32_t NumOfAnchors0, NumOfAnchors1;
+  int32_t n_blocks, n_cigar;
+  uint64_t cigar_off;                    /* into the cigar array: BAM-encoded ops (len << 4 | op; '=' 7, 'X' 8, 'I' 1, 'D' 2) */
+} lra_b200_record;
+
+typedef struct lra_b200_map_result {     /* caller-owned host buffers; *_cap in elements */
+  int32_t *status;                       /* [n_reads] 0 mapped, 1 unaligned, >= 2 internal capacity error (the read is reported unaligned) */
+  int32_t *n_aln;                        /* [n_reads] alignments.size() */
+  int32_t *aln_nseg, *aln_seg0, *aln_rank;   /* [n_reads * 4] per alignment slot: segments, first record, and the slot printed a-th (AlignmentsOrder) */
+  lra_b200_record *records; uint64_t record_cap; uint64_t n_records;
+  uint32_t *cigar; uint64_t cigar_cap; uint64_t n_cigar;
+  uint64_t aligned_bases;                /* out: sum of qEnd - qStart over the non-supplementary, non-secondary segments */
+} lra_b200_map_result;
+
+typedef struct lra_b200_mapper lra_b200_mapper;
+/* genome: contigs concatenated (ASCII, upper-cased as Genome::Read does); hdr_pos[n_contigs + 1] cumulative offsets; the <ref>.mms tuples (t, pos);
+ * the <ref>.gli arrays (seq_offsets / tuple_boundaries have n_regions entries, MMIndex.h:138-151). */
+int lra_b200_mapper_create(lra_b200_ctx *ctx, const lra_b200_map_opts *opts, const char *genome_ascii, uint64_t genome_len, const uint64_t *hdr_pos, int32_t n_contigs,
+                           const uint64_t *mms_t, const uint32_t *mms_pos, uint64_t n_mms, const uint64_t *gli_seq_offsets, const uint64_t *gli_tuple_boundaries,
+                           int32_t gli_n_regions, const uint32_t *gli_minimizers, uint64_t gli_n_min, lra_b200_mapper **out);
+void lra_b200_mapper_destroy(lra_b200_ctx *ctx, lra_b200_mapper *m);
+/* reads: ASCII bases of all reads concatenated (upper case), read r = [read_off[r], +read_len[r]).  Records of read r come back at
+ * aln_seg0 .. in SegAlignment order. */
+int lra_b200_map_batch(lra_b200_ctx *ctx, lra_b200_mapper *m, const char *reads_ascii, uint64_t reads_len, const uint64_t *read_off, const uint32_t *read_len,
+                       int32_t n_reads, lra_b200_map_result *res);
+/* SAM text of the batch in input order (Alignment::PrintSAM, Alignment.h:658-808; unaligned reads: SimplePrintSAM :811-832; order of the
+ * segments: OUTPUT, Mapping_ultility.h:465-494).  names: n_reads NUL-terminated strings back to back; contig_names likewise.  Returns the
+ * number of bytes written, or -(required size) when cap is too small.  Pure host code. */
+int64_t lra_b200_format_sam(const lra_b200_map_opts *opts, const lra_b200_map_result *res, int32_t n_reads, const char *names, const char *reads_ascii,
+                            const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, int32_t n_contigs, int32_t runtime, char *out, int64_t cap);
+
 /* ---- per-kernel timing of the last batch call (CUDA events on the context's stream) ---------------------------- */
 typedef struct lra_b200_kernel_stat {
   char name[48];

@@ -63,6 +63,31 @@ class _SdpResult(C.Structure):
                 ("cl_of_frag", C.c_void_p), ("arena_peak", C.c_uint64)]
 
 
+class MapOpts(C.Structure):
+    """lra_b200_map_opts (include/lra_b200.h)."""
+    _fields_ = [(n, C.c_int32) for n in ("globalK", "globalW", "globalMaxFreq", "localW", "localMaxFreq", "smallK", "smallW", "cleanMaxDiag", "minDiagCluster",
+                                         "cleanClustersize", "SecondCleanMinDiagCluster", "SecondCleanMaxDiag", "punish_anchorfreq", "anchorPerlength", "NumAln",
+                                         "PrintNumAln", "splitdist", "readType")] + \
+               [(n, C.c_float) for n in ("initial_anchorbonus", "second_anchorbonus", "alnthres", "anchorstoosparse")] + \
+               [(n, C.c_int32) for n in ("refineSpaceDist", "window", "limitrefine", "RefineBySDP", "localMatch", "localMismatch", "localIndel", "localBand", "refineBand",
+                                         "hardClip", "bypassClustering")] + \
+               [(n, C.c_float) for n in ("gapopen", "gapextend", "gaproot")] + \
+               [(n, C.c_int32) for n in ("gapCeiling1", "gapCeiling2", "localIndexWindow", "localIndexMaxFreq")]
+
+
+# lra_b200_record
+RECORD = np.dtype([(n, "<i4") for n in ("read", "chain", "seg", "n_seg")] + [("flag", "<u4")] +
+                  [(n, "<i4") for n in ("chrom", "strand", "mapq", "order", "typeofaln", "supplementary")] +
+                  [(n, "<u4") for n in ("tStart", "tEnd", "qStart", "qEnd")] + [(n, "<i4") for n in ("preClip", "sufClip")] +
+                  [(n, "<i4") for n in ("nm", "nmm", "nins", "ndel", "tins", "tdel", "nSmallDel", "nMedDel", "nLargeDel", "nSmallIns", "nMedIns", "nLargeIns")] +
+                  [("value", "<f4")] + [(n, "<i4") for n in ("NumOfAnchors0", "NumOfAnchors1", "n_blocks", "n_cigar")] + [("cigar_off", "<u8")])
+
+
+class _MapResult(C.Structure):
+    _fields_ = [("status", C.c_void_p), ("n_aln", C.c_void_p), ("aln_nseg", C.c_void_p), ("aln_seg0", C.c_void_p), ("aln_rank", C.c_void_p), ("records", C.c_void_p),
+                ("record_cap", C.c_uint64), ("n_records", C.c_uint64), ("cigar", C.c_void_p), ("cigar_cap", C.c_uint64), ("n_cigar", C.c_uint64), ("aligned_bases", C.c_uint64)]
+
+
 class _SeedReads(C.Structure):
     _fields_ = [("read_off", C.c_void_p), ("read_len", C.c_void_p), ("n_reads", C.c_int32), ("k", C.c_int32), ("w", C.c_int32),
                 ("max_freq", C.c_int64)]
@@ -295,6 +320,15 @@ def load_library():
     L.lra_b200_calc_stats_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_IrSegments), C.c_void_p, C.POINTER(_StatsResult)]
     L.lra_b200_sdp_batch.argtypes = [C.c_void_p, C.POINTER(_SdpProblems), C.POINTER(_SdpResult)]
     L.lra_b200_init_pwl.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lra_b200_map_opts_preset.argtypes = [C.c_char_p, C.POINTER(MapOpts)]
+    L.lra_b200_format_sam.restype = C.c_int64
+    L.lra_b200_format_sam.argtypes = [C.POINTER(MapOpts), C.POINTER(_MapResult), C.c_int32, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int32, C.c_int32,
+                                      C.c_void_p, C.c_int64]
+    L.lra_b200_mapper_create.argtypes = [C.c_void_p, C.POINTER(MapOpts), C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                         C.c_int32, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    L.lra_b200_mapper_destroy.argtypes = [C.c_void_p, C.c_void_p]
+    L.lra_b200_mapper_destroy.restype = None
+    L.lra_b200_map_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(_MapResult)]
     L.lra_b200_last_kernel_stats.argtypes = [C.c_void_p, C.POINTER(KernelStat), C.c_int]
     L.lra_b200_launch_count.argtypes = [C.c_void_p]
     L.lra_b200_launch_count.restype = C.c_uint64
@@ -307,6 +341,78 @@ def init_pwl(gapopen, gapextend, gaproot, ceil1, ceil2):
     stops = np.zeros(25, np.int64); slope = np.zeros(25, np.float32); inter = np.zeros(25, np.float32)
     load_library().lra_b200_init_pwl(gapopen, gapextend, gaproot, ceil1, ceil2, stops.ctypes.data, slope.ctypes.data, inter.ctypes.data)
     return stops, slope, inter, ceil1, ceil2
+
+
+def map_opts_preset(mode):
+    """The align preset of `lra align -ONT | -CLR` (lra.cpp:339-431)."""
+    o = MapOpts()
+    rc = load_library().lra_b200_map_opts_preset(mode.encode(), C.byref(o))
+    if rc:
+        raise LraB200Error(rc, "unknown / unsupported preset %r" % mode)
+    return o
+
+
+def read_mms(path):
+    """<ref>.mms (MMIndex.h:402-424): dict(k, names, pos (cumulative contig offsets), t (uint64 tuples), pos_t (uint32 positions))."""
+    d = open(path, "rb").read()
+    n = int(np.frombuffer(d, np.int64, 1, 0)[0]); k = int(np.frombuffer(d, np.int32, 1, 8)[0])
+    nc = int(np.frombuffer(d, np.int32, 1, 12)[0]); o = 16
+    names = []
+    for _ in range(nc):
+        ln = int(np.frombuffer(d, np.int32, 1, o)[0]); o += 4
+        names.append(d[o:o + ln].decode()); o += ln
+    hdr = np.frombuffer(d, np.uint64, nc + 1, o).copy(); o += 8 * (nc + 1)
+    rec = np.frombuffer(d, np.dtype([("t", "<u8"), ("pos", "<u4"), ("pad", "<u4")]), n, o)
+    return dict(k=k, names=names, hdr=hdr, t=np.ascontiguousarray(rec["t"]), pos=np.ascontiguousarray(rec["pos"]))
+
+
+def _map_result_struct(res):
+    return _MapResult(_ptr(res["status"]), _ptr(res["n_aln"]), _ptr(res["aln_nseg"]), _ptr(res["aln_seg0"]), _ptr(res["aln_rank"]), res["records"].ctypes.data,
+                      len(res["records"]), int(res["n_records"]), _ptr(res["cigar"]), len(res["cigar"]), int(res["n_cigar"]), int(res.get("aligned_bases", 0)))
+
+
+def format_sam(opts, res, names, reads, read_off, read_len, contig_names, runtime=0):
+    """SAM records of a batch (lra_b200_format_sam): Alignment::PrintSAM for every printed segment, SimplePrintSAM for unaligned reads."""
+    L = load_library()
+    ms = _map_result_struct(res)
+    nm = b"".join(n.encode() + b"\0" for n in names); cn = b"".join(n.encode() + b"\0" for n in contig_names)
+    reads = np.ascontiguousarray(reads, np.uint8); ro = np.ascontiguousarray(read_off, np.uint64); rl = np.ascontiguousarray(read_len, np.uint32)
+    need = -L.lra_b200_format_sam(C.byref(opts), C.byref(ms), len(names), nm, reads.ctypes.data, ro.ctypes.data, rl.ctypes.data, cn, len(contig_names), runtime, None, 0)
+    buf = C.create_string_buffer(int(need) + 16)
+    n = L.lra_b200_format_sam(C.byref(opts), C.byref(ms), len(names), nm, reads.ctypes.data, ro.ctypes.data, rl.ctypes.data, cn, len(contig_names), runtime, buf, need + 16)
+    return buf.raw[:n].decode()
+
+
+class Mapper:
+    """lra_b200_mapper: the MapRead seam for one reference (genome + <ref>.mms + <ref>.gli) and one preset."""
+
+    def __init__(self, ctx, opts, genome, hdr, mms, gli=None):
+        self.ctx = ctx; self.opts = opts
+        g = np.ascontiguousarray(genome, np.uint8); hdr = np.ascontiguousarray(hdr, np.uint64)
+        h = C.c_void_p()
+        if gli is not None:
+            so = np.ascontiguousarray(gli["seq_offsets"], np.uint64); tb = np.ascontiguousarray(gli["tuple_boundaries"], np.uint64); mn = np.ascontiguousarray(gli["minimizers"], np.uint32)
+            args = (_ptr(so), _ptr(tb), len(so), _ptr(mn), len(mn))
+        else:
+            args = (None, None, 0, None, 0)
+        t = np.ascontiguousarray(mms["t"], np.uint64); p = np.ascontiguousarray(mms["pos"], np.uint32)
+        ctx._check(ctx.lib.lra_b200_mapper_create(ctx.h, C.byref(opts), _ptr(g), len(g), _ptr(hdr), len(hdr) - 1, _ptr(t), _ptr(p), len(t), *args, C.byref(h)))
+        self.h = h
+
+    def map_batch(self, reads, read_off, read_len, record_cap=None, cigar_cap=None):
+        reads = np.ascontiguousarray(reads, np.uint8); ro = np.ascontiguousarray(read_off, np.uint64); rl = np.ascontiguousarray(read_len, np.uint32)
+        n = len(rl)
+        record_cap = record_cap or 3 * n + 1024; cigar_cap = cigar_cap or int(rl.sum()) + 64 * n + 4096
+        res = dict(status=np.zeros(max(n, 1), np.int32), n_aln=np.zeros(max(n, 1), np.int32), aln_nseg=np.zeros(4 * max(n, 1), np.int32), aln_seg0=np.zeros(4 * max(n, 1), np.int32),
+                   aln_rank=np.zeros(4 * max(n, 1), np.int32), records=np.zeros(record_cap, RECORD), n_records=0, cigar=np.zeros(cigar_cap, np.uint32), n_cigar=0)
+        ms = _map_result_struct(res)
+        self.ctx._check(self.ctx.lib.lra_b200_map_batch(self.ctx.h, self.h, _ptr(reads), len(reads), _ptr(ro), _ptr(rl), n, C.byref(ms)))
+        res["n_records"] = int(ms.n_records); res["n_cigar"] = int(ms.n_cigar); res["aligned_bases"] = int(ms.aligned_bases)
+        return res
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.lra_b200_mapper_destroy(self.ctx.h, self.h); self.h = None
 
 
 def _ptr(a):

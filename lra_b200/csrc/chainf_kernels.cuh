@@ -25,9 +25,7 @@ struct ChainfBatch {
 __device__ __forceinline__ int cf_sgn(int v) { return v >= 0; }
 __device__ __forceinline__ int cf_abs(int v) { return v < 0 ? -v : v; }
 
-__global__ void __launch_bounds__(128) chainf_kernel(ChainfBatch b) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= b.n_chains) return;
+__device__ __noinline__ void chainf_one(const ChainfBatch &b, const int ch) {
   const unsigned long long o = b.off[ch];
   const int n = (int)(b.off[ch + 1] - o);
   const uint32_t *q = b.q + o, *t = b.t + o, *len = b.len + o;
@@ -119,6 +117,12 @@ __global__ void __launch_bounds__(128) chainf_kernel(ChainfBatch b) {
       if (keep[SVpos[c - 1]] == 1 && cf_sgn(SV[c]) != cf_sgn(SV[c - 1]) && SV[c] != 0 && SV[c - 1] != 0 && SVpos[c] - SVpos[c - 1] == 1)
         for (int i = SVpos[c - 1]; i < SVpos[c]; i++) if (len[i] < 50) keep[i] = 0;
   }
+}
+
+__global__ void __launch_bounds__(128) chainf_kernel(ChainfBatch b) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= b.n_chains) return;
+  chainf_one(b, ch);
 }
 
 }  // namespace lra

@@ -87,9 +87,7 @@ __device__ __forceinline__ void cod_second_round(int32_t *count, int out_counter
   for (int i = os; i < oe; i++) { if (fw[i] && rv[i]) { orig[i] = 1; count[i] = out_counter; } else orig[i] = 0; }
 }
 
-__global__ void __launch_bounds__(64) cod_kernel(CodBatch b) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= b.n_lists) return;
+__device__ __noinline__ void cod_one(const CodBatch &b, const int s) {
   const unsigned long long o = b.off[s];
   const int n = (int)(b.off[s + 1] - o);
   const uint32_t *q = b.q + o, *t = b.t + o;
@@ -177,6 +175,12 @@ __global__ void __launch_bounds__(64) cod_kernel(CodBatch b) {
   }
   if (m > 0) emit(m);
   b.n_cl[s] = ncl;
+}
+
+__global__ void __launch_bounds__(64) cod_kernel(CodBatch b) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= b.n_lists) return;
+  cod_one(b, s);
 }
 
 }  // namespace lra

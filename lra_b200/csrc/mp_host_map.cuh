@@ -1,0 +1,368 @@
+// Host side of the MapRead seam (included at the end of lra_b200.cu): the align presets, lra_b200_mapper_create / lra_b200_map_batch /
+// lra_b200_mapper_destroy (packs the reads, builds their LocalIndex images, runs the mapper worker kernel, the a19 / a21 batch kernels and the
+// finalize kernel, copies the records home) and the SAM emitter (Alignment::PrintSAM, host code).
+#pragma once
+#include <sstream>
+#include <algorithm>
+#include "mp_map.cuh"
+
+// ---- presets (lra.cpp:339-431 on top of Options.h:123-240) -------------------------------------------------------------------------------------
+extern "C" int lra_b200_map_opts_preset(const char *mode, lra_b200_map_opts *o) {
+  if (!mode || !o) return LRA_B200_EINVAL;
+  memset(o, 0, sizeof *o);
+  // defaults
+  o->globalK = 17; o->globalW = 10; o->globalMaxFreq = 50; o->localW = 5; o->localMaxFreq = 30; o->smallK = 10; o->smallW = 5;
+  o->cleanMaxDiag = 100; o->minDiagCluster = 10; o->cleanClustersize = 100; o->SecondCleanMinDiagCluster = 40; o->SecondCleanMaxDiag = 10; o->punish_anchorfreq = 10;
+  o->anchorPerlength = 10; o->NumAln = 3; o->PrintNumAln = 1; o->splitdist = 50000; o->readType = 0;
+  o->initial_anchorbonus = 1.0f; o->second_anchorbonus = 2.0f; o->alnthres = 0.7f; o->anchorstoosparse = 0.01f;
+  o->refineSpaceDist = 10000; o->window = 100; o->limitrefine = 1; o->RefineBySDP = 1;
+  o->localMatch = 4; o->localMismatch = -3; o->localIndel = -4; o->localBand = 15; o->refineBand = 7; o->hardClip = 0; o->bypassClustering = 0;
+  o->gapopen = 2.0f; o->gapextend = 10.0f; o->gaproot = 2.0f; o->gapCeiling1 = 1500; o->gapCeiling2 = 3000; o->localIndexWindow = 2048; o->localIndexMaxFreq = 15;
+  std::string m(mode);
+  if (!m.empty() && m[0] == '-') m = m.substr(1);
+  for (auto &c : m) c = (char)toupper(c);
+  if (m == "CLR") {
+    o->globalK = 15; o->globalW = 10; o->globalMaxFreq = 250; o->localW = 5; o->localMaxFreq = 15; o->readType = 1; o->refineBand = 20;
+    o->gaproot = 1.5f; o->gapextend = 10.0f; o->gapopen = 7.0f; o->initial_anchorbonus = 15.0f; o->localMismatch = -1; o->localIndel = -2;
+    o->gapCeiling1 = 1500; o->gapCeiling2 = 3000; o->NumAln = 2; o->PrintNumAln = 1; o->cleanMaxDiag = 200; o->SecondCleanMaxDiag = 120; o->SecondCleanMinDiagCluster = 10;
+    o->refineSpaceDist = 30000; o->minDiagCluster = 3; o->bypassClustering = 1; o->punish_anchorfreq = 5; o->anchorPerlength = 5; o->cleanClustersize = 100;
+    o->anchorstoosparse = 0.005f; o->hardClip = 1; o->alnthres = 0.50f; o->second_anchorbonus = 6.0f;
+  } else if (m == "ONT") {
+    o->globalK = 17; o->globalW = 10; o->globalMaxFreq = 150; o->localW = 5; o->localMaxFreq = 15; o->readType = 0;
+    o->gaproot = 1.5f; o->gapextend = 10.0f; o->gapopen = 7.0f; o->initial_anchorbonus = 20.0f; o->localMismatch = -1; o->localIndel = -2;
+    o->gapCeiling1 = 1500; o->gapCeiling2 = 3000; o->NumAln = 2; o->PrintNumAln = 1; o->cleanMaxDiag = 200; o->SecondCleanMaxDiag = 100; o->SecondCleanMinDiagCluster = 10;
+    o->refineSpaceDist = 30000; o->minDiagCluster = 3; o->bypassClustering = 1; o->punish_anchorfreq = 5; o->anchorPerlength = 5; o->cleanClustersize = 100;
+    o->anchorstoosparse = 0.005f; o->hardClip = 1; o->alnthres = 0.65f;
+  } else return LRA_B200_EINVAL;      // the high-accuracy presets (-CCS, -CONTIG) take MapRead_highacc, which this library does not map yet
+  return LRA_B200_OK;
+}
+
+// ---- SAM emitter (Alignment.h:658-808, 811-832; Mapping_ultility.h:457-494) -------------------------------------------------------------------
+static void mp_cigar_string(const uint32_t *cig, int n, std::string &out) {
+  static const char ops[] = "MIDNSHP=X";
+  char buf[16];
+  for (int i = 0; i < n; i++) { const int l = snprintf(buf, sizeof buf, "%u%c", cig[i] >> 4, ops[cig[i] & 15u]); out.append(buf, l); }
+}
+static const unsigned char *mp_revcomp_table() {
+  static unsigned char T[256]; static bool init = false;
+  if (!init) { for (int i = 0; i < 256; i++) T[i] = 'N'; T['A'] = 'T'; T['C'] = 'G'; T['G'] = 'C'; T['T'] = 'A'; T['a'] = 't'; T['c'] = 'g'; T['g'] = 'c'; T['t'] = 'a'; T['n'] = 'n'; init = true; }
+  return T;
+}
+
+extern "C" int64_t lra_b200_format_sam(const lra_b200_map_opts *opts, const lra_b200_map_result *res, int32_t n_reads, const char *names, const char *reads_ascii,
+                                       const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, int32_t n_contigs, int32_t runtime, char *out,
+                                       int64_t cap) {
+  if (!opts || !res || n_reads < 0 || !names || !reads_ascii || !read_off || !read_len || !contig_names) return 0;
+  std::vector<const char *> cname(n_contigs);
+  { const char *p = contig_names; for (int c = 0; c < n_contigs; c++) { cname[c] = p; p += strlen(p) + 1; } }
+  const unsigned char *RC = mp_revcomp_table();
+  std::string text, rc, cig, sa;
+  const char *np = names;
+  for (int r = 0; r < n_reads; r++) {
+    const char *name = np; np += strlen(np) + 1;
+    const char *seq = reads_ascii + read_off[r]; const uint32_t L = read_len[r];
+    const int na = res->status[r] == 0 ? res->n_aln[r] : 0;
+    bool printed = false;
+    if (na > 0 && res->aln_nseg[4 * r + res->aln_rank[4 * r]] > 0) {
+      bool have_rc = false;
+      const int lim = na < opts->PrintNumAln ? na : opts->PrintNumAln;
+      for (int a = 0; a < lim; a++) {
+        const int slot = res->aln_rank[4 * r + a];
+        const int ns = res->aln_nseg[4 * r + slot], s0 = res->aln_seg0[4 * r + slot];
+        for (int s = ns - 1; s >= 0; s--) {
+          const lra_b200_record &x = res->records[s0 + s];
+          printed = true;
+          std::ostringstream o;
+          o << name << "\t";
+          const char *rd = seq;
+          if (x.strand == 1) {
+            if (!have_rc) { rc.resize(L); for (uint32_t i = 0; i < L; i++) rc[L - 1 - i] = (char)RC[(unsigned char)seq[i]]; have_rc = true; }
+            rd = rc.data();
+          }
+          if (x.n_blocks == 0) { o << "4\t*\t0\t0\t*\t*\t0\t0\t"; o.write(rd, L); o << "\t*"; }
+          else {
+            o << (unsigned int)x.flag << "\t" << cname[x.chrom] << "\t" << x.tStart + 1 << "\t" << (unsigned int)(unsigned char)x.mapq << "\t";
+            char clipOp = 'S';
+            if (x.supplementary && opts->hardClip) clipOp = 'H';
+            if (x.preClip > 0) o << x.preClip << clipOp;
+            cig.clear(); mp_cigar_string(res->cigar + x.cigar_off, x.n_cigar, cig);
+            o << cig;
+            if (x.sufClip > 0) o << x.sufClip << clipOp;
+            o << "\t*\t0\t" << x.tEnd - x.tStart << "\t";
+            if (!x.supplementary) o.write(rd, L);
+            else if (opts->hardClip) o.write(rd + x.qStart, x.qEnd - x.qStart);
+            else o.write(rd, L);
+            o << "\t*";
+            o << "\tNM:i:" << x.nmm + x.ndel + x.nins << "\tMM:i:" << x.nmm + x.ndel + x.nins << "\tNX:i:" << x.nmm << "\tND:i:" << x.ndel << "\tTD:i:" << x.tdel
+              << "\tNI:i:" << x.nins << "\tTI:i:" << x.tins << "\tNV:f:" << x.value << "\tAS:i:" << (int)x.value << "\tAO:i:" << x.order << "\tN0:i:" << x.NumOfAnchors0
+              << "\tRT:i:" << runtime;
+            o << "\tTP:A:" << (x.typeofaln == 0 ? "P" : (x.typeofaln == 1 ? "S" : "I"));
+            o << "\tSD:i:" << x.nSmallDel << "\tME:i:" << x.nMedDel << "\tLD:i:" << x.nLargeDel << "\tSI:i:" << x.nSmallIns << "\tMI:i:" << x.nMedIns << "\tLI:i:" << x.nLargeIns;
+            if (ns > 1) o << "\tSA:Z:";
+            for (int ag = ns - 1; ag >= 0; ag--) {
+              if (ag == s) continue;
+              const lra_b200_record &y = res->records[s0 + ag];
+              o << (y.n_blocks == 0 ? "*" : cname[y.chrom]) << "," << y.tStart + 1 << "," << (y.strand == 0 ? "+" : "-") << ",";
+              if (y.preClip > 0) o << y.preClip << 'S';
+              cig.clear(); mp_cigar_string(res->cigar + y.cigar_off, y.n_cigar, cig);
+              o << cig;
+              if (y.sufClip > 0) o << y.sufClip << 'S';
+              o << "," << (unsigned int)(unsigned char)y.mapq << "," << y.nm << ";";
+            }
+          }
+          o << "\n";
+          text += o.str();
+        }
+      }
+    }
+    if (!printed) {      // output_unaligned -> SimplePrintSAM of an Alignment without blocks
+      text += name; text += "\t4\t*\t0\t0\t*\t*\t0\t0\t"; text.append(seq, L); text += "\t*\n";
+    }
+  }
+  if ((int64_t)text.size() > cap || !out) return -(int64_t)text.size();
+  memcpy(out, text.data(), text.size());
+  return (int64_t)text.size();
+}
+
+// ---- the mapper ---------------------------------------------------------------------------------------------------------------------------------
+struct lra_b200_mapper {
+  lra_b200_map_opts opts;
+  lra_b200_seq *genome = nullptr;
+  lra_b200_index *index = nullptr;
+  lra_b200_lindex *gl = nullptr;
+  unsigned long long *d_hdr = nullptr; int n_hdr = 0;
+  std::vector<uint64_t> h_hdr;
+  lra::mp::Pwl *d_pwl = nullptr;
+  float log_lut[2001];
+  float logf_len[8];
+  // per batch
+  lra_b200_seq *reads = nullptr;          // forward strands at [0, Npad), reverse complements at [Npad, 2 Npad)
+  lra_b200_lindex *rl[2] = {nullptr, nullptr};
+  DevBuf b[40];
+  int *h_pin = nullptr;
+};
+
+struct lra_b200_index_internal_view { const unsigned long long *t; const uint32_t *pos; uint64_t n; };
+
+namespace lra { namespace mp {
+// SegRec -> the a19 / a21 segment arrays
+__global__ void seg_to_ir_kernel(const SegRec *seg, int n, const unsigned long long *read_off, const uint32_t *read_len, unsigned long long rc_shift,
+                                 const unsigned long long *hdr_pos, unsigned long long *blk_off, int32_t *blk_cnt, uint32_t *q_base, uint32_t *t_base, int32_t *rlen,
+                                 int32_t *clen) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const SegRec x = seg[s];
+  blk_off[s] = x.blk_off; blk_cnt[s] = x.blk_cnt;
+  q_base[s] = (uint32_t)(read_off[x.read] + (x.strand ? rc_shift : 0ull));
+  t_base[s] = (uint32_t)hdr_pos[x.chrom];
+  rlen[s] = (int32_t)read_len[x.read]; clen[s] = (int32_t)(hdr_pos[x.chrom + 1] - hdr_pos[x.chrom]);
+}
+}}
+
+extern "C" void lra_b200_mapper_destroy(lra_b200_ctx *ctx, lra_b200_mapper *m) {
+  if (!m) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  if (m->genome) lra_b200_seq_free(ctx, m->genome);
+  if (m->index) lra_b200_index_free(ctx, m->index);
+  if (m->gl) lra_b200_lindex_free(ctx, m->gl);
+  if (m->reads) lra_b200_seq_free(ctx, m->reads);
+  for (int s = 0; s < 2; s++) if (m->rl[s]) lra_b200_lindex_free(ctx, m->rl[s]);
+  if (m->d_hdr) cudaFree(m->d_hdr);
+  if (m->d_pwl) cudaFree(m->d_pwl);
+  for (DevBuf &b : m->b) if (b.p) cudaFree(b.p);
+  if (m->h_pin) cudaFreeHost(m->h_pin);
+  delete m;
+}
+
+extern "C" int lra_b200_mapper_create(lra_b200_ctx *ctx, const lra_b200_map_opts *opts, const char *genome_ascii, uint64_t genome_len, const uint64_t *hdr_pos,
+                                      int32_t n_contigs, const uint64_t *mms_t, const uint32_t *mms_pos, uint64_t n_mms, const uint64_t *gli_seq_offsets,
+                                      const uint64_t *gli_tuple_boundaries, int32_t gli_n_regions, const uint32_t *gli_minimizers, uint64_t gli_n_min,
+                                      lra_b200_mapper **out) {
+  if (!ctx || !opts || !genome_ascii || !hdr_pos || n_contigs < 1 || !mms_t || !mms_pos || !out) return fail(ctx, LRA_B200_EINVAL, "mapper_create: NULL argument");
+  if (!opts->bypassClustering) return fail(ctx, LRA_B200_EINVAL, "mapper_create: only the low-accuracy presets (-ONT, -CLR: MapRead_lowacc) are implemented");
+  if (hdr_pos[n_contigs] != genome_len || genome_len >= (1ull << 32)) return fail(ctx, LRA_B200_EINVAL, "mapper_create: header offsets do not cover the genome (or >= 2^32 bases)");
+  *out = nullptr;
+  CU(cudaSetDevice(ctx->device));
+  lra_b200_mapper *m = new lra_b200_mapper();
+  m->opts = *opts;
+  int rc;
+  if ((rc = lra_b200_seq_upload(ctx, genome_ascii, genome_len, &m->genome))) { lra_b200_mapper_destroy(ctx, m); return rc; }
+  if ((rc = lra_b200_index_upload(ctx, mms_t, mms_pos, n_mms, &m->index))) { lra_b200_mapper_destroy(ctx, m); return rc; }
+  std::vector<uint64_t> starts(n_contigs); std::vector<uint32_t> lens(n_contigs);
+  for (int c = 0; c < n_contigs; c++) { starts[c] = hdr_pos[c]; lens[c] = (uint32_t)(hdr_pos[c + 1] - hdr_pos[c]); }
+  if (gli_seq_offsets && gli_tuple_boundaries && gli_n_regions > 0) {
+    (void)gli_n_min;
+    rc = lra_b200_lindex_upload(ctx, starts.data(), lens.data(), n_contigs, opts->localIndexWindow, gli_seq_offsets, gli_tuple_boundaries, gli_minimizers,
+                                (uint64_t)gli_n_regions - 1, &m->gl);
+  } else rc = lra_b200_lindex_build(ctx, m->genome, starts.data(), lens.data(), n_contigs, opts->smallK, opts->smallW, opts->localIndexWindow, opts->localIndexMaxFreq, &m->gl);
+  if (rc) { lra_b200_mapper_destroy(ctx, m); return rc; }
+  m->n_hdr = n_contigs; m->h_hdr.assign(hdr_pos, hdr_pos + n_contigs + 1);
+  if (cudaMalloc(&m->d_hdr, (size_t)(n_contigs + 1) * 8) != cudaSuccess || cudaMalloc(&m->d_pwl, sizeof(lra::mp::Pwl)) != cudaSuccess ||
+      cudaHostAlloc((void **)&m->h_pin, 256, cudaHostAllocDefault) != cudaSuccess) { lra_b200_mapper_destroy(ctx, m); return fail(ctx, LRA_B200_ECUDA, "mapper_create: allocation failed"); }
+  lra::mp::Pwl hp; int64_t stops[25]; float slope[25], inter[25];
+  lra_b200_init_pwl(opts->gapopen, opts->gapextend, opts->gaproot, opts->gapCeiling1, opts->gapCeiling2, stops, slope, inter);
+  mp_fill_pwl(hp, stops, slope, inter, opts->gapCeiling1, opts->gapCeiling2);
+  cudaMemcpyAsync(m->d_hdr, hdr_pos, (size_t)(n_contigs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(m->d_pwl, &hp, sizeof hp, cudaMemcpyHostToDevice, ctx->stream);
+  CU(cudaStreamSynchronize(ctx->stream));
+  // CreateLookUpTable (LogLookUpTable.h:9-15) with the host logf
+  { int k = 0; for (int i = 1; i <= 10001; i += 5) m->log_lut[k++] = logf((float)i); }
+  for (int i = 0; i < 8; i++) m->logf_len[i] = i > 0 ? logf((float)i) : 0.0f;
+  *out = m;
+  return LRA_B200_OK;
+}
+
+extern "C" int lra_b200_map_batch(lra_b200_ctx *ctx, lra_b200_mapper *m, const char *reads_ascii, uint64_t reads_len, const uint64_t *read_off, const uint32_t *read_len,
+                                  int32_t n_reads, lra_b200_map_result *res) {
+  using namespace lra::mp;
+  if (!ctx || !m || !res || n_reads < 0 || (n_reads && (!reads_ascii || !read_off || !read_len))) return fail(ctx, LRA_B200_EINVAL, "map_batch: NULL argument");
+  if (!res->status || !res->n_aln || !res->aln_nseg || !res->aln_seg0 || !res->aln_rank || !res->records || !res->cigar) return fail(ctx, LRA_B200_EINVAL, "map_batch: NULL result array");
+  CU(cudaSetDevice(ctx->device));
+  res->n_records = 0; res->n_cigar = 0; res->aligned_bases = 0;
+  std::vector<lra_b200_kernel_stat> all;
+  if (n_reads == 0) { ctx->stats.clear(); return LRA_B200_OK; }
+  uint32_t maxL = 0;
+  for (int r = 0; r < n_reads; r++) {
+    if (read_off[r] + read_len[r] > reads_len) return fail(ctx, LRA_B200_EINVAL, "map_batch: read %d ends beyond the buffer", r);
+    if (r && read_off[r] < read_off[r - 1] + read_len[r - 1]) return fail(ctx, LRA_B200_EINVAL, "map_batch: reads overlap or are not in ascending order at %d", r);
+    maxL = read_len[r] > maxL ? read_len[r] : maxL;
+  }
+  const unsigned long long Npad = ((unsigned long long)reads_len + 127ull) & ~63ull;
+  if (2 * Npad >= (1ull << 32)) return fail(ctx, LRA_B200_EINVAL, "map_batch: more than 2^31 bases in one batch");
+  cudaStream_t st = ctx->stream;
+  int rc;
+  // ---- reads: pack the forward strands into [0, Npad), reverse complements into [Npad, 2 Npad)
+  if (!m->reads) m->reads = new lra_b200_seq();
+  if ((rc = seq_reserve(ctx, m->reads, 2 * Npad))) return rc;
+  CU(cudaMemsetAsync(m->reads->b2, 0, (m->reads->cap_groups * 2 + 8) * 4, st));
+  CU(cudaMemsetAsync(m->reads->nm, 0xFF, (m->reads->cap_groups + 8) * 4, st));
+  if (reads_len + 64 > m->reads->ascii_cap) {
+    if (m->reads->ascii_dev) { CU(cudaStreamSynchronize(st)); CU(cudaFree(m->reads->ascii_dev)); m->reads->ascii_dev = nullptr; }
+    const uint64_t cap = reads_len + reads_len / 4 + 256;
+    CU(cudaMalloc((void **)&m->reads->ascii_dev, cap)); m->reads->ascii_cap = cap;
+  }
+  CU(cudaMemcpyAsync(m->reads->ascii_dev, reads_ascii, reads_len, cudaMemcpyHostToDevice, st));
+  { const uint64_t groups = (reads_len + 31) / 32 + 1;
+    lra::seq_pack_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(m->reads->ascii_dev, reads_len, m->reads->b2, m->reads->nm, groups); ctx->launches++; }
+  m->reads->n = 2 * Npad;
+  DevBuf *B = m->b;
+  if ((rc = ensure(ctx, B[0], (size_t)n_reads * 8)) || (rc = ensure(ctx, B[1], (size_t)n_reads * 4))) return rc;
+  CU(cudaMemcpyAsync(B[0].p, read_off, (size_t)n_reads * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B[1].p, read_len, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
+  lra::seq_revcomp_kernel<<<(unsigned)((n_reads + 7) / 8), 256, 0, st>>>(lra::SeqView{m->reads->b2, m->reads->nm, Npad}, (const unsigned long long *)B[0].p,
+                                                                         (const uint32_t *)B[1].p, n_reads, m->reads->b2 + Npad / 16, m->reads->nm + Npad / 32);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  // ---- a12: LocalIndex::IndexSeq of every read, both strands (Map_lowacc.h:246-250)
+  std::vector<uint64_t> rc_off(n_reads);
+  for (int r = 0; r < n_reads; r++) rc_off[r] = read_off[r] + Npad;
+  ctx->keep_stats = false;
+  if ((rc = lra_b200_lindex_build(ctx, m->reads, read_off, read_len, n_reads, m->opts.smallK, m->opts.smallW, m->opts.localIndexWindow, m->opts.localIndexMaxFreq, &m->rl[0]))) return rc;
+  all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
+  if ((rc = lra_b200_lindex_build(ctx, m->reads, rc_off.data(), read_len, n_reads, m->opts.smallK, m->opts.smallW, m->opts.localIndexWindow, m->opts.localIndexMaxFreq, &m->rl[1]))) return rc;
+  all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
+  // ---- the mapper worker kernel
+  unsigned long long total_bases = 0; for (int r = 0; r < n_reads; r++) total_bases += read_len[r];
+  const size_t seg_cap = (size_t)n_reads * 3 + 1024;
+  const size_t blk_cap = (size_t)(total_bases / 2) + (size_t)n_reads * 64 + 4096;
+  int warps = ctx->n_sm * 8; if (warps > n_reads) warps = n_reads;
+  size_t per = (size_t)maxL * 1536 + (24u << 20);
+  size_t free_b = 0, tot_b = 0; cudaMemGetInfo(&free_b, &tot_b);
+  while ((size_t)warps * per > free_b / 2 && warps > ctx->n_sm) warps -= ctx->n_sm;
+  if ((rc = ensure(ctx, B[2], (size_t)n_reads * 4)) || (rc = ensure(ctx, B[3], (size_t)n_reads * 4)) || (rc = ensure(ctx, B[4], (size_t)n_reads * 16)) ||
+      (rc = ensure(ctx, B[5], (size_t)n_reads * 16)) || (rc = ensure(ctx, B[6], seg_cap * sizeof(SegRec))) || (rc = ensure(ctx, B[7], blk_cap * 12)) ||
+      (rc = ensure(ctx, B[8], 256)) || (rc = ensure(ctx, B[9], (size_t)warps * per)) || (rc = ensure(ctx, B[10], (size_t)n_reads * 4)))
+    return rc;
+  CU(cudaMemsetAsync(B[8].p, 0, 256, st));
+  // longest reads first (the tail of the batch is then made of short reads)
+  { std::vector<int> ord(n_reads); for (int r = 0; r < n_reads; r++) ord[r] = r;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return read_len[a] > read_len[b2]; });
+    CU(cudaMemcpyAsync(B[10].p, ord.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, st)); CU(cudaStreamSynchronize(st)); }
+  MapBatch mb;
+  mb.C.o = m->opts; mb.C.pwl = m->d_pwl;
+  mb.C.ix.genome = lra::SeqView{m->genome->b2, m->genome->nm, m->genome->n}; mb.C.ix.hdr_pos = m->d_hdr; mb.C.ix.n_hdr = m->n_hdr;
+  mb.C.ix.idx_t = (const unsigned long long *)m->index->t; mb.C.ix.idx_pos = m->index->pos; mb.C.ix.n_idx = (long long)m->index->n;
+  mb.C.ix.gl = lidx_view(m->gl);
+  mb.C.rd.fwd = lra::SeqView{m->reads->b2, m->reads->nm, Npad}; mb.C.rd.rc = lra::SeqView{m->reads->b2 + Npad / 16, m->reads->nm + Npad / 32, Npad};
+  mb.C.rd.read_off = (const unsigned long long *)B[0].p; mb.C.rd.read_len = (const uint32_t *)B[1].p; mb.C.rd.n_reads = n_reads;
+  mb.C.rd.rd[0] = lidx_view(m->rl[0]); mb.C.rd.rd[1] = lidx_view(m->rl[1]);
+  // (the reverse-complement image was built over arena offsets read_off + Npad; the worker only uses window offsets relative to the image's own seq_start)
+  mb.out.status = (int *)B[2].p; mb.out.n_chains = (int *)B[3].p; mb.out.chain_nseg = (int *)B[4].p; mb.out.chain_seg0 = (int *)B[5].p;
+  mb.out.seg = (SegRec *)B[6].p; mb.out.seg_cap = (int)seg_cap; mb.out.seg_cursor = (unsigned long long *)B[8].p; mb.out.blocks = (uint32_t *)B[7].p; mb.out.blk_cap = blk_cap;
+  mb.out.blk_cursor = (unsigned long long *)((char *)B[8].p + 8); mb.out.err = (int *)((char *)B[8].p + 16); mb.out.peak = (unsigned long long *)((char *)B[8].p + 24);
+  mb.arena = (unsigned char *)B[9].p; mb.arena_per_warp = per; mb.work = (int *)((char *)B[8].p + 32); mb.order = (const int *)B[10].p;
+  cudaEventRecord(ctx->ev[0], st);
+  map_reads_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(mb);
+  cudaEventRecord(ctx->ev[1], st);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  unsigned long long hcur[4];
+  CU(cudaMemcpyAsync(hcur, B[8].p, 32, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  { lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "map_reads"); cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]);
+    s2.jobs = (uint64_t)n_reads; s2.algo_bytes = total_bases + 2 * ((total_bases + 3) / 4); all.push_back(s2); }
+  const int S = (int)(hcur[0] >> 40); const unsigned long long NB = hcur[0] & ((1ull << 40) - 1ull);
+  const int kerr = (int)(hcur[2] & 0xffffffffull);
+  if (kerr & 3) return fail(ctx, LRA_B200_EOVERFLOW, "map_batch: segment / block capacity exceeded (%d segments, %llu blocks)", S, NB);
+  if ((uint64_t)S > res->record_cap) { res->n_records = (uint64_t)S; return fail(ctx, LRA_B200_EOVERFLOW, "map_batch: record capacity %llu too small, %d needed", (unsigned long long)res->record_cap, S); }
+  // ---- a19 IndelRefineAlignment and a21 CalculateStatistics over all segments
+  if ((rc = ensure(ctx, B[11], (size_t)(S + 1) * 8)) || (rc = ensure(ctx, B[12], (size_t)(S + 1) * 4)) || (rc = ensure(ctx, B[13], (size_t)(S + 1) * 4)) ||
+      (rc = ensure(ctx, B[14], (size_t)(S + 1) * 4)) || (rc = ensure(ctx, B[15], (size_t)(S + 1) * 4)) || (rc = ensure(ctx, B[16], (size_t)(S + 1) * 4)))
+    return rc;
+  const size_t ir_cap = (size_t)NB * 2 + (size_t)S * 64 + 1024;
+  const size_t cig_cap = (size_t)total_bases / 2 + (size_t)NB * 4 + (size_t)S * 16 + 1024;
+  if ((rc = ensure(ctx, B[17], (size_t)(S + 1) * 4)) || (rc = ensure(ctx, B[18], (size_t)(S + 1) * 8)) || (rc = ensure(ctx, B[19], ir_cap * 12)) ||
+      (rc = ensure(ctx, B[20], (size_t)(S + 1) * 64)) || (rc = ensure(ctx, B[21], (size_t)(S + 1) * 4)) || (rc = ensure(ctx, B[22], (size_t)(S + 2) * 8)) ||
+      (rc = ensure(ctx, B[23], cig_cap * 4)) || (rc = ensure(ctx, B[24], (size_t)(S + 1) * sizeof(lra_b200_record))) || (rc = ensure(ctx, B[25], (size_t)n_reads * 16)) ||
+      (rc = ensure(ctx, B[26], 64)))
+    return rc;
+  lra_b200_ir_seg_result ir; memset(&ir, 0, sizeof ir);
+  lra_b200_stats_result sr; memset(&sr, 0, sizeof sr);
+  if (S > 0) {
+    seg_to_ir_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>((const SegRec *)B[6].p, S, (const unsigned long long *)B[0].p, (const uint32_t *)B[1].p, Npad, m->d_hdr,
+                                                                 (unsigned long long *)B[11].p, (int32_t *)B[12].p, (uint32_t *)B[13].p, (uint32_t *)B[14].p, (int32_t *)B[15].p,
+                                                                 (int32_t *)B[16].p);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    lra_b200_ir_segments sg; memset(&sg, 0, sizeof sg);
+    sg.blocks_in = (const uint32_t *)B[7].p; sg.blk_off = (const uint64_t *)B[11].p; sg.blk_cnt = (const int32_t *)B[12].p; sg.q_base = (const uint32_t *)B[13].p;
+    sg.t_base = (const uint32_t *)B[14].p; sg.read_len = (const int32_t *)B[15].p; sg.contig_len = (const int32_t *)B[16].p; sg.n_blocks_in = NB; sg.n_segments = S;
+    sg.refine_band = m->opts.refineBand; sg.match = m->opts.localMatch; sg.mismatch = m->opts.localMismatch; sg.indel = m->opts.localIndel; sg.end_align = 0;
+    ir.n_blocks = (int32_t *)B[17].p; ir.block_off = (uint64_t *)B[18].p; ir.blocks = (uint32_t *)B[19].p; ir.block_cap = ir_cap;
+    if ((rc = lra_b200_indel_refine_batch_device(ctx, m->reads, m->genome, &sg, &ir))) return rc;
+    all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
+    lra_b200_ir_segments s2 = sg;
+    s2.blocks_in = ir.blocks; s2.blk_off = ir.block_off; s2.blk_cnt = ir.n_blocks; s2.n_blocks_in = ir.n_blocks_total;
+    sr.stats = (int32_t *)B[20].p; sr.value = (float *)B[21].p; sr.cigar_off = (uint64_t *)B[22].p; sr.cigar = (uint32_t *)B[23].p; sr.cigar_cap = cig_cap;
+    if ((rc = lra_b200_calc_stats_batch_device(ctx, m->reads, m->genome, &s2, m->log_lut, &sr))) return rc;
+    all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
+  }
+  // ---- finalize
+  CU(cudaMemcpyAsync(B[26].p, m->logf_len, 32, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync((char *)B[26].p + 32, 0, 8, st));
+  FinalBatch fb;
+  fb.n_reads = n_reads; fb.o = m->opts; fb.read_off = (const unsigned long long *)B[0].p; fb.read_len = (const uint32_t *)B[1].p; fb.status = (const int *)B[2].p;
+  fb.n_chains = (const int *)B[3].p; fb.chain_nseg = (const int *)B[4].p; fb.chain_seg0 = (const int *)B[5].p; fb.seg = (const SegRec *)B[6].p;
+  fb.ir_nblk = (const int32_t *)B[17].p; fb.ir_off = (const unsigned long long *)B[18].p; fb.ir_blocks = (const uint32_t *)B[19].p;
+  fb.stats = (const int32_t *)B[20].p; fb.value = (const float *)B[21].p; fb.cigar_off = (const unsigned long long *)B[22].p; fb.logf_len = (const float *)B[26].p;
+  fb.rec = (lra_b200_record *)B[24].p; fb.rank = (int *)B[25].p; fb.aligned_bases = (unsigned long long *)((char *)B[26].p + 32);
+  map_finalize_kernel<<<(unsigned)((n_reads + 127) / 128), 128, 0, st>>>(fb);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  // ---- records home
+  CU(cudaMemcpyAsync(res->status, B[2].p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->n_aln, B[3].p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->aln_nseg, B[4].p, (size_t)n_reads * 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->aln_seg0, B[5].p, (size_t)n_reads * 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res->aln_rank, B[25].p, (size_t)n_reads * 16, cudaMemcpyDeviceToHost, st));
+  if (S > 0) CU(cudaMemcpyAsync(res->records, B[24].p, (size_t)S * sizeof(lra_b200_record), cudaMemcpyDeviceToHost, st));
+  if (sr.n_cigar_total > res->cigar_cap) { res->n_cigar = sr.n_cigar_total; return fail(ctx, LRA_B200_EOVERFLOW, "map_batch: cigar capacity %llu too small, %llu needed", (unsigned long long)res->cigar_cap, (unsigned long long)sr.n_cigar_total); }
+  if (sr.n_cigar_total) CU(cudaMemcpyAsync(res->cigar, B[23].p, (size_t)sr.n_cigar_total * 4, cudaMemcpyDeviceToHost, st));
+  unsigned long long ab = 0;
+  CU(cudaMemcpyAsync(&ab, (char *)B[26].p + 32, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  res->n_records = (uint64_t)S; res->n_cigar = sr.n_cigar_total; res->aligned_bases = ab;
+  ctx->stats = all;
+  if (kerr & 4) return fail(ctx, LRA_B200_EINTERNAL, "map_batch: worker scratch exhausted inside TrimOverlappedAnchors");
+  return LRA_B200_OK;
+}

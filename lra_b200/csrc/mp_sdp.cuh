@@ -45,7 +45,7 @@ struct SdpFam {
 // lanes grow the lists of different sub-problems concurrently.  (The reference re-runs Maximization over entries it has
 // already seen whenever `now` moves backwards, so the lists have no bound in terms of m.)
 struct SdpDyn { unsigned long long *top; unsigned char *base; unsigned long long cap; int *err; unsigned long long base_off; };
-__device__ inline bool sdp_grow(const SdpDyn &D, int2 *&arr, int &cap, int used) {
+__device__ __noinline__ bool sdp_grow(const SdpDyn &D, int2 *&arr, int &cap, int used) {
   const int ncap = cap * 2 + 16;
   const unsigned long long bytes = ((unsigned long long)ncap * sizeof(int2) + 15ull) & ~15ull;
   const unsigned long long off = atomicAdd(D.top, bytes);
@@ -117,7 +117,7 @@ __device__ __forceinline__ int sdp_find_boundary(int first, int last, int a, int
 // Maximization (SubRountine.h:357-458): advances the candidate list of one sub-problem from `last` to `now`
 #define SDP_PUSH_B(v) do { if (nB >= s.capB && !sdp_grow(D, s.Bk, s.capB, nB)) { s.nS = nS; s.nB = nB; return false; } s.Bk[nB++] = (v); } while (0)
 #define SDP_PUSH_S(v) do { if (nS >= s.capS && !sdp_grow(D, s.S, s.capS, nS)) { s.nS = nS; s.nB = nB; return false; } s.S[nS++] = (v); } while (0)
-__device__ inline bool sdp_maximization(SdpSub &s, const Pwl &P, const SdpDyn &D) {
+__device__ __noinline__ bool sdp_maximization(SdpSub &s, const Pwl &P, const SdpDyn &D) {
   const int n = s.n, m = s.m;
   int nS = s.nS, nB = s.nB;
   for (unsigned i = (unsigned)(s.last + 1); i <= (unsigned)s.now; ++i) {
@@ -154,7 +154,7 @@ __device__ inline bool sdp_maximization(SdpSub &s, const Pwl &P, const SdpDyn &D
 
 // one start point against one sub-problem (the body of the k loops of ProcessPoint, SparseDP.h:1029-1063); returns false
 // when the sub-problem is skipped, else Ev and the Ei index
-__device__ inline bool sdp_eval_start(SdpSub &s, long long diag, int desc, float bonus, const Pwl &P, const SdpDyn &D, float &ev, int &i1out) {
+__device__ __noinline__ bool sdp_eval_start(SdpSub &s, long long diag, int desc, float bonus, const Pwl &P, const SdpDyn &D, float &ev, int &i1out) {
   if (s.m == 0 || s.n == 0) return false;      // Di.empty(); a kept one-sided node with Ei empty is never in a B list
   const int t = sdp_lb(s.Ei, s.n, diag, desc);
   if (t < 0) return false;
@@ -182,7 +182,7 @@ __device__ inline bool sdp_eval_start(SdpSub &s, long long diag, int desc, float
 __device__ __forceinline__ const SdpPt &sdp_pt(const SdpWork &W, const SdpFam &F, int pos) { return F.cols ? W.H1[W.H2[pos]] : W.H1[pos]; }
 
 // collect the diagonals of the points of rows/cols [s,e) with ind == DE of this family; flag rows that have one
-__device__ inline int sdp_scan(SdpWork &W, const SdpFam &F, int s, int e, int DE, long long *out) {
+__device__ __noinline__ int sdp_scan(SdpWork &W, const SdpFam &F, int s, int e, int DE, long long *out) {
   const int *vs = F.cols ? W.colS : W.rowS, *ve = F.cols ? W.colE : W.rowE;
   const int *rof = F.cols ? W.colOfPos : W.rowOf;
   const int p0 = vs[s], p1 = ve[e - 1];
@@ -203,7 +203,7 @@ __device__ inline int sdp_scan(SdpWork &W, const SdpFam &F, int s, int e, int DE
   return cnt;
 }
 // sort + unique `a[0..cnt)` (scratch, capacity next_pow2(cnt)), write the distinct values to dst in ascending / descending order
-__device__ inline int sdp_sort_unique(long long *a, int cnt, long long *dst, int desc) {
+__device__ __noinline__ int sdp_sort_unique(long long *a, int cnt, long long *dst, int desc) {
   if (cnt == 0) return 0;
   const int P = next_pow2(cnt);
   for (int i = cnt + lane_id(); i < P; i += kLanes) a[i] = 0x7fffffffffffffffll;
@@ -224,7 +224,7 @@ __device__ inline int sdp_sort_unique(long long *a, int cnt, long long *dst, int
   return u;
 }
 // push node number n into the A or B list of every flagged row of [s,e); clears the flags
-__device__ inline void sdp_push_ss(SdpWork &W, SdpFam &F, int s, int e, int n, bool toA, bool toB) {
+__device__ __noinline__ void sdp_push_ss(SdpWork &W, SdpFam &F, int s, int e, int n, bool toA, bool toB) {
   for (int r = s + lane_id(); r < e; r += kLanes) {
     if (W.flag[r]) {
       if (toA) { F.ssA[(long long)r * F.stride + F.nA[r]] = (uint32_t)n; F.nA[r]++; }
@@ -240,7 +240,7 @@ __device__ inline void sdp_clear_flags(SdpWork &W, int s, int e) {
 }
 
 // allocate and initialise the arrays of a kept two-sided node (Decide_Eb_Db_*, DivideSubBy*.h)
-__device__ inline bool sdp_setup_sub(SdpSub &s, int desc, Arena &ar) {
+__device__ __noinline__ bool sdp_setup_sub(SdpSub &s, int desc, Arena &ar) {
   const int m = s.m, n = s.n;
   s.Dv = ar.alloc<float>(m); s.Dp = ar.alloc<uint32_t>(m); s.Db = ar.alloc<int>(m);
   s.Ev = ar.alloc<float>(n); s.Ep = ar.alloc<uint32_t>(n); s.Eb = ar.alloc<int>(n);
@@ -283,7 +283,7 @@ __device__ inline bool sdp_setup_sub(SdpSub &s, int desc, Arena &ar) {
 }
 
 // DivideSubProbBy{Row1,Col1,Row2,Col2}: pre-order numbering with dropped nodes, explicit stack
-__device__ inline bool sdp_divide(SdpWork &W, SdpFam &F, Arena &ar) {
+__device__ __noinline__ bool sdp_divide(SdpWork &W, SdpFam &F, Arena &ar) {
   const int V = F.cols ? W.C : W.R;
   F.nsub = 0;
   if (V == 0) return true;
@@ -375,7 +375,7 @@ __device__ __forceinline__ void sdp_put_pair(SdpPt *H, int at, uint32_t frag, ui
 }
 
 // mode 0: pure matches of all clusters (SparseDP.h:2139); 1: one cluster `only_cl` (:2287); 2: forward only (SparseDP_Forward.h:312)
-__device__ inline bool sdp_build(SdpWork &W, const SdpAnchors &A, int mode, int only_cl, float rate, int irate, Arena &ar) {
+__device__ __noinline__ bool sdp_build(SdpWork &W, const SdpAnchors &A, int mode, int only_cl, float rate, int irate, Arena &ar) {
   // count points
   int N = 0, f0 = 0, f1 = A.nfrag;
   if (mode == 0) { N = 2 * A.nfrag; for (int c = 0; c < A.ncl; c++) { const int sz = A.cl_off[c + 1] - A.cl_off[c]; if (sz == 1) N += 2; else if (sz > 1) N += 4; } }
@@ -504,7 +504,7 @@ __device__ inline bool sdp_open_dyn(SdpWork &W, Arena &ar) {
 }
 
 // ---- ProcessPoint (SparseDP.h:1016-1350; forward-only: SparseDP_Forward.h:37-130) ------------------------------------
-__device__ inline void sdp_process(SdpWork &W, const SdpAnchors &A, int f0, int mode, float rate, int irate, const Pwl &P) {
+__device__ __noinline__ void sdp_process(SdpWork &W, const SdpAnchors &A, int f0, int mode, float rate, int irate, const Pwl &P) {
   const int lane = lane_id();
   for (int i = 0; i < W.N; i++) {
     const SdpPt pt = W.H1[i];
@@ -564,7 +564,7 @@ __device__ __forceinline__ uint32_t sdp_prev_frag(const SdpWork &W, const SdpVal
   return s.Dp[s.Ep[v.prev_ind]];
 }
 // plain traceback; returns the chain length (chain and link need room for nfrag entries)
-__device__ inline int sdp_traceback(const SdpWork &W, uint32_t i, uint32_t *chain, uint8_t *link) {
+__device__ __noinline__ int sdp_traceback(const SdpWork &W, uint32_t i, uint32_t *chain, uint8_t *link) {
   int n = 0;
   chain[n++] = i;
   while (W.val[i].prev_sub != -1 && W.val[i].prev_ind != -1) {
@@ -577,7 +577,7 @@ __device__ inline int sdp_traceback(const SdpWork &W, uint32_t i, uint32_t *chai
   return n;
 }
 // traceback that refuses anchors already used by an earlier chain (chain is dropped as a whole)
-__device__ inline int sdp_traceback_used(const SdpWork &W, uint32_t i, uint32_t *chain, uint8_t *link, uint8_t *used) {
+__device__ __noinline__ int sdp_traceback_used(const SdpWork &W, uint32_t i, uint32_t *chain, uint8_t *link, uint8_t *used) {
   int n = 0;
   if (used[i]) return 0;
   chain[n++] = i; used[i] = 1;

@@ -24,7 +24,7 @@ __device__ __forceinline__ bool sdp_overlaps_on_t(uint32_t TStart, uint32_t TEnd
 }
 
 // mode 0.  chains[c].chain / link must have room for A.nfrag entries each.  Returns the number of chains (<= NumAln), -1 on arena overflow.
-__device__ inline int sdp_pure_matches(const SdpAnchors &A, float rate, float alnthres, int NumAln, int read_len, const Pwl &P, Arena &ar,
+__device__ __noinline__ int sdp_pure_matches(const SdpAnchors &A, float rate, float alnthres, int NumAln, int read_len, const Pwl &P, Arena &ar,
                                        SdpChain *chains, int *cl_of_frag /* optional [nfrag] */) {
   const unsigned long long mk = ar.mark();
   SdpWork W;
@@ -78,7 +78,7 @@ __device__ inline int sdp_pure_matches(const SdpAnchors &A, float rate, float al
 }
 
 // mode 1 (one cluster).  Returns the chain length (0 for an empty cluster), -1 on arena overflow; chain holds cluster-local indices.
-__device__ inline int sdp_one_cluster(const SdpAnchors &A, int cl, float rate, const Pwl &P, Arena &ar, uint32_t *chain, uint8_t *link, float *value) {
+__device__ __noinline__ int sdp_one_cluster(const SdpAnchors &A, int cl, float rate, const Pwl &P, Arena &ar, uint32_t *chain, uint8_t *link, float *value) {
   const int f0 = A.cl_off[cl], nf = A.cl_off[cl + 1] - f0;
   if (nf == 0) return 0;
   const unsigned long long mk = ar.mark();
@@ -102,7 +102,7 @@ __device__ inline int sdp_one_cluster(const SdpAnchors &A, int cl, float rate, c
 }
 
 // mode 2 (forward only, SparseDP_ForwardOnly).  A.q/t/len are the anchors, no clusters.  Returns the chain length.
-__device__ inline int sdp_forward_only(const SdpAnchors &A, int irate, const Pwl &P, Arena &ar, uint32_t *chain, float *value) {
+__device__ __noinline__ int sdp_forward_only(const SdpAnchors &A, int irate, const Pwl &P, Arena &ar, uint32_t *chain, float *value) {
   if (A.nfrag == 0) return 0;
   const unsigned long long mk = ar.mark();
   SdpWork W;

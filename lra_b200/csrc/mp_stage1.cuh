@@ -1,0 +1,309 @@
+// Mapper worker, first half of MapRead_lowacc: seeding (MapRead.h:169-203), CleanMatches (Clustering.h:1840-1908), the first LinearExtend
+// (Map_lowacc.h:132-153, LinearExtend.h:658-716), the first SparseDP + RemoveSpuriousJump (Map_lowacc.h:184-191).
+// Serial scans whose state runs from anchor to anchor (minimizer window, the CompareLists galloping, CleanOffDiagonal's run counters,
+// LinearExtend's m / n cursors) are replayed by lane 0 with the pinned device routines of the stage kernels (seed_kernels.cuh, cod_kernels.cuh);
+// sorts, strand tests, compactions and the sparse DP use all lanes.
+#pragma once
+#include "mp_types.cuh"
+#include "mp_sdp_driver.cuh"
+#include "seed_kernels.cuh"
+#include "cod_kernels.cuh"
+#include "chainf_kernels.cuh"
+
+namespace lra {
+namespace mp {
+
+struct MpCtx {
+  MpOpts o;
+  MpIndex ix;
+  MpReads rd;
+  const Pwl *pwl;
+};
+
+struct MpMatch { uint32_t q, t; unsigned long long qt; };
+struct MpKey { unsigned long long k; uint32_t q, idx; };
+
+__device__ __forceinline__ uint32_t contig_len(const MpIndex &ix, int c) { return (uint32_t)(ix.hdr_pos[c + 1] - ix.hdr_pos[c]); }
+
+// sort `n` records by (k, q, idx) and leave the permutation in keys[].idx; keys has room for next_pow2(n)
+__device__ __noinline__ void mp_sort_keys(MpKey *keys, int n) {
+  const int P = next_pow2(n > 0 ? n : 1);
+  for (int i = n + lane_id(); i < P; i += kLanes) { keys[i].k = ~0ull; keys[i].q = 0xffffffffu; keys[i].idx = 0xffffffffu; }
+  wsort_pow2(keys, P, [](const MpKey &a, const MpKey &b) { if (a.k != b.k) return a.k < b.k; if (a.q != b.q) return a.q < b.q; return a.idx < b.idx; });
+}
+
+// Checkbp (LinearExtend.h:50-85): extend after anchor `cur` by exact base comparison until `next`; t chromosome-relative
+__device__ __noinline__ void mp_checkbp(const MpCtx &C, unsigned long long roff, uint32_t readLen, unsigned long long coff, uint32_t chromLen, uint32_t cq, uint32_t ct,
+                                  uint32_t nq, uint32_t nt, int strand, int K, uint32_t &qe, uint32_t &te) {
+  uint32_t curQ, curT, nextQ, nextT;
+  if (strand == 0) {
+    curQ = cq + K; curT = chromLen < ct + K ? chromLen : ct + K;
+    nextQ = nq; nextT = chromLen < nt ? chromLen : nt;
+    while (curQ < readLen && curT < chromLen && nextQ > curQ && nextT > curT && seq_code(C.ix.genome, coff + curT) == seq_code(C.rd.fwd, roff + curQ)) { curQ++; curT++; }
+  } else {
+    curQ = cq + K; curT = (chromLen - 1u) < (ct - 1u) ? (chromLen - 1u) : (ct - 1u);
+    nextQ = nq; nextT = (chromLen - 1u) < (nt + K - 1u) ? (chromLen - 1u) : (nt + K - 1u);
+    while (curQ < readLen && nextQ > curQ && nextT < curT && curT < chromLen && seq_code(C.ix.genome, coff + curT) == seq_code(C.rd.fwd, roff + curQ)) { curQ++; curT--; }
+  }
+  qe = curQ; te = curT;
+}
+
+// LinearExtend, GenomePairs overload (LinearExtend.h:658-716), sorting excluded; appends to (oq, ot, ol) from index o0; returns the new count.
+// Serial (called by one lane).
+__device__ __noinline__ int mp_linear_extend(const MpCtx &C, unsigned long long roff, uint32_t readLen, int chrom, const uint32_t *q, const uint32_t *t, int np, int strand,
+                                       int K, uint32_t *oq, uint32_t *ot, int *ol, int o0) {
+  const unsigned long long coff = C.ix.hdr_pos[chrom];
+  const uint32_t chromLen = contig_len(C.ix, chrom);
+  int n = 1, m = 0, o = o0;
+  while (n < np) {
+    long long curDiag, nextDiag;
+    if (strand == 0) { curDiag = (long long)q[n - 1] - (long long)t[n - 1]; nextDiag = (long long)q[n] - (long long)t[n]; }
+    else { curDiag = (long long)q[n - 1] + (long long)t[n - 1]; nextDiag = (long long)q[n] + (long long)t[n]; }
+    if (curDiag == nextDiag) {
+      if (q[n] < q[n - 1] + (uint32_t)K) n++;
+      else {
+        uint32_t qe, te;
+        mp_checkbp(C, roff, readLen, coff, chromLen, q[n - 1], t[n - 1], q[n], t[n], strand, K, qe, te);
+        if (strand == 0 && qe == q[n] && te == t[n]) n++;
+        else if (strand == 1 && qe == q[n] && te == t[n] + (uint32_t)K - 1u) n++;
+        else {
+          oq[o] = q[m]; ot[o] = strand == 0 ? t[m] : te + 1u; ol[o] = (int)(qe - q[m]); o++;
+          m = n; n++;
+        }
+      }
+    } else {
+      oq[o] = q[m]; ot[o] = strand == 0 ? t[m] : t[n - 1]; ol[o] = (int)(q[n - 1] + (uint32_t)K - q[m]); o++;
+      m = n; n++;
+    }
+  }
+  if (n == np) { oq[o] = q[m]; ot[o] = strand == 0 ? t[m] : t[n - 1]; ol[o] = (int)(q[n - 1] + (uint32_t)K - q[m]); o++; }
+  return o;
+}
+
+// DecideCoordinates (LinearExtend.h:105-128) over anchors [a0, a1) of a cluster set entry
+__device__ __noinline__ void mp_decide_coordinates(ClusterSet &S, int c, int strand, int chrom, float freq) {
+  const int a0 = S.off[c], a1 = S.off[c + 1];
+  if (a1 == a0) return;
+  uint32_t qS = S.q[a0], qE = qS + (uint32_t)S.len[a0], tS = S.t[a0], tE = tS + (uint32_t)S.len[a0];
+  for (int n = a0 + 1; n < a1; n++) {
+    qS = S.q[n] < qS ? S.q[n] : qS; qE = S.q[n] + (uint32_t)S.len[n] > qE ? S.q[n] + (uint32_t)S.len[n] : qE;
+    tS = S.t[n] < tS ? S.t[n] : tS; tE = S.t[n] + (uint32_t)S.len[n] > tE ? S.t[n] + (uint32_t)S.len[n] : tE;
+  }
+  S.qS[c] = qS; S.qE[c] = qE; S.tS[c] = tS; S.tE[c] = tE; S.strand[c] = strand; S.chrom[c] = chrom; S.freq[c] = freq;
+}
+
+__device__ __noinline__ bool mp_alloc_clusterset(ClusterSet &S, Arena &ar, int cap_cl, int cap_a, bool with_len) {
+  S.cap_cl = cap_cl; S.cap_a = cap_a; S.ncl = 0;
+  S.q = ar.alloc<uint32_t>(cap_a + 1); S.t = ar.alloc<uint32_t>(cap_a + 1); S.len = with_len ? ar.alloc<int>(cap_a + 1) : (int *)0;
+  S.off = ar.alloc<int>(cap_cl + 2);
+  S.qS = ar.alloc<uint32_t>(cap_cl + 1); S.qE = ar.alloc<uint32_t>(cap_cl + 1); S.tS = ar.alloc<uint32_t>(cap_cl + 1); S.tE = ar.alloc<uint32_t>(cap_cl + 1);
+  S.strand = ar.alloc<int>(cap_cl + 1); S.chrom = ar.alloc<int>(cap_cl + 1); S.freq = ar.alloc<float>(cap_cl + 1);
+  return !ar.overflow;
+}
+
+// the keep mask of a chain filter (Chain.h:546-960, chainf_kernels.cuh) over the anchors of a chain; serial.  scratch: 3 * n ints + n bytes + SoA copies
+__device__ __noinline__ void mp_chain_filter(int mode, const ClusterSet &S, UChain &ch, Arena &ar, bool compact_link) {
+  const int n = ch.n;
+  if (n < 2) return;
+  const unsigned long long mk = ar.mark();
+  uint32_t *q = ar.alloc<uint32_t>(n), *t = ar.alloc<uint32_t>(n), *len = ar.alloc<uint32_t>(n);
+  uint8_t *st = ar.alloc<uint8_t>(n), *keep = ar.alloc<uint8_t>(n);
+  int32_t *sv = ar.alloc<int32_t>(n), *svp = ar.alloc<int32_t>(n), *svg = ar.alloc<int32_t>(n);
+  unsigned long long *off = ar.alloc<unsigned long long>(2);
+  if (ar.overflow) { ar.release(mk); return; }
+  for (int i = lane_id(); i < n; i += kLanes) {
+    const int a = S.off[ch.cl[i]] + (int)ch.idx[i];
+    q[i] = S.q[a]; t[i] = S.t[a]; len[i] = (uint32_t)S.len[a]; st[i] = (uint8_t)(S.strand[ch.cl[i]] != 0);
+  }
+  if (lane_id() == 0) { off[0] = 0; off[1] = (unsigned long long)n; }
+  wsync();
+  int m = 0;
+  if (lane_id() == 0) {
+    ChainfBatch b; b.n_chains = 1; b.mode = mode; b.off = off; b.q = q; b.t = t; b.len = len; b.strand = st; b.keep = keep; b.sv = sv; b.svpos = svp; b.svg = svg;
+    chainf_one(b, 0);
+    for (int i = 0; i < n; i++) {
+      if (keep[i]) {
+        ch.idx[m] = ch.idx[i]; ch.cl[m] = ch.cl[i];
+        if (compact_link && ch.nlink > 0 && m >= 1) ch.link[m - 1] = ch.link[i - 1];
+        m++;
+      }
+    }
+  }
+  wsync();
+  m = bcast(m, 0);
+  ch.n = m;
+  if (compact_link && ch.nlink > 0) ch.nlink = m - 1;     // (m == 0 would be resize(-1) in the reference: not reachable, at least two anchors survive)
+  ar.release(mk);
+}
+
+// ---- seeding + CleanMatches + LinearExtend + first SparseDP for one read.  Returns MP_OK with `ext` (extended clusters, global t) and
+// `chains` (nch of them), or MP_UNALIGNED / an error.
+__device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterSet &ext, UChain *&chains, int &nch) {
+  const int lane = lane_id();
+  const MpOpts &O = C.o;
+  const unsigned long long roff = C.rd.read_off[r];
+  const uint32_t L = C.rd.read_len[r];
+  nch = 0;
+  // ---- a2 / a3: minimizers of the read, std::sort (MapRead.h:181-185)
+  unsigned long long *mm_t = ar.alloc<unsigned long long>((unsigned long long)L + 2);
+  uint32_t *mm_p = ar.alloc<uint32_t>((unsigned long long)L + 2);
+  if (ar.overflow) return MP_ERR_ARENA;
+  int n_mm = 0;
+  if (lane == 0) { n_mm = (int)mm_scan<true>(C.rd.fwd, roff, L, O.globalK, O.globalW, mm_t, mm_p); mm_sort(MmRef{mm_t, mm_p}, (long)n_mm); }
+  wsync();
+  n_mm = bcast(n_mm, 0);
+  // ---- a4: CompareLists against the global index (MapRead.h:190); matches land in the open end of the arena
+  const unsigned long long top0 = (ar.top + 15ull) & ~15ull;
+  const unsigned long long room = ar.cap > top0 ? (ar.cap - top0) / sizeof(MpMatch) : 0ull;
+  MpMatch *M = (MpMatch *)(ar.base + top0);
+  long long n_match = 0;
+  if (lane == 0) {
+    const uint32_t *idx_pos = C.ix.idx_pos;
+    mm_compare(mm_t, (long)n_mm, C.ix.idx_t, (long)C.ix.n_idx, (long long)O.globalMaxFreq, [&](long qi, long ti) {
+      if ((unsigned long long)n_match < room) { MpMatch x; x.q = mm_p[qi]; x.t = idx_pos[ti]; x.qt = mm_t[qi]; M[n_match] = x; }
+      n_match++;
+    });
+  }
+  wsync();
+  n_match = bcast(n_match, 0);
+  if ((unsigned long long)n_match > room / 4) return MP_ERR_ARENA;        // leave room for the stages below
+  ar.alloc<MpMatch>((unsigned long long)n_match);
+  const int NM = (int)n_match;
+  if (NM == 0) return MP_UNALIGNED;
+  // ---- a5: SeparateMatchesByStrand (MapRead.h:109-150): strncmp(read + q, genome + t, K) == 0 -> forward
+  uint8_t *mstr = ar.alloc<uint8_t>(NM);
+  if (ar.overflow) return MP_ERR_ARENA;
+  for (int i = lane; i < NM; i += kLanes) {
+    int differ = 0;
+    for (int j = 0; j < O.globalK && !differ; j++) differ = seq_code(C.rd.fwd, roff + M[i].q + j) != seq_code(C.ix.genome, (unsigned long long)M[i].t + j);
+    mstr[i] = (uint8_t)differ;
+  }
+  wsync();
+  // ---- CleanMatches per strand (Clustering.h:1840-1908): DiagonalSort / AntiDiagonalSort, CleanOffDiagonal, clusters with their matches
+  ClusterSet raw;
+  if (!mp_alloc_clusterset(raw, ar, NM, NM, false)) return MP_ERR_ARENA;
+  if (lane == 0) raw.off[0] = 0;
+  int n_raw_a = 0;
+  int repetitive = 0;
+  for (int s = 0; s < 2; s++) {
+    const unsigned long long mk = ar.mark();
+    // gather this strand's matches (order is irrelevant: the sort key below is total up to identical records)
+    MpKey *keys = ar.alloc<MpKey>((unsigned long long)next_pow2(NM));
+    if (ar.overflow) return MP_ERR_ARENA;
+    int ns = 0;
+    for (int b = 0; b < NM; b += kLanes) {
+      const int i = b + lane;
+      const bool take = i < NM && mstr[i] == s;
+      const unsigned mk2 = ballot(take);
+      if (take) {
+        MpKey k;
+        if (s == 0) k.k = (unsigned long long)((long long)M[i].q - (long long)M[i].t + (1ll << 33));
+        else k.k = (unsigned long long)(uint32_t)(M[i].q + M[i].t);
+        k.q = M[i].q; k.idx = (uint32_t)i;
+        keys[ns + __popc(mk2 & lanemask_lt())] = k;
+      }
+      ns += __popc(mk2);
+    }
+    wsync();
+    if (ns == 0) { ar.release(mk); continue; }
+    mp_sort_keys(keys, ns);
+    uint32_t *sq = ar.alloc<uint32_t>(ns), *stt = ar.alloc<uint32_t>(ns);
+    unsigned long long *sqt = ar.alloc<unsigned long long>(ns);
+    uint8_t *keep = ar.alloc<uint8_t>(ns), *flags = ar.alloc<uint8_t>(3ull * ns + 3), *hused = ar.alloc<uint8_t>(4ull * ns + 8);
+    float *freq = ar.alloc<float>(ns), *clf = ar.alloc<float>(ns);
+    int32_t *cnt = ar.alloc<int32_t>(ns), *cl = ar.alloc<int32_t>(7ull * ns), *ncl_p = ar.alloc<int32_t>(2);
+    unsigned long long *hkeys = ar.alloc<unsigned long long>(4ull * ns + 8), *off = ar.alloc<unsigned long long>(2);
+    uint8_t *sstr = ar.alloc<uint8_t>(2);
+    if (ar.overflow) return MP_ERR_ARENA;
+    for (int i = lane; i < ns; i += kLanes) { const MpMatch &x = M[keys[i].idx]; sq[i] = x.q; stt[i] = x.t; sqt[i] = x.qt; }
+    if (lane == 0) { off[0] = 0; off[1] = (unsigned long long)ns; sstr[0] = (uint8_t)s; }
+    wsync();
+    if (lane == 0) {
+      CodBatch b;
+      b.n_lists = 1; b.off = off; b.q = sq; b.t = stt; b.qt = sqt; b.strand = sstr;
+      b.o.cleanMaxDiag = O.cleanMaxDiag; b.o.minDiagCluster = O.minDiagCluster; b.o.bypassClustering = 1; b.o.cleanClustersize = O.cleanClustersize;
+      b.o.SecondCleanMinDiagCluster = O.SecondCleanMinDiagCluster; b.o.punish_anchorfreq = O.punish_anchorfreq; b.o.anchorPerlength = O.anchorPerlength;
+      b.o.SecondCleanMaxDiag = O.SecondCleanMaxDiag; b.o.ExtractDiagonalFromClean = 1; b.o.globalK = O.globalK;
+      b.hdr_pos = C.ix.hdr_pos; b.n_hdr = C.ix.n_hdr;
+      b.keep = keep; b.freq = freq; b.cnt = cnt; b.cl = cl; b.cl_freq = clf; b.n_cl = ncl_p; b.flags = flags; b.hkeys = hkeys; b.hused = hused;
+      cod_one(b, 0);
+      // the cleaned list is the concatenation of the clusters' matches (cluster ranges index the compacted list)
+      int m = 0;
+      for (int i = 0; i < ns; i++) if (keep[i]) { raw.q[n_raw_a + m] = sq[i]; raw.t[n_raw_a + m] = stt[i]; m++; }
+      const int nc = ncl_p[0];
+      for (int c = 0; c < nc; c++) {
+        const int k = raw.ncl + c;
+        raw.off[k + 1] = n_raw_a + cl[7 * c + 1];
+        raw.qS[k] = (uint32_t)cl[7 * c + 2]; raw.qE[k] = (uint32_t)cl[7 * c + 3]; raw.tS[k] = (uint32_t)cl[7 * c + 4]; raw.tE[k] = (uint32_t)cl[7 * c + 5];
+        raw.chrom[k] = cl[7 * c + 6]; raw.strand[k] = s; raw.freq[k] = clf[c];
+      }
+      ncl_p[1] = m;
+    }
+    wsync();
+    raw.ncl += ncl_p[0]; n_raw_a += ncl_p[1];
+    wsync();
+    ar.release(mk);
+  }
+  if (raw.ncl == 0) return MP_UNALIGNED;
+  for (int c = 0; c < raw.ncl; c++) {
+    const float f = raw.freq[c];
+    if (f > 1.0f && f <= 2.0f && raw.off[c + 1] - raw.off[c] >= 500) repetitive = 1;
+  }
+  // ---- LinearExtend on the raw K-mers of every cluster (Map_lowacc.h:118-153): t chromosome-relative inside, global again afterwards
+  if (!mp_alloc_clusterset(ext, ar, raw.ncl, n_raw_a, true)) return MP_ERR_ARENA;
+  if (lane == 0) {
+    ext.off[0] = 0;
+    int o = 0;
+    for (int d = 0; d < raw.ncl; d++) {
+      const int chrom = raw.chrom[d];
+      const uint32_t coff = (uint32_t)C.ix.hdr_pos[chrom];
+      const int a0 = raw.off[d], np = raw.off[d + 1] - a0;
+      for (int m = 0; m < np; m++) raw.t[a0 + m] -= coff;
+      const int o1 = mp_linear_extend(C, roff, L, chrom, raw.q + a0, raw.t + a0, np, raw.strand[d], O.globalK, ext.q, ext.t, ext.len, o);
+      ext.off[d + 1] = o1;
+      ext.strand[d] = -1; ext.chrom[d] = 0; ext.freq[d] = 0.0f; ext.qS[d] = 0xffffffffu; ext.qE[d] = 0; ext.tS[d] = 0xffffffffu; ext.tE[d] = 0;
+      mp_decide_coordinates(ext, d, raw.strand[d], chrom, raw.freq[d]);
+      for (int m = o; m < o1; m++) ext.t[m] += coff;
+      ext.tS[d] += coff; ext.tE[d] += coff;
+      o = o1;
+    }
+  }
+  wsync();
+  ext.ncl = raw.ncl;
+  const int NE = ext.off[ext.ncl];
+  // ---- first SparseDP on all anchors (Map_lowacc.h:184-188) + RemoveSpuriousJump
+  const float match_rate = repetitive ? 3.0f : O.initial_anchorbonus;
+  const int NA = O.NumAln < 8 ? O.NumAln : 8;
+  chains = ar.alloc<UChain>(NA);
+  SdpChain *sc = ar.alloc<SdpChain>(NA);
+  int *cl_of = ar.alloc<int>(NE + 1);
+  uint8_t *clst = ar.alloc<uint8_t>(ext.ncl + 1);
+  uint32_t *cbuf = ar.alloc<uint32_t>((unsigned long long)NA * (NE + 1));
+  uint8_t *lbuf = ar.alloc<uint8_t>((unsigned long long)NA * (NE + 1));
+  int *clbuf = ar.alloc<int>((unsigned long long)NA * (NE + 1));
+  if (ar.overflow) return MP_ERR_ARENA;
+  for (int c = lane; c < ext.ncl; c += kLanes) clst[c] = (uint8_t)(ext.strand[c] != 0);
+  if (lane == 0) for (int c = 0; c < NA; c++) { sc[c].chain = cbuf + (unsigned long long)c * (NE + 1); sc[c].link = lbuf + (unsigned long long)c * (NE + 1); sc[c].n = 0; }
+  wsync();
+  SdpAnchors A; A.q = ext.q; A.t = ext.t; A.len = ext.len; A.nfrag = NE; A.cl_off = ext.off; A.cl_strand = clst; A.ncl = ext.ncl;
+  const int nc = sdp_pure_matches(A, match_rate, O.alnthres, NA, (int)L, *C.pwl, ar, sc, cl_of);
+  if (nc < 0) return MP_ERR_ARENA;
+  wsync();
+  for (int c = 0; c < nc; c++) {
+    UChain u;
+    u.idx = sc[c].chain; u.link = sc[c].link; u.cl = clbuf + (unsigned long long)c * (NE + 1);
+    u.n = sc[c].n; u.nlink = u.n - 1; u.FirstSDPValue = sc[c].value; u.NumOfAnchors0 = u.n; u.NumOfAnchors1 = 0;
+    u.QStart = sc[c].QStart; u.QEnd = sc[c].QEnd; u.TStart = sc[c].TStart; u.TEnd = sc[c].TEnd;
+    for (int i = lane; i < u.n; i += kLanes) { const int f = (int)u.idx[i]; const int k = cl_of[f]; u.cl[i] = k; u.idx[i] = (uint32_t)(f - ext.off[k]); }
+    wsync();
+    mp_chain_filter(5, ext, u, ar, true);       // RemoveSpuriousJump
+    if (lane == 0) chains[c] = u;
+    wsync();
+  }
+  nch = nc;
+  if (nc == 0) return MP_UNALIGNED;
+  return MP_OK;
+}
+
+}  // namespace mp
+}  // namespace lra

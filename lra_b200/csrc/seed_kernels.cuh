@@ -90,7 +90,7 @@ constexpr int kSeedMaxW = 64;
 // ---- a2 (literal): the minimizers of seq[off, off + seqLen) into (ot, op); returns their number.  CANON: StoreMinimizers (MinCount.h:7-179, the smaller of
 // the tuple and its reverse complement, strand in the top bit); !CANON: StoreMinimizers_noncanonical (MinCount.h:181-337, forward tuples only)
 template <bool CANON>
-__device__ uint32_t mm_scan(const SeqView &seq, unsigned long long off, uint32_t seqLen, int k, int w, unsigned long long *ot, uint32_t *op) {
+__device__ __noinline__ uint32_t mm_scan(const SeqView &seq, unsigned long long off, uint32_t seqLen, int k, int w, unsigned long long *ot, uint32_t *op) {
   uint32_t n_out = 0;
   if (seqLen < (uint32_t)k) return 0;
   const int windowSpan = w + k - 1;
@@ -230,7 +230,7 @@ __device__ __forceinline__ void mm_heap_sort(const MmRef &v, long first, long la
   }
 }
 
-__device__ inline void mm_sort(const MmRef &v, long n) {
+__device__ __noinline__ void mm_sort(const MmRef &v, long n) {
   if (n <= 1) return;
   long lg = 0;
   { unsigned long x = (unsigned long)n; while (x > 1) { x >>= 1; lg++; } }

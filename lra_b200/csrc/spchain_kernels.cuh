@@ -44,9 +44,7 @@ __device__ __forceinline__ int spc_hdr_find(const unsigned long long *pos, int n
   return lo - 1;
 }
 
-__global__ void __launch_bounds__(64) spchain_kernel(SpChainBatch b) {
-  const int k = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x);
-  if (k >= b.n_chains) return;
+__device__ __noinline__ void spchain_one(const SpChainBatch &b, const int k) {
   const unsigned long long a0 = b.c_off[k];
   const int n = (int)(b.c_off[k + 1] - a0);
   const uint32_t *q = b.q + a0, *t = b.t + a0;
@@ -189,6 +187,12 @@ __global__ void __launch_bounds__(64) spchain_kernel(SpChainBatch b) {
   sp_off[nk] = o; ci_off[nk] = oc;
   for (int i = 0; i < nsl; i++) b.sp_link[a0 + i] = SL[i];
   b.n_sp[k] = nk; b.n_link[k] = nsl;
+}
+
+__global__ void __launch_bounds__(64) spchain_kernel(SpChainBatch b) {
+  const int k = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x);
+  if (k >= b.n_chains) return;
+  spchain_one(b, k);
 }
 
 }  // namespace lra

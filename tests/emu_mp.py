@@ -28,6 +28,10 @@ def lib(lanes=32):
     srcs += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         cpps = [s for s in srcs if s.endswith(".cpp")]
+        if lanes == 1:      # the 1-lane build binds the in-worker AffineOneGapAlign to the pinned C restatement (see mp_aog.cuh)
+            obj = os.path.join(MPD, "aog_port.o")
+            subprocess.run(["gcc", "-std=c11", "-O2", "-fPIC", "-c", os.path.join(os.path.dirname(HERE), "oracle", "aog.c"), "-o", obj], check=True)
+            cpps.append(obj)
         subprocess.run(["g++", "-std=c++17", "-O2" if lanes == 1 else "-O1", "-DLRA_EMU", "-DMP_LANES=%d" % lanes] + (["-DMP_DEBUG", "-g"] if os.environ.get("MP_DEBUG") else []) + [ "-I" + SIMT, "-I" + CSRC, "-fPIC", "-shared"] + cpps +
                        ["-o", so], check=True)
     L = C.CDLL(so)

@@ -30,3 +30,67 @@ extern "C" int emu_sdp_batch(int n_prob, int max_aln, const int *mode, const uin
   emu::launch(dim3(1), dim3(MP_LANES), 0, [&] { sdp_batch_kernel(b); });
   return err;
 }
+
+// ---- the mapper worker (map_reads_kernel) and map_finalize_kernel under the emulator ------------------------------------------------
+#include "mp_map.cuh"
+#include "seq_kernels.cuh"
+
+namespace {
+struct Packed { std::vector<uint32_t> b2, nm; SeqView view; };
+void pack_ascii(const uint8_t *ascii, uint64_t n, Packed &p) {
+  // host packing with the alphabet of seq_pack_kernel: A,C,G,T (either case) -> 0..3, everything else -> N
+  p.b2.assign((n + 15) / 16 + 8, 0); p.nm.assign((n + 31) / 32 + 8, 0xFFFFFFFFu);
+  for (uint64_t i = 0; i < n; i++) {
+    int c;
+    switch (ascii[i]) { case 'A': case 'a': c = 0; break; case 'C': case 'c': c = 1; break; case 'G': case 'g': c = 2; break; case 'T': case 't': c = 3; break; default: c = 4; }
+    if (c < 4) { p.b2[i >> 4] |= (uint32_t)c << (2 * (i & 15)); p.nm[i >> 5] &= ~(1u << (i & 31)); }
+  }
+  p.view = SeqView{p.b2.data(), p.nm.data(), n};
+}
+}  // namespace
+
+extern "C" int emu_map_reads(const uint8_t *reads_fwd, const uint8_t *reads_rc, uint64_t rn, const uint64_t *read_off, const uint32_t *read_len, int n_reads,
+                             const uint8_t *genome, uint64_t gn, const uint64_t *hdr_pos, int n_hdr, const uint64_t *idx_t, const uint32_t *idx_pos, int64_t n_idx,
+                             const uint64_t *gl_win_off, const uint64_t *gl_bnd, const uint32_t *gl_mins, int gl_n_win,
+                             const uint32_t *rf_win_first, const uint64_t *rf_win_off, const uint64_t *rf_bnd, const uint32_t *rf_mins,
+                             const uint32_t *rr_win_first, const uint64_t *rr_win_off, const uint64_t *rr_bnd, const uint32_t *rr_mins,
+                             const MpOpts *opts, const int64_t *stops, const float *slope, const float *inter, int ceil1, int ceil2,
+                             int *status, int *n_chains, int *chain_nseg, int *chain_seg0, SegRec *seg, int seg_cap, uint32_t *blocks, uint64_t blk_cap,
+                             uint64_t *counts /* n_seg, n_blk, err, peak */, uint64_t arena_bytes) {
+  Packed pf, pr, pg; pack_ascii(reads_fwd, rn, pf); pack_ascii(reads_rc, rn, pr); pack_ascii(genome, gn, pg);
+  Pwl pwl; for (int i = 0; i < 25; i++) { pwl.stops[i] = stops[i]; pwl.slope[i] = slope[i]; pwl.inter[i] = inter[i]; } pwl.ceil1 = ceil1; pwl.ceil2 = ceil2;
+  std::vector<unsigned char> arena(arena_bytes + 64);
+  unsigned char *base = arena.data(); while (((uintptr_t)base) & 15) base++;
+  MapBatch b;
+  b.C.o = *opts; b.C.pwl = &pwl;
+  b.C.ix.genome = pg.view; b.C.ix.hdr_pos = (const unsigned long long *)hdr_pos; b.C.ix.n_hdr = n_hdr; b.C.ix.idx_t = (const unsigned long long *)idx_t; b.C.ix.idx_pos = idx_pos;
+  b.C.ix.n_idx = n_idx;
+  b.C.ix.gl = LidxView{(const unsigned long long *)gl_win_off, nullptr, (const unsigned long long *)gl_bnd, gl_mins, nullptr, nullptr, nullptr, gl_n_win, n_hdr};
+  b.C.rd.fwd = pf.view; b.C.rd.rc = pr.view; b.C.rd.read_off = (const unsigned long long *)read_off; b.C.rd.read_len = read_len; b.C.rd.n_reads = n_reads;
+  b.C.rd.rd[0] = LidxView{(const unsigned long long *)rf_win_off, nullptr, (const unsigned long long *)rf_bnd, rf_mins, rf_win_first, (const unsigned long long *)read_off, read_len, 0, n_reads};
+  b.C.rd.rd[1] = LidxView{(const unsigned long long *)rr_win_off, nullptr, (const unsigned long long *)rr_bnd, rr_mins, rr_win_first, (const unsigned long long *)read_off, read_len, 0, n_reads};
+  unsigned long long cur[4] = {0, 0, 0, 0}; int err = 0, work = 0;
+  b.out.status = status; b.out.n_chains = n_chains; b.out.chain_nseg = chain_nseg; b.out.chain_seg0 = chain_seg0;
+  b.out.seg = seg; b.out.seg_cap = seg_cap; b.out.seg_cursor = &cur[0]; b.out.blocks = blocks; b.out.blk_cap = blk_cap; b.out.blk_cursor = &cur[1]; b.out.err = &err;
+  b.out.peak = &cur[2];
+  b.arena = base; b.arena_per_warp = arena_bytes; b.work = &work; b.order = nullptr;
+  emu::launch(dim3(1), dim3(MP_LANES), 0, [&] { map_reads_kernel(b); });
+  counts[0] = cur[0] >> 40; counts[1] = cur[0] & ((1ull << 40) - 1ull); counts[2] = (uint64_t)err; counts[3] = cur[2];
+  return err;
+}
+
+extern "C" int emu_map_finalize(int n_reads, const MpOpts *opts, const uint64_t *read_off, const uint32_t *read_len, const int *status, const int *n_chains,
+                                const int *chain_nseg, const int *chain_seg0, const SegRec *seg, const int32_t *ir_nblk, const uint64_t *ir_off, const uint32_t *ir_blocks,
+                                const int32_t *stats, const float *value, const uint64_t *cigar_off, const float *logf_len, lra_b200_record *rec, int *rank,
+                                uint64_t *aligned_bases) {
+  FinalBatch b;
+  b.n_reads = n_reads; b.o = *opts; b.read_off = (const unsigned long long *)read_off; b.read_len = read_len; b.status = status; b.n_chains = n_chains;
+  b.chain_nseg = chain_nseg; b.chain_seg0 = chain_seg0; b.seg = seg; b.ir_nblk = ir_nblk; b.ir_off = (const unsigned long long *)ir_off; b.ir_blocks = ir_blocks;
+  b.stats = stats; b.value = value; b.cigar_off = (const unsigned long long *)cigar_off; b.logf_len = logf_len; b.rec = rec; b.rank = rank;
+  b.aligned_bases = (unsigned long long *)aligned_bases;
+  emu::launch(dim3((unsigned)((n_reads + 127) / 128)), dim3(128), 0, [&] { map_finalize_kernel(b); });
+  return 0;
+}
+extern "C" int emu_sizeof_segrec() { return (int)sizeof(SegRec); }
+extern "C" int emu_sizeof_mpopts() { return (int)sizeof(MpOpts); }
+extern "C" int emu_sizeof_record() { return (int)sizeof(lra_b200_record); }
