@@ -1,0 +1,81 @@
+"""End-to-end parity of the MapRead seam (lra_b200_map_batch) with the reference: the SAM text of `oracle/_ref/lra_ref align -MODE -t 1 -p s`
+on seeded synthetic reads must be reproduced byte for byte after canonicalisation (drop @PG, mask RT:i, sort records).
+CPU: the mapper worker + finalize kernels under the SIMT emulator with the reference standing in for the separately tested a12 / a19 / a21 kernels
+(tests/mapemu.py).  GPU: everything through the C ABI."""
+import os
+import re
+import sys
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import mapgen  # noqa: E402
+
+
+def canon_ours(text):
+    return sorted(re.sub(r"\tRT:i:\d+", "\tRT:i:0", l) + "\n" for l in text.split("\n") if l)
+
+
+def diff_report(ours, ref, limit=5):
+    out = []
+    for a, b in zip(ours, ref):
+        if a != b:
+            fa, fb = a.split("\t"), b.split("\t")
+            d = [i for i, (x, y) in enumerate(zip(fa, fb)) if x != y]
+            out.append((fa[0], d, [(fa[i][:40], fb[i][:40]) for i in d if i not in (5, 9)][:4]))
+            if len(out) >= limit:
+                break
+    return out
+
+
+@pytest.mark.parametrize("preset,n_reads,repeats", [("ont", 60, False), ("clr", 60, True)])
+def test_map_emulated_matches_reference_sam(preset, n_reads, repeats, tmp_path):
+    import mapemu
+    w = mapgen.workdir(tmp_path, preset, n_reads=n_reads, ref_len=1_500_000, contigs=3, repeats=repeats)
+    _, ref = mapgen.canonical_sam(mapgen.reference_sam(w))
+    inp, mo, res, text = mapemu.run(w, lanes=1)
+    assert mo["err"] == 0 and (mo["status"] <= 1).all()
+    ours = canon_ours(text)
+    assert len(ours) == len(ref)
+    assert ours == ref, diff_report(ours, ref)
+
+
+def test_map_emulated_32_lanes(tmp_path):
+    import mapemu
+    w = mapgen.workdir(tmp_path, "ont", n_reads=2, ref_len=300_000, contigs=2, repeats=False)
+    _, ref = mapgen.canonical_sam(mapgen.reference_sam(w))
+    inp, mo, res, text = mapemu.run(w, lanes=32)
+    assert canon_ours(text) == ref
+
+
+def gpu_sam(w, batch=None):
+    import lra_b200
+    import mapemu
+    inp = mapemu.load_inputs(w)
+    ctx = lra_b200.Context(0)
+    mp = lra_b200.Mapper(ctx, inp["opts"], inp["genome"], inp["hdr"], inp["mms"], inp["gli"])
+    n = len(inp["read_len"]); batch = batch or n
+    text = []
+    stats = dict(status=[], n_records=0)
+    for s in range(0, n, batch):
+        e = min(n, s + batch)
+        o0 = int(inp["read_off"][s]); o1 = int(inp["read_off"][e - 1]) + int(inp["read_len"][e - 1])
+        res = mp.map_batch(inp["reads"][o0:o1], inp["read_off"][s:e] - np.uint64(o0), inp["read_len"][s:e])
+        stats["status"].append(res["status"][:e - s].copy()); stats["n_records"] += res["n_records"]
+        text.append(lra_b200.format_sam(inp["opts"], res, inp["names"][s:e], inp["reads"][o0:o1], inp["read_off"][s:e] - np.uint64(o0), inp["read_len"][s:e], inp["contig_names"]))
+    mp.close(); ctx.close()
+    stats["status"] = np.concatenate(stats["status"])
+    return "".join(text), stats
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset,n_reads,repeats,batch", [("ont", 1000, False, None), ("clr", 1000, False, 400), ("ont", 600, True, None), ("clr", 600, True, 250)])
+def test_map_batch_gpu_matches_reference_sam(preset, n_reads, repeats, batch, tmp_path):
+    w = mapgen.workdir(tmp_path, preset, n_reads=n_reads, ref_len=5_000_000, contigs=3, repeats=repeats)
+    _, ref = mapgen.canonical_sam(mapgen.reference_sam(w))
+    text, st = gpu_sam(w, batch)
+    assert (st["status"] <= 1).all(), np.bincount(st["status"])
+    ours = canon_ours(text)
+    assert len(ours) == len(ref)
+    assert ours == ref, diff_report(ours, ref)
