@@ -72,8 +72,10 @@ __device__ __noinline__ bool mp_refine_linear(const MpCtx &C, int r, Arena &ar, 
   if (ar.overflow) return false;
   int nb = 0;
   const SeqView &rs = str ? C.rd.rc : C.rd.fwd;
+  const unsigned long long tk = mp_clock();
   mp_aog(rs, (uint32_t)(C.rd.read_off[r] + curReadEnd), qLen, C.ix.genome, (uint32_t)(C.ix.hdr_pos[chrom] + curGenomeEnd), tLen, O.localMatch, O.localMismatch,
          O.localIndel, band, ar, blk, capb, &nb, errp);
+  mp_tick(C, PF_AOG, tk);
   if (nb < 0) return false;
   wsync();
   bool ok = true;
@@ -119,7 +121,9 @@ __device__ __noinline__ bool mp_refined_alignment_btwn(const MpCtx &C, int r, Ar
   else if (maxd < 500) { tK = 9; tW = 7; tMaxFreq = 50; minRatio = (float)(0.5 / 69.1); }
   else { tK = 12; tW = 7; minRatio = (float)(0.5 / 140.2); }
   uint32_t *fq = 0, *ft = 0, *rq = 0, *rt = 0; float identity = 0.0f;
+  unsigned long long tk = mp_clock();
   int nfor = mp_refine_space(C, r, ar, tK, tW, refineSpaceDiag, false, tMaxFreq, chrom, nextReadStart, curReadEnd, nextGenomeStart, curGenomeEnd, str, 0, 0, &fq, &ft, &identity);
+  tk = mp_tick(C, PF_REFINE_SPACE, tk);
   if (nfor < 0) return false;
   const int minDist = (int)mind;
   uint32_t *bq = fq, *bt = ft; int nb = nfor;
@@ -168,7 +172,9 @@ __device__ __noinline__ bool mp_refined_alignment_btwn(const MpCtx &C, int r, Ar
   float *ivp = ar.alloc<float>(1);
   if (ar.overflow) return false;
   SdpAnchors A; A.q = eq; A.t = et; A.len = el; A.nfrag = ne; A.cl_off = 0; A.cl_strand = 0; A.ncl = 0;
+  tk = mp_clock();
   int nbc = sdp_forward_only(A, 2, *C.pwl, ar, bchain, ivp);
+  tk = mp_tick(C, PF_SDP3, tk);
   if (nbc < 0) return false;
   wsync();
   const float inv_value = *ivp;

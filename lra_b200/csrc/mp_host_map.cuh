@@ -266,20 +266,26 @@ extern "C" int lra_b200_map_batch(lra_b200_ctx *ctx, lra_b200_mapper *m, const c
   const size_t seg_cap = (size_t)n_reads * 3 + 1024;
   const size_t blk_cap = (size_t)(total_bases / 2) + (size_t)n_reads * 64 + 4096;
   int warps = ctx->n_sm * 8; if (warps > n_reads) warps = n_reads;
-  size_t per = (size_t)maxL * 1536 + (24u << 20);
+  int warps_max = ctx->n_sm * 16; if (getenv("LRA_B200_MAP_WARPS_PER_SM")) warps_max = ctx->n_sm * atoi(getenv("LRA_B200_MAP_WARPS_PER_SM"));
+  warps = warps_max < n_reads ? warps_max : n_reads;
+  // measured worker scratch: < 10 MB for reads up to 60 kb (SparseDP sub-problems dominate); the arena is kept across batches
+  size_t per = (size_t)maxL * 384 + (16u << 20);
   size_t free_b = 0, tot_b = 0; cudaMemGetInfo(&free_b, &tot_b);
-  while ((size_t)warps * per > free_b / 2 && warps > ctx->n_sm) warps -= ctx->n_sm;
+  const size_t budget = (free_b + B[9].cap) / 2;
+  while ((size_t)warps * per > budget && warps > ctx->n_sm) warps -= ctx->n_sm;
   if ((rc = ensure(ctx, B[2], (size_t)n_reads * 4)) || (rc = ensure(ctx, B[3], (size_t)n_reads * 4)) || (rc = ensure(ctx, B[4], (size_t)n_reads * 16)) ||
       (rc = ensure(ctx, B[5], (size_t)n_reads * 16)) || (rc = ensure(ctx, B[6], seg_cap * sizeof(SegRec))) || (rc = ensure(ctx, B[7], blk_cap * 12)) ||
-      (rc = ensure(ctx, B[8], 256)) || (rc = ensure(ctx, B[9], (size_t)warps * per)) || (rc = ensure(ctx, B[10], (size_t)n_reads * 4)))
+      (rc = ensure(ctx, B[8], 256)) || (rc = ensure(ctx, B[9], (size_t)warps * per)) || (rc = ensure(ctx, B[10], (size_t)n_reads * 4)) ||
+      (rc = ensure(ctx, B[27], (size_t)(warps + 4) * lra::mp::kProfStages * 8)))
     return rc;
   CU(cudaMemsetAsync(B[8].p, 0, 256, st));
+  CU(cudaMemsetAsync(B[27].p, 0, (size_t)(warps + 4) * lra::mp::kProfStages * 8, st));
   // longest reads first (the tail of the batch is then made of short reads)
   { std::vector<int> ord(n_reads); for (int r = 0; r < n_reads; r++) ord[r] = r;
     std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return read_len[a] > read_len[b2]; });
     CU(cudaMemcpyAsync(B[10].p, ord.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, st)); CU(cudaStreamSynchronize(st)); }
   MapBatch mb;
-  mb.C.o = m->opts; mb.C.pwl = m->d_pwl;
+  mb.C.o = m->opts; mb.C.pwl = m->d_pwl; mb.C.prof = getenv("LRA_B200_MAP_PROFILE") ? (unsigned long long *)B[27].p : nullptr;
   mb.C.ix.genome = lra::SeqView{m->genome->b2, m->genome->nm, m->genome->n}; mb.C.ix.hdr_pos = m->d_hdr; mb.C.ix.n_hdr = m->n_hdr;
   mb.C.ix.idx_t = (const unsigned long long *)m->index->t; mb.C.ix.idx_pos = m->index->pos; mb.C.ix.n_idx = (long long)m->index->n;
   mb.C.ix.gl = lidx_view(m->gl);
@@ -301,6 +307,18 @@ extern "C" int lra_b200_map_batch(lra_b200_ctx *ctx, lra_b200_mapper *m, const c
   CU(cudaStreamSynchronize(st));
   { lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "map_reads"); cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]);
     s2.jobs = (uint64_t)n_reads; s2.algo_bytes = total_bases + 2 * ((total_bases + 3) / 4); all.push_back(s2); }
+  if (mb.C.prof) {
+    std::vector<unsigned long long> hp((size_t)(warps + 4) * lra::mp::kProfStages);
+    CU(cudaMemcpy(hp.data(), B[27].p, hp.size() * 8, cudaMemcpyDeviceToHost));
+    static const char *nm[lra::mp::kProfStages] = {"minimizers+sort", "CompareLists(global)", "strand+CleanMatches", "LinearExtend#1", "SparseDP#1", "SPLITChain", "Refine_splitchain",
+                                                   "Refine_Btwnsplitchain", "LinearExtend#2+Trim", "SparseDP#2+filters", "LocalRefineAlignment(all)", "  AffineOneGapAlign", "  RefineSpace",
+                                                   "  SparseDP#3", "output", ""};
+    unsigned long long tot[lra::mp::kProfStages] = {0}; unsigned long long all_c = 0;
+    for (int wv = 0; wv < warps; wv++) for (int s = 0; s < lra::mp::kProfStages; s++) tot[s] += hp[(size_t)wv * lra::mp::kProfStages + s];
+    for (int s = 0; s < 11; s++) all_c += tot[s]; all_c += tot[14];
+    fprintf(stderr, "[lra_b200 map profile] %d warps, arena %zu MB/warp, peak %.1f MB; share of worker cycles:\n", warps, per >> 20, (double)hcur[3] / 1e6);
+    for (int s = 0; s < 15; s++) fprintf(stderr, "  %-28s %6.2f %%\n", nm[s], all_c ? 100.0 * (double)tot[s] / (double)all_c : 0.0);
+  }
   const int S = (int)(hcur[0] >> 40); const unsigned long long NB = hcur[0] & ((1ull << 40) - 1ull);
   const int kerr = (int)(hcur[2] & 0xffffffffull);
   if (kerr & 3) return fail(ctx, LRA_B200_EOVERFLOW, "map_batch: segment / block capacity exceeded (%d segments, %llu blocks)", S, NB);

@@ -31,15 +31,19 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
   const MpOpts &O = C.o;
   const uint32_t L = C.rd.read_len[r];
   nseg_out = 0; seg0_out = 0;
+  unsigned long long tk = mp_clock();
   SplitSet sp;
   if (!mp_split_chain(C, ext, chain, ar, sp)) return -MP_ERR_ARENA;
+  tk = mp_tick(C, PF_SPLIT, tk);
   if (sp.n == 0) return 1;
   // ---- Refine_splitchain, Refine_Btwnsplitchain
   RCluster *RC = ar.alloc<RCluster>(sp.n);
   RSeg *nodes = ar.alloc<RSeg>(sp.n);
   if (ar.overflow) return -MP_ERR_ARENA;
   for (int ph = 0; ph < sp.n; ph++) if (!mp_refine_splitchain(C, r, ext, chain, sp, ph, ar, RC[ph], nodes + ph)) return -MP_ERR_ARENA;
+  tk = mp_tick(C, PF_REFINE_SPLIT, tk);
   if (!mp_refine_btwn_splitchain(C, r, ar, sp, RC)) return -MP_ERR_ARENA;
+  tk = mp_tick(C, PF_REFINE_BTWN, tk);
   // ---- MergeChain (ChainRefine.h:767-802): groups of consecutive refined clusters
   int *grp = ar.alloc<int>(sp.n + 1);     // group id of every refined cluster
   int *ng_p = ar.alloc<int>(2);
@@ -118,6 +122,7 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
     }
     wsync();
   }
+  tk = mp_tick(C, PF_LEXT2, tk);
   if (total_refined == 0) return 1;
   // ---- second SparseDP per extended cluster + RemovePairedIndels + RemoveSpuriousAnchors
   UChain *uc = ar.alloc<UChain>(ng);
@@ -147,6 +152,7 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
     if (lane == 0) uc[g] = u;
     wsync();
   }
+  tk = mp_tick(C, PF_SDP2, tk);
   // LargestSplitChain
   int LSC = 0;
   for (int g = 1; g < ng; g++) if (uc[g].n > uc[LSC].n) LSC = g;
@@ -162,6 +168,7 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
   if (ar.overflow) return -MP_ERR_ARENA;
   if (!mp_local_refine_alignment(C, r, ar, B, xs, uc, ng, LSC)) return ar.overflow ? -MP_ERR_ARENA : -MP_ERR_CAP;
   wsync();
+  tk = mp_tick(C, PF_LOCAL_REFINE, tk);
   if (B.nseg == 0) { nseg_out = 0; return 0; }
   // ---- hand the segments to the global lists
   // one atomic reserves the segment ids (high 24 bits) and the block range (low 40 bits) together, so that in segment order the block offsets are
@@ -185,6 +192,7 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
   }
   wsync();
   nseg_out = B.nseg; seg0_out = (int)s0;
+  tk = mp_tick(C, PF_OUTPUT, tk);
   return 0;
 }
 
@@ -228,7 +236,7 @@ struct MapBatch {
   const int *order;                       // optional: reads in decreasing length (longest first)
 };
 
-__global__ void __launch_bounds__(128) map_reads_kernel(MapBatch b) {
+__global__ void __launch_bounds__(128, 4) map_reads_kernel(MapBatch b) {
   const int warps_per_block = (int)blockDim.x / kLanes;
   const int wid = (int)blockIdx.x * warps_per_block + (int)threadIdx.x / kLanes;
   Arena ar; ar.init(b.arena + (unsigned long long)wid * b.arena_per_warp, b.arena_per_warp);

@@ -18,7 +18,31 @@ struct MpCtx {
   MpIndex ix;
   MpReads rd;
   const Pwl *pwl;
+  unsigned long long *prof;               // optional [n_warps][kProfStages] clock64 totals per stage (lane 0)
 };
+
+// ---- stage profile of the worker kernel (clock64 deltas accumulated per warp; summed on the host)
+enum { PF_MINIMIZERS = 0, PF_COMPARE, PF_STRAND_CLEAN, PF_LEXT1, PF_SDP1, PF_SPLIT, PF_REFINE_SPLIT, PF_REFINE_BTWN, PF_LEXT2, PF_SDP2, PF_LOCAL_REFINE, PF_AOG, PF_REFINE_SPACE,
+       PF_SDP3, PF_OUTPUT, kProfStages = 16 };
+__device__ __forceinline__ unsigned long long mp_clock() {
+#ifdef LRA_EMU
+  return 0ull;
+#else
+  return (unsigned long long)clock64();
+#endif
+}
+__device__ __forceinline__ unsigned long long mp_tick(const MpCtx &C, int stage, unsigned long long t0) {
+#ifdef LRA_EMU
+  (void)C; (void)stage; (void)t0; return 0ull;
+#else
+  const unsigned long long t1 = (unsigned long long)clock64();
+  if (C.prof && (threadIdx.x & 31u) == 0) {
+    const unsigned wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    C.prof[(unsigned long long)wid * kProfStages + stage] += t1 - t0;
+  }
+  return t1;
+#endif
+}
 
 struct MpMatch { uint32_t q, t; unsigned long long qt; };
 struct MpKey { unsigned long long k; uint32_t q, idx; };
@@ -148,10 +172,12 @@ __device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterS
   unsigned long long *mm_t = ar.alloc<unsigned long long>((unsigned long long)L + 2);
   uint32_t *mm_p = ar.alloc<uint32_t>((unsigned long long)L + 2);
   if (ar.overflow) return MP_ERR_ARENA;
+  unsigned long long tk = mp_clock();
   int n_mm = 0;
   if (lane == 0) { n_mm = (int)mm_scan<true>(C.rd.fwd, roff, L, O.globalK, O.globalW, mm_t, mm_p); mm_sort(MmRef{mm_t, mm_p}, (long)n_mm); }
   wsync();
   n_mm = bcast(n_mm, 0);
+  tk = mp_tick(C, PF_MINIMIZERS, tk);
   // ---- a4: CompareLists against the global index (MapRead.h:190); matches land in the open end of the arena
   const unsigned long long top0 = (ar.top + 15ull) & ~15ull;
   const unsigned long long room = ar.cap > top0 ? (ar.cap - top0) / sizeof(MpMatch) : 0ull;
@@ -166,6 +192,7 @@ __device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterS
   }
   wsync();
   n_match = bcast(n_match, 0);
+  tk = mp_tick(C, PF_COMPARE, tk);
   if ((unsigned long long)n_match > room / 4) return MP_ERR_ARENA;        // leave room for the stages below
   ar.alloc<MpMatch>((unsigned long long)n_match);
   const int NM = (int)n_match;
@@ -249,6 +276,7 @@ __device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterS
     const float f = raw.freq[c];
     if (f > 1.0f && f <= 2.0f && raw.off[c + 1] - raw.off[c] >= 500) repetitive = 1;
   }
+  tk = mp_tick(C, PF_STRAND_CLEAN, tk);
   // ---- LinearExtend on the raw K-mers of every cluster (Map_lowacc.h:118-153): t chromosome-relative inside, global again afterwards
   if (!mp_alloc_clusterset(ext, ar, raw.ncl, n_raw_a, true)) return MP_ERR_ARENA;
   if (lane == 0) {
@@ -271,6 +299,7 @@ __device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterS
   wsync();
   ext.ncl = raw.ncl;
   const int NE = ext.off[ext.ncl];
+  tk = mp_tick(C, PF_LEXT1, tk);
   // ---- first SparseDP on all anchors (Map_lowacc.h:184-188) + RemoveSpuriousJump
   const float match_rate = repetitive ? 3.0f : O.initial_anchorbonus;
   const int NA = O.NumAln < 8 ? O.NumAln : 8;
@@ -301,6 +330,7 @@ __device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterS
     wsync();
   }
   nch = nc;
+  tk = mp_tick(C, PF_SDP1, tk);
   if (nc == 0) return MP_UNALIGNED;
   return MP_OK;
 }

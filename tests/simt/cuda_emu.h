@@ -22,7 +22,7 @@
 #define __host__
 #define __global__ static
 #define __forceinline__ inline __attribute__((always_inline))
-#define __noinline__ __attribute__((noinline))
+#define __noinline__ inline __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __shared__ static
 

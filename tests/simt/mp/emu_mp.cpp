@@ -62,7 +62,7 @@ extern "C" int emu_map_reads(const uint8_t *reads_fwd, const uint8_t *reads_rc, 
   std::vector<unsigned char> arena(arena_bytes + 64);
   unsigned char *base = arena.data(); while (((uintptr_t)base) & 15) base++;
   MapBatch b;
-  b.C.o = *opts; b.C.pwl = &pwl;
+  b.C.o = *opts; b.C.pwl = &pwl; b.C.prof = nullptr;
   b.C.ix.genome = pg.view; b.C.ix.hdr_pos = (const unsigned long long *)hdr_pos; b.C.ix.n_hdr = n_hdr; b.C.ix.idx_t = (const unsigned long long *)idx_t; b.C.ix.idx_pos = idx_pos;
   b.C.ix.n_idx = n_idx;
   b.C.ix.gl = LidxView{(const unsigned long long *)gl_win_off, nullptr, (const unsigned long long *)gl_bnd, gl_mins, nullptr, nullptr, nullptr, gl_n_win, n_hdr};
