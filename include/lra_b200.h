@@ -865,6 +865,18 @@ void lra_b200_mapper_destroy(lra_b200_ctx *ctx, lra_b200_mapper *m);
  * aln_seg0 .. in SegAlignment order. */
 int lra_b200_map_batch(lra_b200_ctx *ctx, lra_b200_mapper *m, const char *reads_ascii, uint64_t reads_len, const uint64_t *read_off, const uint32_t *read_len,
                        int32_t n_reads, lra_b200_map_result *res);
+/* The same in three steps, for callers that keep batches resident (double buffering, multi-GPU shards; bench.py's `value` leg):
+ * lra_b200_readset_upload  host ASCII reads -> packed forward strands + reverse complements + descriptors in HBM (H2D inside);
+ * lra_b200_map_resident    every kernel of the path over a resident batch, records left in the mapper's device buffers;
+ * lra_b200_map_download    records of the last lra_b200_map_resident call -> caller-owned host buffers (D2H inside).
+ * lra_b200_map_batch == upload + resident + download.  `reads_ascii` and the arrays of lra_b200_map_result may be host or device pointers (the copies
+ * use cudaMemcpyDefault), so a shard received over NCCL is mapped, and its records sent back, without a host bounce; read_off / read_len are host arrays. */
+typedef struct lra_b200_readset lra_b200_readset;
+int lra_b200_readset_upload(lra_b200_ctx *ctx, const char *reads_ascii, uint64_t reads_len, const uint64_t *read_off, const uint32_t *read_len, int32_t n_reads,
+                            lra_b200_readset **out);
+void lra_b200_readset_free(lra_b200_ctx *ctx, lra_b200_readset *rs);
+int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, const lra_b200_readset *rs);
+int lra_b200_map_download(lra_b200_ctx *ctx, lra_b200_mapper *m, lra_b200_map_result *res);
 /* SAM text of the batch in input order (Alignment::PrintSAM, Alignment.h:658-808; unaligned reads: SimplePrintSAM :811-832; order of the
  * segments: OUTPUT, Mapping_ultility.h:465-494).  names: n_reads NUL-terminated strings back to back; contig_names likewise.  Returns the
  * number of bytes written, or -(required size) when cap is too small.  Pure host code. */

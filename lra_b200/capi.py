@@ -246,7 +246,7 @@ class KernelStat(C.Structure):
 
 
 def library_path():
-    return os.path.join(_HERE, "liblra_b200.so")
+    return os.environ.get("LRA_B200_LIB") or os.path.join(_HERE, "liblra_b200.so")
 
 
 def load_library():
@@ -329,6 +329,11 @@ def load_library():
     L.lra_b200_mapper_destroy.argtypes = [C.c_void_p, C.c_void_p]
     L.lra_b200_mapper_destroy.restype = None
     L.lra_b200_map_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(_MapResult)]
+    L.lra_b200_readset_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+    L.lra_b200_readset_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.lra_b200_readset_free.restype = None
+    L.lra_b200_map_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lra_b200_map_download.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_MapResult)]
     L.lra_b200_last_kernel_stats.argtypes = [C.c_void_p, C.POINTER(KernelStat), C.c_int]
     L.lra_b200_launch_count.argtypes = [C.c_void_p]
     L.lra_b200_launch_count.restype = C.c_uint64
@@ -383,6 +388,36 @@ def format_sam(opts, res, names, reads, read_off, read_len, contig_names, runtim
     return buf.raw[:n].decode()
 
 
+def names_blob(names):
+    """n NUL-terminated strings back to back (the `names` / `contig_names` argument of lra_b200_format_sam)."""
+    return b"".join(n.encode() + b"\0" for n in names)
+
+
+def format_sam_into(opts, res, names_b, reads, read_off, read_len, contig_b, n_contigs, out, runtime=0):
+    """lra_b200_format_sam into a caller-owned uint8 buffer (one pass); returns the number of bytes written."""
+    L = load_library()
+    ms = _map_result_struct(res)
+    reads = np.ascontiguousarray(reads, np.uint8); ro = np.ascontiguousarray(read_off, np.uint64); rl = np.ascontiguousarray(read_len, np.uint32)
+    n = L.lra_b200_format_sam(C.byref(opts), C.byref(ms), len(rl), names_b, reads.ctypes.data, ro.ctypes.data, rl.ctypes.data, contig_b, n_contigs, runtime, out.ctypes.data, len(out))
+    if n < 0:
+        raise LraB200Error(EOVERFLOW, "format_sam: buffer of %d bytes too small, %d needed" % (len(out), -n))
+    return int(n)
+
+
+_PART_KEYS = ("status", "n_aln", "aln_nseg", "aln_seg0", "aln_rank", "records", "cigar")
+
+
+def result_from_parts(parts):
+    """Inverse of Mapper.download_device: 1-D CPU tensors (per-read arrays, record bytes, cigar words, [n_records, n_cigar, aligned_bases]) -> the result dict."""
+    res = {}
+    for k, t in zip(_PART_KEYS, parts):
+        a = t.numpy()
+        res[k] = a.view(RECORD) if k == "records" else a
+    meta = parts[len(_PART_KEYS)].numpy()
+    res["n_records"] = int(meta[0]); res["n_cigar"] = int(meta[1]); res["aligned_bases"] = int(meta[2])
+    return res
+
+
 class Mapper:
     """lra_b200_mapper: the MapRead seam for one reference (genome + <ref>.mms + <ref>.gli) and one preset."""
 
@@ -399,14 +434,61 @@ class Mapper:
         ctx._check(ctx.lib.lra_b200_mapper_create(ctx.h, C.byref(opts), _ptr(g), len(g), _ptr(hdr), len(hdr) - 1, _ptr(t), _ptr(p), len(t), *args, C.byref(h)))
         self.h = h
 
-    def map_batch(self, reads, read_off, read_len, record_cap=None, cigar_cap=None):
+    @staticmethod
+    def _result_buffers(n, bases, record_cap=None, cigar_cap=None):
+        record_cap = record_cap or 3 * n + 1024; cigar_cap = cigar_cap or int(bases) + 64 * n + 4096
+        return dict(status=np.zeros(max(n, 1), np.int32), n_aln=np.zeros(max(n, 1), np.int32), aln_nseg=np.zeros(4 * max(n, 1), np.int32), aln_seg0=np.zeros(4 * max(n, 1), np.int32),
+                    aln_rank=np.zeros(4 * max(n, 1), np.int32), records=np.zeros(record_cap, RECORD), n_records=0, cigar=np.zeros(cigar_cap, np.uint32), n_cigar=0)
+
+    def map_batch(self, reads, read_off, read_len, record_cap=None, cigar_cap=None, res=None):
+        """MapRead over a batch of reads given as host buffers (H2D of the reads and D2H of the records inside the call)."""
         reads = np.ascontiguousarray(reads, np.uint8); ro = np.ascontiguousarray(read_off, np.uint64); rl = np.ascontiguousarray(read_len, np.uint32)
         n = len(rl)
-        record_cap = record_cap or 3 * n + 1024; cigar_cap = cigar_cap or int(rl.sum()) + 64 * n + 4096
-        res = dict(status=np.zeros(max(n, 1), np.int32), n_aln=np.zeros(max(n, 1), np.int32), aln_nseg=np.zeros(4 * max(n, 1), np.int32), aln_seg0=np.zeros(4 * max(n, 1), np.int32),
-                   aln_rank=np.zeros(4 * max(n, 1), np.int32), records=np.zeros(record_cap, RECORD), n_records=0, cigar=np.zeros(cigar_cap, np.uint32), n_cigar=0)
+        res = res if res is not None else self._result_buffers(n, rl.sum(), record_cap, cigar_cap)
         ms = _map_result_struct(res)
         self.ctx._check(self.ctx.lib.lra_b200_map_batch(self.ctx.h, self.h, _ptr(reads), len(reads), _ptr(ro), _ptr(rl), n, C.byref(ms)))
+        res["n_records"] = int(ms.n_records); res["n_cigar"] = int(ms.n_cigar); res["aligned_bases"] = int(ms.aligned_bases)
+        return res
+
+    def upload(self, reads, read_off, read_len):
+        """lra_b200_readset_upload: the batch packed and resident in HBM; returns an opaque handle (free with free_readset)."""
+        reads = np.ascontiguousarray(reads, np.uint8); ro = np.ascontiguousarray(read_off, np.uint64); rl = np.ascontiguousarray(read_len, np.uint32)
+        h = C.c_void_p()
+        self.ctx._check(self.ctx.lib.lra_b200_readset_upload(self.ctx.h, _ptr(reads), len(reads), _ptr(ro), _ptr(rl), len(rl), C.byref(h)))
+        return h
+
+    def upload_device(self, reads_t, read_off, read_len):
+        """lra_b200_readset_upload from a uint8 CUDA tensor (a shard received over NCCL): no host bounce of the bases."""
+        ro = np.ascontiguousarray(read_off, np.uint64); rl = np.ascontiguousarray(read_len, np.uint32)
+        h = C.c_void_p()
+        self.ctx._check(self.ctx.lib.lra_b200_readset_upload(self.ctx.h, C.c_void_p(reads_t.data_ptr()), int(reads_t.numel()), _ptr(ro), _ptr(rl), len(rl), C.byref(h)))
+        return h
+
+    def download_device(self, n, bases, device):
+        """lra_b200_map_download into CUDA tensors (to be sent over NCCL): [status, n_aln, aln_nseg, aln_seg0, aln_rank, record bytes, cigar, meta]."""
+        import torch
+        record_cap = 3 * n + 1024; cigar_cap = int(bases) + 64 * n + 4096
+        t = dict(status=torch.empty(max(n, 1), dtype=torch.int32, device=device), n_aln=torch.empty(max(n, 1), dtype=torch.int32, device=device),
+                 aln_nseg=torch.empty(4 * max(n, 1), dtype=torch.int32, device=device), aln_seg0=torch.empty(4 * max(n, 1), dtype=torch.int32, device=device),
+                 aln_rank=torch.empty(4 * max(n, 1), dtype=torch.int32, device=device), records=torch.empty(record_cap * RECORD.itemsize, dtype=torch.uint8, device=device),
+                 cigar=torch.empty(cigar_cap, dtype=torch.int32, device=device))
+        ms = _MapResult(*(C.c_void_p(t[k].data_ptr()) for k in ("status", "n_aln", "aln_nseg", "aln_seg0", "aln_rank")), t["records"].data_ptr(), record_cap, 0,
+                        C.c_void_p(t["cigar"].data_ptr()), cigar_cap, 0, 0)
+        self.ctx._check(self.ctx.lib.lra_b200_map_download(self.ctx.h, self.h, C.byref(ms)))
+        nr, nc = int(ms.n_records), int(ms.n_cigar)
+        meta = torch.tensor([nr, nc, int(ms.aligned_bases)], dtype=torch.int64, device=device)
+        return [t["status"][:n], t["n_aln"][:n], t["aln_nseg"][:4 * n], t["aln_seg0"][:4 * n], t["aln_rank"][:4 * n], t["records"][:nr * RECORD.itemsize], t["cigar"][:nc].view(torch.int32), meta]
+
+    def free_readset(self, h):
+        self.ctx.lib.lra_b200_readset_free(self.ctx.h, h)
+
+    def map_resident(self, readset):
+        self.ctx._check(self.ctx.lib.lra_b200_map_resident(self.ctx.h, self.h, readset))
+
+    def map_download(self, n, bases, res=None):
+        res = res if res is not None else self._result_buffers(n, bases)
+        ms = _map_result_struct(res)
+        self.ctx._check(self.ctx.lib.lra_b200_map_download(self.ctx.h, self.h, C.byref(ms)))
         res["n_records"] = int(ms.n_records); res["n_cigar"] = int(ms.n_cigar); res["aligned_bases"] = int(ms.aligned_bases)
         return res
 

@@ -102,7 +102,8 @@ struct Arena {
   unsigned char *base;
   unsigned long long cap, top, peak;
   int overflow;
-  __device__ __forceinline__ void init(void *b, unsigned long long c) { base = (unsigned char *)b; cap = c; top = 0; peak = 0; overflow = 0; }
+  int phase;                              // CTA phase barriers this warp has passed for its current read (mp_phase)
+  __device__ __forceinline__ void init(void *b, unsigned long long c) { base = (unsigned char *)b; cap = c; top = 0; peak = 0; overflow = 0; phase = 0; }
   template <class T> __device__ __forceinline__ T *alloc(unsigned long long n) {
     unsigned long long t = (top + 15ull) & ~15ull;
     unsigned long long e = t + n * sizeof(T);
@@ -115,6 +116,20 @@ struct Arena {
   __device__ __forceinline__ void release(unsigned long long m) { top = m; }
   __device__ __forceinline__ unsigned long long avail() const { return cap - ((top + 15ull) & ~15ull); }
 };
+
+// ---- phase alignment of the warps of a CTA.  The worker is instruction-fetch bound when its warps run different stages of the (800 KB) path at
+// the same time (ncu: 30 of 39 stall cycles per instruction are no_instruction with 16 unaligned warps per SM), so the warps of a CTA take a group
+// of reads through the stages in lock step: one CTA barrier closes every stage.  A barrier only counts arrivals, so a warp whose read leaves the
+// path early (unaligned, capacity error, fewer chains) catches up with mp_phase_upto and idles at no cost to the others.
+__device__ __forceinline__ void mp_phase(Arena &ar) {
+  ar.phase++;
+#if !defined(LRA_EMU)
+  __syncthreads();
+#endif
+}
+__device__ __forceinline__ void mp_phase_upto(Arena &ar, int n) { while (ar.phase < n) mp_phase(ar); }
+constexpr int kPhasesStage1 = 4;          // minimizers+sort | CompareLists | strand+CleanMatches+LinearExtend | first SparseDP
+constexpr int kPhasesChain = 6;           // SPLITChain+Refine_splitchain | Refine_Btwnsplitchain | MergeChain+LinearExtend | second SparseDP | LocalRefineAlignment | output
 
 __device__ __forceinline__ int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 

@@ -124,6 +124,8 @@ extern "C" int64_t lra_b200_format_sam(const lra_b200_map_opts *opts, const lra_
   return (int64_t)text.size();
 }
 
+struct lra_b200_readset;
+extern "C" void lra_b200_readset_free(lra_b200_ctx *ctx, lra_b200_readset *rs);
 // ---- the mapper ---------------------------------------------------------------------------------------------------------------------------------
 struct lra_b200_mapper {
   lra_b200_map_opts opts;
@@ -136,8 +138,9 @@ struct lra_b200_mapper {
   float log_lut[2001];
   float logf_len[8];
   // per batch
-  lra_b200_seq *reads = nullptr;          // forward strands at [0, Npad), reverse complements at [Npad, 2 Npad)
+  struct lra_b200_readset *own = nullptr; // the batch of lra_b200_map_batch (host buffers in, records out)
   lra_b200_lindex *rl[2] = {nullptr, nullptr};
+  int last_reads = 0, last_S = 0, last_kerr = 0; uint64_t last_ncig = 0;
   DevBuf b[40];
   int *h_pin = nullptr;
 };
@@ -165,7 +168,7 @@ extern "C" void lra_b200_mapper_destroy(lra_b200_ctx *ctx, lra_b200_mapper *m) {
   if (m->genome) lra_b200_seq_free(ctx, m->genome);
   if (m->index) lra_b200_index_free(ctx, m->index);
   if (m->gl) lra_b200_lindex_free(ctx, m->gl);
-  if (m->reads) lra_b200_seq_free(ctx, m->reads);
+  if (m->own) lra_b200_readset_free(ctx, m->own);
   for (int s = 0; s < 2; s++) if (m->rl[s]) lra_b200_lindex_free(ctx, m->rl[s]);
   if (m->d_hdr) cudaFree(m->d_hdr);
   if (m->d_pwl) cudaFree(m->d_pwl);
@@ -212,93 +215,135 @@ extern "C" int lra_b200_mapper_create(lra_b200_ctx *ctx, const lra_b200_map_opts
   return LRA_B200_OK;
 }
 
-extern "C" int lra_b200_map_batch(lra_b200_ctx *ctx, lra_b200_mapper *m, const char *reads_ascii, uint64_t reads_len, const uint64_t *read_off, const uint32_t *read_len,
-                                  int32_t n_reads, lra_b200_map_result *res) {
-  using namespace lra::mp;
-  if (!ctx || !m || !res || n_reads < 0 || (n_reads && (!reads_ascii || !read_off || !read_len))) return fail(ctx, LRA_B200_EINVAL, "map_batch: NULL argument");
-  if (!res->status || !res->n_aln || !res->aln_nseg || !res->aln_seg0 || !res->aln_rank || !res->records || !res->cigar) return fail(ctx, LRA_B200_EINVAL, "map_batch: NULL result array");
+
+// ---- a batch of reads resident on the device (packed forward strands + reverse complements, descriptors, longest-first order) ----------------------
+struct lra_b200_readset {
+  lra_b200_seq *reads = nullptr;          // forward strands at [0, Npad), reverse complements at [Npad, 2 Npad)
+  DevBuf off, len, order;
+  std::vector<uint64_t> h_off, h_rc_off; std::vector<uint32_t> h_len;
+  int n_reads = 0; unsigned long long Npad = 0, total_bases = 0; uint32_t maxL = 0;
+};
+
+extern "C" void lra_b200_readset_free(lra_b200_ctx *ctx, lra_b200_readset *rs) {
+  if (!rs) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  if (rs->reads) lra_b200_seq_free(ctx, rs->reads);
+  for (DevBuf *b : {&rs->off, &rs->len, &rs->order}) if (b->p) cudaFree(b->p);
+  delete rs;
+}
+
+static int readset_fill(lra_b200_ctx *ctx, lra_b200_readset *rs, const char *reads_ascii, uint64_t reads_len, const uint64_t *read_off, const uint32_t *read_len, int32_t n_reads) {
   CU(cudaSetDevice(ctx->device));
-  res->n_records = 0; res->n_cigar = 0; res->aligned_bases = 0;
-  std::vector<lra_b200_kernel_stat> all;
-  if (n_reads == 0) { ctx->stats.clear(); return LRA_B200_OK; }
-  uint32_t maxL = 0;
+  rs->n_reads = n_reads; rs->maxL = 0; rs->total_bases = 0; rs->Npad = 0;
+  if (n_reads == 0) return LRA_B200_OK;
+  uint32_t maxL = 0; unsigned long long total_bases = 0;
   for (int r = 0; r < n_reads; r++) {
-    if (read_off[r] + read_len[r] > reads_len) return fail(ctx, LRA_B200_EINVAL, "map_batch: read %d ends beyond the buffer", r);
-    if (r && read_off[r] < read_off[r - 1] + read_len[r - 1]) return fail(ctx, LRA_B200_EINVAL, "map_batch: reads overlap or are not in ascending order at %d", r);
-    maxL = read_len[r] > maxL ? read_len[r] : maxL;
+    if (read_off[r] + read_len[r] > reads_len) return fail(ctx, LRA_B200_EINVAL, "readset_upload: read %d ends beyond the buffer", r);
+    if (r && read_off[r] < read_off[r - 1] + read_len[r - 1]) return fail(ctx, LRA_B200_EINVAL, "readset_upload: reads overlap or are not in ascending order at %d", r);
+    maxL = read_len[r] > maxL ? read_len[r] : maxL; total_bases += read_len[r];
   }
   const unsigned long long Npad = ((unsigned long long)reads_len + 127ull) & ~63ull;
-  if (2 * Npad >= (1ull << 32)) return fail(ctx, LRA_B200_EINVAL, "map_batch: more than 2^31 bases in one batch");
+  if (2 * Npad >= (1ull << 32)) return fail(ctx, LRA_B200_EINVAL, "readset_upload: more than 2^31 bases in one batch");
   cudaStream_t st = ctx->stream;
   int rc;
   // ---- reads: pack the forward strands into [0, Npad), reverse complements into [Npad, 2 Npad)
-  if (!m->reads) m->reads = new lra_b200_seq();
-  if ((rc = seq_reserve(ctx, m->reads, 2 * Npad))) return rc;
-  CU(cudaMemsetAsync(m->reads->b2, 0, (m->reads->cap_groups * 2 + 8) * 4, st));
-  CU(cudaMemsetAsync(m->reads->nm, 0xFF, (m->reads->cap_groups + 8) * 4, st));
-  if (reads_len + 64 > m->reads->ascii_cap) {
-    if (m->reads->ascii_dev) { CU(cudaStreamSynchronize(st)); CU(cudaFree(m->reads->ascii_dev)); m->reads->ascii_dev = nullptr; }
+  if (!rs->reads) rs->reads = new lra_b200_seq();
+  if ((rc = seq_reserve(ctx, rs->reads, 2 * Npad))) return rc;
+  CU(cudaMemsetAsync(rs->reads->b2, 0, (rs->reads->cap_groups * 2 + 8) * 4, st));
+  CU(cudaMemsetAsync(rs->reads->nm, 0xFF, (rs->reads->cap_groups + 8) * 4, st));
+  if (reads_len + 64 > rs->reads->ascii_cap) {
+    if (rs->reads->ascii_dev) { CU(cudaStreamSynchronize(st)); CU(cudaFree(rs->reads->ascii_dev)); rs->reads->ascii_dev = nullptr; }
     const uint64_t cap = reads_len + reads_len / 4 + 256;
-    CU(cudaMalloc((void **)&m->reads->ascii_dev, cap)); m->reads->ascii_cap = cap;
+    CU(cudaMalloc((void **)&rs->reads->ascii_dev, cap)); rs->reads->ascii_cap = cap;
   }
-  CU(cudaMemcpyAsync(m->reads->ascii_dev, reads_ascii, reads_len, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(rs->reads->ascii_dev, reads_ascii, reads_len, cudaMemcpyDefault, st));   // host or device source (UVA)
   { const uint64_t groups = (reads_len + 31) / 32 + 1;
-    lra::seq_pack_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(m->reads->ascii_dev, reads_len, m->reads->b2, m->reads->nm, groups); ctx->launches++; }
-  m->reads->n = 2 * Npad;
-  DevBuf *B = m->b;
-  if ((rc = ensure(ctx, B[0], (size_t)n_reads * 8)) || (rc = ensure(ctx, B[1], (size_t)n_reads * 4))) return rc;
-  CU(cudaMemcpyAsync(B[0].p, read_off, (size_t)n_reads * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(B[1].p, read_len, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
-  lra::seq_revcomp_kernel<<<(unsigned)((n_reads + 7) / 8), 256, 0, st>>>(lra::SeqView{m->reads->b2, m->reads->nm, Npad}, (const unsigned long long *)B[0].p,
-                                                                         (const uint32_t *)B[1].p, n_reads, m->reads->b2 + Npad / 16, m->reads->nm + Npad / 32);
+    lra::seq_pack_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(rs->reads->ascii_dev, reads_len, rs->reads->b2, rs->reads->nm, groups); ctx->launches++; }
+  rs->reads->n = 2 * Npad;
+  if ((rc = ensure(ctx, rs->off, (size_t)n_reads * 8)) || (rc = ensure(ctx, rs->len, (size_t)n_reads * 4))) return rc;
+  CU(cudaMemcpyAsync(rs->off.p, read_off, (size_t)n_reads * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(rs->len.p, read_len, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
+  lra::seq_revcomp_kernel<<<(unsigned)((n_reads + 7) / 8), 256, 0, st>>>(lra::SeqView{rs->reads->b2, rs->reads->nm, Npad}, (const unsigned long long *)rs->off.p,
+                                                                         (const uint32_t *)rs->len.p, n_reads, rs->reads->b2 + Npad / 16, rs->reads->nm + Npad / 32);
   ctx->launches++;
   CU(cudaGetLastError());
+  // longest reads first (the tail of the batch is then made of short reads)
+  if ((rc = ensure(ctx, rs->order, (size_t)n_reads * 4))) return rc;
+  { std::vector<int> ord(n_reads); for (int r = 0; r < n_reads; r++) ord[r] = r;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return read_len[a] > read_len[b2]; });
+    CU(cudaMemcpyAsync(rs->order.p, ord.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, st)); CU(cudaStreamSynchronize(st)); }
+  rs->h_off.assign(read_off, read_off + n_reads); rs->h_len.assign(read_len, read_len + n_reads); rs->h_rc_off.resize(n_reads);
+  for (int r = 0; r < n_reads; r++) rs->h_rc_off[r] = read_off[r] + Npad;
+  rs->Npad = Npad; rs->maxL = maxL; rs->total_bases = total_bases;
+  return LRA_B200_OK;
+}
+
+extern "C" int lra_b200_readset_upload(lra_b200_ctx *ctx, const char *reads_ascii, uint64_t reads_len, const uint64_t *read_off, const uint32_t *read_len, int32_t n_reads,
+                                       lra_b200_readset **out) {
+  if (!ctx || !out || n_reads < 0 || (n_reads && (!reads_ascii || !read_off || !read_len))) return fail(ctx, LRA_B200_EINVAL, "readset_upload: NULL argument");
+  *out = nullptr;
+  lra_b200_readset *rs = new lra_b200_readset();
+  const int rc = readset_fill(ctx, rs, reads_ascii, reads_len, read_off, read_len, n_reads);
+  if (rc) { lra_b200_readset_free(ctx, rs); return rc; }
+  *out = rs;
+  return LRA_B200_OK;
+}
+
+// every kernel of the path over a resident batch; the records stay in the mapper's device buffers until lra_b200_map_download
+extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, const lra_b200_readset *rs) {
+  using namespace lra::mp;
+  if (!ctx || !m || !rs) return fail(ctx, LRA_B200_EINVAL, "map_resident: NULL argument");
+  CU(cudaSetDevice(ctx->device));
+  const int n_reads = rs->n_reads; const unsigned long long Npad = rs->Npad, total_bases = rs->total_bases; const uint32_t maxL = rs->maxL;
+  m->last_reads = n_reads; m->last_S = 0; m->last_ncig = 0; m->last_kerr = 0;
+  std::vector<lra_b200_kernel_stat> all;
+  if (n_reads == 0) { ctx->stats.clear(); return LRA_B200_OK; }
+  cudaStream_t st = ctx->stream;
+  int rc;
+  DevBuf *B = m->b;
   // ---- a12: LocalIndex::IndexSeq of every read, both strands (Map_lowacc.h:246-250)
-  std::vector<uint64_t> rc_off(n_reads);
-  for (int r = 0; r < n_reads; r++) rc_off[r] = read_off[r] + Npad;
   ctx->keep_stats = false;
-  if ((rc = lra_b200_lindex_build(ctx, m->reads, read_off, read_len, n_reads, m->opts.smallK, m->opts.smallW, m->opts.localIndexWindow, m->opts.localIndexMaxFreq, &m->rl[0]))) return rc;
+  if ((rc = lra_b200_lindex_build(ctx, rs->reads, rs->h_off.data(), rs->h_len.data(), n_reads, m->opts.smallK, m->opts.smallW, m->opts.localIndexWindow, m->opts.localIndexMaxFreq, &m->rl[0]))) return rc;
   all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
-  if ((rc = lra_b200_lindex_build(ctx, m->reads, rc_off.data(), read_len, n_reads, m->opts.smallK, m->opts.smallW, m->opts.localIndexWindow, m->opts.localIndexMaxFreq, &m->rl[1]))) return rc;
+  if ((rc = lra_b200_lindex_build(ctx, rs->reads, rs->h_rc_off.data(), rs->h_len.data(), n_reads, m->opts.smallK, m->opts.smallW, m->opts.localIndexWindow, m->opts.localIndexMaxFreq, &m->rl[1]))) return rc;
   all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
   // ---- the mapper worker kernel
-  unsigned long long total_bases = 0; for (int r = 0; r < n_reads; r++) total_bases += read_len[r];
   const size_t seg_cap = (size_t)n_reads * 3 + 1024;
   const size_t blk_cap = (size_t)(total_bases / 2) + (size_t)n_reads * 64 + 4096;
-  int warps = ctx->n_sm * 8; if (warps > n_reads) warps = n_reads;
-  int warps_max = ctx->n_sm * 16; if (getenv("LRA_B200_MAP_WARPS_PER_SM")) warps_max = ctx->n_sm * atoi(getenv("LRA_B200_MAP_WARPS_PER_SM"));
-  warps = warps_max < n_reads ? warps_max : n_reads;
+  // one CTA of `bw` warps per SM (phase-aligned groups of reads, mp_phase); LRA_B200_MAP_BLOCK_WARPS / _BLOCKS_PER_SM for experiments
+  int bw = 16; if (getenv("LRA_B200_MAP_BLOCK_WARPS")) bw = atoi(getenv("LRA_B200_MAP_BLOCK_WARPS"));
+  if (bw < 1) bw = 1; if (bw > 16) bw = 16;
+  int blocks = ctx->n_sm;
+  if ((long long)blocks * bw > (long long)n_reads) blocks = (n_reads + bw - 1) / bw;
+  int warps = blocks * bw;
   // measured worker scratch: < 10 MB for reads up to 60 kb (SparseDP sub-problems dominate); the arena is kept across batches
   size_t per = (size_t)maxL * 384 + (16u << 20);
+  if (getenv("LRA_B200_MAP_ARENA_MB")) per = (size_t)atoi(getenv("LRA_B200_MAP_ARENA_MB")) << 20;
   size_t free_b = 0, tot_b = 0; cudaMemGetInfo(&free_b, &tot_b);
   const size_t budget = (free_b + B[9].cap) / 2;
-  while ((size_t)warps * per > budget && warps > ctx->n_sm) warps -= ctx->n_sm;
+  while ((size_t)warps * per > budget && blocks > 1) { blocks--; warps = blocks * bw; }
   if ((rc = ensure(ctx, B[2], (size_t)n_reads * 4)) || (rc = ensure(ctx, B[3], (size_t)n_reads * 4)) || (rc = ensure(ctx, B[4], (size_t)n_reads * 16)) ||
       (rc = ensure(ctx, B[5], (size_t)n_reads * 16)) || (rc = ensure(ctx, B[6], seg_cap * sizeof(SegRec))) || (rc = ensure(ctx, B[7], blk_cap * 12)) ||
-      (rc = ensure(ctx, B[8], 256)) || (rc = ensure(ctx, B[9], (size_t)warps * per)) || (rc = ensure(ctx, B[10], (size_t)n_reads * 4)) ||
+      (rc = ensure(ctx, B[8], 256)) || (rc = ensure(ctx, B[9], (size_t)warps * per)) ||
       (rc = ensure(ctx, B[27], (size_t)(warps + 4) * lra::mp::kProfStages * 8)))
     return rc;
   CU(cudaMemsetAsync(B[8].p, 0, 256, st));
   CU(cudaMemsetAsync(B[27].p, 0, (size_t)(warps + 4) * lra::mp::kProfStages * 8, st));
-  // longest reads first (the tail of the batch is then made of short reads)
-  { std::vector<int> ord(n_reads); for (int r = 0; r < n_reads; r++) ord[r] = r;
-    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b2) { return read_len[a] > read_len[b2]; });
-    CU(cudaMemcpyAsync(B[10].p, ord.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, st)); CU(cudaStreamSynchronize(st)); }
   MapBatch mb;
   mb.C.o = m->opts; mb.C.pwl = m->d_pwl; mb.C.prof = getenv("LRA_B200_MAP_PROFILE") ? (unsigned long long *)B[27].p : nullptr;
   mb.C.ix.genome = lra::SeqView{m->genome->b2, m->genome->nm, m->genome->n}; mb.C.ix.hdr_pos = m->d_hdr; mb.C.ix.n_hdr = m->n_hdr;
   mb.C.ix.idx_t = (const unsigned long long *)m->index->t; mb.C.ix.idx_pos = m->index->pos; mb.C.ix.n_idx = (long long)m->index->n;
   mb.C.ix.gl = lidx_view(m->gl);
-  mb.C.rd.fwd = lra::SeqView{m->reads->b2, m->reads->nm, Npad}; mb.C.rd.rc = lra::SeqView{m->reads->b2 + Npad / 16, m->reads->nm + Npad / 32, Npad};
-  mb.C.rd.read_off = (const unsigned long long *)B[0].p; mb.C.rd.read_len = (const uint32_t *)B[1].p; mb.C.rd.n_reads = n_reads;
+  mb.C.rd.fwd = lra::SeqView{rs->reads->b2, rs->reads->nm, Npad}; mb.C.rd.rc = lra::SeqView{rs->reads->b2 + Npad / 16, rs->reads->nm + Npad / 32, Npad};
+  mb.C.rd.read_off = (const unsigned long long *)rs->off.p; mb.C.rd.read_len = (const uint32_t *)rs->len.p; mb.C.rd.n_reads = n_reads;
   mb.C.rd.rd[0] = lidx_view(m->rl[0]); mb.C.rd.rd[1] = lidx_view(m->rl[1]);
   // (the reverse-complement image was built over arena offsets read_off + Npad; the worker only uses window offsets relative to the image's own seq_start)
   mb.out.status = (int *)B[2].p; mb.out.n_chains = (int *)B[3].p; mb.out.chain_nseg = (int *)B[4].p; mb.out.chain_seg0 = (int *)B[5].p;
   mb.out.seg = (SegRec *)B[6].p; mb.out.seg_cap = (int)seg_cap; mb.out.seg_cursor = (unsigned long long *)B[8].p; mb.out.blocks = (uint32_t *)B[7].p; mb.out.blk_cap = blk_cap;
   mb.out.blk_cursor = (unsigned long long *)((char *)B[8].p + 8); mb.out.err = (int *)((char *)B[8].p + 16); mb.out.peak = (unsigned long long *)((char *)B[8].p + 24);
-  mb.arena = (unsigned char *)B[9].p; mb.arena_per_warp = per; mb.work = (int *)((char *)B[8].p + 32); mb.order = (const int *)B[10].p;
+  mb.arena = (unsigned char *)B[9].p; mb.arena_per_warp = per; mb.work = (int *)((char *)B[8].p + 32); mb.order = (const int *)rs->order.p;
   cudaEventRecord(ctx->ev[0], st);
-  map_reads_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(mb);
+  map_reads_kernel<<<(unsigned)blocks, (unsigned)(bw * 32), 0, st>>>(mb);
   cudaEventRecord(ctx->ev[1], st);
   ctx->launches++;
   CU(cudaGetLastError());
@@ -322,7 +367,6 @@ extern "C" int lra_b200_map_batch(lra_b200_ctx *ctx, lra_b200_mapper *m, const c
   const int S = (int)(hcur[0] >> 40); const unsigned long long NB = hcur[0] & ((1ull << 40) - 1ull);
   const int kerr = (int)(hcur[2] & 0xffffffffull);
   if (kerr & 3) return fail(ctx, LRA_B200_EOVERFLOW, "map_batch: segment / block capacity exceeded (%d segments, %llu blocks)", S, NB);
-  if ((uint64_t)S > res->record_cap) { res->n_records = (uint64_t)S; return fail(ctx, LRA_B200_EOVERFLOW, "map_batch: record capacity %llu too small, %d needed", (unsigned long long)res->record_cap, S); }
   // ---- a19 IndelRefineAlignment and a21 CalculateStatistics over all segments
   if ((rc = ensure(ctx, B[11], (size_t)(S + 1) * 8)) || (rc = ensure(ctx, B[12], (size_t)(S + 1) * 4)) || (rc = ensure(ctx, B[13], (size_t)(S + 1) * 4)) ||
       (rc = ensure(ctx, B[14], (size_t)(S + 1) * 4)) || (rc = ensure(ctx, B[15], (size_t)(S + 1) * 4)) || (rc = ensure(ctx, B[16], (size_t)(S + 1) * 4)))
@@ -337,7 +381,7 @@ extern "C" int lra_b200_map_batch(lra_b200_ctx *ctx, lra_b200_mapper *m, const c
   lra_b200_ir_seg_result ir; memset(&ir, 0, sizeof ir);
   lra_b200_stats_result sr; memset(&sr, 0, sizeof sr);
   if (S > 0) {
-    seg_to_ir_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>((const SegRec *)B[6].p, S, (const unsigned long long *)B[0].p, (const uint32_t *)B[1].p, Npad, m->d_hdr,
+    seg_to_ir_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>((const SegRec *)B[6].p, S, (const unsigned long long *)rs->off.p, (const uint32_t *)rs->len.p, Npad, m->d_hdr,
                                                                  (unsigned long long *)B[11].p, (int32_t *)B[12].p, (uint32_t *)B[13].p, (uint32_t *)B[14].p, (int32_t *)B[15].p,
                                                                  (int32_t *)B[16].p);
     ctx->launches++;
@@ -347,19 +391,19 @@ extern "C" int lra_b200_map_batch(lra_b200_ctx *ctx, lra_b200_mapper *m, const c
     sg.t_base = (const uint32_t *)B[14].p; sg.read_len = (const int32_t *)B[15].p; sg.contig_len = (const int32_t *)B[16].p; sg.n_blocks_in = NB; sg.n_segments = S;
     sg.refine_band = m->opts.refineBand; sg.match = m->opts.localMatch; sg.mismatch = m->opts.localMismatch; sg.indel = m->opts.localIndel; sg.end_align = 0;
     ir.n_blocks = (int32_t *)B[17].p; ir.block_off = (uint64_t *)B[18].p; ir.blocks = (uint32_t *)B[19].p; ir.block_cap = ir_cap;
-    if ((rc = lra_b200_indel_refine_batch_device(ctx, m->reads, m->genome, &sg, &ir))) return rc;
+    if ((rc = lra_b200_indel_refine_batch_device(ctx, rs->reads, m->genome, &sg, &ir))) return rc;
     all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
     lra_b200_ir_segments s2 = sg;
     s2.blocks_in = ir.blocks; s2.blk_off = ir.block_off; s2.blk_cnt = ir.n_blocks; s2.n_blocks_in = ir.n_blocks_total;
     sr.stats = (int32_t *)B[20].p; sr.value = (float *)B[21].p; sr.cigar_off = (uint64_t *)B[22].p; sr.cigar = (uint32_t *)B[23].p; sr.cigar_cap = cig_cap;
-    if ((rc = lra_b200_calc_stats_batch_device(ctx, m->reads, m->genome, &s2, m->log_lut, &sr))) return rc;
+    if ((rc = lra_b200_calc_stats_batch_device(ctx, rs->reads, m->genome, &s2, m->log_lut, &sr))) return rc;
     all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
   }
   // ---- finalize
   CU(cudaMemcpyAsync(B[26].p, m->logf_len, 32, cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync((char *)B[26].p + 32, 0, 8, st));
   FinalBatch fb;
-  fb.n_reads = n_reads; fb.o = m->opts; fb.read_off = (const unsigned long long *)B[0].p; fb.read_len = (const uint32_t *)B[1].p; fb.status = (const int *)B[2].p;
+  fb.n_reads = n_reads; fb.o = m->opts; fb.read_off = (const unsigned long long *)rs->off.p; fb.read_len = (const uint32_t *)rs->len.p; fb.status = (const int *)B[2].p;
   fb.n_chains = (const int *)B[3].p; fb.chain_nseg = (const int *)B[4].p; fb.chain_seg0 = (const int *)B[5].p; fb.seg = (const SegRec *)B[6].p;
   fb.ir_nblk = (const int32_t *)B[17].p; fb.ir_off = (const unsigned long long *)B[18].p; fb.ir_blocks = (const uint32_t *)B[19].p;
   fb.stats = (const int32_t *)B[20].p; fb.value = (const float *)B[21].p; fb.cigar_off = (const unsigned long long *)B[22].p; fb.logf_len = (const float *)B[26].p;
@@ -367,20 +411,47 @@ extern "C" int lra_b200_map_batch(lra_b200_ctx *ctx, lra_b200_mapper *m, const c
   map_finalize_kernel<<<(unsigned)((n_reads + 127) / 128), 128, 0, st>>>(fb);
   ctx->launches++;
   CU(cudaGetLastError());
-  // ---- records home
-  CU(cudaMemcpyAsync(res->status, B[2].p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(res->n_aln, B[3].p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(res->aln_nseg, B[4].p, (size_t)n_reads * 16, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(res->aln_seg0, B[5].p, (size_t)n_reads * 16, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(res->aln_rank, B[25].p, (size_t)n_reads * 16, cudaMemcpyDeviceToHost, st));
-  if (S > 0) CU(cudaMemcpyAsync(res->records, B[24].p, (size_t)S * sizeof(lra_b200_record), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  m->last_S = S; m->last_ncig = sr.n_cigar_total; m->last_kerr = kerr;
+  ctx->stats = all;
+  if (kerr & 4) return fail(ctx, LRA_B200_EINTERNAL, "map_batch: worker scratch exhausted inside TrimOverlappedAnchors");
+  return LRA_B200_OK;
+}
+
+// records of the last lra_b200_map_resident call -> caller-owned host buffers
+extern "C" int lra_b200_map_download(lra_b200_ctx *ctx, lra_b200_mapper *m, lra_b200_map_result *res) {
+  if (!ctx || !m || !res) return fail(ctx, LRA_B200_EINVAL, "map_download: NULL argument");
+  if (!res->status || !res->n_aln || !res->aln_nseg || !res->aln_seg0 || !res->aln_rank || !res->records || !res->cigar) return fail(ctx, LRA_B200_EINVAL, "map_download: NULL result array");
+  CU(cudaSetDevice(ctx->device));
+  res->n_records = 0; res->n_cigar = 0; res->aligned_bases = 0;
+  const int n_reads = m->last_reads, S = m->last_S;
+  if (n_reads == 0) return LRA_B200_OK;
+  cudaStream_t st = ctx->stream;
+  DevBuf *B = m->b;
+  struct { uint64_t n_cigar_total; } sr = {m->last_ncig};
+  if ((uint64_t)S > res->record_cap) { res->n_records = (uint64_t)S; return fail(ctx, LRA_B200_EOVERFLOW, "map_batch: record capacity %llu too small, %d needed", (unsigned long long)res->record_cap, S); }
+  CU(cudaMemcpyAsync(res->status, B[2].p, (size_t)n_reads * 4, cudaMemcpyDefault, st));
+  CU(cudaMemcpyAsync(res->n_aln, B[3].p, (size_t)n_reads * 4, cudaMemcpyDefault, st));
+  CU(cudaMemcpyAsync(res->aln_nseg, B[4].p, (size_t)n_reads * 16, cudaMemcpyDefault, st));
+  CU(cudaMemcpyAsync(res->aln_seg0, B[5].p, (size_t)n_reads * 16, cudaMemcpyDefault, st));
+  CU(cudaMemcpyAsync(res->aln_rank, B[25].p, (size_t)n_reads * 16, cudaMemcpyDefault, st));
+  if (S > 0) CU(cudaMemcpyAsync(res->records, B[24].p, (size_t)S * sizeof(lra_b200_record), cudaMemcpyDefault, st));
   if (sr.n_cigar_total > res->cigar_cap) { res->n_cigar = sr.n_cigar_total; return fail(ctx, LRA_B200_EOVERFLOW, "map_batch: cigar capacity %llu too small, %llu needed", (unsigned long long)res->cigar_cap, (unsigned long long)sr.n_cigar_total); }
-  if (sr.n_cigar_total) CU(cudaMemcpyAsync(res->cigar, B[23].p, (size_t)sr.n_cigar_total * 4, cudaMemcpyDeviceToHost, st));
+  if (sr.n_cigar_total) CU(cudaMemcpyAsync(res->cigar, B[23].p, (size_t)sr.n_cigar_total * 4, cudaMemcpyDefault, st));
   unsigned long long ab = 0;
   CU(cudaMemcpyAsync(&ab, (char *)B[26].p + 32, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   res->n_records = (uint64_t)S; res->n_cigar = sr.n_cigar_total; res->aligned_bases = ab;
-  ctx->stats = all;
-  if (kerr & 4) return fail(ctx, LRA_B200_EINTERNAL, "map_batch: worker scratch exhausted inside TrimOverlappedAnchors");
   return LRA_B200_OK;
+}
+
+extern "C" int lra_b200_map_batch(lra_b200_ctx *ctx, lra_b200_mapper *m, const char *reads_ascii, uint64_t reads_len, const uint64_t *read_off, const uint32_t *read_len,
+                                  int32_t n_reads, lra_b200_map_result *res) {
+  if (!ctx || !m || !res || n_reads < 0 || (n_reads && (!reads_ascii || !read_off || !read_len))) return fail(ctx, LRA_B200_EINVAL, "map_batch: NULL argument");
+  if (!res->status || !res->n_aln || !res->aln_nseg || !res->aln_seg0 || !res->aln_rank || !res->records || !res->cigar) return fail(ctx, LRA_B200_EINVAL, "map_batch: NULL result array");
+  if (!m->own) m->own = new lra_b200_readset();
+  int rc;
+  if ((rc = readset_fill(ctx, m->own, reads_ascii, reads_len, read_off, read_len, n_reads))) return rc;
+  if ((rc = lra_b200_map_resident(ctx, m, m->own))) return rc;
+  return lra_b200_map_download(ctx, m, res);
 }

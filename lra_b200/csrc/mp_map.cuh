@@ -42,8 +42,10 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
   if (ar.overflow) return -MP_ERR_ARENA;
   for (int ph = 0; ph < sp.n; ph++) if (!mp_refine_splitchain(C, r, ext, chain, sp, ph, ar, RC[ph], nodes + ph)) return -MP_ERR_ARENA;
   tk = mp_tick(C, PF_REFINE_SPLIT, tk);
+  mp_phase(ar);
   if (!mp_refine_btwn_splitchain(C, r, ar, sp, RC)) return -MP_ERR_ARENA;
   tk = mp_tick(C, PF_REFINE_BTWN, tk);
+  mp_phase(ar);
   // ---- MergeChain (ChainRefine.h:767-802): groups of consecutive refined clusters
   int *grp = ar.alloc<int>(sp.n + 1);     // group id of every refined cluster
   int *ng_p = ar.alloc<int>(2);
@@ -123,6 +125,7 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
     wsync();
   }
   tk = mp_tick(C, PF_LEXT2, tk);
+  mp_phase(ar);
   if (total_refined == 0) return 1;
   // ---- second SparseDP per extended cluster + RemovePairedIndels + RemoveSpuriousAnchors
   UChain *uc = ar.alloc<UChain>(ng);
@@ -153,6 +156,7 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
     wsync();
   }
   tk = mp_tick(C, PF_SDP2, tk);
+  mp_phase(ar);
   // LargestSplitChain
   int LSC = 0;
   for (int g = 1; g < ng; g++) if (uc[g].n > uc[LSC].n) LSC = g;
@@ -169,6 +173,7 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
   if (!mp_local_refine_alignment(C, r, ar, B, xs, uc, ng, LSC)) return ar.overflow ? -MP_ERR_ARENA : -MP_ERR_CAP;
   wsync();
   tk = mp_tick(C, PF_LOCAL_REFINE, tk);
+  mp_phase(ar);
   if (B.nseg == 0) { nseg_out = 0; return 0; }
   // ---- hand the segments to the global lists
   // one atomic reserves the segment ids (high 24 bits) and the block range (low 40 bits) together, so that in segment order the block offsets are
@@ -203,7 +208,10 @@ __device__ __noinline__ void mp_map_read(const MpCtx &C, int r, Arena &ar, const
   int nseg[kMaxChains], seg0[kMaxChains];
   for (int p = 0; p < kMaxChains; p++) { nseg[p] = 0; seg0[p] = 0; }
   ClusterSet ext; UChain *chains = 0; int nch = 0;
+  ar.phase = 0;
+  const int PB = (C.o.NumAln < kMaxChains ? C.o.NumAln : kMaxChains);      // chains a read can have (uniform over the batch)
   status = mp_stage1(C, r, ar, ext, chains, nch);
+  mp_phase_upto(ar, kPhasesStage1);
   if (status == MP_OK) {
     const unsigned long long mk = ar.mark();
     for (int p = 0; p < nch && p < kMaxChains; p++) {
@@ -212,6 +220,7 @@ __device__ __noinline__ void mp_map_read(const MpCtx &C, int r, Arena &ar, const
       const UChain ch = chains[p];
       int ns = 0, s0 = 0;
       const int rc = mp_map_chain(C, r, ar, ext, ch, p, out, ns, s0);
+      mp_phase_upto(ar, kPhasesStage1 + kPhasesChain * (p + 1));
       if (rc < 0) { status = -rc; break; }
       if (rc == 1) { if (p == 0) status = MP_UNALIGNED; break; }
       // alignments.resize(+1) happened for this chain; p == 0 without a segment makes the read unaligned (Map_lowacc.h:577-580)
@@ -219,6 +228,7 @@ __device__ __noinline__ void mp_map_read(const MpCtx &C, int r, Arena &ar, const
       nseg[n_al] = ns; seg0[n_al] = s0; n_al++;
     }
   }
+  mp_phase_upto(ar, kPhasesStage1 + kPhasesChain * PB);
   if (status != MP_OK) n_al = 0;
   if (lane == 0) {
     out.status[r] = status; out.n_chains[r] = n_al;
@@ -236,17 +246,33 @@ struct MapBatch {
   const int *order;                       // optional: reads in decreasing length (longest first)
 };
 
-__global__ void __launch_bounds__(128, 4) map_reads_kernel(MapBatch b) {
+// One CTA per SM; its warps take a group of consecutive reads of the length-sorted order (similar lengths, similar stage times) through the
+// stages in lock step (mp_phase).  blockDim.x = 32 * warps per CTA (host: 16).
+__global__ void __launch_bounds__(512, 1) map_reads_kernel(MapBatch b) {
   const int warps_per_block = (int)blockDim.x / kLanes;
-  const int wid = (int)blockIdx.x * warps_per_block + (int)threadIdx.x / kLanes;
+  const int wib = (int)threadIdx.x / kLanes;
+  const int wid = (int)blockIdx.x * warps_per_block + wib;
   Arena ar; ar.init(b.arena + (unsigned long long)wid * b.arena_per_warp, b.arena_per_warp);
+  const int PB = (b.C.o.NumAln < kMaxChains ? b.C.o.NumAln : kMaxChains);
+#if !defined(LRA_EMU)
+  __shared__ int s_base;
+#endif
   for (;;) {
-    int w = 0;
-    if (lane_id() == 0) w = atomicAdd(b.work, 1);
-    w = bcast(w, 0);
-    if (w >= b.C.rd.n_reads) break;
-    const int r = b.order ? b.order[w] : w;
-    mp_map_read(b.C, r, ar, b.out);
+    int base;
+#if !defined(LRA_EMU)
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = atomicAdd(b.work, warps_per_block);
+    __syncthreads();
+    base = s_base;
+#else
+    base = 0;
+    if (lane_id() == 0) base = atomicAdd(b.work, warps_per_block);
+    base = bcast(base, 0);
+#endif
+    if (base >= b.C.rd.n_reads) break;
+    const int w = base + wib;
+    if (w < b.C.rd.n_reads) mp_map_read(b.C, b.order ? b.order[w] : w, ar, b.out);
+    else { ar.phase = 0; mp_phase_upto(ar, kPhasesStage1 + kPhasesChain * PB); }
   }
 }
 

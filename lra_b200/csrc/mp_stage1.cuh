@@ -178,6 +178,7 @@ __device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterS
   wsync();
   n_mm = bcast(n_mm, 0);
   tk = mp_tick(C, PF_MINIMIZERS, tk);
+  mp_phase(ar);
   // ---- a4: CompareLists against the global index (MapRead.h:190); matches land in the open end of the arena
   const unsigned long long top0 = (ar.top + 15ull) & ~15ull;
   const unsigned long long room = ar.cap > top0 ? (ar.cap - top0) / sizeof(MpMatch) : 0ull;
@@ -193,6 +194,7 @@ __device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterS
   wsync();
   n_match = bcast(n_match, 0);
   tk = mp_tick(C, PF_COMPARE, tk);
+  mp_phase(ar);
   if ((unsigned long long)n_match > room / 4) return MP_ERR_ARENA;        // leave room for the stages below
   ar.alloc<MpMatch>((unsigned long long)n_match);
   const int NM = (int)n_match;
@@ -300,6 +302,7 @@ __device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterS
   ext.ncl = raw.ncl;
   const int NE = ext.off[ext.ncl];
   tk = mp_tick(C, PF_LEXT1, tk);
+  mp_phase(ar);
   // ---- first SparseDP on all anchors (Map_lowacc.h:184-188) + RemoveSpuriousJump
   const float match_rate = repetitive ? 3.0f : O.initial_anchorbonus;
   const int NA = O.NumAln < 8 ? O.NumAln : 8;
