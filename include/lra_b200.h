@@ -176,6 +176,15 @@ int lra_b200_indel_refine_batch_device(lra_b200_ctx *ctx, const lra_b200_seq *q,
 typedef struct lra_b200_index lra_b200_index;
 int lra_b200_index_upload(lra_b200_ctx *ctx, const uint64_t *t, const uint32_t *pos, uint64_t n, lra_b200_index **out);
 void lra_b200_index_free(lra_b200_ctx *ctx, lra_b200_index *idx);
+/* `lra index -MODE` / `lra global` on the device (StoreIndex, MMIndex.h:286-399): canonical (k, w) minimizers of every contig (StoreMinimizers,
+ * MinCount.h:7-179) with the contig offset added to pos, sorted by the masked tuple, tuples occurring more than max_freq times removed, at most
+ * per_window minimizers kept per win_size window of the genome (lowest multiplicity first, CountSort order), RemoveFrequent.  The index presets
+ * (lra.cpp:884-911): -ONT / -CCS 17,10,150,15,1; -CLR 15,10,250,12,1; -CONTIG 19,10,30,20,1.  The result is the image lra_b200_index_upload makes
+ * of <ref>.mms; inside a run of equal tuples the entries are ordered by position (std::sort leaves them in introsort's order). */
+int lra_b200_gindex_build(lra_b200_ctx *ctx, const lra_b200_seq *genome, const uint64_t *contig_start, const uint32_t *contig_len, int32_t n_contigs, int32_t k, int32_t w,
+                          int32_t max_freq, int32_t win_size, int32_t per_window, lra_b200_index **out);
+uint64_t lra_b200_index_size(const lra_b200_index *idx);
+int lra_b200_index_download(lra_b200_ctx *ctx, const lra_b200_index *idx, uint64_t *t, uint32_t *pos);
 
 /* reads: a packed arena holding the forward strands; read r = [read_off[r], read_off[r] + read_len[r]).  *out_rc must be NULL or an
  * arena of an earlier call, which is then re-used (no allocation in the steady state of a batch loop). */

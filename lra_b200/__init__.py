@@ -6,5 +6,5 @@ functions for this path.  There is no CPU implementation here: importing works a
 the CUDA library and a GPU and raises otherwise.
 """
 from .capi import (  # noqa: F401
-    Context, LraB200Error, SeqArena, LocalIndexImage, CreateLookUpTable, write_gli, read_gli, split_chain_view, AffineOneGapAlign, AffineOneGapAlignBatch, IndelRefineAlignment, library_path, load_library, init_pwl, map_opts_preset, read_mms, format_sam, Mapper, MapOpts, RECORD,
+    Context, LraB200Error, SeqArena, LocalIndexImage, CreateLookUpTable, write_gli, read_gli, split_chain_view, AffineOneGapAlign, AffineOneGapAlignBatch, IndelRefineAlignment, library_path, load_library, init_pwl, map_opts_preset, read_mms, format_sam, Mapper, MapOpts, RECORD, write_mms, build_index_files, INDEX_PRESET,
 )

@@ -329,6 +329,12 @@ def load_library():
     L.lra_b200_mapper_destroy.argtypes = [C.c_void_p, C.c_void_p]
     L.lra_b200_mapper_destroy.restype = None
     L.lra_b200_map_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(_MapResult)]
+    L.lra_b200_gindex_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    L.lra_b200_index_size.argtypes = [C.c_void_p]
+    L.lra_b200_index_size.restype = C.c_uint64
+    L.lra_b200_index_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lra_b200_index_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.lra_b200_index_free.restype = None
     L.lra_b200_readset_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
     L.lra_b200_readset_free.argtypes = [C.c_void_p, C.c_void_p]
     L.lra_b200_readset_free.restype = None
@@ -988,6 +994,19 @@ class Context:
         self._check(self.lib.lra_b200_lindex_build(self.h, seq.handle, _ptr(ss), _ptr(sl), len(ss), k, w, window, max_freq, C.byref(h)))
         return LocalIndexImage(self, h)
 
+    def gindex_build(self, seq, contig_start, contig_len, k=17, w=10, max_freq=150, win_size=15, per_window=1):
+        """`lra index` / `lra global` on the device (StoreIndex, MMIndex.h:286-399).  Returns (t uint64[n], pos uint32[n]): the records of <ref>.mms."""
+        cs = np.ascontiguousarray(contig_start, np.uint64); cl = np.ascontiguousarray(contig_len, np.uint32)
+        h = C.c_void_p()
+        self._check(self.lib.lra_b200_gindex_build(self.h, seq.handle, _ptr(cs), _ptr(cl), len(cs), k, w, max_freq, win_size, per_window, C.byref(h)))
+        try:
+            n = int(self.lib.lra_b200_index_size(h))
+            t = np.zeros(n, np.uint64); pos = np.zeros(n, np.uint32)
+            self._check(self.lib.lra_b200_index_download(self.h, h, _ptr(t) if n else None, _ptr(pos) if n else None))
+        finally:
+            self.lib.lra_b200_index_free(self.h, h)
+        return t, pos
+
     def lindex_upload(self, seq_start, seq_len, window, win_off, bnd, mins):
         ss = np.ascontiguousarray(seq_start, np.uint64); sl = np.ascontiguousarray(seq_len, np.uint32)
         wo = np.ascontiguousarray(win_off, np.uint64); bd = np.ascontiguousarray(bnd, np.uint64); mn = np.ascontiguousarray(mins, np.uint32)
@@ -1183,6 +1202,52 @@ def write_gli(path, k, w, window, seq_offsets, tuple_boundaries, minimizers):
         f.write(np.array([k, w, window, len(so)], np.int32).tobytes())
         f.write(so.tobytes()); f.write(tb.tobytes())
         f.write(np.array([len(mn)], np.uint64).tobytes()); f.write(mn.tobytes())
+
+
+INDEX_PRESET = {   # lra.cpp:884-911 (global) and the LocalIndex the same command writes (k 10, w 5, window 2048, maxFreq 15)
+    "ont": dict(k=17, w=10, max_freq=150, win_size=15, per_window=1), "ccs": dict(k=17, w=10, max_freq=150, win_size=15, per_window=1),
+    "clr": dict(k=15, w=10, max_freq=250, win_size=12, per_window=1), "contig": dict(k=19, w=10, max_freq=30, win_size=20, per_window=1)}
+
+
+def write_mms(path, k, names, hdr, t, pos):
+    """<ref>.mms as WriteIndex lays it out (MMIndex.h:414-422): int64 n, int k, Header (int nContigs; per contig int len + name; uint64 pos[n+1]),
+    GenomeTuple[n] (uint64 t, uint32 pos, 4 bytes of padding)."""
+    t = np.ascontiguousarray(t, np.uint64); pos = np.ascontiguousarray(pos, np.uint32)
+    with open(path, "wb") as f:
+        f.write(np.array([len(t)], np.int64).tobytes()); f.write(np.array([k], np.int32).tobytes())
+        f.write(np.array([len(names)], np.int32).tobytes())
+        for n in names:
+            b = n.encode(); f.write(np.array([len(b)], np.int32).tobytes()); f.write(b)
+        f.write(np.ascontiguousarray(hdr, np.uint64).tobytes())
+        CH = 1 << 24
+        for a in range(0, len(t), CH):
+            rec = np.zeros(min(CH, len(t) - a), np.dtype([("t", "<u8"), ("pos", "<u4"), ("pad", "<u4")]))
+            rec["t"] = t[a:a + CH]; rec["pos"] = pos[a:a + CH]
+            f.write(rec.tobytes())
+
+
+def build_index_files(fasta_path, contigs, preset, device=0, ctx=None):
+    """`lra index -MODE ref.fa` on the GPU: writes <fasta>.mms and <fasta>.gli in the reference's formats (the reference loads them).
+    contigs: list of (name, uint8 ASCII array) as in the FASTA.  Returns dict(n_mms, n_gli)."""
+    own = ctx is None
+    ctx = ctx or Context(device)
+    pr = INDEX_PRESET[preset]
+    lens = np.array([len(s) for _, s in contigs], np.uint32)
+    start = np.zeros(len(contigs), np.uint64); start[1:] = np.cumsum(lens[:-1].astype(np.uint64))
+    hdr = np.concatenate([start, [np.uint64(int(start[-1]) + int(lens[-1]))]]).astype(np.uint64)
+    arena = ctx.seq_upload(np.concatenate([s for _, s in contigs]))
+    try:
+        t, pos = ctx.gindex_build(arena, start, lens, **pr)
+        write_mms(fasta_path + ".mms", pr["k"], [n for n, _ in contigs], hdr, t, pos)
+        img = ctx.lindex_build(arena, start, lens, k=10, w=5, window=2048, max_freq=15)
+        wo, bd, mn = img.download()
+        write_gli(fasta_path + ".gli", 10, 5, 2048, wo, bd, mn)
+        img.free()
+    finally:
+        arena.free()
+        if own:
+            ctx.close()
+    return dict(n_mms=len(t), n_gli=len(mn))
 
 
 def read_gli(path):

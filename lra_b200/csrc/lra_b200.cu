@@ -1075,3 +1075,4 @@ extern "C" int lra_b200_calc_stats_batch_device(lra_b200_ctx *ctx, const lra_b20
 #include "lref_host.cuh"
 #include "mp_host.cuh"
 #include "mp_host_map.cuh"
+#include "gidx_host.cuh"

@@ -3,6 +3,7 @@
 // finalize kernel, copies the records home) and the SAM emitter (Alignment::PrintSAM, host code).
 #pragma once
 #include <sstream>
+#include <thread>
 #include <algorithm>
 #include "mp_map.cuh"
 
@@ -38,15 +39,81 @@ extern "C" int lra_b200_map_opts_preset(const char *mode, lra_b200_map_opts *o) 
 }
 
 // ---- SAM emitter (Alignment.h:658-808, 811-832; Mapping_ultility.h:457-494) -------------------------------------------------------------------
-static void mp_cigar_string(const uint32_t *cig, int n, std::string &out) {
-  static const char ops[] = "MIDNSHP=X";
-  char buf[16];
-  for (int i = 0; i < n; i++) { const int l = snprintf(buf, sizeof buf, "%u%c", cig[i] >> 4, ops[cig[i] & 15u]); out.append(buf, l); }
-}
 static const unsigned char *mp_revcomp_table() {
   static unsigned char T[256]; static bool init = false;
   if (!init) { for (int i = 0; i < 256; i++) T[i] = 'N'; T['A'] = 'T'; T['C'] = 'G'; T['G'] = 'C'; T['T'] = 'A'; T['a'] = 't'; T['c'] = 'g'; T['g'] = 'c'; T['t'] = 'a'; T['n'] = 'n'; init = true; }
   return T;
+}
+
+// appender with the ostream formatting the reference relies on (operator<< of integers, chars, strings and one float with the default precision)
+struct SamOut {
+  std::string s;
+  void put(const char *p, size_t n) { s.append(p, n); }
+  void put(const char *p) { s.append(p); }
+  void put(char c) { s.push_back(c); }
+  void u(unsigned long long v) { char b[24]; int n = 0; do { b[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) s.push_back(b[--n]); }
+  void i(long long v) { if (v < 0) { s.push_back('-'); u((unsigned long long)(-(v + 1)) + 1ull); } else u((unsigned long long)v); }
+  void f(float v) { char b[48]; const int n = snprintf(b, sizeof b, "%g", (double)v); s.append(b, (size_t)n); }     // ostream default: %g, 6 significant digits
+  void cigar(const uint32_t *cig, int n) { static const char ops[] = "MIDNSHP=X"; for (int k = 0; k < n; k++) { u(cig[k] >> 4); s.push_back(ops[cig[k] & 15u]); } }
+};
+
+static void mp_format_read(SamOut &o, const lra_b200_map_opts *opts, const lra_b200_map_result *res, int r, const char *name, const char *seq, uint32_t L,
+                           const std::vector<const char *> &cname, int runtime, std::string &rc) {
+  const unsigned char *RC = mp_revcomp_table();
+  const int na = res->status[r] == 0 ? res->n_aln[r] : 0;
+  bool printed = false;
+  if (na > 0 && res->aln_nseg[4 * r + res->aln_rank[4 * r]] > 0) {
+    bool have_rc = false;
+    const int lim = na < opts->PrintNumAln ? na : opts->PrintNumAln;
+    for (int a = 0; a < lim; a++) {
+      const int slot = res->aln_rank[4 * r + a];
+      const int ns = res->aln_nseg[4 * r + slot], s0 = res->aln_seg0[4 * r + slot];
+      for (int sgi = ns - 1; sgi >= 0; sgi--) {
+        const lra_b200_record &x = res->records[s0 + sgi];
+        printed = true;
+        o.put(name); o.put('\t');
+        const char *rd = seq;
+        if (x.strand == 1) {
+          if (!have_rc) { rc.resize(L); for (uint32_t k = 0; k < L; k++) rc[L - 1 - k] = (char)RC[(unsigned char)seq[k]]; have_rc = true; }
+          rd = rc.data();
+        }
+        if (x.n_blocks == 0) { o.put("4\t*\t0\t0\t*\t*\t0\t0\t"); o.put(rd, L); o.put("\t*"); }
+        else {
+          o.u(x.flag); o.put('\t'); o.put(cname[x.chrom]); o.put('\t'); o.u(x.tStart + 1u); o.put('\t'); o.u((unsigned char)x.mapq); o.put('\t');
+          char clipOp = 'S';
+          if (x.supplementary && opts->hardClip) clipOp = 'H';
+          if (x.preClip > 0) { o.i(x.preClip); o.put(clipOp); }
+          o.cigar(res->cigar + x.cigar_off, x.n_cigar);
+          if (x.sufClip > 0) { o.i(x.sufClip); o.put(clipOp); }
+          o.put("\t*\t0\t"); o.u(x.tEnd - x.tStart); o.put('\t');
+          if (!x.supplementary) o.put(rd, L);
+          else if (opts->hardClip) o.put(rd + x.qStart, x.qEnd - x.qStart);
+          else o.put(rd, L);
+          o.put("\t*");
+          o.put("\tNM:i:"); o.i(x.nmm + x.ndel + x.nins); o.put("\tMM:i:"); o.i(x.nmm + x.ndel + x.nins); o.put("\tNX:i:"); o.i(x.nmm); o.put("\tND:i:"); o.i(x.ndel);
+          o.put("\tTD:i:"); o.i(x.tdel); o.put("\tNI:i:"); o.i(x.nins); o.put("\tTI:i:"); o.i(x.tins); o.put("\tNV:f:"); o.f(x.value); o.put("\tAS:i:"); o.i((int)x.value);
+          o.put("\tAO:i:"); o.i(x.order); o.put("\tN0:i:"); o.i(x.NumOfAnchors0); o.put("\tRT:i:"); o.i(runtime);
+          o.put("\tTP:A:"); o.put(x.typeofaln == 0 ? 'P' : (x.typeofaln == 1 ? 'S' : 'I'));
+          o.put("\tSD:i:"); o.i(x.nSmallDel); o.put("\tME:i:"); o.i(x.nMedDel); o.put("\tLD:i:"); o.i(x.nLargeDel); o.put("\tSI:i:"); o.i(x.nSmallIns); o.put("\tMI:i:"); o.i(x.nMedIns);
+          o.put("\tLI:i:"); o.i(x.nLargeIns);
+          if (ns > 1) o.put("\tSA:Z:");
+          for (int ag = ns - 1; ag >= 0; ag--) {
+            if (ag == sgi) continue;
+            const lra_b200_record &y = res->records[s0 + ag];
+            o.put(y.n_blocks == 0 ? "*" : cname[y.chrom]); o.put(','); o.u(y.tStart + 1u); o.put(','); o.put(y.strand == 0 ? '+' : '-'); o.put(',');
+            if (y.preClip > 0) { o.i(y.preClip); o.put('S'); }
+            o.cigar(res->cigar + y.cigar_off, y.n_cigar);
+            if (y.sufClip > 0) { o.i(y.sufClip); o.put('S'); }
+            o.put(','); o.u((unsigned char)y.mapq); o.put(','); o.i(y.nm); o.put(';');
+          }
+        }
+        o.put('\n');
+      }
+    }
+  }
+  if (!printed) {      // output_unaligned -> SimplePrintSAM of an Alignment without blocks
+    o.put(name); o.put("\t4\t*\t0\t0\t*\t*\t0\t0\t"); o.put(seq, L); o.put("\t*\n");
+  }
 }
 
 extern "C" int64_t lra_b200_format_sam(const lra_b200_map_opts *opts, const lra_b200_map_result *res, int32_t n_reads, const char *names, const char *reads_ascii,
@@ -55,73 +122,30 @@ extern "C" int64_t lra_b200_format_sam(const lra_b200_map_opts *opts, const lra_
   if (!opts || !res || n_reads < 0 || !names || !reads_ascii || !read_off || !read_len || !contig_names) return 0;
   std::vector<const char *> cname(n_contigs);
   { const char *p = contig_names; for (int c = 0; c < n_contigs; c++) { cname[c] = p; p += strlen(p) + 1; } }
-  const unsigned char *RC = mp_revcomp_table();
-  std::string text, rc, cig, sa;
-  const char *np = names;
-  for (int r = 0; r < n_reads; r++) {
-    const char *name = np; np += strlen(np) + 1;
-    const char *seq = reads_ascii + read_off[r]; const uint32_t L = read_len[r];
-    const int na = res->status[r] == 0 ? res->n_aln[r] : 0;
-    bool printed = false;
-    if (na > 0 && res->aln_nseg[4 * r + res->aln_rank[4 * r]] > 0) {
-      bool have_rc = false;
-      const int lim = na < opts->PrintNumAln ? na : opts->PrintNumAln;
-      for (int a = 0; a < lim; a++) {
-        const int slot = res->aln_rank[4 * r + a];
-        const int ns = res->aln_nseg[4 * r + slot], s0 = res->aln_seg0[4 * r + slot];
-        for (int s = ns - 1; s >= 0; s--) {
-          const lra_b200_record &x = res->records[s0 + s];
-          printed = true;
-          std::ostringstream o;
-          o << name << "\t";
-          const char *rd = seq;
-          if (x.strand == 1) {
-            if (!have_rc) { rc.resize(L); for (uint32_t i = 0; i < L; i++) rc[L - 1 - i] = (char)RC[(unsigned char)seq[i]]; have_rc = true; }
-            rd = rc.data();
-          }
-          if (x.n_blocks == 0) { o << "4\t*\t0\t0\t*\t*\t0\t0\t"; o.write(rd, L); o << "\t*"; }
-          else {
-            o << (unsigned int)x.flag << "\t" << cname[x.chrom] << "\t" << x.tStart + 1 << "\t" << (unsigned int)(unsigned char)x.mapq << "\t";
-            char clipOp = 'S';
-            if (x.supplementary && opts->hardClip) clipOp = 'H';
-            if (x.preClip > 0) o << x.preClip << clipOp;
-            cig.clear(); mp_cigar_string(res->cigar + x.cigar_off, x.n_cigar, cig);
-            o << cig;
-            if (x.sufClip > 0) o << x.sufClip << clipOp;
-            o << "\t*\t0\t" << x.tEnd - x.tStart << "\t";
-            if (!x.supplementary) o.write(rd, L);
-            else if (opts->hardClip) o.write(rd + x.qStart, x.qEnd - x.qStart);
-            else o.write(rd, L);
-            o << "\t*";
-            o << "\tNM:i:" << x.nmm + x.ndel + x.nins << "\tMM:i:" << x.nmm + x.ndel + x.nins << "\tNX:i:" << x.nmm << "\tND:i:" << x.ndel << "\tTD:i:" << x.tdel
-              << "\tNI:i:" << x.nins << "\tTI:i:" << x.tins << "\tNV:f:" << x.value << "\tAS:i:" << (int)x.value << "\tAO:i:" << x.order << "\tN0:i:" << x.NumOfAnchors0
-              << "\tRT:i:" << runtime;
-            o << "\tTP:A:" << (x.typeofaln == 0 ? "P" : (x.typeofaln == 1 ? "S" : "I"));
-            o << "\tSD:i:" << x.nSmallDel << "\tME:i:" << x.nMedDel << "\tLD:i:" << x.nLargeDel << "\tSI:i:" << x.nSmallIns << "\tMI:i:" << x.nMedIns << "\tLI:i:" << x.nLargeIns;
-            if (ns > 1) o << "\tSA:Z:";
-            for (int ag = ns - 1; ag >= 0; ag--) {
-              if (ag == s) continue;
-              const lra_b200_record &y = res->records[s0 + ag];
-              o << (y.n_blocks == 0 ? "*" : cname[y.chrom]) << "," << y.tStart + 1 << "," << (y.strand == 0 ? "+" : "-") << ",";
-              if (y.preClip > 0) o << y.preClip << 'S';
-              cig.clear(); mp_cigar_string(res->cigar + y.cigar_off, y.n_cigar, cig);
-              o << cig;
-              if (y.sufClip > 0) o << y.sufClip << 'S';
-              o << "," << (unsigned int)(unsigned char)y.mapq << "," << y.nm << ";";
-            }
-          }
-          o << "\n";
-          text += o.str();
-        }
-      }
-    }
-    if (!printed) {      // output_unaligned -> SimplePrintSAM of an Alignment without blocks
-      text += name; text += "\t4\t*\t0\t0\t*\t*\t0\t0\t"; text.append(seq, L); text += "\t*\n";
-    }
-  }
-  if ((int64_t)text.size() > cap || !out) return -(int64_t)text.size();
-  memcpy(out, text.data(), text.size());
-  return (int64_t)text.size();
+  std::vector<const char *> rname(n_reads);
+  { const char *p = names; for (int r = 0; r < n_reads; r++) { rname[r] = p; p += strlen(p) + 1; } }
+  // host threads over contiguous, base-balanced runs of reads (the text of a read depends on that read only); pieces are concatenated in input order
+  unsigned long long total = 0; for (int r = 0; r < n_reads; r++) total += read_len[r];
+  int T = (int)std::thread::hardware_concurrency(); if (T < 1) T = 1; if (T > 32) T = 32;
+  if (total < (1u << 20)) T = 1;
+  if (getenv("LRA_B200_SAM_THREADS")) T = atoi(getenv("LRA_B200_SAM_THREADS"));
+  if (T < 1) T = 1;
+  if (T > n_reads) T = n_reads > 0 ? n_reads : 1;
+  std::vector<int> cut(T + 1, n_reads); cut[0] = 0;
+  { unsigned long long acc = 0; int t = 1; for (int r = 0; r < n_reads && t < T; r++) { acc += read_len[r]; if (acc * T >= total * t) cut[t++] = r + 1; } }
+  std::vector<SamOut> piece(T);
+  auto work = [&](int t) {
+    std::string rc;
+    unsigned long long b = 0; for (int r = cut[t]; r < cut[t + 1]; r++) b += read_len[r];
+    piece[t].s.reserve((size_t)(b + b / 2) + 4096);
+    for (int r = cut[t]; r < cut[t + 1]; r++) mp_format_read(piece[t], opts, res, r, rname[r], reads_ascii + read_off[r], read_len[r], cname, runtime, rc);
+  };
+  if (T == 1) work(0);
+  else { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(work, t); for (auto &x : th) x.join(); }
+  size_t n = 0; for (auto &p : piece) n += p.s.size();
+  if ((int64_t)n > cap || !out) return -(int64_t)n;
+  size_t at = 0; for (auto &p : piece) { memcpy(out + at, p.s.data(), p.s.size()); at += p.s.size(); }
+  return (int64_t)n;
 }
 
 struct lra_b200_readset;
@@ -312,7 +336,7 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
   const size_t blk_cap = (size_t)(total_bases / 2) + (size_t)n_reads * 64 + 4096;
   // one CTA of `bw` warps per SM (phase-aligned groups of reads, mp_phase); LRA_B200_MAP_BLOCK_WARPS / _BLOCKS_PER_SM for experiments
   int bw = 16; if (getenv("LRA_B200_MAP_BLOCK_WARPS")) bw = atoi(getenv("LRA_B200_MAP_BLOCK_WARPS"));
-  if (bw < 1) bw = 1; if (bw > 16) bw = 16;
+  if (bw < 1) bw = 1; if (bw > MP_BLOCK_THREADS / 32) bw = MP_BLOCK_THREADS / 32;
   int blocks = ctx->n_sm;
   if ((long long)blocks * bw > (long long)n_reads) blocks = (n_reads + bw - 1) / bw;
   int warps = blocks * bw;

@@ -248,7 +248,10 @@ struct MapBatch {
 
 // One CTA per SM; its warps take a group of consecutive reads of the length-sorted order (similar lengths, similar stage times) through the
 // stages in lock step (mp_phase).  blockDim.x = 32 * warps per CTA (host: 16).
-__global__ void __launch_bounds__(512, 1) map_reads_kernel(MapBatch b) {
+#ifndef MP_BLOCK_THREADS
+#define MP_BLOCK_THREADS 512
+#endif
+__global__ void __launch_bounds__(MP_BLOCK_THREADS, 1) map_reads_kernel(MapBatch b) {
   const int warps_per_block = (int)blockDim.x / kLanes;
   const int wib = (int)threadIdx.x / kLanes;
   const int wid = (int)blockIdx.x * warps_per_block + wib;
