@@ -340,8 +340,10 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
   int blocks = ctx->n_sm;
   if ((long long)blocks * bw > (long long)n_reads) blocks = (n_reads + bw - 1) / bw;
   int warps = blocks * bw;
-  // measured worker scratch: < 10 MB for reads up to 60 kb (SparseDP sub-problems dominate); the arena is kept across batches
-  size_t per = (size_t)maxL * 384 + (16u << 20);
+  // worker scratch, measured on ONT / CLR reads: peak 14.4 MB for a 100 kb read, ~150 B per base (SparseDP sub-problems dominate).  The first pass
+  // gives every warp 4 MB + 192 B per base of the longest read; a read that still runs out (status MP_ERR_ARENA) is mapped again below with 8x
+  // that on fewer warps.  The arena is kept across batches.
+  size_t per = (size_t)maxL * 192 + (4u << 20);
   if (getenv("LRA_B200_MAP_ARENA_MB")) per = (size_t)atoi(getenv("LRA_B200_MAP_ARENA_MB")) << 20;
   size_t free_b = 0, tot_b = 0; cudaMemGetInfo(&free_b, &tot_b);
   const size_t budget = (free_b + B[9].cap) / 2;
@@ -365,28 +367,56 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
   mb.out.status = (int *)B[2].p; mb.out.n_chains = (int *)B[3].p; mb.out.chain_nseg = (int *)B[4].p; mb.out.chain_seg0 = (int *)B[5].p;
   mb.out.seg = (SegRec *)B[6].p; mb.out.seg_cap = (int)seg_cap; mb.out.seg_cursor = (unsigned long long *)B[8].p; mb.out.blocks = (uint32_t *)B[7].p; mb.out.blk_cap = blk_cap;
   mb.out.blk_cursor = (unsigned long long *)((char *)B[8].p + 8); mb.out.err = (int *)((char *)B[8].p + 16); mb.out.peak = (unsigned long long *)((char *)B[8].p + 24);
-  mb.arena = (unsigned char *)B[9].p; mb.arena_per_warp = per; mb.work = (int *)((char *)B[8].p + 32); mb.order = (const int *)rs->order.p;
+  mb.arena = (unsigned char *)B[9].p; mb.arena_per_warp = per; mb.work = (int *)((char *)B[8].p + 32); mb.order = (const int *)rs->order.p; mb.n_work = n_reads;
   cudaEventRecord(ctx->ev[0], st);
   map_reads_kernel<<<(unsigned)blocks, (unsigned)(bw * 32), 0, st>>>(mb);
   cudaEventRecord(ctx->ev[1], st);
   ctx->launches++;
   CU(cudaGetLastError());
   unsigned long long hcur[4];
+  { // second pass for the reads whose scratch did not fit
+    std::vector<int> hst(n_reads);
+    CU(cudaMemcpyAsync(hst.data(), B[2].p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    { lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "map_reads"); cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]);
+      s2.jobs = (uint64_t)n_reads; s2.algo_bytes = total_bases + 2 * ((total_bases + 3) / 4); all.push_back(s2); }
+    std::vector<int> redo;
+    for (int r = 0; r < n_reads; r++) if (hst[r] == MP_ERR_ARENA) redo.push_back(r);
+    if (!redo.empty() && !getenv("LRA_B200_MAP_NO_RETRY")) {
+      std::stable_sort(redo.begin(), redo.end(), [&](int a, int b2) { return rs->h_len[a] > rs->h_len[b2]; });
+      const size_t per2 = per * 8;
+      int blocks2 = (int)((redo.size() + bw - 1) / bw); if (blocks2 > ctx->n_sm) blocks2 = ctx->n_sm;
+      while ((size_t)blocks2 * bw * per2 > B[9].cap && blocks2 > 1) blocks2--;
+      int bw2 = bw; while ((size_t)blocks2 * bw2 * per2 > B[9].cap && bw2 > 1) bw2--;
+      if ((size_t)blocks2 * bw2 * per2 <= B[9].cap) {
+        if ((rc = ensure(ctx, B[28], redo.size() * 4))) return rc;
+        CU(cudaMemcpyAsync(B[28].p, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync((char *)B[8].p + 32, 0, 4, st));
+        MapBatch mb2 = mb; mb2.order = (const int *)B[28].p; mb2.n_work = (int)redo.size(); mb2.arena_per_warp = per2;
+        cudaEventRecord(ctx->ev[0], st);
+        map_reads_kernel<<<(unsigned)blocks2, (unsigned)(bw2 * 32), 0, st>>>(mb2);
+        cudaEventRecord(ctx->ev[1], st);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(st));
+        lra_b200_kernel_stat s3; memset(&s3, 0, sizeof s3); snprintf(s3.name, sizeof s3.name, "map_reads(retry, 8x scratch)"); cudaEventElapsedTime(&s3.ms, ctx->ev[0], ctx->ev[1]);
+        s3.jobs = (uint64_t)redo.size(); all.push_back(s3);
+      }
+    }
+  }
   CU(cudaMemcpyAsync(hcur, B[8].p, 32, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  { lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "map_reads"); cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]);
-    s2.jobs = (uint64_t)n_reads; s2.algo_bytes = total_bases + 2 * ((total_bases + 3) / 4); all.push_back(s2); }
   if (mb.C.prof) {
     std::vector<unsigned long long> hp((size_t)(warps + 4) * lra::mp::kProfStages);
     CU(cudaMemcpy(hp.data(), B[27].p, hp.size() * 8, cudaMemcpyDeviceToHost));
     static const char *nm[lra::mp::kProfStages] = {"minimizers+sort", "CompareLists(global)", "strand+CleanMatches", "LinearExtend#1", "SparseDP#1", "SPLITChain", "Refine_splitchain",
                                                    "Refine_Btwnsplitchain", "LinearExtend#2+Trim", "SparseDP#2+filters", "LocalRefineAlignment(all)", "  AffineOneGapAlign", "  RefineSpace",
-                                                   "  SparseDP#3", "output", ""};
+                                                   "  SparseDP#3", "output", "phase barriers"};
     unsigned long long tot[lra::mp::kProfStages] = {0}; unsigned long long all_c = 0;
     for (int wv = 0; wv < warps; wv++) for (int s = 0; s < lra::mp::kProfStages; s++) tot[s] += hp[(size_t)wv * lra::mp::kProfStages + s];
-    for (int s = 0; s < 11; s++) all_c += tot[s]; all_c += tot[14];
+    for (int s = 0; s < 11; s++) all_c += tot[s]; all_c += tot[14] + tot[15];
     fprintf(stderr, "[lra_b200 map profile] %d warps, arena %zu MB/warp, peak %.1f MB; share of worker cycles:\n", warps, per >> 20, (double)hcur[3] / 1e6);
-    for (int s = 0; s < 15; s++) fprintf(stderr, "  %-28s %6.2f %%\n", nm[s], all_c ? 100.0 * (double)tot[s] / (double)all_c : 0.0);
+    for (int s = 0; s < 16; s++) fprintf(stderr, "  %-28s %6.2f %%\n", nm[s], all_c ? 100.0 * (double)tot[s] / (double)all_c : 0.0);
   }
   const int S = (int)(hcur[0] >> 40); const unsigned long long NB = hcur[0] & ((1ull << 40) - 1ull);
   const int kerr = (int)(hcur[2] & 0xffffffffull);

@@ -43,9 +43,11 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
   for (int ph = 0; ph < sp.n; ph++) if (!mp_refine_splitchain(C, r, ext, chain, sp, ph, ar, RC[ph], nodes + ph)) return -MP_ERR_ARENA;
   tk = mp_tick(C, PF_REFINE_SPLIT, tk);
   mp_phase(ar);
+  tk = mp_tick(C, PF_BARRIER, tk);
   if (!mp_refine_btwn_splitchain(C, r, ar, sp, RC)) return -MP_ERR_ARENA;
   tk = mp_tick(C, PF_REFINE_BTWN, tk);
   mp_phase(ar);
+  tk = mp_tick(C, PF_BARRIER, tk);
   // ---- MergeChain (ChainRefine.h:767-802): groups of consecutive refined clusters
   int *grp = ar.alloc<int>(sp.n + 1);     // group id of every refined cluster
   int *ng_p = ar.alloc<int>(2);
@@ -126,6 +128,7 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
   }
   tk = mp_tick(C, PF_LEXT2, tk);
   mp_phase(ar);
+  tk = mp_tick(C, PF_BARRIER, tk);
   if (total_refined == 0) return 1;
   // ---- second SparseDP per extended cluster + RemovePairedIndels + RemoveSpuriousAnchors
   UChain *uc = ar.alloc<UChain>(ng);
@@ -157,6 +160,7 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
   }
   tk = mp_tick(C, PF_SDP2, tk);
   mp_phase(ar);
+  tk = mp_tick(C, PF_BARRIER, tk);
   // LargestSplitChain
   int LSC = 0;
   for (int g = 1; g < ng; g++) if (uc[g].n > uc[LSC].n) LSC = g;
@@ -174,6 +178,7 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
   wsync();
   tk = mp_tick(C, PF_LOCAL_REFINE, tk);
   mp_phase(ar);
+  tk = mp_tick(C, PF_BARRIER, tk);
   if (B.nseg == 0) { nseg_out = 0; return 0; }
   // ---- hand the segments to the global lists
   // one atomic reserves the segment ids (high 24 bits) and the block range (low 40 bits) together, so that in segment order the block offsets are
@@ -243,7 +248,8 @@ struct MapBatch {
   MapOut out;
   unsigned char *arena; unsigned long long arena_per_warp;
   int *work;                              // dynamic read counter
-  const int *order;                       // optional: reads in decreasing length (longest first)
+  const int *order;                       // optional: reads in decreasing length (longest first), or the reads of a retry pass
+  int n_work;                             // reads to map in this launch (entries of `order`)
 };
 
 // One CTA per SM; its warps take a group of consecutive reads of the length-sorted order (similar lengths, similar stage times) through the
@@ -272,9 +278,9 @@ __global__ void __launch_bounds__(MP_BLOCK_THREADS, 1) map_reads_kernel(MapBatch
     if (lane_id() == 0) base = atomicAdd(b.work, warps_per_block);
     base = bcast(base, 0);
 #endif
-    if (base >= b.C.rd.n_reads) break;
+    if (base >= b.n_work) break;
     const int w = base + wib;
-    if (w < b.C.rd.n_reads) mp_map_read(b.C, b.order ? b.order[w] : w, ar, b.out);
+    if (w < b.n_work) mp_map_read(b.C, b.order ? b.order[w] : w, ar, b.out);
     else { ar.phase = 0; mp_phase_upto(ar, kPhasesStage1 + kPhasesChain * PB); }
   }
 }

@@ -4,6 +4,8 @@
 // LinearExtend's m / n cursors) are replayed by lane 0 with the pinned device routines of the stage kernels (seed_kernels.cuh, cod_kernels.cuh);
 // sorts, strand tests, compactions and the sparse DP use all lanes.
 #pragma once
+#include "mm_range.cuh"
+#include "mp_compare.cuh"
 #include "mp_types.cuh"
 #include "mp_sdp_driver.cuh"
 #include "seed_kernels.cuh"
@@ -23,7 +25,7 @@ struct MpCtx {
 
 // ---- stage profile of the worker kernel (clock64 deltas accumulated per warp; summed on the host)
 enum { PF_MINIMIZERS = 0, PF_COMPARE, PF_STRAND_CLEAN, PF_LEXT1, PF_SDP1, PF_SPLIT, PF_REFINE_SPLIT, PF_REFINE_BTWN, PF_LEXT2, PF_SDP2, PF_LOCAL_REFINE, PF_AOG, PF_REFINE_SPACE,
-       PF_SDP3, PF_OUTPUT, kProfStages = 16 };
+       PF_SDP3, PF_OUTPUT, PF_BARRIER, kProfStages = 16 };
 __device__ __forceinline__ unsigned long long mp_clock() {
 #ifdef LRA_EMU
   return 0ull;
@@ -160,6 +162,68 @@ __device__ __noinline__ void mp_chain_filter(int mode, const ClusterSet &S, UCha
   ar.release(mk);
 }
 
+// ---- a2 warp-parallel: StoreMinimizers of the read, one lane per chunk of 256 loop steps (mm_range.cuh), compacted in place.  Returns the number of
+// minimizers in (mm_t, mm_p), or -1 when a chunk's entry state is not provably the sequential one (the caller falls back to the literal scan).
+__device__ __noinline__ int mp_minimizers_warp(const SeqView &seq, unsigned long long roff, uint32_t L, int k, int w, unsigned long long *mm_t, uint32_t *mm_p) {
+  const int lane = lane_id();
+  if (L < (uint32_t)(w + k - 1)) return 0;
+  const int CH = 256, WARM = 64;
+  const int steps = (int)(L - (uint32_t)k + 1u);
+  const int nch = (steps + CH - 1) / CH;
+  int total = 0;
+  for (int c0 = 0; c0 < nch; c0 += kLanes) {
+    const int c = c0 + lane;
+    uint32_t n = 0; bool unc = false;
+    if (c < nch) {
+      const uint32_t pb = (uint32_t)c * CH, pe = c == nch - 1 ? 0xffffffffu : pb + CH;
+      const uint32_t s0 = pb > (uint32_t)WARM ? pb - WARM : 0u;
+      bool certain;
+      n = gidx_scan_range<true>(seq, roff, L, k, w, s0, pb, pe, mm_t + pb, mm_p + pb, 0u, certain);
+      if (n == 0xffffffffu) { unc = true; n = 0; }
+    }
+    if (wany(unc)) return -1;
+    wsync();
+    // move the chunks of this round down to the end of the list, in order (destination never ahead of the source)
+    for (int j = 0; j < kLanes && c0 + j < nch; j++) {
+      const int nj = (int)bcast(n, j), src = (c0 + j) * CH;
+      if (src != total) {
+        for (int i0 = 0; i0 < nj; i0 += kLanes) {
+          const int i = i0 + lane;
+          unsigned long long tv = 0; uint32_t pv = 0;
+          if (i < nj) { tv = mm_t[src + i]; pv = mm_p[src + i]; }
+          wsync();
+          if (i < nj) { mm_t[total + i] = tv; mm_p[total + i] = pv; }
+          wsync();
+        }
+      }
+      total += nj;
+    }
+  }
+  return total;
+}
+
+// ---- a3 warp-parallel: std::sort(readmm) on the masked tuple (MapRead.h:185).  With all keys distinct every sort gives the same list; equal keys
+// (the same k-mer twice in the read) leave introsort's order in the reference, so that case is sent back to the literal replay (returns false,
+// the arrays untouched).
+__device__ __noinline__ bool mp_sort_minimizers_warp(Arena &ar, unsigned long long *mm_t, uint32_t *mm_p, int n) {
+  if (n < 2) return true;
+  const int lane = lane_id();
+  const unsigned long long mk = ar.mark();
+  MpKey *keys = ar.alloc<MpKey>((unsigned long long)next_pow2(n));
+  unsigned long long *tt = ar.alloc<unsigned long long>(n);
+  if (ar.overflow) { ar.overflow = 0; ar.release(mk); return false; }
+  for (int i = lane; i < n; i += kLanes) { keys[i].k = mm_t[i] & kForMask; keys[i].q = mm_p[i]; keys[i].idx = (uint32_t)i; tt[i] = mm_t[i]; }
+  wsync();
+  mp_sort_keys(keys, n);
+  bool dup = false;
+  for (int i = 1 + lane; i < n; i += kLanes) dup = dup || keys[i].k == keys[i - 1].k;
+  if (wany(dup)) { ar.release(mk); return false; }
+  for (int i = lane; i < n; i += kLanes) { mm_t[i] = tt[keys[i].idx]; mm_p[i] = keys[i].q; }
+  wsync();
+  ar.release(mk);
+  return true;
+}
+
 // ---- seeding + CleanMatches + LinearExtend + first SparseDP for one read.  Returns MP_OK with `ext` (extended clusters, global t) and
 // `chains` (nch of them), or MP_UNALIGNED / an error.
 __device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterSet &ext, UChain *&chains, int &nch) {
@@ -174,27 +238,56 @@ __device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterS
   if (ar.overflow) return MP_ERR_ARENA;
   unsigned long long tk = mp_clock();
   int n_mm = 0;
-  if (lane == 0) { n_mm = (int)mm_scan<true>(C.rd.fwd, roff, L, O.globalK, O.globalW, mm_t, mm_p); mm_sort(MmRef{mm_t, mm_p}, (long)n_mm); }
-  wsync();
-  n_mm = bcast(n_mm, 0);
+  n_mm = mp_minimizers_warp(C.rd.fwd, roff, L, O.globalK, O.globalW, mm_t, mm_p);
+  if (n_mm < 0) {           // low-complexity stretch: literal scan
+    if (lane == 0) n_mm = (int)mm_scan<true>(C.rd.fwd, roff, L, O.globalK, O.globalW, mm_t, mm_p);
+    wsync();
+    n_mm = bcast(n_mm, 0);
+  }
+  if (!mp_sort_minimizers_warp(ar, mm_t, mm_p, n_mm)) {
+    if (lane == 0) mm_sort(MmRef{mm_t, mm_p}, (long)n_mm);
+    wsync();
+  }
   tk = mp_tick(C, PF_MINIMIZERS, tk);
   mp_phase(ar);
+  tk = mp_tick(C, PF_BARRIER, tk);
   // ---- a4: CompareLists against the global index (MapRead.h:190); matches land in the open end of the arena
   const unsigned long long top0 = (ar.top + 15ull) & ~15ull;
   const unsigned long long room = ar.cap > top0 ? (ar.cap - top0) / sizeof(MpMatch) : 0ull;
   MpMatch *M = (MpMatch *)(ar.base + top0);
   long long n_match = 0;
-  if (lane == 0) {
+  {
+    // the plan's arrays live above the match list's start only until the matches are written: plan first (arena), then the matches behind it
+    const unsigned long long mkp = ar.mark();
+    CmpPlan *plan = ar.alloc<CmpPlan>((unsigned long long)n_mm + 2);
+    if (ar.overflow) return MP_ERR_ARENA;
+    const int np = mp_compare_plan(mm_t, n_mm, C.ix.idx_t, C.ix.n_idx, (long long)O.globalMaxFreq, ar, plan);
+    if (np < 0) return MP_ERR_ARENA;
+    const unsigned long long top1 = (ar.top + 15ull) & ~15ull;
+    const unsigned long long room1 = ar.cap > top1 ? (ar.cap - top1) / sizeof(MpMatch) : 0ull;
+    MpMatch *M1 = (MpMatch *)(ar.base + top1);
     const uint32_t *idx_pos = C.ix.idx_pos;
-    mm_compare(mm_t, (long)n_mm, C.ix.idx_t, (long)C.ix.n_idx, (long long)O.globalMaxFreq, [&](long qi, long ti) {
-      if ((unsigned long long)n_match < room) { MpMatch x; x.q = mm_p[qi]; x.t = idx_pos[ti]; x.qt = mm_t[qi]; M[n_match] = x; }
-      n_match++;
+    n_match = mp_compare_expand(plan, np, [&](long long slot, int qi, uint32_t ti) {
+      if ((unsigned long long)slot < room1) { MpMatch x; x.q = mm_p[qi]; x.t = idx_pos[ti]; x.qt = mm_t[qi]; M1[slot] = x; }
     });
+    if ((unsigned long long)n_match > room1) return MP_ERR_ARENA;
+    // slide the matches down to where the plan started (M == the open end of the arena before the plan)
+    ar.release(mkp);
+    if ((unsigned char *)M1 != (unsigned char *)M) {
+      for (long long b0 = 0; b0 < n_match; b0 += kLanes) {
+        const long long i = b0 + lane;
+        MpMatch x; x.q = 0; x.t = 0; x.qt = 0;
+        if (i < n_match) x = M1[i];
+        wsync();
+        if (i < n_match) M[i] = x;
+        wsync();
+      }
+    }
   }
   wsync();
-  n_match = bcast(n_match, 0);
   tk = mp_tick(C, PF_COMPARE, tk);
   mp_phase(ar);
+  tk = mp_tick(C, PF_BARRIER, tk);
   if ((unsigned long long)n_match > room / 4) return MP_ERR_ARENA;        // leave room for the stages below
   ar.alloc<MpMatch>((unsigned long long)n_match);
   const int NM = (int)n_match;
@@ -303,6 +396,7 @@ __device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterS
   const int NE = ext.off[ext.ncl];
   tk = mp_tick(C, PF_LEXT1, tk);
   mp_phase(ar);
+  tk = mp_tick(C, PF_BARRIER, tk);
   // ---- first SparseDP on all anchors (Map_lowacc.h:184-188) + RemoveSpuriousJump
   const float match_rate = repetitive ? 3.0f : O.initial_anchorbonus;
   const int NA = O.NumAln < 8 ? O.NumAln : 8;

@@ -73,7 +73,7 @@ extern "C" int emu_map_reads(const uint8_t *reads_fwd, const uint8_t *reads_rc, 
   b.out.status = status; b.out.n_chains = n_chains; b.out.chain_nseg = chain_nseg; b.out.chain_seg0 = chain_seg0;
   b.out.seg = seg; b.out.seg_cap = seg_cap; b.out.seg_cursor = &cur[0]; b.out.blocks = blocks; b.out.blk_cap = blk_cap; b.out.blk_cursor = &cur[1]; b.out.err = &err;
   b.out.peak = &cur[2];
-  b.arena = base; b.arena_per_warp = arena_bytes; b.work = &work; b.order = nullptr;
+  b.arena = base; b.arena_per_warp = arena_bytes; b.work = &work; b.order = nullptr; b.n_work = n_reads;
   emu::launch(dim3(1), dim3(MP_LANES), 0, [&] { map_reads_kernel(b); });
   counts[0] = cur[0] >> 40; counts[1] = cur[0] & ((1ull << 40) - 1ull); counts[2] = (uint64_t)err; counts[3] = cur[2];
   return err;
@@ -94,3 +94,23 @@ extern "C" int emu_map_finalize(int n_reads, const MpOpts *opts, const uint64_t 
 extern "C" int emu_sizeof_segrec() { return (int)sizeof(SegRec); }
 extern "C" int emu_sizeof_mpopts() { return (int)sizeof(MpOpts); }
 extern "C" int emu_sizeof_record() { return (int)sizeof(lra_b200_record); }
+
+// ---- CompareLists: the worker's planned form (mp_compare.cuh) and the literal device form (seed_kernels.cuh) on the same lists
+extern "C" long long emu_compare_plan(const uint64_t *qt, int nq, const uint64_t *tt, long long nt, long long maxFreq, int32_t *out_q, uint32_t *out_t, long long cap) {
+  std::vector<unsigned char> arena((size_t)nq * 64 + (1 << 20));
+  unsigned char *base = arena.data(); while (((uintptr_t)base) & 15) base++;
+  long long total = 0;
+  emu::launch(dim3(1), dim3(MP_LANES), 0, [&] {
+    Arena ar; ar.init(base, arena.size() - 32);
+    CmpPlan *plan = ar.alloc<CmpPlan>((unsigned long long)nq + 2);
+    const int np = mp_compare_plan((const unsigned long long *)qt, nq, (const unsigned long long *)tt, nt, maxFreq, ar, plan);
+    const long long n = mp_compare_expand(plan, np < 0 ? 0 : np, [&](long long slot, int qi, uint32_t ti) { if (slot < cap) { out_q[slot] = qi; out_t[slot] = ti; } });
+    if (lane_id() == 0) total = np < 0 ? -1 : n;
+  });
+  return total;
+}
+extern "C" long long emu_compare_literal(const uint64_t *qt, int nq, const uint64_t *tt, long long nt, long long maxFreq, int32_t *out_q, uint32_t *out_t, long long cap) {
+  long long n = 0;
+  lra::mm_compare((const unsigned long long *)qt, (long)nq, (const unsigned long long *)tt, (long)nt, maxFreq, [&](long qi, long ti) { if (n < cap) { out_q[n] = (int32_t)qi; out_t[n] = (uint32_t)ti; } n++; });
+  return n;
+}

@@ -79,3 +79,17 @@ def test_map_batch_gpu_matches_reference_sam(preset, n_reads, repeats, batch, tm
     ours = canon_ours(text)
     assert len(ours) == len(ref)
     assert ours == ref, diff_report(ours, ref)
+
+
+@pytest.mark.gpu
+def test_map_batch_gpu_small_scratch_retries(tmp_path, monkeypatch):
+    """Reads whose worker scratch does not fit the first pass (forced here with 2 MB arenas) are mapped again with 8x the scratch: same SAM."""
+    w = mapgen.workdir(tmp_path, "ont", n_reads=300, ref_len=5_000_000, contigs=3, repeats=False)
+    _, ref = mapgen.canonical_sam(mapgen.reference_sam(w))
+    monkeypatch.setenv("LRA_B200_MAP_ARENA_MB", "2")
+    text, st = gpu_sam(w, None)
+    assert (st["status"] <= 1).all(), np.bincount(st["status"])
+    assert canon_ours(text) == ref
+    monkeypatch.setenv("LRA_B200_MAP_NO_RETRY", "1")
+    text2, st2 = gpu_sam(w, None)
+    assert (st2["status"] == 2).any()           # the first pass alone does leave reads behind at this size
