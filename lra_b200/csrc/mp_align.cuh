@@ -13,7 +13,11 @@ struct SegBuild {
   int *seg_start;                         // first block of every segment
   int *seg_strand, *seg_chrom, *seg_n0, *seg_n1, *seg_supp; float *seg_val;
   int nseg, cap_seg;
+  // RefineByLinearAlignment calls are independent of one another: they are queued (a placeholder block with length 0 holds the job index) and
+  // aligned 32 at a time, one per lane, by mp_flush_aog; the placeholders are then replaced by the jobs' blocks
+  struct AogJob *jobs; int njobs, cap_jobs;
 };
+struct AogJob { uint32_t qoff, toff, addq, addt; int qLen, tLen, band, str; };
 __device__ __forceinline__ bool sb_push_block(SegBuild &B, uint32_t q, uint32_t t, uint32_t len) {
   if (B.nblk >= B.cap) return false;
   if (lane_id() == 0) { B.blk[3 * B.nblk] = q; B.blk[3 * B.nblk + 1] = t; B.blk[3 * B.nblk + 2] = len; }
@@ -54,6 +58,161 @@ __device__ __noinline__ void mp_trim_overlapped(uint32_t *q, uint32_t *t, int *l
   }
 }
 
+// One AffineOneGapAlign job by one lane: the one-sided case with an even doubled half-width K <= 14 and at most kLaneAogRows rows, i.e. the body
+// of aog_thread_kernel<K> (aog_kernels.cuh) with K at run time.  Blocks go to `out` in the reference's order; returns their number.
+constexpr int kLaneAogRows = 96;
+__device__ __forceinline__ bool mp_aog_lane_ok(int qLen, int tLen, int k_in) {
+  const AogShape s = aog_shape(qLen, tLen, k_in, 0);
+  return s.cls < kAogThreadClasses && s.rows <= kLaneAogRows;
+}
+__device__ __noinline__ int mp_aog_lane(const SeqView &q, uint32_t qoff, int qLen, const SeqView &t, uint32_t toff, int tLen, int m, int mm, int indel, int k_in, uint32_t *out) {
+  const AogShape sh = aog_shape(qLen, tLen, k_in, 0);
+  const int K = sh.k, W = 2 * K + 1;
+  const int diag = sh.diag, qB = sh.qB, tB = sh.tB;
+  const bool keep0 = !((qLen >= tLen && diag - K - 1 >= 0) || (qLen <= tLen && diag >= 2));
+  unsigned long long tb[kLaneAogRows + 1];
+  int prev[31];
+  for (int c = 0; c <= W; c++) { const int i = c - K; prev[c] = (i < 0 || i > K) ? kMissing : indel * i; }
+  SeqStream qs, ts;
+  qs.init(q, qoff); ts.init(t, toff);
+  unsigned long long qw = 0, qn = 0;
+  int qnext = 1;
+  for (int c = K; c <= 2 * K; c++) {
+    int code = 0;
+    if (qnext <= qLen) code = qs.next();
+    qnext++;
+    qw |= (unsigned long long)(code & 3) << (2 * c);
+    qn |= (unsigned long long)(code == 4 ? 1 : 0) << (2 * c);
+  }
+  const unsigned long long kOdd = 0x5555555555555555ull;
+  const int rows = tB - 1;
+  for (int j = 1; j <= rows; j++) {
+    const int tc = ts.next();
+    unsigned long long e;
+    if (tc == 4) e = qn;
+    else { const unsigned long long x = qw ^ ((unsigned long long)tc * kOdd); e = ~(x | (x >> 1)) & kOdd & ~qn; }
+    int run = (j == K + 1 && keep0) ? indel * (K + 1) : kMissing;
+    unsigned long long bits = 0;
+    for (int c = 0; c < W; c++) {
+      const int sM = prev[c] + (((e >> (2 * c)) & 1ull) ? m : mm);
+      const int sD = prev[c + 1] + indel;
+      const int sI = run + indel;
+      const int best = imax(sI, imax(sD, sM));
+      const int arrow = (best == sI) ? AR_LEFT : ((best == sD) ? AR_DOWN : AR_DIAG);
+      bits |= (unsigned long long)arrow << (2 * c);
+      prev[c] = best;
+      run = best;
+    }
+    tb[j] = bits;
+    qw >>= 2; qn >>= 2;
+    int code = 0;
+    if (qnext <= qLen) code = qs.next();
+    qnext++;
+    qw |= (unsigned long long)(code & 3) << (4 * K);
+    qn |= (unsigned long long)(code == 4 ? 1 : 0) << (4 * K);
+  }
+  int nb = 0;
+  { int i = qB - 1, j = tB - 1, run = 0;
+    while (i > 0 && j > 0) {
+      const int a = (int)((tb[j] >> (2 * (i - j + K))) & 3ull);
+      if (a == AR_DIAG) { run++; i--; j--; } else { if (run) { nb++; run = 0; } if (a == AR_LEFT) i--; else j--; }
+    }
+    if (run) nb++; }
+  { int i = qB - 1, j = tB - 1, run = 0, r = nb - 1;
+    while (i > 0 && j > 0) {
+      const int a = (int)((tb[j] >> (2 * (i - j + K))) & 3ull);
+      if (a == AR_DIAG) { run++; i--; j--; }
+      else { if (run) { out[3 * r] = (uint32_t)i; out[3 * r + 1] = (uint32_t)j; out[3 * r + 2] = (uint32_t)run; r--; run = 0; } if (a == AR_LEFT) i--; else j--; }
+    }
+    if (run) { out[3 * r] = (uint32_t)i; out[3 * r + 1] = (uint32_t)j; out[3 * r + 2] = (uint32_t)run; } }
+  return nb;
+}
+
+// Run the queued RefineByLinearAlignment jobs and splice their blocks into the segment's block list
+__device__ __noinline__ bool mp_flush_aog(const MpCtx &C, int r, Arena &ar, SegBuild &B) {
+  const int nj = B.njobs;
+  if (nj == 0) return true;
+  const int lane = lane_id();
+  const MpOpts &O = C.o;
+  const unsigned long long tk = mp_clock();
+  const unsigned long long mk = ar.mark();
+  int *joff = ar.alloc<int>(nj + 1), *jnb = ar.alloc<int>(nj);
+  int *newpos = ar.alloc<int>(B.nblk + 1);
+  int *errp = ar.alloc<int>(1);
+  if (ar.overflow) return false;
+  // capacity of every job's block list: min(qLen, tLen) + 2 triples
+  int carry = 0;
+  for (int b0 = 0; b0 < nj; b0 += kLanes) {
+    const int j = b0 + lane;
+    const int c = j < nj ? imin(B.jobs[j].qLen, B.jobs[j].tLen) + 2 : 0;
+    const int incl = wscan_incl(c);
+    if (j < nj) joff[j] = carry + incl - c;
+    carry += bcast(incl, kLanes - 1);
+  }
+  if (lane == 0) joff[nj] = carry;
+  wsync();
+  uint32_t *jblk = ar.alloc<uint32_t>(3ull * (unsigned long long)(carry > 0 ? carry : 1));
+  if (ar.overflow) return false;
+  // one job per lane where the thread form applies
+  bool pending = false;
+  for (int j = lane; j < nj; j += kLanes) {
+    const AogJob &J = B.jobs[j];
+    if (mp_aog_lane_ok(J.qLen, J.tLen, J.band)) {
+      const SeqView &rs = J.str ? C.rd.rc : C.rd.fwd;
+      jnb[j] = mp_aog_lane(rs, J.qoff, J.qLen, C.ix.genome, J.toff, J.tLen, O.localMatch, O.localMismatch, O.localIndel, J.band, jblk + 3ull * joff[j]);
+    } else { jnb[j] = -2; pending = true; }
+  }
+  wsync();
+  // the rest one after the other on the whole warp
+  if (wany(pending)) {
+    for (int j = 0; j < nj; j++) {
+      if (jnb[j] != -2) continue;
+      const AogJob J = B.jobs[j];
+      const SeqView &rs = J.str ? C.rd.rc : C.rd.fwd;
+      int nb = 0;
+      mp_aog(rs, J.qoff, J.qLen, C.ix.genome, J.toff, J.tLen, O.localMatch, O.localMismatch, O.localIndel, J.band, ar, jblk + 3ull * joff[j], joff[j + 1] - joff[j], &nb, errp);
+      if (nb < 0) return false;
+      wsync();
+      if (lane == 0) jnb[j] = nb;
+      wsync();
+    }
+  }
+  // new position of every block of the list (a placeholder becomes its job's blocks)
+  carry = 0;
+  for (int b0 = 0; b0 < B.nblk; b0 += kLanes) {
+    const int i = b0 + lane;
+    int c = 0;
+    if (i < B.nblk) c = (B.blk[3 * i + 2] == 0u && B.blk[3 * i + 1] == 0xffffffffu) ? jnb[B.blk[3 * i]] : 1;
+    const int incl = wscan_incl(c);
+    if (i < B.nblk) newpos[i] = carry + incl - c;
+    carry += bcast(incl, kLanes - 1);
+  }
+  if (lane == 0) newpos[B.nblk] = carry;
+  wsync();
+  const int total = carry;
+  if (total > B.cap) return false;
+  uint32_t *tmp = ar.alloc<uint32_t>(3ull * (unsigned long long)(total > 0 ? total : 1));
+  if (ar.overflow) return false;
+  for (int i = lane; i < B.nblk; i += kLanes) {
+    const int at = newpos[i];
+    if (!(B.blk[3 * i + 2] == 0u && B.blk[3 * i + 1] == 0xffffffffu)) { tmp[3 * at] = B.blk[3 * i]; tmp[3 * at + 1] = B.blk[3 * i + 1]; tmp[3 * at + 2] = B.blk[3 * i + 2]; }
+    else {
+      const int j = (int)B.blk[3 * i];
+      const AogJob &J = B.jobs[j];
+      const uint32_t *src = jblk + 3ull * joff[j];
+      for (int x = 0; x < jnb[j]; x++) { tmp[3 * (at + x)] = src[3 * x] + J.addq; tmp[3 * (at + x) + 1] = src[3 * x + 1] + J.addt; tmp[3 * (at + x) + 2] = src[3 * x + 2]; }
+    }
+  }
+  wsync();
+  for (int sgi = lane; sgi < B.nseg; sgi += kLanes) B.seg_start[sgi] = newpos[B.seg_start[sgi]];
+  for (int i = lane; i < 3 * total; i += kLanes) B.blk[i] = tmp[i];
+  wsync();
+  B.nblk = total; B.njobs = 0;
+  ar.release(mk);
+  mp_tick(C, PF_AOG, tk);
+  return true;
+}
+
 // RefineByLinearAlignment (LocalRefineAlignment.h:144-185): AffineOneGapAlign between two anchors, blocks appended to the current segment
 __device__ __noinline__ bool mp_refine_linear(const MpCtx &C, int r, Arena &ar, SegBuild &B, uint32_t curReadEnd, uint32_t curGenomeEnd, uint32_t nextReadStart,
                                         uint32_t nextGenomeStart, int str, int chrom) {
@@ -65,24 +224,18 @@ __device__ __noinline__ bool mp_refine_linear(const MpCtx &C, int r, Arena &ar, 
   const int qLen = (int)(nextReadStart - curReadEnd), tLen = (int)(nextGenomeStart - curGenomeEnd);
   int drift = qLen - tLen; if (drift < 0) drift = -drift;
   const int band = (drift * 2 + 1) < O.localBand ? (drift * 2 + 1) : O.localBand;
-  const unsigned long long mk = ar.mark();
-  const int capb = (qLen < tLen ? qLen : tLen) + 2;
-  uint32_t *blk = ar.alloc<uint32_t>(3ull * (capb > 0 ? capb : 1));
-  int *errp = ar.alloc<int>(1);
-  if (ar.overflow) return false;
-  int nb = 0;
-  const SeqView &rs = str ? C.rd.rc : C.rd.fwd;
-  const unsigned long long tk = mp_clock();
-  mp_aog(rs, (uint32_t)(C.rd.read_off[r] + curReadEnd), qLen, C.ix.genome, (uint32_t)(C.ix.hdr_pos[chrom] + curGenomeEnd), tLen, O.localMatch, O.localMismatch,
-         O.localIndel, band, ar, blk, capb, &nb, errp);
-  mp_tick(C, PF_AOG, tk);
-  if (nb < 0) return false;
+  if (B.njobs >= B.cap_jobs && !mp_flush_aog(C, r, ar, B)) return false;
+  if (B.nblk >= B.cap) return false;
+  if (lane_id() == 0) {
+    AogJob J;
+    J.qoff = (uint32_t)(C.rd.read_off[r] + curReadEnd); J.toff = (uint32_t)(C.ix.hdr_pos[chrom] + curGenomeEnd); J.addq = curReadEnd; J.addt = curGenomeEnd;
+    J.qLen = qLen; J.tLen = tLen; J.band = band; J.str = str;
+    B.jobs[B.njobs] = J;
+    B.blk[3 * B.nblk] = (uint32_t)B.njobs; B.blk[3 * B.nblk + 1] = 0xffffffffu; B.blk[3 * B.nblk + 2] = 0u;      // placeholder: length 0 at t = 2^32 - 1
+  }
+  B.njobs++; B.nblk++;
   wsync();
-  bool ok = true;
-  for (int i = 0; i < nb; i++) ok = ok && sb_push_block(B, blk[3 * i] + curReadEnd, blk[3 * i + 1] + curGenomeEnd, blk[3 * i + 2]);
-  wsync();
-  ar.release(mk);
-  return ok;
+  return true;
 }
 
 struct GapState { bool inversion, breakalignment; };
@@ -128,7 +281,12 @@ __device__ __noinline__ bool mp_refined_alignment_btwn(const MpCtx &C, int r, Ar
   const int minDist = (int)mind;
   uint32_t *bq = fq, *bt = ft; int nb = nfor;
   bool inversion = false;
-  const int cur_seg_blocks = B.nblk - B.seg_start[B.nseg - 1];
+  // (the number of blocks of the current segment enters the test: the queued linear alignments are run first when the other two conditions hold)
+  int cur_seg_blocks = 0;
+  if (__fdiv_rn((float)nfor, (float)minDist) < minRatio && identity < 0.8f) {
+    if (!mp_flush_aog(C, r, ar, B)) return false;
+    cur_seg_blocks = B.nblk - B.seg_start[B.nseg - 1];
+  }
   if (__fdiv_rn((float)nfor, (float)minDist) < minRatio && cur_seg_blocks >= 5 && identity < 0.8f) {
     const uint32_t temp = curReadEnd;
     curReadEnd = L - nextReadStart; nextReadStart = L - temp;
@@ -269,7 +427,7 @@ __device__ __noinline__ bool mp_local_refine_alignment(const MpCtx &C, int r, Ar
     if (lane_id() == 0) B.seg_strand[B.nseg - 1] = str;
     wsync();
   }
-  return true;
+  return mp_flush_aog(C, r, ar, B);
 }
 
 }  // namespace mp

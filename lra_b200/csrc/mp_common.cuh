@@ -103,7 +103,24 @@ struct Arena {
   unsigned long long cap, top, peak;
   int overflow;
   int phase;                              // CTA phase barriers this warp has passed for its current read (mp_phase)
-  __device__ __forceinline__ void init(void *b, unsigned long long c) { base = (unsigned char *)b; cap = c; top = 0; peak = 0; overflow = 0; phase = 0; }
+  unsigned long long *prof;               // optional cycle counters of this warp (LRA_B200_MAP_PROFILE)
+  __device__ __forceinline__ void init(void *b, unsigned long long c) { base = (unsigned char *)b; cap = c; top = 0; peak = 0; overflow = 0; phase = 0; prof = nullptr; }
+  __device__ __forceinline__ unsigned long long tick(int slot, unsigned long long t0) {
+#ifdef LRA_EMU
+    (void)slot; (void)t0; return 0ull;
+#else
+    const unsigned long long t1 = (unsigned long long)clock64();
+    if (prof && (threadIdx.x & 31u) == 0) prof[slot] += t1 - t0;
+    return t1;
+#endif
+  }
+  __device__ __forceinline__ unsigned long long now() const {
+#ifdef LRA_EMU
+    return 0ull;
+#else
+    return (unsigned long long)clock64();
+#endif
+  }
   template <class T> __device__ __forceinline__ T *alloc(unsigned long long n) {
     unsigned long long t = (top + 15ull) & ~15ull;
     unsigned long long e = t + n * sizeof(T);

@@ -411,12 +411,12 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
     CU(cudaMemcpy(hp.data(), B[27].p, hp.size() * 8, cudaMemcpyDeviceToHost));
     static const char *nm[lra::mp::kProfStages] = {"minimizers+sort", "CompareLists(global)", "strand+CleanMatches", "LinearExtend#1", "SparseDP#1", "SPLITChain", "Refine_splitchain",
                                                    "Refine_Btwnsplitchain", "LinearExtend#2+Trim", "SparseDP#2+filters", "LocalRefineAlignment(all)", "  AffineOneGapAlign", "  RefineSpace",
-                                                   "  SparseDP#3", "output", "phase barriers"};
+                                                   "  SparseDP#3", "output", "phase barriers", "  [all SDP] points+sorts", "  [all SDP] divide", "  [all SDP] ProcessPoint", "", "", "", "", ""};
     unsigned long long tot[lra::mp::kProfStages] = {0}; unsigned long long all_c = 0;
     for (int wv = 0; wv < warps; wv++) for (int s = 0; s < lra::mp::kProfStages; s++) tot[s] += hp[(size_t)wv * lra::mp::kProfStages + s];
     for (int s = 0; s < 11; s++) all_c += tot[s]; all_c += tot[14] + tot[15];
     fprintf(stderr, "[lra_b200 map profile] %d warps, arena %zu MB/warp, peak %.1f MB; share of worker cycles:\n", warps, per >> 20, (double)hcur[3] / 1e6);
-    for (int s = 0; s < 16; s++) fprintf(stderr, "  %-28s %6.2f %%\n", nm[s], all_c ? 100.0 * (double)tot[s] / (double)all_c : 0.0);
+    for (int s = 0; s < 19; s++) fprintf(stderr, "  %-28s %6.2f %%\n", nm[s], all_c ? 100.0 * (double)tot[s] / (double)all_c : 0.0);
   }
   const int S = (int)(hcur[0] >> 40); const unsigned long long NB = hcur[0] & ((1ull << 40) - 1ull);
   const int kerr = (int)(hcur[2] & 0xffffffffull);

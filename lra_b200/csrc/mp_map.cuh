@@ -173,6 +173,8 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
   B.blk = ar.alloc<uint32_t>(3ull * max_blocks);
   B.seg_start = ar.alloc<int>(kMaxSegPerChain + 1); B.seg_strand = ar.alloc<int>(kMaxSegPerChain); B.seg_chrom = ar.alloc<int>(kMaxSegPerChain);
   B.seg_n0 = ar.alloc<int>(kMaxSegPerChain); B.seg_n1 = ar.alloc<int>(kMaxSegPerChain); B.seg_supp = ar.alloc<int>(kMaxSegPerChain); B.seg_val = ar.alloc<float>(kMaxSegPerChain);
+  B.cap_jobs = 4096; B.njobs = 0;
+  B.jobs = ar.alloc<AogJob>(B.cap_jobs);
   if (ar.overflow) return -MP_ERR_ARENA;
   if (!mp_local_refine_alignment(C, r, ar, B, xs, uc, ng, LSC)) return ar.overflow ? -MP_ERR_ARENA : -MP_ERR_CAP;
   wsync();
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(MP_BLOCK_THREADS, 1) map_reads_kernel(MapBatch
   const int wib = (int)threadIdx.x / kLanes;
   const int wid = (int)blockIdx.x * warps_per_block + wib;
   Arena ar; ar.init(b.arena + (unsigned long long)wid * b.arena_per_warp, b.arena_per_warp);
+  if (b.C.prof) ar.prof = b.C.prof + (unsigned long long)wid * kProfStages;
   const int PB = (b.C.o.NumAln < kMaxChains ? b.C.o.NumAln : kMaxChains);
 #if !defined(LRA_EMU)
   __shared__ int s_base;

@@ -376,6 +376,7 @@ __device__ __forceinline__ void sdp_put_pair(SdpPt *H, int at, uint32_t frag, ui
 
 // mode 0: pure matches of all clusters (SparseDP.h:2139); 1: one cluster `only_cl` (:2287); 2: forward only (SparseDP_Forward.h:312)
 __device__ __noinline__ bool sdp_build(SdpWork &W, const SdpAnchors &A, int mode, int only_cl, float rate, int irate, Arena &ar) {
+  unsigned long long tk_ = ar.now();
   // count points
   int N = 0, f0 = 0, f1 = A.nfrag;
   if (mode == 0) { N = 2 * A.nfrag; for (int c = 0; c < A.ncl; c++) { const int sz = A.cl_off[c + 1] - A.cl_off[c]; if (sz == 1) N += 2; else if (sz > 1) N += 4; } }
@@ -472,6 +473,7 @@ __device__ __noinline__ bool sdp_build(SdpWork &W, const SdpAnchors &A, int mode
   for (int i = lane_id(); i <= N; i += kLanes) W.flag[i] = 0;
   wsync();
   W.R = R; W.C = C;
+  tk_ = ar.tick(16, tk_);
   // families
   const int nf = mode == 2 ? 2 : 4;
   for (int f = 0; f < 4; f++) {
@@ -490,6 +492,7 @@ __device__ __noinline__ bool sdp_build(SdpWork &W, const SdpAnchors &A, int mode
     wsync();
     if (!sdp_divide(W, F, ar)) return false;
   }
+  tk_ = ar.tick(17, tk_);
   return true;
 }
 // hand the rest of the arena to the growth heap (call after every uniform allocation the problem still needs)

@@ -34,7 +34,7 @@ __device__ __noinline__ int sdp_pure_matches(const SdpAnchors &A, float rate, fl
   uint8_t *used = ar.alloc<uint8_t>(n > 0 ? n : 1);
   int *nch_p = ar.alloc<int>(1);
   if (ar.overflow || !sdp_open_dyn(W, ar)) { ar.release(mk); return -1; }
-  sdp_process(W, A, 0, 0, rate, 0, P);
+  { const unsigned long long tp_ = ar.now(); sdp_process(W, A, 0, 0, rate, 0, P); ar.tick(18, tp_); }
   { const unsigned long long e = W.dyn.base_off + *W.dyn.top; if (e > ar.peak) ar.peak = e; }
   if (*W.dyn.err) { ar.release(mk); return -1; }
   for (int i = lane_id(); i < n; i += kLanes) { order[i] = i; used[i] = 0; if (cl_of_frag) cl_of_frag[i] = W.val[i].cl; }
@@ -86,7 +86,7 @@ __device__ __noinline__ int sdp_one_cluster(const SdpAnchors &A, int cl, float r
   if (!sdp_build(W, A, 1, cl, rate, 0, ar)) { ar.release(mk); return -1; }
   int *res = ar.alloc<int>(2);
   if (ar.overflow || !sdp_open_dyn(W, ar)) { ar.release(mk); return -1; }
-  sdp_process(W, A, f0, 1, rate, 0, P);
+  { const unsigned long long tp_ = ar.now(); sdp_process(W, A, f0, 1, rate, 0, P); ar.tick(18, tp_); }
   { const unsigned long long e = W.dyn.base_off + *W.dyn.top; if (e > ar.peak) ar.peak = e; }
   if (*W.dyn.err) { ar.release(mk); return -1; }
   if (lane_id() == 0) {
@@ -110,7 +110,7 @@ __device__ __noinline__ int sdp_forward_only(const SdpAnchors &A, int irate, con
   int *res = ar.alloc<int>(2);
   uint8_t *link = ar.alloc<uint8_t>(A.nfrag + 1);
   if (ar.overflow || !sdp_open_dyn(W, ar)) { ar.release(mk); return -1; }
-  sdp_process(W, A, 0, 2, 0.0f, irate, P);
+  { const unsigned long long tp_ = ar.now(); sdp_process(W, A, 0, 2, 0.0f, irate, P); ar.tick(18, tp_); }
   { const unsigned long long e = W.dyn.base_off + *W.dyn.top; if (e > ar.peak) ar.peak = e; }
   if (*W.dyn.err) { ar.release(mk); return -1; }
   if (lane_id() == 0) {

@@ -25,7 +25,7 @@ struct MpCtx {
 
 // ---- stage profile of the worker kernel (clock64 deltas accumulated per warp; summed on the host)
 enum { PF_MINIMIZERS = 0, PF_COMPARE, PF_STRAND_CLEAN, PF_LEXT1, PF_SDP1, PF_SPLIT, PF_REFINE_SPLIT, PF_REFINE_BTWN, PF_LEXT2, PF_SDP2, PF_LOCAL_REFINE, PF_AOG, PF_REFINE_SPACE,
-       PF_SDP3, PF_OUTPUT, PF_BARRIER, kProfStages = 16 };
+       PF_SDP3, PF_OUTPUT, PF_BARRIER, PF_SDP_POINTS, PF_SDP_DIVIDE, PF_SDP_PROCESS, PF_SDP_TRACE, kProfStages = 24 };
 __device__ __forceinline__ unsigned long long mp_clock() {
 #ifdef LRA_EMU
   return 0ull;
