@@ -892,6 +892,12 @@ int lra_b200_map_download(lra_b200_ctx *ctx, lra_b200_mapper *m, lra_b200_map_re
 int64_t lra_b200_format_sam(const lra_b200_map_opts *opts, const lra_b200_map_result *res, int32_t n_reads, const char *names, const char *reads_ascii,
                             const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, int32_t n_contigs, int32_t runtime, char *out, int64_t cap);
 
+/* The other printers of OUTPUT (Mapping_ultility.h:465-494): fmt 's' SAM, 'p' PAF (Alignment::PrintPAF, Alignment.h:600-656; `-p p`, the reference's
+ * default), 'c' PAF with CG:z: (`-p pc`), 'b' BED (PrintBed :591-598).  contig_len[n_contigs] is the `genomeLen` column of PAF. */
+int64_t lra_b200_format_records(const lra_b200_map_opts *opts, const lra_b200_map_result *res, int32_t n_reads, const char *names, const char *reads_ascii,
+                                const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, const uint64_t *contig_len, int32_t n_contigs,
+                                int32_t fmt, int32_t runtime, char *out, int64_t cap);
+
 /* ---- per-kernel timing of the last batch call (CUDA events on the context's stream) ---------------------------- */
 typedef struct lra_b200_kernel_stat {
   char name[48];

@@ -57,8 +57,9 @@ struct SamOut {
   void cigar(const uint32_t *cig, int n) { static const char ops[] = "MIDNSHP=X"; for (int k = 0; k < n; k++) { u(cig[k] >> 4); s.push_back(ops[cig[k] & 15u]); } }
 };
 
+// fmt: 's' SAM (Alignment::PrintSAM, Alignment.h:658-808), 'p' PAF, 'c' PAF with CG:z: (-p pc; PrintPAF :600-656), 'b' BED (PrintBed :591-598)
 static void mp_format_read(SamOut &o, const lra_b200_map_opts *opts, const lra_b200_map_result *res, int r, const char *name, const char *seq, uint32_t L,
-                           const std::vector<const char *> &cname, int runtime, std::string &rc) {
+                           const std::vector<const char *> &cname, const uint64_t *contig_len, int runtime, std::string &rc, char fmt) {
   const unsigned char *RC = mp_revcomp_table();
   const int na = res->status[r] == 0 ? res->n_aln[r] : 0;
   bool printed = false;
@@ -71,6 +72,34 @@ static void mp_format_read(SamOut &o, const lra_b200_map_opts *opts, const lra_b
       for (int sgi = ns - 1; sgi >= 0; sgi--) {
         const lra_b200_record &x = res->records[s0 + sgi];
         printed = true;
+        if (fmt == 'b') {
+          o.put(x.n_blocks ? cname[x.chrom] : ""); o.put('\t'); o.u(x.tStart); o.put('\t'); o.u(x.tEnd); o.put('\t'); o.i((int)(unsigned char)x.mapq); o.put('\t'); o.put(name); o.put('\t');
+          o.u(L); o.put('\t'); o.u(x.qStart); o.put('\t'); o.u(x.qEnd); o.put('\t'); o.i(x.nm); o.put('\t'); o.i(x.nmm); o.put('\t'); o.i(x.nins); o.put('\t'); o.i(x.ndel); o.put('\t');
+          o.f(x.value); o.put('\t'); o.u(x.flag); o.put('\t'); o.i(x.NumOfAnchors1); o.put('\t'); o.f((float)x.NumOfAnchors1 / (float)L); o.put('\n');
+          continue;
+        }
+        if (fmt == 'p' || fmt == 'c') {
+          o.put(name); o.put('\t'); o.u(L); o.put('\t');
+          if (x.strand == 0) { o.u(x.qStart); o.put('\t'); o.u(x.qEnd); o.put('\t'); }
+          else { o.u(L - x.qEnd); o.put('\t'); o.u(L - x.qStart); o.put('\t'); }
+          o.put(x.strand == 1 ? '-' : '+'); o.put('\t'); o.put(x.n_blocks ? cname[x.chrom] : ""); o.put('\t'); o.u(x.n_blocks && contig_len ? contig_len[x.chrom] : 0ull); o.put('\t');
+          o.u(x.tStart); o.put('\t'); o.u(x.tEnd); o.put('\t'); o.i(x.nm); o.put('\t'); o.i(x.nm + x.nmm + x.ndel + x.nins); o.put('\t'); o.i((int)(unsigned char)x.mapq);
+          o.put("\tOR:i:"); o.i(x.order); o.put("\tNM:i:"); o.i(x.nmm + x.ndel + x.nins); o.put("\tNX:i:"); o.i(x.nmm); o.put("\tND:i:"); o.i(x.ndel); o.put("\tTD:i:"); o.i(x.tdel);
+          o.put("\tNI:i:"); o.i(x.nins); o.put("\tTI:i:"); o.i(x.tins);
+          o.put("\tSD:i:"); o.i(x.nSmallDel); o.put("\tME:i:"); o.i(x.nMedDel); o.put("\tLD:i:"); o.i(x.nLargeDel); o.put("\tSI:i:"); o.i(x.nSmallIns); o.put("\tMI:i:"); o.i(x.nMedIns);
+          o.put("\tLI:i:"); o.i(x.nLargeIns); o.put("\tN0:i:"); o.i(x.NumOfAnchors0); o.put("\tNV:f:"); o.f(x.value); o.put("\tAS:i:"); o.i((int)x.value);
+          o.put("\tTP:A:"); o.put(x.typeofaln == 0 ? 'P' : (x.typeofaln == 1 ? 'S' : 'I'));
+          if (x.NumOfAnchors1 > 0) { o.put("\tNA:i:"); o.i(x.NumOfAnchors1); }
+          if (runtime > 0) { o.put("\tRT:i:"); o.i(runtime); }
+          if (fmt == 'c') {
+            o.put("\tCG:z:");
+            if (x.preClip > 0) { o.i(x.preClip); o.put('S'); }
+            o.cigar(res->cigar + x.cigar_off, x.n_cigar);
+            if (x.sufClip > 0) { o.i(x.sufClip); o.put('S'); }
+          }
+          o.put('\n');
+          continue;
+        }
         o.put(name); o.put('\t');
         const char *rd = seq;
         if (x.strand == 1) {
@@ -111,14 +140,24 @@ static void mp_format_read(SamOut &o, const lra_b200_map_opts *opts, const lra_b
       }
     }
   }
-  if (!printed) {      // output_unaligned -> SimplePrintSAM of an Alignment without blocks
+  if (!printed && fmt == 's') {      // output_unaligned -> SimplePrintSAM of an Alignment without blocks (SAM only, Mapping_ultility.h:457-463)
     o.put(name); o.put("\t4\t*\t0\t0\t*\t*\t0\t0\t"); o.put(seq, L); o.put("\t*\n");
   }
 }
 
+extern "C" int64_t lra_b200_format_records(const lra_b200_map_opts *opts, const lra_b200_map_result *res, int32_t n_reads, const char *names, const char *reads_ascii,
+                                           const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, const uint64_t *contig_len, int32_t n_contigs,
+                                           int32_t fmt, int32_t runtime, char *out, int64_t cap);
 extern "C" int64_t lra_b200_format_sam(const lra_b200_map_opts *opts, const lra_b200_map_result *res, int32_t n_reads, const char *names, const char *reads_ascii,
                                        const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, int32_t n_contigs, int32_t runtime, char *out,
                                        int64_t cap) {
+  return lra_b200_format_records(opts, res, n_reads, names, reads_ascii, read_off, read_len, contig_names, nullptr, n_contigs, 's', runtime, out, cap);
+}
+
+extern "C" int64_t lra_b200_format_records(const lra_b200_map_opts *opts, const lra_b200_map_result *res, int32_t n_reads, const char *names, const char *reads_ascii,
+                                           const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, const uint64_t *contig_len, int32_t n_contigs,
+                                           int32_t fmt, int32_t runtime, char *out, int64_t cap) {
+  if (fmt != 's' && fmt != 'p' && fmt != 'c' && fmt != 'b') return 0;
   if (!opts || !res || n_reads < 0 || !names || !reads_ascii || !read_off || !read_len || !contig_names) return 0;
   std::vector<const char *> cname(n_contigs);
   { const char *p = contig_names; for (int c = 0; c < n_contigs; c++) { cname[c] = p; p += strlen(p) + 1; } }
@@ -138,7 +177,7 @@ extern "C" int64_t lra_b200_format_sam(const lra_b200_map_opts *opts, const lra_
     std::string rc;
     unsigned long long b = 0; for (int r = cut[t]; r < cut[t + 1]; r++) b += read_len[r];
     piece[t].s.reserve((size_t)(b + b / 2) + 4096);
-    for (int r = cut[t]; r < cut[t + 1]; r++) mp_format_read(piece[t], opts, res, r, rname[r], reads_ascii + read_off[r], read_len[r], cname, runtime, rc);
+    for (int r = cut[t]; r < cut[t + 1]; r++) mp_format_read(piece[t], opts, res, r, rname[r], reads_ascii + read_off[r], read_len[r], cname, contig_len, runtime, rc, (char)fmt);
   };
   if (T == 1) work(0);
   else { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(work, t); for (auto &x : th) x.join(); }
@@ -335,7 +374,7 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
   const size_t seg_cap = (size_t)n_reads * 3 + 1024;
   const size_t blk_cap = (size_t)(total_bases / 2) + (size_t)n_reads * 64 + 4096;
   // one CTA of `bw` warps per SM (phase-aligned groups of reads, mp_phase); LRA_B200_MAP_BLOCK_WARPS / _BLOCKS_PER_SM for experiments
-  int bw = 16; if (getenv("LRA_B200_MAP_BLOCK_WARPS")) bw = atoi(getenv("LRA_B200_MAP_BLOCK_WARPS"));
+  int bw = MP_BLOCK_THREADS / 32; if (getenv("LRA_B200_MAP_BLOCK_WARPS")) bw = atoi(getenv("LRA_B200_MAP_BLOCK_WARPS"));
   if (bw < 1) bw = 1; if (bw > MP_BLOCK_THREADS / 32) bw = MP_BLOCK_THREADS / 32;
   int blocks = ctx->n_sm;
   if ((long long)blocks * bw > (long long)n_reads) blocks = (n_reads + bw - 1) / bw;

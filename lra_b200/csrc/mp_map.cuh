@@ -255,9 +255,10 @@ struct MapBatch {
 };
 
 // One CTA per SM; its warps take a group of consecutive reads of the length-sorted order (similar lengths, similar stage times) through the
-// stages in lock step (mp_phase).  blockDim.x = 32 * warps per CTA (host: 16).
+// stages in lock step (mp_phase).  blockDim.x = 32 * warps per CTA (host: 24 warps, 80 registers per thread: measured 576 ms per 16 k ONT reads
+// against 633 ms for 16 warps with 128 registers and 692+ ms for 32 warps with 64, profiles/r02_experiments.md).
 #ifndef MP_BLOCK_THREADS
-#define MP_BLOCK_THREADS 512
+#define MP_BLOCK_THREADS 768
 #endif
 __global__ void __launch_bounds__(MP_BLOCK_THREADS, 1) map_reads_kernel(MapBatch b) {
   const int warps_per_block = (int)blockDim.x / kLanes;
