@@ -22,11 +22,23 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+CLI_SRC = os.path.join(HERE, "cli", "lra_b200_cli.cpp")
+CLI_OUT = os.path.join(HERE, "lra_b200")
+
+
+def build_cli(force=False):
+    """The C++ host program above the C ABI (`lra_b200 index|align`, lra_b200/cli/): plain g++, linked against liblra_b200.so."""
+    if not force and os.path.exists(CLI_OUT) and os.path.getmtime(CLI_OUT) > max(os.path.getmtime(CLI_SRC), os.path.getmtime(OUT)):
+        return CLI_OUT
+    subprocess.run(["g++", "-std=c++17", "-O2", CLI_SRC, "-o", CLI_OUT, "-L" + HERE, "-llra_b200", "-Wl,-rpath,$ORIGIN"], check=True)
+    return CLI_OUT
+
+
 def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", OUT]
-    subprocess.run(cmd, check=True)
+    if force or needs_build():
+        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", OUT]
+        subprocess.run(cmd, check=True)
+    build_cli(force)
     return OUT
 
 
