@@ -385,7 +385,7 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
   size_t per = (size_t)maxL * 192 + (4u << 20);
   if (getenv("LRA_B200_MAP_ARENA_MB")) per = (size_t)atoi(getenv("LRA_B200_MAP_ARENA_MB")) << 20;
   size_t free_b = 0, tot_b = 0; cudaMemGetInfo(&free_b, &tot_b);
-  const size_t budget = (free_b + B[9].cap) / 2;
+  const size_t budget = (free_b + B[9].cap) / 10 * 8;      // the rest of the batch (records, blocks, a19 / a21 buffers) needs a few GB
   while ((size_t)warps * per > budget && blocks > 1) { blocks--; warps = blocks * bw; }
   if ((rc = ensure(ctx, B[2], (size_t)n_reads * 4)) || (rc = ensure(ctx, B[3], (size_t)n_reads * 4)) || (rc = ensure(ctx, B[4], (size_t)n_reads * 16)) ||
       (rc = ensure(ctx, B[5], (size_t)n_reads * 16)) || (rc = ensure(ctx, B[6], seg_cap * sizeof(SegRec))) || (rc = ensure(ctx, B[7], blk_cap * 12)) ||

@@ -282,75 +282,156 @@ __device__ __noinline__ bool sdp_setup_sub(SdpSub &s, int desc, Arena &ar) {
   return true;
 }
 
-// DivideSubProbBy{Row1,Col1,Row2,Col2}: pre-order numbering with dropped nodes, explicit stack
+// DivideSubProbBy{Row1,Col1,Row2,Col2}: pre-order numbering with dropped nodes, explicit stack.
+// The reference collects and sorts the diagonals of a node's points at every node (O(N log^2 N) per level with a sorting network).  Here the D and
+// the E points of the family are sorted by diagonal ONCE; a node owns the segment of each list that holds the points of its rows, still sorted, and
+// hands its two halves to its children with a stable partition by row (ping-pong between two buffers by depth).  A node's Di / Ei are the distinct
+// diagonals of the segment of its D half / E half.  Numbering, kept / dropped nodes, the SS lists and the sub-problem set-up are as before.
+struct SdpDE { long long d; int row; int pad; };
+// distinct diagonals of the sorted segment a[0..cnt) -> dst (ascending, or descending when desc); returns their number
+__device__ __noinline__ int sdp_unique_sorted(const SdpDE *a, int cnt, long long *dst, int desc) {
+  int u = 0;
+  for (int b = 0; b < cnt; b += kLanes) {
+    const int i = b + lane_id();
+    const bool keep = i < cnt && (i == 0 || a[i].d != a[i - 1].d);
+    const unsigned mk = ballot(keep);
+    if (keep) dst[u + __popc(mk & lanemask_lt())] = a[i].d;
+    u += __popc(mk);
+  }
+  wsync();
+  if (desc) {
+    for (int i = lane_id(); i < u / 2; i += kLanes) { const long long x = dst[i]; dst[i] = dst[u - 1 - i]; dst[u - 1 - i] = x; }
+    wsync();
+  }
+  return u;
+}
+// stable partition of src[lo, hi) by row < med into dst[lo, hi); returns the size of the left part
+__device__ __noinline__ int sdp_partition(const SdpDE *src, SdpDE *dst, int lo, int hi, int med) {
+  int nl = 0;
+  for (int b = lo; b < hi; b += kLanes) { const int i = b + lane_id(); nl += __popc(ballot(i < hi && src[i].row < med)); }
+  int cl = 0, cr = 0;
+  for (int b = lo; b < hi; b += kLanes) {
+    const int i = b + lane_id();
+    const bool in = i < hi;
+    SdpDE x; x.d = 0; x.row = 0; x.pad = 0;
+    if (in) x = src[i];
+    const bool left = in && x.row < med, right = in && !left;
+    const unsigned ml = ballot(left), mr = ballot(right);
+    if (left) dst[lo + cl + __popc(ml & lanemask_lt())] = x;
+    if (right) dst[lo + nl + cr + __popc(mr & lanemask_lt())] = x;
+    cl += __popc(ml); cr += __popc(mr);
+  }
+  wsync();
+  return nl;
+}
+// push node number n into the A or B list of every row of [s,e) that has a D (A) / an E (B) point of the family
+__device__ __noinline__ void sdp_push_ss2(SdpFam &F, const uint8_t *has, int s, int e, int n, bool toA, bool toB) {
+  for (int r = s + lane_id(); r < e; r += kLanes) {
+    if (toA && (has[r] & 1)) { F.ssA[(long long)r * F.stride + F.nA[r]] = (uint32_t)n; F.nA[r]++; }
+    if (toB && (has[r] & 2)) { F.ssB[(long long)r * F.stride + F.nB[r]] = (uint32_t)n; F.nB[r]++; }
+  }
+  wsync();
+}
+
 __device__ __noinline__ bool sdp_divide(SdpWork &W, SdpFam &F, Arena &ar) {
   const int V = F.cols ? W.C : W.R;
   F.nsub = 0;
   if (V == 0) return true;
-  int stS[72], stE[72]; int sp = 0;
-  stS[0] = 0; stE[0] = V; sp = 1;
+  // ---- the family's D and E points (diagonal, row), sorted by diagonal; has[r]: bit 0 row r has a D point, bit 1 an E point
+  const int *rof = F.cols ? W.colOfPos : W.rowOf;
+  const int N = W.N, P2 = next_pow2(N > 0 ? N : 1);
+  SdpDE *bufD[2], *bufE[2];
+  bufD[0] = ar.alloc<SdpDE>(P2); bufD[1] = ar.alloc<SdpDE>(N > 0 ? N : 1); bufE[0] = ar.alloc<SdpDE>(P2); bufE[1] = ar.alloc<SdpDE>(N > 0 ? N : 1);
+  uint8_t *has = ar.alloc<uint8_t>(V);
+  if (ar.overflow) return false;
+  for (int r = lane_id(); r < V; r += kLanes) has[r] = 0;
+  wsync();
+  int nD = 0, nE = 0;
+  for (int b = 0; b < N; b += kLanes) {
+    const int p = b + lane_id();
+    bool tD = false, tE = false; SdpDE x; x.d = 0; x.row = 0; x.pad = 0;
+    if (p < N) {
+      const SdpPt &pt = sdp_pt(W, F, p);
+      if ((int)((pt.fl >> 1) & 1u) == F.inv) { tD = (pt.fl & 1u) == 0u; tE = !tD; x.d = sdp_diag(pt, F.inv); x.row = rof[p]; }
+    }
+    const unsigned mD = ballot(tD), mE = ballot(tE);
+    if (tD) bufD[0][nD + __popc(mD & lanemask_lt())] = x;
+    if (tE) bufE[0][nE + __popc(mE & lanemask_lt())] = x;
+    nD += __popc(mD); nE += __popc(mE);
+  }
+  wsync();
+  // (rows are contiguous in family order, so the flag writes of one pass never collide on a byte with different values: a row's D and E bits are
+  //  set by separate passes)
+  for (int i = lane_id(); i < nD; i += kLanes) has[bufD[0][i].row] |= 1;
+  wsync();
+  for (int i = lane_id(); i < nE; i += kLanes) has[bufE[0][i].row] |= 2;
+  wsync();
+  if (nD == 0 && nE == 0) return true;                 // the root is dropped: no sub-problems
+  { const int PD = next_pow2(nD > 0 ? nD : 1), PE = next_pow2(nE > 0 ? nE : 1);
+    for (int i = nD + lane_id(); i < PD; i += kLanes) { bufD[0][i].d = 0x7fffffffffffffffll; bufD[0][i].row = 0x7fffffff; }
+    for (int i = nE + lane_id(); i < PE; i += kLanes) { bufE[0][i].d = 0x7fffffffffffffffll; bufE[0][i].row = 0x7fffffff; }
+    wsync();
+    auto less = [](const SdpDE &x, const SdpDE &y) { return x.d < y.d; };
+    if (nD > 1) wsort_pow2(bufD[0], PD, less);
+    if (nE > 1) wsort_pow2(bufE[0], PE, less); }
+  int stS[72], stE[72], stDl[72], stDh[72], stEl[72], stEh[72], stDep[72]; int sp = 0;
+  stS[0] = 0; stE[0] = V; stDl[0] = 0; stDh[0] = nD; stEl[0] = 0; stEh[0] = nE; stDep[0] = 0; sp = 1;
   while (sp > 0) {
     --sp;
-    const int start = stS[sp], end = stE[sp];
+    const int start = stS[sp], end = stE[sp], dlo = stDl[sp], dhi = stDh[sp], elo = stEl[sp], ehi = stEh[sp], dep = stDep[sp];
     if (F.nsub >= F.cap) { ar.overflow = 1; return false; }
     SdpSub s; s.m = s.n = 0; s.now = 0; s.last = -1; s.nB = 0; s.nS = 0; s.capB = s.capS = 0;
     s.Di = s.Ei = 0; s.Dv = s.Ev = 0; s.Dp = s.Ep = 0; s.Db = s.Eb = 0; s.Bk = s.S = 0;
     const int n = F.nsub;
-    const unsigned long long mk0 = ar.mark();
+    const SdpDE *curD = bufD[dep & 1], *curE = bufE[dep & 1];
     if (end == start + 1) {
       // leaf: starts and ends of one row
-      const int cE = sdp_scan(W, F, start, end, 1, W.tmp);
-      long long *tmp2 = W.tmp + next_pow2(cE > 0 ? cE : 1);
-      const int cD = sdp_scan(W, F, start, end, 0, tmp2);
+      const int cE = ehi - elo, cD = dhi - dlo;
       if (cE != 0 && cD != 0) {
         s.Ei = ar.alloc<long long>(cE); s.Di = ar.alloc<long long>(cD);
         if (ar.overflow) return false;
-        s.n = sdp_sort_unique(W.tmp, cE, s.Ei, F.desc);
-        s.m = sdp_sort_unique(tmp2, cD, s.Di, F.desc);
-        sdp_push_ss(W, F, start, end, n, true, true);
+        s.n = sdp_unique_sorted(curE + elo, cE, s.Ei, F.desc);
+        s.m = sdp_unique_sorted(curD + dlo, cD, s.Di, F.desc);
+        sdp_push_ss2(F, has, start, end, n, true, true);
         if (!sdp_setup_sub(s, F.desc, ar)) return false;
         if (lane_id() == 0) F.sub[n] = s;
         wsync();
         F.nsub++;
-      } else {
-        sdp_clear_flags(W, start, end);
-        ar.release(mk0);
       }
       continue;
     }
     const int med = (start + end) / 2;
     const int dS = F.swp ? med : start, dE = F.swp ? end : med;     // the half the D (end) points come from
     const int eS = F.swp ? start : med, eE = F.swp ? med : end;     // the half the E (start) points come from
-    int cD, cE;
+    SdpDE *nxtD = bufD[(dep + 1) & 1], *nxtE = bufE[(dep + 1) & 1];
+    const int dl = sdp_partition(curD, nxtD, dlo, dhi, med);        // rows < med in [dlo, dlo + dl), the rest behind
+    const int el = sdp_partition(curE, nxtE, elo, ehi, med);
+    // segments of the halves in the next buffer
+    const int ldl = dlo, ldh = dlo + dl, rdl = dlo + dl, rdh = dhi;   // D points of the left / right half of the rows
+    const int lel = elo, leh = elo + el, rel = elo + el, reh = ehi;   // E points of the left / right half
+    const int Ddl = F.swp ? rdl : ldl, Ddh = F.swp ? rdh : ldh;       // D points of the D half
+    const int Eel = F.swp ? lel : rel, Eeh = F.swp ? leh : reh;       // E points of the E half
+    const int cD = Ddh - Ddl, cE = Eeh - Eel;
     if (!F.swp) {
-      cD = sdp_scan(W, F, dS, dE, 0, W.tmp);
-      if (cD) { s.Di = ar.alloc<long long>(cD); if (ar.overflow) return false; s.m = sdp_sort_unique(W.tmp, cD, s.Di, F.desc); }
-      sdp_push_ss(W, F, dS, dE, n, true, false);
-      cE = sdp_scan(W, F, eS, eE, 1, W.tmp);
-      if (cE) { s.Ei = ar.alloc<long long>(cE); if (ar.overflow) return false; s.n = sdp_sort_unique(W.tmp, cE, s.Ei, F.desc); }
-      sdp_push_ss(W, F, eS, eE, n, false, true);
+      if (cD) { s.Di = ar.alloc<long long>(cD); if (ar.overflow) return false; s.m = sdp_unique_sorted(nxtD + Ddl, cD, s.Di, F.desc); }
+      if (cE) { s.Ei = ar.alloc<long long>(cE); if (ar.overflow) return false; s.n = sdp_unique_sorted(nxtE + Eel, cE, s.Ei, F.desc); }
     } else {
-      cE = sdp_scan(W, F, eS, eE, 1, W.tmp);
-      if (cE) { s.Ei = ar.alloc<long long>(cE); if (ar.overflow) return false; s.n = sdp_sort_unique(W.tmp, cE, s.Ei, F.desc); }
-      sdp_push_ss(W, F, eS, eE, n, false, true);
-      cD = sdp_scan(W, F, dS, dE, 0, W.tmp);
-      if (cD) { s.Di = ar.alloc<long long>(cD); if (ar.overflow) return false; s.m = sdp_sort_unique(W.tmp, cD, s.Di, F.desc); }
-      sdp_push_ss(W, F, dS, dE, n, true, false);
+      if (cE) { s.Ei = ar.alloc<long long>(cE); if (ar.overflow) return false; s.n = sdp_unique_sorted(nxtE + Eel, cE, s.Ei, F.desc); }
+      if (cD) { s.Di = ar.alloc<long long>(cD); if (ar.overflow) return false; s.m = sdp_unique_sorted(nxtD + Ddl, cD, s.Di, F.desc); }
     }
-    if (s.n == 0 && s.m == 0) { ar.release(mk0); continue; }
+    if (s.n == 0 && s.m == 0) continue;
+    sdp_push_ss2(F, has, dS, dE, n, true, false);
+    sdp_push_ss2(F, has, eS, eE, n, false, true);
     if (s.n != 0 && s.m != 0) { if (!sdp_setup_sub(s, F.desc, ar)) return false; }
     if (lane_id() == 0) F.sub[n] = s;
     wsync();
     F.nsub++;
-    // children: the first visited is pushed last
-    const bool goD = s.m != 0, goE = s.n != 0;   // D half / E half
-    if (!F.swp) {     // visit [start,med) (the D half) first, then [med,end)
-      if (goE) { stS[sp] = eS; stE[sp] = eE; sp++; }
-      if (goD) { stS[sp] = dS; stE[sp] = dE; sp++; }
-    } else {          // Col2: visit [med,end) (the D half) first, then [start,med)
-      if (goE) { stS[sp] = eS; stE[sp] = eE; sp++; }
-      if (goD) { stS[sp] = dS; stE[sp] = dE; sp++; }
-    }
+    // children: the first visited (the D half) is pushed last; a half keeps BOTH its D and its E points
+    const bool goD = s.m != 0, goE = s.n != 0;
+    const int Dhalf_dl = Ddl, Dhalf_dh = Ddh, Dhalf_el = F.swp ? rel : lel, Dhalf_eh = F.swp ? reh : leh;
+    const int Ehalf_dl = F.swp ? ldl : rdl, Ehalf_dh = F.swp ? ldh : rdh, Ehalf_el = Eel, Ehalf_eh = Eeh;
+    if (goE) { stS[sp] = eS; stE[sp] = eE; stDl[sp] = Ehalf_dl; stDh[sp] = Ehalf_dh; stEl[sp] = Ehalf_el; stEh[sp] = Ehalf_eh; stDep[sp] = dep + 1; sp++; }
+    if (goD) { stS[sp] = dS; stE[sp] = dE; stDl[sp] = Dhalf_dl; stDh[sp] = Dhalf_dh; stEl[sp] = Dhalf_el; stEh[sp] = Dhalf_eh; stDep[sp] = dep + 1; sp++; }
   }
   return true;
 }
