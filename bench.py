@@ -331,11 +331,12 @@ def main():
     res_host = None
     if rank == 0:
         nbases = max(int(h["len32"].sum()) for h in host)
-        res_host = [lra_b200.Mapper._result_buffers(Rg, nbases) for _ in range(2)]
-        for rh in res_host:
-            for k in ("status", "n_aln", "aln_nseg", "aln_seg0", "aln_rank", "records", "cigar"):
-                t = torch.from_numpy(rh[k].view(np.uint8)).pin_memory()
-                rh[k] = t.numpy().view(rh[k].dtype)
+        if world == 1:      # (N > 1: the records arrive as device tensors and are copied home shard by shard)
+            res_host = [lra_b200.Mapper._result_buffers(Rg, nbases) for _ in range(2)]
+            for rh in res_host:
+                for k in ("status", "n_aln", "aln_nseg", "aln_seg0", "aln_rank", "records", "cigar"):
+                    t = torch.from_numpy(rh[k].view(np.uint8)).pin_memory()
+                    rh[k] = t.numpy().view(rh[k].dtype)
         sam_bufs = [np.empty(int(nbases * 1.6) + 1024 * Rg, np.uint8) for _ in range(2)]
     # SAM text of step s is formatted by a host thread (lra_b200_format_sam releases the GIL and uses all cores) while step s + 1 is on the GPU
     from concurrent.futures import ThreadPoolExecutor

@@ -450,12 +450,12 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
     CU(cudaMemcpy(hp.data(), B[27].p, hp.size() * 8, cudaMemcpyDeviceToHost));
     static const char *nm[lra::mp::kProfStages] = {"minimizers+sort", "CompareLists(global)", "strand+CleanMatches", "LinearExtend#1", "SparseDP#1", "SPLITChain", "Refine_splitchain",
                                                    "Refine_Btwnsplitchain", "LinearExtend#2+Trim", "SparseDP#2+filters", "LocalRefineAlignment(all)", "  AffineOneGapAlign", "  RefineSpace",
-                                                   "  SparseDP#3", "output", "phase barriers", "  [all SDP] points+sorts", "  [all SDP] divide", "  [all SDP] ProcessPoint", "", "", "", "", ""};
+                                                   "  SparseDP#3", "output", "phase barriers", "  [all SDP] points+sorts", "  [all SDP] divide", "  [all SDP] ProcessPoint", "    divide: partition", "    divide: unique", "    divide: SS lists", "    divide: sub-problem set-up", "    divide: node bookkeeping"};
     unsigned long long tot[lra::mp::kProfStages] = {0}; unsigned long long all_c = 0;
     for (int wv = 0; wv < warps; wv++) for (int s = 0; s < lra::mp::kProfStages; s++) tot[s] += hp[(size_t)wv * lra::mp::kProfStages + s];
     for (int s = 0; s < 11; s++) all_c += tot[s]; all_c += tot[14] + tot[15];
     fprintf(stderr, "[lra_b200 map profile] %d warps, arena %zu MB/warp, peak %.1f MB; share of worker cycles:\n", warps, per >> 20, (double)hcur[3] / 1e6);
-    for (int s = 0; s < 19; s++) fprintf(stderr, "  %-28s %6.2f %%\n", nm[s], all_c ? 100.0 * (double)tot[s] / (double)all_c : 0.0);
+    for (int s = 0; s < 24; s++) fprintf(stderr, "  %-28s %6.2f %%\n", nm[s], all_c ? 100.0 * (double)tot[s] / (double)all_c : 0.0);
   }
   const int S = (int)(hcur[0] >> 40); const unsigned long long NB = hcur[0] & ((1ull << 40) - 1ull);
   const int kerr = (int)(hcur[2] & 0xffffffffull);
@@ -506,6 +506,12 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(st));
   m->last_S = S; m->last_ncig = sr.n_cigar_total; m->last_kerr = kerr;
+  // algorithmic bytes of the whole path per batch: ASCII in, packed forward + reverse strands, one 32-byte sector per global-index probe
+  // (2 L / (w + 1) read minimizers), the reference bases and LocalIndex slices under the reads (~ the read bases), CIGAR words and records out
+  for (auto &k : all)
+    if (!strcmp(k.name, "map_reads"))
+      k.algo_bytes = total_bases + 2 * ((total_bases + 3) / 4) + 32ull * (2ull * total_bases / (unsigned long long)(m->opts.globalW + 1)) + (total_bases + 3) / 4 +
+                     (unsigned long long)(1.44 * (double)total_bases) + 4ull * sr.n_cigar_total + 64ull * (unsigned long long)S;
   ctx->stats = all;
   if (kerr & 4) return fail(ctx, LRA_B200_EINTERNAL, "map_batch: worker scratch exhausted inside TrimOverlappedAnchors");
   return LRA_B200_OK;

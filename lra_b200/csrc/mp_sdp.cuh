@@ -374,6 +374,8 @@ __device__ __noinline__ bool sdp_divide(SdpWork &W, SdpFam &F, Arena &ar) {
     auto less = [](const SdpDE &x, const SdpDE &y) { return x.d < y.d; };
     if (nD > 1) wsort_pow2(bufD[0], PD, less);
     if (nE > 1) wsort_pow2(bufE[0], PE, less); }
+  unsigned long long tq_ = ar.now();
+  tq_ = ar.now();
   int stS[72], stE[72], stDl[72], stDh[72], stEl[72], stEh[72], stDep[72]; int sp = 0;
   stS[0] = 0; stE[0] = V; stDl[0] = 0; stDh[0] = nD; stEl[0] = 0; stEh[0] = nE; stDep[0] = 0; sp = 1;
   while (sp > 0) {
@@ -390,10 +392,14 @@ __device__ __noinline__ bool sdp_divide(SdpWork &W, SdpFam &F, Arena &ar) {
       if (cE != 0 && cD != 0) {
         s.Ei = ar.alloc<long long>(cE); s.Di = ar.alloc<long long>(cD);
         if (ar.overflow) return false;
+        tq_ = ar.tick(23, tq_);
         s.n = sdp_unique_sorted(curE + elo, cE, s.Ei, F.desc);
         s.m = sdp_unique_sorted(curD + dlo, cD, s.Di, F.desc);
+        tq_ = ar.tick(20, tq_);
         sdp_push_ss2(F, has, start, end, n, true, true);
+        tq_ = ar.tick(21, tq_);
         if (!sdp_setup_sub(s, F.desc, ar)) return false;
+        tq_ = ar.tick(22, tq_);
         if (lane_id() == 0) F.sub[n] = s;
         wsync();
         F.nsub++;
@@ -404,8 +410,10 @@ __device__ __noinline__ bool sdp_divide(SdpWork &W, SdpFam &F, Arena &ar) {
     const int dS = F.swp ? med : start, dE = F.swp ? end : med;     // the half the D (end) points come from
     const int eS = F.swp ? start : med, eE = F.swp ? med : end;     // the half the E (start) points come from
     SdpDE *nxtD = bufD[(dep + 1) & 1], *nxtE = bufE[(dep + 1) & 1];
+    tq_ = ar.tick(23, tq_);
     const int dl = sdp_partition(curD, nxtD, dlo, dhi, med);        // rows < med in [dlo, dlo + dl), the rest behind
     const int el = sdp_partition(curE, nxtE, elo, ehi, med);
+    tq_ = ar.tick(19, tq_);
     // segments of the halves in the next buffer
     const int ldl = dlo, ldh = dlo + dl, rdl = dlo + dl, rdh = dhi;   // D points of the left / right half of the rows
     const int lel = elo, leh = elo + el, rel = elo + el, reh = ehi;   // E points of the left / right half
@@ -419,10 +427,13 @@ __device__ __noinline__ bool sdp_divide(SdpWork &W, SdpFam &F, Arena &ar) {
       if (cE) { s.Ei = ar.alloc<long long>(cE); if (ar.overflow) return false; s.n = sdp_unique_sorted(nxtE + Eel, cE, s.Ei, F.desc); }
       if (cD) { s.Di = ar.alloc<long long>(cD); if (ar.overflow) return false; s.m = sdp_unique_sorted(nxtD + Ddl, cD, s.Di, F.desc); }
     }
+    tq_ = ar.tick(20, tq_);
     if (s.n == 0 && s.m == 0) continue;
     sdp_push_ss2(F, has, dS, dE, n, true, false);
     sdp_push_ss2(F, has, eS, eE, n, false, true);
+    tq_ = ar.tick(21, tq_);
     if (s.n != 0 && s.m != 0) { if (!sdp_setup_sub(s, F.desc, ar)) return false; }
+    tq_ = ar.tick(22, tq_);
     if (lane_id() == 0) F.sub[n] = s;
     wsync();
     F.nsub++;
