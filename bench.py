@@ -272,6 +272,8 @@ def main():
     mapper = lra_b200.Mapper(ctx, ref["opts"], ref["genome"], ref["hdr"], ref["mms"], ref["gli"])
     sys.stderr.write("[bench] rank %d: index image resident in %.1f s\n" % (rank, time.time() - t0))
     gt = torch.from_numpy(ref["genome"]).to(dev)
+    for k in ("genome", "mms", "gli"):      # the host copies are not needed any more (8 ranks x 10 GB otherwise)
+        ref[k] = None
     R = args.reads_per_step
     K, W = args.steps, args.warmup
 

@@ -189,6 +189,10 @@ __device__ __noinline__ int lt_scan_window(uint32_t *v, const SeqView &seq, unsi
 __global__ void __launch_bounds__(32 * kLidxWarps) lidx_window_kernel(LidxBuild b) {
   __shared__ uint32_t sm[kLidxWarps][kLidxMaxWindow];
   __shared__ uint32_t nm_sm[kLidxWarps][68];
+  // the window's packed bases (2048 / 16 words + the 16-byte alignment slack on both sides) and N mask, staged by the copy engine
+  alignas(16) __shared__ uint32_t b2_sm[kLidxWarps][136];
+  alignas(16) __shared__ uint32_t nmraw_sm[kLidxWarps][72];
+  alignas(8) __shared__ unsigned long long mbar[kLidxWarps];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int wi = (int)(blockIdx.x * kLidxWarps + wib);
   if (wi >= b.n_win) return;
@@ -196,12 +200,23 @@ __global__ void __launch_bounds__(32 * kLidxWarps) lidx_window_kernel(LidxBuild 
   const unsigned long long off = b.win_off[wi];
   const uint32_t len = b.win_len[wi];
   const int k = b.k;
+  const unsigned long long wlo = (off >> 4) & ~3ull, mlo = (off >> 5) & ~3ull;      // first staged word of each plane (16-byte aligned)
+  if (lane == 0) bulk_mbar_init(&mbar[wib], 1);
+  __syncwarp();
+  if (lane == 0) {
+    bulk_mbar_expect(&mbar[wib], 136u * 4u + 72u * 4u);
+    bulk_g2s(b2_sm[wib], b.seq.b2 + wlo, 136u * 4u, &mbar[wib]);
+    bulk_g2s(nmraw_sm[wib], b.seq.nm + mlo, 72u * 4u, &mbar[wib]);
+  }
+  bulk_mbar_wait(&mbar[wib], 0u);
+  __syncwarp();
+  const uint32_t *b2w = b2_sm[wib], *nmr = nmraw_sm[wib];
   // 1. k-mer code of every position p <= len - k: bases p .. p+k-1, first base in the most significant digit (StoreTuple)
   const uint32_t kmask = (k >= 10) ? 0xFFFFFu : ((1u << (2 * k)) - 1u);
   if (len >= (uint32_t)k) {
     for (uint32_t p = lane; p + (uint32_t)k <= len; p += 32) {
       const unsigned long long a = off + p;
-      const uint32_t w0 = b.seq.b2[a >> 4], w1 = b.seq.b2[(a >> 4) + 1];
+      const uint32_t w0 = b2w[(a >> 4) - wlo], w1 = b2w[(a >> 4) + 1 - wlo];
       const unsigned long long two = ((unsigned long long)w1 << 32) | w0;
       uint32_t bits = (uint32_t)(two >> ((uint32_t)(a & 15) * 2));     // base a in bits 0..1, a+1 in bits 2..3, ...
       uint32_t code = 0;
@@ -228,7 +243,7 @@ __global__ void __launch_bounds__(32 * kLidxWarps) lidx_window_kernel(LidxBuild 
     uint32_t *nmw = nm_sm[wib];
     for (int j = lane; j < 65; j += 32) {
       const unsigned long long a = off + 32ull * j;
-      const uint32_t w0 = b.seq.nm[a >> 5], w1 = b.seq.nm[(a >> 5) + 1];
+      const uint32_t w0 = nmr[(a >> 5) - mlo], w1 = nmr[(a >> 5) + 1 - mlo];
       const unsigned long long two = ((unsigned long long)w1 << 32) | w0;
       uint32_t bits = (uint32_t)(two >> (uint32_t)(a & 31));
       const int rem = (int)len - 32 * j;               // bases beyond the window count as N-free here (never inside a span)

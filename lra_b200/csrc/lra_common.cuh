@@ -60,6 +60,52 @@ struct SeqStream {
   }
 };
 
+// ---- 1-D bulk copy global -> shared through the copy engine (cp.async.bulk, SASS UBLKCP) with an mbarrier for completion: no tensor map needed.
+// dst, src and bytes must be multiples of 16.  One elected lane arms the barrier with the byte count and issues the copies; every lane that will
+// read the tile waits on the barrier's phase.  (The emulator copies at issue time.)
+__device__ __forceinline__ void bulk_mbar_init(unsigned long long *mbar, int arrivals) {
+#ifndef LRA_EMU
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(arrivals));
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+#else
+  (void)mbar; (void)arrivals;
+#endif
+}
+__device__ __forceinline__ void bulk_mbar_expect(unsigned long long *mbar, uint32_t bytes) {
+#ifndef LRA_EMU
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+#else
+  (void)mbar; (void)bytes;
+#endif
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *mbar) {
+#ifndef LRA_EMU
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst), a = (uint32_t)__cvta_generic_to_shared(mbar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d), "l"(gsrc), "r"(bytes), "r"(a) : "memory");
+#else
+  (void)mbar;
+  for (uint32_t i = 0; i < bytes; i++) ((unsigned char *)smem_dst)[i] = ((const unsigned char *)gsrc)[i];
+#endif
+}
+__device__ __forceinline__ void bulk_mbar_wait(unsigned long long *mbar, uint32_t phase) {
+#ifndef LRA_EMU
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(a), "r"(phase) : "memory");
+#else
+  (void)mbar; (void)phase;
+#endif
+}
+
 // 4-byte asynchronous global -> shared copy (LDGSTS): the prefetches of the row-pipeline kernel never pass through registers,
 // so no scoreboard wait can end up in the dependent chain.  Completion: cp_async_wait_all() by the issuing thread, then a
 // warp barrier before other lanes read.  (The emulator copies at issue time.)
