@@ -100,11 +100,11 @@ __device__ __forceinline__ int wscan_incl(int v) {
 // ---- per-worker bump arena with stack discipline (mark / release), replaces the function-local std::vectors of the reference
 struct Arena {
   unsigned char *base;
-  unsigned long long cap, top, peak;
+  unsigned long long cap, top, peak, cap0;
   int overflow;
   int phase;                              // CTA phase barriers this warp has passed for its current read (mp_phase)
   unsigned long long *prof;               // optional cycle counters of this warp (LRA_B200_MAP_PROFILE)
-  __device__ __forceinline__ void init(void *b, unsigned long long c) { base = (unsigned char *)b; cap = c; top = 0; peak = 0; overflow = 0; phase = 0; prof = nullptr; }
+  __device__ __forceinline__ void init(void *b, unsigned long long c) { base = (unsigned char *)b; cap = c & ~15ull; cap0 = cap; top = 0; peak = 0; overflow = 0; phase = 0; prof = nullptr; }
   __device__ __forceinline__ unsigned long long tick(int slot, unsigned long long t0) {
 #ifdef LRA_EMU
     (void)slot; (void)t0; return 0ull;
@@ -126,9 +126,20 @@ struct Arena {
     unsigned long long e = t + n * sizeof(T);
     if (e > cap) { overflow = 1; return (T *)0; }
     top = e;
-    if (e > peak) peak = e;
+    if (e + (cap0 - cap) > peak) peak = e + (cap0 - cap);
     return (T *)(base + t);
   }
+  // temporaries from the far end of the arena (released by restoring `cap`): scratch that must not sit under allocations that outlive it
+  template <class T> __device__ __forceinline__ T *alloc_hi(unsigned long long n) {
+    const unsigned long long bytes = (n * sizeof(T) + 15ull) & ~15ull;
+    const unsigned long long t = (top + 15ull) & ~15ull;
+    if (bytes > cap || t > cap - bytes) { overflow = 1; return (T *)0; }
+    cap -= bytes;
+    if (t + (cap0 - cap) > peak) peak = t + (cap0 - cap);
+    return (T *)(base + cap);
+  }
+  __device__ __forceinline__ unsigned long long mark_hi() const { return cap; }
+  __device__ __forceinline__ void release_hi(unsigned long long m) { cap = m; }
   __device__ __forceinline__ unsigned long long mark() const { return top; }
   __device__ __forceinline__ void release(unsigned long long m) { top = m; }
   __device__ __forceinline__ unsigned long long avail() const { return cap - ((top + 15ull) & ~15ull); }

@@ -380,9 +380,9 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
   if ((long long)blocks * bw > (long long)n_reads) blocks = (n_reads + bw - 1) / bw;
   int warps = blocks * bw;
   // worker scratch, measured on ONT / CLR reads: peak 14.4 MB for a 100 kb read, ~150 B per base (SparseDP sub-problems dominate).  The first pass
-  // gives every warp 4 MB + 192 B per base of the longest read; a read that still runs out (status MP_ERR_ARENA) is mapped again below with 8x
+  // gives every warp 4 MB + 256 B per base of the longest read (measured peak: 21 MB for a 100 kb read); a read that still runs out (status MP_ERR_ARENA) is mapped again below with 8x
   // that on fewer warps.  The arena is kept across batches.
-  size_t per = (size_t)maxL * 192 + (4u << 20);
+  size_t per = (size_t)maxL * 256 + (4u << 20);
   if (getenv("LRA_B200_MAP_ARENA_MB")) per = (size_t)atoi(getenv("LRA_B200_MAP_ARENA_MB")) << 20;
   size_t free_b = 0, tot_b = 0; cudaMemGetInfo(&free_b, &tot_b);
   const size_t budget = (free_b + B[9].cap) / 10 * 8;      // the rest of the batch (records, blocks, a19 / a21 buffers) needs a few GB

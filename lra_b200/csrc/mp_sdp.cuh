@@ -333,7 +333,143 @@ __device__ __noinline__ void sdp_push_ss2(SdpFam &F, const uint8_t *has, int s, 
   wsync();
 }
 
-__device__ __noinline__ bool sdp_divide(SdpWork &W, SdpFam &F, Arena &ar) {
+// ---- small subtrees of the divide-and-conquer tree, one per LANE ------------------------------------------------------------------------------
+// Most nodes of the tree are small (a tree over V rows has V leaves), and a warp-wide pass over a node of a few points costs the same few hundred
+// instructions as over a node of a thousand.  Subtrees of at most kSdpSmallRows rows are therefore taken out of the warp's traversal: their number of
+// kept nodes depends only on the point counts of their rows (computed for all of them, one per lane, from prefix counts), so the warp's traversal
+// can skip over them and keep numbering; afterwards every lane builds one small subtree serially (same partition / unique / set-up, plain loops),
+// in its own slice of the two list buffers and of a private heap.
+constexpr int kSdpSmallRows = 16;
+struct SdpLaneHeap {
+  unsigned char *p, *end; int ovf;
+  template <class T> __device__ __forceinline__ T *alloc(int n) {
+    unsigned char *q = (unsigned char *)(((unsigned long long)p + 15ull) & ~15ull);
+    unsigned char *e = q + (unsigned long long)(n > 0 ? n : 0) * sizeof(T);
+    if (e > end) { ovf = 1; return (T *)0; }
+    p = e;
+    return (T *)q;
+  }
+};
+struct SdpSmallJob { int start, end, dlo, dhi, elo, ehi, dep, base; unsigned long long heap_off, heap_len; };
+
+// number of kept nodes of the subtree over rows [s, e) (the subtree root is assumed to be visited)
+__device__ __noinline__ int sdp_subtree_size(const int *PD, const int *PE, int s0, int e0, int swp) {
+  int stS[24], stE[24], sp = 0, total = 0;
+  stS[0] = s0; stE[0] = e0; sp = 1;
+  while (sp > 0) {
+    --sp;
+    const int s = stS[sp], e = stE[sp];
+    if (e == s + 1) { if (PD[e] - PD[s] != 0 && PE[e] - PE[s] != 0) total++; continue; }
+    const int med = (s + e) / 2;
+    const int dS = swp ? med : s, dE = swp ? e : med, eS = swp ? s : med, eE = swp ? med : e;
+    const int cd = PD[dE] - PD[dS], ce = PE[eE] - PE[eS];
+    if (cd == 0 && ce == 0) continue;
+    total++;
+    if (ce) { stS[sp] = eS; stE[sp] = eE; sp++; }
+    if (cd) { stS[sp] = dS; stE[sp] = dE; sp++; }
+  }
+  return total;
+}
+
+__device__ __forceinline__ int sdp_unique_serial(const SdpDE *a, int cnt, long long *dst, int desc) {
+  int u = 0;
+  for (int i = 0; i < cnt; i++) if (i == 0 || a[i].d != a[i - 1].d) dst[u++] = a[i].d;
+  if (desc) for (int i = 0; i < u / 2; i++) { const long long x = dst[i]; dst[i] = dst[u - 1 - i]; dst[u - 1 - i] = x; }
+  return u;
+}
+__device__ __forceinline__ int sdp_partition_serial(const SdpDE *src, SdpDE *dst, int lo, int hi, int med) {
+  int nl = 0;
+  for (int i = lo; i < hi; i++) nl += src[i].row < med ? 1 : 0;
+  int cl = lo, cr = lo + nl;
+  for (int i = lo; i < hi; i++) { if (src[i].row < med) dst[cl++] = src[i]; else dst[cr++] = src[i]; }
+  return nl;
+}
+__device__ __forceinline__ void sdp_push_ss_serial(SdpFam &F, const uint8_t *has, int s, int e, int n, bool toA, bool toB) {
+  for (int r = s; r < e; r++) {
+    if (toA && (has[r] & 1)) { F.ssA[(long long)r * F.stride + F.nA[r]] = (uint32_t)n; F.nA[r]++; }
+    if (toB && (has[r] & 2)) { F.ssB[(long long)r * F.stride + F.nB[r]] = (uint32_t)n; F.nB[r]++; }
+  }
+}
+__device__ __forceinline__ bool sdp_setup_sub_serial(SdpSub &s, int desc, SdpLaneHeap &H) {
+  const int m = s.m, n = s.n;
+  s.Dv = H.alloc<float>(m); s.Dp = H.alloc<uint32_t>(m); s.Db = H.alloc<int>(m);
+  s.Ev = H.alloc<float>(n); s.Ep = H.alloc<uint32_t>(n); s.Eb = H.alloc<int>(n);
+  s.capB = 2 * m + 4; s.capS = m + 3;
+  s.Bk = H.alloc<int2>(s.capB); s.S = H.alloc<int2>(s.capS);
+  if (H.ovf) return false;
+  for (int i = 0; i < m; i++) { s.Dv[i] = 0.0f; s.Dp[i] = 0; }
+  for (int i = 0; i < n; i++) { s.Ev[i] = 0.0f; s.Ep[i] = 0; s.Eb[i] = -1; }
+  for (int i = 0; i < m; i++) {
+    int db = -1;
+    if (!desc) { const int t = lower_bound_idx(s.Ei, n, s.Di[i]); if (t < n) db = t; }
+    else {
+      int first = 0, count = n;
+      while (count > 0) { int step = count >> 1; if (s.Ei[n - 1 - (first + step)] < s.Di[i]) { first += step + 1; count -= step + 1; } else count = step; }
+      if (first != 0) db = n - first;
+    }
+    s.Db[i] = db;
+    if (db >= 0 && s.Eb[db] < i) s.Eb[db] = i;
+  }
+  int carry = -1;
+  for (int i = 0; i < n; i++) { if (s.Eb[i] < carry) s.Eb[i] = carry; else carry = s.Eb[i]; }
+  s.now = 0; s.last = -1; s.nB = 0; s.nS = 1;
+  s.S[0] = make_int2(-1, n + 1);
+  return true;
+}
+// one small subtree, serially (called by one lane per subtree)
+__device__ __noinline__ bool sdp_subtree_lane(SdpFam &F, const uint8_t *has, SdpDE *const *bufD, SdpDE *const *bufE, const SdpSmallJob &J, SdpLaneHeap &H) {
+  int stS[24], stE[24], stDl[24], stDh[24], stEl[24], stEh[24], stDep[24]; int sp = 0;
+  stS[0] = J.start; stE[0] = J.end; stDl[0] = J.dlo; stDh[0] = J.dhi; stEl[0] = J.elo; stEh[0] = J.ehi; stDep[0] = J.dep; sp = 1;
+  int num = J.base;
+  while (sp > 0) {
+    --sp;
+    const int start = stS[sp], end = stE[sp], dlo = stDl[sp], dhi = stDh[sp], elo = stEl[sp], ehi = stEh[sp], dep = stDep[sp];
+    SdpSub s; s.m = s.n = 0; s.now = 0; s.last = -1; s.nB = 0; s.nS = 0; s.capB = s.capS = 0;
+    s.Di = s.Ei = 0; s.Dv = s.Ev = 0; s.Dp = s.Ep = 0; s.Db = s.Eb = 0; s.Bk = s.S = 0;
+    const SdpDE *curD = bufD[dep & 1], *curE = bufE[dep & 1];
+    if (end == start + 1) {
+      const int cE = ehi - elo, cD = dhi - dlo;
+      if (cE != 0 && cD != 0) {
+        s.Ei = H.alloc<long long>(cE); s.Di = H.alloc<long long>(cD);
+        if (H.ovf) return false;
+        s.n = sdp_unique_serial(curE + elo, cE, s.Ei, F.desc);
+        s.m = sdp_unique_serial(curD + dlo, cD, s.Di, F.desc);
+        sdp_push_ss_serial(F, has, start, end, num, true, true);
+        if (!sdp_setup_sub_serial(s, F.desc, H)) return false;
+        F.sub[num] = s;
+        num++;
+      }
+      continue;
+    }
+    const int med = (start + end) / 2;
+    const int dS = F.swp ? med : start, dE = F.swp ? end : med;
+    const int eS = F.swp ? start : med, eE = F.swp ? med : end;
+    SdpDE *nxtD = bufD[(dep + 1) & 1], *nxtE = bufE[(dep + 1) & 1];
+    const int dl = sdp_partition_serial(curD, nxtD, dlo, dhi, med);
+    const int el = sdp_partition_serial(curE, nxtE, elo, ehi, med);
+    const int ldl = dlo, ldh = dlo + dl, rdl = dlo + dl, rdh = dhi;
+    const int lel = elo, leh = elo + el, rel = elo + el, reh = ehi;
+    const int Ddl = F.swp ? rdl : ldl, Ddh = F.swp ? rdh : ldh;
+    const int Eel = F.swp ? lel : rel, Eeh = F.swp ? leh : reh;
+    const int cD = Ddh - Ddl, cE = Eeh - Eel;
+    if (cD) { s.Di = H.alloc<long long>(cD); if (H.ovf) return false; s.m = sdp_unique_serial(nxtD + Ddl, cD, s.Di, F.desc); }
+    if (cE) { s.Ei = H.alloc<long long>(cE); if (H.ovf) return false; s.n = sdp_unique_serial(nxtE + Eel, cE, s.Ei, F.desc); }
+    if (s.n == 0 && s.m == 0) continue;
+    sdp_push_ss_serial(F, has, dS, dE, num, true, false);
+    sdp_push_ss_serial(F, has, eS, eE, num, false, true);
+    if (s.n != 0 && s.m != 0) { if (!sdp_setup_sub_serial(s, F.desc, H)) return false; }
+    F.sub[num] = s;
+    num++;
+    const bool goD = s.m != 0, goE = s.n != 0;
+    const int Dhalf_el = F.swp ? rel : lel, Dhalf_eh = F.swp ? reh : leh;
+    const int Ehalf_dl = F.swp ? ldl : rdl, Ehalf_dh = F.swp ? ldh : rdh;
+    if (goE) { stS[sp] = eS; stE[sp] = eE; stDl[sp] = Ehalf_dl; stDh[sp] = Ehalf_dh; stEl[sp] = Eel; stEh[sp] = Eeh; stDep[sp] = dep + 1; sp++; }
+    if (goD) { stS[sp] = dS; stE[sp] = dE; stDl[sp] = Ddl; stDh[sp] = Ddh; stEl[sp] = Dhalf_el; stEh[sp] = Dhalf_eh; stDep[sp] = dep + 1; sp++; }
+  }
+  return true;
+}
+
+__device__ __noinline__ bool sdp_divide_impl(SdpWork &W, SdpFam &F, Arena &ar) {
   const int V = F.cols ? W.C : W.R;
   F.nsub = 0;
   if (V == 0) return true;
@@ -341,8 +477,8 @@ __device__ __noinline__ bool sdp_divide(SdpWork &W, SdpFam &F, Arena &ar) {
   const int *rof = F.cols ? W.colOfPos : W.rowOf;
   const int N = W.N, P2 = next_pow2(N > 0 ? N : 1);
   SdpDE *bufD[2], *bufE[2];
-  bufD[0] = ar.alloc<SdpDE>(P2); bufD[1] = ar.alloc<SdpDE>(N > 0 ? N : 1); bufE[0] = ar.alloc<SdpDE>(P2); bufE[1] = ar.alloc<SdpDE>(N > 0 ? N : 1);
-  uint8_t *has = ar.alloc<uint8_t>(V);
+  bufD[0] = ar.alloc_hi<SdpDE>(P2); bufD[1] = ar.alloc_hi<SdpDE>(N > 0 ? N : 1); bufE[0] = ar.alloc_hi<SdpDE>(P2); bufE[1] = ar.alloc_hi<SdpDE>(N > 0 ? N : 1);
+  uint8_t *has = ar.alloc_hi<uint8_t>(V);
   if (ar.overflow) return false;
   for (int r = lane_id(); r < V; r += kLanes) has[r] = 0;
   wsync();
@@ -374,13 +510,67 @@ __device__ __noinline__ bool sdp_divide(SdpWork &W, SdpFam &F, Arena &ar) {
     auto less = [](const SdpDE &x, const SdpDE &y) { return x.d < y.d; };
     if (nD > 1) wsort_pow2(bufD[0], PD, less);
     if (nE > 1) wsort_pow2(bufE[0], PE, less); }
-  unsigned long long tq_ = ar.now();
-  tq_ = ar.now();
+  // ---- prefix counts of the D / E points over the rows, the small subtrees of the (fixed, midpoint-split) tree and their numbers of kept nodes
+  int *PD = ar.alloc_hi<int>(V + 1), *PE = ar.alloc_hi<int>(V + 1);
+  const int max_slots = 2 * (V / kSdpSmallRows) + 4;
+  int *slotS = ar.alloc_hi<int>(max_slots), *slotE = ar.alloc_hi<int>(max_slots), *slotSize = ar.alloc_hi<int>(max_slots), *slotOf = ar.alloc_hi<int>(V + 1);
+  SdpSmallJob *jobs = ar.alloc_hi<SdpSmallJob>(max_slots);
+  int *nslot_p = ar.alloc_hi<int>(4);
+  if (ar.overflow) return false;
+  for (int r = lane_id(); r <= V; r += kLanes) { PD[r] = 0; PE[r] = 0; }
+  wsync();
+  for (int i = lane_id(); i < nD; i += kLanes) atomicAdd(&PD[bufD[0][i].row + 1], 1);
+  for (int i = lane_id(); i < nE; i += kLanes) atomicAdd(&PE[bufE[0][i].row + 1], 1);
+  wsync();
+  { int cd = 0, ce = 0;          // inclusive scans in place: P[r] = points in rows < r
+    for (int b = 0; b <= V; b += kLanes) {
+      const int r = b + lane_id();
+      const int vd = r <= V ? PD[r] : 0, ve = r <= V ? PE[r] : 0;
+      const int id = wscan_incl(vd), ie = wscan_incl(ve);
+      if (r <= V) { PD[r] = cd + id; PE[r] = ce + ie; }
+      cd += bcast(id, kLanes - 1); ce += bcast(ie, kLanes - 1);
+    } }
+  wsync();
+  if (lane_id() == 0) {
+    int ss[72], se[72], sp0 = 0, ns = 0;
+    ss[0] = 0; se[0] = V; sp0 = 1;
+    while (sp0 > 0) {
+      --sp0;
+      const int a0 = ss[sp0], e0 = se[sp0];
+      if (e0 - a0 <= kSdpSmallRows) { slotS[ns] = a0; slotE[ns] = e0; slotOf[a0] = ns; ns++; continue; }
+      const int med = (a0 + e0) / 2;
+      ss[sp0] = a0; se[sp0] = med; sp0++;
+      ss[sp0] = med; se[sp0] = e0; sp0++;
+    }
+    nslot_p[0] = ns;
+  }
+  wsync();
+  const int nslots = nslot_p[0];
+  for (int k = lane_id(); k < nslots; k += kLanes) slotSize[k] = sdp_subtree_size(PD, PE, slotS[k], slotE[k], F.swp);
+  wsync();
+  int njobs = 0;
+  unsigned long long heap_total = 0;
   int stS[72], stE[72], stDl[72], stDh[72], stEl[72], stEh[72], stDep[72]; int sp = 0;
   stS[0] = 0; stE[0] = V; stDl[0] = 0; stDh[0] = nD; stEl[0] = 0; stEh[0] = nE; stDep[0] = 0; sp = 1;
   while (sp > 0) {
     --sp;
     const int start = stS[sp], end = stE[sp], dlo = stDl[sp], dhi = stDh[sp], elo = stEl[sp], ehi = stEh[sp], dep = stDep[sp];
+    if (end - start <= kSdpSmallRows) {
+      const int k = slotOf[start], sz = slotSize[k];
+      if (F.nsub + sz > F.cap) { ar.overflow = 1; return false; }
+      if (sz > 0) {
+        const unsigned long long pD = (unsigned long long)(dhi - dlo), pE = (unsigned long long)(ehi - elo);
+        int lv = 1; while ((1 << (lv - 1)) < end - start) lv++;             // levels of the subtree
+        const unsigned long long need = (unsigned long long)lv * (44ull * pD + 20ull * pE) + 416ull * (unsigned long long)(end - start) + 256ull;
+        if (lane_id() == 0) {
+          SdpSmallJob J; J.start = start; J.end = end; J.dlo = dlo; J.dhi = dhi; J.elo = elo; J.ehi = ehi; J.dep = dep; J.base = F.nsub; J.heap_off = heap_total; J.heap_len = need;
+          jobs[njobs] = J;
+        }
+        njobs++; heap_total += need;
+        F.nsub += sz;
+      }
+      continue;
+    }
     if (F.nsub >= F.cap) { ar.overflow = 1; return false; }
     SdpSub s; s.m = s.n = 0; s.now = 0; s.last = -1; s.nB = 0; s.nS = 0; s.capB = s.capS = 0;
     s.Di = s.Ei = 0; s.Dv = s.Ev = 0; s.Dp = s.Ep = 0; s.Db = s.Eb = 0; s.Bk = s.S = 0;
@@ -392,14 +582,10 @@ __device__ __noinline__ bool sdp_divide(SdpWork &W, SdpFam &F, Arena &ar) {
       if (cE != 0 && cD != 0) {
         s.Ei = ar.alloc<long long>(cE); s.Di = ar.alloc<long long>(cD);
         if (ar.overflow) return false;
-        tq_ = ar.tick(23, tq_);
         s.n = sdp_unique_sorted(curE + elo, cE, s.Ei, F.desc);
         s.m = sdp_unique_sorted(curD + dlo, cD, s.Di, F.desc);
-        tq_ = ar.tick(20, tq_);
         sdp_push_ss2(F, has, start, end, n, true, true);
-        tq_ = ar.tick(21, tq_);
         if (!sdp_setup_sub(s, F.desc, ar)) return false;
-        tq_ = ar.tick(22, tq_);
         if (lane_id() == 0) F.sub[n] = s;
         wsync();
         F.nsub++;
@@ -410,10 +596,8 @@ __device__ __noinline__ bool sdp_divide(SdpWork &W, SdpFam &F, Arena &ar) {
     const int dS = F.swp ? med : start, dE = F.swp ? end : med;     // the half the D (end) points come from
     const int eS = F.swp ? start : med, eE = F.swp ? med : end;     // the half the E (start) points come from
     SdpDE *nxtD = bufD[(dep + 1) & 1], *nxtE = bufE[(dep + 1) & 1];
-    tq_ = ar.tick(23, tq_);
     const int dl = sdp_partition(curD, nxtD, dlo, dhi, med);        // rows < med in [dlo, dlo + dl), the rest behind
     const int el = sdp_partition(curE, nxtE, elo, ehi, med);
-    tq_ = ar.tick(19, tq_);
     // segments of the halves in the next buffer
     const int ldl = dlo, ldh = dlo + dl, rdl = dlo + dl, rdh = dhi;   // D points of the left / right half of the rows
     const int lel = elo, leh = elo + el, rel = elo + el, reh = ehi;   // E points of the left / right half
@@ -427,13 +611,10 @@ __device__ __noinline__ bool sdp_divide(SdpWork &W, SdpFam &F, Arena &ar) {
       if (cE) { s.Ei = ar.alloc<long long>(cE); if (ar.overflow) return false; s.n = sdp_unique_sorted(nxtE + Eel, cE, s.Ei, F.desc); }
       if (cD) { s.Di = ar.alloc<long long>(cD); if (ar.overflow) return false; s.m = sdp_unique_sorted(nxtD + Ddl, cD, s.Di, F.desc); }
     }
-    tq_ = ar.tick(20, tq_);
     if (s.n == 0 && s.m == 0) continue;
     sdp_push_ss2(F, has, dS, dE, n, true, false);
     sdp_push_ss2(F, has, eS, eE, n, false, true);
-    tq_ = ar.tick(21, tq_);
     if (s.n != 0 && s.m != 0) { if (!sdp_setup_sub(s, F.desc, ar)) return false; }
-    tq_ = ar.tick(22, tq_);
     if (lane_id() == 0) F.sub[n] = s;
     wsync();
     F.nsub++;
@@ -444,7 +625,28 @@ __device__ __noinline__ bool sdp_divide(SdpWork &W, SdpFam &F, Arena &ar) {
     if (goE) { stS[sp] = eS; stE[sp] = eE; stDl[sp] = Ehalf_dl; stDh[sp] = Ehalf_dh; stEl[sp] = Ehalf_el; stEh[sp] = Ehalf_eh; stDep[sp] = dep + 1; sp++; }
     if (goD) { stS[sp] = dS; stE[sp] = dE; stDl[sp] = Dhalf_dl; stDh[sp] = Dhalf_dh; stEl[sp] = Dhalf_el; stEh[sp] = Dhalf_eh; stDep[sp] = dep + 1; sp++; }
   }
+  // ---- the small subtrees, one per lane
+  wsync();
+  if (njobs > 0) {
+    unsigned char *heap = ar.alloc<unsigned char>(heap_total + 16);
+    if (ar.overflow) return false;
+    bool bad = false;
+    for (int j = lane_id(); j < njobs; j += kLanes) {
+      const SdpSmallJob J = jobs[j];
+      SdpLaneHeap H; H.p = heap + J.heap_off; H.end = H.p + J.heap_len; H.ovf = 0;
+      if (!sdp_subtree_lane(F, has, bufD, bufE, J, H)) bad = true;
+    }
+    wsync();
+    if (wany(bad)) { ar.overflow = 1; return false; }
+  }
   return true;
+}
+
+__device__ __forceinline__ bool sdp_divide(SdpWork &W, SdpFam &F, Arena &ar) {
+  const unsigned long long hi = ar.mark_hi();          // the list buffers, prefix counts and subtree queue live at the far end of the arena
+  const bool ok = sdp_divide_impl(W, F, ar);
+  ar.release_hi(hi);
+  return ok;
 }
 
 // ---- problem set-up ----------------------------------------------------------------------------------------------
