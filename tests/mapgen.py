@@ -22,7 +22,7 @@ def have_reference_binaries():
     return os.path.exists(REF_BIN) and os.path.exists(CAP_BIN)
 
 
-def workdir(tmp, preset, n_reads, ref_len=5_000_000, contigs=3, repeats=False, seed=None):
+def workdir(tmp, preset, n_reads, ref_len=5_000_000, contigs=3, repeats=False, seed=None, sv=False):
     """Creates <tmp>/ref.fa (+ .mms / .gli written by the reference) and <tmp>/reads.fa; returns a dict of paths."""
     tmp = str(tmp)
     os.makedirs(tmp, exist_ok=True)
@@ -31,7 +31,8 @@ def workdir(tmp, preset, n_reads, ref_len=5_000_000, contigs=3, repeats=False, s
         ref = synth.add_repeats(ref)
     w = dict(dir=tmp, preset=preset, ref=os.path.join(tmp, "ref.fa"), reads=os.path.join(tmp, "reads.fa"), n_reads=n_reads)
     synth.write_fasta(w["ref"], ref)
-    reads = synth.gen_reads(ref, n_reads, PROFILE[preset], SEED[preset] if seed is None else seed)
+    gen = synth.gen_sv_reads if sv else synth.gen_reads      # sv: deletions, insertions, inversions, translocations, duplications inside the reads
+    reads = gen(ref, n_reads, PROFILE[preset], SEED[preset] if seed is None else seed)
     synth.write_fasta(w["reads"], reads, width=1 << 30)
     subprocess.run([REF_BIN, "index", MODE[preset], w["ref"]], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     w["ref_records"] = ref

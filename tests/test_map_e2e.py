@@ -70,7 +70,7 @@ def gpu_sam(w, batch=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("preset,n_reads,repeats,batch", [("ont", 1000, False, None), ("clr", 1000, False, 400), ("ont", 600, True, None), ("clr", 600, True, 250)])
+@pytest.mark.parametrize("preset,n_reads,repeats,batch", [("ont", 1000, False, None), ("clr", 1000, False, 400), ("ont", 600, True, None), ("clr", 600, True, 250), ("ont", 4000, True, 1500)])
 def test_map_batch_gpu_matches_reference_sam(preset, n_reads, repeats, batch, tmp_path):
     w = mapgen.workdir(tmp_path, preset, n_reads=n_reads, ref_len=5_000_000, contigs=3, repeats=repeats)
     _, ref = mapgen.canonical_sam(mapgen.reference_sam(w))
@@ -93,3 +93,83 @@ def test_map_batch_gpu_small_scratch_retries(tmp_path, monkeypatch):
     monkeypatch.setenv("LRA_B200_MAP_NO_RETRY", "1")
     text2, st2 = gpu_sam(w, None)
     assert (st2["status"] == 2).any()           # the first pass alone does leave reads behind at this size
+
+
+def test_map_emulated_structural_variant_reads(tmp_path):
+    """Reads with a deletion / insertion / inversion / translocation / duplication inside: split chains of every type, inversion probing,
+    supplementary segments and SA:Z tags (emulator, one lane)."""
+    import mapemu
+    w = mapgen.workdir(tmp_path, "ont", n_reads=30, ref_len=1_500_000, contigs=3, repeats=False, sv=True)
+    _, ref = mapgen.canonical_sam(mapgen.reference_sam(w))
+    inp, mo, res, text = mapemu.run(w, lanes=1)
+    assert mo["err"] == 0 and (mo["status"] <= 1).all()
+    ours = canon_ours(text)
+    assert sum("SA:Z:" in l for l in ref) >= 5          # the case really has multi-segment alignments
+    assert len(ours) == len(ref)
+    assert ours == ref, diff_report(ours, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", ["ont", "clr"])
+def test_map_batch_gpu_structural_variant_reads(preset, tmp_path):
+    w = mapgen.workdir(tmp_path, preset, n_reads=360, ref_len=5_000_000, contigs=3, repeats=False, sv=True)
+    _, ref = mapgen.canonical_sam(mapgen.reference_sam(w))
+    text, st = gpu_sam(w, None)
+    assert (st["status"] <= 1).all(), np.bincount(st["status"])
+    ours = canon_ours(text)
+    assert sum("SA:Z:" in l for l in ref) >= 50
+    assert len(ours) == len(ref)
+    assert ours == ref, diff_report(ours, ref)
+
+
+def edge_case_workdir(tmp_path, preset):
+    """Degenerate reads: shorter than k, shorter than a minimizer window, all N, N runs, homopolymer, dinucleotide repeat, an exact copy of the
+    reference, a read covering a whole small contig, the same read twice."""
+    import synth
+    w = mapgen.workdir(tmp_path, preset, n_reads=4, ref_len=600_000, contigs=3, repeats=False)
+    ref = w["ref_records"]
+    rng = np.random.default_rng(9)
+    B = np.frombuffer(b"ACGT", np.uint8)
+    c0 = ref[0][1]
+    reads = list(w["read_records"])
+    reads.append(("short10", c0[1000:1010].copy()))
+    reads.append(("short25", c0[2000:2025].copy()))
+    reads.append(("short200", c0[3000:3200].copy()))
+    reads.append(("allN", np.full(700, ord("N"), np.uint8)))
+    x = c0[50000:58000].copy(); x[1000:1400] = ord("N"); x[5000] = ord("N")
+    reads.append(("withN", x))
+    reads.append(("polyA", np.full(3000, ord("A"), np.uint8)))
+    reads.append(("dinuc", np.tile(np.frombuffer(b"AC", np.uint8), 2000)))
+    reads.append(("exact", c0[100000:112000].copy()))
+    reads.append(("exact_rc", synth.COMP[c0[120000:129000][::-1]]))
+    reads.append(("random", B[rng.integers(0, 4, 6000)]))
+    reads.append(("dup1", reads[0][1].copy())); reads.append(("dup2", reads[0][1].copy()))
+    reads.append(("contig_end", ref[1][1][-7000:].copy()))
+    reads.append(("contig_start", ref[2][1][:7000].copy()))
+    reads.append(("across_contigs", np.concatenate([ref[0][1][-4000:], ref[1][1][:4000]])))
+    synth.write_fasta(w["reads"], reads, width=1 << 30)
+    w["read_records"] = reads
+    return w
+
+
+def test_map_emulated_edge_case_reads(tmp_path):
+    import mapemu
+    w = edge_case_workdir(tmp_path, "ont")
+    _, ref = mapgen.canonical_sam(mapgen.reference_sam(w))
+    inp, mo, res, text = mapemu.run(w, lanes=1)
+    assert mo["err"] == 0 and (mo["status"] <= 1).all()
+    ours = canon_ours(text)
+    assert len(ours) == len(ref)
+    assert ours == ref, diff_report(ours, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", ["ont", "clr"])
+def test_map_batch_gpu_edge_case_reads(preset, tmp_path):
+    w = edge_case_workdir(tmp_path, preset)
+    _, ref = mapgen.canonical_sam(mapgen.reference_sam(w))
+    text, st = gpu_sam(w, None)
+    assert (st["status"] <= 1).all(), np.bincount(st["status"])
+    ours = canon_ours(text)
+    assert len(ours) == len(ref)
+    assert ours == ref, diff_report(ours, ref)

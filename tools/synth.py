@@ -214,3 +214,50 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def gen_sv_reads(ref, n_reads, profile, seed, err=None):
+    """Reads with structural differences from the reference (for the multi-segment paths: split chains, inversion probing, supplementary
+    segments, SA:Z): per read one of deletion (0.5-8 kb of reference skipped), insertion (0.3-3 kb of random sequence), inversion (0.5-4 kb
+    reverse-complemented in place), translocation (second half from another locus / contig), tandem duplication (1-3 kb repeated), or none."""
+    rng = np.random.default_rng(seed)
+    err = PROFILE_ERR[profile] if err is None else err
+    lens = read_lengths(profile, n_reads, rng)
+    out = []
+    kinds = ["del", "ins", "inv", "tra", "dup", "none"]
+    for i in range(n_reads):
+        c = int(rng.integers(0, len(ref)))
+        name, seq = ref[c]
+        L = int(min(max(lens[i], 6000), len(seq) - 20000))
+        start = int(rng.integers(0, len(seq) - L - 10000))
+        kind = kinds[i % len(kinds)]
+        a = L // 3 + int(rng.integers(0, L // 3))
+        if kind == "del":
+            d = int(rng.integers(500, 8000))
+            frag = np.concatenate([seq[start:start + a], seq[start + a + d:start + L + d]])
+        elif kind == "ins":
+            d = int(rng.integers(300, 3000))
+            frag = np.concatenate([seq[start:start + a], BASES[rng.integers(0, 4, size=d, dtype=np.uint8)], seq[start + a:start + L]])
+        elif kind == "inv":
+            d = int(rng.integers(500, 4000))
+            d = min(d, L - a - 100)
+            frag = np.concatenate([seq[start:start + a], COMP[seq[start + a:start + a + d][::-1]], seq[start + a + d:start + L]])
+        elif kind == "tra":
+            c2 = int(rng.integers(0, len(ref)))
+            s2 = ref[c2][1]
+            b = int(rng.integers(0, len(s2) - L))
+            piece = s2[b:b + L - a]
+            if rng.integers(0, 2):
+                piece = COMP[piece[::-1]]
+            frag = np.concatenate([seq[start:start + a], piece])
+        elif kind == "dup":
+            d = int(rng.integers(1000, 3000))
+            d = min(d, a)
+            frag = np.concatenate([seq[start:start + a], seq[start + a - d:start + a], seq[start + a:start + L]])
+        else:
+            frag = seq[start:start + L]
+        strand = int(rng.integers(0, 2))
+        if strand:
+            frag = COMP[frag[::-1]]
+        out.append(("sv%d_%s_%s_%d_%s" % (i, kind, name, start, "-" if strand else "+"), mutate(frag, err, rng)))
+    return out
