@@ -30,7 +30,7 @@ def build_cli(force=False):
     """The C++ host program above the C ABI (`lra_b200 index|align`, lra_b200/cli/): plain g++, linked against liblra_b200.so."""
     if not force and os.path.exists(CLI_OUT) and os.path.getmtime(CLI_OUT) > max(os.path.getmtime(CLI_SRC), os.path.getmtime(OUT)):
         return CLI_OUT
-    subprocess.run(["g++", "-std=c++17", "-O2", CLI_SRC, "-o", CLI_OUT, "-L" + HERE, "-llra_b200", "-Wl,-rpath,$ORIGIN"], check=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", CLI_SRC, "-o", CLI_OUT, "-L" + HERE, "-llra_b200", "-lz", "-pthread", "-Wl,-rpath,$ORIGIN"], check=True)
     return CLI_OUT
 
 

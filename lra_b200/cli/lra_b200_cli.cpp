@@ -6,7 +6,8 @@
 //
 // Plain C++ (no CUDA, no torch): everything on the device goes through liblra_b200.so.  What it keeps of the reference's host side:
 //   * Genome::Read (Genome.h:115-138): contigs upper-cased, name = first token of the header line;
-//   * Input::GetNext for FASTA / FASTQ (Input.h:182-290): name = first token, blanks dropped, bases upper-cased, several files chained;
+//   * Input::GetNext for FASTA / FASTQ (Input.h:182-290), plain or gzip: name = first token, blanks dropped, bases upper-cased, several files chained;
+//     FASTA is parsed on all host threads;
 //   * ReadIndex / LocalIndex::Read (MMIndex.h:154-173, 402-412): the on-disk .mms / .gli formats, globalK taken from the .mms;
 //   * the SAM header (@PG line, Header::WriteSAMHeader, Genome.h:85-89) and the printers through lra_b200_format_records.
 // Reads are mapped in batches of --batch-bases bases; records come back in input order (the reference's order with -t 1).
@@ -18,7 +19,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
+#include <zlib.h>
 #include "../../include/lra_b200.h"
 
 namespace {
@@ -29,14 +32,21 @@ struct Fasta {                      // sequences back to back + names + offsets
   std::vector<uint64_t> off;        // n + 1 entries
 };
 
+// whole file into memory; gzip-compressed files are inflated through zlib (gzread also passes plain files through, as the reference's kseq does)
 bool slurp(const std::string &path, std::string &out) {
-  FILE *f = fopen(path.c_str(), "rb");
+  gzFile f = gzopen(path.c_str(), "rb");
   if (!f) return false;
-  fseek(f, 0, SEEK_END); const long n = ftell(f); fseek(f, 0, SEEK_SET);
-  out.resize((size_t)n);
-  const size_t got = n ? fread(&out[0], 1, (size_t)n, f) : 0;
-  fclose(f);
-  return got == (size_t)n;
+  gzbuffer(f, 1 << 20);
+  out.clear();
+  std::vector<char> buf(8u << 20);
+  for (;;) {
+    const int n = gzread(f, buf.data(), (unsigned)buf.size());
+    if (n < 0) { gzclose(f); return false; }
+    if (n == 0) break;
+    out.append(buf.data(), (size_t)n);
+  }
+  gzclose(f);
+  return true;
 }
 
 std::string first_token(const char *p, const char *e) {   // after the leading '>' / '@'
@@ -78,8 +88,40 @@ bool parse_reads(const std::string &text, Fasta &fa) {
   return true;
 }
 
+// the same on host threads: the text is cut at record starts ('>' at a line start; FASTQ is parsed by one thread because '@' is also a
+// quality character), the pieces are parsed independently and concatenated in order
+bool parse_reads_mt(const std::string &text, Fasta &fa, int threads) {
+  if (text.empty()) { if (fa.off.empty()) fa.off.push_back(0); return true; }
+  if (threads < 2 || text.size() < (8u << 20) || text[0] != '>') return parse_reads(text, fa);
+  std::vector<size_t> cut(1, 0);
+  for (int t = 1; t < threads; t++) {
+    size_t p = text.size() * (size_t)t / (size_t)threads;
+    const char *q = nullptr;
+    while (p < text.size() && (q = (const char *)memchr(text.data() + p, '>', text.size() - p))) {
+      p = (size_t)(q - text.data());
+      if (p == 0 || text[p - 1] == '\n') break;
+      p++;
+    }
+    if (!q || p >= text.size()) break;
+    if (p > cut.back()) cut.push_back(p);
+  }
+  cut.push_back(text.size());
+  const int np = (int)cut.size() - 1;
+  std::vector<Fasta> part(np);
+  std::vector<std::thread> th;
+  for (int i = 0; i < np; i++) th.emplace_back([&, i] { std::string piece(text.data() + cut[i], cut[i + 1] - cut[i]); parse_reads(piece, part[i]); });
+  for (auto &x : th) x.join();
+  if (fa.off.empty()) fa.off.push_back(0);
+  for (int i = 0; i < np; i++) {
+    const uint64_t base = fa.seq.size();
+    fa.seq += part[i].seq;
+    for (size_t r = 0; r < part[i].names.size(); r++) { fa.names.push_back(std::move(part[i].names[r])); fa.off.push_back(base + part[i].off[r + 1]); }
+  }
+  return true;
+}
+
 // Genome::Read: kseq semantics (sequence = all non-blank characters of the record's lines), upper-cased
-bool parse_genome(const std::string &text, Fasta &fa) { return parse_reads(text, fa); }
+bool parse_genome(const std::string &text, Fasta &fa) { return parse_reads_mt(text, fa, (int)std::thread::hardware_concurrency()); }
 
 struct Preset { int k, w, max_freq, win, per_window; };
 bool index_preset(const std::string &m, Preset &p) {      // lra.cpp:884-911
@@ -242,7 +284,7 @@ int run_align(int argc, char **argv, const std::string &cmdline) {
   for (const std::string &in : inputs) {
     std::string t2;
     if (!slurp(in, t2)) { fprintf(stderr, "Cannot open reads %s\n", in.c_str()); return 1; }
-    parse_reads(t2, rd);
+    parse_reads_mt(t2, rd, (int)std::thread::hardware_concurrency());
   }
   const size_t n_reads = rd.names.size();
   std::vector<char> textbuf;

@@ -53,3 +53,12 @@ def test_cli_index_and_align_match_the_reference(tmp_path):
         ours = lines(o)
         assert len(ours) == len(ref_out[fmt]), fmt
         assert ours == ref_out[fmt], (fmt, [(a, b) for a, b in zip(ours, ref_out[fmt]) if a != b][:2])
+    # the same reads as gzip-compressed FASTQ (qualities ignored by the printers, as for FASTA input): identical SAM
+    import gzip
+    fq = str(tmp_path / "reads.fq.gz")
+    with gzip.open(fq, "wb") as f:
+        for name, seq in w["read_records"]:
+            f.write(b"@" + name.encode() + b" extra words\n" + seq.tobytes().lower() + b"\n+\n" + b"I" * len(seq) + b"\n")
+    o = str(tmp_path / "ours_fq.s")
+    subprocess.run([CLI, "align", "-ONT", w["ref"], fq, "-p", "s", "-o", o], check=True)
+    assert lines(o) == ref_out["s"]
