@@ -898,6 +898,12 @@ int64_t lra_b200_format_records(const lra_b200_map_opts *opts, const lra_b200_ma
                                 const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, const uint64_t *contig_len, int32_t n_contigs,
                                 int32_t fmt, int32_t runtime, char *out, int64_t cap);
 
+/* The same with the QUAL column of FASTQ input (quals_ascii: one quality string per read at the offsets of reads_ascii, or NULL for '*').  As in
+ * Alignment::PrintSAM (Alignment.h:719-732) the string is printed as given (not reversed with the strand) and hard-clipped like SEQ. */
+int64_t lra_b200_format_records_qual(const lra_b200_map_opts *opts, const lra_b200_map_result *res, int32_t n_reads, const char *names, const char *reads_ascii,
+                                     const char *quals_ascii, const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, const uint64_t *contig_len,
+                                     int32_t n_contigs, int32_t fmt, int32_t runtime, char *out, int64_t cap);
+
 /* ---- per-kernel timing of the last batch call (CUDA events on the context's stream) ---------------------------- */
 typedef struct lra_b200_kernel_stat {
   char name[48];

@@ -28,6 +28,7 @@ namespace {
 
 struct Fasta {                      // sequences back to back + names + offsets
   std::string seq;
+  std::string qual;                 // FASTQ: quality strings at the same offsets (blanks dropped); empty for FASTA
   std::vector<std::string> names;
   std::vector<uint64_t> off;        // n + 1 entries
 };
@@ -79,7 +80,12 @@ bool parse_reads(const std::string &text, Fasta &fa) {
       nl = (const char *)memchr(p, '\n', (size_t)(e - p)); le = nl ? nl : e;
       for (const char *c = p; c < le; c++) if (*c != ' ' && *c != '\r') fa.seq.push_back((char)toupper((unsigned char)*c));
       p = nl ? nl + 1 : e;
-      for (int k = 0; k < 2 && p < e; k++) { nl = (const char *)memchr(p, '\n', (size_t)(e - p)); p = nl ? nl + 1 : e; }   // '+' line, qualities
+      nl = (const char *)memchr(p, '\n', (size_t)(e - p)); p = nl ? nl + 1 : e;                                           // '+' line
+      nl = (const char *)memchr(p, '\n', (size_t)(e - p)); le = nl ? nl : e;
+      fa.qual.resize(fa.off.back(), '!');                                                                                  // (earlier FASTA records of a mixed input)
+      for (const char *c = p; c < le; c++) if (*c != ' ' && *c != '\r') fa.qual.push_back(*c);
+      fa.qual.resize(fa.seq.size(), '!');
+      p = nl ? nl + 1 : e;
       fa.off.push_back(fa.seq.size());
     } else {
       p = nl ? nl + 1 : e;      // blank line
@@ -115,6 +121,7 @@ bool parse_reads_mt(const std::string &text, Fasta &fa, int threads) {
   for (int i = 0; i < np; i++) {
     const uint64_t base = fa.seq.size();
     fa.seq += part[i].seq;
+    if (!part[i].qual.empty()) { fa.qual.resize(base, '!'); fa.qual += part[i].qual; }
     for (size_t r = 0; r < part[i].names.size(); r++) { fa.names.push_back(std::move(part[i].names[r])); fa.off.push_back(base + part[i].off[r + 1]); }
   }
   return true;
@@ -304,10 +311,11 @@ int run_align(int argc, char **argv, const std::string &cmdline) {
     if (lra_b200_map_batch(ctx, m, base, bases, off.data(), len.data(), n, &res)) return die(ctx, "map_batch");
     std::string names;
     for (int i = 0; i < n; i++) { names += rd.names[r0 + i]; names.push_back('\0'); if (status[i] == 0 && n_aln[i] > 0) mapped++; }
-    int64_t need = lra_b200_format_records(&opts, &res, n, names.data(), base, off.data(), len.data(), cnames.data(), clen.data(), nc, f, 0, nullptr, 0);
+    const char *qbase = rd.qual.size() == rd.seq.size() && !rd.qual.empty() ? rd.qual.data() + rd.off[r0] : nullptr;
+    int64_t need = lra_b200_format_records_qual(&opts, &res, n, names.data(), base, qbase, off.data(), len.data(), cnames.data(), clen.data(), nc, f, 0, nullptr, 0);
     need = -need;
     textbuf.resize((size_t)need + 16);
-    const int64_t got = lra_b200_format_records(&opts, &res, n, names.data(), base, off.data(), len.data(), cnames.data(), clen.data(), nc, f, 0, textbuf.data(), need + 16);
+    const int64_t got = lra_b200_format_records_qual(&opts, &res, n, names.data(), base, qbase, off.data(), len.data(), cnames.data(), clen.data(), nc, f, 0, textbuf.data(), need + 16);
     if (got > 0) fwrite(textbuf.data(), 1, (size_t)got, out);
     r0 = r1;
   }

@@ -59,7 +59,7 @@ struct SamOut {
 
 // fmt: 's' SAM (Alignment::PrintSAM, Alignment.h:658-808), 'p' PAF, 'c' PAF with CG:z: (-p pc; PrintPAF :600-656), 'b' BED (PrintBed :591-598)
 static void mp_format_read(SamOut &o, const lra_b200_map_opts *opts, const lra_b200_map_result *res, int r, const char *name, const char *seq, uint32_t L,
-                           const std::vector<const char *> &cname, const uint64_t *contig_len, int runtime, std::string &rc, char fmt) {
+                           const std::vector<const char *> &cname, const uint64_t *contig_len, int runtime, std::string &rc, char fmt, const char *qual) {
   const unsigned char *RC = mp_revcomp_table();
   const int na = res->status[r] == 0 ? res->n_aln[r] : 0;
   bool printed = false;
@@ -106,7 +106,7 @@ static void mp_format_read(SamOut &o, const lra_b200_map_opts *opts, const lra_b
           if (!have_rc) { rc.resize(L); for (uint32_t k = 0; k < L; k++) rc[L - 1 - k] = (char)RC[(unsigned char)seq[k]]; have_rc = true; }
           rd = rc.data();
         }
-        if (x.n_blocks == 0) { o.put("4\t*\t0\t0\t*\t*\t0\t0\t"); o.put(rd, L); o.put("\t*"); }
+        if (x.n_blocks == 0) { o.put("4\t*\t0\t0\t*\t*\t0\t0\t"); o.put(rd, L); o.put('\t'); if (qual) o.put(qual, L); else o.put('*'); }
         else {
           o.u(x.flag); o.put('\t'); o.put(cname[x.chrom]); o.put('\t'); o.u(x.tStart + 1u); o.put('\t'); o.u((unsigned char)x.mapq); o.put('\t');
           char clipOp = 'S';
@@ -118,7 +118,11 @@ static void mp_format_read(SamOut &o, const lra_b200_map_opts *opts, const lra_b
           if (!x.supplementary) o.put(rd, L);
           else if (opts->hardClip) o.put(rd + x.qStart, x.qEnd - x.qStart);
           else o.put(rd, L);
-          o.put("\t*");
+          // QUAL (Alignment.h:719-732): as given in the input, not reversed with the strand; hard-clipped like SEQ
+          o.put('\t');
+          if (!qual || qual[0] == '*') o.put('*');
+          else if (x.supplementary && opts->hardClip) o.put(qual + x.qStart, x.qEnd - x.qStart);
+          else o.put(qual, L);
           o.put("\tNM:i:"); o.i(x.nmm + x.ndel + x.nins); o.put("\tMM:i:"); o.i(x.nmm + x.ndel + x.nins); o.put("\tNX:i:"); o.i(x.nmm); o.put("\tND:i:"); o.i(x.ndel);
           o.put("\tTD:i:"); o.i(x.tdel); o.put("\tNI:i:"); o.i(x.nins); o.put("\tTI:i:"); o.i(x.tins); o.put("\tNV:f:"); o.f(x.value); o.put("\tAS:i:"); o.i((int)x.value);
           o.put("\tAO:i:"); o.i(x.order); o.put("\tN0:i:"); o.i(x.NumOfAnchors0); o.put("\tRT:i:"); o.i(runtime);
@@ -141,7 +145,7 @@ static void mp_format_read(SamOut &o, const lra_b200_map_opts *opts, const lra_b
     }
   }
   if (!printed && fmt == 's') {      // output_unaligned -> SimplePrintSAM of an Alignment without blocks (SAM only, Mapping_ultility.h:457-463)
-    o.put(name); o.put("\t4\t*\t0\t0\t*\t*\t0\t0\t"); o.put(seq, L); o.put("\t*\n");
+    o.put(name); o.put("\t4\t*\t0\t0\t*\t*\t0\t0\t"); o.put(seq, L); o.put('\t'); if (qual) o.put(qual, L); else o.put('*'); o.put('\n');
   }
 }
 
@@ -154,9 +158,17 @@ extern "C" int64_t lra_b200_format_sam(const lra_b200_map_opts *opts, const lra_
   return lra_b200_format_records(opts, res, n_reads, names, reads_ascii, read_off, read_len, contig_names, nullptr, n_contigs, 's', runtime, out, cap);
 }
 
+extern "C" int64_t lra_b200_format_records_qual(const lra_b200_map_opts *opts, const lra_b200_map_result *res, int32_t n_reads, const char *names, const char *reads_ascii,
+                                                const char *quals_ascii, const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, const uint64_t *contig_len,
+                                                int32_t n_contigs, int32_t fmt, int32_t runtime, char *out, int64_t cap);
 extern "C" int64_t lra_b200_format_records(const lra_b200_map_opts *opts, const lra_b200_map_result *res, int32_t n_reads, const char *names, const char *reads_ascii,
                                            const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, const uint64_t *contig_len, int32_t n_contigs,
                                            int32_t fmt, int32_t runtime, char *out, int64_t cap) {
+  return lra_b200_format_records_qual(opts, res, n_reads, names, reads_ascii, nullptr, read_off, read_len, contig_names, contig_len, n_contigs, fmt, runtime, out, cap);
+}
+extern "C" int64_t lra_b200_format_records_qual(const lra_b200_map_opts *opts, const lra_b200_map_result *res, int32_t n_reads, const char *names, const char *reads_ascii,
+                                                const char *quals_ascii, const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, const uint64_t *contig_len,
+                                                int32_t n_contigs, int32_t fmt, int32_t runtime, char *out, int64_t cap) {
   if (fmt != 's' && fmt != 'p' && fmt != 'c' && fmt != 'b') return 0;
   if (!opts || !res || n_reads < 0 || !names || !reads_ascii || !read_off || !read_len || !contig_names) return 0;
   std::vector<const char *> cname(n_contigs);
@@ -177,7 +189,7 @@ extern "C" int64_t lra_b200_format_records(const lra_b200_map_opts *opts, const 
     std::string rc;
     unsigned long long b = 0; for (int r = cut[t]; r < cut[t + 1]; r++) b += read_len[r];
     piece[t].s.reserve((size_t)(b + b / 2) + 4096);
-    for (int r = cut[t]; r < cut[t + 1]; r++) mp_format_read(piece[t], opts, res, r, rname[r], reads_ascii + read_off[r], read_len[r], cname, contig_len, runtime, rc, (char)fmt);
+    for (int r = cut[t]; r < cut[t + 1]; r++) mp_format_read(piece[t], opts, res, r, rname[r], reads_ascii + read_off[r], read_len[r], cname, contig_len, runtime, rc, (char)fmt, quals_ascii ? quals_ascii + read_off[r] : nullptr);
   };
   if (T == 1) work(0);
   else { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(work, t); for (auto &x : th) x.join(); }

@@ -53,12 +53,17 @@ def test_cli_index_and_align_match_the_reference(tmp_path):
         ours = lines(o)
         assert len(ours) == len(ref_out[fmt]), fmt
         assert ours == ref_out[fmt], (fmt, [(a, b) for a, b in zip(ours, ref_out[fmt]) if a != b][:2])
-    # the same reads as gzip-compressed FASTQ (qualities ignored by the printers, as for FASTA input): identical SAM
+    # FASTQ input (lower-case bases, extra words in the header, qualities): plain for the reference, gzip-compressed for the CLI
     import gzip
-    fq = str(tmp_path / "reads.fq.gz")
-    with gzip.open(fq, "wb") as f:
+    rng = __import__("numpy").random.default_rng(3)
+    fqp = str(tmp_path / "reads.fq"); fq = fqp + ".gz"
+    with open(fqp, "wb") as f1, gzip.open(fq, "wb") as f2:
         for name, seq in w["read_records"]:
-            f.write(b"@" + name.encode() + b" extra words\n" + seq.tobytes().lower() + b"\n+\n" + b"I" * len(seq) + b"\n")
-    o = str(tmp_path / "ours_fq.s")
+            q = (rng.integers(35, 75, size=len(seq)).astype("uint8")).tobytes()
+            rec = b"@" + name.encode() + b" extra words\n" + seq.tobytes().lower() + b"\n+\n" + q + b"\n"
+            f1.write(rec); f2.write(rec)
+    o_ref = str(tmp_path / "ref_fq.s"); o = str(tmp_path / "ours_fq.s")
+    subprocess.run([mapgen.REF_BIN, "align", "-ONT", w["ref"], fqp, "-t", "1", "-p", "s", "-o", o_ref], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     subprocess.run([CLI, "align", "-ONT", w["ref"], fq, "-p", "s", "-o", o], check=True)
-    assert lines(o) == ref_out["s"]
+    a, b = lines(o), lines(o_ref)
+    assert len(a) == len(b) and a == b, [(x[:80], y[:80]) for x, y in zip(a, b) if x != y][:2]
