@@ -42,7 +42,7 @@ struct IrBatch {
   int32_t *max_width;       // per group
 };
 
-constexpr int kIrClsW24 = 0, kIrClsW64 = 1, kIrClsGeneric = 2, kIrClsWarp32 = 3, kIrClsPipe = 4, kIrNumCls = 5;
+constexpr int kIrClsW24 = 0, kIrClsW64 = 1, kIrClsGeneric = 2, kIrClsWarp32 = 3, kIrClsPipe = 4, kIrClsWarp64 = 5, kIrNumCls = 6;
 constexpr int kIrPipeSpan = 24;        // rows over which the band may advance at most kIrPipeMaxAdvance for the pipeline kernel
 constexpr int kIrPipeMaxAdvance = 64;
 constexpr int kIrWarpMinRows = 192;   // longer groups of width <= 32 go to the warp-per-group kernel
@@ -83,13 +83,17 @@ __global__ void __launch_bounds__(128) ir_classify_kernel(IrBatch b, AogPlan *pl
     // no_warp: 1 = thread kernels only, 2 = long groups through the scan kernel only.  The longest groups (rows >= long_rows)
     // take the scan kernel, whose latency per row is lower; the row-pipeline kernel has the higher throughput for the rest.
     const bool longGroup = mw <= 32 && rows >= kIrWarpMinRows && no_warp != 1;
-    const int cls = longGroup ? ((no_warp == 2 || (bad & 2) || rows >= long_rows) ? kIrClsWarp32 : kIrClsPipe) : mw <= 24 ? kIrClsW24 : (mw <= 64 ? kIrClsW64 : kIrClsGeneric);
-    unsigned long long words = longGroup ? (unsigned long long)rows * 6ull + 8ull + 3ull * ((unsigned long long)rows + (unsigned long long)b.q_seq_len[g] + 4ull) : cls == kIrClsGeneric ? ((unsigned long long)rows * (unsigned long long)mw + 3ull) / 4ull + 2ull * (unsigned long long)mw + 4ull
+    // long groups of width 33..64 (CLR: refineBand 20): the two-cells-per-lane form of the warp kernel
+    const bool longWide = mw > 32 && mw <= 64 && rows >= kIrWarpMinRows && no_warp != 1;
+    const int cls = longGroup ? ((no_warp == 2 || (bad & 2) || rows >= long_rows) ? kIrClsWarp32 : kIrClsPipe) : longWide ? kIrClsWarp64 : mw <= 24 ? kIrClsW24 : (mw <= 64 ? kIrClsW64 : kIrClsGeneric);
+    unsigned long long words = longGroup ? (unsigned long long)rows * 6ull + 8ull + 3ull * ((unsigned long long)rows + (unsigned long long)b.q_seq_len[g] + 4ull)
+                               : longWide ? (unsigned long long)rows * 10ull + 8ull + 3ull * ((unsigned long long)rows + (unsigned long long)b.q_seq_len[g] + 4ull)
+                               : cls == kIrClsGeneric ? ((unsigned long long)rows * (unsigned long long)mw + 3ull) / 4ull + 2ull * (unsigned long long)mw + 4ull
                                                            : (unsigned long long)rows * (unsigned long long)ir_words(cls == kIrClsW24 ? 24 : 64);
     words = (words + 1ull) & ~1ull;   // keep every group's arrows 8-byte aligned
     b.tb_off[g] = atomicAdd(tb_cursor, words);
     b.max_width[g] = mw;
-    const int bucket = kAogBuckets - 1 - imin(longGroup ? rows >> 8 : rows >> 3, kAogBuckets - 1);
+    const int bucket = kAogBuckets - 1 - imin((longGroup || longWide) ? rows >> 8 : rows >> 3, kAogBuckets - 1);
     const uint32_t bin = (uint32_t)(cls * kAogBuckets + bucket);
     bin_of_group[g] = bin;
     atomicAdd(&plan->hist[bin], 1u);
@@ -506,6 +510,210 @@ __global__ void __launch_bounds__(128) ir_dp_warp_kernel(IrBatch b, AogPlan *pla
     // one traceback walk: blocks come out last-first into the group's scratch, then are copied in forward order
     uint32_t *rb = tbw + (unsigned long long)rows * 5ull + 8ull;
     int nb = ir_walk_planes<2>(tbw, qS, qE, rows, tStart, rb, 0, lane);
+    if (nb < 0) { if (lane == 0) atomicOr(b.err, 16); nb = 0; }
+    unsigned long long slot = aog_reserve_blocks(AogBatch{b.q, b.t, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, nullptr,
+                                                          nullptr, b.blocks, b.block_cap, b.block_cursor, b.err},
+                                                 lane == 0 ? nb : 0, lane, &plan->cls_blocks[cls]);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (lane == 0) { b.n_blocks[g] = nb; b.block_off[g] = slot; }
+    __syncwarp();
+    if (slot != ~0ull) {
+      uint32_t *out = b.blocks + 3ull * slot;
+      for (int i = lane; i < 3 * nb; i += 32) { const int r = i / 3, c = i - 3 * r; out[i] = rb[3 * (nb - 1 - r) + c]; }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- warp per group, width <= 64
+// The same kernel with TWO band cells per lane (cell x = lane + 32 c): CLR's refineBand 20 makes rows of 41..64 cells.  The two prefix-max
+// scans of a row run over the low half, then over the high half seeded with the low half's totals; arrows are 5 bit-planes of 64 bits
+// (two ballots each) = 10 words per row.
+template <int MODE>
+__device__ __forceinline__ int ir_walk_planes64(const uint32_t *tb, const int32_t *qS, const int32_t *qE, int rows, int tStart, uint32_t *out, int nb, int lane) {
+  int t = rows - 1;
+  int qs = qS[t];
+  int x = qE[t] - qs;
+  int mat = 0, run = 0, lastOp = -1, count = 0;
+  long guard = 0;
+  const long guardMax = 4L * rows + 4L * (qE[rows - 1] - qS[0]) + 64;
+  auto emit = [&](uint32_t qq, uint32_t tt, uint32_t ln) {
+    if (MODE != 0 && lane == 0) { const int r = (MODE == 1) ? nb - 1 - count : count; out[3 * r] = qq; out[3 * r + 1] = tt; out[3 * r + 2] = ln; }
+    count++;
+  };
+  int top = -1;                 // rows [top-31, top] are held: lane l has row top-l
+  unsigned long long p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0;
+  int rqs = 0;
+  while (true) {
+    if (++guard > guardMax) return -1;
+    if (t == 0) {
+      if (x > 0) {
+        if (mat != 0) return -1;
+        if (run > 0) { emit((uint32_t)(qs + x + 1), (uint32_t)(tStart + 1), (uint32_t)run); run = 0; }
+        else if (lastOp == IR_DOWN) emit((uint32_t)(qs + x + 1), (uint32_t)(tStart + 1), 0u);
+        lastOp = IR_LEFT; x = 0;
+      }
+      run += 1;
+      emit((uint32_t)qs, (uint32_t)tStart, (uint32_t)run);
+      break;
+    }
+    if (top < 0 || t > top || t < top - 31) {
+      top = t;
+      const int r = top - lane;
+      if (r >= 1) {
+        const uint32_t *w = tb + (unsigned long long)r * 10ull;
+        p0 = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32); p1 = (unsigned long long)w[2] | ((unsigned long long)w[3] << 32);
+        p2 = (unsigned long long)w[4] | ((unsigned long long)w[5] << 32); p3 = (unsigned long long)w[6] | ((unsigned long long)w[7] << 32);
+        p4 = (unsigned long long)w[8] | ((unsigned long long)w[9] << 32);
+      }
+      rqs = (r >= 1) ? qS[r - 1] : 0;
+    }
+    const int src = top - t;
+    const unsigned long long w0 = __shfl_sync(0xffffffffu, p0, src), w1 = __shfl_sync(0xffffffffu, p1, src), w2 = __shfl_sync(0xffffffffu, p2, src);
+    const unsigned long long w3 = __shfl_sync(0xffffffffu, p3, src), w4 = __shfl_sync(0xffffffffu, p4, src);
+    const int pqs = __shfl_sync(0xffffffffu, rqs, src);
+    const int a = (int)(((w0 >> x) & 1ull) | (((w1 >> x) & 1ull) << 1) | (((w2 >> x) & 1ull) << 2));
+    const int dbit = (int)((w3 >> x) & 1ull), ibit = (int)((w4 >> x) & 1ull);
+    int op, nt = t, nx = x, nmat = mat;
+    if (mat == 0) {
+      if (a == IR_DELCLOSE) { op = -1; nmat = 1; }
+      else if (a == IR_INSCLOSE) { op = -1; nmat = 2; }
+      else if (a == IR_DIAG) { op = IR_DIAG; nt = t - 1; }
+      else if (a == IR_LEFT) { op = IR_LEFT; nx = x - 1; }
+      else if (a == IR_DOWN) { op = IR_DOWN; nt = t - 1; }
+      else return -1;
+    } else if (mat == 1) { op = IR_DOWN; nmat = dbit ? 1 : 0; nt = t - 1; }
+    else { op = IR_LEFT; nmat = ibit ? 2 : 0; nx = x - 1; }
+    if (op >= 0) {
+      const int q = qs + x;
+      if (op == IR_DIAG) run++;
+      else {
+        if (run > 0) { emit((uint32_t)(q + 1), (uint32_t)(tStart + t + 1), (uint32_t)run); run = 0; }
+        else if (lastOp != -1 && lastOp != op) emit((uint32_t)(q + 1), (uint32_t)(tStart + t + 1), 0u);
+      }
+      lastOp = op;
+    }
+    if (nt != t) { const int q = qs + x; nx = (op == IR_DIAG ? q - 1 : q) - pqs; qs = pqs; }
+    t = nt; x = nx; mat = nmat;
+    if (x < 0 || x > 63) return -1;
+  }
+  return count;
+}
+
+__global__ void __launch_bounds__(128) ir_dp_warp64_kernel(IrBatch b, AogPlan *plan, const uint32_t *sorted) {
+  constexpr int cls = kIrClsWarp64;
+  __shared__ int sM[4][66];
+  __shared__ int sD[4][66];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  int *rowM = sM[wib], *rowD = sD[wib];
+  const uint32_t begin = plan->bin_start[cls * kAogBuckets];
+  const uint32_t end = plan->bin_start[(cls + 1) * kAogBuckets];
+  const int match = b.match, mismatch = b.mismatch, gap = b.gap, gapOpen = 2 * b.gap + 1;
+  for (;;) {
+    uint32_t w = 0;
+    if (lane == 0) w = atomicAdd(&plan->work[cls], 1u);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (begin + w >= end) break;
+    const int g = (int)sorted[begin + w];
+    const int rows = b.t_len[g];
+    const int tStart = b.t_start[g];
+    const int32_t *qS = b.band + b.band_off[g];
+    const int32_t *qE = qS + rows;
+    uint32_t *tbw = b.tb + b.tb_off[g];
+    const uint64_t qbase = (uint64_t)b.q_base[g];
+    const uint32_t tbase = b.t_base[g];
+    int qsPrev = qS[0];
+    int lenPrev = qE[0] - qsPrev + 1;
+    __syncwarp();
+    rowM[lane] = lane * gap; rowM[lane + 32] = (lane + 32) * gap;
+    rowD[lane] = kIrBad; rowD[lane + 32] = kIrBad;
+    __syncwarp();
+    auto qcode_at = [&](int pos) -> int { const uint64_t p = qbase + (uint64_t)pos; return p < b.q.n ? seq_code(b.q, p) : 5; };
+    for (int t0 = 1; t0 < rows; t0 += 32) {
+      const int rr = t0 + lane;
+      const int pqs = rr < rows ? qS[rr] : 0, pqe = rr < rows ? qE[rr] : 0;
+      const int ptc = rr < rows ? seq_code(b.t, (uint64_t)(uint32_t)(tbase + (uint32_t)(tStart + rr))) : 5;
+      const int nrow = imin(32, rows - t0);
+      for (int l = 0; l < nrow; l++) {
+        const int t = t0 + l;
+        const int qs = __shfl_sync(0xffffffffu, pqs, l), qe = __shfl_sync(0xffffffffu, pqe, l), tc = __shfl_sync(0xffffffffu, ptc, l);
+        const int len = qe - qs + 1;
+        const int off = qs - qsPrev;
+        const int rowEnd = (t == rows - 1) ? len : len - 1;
+        int a[2], D[2], dbit[2], mS[2], dS[2]; bool valid[2];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const int x = lane + 32 * c;
+          const int qc = qcode_at(qs + x);
+          const int xp = x + off;
+          const bool upIn = xp <= lenPrev - 1;
+          const bool upOk = xp < lenPrev - 1;
+          const bool diagOk = upIn && !(xp - 1 == 0 && t != 1);
+          const int Mup = upIn ? rowM[xp] : kIrBad;
+          const int Dup = upIn ? rowD[xp] : kIrBad;
+          const int Mdg = (upIn && xp >= 1) ? rowM[xp - 1] : kIrBad;
+          valid[c] = x >= 1 && x < rowEnd;
+          const int delOpen = upOk ? Mup + gapOpen : kIrBad;
+          const int delExt = upOk ? Dup : kIrBad;
+          D[c] = imax(delOpen, delExt);
+          dbit[c] = (D[c] == delOpen) ? 0 : 1;
+          mS[c] = diagOk ? Mdg + (qc == tc ? match : mismatch) : kIrBad;
+          dS[c] = upOk ? Mup + gap : kIrBad;
+          a[c] = valid[c] ? imax(imax(mS[c], dS[c]), D[c]) : (x == 0 ? kIrBad : kIrNeg);
+        }
+        __syncwarp();
+        // inclusive prefix maxima over the 64 cells: u = a - x gap (for L), pm = a (for I and the gap-open term)
+        int u0 = a[0] - lane * gap, pm0 = a[0];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int uu = __shfl_up_sync(0xffffffffu, u0, o), pp = __shfl_up_sync(0xffffffffu, pm0, o);
+          if (lane >= o) { u0 = imax(u0, uu); pm0 = imax(pm0, pp); }
+        }
+        const int cu = __shfl_sync(0xffffffffu, u0, 31), cp = __shfl_sync(0xffffffffu, pm0, 31);
+        int u1 = a[1] - (lane + 32) * gap, pm1 = a[1];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int uu = __shfl_up_sync(0xffffffffu, u1, o), pp = __shfl_up_sync(0xffffffffu, pm1, o);
+          if (lane >= o) { u1 = imax(u1, uu); pm1 = imax(pm1, pp); }
+        }
+        u1 = imax(u1, cu); pm1 = imax(pm1, cp);
+        int pmx0 = __shfl_up_sync(0xffffffffu, pm0, 1); if (lane == 0) pmx0 = kIrNeg;
+        int pmx1 = __shfl_up_sync(0xffffffffu, pm1, 1); if (lane == 0) pmx1 = cp;
+        int M[2], I[2];
+        { const int L = u0 + lane * gap; I[0] = imax(kIrBad, pmx0 + gapOpen); M[0] = (lane == 0) ? kIrBad : imax(imax(L, pmx0 + gapOpen), kIrBad); }
+        { const int L = u1 + (lane + 32) * gap; I[1] = imax(kIrBad, pmx1 + gapOpen); M[1] = imax(imax(L, pmx1 + gapOpen), kIrBad); }
+        int Ml0 = __shfl_up_sync(0xffffffffu, M[0], 1); if (lane == 0) Ml0 = kIrBad;
+        const int M0last = __shfl_sync(0xffffffffu, M[0], 31);
+        int Ml1 = __shfl_up_sync(0xffffffffu, M[1], 1); if (lane == 0) Ml1 = M0last;
+        const int Mleft[2] = {Ml0, Ml1};
+        uint32_t pl[10];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const int iS = Mleft[c] + gap;
+          const int ibit = (I[c] == Mleft[c] + gapOpen) ? 0 : 1;
+          const int arrow = (M[c] == mS[c]) ? IR_DIAG : (M[c] == iS) ? IR_LEFT : (M[c] == dS[c]) ? IR_DOWN : (M[c] == D[c]) ? IR_DELCLOSE : IR_INSCLOSE;
+          pl[0 + c] = __ballot_sync(0xffffffffu, valid[c] && (arrow & 1));
+          pl[2 + c] = __ballot_sync(0xffffffffu, valid[c] && (arrow & 2));
+          pl[4 + c] = __ballot_sync(0xffffffffu, valid[c] && (arrow & 4));
+          pl[6 + c] = __ballot_sync(0xffffffffu, valid[c] && dbit[c]);
+          pl[8 + c] = __ballot_sync(0xffffffffu, valid[c] && ibit);
+        }
+        if (lane < 10) {
+          uint32_t v = 0;
+#pragma unroll
+          for (int k = 0; k < 10; k++) if (lane == k) v = pl[k];
+          tbw[(unsigned long long)t * 10ull + (unsigned)lane] = v;
+        }
+        rowM[lane] = M[0]; rowM[lane + 32] = M[1];
+        rowD[lane] = valid[0] ? D[0] : kIrBad; rowD[lane + 32] = valid[1] ? D[1] : kIrBad;
+        __syncwarp();
+        qsPrev = qs; lenPrev = len;
+      }
+    }
+    __syncwarp();
+    uint32_t *rb = tbw + (unsigned long long)rows * 10ull + 8ull;
+    int nb = ir_walk_planes64<2>(tbw, qS, qE, rows, tStart, rb, 0, lane);
     if (nb < 0) { if (lane == 0) atomicOr(b.err, 16); nb = 0; }
     unsigned long long slot = aog_reserve_blocks(AogBatch{b.q, b.t, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, nullptr,
                                                           nullptr, b.blocks, b.block_cap, b.block_cursor, b.err},

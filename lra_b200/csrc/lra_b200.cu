@@ -573,6 +573,10 @@ static int ir_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b20
     launched.push_back({kIrClsPipe, evi}); recs(S[1]); { static const bool two = getenv("LRA_B200_IR_PIPE2") != nullptr;
       if (two) ir_dp_pipe_kernel<2><<<pb, 128, 0, S[1]>>>(b, plan, sorted, kIrClsPipe); else ir_dp_pipe_kernel<1><<<pb, 128, 0, S[1]>>>(b, plan, sorted, kIrClsPipe); } recs(S[1]); ctx->launches++;
   }
+  if (cnt[kIrClsWarp64]) {
+    unsigned wb = (cnt[kIrClsWarp64] + 3) / 4; const unsigned wcap = (unsigned)ctx->n_sm * 16u; if (wb > wcap) wb = wcap;
+    launched.push_back({kIrClsWarp64, evi}); recs(S[0]); ir_dp_warp64_kernel<<<wb, 128, 0, S[0]>>>(b, plan, sorted); recs(S[0]); ctx->launches++;
+  }
   if (cnt[kIrClsGeneric]) { launched.push_back({kIrClsGeneric, evi}); recs(S[2]); ir_dp_generic_kernel<<<blocks_for(cnt[kIrClsGeneric]), 64, 0, S[2]>>>(b, plan, sorted); recs(S[2]); ctx->launches++; }
   if (cnt[kIrClsW64]) { launched.push_back({kIrClsW64, evi}); recs(S[3]); ir_dp_thread_kernel<64><<<blocks_for(cnt[kIrClsW64]), 64, 0, S[3]>>>(b, plan, sorted, kIrClsW64); recs(S[3]); ctx->launches++; }
   if (cnt[kIrClsW24]) { launched.push_back({kIrClsW24, evi}); recs(S[2]); ir_dp_thread_kernel<24><<<blocks_for(cnt[kIrClsW24]), 64, 0, S[2]>>>(b, plan, sorted, kIrClsW24); recs(S[2]); ctx->launches++; }
@@ -585,7 +589,7 @@ static int ir_run_device(lra_b200_ctx *ctx, const lra_b200_seq *q, const lra_b20
   res->n_blocks_total = ctx->h_misc[0];
   res->cells = ctx->h_misc[3];
   const int err = *(int *)((char *)ctx->h_misc + 8);
-  static const char *names[kIrNumCls] = {"ir_dp_thread<W=24>", "ir_dp_thread<W=64>", "ir_dp_generic", "ir_dp_warp<W=32>", "ir_dp_pipe<W=32>"};
+  static const char *names[kIrNumCls] = {"ir_dp_thread<W=24>", "ir_dp_thread<W=64>", "ir_dp_generic", "ir_dp_warp<W=32>", "ir_dp_pipe<W=32>", "ir_dp_warp<W=64>"};
   {
     lra_b200_kernel_stat s;
     memset(&s, 0, sizeof s);

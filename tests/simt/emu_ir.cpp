@@ -35,6 +35,7 @@ static uint64_t run_ir_dp(IrBatch &b, int force_generic, std::vector<uint32_t> &
   if (cnt(kIrClsW64)) emu::launch(dim3(2), dim3(64), 0, [&] { ir_dp_thread_kernel<64>(b, plan, sorted.data(), kIrClsW64); });
   if (cnt(kIrClsGeneric)) emu::launch(dim3(2), dim3(64), 0, [&] { ir_dp_generic_kernel(b, plan, sorted.data()); });
   if (cnt(kIrClsWarp32)) emu::launch(dim3(2), dim3(128), 0, [&] { ir_dp_warp_kernel(b, plan, sorted.data()); });
+  if (cnt(kIrClsWarp64)) emu::launch(dim3(2), dim3(128), 0, [&] { ir_dp_warp64_kernel(b, plan, sorted.data()); });
   if (cnt(kIrClsPipe)) emu::launch(dim3(2), dim3(128), 0, [&] { if (force_generic == 5) ir_dp_pipe_kernel<2>(b, plan, sorted.data(), kIrClsPipe); else ir_dp_pipe_kernel<1>(b, plan, sorted.data(), kIrClsPipe); });
   return cells;
 }
