@@ -668,7 +668,8 @@ __device__ __forceinline__ void sdp_put_pair(SdpPt *H, int at, uint32_t frag, ui
   H[at] = s; H[at + 1] = e;
 }
 
-// mode 0: pure matches of all clusters (SparseDP.h:2139); 1: one cluster `only_cl` (:2287); 2: forward only (SparseDP_Forward.h:312)
+// mode 0: pure matches of all clusters (SparseDP.h:2139); 1: one cluster `only_cl` (:2287); 2: forward only (SparseDP_Forward.h:312);
+// 3: the Cluster_SameDiag anchors of the clusters of a split chain (:1766, high-accuracy pipeline): like 0 without the boundary pairs
 __device__ __noinline__ bool sdp_build(SdpWork &W, const SdpAnchors &A, int mode, int only_cl, float rate, int irate, Arena &ar) {
   unsigned long long tk_ = ar.now();
   // count points
@@ -707,6 +708,15 @@ __device__ __noinline__ bool sdp_build(SdpWork &W, const SdpAnchors &A, int mode
       const int g = f0 + i;
       if (st == 0) sdp_put_pair(W.H1, 2 * i, (uint32_t)i, A.q[g], A.t[g], A.len[g], only_cl, 0, 1);
       else sdp_put_pair(W.H1, 2 * i, (uint32_t)i, A.q[g], A.t[g], A.len[g], only_cl, 1, 0);
+    }
+  } else if (mode == 3) {
+    for (int c = 0; c < A.ncl; c++) {
+      const int o = A.cl_off[c], sz = A.cl_off[c + 1] - o, st = A.cl_strand[c];
+      for (int i = lane_id(); i < sz; i += kLanes) {
+        const uint32_t g = (uint32_t)(o + i);
+        if (st == 0) sdp_put_pair(W.H1, 2 * (int)g, g, A.q[g], A.t[g], A.len[g], c, 0, 1);
+        else sdp_put_pair(W.H1, 2 * (int)g, g, A.q[g], A.t[g], A.len[g], c, 1, 0);
+      }
     }
   } else {
     for (int i = lane_id(); i < A.nfrag; i += kLanes) sdp_put_pair(W.H1, 2 * i, (uint32_t)i, A.q[i], A.t[i], A.len[i], 0, 0, 1);

@@ -101,6 +101,31 @@ __device__ __noinline__ int sdp_one_cluster(const SdpAnchors &A, int cl, float r
   return n;
 }
 
+// mode 3 (SparseDP.h:1766): the same-diagonal anchors of the clusters of one split chain (A.cl_off / A.cl_strand in split-chain order), value =
+// length x second_anchorbonus, one chain from the best anchor.  Returns the chain length; chain holds indices into the concatenation (the
+// FinalChain's (ClusterIndex, chain) pair is (cluster of the index, index - cl_off[cluster])).
+__device__ __noinline__ int sdp_samediag_chain(const SdpAnchors &A, float rate, const Pwl &P, Arena &ar, uint32_t *chain, uint8_t *link, float *value) {
+  if (A.nfrag == 0) return 0;
+  const unsigned long long mk = ar.mark();
+  SdpWork W;
+  if (!sdp_build(W, A, 3, 0, rate, 0, ar)) { ar.release(mk); return -1; }
+  int *res = ar.alloc<int>(2);
+  if (ar.overflow || !sdp_open_dyn(W, ar)) { ar.release(mk); return -1; }
+  { const unsigned long long tp_ = ar.now(); sdp_process(W, A, 0, 3, rate, 0, P); ar.tick(18, tp_); }
+  { const unsigned long long e = W.dyn.base_off + *W.dyn.top; if (e > ar.peak) ar.peak = e; }
+  if (*W.dyn.err) { ar.release(mk); return -1; }
+  if (lane_id() == 0) {
+    float mx = 0.0f; uint32_t pos = 0;
+    for (int l = 0; l < A.nfrag; l++) if (W.val[l].val > mx) { mx = W.val[l].val; pos = (uint32_t)l; }
+    *value = mx;
+    res[0] = sdp_traceback(W, pos, chain, link);
+  }
+  wsync();
+  const int n = res[0];
+  ar.release(mk);
+  return n;
+}
+
 // mode 2 (forward only, SparseDP_ForwardOnly).  A.q/t/len are the anchors, no clusters.  Returns the chain length.
 __device__ __noinline__ int sdp_forward_only(const SdpAnchors &A, int irate, const Pwl &P, Arena &ar, uint32_t *chain, float *value) {
   if (A.nfrag == 0) return 0;
@@ -128,7 +153,7 @@ __device__ __noinline__ int sdp_forward_only(const SdpAnchors &A, int irate, con
 // ---- stand-alone batch (lra_b200_sdp_batch): one problem per warp ------------------------------------------------------
 struct SdpBatch {
   int n_prob, max_aln;
-  const int *mode;                         // 0 pure matches, 1 one cluster, 2 forward only
+  const int *mode;                         // 0 pure matches, 1 one cluster, 2 forward only, 3 same-diagonal anchors of a split chain
   const unsigned long long *frag_off;      // [n_prob + 1] into q / t / len
   const uint32_t *q, *t; const int32_t *len;
   const unsigned long long *cl_off_off;    // [n_prob + 1] into cl_off (ncl + 1 entries per problem, problem-relative) and cl_strand (ncl + 1 slots)
@@ -168,6 +193,10 @@ __global__ void __launch_bounds__(128) sdp_batch_kernel(SdpBatch b) {
       float v = 0.0f; float *vp = b.chain_val + p * b.max_aln;
       const int n = sdp_one_cluster(A, b.only_cl[p], b.rate[p], *b.pwl, ar, cb, lb, vp);
       (void)v;
+      if (n < 0) nch = -1; else { nch = 1; if (lane_id() == 0) b.chain_len[p * b.max_aln] = n; }
+    } else if (mode == 3) {
+      float *vp = b.chain_val + p * b.max_aln;
+      const int n = sdp_samediag_chain(A, b.rate[p], *b.pwl, ar, cb, lb, vp);
       if (n < 0) nch = -1; else { nch = 1; if (lane_id() == 0) b.chain_len[p * b.max_aln] = n; }
     } else {
       float *vp = b.chain_val + p * b.max_aln;

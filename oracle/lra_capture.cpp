@@ -82,6 +82,7 @@ static inline void IndelRefineAlignment_logged(Read &read, Genome &genome, Align
 //           {n_chains} then per chain {n, value(f32), QStart, QEnd, TStart, TEnd} chain[n] (global fragment index) link[n-1]
 //   kind 1: {1, strand, nfrag, rate(f32)} q t len {n, value(f32)} chain[n] link[n-1]
 //   kind 2: {2, nfrag, rate} q t len {n, value(f32)} chain[n]
+//   kind 3: see below
 #include "SparseDP.h"
 #include "SparseDP_Forward.h"
 static FILE *lra_cap_sdp_fp() {
@@ -132,8 +133,26 @@ static inline int SparseDP_logged(int ClusterIndex, vector<Cluster> &FragInput, 
   }
   return r;
 }
+// kind 3 (SparseDP.h:1766, the high-accuracy pipeline's second SparseDP over the Cluster_SameDiag anchors of a split chain):
+//   {3, n_cl, nfrag, rate(f32)} cl_off[n_cl+1] cl_strand[n_cl] q[nfrag] t[nfrag] len[nfrag] {n, value(f32)} chain[n] (index into the concatenation)
 static inline int SparseDP_logged(SplitChain &inputChain, vector<Cluster_SameDiag *> &FragInput, FinalChain &finalchain, const Options &opts, const vector<float> &LookUpTable, Read &read) {
-  return SparseDP(inputChain, FragInput, finalchain, opts, LookUpTable, read);
+  FILE *fp = lra_cap_sdp_fp();
+  int un = read.unaligned;
+  int r = SparseDP(inputChain, FragInput, finalchain, opts, LookUpTable, read);
+  if (fp && !un && inputChain.size() > 0) {
+    const int ncl = inputChain.size();
+    std::vector<int> off(ncl + 1, 0);
+    for (int c = 0; c < ncl; c++) off[c + 1] = off[c] + FragInput[inputChain[c]]->size();
+    cap_w32(fp, 3); cap_w32(fp, ncl); cap_w32(fp, off[ncl]); cap_wf(fp, opts.second_anchorbonus);
+    for (int c = 0; c <= ncl; c++) cap_w32(fp, off[c]);
+    for (int c = 0; c < ncl; c++) cap_w32(fp, FragInput[inputChain[c]]->strand);
+    for (int c = 0; c < ncl; c++) for (int i = 0; i < FragInput[inputChain[c]]->size(); i++) cap_w32(fp, FragInput[inputChain[c]]->GetqStart(i));
+    for (int c = 0; c < ncl; c++) for (int i = 0; i < FragInput[inputChain[c]]->size(); i++) cap_w32(fp, FragInput[inputChain[c]]->GettStart(i));
+    for (int c = 0; c < ncl; c++) for (int i = 0; i < FragInput[inputChain[c]]->size(); i++) cap_w32(fp, FragInput[inputChain[c]]->length(i));
+    cap_w32(fp, finalchain.chain.size()); cap_wf(fp, finalchain.SecondSDPValue);
+    for (size_t s = 0; s < finalchain.chain.size(); s++) cap_w32(fp, finalchain.chain[s] + FragInput[finalchain.ClusterIndex[s]]->matchStart);
+  }
+  return r;
 }
 static inline int SparseDP_logged(vector<Cluster> &FragInput, vector<Primary_chain> &Primary_chains, const Options &opts, const vector<float> &LookUpTable, Read &read, float &rate) {
   return SparseDP(FragInput, Primary_chains, opts, LookUpTable, read, rate);

@@ -49,6 +49,18 @@ def parse_capture(path, limit=None):
             n = int(a[i]); val = f[i + 1]; i += 2
             ch = a[i:i + n].copy(); i += n
             rec["chains"] = [dict(n=n, value=np.float32(val), chain=ch, link=np.zeros(0, np.uint8))]
+        elif kind == 3:
+            n_cl, nfrag = int(a[i + 1]), int(a[i + 2])
+            rec = dict(kind=3, rate=float(f[i + 3]))
+            i += 4
+            rec["cl_off"] = a[i:i + n_cl + 1].astype(np.int32); i += n_cl + 1
+            rec["cl_strand"] = a[i:i + n_cl].astype(np.uint8); i += n_cl
+            rec["q"] = a[i:i + nfrag].copy(); i += nfrag
+            rec["t"] = a[i:i + nfrag].copy(); i += nfrag
+            rec["len"] = a[i:i + nfrag].astype(np.int32); i += nfrag
+            n = int(a[i]); val = f[i + 1]; i += 2
+            ch = a[i:i + n].copy(); i += n
+            rec["chains"] = [dict(n=n, value=np.float32(val), chain=ch, link=np.zeros(0, np.uint8))]
         else:
             raise ValueError("bad capture stream at word %d" % i)
         out.append(rec)

@@ -16,7 +16,8 @@ import synth  # noqa: E402
 import sdpgen  # noqa: E402
 import mapgen  # noqa: E402
 
-PRESET = {"ont": dict(pwl=(7.0, 10.0, 1.5, 1500, 3000), alnthres=0.65, NumAln=2), "clr": dict(pwl=(7.0, 10.0, 1.5, 1500, 3000), alnthres=0.5, NumAln=2)}
+PRESET = {"ont": dict(pwl=(7.0, 10.0, 1.5, 1500, 3000), alnthres=0.65, NumAln=2), "clr": dict(pwl=(7.0, 10.0, 1.5, 1500, 3000), alnthres=0.5, NumAln=2),
+          "ccs": dict(pwl=(4.0, 15.0, 1.5, 2000, 3000), alnthres=0.7, NumAln=2)}
 
 
 def ref_pwl(p):
@@ -61,6 +62,43 @@ def test_sdp_gpu_on_captured_calls(preset, n_reads, repeats, tmp_path):
     recs = sdpgen.parse_capture(mapgen.capture_sdp(w))
     assert len(recs) >= 2 * n_reads - 20
     P = PRESET[preset]
+    ctx = lra_b200.Context(0)
+    pwl = lra_b200.init_pwl(*P["pwl"])
+    bad = []
+    for s in range(0, len(recs), 2048):
+        sub = recs[s:s + 2048]
+        pb = sdpgen.pack(sub)
+        out = ctx.sdp_batch(pb, pwl, P["alnthres"], P["NumAln"])
+        bad += [(s + k, m) for k, m in sdpgen.compare(sub, pb, out, 2)]
+    ctx.close()
+    assert bad == [], bad[:10]
+
+
+def test_sdp_emulated_on_captured_highacc_calls(tmp_path):
+    """SparseDP.h:1766 (the second SparseDP of the high-accuracy pipeline, over the Cluster_SameDiag anchors of a split chain) on the calls of a
+    real `lra align -CCS` run: chain and float value bit-identical (the :1956 driver of the same run is not on the device yet and is skipped)."""
+    import emu_mp
+    w = mapgen.workdir(tmp_path, "ccs", n_reads=60, ref_len=600_000, contigs=2, repeats=True)
+    recs = [r for r in sdpgen.parse_capture(mapgen.capture_sdp(w)) if r["kind"] == 3]
+    assert len(recs) >= 50
+    P = PRESET["ccs"]
+    pb = sdpgen.pack(recs)
+    out = emu_mp.sdp_batch(pb, ref_pwl(P["pwl"]), P["alnthres"], P["NumAln"], lanes=1)
+    assert out["err"] == 0
+    assert sdpgen.compare(recs, pb, out, 2) == []
+    sub = recs[:4]
+    pb = sdpgen.pack(sub)
+    out = emu_mp.sdp_batch(pb, ref_pwl(P["pwl"]), P["alnthres"], P["NumAln"], lanes=32)
+    assert sdpgen.compare(sub, pb, out, 2) == []
+
+
+@pytest.mark.gpu
+def test_sdp_gpu_on_captured_highacc_calls(tmp_path):
+    import lra_b200
+    w = mapgen.workdir(tmp_path, "ccs", n_reads=1500, ref_len=5_000_000, contigs=3, repeats=True)
+    recs = [r for r in sdpgen.parse_capture(mapgen.capture_sdp(w)) if r["kind"] == 3]
+    assert len(recs) >= 1400
+    P = PRESET["ccs"]
     ctx = lra_b200.Context(0)
     pwl = lra_b200.init_pwl(*P["pwl"])
     bad = []
