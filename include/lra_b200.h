@@ -778,6 +778,12 @@ int lra_b200_global_chain_batch(lra_b200_ctx *ctx, const int32_t *frag, const ui
  *            SparseDP.h:2287-2440 (second SDP, Map_lowacc.h:535)
  *   mode 2:  int SparseDP_ForwardOnly(const GenomePairs&, const vector<int> &MatchLengths, vector<unsigned int> &chain, ..., int rate)
  *            SparseDP_Forward.h:312-490 (third SDP, LocalRefineAlignment.h:377)
+ *   mode 3:  int SparseDP(SplitChain &inputChain, vector<Cluster_SameDiag*> &FragInput, FinalChain&, ...)   SparseDP.h:1766-1952 (second SDP of
+ *            MapRead_highacc, LocalRefineAlignment.h:563): the same-diagonal anchors (GetqStart, GettStart, length) of the clusters of the split chain,
+ *            in split-chain order, as anchors grouped by cl_off / cl_strand; rate = opts.second_anchorbonus; chain = indices into the concatenation
+ *   mode 4:  int SparseDP(vector<Cluster> &FragInput, vector<Primary_chain>&, ..., float &rate)   SparseDP.h:1956-2135 (first SDP of MapRead_highacc on
+ *            the split clusters, Map_highacc.h:229) incl. DecidePrimaryChains :1586-1652: every fragment is a box with four points; chains of
+ *            Primary_chains[0] with value, box and NumOfAnchors0
  * Problem p owns the anchors frag_off[p] .. frag_off[p+1] (q = first.pos, t = second.pos, len = matchesLengths), grouped into clusters by
  * cl_off[cl_off_off[p] ..] (ncl + 1 problem-relative offsets) with strands cl_strand[cl_off_off[p] ..].  rate = the anchor bonus (mode 0:
  * the `rate` argument, mode 1: opts.second_anchorbonus), irate = the integer rate of mode 2.  The gap cost is the reference's PWL_w over
@@ -802,6 +808,12 @@ typedef struct lra_b200_sdp_problems {
   int32_t num_aln;         /* opts.NumAln */
   const int64_t *pwl_stops; const float *pwl_slope; const float *pwl_inter;   /* 25 entries each */
   int32_t ceil1, ceil2;    /* opts.gapCeiling1 / 2 */
+  /* mode 4 only (may be NULL otherwise), one entry per fragment at frag_off: q / t above are the box starts (qStart, tStart) */
+  const uint32_t *q_end, *t_end;   /* Cluster::qEnd, tEnd */
+  const uint8_t *frag_strand;      /* Cluster::strand */
+  const float *frag_val;           /* Cluster::Val */
+  const int32_t *frag_n0;          /* Cluster::NumofAnchors0 */
+  int32_t global_k;                /* opts.globalK (the value threshold of DecidePrimaryChains, SparseDP.h:1593) */
 } lra_b200_sdp_problems;
 typedef struct lra_b200_sdp_result {
   int32_t *n_chains;       /* [n_prob] */
@@ -812,6 +824,7 @@ typedef struct lra_b200_sdp_result {
   uint8_t *link;           /* [max_aln * total anchors] */
   int32_t *cl_of_frag;     /* [total anchors] (mode 0: cluster of every anchor) */
   uint64_t arena_peak;     /* out: largest per-problem scratch use in bytes */
+  int32_t *num_anchors0;   /* [n_prob * max_aln] mode 4: CHain::NumOfAnchors0 (may be NULL) */
 } lra_b200_sdp_result;
 int lra_b200_sdp_batch(lra_b200_ctx *ctx, const lra_b200_sdp_problems *problems, lra_b200_sdp_result *res);
 /* InitPWL (SubRountine.h:43-101): the piece-wise-linear gap cost tables for (opts.gapopen, opts.gapextend, opts.gaproot), 25 entries each. */

@@ -55,12 +55,13 @@ class _SdpProblems(C.Structure):
     _fields_ = [("n_prob", C.c_int32), ("max_aln", C.c_int32), ("mode", C.c_void_p), ("frag_off", C.c_void_p), ("q", C.c_void_p), ("t", C.c_void_p), ("len", C.c_void_p),
                 ("cl_off_off", C.c_void_p), ("cl_off", C.c_void_p), ("cl_strand", C.c_void_p), ("only_cl", C.c_void_p), ("rate", C.c_void_p), ("irate", C.c_void_p),
                 ("read_len", C.c_void_p), ("alnthres", C.c_float), ("num_aln", C.c_int32), ("pwl_stops", C.c_void_p), ("pwl_slope", C.c_void_p), ("pwl_inter", C.c_void_p),
-                ("ceil1", C.c_int32), ("ceil2", C.c_int32)]
+                ("ceil1", C.c_int32), ("ceil2", C.c_int32), ("q_end", C.c_void_p), ("t_end", C.c_void_p), ("frag_strand", C.c_void_p), ("frag_val", C.c_void_p),
+                ("frag_n0", C.c_void_p), ("global_k", C.c_int32)]
 
 
 class _SdpResult(C.Structure):
     _fields_ = [("n_chains", C.c_void_p), ("chain_len", C.c_void_p), ("chain_val", C.c_void_p), ("bounds", C.c_void_p), ("chain", C.c_void_p), ("link", C.c_void_p),
-                ("cl_of_frag", C.c_void_p), ("arena_peak", C.c_uint64)]
+                ("cl_of_frag", C.c_void_p), ("arena_peak", C.c_uint64), ("num_anchors0", C.c_void_p)]
 
 
 class MapOpts(C.Structure):
@@ -977,8 +978,10 @@ class Context:
         keep = [np.ascontiguousarray(pwl[0], np.int64), np.ascontiguousarray(pwl[1], np.float32), np.ascontiguousarray(pwl[2], np.float32)]
         pr = _SdpProblems(n, max_aln, _ptr(pb["mode"]), _ptr(pb["frag_off"]), _ptr(pb["q"]), _ptr(pb["t"]), _ptr(pb["len"]), _ptr(pb["cl_off_off"]), _ptr(pb["cl_off"]),
                           _ptr(pb["cl_strand"]), _ptr(pb["only_cl"]), _ptr(pb["rate"]), _ptr(pb["irate"]), _ptr(pb["read_len"]), alnthres, num_aln,
-                          _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), int(pwl[3]), int(pwl[4]))
-        rs = _SdpResult(_ptr(o["n_chains"]), _ptr(o["chain_len"]), _ptr(o["chain_val"]), _ptr(o["bounds"]), _ptr(o["chain"]), _ptr(o["link"]), _ptr(o["cl_of_frag"]), 0)
+                          _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), int(pwl[3]), int(pwl[4]),
+                          *((_ptr(pb["qe"]), _ptr(pb["te"]), _ptr(pb["fstrand"]), _ptr(pb["fval"]), _ptr(pb["fn0"]), int(pb["globalK"])) if "qe" in pb else (None, None, None, None, None, 0)))
+        o["n0"] = np.zeros(max(n * max_aln, 1), np.int32)
+        rs = _SdpResult(_ptr(o["n_chains"]), _ptr(o["chain_len"]), _ptr(o["chain_val"]), _ptr(o["bounds"]), _ptr(o["chain"]), _ptr(o["link"]), _ptr(o["cl_of_frag"]), 0, _ptr(o["n0"]))
         self._check(self.lib.lra_b200_sdp_batch(self.h, C.byref(pr), C.byref(rs)))
         o["peak"] = int(rs.arena_peak); o["err"] = 0
         return o

@@ -46,10 +46,11 @@ extern "C" int lra_b200_sdp_batch(lra_b200_ctx *ctx, const lra_b200_sdp_problems
     if (pr->frag_off[p + 1] < pr->frag_off[p] || pr->cl_off_off[p + 1] < pr->cl_off_off[p] + 1) return fail(ctx, LRA_B200_EINVAL, "sdp_batch: offsets of problem %d", p);
     const size_t nf = (size_t)(pr->frag_off[p + 1] - pr->frag_off[p]);
     if (nf > (1u << 22)) return fail(ctx, LRA_B200_EINVAL, "sdp_batch: problem %d has more than 2^22 anchors", p);
-    if (pr->mode[p] < 0 || pr->mode[p] > 2) return fail(ctx, LRA_B200_EINVAL, "sdp_batch: mode of problem %d", p);
+    if (pr->mode[p] < 0 || pr->mode[p] > 4) return fail(ctx, LRA_B200_EINVAL, "sdp_batch: mode of problem %d", p);
+    if (pr->mode[p] == 4 && (!pr->q_end || !pr->t_end || !pr->frag_strand || !pr->frag_val || !pr->frag_n0)) return fail(ctx, LRA_B200_EINVAL, "sdp_batch: mode 4 needs q_end / t_end / frag_strand / frag_val / frag_n0");
     const int ncl = (int)(pr->cl_off_off[p + 1] - pr->cl_off_off[p]) - 1;
     if (pr->mode[p] == 1 && (pr->only_cl[p] < 0 || pr->only_cl[p] >= ncl)) return fail(ctx, LRA_B200_EINVAL, "sdp_batch: cluster index of problem %d", p);
-    if (pr->mode[p] != 2) {
+    if (pr->mode[p] != 2 && pr->mode[p] != 4) {
       const int32_t *co = pr->cl_off + pr->cl_off_off[p];
       if (co[0] != 0 || (size_t)co[ncl] != nf) return fail(ctx, LRA_B200_EINVAL, "sdp_batch: cluster offsets of problem %d do not cover its anchors", p);
       for (int c = 0; c < ncl; c++) if (co[c + 1] < co[c]) return fail(ctx, LRA_B200_EINVAL, "sdp_batch: cluster offsets of problem %d not ascending", p);
@@ -83,6 +84,17 @@ extern "C" int lra_b200_sdp_batch(lra_b200_ctx *ctx, const lra_b200_sdp_problems
   b.n_chains = (int *)B[13].p; b.chain_len = (int *)B[14].p; b.chain_val = (float *)B[15].p; b.bounds = (uint32_t *)B[16].p; b.chain = (uint32_t *)B[17].p;
   b.link = (uint8_t *)B[18].p; b.cl_of_frag = (int *)B[19].p; b.arena = (unsigned char *)B[20].p; b.arena_per_warp = per; b.err = (int *)B[21].p;
   b.peak = (unsigned long long *)((char *)B[21].p + 8);
+  b.qe = b.te = nullptr; b.fstrand = nullptr; b.fval = nullptr; b.fn0 = nullptr; b.out_n0 = nullptr; b.globalK = pr->global_k;
+  if (pr->q_end && pr->t_end && pr->frag_strand && pr->frag_val && pr->frag_n0 && NF) {
+    DevBuf *X = ctx->mp + 24;
+    const size_t xs[6] = {NF * 4 + 16, NF * 4 + 16, NF + 16, NF * 4 + 16, NF * 4 + 16, (size_t)n * MA * 4 + 16};
+    for (int i = 0; i < 6; i++) if ((rc = ensure(ctx, X[i], xs[i]))) return rc;
+    CU(cudaMemcpyAsync(X[0].p, pr->q_end, NF * 4, cudaMemcpyHostToDevice, st)); CU(cudaMemcpyAsync(X[1].p, pr->t_end, NF * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(X[2].p, pr->frag_strand, NF, cudaMemcpyHostToDevice, st)); CU(cudaMemcpyAsync(X[3].p, pr->frag_val, NF * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(X[4].p, pr->frag_n0, NF * 4, cudaMemcpyHostToDevice, st)); CU(cudaMemsetAsync(X[5].p, 0, xs[5], st));
+    b.qe = (const uint32_t *)X[0].p; b.te = (const uint32_t *)X[1].p; b.fstrand = (const uint8_t *)X[2].p; b.fval = (const float *)X[3].p; b.fn0 = (const int32_t *)X[4].p;
+    b.out_n0 = (int *)X[5].p;
+  }
   CU(cudaMemsetAsync(B[14].p, 0, sz[14], st)); CU(cudaMemsetAsync(B[15].p, 0, sz[15], st)); CU(cudaMemsetAsync(B[16].p, 0, sz[16], st));
   cudaEventRecord(ctx->ev[0], st);
   sdp_batch_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(b);
@@ -98,6 +110,7 @@ extern "C" int lra_b200_sdp_batch(lra_b200_ctx *ctx, const lra_b200_sdp_problems
     CU(cudaMemcpyAsync(res->link, b.link, NF * MA, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(res->cl_of_frag, b.cl_of_frag, NF * 4, cudaMemcpyDeviceToHost, st));
   }
+  if (b.out_n0 && res->num_anchors0) CU(cudaMemcpyAsync(res->num_anchors0, b.out_n0, (size_t)n * MA * 4, cudaMemcpyDeviceToHost, st));
   unsigned long long h[2] = {0, 0};
   CU(cudaMemcpyAsync(h, B[21].p, 16, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));

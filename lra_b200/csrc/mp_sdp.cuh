@@ -652,7 +652,9 @@ __device__ __forceinline__ bool sdp_divide(SdpWork &W, SdpFam &F, Arena &ar) {
 // ---- problem set-up ----------------------------------------------------------------------------------------------
 struct SdpAnchors {          // concatenated anchors of the clusters of one problem
   const uint32_t *q, *t; const int32_t *len; int nfrag;
-  const int *cl_off; const uint8_t *cl_strand; int ncl;      // mode 0 / 1
+  const int *cl_off; const uint8_t *cl_strand; int ncl;      // mode 0 / 1 / 3
+  // mode 4 (split clusters as fragments, SparseDP.h:1956): boxes (q, t = starts; qe, te = ends), per-fragment strand, value (Cluster::Val) and NumofAnchors0
+  const uint32_t *qe, *te; const uint8_t *fstrand; const float *fval; const int32_t *fn0;
 };
 
 __device__ __forceinline__ void sdp_put_pair(SdpPt *H, int at, uint32_t frag, uint32_t qs, uint32_t ts, int len, int cl, int pair, int strand) {
@@ -669,13 +671,15 @@ __device__ __forceinline__ void sdp_put_pair(SdpPt *H, int at, uint32_t frag, ui
 }
 
 // mode 0: pure matches of all clusters (SparseDP.h:2139); 1: one cluster `only_cl` (:2287); 2: forward only (SparseDP_Forward.h:312);
-// 3: the Cluster_SameDiag anchors of the clusters of a split chain (:1766, high-accuracy pipeline): like 0 without the boundary pairs
+// 3: the Cluster_SameDiag anchors of the clusters of a split chain (:1766, high-accuracy pipeline): like 0 without the boundary pairs;
+// 4: split clusters as fragments with four points each (:1956, the first SparseDP of the high-accuracy pipeline)
 __device__ __noinline__ bool sdp_build(SdpWork &W, const SdpAnchors &A, int mode, int only_cl, float rate, int irate, Arena &ar) {
   unsigned long long tk_ = ar.now();
   // count points
   int N = 0, f0 = 0, f1 = A.nfrag;
   if (mode == 0) { N = 2 * A.nfrag; for (int c = 0; c < A.ncl; c++) { const int sz = A.cl_off[c + 1] - A.cl_off[c]; if (sz == 1) N += 2; else if (sz > 1) N += 4; } }
   else if (mode == 1) { f0 = A.cl_off[only_cl]; f1 = A.cl_off[only_cl + 1]; N = 2 * (f1 - f0); }
+  else if (mode == 4) N = 4 * A.nfrag;
   else N = 2 * A.nfrag;
   W.N = N; W.nfrag = mode == 1 ? f1 - f0 : A.nfrag;
   const int P = next_pow2(N > 0 ? N : 1);
@@ -709,6 +713,16 @@ __device__ __noinline__ bool sdp_build(SdpWork &W, const SdpAnchors &A, int mode
       if (st == 0) sdp_put_pair(W.H1, 2 * i, (uint32_t)i, A.q[g], A.t[g], A.len[g], only_cl, 0, 1);
       else sdp_put_pair(W.H1, 2 * i, (uint32_t)i, A.q[g], A.t[g], A.len[g], only_cl, 1, 0);
     }
+  } else if (mode == 4) {
+    // s1 (qS+1, tS+1), e1 (qE-1, tE-1) forward; s2 (qS+1, tE-1), e2 (qE-1, tS+1) backward; orient = strand 0 (SparseDP.h:1960-2012)
+    for (int i = lane_id(); i < A.nfrag; i += kLanes) {
+      const uint32_t or_ = A.fstrand[i] == 0 ? 1u : 0u;
+      SdpPt x; x.frag = (uint32_t)i; x.cl = 0;
+      x.q = A.q[i] + 1u; x.t = A.t[i] + 1u; x.fl = 1u | 2u | (or_ << 2); x.src = (uint32_t)(4 * i); W.H1[4 * i] = x;
+      x.q = A.qe[i] - 1u; x.t = A.te[i] - 1u; x.fl = 0u | 2u | (or_ << 2); x.src = (uint32_t)(4 * i + 1); W.H1[4 * i + 1] = x;
+      x.q = A.q[i] + 1u; x.t = A.te[i] - 1u; x.fl = 1u | 0u | (or_ << 2); x.src = (uint32_t)(4 * i + 2); W.H1[4 * i + 2] = x;
+      x.q = A.qe[i] - 1u; x.t = A.t[i] + 1u; x.fl = 0u | 0u | (or_ << 2); x.src = (uint32_t)(4 * i + 3); W.H1[4 * i + 3] = x;
+    }
   } else if (mode == 3) {
     for (int c = 0; c < A.ncl; c++) {
       const int o = A.cl_off[c], sz = A.cl_off[c + 1] - o, st = A.cl_strand[c];
@@ -726,6 +740,7 @@ __device__ __noinline__ bool sdp_build(SdpWork &W, const SdpAnchors &A, int mode
     SdpVal v; v.prev_sub = -1; v.prev_ind = -1; v.prev = 1; v.inv = 1; v.orient = 1; v.cl = 0;
     const int g = f0 + i;
     if (mode == 2) v.val = (float)(A.len[g] * irate);
+    else if (mode == 4) v.val = __fmul_rn(A.fval[g], rate);
     else v.val = __fmul_rn((float)A.len[g], rate);
     W.val[i] = v;
   }
@@ -825,6 +840,7 @@ __device__ __noinline__ void sdp_process(SdpWork &W, const SdpAnchors &A, int f0
       const int nR = FR.nB[row], nC = FC.nB[col], total = nR + nC;
       float bonus;
       if (mode == 2) bonus = (float)(A.len[f0 + ii] * irate);
+      else if (mode == 4) bonus = __fmul_rn(A.fval[f0 + ii], rate);
       else bonus = __fmul_rn(rate, (float)A.len[f0 + ii]);
       SdpVal v = W.val[ii];
       for (int b = 0; b < total; b += kLanes) {

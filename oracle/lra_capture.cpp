@@ -154,8 +154,33 @@ static inline int SparseDP_logged(SplitChain &inputChain, vector<Cluster_SameDia
   }
   return r;
 }
+// kind 4 (SparseDP.h:1956, the first SparseDP of the high-accuracy pipeline over the split clusters):
+//   {4, nfrag, rate(f32), alnthres(f32), globalK, NumAln, read_len} qS[n] qE[n] tS[n] tE[n] strand[n] Val(f32)[n] NumofAnchors0[n]
+//   {n_chains} then per chain of Primary_chains[0] {n, value(f32), qStart, qEnd, tStart, tEnd, NumOfAnchors0} ch[n] link[n-1]
 static inline int SparseDP_logged(vector<Cluster> &FragInput, vector<Primary_chain> &Primary_chains, const Options &opts, const vector<float> &LookUpTable, Read &read, float &rate) {
-  return SparseDP(FragInput, Primary_chains, opts, LookUpTable, read, rate);
+  FILE *fp = lra_cap_sdp_fp();
+  size_t p0 = Primary_chains.size();
+  int r = SparseDP(FragInput, Primary_chains, opts, LookUpTable, read, rate);
+  if (fp && FragInput.size() > 0 && p0 == 0) {
+    const size_t n = FragInput.size();
+    cap_w32(fp, 4); cap_w32(fp, n); cap_wf(fp, rate); cap_wf(fp, opts.alnthres); cap_w32(fp, opts.globalK); cap_w32(fp, opts.NumAln); cap_w32(fp, read.length);
+    for (size_t i = 0; i < n; i++) cap_w32(fp, FragInput[i].qStart);
+    for (size_t i = 0; i < n; i++) cap_w32(fp, FragInput[i].qEnd);
+    for (size_t i = 0; i < n; i++) cap_w32(fp, FragInput[i].tStart);
+    for (size_t i = 0; i < n; i++) cap_w32(fp, FragInput[i].tEnd);
+    for (size_t i = 0; i < n; i++) cap_w32(fp, FragInput[i].strand);
+    for (size_t i = 0; i < n; i++) cap_wf(fp, FragInput[i].Val);
+    for (size_t i = 0; i < n; i++) cap_w32(fp, FragInput[i].NumofAnchors0);
+    const size_t nc = Primary_chains.size() ? Primary_chains[0].chains.size() : 0;
+    cap_w32(fp, nc);
+    for (size_t c = 0; c < nc; c++) {
+      CHain &ch = Primary_chains[0].chains[c];
+      cap_w32(fp, ch.ch.size()); cap_wf(fp, ch.value); cap_w32(fp, ch.qStart); cap_w32(fp, ch.qEnd); cap_w32(fp, ch.tStart); cap_w32(fp, ch.tEnd); cap_w32(fp, ch.NumOfAnchors0);
+      for (size_t x = 0; x < ch.ch.size(); x++) cap_w32(fp, ch.ch[x]);
+      for (size_t x = 0; x + 1 < ch.ch.size(); x++) cap_w32(fp, x < ch.link.size() ? (uint32_t)ch.link[x] : 255u);
+    }
+  }
+  return r;
 }
 static inline int SparseDP_ForwardOnly_logged(const GenomePairs &FragInput, const vector<int> &MatchLengths, std::vector<unsigned int> &chain, const Options &opts,
                                               const std::vector<float> &LookUpTable, float &inv_value, int &inv_NumOfAnchors, int rate = 5) {

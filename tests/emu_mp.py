@@ -38,6 +38,8 @@ def lib(lanes=32):
     L.emu_sdp_batch.restype = C.c_int
     L.emu_sdp_batch.argtypes = [C.c_int, C.c_int, _i32p, _u64p, _u32p, _u32p, _i32p, _u64p, _i32p, _u8p, _i32p, _f32p, _i32p, _i32p, C.c_float, C.c_int,
                                 _i64p, _f32p, _f32p, C.c_int, C.c_int, _i32p, _i32p, _f32p, _u32p, _u32p, _u8p, _i32p, C.c_uint64, _u64p]
+    L.emu_sdp_batch_ext.restype = C.c_int
+    L.emu_sdp_batch_ext.argtypes = L.emu_sdp_batch.argtypes + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _i32p]
     _libs[lanes] = L
     return L
 
@@ -51,6 +53,14 @@ def sdp_batch(pb, pwl, alnthres, NumAln, max_aln=2, lanes=32, arena_bytes=256 <<
                bounds=np.zeros(4 * n * max_aln, np.uint32), chain=np.zeros(max(1, nf * max_aln), np.uint32), link=np.zeros(max(1, nf * max_aln), np.uint8),
                cl_of_frag=np.zeros(max(1, nf), np.int32))
     peak = np.zeros(1, np.uint64)
+    if "qe" in pb:
+        out["n0"] = np.zeros(n * max_aln, np.int32)
+        err = L.emu_sdp_batch_ext(n, max_aln, pb["mode"], pb["frag_off"], pb["q"], pb["t"], pb["len"], pb["cl_off_off"], pb["cl_off"], pb["cl_strand"], pb["only_cl"],
+                                  pb["rate"], pb["irate"], pb["read_len"], alnthres, NumAln, pwl[0], pwl[1], pwl[2], pwl[3], pwl[4],
+                                  out["n_chains"], out["chain_len"], out["chain_val"], out["bounds"], out["chain"], out["link"], out["cl_of_frag"], arena_bytes, peak,
+                                  pb["qe"].ctypes.data, pb["te"].ctypes.data, pb["fstrand"].ctypes.data, pb["fval"].ctypes.data, pb["fn0"].ctypes.data, pb["globalK"], out["n0"])
+        out["err"] = err; out["peak"] = int(peak[0])
+        return out
     err = L.emu_sdp_batch(n, max_aln, pb["mode"], pb["frag_off"], pb["q"], pb["t"], pb["len"], pb["cl_off_off"], pb["cl_off"], pb["cl_strand"], pb["only_cl"],
                           pb["rate"], pb["irate"], pb["read_len"], alnthres, NumAln, pwl[0], pwl[1], pwl[2], pwl[3], pwl[4],
                           out["n_chains"], out["chain_len"], out["chain_val"], out["bounds"], out["chain"], out["link"], out["cl_of_frag"], arena_bytes, peak)

@@ -61,6 +61,27 @@ def parse_capture(path, limit=None):
             n = int(a[i]); val = f[i + 1]; i += 2
             ch = a[i:i + n].copy(); i += n
             rec["chains"] = [dict(n=n, value=np.float32(val), chain=ch, link=np.zeros(0, np.uint8))]
+        elif kind == 4:
+            nfrag = int(a[i + 1])
+            rec = dict(kind=4, rate=float(f[i + 2]), alnthres=float(f[i + 3]), globalK=int(a[i + 4]), NumAln=int(a[i + 5]), read_len=int(a[i + 6]),
+                       cl_off=np.array([0, nfrag], np.int32), cl_strand=np.array([0], np.uint8))
+            i += 7
+            rec["q"] = a[i:i + nfrag].copy(); i += nfrag
+            rec["qe"] = a[i:i + nfrag].copy(); i += nfrag
+            rec["t"] = a[i:i + nfrag].copy(); i += nfrag
+            rec["te"] = a[i:i + nfrag].copy(); i += nfrag
+            rec["fstrand"] = a[i:i + nfrag].astype(np.uint8); i += nfrag
+            rec["fval"] = f[i:i + nfrag].copy(); i += nfrag
+            rec["fn0"] = a[i:i + nfrag].astype(np.int32); i += nfrag
+            rec["len"] = np.zeros(nfrag, np.int32)
+            nch = int(a[i]); i += 1
+            chains = []
+            for _ in range(nch):
+                n = int(a[i]); val = f[i + 1]; b = a[i + 2:i + 6].copy(); n0 = int(a[i + 6]); i += 7
+                ch = a[i:i + n].copy(); i += n
+                lk = a[i:i + max(0, n - 1)].astype(np.uint8); i += max(0, n - 1)
+                chains.append(dict(n=n, value=np.float32(val), bounds=b, n0=n0, chain=ch, link=lk))
+            rec["chains"] = chains
         else:
             raise ValueError("bad capture stream at word %d" % i)
         out.append(rec)
@@ -75,7 +96,13 @@ def pack(recs):
         frag_off[k + 1] = frag_off[k] + len(r["q"])
         cl_off_off[k + 1] = cl_off_off[k] + len(r["cl_off"])
     cat = lambda key, dt: np.ascontiguousarray(np.concatenate([np.asarray(r[key], dt) for r in recs])) if n else np.zeros(0, dt)
-    return dict(mode=np.array([r["kind"] for r in recs], np.int32), frag_off=frag_off, q=cat("q", np.uint32), t=cat("t", np.uint32), len=cat("len", np.int32),
+    ext = {}
+    if any(r["kind"] == 4 for r in recs):
+        z = lambda r, key, dt: np.asarray(r[key], dt) if key in r else np.zeros(len(r["q"]), dt)
+        for key, dt in (("qe", np.uint32), ("te", np.uint32), ("fstrand", np.uint8), ("fval", np.float32), ("fn0", np.int32)):
+            ext[key] = np.ascontiguousarray(np.concatenate([z(r, key, dt) for r in recs]))
+        ext["globalK"] = int([r for r in recs if r["kind"] == 4][0]["globalK"])
+    return dict(ext, mode=np.array([r["kind"] for r in recs], np.int32), frag_off=frag_off, q=cat("q", np.uint32), t=cat("t", np.uint32), len=cat("len", np.int32),
                 cl_off_off=cl_off_off, cl_off=cat("cl_off", np.int32),
                 cl_strand=np.ascontiguousarray(np.concatenate([np.append(np.asarray(r["cl_strand"], np.uint8), 0) for r in recs]).astype(np.uint8)),
                 only_cl=np.zeros(n, np.int32), rate=np.array([r.get("rate", 0.0) for r in recs], np.float32),
@@ -89,7 +116,7 @@ def compare(recs, pb, out, max_aln):
         exp = r["chains"]
         fo = int(pb["frag_off"][k]); nf = int(pb["frag_off"][k + 1]) - fo
         nch = int(out["n_chains"][k])
-        if r["kind"] != 0:
+        if r["kind"] not in (0, 4):
             e = exp[0]
             n = int(out["chain_len"][k * max_aln])
             if n != e["n"]: bad.append((k, "len %d != %d" % (n, e["n"]))); continue
@@ -108,4 +135,5 @@ def compare(recs, pb, out, max_aln):
             if not (out["link"][base:base + n - 1] == e["link"]).all(): bad.append((k, "chain %d link" % c)); break
             if out["chain_val"][o].view(np.uint32) != np.float32(e["value"]).view(np.uint32): bad.append((k, "chain %d value" % c)); break
             if not (out["bounds"][4 * o:4 * o + 4] == e["bounds"]).all(): bad.append((k, "chain %d bounds" % c)); break
+            if r["kind"] == 4 and int(out["n0"][o]) != e["n0"]: bad.append((k, "chain %d NumOfAnchors0" % c)); break
     return bad

@@ -12,11 +12,12 @@ using namespace lra::mp;
 
 extern "C" int emu_mp_lanes() { return MP_LANES; }
 
-extern "C" int emu_sdp_batch(int n_prob, int max_aln, const int *mode, const uint64_t *frag_off, const uint32_t *q, const uint32_t *t, const int32_t *len,
-                             const uint64_t *cl_off_off, const int *cl_off, const uint8_t *cl_strand, const int *only_cl, const float *rate, const int *irate,
-                             const int *read_len, float alnthres, int NumAln, const int64_t *stops, const float *slope, const float *inter, int ceil1, int ceil2,
-                             int *n_chains, int *chain_len, float *chain_val, uint32_t *bounds, uint32_t *chain, uint8_t *link, int *cl_of_frag,
-                             uint64_t arena_bytes, uint64_t *peak) {
+extern "C" int emu_sdp_batch_ext(int n_prob, int max_aln, const int *mode, const uint64_t *frag_off, const uint32_t *q, const uint32_t *t, const int32_t *len,
+                                 const uint64_t *cl_off_off, const int *cl_off, const uint8_t *cl_strand, const int *only_cl, const float *rate, const int *irate,
+                                 const int *read_len, float alnthres, int NumAln, const int64_t *stops, const float *slope, const float *inter, int ceil1, int ceil2,
+                                 int *n_chains, int *chain_len, float *chain_val, uint32_t *bounds, uint32_t *chain, uint8_t *link, int *cl_of_frag,
+                                 uint64_t arena_bytes, uint64_t *peak,
+                                 const uint32_t *qe, const uint32_t *te, const uint8_t *fstrand, const float *fval, const int32_t *fn0, int globalK, int *out_n0) {
   Pwl pwl; for (int i = 0; i < 25; i++) { pwl.stops[i] = stops[i]; pwl.slope[i] = slope[i]; pwl.inter[i] = inter[i]; } pwl.ceil1 = ceil1; pwl.ceil2 = ceil2;
   std::vector<unsigned char> arena(arena_bytes + 64);
   int err = 0;
@@ -25,10 +26,19 @@ extern "C" int emu_sdp_batch(int n_prob, int max_aln, const int *mode, const uin
   b.cl_off_off = (const unsigned long long *)cl_off_off; b.cl_off = cl_off; b.cl_strand = cl_strand; b.only_cl = only_cl; b.rate = rate; b.irate = irate;
   b.read_len = read_len; b.alnthres = alnthres; b.NumAln = NumAln; b.pwl = &pwl;
   b.n_chains = n_chains; b.chain_len = chain_len; b.chain_val = chain_val; b.bounds = bounds; b.chain = chain; b.link = link; b.cl_of_frag = cl_of_frag;
+  b.qe = qe; b.te = te; b.fstrand = fstrand; b.fval = fval; b.fn0 = fn0; b.globalK = globalK; b.out_n0 = out_n0;
   unsigned char *base = arena.data(); while (((uintptr_t)base) & 15) base++;
   b.arena = base; b.arena_per_warp = arena_bytes; b.err = &err; b.peak = (unsigned long long *)peak;
   emu::launch(dim3(1), dim3(MP_LANES), 0, [&] { sdp_batch_kernel(b); });
   return err;
+}
+extern "C" int emu_sdp_batch(int n_prob, int max_aln, const int *mode, const uint64_t *frag_off, const uint32_t *q, const uint32_t *t, const int32_t *len,
+                             const uint64_t *cl_off_off, const int *cl_off, const uint8_t *cl_strand, const int *only_cl, const float *rate, const int *irate,
+                             const int *read_len, float alnthres, int NumAln, const int64_t *stops, const float *slope, const float *inter, int ceil1, int ceil2,
+                             int *n_chains, int *chain_len, float *chain_val, uint32_t *bounds, uint32_t *chain, uint8_t *link, int *cl_of_frag,
+                             uint64_t arena_bytes, uint64_t *peak) {
+  return emu_sdp_batch_ext(n_prob, max_aln, mode, frag_off, q, t, len, cl_off_off, cl_off, cl_strand, only_cl, rate, irate, read_len, alnthres, NumAln, stops, slope, inter, ceil1,
+                           ceil2, n_chains, chain_len, chain_val, bounds, chain, link, cl_of_frag, arena_bytes, peak, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
 }
 
 // ---- the mapper worker (map_reads_kernel) and map_finalize_kernel under the emulator ------------------------------------------------

@@ -76,11 +76,12 @@ def test_sdp_gpu_on_captured_calls(preset, n_reads, repeats, tmp_path):
 
 def test_sdp_emulated_on_captured_highacc_calls(tmp_path):
     """SparseDP.h:1766 (the second SparseDP of the high-accuracy pipeline, over the Cluster_SameDiag anchors of a split chain) on the calls of a
-    real `lra align -CCS` run: chain and float value bit-identical (the :1956 driver of the same run is not on the device yet and is skipped)."""
+    real `lra align -CCS` run, and SparseDP.h:1956 (the first one, over the split clusters, with DecidePrimaryChains :1586): chains, link bits,
+    float value bits, boxes, NumOfAnchors0 bit-identical."""
     import emu_mp
     w = mapgen.workdir(tmp_path, "ccs", n_reads=60, ref_len=600_000, contigs=2, repeats=True)
-    recs = [r for r in sdpgen.parse_capture(mapgen.capture_sdp(w)) if r["kind"] == 3]
-    assert len(recs) >= 50
+    recs = [r for r in sdpgen.parse_capture(mapgen.capture_sdp(w)) if r["kind"] in (3, 4)]
+    assert sum(r["kind"] == 3 for r in recs) >= 50 and sum(r["kind"] == 4 for r in recs) >= 50
     P = PRESET["ccs"]
     pb = sdpgen.pack(recs)
     out = emu_mp.sdp_batch(pb, ref_pwl(P["pwl"]), P["alnthres"], P["NumAln"], lanes=1)
@@ -96,8 +97,8 @@ def test_sdp_emulated_on_captured_highacc_calls(tmp_path):
 def test_sdp_gpu_on_captured_highacc_calls(tmp_path):
     import lra_b200
     w = mapgen.workdir(tmp_path, "ccs", n_reads=1500, ref_len=5_000_000, contigs=3, repeats=True)
-    recs = [r for r in sdpgen.parse_capture(mapgen.capture_sdp(w)) if r["kind"] == 3]
-    assert len(recs) >= 1400
+    recs = [r for r in sdpgen.parse_capture(mapgen.capture_sdp(w)) if r["kind"] in (3, 4)]
+    assert sum(r["kind"] == 3 for r in recs) >= 1400 and sum(r["kind"] == 4 for r in recs) >= 1400
     P = PRESET["ccs"]
     ctx = lra_b200.Context(0)
     pwl = lra_b200.init_pwl(*P["pwl"])
