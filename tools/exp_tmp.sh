@@ -1,3 +1,3 @@
 cd /root/repo
-for lr in 0 192 2000; do echo "== LRA_B200_IR_LONG_ROWS=$lr"; LRA_B200_IR_LONG_ROWS=$lr python tools/map_timing.py --preset ont --reads 16384 --reps 2 --no-ref 2>&1 | grep -E "rep 1|ir_dp|ir_band"; done
-echo "== serial classes"; LRA_B200_SERIAL=1 python tools/map_timing.py --preset ont --reads 16384 --reps 2 --no-ref 2>&1 | grep -E "rep 1|ir_dp|ir_band"
+ncu --section SourceCounters --section WarpStateStats --clock-control none --import-source on -k regex:ir_dp_warp_kernel -c 1 -f -o gpurun_out/r02y_irw python tools/map_timing.py --preset ont --reads 4096 --reps 1 --no-ref > gpurun_out/r02y_irwarp.log 2>&1
+ls -la gpurun_out/r02y_irw.ncu-rep
