@@ -88,7 +88,6 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
           const unsigned long long mk = ar.mark();
           MpKey *keys = ar.alloc<MpKey>((unsigned long long)next_pow2(n));
           uint32_t *gq = ar.alloc<uint32_t>(n), *gt = ar.alloc<uint32_t>(n), *sq = ar.alloc<uint32_t>(n), *stt = ar.alloc<uint32_t>(n);
-          int *o_p = ar.alloc<int>(1);
           if (ar.overflow) return -MP_ERR_ARENA;
           if (lane == 0) { int k = 0; for (RSeg *s = rc.head; s; s = s->next) for (int i = 0; i < s->n; i++) { gq[k] = s->q[i]; gt[k] = s->t[i]; k++; } }
           wsync();
@@ -97,9 +96,7 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
           mp_sort_keys(keys, n);
           for (int i = lane; i < n; i += kLanes) { sq[i] = gq[keys[i].idx]; stt[i] = gt[keys[i].idx]; }
           wsync();
-          if (lane == 0) o_p[0] = mp_linear_extend(C, C.rd.read_off[r], L, chrom, sq, stt, n, st, O.smallK, xs.q, xs.t, xs.len, o);
-          wsync();
-          o = o_p[0];
+          o = mp_linear_extend_warp(C, C.rd.read_off[r], L, chrom, sq, stt, n, st, O.smallK, xs.q, xs.t, xs.len, o);
           ar.release(mk);
         }
         t++;

@@ -106,6 +106,49 @@ __device__ __noinline__ int mp_linear_extend(const MpCtx &C, unsigned long long 
   return o;
 }
 
+// The same on the whole warp.  Whether the run of co-diagonal anchors ends between anchors n-1 and n depends on that pair alone (same diagonal?
+// overlapping K-mers? does the exact extension from n-1 reach n?), so every lane decides one pair; the start m of the run a break closes is the
+// previous break (a warp max-scan), the output slot the number of earlier breaks.
+__device__ __noinline__ int mp_linear_extend_warp(const MpCtx &C, unsigned long long roff, uint32_t readLen, int chrom, const uint32_t *q, const uint32_t *t, int np, int strand,
+                                            int K, uint32_t *oq, uint32_t *ot, int *ol, int o0) {
+  if (np <= 0) return o0;
+  const int lane = lane_id();
+  const unsigned long long coff = C.ix.hdr_pos[chrom];
+  const uint32_t chromLen = contig_len(C.ix, chrom);
+  int o = o0, m_carry = 0;
+  for (int b = 1; b < np; b += kLanes) {
+    const int n = b + lane;
+    bool brk = false, typeA = false; uint32_t qe = 0, te = 0;
+    if (n < np) {
+      long long curDiag, nextDiag;
+      if (strand == 0) { curDiag = (long long)q[n - 1] - (long long)t[n - 1]; nextDiag = (long long)q[n] - (long long)t[n]; }
+      else { curDiag = (long long)q[n - 1] + (long long)t[n - 1]; nextDiag = (long long)q[n] + (long long)t[n]; }
+      if (curDiag != nextDiag) brk = true;
+      else if (!(q[n] < q[n - 1] + (uint32_t)K)) {
+        mp_checkbp(C, roff, readLen, coff, chromLen, q[n - 1], t[n - 1], q[n], t[n], strand, K, qe, te);
+        const bool reach = strand == 0 ? (qe == q[n] && te == t[n]) : (qe == q[n] && te == t[n] + (uint32_t)K - 1u);
+        if (!reach) { brk = true; typeA = true; }
+      }
+    }
+    const unsigned mk = ballot(brk);
+    // start of the run this break closes: the n of the previous break (in this chunk: highest lower lane with a break; else the carry)
+    int m = m_carry;
+    { const unsigned lower = mk & lanemask_lt(); if (lower) m = b + (31 - __clz((int)lower)); }
+    if (brk) {
+      const int at = o + __popc(mk & lanemask_lt());
+      oq[at] = q[m];
+      if (typeA) { ot[at] = strand == 0 ? t[m] : te + 1u; ol[at] = (int)(qe - q[m]); }
+      else { ot[at] = strand == 0 ? t[m] : t[n - 1]; ol[at] = (int)(q[n - 1] + (uint32_t)K - q[m]); }
+    }
+    o += __popc(mk);
+    if (mk) m_carry = b + (31 - __clz((int)mk));
+  }
+  if (lane == 0) { oq[o] = q[m_carry]; ot[o] = strand == 0 ? t[m_carry] : t[np - 1]; ol[o] = (int)(q[np - 1] + (uint32_t)K - q[m_carry]); }
+  o++;
+  wsync();
+  return o;
+}
+
 // DecideCoordinates (LinearExtend.h:105-128) over anchors [a0, a1) of a cluster set entry
 __device__ __noinline__ void mp_decide_coordinates(ClusterSet &S, int c, int strand, int chrom, float freq) {
   const int a0 = S.off[c], a1 = S.off[c + 1];
@@ -374,20 +417,25 @@ __device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterS
   tk = mp_tick(C, PF_STRAND_CLEAN, tk);
   // ---- LinearExtend on the raw K-mers of every cluster (Map_lowacc.h:118-153): t chromosome-relative inside, global again afterwards
   if (!mp_alloc_clusterset(ext, ar, raw.ncl, n_raw_a, true)) return MP_ERR_ARENA;
-  if (lane == 0) {
-    ext.off[0] = 0;
+  {
+    if (lane == 0) ext.off[0] = 0;
     int o = 0;
     for (int d = 0; d < raw.ncl; d++) {
       const int chrom = raw.chrom[d];
       const uint32_t coff = (uint32_t)C.ix.hdr_pos[chrom];
       const int a0 = raw.off[d], np = raw.off[d + 1] - a0;
-      for (int m = 0; m < np; m++) raw.t[a0 + m] -= coff;
-      const int o1 = mp_linear_extend(C, roff, L, chrom, raw.q + a0, raw.t + a0, np, raw.strand[d], O.globalK, ext.q, ext.t, ext.len, o);
-      ext.off[d + 1] = o1;
-      ext.strand[d] = -1; ext.chrom[d] = 0; ext.freq[d] = 0.0f; ext.qS[d] = 0xffffffffu; ext.qE[d] = 0; ext.tS[d] = 0xffffffffu; ext.tE[d] = 0;
-      mp_decide_coordinates(ext, d, raw.strand[d], chrom, raw.freq[d]);
-      for (int m = o; m < o1; m++) ext.t[m] += coff;
-      ext.tS[d] += coff; ext.tE[d] += coff;
+      for (int m = lane; m < np; m += kLanes) raw.t[a0 + m] -= coff;
+      wsync();
+      const int o1 = mp_linear_extend_warp(C, roff, L, chrom, raw.q + a0, raw.t + a0, np, raw.strand[d], O.globalK, ext.q, ext.t, ext.len, o);
+      if (lane == 0) {
+        ext.off[d + 1] = o1;
+        ext.strand[d] = -1; ext.chrom[d] = 0; ext.freq[d] = 0.0f; ext.qS[d] = 0xffffffffu; ext.qE[d] = 0; ext.tS[d] = 0xffffffffu; ext.tE[d] = 0;
+        mp_decide_coordinates(ext, d, raw.strand[d], chrom, raw.freq[d]);
+      }
+      wsync();
+      for (int m = o + lane; m < o1; m += kLanes) ext.t[m] += coff;
+      if (lane == 0) { ext.tS[d] += coff; ext.tE[d] += coff; }
+      wsync();
       o = o1;
     }
   }
