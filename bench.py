@@ -286,6 +286,7 @@ def main():
         a, ro, rl, nm = chunk(s, rank)
         shards.append((mapper.upload(a, ro, rl), len(rl), int(rl.sum())))
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()        # the read generator's temporaries go back to the driver before the library sizes its worker arenas
 
     def barrier():
         if world > 1:

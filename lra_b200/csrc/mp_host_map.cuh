@@ -397,11 +397,23 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
   size_t per = (size_t)maxL * 256 + (4u << 20);
   if (getenv("LRA_B200_MAP_ARENA_MB")) per = (size_t)atoi(getenv("LRA_B200_MAP_ARENA_MB")) << 20;
   size_t free_b = 0, tot_b = 0; cudaMemGetInfo(&free_b, &tot_b);
-  const size_t budget = (free_b + B[9].cap) / 10 * 8;      // the rest of the batch (records, blocks, a19 / a21 buffers) needs a few GB
+  // the worker arenas take at most 70 % of what is free (the rest of the batch -- records, blocks, a19 / a21 buffers -- needs a few GB); the
+  // allocation is exact (no growth slack) and, should it still fail (another allocator holding memory), retried with fewer CTAs
+  const size_t budget = (free_b + B[9].cap) / 10 * 7;
   while ((size_t)warps * per > budget && blocks > 1) { blocks--; warps = blocks * bw; }
+  if (B[9].cap < (size_t)warps * per) {
+    if (B[9].p) { CU(cudaStreamSynchronize(st)); CU(cudaFree(B[9].p)); B[9].p = nullptr; B[9].cap = 0; }
+    for (;;) {
+      if (cudaMalloc(&B[9].p, (size_t)warps * per) == cudaSuccess) { B[9].cap = (size_t)warps * per; break; }
+      cudaGetLastError();
+      B[9].p = nullptr;
+      if (blocks <= 1) return fail(ctx, LRA_B200_ECUDA, "map_batch: no memory for the worker arenas (%zu bytes per warp)", per);
+      blocks -= (blocks + 3) / 4; warps = blocks * bw;
+    }
+  }
   if ((rc = ensure(ctx, B[2], (size_t)n_reads * 4)) || (rc = ensure(ctx, B[3], (size_t)n_reads * 4)) || (rc = ensure(ctx, B[4], (size_t)n_reads * 16)) ||
       (rc = ensure(ctx, B[5], (size_t)n_reads * 16)) || (rc = ensure(ctx, B[6], seg_cap * sizeof(SegRec))) || (rc = ensure(ctx, B[7], blk_cap * 12)) ||
-      (rc = ensure(ctx, B[8], 256)) || (rc = ensure(ctx, B[9], (size_t)warps * per)) ||
+      (rc = ensure(ctx, B[8], 256)) ||
       (rc = ensure(ctx, B[27], (size_t)(warps + 4) * lra::mp::kProfStages * 8)))
     return rc;
   CU(cudaMemsetAsync(B[8].p, 0, 256, st));
