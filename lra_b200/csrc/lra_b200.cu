@@ -899,6 +899,12 @@ extern "C" int lra_b200_seed_batch(lra_b200_ctx *ctx, const lra_b200_seq *reads,
   ctx->stats.clear();
   res->n_matches = 0;
   if (R == 0) return LRA_B200_OK;
+  if (!in->read_off || !in->read_len) return fail(ctx, LRA_B200_EINVAL, "seed_batch: NULL read descriptors");
+  // the minimizer scratch is indexed by read_off: reads must lie inside the arena, in ascending order, without overlap
+  for (int r = 0; r < R; r++) {
+    if (in->read_off[r] + in->read_len[r] > reads->n) return fail(ctx, LRA_B200_EINVAL, "seed_batch: read %d ends beyond the arena", r);
+    if (r && in->read_off[r] < in->read_off[r - 1] + in->read_len[r - 1]) return fail(ctx, LRA_B200_EINVAL, "seed_batch: reads overlap or are not in ascending order at %d", r);
+  }
   int rc;
   DevBuf *B = ctx->sd;
   const size_t mmcap = (size_t)reads->n + 64;

@@ -1514,10 +1514,11 @@ extern "C" int lra_b200_store_diagonal_batch(lra_b200_ctx *ctx, const lra_b200_c
 // ---------------------------------------------------------------------------------------------------- TrimSplitChainDiagonal
 extern "C" int lra_b200_trim_splitchains_batch(lra_b200_ctx *ctx, const uint32_t *cq, const uint32_t *ct, const uint64_t *c_off, const uint8_t *strand, int32_t n_chains,
                                                uint32_t *q, uint32_t *t, const uint64_t *m_off, uint8_t *keep, int32_t *removed) {
-  if (!ctx || !c_off || !m_off || !strand || !removed || n_chains < 0) return fail(ctx, LRA_B200_EINVAL, "trim_splitchains_batch: bad argument");
+  if (!ctx || n_chains < 0) return fail(ctx, LRA_B200_EINVAL, "trim_splitchains_batch: bad argument");
   CU(cudaSetDevice(ctx->device));
   ctx->stats.clear();
-  if (n_chains == 0) return LRA_B200_OK;
+  if (n_chains == 0) return LRA_B200_OK;          // an empty batch needs no arrays
+  if (!c_off || !m_off || !strand || !removed) return fail(ctx, LRA_B200_EINVAL, "trim_splitchains_batch: bad argument");
   const size_t A = (size_t)c_off[n_chains], M = (size_t)m_off[n_chains], C1 = (size_t)n_chains;
   if (M > 0x7FFFFFF0ull) return fail(ctx, LRA_B200_EINVAL, "trim_splitchains_batch: more than 2^31 anchors in one batch");
   if ((A && (!cq || !ct)) || (M && (!q || !t || !keep))) return fail(ctx, LRA_B200_EINVAL, "trim_splitchains_batch: NULL array");

@@ -55,3 +55,18 @@ def test_seed_overflow_and_revcomp(ctx):
         o, L = int(case["read_off"][r]), int(case["read_len"][r])
         assert (got[o:o + L] == lut[seedgen.COMP[case["arena"][o:o + L][::-1]]]).all()
     ctx.index_free(idx); reads.free(); genome.free(); rc.free()
+
+
+def test_seed_batch_rejects_bad_read_descriptors(ctx):
+    """reads beyond the arena, overlapping or out of order are refused (the minimizer scratch is indexed by read_off)"""
+    from lra_b200 import capi
+    case = seedgen.make_case(7, glen=50000, n_reads=4, k=17, w=10)
+    reads = ctx.seq_upload(case["arena"][:-16]); genome = ctx.seq_upload(case["genome"][:-16])
+    idx = ctx.index_upload(case["idx_t"], case["idx_pos"])
+    ro, rl = case["read_off"].copy(), case["read_len"].copy()
+    for bad_off, bad_len in ((ro, np.where(np.arange(len(rl)) == len(rl) - 1, rl + 10 ** 6, rl).astype(rl.dtype)), (ro[::-1].copy(), rl[::-1].copy()),
+                             (np.where(np.arange(len(ro)) == 1, ro[0] + 1, ro).astype(ro.dtype), rl)):
+        with pytest.raises(capi.LraB200Error) as e:
+            ctx.seed_batch(reads, genome, idx, bad_off, bad_len, 17, 10, 150)
+        assert e.value.code == capi.EINVAL
+    ctx.index_free(idx); reads.free(); genome.free()
