@@ -217,7 +217,7 @@ def run_reference(args):
                        "reads_per_step_timed": S},
             "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def gpu_builder_available():
@@ -235,8 +235,26 @@ def pinned(a):
     return t
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly one JSON line: everything else that writes to fd 1 (the NCCL version banner, library chatter) goes to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
     args = parse()
+    quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -471,7 +489,7 @@ def main():
         line["cpu_baseline"] = {"value": S / dt, "unit": "reads/s", "gbp_per_s": aligned_bases_of_sam(os.path.join(d, "ref_arm.sam")) / dt / 1e9, "cores": cores, "kind": "reference",
                                 "sample": "first %d reads of an e2e batch: `lra_ref align %s ref.fa sample.fa -t %d -p s`, wall %.2f s minus index load %.2f s (one-read run)"
                                           % (S, MODE[args.preset], cores, t_all, t_load)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 

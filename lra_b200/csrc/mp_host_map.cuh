@@ -195,7 +195,11 @@ extern "C" int64_t lra_b200_format_records_qual(const lra_b200_map_opts *opts, c
   else { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(work, t); for (auto &x : th) x.join(); }
   size_t n = 0; for (auto &p : piece) n += p.s.size();
   if ((int64_t)n > cap || !out) return -(int64_t)n;
-  size_t at = 0; for (auto &p : piece) { memcpy(out + at, p.s.data(), p.s.size()); at += p.s.size(); }
+  std::vector<size_t> at(T + 1, 0);
+  for (int t = 0; t < T; t++) at[t + 1] = at[t] + piece[t].s.size();
+  auto copy = [&](int t) { memcpy(out + at[t], piece[t].s.data(), piece[t].s.size()); };
+  if (T == 1) copy(0);
+  else { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(copy, t); for (auto &x : th) x.join(); }
   return (int64_t)n;
 }
 
