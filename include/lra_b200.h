@@ -849,8 +849,10 @@ typedef struct lra_b200_map_opts {      /* the Options members the path reads (O
   float gapopen, gapextend, gaproot;
   int32_t gapCeiling1, gapCeiling2;
   int32_t localIndexWindow, localIndexMaxFreq;
+  /* read by MapRead_highacc only (-CCS, -CONTIG; Map_highacc.h:37-798) */
+  int32_t HighlyAccurate, maxDiag, maxGap, RoughClustermaxGap, minClusterSize, minUniqueStretchNum, minUniqueStretchDist, merge_dist;
 } lra_b200_map_opts;
-/* the align preset of `lra align -ONT | -CLR` (lra.cpp:339-431) on top of the defaults (Options.h:123-240); globalK is overwritten
+/* the align preset of `lra align -ONT | -CLR | -CCS | -CONTIG` (lra.cpp:268-431) on top of the defaults (Options.h:123-240); globalK is overwritten
  * by the value stored in <ref>.mms (MMIndex.h:409), smallK / smallW by the <ref>.gli header */
 int lra_b200_map_opts_preset(const char *mode, lra_b200_map_opts *opts);
 

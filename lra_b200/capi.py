@@ -73,7 +73,8 @@ class MapOpts(C.Structure):
                [(n, C.c_int32) for n in ("refineSpaceDist", "window", "limitrefine", "RefineBySDP", "localMatch", "localMismatch", "localIndel", "localBand", "refineBand",
                                          "hardClip", "bypassClustering")] + \
                [(n, C.c_float) for n in ("gapopen", "gapextend", "gaproot")] + \
-               [(n, C.c_int32) for n in ("gapCeiling1", "gapCeiling2", "localIndexWindow", "localIndexMaxFreq")]
+               [(n, C.c_int32) for n in ("gapCeiling1", "gapCeiling2", "localIndexWindow", "localIndexMaxFreq", "HighlyAccurate", "maxDiag", "maxGap", "RoughClustermaxGap",
+                                         "minClusterSize", "minUniqueStretchNum", "minUniqueStretchDist", "merge_dist")]
 
 
 # lra_b200_record

@@ -47,9 +47,7 @@ struct SwitchIndexBatch {
   int32_t *n_out, *nl_out;           // [n_chains]
 };
 
-__global__ void __launch_bounds__(64) switchindex_kernel(SwitchIndexBatch b) {
-  const int k = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x);
-  if (k >= b.n_chains) return;
+__device__ __noinline__ void switchindex_one(const SwitchIndexBatch &b, const int k) {
   const unsigned long long a0 = b.c_off[k];
   int n = (int)(b.c_off[k + 1] - a0);
   int32_t *ch = b.ch + a0, *ss = b.ss + a0, *se = b.se + a0, *newch = b.newch + a0;
@@ -103,6 +101,12 @@ __global__ void __launch_bounds__(64) switchindex_kernel(SwitchIndexBatch b) {
     n = sc; nl = sc - 1 > 0 ? sc - 1 : 0;
   }
   b.n_out[k] = n; b.nl_out[k] = nl;
+}
+
+__global__ void __launch_bounds__(64) switchindex_kernel(SwitchIndexBatch b) {
+  const int k = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x);
+  if (k >= b.n_chains) return;
+  switchindex_one(b, k);
 }
 
 // a17: SwitchToOriginalAnchors (reference LocalRefineAlignment.h:187-198).  Entry i of a FinalChain names run k = chain[i] of the same-diagonal runs

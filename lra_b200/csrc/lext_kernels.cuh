@@ -227,9 +227,7 @@ __device__ __forceinline__ bool lext_check_overlap(uint32_t q, uint32_t t, uint3
   return false;
 }
 
-__global__ void __launch_bounds__(128) lextc_walk_kernel(LextChainBatch b) {
-  const int u = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x);
-  if (u >= b.n_units) return;
+__device__ __noinline__ void lextc_walk_one(const LextChainBatch &b, const int u) {
   const uint32_t cm = b.unit_cl[u];
   const unsigned long long a = b.cl_off[cm];
   const long size = (long)(b.cl_off[cm + 1] - a);
@@ -292,6 +290,12 @@ __global__ void __launch_bounds__(128) lextc_walk_kernel(LextChainBatch b) {
   }
   b.cnt[u] = no;
   b.u_overlap[u] = ovl;
+}
+
+__global__ void __launch_bounds__(128) lextc_walk_kernel(LextChainBatch b) {
+  const int u = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x);
+  if (u >= b.n_units) return;
+  lextc_walk_one(b, u);
 }
 
 // one warp per unit, after the scan of cnt[]

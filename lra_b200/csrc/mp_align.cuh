@@ -382,11 +382,13 @@ __device__ __noinline__ bool mp_refined_alignment_btwn(const MpCtx &C, int r, Ar
 }
 
 // LocalRefineAlignment, pure-matches form (LocalRefineAlignment.h:884-1030), for the ultimate chains uc[0..nuc) of one chain p
-__device__ __noinline__ bool mp_local_refine_alignment(const MpCtx &C, int r, Arena &ar, SegBuild &B, const ClusterSet &S, UChain *uc, int nuc, int LSC) {
+// min_n: 2 for the pure-matches form (`size() <= 1` is skipped), 1 for the high-accuracy form (:553-768, only an empty chain is skipped; the two bodies are
+// otherwise the same)
+__device__ __noinline__ bool mp_local_refine_alignment(const MpCtx &C, int r, Arena &ar, SegBuild &B, const ClusterSet &S, UChain *uc, int nuc, int LSC, int min_n) {
   const uint32_t L = C.rd.read_len[r];
   for (int st = 0; st < nuc; st++) {
     const UChain &ch = uc[st];
-    if (ch.n <= 1) continue;
+    if (ch.n < min_n) continue;
     const int start = 0, end = ch.n - 1;
     const int str = S.strand[ch.cl[start]] != 0 ? 1 : 0;
     const int chrom = S.chrom[ch.cl[start]];

@@ -19,6 +19,8 @@ extern "C" int lra_b200_map_opts_preset(const char *mode, lra_b200_map_opts *o) 
   o->refineSpaceDist = 10000; o->window = 100; o->limitrefine = 1; o->RefineBySDP = 1;
   o->localMatch = 4; o->localMismatch = -3; o->localIndel = -4; o->localBand = 15; o->refineBand = 7; o->hardClip = 0; o->bypassClustering = 0;
   o->gapopen = 2.0f; o->gapextend = 10.0f; o->gaproot = 2.0f; o->gapCeiling1 = 1500; o->gapCeiling2 = 3000; o->localIndexWindow = 2048; o->localIndexMaxFreq = 15;
+  o->HighlyAccurate = 0; o->maxDiag = 500; o->maxGap = 5000; o->RoughClustermaxGap = 1000; o->minClusterSize = 2; o->minUniqueStretchNum = 1; o->minUniqueStretchDist = 50;
+  o->merge_dist = 100;
   std::string m(mode);
   if (!m.empty() && m[0] == '-') m = m.substr(1);
   for (auto &c : m) c = (char)toupper(c);
@@ -34,7 +36,19 @@ extern "C" int lra_b200_map_opts_preset(const char *mode, lra_b200_map_opts *o) 
     o->gapCeiling1 = 1500; o->gapCeiling2 = 3000; o->NumAln = 2; o->PrintNumAln = 1; o->cleanMaxDiag = 200; o->SecondCleanMaxDiag = 100; o->SecondCleanMinDiagCluster = 10;
     o->refineSpaceDist = 30000; o->minDiagCluster = 3; o->bypassClustering = 1; o->punish_anchorfreq = 5; o->anchorPerlength = 5; o->cleanClustersize = 100;
     o->anchorstoosparse = 0.005f; o->hardClip = 1; o->alnthres = 0.65f;
-  } else return LRA_B200_EINVAL;      // the high-accuracy presets (-CCS, -CONTIG) take MapRead_highacc, which this library does not map yet
+  } else if (m == "CCS") {
+    o->globalK = 25; o->globalW = 20; o->globalMaxFreq = 150; o->localMaxFreq = 15; o->readType = 2;
+    o->gaproot = 1.5f; o->gapextend = 15.0f; o->gapopen = 4.0f; o->initial_anchorbonus = 10.0f; o->gapCeiling1 = 2000; o->gapCeiling2 = 3000; o->HighlyAccurate = 1;
+    o->NumAln = 2; o->PrintNumAln = 1; o->merge_dist = 100; o->RoughClustermaxGap = 500; o->maxGap = 400; o->cleanMaxDiag = 150; o->SecondCleanMaxDiag = 100;
+    o->SecondCleanMinDiagCluster = 30; o->minDiagCluster = 10; o->minClusterSize = 10; o->cleanClustersize = 100; o->punish_anchorfreq = 10; o->anchorPerlength = 10;
+    o->refineSpaceDist = 30000; o->anchorstoosparse = 0.005f; o->hardClip = 1;
+  } else if (m == "CONTIG") {
+    o->globalK = 19; o->globalW = 10; o->globalMaxFreq = 30; o->localMaxFreq = 15; o->readType = 3; o->refineBand = 50;
+    o->gaproot = 1.5f; o->gapextend = 20.0f; o->gapopen = 4.0f; o->gapCeiling1 = 3000; o->gapCeiling2 = 5000; o->HighlyAccurate = 1; o->initial_anchorbonus = 1.0f;
+    o->maxDiag = 100; o->maxGap = 500; o->RoughClustermaxGap = 500; o->NumAln = 2; o->PrintNumAln = 1; o->anchorstoosparse = 0.005f; o->merge_dist = 100;
+    o->cleanMaxDiag = 150; o->SecondCleanMaxDiag = 100; o->SecondCleanMinDiagCluster = 30; o->minDiagCluster = 30; o->minClusterSize = 10; o->refineSpaceDist = 50000;
+    o->cleanClustersize = 100; o->punish_anchorfreq = 10; o->anchorPerlength = 10; o->hardClip = 1;
+  } else return LRA_B200_EINVAL;
   return LRA_B200_OK;
 }
 

@@ -24,6 +24,9 @@ struct MapOut {
   unsigned long long *peak;               // arena high-water mark
 };
 
+__device__ __noinline__ bool mp_segbuild_alloc(SegBuild &B, Arena &ar, const UChain *uc, int ng, uint32_t L);
+__device__ __noinline__ int mp_emit_segments(int r, int p, const SegBuild &B, const MapOut &out, int &nseg_out, int &seg0_out);
+
 // one chain p of a read: everything from SPLITChain to LocalRefineAlignment.  Returns 0 ok (segments appended, possibly none),
 // 1 "this chain ends the loop over chains" (Map_lowacc.h: unaligned for p == 0, break for p > 0), < 0 error
 __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const ClusterSet &ext, const UChain &chain, int p, const MapOut &out, int &nseg_out, int &seg0_out) {
@@ -162,22 +165,35 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
   int LSC = 0;
   for (int g = 1; g < ng; g++) if (uc[g].n > uc[LSC].n) LSC = g;
   // ---- LocalRefineAlignment -> segments
+  SegBuild B;
+  if (!mp_segbuild_alloc(B, ar, uc, ng, L)) return -MP_ERR_ARENA;
+  if (!mp_local_refine_alignment(C, r, ar, B, xs, uc, ng, LSC, 2)) return ar.overflow ? -MP_ERR_ARENA : -MP_ERR_CAP;
+  wsync();
+  tk = mp_tick(C, PF_LOCAL_REFINE, tk);
+  mp_phase(ar);
+  tk = mp_tick(C, PF_BARRIER, tk);
+  const int rc_emit = mp_emit_segments(r, p, B, out, nseg_out, seg0_out);
+  tk = mp_tick(C, PF_OUTPUT, tk);
+  return rc_emit;
+}
+
+// the SegBuild of one chain: room for the anchors of its ultimate chains and for the linear alignments between them
+__device__ __noinline__ bool mp_segbuild_alloc(SegBuild &B, Arena &ar, const UChain *uc, int ng, uint32_t L) {
   int max_blocks = 64;
   for (int g = 0; g < ng; g++) max_blocks += 2 * uc[g].n + 8;
   max_blocks += (int)(L / 2u) + (int)(L / 8u);     // blocks of the linear alignments between the anchors (a block covers at least one base, gaps at least one more)
-  SegBuild B;
   B.cap = max_blocks; B.nblk = 0; B.nseg = 0; B.cap_seg = kMaxSegPerChain;
   B.blk = ar.alloc<uint32_t>(3ull * max_blocks);
   B.seg_start = ar.alloc<int>(kMaxSegPerChain + 1); B.seg_strand = ar.alloc<int>(kMaxSegPerChain); B.seg_chrom = ar.alloc<int>(kMaxSegPerChain);
   B.seg_n0 = ar.alloc<int>(kMaxSegPerChain); B.seg_n1 = ar.alloc<int>(kMaxSegPerChain); B.seg_supp = ar.alloc<int>(kMaxSegPerChain); B.seg_val = ar.alloc<float>(kMaxSegPerChain);
   B.cap_jobs = 4096; B.njobs = 0;
   B.jobs = ar.alloc<AogJob>(B.cap_jobs);
-  if (ar.overflow) return -MP_ERR_ARENA;
-  if (!mp_local_refine_alignment(C, r, ar, B, xs, uc, ng, LSC)) return ar.overflow ? -MP_ERR_ARENA : -MP_ERR_CAP;
-  wsync();
-  tk = mp_tick(C, PF_LOCAL_REFINE, tk);
-  mp_phase(ar);
-  tk = mp_tick(C, PF_BARRIER, tk);
+  return !ar.overflow;
+}
+
+// hand the segments of chain p of read r to the global lists.  Returns 0 (also with no segment), < 0 on a capacity error.
+__device__ __noinline__ int mp_emit_segments(int r, int p, const SegBuild &B, const MapOut &out, int &nseg_out, int &seg0_out) {
+  const int lane = lane_id();
   if (B.nseg == 0) { nseg_out = 0; return 0; }
   // ---- hand the segments to the global lists
   // one atomic reserves the segment ids (high 24 bits) and the block range (low 40 bits) together, so that in segment order the block offsets are
@@ -201,9 +217,14 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
   }
   wsync();
   nseg_out = B.nseg; seg0_out = (int)s0;
-  tk = mp_tick(C, PF_OUTPUT, tk);
   return 0;
 }
+
+}  // namespace mp
+}  // namespace lra
+#include "mp_highacc.cuh"
+namespace lra {
+namespace mp {
 
 __device__ __noinline__ void mp_map_read(const MpCtx &C, int r, Arena &ar, const MapOut &out) {
   const int lane = lane_id();
@@ -214,6 +235,28 @@ __device__ __noinline__ void mp_map_read(const MpCtx &C, int r, Arena &ar, const
   ClusterSet ext; UChain *chains = 0; int nch = 0;
   ar.phase = 0;
   const int PB = (C.o.NumAln < kMaxChains ? C.o.NumAln : kMaxChains);      // chains a read can have (uniform over the batch)
+  if (C.o.HighlyAccurate) {
+    // MapRead_highacc (Map_highacc.h:37-798): every chain of Primary_chains[0] becomes an alignment (:690-735)
+    HaState *S = ar.alloc<HaState>(1);
+    HaState hs;
+    status = ar.overflow ? MP_ERR_ARENA : mp_stage1_highacc(C, r, ar, hs);
+    (void)S;
+    mp_phase_upto(ar, kPhasesStage1);
+    if (status == MP_OK) {
+      const unsigned long long mk = ar.mark();
+      for (int h = 0; h < hs.H.nch && h < kMaxChains; h++) {
+        if (hs.H.n[h] == 0) continue;
+        ar.release(mk);
+        wsync();
+        int ns = 0, s0 = 0;
+        const int rc = mp_map_chain_highacc(C, r, ar, hs, h, out, ns, s0);
+        mp_phase_upto(ar, kPhasesStage1 + kPhasesChain * (h + 1));
+        if (rc < 0) { status = -rc; break; }
+        nseg[n_al] = ns; seg0[n_al] = s0; n_al++;
+      }
+      if (status == MP_OK && n_al == 0) status = MP_UNALIGNED;
+    }
+  } else {
   status = mp_stage1(C, r, ar, ext, chains, nch);
   mp_phase_upto(ar, kPhasesStage1);
   if (status == MP_OK) {
@@ -231,6 +274,7 @@ __device__ __noinline__ void mp_map_read(const MpCtx &C, int r, Arena &ar, const
       if (p == 0 && ns == 0) { status = MP_UNALIGNED; break; }
       nseg[n_al] = ns; seg0[n_al] = s0; n_al++;
     }
+  }
   }
   mp_phase_upto(ar, kPhasesStage1 + kPhasesChain * PB);
   if (status != MP_OK) n_al = 0;
@@ -300,6 +344,9 @@ struct FinalBatch {
   const int32_t *ir_nblk; const unsigned long long *ir_off; const uint32_t *ir_blocks;
   const int32_t *stats; const float *value; const unsigned long long *cigar_off;
   const float *logf_len;                  // host-built: logf(len) for len = 0..kMaxChains
+  const int32_t *stats_first;             // MapRead_highacc calls CalculateStatistics twice (Map_highacc.h:720, 729) and tdel / tins / the six size-class counters
+                                          // are never reset (Alignment.h:418-505): the printed values are the sums over both calls.  nullptr: one call
+  const float *seg_l;                     // host-built (glibc logf), presets without bypassClustering: value > 3 ? logf(value / globalK) : 0 per segment
   lra_b200_record *rec;                   // [n_seg]
   int *rank;                              // [n_reads][kMaxChains]
   unsigned long long *aligned_bases;
@@ -345,6 +392,10 @@ __global__ void __launch_bounds__(128) map_finalize_kernel(FinalBatch b) {
       // members after one CalculateStatistics call: the D count lands in `nins`, the I count in `ndel` (Alignment.h:414 vs :516)
       x.nm = st[0]; x.nmm = st[1]; x.nins = st[2]; x.ndel = st[3]; x.tdel = st[4]; x.tins = st[5];
       x.nSmallDel = st[6]; x.nMedDel = st[7]; x.nLargeDel = st[8]; x.nSmallIns = st[9]; x.nMedIns = st[10]; x.nLargeIns = st[11];
+      if (b.stats_first) {
+        const int32_t *s1 = b.stats_first + 16ll * (s0 + s);
+        x.tdel += s1[4]; x.tins += s1[5]; x.nSmallDel += s1[6]; x.nMedDel += s1[7]; x.nLargeDel += s1[8]; x.nSmallIns += s1[9]; x.nMedIns += s1[10]; x.nLargeIns += s1[11];
+      }
       x.value = b.value[s0 + s];
       x.NumOfAnchors0 = sg.NumOfAnchors0; x.NumOfAnchors1 = sg.NumOfAnchors1;
       x.cigar_off = b.cigar_off[s0 + s]; x.n_cigar = (int)(b.cigar_off[s0 + s + 1] - b.cigar_off[s0 + s]);
@@ -372,16 +423,21 @@ __global__ void __launch_bounds__(128) map_finalize_kernel(FinalBatch b) {
   for (int s = ns - 1; s >= 0; s--) {
     lra_b200_record &rc = b.rec[s0 + s];
     const int n0 = rc.NumOfAnchors0;
-    if (na > 1) y = __fdiv_rn((float)gn0[a], (float)gn0[idx[1]]);
-    float pen = __fmul_rn(n0 > 10 ? 1.0f : 0.05f, (float)n0);
-    pen = __fmul_rn(n0 >= 5 ? 1.0f : 0.02f, pen);
+    if (na > 1 && b.o.bypassClustering) y = __fdiv_rn((float)gn0[a], (float)gn0[idx[1]]);
+    float pen;
+    if (!b.o.bypassClustering) { pen = __fmul_rn(n0 > 20 ? 1.0f : 0.05f, (float)n0); pen = __fmul_rn(n0 >= 5 ? 1.0f : 0.1f, pen); y = 1.0f; }
+    else { pen = __fmul_rn(n0 > 10 ? 1.0f : 0.05f, (float)n0); pen = __fmul_rn(n0 >= 5 ? 1.0f : 0.02f, pen); }
+    const float l = b.o.bypassClustering ? 1.0f : b.seg_l[s0 + s];
     const int den = rc.nmm + rc.ndel + rc.nins;
     float identity = den == 0 ? 1.0f : __fdiv_rn((float)rc.nm, (float)den);
     identity = identity < 1 ? identity : 1;
     long long mapq;
-    if (na == 1) mapq = (long long)x86_f2i(__fmul_rn(__fmul_rn(pen, q_coef), identity));
-    else {
+    if (na == 1) {
+      if (!b.o.bypassClustering) mapq = (long long)x86_f2i(__fmul_rn(__fmul_rn(__fmul_rn(pen, q_coef), l), identity));
+      else mapq = (long long)x86_f2i(__fmul_rn(__fmul_rn(pen, q_coef), identity));
+    } else {
       if (x >= 0.990f) mapq = (long long)x86_f2i(__fmul_rn(__fmul_rn(__fmul_rn(pen, __fsub_rn(1.0f, x)), y), identity));
+      else if (!b.o.bypassClustering) mapq = (long long)x86_f2i(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(pen, q_coef), __fsub_rn(1.0f, x)), l), y), identity));
       else mapq = (long long)x86_f2i(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(pen, q_coef), __fsub_rn(1.0f, x)), y), identity));
       mapq -= (long long)x86_f2i(__fadd_rn(__fmul_rn(4.343f, b.logf_len[na]), .499f));
     }

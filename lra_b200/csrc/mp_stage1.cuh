@@ -267,14 +267,14 @@ __device__ __noinline__ bool mp_sort_minimizers_warp(Arena &ar, unsigned long lo
   return true;
 }
 
-// ---- seeding + CleanMatches + LinearExtend + first SparseDP for one read.  Returns MP_OK with `ext` (extended clusters, global t) and
-// `chains` (nch of them), or MP_UNALIGNED / an error.
-__device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterSet &ext, UChain *&chains, int &nch) {
+// ---- seeding + the sort / CleanOffDiagonal of each strand's matches for one read (MapRead.h:169-203; the common head of CleanMatches, Clustering.h:1840-1908,
+// and MatchesToFineClusters, :1555-1676).  Returns MP_OK with `raw`: the cleaned matches of strand 0 then strand 1 (global t) and the clusters
+// CleanOffDiagonal cut them into (ranges, boxes, anchorfreq; chrom only under bypassClustering), n_raw_a anchors in all.
+__device__ __noinline__ int mp_seed_clean(const MpCtx &C, int r, Arena &ar, ClusterSet &raw, int &n_raw_a_out) {
   const int lane = lane_id();
   const MpOpts &O = C.o;
   const unsigned long long roff = C.rd.read_off[r];
   const uint32_t L = C.rd.read_len[r];
-  nch = 0;
   // ---- a2 / a3: minimizers of the read, std::sort (MapRead.h:181-185)
   unsigned long long *mm_t = ar.alloc<unsigned long long>((unsigned long long)L + 2);
   uint32_t *mm_p = ar.alloc<uint32_t>((unsigned long long)L + 2);
@@ -345,11 +345,9 @@ __device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterS
   }
   wsync();
   // ---- CleanMatches per strand (Clustering.h:1840-1908): DiagonalSort / AntiDiagonalSort, CleanOffDiagonal, clusters with their matches
-  ClusterSet raw;
   if (!mp_alloc_clusterset(raw, ar, NM, NM, false)) return MP_ERR_ARENA;
   if (lane == 0) raw.off[0] = 0;
   int n_raw_a = 0;
-  int repetitive = 0;
   for (int s = 0; s < 2; s++) {
     const unsigned long long mk = ar.mark();
     // gather this strand's matches (order is irrelevant: the sort key below is total up to identical records)
@@ -386,7 +384,7 @@ __device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterS
     if (lane == 0) {
       CodBatch b;
       b.n_lists = 1; b.off = off; b.q = sq; b.t = stt; b.qt = sqt; b.strand = sstr;
-      b.o.cleanMaxDiag = O.cleanMaxDiag; b.o.minDiagCluster = O.minDiagCluster; b.o.bypassClustering = 1; b.o.cleanClustersize = O.cleanClustersize;
+      b.o.cleanMaxDiag = O.cleanMaxDiag; b.o.minDiagCluster = O.minDiagCluster; b.o.bypassClustering = O.bypassClustering; b.o.cleanClustersize = O.cleanClustersize;
       b.o.SecondCleanMinDiagCluster = O.SecondCleanMinDiagCluster; b.o.punish_anchorfreq = O.punish_anchorfreq; b.o.anchorPerlength = O.anchorPerlength;
       b.o.SecondCleanMaxDiag = O.SecondCleanMaxDiag; b.o.ExtractDiagonalFromClean = 1; b.o.globalK = O.globalK;
       b.hdr_pos = C.ix.hdr_pos; b.n_hdr = C.ix.n_hdr;
@@ -409,12 +407,28 @@ __device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterS
     wsync();
     ar.release(mk);
   }
+  tk = mp_tick(C, PF_STRAND_CLEAN, tk);
+  n_raw_a_out = n_raw_a;
+  return MP_OK;
+}
+
+// ---- seeding + CleanMatches + LinearExtend + first SparseDP for one read.  Returns MP_OK with `ext` (extended clusters, global t) and
+// `chains` (nch of them), or MP_UNALIGNED / an error.
+__device__ __noinline__ int mp_stage1(const MpCtx &C, int r, Arena &ar, ClusterSet &ext, UChain *&chains, int &nch) {
+  const int lane = lane_id();
+  const MpOpts &O = C.o;
+  const unsigned long long roff = C.rd.read_off[r];
+  const uint32_t L = C.rd.read_len[r];
+  nch = 0;
+  ClusterSet raw; int n_raw_a = 0;
+  { const int rc = mp_seed_clean(C, r, ar, raw, n_raw_a); if (rc != MP_OK) return rc; }
+  unsigned long long tk = mp_clock();
+  int repetitive = 0;
   if (raw.ncl == 0) return MP_UNALIGNED;
   for (int c = 0; c < raw.ncl; c++) {
     const float f = raw.freq[c];
     if (f > 1.0f && f <= 2.0f && raw.off[c + 1] - raw.off[c] >= 500) repetitive = 1;
   }
-  tk = mp_tick(C, PF_STRAND_CLEAN, tk);
   // ---- LinearExtend on the raw K-mers of every cluster (Map_lowacc.h:118-153): t chromosome-relative inside, global again afterwards
   if (!mp_alloc_clusterset(ext, ar, raw.ncl, n_raw_a, true)) return MP_ERR_ARENA;
   {

@@ -50,9 +50,7 @@ struct SplitBatch {
 };
 
 template <bool EMIT>
-__global__ void __launch_bounds__(64) split_kernel(SplitBatch b) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= b.n_reads) return;
+__device__ __noinline__ void split_one(const SplitBatch &b, const int r) {
   const unsigned long long c0 = b.cl_off[r];
   const int n = (int)(b.cl_off[r + 1] - c0);
   const uint32_t *box = b.box + 4 * c0;
@@ -176,6 +174,13 @@ __global__ void __launch_bounds__(64) split_kernel(SplitBatch b) {
     if (nn < ns) ic_n = (int)sp[6 * nn + 5];
   }
   s0[nn - 1] = (int32_t)((long long)(moff[ic_m + 1] - moff[ic_m]) - matchS);
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(64) split_kernel(SplitBatch b) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= b.n_reads) return;
+  split_one<EMIT>(b, r);
 }
 
 }  // namespace lra

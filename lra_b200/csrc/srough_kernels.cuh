@@ -28,9 +28,7 @@ struct SplitRoughBatch {
   int32_t *p_cluster, *p_start, *p_end;
 };
 
-__global__ void __launch_bounds__(64) split_rough_kernel(SplitRoughBatch b) {
-  const int l = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x);
-  if (l >= b.n_lists) return;
+__device__ __noinline__ void split_rough_one(const SplitRoughBatch &b, const int l) {
   const unsigned long long a0 = b.l_off[l], c0 = b.lr_off[l], base = a0 + c0;
   const int n_rough = (int)(b.lr_off[l + 1] - c0);
   const uint32_t *q = b.q + a0, *t = b.t + a0;
@@ -95,6 +93,12 @@ __global__ void __launch_bounds__(64) split_rough_kernel(SplitRoughBatch b) {
     }
   }
   b.n_split[l] = ns; b.n_piece[l] = np;
+}
+
+__global__ void __launch_bounds__(64) split_rough_kernel(SplitRoughBatch b) {
+  const int l = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x);
+  if (l >= b.n_lists) return;
+  split_rough_one(b, l);
 }
 
 // StoreDiagonalClusters (reference Clustering.h:1442-1487, RemoveSuperRepetitiveClusters :1432-1439): the clusters CleanMatches makes from the cleaned,

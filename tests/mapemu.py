@@ -42,7 +42,7 @@ def _bind(L):
                                 _i32p, _i32p, _i32p, _i32p, C.c_void_p, C.c_int, _u32p, C.c_uint64, _u64p, C.c_uint64]
     L.emu_map_finalize.restype = C.c_int
     L.emu_map_finalize.argtypes = [C.c_int, C.c_void_p, _u64p, _u32p, _i32p, _i32p, _i32p, _i32p, C.c_void_p, _i32p, _u64p, _u32p, _i32p, _f32p, _u64p, _f32p,
-                                   C.c_void_p, _i32p, _u64p]
+                                   C.c_void_p, _i32p, _u64p, _f32p, C.c_void_p]
     L._map_bound = True
 
 
@@ -114,7 +114,7 @@ def refine_and_stats(inp, mo):
     sb = dict(q_arena=q_arena, blocks_in=mo["blocks"][:3 * mo["n_blk"]].reshape(-1, 3), blk_off=seg["blk_off"].astype(np.uint64), blk_cnt=seg["blk_cnt"].astype(np.int32),
               q_base=(inp["read_off"][seg["read"]] + np.uint64(N) * seg["strand"].astype(np.uint64)).astype(np.uint32),
               read_len=inp["read_len"][seg["read"]].astype(np.int32), contig_len=(hdr[seg["chrom"] + 1] - hdr[seg["chrom"]]).astype(np.int32),
-              k=o.refineBand, match=o.localMatch, mismatch=o.localMismatch, indel=o.localIndel, end_align=0)
+              k=o.refineBand, match=o.localMatch, mismatch=o.localMismatch, indel=o.localIndel, end_align=1 if o.HighlyAccurate else 0)
     t_base = hdr[seg["chrom"]].astype(np.uint32)
     g_arena = np.concatenate([inp["genome"], np.zeros(64, np.uint8)])
     if S == 0:
@@ -143,8 +143,12 @@ def finalize(inp, mo, rs, lanes=1):
     assert L.emu_sizeof_record() == capi.RECORD.itemsize
     rank = np.zeros(4 * n, np.int32); ab = np.zeros(1, np.uint64)
     logf_len = np.array([0.0] + [np.log(np.float32(i)) for i in range(1, 8)], np.float32)
+    libm = C.CDLL("libm.so.6"); libm.logf.restype = C.c_float; libm.logf.argtypes = [C.c_float]
+    K = np.float32(inp["opts"].globalK)
+    seg_l = np.array([libm.logf(np.float32(v) / K) if v > 3 else 0.0 for v in rs["value"][:max(S, 1)]], np.float32)
     L.emu_map_finalize(n, C.addressof(inp["opts"]), inp["read_off"], inp["read_len"], mo["status"], mo["n_chains"], mo["chain_nseg"], mo["chain_seg0"], mo["seg"].ctypes.data,
-                       rs["ir_n"], rs["ir_off"], rs["ir_blocks"], rs["stats"], rs["value"], rs["cigar_off"], logf_len, rec.ctypes.data, rank, ab)
+                       rs["ir_n"], rs["ir_off"], rs["ir_blocks"], rs["stats"], rs["value"], rs["cigar_off"], logf_len, rec.ctypes.data, rank, ab, seg_l,
+                       rs.get("stats_first", rs["stats"]).ctypes.data if inp["opts"].HighlyAccurate else None)
     return dict(status=mo["status"], n_aln=mo["n_chains"], aln_nseg=mo["chain_nseg"], aln_seg0=mo["chain_seg0"], aln_rank=rank, records=rec, n_records=S, cigar=rs["cigar"],
                 n_cigar=int(rs["cigar_off"][-1]), aligned_bases=int(ab[0]))
 

@@ -92,11 +92,11 @@ extern "C" int emu_map_reads(const uint8_t *reads_fwd, const uint8_t *reads_rc, 
 extern "C" int emu_map_finalize(int n_reads, const MpOpts *opts, const uint64_t *read_off, const uint32_t *read_len, const int *status, const int *n_chains,
                                 const int *chain_nseg, const int *chain_seg0, const SegRec *seg, const int32_t *ir_nblk, const uint64_t *ir_off, const uint32_t *ir_blocks,
                                 const int32_t *stats, const float *value, const uint64_t *cigar_off, const float *logf_len, lra_b200_record *rec, int *rank,
-                                uint64_t *aligned_bases) {
+                                uint64_t *aligned_bases, const float *seg_l, const int32_t *stats_first) {
   FinalBatch b;
   b.n_reads = n_reads; b.o = *opts; b.read_off = (const unsigned long long *)read_off; b.read_len = read_len; b.status = status; b.n_chains = n_chains;
   b.chain_nseg = chain_nseg; b.chain_seg0 = chain_seg0; b.seg = seg; b.ir_nblk = ir_nblk; b.ir_off = (const unsigned long long *)ir_off; b.ir_blocks = ir_blocks;
-  b.stats = stats; b.value = value; b.cigar_off = (const unsigned long long *)cigar_off; b.logf_len = logf_len; b.rec = rec; b.rank = rank;
+  b.stats = stats; b.value = value; b.cigar_off = (const unsigned long long *)cigar_off; b.logf_len = logf_len; b.seg_l = seg_l; b.stats_first = stats_first; b.rec = rec; b.rank = rank;
   b.aligned_bases = (unsigned long long *)aligned_bases;
   emu::launch(dim3((unsigned)((n_reads + 127) / 128)), dim3(128), 0, [&] { map_finalize_kernel(b); });
   return 0;
