@@ -460,6 +460,143 @@ __device__ __noinline__ bool mp_refine_btwn_clusters_chain(const MpCtx &C, int r
   return true;
 }
 
+// REFINEclusters (ClusterRefine.h:45-240) for cluster c of F -> refined cluster R (anchors of the LocalIndex k-mers, t chromosome-relative).  The window
+// walk is stateless per genome window (a12 / a13 form, lref_kernels.cuh); the window pairs are compared one per lane (count, scan, emit).
+__device__ __noinline__ bool mp_refine_cluster(const MpCtx &C, int r, const ClusterSet &F, int c, Arena &ar, RCluster &R, RSeg *node) {
+  const int lane = lane_id();
+  const MpOpts &O = C.o;
+  const uint32_t L = C.rd.read_len[r];
+  const int a0 = F.off[c], nm = F.off[c + 1] - a0;
+  const int Strand = F.strand[c] != 0 ? 1 : 0;
+  const int first = lref_hdr_find(C.ix.hdr_pos, C.ix.n_hdr, (unsigned long long)F.tS[c] + 1ull), last = lref_hdr_find(C.ix.hdr_pos, C.ix.n_hdr, (unsigned long long)F.tE[c]);
+  if (lane == 0) { R.head = R.tail = 0; R.n = 0; R.qS = 0xffffffffu; R.qE = 0; R.tS = 0xffffffffu; R.tE = 0; R.strand = Strand; R.chrom = first; R.refinespace = 0; R.freq = F.freq[c]; }
+  wsync();
+  if (nm == 0 || first != last) return true;
+  const int chrom = first;
+  const uint32_t chromOffset = (uint32_t)C.ix.hdr_pos[chrom], chromEndOffset = (uint32_t)C.ix.hdr_pos[last + 1];
+  const unsigned long long mk = ar.mark();
+  uint32_t *mq = ar.alloc<uint32_t>(nm), *mt = ar.alloc<uint32_t>(nm);
+  MpKey *keys = ar.alloc<MpKey>((unsigned long long)next_pow2(nm));
+  if (ar.overflow) return false;
+  long long maxDN = -(1ll << 62), minDN = (1ll << 62);
+  for (int i = lane; i < nm; i += kLanes) {
+    uint32_t q = F.q[a0 + i];
+    if (Strand == 1) q = L - (q + (uint32_t)O.globalK);            // SwapStrand(read, opts, clusters[ph], opts.globalK)
+    const uint32_t t = F.t[a0 + i] - chromOffset;
+    const long long d = (long long)t - (long long)q;
+    maxDN = d > maxDN ? d : maxDN; minDN = d < minDN ? d : minDN;
+    keys[i].k = ((unsigned long long)t << 32) | q; keys[i].q = 0; keys[i].idx = (uint32_t)i;
+  }
+  maxDN = wmax(maxDN) + 100; minDN = wmin(minDN) - 100;
+  wsync();
+  mp_sort_keys(keys, nm);                                          // CartesianTargetSort
+  for (int i = lane; i < nm; i += kLanes) { mt[i] = (uint32_t)(keys[i].k >> 32); mq[i] = (uint32_t)keys[i].k; }
+  wsync();
+  uint32_t bqs = F.qS[c], bqe = F.qE[c];
+  if (Strand == 1) { const uint32_t t = bqs; bqs = L - bqe; bqe = L - t; }
+  const uint32_t tStart = F.tS[c], tEnd = F.tE[c];
+  const uint32_t bts = tStart - chromOffset, bte = tEnd - chromOffset;
+  const uint32_t W = (uint32_t)O.window;
+  const uint32_t wts = chromOffset + W > tStart ? chromOffset : tStart - W;
+  const uint32_t wte = tEnd + W > chromEndOffset ? chromEndOffset - 1u : tEnd + W;
+  const LidxView &gl = C.ix.gl;
+  const unsigned long long gend = gl.win_off[gl.n_win];
+  const int ls = lref_lookup(gl.win_off, gl.n_win, 0ull, gend, wts), le = lref_lookup(gl.win_off, gl.n_win, 0ull, gend, wte);
+  const LidxView &rdx = C.rd.rd[Strand];
+  const int wf = (int)rdx.win_first[r], nw = (int)rdx.win_first[r + 1] - wf;
+  const unsigned long long rbase = rdx.seq_start[r], rend = rbase + L;
+  RsTask *tasks = 0;
+  int n_tasks = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    int nt = 0;
+    if (lane == 0) {
+      for (int lsi = ls; lsi <= le; lsi++) {
+        if (lsi >= gl.n_win) continue;
+        const unsigned long long o0 = gl.win_off[lsi], o1 = gl.win_off[lsi + 1];
+        if (o0 < chromOffset || o1 < chromOffset) continue;
+        const uint32_t gStart = (uint32_t)(o0 - chromOffset), gEnd = (uint32_t)(o1 - 1 - chromOffset);
+        if (gStart >= gEnd) continue;
+        int matchStart, matchEnd;
+        { int lo = 0, len = nm;
+          while (len > 0) { const int half = len >> 1; if (mt[lo + half] < gStart) { lo += half + 1; len -= half + 1; } else len = half; }
+          matchStart = lo; }
+        { int lo = matchStart, len = nm - matchStart;
+          while (len > 0) {
+            const int half = len >> 1, mid = lo + half;
+            const bool less = (gEnd != mt[mid]) ? (gEnd < mt[mid]) : (0u < mq[mid]);
+            if (less) len = half; else { lo = mid + 1; len -= half + 1; }
+          }
+          matchEnd = lo; }
+        if (matchEnd == nm) matchEnd--;
+        if (matchStart >= nm) continue;
+        uint32_t readStart = mq[matchStart], readEnd = mq[matchEnd];
+        if (readStart == readEnd) { if (lsi > ls && readStart > 0u) readStart = 0u; }     // prev_readEnd is 0 at its only read (ClusterRefine.h:152,162)
+        if (lsi == ls) readStart = readStart < W ? 0u : readStart - W;
+        if (lsi == le) readEnd = readEnd + W > L ? L : readEnd + W;
+        if (readStart > readEnd) continue;
+        const int qis = lref_lookup(rdx.win_off + wf, nw, rbase, rend, readStart);
+        const int qie = lref_lookup(rdx.win_off + wf, nw, rbase, rend, readEnd < L - 1 ? readEnd : L - 1);
+        for (int qi = qis; qi <= qie; qi++) {
+          if (pass == 1) {
+            RsTask tk; tk.lsi = lsi; tk.qw = wf + qi; tk.gStart = gStart; tk.rsStart = (uint32_t)(rdx.win_off[wf + qi] - rbase); tk.bmin = minDN; tk.bmax = maxDN;
+            tasks[nt] = tk;
+          }
+          nt++;
+        }
+      }
+    }
+    wsync();
+    nt = bcast(nt, 0);
+    if (pass == 0) {
+      n_tasks = nt;
+      if (n_tasks == 0) break;
+      tasks = ar.alloc<RsTask>(n_tasks);
+      if (ar.overflow) return false;
+    }
+  }
+  if (n_tasks == 0) { ar.release(mk); return true; }
+  const long maxFreq = (long)O.localMaxFreq;
+  int *cnt = ar.alloc<int>(n_tasks + 1);
+  if (ar.overflow) return false;
+  for (int k = lane; k < n_tasks; k += kLanes) {
+    const RsTask tk = tasks[k];
+    const uint32_t *q = rdx.mins + rdx.bnd[tk.qw]; const long nq = (long)(rdx.bnd[tk.qw + 1] - rdx.bnd[tk.qw]);
+    const uint32_t *t = gl.mins + gl.bnd[tk.lsi]; const long nt = (long)(gl.bnd[tk.lsi + 1] - gl.bnd[tk.lsi]);
+    int cc = 0;
+    lt_compare(q, nq, t, nt, maxFreq, [&](long qi, long ti) {
+      const uint32_t qp = (q[qi] >> 20) + tk.rsStart, tp = (t[ti] >> 20) + tk.gStart;
+      const long long d = (long long)tp - (long long)qp;
+      if (d >= tk.bmin && d <= tk.bmax && qp >= bqs && qp < bqe && tp >= bts && tp < bte) cc++;
+    });
+    cnt[k] = cc;
+  }
+  wsync();
+  int total = 0;
+  if (lane == 0) { for (int k = 0; k < n_tasks; k++) { const int cc = cnt[k]; cnt[k] = total; total += cc; } cnt[n_tasks] = total; }
+  wsync();
+  total = bcast(total, 0);
+  if (total == 0) { ar.release(mk); return true; }
+  uint32_t *rq = ar.alloc<uint32_t>(total), *rt = ar.alloc<uint32_t>(total);
+  if (ar.overflow) return false;
+  for (int k = lane; k < n_tasks; k += kLanes) {
+    const RsTask tk = tasks[k];
+    if (cnt[k + 1] == cnt[k]) continue;
+    const uint32_t *q = rdx.mins + rdx.bnd[tk.qw]; const long nq = (long)(rdx.bnd[tk.qw + 1] - rdx.bnd[tk.qw]);
+    const uint32_t *t = gl.mins + gl.bnd[tk.lsi]; const long nt = (long)(gl.bnd[tk.lsi + 1] - gl.bnd[tk.lsi]);
+    int o = cnt[k];
+    lt_compare(q, nq, t, nt, maxFreq, [&](long qi, long ti) {
+      const uint32_t qp = (q[qi] >> 20) + tk.rsStart, tp = (t[ti] >> 20) + tk.gStart;
+      const long long d = (long long)tp - (long long)qp;
+      if (d >= tk.bmin && d <= tk.bmax && qp >= bqs && qp < bqe && tp >= bts && tp < bte) { rq[o] = qp; rt[o] = tp; o++; }
+    });
+  }
+  wsync();
+  if (Strand == 1) { for (int i = lane; i < total; i += kLanes) rq[i] = L - (rq[i] + (uint32_t)O.smallK); wsync(); }
+  if (lane == 0) { rc_append(R, node, rq, rt, total); rc_set_boundaries(R, O.smallK); }
+  wsync();
+  return true;
+}
+
 // state of a read between the stages
 struct HaState {
   HaChains H;
@@ -493,11 +630,21 @@ __device__ __noinline__ int mp_stage1_highacc(const MpCtx &C, int r, Arena &ar, 
     const int c = keep[p];
     if (__fdiv_rn((float)fc_size(F, c), (float)(uint32_t)(F.qE[c] - F.qS[c])) <= 0.01f && L <= 50000u) sparse = 1;
   }
-  if (sparse) return MP_ERR_UNSUPPORTED;
-  // ---- RefinedClusters = the clusters themselves, t chromosome-relative (:449-461)
   RCluster *RC = ar.alloc<RCluster>(nkeep);
   RSeg *nodes = ar.alloc<RSeg>(nkeep);
   if (ar.overflow) return MP_ERR_ARENA;
+  if (sparse) {
+    // ---- REFINEclusters with the LocalIndex k-mers (smallOpts.globalK / globalW = the index's k / w, :427-441)
+    for (int p = 0; p < nkeep; p++) if (!mp_refine_cluster(C, r, F, keep[p], ar, RC[p], nodes + p)) return MP_ERR_ARENA;
+    // chain entries whose refined cluster came back empty are dropped (:475-486); the links stay as they are
+    int *ncp = ar.alloc<int>(kMaxChains);
+    if (ar.overflow) return MP_ERR_ARENA;
+    if (lane == 0) for (int h = 0; h < H.nch; h++) { int cp = 0; for (int i = 0; i < H.n[h]; i++) if (RC[H.ch[h][i]].n != 0) H.ch[h][cp++] = H.ch[h][i]; ncp[h] = cp; }
+    wsync();
+    for (int h = 0; h < H.nch; h++) H.n[h] = ncp[h];
+    if (H.nch == 0 || H.n[0] == 0) return MP_UNALIGNED;
+  } else {
+  // ---- RefinedClusters = the clusters themselves, t chromosome-relative (:449-461)
   for (int p = 0; p < nkeep; p++) {
     const int c = keep[p];
     const uint32_t coff = (uint32_t)C.ix.hdr_pos[F.chrom[c]];
@@ -510,8 +657,9 @@ __device__ __noinline__ int mp_stage1_highacc(const MpCtx &C, int r, Arena &ar, 
       rc_append(R, nodes + p, F.q + a0, F.t + a0, n);
     }
   }
+  }
   wsync();
-  const int K = O.globalK, W = O.globalW;
+  const int K = sparse ? O.smallK : O.globalK, W = sparse ? O.smallW : O.globalW;
   for (int h = 0; h < H.nch; h++) {
     if (H.n[h] == 0) continue;
     if (!mp_refine_btwn_clusters_chain(C, r, ar, K, W, H.ch[h], H.n[h], RC)) return MP_ERR_ARENA;

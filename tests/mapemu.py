@@ -121,18 +121,44 @@ def refine_and_stats(inp, mo):
         return dict(ir_n=np.zeros(1, np.int32), ir_off=np.zeros(1, np.uint64), ir_blocks=np.zeros(3, np.uint32), stats=np.zeros(16, np.int32), value=np.zeros(1, np.float32),
                     cigar_off=np.zeros(2, np.uint64), cigar=np.zeros(1, np.uint32))
     n, off, blocks = po.indel_refine_batch_ref(sb, g_arena, t_base, nthreads=4)
-    stats = np.zeros(16 * S, np.int32); value = np.zeros(S, np.float32); cig_off = np.zeros(S + 1, np.uint64); cigs = []
+    bl = [blocks[int(off[s]):int(off[s]) + int(n[s])].copy() for s in range(S)]
     opmap = {"=": 7, "X": 8, "I": 1, "D": 2, "M": 0}
     import re
-    for s in range(S):
-        b = blocks[int(off[s]):int(off[s]) + int(n[s])]
+
+    def seqs(s):
         qb = int(sb["q_base"][s]); rl = int(sb["read_len"][s]); tb = int(t_base[s]); cl = int(sb["contig_len"][s])
-        st, v, cig = po.calc_stats_ref(q_arena[qb:qb + rl].tobytes(), g_arena[tb:tb + cl].tobytes(), b)
-        stats[16 * s:16 * s + 16] = st; value[s] = v
-        ops = np.array([(int(l) << 4) | opmap[c] for l, c in re.findall(r"(\d+)([=XIDM])", cig)], np.uint32)
-        cigs.append(ops); cig_off[s + 1] = cig_off[s] + np.uint64(len(ops))
+        return q_arena[qb:qb + rl], g_arena[tb:tb + cl], rl
+
+    def all_stats():
+        stats = np.zeros(16 * S, np.int32); value = np.zeros(S, np.float32); cig_off = np.zeros(S + 1, np.uint64); cigs = []
+        for s in range(S):
+            rd, gn, _ = seqs(s)
+            st, v, cig = po.calc_stats_ref(rd.tobytes(), gn.tobytes(), bl[s])
+            stats[16 * s:16 * s + 16] = st; value[s] = v
+            ops = np.array([(int(l) << 4) | opmap[c] for l, c in re.findall(r"(\d+)([=XIDM])", cig)], np.uint32)
+            cigs.append(ops); cig_off[s + 1] = cig_off[s] + np.uint64(len(ops))
+        return stats, value, cig_off, cigs
+
+    stats, value, cig_off, cigs = all_stats()
+    extra = {}
+    if o.HighlyAccurate:
+        # Map_highacc.h:722-731: RefineBreakpoint between consecutive segments of every alignment, then CalculateStatistics again (stand-in: the reference)
+        extra["stats_first"] = stats
+        nrd = len(inp["read_len"])
+        for r in range(nrd):
+            for a in range(int(mo["n_chains"][r])):
+                ns = int(mo["chain_nseg"][4 * r + a]); s0 = int(mo["chain_seg0"][4 * r + a])
+                for k in range(1, ns):
+                    li, ri = s0 + k, s0 + k - 1
+                    lrd, lgn, rl = seqs(li); rrd, rgn, _ = seqs(ri)
+                    if len(bl[li]) == 0 or len(bl[ri]) == 0:
+                        continue
+                    bl[li], bl[ri] = po.refine_breakpoint_ref(lrd, rrd, rl, lgn, rgn, bl[li], int(seg["strand"][li]), bl[ri], int(seg["strand"][ri]))
+        stats, value, cig_off, cigs = all_stats()
+    n = np.array([len(b) for b in bl], np.int32); off = np.zeros(S, np.uint64); off[1:] = np.cumsum(n[:-1].astype(np.uint64))
+    blocks = np.concatenate([b.reshape(-1, 3) for b in bl] + [np.zeros((1, 3), np.uint32)])
     return dict(ir_n=n, ir_off=off, ir_blocks=np.ascontiguousarray(blocks.reshape(-1)), stats=stats, value=value, cigar_off=cig_off,
-                cigar=np.ascontiguousarray(np.concatenate(cigs + [np.zeros(1, np.uint32)])))
+                cigar=np.ascontiguousarray(np.concatenate(cigs + [np.zeros(1, np.uint32)])), **extra)
 
 
 def finalize(inp, mo, rs, lanes=1):

@@ -14,8 +14,8 @@ import synth  # noqa: E402
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "lra_ref")
 CAP_BIN = os.path.join(ROOT, "oracle", "_ref", "lra_capture")
 MODE = {"ont": "-ONT", "clr": "-CLR", "ccs": "-CCS", "contig": "-CONTIG"}
-PROFILE = {"ont": "ont", "clr": "clr", "ccs": "ccs10k"}
-SEED = {"ont": 2, "clr": 4, "ccs": 11}
+PROFILE = {"ont": "ont", "clr": "clr", "ccs": "ccs10k", "contig": "contig"}
+SEED = {"ont": 2, "clr": 4, "ccs": 11, "contig": 17}
 
 
 def have_reference_binaries():

@@ -29,10 +29,13 @@ def diff_report(ours, ref, limit=5):
     return out
 
 
-@pytest.mark.parametrize("preset,n_reads,repeats", [("ont", 60, False), ("clr", 60, True)])
-def test_map_emulated_matches_reference_sam(preset, n_reads, repeats, tmp_path):
+@pytest.mark.parametrize("preset,n_reads,repeats,sv", [("ont", 60, False, False), ("clr", 60, True, False), ("ccs", 80, True, False), ("ccs", 48, False, True),
+                                                       ("contig", 6, False, True)])
+def test_map_emulated_matches_reference_sam(preset, n_reads, repeats, sv, tmp_path):
+    """-CCS / -CONTIG take MapRead_highacc (Map_highacc.h:37-798): fine clusters, split clusters, both high-accuracy SparseDPs, RefineBreakpoint between the
+    segments of the reads with structural variants (sv: deletions, insertions, inversions, translocations, duplications)."""
     import mapemu
-    w = mapgen.workdir(tmp_path, preset, n_reads=n_reads, ref_len=1_500_000, contigs=3, repeats=repeats)
+    w = mapgen.workdir(tmp_path, preset, n_reads=n_reads, ref_len=1_500_000, contigs=3, repeats=repeats, sv=sv)
     _, ref = mapgen.canonical_sam(mapgen.reference_sam(w))
     inp, mo, res, text = mapemu.run(w, lanes=1)
     assert mo["err"] == 0 and (mo["status"] <= 1).all()
