@@ -255,7 +255,6 @@ int run_align(int argc, char **argv, const std::string &cmdline) {
     else if (a[0] != '-') { if (ref.empty()) ref = a; else inputs.push_back(a); }
   }
   if (ref.empty() || inputs.empty()) { fprintf(stderr, "usage: lra_b200 align -CLR|-ONT ref.fa reads.fa [-t N] [-p s|p|pc|b] [-o out]\n"); return 1; }
-  if (mode == "-CCS" || mode == "-CONTIG") { fprintf(stderr, "lra_b200 align: %s takes MapRead_highacc, which this library does not map yet (-ONT, -CLR are implemented)\n", mode.c_str()); return 2; }
   const char f = fmt == "s" ? 's' : fmt == "p" ? 'p' : fmt == "pc" ? 'c' : fmt == "b" ? 'b' : 0;
   if (!f) { fprintf(stderr, "lra_b200 align: -p %s is not supported (s, p, pc, b)\n", fmt.c_str()); return 1; }
   std::string text; Fasta g;

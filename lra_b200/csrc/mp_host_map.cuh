@@ -275,7 +275,8 @@ extern "C" int lra_b200_mapper_create(lra_b200_ctx *ctx, const lra_b200_map_opts
                                       const uint64_t *gli_tuple_boundaries, int32_t gli_n_regions, const uint32_t *gli_minimizers, uint64_t gli_n_min,
                                       lra_b200_mapper **out) {
   if (!ctx || !opts || !genome_ascii || !hdr_pos || n_contigs < 1 || !mms_t || !mms_pos || !out) return fail(ctx, LRA_B200_EINVAL, "mapper_create: NULL argument");
-  if (!opts->bypassClustering) return fail(ctx, LRA_B200_EINVAL, "mapper_create: only the low-accuracy presets (-ONT, -CLR: MapRead_lowacc) are implemented");
+  if (!opts->bypassClustering && !opts->HighlyAccurate)
+    return fail(ctx, LRA_B200_EINVAL, "mapper_create: neither bypassClustering (-ONT, -CLR: MapRead_lowacc) nor HighlyAccurate (-CCS, -CONTIG: MapRead_highacc) is set");
   if (hdr_pos[n_contigs] != genome_len || genome_len >= (1ull << 32)) return fail(ctx, LRA_B200_EINVAL, "mapper_create: header offsets do not cover the genome (or >= 2^32 bases)");
   *out = nullptr;
   CU(cudaSetDevice(ctx->device));
@@ -506,7 +507,30 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
   if ((rc = ensure(ctx, B[11], (size_t)(S + 1) * 8)) || (rc = ensure(ctx, B[12], (size_t)(S + 1) * 4)) || (rc = ensure(ctx, B[13], (size_t)(S + 1) * 4)) ||
       (rc = ensure(ctx, B[14], (size_t)(S + 1) * 4)) || (rc = ensure(ctx, B[15], (size_t)(S + 1) * 4)) || (rc = ensure(ctx, B[16], (size_t)(S + 1) * 4)))
     return rc;
-  const size_t ir_cap = (size_t)NB * 2 + (size_t)S * 64 + 1024;
+  // MapRead_highacc (Map_highacc.h:716-731): IndelRefineAlignment(endAlign = true), CalculateStatistics, RefineBreakpoint between consecutive segments of an
+  // alignment, CalculateStatistics again.  The alignments with several segments are rare (reads across structural variants): their pairs are
+  // refined round by round (segment s against s - 1; a segment is the left side of one pair and the right side of the next) and the new block lists are
+  // appended behind the IndelRefine output.
+  const bool HA = m->opts.HighlyAccurate != 0;
+  struct HaAln { int seg0, nseg; };
+  std::vector<HaAln> multi;
+  std::vector<SegRec> h_seg;
+  size_t rbp_slack = 0;
+  if (HA && S > 0) {
+    std::vector<int> h_nch(n_reads), h_nseg((size_t)n_reads * 4), h_seg0((size_t)n_reads * 4);
+    CU(cudaMemcpyAsync(h_nch.data(), B[3].p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_nseg.data(), B[4].p, (size_t)n_reads * 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_seg0.data(), B[5].p, (size_t)n_reads * 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int r = 0; r < n_reads; r++) for (int a = 0; a < h_nch[r] && a < 4; a++) if (h_nseg[(size_t)r * 4 + a] > 1) multi.push_back(HaAln{h_seg0[(size_t)r * 4 + a], h_nseg[(size_t)r * 4 + a]});
+    if (!multi.empty()) {
+      h_seg.resize(S);
+      CU(cudaMemcpyAsync(h_seg.data(), B[6].p, (size_t)S * sizeof(SegRec), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      for (const HaAln &a : multi) for (int k = 0; k < a.nseg; k++) rbp_slack += 2 * (2 * (size_t)h_seg[a.seg0 + k].blk_cnt + 64 + 2 * (size_t)lra::kRbpCap);
+    }
+  }
+  const size_t ir_cap = (size_t)NB * 2 + (size_t)S * 64 + 1024 + rbp_slack;
   const size_t cig_cap = (size_t)total_bases / 2 + (size_t)NB * 4 + (size_t)S * 16 + 1024;
   if ((rc = ensure(ctx, B[17], (size_t)(S + 1) * 4)) || (rc = ensure(ctx, B[18], (size_t)(S + 1) * 8)) || (rc = ensure(ctx, B[19], ir_cap * 12)) ||
       (rc = ensure(ctx, B[20], (size_t)(S + 1) * 64)) || (rc = ensure(ctx, B[21], (size_t)(S + 1) * 4)) || (rc = ensure(ctx, B[22], (size_t)(S + 2) * 8)) ||
@@ -524,7 +548,7 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
     lra_b200_ir_segments sg; memset(&sg, 0, sizeof sg);
     sg.blocks_in = (const uint32_t *)B[7].p; sg.blk_off = (const uint64_t *)B[11].p; sg.blk_cnt = (const int32_t *)B[12].p; sg.q_base = (const uint32_t *)B[13].p;
     sg.t_base = (const uint32_t *)B[14].p; sg.read_len = (const int32_t *)B[15].p; sg.contig_len = (const int32_t *)B[16].p; sg.n_blocks_in = NB; sg.n_segments = S;
-    sg.refine_band = m->opts.refineBand; sg.match = m->opts.localMatch; sg.mismatch = m->opts.localMismatch; sg.indel = m->opts.localIndel; sg.end_align = 0;
+    sg.refine_band = m->opts.refineBand; sg.match = m->opts.localMatch; sg.mismatch = m->opts.localMismatch; sg.indel = m->opts.localIndel; sg.end_align = HA ? 1 : 0;
     ir.n_blocks = (int32_t *)B[17].p; ir.block_off = (uint64_t *)B[18].p; ir.blocks = (uint32_t *)B[19].p; ir.block_cap = ir_cap;
     if ((rc = lra_b200_indel_refine_batch_device(ctx, rs->reads, m->genome, &sg, &ir))) return rc;
     all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
@@ -533,6 +557,86 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
     sr.stats = (int32_t *)B[20].p; sr.value = (float *)B[21].p; sr.cigar_off = (uint64_t *)B[22].p; sr.cigar = (uint32_t *)B[23].p; sr.cigar_cap = cig_cap;
     if ((rc = lra_b200_calc_stats_batch_device(ctx, rs->reads, m->genome, &s2, m->log_lut, &sr))) return rc;
     all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
+    if (HA && !multi.empty()) {
+      if ((rc = ensure(ctx, B[29], (size_t)(S + 1) * 64))) return rc;
+      CU(cudaMemcpyAsync(B[29].p, B[20].p, (size_t)S * 64, cudaMemcpyDeviceToDevice, st));
+      std::vector<int32_t> h_nb(S); std::vector<uint64_t> h_bo(S);
+      CU(cudaMemcpyAsync(h_nb.data(), B[17].p, (size_t)S * 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(h_bo.data(), B[18].p, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      uint64_t cursor = ir.n_blocks_total;
+      lra_b200_seq fwd_v = *rs->reads, rc_v = *rs->reads;
+      fwd_v.n = Npad; rc_v.b2 += Npad / 16; rc_v.nm += Npad / 32; rc_v.n = Npad;
+      uint32_t *blk = (uint32_t *)B[19].p;
+      int max_seg = 0; for (const HaAln &a : multi) max_seg = a.nseg > max_seg ? a.nseg : max_seg;
+      for (int j = 1; j < max_seg; j++) {
+        std::vector<int> li, ri;
+        for (const HaAln &a : multi) if (a.nseg > j && h_nb[a.seg0 + j] > 0 && h_nb[a.seg0 + j - 1] > 0) { li.push_back(a.seg0 + j); ri.push_back(a.seg0 + j - 1); }
+        const size_t P = li.size();
+        if (P == 0) continue;
+        std::vector<uint32_t> lf(P * 3), ll(P * 3), rf(P * 3), rl(P * 3), rlen(P), lcl(P), rcl(P);
+        std::vector<uint8_t> ls(P), rsd(P);
+        std::vector<uint64_t> roff(P), lco(P), rco(P);
+        for (size_t p = 0; p < P; p++) {
+          const int l = li[p], r_ = ri[p];
+          CU(cudaMemcpyAsync(&lf[p * 3], blk + 3 * h_bo[l], 12, cudaMemcpyDeviceToHost, st));
+          CU(cudaMemcpyAsync(&ll[p * 3], blk + 3 * (h_bo[l] + (uint64_t)h_nb[l] - 1), 12, cudaMemcpyDeviceToHost, st));
+          CU(cudaMemcpyAsync(&rf[p * 3], blk + 3 * h_bo[r_], 12, cudaMemcpyDeviceToHost, st));
+          CU(cudaMemcpyAsync(&rl[p * 3], blk + 3 * (h_bo[r_] + (uint64_t)h_nb[r_] - 1), 12, cudaMemcpyDeviceToHost, st));
+          ls[p] = (uint8_t)h_seg[l].strand; rsd[p] = (uint8_t)h_seg[r_].strand;
+          roff[p] = rs->h_off[h_seg[l].read]; rlen[p] = rs->h_len[h_seg[l].read];
+          lco[p] = m->h_hdr[h_seg[l].chrom]; lcl[p] = (uint32_t)(m->h_hdr[h_seg[l].chrom + 1] - m->h_hdr[h_seg[l].chrom]);
+          rco[p] = m->h_hdr[h_seg[r_].chrom]; rcl[p] = (uint32_t)(m->h_hdr[h_seg[r_].chrom + 1] - m->h_hdr[h_seg[r_].chrom]);
+        }
+        CU(cudaStreamSynchronize(st));
+        lra_b200_breakpoints bp; memset(&bp, 0, sizeof bp);
+        bp.n_pairs = (int32_t)P; bp.lf = lf.data(); bp.ll = ll.data(); bp.rf = rf.data(); bp.rl = rl.data(); bp.lstrand = ls.data(); bp.rstrand = rsd.data();
+        bp.read_off = roff.data(); bp.read_len = rlen.data(); bp.lchrom_off = lco.data(); bp.rchrom_off = rco.data(); bp.lchrom_len = lcl.data(); bp.rchrom_len = rcl.data();
+        std::vector<int32_t> mode(P * 2), n_out(P * 2), refined(P);
+        std::vector<uint32_t> bound(P * 6), outb(P * 2 * (size_t)lra::kRbpCap * 3);
+        lra_b200_breakpoint_result br; br.mode = mode.data(); br.n_out = n_out.data(); br.bound = bound.data(); br.out = outb.data(); br.refined = refined.data();
+        if ((rc = lra_b200_refine_breakpoint_batch(ctx, &fwd_v, &rc_v, m->genome, &bp, &br))) return rc;
+        all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
+        for (size_t p = 0; p < P; p++) for (int side = 0; side < 2; side++) {
+          const int md = mode[2 * p + side], no = n_out[2 * p + side], x = side == 0 ? li[p] : ri[p];
+          if (md != 1 && md != 2) continue;
+          const uint64_t n_old = (uint64_t)h_nb[x];
+          if (cursor + n_old + (uint64_t)no > ir_cap) return fail(ctx, LRA_B200_EOVERFLOW, "map_batch: block capacity exceeded while splicing refined breakpoints");
+          uint32_t *dst = blk + 3 * cursor;
+          const uint32_t *src = blk + 3 * h_bo[x];
+          const uint32_t *nb_ = &outb[(2 * p + side) * (size_t)lra::kRbpCap * 3], *bd = &bound[(2 * p + side) * 3];
+          if (md == 1) {
+            CU(cudaMemcpyAsync(dst, src, n_old * 12, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(dst + 3 * (n_old - 1), bd, 12, cudaMemcpyHostToDevice, st));
+            if (no) CU(cudaMemcpyAsync(dst + 3 * n_old, nb_, (size_t)no * 12, cudaMemcpyHostToDevice, st));
+          } else {
+            if (no) CU(cudaMemcpyAsync(dst, nb_, (size_t)no * 12, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(dst + 3 * (size_t)no, src, n_old * 12, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpyAsync(dst + 3 * (size_t)no, bd, 12, cudaMemcpyHostToDevice, st));
+          }
+          h_bo[x] = cursor; h_nb[x] = (int32_t)(n_old + (uint64_t)no); cursor += n_old + (uint64_t)no;
+        }
+        CU(cudaStreamSynchronize(st));
+      }
+      CU(cudaMemcpyAsync(B[17].p, h_nb.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(B[18].p, h_bo.data(), (size_t)S * 8, cudaMemcpyHostToDevice, st));
+      CU(cudaStreamSynchronize(st));
+      s2.n_blocks_in = cursor;
+      if ((rc = lra_b200_calc_stats_batch_device(ctx, rs->reads, m->genome, &s2, m->log_lut, &sr))) return rc;
+      all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
+    }
+  }
+  // SimpleMapQV without bypassClustering reads logf(value / globalK) per segment (Mapping_ultility.h:524, 564): evaluated with the host libm, as in the reference
+  if (!m->opts.bypassClustering) {
+    if ((rc = ensure(ctx, B[30], (size_t)(S + 1) * 4))) return rc;
+    if (S > 0) {
+      std::vector<float> hv(S);
+      CU(cudaMemcpyAsync(hv.data(), B[21].p, (size_t)S * 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      for (int i = 0; i < S; i++) hv[i] = hv[i] > 3 ? logf(hv[i] / m->opts.globalK) : 0.0f;
+      CU(cudaMemcpyAsync(B[30].p, hv.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
+      CU(cudaStreamSynchronize(st));
+    }
   }
   // ---- finalize
   CU(cudaMemcpyAsync(B[26].p, m->logf_len, 32, cudaMemcpyHostToDevice, st));
@@ -542,6 +646,8 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
   fb.n_chains = (const int *)B[3].p; fb.chain_nseg = (const int *)B[4].p; fb.chain_seg0 = (const int *)B[5].p; fb.seg = (const SegRec *)B[6].p;
   fb.ir_nblk = (const int32_t *)B[17].p; fb.ir_off = (const unsigned long long *)B[18].p; fb.ir_blocks = (const uint32_t *)B[19].p;
   fb.stats = (const int32_t *)B[20].p; fb.value = (const float *)B[21].p; fb.cigar_off = (const unsigned long long *)B[22].p; fb.logf_len = (const float *)B[26].p;
+  fb.stats_first = HA ? (const int32_t *)((!multi.empty() && S > 0) ? B[29].p : B[20].p) : nullptr;
+  fb.seg_l = m->opts.bypassClustering ? nullptr : (const float *)B[30].p;
   fb.rec = (lra_b200_record *)B[24].p; fb.rank = (int *)B[25].p; fb.aligned_bases = (unsigned long long *)((char *)B[26].p + 32);
   map_finalize_kernel<<<(unsigned)((n_reads + 127) / 128), 128, 0, st>>>(fb);
   ctx->launches++;

@@ -44,9 +44,10 @@ def test_map_emulated_matches_reference_sam(preset, n_reads, repeats, sv, tmp_pa
     assert ours == ref, diff_report(ours, ref)
 
 
-def test_map_emulated_32_lanes(tmp_path):
+@pytest.mark.parametrize("preset", ["ont", "ccs"])
+def test_map_emulated_32_lanes(preset, tmp_path):
     import mapemu
-    w = mapgen.workdir(tmp_path, "ont", n_reads=2, ref_len=300_000, contigs=2, repeats=False)
+    w = mapgen.workdir(tmp_path, preset, n_reads=2, ref_len=300_000, contigs=2, repeats=False, sv=preset == "ccs")
     _, ref = mapgen.canonical_sam(mapgen.reference_sam(w))
     inp, mo, res, text = mapemu.run(w, lanes=32)
     assert canon_ours(text) == ref
@@ -73,7 +74,8 @@ def gpu_sam(w, batch=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("preset,n_reads,repeats,batch", [("ont", 1000, False, None), ("clr", 1000, False, 400), ("ont", 600, True, None), ("clr", 600, True, 250), ("ont", 4000, True, 1500)])
+@pytest.mark.parametrize("preset,n_reads,repeats,batch", [("ont", 1000, False, None), ("clr", 1000, False, 400), ("ont", 600, True, None), ("clr", 600, True, 250), ("ont", 4000, True, 1500),
+                                                          ("ccs", 1000, False, None), ("ccs", 1000, True, 300), ("contig", 24, False, None)])
 def test_map_batch_gpu_matches_reference_sam(preset, n_reads, repeats, batch, tmp_path):
     w = mapgen.workdir(tmp_path, preset, n_reads=n_reads, ref_len=5_000_000, contigs=3, repeats=repeats)
     _, ref = mapgen.canonical_sam(mapgen.reference_sam(w))
@@ -113,14 +115,14 @@ def test_map_emulated_structural_variant_reads(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("preset", ["ont", "clr"])
-def test_map_batch_gpu_structural_variant_reads(preset, tmp_path):
-    w = mapgen.workdir(tmp_path, preset, n_reads=360, ref_len=5_000_000, contigs=3, repeats=False, sv=True)
+@pytest.mark.parametrize("preset,n_reads", [("ont", 360), ("clr", 360), ("ccs", 360), ("contig", 30)])
+def test_map_batch_gpu_structural_variant_reads(preset, n_reads, tmp_path):
+    w = mapgen.workdir(tmp_path, preset, n_reads=n_reads, ref_len=5_000_000, contigs=3, repeats=False, sv=True)
     _, ref = mapgen.canonical_sam(mapgen.reference_sam(w))
     text, st = gpu_sam(w, None)
     assert (st["status"] <= 1).all(), np.bincount(st["status"])
     ours = canon_ours(text)
-    assert sum("SA:Z:" in l for l in ref) >= 50
+    assert sum("SA:Z:" in l for l in ref) >= n_reads // 8
     assert len(ours) == len(ref)
     assert ours == ref, diff_report(ours, ref)
 
@@ -155,9 +157,10 @@ def edge_case_workdir(tmp_path, preset):
     return w
 
 
-def test_map_emulated_edge_case_reads(tmp_path):
+@pytest.mark.parametrize("preset", ["ont", "ccs"])
+def test_map_emulated_edge_case_reads(preset, tmp_path):
     import mapemu
-    w = edge_case_workdir(tmp_path, "ont")
+    w = edge_case_workdir(tmp_path, preset)
     _, ref = mapgen.canonical_sam(mapgen.reference_sam(w))
     inp, mo, res, text = mapemu.run(w, lanes=1)
     assert mo["err"] == 0 and (mo["status"] <= 1).all()
@@ -167,7 +170,7 @@ def test_map_emulated_edge_case_reads(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("preset", ["ont", "clr"])
+@pytest.mark.parametrize("preset", ["ont", "clr", "ccs", "contig"])
 def test_map_batch_gpu_edge_case_reads(preset, tmp_path):
     w = edge_case_workdir(tmp_path, preset)
     _, ref = mapgen.canonical_sam(mapgen.reference_sam(w))
