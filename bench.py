@@ -36,8 +36,9 @@ for p in (ROOT, os.path.join(ROOT, "tools")):
 import synth  # noqa: E402
 
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "lra_ref")
-MODE = {"ont": "-ONT", "clr": "-CLR"}
-SEED = {"ont": 2, "clr": 4}
+MODE = {"ont": "-ONT", "clr": "-CLR", "ccs": "-CCS"}
+SEED = {"ont": 2, "clr": 4, "ccs": 11}
+PROFILE = {"ont": "ont", "clr": "clr", "ccs": "hifi"}      # tools/synth.py read profiles; ccs = BASELINE configs[2] (HiFi, 15 kb, 0.5 % error)
 METRIC = "reads/sec (whole MapRead path: reads in, alignment records out)"
 
 
@@ -47,7 +48,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--preset", default="ont", choices=["ont", "clr"])
+    ap.add_argument("--preset", default="ont", choices=["ont", "clr", "ccs"])
     ap.add_argument("--reads-per-step", type=int, default=16384, help="reads per step and per GPU")
     ap.add_argument("--genome-len", type=int, default=3_000_000_000)
     ap.add_argument("--contigs", type=int, default=24)
@@ -111,9 +112,11 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------------------------- workload
 def workload_name(args):
-    return ("BASELINE configs[1]: synthetic ONT reads (log-normal lengths, N50 20 kb, 8%% i.i.d. error sub:ins:del 1:1:1) vs a %.3g Gb synthetic "
-            "reference (%d contigs, uniform ACGT, seed 1234), lra align %s; %d reads per step per GPU"
-            % (args.genome_len / 1e9, args.contigs, MODE[args.preset], args.reads_per_step)).replace("ONT reads", "%s reads" % args.preset.upper())
+    reads = {"ont": "BASELINE configs[1]: synthetic ONT reads (log-normal lengths, N50 20 kb, 8% i.i.d. error sub:ins:del 1:1:1)",
+             "clr": "BASELINE configs[3]: synthetic CLR reads (log-normal lengths, N50 12 kb, 12% i.i.d. error sub:ins:del 1:1:1)",
+             "ccs": "BASELINE configs[2]: synthetic HiFi reads (15 kb +- 2 kb, 0.5% i.i.d. error sub:ins:del 1:1:1)"}[args.preset]
+    return ("%s vs a %.3g Gb synthetic reference (%d contigs, uniform ACGT, seed 1234), lra align %s; %d reads per step per GPU"
+            % (reads, args.genome_len / 1e9, args.contigs, MODE[args.preset], args.reads_per_step))
 
 
 def build_workdir(args, builder, device=None):
@@ -196,7 +199,7 @@ def run_reference(args):
     vals, walls, loads, gbp = [], [], [], []
     t_load = None
     for i in range(args.warmup + args.steps):
-        a, ro, rl, nm = synth.gen_reads_torch(gt, ref["hdr"], ref["names"], S, args.preset, SEED[args.preset] * 1000 + max(0, i - args.warmup), dev)
+        a, ro, rl, nm = synth.gen_reads_torch(gt, ref["hdr"], ref["names"], S, PROFILE[args.preset], SEED[args.preset] * 1000 + max(0, i - args.warmup), dev)
         fa = os.path.join(d, "sample.fa")
         synth.write_reads_fasta(fa, a, ro, rl, nm)
         if t_load is None:
@@ -296,7 +299,7 @@ def main():
     K, W = args.steps, args.warmup
 
     def chunk(step, r):
-        return synth.gen_reads_torch(gt, ref["hdr"], ref["names"], R, args.preset, SEED[args.preset] * 100000 + step * 64 + r, dev)
+        return synth.gen_reads_torch(gt, ref["hdr"], ref["names"], R, PROFILE[args.preset], SEED[args.preset] * 100000 + step * 64 + r, dev)
 
     # ---- value leg: every rank's shard of every step resident before the clock starts
     shards = []
