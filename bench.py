@@ -492,6 +492,23 @@ def main():
         line["cpu_baseline"] = {"value": S / dt, "unit": "reads/s", "gbp_per_s": aligned_bases_of_sam(os.path.join(d, "ref_arm.sam")) / dt / 1e9, "cores": cores, "kind": "reference",
                                 "sample": "first %d reads of an e2e batch: `lra_ref align %s ref.fa sample.fa -t %d -p s`, wall %.2f s minus index load %.2f s (one-read run)"
                                           % (S, MODE[args.preset], cores, t_all, t_load)}
+        # parity at bench scale: the same sample through lra_b200_map_batch + the SAM emitter, record for record against the reference's SAM
+        try:
+            import re
+            o1 = int(hb["off"][S - 1]) + int(hb["len32"][S - 1])
+            arr = hb["ascii"].numpy()[:o1]
+            off_s = np.ascontiguousarray(hb["off"][:S]).astype(np.uint64); len_s = np.ascontiguousarray(hb["len32"][:S]).astype(np.uint32)
+            res_s = mapper.map_batch(arr, off_s, len_s)
+            text = lra_b200.format_sam(ref["opts"], res_s, hb["names"][:S], arr, off_s, len_s, contig_names)
+            canon = lambda l: re.sub(r"\tRT:i:\d+", "\tRT:i:0", l.rstrip("\n"))
+            ours = sorted(canon(l) for l in text.split("\n") if l)
+            with open(os.path.join(d, "ref_arm.sam")) as f:
+                theirs = sorted(canon(l) for l in f if l.strip() and not l.startswith("@"))
+            same = sum(1 for a, b in zip(ours, theirs) if a == b) if len(ours) == len(theirs) else len(set(ours) & set(theirs))
+            line["parity_sample"] = {"reads": int(S), "reference_records": len(theirs), "our_records": len(ours), "identical_records": int(same),
+                                     "identical": bool(ours == theirs), "what": "SAM records of the cpu_baseline sample, `lra_ref align` vs lra_b200_map_batch + lra_b200_format_sam (RT:i masked, sorted)"}
+        except Exception as e:      # the check must not cost the bench line
+            line["parity_sample"] = {"error": repr(e)[:200]}
     emit(line)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()

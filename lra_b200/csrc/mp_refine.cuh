@@ -5,7 +5,7 @@
 // pair per lane (count, scan, emit: anchors land in the reference's order) and AffineOneGapAlign uses the whole warp.
 #pragma once
 #include "mp_stage1.cuh"
-#include "mp_aog.cuh"
+#include "mp_aog_band.cuh"
 #include "spchain_kernels.cuh"
 
 namespace lra {
@@ -311,7 +311,7 @@ __device__ __noinline__ int mp_refine_space(const MpCtx &C, int r, Arena &ar, in
     int *errp = ar.alloc<int>(1);
     if (ar.overflow) return -1;
     int nb = 0;
-    mp_aog(rs, (uint32_t)(roff + qs), (int)qlen, C.ix.genome, (uint32_t)(coff + tshift), (int)tlen, O.localMatch, O.localMismatch, O.localIndel, 30, ar, blk, capb, &nb, errp);
+    mp_aog_any(rs, (uint32_t)(roff + qs), (int)qlen, C.ix.genome, (uint32_t)(coff + tshift), (int)tlen, O.localMatch, O.localMismatch, O.localIndel, 30, ar, blk, capb, &nb, errp);
     if (nb < 0) return -1;
     wsync();
     int nMatch = 0;
