@@ -15,7 +15,6 @@
 namespace lra {
 namespace mp {
 
-constexpr int MP_ERR_UNSUPPORTED = 4;     // a branch of MapRead_highacc that is not built (REFINEclusters of sparse clusters)
 
 __device__ __forceinline__ long long ha_labs(long long x) { return x < 0 ? -x : x; }
 // DiagonalDifference / minGapDifference (Clustering.h:503-537) on anchors a, b of a list
@@ -503,8 +502,9 @@ __device__ __noinline__ bool mp_refine_cluster(const MpCtx &C, int r, const Clus
   const unsigned long long gend = gl.win_off[gl.n_win];
   const int ls = lref_lookup(gl.win_off, gl.n_win, 0ull, gend, wts), le = lref_lookup(gl.win_off, gl.n_win, 0ull, gend, wte);
   const LidxView &rdx = C.rd.rd[Strand];
-  const int wf = (int)rdx.win_first[r], nw = (int)rdx.win_first[r + 1] - wf;
-  const unsigned long long rbase = rdx.seq_start[r], rend = rbase + L;
+  const int rsq = C.rd.lidx_slot ? C.rd.lidx_slot[r] : r;
+  const int wf = (int)rdx.win_first[rsq], nw = (int)rdx.win_first[rsq + 1] - wf;
+  const unsigned long long rbase = rdx.seq_start[rsq], rend = rbase + L;
   RsTask *tasks = 0;
   int n_tasks = 0;
   for (int pass = 0; pass < 2; pass++) {
@@ -633,6 +633,7 @@ __device__ __noinline__ int mp_stage1_highacc(const MpCtx &C, int r, Arena &ar, 
   RCluster *RC = ar.alloc<RCluster>(nkeep);
   RSeg *nodes = ar.alloc<RSeg>(nkeep);
   if (ar.overflow) return MP_ERR_ARENA;
+  if (sparse && (C.rd.rd[0].win_off == nullptr || (C.rd.lidx_slot && C.rd.lidx_slot[r] < 0))) return MP_NEED_LIDX;     // the host indexes the read and maps it again
   if (sparse) {
     // ---- REFINEclusters with the LocalIndex k-mers (smallOpts.globalK / globalW = the index's k / w, :427-441)
     for (int p = 0; p < nkeep; p++) if (!mp_refine_cluster(C, r, F, keep[p], ar, RC[p], nodes + p)) return MP_ERR_ARENA;
@@ -709,9 +710,9 @@ __device__ __noinline__ int mp_stage1_highacc(const MpCtx &C, int r, Arena &ar, 
       for (int i = 0; i < n; i++) {
         RCluster &R = RC[H.ch[h][i]];
         const int m = R.n;
+        { int k = 0;
+          for (RSeg *s = R.head; s; s = s->next) { const int sn = s->n; for (int j = lane; j < sn; j += kLanes) { tmpq[o + k + j] = s->q[j]; tmpt[o + k + j] = s->t[j]; } k += sn; } }
         if (lane == 0) {
-          int k = 0;
-          for (RSeg *s = R.head; s; s = s->next) for (int j = 0; j < s->n; j++) { tmpq[o + k] = s->q[j]; tmpt[o + k] = s->t[j]; k++; }
           cl_off[i] = (unsigned long long)o; slot_off[i] = (unsigned long long)o; unit_cl[i] = (uint32_t)i; unit_edge[i] = (uint8_t)((i == 0 ? 1 : 0) | (i == n - 1 ? 2 : 0));
           cl_box[4 * i] = R.qS; cl_box[4 * i + 1] = R.qE; cl_box[4 * i + 2] = R.tS; cl_box[4 * i + 3] = R.tE; cl_strand[i] = (uint8_t)(R.strand != 0); cl_freq[i] = R.freq;
           chrom_off[i] = C.ix.hdr_pos[R.chrom]; chrom_len[i] = contig_len(C.ix, R.chrom); read_off[i] = C.rd.read_off[r]; read_len[i] = L;
@@ -756,22 +757,30 @@ __device__ __noinline__ int mp_stage1_highacc(const MpCtx &C, int r, Arena &ar, 
         xs.strand[xc] = -1; xs.chrom[xc] = R.chrom; xs.freq[xc] = R.freq; xs.qS[xc] = 0xffffffffu; xs.qE[xc] = 0; xs.tS[xc] = 0xffffffffu; xs.tE[xc] = 0;
         if (R.n > 0) mp_decide_coordinates(xs, xc, R.strand, R.chrom, R.freq);
         if (cn > 0) mp_trim_overlapped(xs.q + xo, xs.t + xo, xs.len + xo, cn, xs.strand[xc], 40, true, tidx);
-        // same-diagonal runs
-        int nr = S.run_off[xc];
+      }
+      wsync();
+      {   // same-diagonal runs (MergeMatchesSameDiag): anchor j opens a run unless it continues the one of j - 1; one anchor per lane, heads compacted by ballot
+        const int nr0 = S.run_off[xc];
+        int nr = nr0;
         const int st = xs.strand[xc];
-        for (int j = 0; j < cn; j++) {
-          bool head = true;
-          if (j > 0) {
-            const uint32_t *Q = xs.q + xo, *T = xs.t + xo; const int *Ln = xs.len + xo; const uint8_t *Ov = S.ovp + xo;
+        const uint32_t *Q = xs.q + xo, *T = xs.t + xo; const int *Ln = xs.len + xo; const uint8_t *Ov = S.ovp + xo;
+        for (int b0 = 0; b0 < cn; b0 += kLanes) {
+          const int j = b0 + lane;
+          bool head = j < cn;
+          if (j < cn && j > 0) {
             const long long dp = st == 0 ? (long long)T[j - 1] - (long long)Q[j - 1] : (long long)Q[j - 1] + (long long)T[j - 1] + (long long)Ln[j - 1];
             const long long dc = st == 0 ? (long long)T[j] - (long long)Q[j] : (long long)Q[j] + (long long)T[j] + (long long)Ln[j];
             const uint32_t prev_qEnd = Q[j - 1] + (uint32_t)Ln[j - 1];
             const long long gd = ha_labs((long long)Q[j] - ((long long)Q[j - 1] + (long long)Ln[j - 1]));
             if (Ov[j - 1] == 0 && Ov[j] == 0 && dp == dc && prev_qEnd < Q[j] && gd <= (long long)O.merge_dist) head = false;
           }
-          if (head) { S.run_s[nr] = j; S.run_e[nr] = j + 1; nr++; } else S.run_e[nr - 1] = j + 1;
+          const unsigned mk3 = ballot(head);
+          if (head) S.run_s[nr + __popc(mk3 & lanemask_lt())] = j;
+          nr += __popc(mk3);
         }
-        S.run_off[xc + 1] = nr;
+        wsync();
+        for (int k = nr0 + lane; k < nr; k += kLanes) S.run_e[k] = k + 1 < nr ? S.run_s[k + 1] : cn;
+        if (lane == 0) S.run_off[xc + 1] = nr;
       }
       wsync();
       xo += cn; xc++;

@@ -395,12 +395,16 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
   cudaStream_t st = ctx->stream;
   int rc;
   DevBuf *B = m->b;
-  // ---- a12: LocalIndex::IndexSeq of every read, both strands (Map_lowacc.h:246-250)
+  // ---- a12: LocalIndex::IndexSeq of every read, both strands (Map_lowacc.h:246-250).  MapRead_highacc builds them too (Map_highacc.h:399-403) but reads them only in
+  // REFINEclusters, i.e. for the few reads with a sparse cluster: those reads come back with MP_NEED_LIDX, are indexed, and mapped again below.
   ctx->keep_stats = false;
-  if ((rc = lra_b200_lindex_build(ctx, rs->reads, rs->h_off.data(), rs->h_len.data(), n_reads, m->opts.smallK, m->opts.smallW, m->opts.localIndexWindow, m->opts.localIndexMaxFreq, &m->rl[0]))) return rc;
-  all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
-  if ((rc = lra_b200_lindex_build(ctx, rs->reads, rs->h_rc_off.data(), rs->h_len.data(), n_reads, m->opts.smallK, m->opts.smallW, m->opts.localIndexWindow, m->opts.localIndexMaxFreq, &m->rl[1]))) return rc;
-  all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
+  const bool lazy_lidx = m->opts.HighlyAccurate != 0 && !getenv("LRA_B200_MAP_EAGER_LIDX");
+  if (!lazy_lidx) {
+    if ((rc = lra_b200_lindex_build(ctx, rs->reads, rs->h_off.data(), rs->h_len.data(), n_reads, m->opts.smallK, m->opts.smallW, m->opts.localIndexWindow, m->opts.localIndexMaxFreq, &m->rl[0]))) return rc;
+    all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
+    if ((rc = lra_b200_lindex_build(ctx, rs->reads, rs->h_rc_off.data(), rs->h_len.data(), n_reads, m->opts.smallK, m->opts.smallW, m->opts.localIndexWindow, m->opts.localIndexMaxFreq, &m->rl[1]))) return rc;
+    all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
+  }
   // ---- the mapper worker kernel
   const size_t seg_cap = (size_t)n_reads * 3 + 1024;
   const size_t blk_cap = (size_t)(total_bases / 2) + (size_t)n_reads * 64 + 4096;
@@ -444,7 +448,9 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
   mb.C.ix.gl = lidx_view(m->gl);
   mb.C.rd.fwd = lra::SeqView{rs->reads->b2, rs->reads->nm, Npad}; mb.C.rd.rc = lra::SeqView{rs->reads->b2 + Npad / 16, rs->reads->nm + Npad / 32, Npad};
   mb.C.rd.read_off = (const unsigned long long *)rs->off.p; mb.C.rd.read_len = (const uint32_t *)rs->len.p; mb.C.rd.n_reads = n_reads;
-  mb.C.rd.rd[0] = lidx_view(m->rl[0]); mb.C.rd.rd[1] = lidx_view(m->rl[1]);
+  mb.C.rd.lidx_slot = nullptr;
+  if (lazy_lidx) { memset(&mb.C.rd.rd[0], 0, sizeof mb.C.rd.rd[0]); memset(&mb.C.rd.rd[1], 0, sizeof mb.C.rd.rd[1]); }
+  else { mb.C.rd.rd[0] = lidx_view(m->rl[0]); mb.C.rd.rd[1] = lidx_view(m->rl[1]); }
   // (the reverse-complement image was built over arena offsets read_off + Npad; the worker only uses window offsets relative to the image's own seq_start)
   mb.out.status = (int *)B[2].p; mb.out.n_chains = (int *)B[3].p; mb.out.chain_nseg = (int *)B[4].p; mb.out.chain_seg0 = (int *)B[5].p;
   mb.out.seg = (SegRec *)B[6].p; mb.out.seg_cap = (int)seg_cap; mb.out.seg_cursor = (unsigned long long *)B[8].p; mb.out.blocks = (uint32_t *)B[7].p; mb.out.blk_cap = blk_cap;
@@ -462,6 +468,36 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
     CU(cudaStreamSynchronize(st));
     { lra_b200_kernel_stat s2; memset(&s2, 0, sizeof s2); snprintf(s2.name, sizeof s2.name, "map_reads"); cudaEventElapsedTime(&s2.ms, ctx->ev[0], ctx->ev[1]);
       s2.jobs = (uint64_t)n_reads; s2.algo_bytes = total_bases + 2 * ((total_bases + 3) / 4); all.push_back(s2); }
+    if (lazy_lidx) {
+      std::vector<int> need;
+      for (int r = 0; r < n_reads; r++) if (hst[r] == MP_NEED_LIDX) need.push_back(r);
+      if (!need.empty()) {
+        const int nn = (int)need.size();
+        std::vector<uint64_t> o0(nn), o1(nn); std::vector<uint32_t> ln(nn); std::vector<int> slot(n_reads, -1);
+        for (int i = 0; i < nn; i++) { o0[i] = rs->h_off[need[i]]; o1[i] = rs->h_rc_off[need[i]]; ln[i] = rs->h_len[need[i]]; slot[need[i]] = i; }
+        if ((rc = lra_b200_lindex_build(ctx, rs->reads, o0.data(), ln.data(), nn, m->opts.smallK, m->opts.smallW, m->opts.localIndexWindow, m->opts.localIndexMaxFreq, &m->rl[0]))) return rc;
+        all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
+        if ((rc = lra_b200_lindex_build(ctx, rs->reads, o1.data(), ln.data(), nn, m->opts.smallK, m->opts.smallW, m->opts.localIndexWindow, m->opts.localIndexMaxFreq, &m->rl[1]))) return rc;
+        all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
+        std::stable_sort(need.begin(), need.end(), [&](int a, int b2) { return rs->h_len[a] > rs->h_len[b2]; });
+        if ((rc = ensure(ctx, B[31], (size_t)n_reads * 4)) || (rc = ensure(ctx, B[32], (size_t)nn * 4))) return rc;
+        CU(cudaMemcpyAsync(B[31].p, slot.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(B[32].p, need.data(), (size_t)nn * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync((char *)B[8].p + 32, 0, 4, st));
+        mb.C.rd.rd[0] = lidx_view(m->rl[0]); mb.C.rd.rd[1] = lidx_view(m->rl[1]); mb.C.rd.lidx_slot = (const int *)B[31].p;
+        MapBatch mbs = mb; mbs.order = (const int *)B[32].p; mbs.n_work = nn;
+        int blocks_s = (nn + bw - 1) / bw; if (blocks_s > blocks) blocks_s = blocks;
+        cudaEventRecord(ctx->ev[0], st);
+        map_reads_kernel<<<(unsigned)blocks_s, (unsigned)(bw * 32), 0, st>>>(mbs);
+        cudaEventRecord(ctx->ev[1], st);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(hst.data(), B[2].p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        lra_b200_kernel_stat s4; memset(&s4, 0, sizeof s4); snprintf(s4.name, sizeof s4.name, "map_reads(REFINEclusters reads)"); cudaEventElapsedTime(&s4.ms, ctx->ev[0], ctx->ev[1]);
+        s4.jobs = (uint64_t)nn; all.push_back(s4);
+      }
+    }
     std::vector<int> redo;
     for (int r = 0; r < n_reads; r++) if (hst[r] == MP_ERR_ARENA) redo.push_back(r);
     if (!redo.empty() && !getenv("LRA_B200_MAP_NO_RETRY")) {
@@ -471,6 +507,18 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
       while ((size_t)blocks2 * bw * per2 > B[9].cap && blocks2 > 1) blocks2--;
       int bw2 = bw; while ((size_t)blocks2 * bw2 * per2 > B[9].cap && bw2 > 1) bw2--;
       if ((size_t)blocks2 * bw2 * per2 <= B[9].cap) {
+        if (lazy_lidx) {      // a read that ran out of scratch may still reach REFINEclusters: index the reads of this pass
+          const int nn = (int)redo.size();
+          std::vector<uint64_t> o0(nn), o1(nn); std::vector<uint32_t> ln(nn); std::vector<int> slot(n_reads, -1);
+          std::vector<int> asc(redo); std::sort(asc.begin(), asc.end());
+          for (int i = 0; i < nn; i++) { o0[i] = rs->h_off[asc[i]]; o1[i] = rs->h_rc_off[asc[i]]; ln[i] = rs->h_len[asc[i]]; slot[asc[i]] = i; }
+          if ((rc = lra_b200_lindex_build(ctx, rs->reads, o0.data(), ln.data(), nn, m->opts.smallK, m->opts.smallW, m->opts.localIndexWindow, m->opts.localIndexMaxFreq, &m->rl[0]))) return rc;
+          if ((rc = lra_b200_lindex_build(ctx, rs->reads, o1.data(), ln.data(), nn, m->opts.smallK, m->opts.smallW, m->opts.localIndexWindow, m->opts.localIndexMaxFreq, &m->rl[1]))) return rc;
+          if ((rc = ensure(ctx, B[31], (size_t)n_reads * 4))) return rc;
+          CU(cudaMemcpyAsync(B[31].p, slot.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
+          CU(cudaStreamSynchronize(st));
+          mb.C.rd.rd[0] = lidx_view(m->rl[0]); mb.C.rd.rd[1] = lidx_view(m->rl[1]); mb.C.rd.lidx_slot = (const int *)B[31].p;
+        }
         if ((rc = ensure(ctx, B[28], redo.size() * 4))) return rc;
         CU(cudaMemcpyAsync(B[28].p, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemsetAsync((char *)B[8].p + 32, 0, 4, st));

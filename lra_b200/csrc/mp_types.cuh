@@ -28,6 +28,8 @@ struct MpReads {
   const uint32_t *read_len;
   int n_reads;
   LidxView rd[2];                         // LocalIndex::IndexSeq of every read, forward / reverse complement (Map_lowacc.h:246-250)
+  const int *lidx_slot;                   // nullptr: rd[] hold every read of the batch (sequence r = read r); else the sequence of read r in rd[], -1 = not indexed
+                                          // (high-accuracy presets index only the reads that reach REFINEclusters, in a second pass)
 };
 
 // anchors of a set of clusters, SoA; cluster c owns [off[c], off[c+1])
@@ -60,7 +62,7 @@ struct SegRec {
 };
 
 // status of a read after the map kernel
-enum { MP_OK = 0, MP_UNALIGNED = 1, MP_ERR_ARENA = 2, MP_ERR_CAP = 3 };
+enum { MP_OK = 0, MP_UNALIGNED = 1, MP_ERR_ARENA = 2, MP_ERR_CAP = 3, MP_ERR_UNSUPPORTED = 4, MP_NEED_LIDX = 5 };
 
 }  // namespace mp
 }  // namespace lra

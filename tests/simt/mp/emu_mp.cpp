@@ -76,7 +76,7 @@ extern "C" int emu_map_reads(const uint8_t *reads_fwd, const uint8_t *reads_rc, 
   b.C.ix.genome = pg.view; b.C.ix.hdr_pos = (const unsigned long long *)hdr_pos; b.C.ix.n_hdr = n_hdr; b.C.ix.idx_t = (const unsigned long long *)idx_t; b.C.ix.idx_pos = idx_pos;
   b.C.ix.n_idx = n_idx;
   b.C.ix.gl = LidxView{(const unsigned long long *)gl_win_off, nullptr, (const unsigned long long *)gl_bnd, gl_mins, nullptr, nullptr, nullptr, gl_n_win, n_hdr};
-  b.C.rd.fwd = pf.view; b.C.rd.rc = pr.view; b.C.rd.read_off = (const unsigned long long *)read_off; b.C.rd.read_len = read_len; b.C.rd.n_reads = n_reads;
+  b.C.rd.fwd = pf.view; b.C.rd.rc = pr.view; b.C.rd.read_off = (const unsigned long long *)read_off; b.C.rd.read_len = read_len; b.C.rd.n_reads = n_reads; b.C.rd.lidx_slot = nullptr;
   b.C.rd.rd[0] = LidxView{(const unsigned long long *)rf_win_off, nullptr, (const unsigned long long *)rf_bnd, rf_mins, rf_win_first, (const unsigned long long *)read_off, read_len, 0, n_reads};
   b.C.rd.rd[1] = LidxView{(const unsigned long long *)rr_win_off, nullptr, (const unsigned long long *)rr_bnd, rr_mins, rr_win_first, (const unsigned long long *)read_off, read_len, 0, n_reads};
   unsigned long long cur[4] = {0, 0, 0, 0}; int err = 0, work = 0;
