@@ -411,7 +411,9 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
   // one CTA of `bw` warps per SM (phase-aligned groups of reads, mp_phase); LRA_B200_MAP_BLOCK_WARPS / _BLOCKS_PER_SM for experiments
   int bw = MP_BLOCK_THREADS / 32; if (getenv("LRA_B200_MAP_BLOCK_WARPS")) bw = atoi(getenv("LRA_B200_MAP_BLOCK_WARPS"));
   if (bw < 1) bw = 1; if (bw > MP_BLOCK_THREADS / 32) bw = MP_BLOCK_THREADS / 32;
-  int blocks = ctx->n_sm;
+  int bps = 1; if (getenv("LRA_B200_MAP_BLOCKS_PER_SM")) bps = atoi(getenv("LRA_B200_MAP_BLOCKS_PER_SM"));
+  if (bps < 1) bps = 1; if (bps * bw > MP_BLOCK_THREADS / 32) bps = (MP_BLOCK_THREADS / 32) / bw;
+  int blocks = ctx->n_sm * bps;
   if ((long long)blocks * bw > (long long)n_reads) blocks = (n_reads + bw - 1) / bw;
   int warps = blocks * bw;
   // worker scratch, measured on ONT / CLR reads: peak 14.4 MB for a 100 kb read, ~150 B per base (SparseDP sub-problems dominate).  The first pass

@@ -127,6 +127,19 @@ def test_map_batch_gpu_structural_variant_reads(preset, n_reads, tmp_path):
     assert ours == ref, diff_report(ours, ref)
 
 
+@pytest.mark.gpu
+def test_map_batch_gpu_megabase_contigs(tmp_path, monkeypatch):
+    """-CONTIG on 1-2 Mb contigs with seeded structural variants (BASELINE configs[4] is 1-10 Mb): worker arenas of hundreds of MB per warp, few CTAs."""
+    monkeypatch.setitem(mapgen.PROFILE, "contig", "contig_long")
+    w = mapgen.workdir(tmp_path, "contig", n_reads=6, ref_len=9_000_000, contigs=3, repeats=False, sv=True)
+    _, ref = mapgen.canonical_sam(mapgen.reference_sam(w))
+    text, st = gpu_sam(w, None)
+    assert (st["status"] <= 1).all(), np.bincount(st["status"])
+    ours = canon_ours(text)
+    assert len(ours) == len(ref)
+    assert ours == ref, diff_report(ours, ref)
+
+
 def edge_case_workdir(tmp_path, preset):
     """Degenerate reads: shorter than k, shorter than a minimizer window, all N, N runs, homopolymer, dinucleotide repeat, an exact copy of the
     reference, a read covering a whole small contig, the same read twice."""

@@ -108,10 +108,12 @@ def read_lengths(profile, n, rng):
         return np.maximum(1000, rng.lognormal(mu, sigma, size=n)).astype(np.int64)
     if profile == "contig":  # assembly contigs scaled to the test references: 100-400 kb
         return rng.integers(100000, 400000, size=n).astype(np.int64)
+    if profile == "contig_long":  # megabase-scale contigs (BASELINE configs[4] is 1-10 Mb)
+        return rng.integers(1000000, 2000000, size=n).astype(np.int64)
     raise ValueError(profile)
 
 
-PROFILE_ERR = {"ccs10k": 0.01, "hifi": 0.005, "ont": 0.08, "clr": 0.12, "contig": 0.001}
+PROFILE_ERR = {"contig_long": 0.001, "ccs10k": 0.01, "hifi": 0.005, "ont": 0.08, "clr": 0.12, "contig": 0.001}
 
 
 def gen_reads(ref, n_reads, profile, seed, err=None):
