@@ -103,8 +103,9 @@ struct Arena {
   unsigned long long cap, top, peak, cap0;
   int overflow;
   int phase;                              // CTA phase barriers this warp has passed for its current read (mp_phase)
+  unsigned phase_mask;                    // bit i: the i-th phase point of a read is a CTA barrier (uniform over the launch; all ones by default)
   unsigned long long *prof;               // optional cycle counters of this warp (LRA_B200_MAP_PROFILE)
-  __device__ __forceinline__ void init(void *b, unsigned long long c) { base = (unsigned char *)b; cap = c & ~15ull; cap0 = cap; top = 0; peak = 0; overflow = 0; phase = 0; prof = nullptr; }
+  __device__ __forceinline__ void init(void *b, unsigned long long c) { base = (unsigned char *)b; cap = c & ~15ull; cap0 = cap; top = 0; peak = 0; overflow = 0; phase = 0; phase_mask = 0xffffffffu; prof = nullptr; }
   __device__ __forceinline__ unsigned long long tick(int slot, unsigned long long t0) {
 #ifdef LRA_EMU
     (void)slot; (void)t0; return 0ull;
@@ -150,10 +151,10 @@ struct Arena {
 // of reads through the stages in lock step: one CTA barrier closes every stage.  A barrier only counts arrivals, so a warp whose read leaves the
 // path early (unaligned, capacity error, fewer chains) catches up with mp_phase_upto and idles at no cost to the others.
 __device__ __forceinline__ void mp_phase(Arena &ar) {
-  ar.phase++;
 #if !defined(LRA_EMU)
-  __syncthreads();
+  if ((ar.phase_mask >> (ar.phase & 31)) & 1u) __syncthreads();
 #endif
+  ar.phase++;
 }
 __device__ __forceinline__ void mp_phase_upto(Arena &ar, int n) { while (ar.phase < n) mp_phase(ar); }
 constexpr int kPhasesStage1 = 4;          // minimizers+sort | CompareLists | strand+CleanMatches+LinearExtend | first SparseDP

@@ -457,6 +457,7 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
   mb.out.status = (int *)B[2].p; mb.out.n_chains = (int *)B[3].p; mb.out.chain_nseg = (int *)B[4].p; mb.out.chain_seg0 = (int *)B[5].p;
   mb.out.seg = (SegRec *)B[6].p; mb.out.seg_cap = (int)seg_cap; mb.out.seg_cursor = (unsigned long long *)B[8].p; mb.out.blocks = (uint32_t *)B[7].p; mb.out.blk_cap = blk_cap;
   mb.out.blk_cursor = (unsigned long long *)((char *)B[8].p + 8); mb.out.err = (int *)((char *)B[8].p + 16); mb.out.peak = (unsigned long long *)((char *)B[8].p + 24);
+  mb.phase_mask = 0xffffffffu; if (getenv("LRA_B200_MAP_PHASE_MASK")) mb.phase_mask = (unsigned)strtoul(getenv("LRA_B200_MAP_PHASE_MASK"), nullptr, 16);
   mb.arena = (unsigned char *)B[9].p; mb.arena_per_warp = per; mb.work = (int *)((char *)B[8].p + 32); mb.order = (const int *)rs->order.p; mb.n_work = n_reads;
   cudaEventRecord(ctx->ev[0], st);
   map_reads_kernel<<<(unsigned)blocks, (unsigned)(bw * 32), 0, st>>>(mb);
@@ -488,9 +489,11 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
         CU(cudaMemsetAsync((char *)B[8].p + 32, 0, 4, st));
         mb.C.rd.rd[0] = lidx_view(m->rl[0]); mb.C.rd.rd[1] = lidx_view(m->rl[1]); mb.C.rd.lidx_slot = (const int *)B[31].p;
         MapBatch mbs = mb; mbs.order = (const int *)B[32].p; mbs.n_work = nn;
-        int blocks_s = (nn + bw - 1) / bw; if (blocks_s > blocks) blocks_s = blocks;
+        // few reads: spread them over all SMs (CTAs of fewer warps) instead of filling a few 24-warp CTAs
+        int bw_s = (nn + ctx->n_sm - 1) / ctx->n_sm; if (bw_s < 1) bw_s = 1; if (bw_s > bw) bw_s = bw;
+        int blocks_s = (nn + bw_s - 1) / bw_s; if (blocks_s > blocks) blocks_s = blocks;
         cudaEventRecord(ctx->ev[0], st);
-        map_reads_kernel<<<(unsigned)blocks_s, (unsigned)(bw * 32), 0, st>>>(mbs);
+        map_reads_kernel<<<(unsigned)blocks_s, (unsigned)(bw_s * 32), 0, st>>>(mbs);
         cudaEventRecord(ctx->ev[1], st);
         ctx->launches++;
         CU(cudaGetLastError());

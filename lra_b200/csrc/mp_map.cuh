@@ -293,6 +293,7 @@ struct MapBatch {
   int *work;                              // dynamic read counter
   const int *order;                       // optional: reads in decreasing length (longest first), or the reads of a retry pass
   int n_work;                             // reads to map in this launch (entries of `order`)
+  unsigned phase_mask;                    // which phase points are CTA barriers (mp_phase)
 };
 
 // One CTA per SM; its warps take a group of consecutive reads of the length-sorted order (similar lengths, similar stage times) through the
@@ -307,6 +308,7 @@ __global__ void __launch_bounds__(MP_BLOCK_THREADS, 1) map_reads_kernel(MapBatch
   const int wid = (int)blockIdx.x * warps_per_block + wib;
   Arena ar; ar.init(b.arena + (unsigned long long)wid * b.arena_per_warp, b.arena_per_warp);
   if (b.C.prof) ar.prof = b.C.prof + (unsigned long long)wid * kProfStages;
+  ar.phase_mask = b.phase_mask;
   const int PB = (b.C.o.NumAln < kMaxChains ? b.C.o.NumAln : kMaxChains);
 #if !defined(LRA_EMU)
   __shared__ int s_base;

@@ -83,7 +83,7 @@ extern "C" int emu_map_reads(const uint8_t *reads_fwd, const uint8_t *reads_rc, 
   b.out.status = status; b.out.n_chains = n_chains; b.out.chain_nseg = chain_nseg; b.out.chain_seg0 = chain_seg0;
   b.out.seg = seg; b.out.seg_cap = seg_cap; b.out.seg_cursor = &cur[0]; b.out.blocks = blocks; b.out.blk_cap = blk_cap; b.out.blk_cursor = &cur[1]; b.out.err = &err;
   b.out.peak = &cur[2];
-  b.arena = base; b.arena_per_warp = arena_bytes; b.work = &work; b.order = nullptr; b.n_work = n_reads;
+  b.arena = base; b.arena_per_warp = arena_bytes; b.work = &work; b.order = nullptr; b.n_work = n_reads; b.phase_mask = 0xffffffffu;
   emu::launch(dim3(1), dim3(MP_LANES), 0, [&] { map_reads_kernel(b); });
   counts[0] = cur[0] >> 40; counts[1] = cur[0] & ((1ull << 40) - 1ull); counts[2] = (uint64_t)err; counts[3] = cur[2];
   return err;
