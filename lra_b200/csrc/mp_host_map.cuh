@@ -280,6 +280,13 @@ extern "C" int lra_b200_mapper_create(lra_b200_ctx *ctx, const lra_b200_map_opts
   if (hdr_pos[n_contigs] != genome_len || genome_len >= (1ull << 32)) return fail(ctx, LRA_B200_EINVAL, "mapper_create: header offsets do not cover the genome (or >= 2^32 bases)");
   *out = nullptr;
   CU(cudaSetDevice(ctx->device));
+  {   // the packed alphabet is A, C, G, T + one "N" code: IUPAC ambiguity bytes compare equal to N here but as raw bytes in the reference (Checkbp, RefineSpace, strncmp)
+    bool plain[256]; for (int i = 0; i < 256; i++) plain[i] = false;
+    for (const char *c = "ACGTNacgtn"; *c; c++) plain[(unsigned char)*c] = true;
+    unsigned long long other = 0;
+    for (uint64_t i = 0; i < genome_len; i++) other += plain[(unsigned char)genome_ascii[i]] ? 0 : 1;
+    if (other) fprintf(stderr, "lra_b200: warning: %llu reference bases outside ACGTN are treated as N; alignments that overlap them may differ from the reference's\n", other);
+  }
   lra_b200_mapper *m = new lra_b200_mapper();
   m->opts = *opts;
   int rc;
