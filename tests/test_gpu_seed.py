@@ -60,7 +60,7 @@ def test_seed_overflow_and_revcomp(ctx):
 def test_seed_batch_rejects_bad_read_descriptors(ctx):
     """reads beyond the arena, overlapping or out of order are refused (the minimizer scratch is indexed by read_off)"""
     from lra_b200 import capi
-    case = seedgen.make_case(7, glen=50000, n_reads=4, k=17, w=10)
+    case = seedgen.make_case(7, glen=120000, n_reads=4, k=17, w=10)
     reads = ctx.seq_upload(case["arena"][:-16]); genome = ctx.seq_upload(case["genome"][:-16])
     idx = ctx.index_upload(case["idx_t"], case["idx_pos"])
     ro, rl = case["read_off"].copy(), case["read_len"].copy()
