@@ -463,7 +463,8 @@ def main():
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if tname in tr.get("kernels", {}):
-            traffic = tr["kernels"][tname]["dram_bytes_per_read"] * R
+            kt = tr["kernels"][tname]
+            traffic = kt.get("by_preset", {}).get(args.preset, kt)["dram_bytes_per_read"] * R
     except Exception:
         pass
     line = {"metric": METRIC, "value": value, "unit": "reads/s", "gbp_per_s": (ab_last / max(1, R)) * value / 1e9,
