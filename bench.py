@@ -370,6 +370,7 @@ def main():
     contig_names = ref["names"]
     h2d = d2h = 0
     sam_bytes = 0
+    pin_pool = {}
 
     def e2e_step(b):
         nonlocal h2d, d2h, sam_bytes
@@ -405,9 +406,20 @@ def main():
             hb = host[b]
             d2h = 0
             shards_res = []
-            for r, parts in enumerate(got):
-                res = capi.result_from_parts([p.cpu() for p in parts])
+            staged = []
+            for r, parts in enumerate(got):      # D2H of every shard's records into pinned buffers that live as long as the slot (re-used across steps)
+                hp = []
+                for i, p in enumerate(parts):
+                    key = (slot, r, i); n_el = int(p.numel())
+                    buf = pin_pool.get(key)
+                    if buf is None or buf.numel() < n_el or buf.dtype != p.dtype:
+                        buf = torch.empty(n_el + n_el // 4 + 16, dtype=p.dtype).pin_memory(); pin_pool[key] = buf
+                    v = buf[:n_el]; v.copy_(p, non_blocking=True); hp.append(v)
+                staged.append(hp)
                 d2h += sum(int(p.numel()) * p.element_size() for p in parts)
+            torch.cuda.synchronize()
+            for hp in staged:
+                res = capi.result_from_parts(hp)
                 ab += res["aligned_bases"]
                 shards_res.append(res)
             if not args.no_sam:
