@@ -437,6 +437,7 @@ extern "C" int lra_b200_sort_matches_batch(lra_b200_ctx *ctx, int32_t mode, uint
   size_t slots = 0;
   for (int s = 0; s < n_seg; s++) {
     if (seg_off[s + 1] < seg_off[s]) return fail(ctx, LRA_B200_EINVAL, "sort_matches_batch: segment offsets not ascending");
+    if (seg_off[s + 1] - seg_off[s] > (1ull << 30)) return fail(ctx, LRA_B200_EINVAL, "sort_matches_batch: segment %d has more than 2^30 anchors (the kernel pads a segment to a power of two in int)", s);
     const size_t n = (size_t)(seg_off[s + 1] - seg_off[s]);
     size_t P = 1; while (P < n) P <<= 1;
     slot[s] = slots;
