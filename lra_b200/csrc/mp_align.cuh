@@ -58,6 +58,68 @@ __device__ __noinline__ void mp_trim_overlapped(uint32_t *q, uint32_t *t, int *l
   }
 }
 
+// The same on the whole warp (cluster form: thr 40, strand aware).  The long anchors are sorted by the LongAnchors key with a warp bitonic sort; the reference's std::sort leaves
+// equal keys (two long anchors with the same start, or the same end on the reverse strand, and the same t) in introsort's order, which decides which of them is `prev`, so a list
+// with equal keys goes to the literal replay above.  Iteration ln of the trim loop reads anchors idx[ln - 1], idx[ln] and writes idx[ln - 1] only, and no earlier iteration writes
+// either, so 32 iterations run at a time: all reads, then all writes (lext_kernels.cuh: lext_trim_warp).  scratch: next_pow2(n) MpKey + n ints from the arena.
+__device__ __noinline__ bool mp_trim_overlapped_warp(uint32_t *q, uint32_t *t, int *len, int n, int strand, int thr, bool cluster_form, Arena &ar) {
+  const int lane = lane_id();
+  if (n <= 0) return true;
+  const unsigned long long mk = ar.mark();
+  int *idx = ar.alloc<int>(n + 1);
+  if (ar.overflow) { ar.release(mk); return false; }
+  int nl = 0;
+  for (int base = 0; base < n; base += kLanes) {
+    const int i = base + lane;
+    const bool is_long = i < n && len[i] >= thr;
+    const unsigned m = ballot(is_long);
+    if (is_long) idx[nl + __popc(m & lanemask_lt())] = i;
+    nl += __popc(m);
+  }
+  wsync();
+  if (nl >= 2) {
+    MpKey *keys = ar.alloc<MpKey>((unsigned long long)next_pow2(nl));
+    if (ar.overflow) { ar.release(mk); return false; }
+    for (int i = lane; i < nl; i += kLanes) {
+      const int a = idx[i];
+      const uint32_t k0 = strand == 0 ? q[a] : ~(q[a] + (uint32_t)len[a]);
+      keys[i].k = ((unsigned long long)k0 << 32) | t[a]; keys[i].q = 0; keys[i].idx = (uint32_t)a;
+    }
+    wsync();
+    mp_sort_keys(keys, nl);
+    bool dup = false;
+    for (int i = 1 + lane; i < nl; i += kLanes) dup = dup || keys[i].k == keys[i - 1].k;
+    if (wany(dup)) {
+      if (lane == 0) mp_trim_overlapped(q, t, len, n, strand, thr, cluster_form, idx);
+      wsync();
+      ar.release(mk);
+      return true;
+    }
+    for (int i = lane; i < nl; i += kLanes) idx[i] = (int)keys[i].idx;
+    wsync();
+    for (int base = 1; base < nl; base += kLanes) {
+      const int ln = base + lane;
+      int prev = 0, cut = 0;
+      if (ln < nl) {
+        prev = idx[ln - 1];
+        const int cur = idx[ln];
+        int overlap_r = 0, overlap_g = 0;
+        const uint32_t pend = q[prev] + (uint32_t)len[prev];
+        if (strand == 0) { if (q[cur] < pend && q[cur] >= pend - 30u) overlap_r = (int)(pend - q[cur]); }
+        else { const uint32_t cend = q[cur] + (uint32_t)len[cur]; if (cend > q[prev] && cend <= q[prev] + 30u) overlap_r = (int)(cend - q[prev]); }
+        const uint32_t ptend = t[prev] + (uint32_t)len[prev];
+        if (t[cur] < ptend && t[cur] >= ptend - 30u) overlap_g = (int)(ptend - t[cur]);
+        if (overlap_r > 0 || overlap_g > 0) cut = (overlap_r > overlap_g ? overlap_r : overlap_g) + 1;
+      }
+      wsync();
+      if (cut) { if (cluster_form && strand == 1) q[prev] += (uint32_t)cut; len[prev] -= cut; }
+      wsync();
+    }
+  }
+  ar.release(mk);
+  return true;
+}
+
 // One AffineOneGapAlign job by one lane: the one-sided case with an even doubled half-width K <= 14 and at most kLaneAogRows rows, i.e. the body
 // of aog_thread_kernel<K> (aog_kernels.cuh) with K at run time.  Blocks go to `out` in the reference's order; returns their number.
 constexpr int kLaneAogRows = 96;

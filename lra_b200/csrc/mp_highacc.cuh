@@ -756,8 +756,9 @@ __device__ __noinline__ int mp_stage1_highacc(const MpCtx &C, int r, Arena &ar, 
         xs.off[xc + 1] = xo + cn;
         xs.strand[xc] = -1; xs.chrom[xc] = R.chrom; xs.freq[xc] = R.freq; xs.qS[xc] = 0xffffffffu; xs.qE[xc] = 0; xs.tS[xc] = 0xffffffffu; xs.tE[xc] = 0;
         if (R.n > 0) mp_decide_coordinates(xs, xc, R.strand, R.chrom, R.freq);
-        if (cn > 0) mp_trim_overlapped(xs.q + xo, xs.t + xo, xs.len + xo, cn, xs.strand[xc], 40, true, tidx);
       }
+      wsync();
+      if (cn > 0 && !mp_trim_overlapped_warp(xs.q + xo, xs.t + xo, xs.len + xo, cn, xs.strand[xc], 40, true, ar)) return MP_ERR_ARENA;
       wsync();
       {   // same-diagonal runs (MergeMatchesSameDiag): anchor j opens a run unless it continues the one of j - 1; one anchor per lane, heads compacted by ballot
         const int nr0 = S.run_off[xc];

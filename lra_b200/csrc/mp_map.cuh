@@ -92,7 +92,7 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
           MpKey *keys = ar.alloc<MpKey>((unsigned long long)next_pow2(n));
           uint32_t *gq = ar.alloc<uint32_t>(n), *gt = ar.alloc<uint32_t>(n), *sq = ar.alloc<uint32_t>(n), *stt = ar.alloc<uint32_t>(n);
           if (ar.overflow) return -MP_ERR_ARENA;
-          if (lane == 0) { int k = 0; for (RSeg *s = rc.head; s; s = s->next) for (int i = 0; i < s->n; i++) { gq[k] = s->q[i]; gt[k] = s->t[i]; k++; } }
+          { int k = 0; for (RSeg *s = rc.head; s; s = s->next) { const int sn = s->n; for (int i = lane; i < sn; i += kLanes) { gq[k + i] = s->q[i]; gt[k + i] = s->t[i]; } k += sn; } }
           wsync();
           for (int i = lane; i < n; i += kLanes) { keys[i].k = (unsigned long long)((long long)gq[i] - (long long)gt[i] + (1ll << 33)); keys[i].q = gq[i]; keys[i].idx = (uint32_t)i; }
           wsync();
@@ -114,15 +114,11 @@ __device__ __noinline__ int mp_map_chain(const MpCtx &C, int r, Arena &ar, const
     }
     xs.ncl = ng;
     // TrimOverlappedAnchors(extend_clusters, 0)
-    if (lane == 0) {
-      for (int g = 0; g < ng; g++) {
-        const int a0 = xs.off[g], n = xs.off[g + 1] - a0;
-        if (n == 0) continue;
-        // scratch for the long-anchor index list: the top of the arena is free here
-        int *idx = (int *)(ar.base + ((ar.top + 15ull) & ~15ull));
-        if (ar.avail() < (unsigned long long)n * 4ull + 64ull) { atomicOr(out.err, 4); continue; }
-        mp_trim_overlapped(xs.q + a0, xs.t + a0, xs.len + a0, n, xs.strand[g], 40, true, idx);
-      }
+    wsync();
+    for (int g = 0; g < ng; g++) {
+      const int a0 = xs.off[g], n = xs.off[g + 1] - a0;
+      if (n == 0) continue;
+      if (!mp_trim_overlapped_warp(xs.q + a0, xs.t + a0, xs.len + a0, n, xs.strand[g], 40, true, ar)) return -MP_ERR_ARENA;
     }
     wsync();
   }
