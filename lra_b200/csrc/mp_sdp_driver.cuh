@@ -39,43 +39,11 @@ __device__ __noinline__ int sdp_pure_matches(const SdpAnchors &A, float rate, fl
   if (*W.dyn.err) { ar.release(mk); return -1; }
   for (int i = lane_id(); i < n; i += kLanes) { order[i] = i; used[i] = 0; if (cl_of_frag) cl_of_frag[i] = W.val[i].cl; }
   wsync();
-  // Fragment_valueOrder (Fragment_Info.h:65-99) is a std::sort by value, descending: the loop below only walks the entries with value >= thres, and where those
-  // values are pairwise distinct (and above the next one) every sort puts them in the same order -- a warp bitonic sort by (value desc, index).  Equal values in that
-  // prefix (exact copies of a chain) leave introsort's order in the reference: that case takes the literal replay.
-  bool sorted_by_warp = false;
-  if (n >= 64) {
-    const int P2 = next_pow2(n);
-    unsigned long long *sk = ar.alloc<unsigned long long>((unsigned long long)P2);
-    int *flag = ar.alloc<int>(1);
-    if (!ar.overflow) {
-      const SdpVal *val = W.val;
-      bool neg = false;
-      for (int i = lane_id(); i < P2; i += kLanes) {
-        if (i < n) { const uint32_t b = __float_as_uint(val[i].val); neg = neg || (b >> 31) != 0u || b == 0x7f800000u || (b & 0x7fffffffu) > 0x7f800000u; sk[i] = ((unsigned long long)(~b) << 32) | (uint32_t)i; }
-        else sk[i] = ~0ull;
-      }
-      wsync();
-      if (!wany(neg)) {
-        wsort_pow2(sk, P2, [](unsigned long long a, unsigned long long b) { return a < b; });
-        const float top = val[(uint32_t)sk[0]].val;
-        const float thres0 = __fmul_rn(alnthres, top);
-        bool tie = false;
-        for (int i = 1 + lane_id(); i < n; i += kLanes) {
-          const float a = val[(uint32_t)sk[i - 1]].val, b = val[(uint32_t)sk[i]].val;
-          if (a >= thres0 && a == b) tie = true;
-        }
-        if (!wany(tie)) { for (int i = lane_id(); i < n; i += kLanes) order[i] = (int)(uint32_t)sk[i]; sorted_by_warp = true; }
-      }
-      wsync();
-      (void)flag;
-    } else { ar.overflow = 0; }
-  }
-  wsync();
   if (lane_id() == 0) {
     int nch = 0;
     if (n > 0) {
       const SdpVal *val = W.val;
-      if (!sorted_by_warp) std_sort_replay(order, n, [val](int a, int b) { return val[a].val > val[b].val; });   // Fragment_valueOrder (Fragment_Info.h:65-99)
+      std_sort_replay(order, n, [val](int a, int b) { return val[a].val > val[b].val; });   // Fragment_valueOrder (Fragment_Info.h:65-99)
       const float thres = __fmul_rn(alnthres, val[order[0]].val);
       int fv = 0;
       while (nch < NumAln && fv < n && val[order[fv]].val >= thres) {

@@ -279,7 +279,6 @@ inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 inline float __uint_as_float(unsigned int x) { float f; memcpy(&f, &x, 4); return f; }
-inline unsigned int __float_as_uint(float f) { unsigned int x; memcpy(&x, &f, 4); return x; }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
