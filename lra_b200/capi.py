@@ -444,7 +444,7 @@ class Mapper:
 
     @staticmethod
     def _result_buffers(n, bases, record_cap=None, cigar_cap=None):
-        record_cap = record_cap or 3 * n + 1024; cigar_cap = cigar_cap or int(bases) + 64 * n + 4096
+        record_cap = record_cap or 3 * n + 1024 + 65536; cigar_cap = cigar_cap or int(bases) + 64 * n + 4096
         return dict(status=np.zeros(max(n, 1), np.int32), n_aln=np.zeros(max(n, 1), np.int32), aln_nseg=np.zeros(4 * max(n, 1), np.int32), aln_seg0=np.zeros(4 * max(n, 1), np.int32),
                     aln_rank=np.zeros(4 * max(n, 1), np.int32), records=np.zeros(record_cap, RECORD), n_records=0, cigar=np.zeros(cigar_cap, np.uint32), n_cigar=0)
 

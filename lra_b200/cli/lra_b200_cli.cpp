@@ -303,7 +303,7 @@ int run_align(int argc, char **argv, const std::string &cmdline) {
     for (int i = 0; i < n; i++) { off[i] = rd.off[r0 + i] - rd.off[r0]; len[i] = (uint32_t)(rd.off[r0 + i + 1] - rd.off[r0 + i]); }
     lra_b200_map_result res; memset(&res, 0, sizeof res);
     std::vector<int32_t> status(n), n_aln(n), nseg(4 * n), seg0(4 * n), rank(4 * n);
-    std::vector<lra_b200_record> recs((size_t)3 * n + 1024); std::vector<uint32_t> cig((size_t)bases + 64ull * n + 4096);
+    std::vector<lra_b200_record> recs((size_t)3 * n + 1024 + 65536); std::vector<uint32_t> cig((size_t)bases + 64ull * n + 4096);
     res.status = status.data(); res.n_aln = n_aln.data(); res.aln_nseg = nseg.data(); res.aln_seg0 = seg0.data(); res.aln_rank = rank.data();
     res.records = recs.data(); res.record_cap = recs.size(); res.cigar = cig.data(); res.cigar_cap = cig.size();
     const char *base = rd.seq.data() + rd.off[r0];

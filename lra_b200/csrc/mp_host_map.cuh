@@ -413,7 +413,7 @@ extern "C" int lra_b200_map_resident(lra_b200_ctx *ctx, lra_b200_mapper *m, cons
     all.insert(all.end(), ctx->stats.begin(), ctx->stats.end());
   }
   // ---- the mapper worker kernel
-  const size_t seg_cap = (size_t)n_reads * 3 + 1024;
+  const size_t seg_cap = (size_t)n_reads * 3 + 1024 + (m->opts.readType == 3 ? 65536 : 0);      // contigs: many segments per read
   const size_t blk_cap = (size_t)(total_bases / 2) + (size_t)n_reads * 64 + 4096;
   // one CTA of `bw` warps per SM (phase-aligned groups of reads, mp_phase); LRA_B200_MAP_BLOCK_WARPS / _BLOCKS_PER_SM for experiments
   int bw = MP_BLOCK_THREADS / 32; if (getenv("LRA_B200_MAP_BLOCK_WARPS")) bw = atoi(getenv("LRA_B200_MAP_BLOCK_WARPS"));

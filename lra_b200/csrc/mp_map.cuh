@@ -9,7 +9,7 @@ namespace lra {
 namespace mp {
 
 constexpr int kMaxChains = 4;            // opts.NumAln is 2 or 3 under every preset
-constexpr int kMaxSegPerChain = 24;
+constexpr int kMaxSegPerChain = 256;         // segments of one alignment (a contig with seeded inversions has a few per inversion)
 
 struct MapOut {
   // per read
