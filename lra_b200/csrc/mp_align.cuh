@@ -288,9 +288,6 @@ __device__ __noinline__ bool mp_refine_linear(const MpCtx &C, int r, Arena &ar, 
   const int band = (drift * 2 + 1) < O.localBand ? (drift * 2 + 1) : O.localBand;
   if (B.njobs >= B.cap_jobs && !mp_flush_aog(C, r, ar, B)) return false;
   if (B.nblk >= B.cap) return false;
-#if defined(LRA_EMU) && defined(MP_TRACE)
-  if (lane_id() == 0) fprintf(stderr, "TRACE aog %d %d %d\n", qLen, tLen, band);
-#endif
   if (lane_id() == 0) {
     AogJob J;
     J.qoff = (uint32_t)(C.rd.read_off[r] + curReadEnd); J.toff = (uint32_t)(C.ix.hdr_pos[chrom] + curGenomeEnd); J.addq = curReadEnd; J.addt = curGenomeEnd;
@@ -340,9 +337,6 @@ __device__ __noinline__ bool mp_refined_alignment_btwn(const MpCtx &C, int r, Ar
   else { tK = 12; tW = 7; minRatio = (float)(0.5 / 140.2); }
   uint32_t *fq = 0, *ft = 0, *rq = 0, *rt = 0; float identity = 0.0f;
   unsigned long long tk = mp_clock();
-#if defined(LRA_EMU) && defined(MP_TRACE)
-  if (lane_id() == 0) fprintf(stderr, "TRACE rs %lld %lld\n", read_dist, genome_dist);
-#endif
   int nfor = mp_refine_space(C, r, ar, tK, tW, refineSpaceDiag, false, tMaxFreq, chrom, nextReadStart, curReadEnd, nextGenomeStart, curGenomeEnd, str, 0, 0, &fq, &ft, &identity);
   tk = mp_tick(C, PF_REFINE_SPACE, tk);
   if (nfor < 0) return false;

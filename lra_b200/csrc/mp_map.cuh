@@ -233,10 +233,8 @@ __device__ __noinline__ void mp_map_read(const MpCtx &C, int r, Arena &ar, const
   const int PB = (C.o.NumAln < kMaxChains ? C.o.NumAln : kMaxChains);      // chains a read can have (uniform over the batch)
   if (C.o.HighlyAccurate) {
     // MapRead_highacc (Map_highacc.h:37-798): every chain of Primary_chains[0] becomes an alignment (:690-735)
-    HaState *S = ar.alloc<HaState>(1);
     HaState hs;
-    status = ar.overflow ? MP_ERR_ARENA : mp_stage1_highacc(C, r, ar, hs);
-    (void)S;
+    status = mp_stage1_highacc(C, r, ar, hs);
     mp_phase_upto(ar, kPhasesStage1);
     if (status == MP_OK) {
       const unsigned long long mk = ar.mark();

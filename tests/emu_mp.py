@@ -32,7 +32,7 @@ def lib(lanes=32):
             obj = os.path.join(MPD, "aog_port.o")
             subprocess.run(["gcc", "-std=c11", "-O2", "-fPIC", "-c", os.path.join(os.path.dirname(HERE), "oracle", "aog.c"), "-o", obj], check=True)
             cpps.append(obj)
-        subprocess.run(["g++", "-std=c++17", "-O2" if lanes == 1 else "-O1", "-DLRA_EMU", "-DMP_LANES=%d" % lanes] + (["-DMP_DEBUG", "-g"] if os.environ.get("MP_DEBUG") else []) + (["-DMP_TRACE", "-include", "cstdio"] if os.environ.get("MP_TRACE") else []) + [ "-I" + SIMT, "-I" + CSRC, "-fPIC", "-shared"] + cpps +
+        subprocess.run(["g++", "-std=c++17", "-O2" if lanes == 1 else "-O1", "-DLRA_EMU", "-DMP_LANES=%d" % lanes] + (["-DMP_DEBUG", "-g"] if os.environ.get("MP_DEBUG") else []) + [ "-I" + SIMT, "-I" + CSRC, "-fPIC", "-shared"] + cpps +
                        ["-o", so], check=True)
     L = C.CDLL(so)
     L.emu_sdp_batch.restype = C.c_int
