@@ -919,6 +919,14 @@ int64_t lra_b200_format_records_qual(const lra_b200_map_opts *opts, const lra_b2
                                      const char *quals_ascii, const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, const uint64_t *contig_len,
                                      int32_t n_contigs, int32_t fmt, int32_t runtime, char *out, int64_t cap);
 
+/* The printers that read the reference bases: fmt 'a' the pairwise view of `-p a` (Alignment::PrintPairwise, Alignment.h:564-589) and, with print_md != 0 and fmt 's', the
+ * MD:Z: tag of `--printMD` (AlignmentStringsToMD, Alignment.h:204-245, :763-767).  genome_ascii: contigs back to back as given to lra_b200_mapper_create, contig c at
+ * contig_off[c].  Other arguments and the return value as lra_b200_format_records_qual (which this call equals for the other formats). */
+int64_t lra_b200_format_records_ref(const lra_b200_map_opts *opts, const lra_b200_map_result *res, int32_t n_reads, const char *names, const char *reads_ascii,
+                                    const char *quals_ascii, const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, const uint64_t *contig_len,
+                                    int32_t n_contigs, const char *genome_ascii, const uint64_t *contig_off, int32_t fmt, int32_t print_md, int32_t runtime, char *out,
+                                    int64_t cap);
+
 /* ---- per-kernel timing of the last batch call (CUDA events on the context's stream) ---------------------------- */
 typedef struct lra_b200_kernel_stat {
   char name[48];

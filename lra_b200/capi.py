@@ -396,6 +396,27 @@ def format_sam(opts, res, names, reads, read_off, read_len, contig_names, runtim
     return buf.raw[:n].decode()
 
 
+def format_records_ref(opts, res, names, reads, read_off, read_len, contig_names, genome, contig_off, fmt="a", print_md=False, runtime=0):
+    """lra_b200_format_records_ref: the printers that read the reference bases -- fmt 'a' (PrintPairwise, `-p a`), or fmt 's' with print_md (MD:Z:, `--printMD`)."""
+    L = load_library()
+    L.lra_b200_format_records_ref.restype = C.c_int64
+    L.lra_b200_format_records_ref.argtypes = [C.POINTER(MapOpts), C.POINTER(_MapResult), C.c_int32, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p,
+                                              C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]
+    ms = _map_result_struct(res)
+    nm = names_blob(names); cn = names_blob(contig_names)
+    reads = np.ascontiguousarray(reads, np.uint8); ro = np.ascontiguousarray(read_off, np.uint64); rl = np.ascontiguousarray(read_len, np.uint32)
+    g = np.ascontiguousarray(genome, np.uint8); co = np.ascontiguousarray(contig_off, np.uint64)
+    clen = np.diff(co).astype(np.uint64)
+    args = (C.byref(opts), C.byref(ms), len(names), nm, reads.ctypes.data, None, ro.ctypes.data, rl.ctypes.data, cn, clen.ctypes.data, len(contig_names), g.ctypes.data, co.ctypes.data,
+            ord(fmt), 1 if print_md else 0, runtime)
+    need = -L.lra_b200_format_records_ref(*args, None, 0)
+    if need <= 0:
+        return ""
+    buf = C.create_string_buffer(int(need) + 16)
+    n = L.lra_b200_format_records_ref(*args, buf, need + 16)
+    return buf.raw[:n].decode()
+
+
 def names_blob(names):
     """n NUL-terminated strings back to back (the `names` / `contig_names` argument of lra_b200_format_sam)."""
     return b"".join(n.encode() + b"\0" for n in names)

@@ -242,7 +242,7 @@ bool read_gli(const std::string &path, int &k, int &w, int &window, std::vector<
 int run_align(int argc, char **argv, const std::string &cmdline) {
   std::string mode = "-ONT", ref, out_path, fmt = "p";      // the reference's default printer is PAF (Options.h:162)
   std::vector<std::string> inputs;
-  int device = 0, print_num = -1; uint64_t batch_bases = 256ull << 20;
+  int device = 0, print_num = -1, print_md = 0; uint64_t batch_bases = 256ull << 20;
   for (int i = 0; i < argc; i++) {
     const std::string a = argv[i];
     if (a == "-ONT" || a == "-CLR" || a == "-CCS" || a == "-CONTIG") mode = a;
@@ -250,13 +250,14 @@ int run_align(int argc, char **argv, const std::string &cmdline) {
     else if (a == "-p" && i + 1 < argc) fmt = argv[++i];
     else if (a == "-o" && i + 1 < argc) out_path = argv[++i];
     else if (a == "--PrintNumAln" && i + 1 < argc) print_num = atoi(argv[++i]);
+    else if (a == "--printMD") print_md = 1;
     else if (a == "--batch-bases" && i + 1 < argc) batch_bases = strtoull(argv[++i], nullptr, 10);
     else if (a == "--device" && i + 1 < argc) device = atoi(argv[++i]);
     else if (a[0] != '-') { if (ref.empty()) ref = a; else inputs.push_back(a); }
   }
-  if (ref.empty() || inputs.empty()) { fprintf(stderr, "usage: lra_b200 align -CLR|-ONT ref.fa reads.fa [-t N] [-p s|p|pc|b] [-o out]\n"); return 1; }
-  const char f = fmt == "s" ? 's' : fmt == "p" ? 'p' : fmt == "pc" ? 'c' : fmt == "b" ? 'b' : 0;
-  if (!f) { fprintf(stderr, "lra_b200 align: -p %s is not supported (s, p, pc, b)\n", fmt.c_str()); return 1; }
+  if (ref.empty() || inputs.empty()) { fprintf(stderr, "usage: lra_b200 align -CLR|-ONT ref.fa reads.fa [-t N] [-p s|p|pc|b|a] [--printMD] [-o out]\n"); return 1; }
+  const char f = fmt == "s" ? 's' : fmt == "p" ? 'p' : fmt == "pc" ? 'c' : fmt == "b" ? 'b' : fmt == "a" ? 'a' : 0;
+  if (!f) { fprintf(stderr, "lra_b200 align: -p %s is not supported (s, p, pc, b, a)\n", fmt.c_str()); return 1; }
   std::string text; Fasta g;
   if (!slurp(ref, text) || !parse_genome(text, g) || g.names.empty()) { fprintf(stderr, "Cannot open target %s\n", ref.c_str()); return 1; }
   text.clear(); text.shrink_to_fit();
@@ -311,10 +312,11 @@ int run_align(int argc, char **argv, const std::string &cmdline) {
     std::string names;
     for (int i = 0; i < n; i++) { names += rd.names[r0 + i]; names.push_back('\0'); if (status[i] == 0 && n_aln[i] > 0) mapped++; }
     const char *qbase = rd.qual.size() == rd.seq.size() && !rd.qual.empty() ? rd.qual.data() + rd.off[r0] : nullptr;
-    int64_t need = lra_b200_format_records_qual(&opts, &res, n, names.data(), base, qbase, off.data(), len.data(), cnames.data(), clen.data(), nc, f, 0, nullptr, 0);
+    int64_t need = lra_b200_format_records_ref(&opts, &res, n, names.data(), base, qbase, off.data(), len.data(), cnames.data(), clen.data(), nc, g.seq.data(), g.off.data(), f, print_md, 0, nullptr, 0);
     need = -need;
     textbuf.resize((size_t)need + 16);
-    const int64_t got = lra_b200_format_records_qual(&opts, &res, n, names.data(), base, qbase, off.data(), len.data(), cnames.data(), clen.data(), nc, f, 0, textbuf.data(), need + 16);
+    const int64_t got = lra_b200_format_records_ref(&opts, &res, n, names.data(), base, qbase, off.data(), len.data(), cnames.data(), clen.data(), nc, g.seq.data(), g.off.data(), f, print_md, 0,
+                                                    textbuf.data(), need + 16);
     if (got > 0) fwrite(textbuf.data(), 1, (size_t)got, out);
     r0 = r1;
   }

@@ -71,9 +71,71 @@ struct SamOut {
   void cigar(const uint32_t *cig, int n) { static const char ops[] = "MIDNSHP=X"; for (int k = 0; k < n; k++) { u(cig[k] >> 4); s.push_back(ops[cig[k] & 15u]); } }
 };
 
-// fmt: 's' SAM (Alignment::PrintSAM, Alignment.h:658-808), 'p' PAF, 'c' PAF with CG:z: (-p pc; PrintPAF :600-656), 'b' BED (PrintBed :591-598)
+// ---- alignment strings of a record (Alignment::CreateAlignmentStrings, Alignment.h:247-333) rebuilt from its CIGAR: '=' / 'X' columns pair a read base with a
+// reference base, 'I' a read base with '-', 'D' '-' with a reference base -- the column order CreateAlignmentStrings emits and AlignStringsToCigar run-length encodes
+static void mp_alignment_strings(const lra_b200_record &x, const uint32_t *cig, const char *rd, const char *contig, std::string &qs, std::string &as, std::string &ts) {
+  auto sm = [](unsigned char c) { switch (c) { case 'C': case 'c': case 1: case 5: return 1; case 'G': case 'g': case 2: case 6: return 2; case 'T': case 't': case 3: case 7: return 3; default: return 0; } };   // seqMap (SeqUtils.h:4-37)
+  qs.clear(); as.clear(); ts.clear();
+  uint32_t q = x.qStart, t = x.tStart;
+  for (int k = 0; k < x.n_cigar; k++) {
+    const uint32_t len = cig[k] >> 4, op = cig[k] & 15u;
+    for (uint32_t l = 0; l < len; l++) {
+      if (op == 1) { qs.push_back(rd[q++]); ts.push_back('-'); as.push_back(' '); }
+      else if (op == 2) { qs.push_back('-'); ts.push_back(contig[t++]); as.push_back(' '); }
+      else { const char a = rd[q++], b = contig[t++]; qs.push_back(a); ts.push_back(b); as.push_back(sm((unsigned char)a) != sm((unsigned char)b) ? '*' : '|'); }
+    }
+  }
+}
+
+// Alignment::AlignmentStringsToMD (Alignment.h:204-245), literally (including the `a and b or c` precedence of its first scan)
+static void mp_md_string(const std::string &queryStr, const std::string &textStr, SamOut &o) {
+  std::string query(queryStr), text(textStr);
+  for (auto &c : query) c = (char)toupper((unsigned char)c);
+  for (auto &c : text) c = (char)toupper((unsigned char)c);
+  const size_t n = text.size();
+  auto T = [&](size_t i) { return i < n ? text[i] : '\0'; };      // std::string::operator[] at size() is the terminator
+  auto Q = [&](size_t i) { return i < query.size() ? query[i] : '\0'; };
+  size_t s = 0;
+  while (s < n) {
+    size_t i = s;
+    int match = 0;
+    while ((i < n && T(i) == Q(i)) || T(i) == '-') { if (T(i) == Q(i)) match++; i++; if (i > n) break; }
+    o.i(match);
+    s = i;
+    if (T(i) != Q(i) && T(i) != '-' && Q(i) != '-') { i++; if (s < n) o.put(text[s]); }
+    else if (T(i) != '-' && Q(i) == '-') {
+      while (i < n && T(i) != '-' && Q(i) == '-') i++;
+      o.put('^'); o.put(text.data() + s, i - s);
+    }
+    while (i < n && T(i) == '-' && Q(i) == '=') i++;
+    s = i;
+  }
+}
+
+// Alignment::PrintPairwise (Alignment.h:564-589)
+static void mp_print_pairwise(SamOut &o, const char *name, const char *chrom, const lra_b200_record &x, const std::string &qs, const std::string &as, const std::string &ts) {
+  o.put(name); o.put('\n');
+  if (x.n_blocks > 0) { o.put("Interval:\t"); o.put(chrom); o.put(':'); o.u(x.tStart); o.put('-'); o.u(x.tStart + x.tEnd); o.put('\n'); }   // refLen is the end position (refStart = 0, :256-332)
+  auto w10 = [&](long long v) { char b[32]; const int n = snprintf(b, sizeof b, "%10lld", v); o.put(b, (size_t)n); };
+  size_t i = 0; long long q = 0, t = 0;
+  while (i < qs.size()) {
+    const size_t end = qs.size() < i + 50 ? qs.size() : i + 50;
+    size_t gq = 0, gt = 0;
+    for (size_t k = i; k < end; k++) { gq += qs[k] == '-'; gt += ts[k] == '-'; }
+    w10(q + (long long)(x.n_blocks > 0 ? x.qStart : 0)); o.put(" q: "); o.put(qs.data() + i, end - i); o.put('\n');
+    q += (long long)(end - i - gq);
+    o.put("              "); o.put(as.data() + i, end - i); o.put('\n');
+    w10(t + (long long)(x.n_blocks > 0 ? x.tStart : 0)); o.put(" t: "); o.put(ts.data() + i, end - i); o.put('\n');
+    t += (long long)(end - i - gt);
+    o.put('\n');
+    i = end;
+  }
+}
+
+// fmt: 's' SAM (Alignment::PrintSAM, Alignment.h:658-808), 'p' PAF, 'c' PAF with CG:z: (-p pc; PrintPAF :600-656), 'b' BED (PrintBed :591-598), 'a' pairwise (PrintPairwise :564-589; needs the genome)
 static void mp_format_read(SamOut &o, const lra_b200_map_opts *opts, const lra_b200_map_result *res, int r, const char *name, const char *seq, uint32_t L,
-                           const std::vector<const char *> &cname, const uint64_t *contig_len, int runtime, std::string &rc, char fmt, const char *qual) {
+                           const std::vector<const char *> &cname, const uint64_t *contig_len, int runtime, std::string &rc, char fmt, const char *qual,
+                           const char *genome = nullptr, const uint64_t *contig_off = nullptr, bool print_md = false) {
   const unsigned char *RC = mp_revcomp_table();
   const int na = res->status[r] == 0 ? res->n_aln[r] : 0;
   bool printed = false;
@@ -114,12 +176,18 @@ static void mp_format_read(SamOut &o, const lra_b200_map_opts *opts, const lra_b
           o.put('\n');
           continue;
         }
-        o.put(name); o.put('\t');
         const char *rd = seq;
         if (x.strand == 1) {
           if (!have_rc) { rc.resize(L); for (uint32_t k = 0; k < L; k++) rc[L - 1 - k] = (char)RC[(unsigned char)seq[k]]; have_rc = true; }
           rd = rc.data();
         }
+        if (fmt == 'a') {
+          std::string qs, as, ts;
+          if (x.n_blocks > 0) mp_alignment_strings(x, res->cigar + x.cigar_off, rd, genome + contig_off[x.chrom], qs, as, ts);
+          mp_print_pairwise(o, name, x.n_blocks ? cname[x.chrom] : "", x, qs, as, ts);
+          continue;
+        }
+        o.put(name); o.put('\t');
         if (x.n_blocks == 0) { o.put("4\t*\t0\t0\t*\t*\t0\t0\t"); o.put(rd, L); o.put('\t'); if (qual) o.put(qual, L); else o.put('*'); }
         else {
           o.u(x.flag); o.put('\t'); o.put(cname[x.chrom]); o.put('\t'); o.u(x.tStart + 1u); o.put('\t'); o.u((unsigned char)x.mapq); o.put('\t');
@@ -143,6 +211,11 @@ static void mp_format_read(SamOut &o, const lra_b200_map_opts *opts, const lra_b
           o.put("\tTP:A:"); o.put(x.typeofaln == 0 ? 'P' : (x.typeofaln == 1 ? 'S' : 'I'));
           o.put("\tSD:i:"); o.i(x.nSmallDel); o.put("\tME:i:"); o.i(x.nMedDel); o.put("\tLD:i:"); o.i(x.nLargeDel); o.put("\tSI:i:"); o.i(x.nSmallIns); o.put("\tMI:i:"); o.i(x.nMedIns);
           o.put("\tLI:i:"); o.i(x.nLargeIns);
+          if (print_md) {      // opts.printMD (Alignment.h:763-767)
+            std::string qs, as, ts;
+            mp_alignment_strings(x, res->cigar + x.cigar_off, rd, genome + contig_off[x.chrom], qs, as, ts);
+            o.put("\tMD:Z:"); mp_md_string(qs, ts, o);
+          }
           if (ns > 1) o.put("\tSA:Z:");
           for (int ag = ns - 1; ag >= 0; ag--) {
             if (ag == sgi) continue;
@@ -180,10 +253,22 @@ extern "C" int64_t lra_b200_format_records(const lra_b200_map_opts *opts, const 
                                            int32_t fmt, int32_t runtime, char *out, int64_t cap) {
   return lra_b200_format_records_qual(opts, res, n_reads, names, reads_ascii, nullptr, read_off, read_len, contig_names, contig_len, n_contigs, fmt, runtime, out, cap);
 }
+extern "C" int64_t lra_b200_format_records_ref(const lra_b200_map_opts *opts, const lra_b200_map_result *res, int32_t n_reads, const char *names, const char *reads_ascii,
+                                               const char *quals_ascii, const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, const uint64_t *contig_len,
+                                               int32_t n_contigs, const char *genome_ascii, const uint64_t *contig_off, int32_t fmt, int32_t print_md, int32_t runtime, char *out,
+                                               int64_t cap);
 extern "C" int64_t lra_b200_format_records_qual(const lra_b200_map_opts *opts, const lra_b200_map_result *res, int32_t n_reads, const char *names, const char *reads_ascii,
                                                 const char *quals_ascii, const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, const uint64_t *contig_len,
                                                 int32_t n_contigs, int32_t fmt, int32_t runtime, char *out, int64_t cap) {
-  if (fmt != 's' && fmt != 'p' && fmt != 'c' && fmt != 'b') return 0;
+  if (fmt == 'a') return 0;      // the pairwise view needs the reference bases: lra_b200_format_records_ref
+  return lra_b200_format_records_ref(opts, res, n_reads, names, reads_ascii, quals_ascii, read_off, read_len, contig_names, contig_len, n_contigs, nullptr, nullptr, fmt, 0, runtime, out, cap);
+}
+extern "C" int64_t lra_b200_format_records_ref(const lra_b200_map_opts *opts, const lra_b200_map_result *res, int32_t n_reads, const char *names, const char *reads_ascii,
+                                               const char *quals_ascii, const uint64_t *read_off, const uint32_t *read_len, const char *contig_names, const uint64_t *contig_len,
+                                               int32_t n_contigs, const char *genome_ascii, const uint64_t *contig_off, int32_t fmt, int32_t print_md, int32_t runtime, char *out,
+                                               int64_t cap) {
+  if (fmt != 's' && fmt != 'p' && fmt != 'c' && fmt != 'b' && fmt != 'a') return 0;
+  if ((fmt == 'a' || print_md) && (!genome_ascii || !contig_off)) return 0;
   if (!opts || !res || n_reads < 0 || !names || !reads_ascii || !read_off || !read_len || !contig_names) return 0;
   std::vector<const char *> cname(n_contigs);
   { const char *p = contig_names; for (int c = 0; c < n_contigs; c++) { cname[c] = p; p += strlen(p) + 1; } }
@@ -203,7 +288,8 @@ extern "C" int64_t lra_b200_format_records_qual(const lra_b200_map_opts *opts, c
     std::string rc;
     unsigned long long b = 0; for (int r = cut[t]; r < cut[t + 1]; r++) b += read_len[r];
     piece[t].s.reserve((size_t)(b + b / 2) + 4096);
-    for (int r = cut[t]; r < cut[t + 1]; r++) mp_format_read(piece[t], opts, res, r, rname[r], reads_ascii + read_off[r], read_len[r], cname, contig_len, runtime, rc, (char)fmt, quals_ascii ? quals_ascii + read_off[r] : nullptr);
+    for (int r = cut[t]; r < cut[t + 1]; r++) mp_format_read(piece[t], opts, res, r, rname[r], reads_ascii + read_off[r], read_len[r], cname, contig_len, runtime, rc, (char)fmt, quals_ascii ? quals_ascii + read_off[r] : nullptr,
+                                                                     genome_ascii, contig_off, print_md != 0 && fmt == 's');
   };
   if (T == 1) work(0);
   else { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back(work, t); for (auto &x : th) x.join(); }

@@ -53,6 +53,15 @@ def test_cli_index_and_align_match_the_reference(tmp_path):
         ours = lines(o)
         assert len(ours) == len(ref_out[fmt]), fmt
         assert ours == ref_out[fmt], (fmt, [(a, b) for a, b in zip(ours, ref_out[fmt]) if a != b][:2])
+    # the printers that read the reference bases: -p a, --printMD
+    o_ref = str(tmp_path / "ref.a"); o = str(tmp_path / "ours.a")
+    subprocess.run([mapgen.REF_BIN, "align", "-ONT", w["ref"], w["reads"], "-t", "1", "-p", "a", "-o", o_ref], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([CLI, "align", "-ONT", w["ref"], w["reads"], "-p", "a", "-o", o], check=True)
+    assert open(o).read() == open(o_ref).read()
+    o_ref = str(tmp_path / "ref.md"); o = str(tmp_path / "ours.md")
+    subprocess.run([mapgen.REF_BIN, "align", "-ONT", w["ref"], w["reads"], "-t", "1", "-p", "s", "--printMD", "-o", o_ref], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([CLI, "align", "-ONT", w["ref"], w["reads"], "-p", "s", "--printMD", "-o", o], check=True)
+    assert lines(o) == lines(o_ref)
     # the high-accuracy preset through the command line (index written by the CLI's own `index -CCS`)
     wc = mapgen.workdir(tmp_path / "ccs", "ccs", n_reads=120, ref_len=3_000_000, contigs=3, repeats=False, sv=True)
     o_ref = str(tmp_path / "ref_ccs.s"); o = str(tmp_path / "ours_ccs.s")
