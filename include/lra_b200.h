@@ -694,7 +694,9 @@ int lra_b200_store_diagonal_batch(lra_b200_ctx *ctx, const lra_b200_cleaned_list
  * Replaces  TrimSplitChainDiagonal(spchain, refined_clusters)  (ChainRefine.h:189-331; Map_lowacc.h:331, right after Refine_splitchain): split chain c owns
  * chain anchors c_off[c] .. c_off[c+1] (cq / ct = SplitChain::qStart(i) / tStart(i) in sptc order) with SplitChain::Strand strand[c], and the refined anchors
  * m_off[c] .. m_off[c+1] of (q, t) = refined_clusters[c].matches.  q and t come back in the order the reference leaves them (CartesianSort; untouched for a
- * chain of one anchor), keep[i] = 0 marks the anchors it erases, removed[c] = its contribution to the return value. */
+ * chain of one anchor), keep[i] = 0 marks the anchors it erases, removed[c] = its contribution to the return value.  A split chain WITHOUT chain anchors is accepted
+ * on the forward strand (its refined anchors are only sorted, as the reference does) and refused with LRA_B200_EINVAL on the reverse strand, where the reference reads
+ * splitchain[size - 1] of an empty chain. */
 int lra_b200_trim_splitchains_batch(lra_b200_ctx *ctx, const uint32_t *cq, const uint32_t *ct, const uint64_t *c_off, const uint8_t *strand, int32_t n_chains,
                                     uint32_t *q, uint32_t *t, const uint64_t *m_off, uint8_t *keep, int32_t *removed);
 
