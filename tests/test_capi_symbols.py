@@ -60,3 +60,24 @@ def test_every_batch_entry_point_has_a_python_binding():
     for s in declared_symbols():
         if s.endswith("_batch") or s.endswith("_batch_device"):
             assert re.search(r"\.lib\.%s\(" % s, src), s
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/lra_b200.h compiles as C11 (no C++ in the boundary) and a C program that takes the address of every declared entry point links against
+    liblra_b200.so and fails loudly, without a GPU, at lra_b200_create (the reference-side binding of INTEGRATION.md is C++, a cgo / FFI binding would be C)."""
+    import subprocess
+    from lra_b200 import capi
+    names = declared_symbols()
+    src = tmp_path / "abi.c"
+    body = "\n".join("  p[%d] = (void *)%s;" % (i, n) for i, n in enumerate(names))
+    src.write_text('#include <stdio.h>\n#include "lra_b200.h"\nint main(void) {\n  void *p[%d];\n%s\n  lra_b200_ctx *ctx = NULL;\n  int rc = lra_b200_create(&ctx, 0);\n'
+                   '  printf("%%d %%p\\n", rc, p[0]);\n  return rc == LRA_B200_OK ? 0 : 3;\n}\n' % (len(names) + 1, body))
+    exe = tmp_path / "abi"
+    so = capi.library_path()
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), so, "-Wl,-rpath," + os.path.dirname(so)], check=True)
+    import torch
+    p = subprocess.run([str(exe)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert p.returncode == 0
+    else:
+        assert p.returncode == 3, (p.returncode, p.stdout, p.stderr)      # LRA_B200_ECUDA: no CPU fallback
